@@ -1,0 +1,249 @@
+/*
+ * mcre.h - C ABI of the B200-native Monte Carlo risk engine (libmcre_b200.so).
+ *
+ * The reference (konstantineder/montecarlo-risk-engine) is pure Python on PyTorch
+ * CPU and has no FFI.  The seam this library sits behind is its Python API
+ * (SimulationController.run_simulation, src/controller/controller.py:663-709); the
+ * entry points below are what that API's hot loops are replaced by.  Each one cites
+ * the reference code whose work it takes over.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All `const double*` /
+ *     `const int32_t*` inputs of *_create are HOST pointers (copied to the device);
+ *     all `d_*` pointers are DEVICE pointers owned by the caller
+ *     (torch.Tensor.data_ptr()).  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, <0 for an invalid argument / plan,
+ *     >0 for a cudaError_t.  mcre_last_error() gives the message (thread local).
+ *   - launches are asynchronous on `stream`; nothing synchronises unless stated.
+ *   - "dual" tables: a model-parameter-dependent scalar is stored as (1+NT) doubles,
+ *     value first, then its tangents w.r.t. the NT model parameters.  NT = 0 when
+ *     sensitivities are off.
+ */
+#ifndef MCRE_H
+#define MCRE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCRE_ABI_VERSION 1
+
+/* ---- enums -------------------------------------------------------------------- */
+enum { MCRE_SCHEME_EULER = 0, MCRE_SCHEME_ANALYTICAL = 2, MCRE_SCHEME_QE = 3 }; /* src/common/enums.py:4-8 */
+enum {
+  MCRE_MODEL_BS = 0,        /* src/models/black_scholes.py       */
+  MCRE_MODEL_BSM = 1,       /* src/models/black_scholes_multi.py */
+  MCRE_MODEL_HESTON = 2,    /* src/models/heston.py              */
+  MCRE_MODEL_VASICEK = 3,   /* src/models/vasicek.py             */
+  MCRE_MODEL_CIRPP = 4,     /* src/models/cirpp.py               */
+  MCRE_MODEL_SCHWARTZ2F = 5 /* src/models/schwartz_two_factor.py */
+};
+
+/* Normal-draw source.  PHILOX: counter-based Philox4x32-10, key=(seed, stream),
+ * counter=(global path id, sub-step, draw block) + Box-Muller in registers.
+ * INJECT: read the reference's own draws (torch.manual_seed(42|43); torch.randn(N,d)
+ * per sub-step, src/engine/engine.py:25, src/models/model.py:47) from device memory:
+ * z[n_sub][n_paths][noise_dim] (and u[n_sub][n_paths] for Heston-QE). */
+enum { MCRE_RNG_PHILOX = 0, MCRE_RNG_INJECT = 1 };
+
+typedef struct {
+  int32_t mode;          /* MCRE_RNG_* */
+  uint64_t seed;         /* Philox key low 64 bits: 42 pre-simulation, 43 main (engine.py:25) */
+  uint64_t stream;       /* Philox key high bits: scenario / sweep index */
+  const double *d_z;     /* INJECT: device, [n_sub][n_paths_total][noise_dim] */
+  const double *d_u;     /* INJECT: device, [n_sub][n_paths_total] (QE uniforms) or NULL */
+  int64_t n_paths_total; /* leading stride of d_z / d_u */
+} mcre_rng;
+
+/* Which slice of the global path range this process simulates (multi-GPU sharding,
+ * SURVEY §8e): global path ids [path_begin, path_begin + n_paths).  Partial sums are
+ * formed per fixed-size chunk of `chunk_paths` global ids and combined in a fixed
+ * binary tree, so results do not depend on the number of GPUs. */
+typedef struct {
+  int64_t path_begin;
+  int64_t n_paths;
+  int32_t chunk_paths; /* multiple of 256; path_begin % chunk_paths == 0 */
+} mcre_shard;
+
+/* ================================================================================
+ * Generic path generator (compatibility / debugging seam)
+ * replaces MonteCarloEngine.generate_paths(), src/engine/engine.py:27-123, and
+ * Model.simulate_time_step_*; materialises paths [n_paths][n_dates][state_dim].
+ * NOT used by the fused hot path.
+ * ============================================================================== */
+typedef struct {
+  int32_t n_models;
+  const int32_t *model_kind;    /* [n_models] MCRE_MODEL_*                                   */
+  const int32_t *model_nassets; /* [n_models] (BSM: number of assets, else 1)                */
+  const double *model_params;   /* concatenated parameters in the reference's order          */
+  const int32_t *model_flags;   /* [n_models] bit0: CIR++ deterministic, bit1: fuzzy smoothing*/
+  int32_t scheme;               /* MCRE_SCHEME_*                                             */
+  int32_t noise_dim, state_dim;
+  int32_t n_sub, n_dates;
+  int32_t n_pre_dates;          /* number of leading dates with dt<=0 (initial state copied) */
+  const double *step_dt;        /* [n_sub] time2 - time1 as the models see it                */
+  const double *step_t1;        /* [n_sub] accumulated start time (engine.py:60)             */
+  const int32_t *step_date;     /* [n_sub] simulation-date index completed by the step or -1 */
+  const double *chol;           /* [n_chol][noise_dim][noise_dim] lower Cholesky factors:
+                                   of the correlation (EULER/QE) or of the step covariance
+                                   (ANALYTICAL, one per distinct dt; model.py:50-73)         */
+  const int32_t *step_chol;     /* [n_sub] index into chol                                   */
+  const double *step_aux;       /* [n_sub][n_models][4] per-step model scalars:
+                                   [0] CIR++ psi(t1) | Schwartz log F0(t2)
+                                   [1],[2] deterministic CIR++ lambda_mkt(t1), lambda_mkt(t2)
+                                   [3] Vasicek / Hull-White mean level theta(t1)             */
+  const double *init_state;     /* [state_dim]                                               */
+} mcre_paths_desc;
+
+int mcre_generate_paths(const mcre_paths_desc *desc, const mcre_rng *rng, const mcre_shard *shard,
+                        double *d_paths /* [n_paths][n_dates][state_dim] */, void *stream);
+
+/* ================================================================================
+ * Interest-rate / credit family (IRC): Vasicek short rate (+ optional CIR++ intensity)
+ * with bonds, swaps and (later) options on them; PV / CE / EPE / ENE / EEPE / PFE / CVA
+ * with thresholds and MPoR-delayed collateral.
+ * Replaces, fused into one pass per path with no path tensor:
+ *   engine.generate_paths           src/engine/engine.py:27-123
+ *   RequestInterface.resolve_requests   src/request_interface/request_interface.py:115-130
+ *   Bond / InterestRateSwap cashflows   src/products/bond.py:165-214, swap.py:142-172
+ *   SimulationController._evaluate_product  src/controller/controller.py:385-471
+ *   NettingSet.compute_unsecured_exposure_profiles  src/products/netting_set.py:156-184
+ *   Metric.evaluate (PV/CE/EPE/ENE/CVA)  src/metrics/*.py
+ * ============================================================================== */
+#define MCRE_IRC_MAX_SETS 4   /* netting sets per launch (host splits larger books)    */
+#define MCRE_IRC_MAX_UNITS 4  /* regression units (products) per pre-simulation launch  */
+#define MCRE_IRC_MAX_LAG 4    /* max exposure-date lag of the MPoR look-back            */
+
+/* per-date flags */
+#define MCRE_DATE_HAS_CASHFLOW 1
+#define MCRE_DATE_HAS_EXPOSURE 2
+#define MCRE_DATE_HAS_METRIC 4
+#define MCRE_DATE_HAS_REGRESSION 8
+
+/* what the main simulation accumulates */
+#define MCRE_ACC_PV 1
+#define MCRE_ACC_POS 2    /* sum relu(E), sum relu(E)^2 per metric date (CE / EPE / EEPE) */
+#define MCRE_ACC_NEG 4    /* sum -relu(-E) and squares per metric date (ENE)               */
+#define MCRE_ACC_CVA 8
+#define MCRE_ACC_SPILL 16 /* write unsecured exposures [set][metric date][path] (PFE)      */
+
+typedef struct {
+  /* ---- models ---- */
+  int32_t nt;            /* number of tangent directions (0, 4 or 8)                         */
+  int32_t scheme;        /* EULER, or ANALYTICAL (Vasicek only)                              */
+  int32_t has_cir;       /* 0: Vasicek only (noise_dim 1); 1: Vasicek + CIR++ (noise_dim 2)  */
+  int32_t cir_deterministic;
+  int32_t vas_noise, cir_noise; /* column of the correlated noise each model consumes       */
+  const double *vas;     /* dual[4]: r0, sigma, theta, a            (vasicek.py:24-27)       */
+  const double *cir;     /* dual[4]: kappa, theta, sigma, y0        (cirpp.py:42-47)         */
+  const double *cir_init;/* dual[1]: initial y (y0, or lambda_mkt(0) when deterministic)     */
+  const double *chol;    /* dual[4]: L00, L01(=0), L10, L11 of the correlation (model.py:66-73) */
+  /* ---- time grid ---- */
+  int32_t n_sub, n_dates, n_pre_dates;
+  const double *step_dt;       /* [n_sub]                                                    */
+  const int32_t *step_date;    /* [n_sub] date index completed by this sub-step or -1        */
+  const double *step_vas;      /* dual[n_sub][2]: ANALYTICAL decay e^{-a dt}, noise std;
+                                  EULER: theta(t1) (Hull-White extension), unused            */
+  const double *step_cir;      /* dual[n_sub][2]: psi(t1), unused | lambda(t1), lambda(t2)   */
+  /* ---- per simulation date ---- */
+  const int32_t *date_flags;   /* [n_dates]                                                  */
+  const int32_t *date_expo;    /* [n_dates] internal exposure index or -1                    */
+  const int32_t *date_metric;  /* [n_dates] metric-date index or -1                          */
+  const int32_t *date_reg;     /* [n_dates] regression-date index or -1 (pre-simulation)     */
+  const int32_t *date_float_off; /* [n_dates+1] CSR offsets into the float-period pool       */
+  const double *float_coef;    /* dual[n_float][2]: alpha, B of P(t1,t2;r)=exp(alpha-B r)    */
+  const double *float_inv_tau; /* [n_float] 1/(t2-t1) of the LIBOR period (vasicek.py:147-151)*/
+  /* ---- netting sets (main simulation) ---- */
+  int32_t n_sets;
+  int32_t n_expo, n_metric;
+  int32_t acc_flags;           /* MCRE_ACC_*                                                 */
+  const double *set_fix;       /* [n_sets][n_dates] fixed cashflow amount paid at the date   */
+  const double *set_float;     /* [n_sets][n_float] weight on LIBOR_j * 1 (already * dt)     */
+  const double *set_threshold; /* [n_sets]                                                   */
+  const int32_t *set_flags;    /* [n_sets] bit0 collateralised, bit1 CVA applies             */
+  const int32_t *set_lag;      /* [n_sets][n_metric] exposure-index lag of the collateral date, -1: none */
+  const double *expo_coef;     /* dual[n_expo][n_sets][3] netted regression coefficients     */
+  const double *expo_basis;    /* [n_expo][2] shift, scale of the explanatory variable       */
+  const double *cva_coef;      /* dual[n_metric][2]: C_k, B_k of S(t_k,t_k+1|y)=C exp(-B y) (cirpp.py:246-285) */
+  double lgd;                  /* 1 - recovery (cva_metric.py:97)                            */
+  /* ---- regression units (pre-simulation) ---- */
+  int32_t n_units, n_reg;
+  const double *unit_fix;      /* [n_units][n_dates]                                         */
+  const double *unit_float;    /* [n_units][n_float]                                         */
+  const int32_t *unit_last_reg;/* [n_units] number of regression dates that see cashflows    */
+  const double *reg_basis;     /* [n_reg][2] shift, scale                                    */
+} mcre_irc_desc;
+
+typedef struct mcre_irc_plan mcre_irc_plan;
+
+int mcre_irc_create(const mcre_irc_desc *desc, mcre_irc_plan **out);
+void mcre_irc_destroy(mcre_irc_plan *plan);
+
+/* Number of accumulator slots of the main simulation / pre-simulation moments. */
+int64_t mcre_irc_main_slots(const mcre_irc_plan *plan);
+int64_t mcre_irc_presim_slots(const mcre_irc_plan *plan);
+/* Bytes of device scratch the pre-simulation needs for `n_paths` local paths. */
+int64_t mcre_irc_presim_scratch_bytes(const mcre_irc_plan *plan, int64_t n_paths);
+int64_t mcre_irc_partial_bytes(const mcre_irc_plan *plan, int64_t n_paths, int32_t chunk_paths, int presim);
+
+/* Pre-simulation (replaces controller._perform_regression, controller.py:272-383, up to
+ * the least-squares solve): accumulates for every regression date k the Gram moments
+ * sum u^0..u^4 and, per unit, sum u^j * Y_k with Y_k = N(t_k) * fp32 suffix sum of the
+ * discounted future cashflows (the FP32 accumulation of controller.py:312-351 is
+ * reproduced bit for bit).  d_moments: [n_reg][5 + 3*n_units] (+ tangents when nt>0).
+ * d_scratch / d_partial sized by the helpers above. */
+int mcre_irc_presim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard,
+                    void *d_scratch, double *d_partial, double *d_moments, void *stream);
+
+/* Upload regression coefficients (after the host solved the normal equations). */
+int mcre_irc_set_coefficients(mcre_irc_plan *plan, const double *expo_coef /* host, dual[n_expo][n_sets][3] */,
+                              void *stream);
+
+/* Main simulation.  d_acc, d_shift: [mcre_irc_main_slots]; d_spill [n_sets][n_metric][n_paths]
+ * or NULL.  Slot layout (NS = n_sets rounded up to 1, 2 or 4; w = 4 + 2*nt):
+ *   [n_metric][NS][w] : sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2), d pos[nt], d neg[nt]
+ *   [NS][w]           : same for (pv, cva) per path totals
+ * with c = d_shift[slot] = the value on global path 0 (written by a one-path pilot launch), so
+ * mean = c + sum/N and the unbiased variance (metric.py:26-35) has no cancellation. */
+int mcre_irc_mainsim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard,
+                     double *d_partial, double *d_acc, double *d_shift, double *d_spill, void *stream);
+
+/* ================================================================================
+ * Exact order statistics per row (PFE), replaces torch.sort + index in
+ * PFEMetric.evaluate_numerically, src/metrics/pfe_metric.py:59-71.
+ * MSB-first radix select on the order-preserving 64-bit image of the doubles, 8 bits
+ * per pass.  Multi-GPU: the caller all-reduces d_hist between count and scan.
+ * ============================================================================== */
+typedef struct mcre_select_plan mcre_select_plan;
+int mcre_select_create(int32_t n_rows, int32_t n_ranks_per_row, mcre_select_plan **out);
+void mcre_select_destroy(mcre_select_plan *p);
+/* ranks: host [n_rows][n_ranks_per_row] global 0-based ranks (may repeat). */
+int mcre_select_begin(mcre_select_plan *p, const int64_t *ranks, void *stream);
+/* one pass = count (fills d_hist [n_rows][n_ranks_per_row][256] uint64) then scan. */
+int mcre_select_count(mcre_select_plan *p, const double *d_values, int64_t row_stride, int64_t n_local,
+                      int32_t pass, uint64_t *d_hist, void *stream);
+int mcre_select_scan(mcre_select_plan *p, int32_t pass, const uint64_t *d_hist, void *stream);
+/* after 8 passes: d_out [n_rows][n_ranks_per_row] the selected values. */
+int mcre_select_finish(mcre_select_plan *p, double *d_out, void *stream);
+
+/* ================================================================================
+ * Utilities
+ * ============================================================================== */
+/* Fixed-order binary-tree sum over chunks: d_partial [n_chunks][n_slots] -> d_out [n_slots]. */
+int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64_t n_slots, double *d_out, void *stream);
+/* Measured FP64 FMA throughput of this GPU (TFLOP/s) from a register-resident DFMA loop;
+ * the roofline denominator for the FP64-pipe-bound kernels. */
+int mcre_dfma_peak(double *tflops_out, void *stream);
+/* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
+int64_t mcre_launch_count(void);
+const char *mcre_last_error(void);
+int mcre_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCRE_H */

@@ -1,0 +1,220 @@
+"""SimulationController with the reference's constructor, attributes and result layout
+(reference: src/controller/controller.py:21-709), executing on hand-written sm_100a
+kernels through the C-ABI library instead of per-sub-step torch ops.
+
+Flow of run_simulation():
+  1. pick the backend (model / product family) and lower the run into flat plan tables
+  2. pre-simulation pass (Philox key 42): Gram / right-hand-side moments per regression
+     date -> host solve of the (degree+1)^2 normal equations
+  3. main pass (Philox key 43): fused path stepping + cashflows + exposure + netting /
+     collateral + metric integrands, block-reduced into per-date accumulators
+  4. finish metrics on the host from O(T) sums; assemble SimulationResults
+"""
+from __future__ import annotations
+
+import logging
+import time
+from collections import defaultdict
+from typing import Sequence
+
+import numpy as np
+
+from common.packages import *
+from common.enums import SimulationScheme
+from controller.simulation_results import SimulationResults
+from maths.regression import PolyomialRegression, RegressionFunction
+from metrics.metric import Metric, MetricType
+from metrics.risk_metrics import RiskMetrics
+from models.model import Model
+from models.model_config import ModelConfig
+from products.netting_set import NettingSet
+
+logger = logging.getLogger(__name__)
+
+_SINGLE_EVAL = {MetricType.PV, MetricType.CVA, MetricType.EEPE, MetricType.CE}
+
+
+class SimulationController:
+    def __init__(self, netting_sets: Sequence[NettingSet], model: Model, risk_metrics: RiskMetrics,
+                 num_paths_mainsim: int, num_paths_presim: int, num_steps: int,
+                 simulation_scheme: SimulationScheme, differentiate: bool = False,
+                 regression_function: RegressionFunction = PolyomialRegression(degree=2)):
+        self.risk_metrics = risk_metrics
+        netting_sets = list(netting_sets)
+        if len(netting_sets) == 0:
+            raise ValueError("Provide at least one netting set.")
+        seen = set()
+        for ns in netting_sets:
+            for p in ns.products:
+                if id(p) in seen:
+                    raise ValueError("A product instance cannot belong to more than one netting set.")
+                seen.add(id(p))
+        self.netting_sets = netting_sets
+        self.products = [p for ns in netting_sets for p in ns.products]
+        self.product_to_netting_set_idx = [i for i, ns in enumerate(netting_sets) for _ in ns.products]
+
+        # exposure grids: metric dates, plus (t - MPoR) look-back dates of collateralised sets
+        self.metric_exposure_timeline = risk_metrics.exposure_timeline.clone()
+        self.exposure_timeline = self._build_internal_exposure_timeline()
+        self._exposure_time_to_idx = {float(t): i for i, t in enumerate(self.exposure_timeline)}
+        self.metric_exposure_indices = torch.tensor(
+            [self._exposure_time_to_idx[float(t)] for t in self.metric_exposure_timeline],
+            dtype=torch.long, device=device)
+        self.netting_set_delayed_exposure_indices = self._build_netting_set_delayed_exposure_indices()
+
+        if risk_metrics.any_xva:
+            if not isinstance(model, ModelConfig):
+                raise Exception("ModelConfig needs to be provided for xVA valuation.")
+            if not all(cp in model.id_to_model for cp in risk_metrics.counterparty_ids):
+                raise Exception("Not all models set for xVA valuation.")
+
+        self.model = model
+        self.num_paths_presim = num_paths_presim
+        self.num_paths_mainsim = num_paths_mainsim
+        self.num_steps = num_steps
+        self.simulation_scheme = simulation_scheme
+        self.differentiate = differentiate
+        self.regression_function = regression_function
+        self.requires_higher_order_derivatives = False
+        for pid, prod in enumerate(self.products):
+            prod.product_id = pid
+        if differentiate:
+            self.model.requires_grad()
+
+        # regression coefficients per product: [exposure date, product state, basis]
+        self.regression_coeffs = []
+        for prod in self.products:
+            prod._allocate_regression_coeffs(regression_function)
+            self.regression_coeffs.append(torch.zeros(
+                (len(self.exposure_timeline), prod.get_num_states(), regression_function.get_degree()),
+                dtype=FLOAT, device=device))
+
+        # simulation grid = product modelling dates U exposure dates, merged on float equality
+        times = {float(t) for p in self.products for t in p.modeling_timeline}
+        times |= {float(t) for t in self.exposure_timeline}
+        self.simulation_timeline = torch.tensor(sorted(times), dtype=FLOAT, device=device)
+        self.requires_regression = any(self._product_requires_regression(p) for p in self.products)
+
+        # ---- execution knobs of this implementation (not in the reference) ----
+        #: Philox key high word: scenario / sweep index (disjoint streams per scenario)
+        self.rng_stream = 0
+        #: parity mode: {"pre": Tensor[n_sub, N_pre, d], "main": Tensor[n_sub, N_main, d]} on the GPU
+        self.injected_normals = None
+        #: pre-simulation scratch is bounded by processing this many local paths at a time
+        self.presim_batch_paths = 1 << 18
+        self.last_timings = {}
+
+    # ------------------------------------------------------------------ timelines
+    def _build_internal_exposure_timeline(self):
+        if not self.risk_metrics.requires_exposure_profiles():
+            return self.risk_metrics.exposure_timeline.clone()
+        times = {float(t) for t in self.risk_metrics.exposure_timeline}
+        for ns in self.netting_sets:
+            if ns.is_collateralized():
+                times.update(float(t) for t in ns.get_collateral_query_times(self.risk_metrics.exposure_timeline))
+        return torch.tensor(sorted(times), dtype=FLOAT, device=device)
+
+    def _build_netting_set_delayed_exposure_indices(self):
+        out = []
+        n = len(self.metric_exposure_timeline)
+        for ns in self.netting_sets:
+            idx = torch.full((n,), -1, dtype=torch.long, device=device)
+            if ns.is_collateralized():
+                delayed = self.metric_exposure_timeline - ns.margin_period_of_risk
+                for m in range(n):
+                    if float(delayed[m]) >= 0.0:
+                        idx[m] = self._exposure_time_to_idx[float(delayed[m])]
+            out.append(idx)
+        return out
+
+    @staticmethod
+    def _make_unique_names(base_names):
+        counts, out = defaultdict(int), []
+        for name in base_names:
+            counts[name] += 1
+            out.append(name if counts[name] == 1 else f"{name}#{counts[name]}")
+        return out
+
+    # ------------------------------------------------------------------ dispatch rules
+    def _product_requires_regression(self, product):
+        if len(product.regression_timeline) > 0:
+            return True
+        if not self.risk_metrics.requires_exposure_profiles():
+            return False
+        return not self._can_use_analytic_exposure_for_product(product)
+
+    def _can_use_analytic_exposure_for_product(self, product):
+        ok = {MetricType.PV, MetricType.EPE, MetricType.PFE}
+        return all(m.metric_type in ok for m in self.risk_metrics.metrics) and product.supports_analytic_exposure(self.model)
+
+    def _can_evaluate_metric_analytically_for_product(self, product, metric):
+        return (metric.metric_type == MetricType.PV
+                and metric.evaluation_type == Metric.EvaluationType.ANALYTICAL
+                and product.supports_analytic_pv(self.model))
+
+    def _can_skip_monte_carlo_for_product(self, product):
+        if self.risk_metrics.requires_exposure_profiles():
+            return False
+        return all(self._can_evaluate_metric_analytically_for_product(product, m) for m in self.risk_metrics.metrics)
+
+    def compute_higher_derivatives(self):
+        self.requires_higher_order_derivatives = True
+
+    def inject_normals(self, pre=None, main=None):
+        """Parity mode: use the given standard-normal draws
+        [n_sub, N, noise_dim] (the reference's torch.randn stream) instead of Philox."""
+        from mcre.runtime import compute_device
+        dev = compute_device()
+        self.injected_normals = {}
+        if pre is not None:
+            self.injected_normals["pre"] = torch.as_tensor(pre, dtype=torch.float64).to(dev).contiguous()
+        if main is not None:
+            self.injected_normals["main"] = torch.as_tensor(main, dtype=torch.float64).to(dev).contiguous()
+
+    # ------------------------------------------------------------------ run
+    def _select_backend(self):
+        from mcre.irc import IrcBackend
+        if IrcBackend.supports(self):
+            return IrcBackend(self)
+        from mcre.equity import EquityBackend
+        if EquityBackend.supports(self):
+            return EquityBackend(self)
+        raise NotImplementedError(
+            f"No CUDA backend for model {type(self.model).__name__} with products "
+            f"{sorted({type(p).__name__ for p in self.products})}")
+
+    def run_simulation(self) -> SimulationResults:
+        t0 = time.perf_counter()
+        if self.requires_higher_order_derivatives:
+            raise NotImplementedError("second-order sensitivities are not implemented (SURVEY §8f item 4)")
+        mc_products = [p for p in self.products if not self._can_skip_monte_carlo_for_product(p)]
+        analytic = [[0.0 for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
+        has_pathwise = [False] * len(self.netting_sets)
+        for pi, p in enumerate(self.products):
+            si = self.product_to_netting_set_idx[pi]
+            if self._can_skip_monte_carlo_for_product(p):
+                for mi, _ in enumerate(self.risk_metrics.metrics):
+                    analytic[si][mi] += float(p.compute_pv_analytically(self.model).squeeze())
+            else:
+                has_pathwise[si] = True
+        raw, timings = None, {"preprocessing": 0.0, "path_generation": 0.0, "request_resolution": 0.0}
+        if mc_products:
+            backend = self._select_backend()
+            raw, timings = backend.run()
+        t3 = time.perf_counter()
+        from mcre.finish import finish_results
+        results, grads = finish_results(self, raw, analytic, has_pathwise)
+        t4 = time.perf_counter()
+        timings["valuation"] = t4 - t3
+        timings["total"] = t4 - t0
+        self.last_timings = timings
+        logger.info(
+            "Simulation completed for %d netting set(s) and %d product(s): "
+            "preprocessing=%.6fs path_generation=%.6fs request_resolution=%.6fs valuation=%.6fs total=%.6fs",
+            len(self.netting_sets), len(self.products), timings["preprocessing"], timings["path_generation"],
+            timings["request_resolution"], timings["valuation"], timings["total"])
+        return SimulationResults(
+            results, grads, [],
+            netting_set_names=self._make_unique_names([ns.get_name() for ns in self.netting_sets]),
+            metric_names=self._make_unique_names([m.get_name() for m in self.risk_metrics.metrics]),
+            model_param_names=self.model.get_model_param_names())

@@ -1,0 +1,92 @@
+// Counter-based normal stream: Philox4x32-10 + Box-Muller, entirely in registers.
+//
+// Stream addressing (shared with oracle/philox.py, bit for bit on the uniforms):
+//   key     = (low 32 bits of seed, low 32 bits of stream)
+//   counter = (path_lo, path_hi, block, kind)      kind 0: normals, 1: uniforms
+//   normal  #n of a path = element (n & 1) of BoxMuller(block n >> 1)
+//   uniform #m of a path = element (m & 1) of the two 53-bit uniforms of block m >> 1
+// so a draw depends only on (seed, stream, global path id, draw index): sharding paths
+// over GPUs or replaying a path in a second pass reproduces it exactly.  Takes the place
+// of torch.manual_seed(42|43) + torch.randn(N, d) per sub-step (src/engine/engine.py:25,
+// src/models/model.py:47).
+#pragma once
+#include <cstdint>
+
+namespace mcre {
+
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ static inline void round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                               uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), hi1 = __umulhi(M1, c2);
+#else
+    uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c0) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c2) >> 32);
+#endif
+    uint32_t lo0 = M0 * c0, lo1 = M1 * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+  }
+  __host__ __device__ inline void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t out[4]) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      round(c0, c1, c2, c3, a, b);
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+
+// 53-bit uniform in (0,1): (k + 0.5) * 2^-53, k from the top 53 bits of (hi:lo).
+__host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
+  uint64_t k = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)k + 0.5) * 1.1102230246251565e-16;
+}
+
+struct RngDev {
+  int mode;             // MCRE_RNG_*
+  uint32_t k0, k1;
+  const double *z;      // injected normals [n_sub][n_total][d]
+  const double *u;      // injected uniforms [n_sub][n_total]
+  long long n_total;
+};
+
+// Sequential normal stream of one path.  All threads of a warp advance in lockstep, so
+// the spare-normal branch is uniform.
+struct NormalStream {
+  Philox ph;
+  uint32_t p_lo, p_hi;
+  uint32_t n;       // next normal index
+  double spare;
+  __device__ inline void init(const RngDev &r, unsigned long long gpath, uint32_t first = 0) {
+    ph.k0 = r.k0; ph.k1 = r.k1;
+    p_lo = (uint32_t)gpath; p_hi = (uint32_t)(gpath >> 32);
+    n = first; spare = 0.0;
+  }
+  __device__ inline void pair(uint32_t block, double &z0, double &z1) const {
+    uint32_t o[4];
+    ph(p_lo, p_hi, block, 0u, o);
+    double u1 = u53(o[0], o[1]), u2 = u53(o[2], o[3]);
+    double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = rad * c; z1 = rad * s;
+  }
+  __device__ inline double next() {
+    double z;
+    if ((n & 1u) == 0u) { pair(n >> 1, z, spare); } else { z = spare; }
+    ++n;
+    return z;
+  }
+  // two consecutive normals starting at an even index (noise_dim 2 fast path)
+  __device__ inline void next2(double &z0, double &z1) { pair(n >> 1, z0, z1); n += 2; }
+  __device__ inline double uniform(uint32_t m) const {
+    uint32_t o[4];
+    ph(p_lo, p_hi, m >> 1, 1u, o);
+    return (m & 1u) ? u53(o[2], o[3]) : u53(o[0], o[1]);
+  }
+};
+
+}  // namespace mcre

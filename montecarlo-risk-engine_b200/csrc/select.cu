@@ -1,0 +1,153 @@
+// Exact order statistics per row by MSB-first radix select (8 bits per pass, 8 passes)
+// on the order-preserving 64-bit image of IEEE doubles.
+//
+// Takes the place of torch.sort(e).values[q_index (+-1)] in PFEMetric
+// (src/metrics/pfe_metric.py:59-71): the PFE needs three adjacent order statistics per
+// exposure date, not a sorted array.  Each pass is count (histogram of the next digit
+// among elements matching the prefix found so far) + scan (pick the bucket holding the
+// wanted rank).  With paths sharded over GPUs the caller sums the histograms over ranks
+// between the two steps; everything else is local.
+#include "common.cuh"
+
+namespace mcre {
+
+__device__ __forceinline__ unsigned long long key_of(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double value_of(unsigned long long k) {
+  unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+constexpr int SEL_MAX_R = 4;
+
+// grid: (blocks_x, n_rows).  hist: [n_rows][R][256].
+__global__ void __launch_bounds__(256) select_count_kernel(const double *values, long long row_stride,
+                                                           long long n_local, int R, int pass,
+                                                           const unsigned long long *prefix,
+                                                           unsigned long long *hist) {
+  __shared__ unsigned int sh[SEL_MAX_R][256];
+  __shared__ unsigned long long pre[SEL_MAX_R];
+  __shared__ int rep[SEL_MAX_R];
+  const int row = blockIdx.y;
+  for (int i = threadIdx.x; i < SEL_MAX_R * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
+  if (threadIdx.x < R) pre[threadIdx.x] = prefix[(size_t)row * R + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // rank slots that share a prefix are counted once (adjacent ranks usually do)
+    for (int r = 0; r < R; ++r) {
+      rep[r] = r;
+      for (int q = 0; q < r; ++q) if (pre[q] == pre[r]) { rep[r] = q; break; }
+    }
+  }
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const double *v = values + (size_t)row * row_stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long k = key_of(v[i]);
+    const unsigned int digit = (unsigned int)(k >> shift) & 0xffu;
+    for (int r = 0; r < R; ++r) {
+      if (rep[r] != r) continue;
+      const bool match = pass == 0 || ((k ^ pre[r]) >> (shift + 8)) == 0ull;
+      if (match) atomicAdd(&sh[r][digit], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R * 256; i += blockDim.x) {
+    const int r = i >> 8, d = i & 255;
+    const unsigned int c = sh[rep[r]][d];
+    if (c) atomicAdd(&hist[((size_t)row * R + r) * 256 + d], (unsigned long long)c);
+  }
+}
+
+// one thread per (row, rank slot)
+__global__ void select_scan_kernel(int n, int pass, const unsigned long long *hist, unsigned long long *prefix,
+                                   long long *remaining) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long *h = hist + (size_t)i * 256;
+  long long k = remaining[i];
+  unsigned long long cum = 0;
+  int d = 0;
+  for (; d < 255; ++d) {
+    if (cum + h[d] > (unsigned long long)k) break;
+    cum += h[d];
+  }
+  remaining[i] = k - (long long)cum;
+  prefix[i] |= (unsigned long long)d << (56 - 8 * pass);
+}
+
+__global__ void select_finish_kernel(int n, const unsigned long long *prefix, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = value_of(prefix[i]);
+}
+
+}  // namespace mcre
+
+using namespace mcre;
+
+struct mcre_select_plan {
+  int n_rows, R;
+  unsigned long long *prefix = nullptr;
+  long long *remaining = nullptr;
+};
+
+extern "C" int mcre_select_create(int32_t n_rows, int32_t n_ranks_per_row, mcre_select_plan **out) {
+  if (!out || n_rows <= 0 || n_ranks_per_row <= 0 || n_ranks_per_row > SEL_MAX_R)
+    return fail(-1, "select: invalid shape%s", "");
+  mcre_select_plan *p = new mcre_select_plan();
+  p->n_rows = n_rows; p->R = n_ranks_per_row;
+  const size_t n = (size_t)n_rows * n_ranks_per_row;
+  MCRE_CUDA(cudaMalloc((void **)&p->prefix, n * 8));
+  MCRE_CUDA(cudaMalloc((void **)&p->remaining, n * 8));
+  *out = p;
+  return 0;
+}
+extern "C" void mcre_select_destroy(mcre_select_plan *p) {
+  if (!p) return;
+  if (p->prefix) cudaFree(p->prefix);
+  if (p->remaining) cudaFree(p->remaining);
+  delete p;
+}
+extern "C" int mcre_select_begin(mcre_select_plan *p, const int64_t *ranks, void *stream) {
+  if (!p || !ranks) return fail(-1, "null argument%s", "");
+  const size_t n = (size_t)p->n_rows * p->R;
+  MCRE_CUDA(cudaMemsetAsync(p->prefix, 0, n * 8, (cudaStream_t)stream));
+  MCRE_CUDA(cudaMemcpyAsync(p->remaining, ranks, n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  MCRE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // `ranks` is pageable host memory
+  return 0;
+}
+extern "C" int mcre_select_count(mcre_select_plan *p, const double *d_values, int64_t row_stride, int64_t n_local,
+                                 int32_t pass, uint64_t *d_hist, void *stream) {
+  if (!p || !d_hist || pass < 0 || pass > 7) return fail(-1, "select: bad argument%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  MCRE_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)p->n_rows * p->R * 256 * 8, st));
+  if (n_local <= 0) return 0;
+  if (!d_values) return fail(-1, "select: null values%s", "");
+  long long bx = (n_local + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (long long)sm_count() * 16 / p->n_rows + 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)p->n_rows);
+  select_count_kernel<<<grid, 256, 0, st>>>(d_values, row_stride, n_local, p->R, pass, p->prefix,
+                                            (unsigned long long *)d_hist);
+  MCRE_LAUNCHED();
+  return 0;
+}
+extern "C" int mcre_select_scan(mcre_select_plan *p, int32_t pass, const uint64_t *d_hist, void *stream) {
+  if (!p || !d_hist) return fail(-1, "null argument%s", "");
+  const int n = p->n_rows * p->R;
+  select_scan_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, pass, (const unsigned long long *)d_hist,
+                                                                        p->prefix, p->remaining);
+  MCRE_LAUNCHED();
+  return 0;
+}
+extern "C" int mcre_select_finish(mcre_select_plan *p, double *d_out, void *stream) {
+  if (!p || !d_out) return fail(-1, "null argument%s", "");
+  const int n = p->n_rows * p->R;
+  select_finish_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, p->prefix, d_out);
+  MCRE_LAUNCHED();
+  return 0;
+}

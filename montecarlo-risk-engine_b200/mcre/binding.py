@@ -1,0 +1,120 @@
+"""ctypes binding of libmcre_b200.so (include/mcre.h).
+
+The library is the product: if it is missing or fails to load, everything that
+simulates raises.  There is deliberately no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libmcre_b200.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+class McreError(RuntimeError):
+    pass
+
+
+class Rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("seed", C.c_uint64), ("stream", C.c_uint64),
+                ("d_z", C.c_void_p), ("d_u", C.c_void_p), ("n_paths_total", C.c_int64)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("path_begin", C.c_int64), ("n_paths", C.c_int64), ("chunk_paths", C.c_int32)]
+
+
+class IrcDesc(C.Structure):
+    _fields_ = [
+        ("nt", C.c_int32), ("scheme", C.c_int32), ("has_cir", C.c_int32), ("cir_deterministic", C.c_int32),
+        ("vas_noise", C.c_int32), ("cir_noise", C.c_int32),
+        ("vas", c_dp), ("cir", c_dp), ("cir_init", c_dp), ("chol", c_dp),
+        ("n_sub", C.c_int32), ("n_dates", C.c_int32), ("n_pre_dates", C.c_int32),
+        ("step_dt", c_dp), ("step_date", c_ip), ("step_vas", c_dp), ("step_cir", c_dp),
+        ("date_flags", c_ip), ("date_expo", c_ip), ("date_metric", c_ip), ("date_reg", c_ip),
+        ("date_float_off", c_ip), ("float_coef", c_dp), ("float_inv_tau", c_dp),
+        ("n_sets", C.c_int32), ("n_expo", C.c_int32), ("n_metric", C.c_int32), ("acc_flags", C.c_int32),
+        ("set_fix", c_dp), ("set_float", c_dp), ("set_threshold", c_dp), ("set_flags", c_ip), ("set_lag", c_ip),
+        ("expo_coef", c_dp), ("expo_basis", c_dp), ("cva_coef", c_dp), ("lgd", C.c_double),
+        ("n_units", C.c_int32), ("n_reg", C.c_int32),
+        ("unit_fix", c_dp), ("unit_float", c_dp), ("unit_last_reg", c_ip), ("reg_basis", c_dp),
+    ]
+
+
+RNG_PHILOX, RNG_INJECT = 0, 1
+SCHEME_EULER, SCHEME_ANALYTICAL, SCHEME_QE = 0, 2, 3
+DATE_HAS_CASHFLOW, DATE_HAS_EXPOSURE, DATE_HAS_METRIC, DATE_HAS_REGRESSION = 1, 2, 4, 8
+ACC_PV, ACC_POS, ACC_NEG, ACC_CVA, ACC_SPILL = 1, 2, 4, 8, 16
+IRC_MAX_SETS, IRC_MAX_UNITS, IRC_MAX_LAG = 4, 4, 4
+
+_lib = None
+
+#: every symbol include/mcre.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "mcre_generate_paths",
+    "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
+    "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim",
+    "mcre_irc_set_coefficients", "mcre_irc_mainsim",
+    "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
+    "mcre_select_scan", "mcre_select_finish",
+    "mcre_tree_reduce", "mcre_dfma_peak", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
+]
+
+
+def lib():
+    """Load (once) and return the CUDA library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McreError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the Monte Carlo hot path.")
+    L = C.CDLL(LIB_PATH)
+    L.mcre_last_error.restype = C.c_char_p
+    L.mcre_launch_count.restype = C.c_int64
+    L.mcre_irc_main_slots.restype = C.c_int64
+    L.mcre_irc_main_slots.argtypes = [C.c_void_p]
+    L.mcre_irc_presim_slots.restype = C.c_int64
+    L.mcre_irc_presim_slots.argtypes = [C.c_void_p]
+    L.mcre_irc_presim_scratch_bytes.restype = C.c_int64
+    L.mcre_irc_presim_scratch_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.mcre_irc_partial_bytes.restype = C.c_int64
+    L.mcre_irc_partial_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int]
+    L.mcre_irc_create.argtypes = [C.POINTER(IrcDesc), C.POINTER(C.c_void_p)]
+    L.mcre_irc_destroy.argtypes = [C.c_void_p]
+    L.mcre_irc_destroy.restype = None
+    L.mcre_irc_presim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
+    L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_tree_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise McreError(f"libmcre_b200 error {rc}: {lib().mcre_last_error().decode()}")
+
+
+def as_dp(a):
+    """numpy float64 array -> (keepalive, double*)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_dp)
+
+
+def as_ip(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+def launch_count():
+    return int(lib().mcre_launch_count())

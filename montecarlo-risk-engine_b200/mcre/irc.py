@@ -1,0 +1,521 @@
+"""Plan compiler + driver for the interest-rate / credit family (IRC).
+
+Lowers (Vasicek [+ CIR++] model, bonds / swaps, netting sets, metrics, timelines) into
+the flat tables of ``mcre_irc_desc`` (include/mcre.h) and drives the two fused CUDA
+passes: pre-simulation moments -> host solve of the 3x3 normal equations -> main
+simulation.  What it takes the place of in the reference:
+  request collection        src/request_interface/request_interface.py:22-97
+  _perform_regression       src/controller/controller.py:272-383
+  evaluate_products         src/controller/controller.py:565-661
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from common.enums import SimulationScheme
+from mcre import binding as B
+from mcre import runtime as RT
+from mcre.dual import D, cholesky_dual
+from mcre.timegrid import build_time_grid
+from metrics.metric import MetricType
+from models.cirpp import CIRPPModel
+from models.model_config import ModelConfig
+from models.vasicek import VasicekModel
+from products.bond import Bond
+from products.swap import InterestRateSwap, IRSType
+
+CHUNK_PATHS = 4096
+
+
+def _packs(duals):
+    return np.concatenate([d.pack() for d in duals]) if duals else np.zeros(0)
+
+
+class LinearLeg:
+    """Fixed and floating cashflow weights of one linear product on its payment dates."""
+
+    def __init__(self):
+        self.fixed = {}   # date -> amount
+        self.floating = {}  # date -> {(t1, t2): weight}
+
+    def add_bond(self, bond: Bond, sign: float):
+        dates = bond.payment_dates.tolist()
+        accr = bond.accrual_fractions()
+        last = len(dates) - 1
+        if bond.is_fixed():
+            k = float(bond.fixed_rate)
+            for i, (d, a) in enumerate(zip(dates, accr)):
+                amt = k * a + (float(bond.notional) if (bond.pays_notional and i == last) else 0.0)
+                self.fixed[d] = self.fixed.get(d, 0.0) + sign * amt
+        else:
+            for i, (d, a, per) in enumerate(zip(dates, accr, bond.libor_periods())):
+                self.floating.setdefault(d, {})
+                self.floating[d][per] = self.floating[d].get(per, 0.0) + sign * a
+                if bond.pays_notional and i == last:
+                    self.fixed[d] = self.fixed.get(d, 0.0) + sign * float(bond.notional)
+
+
+def linear_leg_of(product):
+    leg = LinearLeg()
+    if isinstance(product, Bond):
+        leg.add_bond(product, 1.0)
+    elif isinstance(product, InterestRateSwap):
+        s = 1.0 if product.irs_type == IRSType.PAYER else -1.0
+        leg.add_bond(product.floating_leg, s)
+        leg.add_bond(product.fixed_leg, -s)
+    else:
+        raise TypeError(type(product))
+    return leg
+
+
+def split_model(model):
+    """(vasicek, cir or None, vas_index, cir_index) or None if not an IRC model."""
+    if isinstance(model, VasicekModel):
+        return model, None, 0, -1
+    if isinstance(model, ModelConfig):
+        ms = model.models
+        vas = [i for i, m in enumerate(ms) if isinstance(m, VasicekModel)]
+        cir = [i for i, m in enumerate(ms) if isinstance(m, CIRPPModel)]
+        if len(vas) == 1 and len(cir) <= 1 and len(vas) + len(cir) == len(ms):
+            if model.id_to_model["numeraire"] != vas[0]:
+                return None
+            return ms[vas[0]], (ms[cir[0]] if cir else None), vas[0], (cir[0] if cir else -1)
+    return None
+
+
+class IrcBackend:
+    @staticmethod
+    def supports(ctrl):
+        if split_model(ctrl.model) is None:
+            return False
+        return all(isinstance(p, (Bond, InterestRateSwap)) for p in ctrl.products)
+
+    def __init__(self, ctrl):
+        self.c = ctrl
+        self.vas, self.cir, self.vas_idx, self.cir_idx = split_model(ctrl.model)
+        self.has_cir = self.cir is not None
+        scheme = ctrl.simulation_scheme
+        if scheme == SimulationScheme.ANALYTICAL and self.has_cir:
+            raise NotImplementedError("Inter covariance not implemented for the requested pair of models.")
+        if scheme not in (SimulationScheme.EULER, SimulationScheme.ANALYTICAL):
+            raise NotImplementedError(f"Scheme {scheme} is not defined for Vasicek / CIR++ models.")
+        self.scheme = scheme
+        self.nt = len(ctrl.model.model_params) if ctrl.differentiate else 0
+        self._keep = []
+
+    # ------------------------------------------------------------------ lowering
+    def _dual_params(self):
+        nt = self.nt
+        if isinstance(self.c.model, ModelConfig):
+            offs = self.c.model.param_offsets()
+            pv = self.vas.dual_params(offs[self.vas_idx], nt)
+            pc = self.cir.dual_params(offs[self.cir_idx], nt) if self.has_cir else None
+        else:
+            pv, pc = self.vas.dual_params(0, nt), None
+        return pv, pc
+
+    def lower(self, set_indices, unit_products):
+        """Build the descriptor for a group of netting sets (main) and regression units
+        (pre-simulation).  Returns (desc, tables) with `tables` keeping numpy arrays alive."""
+        c, nt = self.c, self.nt
+        w = 1 + nt
+        pv, pc = self._dual_params()
+        t0 = self.vas.t0()
+        grid = build_time_grid(t0, c.simulation_timeline.tolist(), c.num_steps)
+        dates = grid.dates
+        date_idx = {t: i for i, t in enumerate(dates)}
+        n_dates, n_sub = len(dates), grid.n_sub
+        zero = D(0.0, None, nt)
+
+        # ---- correlation / Cholesky -------------------------------------------------
+        if isinstance(c.model, ModelConfig) and self.has_cir:
+            sub = [None, None]
+            sub[self.vas_idx], sub[self.cir_idx] = pv, pc
+            corr = c.model.joint_correlation(self.scheme, sub)
+            L = cholesky_dual(corr)
+            chol = [L[0][0], L[0][1], L[1][0], L[1][1]]
+        else:
+            one = D(1.0, None, nt)
+            chol = [one, zero, zero, one]
+
+        # ---- per-step model scalars --------------------------------------------------
+        step_vas, step_cir = [], []
+        for s in range(n_sub):
+            if self.scheme == SimulationScheme.ANALYTICAL:
+                decay, _ = self.vas.exact_step_constants(pv, grid.dt[s])
+                _, nstd = self.vas.exact_step_constants(pv, grid.dt_nominal[s])
+                step_vas += [decay, nstd]
+            else:
+                step_vas += [self.vas.mean_level(pv, grid.t1[s]), zero]
+            if self.has_cir:
+                if self.cir.deterministic:
+                    step_cir += [D(self.cir.market_hazard(grid.t1[s]), None, nt),
+                                 D(self.cir.market_hazard(grid.t2[s]), None, nt)]
+                else:
+                    step_cir += [self.cir.psi(pc, grid.t1[s]), zero]
+        if self.has_cir:
+            cir_init = D(self.cir.market_hazard(t0), None, nt) if self.cir.deterministic else pc[3]
+
+        # ---- cashflow tables ---------------------------------------------------------
+        sets = [c.netting_sets[i] for i in set_indices]
+        need_pv = c.risk_metrics.requires_discounted_cashflows()
+        set_legs = [[linear_leg_of(p) for p in ns.products] for ns in sets]
+        unit_legs = [linear_leg_of(p) for p in unit_products]
+        float_keys = [[] for _ in range(n_dates)]   # per date: list of (t1,t2)
+        for leg in [l for legs in set_legs for l in legs] + unit_legs:
+            for d, per in leg.floating.items():
+                for key in per:
+                    if key not in float_keys[date_idx[d]]:
+                        float_keys[date_idx[d]].append(key)
+        float_off = [0]
+        for di in range(n_dates):
+            float_off.append(float_off[-1] + len(float_keys[di]))
+        n_float = float_off[-1]
+        float_pos = {(di, key): float_off[di] + j for di in range(n_dates) for j, key in enumerate(float_keys[di])}
+        float_coef, float_inv_tau = [], np.zeros(n_float)
+        for di in range(n_dates):
+            for key in float_keys[di]:
+                alpha, Bc = self.vas.bond_coefficients(pv, key[0], key[1])
+                float_coef += [alpha, Bc]
+                float_inv_tau[float_pos[(di, key)]] = 1.0 / (key[1] - key[0])
+
+        def leg_tables(legs_per_row):
+            fix = np.zeros((len(legs_per_row), n_dates))
+            flo = np.zeros((len(legs_per_row), max(n_float, 1)))[:, :n_float]
+            for r, legs in enumerate(legs_per_row):
+                for leg in legs:
+                    for d, amt in leg.fixed.items():
+                        fix[r, date_idx[d]] += amt
+                    for d, per in leg.floating.items():
+                        for key, wgt in per.items():
+                            flo[r, float_pos[(date_idx[d], key)]] += wgt
+            return fix, flo
+
+        set_fix, set_float = leg_tables(set_legs)
+        unit_fix, unit_float = leg_tables([[l] for l in unit_legs])
+
+        # ---- date tables -------------------------------------------------------------
+        expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
+        metric_times = c.metric_exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
+        n_expo, n_metric = len(expo_times), len(metric_times)
+        flags = np.zeros(n_dates, dtype=np.int32)
+        date_expo = np.full(n_dates, -1, dtype=np.int32)
+        date_metric = np.full(n_dates, -1, dtype=np.int32)
+        date_reg = np.full(n_dates, -1, dtype=np.int32)
+        cash_dates = set()
+        for leg in [l for legs in set_legs for l in legs] + unit_legs:
+            cash_dates.update(leg.fixed.keys())
+            cash_dates.update(leg.floating.keys())
+        for d in cash_dates:
+            flags[date_idx[d]] |= B.DATE_HAS_CASHFLOW
+        for e, t in enumerate(expo_times):
+            flags[date_idx[t]] |= B.DATE_HAS_EXPOSURE | B.DATE_HAS_REGRESSION
+            date_expo[date_idx[t]] = e
+            date_reg[date_idx[t]] = e
+        for m, t in enumerate(metric_times):
+            flags[date_idx[t]] |= B.DATE_HAS_METRIC
+            date_metric[date_idx[t]] = m
+
+        # regression basis: standardise the explanatory variable r(t) with its Vasicek
+        # mean / std (pure conditioning aid; the fitted values do not depend on it)
+        r0, sig, th, a = (x.v for x in pv)
+        basis = np.zeros((n_expo, 2))
+        for e, t in enumerate(expo_times):
+            tau = t - t0
+            if tau <= 0:
+                basis[e] = (r0, 1.0)
+            else:
+                mean = th + (r0 - th) * math.exp(-a * tau)
+                std = sig * math.sqrt((1.0 - math.exp(-2.0 * a * tau)) / (2.0 * a))
+                basis[e] = (mean, 1.0 / std if std > 0 else 1.0)
+
+        # ---- netting-set terms ---------------------------------------------------------
+        metrics = c.risk_metrics.metrics
+        acc = 0
+        if need_pv:
+            acc |= B.ACC_PV
+        kinds = {m.metric_type for m in metrics}
+        if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
+            acc |= B.ACC_POS
+        if MetricType.ENE in kinds:
+            acc |= B.ACC_NEG
+        if MetricType.PFE in kinds:
+            acc |= B.ACC_SPILL
+        cva_metrics = [m for m in metrics if m.metric_type == MetricType.CVA]
+        lgd = 0.0
+        cva_coef = [zero] * (2 * n_metric)
+        cva_metric = None
+        if cva_metrics:
+            if len({m.counterparty_id for m in cva_metrics}) > 1 or len({m.recovery_rate for m in cva_metrics}) > 1:
+                raise NotImplementedError("one CVA counterparty / recovery per run is supported for now")
+            cva_metric = cva_metrics[0]
+            if not self.has_cir or cva_metric.counterparty_id not in self.cir.asset_ids:
+                raise Exception("Not all models set for xVA valuation.")
+            acc |= B.ACC_CVA
+            lgd = 1.0 - cva_metric.recovery_rate
+            cva_coef = []
+            for m in range(n_metric):
+                if m < n_metric - 1:
+                    Ck, Bk = self.cir.conditional_survival_coefficients(pc, metric_times[m], metric_times[m + 1])
+                    cva_coef += [Ck, Bk]
+                else:
+                    cva_coef += [zero, zero]
+        set_thr = np.array([ns.threshold for ns in sets], dtype=np.float64)
+        set_flags = np.zeros(len(sets), dtype=np.int32)
+        set_lag = np.full((len(sets), max(n_metric, 1)), -1, dtype=np.int32)[:, :n_metric]
+        for r, (si, ns) in enumerate(zip(set_indices, sets)):
+            if ns.is_collateralized():
+                set_flags[r] |= 1
+                delayed = c.netting_set_delayed_exposure_indices[si].tolist()
+                for m in range(n_metric):
+                    if delayed[m] >= 0:
+                        lag = int(c.metric_exposure_indices[m]) - delayed[m]
+                        if lag >= B.IRC_MAX_LAG:
+                            raise NotImplementedError(
+                                f"MPoR look-back spans {lag} exposure dates; the fused kernel keeps {B.IRC_MAX_LAG - 1}")
+                        set_lag[r, m] = lag
+            if cva_metric is not None and (ns.counterparty_id is None or ns.counterparty_id == cva_metric.counterparty_id):
+                set_flags[r] |= 2
+
+        t = {}  # keep-alive of every host array referenced by the descriptor
+        d = B.IrcDesc()
+        d.nt, d.scheme = nt, (B.SCHEME_ANALYTICAL if self.scheme == SimulationScheme.ANALYTICAL else B.SCHEME_EULER)
+        d.has_cir = int(self.has_cir)
+        d.cir_deterministic = int(self.has_cir and self.cir.deterministic)
+        d.vas_noise = self.vas_idx if self.has_cir else 0
+        d.cir_noise = self.cir_idx if self.has_cir else 0
+
+        def fp(name, arr):
+            t[name], ptr = B.as_dp(arr)
+            return ptr
+
+        def ip(name, arr):
+            t[name], ptr = B.as_ip(arr)
+            return ptr
+
+        d.vas = fp("vas", _packs(pv))
+        d.cir = fp("cir", _packs(pc) if self.has_cir else np.zeros(1))
+        d.cir_init = fp("cir_init", cir_init.pack() if self.has_cir else np.zeros(1))
+        d.chol = fp("chol", _packs(chol))
+        d.n_sub, d.n_dates, d.n_pre_dates = n_sub, n_dates, grid.n_pre_dates
+        d.step_dt = fp("step_dt", np.array(grid.dt))
+        d.step_date = ip("step_date", np.array(grid.date_after))
+        d.step_vas = fp("step_vas", _packs(step_vas))
+        d.step_cir = fp("step_cir", _packs(step_cir) if self.has_cir else np.zeros(1))
+        d.date_flags, d.date_expo = ip("flags", flags), ip("date_expo", date_expo)
+        d.date_metric, d.date_reg = ip("date_metric", date_metric), ip("date_reg", date_reg)
+        d.date_float_off = ip("float_off", np.array(float_off))
+        d.float_coef = fp("float_coef", _packs(float_coef) if float_coef else np.zeros(1))
+        d.float_inv_tau = fp("float_inv_tau", float_inv_tau if n_float else np.zeros(1))
+        d.n_sets, d.n_expo, d.n_metric, d.acc_flags = len(sets), n_expo, n_metric, acc
+        d.set_fix, d.set_float = fp("set_fix", set_fix), fp("set_float", set_float if n_float else np.zeros(1))
+        d.set_threshold, d.set_flags = fp("set_thr", set_thr), ip("set_flags", set_flags)
+        d.set_lag = ip("set_lag", set_lag if n_metric else np.zeros(1))
+        d.expo_coef = fp("expo_coef", np.zeros(max(n_expo * len(sets) * 3 * w, 1)))
+        d.expo_basis = fp("expo_basis", basis if n_expo else np.zeros(1))
+        d.cva_coef = fp("cva_coef", _packs(cva_coef) if n_metric else np.zeros(1))
+        d.lgd = lgd
+        d.n_units, d.n_reg = len(unit_products), n_expo
+        d.unit_fix = fp("unit_fix", unit_fix if unit_products else np.zeros(1))
+        d.unit_float = fp("unit_float", unit_float if (unit_products and n_float) else np.zeros(1))
+        d.unit_last_reg = ip("unit_last_reg", np.zeros(max(len(unit_products), 1)))
+        d.reg_basis = fp("reg_basis", basis if n_expo else np.zeros(1))
+        info = dict(grid=grid, n_expo=n_expo, n_metric=n_metric, basis=basis, acc=acc,
+                    set_flags=set_flags, noise_dim=2 if self.has_cir else 1, n_float=n_float)
+        return d, t, info
+
+    def param_used(self, kind):
+        """Which model parameters a metric's value is connected to (the reference returns
+        None from autograd for unconnected ones, controller.py:618-624)."""
+        n = len(self.c.model.model_params)
+        if not isinstance(self.c.model, ModelConfig):
+            return [True] * n
+        offs = self.c.model.param_offsets()
+        used = [False] * n
+        for i in range(4):
+            used[offs[self.vas_idx] + i] = True
+        if self.has_cir and kind == MetricType.CVA and not self.cir.deterministic:
+            for i in range(4):
+                used[offs[self.cir_idx] + i] = True
+        return used
+
+    # ------------------------------------------------------------------ execution
+    def _rng(self, seed, inject, n_total):
+        r = B.Rng()
+        r.seed, r.stream = seed, self.c.rng_stream
+        if inject is not None:
+            r.mode = B.RNG_INJECT
+            r.d_z = inject.data_ptr()
+            r.d_u = None
+            r.n_paths_total = n_total
+        else:
+            r.mode = B.RNG_PHILOX
+            r.n_paths_total = n_total
+        return r
+
+    def presim_coefficients(self, products, dev):
+        """Regression coefficients [product][n_expo][3] in the standardised basis."""
+        c = self.c
+        L = B.lib()
+        n_pre = c.num_paths_presim
+        out = {}
+        if n_pre <= 0:
+            raise ValueError("Exposure metrics need a pre-simulation: num_paths_presim must be positive.")
+        inject = c.injected_normals.get("pre") if c.injected_normals else None
+        for g0 in range(0, len(products), B.IRC_MAX_UNITS):
+            group = products[g0:g0 + B.IRC_MAX_UNITS]
+            desc, keep, info = self.lower([], group)
+            plan = C.c_void_p()
+            B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
+            try:
+                begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
+                slots = L.mcre_irc_presim_slots(plan)
+                moments = torch.zeros(slots, dtype=torch.float64, device=dev)
+                # bound the scratch: process the local paths in batches of whole chunks
+                batch = max(CHUNK_PATHS, (c.presim_batch_paths // CHUNK_PATHS) * CHUNK_PATHS)
+                for b0 in range(0, count, batch):
+                    bn = min(batch, count - b0)
+                    scratch = torch.empty(L.mcre_irc_presim_scratch_bytes(plan, bn), dtype=torch.uint8, device=dev)
+                    partial = torch.empty(L.mcre_irc_partial_bytes(plan, bn, CHUNK_PATHS, 1) // 8 + 1,
+                                          dtype=torch.float64, device=dev)
+                    part_m = torch.zeros(slots, dtype=torch.float64, device=dev)
+                    rng = self._rng(42, inject, n_pre)
+                    sh = B.Shard(begin + b0, bn, CHUNK_PATHS)
+                    B.check(L.mcre_irc_presim(plan, C.byref(rng), C.byref(sh), scratch.data_ptr(),
+                                              partial.data_ptr(), part_m.data_ptr(), RT.stream_ptr()))
+                    moments += part_m
+                    del scratch, partial
+                moments = RT.all_reduce_tree(moments)
+                mom = moments.cpu().numpy().reshape(info["n_expo"], -1)
+            finally:
+                L.mcre_irc_destroy(plan)
+            nu = 1 if len(group) <= 1 else (2 if len(group) <= 2 else 4)
+            assert mom.shape[1] == 5 + 3 * nu
+            for u, prod in enumerate(group):
+                coefs = np.zeros((info["n_expo"], 3))
+                for k in range(info["n_expo"]):
+                    m = mom[k, :5]
+                    G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
+                    rhs = mom[k, 5 + 3 * u: 8 + 3 * u]
+                    coefs[k] = solve_normal_equations(G, rhs)
+                out[id(prod)] = (coefs, info["basis"])
+        return out
+
+    def run(self):
+        c = self.c
+        dev = RT.compute_device()
+        L = B.lib()
+        n_main = c.num_paths_mainsim
+        n_sets = len(c.netting_sets)
+        need_expo = c.risk_metrics.requires_exposure_profiles()
+        timings = {}
+        import time
+        t0 = time.perf_counter()
+        coef_by_product = {}
+        if c.requires_regression:
+            prods = [p for p in c.products if c._product_requires_regression(p)]
+            coef_by_product = self.presim_coefficients(prods, dev)
+            # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
+            for p in prods:
+                coefs, basis = coef_by_product[id(p)]
+                c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coefs, basis))
+        torch.cuda.synchronize(dev)
+        timings["preprocessing"] = time.perf_counter() - t0
+        t1 = time.perf_counter()
+
+        results = [None] * n_sets
+        inject = c.injected_normals.get("main") if c.injected_normals else None
+        group_size = B.IRC_MAX_SETS if self.nt == 0 else 2
+        for g0 in range(0, n_sets, group_size):
+            idxs = list(range(g0, min(g0 + group_size, n_sets)))
+            desc, keep, info = self.lower(idxs, [])
+            w = 1 + self.nt
+            n_expo, n_metric = info["n_expo"], info["n_metric"]
+            coef = np.zeros((max(n_expo, 1), len(idxs), 3, w))
+            for r, si in enumerate(idxs):
+                for p in c.netting_sets[si].products:
+                    if id(p) in coef_by_product:
+                        coef[:n_expo, r, :, 0] += coef_by_product[id(p)][0]
+            plan = C.c_void_p()
+            B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
+            try:
+                coef_flat, coef_ptr = B.as_dp(coef[:n_expo])
+                B.check(L.mcre_irc_set_coefficients(plan, coef_ptr, RT.stream_ptr()))
+                begin, count = RT.shard_range(n_main, CHUNK_PATHS)
+                slots = L.mcre_irc_main_slots(plan)
+                acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                partial = torch.empty(L.mcre_irc_partial_bytes(plan, max(count, 1), CHUNK_PATHS, 0) // 8 + 1,
+                                      dtype=torch.float64, device=dev)
+                spill = None
+                if info["acc"] & B.ACC_SPILL:
+                    spill = torch.empty((len(idxs), n_metric, max(count, 1)), dtype=torch.float64, device=dev)
+                rng = self._rng(43, inject, n_main)
+                sh = B.Shard(begin, count, CHUNK_PATHS)
+                B.check(L.mcre_irc_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                           shift.data_ptr(), spill.data_ptr() if spill is not None else None,
+                                           RT.stream_ptr()))
+                acc = RT.all_reduce_tree(acc)
+                acc_h = acc.cpu().numpy()
+                shift_h = shift.cpu().numpy()
+                quant = None
+                if spill is not None:
+                    from mcre.select import order_statistics
+                    quant = order_statistics(c, spill, count, n_main)
+            finally:
+                L.mcre_irc_destroy(plan)
+            ns_t = 1 if len(idxs) <= 1 else (2 if len(idxs) <= 2 else 4)
+            nv = 4 + 2 * self.nt
+            acc_h = acc_h.reshape(n_metric + 1, ns_t, nv)
+            shift_h = shift_h.reshape(n_metric + 1, ns_t, nv)
+            from mcre.finish import irc_raw_to_neutral
+            for r, si in enumerate(idxs):
+                res = irc_raw_to_neutral(acc_h[:, r, :], shift_h[:, r, :], n_main, self.nt, n_metric, info["acc"])
+                if quant is not None:
+                    res["pfe"] = quant[r]
+                res["param_used"] = self.param_used
+                results[si] = res
+        torch.cuda.synchronize(dev)
+        timings["path_generation"] = time.perf_counter() - t1
+        timings["request_resolution"] = 0.0
+        return results, timings
+
+
+def solve_normal_equations(G, rhs):
+    """Minimum-norm least-squares solution of G c = rhs (G = Gram matrix of the basis).
+
+    The reference solves the tall system with LAPACK gelsy (controller.py:368-374), which
+    returns the minimum-norm solution for rank-deficient designs (at t = 0 every path has
+    the same explanatory value).  Same convention here via an SVD pseudo-inverse of the
+    symmetrically equilibrated Gram matrix."""
+    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
+    if not np.all(np.isfinite(G)) or d[0] == 0.0:
+        return np.zeros(3)
+    live = d > 0.0
+    scale = np.where(live, d, 1.0)
+    Gs = G / np.outer(scale, scale)
+    # min-norm must be taken in the *unscaled* coefficients to match gelsy; for the
+    # rank-deficient (constant regressor) case solve that directly.
+    u, s, vt = np.linalg.svd(Gs)
+    tol = 1e-10 * s[0]
+    rank = int(np.sum(s > tol))
+    if rank == 3:
+        return np.linalg.solve(Gs, rhs / scale) / scale
+    u2, s2, vt2 = np.linalg.svd(G)
+    keep = s2 > 1e-10 * s2[0]
+    return (vt2[keep].T * (1.0 / s2[keep])) @ (u2[:, keep].T @ rhs)
+
+
+def to_raw_basis(coefs, basis):
+    """Coefficients of [1, u, u^2], u = (x - shift) * scale  ->  coefficients of [1, x, x^2]."""
+    sh, sc = basis[:, 0], basis[:, 1]
+    c0, c1, c2 = coefs[:, 0], coefs[:, 1], coefs[:, 2]
+    out = np.empty_like(coefs)
+    out[:, 2] = c2 * sc * sc
+    out[:, 1] = c1 * sc - 2.0 * c2 * sc * sc * sh
+    out[:, 0] = c0 - c1 * sc * sh + c2 * sc * sc * sh * sh
+    return out

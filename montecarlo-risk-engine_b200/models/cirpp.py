@@ -1,0 +1,112 @@
+"""CIR++ default-intensity model: lambda(t) = y(t) + psi(t)
+(reference: src/models/cirpp.py:6-317, src/helpers/cs_helper.py:80-107).
+
+All deterministic ingredients (market hazard, psi shift, CIR A/B functions, the
+conditional-survival prefactor) are scalars per date; they are evaluated here on
+the host as dual numbers and shipped to the kernels as per-step / per-date
+tables."""
+from models.model import *
+from mcre.dual import D, dexp, dsqrt, dlog, dval
+
+
+class CIRPPModel(Model):
+    KIND = 4  # MCRE_MODEL_CIRPP
+
+    def __init__(self, calibration_date, asset_id, hazard_rates, kappa, theta, volatility, y0,
+                 deterministic=False):
+        super().__init__(calibration_date=calibration_date, state_dim=2, asset_ids=[asset_id])
+        assert 2 * kappa * theta - volatility ** 2 > 0 and y0 > 0, "Feller condition not met."
+        # parameter order: [kappa, theta, sigma, y0]
+        self.model_params = [torch.tensor(float(v), dtype=FLOAT, device=device)
+                             for v in (kappa, theta, volatility, y0)]
+        self.tenors = torch.tensor(list(hazard_rates.keys()), dtype=FLOAT, device=device)
+        self.hazard_rates = torch.tensor(list(hazard_rates.values()), dtype=FLOAT, device=device)
+        self.deterministic = deterministic
+
+    def get_kappa(self):
+        return torch.stack([self.model_params[0]])
+
+    def get_theta(self):
+        return torch.stack([self.model_params[1]])
+
+    def get_sigma(self):
+        return torch.stack([self.model_params[2]])
+
+    def get_y0(self):
+        return torch.stack([self.model_params[3]])
+
+    def get_model_param_names(self):
+        return ["kappa", "theta", "sigma", "y0"]
+
+    # -- market curve (not model parameters: no tangents) ---------------------
+    def market_hazard(self, t):
+        """Piecewise-constant hazard, right-closed buckets, flat after the last tenor."""
+        ten, haz = self.tenors.tolist(), self.hazard_rates.tolist()
+        for tt, h in zip(ten, haz):
+            if t <= tt:
+                return h
+        return haz[-1]
+
+    def market_survival(self, t):
+        """S_m(0,t) from the piecewise-constant hazards (cs_helper.py:80-107)."""
+        import math
+        ten, haz = self.tenors.tolist(), self.hazard_rates.tolist()
+        surv, prev, idx = 1.0, 0.0, len(ten) - 1
+        for i, mat in enumerate(ten):
+            if mat <= t:
+                surv *= math.exp(-haz[i] * (mat - prev))
+                prev = mat
+            else:
+                idx = i
+                break
+        dt = t - prev
+        if dt > 0:
+            surv *= math.exp(-haz[idx] * dt)
+        return surv
+
+    # -- CIR building blocks (reference: cirpp.py:85-142) ---------------------
+    @staticmethod
+    def _h(p):
+        return dsqrt(p[0] * p[0] + 2.0 * p[2] * p[2])
+
+    def cir_A(self, p, tau):
+        kappa, theta, sigma = p[0], p[1], p[2]
+        h = self._h(p)
+        num = 2.0 * h * dexp(0.5 * (kappa + h) * tau)
+        den = 2.0 * h + (kappa + h) * (dexp(h * tau) - 1.0)
+        return (num / den) ** ((2.0 * kappa * theta) / (sigma * sigma))
+
+    def cir_B(self, p, tau):
+        kappa = p[0]
+        h = self._h(p)
+        e = dexp(h * tau) - 1.0
+        return (2.0 * e) / (2.0 * h + (kappa + h) * e)
+
+    def psi(self, p, t):
+        """Deterministic shift psi(t) = lambda_mkt(t) + D(t) - y0 E(t)."""
+        kappa, theta, sigma, y0 = p
+        h = self._h(p)
+        et = dexp(h * t)
+        den = 2.0 * h + (kappa + h) * (et - 1.0)
+        Dt = (2.0 * kappa * theta / (sigma * sigma)) * (0.5 * (kappa + h) - (h * (kappa + h) * et) / den)
+        Et = (4.0 * h * h * et) / (den * den)
+        return self.market_hazard(t) + Dt - y0 * Et
+
+    def conditional_survival_coefficients(self, p, t, T):
+        """(C, B) with S(t,T | y_t) = C * exp(-B * y_t) (reference: cirpp.py:246-285).
+        Deterministic mode: S = S_m(0,T)/S_m(0,t), i.e. (ratio, 0)."""
+        nt = p[0].t.shape[0]
+        if self.deterministic:
+            return D(self.market_survival(T) / self.market_survival(t), None, nt), D(0.0, None, nt)
+        y0 = p[3]
+        A0t, A0T = self.cir_A(p, t), self.cir_A(p, T)
+        B0t, B0T = self.cir_B(p, t), self.cir_B(p, T)
+        pref = (self.market_survival(T) / self.market_survival(t)) * (A0t / A0T) * dexp(B0T * y0 - B0t * y0)
+        return pref * self.cir_A(p, T - t), self.cir_B(p, T - t)
+
+    # -- host helpers used by tests (closed form, tensors in / out) -----------
+    def survival_probability(self, t, T, y_t):
+        t, T = float(torch.as_tensor(t)), float(torch.as_tensor(T))
+        C, B = self.conditional_survival_coefficients(self.dual_params(), t, T)
+        y = torch.as_tensor(y_t, dtype=FLOAT)
+        return C.v * torch.exp(-B.v * y)

@@ -1,0 +1,35 @@
+"""Discretely monitored single / double barrier option with an always-fuzzy
+barrier indicator (reference: src/products/barrier_option.py:15-314)."""
+from products.product import *
+from products.product import _ft
+
+
+class BarrierOptionType(Enum):
+    DOWNANDOUT = "Down-And-Out"
+    UPANDOUT = "Up-And-Out"
+    DOWNANDIN = "Down-And-In"
+    UPANDIN = "Up-And-In"
+
+
+class BarrierOption(Product):
+    FUZZY_EPS = 0.05
+
+    def __init__(self, startdate, maturity, strike, num_observation_timepoints, option_type, barrier1,
+                 barrier_option_type1, barrier2=None, barrier_option_type2=None, asset_id=None):
+        super().__init__(asset_ids=[asset_id], product_family=ProductFamily.BARRIER_PATH_TERMINAL)
+        self.strike = _ft([strike])
+        self.maturity = _ft([maturity])
+        self.product_timeline = _ft([maturity])
+        self.modeling_timeline = torch.linspace(startdate, maturity, num_observation_timepoints,
+                                                dtype=FLOAT, device=device)
+        self.barrier1 = _ft([barrier1])
+        self.barrier_option_type1 = barrier_option_type1
+        self.barrier2 = None if barrier2 is None else _ft([barrier2])
+        self.barrier_option_type2 = barrier_option_type2
+        self.option_type = option_type
+        self.use_brownian_bridge = False
+
+    def set_use_brownian_bridge(self):
+        # Brownian-bridge correction draws from a numpy RNG in the reference
+        # (barrier_option.py:49-50, 138-222); SURVEY §8f item 4 ("next").
+        raise NotImplementedError("Brownian-bridge barrier monitoring is not implemented yet.")

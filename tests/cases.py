@@ -1,0 +1,148 @@
+"""Shared scenario builders for the tests: each returns this repo's host objects for one
+of the reference's test / benchmark configurations."""
+import numpy as np
+
+HAZARDS = {0.5: 0.006402303360855854, 1.0: 0.01553038972325307, 2.0: 0.009729741230773657,
+           3.0: 0.015552544648116201, 4.0: 0.021196186202801115, 5.0: 0.02284319986706472,
+           7.0: 0.010111423894480876, 10.0: 0.00613267811172937, 15.0: 0.0036969930706003337,
+           20.0: 0.003791311459217732}
+
+
+def wwr_cva(ns_module, rho=0.3, maturity=10.0, n_expo=41, extra_metrics=True, vol=0.2, speed=0.02,
+            deterministic=False):
+    """Vasicek + CIR++ payer swap, CVA (+PV, EPE) - tests/pytests/test_cva.py:113-182."""
+    m = ns_module
+    vas = m.VasicekModel(0., 0.03, 0.05, speed, vol, asset_id="irs")
+    cir = m.CIRPPModel(0., "GM", HAZARDS, 0.1, 0.01, 0.02, 0.0001, deterministic=deterministic)
+    model = m.ModelConfig([vas, cir], inter_asset_correlation_matrix=np.array([rho]))
+    irs = m.InterestRateSwap(0.0, maturity, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER, asset_id="irs")
+    sets = [m.NettingSet(name="irs", products=[irs], counterparty_id="GM")]
+    metrics = [m.CVAMetric("GM", 0.4)]
+    if extra_metrics:
+        metrics += [m.PVMetric(), m.EPEMetric()]
+    return model, sets, metrics, np.linspace(0, maturity, n_expo)
+
+
+def vasicek_irs_collateral(ns_module, mpor=0.25, threshold=0.0, n_dates=21, maturity=5.0):
+    """Vasicek payer IRS, uncollateralised + MPoR-collateralised netting sets, full metric
+    set - tests/exposure_tests/ee_pfe_swap_collateralized.py:58-107 (config 2)."""
+    m = ns_module
+    model = m.VasicekModel(0., 0.03, 0.05, 0.02, 0.02)
+    a = m.InterestRateSwap(0.0, maturity, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    b = m.InterestRateSwap(0.0, maturity, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    sets = [m.NettingSet(name="irs_uncollateralized", products=[a], threshold=threshold),
+            m.NettingSet(name="irs_collateralized", products=[b], margin_period_of_risk=mpor, threshold=threshold)]
+    metrics = [m.PVMetric(), m.CEMetric(), m.EPEMetric(), m.ENEMetric(), m.EEPEMetric(), m.PFEMetric(0.95)]
+    return model, sets, metrics, np.linspace(0.0, maturity, n_dates)
+
+
+def bs_european(ns_module, spot=120.0, sigma=0.2, rate=0.05, strike=100.0, T=2.0):
+    """Config 1: BS European call PV + pathwise delta/vega/rho (tests/pytests/test_pv_european_option.py:36-85)."""
+    m = ns_module
+    model = m.BlackScholesModel(0, spot, rate, sigma)
+    opt = m.EuropeanOption(m.Equity(), T, strike, m.OptionType.CALL)
+    return model, [m.NettingSet(name="call", products=[opt])], [m.PVMetric()], None
+
+
+def bermudan_swaption(ns_module, n_ex=8, a=0.002, vol=0.2):
+    """Config 4 (reduced): Vasicek Bermudan payer swaption, EPE + PFE
+    (tests/exposure_tests/ee_pfe_bermudan_swaption.py:21-68)."""
+    m = ns_module
+    model = m.VasicekModel(0., 0.03, 0.05, a, vol)
+    last = 0.25 * n_ex
+    swap = m.InterestRateSwap(0.0, last + 1.0, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    ex = [0.25 * (i + 1) for i in range(n_ex)]
+    opt = m.BermudanOption(swap, ex, 0.0, m.OptionType.CALL)
+    tl = np.array([0.25 * i for i in range(n_ex + 1)])
+    return model, [m.NettingSet(name="bermudan", products=[opt])], [m.EPEMetric(), m.PFEMetric(0.95), m.PVMetric()], tl
+
+
+def heston_european(ns_module):
+    """Heston QE European call (tests/pytests/test_pv_european_option_heston.py:44-74)."""
+    m = ns_module
+    model = m.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    opt = m.EuropeanOption(m.Equity(), 1.0, 100.0, m.OptionType.CALL)
+    return model, [m.NettingSet(name="call", products=[opt])], [m.PVMetric()], None
+
+
+def heston_path_dependent(ns_module):
+    """Config 5 (single-asset part the reference pins): Heston QE up-and-out barrier call and
+    arithmetic Asian call, 13 monthly monitoring dates."""
+    m = ns_module
+    model = m.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    bar = m.BarrierOption(0.0, 1.0, 100.0, 13, m.OptionType.CALL, 140.0, m.BarrierOptionType.UPANDOUT)
+    asian = m.AsianOption(0.0, 1.0, 100.0, 13, m.OptionType.CALL)
+    return model, [m.NettingSet(name="barrier", products=[bar]), m.NettingSet(name="asian", products=[asian])], [m.PVMetric()], None
+
+
+def bs_basket(ns_module, euler=False):
+    """4 x BS in a ModelConfig, arithmetic + geometric basket (tests/pytests/test_model_config.py:18-126)."""
+    m = ns_module
+    ids = ["asset1", "asset2", "asset3", "asset4"]
+    models = [m.BlackScholesModel(0.0, 100.0, 0.0, 0.4, asset_id=a) for a in ids]
+    model = m.ModelConfig(models, inter_asset_correlation_matrix=np.array([[0.5] for _ in range(6)]))
+    w = [0.25] * 4
+    b1 = m.BasketOption(1.0, ids, w, 100, m.OptionType.CALL, m.BasketOptionType.ARITHMETIC, False)
+    b1.name = "basket_arithmetic"
+    b2 = m.BasketOption(1.0, ids, w, 100, m.OptionType.CALL, m.BasketOptionType.GEOMETRIC)
+    b2.name = "basket_geometric"
+    return model, [m.NettingSet(name=b1.get_name(), products=[b1]), m.NettingSet(name=b2.get_name(), products=[b2])], [m.PVMetric()], None
+
+
+#: name -> (builder, builder kwargs, run kwargs)
+GOLDEN_CASES = {
+    "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
+    "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
+    "wwr_cva_greeks": (wwr_cva, dict(rho=0.5, n_expo=11, maturity=2.5), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=True)),
+    "cva_deterministic": (wwr_cva, dict(rho=0.0, deterministic=True, n_expo=21, maturity=5.0), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
+    "irs_collateral": (vasicek_irs_collateral, dict(mpor=0.25), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="EULER", differentiate=False)),
+    "irs_collateral_offgrid": (vasicek_irs_collateral, dict(mpor=10 / 252, threshold=0.005), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="EULER", differentiate=False)),
+    "irs_analytical": (vasicek_irs_collateral, dict(mpor=0.5, n_dates=11, maturity=2.5), dict(n_main=2048, n_pre=2048, num_steps=3, scheme="ANALYTICAL", differentiate=False)),
+    "bs_european": (bs_european, dict(), dict(n_main=100000, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
+    "bs_european_euler": (bs_european, dict(T=1.0), dict(n_main=20000, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
+    "bermudan_swaption": (bermudan_swaption, dict(), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="EULER", differentiate=False)),
+    "heston_european": (heston_european, dict(), dict(n_main=8192, n_pre=0, num_steps=20, scheme="QE", differentiate=False)),
+    "heston_european_greeks": (heston_european, dict(), dict(n_main=4096, n_pre=0, num_steps=10, scheme="QE", differentiate=True)),
+    "heston_path_dependent": (heston_path_dependent, dict(), dict(n_main=4096, n_pre=0, num_steps=4, scheme="QE", differentiate=True)),
+    "bs_basket": (bs_basket, dict(), dict(n_main=8192, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
+}
+
+
+class Namespace:
+    """Bundle of the API classes, taken either from this repo or from the reference."""
+
+    def __init__(self):
+        from common.enums import SimulationScheme
+        from controller.controller import SimulationController
+        from metrics.ce_metric import CEMetric
+        from metrics.cva_metric import CVAMetric
+        from metrics.eepe_metric import EEPEMetric
+        from metrics.ene_metric import ENEMetric
+        from metrics.epe_metric import EPEMetric
+        from metrics.pfe_metric import PFEMetric
+        from metrics.pv_metric import PVMetric
+        from metrics.risk_metrics import RiskMetrics
+        from models.black_scholes import BlackScholesModel
+        from models.black_scholes_multi import BlackScholesMulti
+        from models.cirpp import CIRPPModel
+        from models.heston import HestonModel
+        from models.model_config import ModelConfig
+        from models.vasicek import VasicekModel
+        from products.asian_option import AsianAveragingType, AsianOption
+        from products.barrier_option import BarrierOption, BarrierOptionType
+        from products.basket_option import BasketOption, BasketOptionType
+        from products.bermudan_option import AmericanOption, BermudanOption
+        from products.binary_option import BinaryOption
+        from products.bond import Bond
+        from products.equity import Equity
+        from products.european_option import EuropeanOption
+        from products.netting_set import NettingSet
+        from products.product import OptionType
+        from products.swap import InterestRateSwap, IRSType
+        self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
+        try:
+            from models.schwartz_two_factor import SchwartzTwoFactorModel
+            self.SchwartzTwoFactorModel = SchwartzTwoFactorModel
+        except Exception:  # pragma: no cover
+            pass
