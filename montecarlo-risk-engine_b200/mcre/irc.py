@@ -329,19 +329,12 @@ class IrcBackend:
         return d, t, info
 
     def param_used(self, kind):
-        """Which model parameters a metric's value is connected to (the reference returns
-        None from autograd for unconnected ones, controller.py:618-624)."""
-        n = len(self.c.model.model_params)
-        if not isinstance(self.c.model, ModelConfig):
-            return [True] * n
-        offs = self.c.model.param_offsets()
-        used = [False] * n
-        for i in range(4):
-            used[offs[self.vas_idx] + i] = True
-        if self.has_cir and kind == MetricType.CVA and not self.cir.deterministic:
-            for i in range(4):
-                used[offs[self.cir_idx] + i] = True
-        return used
+        """Which model parameters a metric's value is connected to.  The reference returns
+        None from autograd only for parameters outside the graph (controller.py:618-624);
+        a ModelConfig writes every sub-model's step into one state tensor
+        (model_config.py:261-276), so all of its parameters are connected and unused ones
+        come back as 0.0 - verified against the reference (tests/golden/wwr_cva_greeks.json)."""
+        return [True] * len(self.c.model.model_params)
 
     # ------------------------------------------------------------------ execution
     def _rng(self, seed, inject, n_total):
