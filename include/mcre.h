@@ -238,6 +238,9 @@ int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64_t n_slots,
 /* Measured FP64 FMA throughput of this GPU (TFLOP/s) from a register-resident DFMA loop;
  * the roofline denominator for the FP64-pipe-bound kernels. */
 int mcre_dfma_peak(double *tflops_out, void *stream);
+/* Test hook for the branch-free FP64 functions of csrc/fastmath.cuh the fused kernels use instead
+ * of libdevice: fn 0 exp, 1 log, 2 sqrt, 3 sin(2 pi x), 4 cos(2 pi x), 5 1/x; y[i] = fn(x[i]). */
+int mcre_fastmath_probe(int32_t fn, const double *d_x, double *d_y, int64_t n, void *stream);
 /* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t mcre_launch_count(void);
 const char *mcre_last_error(void);

@@ -7,6 +7,16 @@
 // (one per exposure date) than the model has parameters, so tangents are propagated
 // forward with the path instead of taping it.
 #pragma once
+#ifdef MCRE_FAST_MATH
+#include "fastmath.cuh"
+#define MCRE_EXP(x) fm_exp(x)
+#define MCRE_LOG(x) fm_log(x)
+#define MCRE_SQRT(x) fm_sqrt(x)
+#else
+#define MCRE_EXP(x) exp(x)
+#define MCRE_LOG(x) log(x)
+#define MCRE_SQRT(x) sqrt(x)
+#endif
 
 namespace mcre {
 
@@ -22,9 +32,9 @@ template <> struct RealOf<0> { typedef double type; };
 // ---- plain double overloads -----------------------------------------------------
 __device__ __forceinline__ double val(double x) { return x; }
 __device__ __forceinline__ double tan_of(double, int) { return 0.0; }
-__device__ __forceinline__ double r_exp(double x) { return exp(x); }
-__device__ __forceinline__ double r_log(double x) { return log(x); }
-__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double r_exp(double x) { return MCRE_EXP(x); }
+__device__ __forceinline__ double r_log(double x) { return MCRE_LOG(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return MCRE_SQRT(x); }
 __device__ __forceinline__ double r_relu(double x) { return fmax(x, 0.0); }
 __device__ __forceinline__ double r_max(double x, double c) { return fmax(x, c); }
 __device__ __forceinline__ double r_mask(double x, bool keep) { return keep ? x : 0.0; }
@@ -92,20 +102,20 @@ template <int N> __device__ __forceinline__ Dual<N> &operator+=(Dual<N> &a, cons
 template <int N> __device__ __forceinline__ Dual<N> &operator+=(Dual<N> &a, double b) { a.v += b; return a; }
 
 template <int N> __device__ __forceinline__ Dual<N> r_exp(const Dual<N> &x) {
-  Dual<N> r; r.v = exp(x.v);
+  Dual<N> r; r.v = MCRE_EXP(x.v);
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = r.v * x.d[i];
   return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> r_log(const Dual<N> &x) {
-  Dual<N> r; r.v = log(x.v); double inv = 1.0 / x.v;
+  Dual<N> r; r.v = MCRE_LOG(x.v); double inv = 1.0 / x.v;
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = inv * x.d[i];
   return r;
 }
 // sqrt with torch's convention d sqrt(0) = inf * 0 -> we use 0 at exactly 0 (the clamp in front kills it)
 template <int N> __device__ __forceinline__ Dual<N> r_sqrt(const Dual<N> &x) {
-  Dual<N> r; r.v = sqrt(x.v); double s = r.v > 0.0 ? 0.5 / r.v : 0.0;
+  Dual<N> r; r.v = MCRE_SQRT(x.v); double s = r.v > 0.0 ? 0.5 / r.v : 0.0;
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = s * x.d[i];
   return r;

@@ -1,0 +1,150 @@
+// Branch-free FP64 elementary functions for the fused Monte Carlo kernels.
+//
+// Why not libdevice: ncu on the first version of irc_main_kernel showed the kernel
+// issue-bound (27 % FP64 instructions): libdevice's exp/log/sincospi carry special-case
+// branches (no interleaving of independent paths across BSSY/BSYNC) and materialise every
+// polynomial coefficient as a 64-bit immediate (2 UMOV per DFMA).  These versions
+//   * are straight-line code (select instead of branch), so the two paths a thread owns
+//     interleave and hide each other's DFMA latency,
+//   * assume the argument ranges the Monte Carlo actually produces (documented per
+//     function) instead of handling NaN / Inf / denormals,
+//   * stay within ~2 ulp (tests/test_fastmath_gpu.py), far inside the 1e-10 parity budget.
+#pragma once
+#include <cstdint>
+
+namespace mcre {
+
+__device__ __forceinline__ double fm_rcp_approx(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double fm_rsqrt_approx(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
+// a / b for normal, finite b (|b| in [1e-300, 1e300]): MUFU seed + 2 Newton steps + residual fix.
+__device__ __forceinline__ double fm_div(double a, double b) {
+  double y = fm_rcp_approx(b);
+  double e = fma(-b, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-b, y, 1.0);
+  y = fma(y, e, y);
+  double q = a * y;
+  return fma(fma(-b, q, a), y, q);
+}
+
+// sqrt(x) for x >= 0 (0 -> 0), normal range.
+__device__ __forceinline__ double fm_sqrt(double x) {
+  const double xs = x > 0.0 ? x : 1.0;
+  double y = fm_rsqrt_approx(xs);
+  double g = xs * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  g = fma(fma(-g, g, xs), h, g);
+  return x > 0.0 ? g : 0.0;
+}
+
+// exp(x) for |x| <= 700.  Cody-Waite reduction, degree-13 Taylor on |r| <= ln2/2
+// (truncation 4e-18 relative), scaling by two exact powers of two.
+__device__ __forceinline__ double fm_exp(double x) {
+  const double L2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  double t = fma(x, L2E, MAGIC);
+  const int n = __double2loint(t);
+  t -= MAGIC;
+  double r = fma(t, -LN2_HI, x);
+  r = fma(t, -LN2_LO, r);
+  double p = 1.6059043836821613e-10;           // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);       // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  // 2^n = 2^(n/2) * 2^(n - n/2): both factors normal for |n| <= 1020
+  const int n1 = n >> 1, n2 = n - n1;
+  const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
+  return p * s1 * s2;
+}
+
+// log(u) for u in [2^-60, 2): mantissa/exponent split, s = (m-1)/(m+1), atanh series to s^21.
+__device__ __forceinline__ double fm_log(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;       // m in [1, 2)
+  const bool big = hi >= 0x3ff6a09f;          // m > sqrt(2) -> m/2, e+1 (keeps |s| <= 0.1716)
+  hi = big ? hi - 0x00100000 : hi;
+  e = big ? e + 1 : e;
+  const double m = __hiloint2double(hi, lo);
+  const double f = m - 1.0;
+  const double s = fm_div(f, m + 1.0);
+  const double z = s * s;
+  double p = 4.7619047619047616e-02;            // 1/21
+  p = fma(p, z, 5.2631578947368418e-02);        // 1/19
+  p = fma(p, z, 5.8823529411764705e-02);        // 1/17
+  p = fma(p, z, 6.6666666666666666e-02);        // 1/15
+  p = fma(p, z, 7.6923076923076927e-02);        // 1/13
+  p = fma(p, z, 9.0909090909090912e-02);        // 1/11
+  p = fma(p, z, 1.1111111111111111e-01);        // 1/9
+  p = fma(p, z, 1.4285714285714285e-01);        // 1/7
+  p = fma(p, z, 2.0000000000000001e-01);        // 1/5
+  p = fma(p, z, 3.3333333333333331e-01);        // 1/3
+  // log m = 2 s + 2 s z p
+  const double two_s = s + s;
+  const double lm = fma(two_s * z, p, two_s);
+  const double ed = (double)e;
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  return fma(ed, LN2_HI, fma(ed, LN2_LO, lm));
+}
+
+// (sin(2 pi u), cos(2 pi u)) for u in [0, 1): reduce a = 2u to a quadrant of width 1/2,
+// Taylor in (pi r) with |pi r| <= pi/4 (sin to x^17, cos to x^18), then swap / negate.
+__device__ __forceinline__ void fm_sincos2pi(double u, double &sn, double &cs) {
+  const double a = u + u;                       // [0, 2)
+  const double MAGIC = 6755399441055744.0;
+  double t = fma(a, 2.0, MAGIC);
+  const int q = __double2loint(t);             // nearest integer to 2a: 0..4
+  t -= MAGIC;
+  const double r = fma(t, -0.5, a);             // [-1/4, 1/4], exact
+  const double x = r * 3.141592653589793116 + r * 1.2246467991473532e-16;
+  const double z = x * x;
+  double ps = 2.8114572543455206e-15;           // 1/17!
+  ps = fma(ps, z, -7.6471637318198164e-13);     // -1/15!
+  ps = fma(ps, z, 1.6059043836821613e-10);      // 1/13!
+  ps = fma(ps, z, -2.505210838544172e-08);      // -1/11!
+  ps = fma(ps, z, 2.7557319223985893e-06);      // 1/9!
+  ps = fma(ps, z, -1.984126984126984e-04);      // -1/7!
+  ps = fma(ps, z, 8.333333333333333e-03);       // 1/5!
+  ps = fma(ps, z, -1.6666666666666666e-01);     // -1/3!
+  const double s0 = fma(x * z, ps, x);
+  double pc = 1.5619206968586225e-16;           // 1/18!
+  pc = fma(pc, z, -4.7794773323873853e-14);     // -1/16!
+  pc = fma(pc, z, 1.1470745597729725e-11);      // 1/14!
+  pc = fma(pc, z, -2.08767569878681e-09);       // -1/12!
+  pc = fma(pc, z, 2.755731922398589e-07);       // 1/10!
+  pc = fma(pc, z, -2.48015873015873e-05);       // -1/8!
+  pc = fma(pc, z, 1.3888888888888889e-03);      // 1/6!
+  pc = fma(pc, z, -4.1666666666666664e-02);     // -1/4!
+  pc = fma(pc, z, 0.5);
+  const double c0 = fma(-z, pc, 1.0);
+  // angle = q*pi/2 + x : rotate by quadrant
+  const bool swap = q & 1;
+  const double sa = swap ? c0 : s0, ca = swap ? s0 : c0;
+  sn = (q & 2) ? -sa : sa;
+  cs = ((q + 1) & 2) ? -ca : ca;
+}
+
+}  // namespace mcre

@@ -6,6 +6,7 @@
 // regression-proxy exposure, threshold / MPoR collateral and the metric integrands.
 // Only block-reduced sums ever reach HBM.  See include/mcre.h for what each entry point
 // replaces in the reference.
+#define MCRE_FAST_MATH 1
 #include "common.cuh"
 #include "philox.cuh"
 #include "dual.cuh"
@@ -28,6 +29,7 @@ struct IrcDev {
   double lgd;
   int n_units, n_reg;
   const double *unit_fix, *unit_float; const double *reg_basis;
+  const double *step_rec, *date_rec;  // packed records of the main kernel
 };
 
 struct ShardDev {
@@ -69,7 +71,8 @@ __device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR
     // exact OU transition; the 1x1 Cholesky factor of the step covariance is nstd (vasicek.py:52-86)
     s.r = mp.theta + (s.r - mp.theta) * decay + nstd * z0;
   } else {
-    s.r = s.r + mp.a * (mp.theta - s.r) * dt + mp.sigma * sq * wv;
+    const R theta_t = T::load(P.step_vas, is * 2 + 0);  // mean level at t1 (constant for Vasicek)
+    s.r = s.r + mp.a * (theta_t - s.r) * dt + mp.sigma * sq * wv;
   }
   if (CIR) {
     const R wc = (P.cir_noise == 1) ? w1 : w0;
@@ -132,24 +135,43 @@ __device__ __forceinline__ R apply_threshold(const R &x, double h) {
 // path 0 takes (written by a one-path "pilot" launch of this same kernel).  Shifting by
 // a sample of the distribution keeps the variance formula free of cancellation and makes
 // degenerate dates (all paths equal, e.g. t = 0) give an exact zero Monte Carlo error.
+//
+// Layout choices that came out of the first ncu profile (profiles/r01_irc_main_v0_*):
+//  * PP paths per thread, evaluated in lock-step: all plan loads, branches and index
+//    arithmetic are shared by the PP paths and their Horner chains interleave;
+//  * every per-step / per-date scalar sits in one packed record (mcre_irc_create packs
+//    them), read with a handful of wide uniform loads instead of ~45 scalar loads;
+//  * MODE 1 ("CVA only": one netting set, no threshold / collateral, no other metric):
+//    relu(E_k) S(0,t_k) = relu(poly) exp(-(logB + logB_lambda)) - two exponentials per date.
 // =====================================================================================
-template <int NT, int NS, bool CIR, int SCHEME>
-__global__ void __launch_bounds__(256) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh, double *partial,
-                                                       double *spill, double *shift, int pilot) {
+constexpr int STEP_HDR = 4;   // dt, sqrt(dt), bits(date index), pad
+constexpr int DATE_HDR = 6;   // bits(flags|(expo+1)<<32), bits((metric+1)|float_off<<32), bits(float_cnt), pad, shift, scale
+
+__device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
+__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
+
+template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE>
+__global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
+                                                                         double *partial, double *spill,
+                                                                         double *shift, int pilot) {
   typedef typename RealOf<NT>::type R;
   typedef RealTraits<R> T;
+  constexpr int W = NT + 1;
   constexpr int NV = 4 + 2 * NT;        // values per (set, date)
   constexpr int NVB = NS * NV;          // values per block_accumulate call
+  constexpr int SR = STEP_HDR + 4 * W;  // packed step record stride
   extern __shared__ double smem[];
   const int nw = blockDim.x >> 5;
   const int n_slots = (P.n_metric + 1) * NVB;
   double *acc = smem;                   // [n_slots]
   double *stage = smem + n_slots;       // [2][nw][NVB]
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  const int DR = (DATE_HDR + 2 * W + 3 * W * P.n_sets + 1) & ~1;  // even: records are read as double2
 
   IrcParams<R, CIR> mp;
   irc_load_params<R, CIR>(P, mp);
   const int acc_flags = P.acc_flags;
+  const bool vas_second = CIR && P.vas_noise == 1, cir_second = CIR && P.cir_noise == 1, cir_det = P.cir_det != 0;
   double thr[NS]; int sflags[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -161,98 +183,141 @@ __global__ void __launch_bounds__(256) irc_main_kernel(IrcDev P, RngDev rng, Sha
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) acc[i] = 0.0;
     __syncthreads();
     int parity = 0;
-    for (int it = 0; it < sh.chunk; it += blockDim.x) {
-      const long long lpath = chunk * sh.chunk + it + threadIdx.x;
-      const bool live = lpath < sh.n_paths;
-      const long long gpath = sh.path_begin + (live ? lpath : 0);
-      NormalStream ns; ns.init(rng, (unsigned long long)gpath);
-      IrcState<R> st;
-      st.r = mp.r0; st.logB = T::zero(); st.y = mp.y0; st.logBl = T::zero();
-      R pv[NS], cva[NS], hist[NS][MCRE_IRC_MAX_LAG];
+    for (int it = 0; it < sh.chunk; it += blockDim.x * PP) {
+      long long lpath[PP], gpath[PP];
+      bool live[PP];
+      NormalStream ns[PP];
+      IrcState<R> st[PP];
+      R pv[PP][NS], cva[PP][NS], hist[PP][NS][MODE == 1 ? 1 : MCRE_IRC_MAX_LAG];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        pv[s] = T::zero(); cva[s] = T::zero();
+      for (int p = 0; p < PP; ++p) {
+        lpath[p] = chunk * sh.chunk + it + p * (int)blockDim.x + threadIdx.x;
+        live[p] = lpath[p] < sh.n_paths;
+        gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
+        ns[p].init(rng, (unsigned long long)gpath[p]);
+        st[p].r = mp.r0; st[p].logB = T::zero(); st[p].y = mp.y0; st[p].logBl = T::zero();
 #pragma unroll
-        for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l) hist[s][l] = T::zero();
+        for (int s = 0; s < NS; ++s) {
+          pv[p][s] = T::zero(); cva[p][s] = T::zero();
+#pragma unroll
+          for (int l = 0; l < (MODE == 1 ? 1 : MCRE_IRC_MAX_LAG); ++l) hist[p][s][l] = T::zero();
+        }
       }
 
       // ---- date evaluation (cashflows -> exposure -> metrics) ------------------------
       auto eval_date = [&](int di) {
-        const int flags = __ldg(P.date_flags + di);
+        const double *dr = P.date_rec + (size_t)di * DR;
+        const double2 h0 = __ldg((const double2 *)dr), h1 = __ldg((const double2 *)dr + 1),
+                      h2 = __ldg((const double2 *)dr + 2);
+        const int flags = lo32(h0.x), e = hi32(h0.x) - 1, m = lo32(h0.y) - 1;
         if (!(flags & (MCRE_DATE_HAS_CASHFLOW | MCRE_DATE_HAS_EXPOSURE | MCRE_DATE_HAS_METRIC))) return;
-        const R invN = r_exp(-st.logB);  // 1 / numeraire, numeraire = exp(logB) (vasicek.py:154-156)
-        if ((flags & MCRE_DATE_HAS_CASHFLOW) && (acc_flags & MCRE_ACC_PV)) {
-          R cf[NS];
+        const double bshift = h2.x, bscale = h2.y;
+        const double *dc = dr + DATE_HDR;   // C[w], B[w], coef[set][3][w]
+        if (MODE == 1) {
+          // CVA-only fast path: contribution at metric dates k < n_metric-1 only
+          if (!(flags & MCRE_DATE_HAS_METRIC) || m >= P.n_metric - 1) return;
+          const R C = T::load(dc, 0), Bc = T::load(dc, 1);
+          const R c0 = T::load(dc, 2), c1 = T::load(dc, 3), c2 = T::load(dc, 4);
 #pragma unroll
-          for (int s = 0; s < NS; ++s) cf[s] = T::lift(s < P.n_sets ? __ldg(P.set_fix + (size_t)s * P.n_dates + di) : 0.0);
-          const int j0 = __ldg(P.date_float_off + di), j1 = __ldg(P.date_float_off + di + 1);
-          for (int j = j0; j < j1; ++j) {
-            // LIBOR from the bond price at the payment date's own short rate (bond.py:55-66)
-            R alpha = T::load(P.float_coef, j * 2 + 0), B = T::load(P.float_coef, j * 2 + 1);
-            R libor = (r_exp(B * st.r - alpha) - 1.0) * __ldg(P.float_inv_tau + j);
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-              if (s < P.n_sets) cf[s] = cf[s] + libor * __ldg(P.set_float + (size_t)s * P.n_float + j);
+          for (int p = 0; p < PP; ++p) {
+            const R u = (st[p].r - bshift) * bscale;
+            const R pos = r_relu(c0 + u * (c1 + u * c2));
+            const R ds = r_exp(-(st[p].logB + st[p].logBl));
+            const R cond = C * r_exp(-(Bc * st[p].y));
+            cva[p][0] = cva[p][0] + pos * ds * (1.0 - cond);
           }
-#pragma unroll
-          for (int s = 0; s < NS; ++s) pv[s] = pv[s] + cf[s] * invN;
+          return;
         }
-        if (flags & MCRE_DATE_HAS_EXPOSURE) {
-          const int e = __ldg(P.date_expo + di);
-          const double shift = __ldg(P.expo_basis + e * 2), scale = __ldg(P.expo_basis + e * 2 + 1);
-          const R u = (st.r - shift) * scale;
+        R invN[PP];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) invN[p] = r_exp(-st[p].logB);  // 1 / numeraire (vasicek.py:154-156)
+        if ((flags & MCRE_DATE_HAS_CASHFLOW) && (acc_flags & MCRE_ACC_PV)) {
+          R cf[PP][NS];
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
+            const double fx = s < P.n_sets ? __ldg(P.set_fix + (size_t)s * P.n_dates + di) : 0.0;
 #pragma unroll
-            for (int l = MCRE_IRC_MAX_LAG - 1; l > 0; --l) hist[s][l] = hist[s][l - 1];
-            if (s < P.n_sets) {
-              const int cb = (e * P.n_sets + s) * 3;
-              R c0 = T::load(P.expo_coef, cb), c1 = T::load(P.expo_coef, cb + 1), c2 = T::load(P.expo_coef, cb + 2);
-              hist[s][0] = (c0 + u * (c1 + u * c2)) * invN;  // continuation / numeraire (controller.py:438-447)
+            for (int p = 0; p < PP; ++p) cf[p][s] = T::lift(fx);
+          }
+          const int j0 = hi32(h0.y), j1 = j0 + lo32(h1.x);
+          for (int j = j0; j < j1; ++j) {
+            // LIBOR from the bond price at the payment date's own short rate (bond.py:55-66)
+            const R alpha = T::load(P.float_coef, j * 2 + 0), B = T::load(P.float_coef, j * 2 + 1);
+            const double inv_tau = __ldg(P.float_inv_tau + j);
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+              const R libor = (r_exp(B * st[p].r - alpha) - 1.0) * inv_tau;
+#pragma unroll
+              for (int s = 0; s < NS; ++s)
+                if (s < P.n_sets) cf[p][s] = cf[p][s] + libor * __ldg(P.set_float + (size_t)s * P.n_float + j);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < PP; ++p)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) pv[p][s] = pv[p][s] + cf[p][s] * invN[p];
+        }
+        if (flags & MCRE_DATE_HAS_EXPOSURE) {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            R c0 = T::zero(), c1 = T::zero(), c2 = T::zero();
+            if (s < P.n_sets) { c0 = T::load(dc, 2 + s * 3); c1 = T::load(dc, 3 + s * 3); c2 = T::load(dc, 4 + s * 3); }
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+#pragma unroll
+              for (int l = MCRE_IRC_MAX_LAG - 1; l > 0; --l) hist[p][s][l] = hist[p][s][l - 1];
+              const R u = (st[p].r - bshift) * bscale;
+              hist[p][s][0] = (c0 + u * (c1 + u * c2)) * invN[p];  // continuation / numeraire (controller.py:438-447)
             }
           }
         }
         if (flags & MCRE_DATE_HAS_METRIC) {
-          const int m = __ldg(P.date_metric + di);
           double vals[NVB];
-          R surv = T::zero(), dflt = T::zero();
+#pragma unroll
+          for (int i = 0; i < NVB; ++i) vals[i] = 0.0;
           const bool cva_date = (acc_flags & MCRE_ACC_CVA) && m < P.n_metric - 1;
+          R dflt[PP];
+#pragma unroll
+          for (int p = 0; p < PP; ++p) dflt[p] = T::zero();
           if (CIR && cva_date) {
             // S(0,t_k) = exp(-logB_lambda); S(t_k,t_k+1 | y) = C exp(-B y)   (cirpp.py:298-317)
-            R C = T::load(P.cva_coef, m * 2), Bc = T::load(P.cva_coef, m * 2 + 1);
-            surv = r_exp(-st.logBl);
-            dflt = surv * (1.0 - C * r_exp(-(Bc * st.y)));
+            const R C = T::load(dc, 0), Bc = T::load(dc, 1);
+#pragma unroll
+            for (int p = 0; p < PP; ++p) dflt[p] = r_exp(-st[p].logBl) * (1.0 - C * r_exp(-(Bc * st[p].y)));
           }
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
-            R unsec;
-            if (sflags[s] & 1) {
-              const int lag = s < P.n_sets ? __ldg(P.set_lag + (size_t)s * P.n_metric + m) : -1;
-              R delayed = T::zero();
-#pragma unroll
-              for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l) if (l == lag) delayed = hist[s][l];
-              unsec = hist[s][0] - apply_threshold(delayed, thr[s]);
-            } else {
-              unsec = apply_threshold(hist[s][0], thr[s]);
-            }
-            const R pos = r_relu(unsec);
-            const R neg = -r_relu(-unsec);
-            if (cva_date && (sflags[s] & 2)) cva[s] = cva[s] + pos * dflt;
-            const double keep = live ? 1.0 : 0.0;
+            const int lag = ((sflags[s] & 1) && s < P.n_sets) ? __ldg(P.set_lag + (size_t)s * P.n_metric + m) : -1;
             const int sb = m * NVB + s * NV;
-            if (pilot) {
-              if (threadIdx.x == 0) { shift[sb + 0] = val(pos); shift[sb + 2] = val(neg); }
-            }
-            const double dp = val(pos) - shift[sb + 0], dn = val(neg) - shift[sb + 2];
-            vals[s * NV + 0] = keep * dp; vals[s * NV + 1] = keep * dp * dp;
-            vals[s * NV + 2] = keep * dn; vals[s * NV + 3] = keep * dn * dn;
+            double sh_pos = 0.0, sh_neg = 0.0;
+            if (!pilot) { sh_pos = shift[sb + 0]; sh_neg = shift[sb + 2]; }
 #pragma unroll
-            for (int k = 0; k < NT; ++k) {
-              vals[s * NV + 4 + k] = keep * tan_of(pos, k);
-              vals[s * NV + 4 + NT + k] = keep * tan_of(neg, k);
+            for (int p = 0; p < PP; ++p) {
+              R unsec;
+              if (sflags[s] & 1) {
+                R delayed = T::zero();
+#pragma unroll
+                for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l) if (l == lag) delayed = hist[p][s][l];
+                unsec = hist[p][s][0] - apply_threshold(delayed, thr[s]);
+              } else {
+                unsec = apply_threshold(hist[p][s][0], thr[s]);
+              }
+              const R pos = r_relu(unsec);
+              const R neg = -r_relu(-unsec);
+              if (cva_date && (sflags[s] & 2)) cva[p][s] = cva[p][s] + pos * dflt[p];
+              if (pilot && p == 0 && threadIdx.x == 0) { shift[sb + 0] = val(pos); shift[sb + 2] = val(neg); }
+              const double keep = live[p] ? 1.0 : 0.0;
+              const double dp = val(pos) - sh_pos, dn = val(neg) - sh_neg;
+              vals[s * NV + 0] += keep * dp; vals[s * NV + 1] += keep * dp * dp;
+              vals[s * NV + 2] += keep * dn; vals[s * NV + 3] += keep * dn * dn;
+#pragma unroll
+              for (int k = 0; k < NT; ++k) {
+                vals[s * NV + 4 + k] += keep * tan_of(pos, k);
+                vals[s * NV + 4 + NT + k] += keep * tan_of(neg, k);
+              }
+              if ((acc_flags & MCRE_ACC_SPILL) && live[p] && s < P.n_sets)
+                spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath[p]] = val(unsec);
             }
-            if ((acc_flags & MCRE_ACC_SPILL) && live && s < P.n_sets)
-              spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath] = val(unsec);
           }
           if ((acc_flags & (MCRE_ACC_POS | MCRE_ACC_NEG)) && !pilot)
             block_accumulate<NVB>(vals, acc, m * NVB, stage, NVB, parity);
@@ -261,30 +326,67 @@ __global__ void __launch_bounds__(256) irc_main_kernel(IrcDev P, RngDev rng, Sha
 
       for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
       for (int is = 0; is < P.n_sub; ++is) {
-        double z0, z1;
-        irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-        irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
-        const int di = __ldg(P.step_date + is);
+        const double *sr = P.step_rec + (size_t)is * SR;
+        const double2 g0 = __ldg((const double2 *)sr), g1 = __ldg((const double2 *)sr + 1);
+        const double dt = g0.x, sq = g0.y;
+        const int di = lo32(g1.x);
+        const R sv0 = T::load(sr + STEP_HDR, 0), sv1 = T::load(sr + STEP_HDR, 1);
+        R sc0 = T::zero(), sc1 = T::zero();
+        if (CIR) { sc0 = T::load(sr + STEP_HDR, 2); sc1 = T::load(sr + STEP_HDR, 3); }
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+          double z0, z1;
+          irc_draw<R, CIR>(rng, ns[p], is, lpath[p], gpath[p], z0, z1);
+          // correlated noise z @ L^T (model.py:46-48)
+          const R w0 = mp.L00 * z0;
+          R w1 = T::zero();
+          if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
+          IrcState<R> &s = st[p];
+          s.logB = s.logB + s.r * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+          if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
+            // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
+            s.r = mp.theta + (s.r - mp.theta) * sv0 + sv1 * z0;
+          } else {
+            const R wv = vas_second ? w1 : w0;
+            s.r = s.r + mp.a * (sv0 - s.r) * dt + mp.sigma * sq * wv;
+          }
+          if (CIR) {
+            const R wc = cir_second ? w1 : w0;
+            if (cir_det) {                    // cirpp.py:155-172
+              s.logBl = s.logBl + sc0 * dt;
+              s.y = sc1;
+            } else {                          // full-truncation Euler, cirpp.py:174-198
+              const R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * r_sqrt(r_relu(s.y)) * sq * wc;
+              s.logBl = s.logBl + (s.y + sc0) * dt;
+              s.y = r_max(yn, 1e-12);
+            }
+          }
+        }
         if (di >= 0) eval_date(di);
       }
       // ---- per-path totals ------------------------------------------------------------
       {
         double vals[NVB];
-        const double keep = live ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) vals[i] = 0.0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          const R c = cva[s] * P.lgd;
           const int sb = P.n_metric * NVB + s * NV;
-          if (pilot) {
-            if (threadIdx.x == 0) { shift[sb + 0] = val(pv[s]); shift[sb + 2] = val(c); }
-          }
-          const double dp = val(pv[s]) - shift[sb + 0], dc = val(c) - shift[sb + 2];
-          vals[s * NV + 0] = keep * dp; vals[s * NV + 1] = keep * dp * dp;
-          vals[s * NV + 2] = keep * dc; vals[s * NV + 3] = keep * dc * dc;
+          double sh_pv = 0.0, sh_cva = 0.0;
+          if (!pilot) { sh_pv = shift[sb + 0]; sh_cva = shift[sb + 2]; }
 #pragma unroll
-          for (int k = 0; k < NT; ++k) {
-            vals[s * NV + 4 + k] = keep * tan_of(pv[s], k);
-            vals[s * NV + 4 + NT + k] = keep * tan_of(c, k);
+          for (int p = 0; p < PP; ++p) {
+            const R c = cva[p][s] * P.lgd;
+            if (pilot && p == 0 && threadIdx.x == 0) { shift[sb + 0] = val(pv[p][s]); shift[sb + 2] = val(c); }
+            const double keep = live[p] ? 1.0 : 0.0;
+            const double dp = val(pv[p][s]) - sh_pv, dcv = val(c) - sh_cva;
+            vals[s * NV + 0] += keep * dp; vals[s * NV + 1] += keep * dp * dp;
+            vals[s * NV + 2] += keep * dcv; vals[s * NV + 3] += keep * dcv * dcv;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+              vals[s * NV + 4 + k] += keep * tan_of(pv[p][s], k);
+              vals[s * NV + 4 + NT + k] += keep * tan_of(c, k);
+            }
           }
         }
         if (!pilot) block_accumulate<NVB>(vals, acc, P.n_metric * NVB, stage, NVB, parity);
@@ -425,8 +527,20 @@ struct mcre_irc_plan {
   DevArray<double> vas, cir, cir_init, chol, step_dt, step_vas, step_cir, float_coef, float_inv_tau, set_fix,
       set_float, set_threshold, expo_coef, expo_basis, cva_coef, unit_fix, unit_float, reg_basis;
   DevArray<int> step_date, date_flags, date_expo, date_metric, date_reg, date_float_off, set_flags, set_lag;
+  DevArray<double> step_rec, date_rec;
+  std::vector<double> h_date_rec;   // host copy: coefficients are patched in after the regression solve
+  std::vector<int> h_date_expo;
+  int date_stride = 0;
   size_t expo_coef_count = 0;
+  bool cva_only = false;
 };
+
+static inline double pack2(int lo, int hi) {
+  long long v = ((long long)(unsigned int)hi << 32) | (unsigned int)lo;
+  double d;
+  memcpy(&d, &v, 8);
+  return d;
+}
 
 static RngDev make_rng(const mcre_rng *r) {
   RngDev d;
@@ -471,6 +585,36 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   UP(cva_coef, c->cva_coef, (size_t)c->n_metric * 2 * w);
   UP(unit_fix, c->unit_fix, (size_t)c->n_units * c->n_dates); UP(unit_float, c->unit_float, (size_t)c->n_units * n_float);
   UP(reg_basis, c->reg_basis, (size_t)c->n_reg * 2);
+  {
+    // packed per-step and per-date records of the main kernel (layout: STEP_HDR / DATE_HDR above)
+    const int SR = STEP_HDR + 4 * w, DR = (DATE_HDR + 2 * w + 3 * w * c->n_sets + 1) & ~1;
+    std::vector<double> srec((size_t)c->n_sub * SR + 2, 0.0);
+    for (int s = 0; s < c->n_sub; ++s) {
+      double *r = srec.data() + (size_t)s * SR;
+      r[0] = c->step_dt[s]; r[1] = sqrt(c->step_dt[s]); r[2] = pack2(c->step_date[s], 0);
+      for (int k = 0; k < 2 * w; ++k) r[STEP_HDR + k] = c->step_vas[(size_t)s * 2 * w + k];
+      if (c->has_cir) for (int k = 0; k < 2 * w; ++k) r[STEP_HDR + 2 * w + k] = c->step_cir[(size_t)s * 2 * w + k];
+    }
+    p->h_date_rec.assign((size_t)c->n_dates * DR + 2, 0.0);
+    p->h_date_expo.assign(c->date_expo, c->date_expo + c->n_dates);
+    p->date_stride = DR;
+    for (int di = 0; di < c->n_dates; ++di) {
+      double *r = p->h_date_rec.data() + (size_t)di * DR;
+      const int e = c->date_expo[di], m = c->date_metric[di];
+      r[0] = pack2(c->date_flags[di], e + 1);
+      r[1] = pack2(m + 1, c->date_float_off[di]);
+      r[2] = pack2(c->date_float_off[di + 1] - c->date_float_off[di], 0);
+      if (e >= 0) { r[4] = c->expo_basis[e * 2]; r[5] = c->expo_basis[e * 2 + 1]; }
+      if (m >= 0 && c->cva_coef) for (int k = 0; k < 2 * w; ++k) r[DATE_HDR + k] = c->cva_coef[(size_t)m * 2 * w + k];
+      if (e >= 0 && c->expo_coef)
+        for (int k = 0; k < 3 * w * c->n_sets; ++k) r[DATE_HDR + 2 * w + k] = c->expo_coef[(size_t)e * 3 * w * c->n_sets + k];
+    }
+    UP(step_rec, srec.data(), srec.size());
+    UP(date_rec, p->h_date_rec.data(), p->h_date_rec.size());
+    // "CVA only" fast mode: one set, CVA the only accumulator, no threshold / collateral
+    p->cva_only = c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA &&
+                  c->set_threshold[0] == 0.0 && (c->set_flags[0] & 1) == 0 && (c->set_flags[0] & 2) != 0;
+  }
 #undef UP
   if (rc) { mcre_irc_destroy(p); return rc; }
   IrcDev &d = p->d;
@@ -488,6 +632,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   d.expo_coef = p->expo_coef.p; d.expo_basis = p->expo_basis.p; d.cva_coef = p->cva_coef.p; d.lgd = c->lgd;
   d.n_units = c->n_units; d.n_reg = c->n_reg;
   d.unit_fix = p->unit_fix.p; d.unit_float = p->unit_float.p; d.reg_basis = p->reg_basis.p;
+  d.step_rec = p->step_rec.p; d.date_rec = p->date_rec.p;
   *out = p;
   return 0;
 }
@@ -500,7 +645,7 @@ extern "C" void mcre_irc_destroy(mcre_irc_plan *p) {
   p->expo_basis.release(); p->cva_coef.release(); p->unit_fix.release(); p->unit_float.release();
   p->reg_basis.release(); p->step_date.release(); p->date_flags.release(); p->date_expo.release();
   p->date_metric.release(); p->date_reg.release(); p->date_float_off.release(); p->set_flags.release();
-  p->set_lag.release();
+  p->set_lag.release(); p->step_rec.release(); p->date_rec.release();
   delete p;
 }
 
@@ -526,6 +671,16 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
   if (p->expo_coef_count == 0) return 0;
   MCRE_CUDA(cudaMemcpyAsync(p->d.expo_coef, coef, p->expo_coef_count * sizeof(double), cudaMemcpyHostToDevice,
                             (cudaStream_t)stream));
+  const int w = 1 + p->d.nt, per_date = 3 * w * p->d.n_sets, DR = p->date_stride;
+  for (int di = 0; di < p->d.n_dates; ++di) {
+    const int e = p->h_date_expo[di];
+    if (e < 0) continue;
+    double *r = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR + 2 * w;
+    for (int k = 0; k < per_date; ++k) r[k] = coef[(size_t)e * per_date + k];
+  }
+  MCRE_CUDA(cudaMemcpyAsync((void *)p->d.date_rec, p->h_date_rec.data(), p->h_date_rec.size() * sizeof(double),
+                            cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  MCRE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // host staging buffers may be reused by the caller
   return 0;
 }
 
@@ -533,14 +688,15 @@ template <int NT, int NS>
 static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *spill,
                        double *shift, cudaStream_t st) {
   const IrcDev &d = p->d;
-  const int threads = 256, nw = threads / 32;
+  constexpr int PP = NT == 0 ? 2 : 1;   // paths per thread
+  const int threads = 128, nw = threads / 32;
   const int nvb = NS * (4 + 2 * NT);
   const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0) return 0;
-#define LAUNCH(CIRV, SCH)                                                                              \
+#define LAUNCH(CIRV, SCH, MODEV)                                                                       \
   do {                                                                                                 \
-    auto k = irc_main_kernel<NT, NS, CIRV, SCH>;                                                       \
+    auto k = irc_main_kernel<NT, NS, CIRV, SCH, PP, MODEV>;                                            \
     if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                    \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));               \
@@ -553,9 +709,11 @@ static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, 
     k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, spill, shift, 0);                    \
     MCRE_LAUNCHED();                                                                                   \
   } while (0)
-  if (d.has_cir) LAUNCH(true, MCRE_SCHEME_EULER);
-  else if (d.scheme == MCRE_SCHEME_ANALYTICAL) LAUNCH(false, MCRE_SCHEME_ANALYTICAL);
-  else LAUNCH(false, MCRE_SCHEME_EULER);
+  if (d.has_cir) {
+    if (NT == 0 && NS == 1 && p->cva_only) LAUNCH(true, MCRE_SCHEME_EULER, (NT == 0 && NS == 1 ? 1 : 0));
+    else LAUNCH(true, MCRE_SCHEME_EULER, 0);
+  } else if (d.scheme == MCRE_SCHEME_ANALYTICAL) LAUNCH(false, MCRE_SCHEME_ANALYTICAL, 0);
+  else LAUNCH(false, MCRE_SCHEME_EULER, 0);
 #undef LAUNCH
   return 0;
 }

@@ -11,6 +11,9 @@
 // src/models/model.py:47).
 #pragma once
 #include <cstdint>
+#ifdef MCRE_FAST_MATH
+#include "fastmath.cuh"
+#endif
 
 namespace mcre {
 
@@ -69,9 +72,14 @@ struct NormalStream {
     uint32_t o[4];
     ph(p_lo, p_hi, block, 0u, o);
     double u1 = u53(o[0], o[1]), u2 = u53(o[2], o[3]);
-    double rad = sqrt(-2.0 * log(u1));
     double s, c;
+#ifdef MCRE_FAST_MATH
+    double rad = fm_sqrt(-2.0 * fm_log(u1));
+    fm_sincos2pi(u2, s, c);
+#else
+    double rad = sqrt(-2.0 * log(u1));
     sincospi(2.0 * u2, &s, &c);
+#endif
     z0 = rad * c; z1 = rad * s;
   }
   __device__ inline double next() {

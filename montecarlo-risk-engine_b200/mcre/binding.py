@@ -62,7 +62,7 @@ SYMBOLS = [
     "mcre_irc_set_coefficients", "mcre_irc_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_finish",
-    "mcre_tree_reduce", "mcre_dfma_peak", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
+    "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_tree_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
+    L.mcre_fastmath_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L
     return L
 
