@@ -213,6 +213,75 @@ int mcre_irc_mainsim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard 
                      double *d_partial, double *d_acc, double *d_shift, double *d_spill, void *stream);
 
 /* ================================================================================
+ * Equity family: Black-Scholes (single / multi asset / ModelConfig of BS models), Heston
+ * (Euler, Andersen QE with fuzzy branching; several correlated Heston assets as an
+ * extension) and Schwartz two-factor, with European / binary / basket / Asian / barrier
+ * payoffs; PV and first-order pathwise sensitivities in one fused pass.
+ * Replaces:
+ *   engine.generate_paths                 src/engine/engine.py:27-123
+ *   BlackScholesModel / BlackScholesMulti  src/models/black_scholes.py:44-85, black_scholes_multi.py:63-96
+ *   HestonModel (Euler, QE)               src/models/heston.py:99-121, 161-253
+ *   SchwartzTwoFactorModel                src/models/schwartz_two_factor.py:147-196
+ *   correlated draws z @ L^T              src/models/model.py:38-73, model_config.py:101-221
+ *   payoffs                               src/products/european_option.py:45-68, binary_option.py:37-42,
+ *                                         basket_option.py:55-78, asian_option.py:51-95, barrier_option.py:65-125
+ *   PVMetric + torch.autograd.grad        src/metrics/pv_metric.py:3-18, src/controller/controller.py:609-627
+ * One lane per (path, asset); lanes of a path exchange normals / spots by warp shuffle.
+ * ============================================================================== */
+enum { MCRE_EQ_BS = 0, MCRE_EQ_HESTON = 1, MCRE_EQ_SCHWARTZ = 2 };
+#define MCRE_EQ_MAX_SETS 4
+/* product kinds / event flags of the tables below */
+enum { MCRE_EQ_EUROPEAN = 0, MCRE_EQ_BINARY = 1, MCRE_EQ_BASKET = 2, MCRE_EQ_ASIAN = 3, MCRE_EQ_BARRIER = 4 };
+#define MCRE_EQ_EV_OBSERVE 1
+#define MCRE_EQ_EV_PAY 2
+#define MCRE_EQ_EV_FIRST 4
+
+typedef struct {
+  int32_t kind;          /* MCRE_EQ_*: every asset of a launch is of this kind                       */
+  int32_t scheme;        /* MCRE_SCHEME_*                                                            */
+  int32_t nt;            /* tangents per lane: 0, or the kind's parameter count (BS 3, Heston 7, Schwartz 6) */
+  int32_t smoothing;     /* Heston fuzzy indicators on (the reference ties this to differentiate)    */
+  int32_t n_assets, noise_dim, n_uniform;
+  const double *asset_par;      /* [n_assets][8] lane parameters: BS spot, sigma, rate | Heston spot, sigma, rate,
+                                   rho, kappa, theta, v0 | Schwartz rate, kappa_s, sigma_s, mu_l, sigma_l, rho   */
+  const int32_t *asset_noise;   /* [n_assets][2] noise columns the asset consumes (second: -1 if none)  */
+  const int32_t *asset_uniform; /* [n_assets] index of the asset's QE uniform within a sub-step          */
+  const int32_t *col_asset;     /* [noise_dim] asset owning noise column j                               */
+  const int32_t *col_elem;      /* [noise_dim] 0 / 1: first or second normal of that asset               */
+  int32_t n_sub, n_dates, n_pre_dates, n_chol;
+  const double *step_dt;        /* [n_sub] time2 - time1                                                 */
+  const double *step_sq;        /* [n_sub] sqrt(dt) (EULER / QE) or sqrt(nominal dt) (ANALYTICAL)        */
+  const int32_t *step_date;     /* [n_sub] simulation date completed by the sub-step or -1               */
+  const int32_t *step_chol;     /* [n_sub] index into chol / chol_dual                                   */
+  const double *step_aux;       /* [n_sub][n_assets] Schwartz: log F0(time2)                             */
+  const double *init_aux;       /* [n_assets] Schwartz: log F0(calibration date)                         */
+  int32_t corr_mode;            /* 0 identity, 1 chol_dual (one asset, two noise sources), 2 chol        */
+  const double *chol;           /* [n_chol][noise_dim][noise_dim] lower factor of the joint correlation  */
+  const double *chol_dual;      /* dual[n_chol][4]: L00, L01, L10, L11 with lane-local tangents          */
+  const int32_t *date_ev_off;   /* [n_dates+1] CSR offsets of the product events per simulation date     */
+  const int32_t *ev_prod;       /* [n_ev] product index                                                  */
+  const int32_t *ev_flags;      /* [n_ev] MCRE_EQ_EV_*                                                   */
+  int32_t n_prod;
+  const double *prod;           /* [n_prod][16]: kind, set, strike, sign(+1 call / -1 put), 1/numeraire,
+                                   d(1/numeraire)/d rate, flags(bit0 geometric, bit1 control variate),
+                                   control-variate constant, payment amount, barrier1, type1 (1 UO, 2 DO, 3 UI,
+                                   4 DI), barrier2, type2 (0: none), n observations, tracker slot, reserved  */
+  const double *prod_w;         /* [n_prod][n_assets] weights of the composite underlying                 */
+  int32_t n_sets;
+} mcre_eq_desc;
+
+typedef struct mcre_eq_plan mcre_eq_plan;
+int mcre_eq_create(const mcre_eq_desc *desc, mcre_eq_plan **out);
+void mcre_eq_destroy(mcre_eq_plan *plan);
+/* Accumulator slots (NS = n_sets rounded up to 1, 2 or 4):
+ *   [NS][3]              : sum(cf - c), sum((cf - c)^2), sum_p payoff_p * d(1/N_p)/d rate
+ *   [n_assets][NS][nt]   : lane-local tangents of sum_p payoff_p / N_p
+ * with c = d_shift[set] = the value on global path 0 (pilot launch). */
+int64_t mcre_eq_slots(const mcre_eq_plan *plan);
+int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                    double *d_acc, double *d_shift, void *stream);
+
+/* ================================================================================
  * Exact order statistics per row (PFE), replaces torch.sort + index in
  * PFEMetric.evaluate_numerically, src/metrics/pfe_metric.py:59-71.
  * MSB-first radix select on the order-preserving 64-bit image of the doubles, 8 bits

@@ -168,6 +168,22 @@ template <int N> struct RealTraits<Dual<N> > {
   __device__ static __forceinline__ Dual<N> lift(double c) { Dual<N> r = dual_zero<N>(); r.v = c; return r; }
 };
 
+// x with its value replaced (tangents kept): used where lanes share a group-reduced value
+// but each keeps the tangents of its own contribution.
+__device__ __forceinline__ double r_with_value(double, double v) { return v; }
+template <int N> __device__ __forceinline__ Dual<N> r_with_value(const Dual<N> &x, double v) { Dual<N> r = x; r.v = v; return r; }
+// independent variable #k of the tangent space
+template <typename R> struct RealVar;
+template <> struct RealVar<double> { __device__ static __forceinline__ double make(double v, int) { return v; } };
+template <int N> struct RealVar<Dual<N> > {
+  __device__ static __forceinline__ Dual<N> make(double v, int k) {
+    Dual<N> r; r.v = v;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.d[i] = (i == k) ? 1.0 : 0.0;
+    return r;
+  }
+};
+
 // Symmetric linear fuzzy indicator (src/maths/maths.py:3-9): hard 1{x>0} or
 // clamp((x+eps)/(2 eps), 0, 1) with slope 1/(2 eps) inside the band.
 __device__ __forceinline__ double r_fuzzy(double x, bool fuzzy, double eps) {

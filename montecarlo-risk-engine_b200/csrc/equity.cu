@@ -1,0 +1,450 @@
+// Equity family: fused path generation + payoff + PV / pathwise-Greek reduction for
+// Black-Scholes (single, multi-asset, ModelConfig of BS models), Heston (Euler, Andersen
+// QE with fuzzy branching; also several correlated Heston assets) and Schwartz two-factor,
+// with European / binary / basket / Asian / barrier payoffs.
+//
+// SIMT mapping: one LANE per (path, asset).  A warp holds floor(32 / A) paths; the A lanes
+// of a path exchange their independent normals with warp shuffles to form the correlated
+// noise (z @ L^T, src/models/model.py:46-48) and reduce weighted spots to basket values the
+// same way.  Every lane carries the tangents of its own asset's state with respect to its
+// own asset's parameters only (3 for Black-Scholes, 7 for Heston, 6 for Schwartz): an
+// asset's path never depends on another asset's parameters, so the full gradient over all
+// model parameters costs (1 + local parameters) x, not (1 + all parameters) x.  The payoff
+// is a function of group-reduced values, so each lane's tangent of it is the part flowing
+// through its own asset; the host scatters the lane-local sums to the global parameter
+// order (and adds the deterministic-numeraire term).
+//
+// Nothing but block-reduced sums reaches HBM.  See include/mcre.h for what this replaces.
+#define MCRE_FAST_MATH 1
+#include "common.cuh"
+#include "philox.cuh"
+#include "dual.cuh"
+#include "heston.cuh"
+#include "reduce.cuh"
+#include "launch.cuh"
+
+namespace mcre {
+
+constexpr int EQ_PR = 16;     // doubles per product record
+constexpr int EQ_NTRK = 2;    // path-dependent trackers per launch
+constexpr int EQ_PAR = 8;     // doubles per asset parameter row
+
+struct EqDev {
+  int kind, scheme, smoothing, n_assets, noise_dim, n_uniform;
+  const double *asset_par; const int *asset_noise, *asset_uniform, *col_asset, *col_elem;
+  int n_sub, n_dates, n_pre_dates;
+  const double *step_dt, *step_sq; const int *step_date, *step_chol;
+  const double *step_aux, *init_aux;
+  int corr_mode; const double *chol, *chol_dual;
+  const int *date_ev_off, *ev_prod, *ev_flags;
+  int n_prod; const double *prod, *prod_w;
+  int n_sets;
+};
+
+enum { EQ_EUROPEAN = MCRE_EQ_EUROPEAN, EQ_BINARY = MCRE_EQ_BINARY, EQ_BASKET = MCRE_EQ_BASKET, EQ_ASIAN = MCRE_EQ_ASIAN, EQ_BARRIER = MCRE_EQ_BARRIER };
+enum { EQ_EV_OBSERVE = MCRE_EQ_EV_OBSERVE, EQ_EV_PAY = MCRE_EQ_EV_PAY, EQ_EV_FIRST = MCRE_EQ_EV_FIRST };
+
+template <int KIND> struct EqParCount;
+template <> struct EqParCount<MCRE_EQ_BS> { static const int n = 3; };
+template <> struct EqParCount<MCRE_EQ_HESTON> { static const int n = 7; };
+template <> struct EqParCount<MCRE_EQ_SCHWARTZ> { static const int n = 6; };
+
+// sum of x over the A lanes of this lane's path group
+__device__ __forceinline__ double group_sum(double x, int base, int A) {
+  double tot = 0.0;
+  for (int j = 0; j < A; ++j) tot += __shfl_sync(0xffffffffu, x, (base + j) & 31);
+  return tot;
+}
+
+template <typename R>
+__device__ __forceinline__ R option_payoff(const R &u, double strike, double sign) {
+  return r_relu((u - strike) * sign);
+}
+
+// barrier survival factor with the always-fuzzy indicator, eps = 0.05 in spot units
+// (src/products/barrier_option.py:66-125, src/maths/maths.py:8-9)
+template <typename R>
+__device__ __forceinline__ R barrier_factor(const R &mx, const R &mn, double barrier, int btype) {
+  const R below = r_fuzzy(barrier - mx, true, 0.05);
+  const R above = r_fuzzy(mn - barrier, true, 0.05);
+  switch (btype) {
+    case 1: return below;            // up-and-out
+    case 2: return above;            // down-and-out
+    case 3: return 1.0 - below;      // up-and-in
+    default: return 1.0 - above;     // down-and-in
+  }
+}
+
+// slot layout: [NS][3] = sum(cf - c), sum((cf - c)^2), sum(payoff * d invN / d r)   then
+//              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p
+template <int KIND, int ALT, int NT, int NS>
+__global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
+                                                      double *shift, int pilot) {
+  typedef typename RealOf<NT>::type R;
+  typedef RealTraits<R> T;
+  typedef RealVar<R> V;
+  constexpr int NP = EqParCount<KIND>::n;
+  constexpr int NVH = NS * 3;
+  constexpr int NVT = NS * (NT > 0 ? NT : 1);
+  constexpr int NVMAX = NVH > NVT ? NVH : NVT;
+  extern __shared__ double smem[];
+  const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int A = P.n_assets, ppw = 32 / A;
+  const int n_slots = NS * 3 + A * NS * NT;
+  double *acc = smem;                 // [n_slots]
+  double *stage = smem + n_slots;     // [2][nw][NVMAX]
+  const int g = lane / A, a = lane - g * A, base = g * A;
+  const bool lane_ok = g < ppw;
+  const int aa = lane_ok ? a : 0;     // ghost lanes replay asset 0 and are masked out
+  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  const int paths_per_iter = nw * ppw;
+
+  // ---- this lane's asset -----------------------------------------------------------
+  R par[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) par[k] = V::make(__ldg(P.asset_par + aa * EQ_PAR + k), k);
+  const int c0 = __ldg(P.asset_noise + aa * 2), c1 = __ldg(P.asset_noise + aa * 2 + 1);
+  const int uidx = __ldg(P.asset_uniform + aa);
+  const int d = P.noise_dim;
+  const bool smooth = P.smoothing != 0;
+
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) acc[i] = 0.0;
+    __syncthreads();
+    int parity = 0;
+    for (int it = 0; it < sh.chunk; it += paths_per_iter) {
+      const int in_chunk = it + warp * ppw + g;
+      const long long lpath = chunk * sh.chunk + in_chunk;
+      const bool live = lane_ok && in_chunk < sh.chunk && lpath < sh.n_paths;
+      const unsigned long long gpath = (unsigned long long)(sh.path_begin + (live ? lpath : 0));
+      NormalStream ns; ns.init(rng, gpath);
+
+      R s0, s1;
+      if constexpr (KIND == MCRE_EQ_BS) { s0 = par[0]; s1 = T::zero(); }
+      else if constexpr (KIND == MCRE_EQ_HESTON) { s0 = r_log(par[0]); s1 = par[6]; }
+      else { s0 = T::zero(); s1 = T::zero(); }
+      double logF = KIND == MCRE_EQ_SCHWARTZ ? __ldg(P.init_aux + aa) : 0.0;
+      R cf[NS], trk_a[EQ_NTRK], trk_b[EQ_NTRK];
+      double numtan[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) { cf[s] = T::zero(); numtan[s] = 0.0; }
+#pragma unroll
+      for (int k = 0; k < EQ_NTRK; ++k) { trk_a[k] = T::zero(); trk_b[k] = T::zero(); }
+
+      auto spot_now = [&]() -> R {
+        if (KIND == MCRE_EQ_BS) return s0;
+        if (KIND == MCRE_EQ_HESTON) return r_exp(s0);
+        return r_exp(logF + s0 + s1);
+      };
+
+      // ---- product events of one simulation date --------------------------------------
+      auto eval_date = [&](int di) {
+        const int e0 = __ldg(P.date_ev_off + di), e1 = __ldg(P.date_ev_off + di + 1);
+        if (e0 == e1) return;
+        const R S = spot_now();
+        for (int e = e0; e < e1; ++e) {
+          const int pi = __ldg(P.ev_prod + e), ef = __ldg(P.ev_flags + e);
+          const double *pr = P.prod + (size_t)pi * EQ_PR;
+          const int kind = (int)__ldg(pr + 0), set = (int)__ldg(pr + 1), pflags = (int)__ldg(pr + 6);
+          const double strike = __ldg(pr + 2), sign = __ldg(pr + 3);
+          const double wgt = __ldg(P.prod_w + (size_t)pi * A + aa);
+          // composite underlying: arithmetic and / or geometric weighted basket of the group's spots
+          const bool need_geo = (kind == EQ_BASKET) && (pflags & 3);
+          const bool need_ari = !(kind == EQ_BASKET && (pflags & 1));
+          R U = T::zero(), G = T::zero();
+          if (need_ari) {
+            const R term = S * wgt;
+            U = r_with_value(term, group_sum(val(term), base, A));
+          }
+          if (need_geo) {
+            const R term = r_log(S + 1e-10) * wgt;      // basket_option.py:62-66
+            G = r_exp(r_with_value(term, group_sum(val(term), base, A)));
+          }
+          const int slot = (int)__ldg(pr + 14);
+          if (ef & EQ_EV_OBSERVE) {
+#pragma unroll
+            for (int k = 0; k < EQ_NTRK; ++k) {
+              if (k != slot) continue;
+              if (kind == EQ_ASIAN) {
+                const R x = (pflags & 1) ? r_log(U + 1e-10) : U;     // asian_option.py:51-69
+                trk_a[k] = (ef & EQ_EV_FIRST) ? x : trk_a[k] + x;
+              } else {                                                // running max / min
+                if ((ef & EQ_EV_FIRST) || val(U) > val(trk_a[k])) trk_a[k] = U;
+                if ((ef & EQ_EV_FIRST) || val(U) < val(trk_b[k])) trk_b[k] = U;
+              }
+            }
+          }
+          if (!(ef & EQ_EV_PAY)) continue;
+          R pay;
+          if (kind == EQ_EUROPEAN) {
+            pay = option_payoff(U, strike, sign);                     // european_option.py:45-68
+          } else if (kind == EQ_BINARY) {
+            const R ind = r_fuzzy(U - strike, true, 1.0);             // binary_option.py:37-42
+            pay = (sign > 0.0 ? ind : 1.0 - ind) * __ldg(pr + 8);
+          } else if (kind == EQ_BASKET) {
+            // control variate (basket_option.py:72-78): classical - geometric (+ closed form, added by the host)
+            pay = option_payoff((pflags & 1) ? G : U, strike, sign);
+            if (pflags & 2) pay = pay - option_payoff(G, strike, sign) + __ldg(pr + 7);
+          } else if (kind == EQ_ASIAN) {
+            const double inv_n = 1.0 / __ldg(pr + 13);
+            R avg = T::zero();
+#pragma unroll
+            for (int k = 0; k < EQ_NTRK; ++k) if (k == slot) avg = trk_a[k] * inv_n;
+            if (pflags & 1) avg = r_exp(avg);
+            pay = option_payoff(avg, strike, sign);
+          } else {
+            R mx = T::zero(), mn = T::zero();
+#pragma unroll
+            for (int k = 0; k < EQ_NTRK; ++k) if (k == slot) { mx = trk_a[k]; mn = trk_b[k]; }
+            pay = option_payoff(U, strike, sign) * barrier_factor(mx, mn, __ldg(pr + 9), (int)__ldg(pr + 10));
+            const int bt2 = (int)__ldg(pr + 12);
+            if (bt2 > 0) pay = pay * barrier_factor(mx, mn, __ldg(pr + 11), bt2);
+          }
+          const double invN = __ldg(pr + 4), dinvN = __ldg(pr + 5);
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+            if (s == set) { cf[s] = cf[s] + pay * invN; numtan[s] += val(pay) * dinvN; }
+        }
+      };
+
+      for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+      for (int is = 0; is < P.n_sub; ++is) {
+        const double dt = __ldg(P.step_dt + is), sq = __ldg(P.step_sq + is);
+        // ---- independent draws of this lane's noise columns -----------------------------
+        double z0 = 0.0, z1 = 0.0, u = 0.5;
+        if (rng.mode == MCRE_RNG_INJECT) {
+          const double *zp = rng.z + ((size_t)is * rng.n_total + gpath) * d;
+          z0 = zp[c0];
+          if (c1 >= 0) z1 = zp[c1];
+          if (KIND == MCRE_EQ_HESTON && ALT == 1) u = rng.u[((size_t)is * rng.n_total + gpath) * P.n_uniform + uidx];
+        } else {
+          const uint32_t n0 = (uint32_t)(is * d + c0);
+          double p0, p1;
+          ns.pair(n0 >> 1, p0, p1);
+          z0 = (n0 & 1u) ? p1 : p0;
+          if (c1 >= 0) {
+            const uint32_t n1 = (uint32_t)(is * d + c1);
+            if ((n1 >> 1) == (n0 >> 1)) z1 = (n1 & 1u) ? p1 : p0;
+            else { ns.pair(n1 >> 1, p0, p1); z1 = (n1 & 1u) ? p1 : p0; }
+          }
+          if (KIND == MCRE_EQ_HESTON && ALT == 1) u = ns.uniform((uint32_t)(is * P.n_uniform + uidx));
+        }
+        // ---- correlate: w = z @ L^T -----------------------------------------------------
+        R w0 = T::lift(z0), w1 = T::lift(z1);
+        if (P.corr_mode == 2) {
+          const double *L = P.chol + (size_t)__ldg(P.step_chol + is) * d * d;
+          double a0 = 0.0, a1 = 0.0;
+          for (int j = 0; j < d; ++j) {
+            const int src = (base + __ldg(P.col_asset + j)) & 31;
+            const double zj = __shfl_sync(0xffffffffu, __ldg(P.col_elem + j) ? z1 : z0, src);
+            a0 += __ldg(L + c0 * d + j) * zj;
+            if (c1 >= 0) a1 += __ldg(L + c1 * d + j) * zj;
+          }
+          w0 = T::lift(a0); w1 = T::lift(a1);
+        } else if (P.corr_mode == 1) {
+          const double *L = P.chol_dual + (size_t)__ldg(P.step_chol + is) * 4 * (NT + 1);
+          w0 = T::load(L, 0) * z0;
+          w1 = T::load(L, 2) * z0 + T::load(L, 3) * z1;
+        }
+        // ---- model step ------------------------------------------------------------------
+        if constexpr (KIND == MCRE_EQ_BS) {
+          const R &sigma = par[1], &rate = par[2];
+          if (ALT == 1) s0 = s0 * r_exp(rate * dt + (sigma * (sq * w0) - 0.5 * dt * sigma * sigma));  // black_scholes.py:44-67
+          else s0 = s0 + (rate * s0 * dt + sigma * s0 * sq * w0);                                     // :69-85
+        } else if constexpr (KIND == MCRE_EQ_HESTON) {
+          if (ALT == 1) heston_qe_step<R>(par[1], par[2], par[3], par[4], par[5], dt, smooth, val(w0), val(w1), u, s0, s1);
+          else heston_euler_step<R>(par[1], par[2], par[4], par[5], dt, sq, w0, w1, s0, s1);
+        } else {
+          const R &kappa = par[1], &ss = par[2], &mu = par[3], &sl = par[4];
+          if (ALT == 1) {            // schwartz_two_factor.py:147-171 (w = covariance-scaled)
+            const R xm = fabs(val(kappa)) <= 1e-12 ? s0 : s0 * r_exp(-(kappa * dt));
+            s0 = xm + w0;
+            s1 = s1 + mu * dt + w1;
+          } else {                   // :173-196
+            s0 = s0 - kappa * s0 * dt + ss * sq * w0;
+            s1 = s1 + mu * dt + sl * sq * w1;
+          }
+          logF = __ldg(P.step_aux + (size_t)is * A + aa);
+        }
+        const int di = __ldg(P.step_date + is);
+        if (di >= 0) eval_date(di);
+      }
+
+      // ---- per-path totals -> block accumulators -------------------------------------------
+      const double keep1 = (live && a == 0) ? 1.0 : 0.0;
+      {
+        double vals[NVH];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (pilot) { if (threadIdx.x == 0) shift[s] = val(cf[s]); }
+          const double x = val(cf[s]) - (pilot ? 0.0 : shift[s]);
+          vals[s * 3 + 0] = keep1 * x; vals[s * 3 + 1] = keep1 * x * x; vals[s * 3 + 2] = keep1 * numtan[s];
+        }
+        if (!pilot) block_accumulate<NVH>(vals, acc, 0, stage, NVMAX, parity);
+      }
+      if (NT > 0 && !pilot) {
+        for (int ap = 0; ap < A; ++ap) {
+          const double keep = (live && a == ap) ? 1.0 : 0.0;
+          double tv[NVT];
+#pragma unroll
+          for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int k = 0; k < NT; ++k) tv[s * NT + k] = keep * tan_of(cf[s], k);
+          block_accumulate<NVT>(tv, acc, NS * 3 + ap * NS * NT, stage, NVMAX, parity);
+        }
+      }
+      if (pilot) return;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) partial[(size_t)chunk * n_slots + i] = acc[i];
+    __syncthreads();
+  }
+}
+
+}  // namespace mcre
+
+// =====================================================================================
+// Host side of the C ABI
+// =====================================================================================
+using namespace mcre;
+
+struct mcre_eq_plan {
+  EqDev d;
+  int nt = 0;
+  DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w;
+  DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
+};
+
+extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
+  if (!c || !out) return fail(-1, "null argument%s", "");
+  if (c->n_assets < 1 || c->n_assets > 32) return fail(-1, "eq: 1..32 assets per path group%s", "");
+  if (c->n_sets < 1 || c->n_sets > MCRE_EQ_MAX_SETS) return fail(-1, "eq: n_sets out of range%s", "");
+  const int np = c->kind == MCRE_EQ_BS ? 3 : c->kind == MCRE_EQ_HESTON ? 7 : c->kind == MCRE_EQ_SCHWARTZ ? 6 : -1;
+  if (np < 0) return fail(-1, "eq: unknown model kind%s", "");
+  if (c->nt != 0 && c->nt != np) return fail(-1, "eq: nt must be 0 or the model's parameter count%s", "");
+  if (c->nt != 0 && c->n_sets > 2) return fail(-3, "eq: at most 2 netting sets per launch when tangents are on%s", "");
+  if (c->corr_mode == 1 && (c->n_assets != 1 || c->noise_dim != 2))
+    return fail(-1, "eq: dual Cholesky needs one asset with two noise sources%s", "");
+  const bool scheme_ok = (c->kind == MCRE_EQ_HESTON) ? (c->scheme == MCRE_SCHEME_EULER || c->scheme == MCRE_SCHEME_QE)
+                                                     : (c->scheme == MCRE_SCHEME_EULER || c->scheme == MCRE_SCHEME_ANALYTICAL);
+  if (!scheme_ok) return fail(-1, "eq: scheme not defined for this model%s", "");
+  for (int p = 0; p < c->n_prod; ++p) {
+    const int slot = (int)c->prod[(size_t)p * EQ_PR + 14], kind = (int)c->prod[(size_t)p * EQ_PR];
+    if ((kind == EQ_ASIAN || kind == EQ_BARRIER) && (slot < 0 || slot >= EQ_NTRK))
+      return fail(-3, "eq: at most 2 path-dependent products per launch%s", "");
+    const int set = (int)c->prod[(size_t)p * EQ_PR + 1];
+    if (set < 0 || set >= c->n_sets) return fail(-1, "eq: product set index out of range%s", "");
+  }
+  mcre_eq_plan *p = new mcre_eq_plan();
+  p->nt = c->nt;
+  const int A = c->n_assets, d = c->noise_dim, n_ev = c->date_ev_off[c->n_dates];
+  int rc = 0;
+#define UP(field, host, count) if (!rc) rc = p->field.upload(host, (size_t)(count))
+  UP(asset_par, c->asset_par, A * EQ_PAR); UP(asset_noise, c->asset_noise, A * 2); UP(asset_uniform, c->asset_uniform, A);
+  UP(col_asset, c->col_asset, d); UP(col_elem, c->col_elem, d);
+  UP(step_dt, c->step_dt, c->n_sub); UP(step_sq, c->step_sq, c->n_sub);
+  UP(step_date, c->step_date, c->n_sub); UP(step_chol, c->step_chol, c->n_sub);
+  UP(step_aux, c->step_aux, (size_t)c->n_sub * A); UP(init_aux, c->init_aux, A);
+  UP(chol, c->chol, c->corr_mode == 2 ? (size_t)c->n_chol * d * d : 0);
+  UP(chol_dual, c->chol_dual, c->corr_mode == 1 ? (size_t)c->n_chol * 4 * (c->nt + 1) : 0);
+  UP(date_ev_off, c->date_ev_off, c->n_dates + 1); UP(ev_prod, c->ev_prod, n_ev); UP(ev_flags, c->ev_flags, n_ev);
+  UP(prod, c->prod, (size_t)c->n_prod * EQ_PR); UP(prod_w, c->prod_w, (size_t)c->n_prod * A);
+#undef UP
+  if (rc) { mcre_eq_destroy(p); return rc; }
+  EqDev &D = p->d;
+  D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
+  D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
+  D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
+  D.col_asset = p->col_asset.p; D.col_elem = p->col_elem.p;
+  D.n_sub = c->n_sub; D.n_dates = c->n_dates; D.n_pre_dates = c->n_pre_dates;
+  D.step_dt = p->step_dt.p; D.step_sq = p->step_sq.p; D.step_date = p->step_date.p; D.step_chol = p->step_chol.p;
+  D.step_aux = p->step_aux.p; D.init_aux = p->init_aux.p;
+  D.corr_mode = c->corr_mode; D.chol = p->chol.p; D.chol_dual = p->chol_dual.p;
+  D.date_ev_off = p->date_ev_off.p; D.ev_prod = p->ev_prod.p; D.ev_flags = p->ev_flags.p;
+  D.n_prod = c->n_prod; D.prod = p->prod.p; D.prod_w = p->prod_w.p; D.n_sets = c->n_sets;
+  *out = p;
+  return 0;
+}
+
+extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
+  if (!p) return;
+  p->asset_par.release(); p->step_dt.release(); p->step_sq.release(); p->step_aux.release(); p->init_aux.release();
+  p->chol.release(); p->chol_dual.release(); p->prod.release(); p->prod_w.release(); p->asset_noise.release();
+  p->asset_uniform.release(); p->col_asset.release(); p->col_elem.release(); p->step_date.release();
+  p->step_chol.release(); p->date_ev_off.release(); p->ev_prod.release(); p->ev_flags.release();
+  delete p;
+}
+
+static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 2 : 4); }
+
+extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
+  const int ns = eq_ns_template(p->d.n_sets);
+  return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt;
+}
+
+template <int KIND, int ALT, int NT, int NS>
+static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
+                     cudaStream_t st) {
+  const EqDev &d = p->d;
+  const int threads = 128, nw = threads / 32;
+  constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVMAX = NVH > NVT ? NVH : NVT;
+  const int n_slots = NS * 3 + d.n_assets * NS * NT;
+  const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
+  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  if (n_chunks == 0) return 0;
+  auto k = eq_main_kernel<KIND, ALT, NT, NS>;
+  int per_sm = 1;
+  MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
+  if (per_sm < 1) return fail(-3, "eq main kernel does not fit%s", "");
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > n_chunks) grid = n_chunks;
+  ShardDev pilot_sh{0, 1, sh.chunk};
+  k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, 1);
+  MCRE_LAUNCHED();
+  k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, shift, 0);
+  MCRE_LAUNCHED();
+  return 0;
+}
+
+template <int KIND, int ALT, int NTK>
+static int eq_dispatch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
+                       cudaStream_t st) {
+  const int ns = eq_ns_template(p->d.n_sets);
+  if (p->nt == 0) {
+    return ns == 1 ? eq_launch<KIND, ALT, 0, 1>(p, rng, sh, partial, shift, st)
+         : ns == 2 ? eq_launch<KIND, ALT, 0, 2>(p, rng, sh, partial, shift, st)
+                   : eq_launch<KIND, ALT, 0, 4>(p, rng, sh, partial, shift, st);
+  }
+  return ns == 1 ? eq_launch<KIND, ALT, NTK, 1>(p, rng, sh, partial, shift, st)
+                 : eq_launch<KIND, ALT, NTK, 2>(p, rng, sh, partial, shift, st);
+}
+
+extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                               double *d_acc, double *d_shift, void *stream) {
+  if (!p || !rng || !d_partial || !d_acc || !d_shift) return fail(-1, "null argument%s", "");
+  int rc = check_shard(shard);
+  if (rc) return rc;
+  if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
+  if (rng->mode == MCRE_RNG_INJECT && p->d.kind == MCRE_EQ_HESTON && p->d.scheme == MCRE_SCHEME_QE && !rng->d_u)
+    return fail(-1, "inject mode: QE needs uniforms%s", "");
+  RngDev r = make_rng(rng);
+  ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int alt = (p->d.scheme == MCRE_SCHEME_EULER) ? 0 : 1;
+  switch (p->d.kind) {
+    case MCRE_EQ_BS:
+      rc = alt ? eq_dispatch<MCRE_EQ_BS, 1, 3>(p, r, sh, d_partial, d_shift, st)
+               : eq_dispatch<MCRE_EQ_BS, 0, 3>(p, r, sh, d_partial, d_shift, st);
+      break;
+    case MCRE_EQ_HESTON:
+      rc = alt ? eq_dispatch<MCRE_EQ_HESTON, 1, 7>(p, r, sh, d_partial, d_shift, st)
+               : eq_dispatch<MCRE_EQ_HESTON, 0, 7>(p, r, sh, d_partial, d_shift, st);
+      break;
+    default:
+      rc = alt ? eq_dispatch<MCRE_EQ_SCHWARTZ, 1, 6>(p, r, sh, d_partial, d_shift, st)
+               : eq_dispatch<MCRE_EQ_SCHWARTZ, 0, 6>(p, r, sh, d_partial, d_shift, st);
+  }
+  if (rc) return rc;
+  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  return mcre_tree_reduce(d_partial, n_chunks, mcre_eq_slots(p), d_acc, stream);
+}

@@ -11,6 +11,7 @@
 #include "philox.cuh"
 #include "dual.cuh"
 #include "reduce.cuh"
+#include "launch.cuh"
 
 namespace mcre {
 
@@ -30,11 +31,6 @@ struct IrcDev {
   int n_units, n_reg;
   const double *unit_fix, *unit_float; const double *reg_basis;
   const double *step_rec, *date_rec;  // packed records of the main kernel
-};
-
-struct ShardDev {
-  long long path_begin, n_paths;
-  int chunk;
 };
 
 // ---- per-path model state ---------------------------------------------------------
@@ -534,26 +530,6 @@ struct mcre_irc_plan {
   size_t expo_coef_count = 0;
   bool cva_only = false;
 };
-
-static inline double pack2(int lo, int hi) {
-  long long v = ((long long)(unsigned int)hi << 32) | (unsigned int)lo;
-  double d;
-  memcpy(&d, &v, 8);
-  return d;
-}
-
-static RngDev make_rng(const mcre_rng *r) {
-  RngDev d;
-  d.mode = r->mode; d.k0 = (uint32_t)r->seed; d.k1 = (uint32_t)r->stream;
-  d.z = r->d_z; d.u = r->d_u; d.n_total = r->n_paths_total;
-  return d;
-}
-static int check_shard(const mcre_shard *s) {
-  if (!s || s->n_paths < 0 || s->chunk_paths <= 0 || s->chunk_paths % 256 != 0)
-    return fail(-2, "invalid shard: chunk_paths must be a positive multiple of 256%s", "");
-  if (s->path_begin % s->chunk_paths != 0) return fail(-2, "invalid shard: path_begin not chunk aligned%s", "");
-  return 0;
-}
 
 extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   if (!c || !out) return fail(-1, "null argument%s", "");

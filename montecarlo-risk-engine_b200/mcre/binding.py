@@ -60,6 +60,7 @@ SYMBOLS = [
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim",
     "mcre_irc_set_coefficients", "mcre_irc_mainsim",
+    "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_finish",
     "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
@@ -94,6 +95,13 @@ def lib():
     L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
     L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_eq_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mcre_eq_destroy.argtypes = [C.c_void_p]
+    L.mcre_eq_destroy.restype = None
+    L.mcre_eq_slots.argtypes = [C.c_void_p]
+    L.mcre_eq_slots.restype = C.c_int64
+    L.mcre_eq_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
     L.mcre_tree_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
     L.mcre_fastmath_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

@@ -1,8 +1,486 @@
-"""Equity family backend (Black-Scholes single / multi asset, ModelConfig of BS models,
-Heston) - placeholder until csrc/equity.cu lands in this round."""
+"""Plan compiler + driver for the equity family (csrc/equity.cu).
+
+Lowers (Black-Scholes single / multi asset / ModelConfig of equity models, Heston, Schwartz
+two-factor; European / binary / basket / Asian / barrier payoffs; PV metrics) into the flat
+tables of ``mcre_eq_desc`` (include/mcre.h) and runs the fused kernel: path stepping,
+correlation, payoff, PV and pathwise sensitivities in one pass, nothing per-path in HBM.
+What it takes the place of in the reference:
+  request collection / resolution   src/request_interface/request_interface.py:22-130
+  evaluate_products (PV branch)     src/controller/controller.py:385-471, 565-661
+  torch.autograd.grad               src/controller/controller.py:609-627
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from common.enums import SimulationScheme
+from mcre import binding as B
+from mcre import runtime as RT
+from mcre.dual import D, cholesky_dual
+from mcre.finish import mean_and_error
+from mcre.timegrid import build_time_grid
+from metrics.metric import MetricType
+from models.black_scholes import BlackScholesModel
+from models.black_scholes_multi import BlackScholesMulti
+from models.heston import HestonModel
+from models.model_config import ModelConfig
+from models.schwartz_two_factor import SchwartzTwoFactorModel
+from products.asian_option import AsianAveragingType, AsianOption
+from products.barrier_option import BarrierOption, BarrierOptionType
+from products.basket_option import BasketOption, BasketOptionType
+from products.binary_option import BinaryOption
+from products.equity import Equity
+from products.european_option import EuropeanOption
+from products.product import OptionType
+
+CHUNK_PATHS = 4096
+EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
+P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER = 0, 1, 2, 3, 4
+EV_OBSERVE, EV_PAY, EV_FIRST = 1, 2, 4
+EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS = 16, 8, 2, 4
+_NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
+_BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
+                 BarrierOptionType.UPANDIN: 3, BarrierOptionType.DOWNANDIN: 4}
+
+
+class EqDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("scheme", C.c_int32), ("nt", C.c_int32), ("smoothing", C.c_int32),
+        ("n_assets", C.c_int32), ("noise_dim", C.c_int32), ("n_uniform", C.c_int32),
+        ("asset_par", B.c_dp), ("asset_noise", B.c_ip), ("asset_uniform", B.c_ip),
+        ("col_asset", B.c_ip), ("col_elem", B.c_ip),
+        ("n_sub", C.c_int32), ("n_dates", C.c_int32), ("n_pre_dates", C.c_int32), ("n_chol", C.c_int32),
+        ("step_dt", B.c_dp), ("step_sq", B.c_dp), ("step_date", B.c_ip), ("step_chol", B.c_ip),
+        ("step_aux", B.c_dp), ("init_aux", B.c_dp),
+        ("corr_mode", C.c_int32), ("chol", B.c_dp), ("chol_dual", B.c_dp),
+        ("date_ev_off", B.c_ip), ("ev_prod", B.c_ip), ("ev_flags", B.c_ip),
+        ("n_prod", C.c_int32), ("prod", B.c_dp), ("prod_w", B.c_dp), ("n_sets", C.c_int32),
+    ]
+
+
+class Asset:
+    """One simulated asset = one lane of a path group."""
+
+    def __init__(self, asset_id, model, par, gmap):
+        self.asset_id, self.model = asset_id, model
+        self.par = par        # lane parameter values in the kernel's order
+        self.gmap = gmap      # lane parameter k -> index in the controller's flattened parameter list
+
+
+def _sub_models(model):
+    return list(model.models) if isinstance(model, ModelConfig) else [model]
+
+
+def family_of(model):
+    """(kind, assets) or None if the model is not an equity-family model."""
+    subs = _sub_models(model)
+    offs = model.param_offsets() if isinstance(model, ModelConfig) else [0]
+    kinds, assets = set(), []
+    for m, off in zip(subs, offs):
+        pv = m.param_values()
+        if isinstance(m, BlackScholesModel):
+            kinds.add(EQ_BS)
+            assets.append(Asset(m.asset_ids[0], m, pv, [off, off + 1, off + 2]))
+        elif isinstance(m, BlackScholesMulti):
+            kinds.add(EQ_BS)
+            n = m.num_assets
+            for a in range(n):
+                assets.append(Asset(m.asset_ids[a], m, [pv[a], pv[n + a], pv[2 * n]],
+                                    [off + a, off + n + a, off + 2 * n]))
+        elif isinstance(m, HestonModel):
+            kinds.add(EQ_HESTON)
+            assets.append(Asset(m.asset_ids[0], m, pv, [off + k for k in range(7)]))
+        elif isinstance(m, SchwartzTwoFactorModel):
+            kinds.add(EQ_SCHWARTZ)
+            assets.append(Asset(m.asset_ids[0], m, pv, [off + k for k in range(6)]))
+        else:
+            return None
+    if len(kinds) != 1:
+        return None
+    kind = kinds.pop()
+    if kind == EQ_SCHWARTZ and len(assets) != 1:
+        return None
+    return kind, assets
+
+
+def _is_equity_product(p):
+    if isinstance(p, EuropeanOption):
+        return isinstance(p.underlying, Equity)
+    return isinstance(p, (BinaryOption, BasketOption, AsianOption, BarrierOption))
 
 
 class EquityBackend:
     @staticmethod
     def supports(ctrl):
-        return False
+        if family_of(ctrl.model) is None:
+            return False
+        if any(m.metric_type != MetricType.PV for m in ctrl.risk_metrics.metrics):
+            return False
+        return all(_is_equity_product(p) for p in ctrl.products)
+
+    def __init__(self, ctrl):
+        self.c = ctrl
+        self.kind, self.assets = family_of(ctrl.model)
+        self.A = len(self.assets)
+        if self.A > 32:
+            raise NotImplementedError("at most 32 jointly simulated assets per path group")
+        scheme = ctrl.simulation_scheme
+        if self.kind == EQ_HESTON:
+            if scheme not in (SimulationScheme.EULER, SimulationScheme.QE):
+                raise NotImplementedError(f"Scheme {scheme} is not defined for the Heston model.")
+            if isinstance(ctrl.model, ModelConfig) and scheme != SimulationScheme.QE:
+                raise NotImplementedError("Several correlated Heston assets are simulated with the QE scheme only.")
+        elif scheme not in (SimulationScheme.EULER, SimulationScheme.ANALYTICAL):
+            raise NotImplementedError(f"Scheme {scheme} is not defined for this model.")
+        self.scheme = scheme
+        self.npar = _NPAR[self.kind]
+        self.nt = self.npar if ctrl.differentiate else 0
+        self.id_to_asset = {a.asset_id: i for i, a in enumerate(self.assets)}
+        subs = _sub_models(ctrl.model)
+        num_idx = ctrl.model.id_to_model["numeraire"] if isinstance(ctrl.model, ModelConfig) else 0
+        self.num_model = subs[num_idx]
+        offs = ctrl.model.param_offsets() if isinstance(ctrl.model, ModelConfig) else [0]
+        self.num_rate_global = offs[num_idx] + self._rate_index(self.num_model)
+        self.num_rate = self.num_model.param_values()[self._rate_index(self.num_model)]
+
+    @staticmethod
+    def _rate_index(m):
+        if isinstance(m, BlackScholesMulti):
+            return 2 * m.num_assets
+        if isinstance(m, SchwartzTwoFactorModel):
+            return 0
+        return 2
+
+    # ------------------------------------------------------------------ lowering
+    def _asset_index(self, asset_id):
+        if self.A == 1:
+            return 0
+        if asset_id not in self.id_to_asset:
+            raise ValueError(f"Asset id '{asset_id}' not found in model asset ids {list(self.id_to_asset)}.")
+        return self.id_to_asset[asset_id]
+
+    def _inv_numeraire(self, t):
+        """1 / N(t) and its rate derivative: deterministic money-market account of the
+        numeraire model (black_scholes.py:104-106, heston.py:272-274)."""
+        tau = t - self.num_model.t0()
+        inv = math.exp(-self.num_rate * tau)
+        return inv, -tau * inv
+
+    def _product_record(self, p, set_local, slot, date_idx):
+        """-> (record[16], weights[A], events [(date index, flags)])."""
+        rec = np.zeros(EQ_PR)
+        w = np.zeros(self.A)
+        rec[1] = set_local
+        rec[14] = -1
+        sign = 1.0 if p.option_type == OptionType.CALL else -1.0
+        rec[2], rec[3] = float(p.strike), sign
+        basket = getattr(p, "basket", None)   # extension: path-dependent payoffs on a weighted basket
+        if isinstance(p, EuropeanOption):
+            rec[0] = P_EUROPEAN
+            w[self._asset_index(p.underlying.get_asset_id())] = 1.0
+            t_pay = float(p.exercise_date)
+            events = [(date_idx[t_pay], EV_PAY)]
+            t_num = t_pay
+        elif isinstance(p, BinaryOption):
+            rec[0] = P_BINARY
+            w[self._asset_index(p.get_asset_id())] = 1.0
+            rec[8] = float(p.payment_amount)
+            t_pay = float(p.maturity)
+            events = [(date_idx[t_pay], EV_PAY)]
+            t_num = t_pay
+        elif isinstance(p, BasketOption):
+            rec[0] = P_BASKET
+            for aid, wi in zip(p.asset_ids, p.weights.tolist()):
+                w[self._asset_index(aid)] += wi
+            geo = p.basket_option_type == BasketOptionType.GEOMETRIC
+            rec[6] = (1 if geo else 0) | (2 if p.use_variation_reduction else 0)
+            if p.use_variation_reduction:
+                rec[7] = float(p.compute_pv_analytically(self.c.model).reshape(-1)[0])
+            t_pay = float(p.maturity)
+            events = [(date_idx[t_pay], EV_PAY)]
+            t_num = t_pay
+        elif isinstance(p, (AsianOption, BarrierOption)):
+            obs = [float(t) for t in p.modeling_timeline]
+            if basket is not None:
+                for aid, wi in zip(*basket):
+                    w[self._asset_index(aid)] += float(wi)
+            else:
+                w[self._asset_index(p.get_asset_id())] = 1.0
+            rec[13], rec[14] = len(obs), slot
+            if isinstance(p, AsianOption):
+                rec[0] = P_ASIAN
+                rec[6] = 1 if p.averaging_type == AsianAveragingType.GEOMETRIC else 0
+            else:
+                rec[0] = P_BARRIER
+                rec[9], rec[10] = float(p.barrier1), _BARRIER_CODE[p.barrier_option_type1]
+                if p.barrier2 is not None and p.barrier_option_type2 is not None:
+                    rec[11], rec[12] = float(p.barrier2), _BARRIER_CODE[p.barrier_option_type2]
+            events = []
+            for i, t in enumerate(obs):
+                f = EV_OBSERVE | (EV_FIRST if i == 0 else 0) | (EV_PAY if i == len(obs) - 1 else 0)
+                events.append((date_idx[t], f))
+            # the reference divides by the numeraire request of index 0 = the FIRST monitoring
+            # date (asian_option.py:90, barrier_option.py:312)
+            t_num = obs[0]
+        else:
+            raise TypeError(type(p))
+        rec[4], rec[5] = self._inv_numeraire(t_num)
+        return rec, w, events
+
+    def _correlation_tables(self, grid, nt):
+        """-> (corr_mode, chol [n_chol,d,d] or None, chol_dual list of D or None, step_chol)."""
+        model, scheme = self.c.model, self.scheme
+        n_sub = grid.n_sub
+        zero_idx = [0] * n_sub
+        if self.kind == EQ_BS:
+            if self.A == 1:
+                return 0, None, None, zero_idx
+            # ANALYTICAL: chol(diag(s) C diag(s) dt) = diag(s sqrt(dt)) chol(C): one factor for all steps
+            if isinstance(model, ModelConfig):
+                ps = [m.dual_params() for m in model.models]
+                corr = [[x.v for x in row] for row in model.joint_correlation(SimulationScheme.EULER, ps)]
+            else:
+                corr = model.correlation_matrix.numpy().tolist()
+            Lm = cholesky_dual([[D(x, None, 0) for x in row] for row in corr])
+            return 2, np.array([[[x.v for x in row] for row in Lm]]), None, zero_idx
+        if self.kind == EQ_HESTON:
+            if self.A == 1:
+                if scheme == SimulationScheme.QE:
+                    return 0, None, None, zero_idx
+                p = self.assets[0].model.dual_params(0, nt)
+                L = cholesky_dual(self.assets[0].model.intra_correlation(scheme, p))
+                return 1, None, [L[0][0], L[0][1], L[1][0], L[1][1]], zero_idx
+            # extension: spot normals of the assets correlated by the ModelConfig's inter-asset
+            # matrix, variance normals independent (QE draws them independently, heston.py:85-90)
+            A = self.A
+            corr = np.eye(2 * A)
+            idx = 0
+            for i in range(A):
+                for j in range(i + 1, A):
+                    rho = float(np.asarray(model.inter_asset_correlation_matrix[idx]).reshape(-1)[0])
+                    corr[2 * i, 2 * j] = corr[2 * j, 2 * i] = rho
+                    idx += 1
+            return 2, np.linalg.cholesky(corr)[None], None, zero_idx
+        # Schwartz two-factor
+        m = self.assets[0].model
+        p = m.dual_params(0, nt)
+        if scheme == SimulationScheme.EULER:
+            L = cholesky_dual(m.intra_correlation(scheme, p))
+            return 1, None, [L[0][0], L[0][1], L[1][0], L[1][1]], zero_idx
+        chol_dual, step_chol, seen = [], [], {}
+        for s in range(n_sub):
+            key = grid.dt_nominal[s]
+            if key not in seen:
+                L = cholesky_dual(m.exact_covariance(p, key))
+                seen[key] = len(chol_dual) // 4
+                chol_dual += [L[0][0], L[0][1], L[1][0], L[1][1]]
+            step_chol.append(seen[key])
+        return 1, None, chol_dual, step_chol
+
+    def lower(self, set_indices):
+        c, nt, A = self.c, self.nt, self.A
+        grid = build_time_grid(self.assets[0].model.t0(), c.simulation_timeline.tolist(), c.num_steps)
+        dates = grid.dates
+        date_idx = {t: i for i, t in enumerate(dates)}
+        n_dates, n_sub = len(dates), grid.n_sub
+        two = self.kind != EQ_BS
+        d = (2 if two else 1) * A
+        asset_noise = np.array([[2 * a, 2 * a + 1] if two else [a, -1] for a in range(A)], dtype=np.int32)
+        col_asset = np.array([j // 2 if two else j for j in range(d)], dtype=np.int32)
+        col_elem = np.array([j % 2 if two else 0 for j in range(d)], dtype=np.int32)
+        par = np.zeros((A, EQ_PAR))
+        for a, asset in enumerate(self.assets):
+            par[a, :self.npar] = asset.par
+        corr_mode, chol, chol_dual, step_chol = self._correlation_tables(grid, nt)
+        analytical = self.scheme == SimulationScheme.ANALYTICAL
+        step_sq = [math.sqrt(x) for x in (grid.dt_nominal if analytical else grid.dt)]
+        step_aux = np.zeros((max(n_sub, 1), A))
+        init_aux = np.zeros(A)
+        if self.kind == EQ_SCHWARTZ:
+            m = self.assets[0].model
+            init_aux[0] = math.log(m.curve_value(m.t0()))
+            for s in range(n_sub):
+                step_aux[s, 0] = math.log(m.curve_value(grid.t2[s]))
+
+        # ---- products / events ------------------------------------------------------------
+        recs, weights, events = [], [], [[] for _ in range(n_dates)]
+        owners = []
+        slot = 0
+        for r, si in enumerate(set_indices):
+            for p in c.netting_sets[si].products:
+                if c._can_skip_monte_carlo_for_product(p):
+                    continue
+                use_slot = -1
+                if isinstance(p, (AsianOption, BarrierOption)):
+                    use_slot = slot
+                    slot += 1
+                rec, w, evs = self._product_record(p, r, use_slot, date_idx)
+                pi = len(recs)
+                recs.append(rec)
+                weights.append(w)
+                owners.append(p)
+                for di, f in evs:
+                    events[di].append((pi, f))
+        if slot > EQ_NTRK:
+            raise NotImplementedError(f"at most {EQ_NTRK} path-dependent products per launch group")
+        ev_off, ev_prod, ev_flags = [0], [], []
+        for di in range(n_dates):
+            for pi, f in events[di]:
+                ev_prod.append(pi)
+                ev_flags.append(f)
+            ev_off.append(len(ev_prod))
+
+        t = {}
+
+        def fp(name, arr):
+            t[name], ptr = B.as_dp(arr)
+            return ptr
+
+        def ip(name, arr):
+            t[name], ptr = B.as_ip(arr)
+            return ptr
+
+        desc = EqDesc()
+        desc.kind = self.kind
+        desc.scheme = {SimulationScheme.EULER: B.SCHEME_EULER, SimulationScheme.ANALYTICAL: B.SCHEME_ANALYTICAL,
+                       SimulationScheme.QE: B.SCHEME_QE}[self.scheme]
+        desc.nt = nt
+        desc.smoothing = int(any(a.model.perform_smoothing for a in self.assets))
+        desc.n_assets, desc.noise_dim = A, d
+        desc.n_uniform = A if (self.kind == EQ_HESTON and self.scheme == SimulationScheme.QE) else 1
+        desc.asset_par = fp("par", par)
+        desc.asset_noise, desc.asset_uniform = ip("noise", asset_noise), ip("uni", np.arange(A))
+        desc.col_asset, desc.col_elem = ip("col_asset", col_asset), ip("col_elem", col_elem)
+        desc.n_sub, desc.n_dates, desc.n_pre_dates = n_sub, n_dates, grid.n_pre_dates
+        desc.n_chol = (len(chol_dual) // 4) if chol_dual else (len(chol) if chol is not None else 0)
+        desc.step_dt = fp("dt", grid.dt if n_sub else [0.0])
+        desc.step_sq = fp("sq", step_sq if n_sub else [0.0])
+        desc.step_date = ip("step_date", grid.date_after if n_sub else [0])
+        desc.step_chol = ip("step_chol", step_chol if n_sub else [0])
+        desc.step_aux, desc.init_aux = fp("step_aux", step_aux), fp("init_aux", init_aux)
+        desc.corr_mode = corr_mode
+        desc.chol = fp("chol", chol if chol is not None else np.zeros(1))
+        desc.chol_dual = fp("chol_dual", np.concatenate([x.pack() for x in chol_dual]) if chol_dual else np.zeros(1))
+        desc.date_ev_off = ip("ev_off", ev_off)
+        desc.ev_prod, desc.ev_flags = ip("ev_prod", ev_prod or [0]), ip("ev_flags", ev_flags or [0])
+        desc.n_prod = len(recs)
+        desc.prod = fp("prod", np.stack(recs) if recs else np.zeros(EQ_PR))
+        desc.prod_w = fp("prod_w", np.stack(weights) if weights else np.zeros(A))
+        desc.n_sets = len(set_indices)
+        info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs)
+        return desc, t, info
+
+    # ------------------------------------------------------------------ execution
+    def _rng(self, seed, n_total):
+        c = self.c
+        r = B.Rng()
+        r.seed, r.stream, r.n_paths_total = seed, c.rng_stream, n_total
+        z = c.injected_normals.get("main") if c.injected_normals else None
+        if z is not None:
+            r.mode, r.d_z = B.RNG_INJECT, z.data_ptr()
+            u = getattr(c, "injected_uniforms", None)
+            u = u.get("main") if u else None
+            if u is not None:
+                dev = RT.compute_device()
+                u = torch.as_tensor(u, dtype=torch.float64).to(dev).contiguous()
+                self._keep_u = u
+                r.d_u = u.data_ptr()
+        else:
+            r.mode = B.RNG_PHILOX
+        return r
+
+    def _control_variate_gradient(self, owners, recs, set_local, n_params):
+        """d/d(params) of the closed-form control-variate constants (basket_option.py:72-78):
+        they enter every path's payoff, so their parameter derivative adds invN * dc."""
+        out = np.zeros(n_params)
+        for p, rec in zip(owners, recs):
+            if int(rec[1]) != set_local or not (isinstance(p, BasketOption) and p.use_variation_reduction):
+                continue
+            params = self.c.model.model_params
+            leaves = [q.detach().clone().requires_grad_(True) for q in params]
+            saved = list(params)
+            try:
+                self._swap_params(leaves)
+                val = p.compute_pv_analytically(self.c.model).reshape(-1)[0]
+                grads = torch.autograd.grad(val, leaves, allow_unused=True)
+            finally:
+                self._swap_params(saved)
+            for i, g in enumerate(grads):
+                if g is not None:
+                    out[i] += rec[4] * float(g)
+        return out
+
+    def _swap_params(self, new):
+        model = self.c.model
+        if isinstance(model, ModelConfig):
+            o = 0
+            for m in model.models:
+                k = len(m.model_params)
+                m.model_params = list(new[o:o + k])
+                o += k
+            model.model_params = [q for m in model.models for q in m.model_params]
+        else:
+            model.model_params = list(new)
+
+    def run(self):
+        c = self.c
+        dev = RT.compute_device()
+        L = B.lib()
+        n_main = c.num_paths_mainsim
+        n_sets = len(c.netting_sets)
+        n_params = len(c.model.model_params)
+        t0 = time.perf_counter()
+        results = [None] * n_sets
+        group = EQ_MAX_SETS if self.nt == 0 else 2
+        # launch groups: up to `group` netting sets and EQ_NTRK path-dependent products each
+        groups, cur, cur_trk = [], [], 0
+        for si, ns in enumerate(c.netting_sets):
+            trk = sum(isinstance(p, (AsianOption, BarrierOption)) for p in ns.products)
+            if cur and (len(cur) >= group or cur_trk + trk > EQ_NTRK):
+                groups.append(cur)
+                cur, cur_trk = [], 0
+            cur.append(si)
+            cur_trk += trk
+        if cur:
+            groups.append(cur)
+        for idxs in groups:
+            desc, keep, info = self.lower(idxs)
+            plan = C.c_void_p()
+            B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
+            try:
+                slots = L.mcre_eq_slots(plan)
+                begin, count = RT.shard_range(n_main, CHUNK_PATHS)
+                n_chunks = max((count + CHUNK_PATHS - 1) // CHUNK_PATHS, 1)
+                acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
+                rng = self._rng(43, n_main)
+                sh = B.Shard(begin, count, CHUNK_PATHS)
+                B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                          shift.data_ptr(), RT.stream_ptr()))
+                acc = RT.all_reduce_tree(acc)
+                acc_h, shift_h = acc.cpu().numpy(), shift.cpu().numpy()
+            finally:
+                L.mcre_eq_destroy(plan)
+            ns_t = 1 if len(idxs) <= 1 else (2 if len(idxs) <= 2 else 4)
+            head = acc_h[:ns_t * 3].reshape(ns_t, 3)
+            tang = acc_h[ns_t * 3:].reshape(self.A, ns_t, self.nt) if self.nt else None
+            for r, si in enumerate(idxs):
+                pv = mean_and_error(head[r, 0], head[r, 1], shift_h[r], n_main)
+                grad = None
+                if self.nt:
+                    grad = np.zeros(n_params)
+                    for a, asset in enumerate(self.assets):
+                        for k, g in enumerate(asset.gmap):
+                            grad[g] += tang[a, r, k] / n_main
+                    grad[self.num_rate_global] += head[r, 2] / n_main
+                    grad += self._control_variate_gradient(info["owners"], info["recs"], r, n_params)
+                results[si] = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+        torch.cuda.synchronize(dev)
+        timings = {"preprocessing": 0.0, "path_generation": time.perf_counter() - t0, "request_resolution": 0.0}
+        return results, timings

@@ -211,7 +211,7 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
         geo = prod.basket_option_type.name == "GEOMETRIC"
         pay = option_payoff(prod, basket(geo))
         if prod.use_variation_reduction:
-            pay = pay - option_payoff(prod, basket(True)) + _f(np.asarray(prod.compute_pv_analytically(ctx.model)))
+            pay = pay - option_payoff(prod, basket(True)) + closed_form_constant(prod, ctx.model, ctx.p)
         return state_matrix, [pay / ctx.numeraire(t)] * S
     if k == "AsianOption":             # asian_option.py:51-95
         obs = modeling_timeline(prod)
@@ -270,6 +270,24 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
             next_state[:, s] = np.where(exercise, np.where(st > 0, st - 1, st), st)
         return next_state, cols
     raise NotImplementedError(k)
+
+
+def closed_form_constant(prod, model, p):
+    """The control variate's closed-form correction term (basket_option.py:72-78).  The reference
+    evaluates it on the model's parameter tensors, so under AAD its parameter derivatives flow into
+    the PV Greeks; here they come from torch.autograd on the same host formula."""
+    if not any(isinstance(x, ad.Dual) for x in p):
+        return _f(np.asarray(prod.compute_pv_analytically(model)))
+    import torch
+    saved = list(model.model_params)
+    leaves = [q.detach().clone().requires_grad_(True) for q in saved]
+    try:
+        model.model_params = leaves
+        val = prod.compute_pv_analytically(model).reshape(-1)[0]
+        grads = torch.autograd.grad(val, leaves, allow_unused=True)
+    finally:
+        model.model_params = saved
+    return ad.Dual(float(val.detach()), np.array([0.0 if g is None else float(g) for g in grads]))
 
 
 def supports_analytic_exposure(prod, model):

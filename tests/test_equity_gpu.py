@@ -1,0 +1,144 @@
+"""Parity of the fused equity kernel (csrc/equity.cu) through the C ABI.
+
+  1. reference goldens: the reference's own torch.randn / torch.rand stream injected, compared
+     with the outputs of the unmodified reference (tests/golden/*.json): PV, MC error 1e-10,
+     pathwise Greeks (kernel tangents vs the reference's autograd) 1e-8 relative
+  2. native Philox vs the oracle run on the same Philox stream (1e-8) and vs the reference
+     golden within 4 combined MC standard errors
+"""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+EQ_CASES = ["bs_european", "bs_european_euler", "heston_european", "heston_european_greeks",
+            "heston_path_dependent", "bs_basket", "bs_basket_euler"]
+RTOL = 1e-10
+
+
+def _check_values(flat, ref, rtol, what, err_rtol=1e-7):
+    for key, (va, ea) in flat.items():
+        vb, eb = ref[key]
+        scale = max(1.0, float(np.nanmax(np.abs(vb))))
+        helpers.assert_close(va, vb, rtol, rtol * scale, f"{what} {key} value")
+        helpers.assert_close(ea, eb, err_rtol, 1e-11 * scale, f"{what} {key} mc error")
+
+
+@pytest.mark.parametrize("name", EQ_CASES)
+def test_injected_draws_match_reference_golden(name):
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    assert res.get_netting_set_names() == gold["sets"]
+    assert res.get_metric_names() == gold["metrics"]
+    assert res.get_model_param_names() == gold["params"]
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _check_values(flat, ref, RTOL, name)
+    if gold["run"]["differentiate"]:
+        for s in gold["sets"]:
+            for m in gold["metrics"]:
+                want = np.array([[0.0 if g is None else g for g in row] for row in gold["derivatives"][f"{s}|{m}"]])
+                got = np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives(s, m)])
+                helpers.assert_close(got, want, 1e-8, 1e-8 * max(1.0, float(np.max(np.abs(want)))),
+                                     f"{name} {s}|{m} derivatives")
+
+
+@pytest.mark.parametrize("name", EQ_CASES)
+def test_philox_matches_oracle_and_reference_statistically(name):
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    flat = helpers.flatten_results(res)
+    _check_values(flat, helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8, name + " philox", err_rtol=1e-6)
+    for key, (v, e) in flat.items():
+        rv, re_ = np.array(gold["values"][key]), np.array(gold["errors"][key])
+        se = np.sqrt(e ** 2 + re_ ** 2)
+        assert np.all(np.abs(v - rv) <= 4.0 * se + 1e-12), f"{name} {key}: {v} vs {rv} (se {se})"
+    if gold["run"]["differentiate"]:
+        for si, s in enumerate(gold["sets"]):
+            for mi, m in enumerate(gold["metrics"]):
+                want = out["grads"][si][mi][0]
+                got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, m)[0]])
+                helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))),
+                                     f"{name} {s}|{m} philox derivatives")
+
+
+def _run(ns, model, sets, metrics, n, steps, scheme, differentiate=False):
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), n, 0, steps, scheme, differentiate)
+    return sc.run_simulation(), sc
+
+
+def test_other_payoffs_and_models_match_oracle():
+    """Payoffs / models without a reference golden of their own: binary, double barrier,
+    geometric Asian, control-variate basket on BlackScholesMulti, Schwartz two-factor
+    (ANALYTICAL and EULER), Heston Euler - CUDA vs oracle on the same Philox stream."""
+    from oracle import risk
+    ns = cases.Namespace()
+    S = ns.SimulationScheme
+    bsm = ns.BlackScholesMulti(0.0, 0.03, ["a", "b", "c"], [100.0, 90.0, 110.0], [0.2, 0.3, 0.25],
+                               np.array([[1.0, 0.5, 0.2], [0.5, 1.0, 0.3], [0.2, 0.3, 1.0]]))
+    sch = ns.SchwartzTwoFactorModel(0.0, [0.0, 0.5, 1.0, 2.0], [50.0, 52.0, 51.0, 55.0], 0.03, 1.2, 0.4, 0.02, 0.15, 0.3)
+    hes = lambda: ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    bs = lambda: ns.BlackScholesModel(0.0, 100.0, 0.05, 0.2)
+
+    def book_single():
+        return [
+            ns.NettingSet("binary", [ns.BinaryOption(1.0, 100.0, 10.0, ns.OptionType.CALL)]),
+            ns.NettingSet("dbl", [ns.BarrierOption(0.0, 1.0, 95.0, 7, ns.OptionType.PUT, 130.0, ns.BarrierOptionType.UPANDOUT,
+                                                  80.0, ns.BarrierOptionType.DOWNANDIN)]),
+            ns.NettingSet("geo_asian+put", [ns.AsianOption(0.25, 1.0, 100.0, 4, ns.OptionType.CALL, ns.AsianAveragingType.GEOMETRIC),
+                                            ns.EuropeanOption(ns.Equity(), 0.5, 100.0, ns.OptionType.PUT)]),
+        ]
+
+    def book_multi():
+        w = [0.3, 0.3, 0.4]
+        return [
+            ns.NettingSet("cv", [ns.BasketOption(1.0, ["a", "b", "c"], w, 100.0, ns.OptionType.CALL,
+                                                 ns.BasketOptionType.ARITHMETIC, True)]),
+            ns.NettingSet("geo_put", [ns.BasketOption(1.0, ["a", "b", "c"], w, 100.0, ns.OptionType.PUT,
+                                                      ns.BasketOptionType.GEOMETRIC)]),
+            ns.NettingSet("single", [ns.EuropeanOption(ns.Equity("b"), 0.5, 90.0, ns.OptionType.CALL),
+                                     ns.BinaryOption(1.0, 100.0, 5.0, ns.OptionType.PUT, asset_id="c")]),
+        ]
+
+    runs = [
+        ("bs_analytical", bs(), book_single(), S.ANALYTICAL, 3, True),
+        ("bs_euler", bs(), book_single(), S.EULER, 3, False),
+        ("heston_euler", hes(), book_single(), S.EULER, 4, True),
+        ("heston_qe", hes(), book_single(), S.QE, 4, False),
+        ("schwartz_analytical", sch, book_single(), S.ANALYTICAL, 2, True),
+        ("schwartz_euler", sch, book_single(), S.EULER, 2, True),
+        ("bsm_analytical", bsm, book_multi(), S.ANALYTICAL, 2, False),
+        ("bsm_euler", bsm, book_multi(), S.EULER, 2, True),
+    ]
+    n = 3000   # ragged: not a multiple of the chunk size
+    for name, model, sets, scheme, steps, diff in runs:
+        metrics = [ns.PVMetric()]
+        res, sc = _run(ns, model, sets, metrics, n, steps, scheme, diff)
+        out = risk.run(model, sets, metrics, None, n, 0, steps, scheme.name, differentiate=diff)
+        for si, s in enumerate(res.get_netting_set_names()):
+            want_v, want_e = out["results"][si][0][0]
+            helpers.assert_close(res.get_results(s, "pv"), [want_v], 1e-8, 1e-9, f"{name} {s} pv")
+            helpers.assert_close(res.get_mc_error(s, "pv"), [want_e], 1e-6, 1e-10, f"{name} {s} err")
+            if diff:
+                want = out["grads"][si][0][0]
+                got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, "pv")[0]])
+                helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))), f"{name} {s} greeks")
+
+
+def test_analytic_pv_shortcut_and_edge_cases():
+    ns = cases.Namespace()
+    model = ns.BlackScholesModel(0, 120.0, 0.05, 0.2)
+    opt = ns.EuropeanOption(ns.Equity(), 2.0, 100.0, ns.OptionType.CALL)
+    # ANALYTICAL evaluation type: no Monte Carlo at all (controller.py:506-533)
+    from metrics.metric import Metric
+    res, _ = _run(ns, model, [ns.NettingSet("call", [opt])], [ns.PVMetric(Metric.EvaluationType.ANALYTICAL)], 16, 1,
+                  ns.SimulationScheme.ANALYTICAL)
+    assert abs(res.get_results("call", "pv")[0] - 31.96484725190807) < 1e-9 and res.get_mc_error("call", "pv")[0] == 0.0
+    # one path: NaN error like the reference; 1 sub-step
+    res, _ = _run(ns, model, [ns.NettingSet("call", [ns.EuropeanOption(ns.Equity(), 2.0, 100.0, ns.OptionType.CALL)])],
+                  [ns.PVMetric()], 1, 1, ns.SimulationScheme.ANALYTICAL)
+    assert np.isfinite(res.get_results("call", "pv")[0]) and np.isnan(res.get_mc_error("call", "pv")[0])
