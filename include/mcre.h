@@ -117,12 +117,14 @@ int mcre_generate_paths(const mcre_paths_desc *desc, const mcre_rng *rng, const 
 #define MCRE_IRC_MAX_SETS 4   /* netting sets per launch (host splits larger books)    */
 #define MCRE_IRC_MAX_UNITS 4  /* regression units (products) per pre-simulation launch  */
 #define MCRE_IRC_MAX_LAG 4    /* max exposure-date lag of the MPoR look-back            */
+#define MCRE_IRC_MAX_BERM 8   /* Bermudan exercise units per launch                     */
 
 /* per-date flags */
 #define MCRE_DATE_HAS_CASHFLOW 1
 #define MCRE_DATE_HAS_EXPOSURE 2
 #define MCRE_DATE_HAS_METRIC 4
 #define MCRE_DATE_HAS_REGRESSION 8
+#define MCRE_DATE_HAS_EXERCISE 16
 
 /* what the main simulation accumulates */
 #define MCRE_ACC_PV 1
@@ -176,6 +178,19 @@ typedef struct {
   const double *unit_float;    /* [n_units][n_float]                                         */
   const int32_t *unit_last_reg;/* [n_units] number of regression dates that see cashflows    */
   const double *reg_basis;     /* [n_reg][2] shift, scale                                    */
+  /* ---- Bermudan exercise units (bermudan_option.py:93-188); n_berm = 0: none ---- */
+  int32_t n_berm;              /* <= MCRE_IRC_MAX_BERM                                       */
+  const int32_t *berm_set;     /* [n_berm] netting-set row the unit's cashflows / exposure go to */
+  const double *berm_strike;   /* [n_berm]                                                   */
+  const double *berm_sign;     /* [n_berm] +1 call, -1 put                                   */
+  const int32_t *date_ex_off;  /* [n_dates+1] CSR offsets of the exercise records per date   */
+  const int32_t *ex_unit;      /* [n_ex] unit of the record                                  */
+  const int32_t *ex_last;      /* [n_ex] 1: last exercise date of the unit (continuation 0)  */
+  const int32_t *ex_term_off;  /* [n_ex+1] CSR offsets into the zero-bond term pool          */
+  const double *ex_const;      /* [n_ex] constant part of the underlying's value             */
+  const double *term_coef;     /* dual[n_term][2] alpha, B of P(t_ex, T_j; r) = exp(alpha - B r) */
+  const double *term_w;        /* [n_term] weight of the zero bond in the underlying's value */
+  const double *ex_basis;      /* [n_ex][2] shift, scale of the explanatory variable         */
 } mcre_irc_desc;
 
 typedef struct mcre_irc_plan mcre_irc_plan;
@@ -202,6 +217,20 @@ int mcre_irc_presim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *
 /* Upload regression coefficients (after the host solved the normal equations). */
 int mcre_irc_set_coefficients(mcre_irc_plan *plan, const double *expo_coef /* host, dual[n_expo][n_sets][3] */,
                               void *stream);
+
+/* Upload the exercise-boundary coefficients of the Bermudan units: ex_coef host dual[n_ex][3]
+ * (continuation value after each exercise date) and expo_coef host dual[n_expo][n_berm][3]
+ * (exposure of a still-alive unit per internal exposure date). */
+int mcre_irc_set_exercise_coefficients(mcre_irc_plan *plan, const double *ex_coef, const double *expo_coef,
+                                       void *stream);
+
+/* Pre-simulation of a Bermudan unit, forward pass (replaces the path generation + request
+ * resolution feeding controller._perform_regression_for_product, controller.py:294-383):
+ * spills x [n_reg][n], numeraire [n_reg][n] and the immediate exercise values imm [n_ex][n]
+ * (all f64, date-major) for the backward induction of mcre_lsm_step. */
+int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *plan, int64_t n_paths);
+int mcre_irc_lsm_forward(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
+                         void *stream);
 
 /* Main simulation.  d_acc, d_shift: [mcre_irc_main_slots]; d_spill [n_sets][n_metric][n_paths]
  * or NULL.  Slot layout (NS = n_sets rounded up to 1, 2 or 4; w = 4 + 2*nt):
@@ -280,6 +309,26 @@ void mcre_eq_destroy(mcre_eq_plan *plan);
 int64_t mcre_eq_slots(const mcre_eq_plan *plan);
 int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                     double *d_acc, double *d_shift, void *stream);
+
+/* ================================================================================
+ * Longstaff-Schwartz backward induction on spilled pre-simulation arrays: one call per
+ * regression date, latest first.  Replaces the roll of compute_normalized_cashflows over
+ * [t_next, last) with its float32 accumulators and the tall lstsq of
+ * controller._perform_regression_for_product (controller.py:312-374) for single-right
+ * exercise products (state 0 = exercised carries no value):
+ *   1. if d_imm != NULL: exercise update at the product date i that enters the window,
+ *        cont = c0 + u (c1 + u c2), u = (x_i - shift_i) scale_i   (coef_i == NULL: cont = 0)
+ *        ex = imm_i > cont;  V <- fp32(fp32(ex ? imm_i / N_i : 0) + (ex ? 0 : V))
+ *   2. moments of regression date k with response Y = N_k * V:
+ *        d_moments[0..4] = sum u^0..u^4, d_moments[5..7] = sum Y u^0..u^2, u = (x_k - shift_k) scale_k
+ * All arrays are device arrays of length n (this rank's pre-simulation paths); d_value is
+ * the running fp32 tail value per path (zero-initialised by the caller).  Per-chunk partial
+ * sums + fixed tree, like the other reductions; multi-GPU callers all-reduce d_moments.
+ * ============================================================================== */
+int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double scale_k,
+                  const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i /* host[3] or NULL */,
+                  double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
+                  double *d_partial, double *d_moments, void *stream);
 
 /* ================================================================================
  * Exact order statistics per row (PFE), replaces torch.sort + index in

@@ -6,394 +6,11 @@
 // regression-proxy exposure, threshold / MPoR collateral and the metric integrands.
 // Only block-reduced sums ever reach HBM.  See include/mcre.h for what each entry point
 // replaces in the reference.
-#define MCRE_FAST_MATH 1
-#include "common.cuh"
-#include "philox.cuh"
-#include "dual.cuh"
-#include "reduce.cuh"
-#include "launch.cuh"
+#include <algorithm>
+#include "irc_main.cuh"
 
 namespace mcre {
 
-struct IrcDev {
-  int nt, scheme, has_cir, cir_det, vas_noise, cir_noise;
-  const double *vas, *cir, *cir_init, *chol;
-  int n_sub, n_dates, n_pre_dates;
-  const double *step_dt; const int *step_date; const double *step_vas, *step_cir;
-  const int *date_flags, *date_expo, *date_metric, *date_reg, *date_float_off;
-  const double *float_coef, *float_inv_tau;
-  int n_float;
-  int n_sets, n_expo, n_metric, acc_flags;
-  const double *set_fix, *set_float, *set_threshold; const int *set_flags, *set_lag;
-  double *expo_coef;  // mutable: uploaded after the regression solve
-  const double *expo_basis, *cva_coef;
-  double lgd;
-  int n_units, n_reg;
-  const double *unit_fix, *unit_float; const double *reg_basis;
-  const double *step_rec, *date_rec;  // packed records of the main kernel
-};
-
-// ---- per-path model state ---------------------------------------------------------
-template <typename R>
-struct IrcState {
-  R r, logB, y, logBl;
-};
-
-template <typename R, bool CIR>
-struct IrcParams {
-  R r0, sigma, theta, a;        // Vasicek
-  R kappa, ctheta, csigma, y0;  // CIR++
-  R L10, L11;                   // Cholesky rows used by the second noise column
-  R L00;
-};
-
-// One sub-step of the joint model (src/models/vasicek.py:52-112, cirpp.py:155-198,
-// model_config.py:223-276).  z0/z1 are the independent draws; the correlated noise is
-// z @ L^T with L the lower Cholesky factor (model.py:46-48).
-template <typename R, bool CIR, int SCHEME>
-__device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR> &mp, IrcState<R> &s, int is,
-                                         double z0, double z1) {
-  typedef RealTraits<R> T;
-  const double dt = __ldg(P.step_dt + is);
-  const double sq = sqrt(dt);
-  R w0 = mp.L00 * z0;
-  R w1 = T::zero();
-  if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
-  const R wv = (CIR && P.vas_noise == 1) ? w1 : w0;
-  // numeraire integral uses the pre-step rate (left Riemann sum)
-  s.logB = s.logB + s.r * dt;
-  if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
-    R decay = T::load(P.step_vas, is * 2 + 0), nstd = T::load(P.step_vas, is * 2 + 1);
-    // exact OU transition; the 1x1 Cholesky factor of the step covariance is nstd (vasicek.py:52-86)
-    s.r = mp.theta + (s.r - mp.theta) * decay + nstd * z0;
-  } else {
-    const R theta_t = T::load(P.step_vas, is * 2 + 0);  // mean level at t1 (constant for Vasicek)
-    s.r = s.r + mp.a * (theta_t - s.r) * dt + mp.sigma * sq * wv;
-  }
-  if (CIR) {
-    const R wc = (P.cir_noise == 1) ? w1 : w0;
-    if (P.cir_det) {
-      R lam1 = T::load(P.step_cir, is * 2 + 0), lam2 = T::load(P.step_cir, is * 2 + 1);
-      s.logBl = s.logBl + lam1 * dt;
-      s.y = lam2;
-    } else {
-      R psi = T::load(P.step_cir, is * 2 + 0);
-      R ypos = r_relu(s.y);
-      R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * r_sqrt(ypos) * sq * wc;
-      s.logBl = s.logBl + (s.y + psi) * dt;
-      s.y = r_max(yn, 1e-12);
-    }
-  }
-}
-
-template <typename R, bool CIR>
-__device__ __forceinline__ void irc_load_params(const IrcDev &P, IrcParams<R, CIR> &mp) {
-  typedef RealTraits<R> T;
-  mp.r0 = T::load(P.vas, 0); mp.sigma = T::load(P.vas, 1); mp.theta = T::load(P.vas, 2); mp.a = T::load(P.vas, 3);
-  mp.L00 = T::load(P.chol, 0);
-  if (CIR) {
-    mp.kappa = T::load(P.cir, 0); mp.ctheta = T::load(P.cir, 1); mp.csigma = T::load(P.cir, 2);
-    mp.y0 = T::load(P.cir_init, 0);
-    mp.L10 = T::load(P.chol, 2); mp.L11 = T::load(P.chol, 3);
-  } else {
-    mp.kappa = mp.ctheta = mp.csigma = mp.y0 = mp.L10 = mp.L11 = T::zero();
-  }
-}
-
-template <typename R, bool CIR>
-__device__ __forceinline__ void irc_draw(const RngDev &rng, NormalStream &ns, int is, long long lpath,
-                                         long long gpath, double &z0, double &z1) {
-  if (rng.mode == MCRE_RNG_INJECT) {
-    const int d = CIR ? 2 : 1;
-    const double *p = rng.z + ((size_t)is * rng.n_total + gpath) * d;
-    z0 = p[0];
-    z1 = CIR ? p[1] : 0.0;
-  } else {
-    if (CIR) ns.next2(z0, z1);
-    else { z0 = ns.next(); z1 = 0.0; }
-  }
-}
-
-// threshold dead-band (src/products/netting_set.py:48-72)
-template <typename R>
-__device__ __forceinline__ R apply_threshold(const R &x, double h) {
-  const double v = val(x);
-  if (v > h) return x - h;
-  if (v < -h) return x + h;
-  return RealTraits<R>::zero();
-}
-
-// =====================================================================================
-// Main simulation kernel
-// slot layout: [n_metric][NS][4+2NT] = pos, pos^2, neg, neg^2, d pos[NT], d neg[NT]
-//              then [NS][4+2NT]      = pv, pv^2, cva, cva^2, d pv[NT], d cva[NT]
-// Value slots hold sum(x - c) and sum((x - c)^2) with c = shift[slot], the value global
-// path 0 takes (written by a one-path "pilot" launch of this same kernel).  Shifting by
-// a sample of the distribution keeps the variance formula free of cancellation and makes
-// degenerate dates (all paths equal, e.g. t = 0) give an exact zero Monte Carlo error.
-//
-// Layout choices that came out of the first ncu profile (profiles/r01_irc_main_v0_*):
-//  * PP paths per thread, evaluated in lock-step: all plan loads, branches and index
-//    arithmetic are shared by the PP paths and their Horner chains interleave;
-//  * every per-step / per-date scalar sits in one packed record (mcre_irc_create packs
-//    them), read with a handful of wide uniform loads instead of ~45 scalar loads;
-//  * MODE 1 ("CVA only": one netting set, no threshold / collateral, no other metric):
-//    relu(E_k) S(0,t_k) = relu(poly) exp(-(logB + logB_lambda)) - two exponentials per date.
-// =====================================================================================
-constexpr int STEP_HDR = 4;   // dt, sqrt(dt), bits(date index), pad
-constexpr int DATE_HDR = 6;   // bits(flags|(expo+1)<<32), bits((metric+1)|float_off<<32), bits(float_cnt), pad, shift, scale
-
-__device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
-__device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
-
-template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE>
-__global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
-                                                                         double *partial, double *spill,
-                                                                         double *shift, int pilot) {
-  typedef typename RealOf<NT>::type R;
-  typedef RealTraits<R> T;
-  constexpr int W = NT + 1;
-  constexpr int NV = 4 + 2 * NT;        // values per (set, date)
-  constexpr int NVB = NS * NV;          // values per block_accumulate call
-  constexpr int SR = STEP_HDR + 4 * W;  // packed step record stride
-  extern __shared__ double smem[];
-  const int nw = blockDim.x >> 5;
-  const int n_slots = (P.n_metric + 1) * NVB;
-  double *acc = smem;                   // [n_slots]
-  double *stage = smem + n_slots;       // [2][nw][NVB]
-  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
-  const int DR = (DATE_HDR + 2 * W + 3 * W * P.n_sets + 1) & ~1;  // even: records are read as double2
-
-  IrcParams<R, CIR> mp;
-  irc_load_params<R, CIR>(P, mp);
-  const int acc_flags = P.acc_flags;
-  const bool vas_second = CIR && P.vas_noise == 1, cir_second = CIR && P.cir_noise == 1, cir_det = P.cir_det != 0;
-  double thr[NS]; int sflags[NS];
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    thr[s] = s < P.n_sets ? __ldg(P.set_threshold + s) : 0.0;
-    sflags[s] = s < P.n_sets ? __ldg(P.set_flags + s) : 0;
-  }
-
-  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) acc[i] = 0.0;
-    __syncthreads();
-    int parity = 0;
-    for (int it = 0; it < sh.chunk; it += blockDim.x * PP) {
-      long long lpath[PP], gpath[PP];
-      bool live[PP];
-      NormalStream ns[PP];
-      IrcState<R> st[PP];
-      R pv[PP][NS], cva[PP][NS], hist[PP][NS][MODE == 1 ? 1 : MCRE_IRC_MAX_LAG];
-#pragma unroll
-      for (int p = 0; p < PP; ++p) {
-        lpath[p] = chunk * sh.chunk + it + p * (int)blockDim.x + threadIdx.x;
-        live[p] = lpath[p] < sh.n_paths;
-        gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
-        ns[p].init(rng, (unsigned long long)gpath[p]);
-        st[p].r = mp.r0; st[p].logB = T::zero(); st[p].y = mp.y0; st[p].logBl = T::zero();
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          pv[p][s] = T::zero(); cva[p][s] = T::zero();
-#pragma unroll
-          for (int l = 0; l < (MODE == 1 ? 1 : MCRE_IRC_MAX_LAG); ++l) hist[p][s][l] = T::zero();
-        }
-      }
-
-      // ---- date evaluation (cashflows -> exposure -> metrics) ------------------------
-      auto eval_date = [&](int di) {
-        const double *dr = P.date_rec + (size_t)di * DR;
-        const double2 h0 = __ldg((const double2 *)dr), h1 = __ldg((const double2 *)dr + 1),
-                      h2 = __ldg((const double2 *)dr + 2);
-        const int flags = lo32(h0.x), e = hi32(h0.x) - 1, m = lo32(h0.y) - 1;
-        if (!(flags & (MCRE_DATE_HAS_CASHFLOW | MCRE_DATE_HAS_EXPOSURE | MCRE_DATE_HAS_METRIC))) return;
-        const double bshift = h2.x, bscale = h2.y;
-        const double *dc = dr + DATE_HDR;   // C[w], B[w], coef[set][3][w]
-        if (MODE == 1) {
-          // CVA-only fast path: contribution at metric dates k < n_metric-1 only
-          if (!(flags & MCRE_DATE_HAS_METRIC) || m >= P.n_metric - 1) return;
-          const R C = T::load(dc, 0), Bc = T::load(dc, 1);
-          const R c0 = T::load(dc, 2), c1 = T::load(dc, 3), c2 = T::load(dc, 4);
-#pragma unroll
-          for (int p = 0; p < PP; ++p) {
-            const R u = (st[p].r - bshift) * bscale;
-            const R pos = r_relu(c0 + u * (c1 + u * c2));
-            const R ds = r_exp(-(st[p].logB + st[p].logBl));
-            const R cond = C * r_exp(-(Bc * st[p].y));
-            cva[p][0] = cva[p][0] + pos * ds * (1.0 - cond);
-          }
-          return;
-        }
-        R invN[PP];
-#pragma unroll
-        for (int p = 0; p < PP; ++p) invN[p] = r_exp(-st[p].logB);  // 1 / numeraire (vasicek.py:154-156)
-        if ((flags & MCRE_DATE_HAS_CASHFLOW) && (acc_flags & MCRE_ACC_PV)) {
-          R cf[PP][NS];
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            const double fx = s < P.n_sets ? __ldg(P.set_fix + (size_t)s * P.n_dates + di) : 0.0;
-#pragma unroll
-            for (int p = 0; p < PP; ++p) cf[p][s] = T::lift(fx);
-          }
-          const int j0 = hi32(h0.y), j1 = j0 + lo32(h1.x);
-          for (int j = j0; j < j1; ++j) {
-            // LIBOR from the bond price at the payment date's own short rate (bond.py:55-66)
-            const R alpha = T::load(P.float_coef, j * 2 + 0), B = T::load(P.float_coef, j * 2 + 1);
-            const double inv_tau = __ldg(P.float_inv_tau + j);
-#pragma unroll
-            for (int p = 0; p < PP; ++p) {
-              const R libor = (r_exp(B * st[p].r - alpha) - 1.0) * inv_tau;
-#pragma unroll
-              for (int s = 0; s < NS; ++s)
-                if (s < P.n_sets) cf[p][s] = cf[p][s] + libor * __ldg(P.set_float + (size_t)s * P.n_float + j);
-            }
-          }
-#pragma unroll
-          for (int p = 0; p < PP; ++p)
-#pragma unroll
-            for (int s = 0; s < NS; ++s) pv[p][s] = pv[p][s] + cf[p][s] * invN[p];
-        }
-        if (flags & MCRE_DATE_HAS_EXPOSURE) {
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            R c0 = T::zero(), c1 = T::zero(), c2 = T::zero();
-            if (s < P.n_sets) { c0 = T::load(dc, 2 + s * 3); c1 = T::load(dc, 3 + s * 3); c2 = T::load(dc, 4 + s * 3); }
-#pragma unroll
-            for (int p = 0; p < PP; ++p) {
-#pragma unroll
-              for (int l = MCRE_IRC_MAX_LAG - 1; l > 0; --l) hist[p][s][l] = hist[p][s][l - 1];
-              const R u = (st[p].r - bshift) * bscale;
-              hist[p][s][0] = (c0 + u * (c1 + u * c2)) * invN[p];  // continuation / numeraire (controller.py:438-447)
-            }
-          }
-        }
-        if (flags & MCRE_DATE_HAS_METRIC) {
-          double vals[NVB];
-#pragma unroll
-          for (int i = 0; i < NVB; ++i) vals[i] = 0.0;
-          const bool cva_date = (acc_flags & MCRE_ACC_CVA) && m < P.n_metric - 1;
-          R dflt[PP];
-#pragma unroll
-          for (int p = 0; p < PP; ++p) dflt[p] = T::zero();
-          if (CIR && cva_date) {
-            // S(0,t_k) = exp(-logB_lambda); S(t_k,t_k+1 | y) = C exp(-B y)   (cirpp.py:298-317)
-            const R C = T::load(dc, 0), Bc = T::load(dc, 1);
-#pragma unroll
-            for (int p = 0; p < PP; ++p) dflt[p] = r_exp(-st[p].logBl) * (1.0 - C * r_exp(-(Bc * st[p].y)));
-          }
-#pragma unroll
-          for (int s = 0; s < NS; ++s) {
-            const int lag = ((sflags[s] & 1) && s < P.n_sets) ? __ldg(P.set_lag + (size_t)s * P.n_metric + m) : -1;
-            const int sb = m * NVB + s * NV;
-            double sh_pos = 0.0, sh_neg = 0.0;
-            if (!pilot) { sh_pos = shift[sb + 0]; sh_neg = shift[sb + 2]; }
-#pragma unroll
-            for (int p = 0; p < PP; ++p) {
-              R unsec;
-              if (sflags[s] & 1) {
-                R delayed = T::zero();
-#pragma unroll
-                for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l) if (l == lag) delayed = hist[p][s][l];
-                unsec = hist[p][s][0] - apply_threshold(delayed, thr[s]);
-              } else {
-                unsec = apply_threshold(hist[p][s][0], thr[s]);
-              }
-              const R pos = r_relu(unsec);
-              const R neg = -r_relu(-unsec);
-              if (cva_date && (sflags[s] & 2)) cva[p][s] = cva[p][s] + pos * dflt[p];
-              if (pilot && p == 0 && threadIdx.x == 0) { shift[sb + 0] = val(pos); shift[sb + 2] = val(neg); }
-              const double keep = live[p] ? 1.0 : 0.0;
-              const double dp = val(pos) - sh_pos, dn = val(neg) - sh_neg;
-              vals[s * NV + 0] += keep * dp; vals[s * NV + 1] += keep * dp * dp;
-              vals[s * NV + 2] += keep * dn; vals[s * NV + 3] += keep * dn * dn;
-#pragma unroll
-              for (int k = 0; k < NT; ++k) {
-                vals[s * NV + 4 + k] += keep * tan_of(pos, k);
-                vals[s * NV + 4 + NT + k] += keep * tan_of(neg, k);
-              }
-              if ((acc_flags & MCRE_ACC_SPILL) && live[p] && s < P.n_sets)
-                spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath[p]] = val(unsec);
-            }
-          }
-          if ((acc_flags & (MCRE_ACC_POS | MCRE_ACC_NEG)) && !pilot)
-            block_accumulate<NVB>(vals, acc, m * NVB, stage, NVB, parity);
-        }
-      };
-
-      for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
-      for (int is = 0; is < P.n_sub; ++is) {
-        const double *sr = P.step_rec + (size_t)is * SR;
-        const double2 g0 = __ldg((const double2 *)sr), g1 = __ldg((const double2 *)sr + 1);
-        const double dt = g0.x, sq = g0.y;
-        const int di = lo32(g1.x);
-        const R sv0 = T::load(sr + STEP_HDR, 0), sv1 = T::load(sr + STEP_HDR, 1);
-        R sc0 = T::zero(), sc1 = T::zero();
-        if (CIR) { sc0 = T::load(sr + STEP_HDR, 2); sc1 = T::load(sr + STEP_HDR, 3); }
-#pragma unroll
-        for (int p = 0; p < PP; ++p) {
-          double z0, z1;
-          irc_draw<R, CIR>(rng, ns[p], is, lpath[p], gpath[p], z0, z1);
-          // correlated noise z @ L^T (model.py:46-48)
-          const R w0 = mp.L00 * z0;
-          R w1 = T::zero();
-          if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
-          IrcState<R> &s = st[p];
-          s.logB = s.logB + s.r * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
-          if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
-            // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
-            s.r = mp.theta + (s.r - mp.theta) * sv0 + sv1 * z0;
-          } else {
-            const R wv = vas_second ? w1 : w0;
-            s.r = s.r + mp.a * (sv0 - s.r) * dt + mp.sigma * sq * wv;
-          }
-          if (CIR) {
-            const R wc = cir_second ? w1 : w0;
-            if (cir_det) {                    // cirpp.py:155-172
-              s.logBl = s.logBl + sc0 * dt;
-              s.y = sc1;
-            } else {                          // full-truncation Euler, cirpp.py:174-198
-              const R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * r_sqrt(r_relu(s.y)) * sq * wc;
-              s.logBl = s.logBl + (s.y + sc0) * dt;
-              s.y = r_max(yn, 1e-12);
-            }
-          }
-        }
-        if (di >= 0) eval_date(di);
-      }
-      // ---- per-path totals ------------------------------------------------------------
-      {
-        double vals[NVB];
-#pragma unroll
-        for (int i = 0; i < NVB; ++i) vals[i] = 0.0;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          const int sb = P.n_metric * NVB + s * NV;
-          double sh_pv = 0.0, sh_cva = 0.0;
-          if (!pilot) { sh_pv = shift[sb + 0]; sh_cva = shift[sb + 2]; }
-#pragma unroll
-          for (int p = 0; p < PP; ++p) {
-            const R c = cva[p][s] * P.lgd;
-            if (pilot && p == 0 && threadIdx.x == 0) { shift[sb + 0] = val(pv[p][s]); shift[sb + 2] = val(c); }
-            const double keep = live[p] ? 1.0 : 0.0;
-            const double dp = val(pv[p][s]) - sh_pv, dcv = val(c) - sh_cva;
-            vals[s * NV + 0] += keep * dp; vals[s * NV + 1] += keep * dp * dp;
-            vals[s * NV + 2] += keep * dcv; vals[s * NV + 3] += keep * dcv * dcv;
-#pragma unroll
-            for (int k = 0; k < NT; ++k) {
-              vals[s * NV + 4 + k] += keep * tan_of(pv[p][s], k);
-              vals[s * NV + 4 + NT + k] += keep * tan_of(c, k);
-            }
-          }
-        }
-        if (!pilot) block_accumulate<NVB>(vals, acc, P.n_metric * NVB, stage, NVB, parity);
-      }
-    }
-    if (pilot) return;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n_slots; i += blockDim.x) partial[(size_t)chunk * n_slots + i] = acc[i];
-    __syncthreads();
-  }
-}
 
 // =====================================================================================
 // Pre-simulation pass A: forward simulation, spills per regression date the explanatory
@@ -464,6 +81,44 @@ __global__ void __launch_bounds__(256) irc_presim_forward_kernel(IrcDev P, RngDe
     if (u < P.n_units && P.n_reg > 0) wbuf[((size_t)u * P.n_reg + (P.n_reg - 1)) * n + lpath] = W[u];
 }
 
+// Pre-simulation of Bermudan units, forward pass: spills per regression date the explanatory
+// variable and the numeraire, and per exercise record the immediate exercise value.
+// scratch: x [n_reg][n] | N [n_reg][n] | imm [n_ex][n], all f64
+template <bool CIR, int SCHEME>
+__global__ void __launch_bounds__(128) irc_lsm_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
+                                                              double *nbuf, double *ibuf) {
+  typedef double R;
+  const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lpath >= sh.n_paths) return;
+  const long long gpath = sh.path_begin + lpath;
+  const long long n = sh.n_paths;
+  IrcParams<R, CIR> mp;
+  irc_load_params<R, CIR>(P, mp);
+  NormalStream ns; ns.init(rng, (unsigned long long)gpath);
+  IrcState<R> st;
+  st.r = mp.r0; st.logB = 0.0; st.y = mp.y0; st.logBl = 0.0;
+  auto eval_date = [&](int di) {
+    const int flags = __ldg(P.date_flags + di);
+    if (flags & MCRE_DATE_HAS_REGRESSION) {
+      const int k = __ldg(P.date_reg + di);
+      xbuf[(size_t)k * n + lpath] = st.r;
+      nbuf[(size_t)k * n + lpath] = exp(st.logB);
+    }
+    if (flags & MCRE_DATE_HAS_EXERCISE) {
+      const int x0 = __ldg(P.date_ex_off + di), x1 = __ldg(P.date_ex_off + di + 1);
+      for (int x = x0; x < x1; ++x) ibuf[(size_t)x * n + lpath] = irc_exercise_value<R>(P, x, st.r);
+    }
+  };
+  for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+  for (int is = 0; is < P.n_sub; ++is) {
+    double z0, z1;
+    irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
+    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    const int di = __ldg(P.step_date + is);
+    if (di >= 0) eval_date(di);
+  }
+}
+
 // Pre-simulation pass B: backward FP32 suffix sums + Gram / right-hand-side moments.
 // slot layout: [n_reg][5 + 3*NU] = sum u^0..u^4, then per unit sum u^0..u^2 * Y
 template <int NU>
@@ -518,24 +173,12 @@ __global__ void __launch_bounds__(256) irc_presim_moments_kernel(IrcDev P, Shard
 // =====================================================================================
 using namespace mcre;
 
-struct mcre_irc_plan {
-  IrcDev d;
-  DevArray<double> vas, cir, cir_init, chol, step_dt, step_vas, step_cir, float_coef, float_inv_tau, set_fix,
-      set_float, set_threshold, expo_coef, expo_basis, cva_coef, unit_fix, unit_float, reg_basis;
-  DevArray<int> step_date, date_flags, date_expo, date_metric, date_reg, date_float_off, set_flags, set_lag;
-  DevArray<double> step_rec, date_rec;
-  std::vector<double> h_date_rec;   // host copy: coefficients are patched in after the regression solve
-  std::vector<int> h_date_expo;
-  int date_stride = 0;
-  size_t expo_coef_count = 0;
-  bool cva_only = false;
-};
-
 extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   if (!c || !out) return fail(-1, "null argument%s", "");
   if (c->nt != 0 && c->nt != 4 && c->nt != 8) return fail(-1, "irc: nt must be 0, 4 or 8%s", "");
   if (c->n_sets < 0 || c->n_sets > MCRE_IRC_MAX_SETS) return fail(-1, "irc: n_sets out of range%s", "");
   if (c->n_units < 0 || c->n_units > MCRE_IRC_MAX_UNITS) return fail(-1, "irc: n_units out of range%s", "");
+  if (c->n_berm < 0 || c->n_berm > MCRE_IRC_MAX_BERM) return fail(-1, "irc: n_berm out of range%s", "");
   if (c->scheme != MCRE_SCHEME_EULER && c->scheme != MCRE_SCHEME_ANALYTICAL)
     return fail(-1, "irc: scheme must be EULER or ANALYTICAL%s", "");
   if (c->scheme == MCRE_SCHEME_ANALYTICAL && c->has_cir)
@@ -561,6 +204,20 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   UP(cva_coef, c->cva_coef, (size_t)c->n_metric * 2 * w);
   UP(unit_fix, c->unit_fix, (size_t)c->n_units * c->n_dates); UP(unit_float, c->unit_float, (size_t)c->n_units * n_float);
   UP(reg_basis, c->reg_basis, (size_t)c->n_reg * 2);
+  const int n_berm = c->n_berm;
+  const int n_ex = (n_berm > 0 && c->date_ex_off) ? c->date_ex_off[c->n_dates] : 0;
+  const int n_term = n_ex > 0 ? c->ex_term_off[n_ex] : 0;
+  if (n_berm > 0) {
+    UP(berm_set, c->berm_set, n_berm); UP(berm_strike, c->berm_strike, n_berm); UP(berm_sign, c->berm_sign, n_berm);
+    UP(date_ex_off, c->date_ex_off, c->n_dates + 1); UP(ex_unit, c->ex_unit, n_ex); UP(ex_last, c->ex_last, n_ex);
+    UP(ex_term_off, c->ex_term_off, n_ex + 1); UP(ex_const, c->ex_const, n_ex);
+    UP(term_coef, c->term_coef, (size_t)n_term * 2 * w); UP(term_w, c->term_w, n_term);
+    UP(ex_basis, c->ex_basis, (size_t)n_ex * 2);
+    p->ex_coef_count = (size_t)n_ex * 3 * w;
+    p->berm_expo_count = (size_t)c->n_expo * n_berm * 3 * w;
+    std::vector<double> zeros(std::max(p->ex_coef_count, p->berm_expo_count) + 1, 0.0);
+    UP(ex_coef, zeros.data(), p->ex_coef_count); UP(berm_expo_coef, zeros.data(), p->berm_expo_count);
+  }
   {
     // packed per-step and per-date records of the main kernel (layout: STEP_HDR / DATE_HDR above)
     const int SR = STEP_HDR + 4 * w, DR = (DATE_HDR + 2 * w + 3 * w * c->n_sets + 1) & ~1;
@@ -609,6 +266,11 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   d.n_units = c->n_units; d.n_reg = c->n_reg;
   d.unit_fix = p->unit_fix.p; d.unit_float = p->unit_float.p; d.reg_basis = p->reg_basis.p;
   d.step_rec = p->step_rec.p; d.date_rec = p->date_rec.p;
+  d.n_berm = n_berm; d.n_ex = n_ex;
+  d.berm_set = p->berm_set.p; d.berm_strike = p->berm_strike.p; d.berm_sign = p->berm_sign.p;
+  d.date_ex_off = p->date_ex_off.p; d.ex_unit = p->ex_unit.p; d.ex_term_off = p->ex_term_off.p; d.ex_last = p->ex_last.p;
+  d.ex_const = p->ex_const.p; d.term_coef = p->term_coef.p; d.term_w = p->term_w.p; d.ex_basis = p->ex_basis.p;
+  d.ex_coef = p->ex_coef.p; d.berm_expo_coef = p->berm_expo_coef.p;
   *out = p;
   return 0;
 }
@@ -622,10 +284,12 @@ extern "C" void mcre_irc_destroy(mcre_irc_plan *p) {
   p->reg_basis.release(); p->step_date.release(); p->date_flags.release(); p->date_expo.release();
   p->date_metric.release(); p->date_reg.release(); p->date_float_off.release(); p->set_flags.release();
   p->set_lag.release(); p->step_rec.release(); p->date_rec.release();
+  p->berm_set.release(); p->date_ex_off.release(); p->ex_unit.release(); p->ex_last.release(); p->ex_term_off.release();
+  p->berm_strike.release(); p->berm_sign.release(); p->ex_const.release(); p->term_coef.release(); p->term_w.release();
+  p->ex_basis.release(); p->ex_coef.release(); p->berm_expo_coef.release();
   delete p;
 }
 
-static int ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 2 : 4); }
 static int nu_template(int n_units) { return n_units <= 1 ? 1 : (n_units <= 2 ? 2 : 4); }
 
 extern "C" int64_t mcre_irc_main_slots(const mcre_irc_plan *p) {
@@ -660,37 +324,47 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
   return 0;
 }
 
-template <int NT, int NS>
-static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *spill,
-                       double *shift, cudaStream_t st) {
+extern "C" int mcre_irc_set_exercise_coefficients(mcre_irc_plan *p, const double *ex_coef, const double *expo_coef,
+                                                  void *stream) {
+  if (!p) return fail(-1, "null argument%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->ex_coef_count && ex_coef)
+    MCRE_CUDA(cudaMemcpyAsync(p->d.ex_coef, ex_coef, p->ex_coef_count * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (p->berm_expo_count && expo_coef)
+    MCRE_CUDA(cudaMemcpyAsync(p->d.berm_expo_coef, expo_coef, p->berm_expo_count * sizeof(double),
+                              cudaMemcpyHostToDevice, st));
+  MCRE_CUDA(cudaStreamSynchronize(st));  // host staging buffers may be reused by the caller
+  return 0;
+}
+
+extern "C" int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *p, int64_t n_paths) {
+  return ((int64_t)2 * p->d.n_reg + p->d.n_ex) * n_paths * 8 + 256;
+}
+
+extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
+                                    void *stream) {
+  if (!p || !rng || !d_scratch) return fail(-1, "null argument%s", "");
+  int rc = check_shard(shard);
+  if (rc) return rc;
+  if (p->d.nt != 0) return fail(-4, "irc lsm: tangents through the regression are not implemented%s", "");
+  if (p->d.n_berm < 1) return fail(-1, "irc lsm: plan has no exercise unit%s", "");
+  if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   const IrcDev &d = p->d;
-  constexpr int PP = NT == 0 ? 2 : 1;   // paths per thread
-  const int threads = 128, nw = threads / 32;
-  const int nvb = NS * (4 + 2 * NT);
-  const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);
-  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
-  if (n_chunks == 0) return 0;
-#define LAUNCH(CIRV, SCH, MODEV)                                                                       \
-  do {                                                                                                 \
-    auto k = irc_main_kernel<NT, NS, CIRV, SCH, PP, MODEV>;                                            \
-    if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    int per_sm = 1;                                                                                    \
-    MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));               \
-    if (per_sm < 1) return fail(-3, "irc main kernel does not fit: too many metric dates x tangents%s", ""); \
-    long long grid = (long long)sm_count() * per_sm;                                                   \
-    if (grid > n_chunks) grid = n_chunks;                                                              \
-    ShardDev pilot_sh{0, 1, sh.chunk};                                                                 \
-    k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, spill, shift, 1);                           \
-    MCRE_LAUNCHED();                                                                                   \
-    k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, spill, shift, 0);                    \
-    MCRE_LAUNCHED();                                                                                   \
-  } while (0)
-  if (d.has_cir) {
-    if (NT == 0 && NS == 1 && p->cva_only) LAUNCH(true, MCRE_SCHEME_EULER, (NT == 0 && NS == 1 ? 1 : 0));
-    else LAUNCH(true, MCRE_SCHEME_EULER, 0);
-  } else if (d.scheme == MCRE_SCHEME_ANALYTICAL) LAUNCH(false, MCRE_SCHEME_ANALYTICAL, 0);
-  else LAUNCH(false, MCRE_SCHEME_EULER, 0);
-#undef LAUNCH
+  if (shard->n_paths == 0) return 0;
+  RngDev r = make_rng(rng);
+  ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = sh.n_paths;
+  double *xbuf = (double *)d_scratch;
+  double *nbuf = xbuf + (size_t)d.n_reg * n;
+  double *ibuf = nbuf + (size_t)d.n_reg * n;
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (d.has_cir) irc_lsm_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
+  else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
+    irc_lsm_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
+  else irc_lsm_forward_kernel<false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
+  MCRE_LAUNCHED();
   return 0;
 }
 
@@ -704,22 +378,8 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
   RngDev r = make_rng(rng);
   ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
   cudaStream_t st = (cudaStream_t)stream;
-  const int ns = ns_template(p->d.n_sets);
-  // tangent builds exist for up to 2 netting sets per launch (register budget); the host
-  // splits larger books into groups and replays the same Philox streams.
-  if (p->d.nt == 0) {
-    rc = ns == 1 ? launch_main<0, 1>(p, r, sh, d_partial, d_spill, d_shift, st)
-       : ns == 2 ? launch_main<0, 2>(p, r, sh, d_partial, d_spill, d_shift, st)
-                 : launch_main<0, 4>(p, r, sh, d_partial, d_spill, d_shift, st);
-  } else if (ns > 2) {
-    return fail(-3, "irc: at most 2 netting sets per launch when tangents are on%s", "");
-  } else if (p->d.nt == 4) {
-    rc = ns == 1 ? launch_main<4, 1>(p, r, sh, d_partial, d_spill, d_shift, st)
-                 : launch_main<4, 2>(p, r, sh, d_partial, d_spill, d_shift, st);
-  } else {
-    rc = ns == 1 ? launch_main<8, 1>(p, r, sh, d_partial, d_spill, d_shift, st)
-                 : launch_main<8, 2>(p, r, sh, d_partial, d_spill, d_shift, st);
-  }
+  rc = p->d.n_berm > 0 ? irc_dispatch_main_berm(p, r, sh, d_partial, d_spill, d_shift, st)
+                       : irc_dispatch_main<false>(p, r, sh, d_partial, d_spill, d_shift, st);
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   return mcre_tree_reduce(d_partial, n_chunks, mcre_irc_main_slots(p), d_acc, stream);

@@ -43,14 +43,17 @@ class IrcDesc(C.Structure):
         ("expo_coef", c_dp), ("expo_basis", c_dp), ("cva_coef", c_dp), ("lgd", C.c_double),
         ("n_units", C.c_int32), ("n_reg", C.c_int32),
         ("unit_fix", c_dp), ("unit_float", c_dp), ("unit_last_reg", c_ip), ("reg_basis", c_dp),
+        ("n_berm", C.c_int32), ("berm_set", c_ip), ("berm_strike", c_dp), ("berm_sign", c_dp),
+        ("date_ex_off", c_ip), ("ex_unit", c_ip), ("ex_last", c_ip), ("ex_term_off", c_ip),
+        ("ex_const", c_dp), ("term_coef", c_dp), ("term_w", c_dp), ("ex_basis", c_dp),
     ]
 
 
 RNG_PHILOX, RNG_INJECT = 0, 1
 SCHEME_EULER, SCHEME_ANALYTICAL, SCHEME_QE = 0, 2, 3
-DATE_HAS_CASHFLOW, DATE_HAS_EXPOSURE, DATE_HAS_METRIC, DATE_HAS_REGRESSION = 1, 2, 4, 8
+DATE_HAS_CASHFLOW, DATE_HAS_EXPOSURE, DATE_HAS_METRIC, DATE_HAS_REGRESSION, DATE_HAS_EXERCISE = 1, 2, 4, 8, 16
 ACC_PV, ACC_POS, ACC_NEG, ACC_CVA, ACC_SPILL = 1, 2, 4, 8, 16
-IRC_MAX_SETS, IRC_MAX_UNITS, IRC_MAX_LAG = 4, 4, 4
+IRC_MAX_SETS, IRC_MAX_UNITS, IRC_MAX_LAG, IRC_MAX_BERM = 4, 4, 4, 8
 
 _lib = None
 
@@ -60,6 +63,7 @@ SYMBOLS = [
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim",
     "mcre_irc_set_coefficients", "mcre_irc_mainsim",
+    "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_finish",
@@ -95,6 +99,13 @@ def lib():
     L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
     L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_irc_set_exercise_coefficients.argtypes = [C.c_void_p, c_dp, c_dp, C.c_void_p]
+    L.mcre_irc_lsm_scratch_bytes.restype = C.c_int64
+    L.mcre_irc_lsm_scratch_bytes.argtypes = [C.c_void_p, C.c_int64]
+    L.mcre_irc_lsm_forward.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p]
+    L.mcre_lsm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                c_dp, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_void_p]
     L.mcre_eq_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.mcre_eq_destroy.argtypes = [C.c_void_p]
     L.mcre_eq_destroy.restype = None

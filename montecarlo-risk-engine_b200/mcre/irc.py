@@ -25,7 +25,9 @@ from metrics.metric import MetricType
 from models.cirpp import CIRPPModel
 from models.model_config import ModelConfig
 from models.vasicek import VasicekModel
+from products.bermudan_option import BermudanOption
 from products.bond import Bond
+from products.product import OptionType
 from products.swap import InterestRateSwap, IRSType
 
 CHUNK_PATHS = 4096
@@ -72,6 +74,59 @@ def linear_leg_of(product):
     return leg
 
 
+def underlying_terms(und, t_obs):
+    """Value of an option underlying observed at t_obs as const + sum_T w_T P(t_obs, T)
+    (reference: bond.py:115-163, swap.py:129-140): the underlying is re-scheduled from the
+    observation date and valued on forward zero bonds, notional included."""
+    const, terms = 0.0, {}
+
+    def add(T, w):
+        nonlocal const
+        if T == t_obs:
+            const += w          # P(t, t) = 1
+            return
+        for key in terms:
+            if abs(key - T) < 1e-9:
+                terms[key] += w
+                return
+        terms[T] = w
+
+    def add_bond(bond, sign):
+        b = bond.with_startdate(t_obs)
+        dates, notional = b.payment_dates.tolist(), float(b.notional)
+        if b.is_fixed():
+            prev = t_obs
+            for d in dates:
+                add(d, sign * notional * float(b.fixed_rate) * (d - prev))
+                prev = d
+        else:
+            starts = [per[0] for per in b.libor_periods()] + [float(b.maturity)]
+            for i in range(len(dates)):
+                add(starts[i], sign * notional)
+                add(starts[i + 1], -sign * notional)
+        if b.pays_notional:
+            add(dates[-1], sign * notional)
+
+    if isinstance(und, Bond):
+        add_bond(und, 1.0)
+    elif isinstance(und, InterestRateSwap):
+        s = 1.0 if und.irs_type == IRSType.PAYER else -1.0
+        swap = und.with_startdate(t_obs)
+        add_bond(swap.floating_leg, s)
+        add_bond(swap.fixed_leg, -s)
+    else:
+        raise TypeError(type(und))
+    return const, sorted(terms.items())
+
+
+def is_linear(p):
+    return isinstance(p, (Bond, InterestRateSwap))
+
+
+def is_rate_bermudan(p):
+    return isinstance(p, BermudanOption) and isinstance(p.underlying, (Bond, InterestRateSwap))
+
+
 def split_model(model):
     """(vasicek, cir or None, vas_index, cir_index) or None if not an IRC model."""
     if isinstance(model, VasicekModel):
@@ -92,7 +147,7 @@ class IrcBackend:
     def supports(ctrl):
         if split_model(ctrl.model) is None:
             return False
-        return all(isinstance(p, (Bond, InterestRateSwap)) for p in ctrl.products)
+        return all(is_linear(p) or is_rate_bermudan(p) for p in ctrl.products)
 
     def __init__(self, ctrl):
         self.c = ctrl
@@ -118,9 +173,24 @@ class IrcBackend:
             pv, pc = self.vas.dual_params(0, nt), None
         return pv, pc
 
-    def lower(self, set_indices, unit_products):
+    def basis_at(self, t):
+        """Standardisation (shift, scale) of the explanatory variable r(t): its Vasicek mean /
+        std (pure conditioning aid; the fitted values do not depend on it)."""
+        pv, _ = self._dual_params()
+        r0, sig, th, a = (x.v for x in pv)
+        tau = t - self.vas.t0()
+        if tau <= 0:
+            return (r0, 1.0)
+        mean = th + (r0 - th) * math.exp(-a * tau)
+        std = sig * math.sqrt((1.0 - math.exp(-2.0 * a * tau)) / (2.0 * a))
+        return (mean, 1.0 / std if std > 0 else 1.0)
+
+    def lower(self, set_indices, unit_products, berm_units=None, reg_times=None):
         """Build the descriptor for a group of netting sets (main) and regression units
-        (pre-simulation).  Returns (desc, tables) with `tables` keeping numpy arrays alive."""
+        (pre-simulation).  `berm_units`: [(BermudanOption, set row)] (default: the Bermudan
+        options of the given sets); `reg_times`: regression dates of the pre-simulation
+        (default: the internal exposure dates).
+        Returns (desc, tables) with `tables` keeping numpy arrays alive."""
         c, nt = self.c, self.nt
         w = 1 + nt
         pv, pc = self._dual_params()
@@ -163,7 +233,11 @@ class IrcBackend:
         # ---- cashflow tables ---------------------------------------------------------
         sets = [c.netting_sets[i] for i in set_indices]
         need_pv = c.risk_metrics.requires_discounted_cashflows()
-        set_legs = [[linear_leg_of(p) for p in ns.products] for ns in sets]
+        set_legs = [[linear_leg_of(p) for p in ns.products if is_linear(p)] for ns in sets]
+        if berm_units is None:
+            berm_units = [(p, r) for r, ns in enumerate(sets) for p in ns.products if is_rate_bermudan(p)]
+        if len(berm_units) > B.IRC_MAX_BERM:
+            raise NotImplementedError(f"at most {B.IRC_MAX_BERM} Bermudan options per launch group")
         unit_legs = [linear_leg_of(p) for p in unit_products]
         float_keys = [[] for _ in range(n_dates)]   # per date: list of (t1,t2)
         for leg in [l for legs in set_legs for l in legs] + unit_legs:
@@ -213,25 +287,42 @@ class IrcBackend:
         for d in cash_dates:
             flags[date_idx[d]] |= B.DATE_HAS_CASHFLOW
         for e, t in enumerate(expo_times):
-            flags[date_idx[t]] |= B.DATE_HAS_EXPOSURE | B.DATE_HAS_REGRESSION
+            flags[date_idx[t]] |= B.DATE_HAS_EXPOSURE
             date_expo[date_idx[t]] = e
-            date_reg[date_idx[t]] = e
+        reg_list = expo_times if reg_times is None else list(reg_times)
+        for k, t in enumerate(reg_list):
+            flags[date_idx[t]] |= B.DATE_HAS_REGRESSION
+            date_reg[date_idx[t]] = k
         for m, t in enumerate(metric_times):
             flags[date_idx[t]] |= B.DATE_HAS_METRIC
             date_metric[date_idx[t]] = m
 
-        # regression basis: standardise the explanatory variable r(t) with its Vasicek
-        # mean / std (pure conditioning aid; the fitted values do not depend on it)
-        r0, sig, th, a = (x.v for x in pv)
-        basis = np.zeros((n_expo, 2))
-        for e, t in enumerate(expo_times):
-            tau = t - t0
-            if tau <= 0:
-                basis[e] = (r0, 1.0)
-            else:
-                mean = th + (r0 - th) * math.exp(-a * tau)
-                std = sig * math.sqrt((1.0 - math.exp(-2.0 * a * tau)) / (2.0 * a))
-                basis[e] = (mean, 1.0 / std if std > 0 else 1.0)
+        basis = np.array([self.basis_at(t) for t in expo_times]).reshape(n_expo, 2)
+        reg_basis = np.array([self.basis_at(t) for t in reg_list]).reshape(len(reg_list), 2)
+
+        # ---- Bermudan exercise units: per date, the zero-bond decomposition of the underlying ----
+        ex_by_date = [[] for _ in range(n_dates)]
+        for b, (prod, _) in enumerate(berm_units):
+            ex_dates = prod.product_timeline.tolist()
+            for i, t in enumerate(ex_dates):
+                ex_by_date[date_idx[t]].append((b, i, t, i == len(ex_dates) - 1))
+        ex_off, ex_unit, ex_last, ex_const, ex_term_off, term_coef, term_w, ex_basis = [0], [], [], [], [0], [], [], []
+        ex_index = {}
+        for di in range(n_dates):
+            for b, i, t, last in ex_by_date[di]:
+                const, terms = underlying_terms(berm_units[b][0].underlying, t)
+                ex_index[(b, i)] = len(ex_unit)
+                ex_unit.append(b)
+                ex_last.append(int(last))
+                ex_const.append(const)
+                for T, wgt in terms:
+                    alpha, Bc = self.vas.bond_coefficients(pv, t, T)
+                    term_coef += [alpha, Bc]
+                    term_w.append(wgt)
+                ex_term_off.append(len(term_w))
+                ex_basis.append(self.basis_at(t))
+                flags[di] |= B.DATE_HAS_EXERCISE
+            ex_off.append(len(ex_unit))
 
         # ---- netting-set terms ---------------------------------------------------------
         metrics = c.risk_metrics.metrics
@@ -319,13 +410,26 @@ class IrcBackend:
         d.expo_basis = fp("expo_basis", basis if n_expo else np.zeros(1))
         d.cva_coef = fp("cva_coef", _packs(cva_coef) if n_metric else np.zeros(1))
         d.lgd = lgd
-        d.n_units, d.n_reg = len(unit_products), n_expo
+        d.n_units, d.n_reg = len(unit_products), len(reg_list)
         d.unit_fix = fp("unit_fix", unit_fix if unit_products else np.zeros(1))
         d.unit_float = fp("unit_float", unit_float if (unit_products and n_float) else np.zeros(1))
         d.unit_last_reg = ip("unit_last_reg", np.zeros(max(len(unit_products), 1)))
-        d.reg_basis = fp("reg_basis", basis if n_expo else np.zeros(1))
-        info = dict(grid=grid, n_expo=n_expo, n_metric=n_metric, basis=basis, acc=acc,
-                    set_flags=set_flags, noise_dim=2 if self.has_cir else 1, n_float=n_float)
+        d.reg_basis = fp("reg_basis", reg_basis if len(reg_list) else np.zeros(1))
+        d.n_berm = len(berm_units)
+        if berm_units:
+            d.berm_set = ip("berm_set", np.array([r for _, r in berm_units]))
+            d.berm_strike = fp("berm_strike", np.array([float(p.strike) for p, _ in berm_units]))
+            d.berm_sign = fp("berm_sign", np.array([1.0 if p.option_type == OptionType.CALL else -1.0
+                                                    for p, _ in berm_units]))
+            d.date_ex_off, d.ex_unit, d.ex_last = ip("ex_off", ex_off), ip("ex_unit", ex_unit), ip("ex_last", ex_last)
+            d.ex_term_off, d.ex_const = ip("ex_term_off", ex_term_off), fp("ex_const", ex_const)
+            d.term_coef = fp("term_coef", _packs(term_coef) if term_coef else np.zeros(1))
+            d.term_w = fp("term_w", term_w if term_w else np.zeros(1))
+            d.ex_basis = fp("ex_basis", np.array(ex_basis))
+        info = dict(grid=grid, n_expo=n_expo, n_metric=n_metric, basis=basis, acc=acc, reg_basis=reg_basis,
+                    set_flags=set_flags, noise_dim=2 if self.has_cir else 1, n_float=n_float,
+                    berm_units=berm_units, ex_index=ex_index, n_ex=len(ex_unit), reg_times=reg_list,
+                    expo_times=expo_times)
         return d, t, info
 
     def param_used(self, kind):
@@ -398,6 +502,79 @@ class IrcBackend:
                 out[id(prod)] = (coefs, info["basis"])
         return out
 
+    def presim_bermudan(self, prod, dev):
+        """Longstaff-Schwartz pre-simulation of one Bermudan option (controller.py:294-383):
+        forward pass spills x, numeraire and immediate values; one fused moments(+exercise
+        update) launch per regression date, latest first; the 3x3 normal equations are solved
+        on the host (multi-GPU: after an all-reduce of the 8 moments).
+        -> (coef per regression date [n_reg][3] in the standardised basis, reg_times, reg_basis)"""
+        from bisect import bisect_left
+        c = self.c
+        L = B.lib()
+        n_pre = c.num_paths_presim
+        if n_pre <= 0:
+            raise ValueError("Exercise products need a pre-simulation: num_paths_presim must be positive.")
+        expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
+        ptl = prod.product_timeline.tolist()
+        reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
+        reg_idx = {t: k for k, t in enumerate(reg_times)}
+        desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
+        n_reg, n_ex = len(reg_times), info["n_ex"]
+        basis = info["reg_basis"]
+        coef = np.zeros((n_reg, 3))
+        inject = c.injected_normals.get("pre") if c.injected_normals else None
+        plan = C.c_void_p()
+        B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
+        try:
+            begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
+            n = max(count, 1)
+            scratch = torch.empty(L.mcre_irc_lsm_scratch_bytes(plan, n) // 8 + 1, dtype=torch.float64, device=dev)
+            rng = self._rng(42, inject, n_pre)
+            sh = B.Shard(begin, count, CHUNK_PATHS)
+            B.check(L.mcre_irc_lsm_forward(plan, C.byref(rng), C.byref(sh), scratch.data_ptr(), RT.stream_ptr()))
+        finally:
+            L.mcre_irc_destroy(plan)
+        xs = scratch[:n_reg * n].view(n_reg, n)
+        ns_ = scratch[n_reg * n:2 * n_reg * n].view(n_reg, n)
+        imm = scratch[2 * n_reg * n:(2 * n_reg + n_ex) * n].view(n_ex, n)
+        value = torch.zeros(n, dtype=torch.float32, device=dev)
+        n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
+        partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
+        moments = torch.zeros(8, dtype=torch.float64, device=dev)
+
+        def step(k, i):
+            """moments of regression date k, after the exercise update at product date i (or None)."""
+            args_i = (None, None, None, None, 0.0, 1.0)
+            if i is not None:
+                ki = reg_idx[ptl[i]]
+                cptr = None
+                if i < len(ptl) - 1:
+                    self._coef_keep, cptr = B.as_dp(coef[ki])
+                args_i = (xs[ki].data_ptr(), ns_[ki].data_ptr(), imm[info["ex_index"][(0, i)]].data_ptr(), cptr,
+                          float(basis[ki, 0]), float(basis[ki, 1]))
+            B.check(L.mcre_lsm_step(xs[k].data_ptr(), ns_[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
+                                    *args_i, value.data_ptr(), count, CHUNK_PATHS, partial.data_ptr(),
+                                    moments.data_ptr(), RT.stream_ptr()))
+
+        last = len(ptl)
+        for k in range(n_reg - 1, -1, -1):
+            t_reg = reg_times[k]
+            pidx = bisect_left(ptl, t_reg)
+            if pidx >= len(ptl):
+                continue      # after the last exercise date: no continuation value (controller.py:303-305)
+            t_next = pidx + 1 if ptl[pidx] == t_reg else pidx
+            if t_next < last:
+                for i in range(last - 1, t_next, -1):   # product dates that are not regression dates
+                    step(k, i)
+                step(k, t_next)
+                last = t_next
+            else:
+                step(k, None)
+            m = RT.all_reduce_tree(moments).cpu().numpy()
+            G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
+            coef[k] = solve_normal_equations(G, m[5:8])
+        return coef, reg_times, basis
+
     def run(self):
         c = self.c
         dev = RT.compute_device()
@@ -409,13 +586,29 @@ class IrcBackend:
         import time
         t0 = time.perf_counter()
         coef_by_product = {}
+        berm_coef = {}
         if c.requires_regression:
-            prods = [p for p in c.products if c._product_requires_regression(p)]
-            coef_by_product = self.presim_coefficients(prods, dev)
+            prods = [p for p in c.products if c._product_requires_regression(p) and is_linear(p)]
+            if prods and need_expo:
+                coef_by_product = self.presim_coefficients(prods, dev)
             # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
             for p in prods:
-                coefs, basis = coef_by_product[id(p)]
-                c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coefs, basis))
+                if id(p) in coef_by_product:
+                    coefs, basis = coef_by_product[id(p)]
+                    degen = [t <= self.vas.t0() for t in c.exposure_timeline.tolist()]
+                    c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coefs, basis, degen))
+            expo_times = c.exposure_timeline.tolist() if need_expo else []
+            for p in c.products:
+                if not is_rate_bermudan(p):
+                    continue
+                coef, reg_times, basis = self.presim_bermudan(p, dev)
+                berm_coef[id(p)] = (coef, {t: k for k, t in enumerate(reg_times)}, basis)
+                raw = to_raw_basis(coef, basis, [t <= self.vas.t0() for t in reg_times])
+                ridx = {t: k for k, t in enumerate(reg_times)}
+                for j, t in enumerate(p.regression_timeline.tolist()):
+                    p.regression_coeffs[j, 1, :] = torch.tensor(raw[ridx[t]])
+                for e, t in enumerate(expo_times):
+                    c.regression_coeffs[p.product_id][e, 1, :] = torch.tensor(raw[ridx[t]])
         torch.cuda.synchronize(dev)
         timings["preprocessing"] = time.perf_counter() - t0
         t1 = time.perf_counter()
@@ -438,6 +631,19 @@ class IrcBackend:
             try:
                 coef_flat, coef_ptr = B.as_dp(coef[:n_expo])
                 B.check(L.mcre_irc_set_coefficients(plan, coef_ptr, RT.stream_ptr()))
+                if info["berm_units"]:
+                    units = info["berm_units"]
+                    exc = np.zeros((max(info["n_ex"], 1), 3, w))
+                    bex = np.zeros((max(n_expo, 1), len(units), 3, w))
+                    for b, (p, _) in enumerate(units):
+                        bc, ridx, _ = berm_coef[id(p)]
+                        for i, t in enumerate(p.product_timeline.tolist()):
+                            exc[info["ex_index"][(b, i)], :, 0] = bc[ridx[t]]
+                        for e, t in enumerate(info["expo_times"]):
+                            bex[e, b, :, 0] = bc[ridx[t]]
+                    exc_k, exc_ptr = B.as_dp(exc)
+                    bex_k, bex_ptr = B.as_dp(bex)
+                    B.check(L.mcre_irc_set_exercise_coefficients(plan, exc_ptr, bex_ptr, RT.stream_ptr()))
                 begin, count = RT.shard_range(n_main, CHUNK_PATHS)
                 slots = L.mcre_irc_main_slots(plan)
                 acc = torch.zeros(slots, dtype=torch.float64, device=dev)
@@ -503,12 +709,19 @@ def solve_normal_equations(G, rhs):
     return (vt2[keep].T * (1.0 / s2[keep])) @ (u2[:, keep].T @ rhs)
 
 
-def to_raw_basis(coefs, basis):
-    """Coefficients of [1, u, u^2], u = (x - shift) * scale  ->  coefficients of [1, x, x^2]."""
+def to_raw_basis(coefs, basis, degenerate=None):
+    """Coefficients of [1, u, u^2], u = (x - shift) * scale  ->  coefficients of [1, x, x^2].
+    `degenerate[k]`: every path has x = shift at date k (t = calibration date); the reference's
+    lstsq then returns the minimum-norm solution in the raw basis: c = f * phi / |phi|^2 with
+    phi = [1, x, x^2] and f the fitted constant."""
     sh, sc = basis[:, 0], basis[:, 1]
     c0, c1, c2 = coefs[:, 0], coefs[:, 1], coefs[:, 2]
     out = np.empty_like(coefs)
     out[:, 2] = c2 * sc * sc
     out[:, 1] = c1 * sc - 2.0 * c2 * sc * sc * sh
     out[:, 0] = c0 - c1 * sc * sh + c2 * sc * sc * sh * sh
+    if degenerate is not None:
+        for k in np.nonzero(np.asarray(degenerate))[0]:
+            phi = np.array([1.0, sh[k], sh[k] * sh[k]])
+            out[k] = coefs[k, 0] * phi / phi.dot(phi)
     return out

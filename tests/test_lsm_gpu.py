@@ -1,0 +1,75 @@
+"""Parity of the Longstaff-Schwartz path (csrc/lsm.cu, Bermudan units of csrc/irc_main.cuh)
+through the C ABI: Vasicek Bermudan payer swaption, EPE + PFE + PV (BASELINE config 4).
+
+  1. the reference's torch.randn stream injected -> outputs of the unmodified reference
+     (tests/golden/bermudan_swaption.json) at 1e-9 relative (the exercise indicator is hard, so
+     agreement at this level means every path took the same exercise decision)
+  2. native Philox vs the oracle on the same stream
+"""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(flat_a, flat_b, rtol, what, err_rtol=1e-7):
+    for key, (va, ea) in flat_a.items():
+        vb, eb = flat_b[key]
+        scale = max(1.0, float(np.nanmax(np.abs(vb))) if len(vb) else 1.0)
+        helpers.assert_close(va, vb, rtol, rtol * scale, f"{what} {key} value")
+        helpers.assert_close(ea, eb, err_rtol, 1e-10 * scale, f"{what} {key} mc error")
+
+
+def test_bermudan_swaption_matches_reference_golden():
+    name = "bermudan_swaption"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    assert res.get_netting_set_names() == gold["sets"]
+    assert res.get_metric_names() == gold["metrics"]
+    assert [float(t) for t in sc.simulation_timeline] == gold["simulation_timeline"]
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _compare(flat, ref, 1e-9, name)
+
+
+@pytest.mark.parametrize("kwargs", [dict(), dict(n_main=5000, n_pre=3000), dict(num_steps=2)])
+def test_bermudan_swaption_philox_matches_oracle(kwargs):
+    name = "bermudan_swaption"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="philox", **kwargs)
+    out, _ = helpers.run_oracle(name, draws="philox", **kwargs)
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8,
+             name + " philox", err_rtol=1e-6)
+    # regression coefficients exposed like the reference's controller.regression_coeffs (raw monomial basis)
+    got = sc.regression_coeffs[0].numpy()          # [T_e, S, 3]
+    want = np.stack([np.asarray(c) for c in out["expo_coeffs"][0]])
+    fit_scale = np.abs(want).max(axis=(1, 2), keepdims=True) + 1e-30
+    assert np.all(np.abs(got - want) <= 1e-6 * fit_scale), "exposure regression coefficients"
+
+
+def test_bermudan_pv_only_and_mixed_book():
+    """PV-only run (regression dates = exercise dates only) and a netting set mixing a swap
+    with a Bermudan swaption, collateralised, all exposure metrics."""
+    from oracle import risk
+    ns = cases.Namespace()
+    model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=6)
+    n = 4096
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics([ns.PVMetric()]), n, n, 1, ns.SimulationScheme.EULER)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, [ns.PVMetric()], None, n, n, 1, "EULER")
+    helpers.assert_close(res.get_results("bermudan", "pv"), [out["results"][0][0][0][0]], 1e-8, 1e-12, "pv only")
+    helpers.assert_close(res.get_mc_error("bermudan", "pv"), [out["results"][0][0][0][1]], 1e-6, 1e-12, "pv only err")
+
+    model, sets, _, tl = cases.bermudan_swaption(ns, n_ex=6)
+    swap = ns.InterestRateSwap(0.0, 2.0, 1.0, 0.035, 0.25, 0.25, ns.IRSType.RECEIVER)
+    mixed = [ns.NettingSet(name="mixed", products=[sets[0].products[0], swap], margin_period_of_risk=0.25, threshold=0.002),
+             ns.NettingSet(name="swap_only", products=[ns.InterestRateSwap(0.0, 1.5, 1.0, 0.03, 0.25, 0.25, ns.IRSType.PAYER)])]
+    metrics = [ns.PVMetric(), ns.CEMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.EEPEMetric(), ns.PFEMetric(0.9)]
+    sc = ns.SimulationController(mixed, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.EULER)
+    res = sc.run_simulation()
+    out = risk.run(model, mixed, metrics, tl, n, n, 1, "EULER")
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names()),
+             1e-8, "mixed book", err_rtol=1e-6)
