@@ -10,8 +10,13 @@ class AsianAveragingType(Enum):
 
 class AsianOption(Product):
     def __init__(self, startdate, maturity, strike, num_observation_timepoints, option_type,
-                 averaging_type=AsianAveragingType.ARITHMETIC, asset_id=None):
+                 averaging_type=AsianAveragingType.ARITHMETIC, asset_id=None, basket=None):
         super().__init__(asset_ids=[asset_id], product_family=ProductFamily.ASIAN_PATH_TERMINAL)
+        #: extension (not in the reference, which monitors one asset): (asset_ids, weights) of a
+        #: weighted arithmetic basket monitored instead of a single spot (BASELINE config 5)
+        self.basket = None if basket is None else (list(basket[0]), [float(w) for w in basket[1]])
+        if self.basket is not None:
+            self.asset_ids = list(self.basket[0])
         self.maturity = _ft([maturity])
         self.strike = _ft([strike])
         self.option_type = option_type

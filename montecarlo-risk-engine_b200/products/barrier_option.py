@@ -15,8 +15,13 @@ class BarrierOption(Product):
     FUZZY_EPS = 0.05
 
     def __init__(self, startdate, maturity, strike, num_observation_timepoints, option_type, barrier1,
-                 barrier_option_type1, barrier2=None, barrier_option_type2=None, asset_id=None):
+                 barrier_option_type1, barrier2=None, barrier_option_type2=None, asset_id=None, basket=None):
         super().__init__(asset_ids=[asset_id], product_family=ProductFamily.BARRIER_PATH_TERMINAL)
+        #: extension (not in the reference, which monitors one asset): (asset_ids, weights) of a
+        #: weighted arithmetic basket monitored instead of a single spot (BASELINE config 5)
+        self.basket = None if basket is None else (list(basket[0]), [float(w) for w in basket[1]])
+        if self.basket is not None:
+            self.asset_ids = list(self.basket[0])
         self.strike = _ft([strike])
         self.maturity = _ft([maturity])
         self.product_timeline = _ft([maturity])

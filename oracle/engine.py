@@ -22,10 +22,14 @@ class InjectedDraws:
 class PhiloxDraws:
     """Same counter-based stream as the CUDA kernels (csrc/philox.cuh)."""
 
-    def __init__(self, seed, n_paths, n_sub, dim, stream=0, path_begin=0, with_uniforms=False):
+    def __init__(self, seed, n_paths, n_sub, dim, stream=0, path_begin=0, with_uniforms=False, n_uniform=1):
         paths = np.arange(path_begin, path_begin + n_paths, dtype=np.uint64)
         self.z = philox.normals(paths, n_sub, dim, seed, stream)
-        self.u = philox.uniforms(paths, n_sub, seed, stream) if with_uniforms else None
+        self.u = None
+        if with_uniforms:
+            # uniform #(s * n_uniform + a) of a path belongs to sub-step s, asset a
+            u = philox.uniforms(paths, n_sub * n_uniform, seed, stream)
+            self.u = u if n_uniform == 1 else u.reshape(n_sub, n_uniform, n_paths).transpose(0, 2, 1).copy()
 
     def normals(self, s):
         return [self.z[s, :, j] for j in range(self.z.shape[2])]

@@ -178,6 +178,19 @@ def initial_state(model, p, n):
 def correlation(model, p, scheme):
     """Matrix (list of lists, entries scalar / Dual) of the noise correlation."""
     k = kind(model)
+    if k == "ModelConfig" and scheme == "QE" and all(kind(m) == "HestonModel" for m in model.models):
+        # BUILD-DEFINED EXTENSION, parity unpinned by the reference (its ModelConfig cannot hold a
+        # HestonModel, model_config.py:106-115): spot normals of the assets correlated by the
+        # inter-asset matrix, variance normals independent (QE, heston.py:85-90).
+        A = len(model.models)
+        C = [[1.0 if i == j else 0.0 for j in range(2 * A)] for i in range(2 * A)]
+        idx = 0
+        for i in range(A):
+            for j in range(i + 1, A):
+                rho = float(np.asarray(model.inter_asset_correlation_matrix[idx], dtype=float).reshape(-1)[0])
+                C[2 * i][2 * j] = C[2 * j][2 * i] = rho
+                idx += 1
+        return C
     if k == "ModelConfig":
         n = len(model.asset_ids)
         C = [[0.0 for _ in range(n)] for _ in range(n)]
@@ -309,9 +322,10 @@ def step(model, p, scheme, t1, t2, state, w, u=None, smoothing=False):
     sq = math.sqrt(dt)
     if k == "ModelConfig":
         out, so, no, po = [], 0, 0, 0
-        for m in model.models:
+        for mi, m in enumerate(model.models):
             sd, nd, npar = state_dim(m), noise_dim(m), len(m.model_params)
-            out += step(m, p[po:po + npar], scheme, t1, t2, state[so:so + sd], w[no:no + nd], u, smoothing)
+            um = u[:, mi] if (u is not None and np.ndim(u) == 2) else u   # one QE uniform per asset
+            out += step(m, p[po:po + npar], scheme, t1, t2, state[so:so + sd], w[no:no + nd], um, smoothing)
             so, no, po = so + sd, no + nd, po + npar
         return out
     if k == "BlackScholesModel":

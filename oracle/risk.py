@@ -161,6 +161,19 @@ def _leg(swap, fixed):
     return _LegView(swap, fixed)
 
 
+def monitored_value(prod, t, ctx):
+    """Spot monitored by a path-dependent option; with the `basket` extension (parity unpinned,
+    the reference monitors one asset) the weighted arithmetic basket of several spots."""
+    basket = getattr(prod, "basket", None)
+    if basket is None:
+        return ctx.spot(asset_of(prod), t)
+    tot = None
+    for a, w in zip(*basket):
+        term = w * ctx.spot(a, t)
+        tot = term if tot is None else tot + term
+    return tot
+
+
 def option_payoff(prod, s):
     k = _f(prod.strike)
     return ad.relu(s - k) if prod.option_type.name == "CALL" else ad.relu(k - s)
@@ -215,7 +228,7 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
         return state_matrix, [pay / ctx.numeraire(t)] * S
     if k == "AsianOption":             # asian_option.py:51-95
         obs = modeling_timeline(prod)
-        spots = [ctx.spot(asset_of(prod), t) for t in obs]
+        spots = [monitored_value(prod, t, ctx) for t in obs]
         if prod.averaging_type.name == "GEOMETRIC":
             tot = None
             for s in spots:
@@ -230,7 +243,7 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
         return state_matrix, [option_payoff(prod, avg) / ctx.numeraire(obs[0])] * S
     if k == "BarrierOption":           # barrier_option.py:65-125, 300-314
         obs = modeling_timeline(prod)
-        spots = [ctx.spot(asset_of(prod), t) for t in obs]
+        spots = [monitored_value(prod, t, ctx) for t in obs]
         mx, mn = spots[0], spots[0]
         for s in spots[1:]:
             mx = ad.where(ad.val(s) > ad.val(mx), s, mx)
@@ -490,7 +503,8 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
                 regress_product(pr, ctx, expo_tl, degree, prod_coeffs[k], expo_coeffs[k])
 
     if draws_main is None:
-        draws_main = E.PhiloxDraws(43, n_main, n_sub, dim, with_uniforms=qe)
+        n_uni = len(M.submodels(model)) if qe else 1
+        draws_main = E.PhiloxDraws(43, n_main, n_sub, dim, with_uniforms=qe, n_uniform=n_uni)
     paths = E.generate_paths(model, p, sim_tl, n_main, num_steps, scheme, draws_main, smoothing)
     ctx = Ctx(model, p, sim_tl, paths, n_main)
 

@@ -75,6 +75,22 @@ def heston_path_dependent(ns_module):
     return model, [m.NettingSet(name="barrier", products=[bar]), m.NettingSet(name="asian", products=[asian])], [m.PVMetric()], None
 
 
+def heston_basket5(ns_module, n_assets=5, n_obs=13, rho_spot=0.5):
+    """Config 5: up-and-out barrier call and arithmetic Asian call on an equally weighted basket of
+    correlated Heston assets (QE).  BUILD-DEFINED EXTENSION: the reference's ModelConfig cannot hold
+    Heston models and its barrier / Asian options monitor one asset - parity unpinned
+    beyond the single-asset case, the oracle composes the pinned single-asset pieces."""
+    m = ns_module
+    ids = [f"h{i}" for i in range(n_assets)]
+    models = [m.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04, asset_id=a) for a in ids]
+    n_pairs = n_assets * (n_assets - 1) // 2
+    model = m.ModelConfig(models, inter_asset_correlation_matrix=np.array([[rho_spot] for _ in range(n_pairs)]))
+    w = [1.0 / n_assets] * n_assets
+    bar = m.BarrierOption(0.0, 1.0, 100.0, n_obs, m.OptionType.CALL, 140.0, m.BarrierOptionType.UPANDOUT, basket=(ids, w))
+    asian = m.AsianOption(0.0, 1.0, 100.0, n_obs, m.OptionType.CALL, basket=(ids, w))
+    return model, [m.NettingSet(name="barrier", products=[bar]), m.NettingSet(name="asian", products=[asian])], [m.PVMetric()], None
+
+
 def bs_basket(ns_module, euler=False):
     """4 x BS in a ModelConfig, arithmetic + geometric basket (tests/pytests/test_model_config.py:18-126)."""
     m = ns_module

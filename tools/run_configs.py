@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Runs the BASELINE.json configurations at full size through the public API
+(SimulationController.run_simulation) on one B200 and prints one JSON line per config:
+wall time of the call, path-steps/s and a few result values.  Not the headline bench
+(bench.py is); used to size and sanity-check the other configs.
+
+    python tools/run_configs.py [1 2 2o 4 5] [--scale-log2 -2]   # --scale shrinks the path counts
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["1", "2", "2o", "4", "5", "5g"])
+    ap.add_argument("--scale-log2", type=int, default=0)
+    ap.add_argument("--repeats", type=int, default=2)
+    args = ap.parse_args()
+    importlib.import_module("montecarlo-risk-engine_b200")
+    import torch
+    import cases
+    from mcre import binding as B
+    ns = cases.Namespace()
+    S = ns.SimulationScheme
+    sc_ = args.scale_log2
+
+    def n(log2):
+        return 1 << max(log2 + sc_, 8)
+
+    def cfg(name):
+        if name == "1":
+            model, sets, metrics, tl = cases.bs_european(ns, spot=100.0, strike=100.0, T=1.0)
+            return dict(model=model, sets=sets, metrics=metrics, tl=None, n_main=100000, n_pre=0, steps=1,
+                        scheme=S.ANALYTICAL, diff=True, sub=1, show=[("call", "pv")])
+        if name in ("2", "2o"):
+            mpor = 0.25 if name == "2" else 10 / 252
+            model, sets, metrics, tl = cases.vasicek_irs_collateral(ns, mpor=mpor, n_dates=121, maturity=30.0)
+            return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(22), n_pre=n(22), steps=1, scheme=S.EULER,
+                        diff=False, sub=120 if name == "2" else 240, show=[("irs_collateralized", "eepe"), ("irs_uncollateralized", "eepe")])
+        if name == "4":
+            model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=40)
+            return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(22), n_pre=n(22), steps=1, scheme=S.EULER,
+                        diff=False, sub=40, show=[("bermudan", "pv")])
+        if name in ("5", "5g"):
+            model, sets, metrics, tl = cases.heston_basket5(ns)
+            diff = name == "5g"
+            return dict(model=model, sets=sets, metrics=metrics, tl=None, n_main=n(24), n_pre=0, steps=21, scheme=S.QE,
+                        diff=diff, sub=252, show=[("barrier", "pv"), ("asian", "pv")])
+        raise SystemExit(f"unknown config {name}")
+
+    for name in args.configs:
+        best, res = None, None
+        for rep in range(args.repeats):
+            c = cfg(name)
+            rm = ns.RiskMetrics(c["metrics"], exposure_timeline=c["tl"]) if c["tl"] is not None else ns.RiskMetrics(c["metrics"])
+            torch.cuda.synchronize()
+            l0 = B.launch_count()
+            t0 = time.perf_counter()
+            ctl = ns.SimulationController(c["sets"], c["model"], rm, c["n_main"], c["n_pre"], c["steps"], c["scheme"], c["diff"])
+            res = ctl.run_simulation()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            launches = B.launch_count() - l0
+        out = {"config": name, "n_main": c["n_main"], "n_pre": c["n_pre"], "sub_steps": c["sub"], "differentiate": c["diff"],
+               "seconds": best, "path_steps_per_s": c["n_main"] * c["sub"] / best, "launches": launches,
+               "timings": {k: round(v, 4) for k, v in ctl.last_timings.items()},
+               "max_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+        for s, m in c["show"]:
+            out[f"{s}|{m}"] = [float(res.get_results(s, m)[0]), float(res.get_mc_error(s, m)[0])]
+            if c["diff"]:
+                out[f"{s}|{m}|d"] = [None if g is None else float(g) for g in res.get_derivatives(s, m)[0]][:7]
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
