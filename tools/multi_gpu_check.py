@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""GPU-count independence check: runs a set of scenarios through the public API with the
+paths sharded over WORLD_SIZE GPUs (torchrun) and writes every result to --out as JSON with
+the doubles' exact bit patterns.  Run once with 1 process and once under torchrun; the two
+files must be identical (disjoint Philox streams keyed by global path id + fixed-order chunk
+tree reduction).
+
+    python tools/multi_gpu_check.py --out gpurun_out/mg1.json
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py --out gpurun_out/mg2.json
+    python tools/multi_gpu_check.py --compare gpurun_out/mg1.json gpurun_out/mg2.json
+"""
+import argparse
+import importlib
+import json
+import os
+import struct
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def bits(x):
+    return struct.pack("<d", float(x)).hex()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out")
+    ap.add_argument("--compare", nargs=2)
+    ap.add_argument("--paths-log2", type=int, default=17)
+    args = ap.parse_args()
+    if args.compare:
+        a, b = (json.load(open(f)) for f in args.compare)
+        bad = [k for k in a if a[k] != b.get(k)]
+        print(json.dumps({"scenarios": len(a), "values": sum(len(v) for v in a.values()), "mismatching_scenarios": bad}))
+        sys.exit(1 if bad or set(a) != set(b) else 0)
+    import torch
+    import torch.distributed as dist
+    importlib.import_module("montecarlo-risk-engine_b200")
+    import cases
+    import helpers
+    from mcre import runtime as RT
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = RT.compute_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = 1 << args.paths_log2
+    out = {}
+    for name in ["wwr_cva", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption", "heston_path_dependent",
+                 "bs_basket_euler"]:
+        res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0))
+        vals = []
+        for s in res.get_netting_set_names():
+            for m in res.get_metric_names():
+                vals += [bits(v) for v in res.get_results(s, m)] + [bits(v) for v in res.get_mc_error(s, m)]
+                if cases.GOLDEN_CASES[name][2]["differentiate"]:
+                    for row in res.get_derivatives(s, m):
+                        vals += [bits(0.0 if g is None else g) for g in row]
+        out[name] = vals
+    ns = cases.Namespace()
+    model, sets, metrics, _ = cases.heston_basket5(ns)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), n, 0, 2, ns.SimulationScheme.QE, True)
+    res = sc.run_simulation()
+    out["heston_basket5"] = [bits(res.get_results(s, "pv")[0]) for s in res.get_netting_set_names()] + \
+        [bits(g) for s in res.get_netting_set_names() for g in res.get_derivatives(s, "pv")[0]]
+    if RT.dist_info()[0] == 0:
+        with open(args.out, "w") as f:
+            json.dump(out, f)
+        print(f"world {world}: wrote {sum(len(v) for v in out.values())} values to {args.out}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
