@@ -7,7 +7,12 @@
 // (one per exposure date) than the model has parameters, so tangents are propagated
 // forward with the path instead of taping it.
 #pragma once
-#ifdef MCRE_FAST_MATH
+#if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
+#include "fastmath.cuh"
+#define MCRE_EXP(x) fm_exp_t(x)
+#define MCRE_LOG(x) fm_log_t(x)
+#define MCRE_SQRT(x) fm_sqrt(x)
+#elif defined(MCRE_FAST_MATH)
 #include "fastmath.cuh"
 #define MCRE_EXP(x) fm_exp(x)
 #define MCRE_LOG(x) fm_log(x)

@@ -15,7 +15,7 @@
 // order (and adds the deterministic-numeraire term).
 //
 // Nothing but block-reduced sums reaches HBM.  See include/mcre.h for what this replaces.
-#define MCRE_FAST_MATH 1
+#define MCRE_FAST_MATH 2
 #include "common.cuh"
 #include "philox.cuh"
 #include "dual.cuh"
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
   typedef typename RealOf<NT>::type R;
   typedef RealTraits<R> T;
   typedef RealVar<R> V;
+  fm_tables_init();
   constexpr int NP = EqParCount<KIND>::n;
   constexpr int NVH = NS * 3;
   constexpr int NVT = NS * (NT > 0 ? NT : 1);

@@ -147,4 +147,117 @@ __device__ __forceinline__ void fm_sincos2pi(double u, double &sn, double &cs) {
   cs = ((q + 1) & 2) ? -ca : ca;
 }
 
+
+#if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
+// =====================================================================================
+// Table-driven variants (second ncu pass, profiles/r01_irc_main_v1_*): the v1 kernel spent
+// ~100 of its 148 FP64 instructions per path-step in the long Taylor polynomials above and
+// 77 instructions materialising their coefficients.  Here the argument is reduced against
+// small tables in SHARED memory (4.6 KB per block, built by fm_tables_init at kernel start
+// with libdevice), so the polynomials shrink to degree 5-7, and the coefficients sit in
+// __constant__ memory (one LDCU.128 per two coefficients instead of four UMOV).
+//   exp   : 2^(n/64)            64 doubles     19 -> 11 FP64 instructions
+//   log   : (1/c_j, log c_j)    128 pairs      25 -> 13
+//   sincos: (sin, cos)(2 pi n/128) 128 pairs   24 -> 14
+// Every kernel that calls these must call fm_tables_init() first.
+// =====================================================================================
+struct FmShared {
+  double exp2t[64];
+  double2 logt[128];
+  double2 sct[128];
+};
+static __shared__ FmShared s_fm;
+
+static __constant__ double FM_C[24] = {
+    // exp: 1/120, 1/24, 1/6, 1/2   (index 0..3)
+    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
+    // exp reduction: 64/ln2, ln2/64 hi, ln2/64 lo, pad   (4..7)
+    92.33248261689366, 0.01083042469326756, 2.9815858271643302e-12, 0.0,
+    // log1p(f)/f - 1: -1/2, 1/3, -1/4, 1/5, -1/6, 1/7, -1/8, pad   (8..15)
+    -0.5, 3.3333333333333331e-01, -0.25, 0.2, -1.6666666666666666e-01, 1.4285714285714285e-01, -0.125, 0.0,
+    // sin: -1/6, 1/120, -1/5040 ; cos: -1/2, 1/24, -1/720 ; 2 pi ; pad   (16..23)
+    -1.6666666666666666e-01, 8.3333333333333332e-03, -1.984126984126984e-04,
+    -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 6.283185307179586, 0.0};
+
+// Builds the shared tables (all threads of the block; ends with a barrier).
+__device__ __forceinline__ void fm_tables_init() {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_fm.exp2t[i] = exp2((double)i * (1.0 / 64.0));
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    // interval j of the mantissa m in [1,2): centre c_j, except the two intervals that touch
+    // u = 1 (j = 0: c = 1, j = 127: c = 2) so that log(u) keeps its relative accuracy there.
+    // Intervals with m >= 1 + 53/128 (~sqrt 2) are folded down by a factor 2 (exponent + 1).
+    double c = 1.0 + ((double)i + 0.5) * (1.0 / 128.0);
+    if (i == 0) c = 1.0;
+    if (i == 127) c = 2.0;
+    const double rc = 1.0 / c;
+    double L = (i == 0 || i == 127) ? 0.0 : -log(i >= 53 ? rc * 2.0 : rc);
+    s_fm.logt[i] = make_double2(rc, L);
+    double sn, cs;
+    sincospi((double)i * (1.0 / 64.0), &sn, &cs);
+    s_fm.sct[i] = make_double2(sn, cs);
+  }
+  __syncthreads();
+}
+
+// exp(x) for |x| <= 700: n = round(64 x / ln2), exp(x) = 2^(n>>6) * T[n&63] * exp(r), |r| <= ln2/128.
+__device__ __forceinline__ double fm_exp_t(double x) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  double t = fma(x, FM_C[4], MAGIC);
+  const int n = __double2loint(t);
+  t -= MAGIC;
+  double r = fma(t, -FM_C[5], x);
+  r = fma(t, -FM_C[6], r);
+  const double T = s_fm.exp2t[n & 63];
+  double p = fma(r, FM_C[0], FM_C[1]);
+  p = fma(p, r, FM_C[2]);
+  p = fma(p, r, FM_C[3]);
+  p = fma(p, r, 1.0);                        // 1 + r/2 + r^2/6 + r^3/24 + r^4/120
+  const double res = fma(T * r, p, T);       // T (1 + r p)
+  // scale by 2^(n>>6) in the exponent field (result stays normal for |x| <= 700)
+  return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+}
+
+// log(u) for u in [2^-60, 2).
+__device__ __forceinline__ double fm_log_t(double u) {
+  const int hi = __double2hiint(u);
+  const int e = ((hi + 0x96000) >> 20) - 1023;          // exponent, +1 when m >= 1 + 53/128
+  const int j = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
+  const double2 tb = s_fm.logt[j];
+  const double f = fma(m, tb.x, -1.0);                    // m / c_j - 1, |f| <= 1/128
+  double p = fma(f, FM_C[14], FM_C[13]);
+  p = fma(p, f, FM_C[12]);
+  p = fma(p, f, FM_C[11]);
+  p = fma(p, f, FM_C[10]);
+  p = fma(p, f, FM_C[9]);
+  p = fma(p, f, FM_C[8]);                                 // -1/2 + f/3 - f^2/4 ...
+  const double lp = fma(f * f, p, f);                     // log1p(f)
+  // (double)e through the 2^52 + 2^31 bias: one integer op + one FP64 add
+  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  return fma(ed, LN2_HI, tb.y) + fma(ed, LN2_LO, lp);
+}
+
+// (sin(2 pi u), cos(2 pi u)) for u in [0, 1): n = round(128 u), angle = 2 pi n/128 + x, |x| <= pi/128.
+__device__ __forceinline__ void fm_sincos2pi_t(double u, double &sn, double &cs) {
+  const double MAGIC = 6755399441055744.0;
+  double t = fma(u, 128.0, MAGIC);
+  const int n = __double2loint(t);
+  t -= MAGIC;
+  const double r = fma(t, -0.0078125, u);                 // exact, [-1/256, 1/256]
+  const double x = r * FM_C[22];
+  const double z = x * x;
+  const double2 tb = s_fm.sct[n & 127];
+  double ps = fma(z, FM_C[18], FM_C[17]);
+  ps = fma(ps, z, FM_C[16]);
+  const double sx = fma(x * z, ps, x);                    // sin x
+  double pc = fma(z, FM_C[21], FM_C[20]);
+  pc = fma(pc, z, FM_C[19]);
+  const double cm = z * pc;                               // cos x - 1
+  // rotate: sin(a + x) = S + (C sx + S cm),  cos(a + x) = C + (C cm - S sx)
+  sn = tb.x + fma(tb.y, sx, tb.x * cm);
+  cs = tb.y + fma(-tb.x, sx, tb.y * cm);
+}
+#endif
+
 }  // namespace mcre

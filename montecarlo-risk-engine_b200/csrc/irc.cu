@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) irc_presim_forward_kernel(IrcDev P, RngDe
                                                                  double *nbuf, float *wbuf) {
   typedef double R;
   typedef RealTraits<R> T;
+  fm_tables_init();
   const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lpath >= sh.n_paths) return;
   const long long gpath = sh.path_begin + lpath;
@@ -88,6 +89,7 @@ template <bool CIR, int SCHEME>
 __global__ void __launch_bounds__(128) irc_lsm_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
                                                               double *nbuf, double *ibuf) {
   typedef double R;
+  fm_tables_init();
   const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lpath >= sh.n_paths) return;
   const long long gpath = sh.path_begin + lpath;

@@ -2,7 +2,7 @@
 // Shared by irc.cu (plain books) and irc_berm.cu (books with Bermudan exercise units) so
 // the two sets of template instantiations compile in parallel.
 #pragma once
-#define MCRE_FAST_MATH 1
+#define MCRE_FAST_MATH 2
 #include "common.cuh"
 #include "philox.cuh"
 #include "dual.cuh"
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev
                                                                          double *shift, int pilot) {
   typedef typename RealOf<NT>::type R;
   typedef RealTraits<R> T;
+  fm_tables_init();
   constexpr int W = NT + 1;
   constexpr int NV = 4 + 2 * NT;        // values per (set, date)
   constexpr int NVB = NS * NV;          // values per block_accumulate call

@@ -73,7 +73,10 @@ struct NormalStream {
     ph(p_lo, p_hi, block, 0u, o);
     double u1 = u53(o[0], o[1]), u2 = u53(o[2], o[3]);
     double s, c;
-#ifdef MCRE_FAST_MATH
+#if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
+    double rad = fm_sqrt(-2.0 * fm_log_t(u1));
+    fm_sincos2pi_t(u2, s, c);
+#elif defined(MCRE_FAST_MATH)
     double rad = fm_sqrt(-2.0 * fm_log(u1));
     fm_sincos2pi(u2, s, c);
 #else

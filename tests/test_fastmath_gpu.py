@@ -45,3 +45,24 @@ def test_sincos_2pi():
     # absolute accuracy (the products rad * cos / rad * sin inherit it): a few 1e-16
     assert np.max(np.abs(_probe(3, u) - s)) < 1e-15
     assert np.max(np.abs(_probe(4, u) - c)) < 1e-15
+
+
+def test_table_driven_variants():
+    """Shared-memory-table versions used by the fused kernels (fastmath.cuh, MCRE_FAST_MATH 2)."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-700, 700, 300000), rng.uniform(-2, 2, 300000), rng.uniform(-60, 5, 200000),
+                        [0.0, -0.0, 1e-300, -1e-17, 700.0, -700.0]])
+    assert _ulp_err(_probe(10, x), np.exp(x)).max() <= 4
+    u = np.concatenate([rng.uniform(0, 1, 600000), 2.0 ** -rng.uniform(0, 54, 200000), 1.0 - 2.0 ** -rng.uniform(1, 53, 200000),
+                        [1.0, 0.5, 2.0 ** -54, 1 - 2.0 ** -53, 1 - 2.0 ** -8, np.nextafter(1 - 2.0 ** -8, 0), 1.4140625 / 2,
+                         np.nextafter(1.4140625 / 2, 0)]])
+    u = u[(u > 0) & (u <= 1.0)]
+    lg, want = _probe(11, u), np.log(u)
+    assert np.all(np.abs(lg - want) <= 4 * np.spacing(np.abs(want)) + 1e-300)
+    v = np.concatenate([rng.uniform(0, 1, 600000), [0.0, 0.25, 0.5, 0.75, 0.125, 1 - 2.0 ** -53, 2.0 ** -54, 1 / 256, 3 / 256]])
+    ld = v.astype(np.longdouble)
+    two_pi = 2 * np.longdouble("3.14159265358979323846264338327950288")
+    s = np.sin(two_pi * ld).astype(np.float64)
+    c = np.cos(two_pi * ld).astype(np.float64)
+    assert np.max(np.abs(_probe(13, v) - s)) < 5e-16
+    assert np.max(np.abs(_probe(14, v) - c)) < 5e-16
