@@ -40,6 +40,13 @@ __device__ __forceinline__ double tan_of(double, int) { return 0.0; }
 __device__ __forceinline__ double r_exp(double x) { return MCRE_EXP(x); }
 __device__ __forceinline__ double r_log(double x) { return MCRE_LOG(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return MCRE_SQRT(x); }
+#if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
+__device__ __forceinline__ double r_sqrt_pos(double x) { return fm_sqrt_pos(x); }
+__device__ __forceinline__ double r_exp_small(double x) { return fm_exp_small(x); }
+#else
+__device__ __forceinline__ double r_sqrt_pos(double x) { return MCRE_SQRT(x); }
+__device__ __forceinline__ double r_exp_small(double x) { return MCRE_EXP(x); }
+#endif
 __device__ __forceinline__ double r_relu(double x) { return fmax(x, 0.0); }
 __device__ __forceinline__ double r_max(double x, double c) { return fmax(x, c); }
 __device__ __forceinline__ double r_mask(double x, bool keep) { return keep ? x : 0.0; }
@@ -123,6 +130,18 @@ template <int N> __device__ __forceinline__ Dual<N> r_sqrt(const Dual<N> &x) {
   Dual<N> r; r.v = MCRE_SQRT(x.v); double s = r.v > 0.0 ? 0.5 / r.v : 0.0;
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = s * x.d[i];
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> r_sqrt_pos(const Dual<N> &x) {
+  Dual<N> r; r.v = r_sqrt_pos(x.v); double s = 0.5 / r.v;
+#pragma unroll
+  MCRE_DUAL_LOOP r.d[i] = s * x.d[i];
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual<N> r_exp_small(const Dual<N> &x) {
+  Dual<N> r; r.v = r_exp_small(x.v);
+#pragma unroll
+  MCRE_DUAL_LOOP r.d[i] = r.v * x.d[i];
   return r;
 }
 // relu / clamp-from-below: subgradient 1 where x > bound else 0 (torch.clamp / relu backward)

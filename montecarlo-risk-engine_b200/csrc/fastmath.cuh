@@ -49,6 +49,27 @@ __device__ __forceinline__ double fm_sqrt(double x) {
   return x > 0.0 ? g : 0.0;
 }
 
+// sqrt(x) for x > 0 (normal range): no zero guard.  MUFU seed (2^-22) + two coupled
+// Goldschmidt iterations; the last step is the residual correction g + (x - g^2) h with the
+// first-iteration h (relative error 2^-44: enough for a correction of relative size 2^-44).
+__device__ __forceinline__ double fm_sqrt_pos(double x) {
+  const double y = fm_rsqrt_approx(x);
+  double g = x * y, h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  return fma(fma(-g, g, x), h, g);
+}
+
+// exp(x) for |x| <= 2^-6 without table or range reduction (Taylor to x^6: 2^-42 / 5040 relative).
+__device__ __forceinline__ double fm_exp_small(double x) {
+  double p = fma(x, 1.3888888888888889e-03, 8.3333333333333332e-03);
+  p = fma(p, x, 4.1666666666666664e-02);
+  p = fma(p, x, 1.6666666666666666e-01);
+  p = fma(p, x, 0.5);
+  p = fma(p, x, 1.0);
+  return fma(p, x, 1.0);
+}
+
 // exp(x) for |x| <= 700.  Cody-Waite reduction, degree-13 Taylor on |r| <= ln2/2
 // (truncation 4e-18 relative), scaling by two exact powers of two.
 __device__ __forceinline__ double fm_exp(double x) {

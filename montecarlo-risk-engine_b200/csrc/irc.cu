@@ -319,6 +319,15 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
     if (e < 0) continue;
     double *r = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR + 2 * w;
     for (int k = 0; k < per_date; ++k) r[k] = coef[(size_t)e * per_date + k];
+    if (p->cva_only) {
+      // the CVA-only kernel mode evaluates the polynomial in the raw basis [1, r, r^2]:
+      // c(u) with u = (r - shift) * scale  ->  c'(r)
+      const double sh = p->h_date_rec[(size_t)di * DR + 4], sc = p->h_date_rec[(size_t)di * DR + 5];
+      const double c0 = r[0], c1 = r[1], c2 = r[2];
+      r[2] = c2 * sc * sc;
+      r[1] = c1 * sc - 2.0 * c2 * sc * sc * sh;
+      r[0] = c0 - c1 * sc * sh + c2 * sc * sc * sh * sh;
+    }
   }
   MCRE_CUDA(cudaMemcpyAsync((void *)p->d.date_rec, p->h_date_rec.data(), p->h_date_rec.size() * sizeof(double),
                             cudaMemcpyHostToDevice, (cudaStream_t)stream));

@@ -164,8 +164,14 @@ constexpr int DATE_HDR = 6;   // bits(flags|(expo+1)<<32), bits((metric+1)|float
 __device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
+#ifndef MCRE_IRC_PP
+#define MCRE_IRC_PP 2      // paths per thread of the value-only builds
+#endif
+#ifndef MCRE_IRC_MINB
+#define MCRE_IRC_MINB 4    // resident 128-thread blocks per SM the value-only builds are compiled for
+#endif
 template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE, bool BERM>
-__global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
+__global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
                                                                          double *partial, double *spill,
                                                                          double *shift, int pilot) {
   typedef typename RealOf<NT>::type R;
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev
   irc_load_params<R, CIR>(P, mp);
   const int acc_flags = P.acc_flags;
   const bool vas_second = CIR && P.vas_noise == 1, cir_second = CIR && P.cir_noise == 1, cir_det = P.cir_det != 0;
+  const bool y_positive = CIR && val(mp.y0) > 0.0;
   double thr[NS]; int sflags[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -234,14 +241,22 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev
         if (MODE == 1) {
           // CVA-only fast path: contribution at metric dates k < n_metric-1 only
           if (!(flags & MCRE_DATE_HAS_METRIC) || m >= P.n_metric - 1) return;
+          // (the host side rewrites the coefficients of this mode in the raw basis [1, r, r^2]:
+          // mcre_irc_set_coefficients)
           const R C = T::load(dc, 0), Bc = T::load(dc, 1);
           const R c0 = T::load(dc, 2), c1 = T::load(dc, 3), c2 = T::load(dc, 4);
+          R xb[PP];
+          bool small = true;
+#pragma unroll
+          for (int p = 0; p < PP; ++p) { xb[p] = -(Bc * st[p].y); small = small && fabs(val(xb[p])) <= 0.015625; }
+          // S(t_k, t_k+1 | y) = C exp(-B y): B y is tiny for any sane intensity, so the whole warp
+          // normally takes the reduction-free Taylor form (uniform branch)
+          const bool all_small = __all_sync(0xffffffffu, small);
 #pragma unroll
           for (int p = 0; p < PP; ++p) {
-            const R u = (st[p].r - bshift) * bscale;
-            const R pos = r_relu(c0 + u * (c1 + u * c2));
+            const R pos = r_relu(c0 + st[p].r * (c1 + st[p].r * c2));
             const R ds = r_exp(-(st[p].logB + st[p].logBl));
-            const R cond = C * r_exp(-(Bc * st[p].y));
+            const R cond = C * (all_small ? r_exp_small(xb[p]) : r_exp(xb[p]));
             cva[p][0] = cva[p][0] + pos * ds * (1.0 - cond);
           }
           return;
@@ -406,7 +421,9 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 1)) irc_main_kernel(IrcDev
               s.logBl = s.logBl + sc0 * dt;
               s.y = sc1;
             } else {                          // full-truncation Euler, cirpp.py:174-198
-              const R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * r_sqrt(r_relu(s.y)) * sq * wc;
+              // y >= 1e-12 after every step (clamp below); with y0 > 0 the relu is the identity
+              const R sy = y_positive ? r_sqrt_pos(s.y) : r_sqrt(r_relu(s.y));
+              const R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * sy * sq * wc;
               s.logBl = s.logBl + (s.y + sc0) * dt;
               s.y = r_max(yn, 1e-12);
             }
@@ -476,7 +493,7 @@ template <int NT, int NS, bool BERM>
 static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *spill,
                        double *shift, cudaStream_t st) {
   const IrcDev &d = p->d;
-  constexpr int PP = NT == 0 ? 2 : 1;   // paths per thread
+  constexpr int PP = NT == 0 ? MCRE_IRC_PP : 1;   // paths per thread
   const int threads = 128, nw = threads / 32;
   const int nvb = NS * (4 + 2 * NT);
   const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);

@@ -4,7 +4,7 @@
 //   key     = (low 32 bits of seed, low 32 bits of stream)
 //   counter = (path_lo, path_hi, block, kind)      kind 0: normals, 1: uniforms
 //   normal  #n of a path = element (n & 1) of BoxMuller(block n >> 1)
-//   uniform #m of a path = element (m & 1) of the two 53-bit uniforms of block m >> 1
+//   uniform #m of a path = element (m & 1) of the two 52-bit uniforms of block m >> 1
 // so a draw depends only on (seed, stream, global path id, draw index): sharding paths
 // over GPUs or replaying a path in a second pass reproduces it exactly.  Takes the place
 // of torch.manual_seed(42|43) + torch.randn(N, d) per sub-step (src/engine/engine.py:25,
@@ -22,12 +22,9 @@ struct Philox {
   __host__ __device__ static inline void round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
                                                uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-#ifdef __CUDA_ARCH__
-    uint32_t hi0 = __umulhi(M0, c0), hi1 = __umulhi(M1, c2);
-#else
-    uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c0) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c2) >> 32);
-#endif
-    uint32_t lo0 = M0 * c0, lo1 = M1 * c2;
+    // one 32x32 -> 64 multiply per product (IMAD.WIDE.U32) instead of separate high / low halves
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
     c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
   }
   __host__ __device__ inline void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -42,10 +39,17 @@ struct Philox {
   }
 };
 
-// 53-bit uniform in (0,1): (k + 0.5) * 2^-53, k from the top 53 bits of (hi:lo).
-__host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
-  uint64_t k = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)k + 0.5) * 1.1102230246251565e-16;
+// 52-bit uniform in (0,1): (k + 0.5) * 2^-52, k = the top 52 bits of (hi:lo).  Built in the
+// mantissa of a double in [1,2) and shifted down with one exact subtraction - no int -> double
+// conversion (I2F.F64.U64 was the longest stall of the v2 profile).
+__host__ __device__ inline double u52(uint32_t hi, uint32_t lo) {
+#ifdef __CUDA_ARCH__
+  const double d = __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+  return d - 0.99999999999999988898;   // 1 - 2^-53: exact, result (2k + 1) * 2^-53
+#else
+  uint64_t k = (((uint64_t)hi << 32) | lo) >> 12;
+  return ((double)k + 0.5) * 2.220446049250313e-16;
+#endif
 }
 
 struct RngDev {
@@ -71,10 +75,10 @@ struct NormalStream {
   __device__ inline void pair(uint32_t block, double &z0, double &z1) const {
     uint32_t o[4];
     ph(p_lo, p_hi, block, 0u, o);
-    double u1 = u53(o[0], o[1]), u2 = u53(o[2], o[3]);
+    double u1 = u52(o[0], o[1]), u2 = u52(o[2], o[3]);
     double s, c;
 #if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
-    double rad = fm_sqrt(-2.0 * fm_log_t(u1));
+    double rad = fm_sqrt_pos(-2.0 * fm_log_t(u1));   // u1 < 1: the argument is strictly positive
     fm_sincos2pi_t(u2, s, c);
 #elif defined(MCRE_FAST_MATH)
     double rad = fm_sqrt(-2.0 * fm_log(u1));
@@ -96,7 +100,7 @@ struct NormalStream {
   __device__ inline double uniform(uint32_t m) const {
     uint32_t o[4];
     ph(p_lo, p_hi, m >> 1, 1u, o);
-    return (m & 1u) ? u53(o[2], o[3]) : u53(o[0], o[1]);
+    return (m & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
   }
 };
 

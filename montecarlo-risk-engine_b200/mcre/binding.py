@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libmcre_b200.so")
+# MCRE_LIB_PATH: kernel-tuning variants of the same library (tools/tune_irc.py); never a fallback
+LIB_PATH = os.environ.get("MCRE_LIB_PATH") or os.path.join(_PKG, "libmcre_b200.so")
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)

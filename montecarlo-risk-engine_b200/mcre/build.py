@@ -24,17 +24,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, extra_flags=(), lib=LIB, tag=""):
+    """extra_flags / lib / tag: tuning variants (tools/tune_irc.py) built next to the product library."""
+    if not force and not _stale() and lib == LIB:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for src in sources():
-        obj = os.path.join(PKG, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(PKG, "build", os.path.basename(src)[:-3] + tag + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -46,8 +47,8 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":

@@ -20,16 +20,17 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def u53(hi, lo):
-    k = ((hi << np.uint64(32)) | lo) >> np.uint64(11)
-    return (k.astype(np.float64) + 0.5) * 1.1102230246251565e-16
+def u52(hi, lo):
+    """(k + 0.5) * 2^-52 with k the top 52 bits of (hi:lo) - same definition as csrc/philox.cuh."""
+    k = ((hi << np.uint64(32)) | lo) >> np.uint64(12)
+    return (k.astype(np.float64) + 0.5) * 2.220446049250313e-16
 
 
 def _blocks(paths, block, kind, seed, stream):
     paths = np.asarray(paths, dtype=np.uint64)
     o = philox4x32(paths & MASK, paths >> np.uint64(32), np.full_like(paths, block), np.full_like(paths, kind),
                    seed, stream)
-    return u53(o[0], o[1]), u53(o[2], o[3])
+    return u52(o[0], o[1]), u52(o[2], o[3])
 
 
 def normal_pair(paths, block, seed, stream):
