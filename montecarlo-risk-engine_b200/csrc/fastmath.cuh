@@ -60,15 +60,6 @@ __device__ __forceinline__ double fm_sqrt_pos(double x) {
   return fma(fma(-g, g, x), h, g);
 }
 
-// exp(x) for |x| <= 2^-6 without table or range reduction (Taylor to x^6: 2^-42 / 5040 relative).
-__device__ __forceinline__ double fm_exp_small(double x) {
-  double p = fma(x, 1.3888888888888889e-03, 8.3333333333333332e-03);
-  p = fma(p, x, 4.1666666666666664e-02);
-  p = fma(p, x, 1.6666666666666666e-01);
-  p = fma(p, x, 0.5);
-  p = fma(p, x, 1.0);
-  return fma(p, x, 1.0);
-}
 
 // exp(x) for |x| <= 700.  Cody-Waite reduction, degree-13 Taylor on |r| <= ln2/2
 // (truncation 4e-18 relative), scaling by two exact powers of two.
@@ -220,64 +211,140 @@ __device__ __forceinline__ void fm_tables_init() {
   __syncthreads();
 }
 
+// ---- lock-step ("PP-wide") forms --------------------------------------------------------
+// The FP64 pipe of this GPU only reaches its 2-cycle issue rate when ONE warp issues several
+// independent DFMAs back to back (tools/probes/dfma_latency.cu: dependent chain 8.1 cycles;
+// 1 chain/warp -> 3.0 cycles per instruction however many warps are resident, 2 chains -> 2.5,
+// 4 chains -> 2.17).  So every function below evaluates PP independent arguments with the
+// operations interleaved in source order; the scalar entry points are the PP = 1 instances.
+#define MCRE_VP _Pragma("unroll") for (int p = 0; p < PP; ++p)
+
 // exp(x) for |x| <= 700: n = round(64 x / ln2), exp(x) = 2^(n>>6) * T[n&63] * exp(r), |r| <= ln2/128.
-__device__ __forceinline__ double fm_exp_t(double x) {
+template <int PP>
+__device__ __forceinline__ void fm_exp_tv(const double (&x)[PP], double (&out)[PP]) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  double t = fma(x, FM_C[4], MAGIC);
-  const int n = __double2loint(t);
-  t -= MAGIC;
-  double r = fma(t, -FM_C[5], x);
-  r = fma(t, -FM_C[6], r);
-  const double T = s_fm.exp2t[n & 63];
-  double p = fma(r, FM_C[0], FM_C[1]);
-  p = fma(p, r, FM_C[2]);
-  p = fma(p, r, FM_C[3]);
-  p = fma(p, r, 1.0);                        // 1 + r/2 + r^2/6 + r^3/24 + r^4/120
-  const double res = fma(T * r, p, T);       // T (1 + r p)
+  double t[PP], r[PP], T[PP], q[PP], tr[PP];
+  int n[PP];
+  MCRE_VP t[p] = fma(x[p], FM_C[4], MAGIC);
+  MCRE_VP n[p] = __double2loint(t[p]);
+  MCRE_VP t[p] -= MAGIC;
+  MCRE_VP T[p] = s_fm.exp2t[n[p] & 63];
+  MCRE_VP r[p] = fma(t[p], -FM_C[5], x[p]);
+  MCRE_VP r[p] = fma(t[p], -FM_C[6], r[p]);
+  MCRE_VP q[p] = fma(r[p], FM_C[0], FM_C[1]);
+  MCRE_VP q[p] = fma(q[p], r[p], FM_C[2]);
+  MCRE_VP q[p] = fma(q[p], r[p], FM_C[3]);
+  MCRE_VP q[p] = fma(q[p], r[p], 1.0);          // 1 + r/2 + r^2/6 + r^3/24 + r^4/120
+  MCRE_VP tr[p] = T[p] * r[p];
+  MCRE_VP q[p] = fma(tr[p], q[p], T[p]);        // T (1 + r q)
   // scale by 2^(n>>6) in the exponent field (result stays normal for |x| <= 700)
-  return __hiloint2double(__double2hiint(res) + ((n >> 6) << 20), __double2loint(res));
+  MCRE_VP out[p] = __hiloint2double(__double2hiint(q[p]) + ((n[p] >> 6) << 20), __double2loint(q[p]));
+}
+__device__ __forceinline__ double fm_exp_t(double x) {
+  const double a[1] = {x};
+  double o[1];
+  fm_exp_tv<1>(a, o);
+  return o[0];
+}
+
+// exp(x) for |x| <= 2^-6 without table or range reduction (Taylor to x^6: 2^-42 / 5040 relative).
+template <int PP>
+__device__ __forceinline__ void fm_exp_smallv(const double (&x)[PP], double (&out)[PP]) {
+  double q[PP];
+  MCRE_VP q[p] = fma(x[p], 1.3888888888888889e-03, 8.3333333333333332e-03);
+  MCRE_VP q[p] = fma(q[p], x[p], 4.1666666666666664e-02);
+  MCRE_VP q[p] = fma(q[p], x[p], 1.6666666666666666e-01);
+  MCRE_VP q[p] = fma(q[p], x[p], 0.5);
+  MCRE_VP q[p] = fma(q[p], x[p], 1.0);
+  MCRE_VP out[p] = fma(q[p], x[p], 1.0);
+}
+
+__device__ __forceinline__ double fm_exp_small(double x) {
+  const double a[1] = {x};
+  double o[1];
+  fm_exp_smallv<1>(a, o);
+  return o[0];
 }
 
 // log(u) for u in [2^-60, 2).
-__device__ __forceinline__ double fm_log_t(double u) {
-  const int hi = __double2hiint(u);
-  const int e = ((hi + 0x96000) >> 20) - 1023;          // exponent, +1 when m >= 1 + 53/128
-  const int j = (hi >> 13) & 127;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(u));
-  const double2 tb = s_fm.logt[j];
-  const double f = fma(m, tb.x, -1.0);                    // m / c_j - 1, |f| <= 1/128
-  double p = fma(f, FM_C[14], FM_C[13]);
-  p = fma(p, f, FM_C[12]);
-  p = fma(p, f, FM_C[11]);
-  p = fma(p, f, FM_C[10]);
-  p = fma(p, f, FM_C[9]);
-  p = fma(p, f, FM_C[8]);                                 // -1/2 + f/3 - f^2/4 ...
-  const double lp = fma(f * f, p, f);                     // log1p(f)
-  // (double)e through the 2^52 + 2^31 bias: one integer op + one FP64 add
-  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+template <int PP>
+__device__ __forceinline__ void fm_log_tv(const double (&u)[PP], double (&out)[PP]) {
   const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-  return fma(ed, LN2_HI, tb.y) + fma(ed, LN2_LO, lp);
+  int hi[PP], e[PP];
+  double m[PP], f[PP], q[PP], ff[PP], ed[PP], a[PP];
+  double2 tb[PP];
+  MCRE_VP hi[p] = __double2hiint(u[p]);
+  MCRE_VP tb[p] = s_fm.logt[(hi[p] >> 13) & 127];
+  MCRE_VP e[p] = ((hi[p] + 0x96000) >> 20) - 1023;     // exponent, +1 when m >= 1 + 53/128
+  MCRE_VP m[p] = __hiloint2double((hi[p] & 0x000fffff) | 0x3ff00000, __double2loint(u[p]));
+  // (double)e through the 2^52 + 2^31 bias: one integer op + one FP64 add
+  MCRE_VP ed[p] = __hiloint2double(0x43300000, e[p] ^ 0x80000000) - 4503601774854144.0;
+  MCRE_VP f[p] = fma(m[p], tb[p].x, -1.0);             // m / c_j - 1, |f| <= 1/128
+  MCRE_VP q[p] = fma(f[p], FM_C[14], FM_C[13]);
+  MCRE_VP ff[p] = f[p] * f[p];
+  MCRE_VP q[p] = fma(q[p], f[p], FM_C[12]);
+  MCRE_VP a[p] = fma(ed[p], LN2_HI, tb[p].y);
+  MCRE_VP q[p] = fma(q[p], f[p], FM_C[11]);
+  MCRE_VP q[p] = fma(q[p], f[p], FM_C[10]);
+  MCRE_VP q[p] = fma(q[p], f[p], FM_C[9]);
+  MCRE_VP q[p] = fma(q[p], f[p], FM_C[8]);             // -1/2 + f/3 - f^2/4 ...
+  MCRE_VP q[p] = fma(ff[p], q[p], f[p]);               // log1p(f)
+  MCRE_VP q[p] = fma(ed[p], LN2_LO, q[p]);
+  MCRE_VP out[p] = a[p] + q[p];
+}
+__device__ __forceinline__ double fm_log_t(double u) {
+  const double a[1] = {u};
+  double o[1];
+  fm_log_tv<1>(a, o);
+  return o[0];
+}
+
+// sqrt(x) for x > 0, PP-wide (same arithmetic as fm_sqrt_pos).
+template <int PP>
+__device__ __forceinline__ void fm_sqrt_posv(const double (&x)[PP], double (&out)[PP]) {
+  double y[PP], g[PP], h[PP], r[PP];
+  MCRE_VP y[p] = fm_rsqrt_approx(x[p]);
+  MCRE_VP g[p] = x[p] * y[p];
+  MCRE_VP h[p] = 0.5 * y[p];
+  MCRE_VP r[p] = fma(-h[p], g[p], 0.5);
+  MCRE_VP g[p] = fma(g[p], r[p], g[p]);
+  MCRE_VP h[p] = fma(h[p], r[p], h[p]);
+  MCRE_VP r[p] = fma(-g[p], g[p], x[p]);
+  MCRE_VP out[p] = fma(r[p], h[p], g[p]);
 }
 
 // (sin(2 pi u), cos(2 pi u)) for u in [0, 1): n = round(128 u), angle = 2 pi n/128 + x, |x| <= pi/128.
-__device__ __forceinline__ void fm_sincos2pi_t(double u, double &sn, double &cs) {
+template <int PP>
+__device__ __forceinline__ void fm_sincos2pi_tv(const double (&u)[PP], double (&sn)[PP], double (&cs)[PP]) {
   const double MAGIC = 6755399441055744.0;
-  double t = fma(u, 128.0, MAGIC);
-  const int n = __double2loint(t);
-  t -= MAGIC;
-  const double r = fma(t, -0.0078125, u);                 // exact, [-1/256, 1/256]
-  const double x = r * FM_C[22];
-  const double z = x * x;
-  const double2 tb = s_fm.sct[n & 127];
-  double ps = fma(z, FM_C[18], FM_C[17]);
-  ps = fma(ps, z, FM_C[16]);
-  const double sx = fma(x * z, ps, x);                    // sin x
-  double pc = fma(z, FM_C[21], FM_C[20]);
-  pc = fma(pc, z, FM_C[19]);
-  const double cm = z * pc;                               // cos x - 1
+  double t[PP], x[PP], z[PP], ps[PP], pc[PP], xz[PP], a[PP], b[PP];
+  double2 tb[PP];
+  MCRE_VP t[p] = fma(u[p], 128.0, MAGIC);
+  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 127];
+  MCRE_VP t[p] -= MAGIC;
+  MCRE_VP x[p] = fma(t[p], -0.0078125, u[p]);          // exact, [-1/256, 1/256]
+  MCRE_VP x[p] = x[p] * FM_C[22];
+  MCRE_VP z[p] = x[p] * x[p];
+  MCRE_VP ps[p] = fma(z[p], FM_C[18], FM_C[17]);
+  MCRE_VP pc[p] = fma(z[p], FM_C[21], FM_C[20]);
+  MCRE_VP xz[p] = x[p] * z[p];
+  MCRE_VP ps[p] = fma(ps[p], z[p], FM_C[16]);
+  MCRE_VP pc[p] = fma(pc[p], z[p], FM_C[19]);
+  MCRE_VP ps[p] = fma(xz[p], ps[p], x[p]);             // sin x
+  MCRE_VP pc[p] = z[p] * pc[p];                        // cos x - 1
   // rotate: sin(a + x) = S + (C sx + S cm),  cos(a + x) = C + (C cm - S sx)
-  sn = tb.x + fma(tb.y, sx, tb.x * cm);
-  cs = tb.y + fma(-tb.x, sx, tb.y * cm);
+  MCRE_VP a[p] = tb[p].x * pc[p];
+  MCRE_VP b[p] = tb[p].y * pc[p];
+  MCRE_VP a[p] = fma(tb[p].y, ps[p], a[p]);
+  MCRE_VP b[p] = fma(-tb[p].x, ps[p], b[p]);
+  MCRE_VP sn[p] = tb[p].x + a[p];
+  MCRE_VP cs[p] = tb[p].y + b[p];
+}
+__device__ __forceinline__ void fm_sincos2pi_t(double u, double &sn, double &cs) {
+  const double a[1] = {u};
+  double s[1], c[1];
+  fm_sincos2pi_tv<1>(a, s, c);
+  sn = s[0]; cs = c[0];
 }
 #endif
 

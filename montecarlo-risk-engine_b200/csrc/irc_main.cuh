@@ -165,10 +165,10 @@ __device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
 #ifndef MCRE_IRC_PP
-#define MCRE_IRC_PP 2      // paths per thread of the value-only builds
+#define MCRE_IRC_PP 4      // paths per thread of the value-only builds (lock-step ILP, see fastmath.cuh)
 #endif
 #ifndef MCRE_IRC_MINB
-#define MCRE_IRC_MINB 4    // resident 128-thread blocks per SM the value-only builds are compiled for
+#define MCRE_IRC_MINB 2    // resident 128-thread blocks per SM the value-only builds are compiled for
 #endif
 template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE, bool BERM>
 __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
@@ -208,14 +208,16 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
     for (int it = 0; it < sh.chunk; it += blockDim.x * PP) {
       long long lpath[PP], gpath[PP];
       bool live[PP];
-      NormalStream ns[PP];
+      NormalStream ns[PP];          // Vasicek only: one normal per step
+      NormalStreamV<PP> nsv;        // Vasicek + CIR++: two normals per step, paths in lock-step
       IrcState<R> st[PP];
       R pv[PP][NS], cva[PP][NS], hist[PP][NS][MODE == 1 ? 1 : MCRE_IRC_MAX_LAG];
       unsigned alive[PP];   // bit b: Bermudan unit b still holds its exercise right
 #pragma unroll
       for (int p = 0; p < PP; ++p) {
         lpath[p] = chunk * sh.chunk + it + p * (int)blockDim.x + threadIdx.x;
-        live[p] = lpath[p] < sh.n_paths;
+        // (PP that does not divide chunk / blockDim: the tail lanes of the last pass idle)
+        live[p] = lpath[p] < sh.n_paths && it + p * (int)blockDim.x + (int)threadIdx.x < sh.chunk;
         gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
         ns[p].init(rng, (unsigned long long)gpath[p]);
         st[p].r = mp.r0; st[p].logB = T::zero(); st[p].y = mp.y0; st[p].logBl = T::zero();
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
           for (int l = 0; l < (MODE == 1 ? 1 : MCRE_IRC_MAX_LAG); ++l) hist[p][s][l] = T::zero();
         }
       }
+      nsv.init(rng, gpath);
 
       // ---- date evaluation (cashflows -> exposure -> metrics) ------------------------
       auto eval_date = [&](int di) {
@@ -238,27 +241,30 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
           return;
         const double bshift = h2.x, bscale = h2.y;
         const double *dc = dr + DATE_HDR;   // C[w], B[w], coef[set][3][w]
-        if (MODE == 1) {
-          // CVA-only fast path: contribution at metric dates k < n_metric-1 only
+        if constexpr (MODE == 1) {
+          // CVA-only fast path (value-only build, R = double): contribution at metric dates
+          // k < n_metric-1 only; every operation runs over the PP paths in lock-step.
           if (!(flags & MCRE_DATE_HAS_METRIC) || m >= P.n_metric - 1) return;
           // (the host side rewrites the coefficients of this mode in the raw basis [1, r, r^2]:
           // mcre_irc_set_coefficients)
-          const R C = T::load(dc, 0), Bc = T::load(dc, 1);
-          const R c0 = T::load(dc, 2), c1 = T::load(dc, 3), c2 = T::load(dc, 4);
-          R xb[PP];
+          const double C = __ldg(dc + 0), Bc = __ldg(dc + 1);
+          const double c0 = __ldg(dc + 2), c1 = __ldg(dc + 3), c2 = __ldg(dc + 4);
+          double xa[PP], xb[PP], ea[PP], eb[PP], pos[PP];
           bool small = true;
-#pragma unroll
-          for (int p = 0; p < PP; ++p) { xb[p] = -(Bc * st[p].y); small = small && fabs(val(xb[p])) <= 0.015625; }
+          MCRE_VP xb[p] = -(Bc * st[p].y);
+          MCRE_VP small = small && fabs(xb[p]) <= 0.015625;
           // S(t_k, t_k+1 | y) = C exp(-B y): B y is tiny for any sane intensity, so the whole warp
           // normally takes the reduction-free Taylor form (uniform branch)
           const bool all_small = __all_sync(0xffffffffu, small);
-#pragma unroll
-          for (int p = 0; p < PP; ++p) {
-            const R pos = r_relu(c0 + st[p].r * (c1 + st[p].r * c2));
-            const R ds = r_exp(-(st[p].logB + st[p].logBl));
-            const R cond = C * (all_small ? r_exp_small(xb[p]) : r_exp(xb[p]));
-            cva[p][0] = cva[p][0] + pos * ds * (1.0 - cond);
-          }
+          MCRE_VP xa[p] = -(st[p].logB + st[p].logBl);
+          MCRE_VP pos[p] = fma(st[p].r, c2, c1);
+          fm_exp_tv<PP>(xa, ea);
+          if (all_small) fm_exp_smallv<PP>(xb, eb);
+          else fm_exp_tv<PP>(xb, eb);
+          MCRE_VP pos[p] = fmax(fma(st[p].r, pos[p], c0), 0.0);
+          MCRE_VP eb[p] = fma(-C, eb[p], 1.0);
+          MCRE_VP pos[p] = pos[p] * ea[p];
+          MCRE_VP cva[p][0] = fma(pos[p], eb[p], cva[p][0]);
           return;
         }
         R invN[PP];
@@ -398,35 +404,53 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
         const R sv0 = T::load(sr + STEP_HDR, 0), sv1 = T::load(sr + STEP_HDR, 1);
         R sc0 = T::zero(), sc1 = T::zero();
         if (CIR) { sc0 = T::load(sr + STEP_HDR, 2); sc1 = T::load(sr + STEP_HDR, 3); }
-#pragma unroll
-        for (int p = 0; p < PP; ++p) {
-          double z0, z1;
-          irc_draw<R, CIR>(rng, ns[p], is, lpath[p], gpath[p], z0, z1);
-          // correlated noise z @ L^T (model.py:46-48)
-          const R w0 = mp.L00 * z0;
-          R w1 = T::zero();
-          if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
-          IrcState<R> &s = st[p];
-          s.logB = s.logB + s.r * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
-          if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
-            // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
-            s.r = mp.theta + (s.r - mp.theta) * sv0 + sv1 * z0;
-          } else {
-            const R wv = vas_second ? w1 : w0;
-            s.r = s.r + mp.a * (sv0 - s.r) * dt + mp.sigma * sq * wv;
+        // ---- draws: PP paths in lock-step (Philox) or the reference's injected stream ----------
+        double z0[PP], z1[PP];
+        if (rng.mode == MCRE_RNG_INJECT) {
+          MCRE_VP {
+            const double *zp = rng.z + ((size_t)is * rng.n_total + gpath[p]) * (CIR ? 2 : 1);
+            z0[p] = zp[0];
+            z1[p] = CIR ? zp[1] : 0.0;
           }
-          if (CIR) {
-            const R wc = cir_second ? w1 : w0;
-            if (cir_det) {                    // cirpp.py:155-172
-              s.logBl = s.logBl + sc0 * dt;
-              s.y = sc1;
-            } else {                          // full-truncation Euler, cirpp.py:174-198
-              // y >= 1e-12 after every step (clamp below); with y0 > 0 the relu is the identity
-              const R sy = y_positive ? r_sqrt_pos(s.y) : r_sqrt(r_relu(s.y));
-              const R yn = s.y + mp.kappa * (mp.ctheta - s.y) * dt + mp.csigma * sy * sq * wc;
-              s.logBl = s.logBl + (s.y + sc0) * dt;
-              s.y = r_max(yn, 1e-12);
+        } else if constexpr (CIR) {
+          nsv.next2(z0, z1);
+        } else {
+          MCRE_VP { z0[p] = ns[p].next(); z1[p] = 0.0; }
+        }
+        // ---- correlated noise z @ L^T (model.py:46-48) and the model step, lock-step over paths ----
+        R w0[PP], w1[PP];
+        MCRE_VP w0[p] = mp.L00 * z0[p];
+        if constexpr (CIR) { MCRE_VP w1[p] = mp.L10 * z0[p] + mp.L11 * z1[p]; }
+        else { MCRE_VP w1[p] = T::zero(); }
+        R rate0[PP];
+        MCRE_VP rate0[p] = st[p].r;
+        if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
+          // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
+          MCRE_VP st[p].r = mp.theta + (st[p].r - mp.theta) * sv0 + sv1 * z0[p];
+        } else {
+          MCRE_VP st[p].r = st[p].r + mp.a * (sv0 - st[p].r) * dt + mp.sigma * sq * (vas_second ? w1[p] : w0[p]);
+        }
+        MCRE_VP st[p].logB = st[p].logB + rate0[p] * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+        if constexpr (CIR) {
+          if (cir_det) {                      // cirpp.py:155-172
+            MCRE_VP { st[p].logBl = st[p].logBl + sc0 * dt; st[p].y = sc1; }
+          } else {                            // full-truncation Euler, cirpp.py:174-198
+            // y >= 1e-12 after every step (clamp below); with y0 > 0 the relu is the identity
+            R sy[PP], yn[PP];
+            if constexpr (NT == 0) {
+              if (y_positive) {
+                double yv[PP];
+                MCRE_VP yv[p] = st[p].y;
+                fm_sqrt_posv<PP>(yv, sy);
+              } else {
+                MCRE_VP sy[p] = r_sqrt(r_relu(st[p].y));
+              }
+            } else {
+              MCRE_VP sy[p] = y_positive ? r_sqrt_pos(st[p].y) : r_sqrt(r_relu(st[p].y));
             }
+            MCRE_VP yn[p] = st[p].y + mp.kappa * (mp.ctheta - st[p].y) * dt + mp.csigma * sy[p] * sq * (cir_second ? w1[p] : w0[p]);
+            MCRE_VP st[p].logBl = st[p].logBl + (st[p].y + sc0) * dt;
+            MCRE_VP st[p].y = r_max(yn[p], 1e-12);
           }
         }
         if (di >= 0) eval_date(di);

@@ -104,4 +104,43 @@ struct NormalStream {
   }
 };
 
+
+#if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
+// PP paths of one thread advanced in lock-step: the ten Philox rounds and every Box-Muller
+// operation are interleaved over the paths in source order, so a warp always has PP independent
+// instructions in flight (see the note on MCRE_VP in fastmath.cuh).  Same streams as NormalStream.
+template <int PP>
+struct NormalStreamV {
+  uint32_t k0, k1;
+  uint32_t p_lo[PP], p_hi[PP];
+  uint32_t n;   // next normal index (even)
+  __device__ inline void init(const RngDev &r, const long long (&gpath)[PP]) {
+    k0 = r.k0; k1 = r.k1; n = 0;
+    MCRE_VP { p_lo[p] = (uint32_t)gpath[p]; p_hi[p] = (uint32_t)((unsigned long long)gpath[p] >> 32); }
+  }
+  // two consecutive normals of every path (noise_dim 2)
+  __device__ inline void next2(double (&z0)[PP], double (&z1)[PP]) {
+    uint32_t c0[PP], c1[PP], c2[PP], c3[PP];
+    const uint32_t block = n >> 1;
+    MCRE_VP { c0[p] = p_lo[p]; c1[p] = p_hi[p]; c2[p] = block; c3[p] = 0u; }
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      MCRE_VP Philox::round(c0[p], c1[p], c2[p], c3[p], a, b);
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    double u1[PP], u2[PP], lg[PP], rad[PP], sn[PP], cs[PP];
+    MCRE_VP u1[p] = u52(c0[p], c1[p]);
+    MCRE_VP u2[p] = u52(c2[p], c3[p]);
+    fm_log_tv<PP>(u1, lg);
+    MCRE_VP lg[p] = -2.0 * lg[p];
+    fm_sincos2pi_tv<PP>(u2, sn, cs);
+    fm_sqrt_posv<PP>(lg, rad);          // u1 < 1: the argument is strictly positive
+    MCRE_VP z0[p] = rad[p] * cs[p];
+    MCRE_VP z1[p] = rad[p] * sn[p];
+    n += 2;
+  }
+};
+#endif
+
 }  // namespace mcre
