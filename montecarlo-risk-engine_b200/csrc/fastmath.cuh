@@ -269,7 +269,7 @@ __device__ __forceinline__ double fm_exp_small(double x) {
 // log(u) for u in [2^-60, 2).
 template <int PP>
 __device__ __forceinline__ void fm_log_tv(const double (&u)[PP], double (&out)[PP]) {
-  const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  const double LN2 = 6.931471805599453094e-01;
   int hi[PP], e[PP];
   double m[PP], f[PP], q[PP], ff[PP], ed[PP], a[PP];
   double2 tb[PP];
@@ -283,13 +283,14 @@ __device__ __forceinline__ void fm_log_tv(const double (&u)[PP], double (&out)[P
   MCRE_VP q[p] = fma(f[p], FM_C[14], FM_C[13]);
   MCRE_VP ff[p] = f[p] * f[p];
   MCRE_VP q[p] = fma(q[p], f[p], FM_C[12]);
-  MCRE_VP a[p] = fma(ed[p], LN2_HI, tb[p].y);
+  // e ln2 + log c_j: |e| <= 60, so the rounding of ln2 costs at most 60 * 2^-54 absolute -
+  // below half an ulp of the result whenever e != 0; for e = 0 the term vanishes
+  MCRE_VP a[p] = fma(ed[p], LN2, tb[p].y);
   MCRE_VP q[p] = fma(q[p], f[p], FM_C[11]);
   MCRE_VP q[p] = fma(q[p], f[p], FM_C[10]);
   MCRE_VP q[p] = fma(q[p], f[p], FM_C[9]);
   MCRE_VP q[p] = fma(q[p], f[p], FM_C[8]);             // -1/2 + f/3 - f^2/4 ...
   MCRE_VP q[p] = fma(ff[p], q[p], f[p]);               // log1p(f)
-  MCRE_VP q[p] = fma(ed[p], LN2_LO, q[p]);
   MCRE_VP out[p] = a[p] + q[p];
 }
 __device__ __forceinline__ double fm_log_t(double u) {
@@ -340,6 +341,36 @@ __device__ __forceinline__ void fm_sincos2pi_tv(const double (&u)[PP], double (&
   MCRE_VP sn[p] = tb[p].x + a[p];
   MCRE_VP cs[p] = tb[p].y + b[p];
 }
+// Box-Muller tail: (rad cos(2 pi v), rad sin(2 pi v)) with v = d - 1 given as the mantissa double
+// d in [1, 2) (no subtraction needed: the reduction works on d directly), the rotation against the
+// table entry fused with the scaling by rad:  rad cos(a + x) = RC + (RC cm - RS sx), RC = rad C ...
+template <int PP>
+__device__ __forceinline__ void fm_polar_tv(const double (&d)[PP], const double (&rad)[PP], double (&zc)[PP],
+                                            double (&zs)[PP]) {
+  const double MAGIC = 6755399441055744.0;
+  double t[PP], x[PP], z[PP], ps[PP], pc[PP], xz[PP], rc[PP], rs[PP];
+  double2 tb[PP];
+  MCRE_VP t[p] = fma(d[p], 128.0, MAGIC - 128.0);       // MAGIC + round(128 v)
+  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 127];
+  MCRE_VP t[p] -= MAGIC - 128.0;                        // round(128 v) + 128
+  MCRE_VP x[p] = fma(t[p], -0.0078125, d[p]);          // v - n/128, exact, [-1/256, 1/256]
+  MCRE_VP x[p] = x[p] * FM_C[22];
+  MCRE_VP rc[p] = rad[p] * tb[p].y;
+  MCRE_VP rs[p] = rad[p] * tb[p].x;
+  MCRE_VP z[p] = x[p] * x[p];
+  MCRE_VP ps[p] = fma(z[p], FM_C[18], FM_C[17]);
+  MCRE_VP pc[p] = fma(z[p], FM_C[21], FM_C[20]);
+  MCRE_VP xz[p] = x[p] * z[p];
+  MCRE_VP ps[p] = fma(ps[p], z[p], FM_C[16]);
+  MCRE_VP pc[p] = fma(pc[p], z[p], FM_C[19]);
+  MCRE_VP ps[p] = fma(xz[p], ps[p], x[p]);             // sin x
+  MCRE_VP pc[p] = z[p] * pc[p];                        // cos x - 1
+  MCRE_VP zc[p] = fma(rc[p], pc[p], rc[p]);
+  MCRE_VP zs[p] = fma(rs[p], pc[p], rs[p]);
+  MCRE_VP zc[p] = fma(-rs[p], ps[p], zc[p]);
+  MCRE_VP zs[p] = fma(rc[p], ps[p], zs[p]);
+}
+
 __device__ __forceinline__ void fm_sincos2pi_t(double u, double &sn, double &cs) {
   const double a[1] = {u};
   double s[1], c[1];

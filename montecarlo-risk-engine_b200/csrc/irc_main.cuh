@@ -164,14 +164,24 @@ constexpr int DATE_HDR = 6;   // bits(flags|(expo+1)<<32), bits((metric+1)|float
 __device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
+// Paths per thread / resident 128-thread blocks per SM of each build.  The FP64 pipe needs
+// in-warp ILP (fastmath.cuh, MCRE_VP): the CVA-only mode (few live values per path) runs 8 paths
+// per thread with 2 blocks per SM (255 registers); the general value-only builds carry
+// per-set cashflow / exposure-history state, so fewer paths fit; tangent builds run one path.
 #ifndef MCRE_IRC_PP
-#define MCRE_IRC_PP 4      // paths per thread of the value-only builds (lock-step ILP, see fastmath.cuh)
+#define MCRE_IRC_PP 8
 #endif
 #ifndef MCRE_IRC_MINB
-#define MCRE_IRC_MINB 2    // resident 128-thread blocks per SM the value-only builds are compiled for
+#define MCRE_IRC_MINB 2
 #endif
+__host__ __device__ constexpr int irc_pp(int nt, int ns, int mode) {
+  return nt > 0 ? 1 : (mode == 1 ? MCRE_IRC_PP : (ns == 1 ? 4 : 2));
+}
+__host__ __device__ constexpr int irc_minb(int nt, int ns, int mode) {
+  return nt > 0 ? 1 : (mode == 1 ? MCRE_IRC_MINB : (ns == 1 ? 2 : 4));
+}
 template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE, bool BERM>
-__global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
+__global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
                                                                          double *partial, double *spill,
                                                                          double *shift, int pilot) {
   typedef typename RealOf<NT>::type R;
@@ -396,6 +406,11 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
       };
 
       for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+#if defined(MCRE_IRC_UNROLL) && MCRE_IRC_UNROLL > 1
+#pragma unroll 2
+#else
+#pragma unroll 1
+#endif
       for (int is = 0; is < P.n_sub; ++is) {
         const double *sr = P.step_rec + (size_t)is * SR;
         const double2 g0 = __ldg((const double2 *)sr), g1 = __ldg((const double2 *)sr + 1);
@@ -417,18 +432,22 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
         } else {
           MCRE_VP { z0[p] = ns[p].next(); z1[p] = 0.0; }
         }
-        // ---- correlated noise z @ L^T (model.py:46-48) and the model step, lock-step over paths ----
-        R w0[PP], w1[PP];
-        MCRE_VP w0[p] = mp.L00 * z0[p];
-        if constexpr (CIR) { MCRE_VP w1[p] = mp.L10 * z0[p] + mp.L11 * z1[p]; }
-        else { MCRE_VP w1[p] = T::zero(); }
+        // ---- model step, lock-step over paths.  The correlated noise z @ L^T (model.py:46-48) is
+        // folded into per-step coefficients: sigma sqrt(dt) (L z)_i = k_i0 z0 + k_i1 z1.
         R rate0[PP];
         MCRE_VP rate0[p] = st[p].r;
         if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
           // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
           MCRE_VP st[p].r = mp.theta + (st[p].r - mp.theta) * sv0 + sv1 * z0[p];
         } else {
-          MCRE_VP st[p].r = st[p].r + mp.a * (sv0 - st[p].r) * dt + mp.sigma * sq * (vas_second ? w1[p] : w0[p]);
+          // r + a (theta_t - r) dt + sigma sqrt(dt) w   (vasicek.py:88-112)
+          const R adt = mp.a * dt, ssq = mp.sigma * sq;
+          const R kv0 = ssq * (vas_second ? mp.L10 : mp.L00);
+          MCRE_VP st[p].r = st[p].r + (sv0 - st[p].r) * adt + kv0 * z0[p];
+          if (vas_second) {
+            const R kv1 = ssq * mp.L11;
+            MCRE_VP st[p].r = st[p].r + kv1 * z1[p];
+          }
         }
         MCRE_VP st[p].logB = st[p].logB + rate0[p] * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
         if constexpr (CIR) {
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
             MCRE_VP { st[p].logBl = st[p].logBl + sc0 * dt; st[p].y = sc1; }
           } else {                            // full-truncation Euler, cirpp.py:174-198
             // y >= 1e-12 after every step (clamp below); with y0 > 0 the relu is the identity
-            R sy[PP], yn[PP];
+            R sy[PP], yn[PP], wn[PP];
             if constexpr (NT == 0) {
               if (y_positive) {
                 double yv[PP];
@@ -448,7 +467,14 @@ __global__ void __launch_bounds__(128, (NT == 0 ? MCRE_IRC_MINB : 1)) irc_main_k
             } else {
               MCRE_VP sy[p] = y_positive ? r_sqrt_pos(st[p].y) : r_sqrt(r_relu(st[p].y));
             }
-            MCRE_VP yn[p] = st[p].y + mp.kappa * (mp.ctheta - st[p].y) * dt + mp.csigma * sy[p] * sq * (cir_second ? w1[p] : w0[p]);
+            const R kdt = mp.kappa * dt, csq = mp.csigma * sq;
+            const R kc0 = csq * (cir_second ? mp.L10 : mp.L00);
+            MCRE_VP wn[p] = kc0 * z0[p];
+            if (cir_second) {
+              const R kc1 = csq * mp.L11;
+              MCRE_VP wn[p] = wn[p] + kc1 * z1[p];
+            }
+            MCRE_VP yn[p] = st[p].y + (mp.ctheta - st[p].y) * kdt + sy[p] * wn[p];
             MCRE_VP st[p].logBl = st[p].logBl + (st[p].y + sc0) * dt;
             MCRE_VP st[p].y = r_max(yn[p], 1e-12);
           }
@@ -517,7 +543,7 @@ template <int NT, int NS, bool BERM>
 static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *spill,
                        double *shift, cudaStream_t st) {
   const IrcDev &d = p->d;
-  constexpr int PP = NT == 0 ? MCRE_IRC_PP : 1;   // paths per thread
+
   const int threads = 128, nw = threads / 32;
   const int nvb = NS * (4 + 2 * NT);
   const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);
@@ -525,7 +551,7 @@ static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, 
   if (n_chunks == 0) return 0;
 #define LAUNCH(CIRV, SCH, MODEV)                                                                       \
   do {                                                                                                 \
-    auto k = irc_main_kernel<NT, NS, CIRV, SCH, PP, MODEV, BERM>;                                            \
+    auto k = irc_main_kernel<NT, NS, CIRV, SCH, irc_pp(NT, NS, MODEV), MODEV, BERM>;                         \
     if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                    \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));               \

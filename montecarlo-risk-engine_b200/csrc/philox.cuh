@@ -3,7 +3,8 @@
 // Stream addressing (shared with oracle/philox.py, bit for bit on the uniforms):
 //   key     = (low 32 bits of seed, low 32 bits of stream)
 //   counter = (path_lo, path_hi, block, kind)      kind 0: normals, 1: uniforms
-//   normal  #n of a path = element (n & 1) of BoxMuller(block n >> 1)
+//   normal  #n of a path = element (n & 1) of BoxMuller(block n >> 1):
+//             sqrt(-2 log u1) (cos, sin)(2 pi u2), u1 = (k1 + 1/2) 2^-52, u2 = k2 2^-52, k = top 52 bits
 //   uniform #m of a path = element (m & 1) of the two 52-bit uniforms of block m >> 1
 // so a draw depends only on (seed, stream, global path id, draw index): sharding paths
 // over GPUs or replaying a path in a second pass reproduces it exactly.  Takes the place
@@ -52,6 +53,11 @@ __host__ __device__ inline double u52(uint32_t hi, uint32_t lo) {
 #endif
 }
 
+// mantissa double in [1, 2) from the top 52 bits of (hi:lo): 1 + k 2^-52
+__device__ inline double mant52(uint32_t hi, uint32_t lo) {
+  return __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+}
+
 struct RngDev {
   int mode;             // MCRE_RNG_*
   uint32_t k0, k1;
@@ -75,19 +81,27 @@ struct NormalStream {
   __device__ inline void pair(uint32_t block, double &z0, double &z1) const {
     uint32_t o[4];
     ph(p_lo, p_hi, block, 0u, o);
-    double u1 = u52(o[0], o[1]), u2 = u52(o[2], o[3]);
-    double s, c;
+    // radius from u1 = (k1 + 1/2) 2^-52 in (0,1); angle from u2 = k2 2^-52 in [0,1)
+    const double u1 = u52(o[0], o[1]);
 #if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
-    double rad = fm_sqrt_pos(-2.0 * fm_log_t(u1));   // u1 < 1: the argument is strictly positive
-    fm_sincos2pi_t(u2, s, c);
-#elif defined(MCRE_FAST_MATH)
-    double rad = fm_sqrt(-2.0 * fm_log(u1));
+    // same arithmetic as NormalStreamV::next2 (the angle reduction works on the mantissa double)
+    const double dd[1] = {mant52(o[2], o[3])};
+    const double rr[1] = {fm_sqrt_pos(-2.0 * fm_log_t(u1))};   // u1 < 1: the argument is strictly positive
+    double zc[1], zs[1];
+    fm_polar_tv<1>(dd, rr, zc, zs);
+    z0 = zc[0]; z1 = zs[0];
+#else
+    const double u2 = mant52(o[2], o[3]) - 1.0;
+    double s, c;
+#if defined(MCRE_FAST_MATH)
+    const double rad = fm_sqrt(-2.0 * fm_log(u1));
     fm_sincos2pi(u2, s, c);
 #else
-    double rad = sqrt(-2.0 * log(u1));
+    const double rad = sqrt(-2.0 * log(u1));
     sincospi(2.0 * u2, &s, &c);
 #endif
     z0 = rad * c; z1 = rad * s;
+#endif
   }
   __device__ inline double next() {
     double z;
@@ -129,15 +143,13 @@ struct NormalStreamV {
       MCRE_VP Philox::round(c0[p], c1[p], c2[p], c3[p], a, b);
       a += 0x9E3779B9u; b += 0xBB67AE85u;
     }
-    double u1[PP], u2[PP], lg[PP], rad[PP], sn[PP], cs[PP];
+    double u1[PP], d2[PP], lg[PP], rad[PP];
     MCRE_VP u1[p] = u52(c0[p], c1[p]);
-    MCRE_VP u2[p] = u52(c2[p], c3[p]);
+    MCRE_VP d2[p] = mant52(c2[p], c3[p]);
     fm_log_tv<PP>(u1, lg);
     MCRE_VP lg[p] = -2.0 * lg[p];
-    fm_sincos2pi_tv<PP>(u2, sn, cs);
     fm_sqrt_posv<PP>(lg, rad);          // u1 < 1: the argument is strictly positive
-    MCRE_VP z0[p] = rad[p] * cs[p];
-    MCRE_VP z1[p] = rad[p] * sn[p];
+    fm_polar_tv<PP>(d2, rad, z0, z1);
     n += 2;
   }
 };

@@ -36,7 +36,8 @@ def _blocks(paths, block, kind, seed, stream):
 def normal_pair(paths, block, seed, stream):
     u1, u2 = _blocks(paths, block, 0, seed, stream)
     rad = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * np.pi * u2
+    # the angle uses k 2^-52 (the mantissa of the second word pair), without the half-step offset
+    ang = 2.0 * np.pi * (u2 - 1.1102230246251565e-16)
     # sincospi(2 u2): evaluate through the reduced argument like the device does
     return rad * np.cos(ang), rad * np.sin(ang)
 

@@ -26,8 +26,10 @@ def main():
     if mode == "build":
         from mcre import build
         for v in variants:
-            pp, minb = v.split("x")
-            build.build(force=True, extra_flags=[f"-DMCRE_IRC_PP={pp}", f"-DMCRE_IRC_MINB={minb}"], lib=lib_of(v), tag="_" + v)
+            pp, rest = v.split("x")
+            minb, _, unroll = rest.partition("u")
+            flags = [f"-DMCRE_IRC_PP={pp}", f"-DMCRE_IRC_MINB={minb}"] + ([f"-DMCRE_IRC_UNROLL={unroll}"] if unroll else [])
+            build.build(force=True, extra_flags=flags, lib=lib_of(v), tag="_" + v)
             print("built", lib_of(v))
     else:
         for v in variants:
