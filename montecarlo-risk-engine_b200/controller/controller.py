@@ -101,7 +101,7 @@ class SimulationController:
         #: parity mode: {"pre": Tensor[n_sub, N_pre, d], "main": Tensor[n_sub, N_main, d]} on the GPU
         self.injected_normals = None
         #: pre-simulation scratch is bounded by processing this many local paths at a time
-        self.presim_batch_paths = 1 << 18
+        self.presim_batch_paths = 1 << 22
         self.last_timings = {}
 
     # ------------------------------------------------------------------ timelines

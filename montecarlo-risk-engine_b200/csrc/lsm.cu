@@ -31,12 +31,13 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
     if (threadIdx.x < LSM_NV) acc[threadIdx.x] = 0.0;
     __syncthreads();
     int parity = 0;
+    // each thread first sums its own paths of the chunk (stride blockDim), the block reduces once
+    double vals[LSM_NV];
+#pragma unroll
+    for (int i = 0; i < LSM_NV; ++i) vals[i] = 0.0;
     for (int it = 0; it < chunk; it += blockDim.x) {
       const long long p = ch * chunk + it + threadIdx.x;
-      double vals[LSM_NV];
-#pragma unroll
-      for (int i = 0; i < LSM_NV; ++i) vals[i] = 0.0;
-      if (p < n) {
+      if (it + (int)threadIdx.x < chunk && p < n) {
         float v = value[p];
         if (imm) {
           const double im = imm[p];
@@ -55,11 +56,11 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
         const double u = (xk[p] - shift_k) * scale_k;
         const double y = nk[p] * (double)v;   // numeraire * total cashflows (controller.py:368)
         const double u2 = u * u;
-        vals[0] = 1.0; vals[1] = u; vals[2] = u2; vals[3] = u2 * u; vals[4] = u2 * u2;
-        vals[5] = y; vals[6] = y * u; vals[7] = y * u2;
+        vals[0] += 1.0; vals[1] += u; vals[2] += u2; vals[3] += u2 * u; vals[4] += u2 * u2;
+        vals[5] += y; vals[6] += y * u; vals[7] += y * u2;
       }
-      block_accumulate<LSM_NV>(vals, acc, 0, stage, LSM_NV, parity);
     }
+    block_accumulate<LSM_NV>(vals, acc, 0, stage, LSM_NV, parity);
     __syncthreads();
     if (threadIdx.x < LSM_NV) partial[ch * LSM_NV + threadIdx.x] = acc[threadIdx.x];
     __syncthreads();

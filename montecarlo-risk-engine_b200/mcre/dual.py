@@ -14,14 +14,31 @@ import math
 import numpy as np
 
 
+_EMPTY = np.zeros(0)
+
+
 class D:
-    """value + tangent vector (length n_params, possibly 0)."""
+    """value + tangent vector (length n_params, possibly 0).
+
+    Plans without sensitivities (n = 0) are the common case and are lowered on every
+    run_simulation() call, so every operator has a value-only fast path that never touches
+    numpy (the empty tangent is one shared array)."""
 
     __slots__ = ("v", "t")
 
     def __init__(self, v, t=None, n=0):
         self.v = float(v)
-        self.t = np.zeros(n) if t is None else np.asarray(t, dtype=np.float64)
+        if t is None:
+            self.t = _EMPTY if n == 0 else np.zeros(n)
+        else:
+            self.t = t if isinstance(t, np.ndarray) and t.dtype == np.float64 else np.asarray(t, dtype=np.float64)
+
+    @staticmethod
+    def _val(v):
+        r = object.__new__(D)
+        r.v = v
+        r.t = _EMPTY
+        return r
 
     # -- helpers -----------------------------------------------------------
     @staticmethod
@@ -47,39 +64,55 @@ class D:
 
     # -- arithmetic --------------------------------------------------------
     def __add__(self, o):
+        if self.t is _EMPTY:
+            return D._val(self.v + (o.v if isinstance(o, D) else o))
         o = self._o(o)
         return D(self.v + o.v, self.t + o.t)
 
     __radd__ = __add__
 
     def __neg__(self):
+        if self.t is _EMPTY:
+            return D._val(-self.v)
         return D(-self.v, -self.t)
 
     def __sub__(self, o):
+        if self.t is _EMPTY:
+            return D._val(self.v - (o.v if isinstance(o, D) else o))
         o = self._o(o)
         return D(self.v - o.v, self.t - o.t)
 
     def __rsub__(self, o):
+        if self.t is _EMPTY:
+            return D._val((o.v if isinstance(o, D) else o) - self.v)
         o = self._o(o)
         return D(o.v - self.v, o.t - self.t)
 
     def __mul__(self, o):
+        if self.t is _EMPTY:
+            return D._val(self.v * (o.v if isinstance(o, D) else o))
         o = self._o(o)
         return D(self.v * o.v, self.t * o.v + self.v * o.t)
 
     __rmul__ = __mul__
 
     def __truediv__(self, o):
+        if self.t is _EMPTY:
+            return D._val(self.v / (o.v if isinstance(o, D) else o))
         o = self._o(o)
         q = self.v / o.v
         return D(q, (self.t - q * o.t) / o.v)
 
     def __rtruediv__(self, o):
+        if self.t is _EMPTY:
+            return D._val((o.v if isinstance(o, D) else o) / self.v)
         return self._o(o) / self
 
     def __pow__(self, p):
         if isinstance(p, D):
             return dexp(p * dlog(self))
+        if self.t is _EMPTY:
+            return D._val(self.v ** p)
         return D(self.v ** p, p * self.v ** (p - 1) * self.t)
 
     def __float__(self):
@@ -93,19 +126,21 @@ def dexp(x):
     if not isinstance(x, D):
         return math.exp(x)
     e = math.exp(x.v)
-    return D(e, e * x.t)
+    return D._val(e) if x.t is _EMPTY else D(e, e * x.t)
 
 
 def dlog(x):
     if not isinstance(x, D):
         return math.log(x)
-    return D(math.log(x.v), x.t / x.v)
+    return D._val(math.log(x.v)) if x.t is _EMPTY else D(math.log(x.v), x.t / x.v)
 
 
 def dsqrt(x):
     if not isinstance(x, D):
         return math.sqrt(x)
     s = math.sqrt(x.v)
+    if x.t is _EMPTY:
+        return D._val(s)
     return D(s, x.t / (2.0 * s) if s > 0.0 else np.zeros_like(x.t))
 
 

@@ -164,6 +164,11 @@ class IrcBackend:
 
     # ------------------------------------------------------------------ lowering
     def _dual_params(self):
+        if getattr(self, "_dual_cache", None) is None:
+            self._dual_cache = self._dual_params_uncached()
+        return self._dual_cache
+
+    def _dual_params_uncached(self):
         nt = self.nt
         if isinstance(self.c.model, ModelConfig):
             offs = self.c.model.param_offsets()
@@ -212,9 +217,12 @@ class IrcBackend:
             one = D(1.0, None, nt)
             chol = [one, zero, zero, one]
 
-        # ---- per-step model scalars --------------------------------------------------
+        # ---- per-step model scalars (shared by the pre-simulation and main plans) ---------
         step_vas, step_cir = [], []
-        for s in range(n_sub):
+        cached = getattr(self, "_step_cache", None)
+        if cached is not None:
+            step_vas, step_cir = cached
+        for s in range(n_sub if cached is None else 0):
             if self.scheme == SimulationScheme.ANALYTICAL:
                 decay, _ = self.vas.exact_step_constants(pv, grid.dt[s])
                 _, nstd = self.vas.exact_step_constants(pv, grid.dt_nominal[s])
@@ -227,6 +235,7 @@ class IrcBackend:
                                  D(self.cir.market_hazard(grid.t2[s]), None, nt)]
                 else:
                     step_cir += [self.cir.psi(pc, grid.t1[s]), zero]
+        self._step_cache = (step_vas, step_cir)
         if self.has_cir:
             cir_init = D(self.cir.market_hazard(t0), None, nt) if self.cir.deterministic else pc[3]
 
@@ -340,7 +349,7 @@ class IrcBackend:
         lgd = 0.0
         cva_coef = [zero] * (2 * n_metric)
         cva_metric = None
-        if cva_metrics:
+        if cva_metrics and sets:
             if len({m.counterparty_id for m in cva_metrics}) > 1 or len({m.recovery_rate for m in cva_metrics}) > 1:
                 raise NotImplementedError("one CVA counterparty / recovery per run is supported for now")
             cva_metric = cva_metrics[0]

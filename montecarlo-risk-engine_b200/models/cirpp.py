@@ -69,18 +69,36 @@ class CIRPPModel(Model):
     def _h(p):
         return dsqrt(p[0] * p[0] + 2.0 * p[2] * p[2])
 
+    def _memo(self, p):
+        """Per-parameter-set cache of A(tau) / B(tau): the plan compiler asks for the same
+        maturities again and again (adjacent exposure dates share an end point)."""
+        key = tuple(id(x) for x in p)
+        cache = getattr(self, "_ab_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, {}, {}, p)          # keeps p alive so the ids stay valid
+            self._ab_cache = cache
+        return cache
+
     def cir_A(self, p, tau):
+        memo = self._memo(p)[1]
+        if tau in memo:
+            return memo[tau]
         kappa, theta, sigma = p[0], p[1], p[2]
         h = self._h(p)
         num = 2.0 * h * dexp(0.5 * (kappa + h) * tau)
         den = 2.0 * h + (kappa + h) * (dexp(h * tau) - 1.0)
-        return (num / den) ** ((2.0 * kappa * theta) / (sigma * sigma))
+        memo[tau] = (num / den) ** ((2.0 * kappa * theta) / (sigma * sigma))
+        return memo[tau]
 
     def cir_B(self, p, tau):
+        memo = self._memo(p)[2]
+        if tau in memo:
+            return memo[tau]
         kappa = p[0]
         h = self._h(p)
         e = dexp(h * tau) - 1.0
-        return (2.0 * e) / (2.0 * h + (kappa + h) * e)
+        memo[tau] = (2.0 * e) / (2.0 * h + (kappa + h) * e)
+        return memo[tau]
 
     def psi(self, p, t):
         """Deterministic shift psi(t) = lambda_mkt(t) + D(t) - y0 E(t)."""
