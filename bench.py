@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_port_rate(n_paths, repeats=1, rho=0.3):
+def cpu_port_rate(n_paths, repeats=1, rho=0.3, n_pre=2048):
     """Times the oracle (numpy restatement of the reference) on a bounded sample of the same
     workload: main-simulation phase only (paths + cashflows + exposure + CVA), coefficients fixed."""
     import cases
@@ -84,7 +84,6 @@ def cpu_port_rate(n_paths, repeats=1, rho=0.3):
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        n_pre = 2048
         pre = engine.torch_reference_draws(42, n_pre, N_STEPS_SIM, 2)
         t_draw0 = time.perf_counter()
         # the reference's own draw procedure: one torch.randn(N, d, float64) per sub-step (model.py:47)
@@ -99,26 +98,62 @@ def cpu_port_rate(n_paths, repeats=1, rho=0.3):
     return n_paths * N_STEPS_SIM / best, best
 
 
+def _cpu_worker(task):
+    """One host core's share of a CPU step (runs in a spawned worker process)."""
+    n_paths, rho = task
+    import torch
+    torch.set_num_threads(1)
+    importlib.import_module("montecarlo-risk-engine_b200")
+    if n_paths == 0:
+        return 0.0          # warm-up task: imports only
+    return cpu_port_rate(n_paths, rho=rho, n_pre=256)[1]   # tiny pre-simulation: the step is the main pass
+
+
+class CpuPool:
+    """The oracle port on ALL host cores: the path range of a CPU step is split over one
+    single-threaded worker process per core (paths are independent, exactly like the GPU
+    sharding); a step's time is the wall clock around the whole map."""
+
+    def __init__(self, workers=None):
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        self.workers = workers or max(1, min(os.cpu_count() or 1, 64))
+        self.pool = cf.ProcessPoolExecutor(self.workers, mp_context=mp.get_context("spawn"))
+        list(self.pool.map(_cpu_worker, [(0, 0.0)] * self.workers))   # import everything once per worker
+
+    def step(self, paths_per_worker, rho):
+        t0 = time.perf_counter()
+        list(self.pool.map(_cpu_worker, [(paths_per_worker, rho)] * self.workers))
+        dt = time.perf_counter() - t0
+        return self.workers * paths_per_worker * N_STEPS_SIM / dt, dt
+
+    def close(self):
+        self.pool.shutdown()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    importlib.import_module("montecarlo-risk-engine_b200")
-    n = 1 << 16
+    pool = CpuPool()
+    per_worker = 1 << 14
+    n = per_worker * pool.workers
     times = []
     for i in range(args.warmup + args.steps):
-        rate, dt = cpu_port_rate(n, rho=float(RHOS[i % len(RHOS)]))
+        rate, dt = pool.step(per_worker, float(RHOS[i % len(RHOS)]))
         if i >= args.warmup:
             times.append(dt)
+    pool.close()
     ms = 1e3 * float(np.mean(times))
     value = n * N_STEPS_SIM / (ms * 1e-3)
-    sample = f"{n} paths x {N_STEPS_SIM} steps per step (main simulation incl. normal generation), torch.randn draws + numpy FP64"
+    sample = (f"{n} paths x {N_STEPS_SIM} steps per step ({per_worker} per worker process, {pool.workers} workers = host cores), "
+              "main simulation incl. normal generation: torch.randn draws + numpy FP64 restatement of the reference")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: Vasicek+CIR++ WWR CVA payer swap, 2^24 paths x 240 steps (bounded CPU sample)",
                        "paths_per_step": n, "sub_steps": N_STEPS_SIM},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.workers, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -257,10 +292,15 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = 1 << 17
-            rate, dt = cpu_port_rate(n_cpu)
-            cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{n_cpu} paths x {N_STEPS_SIM} steps, oracle (torch.randn draws + numpy FP64 restatement), main simulation, {dt:.1f} s"}
+            pool = CpuPool()
+            per_worker = 1 << 14
+            pool.step(per_worker, 0.3)
+            rate, dt = max((pool.step(per_worker, 0.3) for _ in range(3)), key=lambda r: r[0])
+            pool.close()
+            cpu = {"value": rate, "unit": UNIT, "cores": pool.workers, "kind": "port",
+                   "sample": f"{per_worker * pool.workers} paths x {N_STEPS_SIM} steps ({per_worker} per worker process, "
+                             f"{pool.workers} workers = host cores), oracle (torch.randn draws + numpy FP64 restatement "
+                             f"of the reference), main simulation, best of 3: {dt:.2f} s"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
