@@ -260,10 +260,12 @@ int mcre_irc_mainsim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard 
 enum { MCRE_EQ_BS = 0, MCRE_EQ_HESTON = 1, MCRE_EQ_SCHWARTZ = 2 };
 #define MCRE_EQ_MAX_SETS 4
 /* product kinds / event flags of the tables below */
-enum { MCRE_EQ_EUROPEAN = 0, MCRE_EQ_BINARY = 1, MCRE_EQ_BASKET = 2, MCRE_EQ_ASIAN = 3, MCRE_EQ_BARRIER = 4 };
+enum { MCRE_EQ_EUROPEAN = 0, MCRE_EQ_BINARY = 1, MCRE_EQ_BASKET = 2, MCRE_EQ_ASIAN = 3, MCRE_EQ_BARRIER = 4,
+       MCRE_EQ_EXERCISE = 5 /* Bermudan / American, src/products/bermudan_option.py:93-188 */ };
 #define MCRE_EQ_EV_OBSERVE 1
 #define MCRE_EQ_EV_PAY 2
 #define MCRE_EQ_EV_FIRST 4
+#define MCRE_EQ_EV_EXERCISE 8
 
 typedef struct {
   int32_t kind;          /* MCRE_EQ_*: every asset of a launch is of this kind                       */
@@ -297,6 +299,11 @@ typedef struct {
                                    4 DI), barrier2, type2 (0: none), n observations, tracker slot, reserved  */
   const double *prod_w;         /* [n_prod][n_assets] weights of the composite underlying                 */
   int32_t n_sets;
+  /* exercise products: per event (same indexing as ev_prod) 8 doubles: c0, c1, c2 of the continuation
+   * value in u = (x - shift) * scale, shift, scale, 1/numeraire(t), d(1/numeraire)/d rate, last-date flag;
+   * prod_x [n_prod][n_assets]: weights picking the explanatory variable x (spot of the option's asset). */
+  const double *ev_data;
+  const double *prod_x;
 } mcre_eq_desc;
 
 typedef struct mcre_eq_plan mcre_eq_plan;
@@ -329,6 +336,18 @@ int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double
                   const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i /* host[3] or NULL */,
                   double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
                   double *d_partial, double *d_moments, void *stream);
+
+/* LSM pre-simulation arrays of an exercise product on equity underlyings, gathered date-major from
+ * materialised pre-simulation paths (mcre_generate_paths with seed 42; the pre-simulation is a small
+ * fraction of the run): x[k][n] explanatory spot and numeraire[k][n] per regression date k,
+ * imm[i][n] = max(sign (U - K), 0) per exercise date i with U = sum_j w_j spot_j.  Spots are state
+ * columns, exponentiated where the model keeps log-spot (Heston, Schwartz).  Host arrays unless d_*. */
+int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, int32_t n_dates, int32_t state_dim,
+                            int32_t n_reg, const int32_t *reg_date, const double *reg_numeraire,
+                            int32_t n_ex, const int32_t *ex_date, int32_t x_col, int32_t x_is_log,
+                            int32_t n_under, const int32_t *under_col, const double *under_w,
+                            const int32_t *under_is_log, double strike, double sign,
+                            double *d_x, double *d_n, double *d_imm, void *stream);
 
 /* ================================================================================
  * Exact order statistics per row (PFE), replaces torch.sort + index in

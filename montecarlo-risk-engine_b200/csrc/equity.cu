@@ -39,10 +39,13 @@ struct EqDev {
   const int *date_ev_off, *ev_prod, *ev_flags;
   int n_prod; const double *prod, *prod_w;
   int n_sets;
+  const double *ev_data, *prod_x;   // exercise products (Bermudan / American)
 };
 
-enum { EQ_EUROPEAN = MCRE_EQ_EUROPEAN, EQ_BINARY = MCRE_EQ_BINARY, EQ_BASKET = MCRE_EQ_BASKET, EQ_ASIAN = MCRE_EQ_ASIAN, EQ_BARRIER = MCRE_EQ_BARRIER };
-enum { EQ_EV_OBSERVE = MCRE_EQ_EV_OBSERVE, EQ_EV_PAY = MCRE_EQ_EV_PAY, EQ_EV_FIRST = MCRE_EQ_EV_FIRST };
+enum { EQ_EUROPEAN = MCRE_EQ_EUROPEAN, EQ_BINARY = MCRE_EQ_BINARY, EQ_BASKET = MCRE_EQ_BASKET, EQ_ASIAN = MCRE_EQ_ASIAN,
+       EQ_BARRIER = MCRE_EQ_BARRIER, EQ_EXERCISE = MCRE_EQ_EXERCISE };
+enum { EQ_EV_OBSERVE = MCRE_EQ_EV_OBSERVE, EQ_EV_PAY = MCRE_EQ_EV_PAY, EQ_EV_FIRST = MCRE_EQ_EV_FIRST,
+       EQ_EV_EXERCISE = MCRE_EQ_EV_EXERCISE };
 
 template <int KIND> struct EqParCount;
 template <> struct EqParCount<MCRE_EQ_BS> { static const int n = 3; };
@@ -162,6 +165,29 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             G = r_exp(r_with_value(term, group_sum(val(term), base, A)));
           }
           const int slot = (int)__ldg(pr + 14);
+          if (ef & EQ_EV_EXERCISE) {
+            // Bermudan / American exercise date (bermudan_option.py:93-131): exercise iff the
+            // immediate value beats the regressed continuation value (hard indicator) and the right
+            // is still alive; tracker a of the product's slot is the alive flag.
+            const double *ed = P.ev_data + (size_t)e * 8;
+            const double xw = __ldg(P.prod_x + (size_t)pi * A + aa);
+            const double X = group_sum(val(S) * xw, base, A);          // explanatory spot
+            const double u = (X - __ldg(ed + 3)) * __ldg(ed + 4);
+            const double cont = __ldg(ed + 7) != 0.0 ? 0.0 : __ldg(ed + 0) + u * (__ldg(ed + 1) + u * __ldg(ed + 2));
+            const R imm = option_payoff(U, strike, sign);
+#pragma unroll
+            for (int k = 0; k < EQ_NTRK; ++k) {
+              if (k != slot) continue;
+              if (ef & EQ_EV_FIRST) trk_a[k] = T::lift(1.0);
+              if (val(trk_a[k]) > 0.5 && val(imm) > cont) {
+                trk_a[k] = T::zero();
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                  if (s == set) { cf[s] = cf[s] + imm * __ldg(ed + 5); numtan[s] += val(imm) * __ldg(ed + 6); }
+              }
+            }
+            continue;
+          }
           if (ef & EQ_EV_OBSERVE) {
 #pragma unroll
             for (int k = 0; k < EQ_NTRK; ++k) {
@@ -312,7 +338,7 @@ using namespace mcre;
 struct mcre_eq_plan {
   EqDev d;
   int nt = 0;
-  DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w;
+  DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w, ev_data, prod_x;
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
 };
 
@@ -331,8 +357,9 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (!scheme_ok) return fail(-1, "eq: scheme not defined for this model%s", "");
   for (int p = 0; p < c->n_prod; ++p) {
     const int slot = (int)c->prod[(size_t)p * EQ_PR + 14], kind = (int)c->prod[(size_t)p * EQ_PR];
-    if ((kind == EQ_ASIAN || kind == EQ_BARRIER) && (slot < 0 || slot >= EQ_NTRK))
-      return fail(-3, "eq: at most 2 path-dependent products per launch%s", "");
+    if ((kind == EQ_ASIAN || kind == EQ_BARRIER || kind == EQ_EXERCISE) && (slot < 0 || slot >= EQ_NTRK))
+      return fail(-3, "eq: at most 2 path-dependent / exercise products per launch%s", "");
+    if (kind == EQ_EXERCISE && (!c->ev_data || !c->prod_x)) return fail(-1, "eq: exercise product without event data%s", "");
     const int set = (int)c->prod[(size_t)p * EQ_PR + 1];
     if (set < 0 || set >= c->n_sets) return fail(-1, "eq: product set index out of range%s", "");
   }
@@ -350,6 +377,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   UP(chol_dual, c->chol_dual, c->corr_mode == 1 ? (size_t)c->n_chol * 4 * (c->nt + 1) : 0);
   UP(date_ev_off, c->date_ev_off, c->n_dates + 1); UP(ev_prod, c->ev_prod, n_ev); UP(ev_flags, c->ev_flags, n_ev);
   UP(prod, c->prod, (size_t)c->n_prod * EQ_PR); UP(prod_w, c->prod_w, (size_t)c->n_prod * A);
+  UP(ev_data, c->ev_data, c->ev_data ? (size_t)n_ev * 8 : 0); UP(prod_x, c->prod_x, c->prod_x ? (size_t)c->n_prod * A : 0);
 #undef UP
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
@@ -363,6 +391,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   D.corr_mode = c->corr_mode; D.chol = p->chol.p; D.chol_dual = p->chol_dual.p;
   D.date_ev_off = p->date_ev_off.p; D.ev_prod = p->ev_prod.p; D.ev_flags = p->ev_flags.p;
   D.n_prod = c->n_prod; D.prod = p->prod.p; D.prod_w = p->prod_w.p; D.n_sets = c->n_sets;
+  D.ev_data = p->ev_data.p; D.prod_x = p->prod_x.p;
   *out = p;
   return 0;
 }
@@ -373,6 +402,7 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->chol.release(); p->chol_dual.release(); p->prod.release(); p->prod_w.release(); p->asset_noise.release();
   p->asset_uniform.release(); p->col_asset.release(); p->col_elem.release(); p->step_date.release();
   p->step_chol.release(); p->date_ev_off.release(); p->ev_prod.release(); p->ev_flags.release();
+  p->ev_data.release(); p->prod_x.release();
   delete p;
 }
 

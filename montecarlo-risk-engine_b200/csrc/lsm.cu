@@ -67,9 +67,66 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
   }
 }
 
+// Gathers the regression / exercise inputs of an equity exercise product from materialised paths
+// [n_paths][n_dates][state_dim]: one thread per path, date-major outputs (coalesced writes).
+__global__ void __launch_bounds__(256) lsm_prepare_equity_kernel(const double *__restrict__ paths, long long n, int n_dates,
+                                                                 int state_dim, int n_reg, const int *reg_date,
+                                                                 const double *reg_num, int n_ex, const int *ex_date,
+                                                                 int x_col, int x_is_log, int n_under, const int *ucol,
+                                                                 const double *uw, const int *ulog, double strike,
+                                                                 double sign, double *x, double *num, double *imm) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double *row = paths + (size_t)p * n_dates * state_dim;
+  for (int k = 0; k < n_reg; ++k) {
+    const double v = row[(size_t)reg_date[k] * state_dim + x_col];
+    x[(size_t)k * n + p] = x_is_log ? exp(v) : v;
+    num[(size_t)k * n + p] = reg_num[k];
+  }
+  for (int i = 0; i < n_ex; ++i) {
+    const double *st = row + (size_t)ex_date[i] * state_dim;
+    double U = 0.0;
+    for (int j = 0; j < n_under; ++j) {
+      const double v = st[ucol[j]];
+      U += uw[j] * (ulog[j] ? exp(v) : v);
+    }
+    imm[(size_t)i * n + p] = fmax((U - strike) * sign, 0.0);
+  }
+}
+
 }  // namespace mcre
 
 using namespace mcre;
+
+extern "C" int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, int32_t n_dates, int32_t state_dim,
+                                       int32_t n_reg, const int32_t *reg_date, const double *reg_numeraire, int32_t n_ex,
+                                       const int32_t *ex_date, int32_t x_col, int32_t x_is_log, int32_t n_under,
+                                       const int32_t *under_col, const double *under_w, const int32_t *under_is_log,
+                                       double strike, double sign, double *d_x, double *d_n, double *d_imm, void *stream) {
+  if (!d_paths || !reg_date || !reg_numeraire || !ex_date || !under_col || !under_w || !under_is_log || !d_x || !d_n || !d_imm)
+    return fail(-1, "null argument%s", "");
+  if (n_paths <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DevArray<int> rd, ed, uc, ul;
+  DevArray<double> rn, uw;
+  int rc = rd.upload(reg_date, n_reg);
+  if (!rc) rc = ed.upload(ex_date, n_ex);
+  if (!rc) rc = uc.upload(under_col, n_under);
+  if (!rc) rc = ul.upload(under_is_log, n_under);
+  if (!rc) rc = rn.upload(reg_numeraire, n_reg);
+  if (!rc) rc = uw.upload(under_w, n_under);
+  if (!rc) {
+    lsm_prepare_equity_kernel<<<(unsigned)((n_paths + 255) / 256), 256, 0, st>>>(
+        d_paths, n_paths, n_dates, state_dim, n_reg, rd.p, rn.p, n_ex, ed.p, x_col, x_is_log, n_under, uc.p, uw.p, ul.p,
+        strike, sign, d_x, d_n, d_imm);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch");
+    else cudaStreamSynchronize(st);   // the temporary index tables are freed below
+  }
+  rd.release(); ed.release(); uc.release(); ul.release(); rn.release(); uw.release();
+  return rc;
+}
 
 extern "C" int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double scale_k, const double *d_xi,
                              const double *d_ni, const double *d_imm, const double *coef_i, double shift_i,

@@ -65,6 +65,7 @@ SYMBOLS = [
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim",
     "mcre_irc_set_coefficients", "mcre_irc_mainsim",
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step",
+    "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_finish",

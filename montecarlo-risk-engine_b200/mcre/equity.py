@@ -33,6 +33,7 @@ from models.schwartz_two_factor import SchwartzTwoFactorModel
 from products.asian_option import AsianAveragingType, AsianOption
 from products.barrier_option import BarrierOption, BarrierOptionType
 from products.basket_option import BasketOption, BasketOptionType
+from products.bermudan_option import BermudanOption
 from products.binary_option import BinaryOption
 from products.equity import Equity
 from products.european_option import EuropeanOption
@@ -40,8 +41,8 @@ from products.product import OptionType
 
 CHUNK_PATHS = 4096
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
-P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER = 0, 1, 2, 3, 4
-EV_OBSERVE, EV_PAY, EV_FIRST = 1, 2, 4
+P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
+EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
 EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS = 16, 8, 2, 4
 _NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
 _BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
@@ -60,6 +61,7 @@ class EqDesc(C.Structure):
         ("corr_mode", C.c_int32), ("chol", B.c_dp), ("chol_dual", B.c_dp),
         ("date_ev_off", B.c_ip), ("ev_prod", B.c_ip), ("ev_flags", B.c_ip),
         ("n_prod", C.c_int32), ("prod", B.c_dp), ("prod_w", B.c_dp), ("n_sets", C.c_int32),
+        ("ev_data", B.c_dp), ("prod_x", B.c_dp),
     ]
 
 
@@ -108,9 +110,19 @@ def family_of(model):
     return kind, assets
 
 
+def is_equity_exercise(p):
+    return isinstance(p, BermudanOption) and isinstance(p.underlying, Equity)
+
+
+def _is_path_dependent(p):
+    return isinstance(p, (AsianOption, BarrierOption)) or is_equity_exercise(p)
+
+
 def _is_equity_product(p):
     if isinstance(p, EuropeanOption):
         return isinstance(p.underlying, Equity)
+    if is_equity_exercise(p):
+        return True
     return isinstance(p, (BinaryOption, BasketOption, AsianOption, BarrierOption))
 
 
@@ -141,6 +153,7 @@ class EquityBackend:
         self.npar = _NPAR[self.kind]
         self.nt = self.npar if ctrl.differentiate else 0
         self.id_to_asset = {a.asset_id: i for i, a in enumerate(self.assets)}
+        self.exercise_coef = {}   # id(product) -> (coef [n_ex, 3] standardised basis, basis [n_ex, 2])
         subs = _sub_models(ctrl.model)
         num_idx = ctrl.model.id_to_model["numeraire"] if isinstance(ctrl.model, ModelConfig) else 0
         self.num_model = subs[num_idx]
@@ -227,6 +240,13 @@ class EquityBackend:
             # the reference divides by the numeraire request of index 0 = the FIRST monitoring
             # date (asian_option.py:90, barrier_option.py:312)
             t_num = obs[0]
+        elif is_equity_exercise(p):
+            rec[0] = P_EXERCISE
+            rec[14] = slot
+            w[self._asset_index(p.underlying.get_asset_id())] = 1.0
+            ex = [float(t) for t in p.product_timeline]
+            events = [(date_idx[t], EV_EXERCISE | (EV_FIRST if i == 0 else 0)) for i, t in enumerate(ex)]
+            t_num = ex[0]
         else:
             raise TypeError(type(p))
         rec[4], rec[5] = self._inv_numeraire(t_num)
@@ -308,7 +328,7 @@ class EquityBackend:
                 step_aux[s, 0] = math.log(m.curve_value(grid.t2[s]))
 
         # ---- products / events ------------------------------------------------------------
-        recs, weights, events = [], [], [[] for _ in range(n_dates)]
+        recs, weights, xweights, events = [], [], [], [[] for _ in range(n_dates)]
         owners = []
         slot = 0
         for r, si in enumerate(set_indices):
@@ -316,23 +336,38 @@ class EquityBackend:
                 if c._can_skip_monte_carlo_for_product(p):
                     continue
                 use_slot = -1
-                if isinstance(p, (AsianOption, BarrierOption)):
+                if _is_path_dependent(p):
                     use_slot = slot
                     slot += 1
                 rec, w, evs = self._product_record(p, r, use_slot, date_idx)
                 pi = len(recs)
                 recs.append(rec)
                 weights.append(w)
+                xw = np.zeros(A)
+                if is_equity_exercise(p):
+                    xw[self._asset_index(p.get_asset_id())] = 1.0   # explanatory variable: spot of the option's asset
+                xweights.append(xw)
                 owners.append(p)
                 for di, f in evs:
                     events[di].append((pi, f))
         if slot > EQ_NTRK:
             raise NotImplementedError(f"at most {EQ_NTRK} path-dependent products per launch group")
-        ev_off, ev_prod, ev_flags = [0], [], []
+        ev_off, ev_prod, ev_flags, ev_data = [0], [], [], []
+        ex_count = {}
         for di in range(n_dates):
             for pi, f in events[di]:
                 ev_prod.append(pi)
                 ev_flags.append(f)
+                row = np.zeros(8)
+                if f & EV_EXERCISE:
+                    p = owners[pi]
+                    i = ex_count.get(pi, 0)
+                    ex_count[pi] = i + 1
+                    coef, basis = self.exercise_coef[id(p)]
+                    row[0:3], row[3:5] = coef[i], basis[i]
+                    row[5], row[6] = self._inv_numeraire(dates[di])
+                    row[7] = 1.0 if i == len(p.product_timeline) - 1 else 0.0
+                ev_data.append(row)
             ev_off.append(len(ev_prod))
 
         t = {}
@@ -372,6 +407,8 @@ class EquityBackend:
         desc.prod = fp("prod", np.stack(recs) if recs else np.zeros(EQ_PR))
         desc.prod_w = fp("prod_w", np.stack(weights) if weights else np.zeros(A))
         desc.n_sets = len(set_indices)
+        desc.ev_data = fp("ev_data", np.stack(ev_data) if ev_data else np.zeros(8))
+        desc.prod_x = fp("prod_x", np.stack(xweights) if xweights else np.zeros(A))
         info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs)
         return desc, t, info
 
@@ -427,6 +464,86 @@ class EquityBackend:
         else:
             model.model_params = list(new)
 
+    def _state_columns(self):
+        """(state column, is log-spot) of every asset in the joint state vector of the path generator."""
+        cols, off = [], 0
+        for m in _sub_models(self.c.model):
+            if isinstance(m, BlackScholesModel):
+                cols.append((off, 0))
+            elif isinstance(m, BlackScholesMulti):
+                cols += [(off + a, 0) for a in range(m.num_assets)]
+            else:                       # Heston [logS, v], Schwartz [logS, x, y]
+                cols.append((off, 1))
+            off += m.state_dim
+        return cols
+
+    def presim_exercise(self, prod, dev):
+        """Longstaff-Schwartz pre-simulation of a Bermudan / American option on equity underlyings
+        (controller.py:294-383): pre-simulation paths from the path generator (seed 42), gathered
+        date-major by mcre_lsm_prepare_equity, then the shared backward induction (mcre/lsm.py)."""
+        from mcre import paths as P
+        from mcre.lsm import backward_induction, to_raw_basis
+        c = self.c
+        L = B.lib()
+        n_pre = c.num_paths_presim
+        if n_pre <= 0:
+            raise ValueError("Exercise products need a pre-simulation: num_paths_presim must be positive.")
+        ptl = prod.product_timeline.tolist()
+        reg_times = sorted(set(prod.regression_timeline.tolist()))
+        sim = c.simulation_timeline.tolist()
+        date_idx = {t: i for i, t in enumerate(sim)}
+        begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
+        n = max(count, 1)
+        inj = c.injected_normals.get("pre") if c.injected_normals else None
+        inj_u = getattr(c, "injected_uniforms", None)
+        inj_u = inj_u.get("pre") if inj_u else None
+        paths = P.generate(c.model, sim, n, c.num_steps, self.scheme, 42, inject_z=inj, inject_u=inj_u,
+                           stream_id=c.rng_stream, path_begin=begin, n_total=n_pre)
+        cols = self._state_columns()
+        xi = self._asset_index(prod.get_asset_id())
+        ui = self._asset_index(prod.underlying.get_asset_id())
+        t0 = self.num_model.t0()
+        n_reg, n_ex = len(reg_times), len(ptl)
+        buf = torch.empty((2 * n_reg + n_ex) * n, dtype=torch.float64, device=dev)
+        xs, nums, imm = buf[:n_reg * n].view(n_reg, n), buf[n_reg * n:2 * n_reg * n].view(n_reg, n), buf[2 * n_reg * n:].view(n_ex, n)
+        keep = []
+
+        def ip(a):
+            arr, ptr = B.as_ip(a)
+            keep.append(arr)
+            return ptr
+
+        def fp(a):
+            arr, ptr = B.as_dp(a)
+            keep.append(arr)
+            return ptr
+
+        L.mcre_lsm_prepare_equity.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, B.c_ip, B.c_dp, C.c_int32,
+                                              B.c_ip, C.c_int32, C.c_int32, C.c_int32, B.c_ip, B.c_dp, B.c_ip, C.c_double,
+                                              C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        sign = 1.0 if prod.option_type == OptionType.CALL else -1.0
+        B.check(L.mcre_lsm_prepare_equity(
+            paths.data_ptr(), count, len(sim), paths.shape[2], n_reg, ip([date_idx[t] for t in reg_times]),
+            fp([math.exp(self.num_rate * (t - t0)) for t in reg_times]), n_ex, ip([date_idx[t] for t in ptl]),
+            cols[xi][0], cols[xi][1], 1, ip([cols[ui][0]]), fp([1.0]), ip([cols[ui][1]]), float(prod.strike), sign,
+            xs.data_ptr(), nums.data_ptr(), imm.data_ptr(), RT.stream_ptr()))
+        del paths
+        # standardisation of the explanatory variable per date: sample mean / std over all ranks
+        live = xs[:, :count] if count else xs[:, :0]
+        mom = torch.stack([torch.full((n_reg,), float(count), dtype=torch.float64, device=dev), live.sum(1), (live * live).sum(1)])
+        mom = RT.all_reduce_tree(mom).cpu().numpy()
+        mean = mom[1] / np.maximum(mom[0], 1.0)
+        var = np.maximum(mom[2] / np.maximum(mom[0], 1.0) - mean * mean, 0.0)
+        std = np.sqrt(var)
+        basis = np.stack([mean, np.where(std > 1e-12 * np.maximum(np.abs(mean), 1.0), 1.0 / np.where(std > 0, std, 1.0), 1.0)], axis=1)
+        coef = backward_induction(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev)
+        ridx = {t: k for k, t in enumerate(reg_times)}
+        rows = [ridx[t] for t in ptl]
+        self.exercise_coef[id(prod)] = (coef[rows], basis[rows])
+        raw = to_raw_basis(coef, basis, [t <= t0 for t in reg_times])
+        for j, t in enumerate(prod.regression_timeline.tolist()):
+            prod.regression_coeffs[j, 1, :] = torch.tensor(raw[ridx[t]])
+
     def run(self):
         c = self.c
         dev = RT.compute_device()
@@ -435,12 +552,16 @@ class EquityBackend:
         n_sets = len(c.netting_sets)
         n_params = len(c.model.model_params)
         t0 = time.perf_counter()
+        for p in c.products:
+            if is_equity_exercise(p):
+                self.presim_exercise(p, dev)
+        t_pre = time.perf_counter() - t0
         results = [None] * n_sets
         group = EQ_MAX_SETS if self.nt == 0 else 2
         # launch groups: up to `group` netting sets and EQ_NTRK path-dependent products each
         groups, cur, cur_trk = [], [], 0
         for si, ns in enumerate(c.netting_sets):
-            trk = sum(isinstance(p, (AsianOption, BarrierOption)) for p in ns.products)
+            trk = sum(_is_path_dependent(p) for p in ns.products)
             if cur and (len(cur) >= group or cur_trk + trk > EQ_NTRK):
                 groups.append(cur)
                 cur, cur_trk = [], 0
@@ -482,5 +603,5 @@ class EquityBackend:
                     grad += self._control_variate_gradient(info["owners"], info["recs"], r, n_params)
                 results[si] = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
         torch.cuda.synchronize(dev)
-        timings = {"preprocessing": 0.0, "path_generation": time.perf_counter() - t0, "request_resolution": 0.0}
+        timings = {"preprocessing": t_pre, "path_generation": time.perf_counter() - t0 - t_pre, "request_resolution": 0.0}
         return results, timings

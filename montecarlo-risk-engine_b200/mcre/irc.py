@@ -20,6 +20,7 @@ from common.enums import SimulationScheme
 from mcre import binding as B
 from mcre import runtime as RT
 from mcre.dual import D, cholesky_dual
+from mcre.lsm import backward_induction, solve_normal_equations, to_raw_basis
 from mcre.timegrid import build_time_grid
 from metrics.metric import MetricType
 from models.cirpp import CIRPPModel
@@ -517,7 +518,6 @@ class IrcBackend:
         update) launch per regression date, latest first; the 3x3 normal equations are solved
         on the host (multi-GPU: after an all-reduce of the 8 moments).
         -> (coef per regression date [n_reg][3] in the standardised basis, reg_times, reg_basis)"""
-        from bisect import bisect_left
         c = self.c
         L = B.lib()
         n_pre = c.num_paths_presim
@@ -526,11 +526,9 @@ class IrcBackend:
         expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
         ptl = prod.product_timeline.tolist()
         reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
-        reg_idx = {t: k for k, t in enumerate(reg_times)}
         desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
         n_reg, n_ex = len(reg_times), info["n_ex"]
         basis = info["reg_basis"]
-        coef = np.zeros((n_reg, 3))
         inject = c.injected_normals.get("pre") if c.injected_normals else None
         plan = C.c_void_p()
         B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
@@ -545,43 +543,10 @@ class IrcBackend:
             L.mcre_irc_destroy(plan)
         xs = scratch[:n_reg * n].view(n_reg, n)
         ns_ = scratch[n_reg * n:2 * n_reg * n].view(n_reg, n)
-        imm = scratch[2 * n_reg * n:(2 * n_reg + n_ex) * n].view(n_ex, n)
-        value = torch.zeros(n, dtype=torch.float32, device=dev)
-        n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
-        partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
-        moments = torch.zeros(8, dtype=torch.float64, device=dev)
-
-        def step(k, i):
-            """moments of regression date k, after the exercise update at product date i (or None)."""
-            args_i = (None, None, None, None, 0.0, 1.0)
-            if i is not None:
-                ki = reg_idx[ptl[i]]
-                cptr = None
-                if i < len(ptl) - 1:
-                    self._coef_keep, cptr = B.as_dp(coef[ki])
-                args_i = (xs[ki].data_ptr(), ns_[ki].data_ptr(), imm[info["ex_index"][(0, i)]].data_ptr(), cptr,
-                          float(basis[ki, 0]), float(basis[ki, 1]))
-            B.check(L.mcre_lsm_step(xs[k].data_ptr(), ns_[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
-                                    *args_i, value.data_ptr(), count, CHUNK_PATHS, partial.data_ptr(),
-                                    moments.data_ptr(), RT.stream_ptr()))
-
-        last = len(ptl)
-        for k in range(n_reg - 1, -1, -1):
-            t_reg = reg_times[k]
-            pidx = bisect_left(ptl, t_reg)
-            if pidx >= len(ptl):
-                continue      # after the last exercise date: no continuation value (controller.py:303-305)
-            t_next = pidx + 1 if ptl[pidx] == t_reg else pidx
-            if t_next < last:
-                for i in range(last - 1, t_next, -1):   # product dates that are not regression dates
-                    step(k, i)
-                step(k, t_next)
-                last = t_next
-            else:
-                step(k, None)
-            m = RT.all_reduce_tree(moments).cpu().numpy()
-            G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
-            coef[k] = solve_normal_equations(G, m[5:8])
+        imm_all = scratch[2 * n_reg * n:(2 * n_reg + n_ex) * n].view(n_ex, n)
+        assert [info["ex_index"][(0, i)] for i in range(len(ptl))] == list(range(len(ptl)))  # one unit: date order
+        imm = imm_all
+        coef = backward_induction(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev)
         return coef, reg_times, basis
 
     def run(self):
@@ -691,46 +656,3 @@ class IrcBackend:
         timings["path_generation"] = time.perf_counter() - t1
         timings["request_resolution"] = 0.0
         return results, timings
-
-
-def solve_normal_equations(G, rhs):
-    """Minimum-norm least-squares solution of G c = rhs (G = Gram matrix of the basis).
-
-    The reference solves the tall system with LAPACK gelsy (controller.py:368-374), which
-    returns the minimum-norm solution for rank-deficient designs (at t = 0 every path has
-    the same explanatory value).  Same convention here via an SVD pseudo-inverse of the
-    symmetrically equilibrated Gram matrix."""
-    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
-    if not np.all(np.isfinite(G)) or d[0] == 0.0:
-        return np.zeros(3)
-    live = d > 0.0
-    scale = np.where(live, d, 1.0)
-    Gs = G / np.outer(scale, scale)
-    # min-norm must be taken in the *unscaled* coefficients to match gelsy; for the
-    # rank-deficient (constant regressor) case solve that directly.
-    u, s, vt = np.linalg.svd(Gs)
-    tol = 1e-10 * s[0]
-    rank = int(np.sum(s > tol))
-    if rank == 3:
-        return np.linalg.solve(Gs, rhs / scale) / scale
-    u2, s2, vt2 = np.linalg.svd(G)
-    keep = s2 > 1e-10 * s2[0]
-    return (vt2[keep].T * (1.0 / s2[keep])) @ (u2[:, keep].T @ rhs)
-
-
-def to_raw_basis(coefs, basis, degenerate=None):
-    """Coefficients of [1, u, u^2], u = (x - shift) * scale  ->  coefficients of [1, x, x^2].
-    `degenerate[k]`: every path has x = shift at date k (t = calibration date); the reference's
-    lstsq then returns the minimum-norm solution in the raw basis: c = f * phi / |phi|^2 with
-    phi = [1, x, x^2] and f the fitted constant."""
-    sh, sc = basis[:, 0], basis[:, 1]
-    c0, c1, c2 = coefs[:, 0], coefs[:, 1], coefs[:, 2]
-    out = np.empty_like(coefs)
-    out[:, 2] = c2 * sc * sc
-    out[:, 1] = c1 * sc - 2.0 * c2 * sc * sc * sh
-    out[:, 0] = c0 - c1 * sc * sh + c2 * sc * sc * sh * sh
-    if degenerate is not None:
-        for k in np.nonzero(np.asarray(degenerate))[0]:
-            phi = np.array([1.0, sh[k], sh[k] * sh[k]])
-            out[k] = coefs[k, 0] * phi / phi.dot(phi)
-    return out

@@ -1,0 +1,109 @@
+"""Longstaff-Schwartz backward induction driver shared by the model families.
+
+The family-specific forward pass spills, date-major on the device, the explanatory variable
+x[k][n] and numeraire N[k][n] per regression date k and the immediate exercise value imm[i][n]
+per exercise date i; this module runs the reference's regression schedule
+(src/controller/controller.py:294-383) over them with one fused `mcre_lsm_step` launch per
+regression date (exercise update of the product date entering the window + 8 moments), an
+all-reduce of the moments over the path-sharding ranks and a host solve of the 3x3 normal
+equations."""
+from __future__ import annotations
+
+from bisect import bisect_left
+
+import numpy as np
+import torch
+
+from mcre import binding as B
+from mcre import runtime as RT
+
+
+def solve_normal_equations(G, rhs):
+    """Minimum-norm least-squares solution of G c = rhs (G = Gram matrix of the basis).
+
+    The reference solves the tall system with LAPACK gelsy (controller.py:368-374), which
+    returns the minimum-norm solution for rank-deficient designs (at t = 0 every path has
+    the same explanatory value).  Same convention here via an SVD pseudo-inverse of the
+    symmetrically equilibrated Gram matrix."""
+    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
+    if not np.all(np.isfinite(G)) or d[0] == 0.0:
+        return np.zeros(3)
+    live = d > 0.0
+    scale = np.where(live, d, 1.0)
+    Gs = G / np.outer(scale, scale)
+    u, s, vt = np.linalg.svd(Gs)
+    tol = 1e-10 * s[0]
+    rank = int(np.sum(s > tol))
+    if rank == 3:
+        return np.linalg.solve(Gs, rhs / scale) / scale
+    # rank deficient (constant regressor): minimum norm in the unscaled coefficients, like gelsy
+    u2, s2, vt2 = np.linalg.svd(G)
+    keep = s2 > 1e-10 * s2[0]
+    return (vt2[keep].T * (1.0 / s2[keep])) @ (u2[:, keep].T @ rhs)
+
+
+def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev):
+    """xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product
+    (exercise) dates; reg_times: regression dates (sorted, contain every product date);
+    basis: [n_reg, 2] (shift, scale).  -> coefficients [n_reg, 3] in the standardised basis."""
+    L = B.lib()
+    n_reg = len(reg_times)
+    n = xs.shape[1]
+    reg_idx = {t: k for k, t in enumerate(reg_times)}
+    coef = np.zeros((n_reg, 3))
+    value = torch.zeros(n, dtype=torch.float32, device=dev)
+    n_chunks = (n + chunk_paths - 1) // chunk_paths
+    partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
+    moments = torch.zeros(8, dtype=torch.float64, device=dev)
+    keep = {}
+
+    def step(k, i):
+        """moments of regression date k, after the exercise update at product date i (or None)."""
+        args_i = (None, None, None, None, 0.0, 1.0)
+        if i is not None:
+            ki = reg_idx[ptl[i]]
+            cptr = None
+            if i < len(ptl) - 1:
+                keep["c"], cptr = B.as_dp(coef[ki])
+            args_i = (xs[ki].data_ptr(), nums[ki].data_ptr(), imm[i].data_ptr(), cptr,
+                      float(basis[ki, 0]), float(basis[ki, 1]))
+        B.check(L.mcre_lsm_step(xs[k].data_ptr(), nums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
+                                *args_i, value.data_ptr(), count, chunk_paths, partial.data_ptr(),
+                                moments.data_ptr(), RT.stream_ptr()))
+
+    last = len(ptl)
+    for k in range(n_reg - 1, -1, -1):
+        t_reg = reg_times[k]
+        pidx = bisect_left(ptl, t_reg)
+        if pidx >= len(ptl):
+            continue      # after the last exercise date: no continuation value (controller.py:303-305)
+        t_next = pidx + 1 if ptl[pidx] == t_reg else pidx
+        if t_next < last:
+            for i in range(last - 1, t_next, -1):   # product dates that are not regression dates
+                step(k, i)
+            step(k, t_next)
+            last = t_next
+        else:
+            step(k, None)
+        m = RT.all_reduce_tree(moments).cpu().numpy()
+        G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
+        coef[k] = solve_normal_equations(G, m[5:8])
+    return coef
+
+
+def to_raw_basis(coefs, basis, degenerate=None):
+    """Coefficients of [1, u, u^2], u = (x - shift) * scale  ->  coefficients of [1, x, x^2].
+    `degenerate[k]`: every path has x = shift at date k (t = calibration date); the reference's
+    lstsq then returns the minimum-norm solution in the raw basis: c = f * phi / |phi|^2 with
+    phi = [1, x, x^2] and f the fitted constant."""
+    sh, sc = basis[:, 0], basis[:, 1]
+    c0, c1, c2 = coefs[:, 0], coefs[:, 1], coefs[:, 2]
+    out = np.empty_like(coefs)
+    out[:, 2] = c2 * sc * sc
+    out[:, 1] = c1 * sc - 2.0 * c2 * sc * sc * sh
+    out[:, 0] = c0 - c1 * sc * sh + c2 * sc * sc * sh * sh
+    if degenerate is not None:
+        for k in np.nonzero(np.asarray(degenerate))[0]:
+            phi = np.array([1.0, sh[k], sh[k] * sh[k]])
+            out[k] = coefs[k, 0] * phi / phi.dot(phi)
+    return out

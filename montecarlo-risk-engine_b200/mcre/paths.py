@@ -115,8 +115,10 @@ def initial_state_values(model):
 
 
 def generate(model, timeline, n_paths, num_steps, scheme, seed, inject_z=None, inject_u=None,
-             grid=None, stream_id=0, init_state=None, identity_chol=False):
-    """-> torch.Tensor [n_paths, n_dates, state_dim] on the compute device."""
+             grid=None, stream_id=0, init_state=None, identity_chol=False, path_begin=0, n_total=None):
+    """-> torch.Tensor [n_paths, n_dates, state_dim] on the compute device.
+    `path_begin` / `n_total`: this process simulates global path ids [path_begin, path_begin + n_paths)
+    of `n_total` (path sharding; injected draws are indexed by global id)."""
     from models.cirpp import CIRPPModel
     from models.schwartz_two_factor import SchwartzTwoFactorModel
     from models.vasicek import VasicekModel
@@ -184,7 +186,7 @@ def generate(model, timeline, n_paths, num_steps, scheme, seed, inject_z=None, i
     d.step_aux = fp(aux)
     d.init_state = fp(initial_state_values(model) if init_state is None else init_state)
     rng = B.Rng()
-    rng.seed, rng.stream, rng.n_paths_total = seed, stream_id, n_paths
+    rng.seed, rng.stream, rng.n_paths_total = seed, stream_id, (n_paths if n_total is None else n_total)
     if inject_z is not None:
         z = torch.as_tensor(inject_z, dtype=torch.float64).to(dev).contiguous()
         keep.append(z)
@@ -196,6 +198,6 @@ def generate(model, timeline, n_paths, num_steps, scheme, seed, inject_z=None, i
     else:
         rng.mode = B.RNG_PHILOX
     out = torch.empty((n_paths, n_dates, state_dim), dtype=torch.float64, device=dev)
-    sh = B.Shard(0, n_paths, 256)
+    sh = B.Shard(path_begin, n_paths, 256)
     B.check(L.mcre_generate_paths(C.byref(d), C.byref(rng), C.byref(sh), out.data_ptr(), RT.stream_ptr()))
     return out

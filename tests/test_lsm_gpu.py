@@ -73,3 +73,61 @@ def test_bermudan_pv_only_and_mixed_book():
     out = risk.run(model, mixed, metrics, tl, n, n, 1, "EULER")
     _compare(helpers.flatten_results(res), helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names()),
              1e-8, "mixed book", err_rtol=1e-6)
+
+
+def _american(ns, n_ex=1000):
+    model = ns.BlackScholesModel(0.0, 100, 0.05, 0.5)
+    prod = ns.AmericanOption(ns.Equity("id"), 3.0, n_ex, 100.0, ns.OptionType.CALL)
+    return model, [ns.NettingSet(name=prod.get_name(), products=[prod])], [ns.PVMetric()]
+
+
+def test_american_option_reference_known_answer():
+    """The reference's own known-answer test (tests/pytests/test_american_option.py:17-61): American call
+    on Black-Scholes, 1000 exercise dates, 100k pre-simulation / 10k main paths, ANALYTICAL scheme,
+    PV = 34.323036543142706 within the reference's threshold 1e-8 - with the reference's torch.randn
+    stream injected, through the LSM kernels and the equity kernel's exercise events."""
+    from oracle import engine
+    ns = cases.Namespace()
+    model, sets, metrics = _american(ns)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), 10000, 100000, 1, ns.SimulationScheme.ANALYTICAL)
+    n_sub, dim = helpers.n_substeps(model, sets, None, metrics, 1)
+    assert (n_sub, dim) == (999, 1)
+    pre = engine.torch_reference_draws(42, 100000, n_sub, dim)
+    main = engine.torch_reference_draws(43, 10000, n_sub, dim)
+    sc.inject_normals(pre=pre.z, main=main.z)
+    res = sc.run_simulation()
+    pv = float(res.get_results(sets[0].get_name(), "pv")[0])
+    assert abs(pv - 34.323036543142706) < 1e-8, pv
+
+
+@pytest.mark.parametrize("which", ["bs_american", "heston_bermudan", "bs4_bermudan_greeks"])
+def test_equity_exercise_philox_matches_oracle(which):
+    from oracle import risk
+    ns = cases.Namespace()
+    S = ns.SimulationScheme
+    if which == "bs_american":
+        model, sets, metrics = _american(ns, n_ex=25)
+        scheme, steps, diff = S.EULER, 2, False
+    elif which == "heston_bermudan":
+        model = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+        put = ns.BermudanOption(ns.Equity(), [0.25, 0.5, 0.75, 1.0], 105.0, ns.OptionType.PUT)
+        sets, metrics = [ns.NettingSet(name="put", products=[put, ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)])], [ns.PVMetric()]
+        scheme, steps, diff = S.QE, 3, False
+    else:
+        ids = ["a", "b", "c", "d"]
+        models = [ns.BlackScholesModel(0.0, 100.0 + 5 * i, 0.02, 0.3 + 0.05 * i, asset_id=a) for i, a in enumerate(ids)]
+        model = ns.ModelConfig(models, inter_asset_correlation_matrix=np.array([[0.4] for _ in range(6)]))
+        put = ns.BermudanOption(ns.Equity("c"), [0.5, 1.0, 1.5], 110.0, ns.OptionType.PUT, asset_id="c")
+        sets, metrics = [ns.NettingSet(name="put_c", products=[put])], [ns.PVMetric()]
+        scheme, steps, diff = S.ANALYTICAL, 2, True
+    n = 5000
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), n, n, steps, scheme, diff)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, metrics, None, n, n, steps, scheme.name, differentiate=diff)
+    name = sets[0].get_name()
+    helpers.assert_close(res.get_results(name, "pv"), [out["results"][0][0][0][0]], 1e-8, 1e-10, which + " pv")
+    helpers.assert_close(res.get_mc_error(name, "pv"), [out["results"][0][0][0][1]], 1e-6, 1e-10, which + " err")
+    if diff:
+        want = out["grads"][0][0][0]
+        got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(name, "pv")[0]])
+        helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))), which + " greeks")

@@ -56,3 +56,20 @@ def test_reference_known_answer_uncorrelated_cva():
     cva, err = out["results"][0][0][0]
     assert abs(cva - 1.114576156484541) < 1e-11
     assert abs(err - 0.0024446898428056294) < 1e-12
+
+
+def test_reference_known_answer_american_option():
+    """The reference's other hard-coded constant (tests/pytests/test_american_option.py:61): American call
+    on Black-Scholes(100, r 5%, sigma 50%), 1000 exercise dates over 3y, 100k pre-simulation and 10k main
+    paths, ANALYTICAL scheme: PV = 34.323036543142706 (reference threshold 1e-8).  Pins the oracle's
+    Longstaff-Schwartz schedule (float32 cashflow roll, per-date lstsq, hard exercise indicator)."""
+    from oracle import engine, risk
+    ns = cases.Namespace()
+    model = ns.BlackScholesModel(0.0, 100, 0.05, 0.5)
+    prod = ns.AmericanOption(ns.Equity("id"), 3.0, 1000, 100.0, ns.OptionType.CALL)
+    sets, metrics = [ns.NettingSet(name=prod.get_name(), products=[prod])], [ns.PVMetric()]
+    n_sub, dim = helpers.n_substeps(model, sets, None, metrics, 1)
+    pre = engine.torch_reference_draws(42, 100000, n_sub, dim)
+    main = engine.torch_reference_draws(43, 10000, n_sub, dim)
+    out = risk.run(model, sets, metrics, None, 10000, 100000, 1, "ANALYTICAL", draws_pre=pre, draws_main=main)
+    assert abs(out["results"][0][0][0][0] - 34.323036543142706) < 1e-8
