@@ -304,6 +304,17 @@ typedef struct {
    * prod_x [n_prod][n_assets]: weights picking the explanatory variable x (spot of the option's asset). */
   const double *ev_data;
   const double *prod_x;
+  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op,
+   * 4 doubles: type (0 none, 1 analytic Black-Scholes value of a European option, european_option.py:123-145),
+   * time to maturity, 1/numeraire(t), pad.  Netting-set terms as in mcre_irc_desc.  acc_flags: MCRE_ACC_POS /
+   * NEG / SPILL.  Adds [n_metric][NS][4] = sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2) to the slots. */
+  int32_t n_expo, n_metric, acc_flags;
+  const int32_t *date_expo;     /* [n_dates] internal exposure index or -1 */
+  const int32_t *date_metric;   /* [n_dates] metric-date index or -1       */
+  const double *xp;             /* [n_expo][n_prod][4]                     */
+  const double *set_threshold;  /* [n_sets]                                */
+  const int32_t *set_flags;     /* [n_sets] bit0 collateralised            */
+  const int32_t *set_lag;       /* [n_sets][n_metric] exposure-index lag of the collateral date, -1: none */
 } mcre_eq_desc;
 
 typedef struct mcre_eq_plan mcre_eq_plan;
@@ -315,7 +326,8 @@ void mcre_eq_destroy(mcre_eq_plan *plan);
  * with c = d_shift[set] = the value on global path 0 (pilot launch). */
 int64_t mcre_eq_slots(const mcre_eq_plan *plan);
 int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
-                    double *d_acc, double *d_shift, void *stream);
+                    double *d_acc, double *d_shift, double *d_spill /* [n_sets][n_metric][n_paths] or NULL */,
+                    void *stream);
 
 /* ================================================================================
  * Longstaff-Schwartz backward induction on spilled pre-simulation arrays: one call per

@@ -40,7 +40,14 @@ struct EqDev {
   int n_prod; const double *prod, *prod_w;
   int n_sets;
   const double *ev_data, *prod_x;   // exercise products (Bermudan / American)
+  // exposure profiles (analytic Black-Scholes exposure of European options, european_option.py:123-145)
+  int n_expo, n_metric, acc_flags;
+  const int *date_expo, *date_metric;
+  const double *xp;                  // [n_expo][n_prod][4]: type (0 none, 1 analytic BS), time to maturity, 1/numeraire(t), pad
+  const double *set_threshold; const int *set_flags, *set_lag;
 };
+constexpr int EQ_XP = 4;
+constexpr int EQ_MAX_LAG = 4;
 
 enum { EQ_EUROPEAN = MCRE_EQ_EUROPEAN, EQ_BINARY = MCRE_EQ_BINARY, EQ_BASKET = MCRE_EQ_BASKET, EQ_ASIAN = MCRE_EQ_ASIAN,
        EQ_BARRIER = MCRE_EQ_BARRIER, EQ_EXERCISE = MCRE_EQ_EXERCISE };
@@ -82,7 +89,7 @@ __device__ __forceinline__ R barrier_factor(const R &mx, const R &mn, double bar
 //              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p
 template <int KIND, int ALT, int NT, int NS>
 __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
-                                                      double *shift, int pilot) {
+                                                      double *shift, double *spill, int pilot) {
   typedef typename RealOf<NT>::type R;
   typedef RealTraits<R> T;
   typedef RealVar<R> V;
@@ -90,11 +97,13 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
   constexpr int NP = EqParCount<KIND>::n;
   constexpr int NVH = NS * 3;
   constexpr int NVT = NS * (NT > 0 ? NT : 1);
-  constexpr int NVMAX = NVH > NVT ? NVH : NVT;
+  constexpr int NVX = NS * 4;                 // exposure values per metric date
+  constexpr int NVMAX = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
   extern __shared__ double smem[];
   const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int A = P.n_assets, ppw = 32 / A;
-  const int n_slots = NS * 3 + A * NS * NT;
+  const int expo_base = NS * 3 + A * NS * NT;
+  const int n_slots = expo_base + P.n_metric * NVX;
   double *acc = smem;                 // [n_slots]
   double *stage = smem + n_slots;     // [2][nw][NVMAX]
   const int g = lane / A, a = lane - g * A, base = g * A;
@@ -129,7 +138,11 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
       else { s0 = T::zero(); s1 = T::zero(); }
       double logF = KIND == MCRE_EQ_SCHWARTZ ? __ldg(P.init_aux + aa) : 0.0;
       R cf[NS], trk_a[EQ_NTRK], trk_b[EQ_NTRK];
-      double numtan[NS];
+      double numtan[NS], hist[NS][EQ_MAX_LAG];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int l = 0; l < EQ_MAX_LAG; ++l) hist[s][l] = 0.0;
 #pragma unroll
       for (int s = 0; s < NS; ++s) { cf[s] = T::zero(); numtan[s] = 0.0; }
 #pragma unroll
@@ -142,6 +155,76 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
       };
 
       // ---- product events of one simulation date --------------------------------------
+      // exposure of the date (after its cashflows, controller.py:417-447), netting, collateral, metrics
+      auto eval_exposure = [&](int di) {
+        if (P.n_expo == 0) return;
+        const int xe = __ldg(P.date_expo + di), m = __ldg(P.date_metric + di);
+        if (xe >= 0) {
+          const double Sv = val(spot_now());
+          double expo[NS];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) expo[s] = 0.0;
+          for (int pi = 0; pi < P.n_prod; ++pi) {
+            const double *op = P.xp + ((size_t)xe * P.n_prod + pi) * EQ_XP;
+            if (__ldg(op) == 0.0) continue;
+            const double *pr = P.prod + (size_t)pi * EQ_PR;
+            const double wgt = __ldg(P.prod_w + (size_t)pi * A + aa);
+            double v = 0.0;
+            if (wgt != 0.0) {
+              // Black-Scholes value of the remaining option at (S_t, T - t), over the numeraire
+              // (european_option.py:70-100, 123-145); evaluated on the lane that owns the asset
+              const double ttm = __ldg(op + 1), K = __ldg(pr + 2), sign = __ldg(pr + 3);
+              const double sigma = val(par[1]), rate = val(par[2]);
+              const double vol_t = sigma * sqrt(ttm);
+              const double d1 = (log(Sv / K) + (rate + 0.5 * sigma * sigma) * ttm) / vol_t, d2 = d1 - vol_t;
+              const double disc = K * exp(-rate * ttm);
+              const double price = sign > 0.0 ? Sv * 0.5 * erfc(-d1 * 0.70710678118654752440) - disc * 0.5 * erfc(-d2 * 0.70710678118654752440)
+                                              : disc * 0.5 * erfc(d2 * 0.70710678118654752440) - Sv * 0.5 * erfc(d1 * 0.70710678118654752440);
+              v = wgt * price * __ldg(op + 2);
+            }
+            const double tot = group_sum(v, base, A);
+            const int set = (int)__ldg(pr + 1);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) if (s == set) expo[s] += tot;
+          }
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+#pragma unroll
+            for (int l = EQ_MAX_LAG - 1; l > 0; --l) hist[s][l] = hist[s][l - 1];
+            hist[s][0] = expo[s];
+          }
+        }
+        if (m >= 0) {
+          double vals[NVX];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            const bool coll = s < P.n_sets && (__ldg(P.set_flags + s) & 1);
+            const double h = s < P.n_sets ? __ldg(P.set_threshold + s) : 0.0;
+            const int lag = coll ? __ldg(P.set_lag + (size_t)s * P.n_metric + m) : -1;
+            auto thr = [h](double x) { return x > h ? x - h : (x < -h ? x + h : 0.0); };   // netting_set.py:48-72
+            double unsec;
+            if (coll) {
+              double delayed = 0.0;
+#pragma unroll
+              for (int l = 0; l < EQ_MAX_LAG; ++l) if (l == lag) delayed = hist[s][l];
+              unsec = hist[s][0] - thr(delayed);
+            } else {
+              unsec = thr(hist[s][0]);
+            }
+            const double pos = fmax(unsec, 0.0), neg = -fmax(-unsec, 0.0);
+            const int sb = expo_base + m * NVX + s * 4;
+            if (pilot) { if (threadIdx.x == 0) { shift[sb + 0] = pos; shift[sb + 2] = neg; } }
+            const double dp = pos - (pilot ? 0.0 : shift[sb + 0]), dn = neg - (pilot ? 0.0 : shift[sb + 2]);
+            const double keep = (live && a == 0) ? 1.0 : 0.0;
+            vals[s * 4 + 0] = keep * dp; vals[s * 4 + 1] = keep * dp * dp;
+            vals[s * 4 + 2] = keep * dn; vals[s * 4 + 3] = keep * dn * dn;
+            if ((P.acc_flags & MCRE_ACC_SPILL) && live && a == 0 && s < P.n_sets && !pilot)
+              spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath] = unsec;
+          }
+          if (!pilot) block_accumulate<NVX>(vals, acc, expo_base + m * NVX, stage, NVMAX, parity);
+        }
+      };
+
       auto eval_date = [&](int di) {
         const int e0 = __ldg(P.date_ev_off + di), e1 = __ldg(P.date_ev_off + di + 1);
         if (e0 == e1) return;
@@ -234,7 +317,7 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
         }
       };
 
-      for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+      for (int di = 0; di < P.n_pre_dates; ++di) { eval_date(di); eval_exposure(di); }
       for (int is = 0; is < P.n_sub; ++is) {
         const double dt = __ldg(P.step_dt + is), sq = __ldg(P.step_sq + is);
         // ---- independent draws of this lane's noise columns -----------------------------
@@ -294,7 +377,7 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
           logF = __ldg(P.step_aux + (size_t)is * A + aa);
         }
         const int di = __ldg(P.step_date + is);
-        if (di >= 0) eval_date(di);
+        if (di >= 0) { eval_date(di); eval_exposure(di); }
       }
 
       // ---- per-path totals -> block accumulators -------------------------------------------
@@ -340,6 +423,8 @@ struct mcre_eq_plan {
   int nt = 0;
   DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w, ev_data, prod_x;
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
+  DevArray<int> date_expo, date_metric, set_flags, set_lag;
+  DevArray<double> xp, set_threshold;
 };
 
 extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
@@ -350,6 +435,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (np < 0) return fail(-1, "eq: unknown model kind%s", "");
   if (c->nt != 0 && c->nt != np) return fail(-1, "eq: nt must be 0 or the model's parameter count%s", "");
   if (c->nt != 0 && c->n_sets > 2) return fail(-3, "eq: at most 2 netting sets per launch when tangents are on%s", "");
+  if (c->nt != 0 && c->n_expo > 0) return fail(-4, "eq: sensitivities of exposure profiles are not implemented%s", "");
   if (c->corr_mode == 1 && (c->n_assets != 1 || c->noise_dim != 2))
     return fail(-1, "eq: dual Cholesky needs one asset with two noise sources%s", "");
   const bool scheme_ok = (c->kind == MCRE_EQ_HESTON) ? (c->scheme == MCRE_SCHEME_EULER || c->scheme == MCRE_SCHEME_QE)
@@ -378,6 +464,12 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   UP(date_ev_off, c->date_ev_off, c->n_dates + 1); UP(ev_prod, c->ev_prod, n_ev); UP(ev_flags, c->ev_flags, n_ev);
   UP(prod, c->prod, (size_t)c->n_prod * EQ_PR); UP(prod_w, c->prod_w, (size_t)c->n_prod * A);
   UP(ev_data, c->ev_data, c->ev_data ? (size_t)n_ev * 8 : 0); UP(prod_x, c->prod_x, c->prod_x ? (size_t)c->n_prod * A : 0);
+  if (c->n_expo > 0) {
+    UP(date_expo, c->date_expo, c->n_dates); UP(date_metric, c->date_metric, c->n_dates);
+    UP(xp, c->xp, (size_t)c->n_expo * c->n_prod * EQ_XP);
+    UP(set_threshold, c->set_threshold, c->n_sets); UP(set_flags, c->set_flags, c->n_sets);
+    UP(set_lag, c->set_lag, (size_t)c->n_sets * c->n_metric);
+  }
 #undef UP
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
@@ -392,6 +484,9 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   D.date_ev_off = p->date_ev_off.p; D.ev_prod = p->ev_prod.p; D.ev_flags = p->ev_flags.p;
   D.n_prod = c->n_prod; D.prod = p->prod.p; D.prod_w = p->prod_w.p; D.n_sets = c->n_sets;
   D.ev_data = p->ev_data.p; D.prod_x = p->prod_x.p;
+  D.n_expo = c->n_expo; D.n_metric = c->n_expo > 0 ? c->n_metric : 0; D.acc_flags = c->acc_flags;
+  D.date_expo = p->date_expo.p; D.date_metric = p->date_metric.p; D.xp = p->xp.p;
+  D.set_threshold = p->set_threshold.p; D.set_flags = p->set_flags.p; D.set_lag = p->set_lag.p;
   *out = p;
   return 0;
 }
@@ -403,6 +498,8 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->asset_uniform.release(); p->col_asset.release(); p->col_elem.release(); p->step_date.release();
   p->step_chol.release(); p->date_ev_off.release(); p->ev_prod.release(); p->ev_flags.release();
   p->ev_data.release(); p->prod_x.release();
+  p->date_expo.release(); p->date_metric.release(); p->set_flags.release(); p->set_lag.release();
+  p->xp.release(); p->set_threshold.release();
   delete p;
 }
 
@@ -410,16 +507,17 @@ static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 
 
 extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
   const int ns = eq_ns_template(p->d.n_sets);
-  return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt;
+  return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4;
 }
 
 template <int KIND, int ALT, int NT, int NS>
 static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
-                     cudaStream_t st) {
+                     double *spill, cudaStream_t st) {
   const EqDev &d = p->d;
   const int threads = 128, nw = threads / 32;
-  constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVMAX = NVH > NVT ? NVH : NVT;
-  const int n_slots = NS * 3 + d.n_assets * NS * NT;
+  constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVX = NS * 4;
+  constexpr int NVMAX = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
+  const int n_slots = NS * 3 + d.n_assets * NS * NT + d.n_metric * NVX;
   const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0) return 0;
@@ -430,32 +528,34 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   long long grid = (long long)sm_count() * per_sm;
   if (grid > n_chunks) grid = n_chunks;
   ShardDev pilot_sh{0, 1, sh.chunk};
-  k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, 1);
+  if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, spill, 1);
   MCRE_LAUNCHED();
-  k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, shift, 0);
+  k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, shift, spill, 0);
   MCRE_LAUNCHED();
   return 0;
 }
 
 template <int KIND, int ALT, int NTK>
 static int eq_dispatch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
-                       cudaStream_t st) {
+                       double *spill, cudaStream_t st) {
   const int ns = eq_ns_template(p->d.n_sets);
   if (p->nt == 0) {
-    return ns == 1 ? eq_launch<KIND, ALT, 0, 1>(p, rng, sh, partial, shift, st)
-         : ns == 2 ? eq_launch<KIND, ALT, 0, 2>(p, rng, sh, partial, shift, st)
-                   : eq_launch<KIND, ALT, 0, 4>(p, rng, sh, partial, shift, st);
+    return ns == 1 ? eq_launch<KIND, ALT, 0, 1>(p, rng, sh, partial, shift, spill, st)
+         : ns == 2 ? eq_launch<KIND, ALT, 0, 2>(p, rng, sh, partial, shift, spill, st)
+                   : eq_launch<KIND, ALT, 0, 4>(p, rng, sh, partial, shift, spill, st);
   }
-  return ns == 1 ? eq_launch<KIND, ALT, NTK, 1>(p, rng, sh, partial, shift, st)
-                 : eq_launch<KIND, ALT, NTK, 2>(p, rng, sh, partial, shift, st);
+  return ns == 1 ? eq_launch<KIND, ALT, NTK, 1>(p, rng, sh, partial, shift, spill, st)
+                 : eq_launch<KIND, ALT, NTK, 2>(p, rng, sh, partial, shift, spill, st);
 }
 
 extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
-                               double *d_acc, double *d_shift, void *stream) {
+                               double *d_acc, double *d_shift, double *d_spill, void *stream) {
   if (!p || !rng || !d_partial || !d_acc || !d_shift) return fail(-1, "null argument%s", "");
   int rc = check_shard(shard);
   if (rc) return rc;
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
+  if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill) return fail(-1, "spill requested but d_spill is null%s", "");
   if (rng->mode == MCRE_RNG_INJECT && p->d.kind == MCRE_EQ_HESTON && p->d.scheme == MCRE_SCHEME_QE && !rng->d_u)
     return fail(-1, "inject mode: QE needs uniforms%s", "");
   RngDev r = make_rng(rng);
@@ -464,16 +564,16 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   const int alt = (p->d.scheme == MCRE_SCHEME_EULER) ? 0 : 1;
   switch (p->d.kind) {
     case MCRE_EQ_BS:
-      rc = alt ? eq_dispatch<MCRE_EQ_BS, 1, 3>(p, r, sh, d_partial, d_shift, st)
-               : eq_dispatch<MCRE_EQ_BS, 0, 3>(p, r, sh, d_partial, d_shift, st);
+      rc = alt ? eq_dispatch<MCRE_EQ_BS, 1, 3>(p, r, sh, d_partial, d_shift, d_spill, st)
+               : eq_dispatch<MCRE_EQ_BS, 0, 3>(p, r, sh, d_partial, d_shift, d_spill, st);
       break;
     case MCRE_EQ_HESTON:
-      rc = alt ? eq_dispatch<MCRE_EQ_HESTON, 1, 7>(p, r, sh, d_partial, d_shift, st)
-               : eq_dispatch<MCRE_EQ_HESTON, 0, 7>(p, r, sh, d_partial, d_shift, st);
+      rc = alt ? eq_dispatch<MCRE_EQ_HESTON, 1, 7>(p, r, sh, d_partial, d_shift, d_spill, st)
+               : eq_dispatch<MCRE_EQ_HESTON, 0, 7>(p, r, sh, d_partial, d_shift, d_spill, st);
       break;
     default:
-      rc = alt ? eq_dispatch<MCRE_EQ_SCHWARTZ, 1, 6>(p, r, sh, d_partial, d_shift, st)
-               : eq_dispatch<MCRE_EQ_SCHWARTZ, 0, 6>(p, r, sh, d_partial, d_shift, st);
+      rc = alt ? eq_dispatch<MCRE_EQ_SCHWARTZ, 1, 6>(p, r, sh, d_partial, d_shift, d_spill, st)
+               : eq_dispatch<MCRE_EQ_SCHWARTZ, 0, 6>(p, r, sh, d_partial, d_shift, d_spill, st);
   }
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;

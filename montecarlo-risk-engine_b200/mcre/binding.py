@@ -114,7 +114,7 @@ def lib():
     L.mcre_eq_slots.argtypes = [C.c_void_p]
     L.mcre_eq_slots.restype = C.c_int64
     L.mcre_eq_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_tree_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
     L.mcre_fastmath_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

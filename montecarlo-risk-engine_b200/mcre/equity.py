@@ -43,7 +43,7 @@ CHUNK_PATHS = 4096
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
 P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
 EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
-EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS = 16, 8, 2, 4
+EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS, EQ_XP, EQ_MAX_LAG = 16, 8, 2, 4, 4, 4
 _NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
 _BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
                  BarrierOptionType.UPANDIN: 3, BarrierOptionType.DOWNANDIN: 4}
@@ -62,6 +62,9 @@ class EqDesc(C.Structure):
         ("date_ev_off", B.c_ip), ("ev_prod", B.c_ip), ("ev_flags", B.c_ip),
         ("n_prod", C.c_int32), ("prod", B.c_dp), ("prod_w", B.c_dp), ("n_sets", C.c_int32),
         ("ev_data", B.c_dp), ("prod_x", B.c_dp),
+        ("n_expo", C.c_int32), ("n_metric", C.c_int32), ("acc_flags", C.c_int32),
+        ("date_expo", B.c_ip), ("date_metric", B.c_ip), ("xp", B.c_dp),
+        ("set_threshold", B.c_dp), ("set_flags", B.c_ip), ("set_lag", B.c_ip),
     ]
 
 
@@ -131,9 +134,13 @@ class EquityBackend:
     def supports(ctrl):
         if family_of(ctrl.model) is None:
             return False
-        if any(m.metric_type != MetricType.PV for m in ctrl.risk_metrics.metrics):
+        if not all(_is_equity_product(p) for p in ctrl.products):
             return False
-        return all(_is_equity_product(p) for p in ctrl.products)
+        if ctrl.risk_metrics.requires_exposure_profiles():
+            # exposure profiles: the analytic Black-Scholes exposure of European options
+            # (the reference's own no-regression branch, controller.py:204-229)
+            return all(ctrl._can_use_analytic_exposure_for_product(p) for p in ctrl.products)
+        return True
 
     def __init__(self, ctrl):
         self.c = ctrl
@@ -409,7 +416,54 @@ class EquityBackend:
         desc.n_sets = len(set_indices)
         desc.ev_data = fp("ev_data", np.stack(ev_data) if ev_data else np.zeros(8))
         desc.prod_x = fp("prod_x", np.stack(xweights) if xweights else np.zeros(A))
-        info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs)
+
+        # ---- exposure profiles ---------------------------------------------------------------
+        n_expo = n_metric = acc = 0
+        if c.risk_metrics.requires_exposure_profiles():
+            if nt:
+                raise NotImplementedError("sensitivities of exposure profiles are not implemented for equity books")
+            expo_times, metric_times = c.exposure_timeline.tolist(), c.metric_exposure_timeline.tolist()
+            n_expo, n_metric = len(expo_times), len(metric_times)
+            date_expo = np.full(n_dates, -1, dtype=np.int32)
+            date_metric = np.full(n_dates, -1, dtype=np.int32)
+            for e, te in enumerate(expo_times):
+                date_expo[date_idx[te]] = e
+            for m, tm in enumerate(metric_times):
+                date_metric[date_idx[tm]] = m
+            xp = np.zeros((n_expo, max(len(recs), 1), EQ_XP))
+            for e, te in enumerate(expo_times):
+                inv = self._inv_numeraire(te)[0]
+                for pi, p in enumerate(owners):
+                    ttm = float(p.exercise_date) - te
+                    if ttm > 0.0:                       # matured options carry no exposure (european_option.py:129-131)
+                        xp[e, pi] = (1.0, ttm, inv, 0.0)
+            kinds = {m.metric_type for m in c.risk_metrics.metrics}
+            if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
+                acc |= B.ACC_POS
+            if MetricType.ENE in kinds:
+                acc |= B.ACC_NEG
+            if MetricType.PFE in kinds:
+                acc |= B.ACC_SPILL
+            sets = [c.netting_sets[i] for i in set_indices]
+            set_flags = np.zeros(len(sets), dtype=np.int32)
+            set_lag = np.full((len(sets), n_metric), -1, dtype=np.int32)
+            for r, (si, ns) in enumerate(zip(set_indices, sets)):
+                if ns.is_collateralized():
+                    set_flags[r] |= 1
+                    delayed = c.netting_set_delayed_exposure_indices[si].tolist()
+                    for m in range(n_metric):
+                        if delayed[m] >= 0:
+                            lag = int(c.metric_exposure_indices[m]) - delayed[m]
+                            if lag >= EQ_MAX_LAG:
+                                raise NotImplementedError(
+                                    f"MPoR look-back spans {lag} exposure dates; the fused kernel keeps {EQ_MAX_LAG - 1}")
+                            set_lag[r, m] = lag
+            desc.date_expo, desc.date_metric = ip("date_expo", date_expo), ip("date_metric", date_metric)
+            desc.xp = fp("xp", xp)
+            desc.set_threshold = fp("set_thr", np.array([ns.threshold for ns in sets], dtype=np.float64))
+            desc.set_flags, desc.set_lag = ip("set_flags", set_flags), ip("set_lag", set_lag)
+        desc.n_expo, desc.n_metric, desc.acc_flags = n_expo, n_metric, acc
+        info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs, n_metric=n_metric, acc=acc)
         return desc, t, info
 
     # ------------------------------------------------------------------ execution
@@ -582,15 +636,27 @@ class EquityBackend:
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 rng = self._rng(43, n_main)
                 sh = B.Shard(begin, count, CHUNK_PATHS)
+                n_metric = info["n_metric"]
+                spill = None
+                if info["acc"] & B.ACC_SPILL:
+                    spill = torch.empty((len(idxs), n_metric, max(count, 1)), dtype=torch.float64, device=dev)
                 B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
-                                          shift.data_ptr(), RT.stream_ptr()))
+                                          shift.data_ptr(), spill.data_ptr() if spill is not None else None,
+                                          RT.stream_ptr()))
                 acc = RT.all_reduce_tree(acc)
                 acc_h, shift_h = acc.cpu().numpy(), shift.cpu().numpy()
+                quant = None
+                if spill is not None:
+                    from mcre.select import order_statistics
+                    quant = order_statistics(c, spill, count, n_main)
             finally:
                 L.mcre_eq_destroy(plan)
             ns_t = 1 if len(idxs) <= 1 else (2 if len(idxs) <= 2 else 4)
             head = acc_h[:ns_t * 3].reshape(ns_t, 3)
-            tang = acc_h[ns_t * 3:].reshape(self.A, ns_t, self.nt) if self.nt else None
+            expo_base = ns_t * 3 + self.A * ns_t * self.nt
+            tang = acc_h[ns_t * 3:expo_base].reshape(self.A, ns_t, self.nt) if self.nt else None
+            xacc = acc_h[expo_base:].reshape(n_metric, ns_t, 4)
+            xshift = shift_h[expo_base:].reshape(n_metric, ns_t, 4)
             for r, si in enumerate(idxs):
                 pv = mean_and_error(head[r, 0], head[r, 1], shift_h[r], n_main)
                 grad = None
@@ -601,7 +667,16 @@ class EquityBackend:
                             grad[g] += tang[a, r, k] / n_main
                     grad[self.num_rate_global] += head[r, 2] / n_main
                     grad += self._control_variate_gradient(info["owners"], info["recs"], r, n_params)
-                results[si] = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+                res = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+                if info["acc"] & B.ACC_POS:
+                    res["pos"] = ([mean_and_error(xacc[m, r, 0], xacc[m, r, 1], xshift[m, r, 0], n_main) for m in range(n_metric)],
+                                  [None] * n_metric)
+                if info["acc"] & B.ACC_NEG:
+                    res["neg"] = ([mean_and_error(xacc[m, r, 2], xacc[m, r, 3], xshift[m, r, 2], n_main) for m in range(n_metric)],
+                                  [None] * n_metric)
+                if quant is not None:
+                    res["pfe"] = quant[r]
+                results[si] = res
         torch.cuda.synchronize(dev)
         timings = {"preprocessing": t_pre, "path_generation": time.perf_counter() - t0 - t_pre, "request_resolution": 0.0}
         return results, timings

@@ -143,6 +143,7 @@ class Namespace:
         from models.black_scholes_multi import BlackScholesMulti
         from models.cirpp import CIRPPModel
         from models.heston import HestonModel
+        from models.hull_white import HullWhiteModel
         from models.model_config import ModelConfig
         from models.vasicek import VasicekModel
         from products.asian_option import AsianAveragingType, AsianOption

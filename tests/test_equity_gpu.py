@@ -164,3 +164,38 @@ def test_heston_basket_extension_matches_oracle():
                 got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, "pv")[0]])
                 assert got.shape == (35,)
                 helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))), f"basket5 {s} greeks")
+
+
+def test_bs_european_analytic_exposure_profiles_match_oracle():
+    """EPE / PFE profiles of European options under Black-Scholes use the analytic exposure
+    BS(S_t, T - t) / N(t) and need no regression (european_option.py:123-145, controller.py:204-229;
+    the reference's tests/pytests/test_netting_sets.py:101-165): CUDA vs oracle on the same Philox stream,
+    with a threshold and an MPoR-collateralised netting set, and the martingale property the
+    reference itself tests (discounted EPE = initial PV before maturity)."""
+    from oracle import risk
+    ns = cases.Namespace()
+    bsm = ns.BlackScholesMulti(0.0, 0.03, ["eq1", "eq2"], [100.0, 110.0], [0.2, 0.25], np.array([[1.0, 0.2], [0.2, 1.0]]))
+    call = lambda a, T, K: ns.EuropeanOption(ns.Equity(a), T, K, ns.OptionType.CALL, asset_id=a)
+    put = lambda a, T, K: ns.EuropeanOption(ns.Equity(a), T, K, ns.OptionType.PUT, asset_id=a)
+    sets = [ns.NettingSet(name="call", products=[call("eq1", 1.0, 100.0)]),
+            ns.NettingSet(name="book", products=[call("eq2", 0.75, 105.0), put("eq1", 1.0, 95.0)], threshold=2.0),
+            ns.NettingSet(name="collateralised", products=[call("eq1", 1.0, 100.0), put("eq2", 0.5, 110.0)], margin_period_of_risk=0.25)]
+    metrics = [ns.EPEMetric(), ns.PFEMetric(0.95), ns.PVMetric()]
+    tl = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    n = 6000
+    for scheme, steps in ((ns.SimulationScheme.ANALYTICAL, 1), (ns.SimulationScheme.EULER, 3)):
+        sc = ns.SimulationController(sets, bsm, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, steps, scheme)
+        assert sc.requires_regression is False and sc._product_requires_regression(sets[0].products[0]) is False
+        res = sc.run_simulation()
+        out = risk.run(bsm, sets, metrics, tl, n, n, steps, scheme.name)
+        got, want = helpers.flatten_results(res), helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names())
+        for key in got:
+            helpers.assert_close(got[key][0], want[key][0], 1e-8, 1e-9, f"{scheme.name} {key} value")
+            helpers.assert_close(got[key][1], want[key][1], 1e-6, 1e-9, f"{scheme.name} {key} mc error")
+    # martingale: the discounted expected exposure of the single call equals its PV at every date before maturity
+    big = ns.SimulationController(sets[:1], bsm, ns.RiskMetrics(metrics, exposure_timeline=tl), 1 << 20, 0, 1,
+                                  ns.SimulationScheme.ANALYTICAL).run_simulation()
+    pv = float(sets[0].products[0].compute_pv_analytically(bsm).reshape(-1)[0])
+    epe, err = np.array(big.get_results("call", "epe")), np.array(big.get_mc_error("call", "epe"))
+    assert abs(epe[0] - pv) < 1e-10 and err[0] == 0.0
+    assert np.all(np.abs(epe[1:4] - pv) <= 4.0 * err[1:4]) and epe[4] == 0.0
