@@ -47,6 +47,13 @@ __device__ __forceinline__ double r_exp_small(double x) { return fm_exp_small(x)
 __device__ __forceinline__ double r_sqrt_pos(double x) { return MCRE_SQRT(x); }
 __device__ __forceinline__ double r_exp_small(double x) { return MCRE_EXP(x); }
 #endif
+#ifdef MCRE_FAST_MATH
+#define MCRE_RCP(x) fm_div(1.0, (x))
+__device__ __forceinline__ double r_div(double a, double b) { return fm_div(a, b); }
+#else
+#define MCRE_RCP(x) (1.0 / (x))
+__device__ __forceinline__ double r_div(double a, double b) { return a / b; }
+#endif
 __device__ __forceinline__ double r_relu(double x) { return fmax(x, 0.0); }
 __device__ __forceinline__ double r_max(double x, double c) { return fmax(x, c); }
 __device__ __forceinline__ double r_mask(double x, bool keep) { return keep ? x : 0.0; }
@@ -87,11 +94,13 @@ template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, 
   return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N> &a, const Dual<N> &b) {
-  Dual<N> r; double inv = 1.0 / b.v; r.v = a.v * inv;
+  Dual<N> r; double inv = MCRE_RCP(b.v); r.v = a.v * inv;
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
   return r;
 }
+template <int N> __device__ __forceinline__ Dual<N> r_div(const Dual<N> &a, const Dual<N> &b) { return a / b; }
+template <int N> __device__ __forceinline__ Dual<N> r_div(const Dual<N> &a, double b) { return a * MCRE_RCP(b); }
 template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, double b) { Dual<N> r = a; r.v += b; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator+(double b, const Dual<N> &a) { Dual<N> r = a; r.v += b; return r; }
 template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N> &a, double b) { Dual<N> r = a; r.v -= b; return r; }
@@ -105,11 +114,12 @@ template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N> &a, 
 template <int N> __device__ __forceinline__ Dual<N> operator*(double b, const Dual<N> &a) { return a * b; }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N> &a, double b) { return a * (1.0 / b); }
 template <int N> __device__ __forceinline__ Dual<N> operator/(double a, const Dual<N> &b) {
-  Dual<N> r; double inv = 1.0 / b.v; r.v = a * inv; double s = -r.v * inv;
+  Dual<N> r; double inv = MCRE_RCP(b.v); r.v = a * inv; double s = -r.v * inv;
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = s * b.d[i];
   return r;
 }
+template <int N> __device__ __forceinline__ Dual<N> r_div(double a, const Dual<N> &b) { return a / b; }
 template <int N> __device__ __forceinline__ Dual<N> &operator+=(Dual<N> &a, const Dual<N> &b) { a = a + b; return a; }
 template <int N> __device__ __forceinline__ Dual<N> &operator+=(Dual<N> &a, double b) { a.v += b; return a; }
 
@@ -120,7 +130,7 @@ template <int N> __device__ __forceinline__ Dual<N> r_exp(const Dual<N> &x) {
   return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> r_log(const Dual<N> &x) {
-  Dual<N> r; r.v = MCRE_LOG(x.v); double inv = 1.0 / x.v;
+  Dual<N> r; r.v = MCRE_LOG(x.v); double inv = MCRE_RCP(x.v);
 #pragma unroll
   MCRE_DUAL_LOOP r.d[i] = inv * x.d[i];
   return r;

@@ -45,9 +45,15 @@ struct EqDev {
   const int *date_expo, *date_metric;
   const double *xp;                  // [n_expo][n_prod][4]: type (0 none, 1 analytic BS), time to maturity, 1/numeraire(t), pad
   const double *set_threshold; const int *set_flags, *set_lag;
+  // sparse form of a single joint Cholesky factor (built by mcre_eq_create): per asset the non-zeros of
+  // the row of its first noise column as (coefficient, source asset << 1 | element); its second column's
+  // row is the identity (Heston QE variance draws are independent).  sp_n = 0: use the dense factor.
+  int sp_n, n_sub_total;
+  const double *sp_coef; const int *sp_src;
 };
 constexpr int EQ_XP = 4;
 constexpr int EQ_MAX_LAG = 4;
+constexpr int EQ_SPNZ = 8;   // non-zeros kept per sparse correlation row
 
 enum { EQ_EUROPEAN = MCRE_EQ_EUROPEAN, EQ_BINARY = MCRE_EQ_BINARY, EQ_BASKET = MCRE_EQ_BASKET, EQ_ASIAN = MCRE_EQ_ASIAN,
        EQ_BARRIER = MCRE_EQ_BARRIER, EQ_EXERCISE = MCRE_EQ_EXERCISE };
@@ -120,6 +126,13 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
   const int uidx = __ldg(P.asset_uniform + aa);
   const int d = P.noise_dim;
   const bool smooth = P.smoothing != 0;
+  double spc[EQ_SPNZ];
+  int sps[EQ_SPNZ];
+#pragma unroll
+  for (int k = 0; k < EQ_SPNZ; ++k) {
+    spc[k] = k < P.sp_n ? __ldg(P.sp_coef + aa * EQ_SPNZ + k) : 0.0;
+    sps[k] = k < P.sp_n ? __ldg(P.sp_src + aa * EQ_SPNZ + k) : 0;
+  }
 
   for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) acc[i] = 0.0;
@@ -131,6 +144,9 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
       const bool live = lane_ok && in_chunk < sh.chunk && lpath < sh.n_paths;
       const unsigned long long gpath = (unsigned long long)(sh.path_begin + (live ? lpath : 0));
       NormalStream ns; ns.init(rng, gpath);
+      QeStepConst<R> qe;
+      qe.dt = -1.0;
+      double u_even = 0.5, u_odd = 0.5;
 
       R s0, s1;
       if constexpr (KIND == MCRE_EQ_BS) { s0 = par[0]; s1 = T::zero(); }
@@ -337,11 +353,26 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             if ((n1 >> 1) == (n0 >> 1)) z1 = (n1 & 1u) ? p1 : p0;
             else { ns.pair(n1 >> 1, p0, p1); z1 = (n1 & 1u) ? p1 : p0; }
           }
-          if (KIND == MCRE_EQ_HESTON && ALT == 1) u = ns.uniform((uint32_t)(is * P.n_uniform + uidx));
+          if (KIND == MCRE_EQ_HESTON && ALT == 1) {
+            // uniform #(asset * n_sub + step): consecutive steps of an asset share a Philox block
+            const uint32_t m = (uint32_t)(uidx * P.n_sub_total + is);
+            if (is == 0 || (m & 1u) == 0u) ns.uniform_pair(m >> 1, u_even, u_odd);
+            u = (m & 1u) ? u_odd : u_even;
+          }
         }
         // ---- correlate: w = z @ L^T -----------------------------------------------------
         R w0 = T::lift(z0), w1 = T::lift(z1);
-        if (P.corr_mode == 2) {
+        if (P.corr_mode == 2 && P.sp_n > 0) {
+          double a0 = 0.0;
+#pragma unroll
+          for (int k = 0; k < EQ_SPNZ; ++k) {
+            if (k < P.sp_n) {
+              const double zj = __shfl_sync(0xffffffffu, (sps[k] & 1) ? z1 : z0, (base + (sps[k] >> 1)) & 31);
+              a0 = fma(spc[k], zj, a0);
+            }
+          }
+          w0 = T::lift(a0);      // w1 = z1: identity row
+        } else if (P.corr_mode == 2) {
           const double *L = P.chol + (size_t)__ldg(P.step_chol + is) * d * d;
           double a0 = 0.0, a1 = 0.0;
           for (int j = 0; j < d; ++j) {
@@ -362,7 +393,10 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
           if (ALT == 1) s0 = s0 * r_exp(rate * dt + (sigma * (sq * w0) - 0.5 * dt * sigma * sigma));  // black_scholes.py:44-67
           else s0 = s0 + (rate * s0 * dt + sigma * s0 * sq * w0);                                     // :69-85
         } else if constexpr (KIND == MCRE_EQ_HESTON) {
-          if (ALT == 1) heston_qe_step<R>(par[1], par[2], par[3], par[4], par[5], dt, smooth, val(w0), val(w1), u, s0, s1);
+          if (ALT == 1) {
+            if (dt != qe.dt) heston_qe_prepare<R>(par[1], par[2], par[3], par[4], par[5], dt, qe);   // uniform: dt is a plan scalar
+            heston_qe_step_c<R>(qe, par[5], smooth, val(w0), val(w1), u, s0, s1);
+          }
           else heston_euler_step<R>(par[1], par[2], par[4], par[5], dt, sq, w0, w1, s0, s1);
         } else {
           const R &kappa = par[1], &ss = par[2], &mu = par[3], &sl = par[4];
@@ -423,8 +457,8 @@ struct mcre_eq_plan {
   int nt = 0;
   DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w, ev_data, prod_x;
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
-  DevArray<int> date_expo, date_metric, set_flags, set_lag;
-  DevArray<double> xp, set_threshold;
+  DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src;
+  DevArray<double> xp, set_threshold, sp_coef;
 };
 
 extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
@@ -470,9 +504,34 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
     UP(set_threshold, c->set_threshold, c->n_sets); UP(set_flags, c->set_flags, c->n_sets);
     UP(set_lag, c->set_lag, (size_t)c->n_sets * c->n_metric);
   }
+  // sparse rows of the joint Cholesky factor (see EqDev)
+  int sp_n = 0;
+  if (c->corr_mode == 2 && c->n_chol == 1 && c->chol) {
+    std::vector<double> coef((size_t)A * EQ_SPNZ, 0.0);
+    std::vector<int> src((size_t)A * EQ_SPNZ, 0);
+    bool ok = true;
+    for (int a = 0; a < A && ok; ++a) {
+      const int r0 = c->asset_noise[a * 2], r1 = c->asset_noise[a * 2 + 1];
+      if (r1 >= 0)
+        for (int j = 0; j < d; ++j) ok = ok && c->chol[(size_t)r1 * d + j] == (j == r1 ? 1.0 : 0.0);
+      int n = 0;
+      for (int j = 0; j < d && ok; ++j) {
+        const double v = c->chol[(size_t)r0 * d + j];
+        if (v == 0.0) continue;
+        if (n == EQ_SPNZ) { ok = false; break; }
+        coef[(size_t)a * EQ_SPNZ + n] = v;
+        src[(size_t)a * EQ_SPNZ + n] = (c->col_asset[j] << 1) | (c->col_elem[j] & 1);
+        ++n;
+      }
+      if (n > sp_n) sp_n = n;
+    }
+    if (!ok) sp_n = 0;
+    if (sp_n > 0) { UP(sp_coef, coef.data(), coef.size()); UP(sp_src, src.data(), src.size()); }
+  }
 #undef UP
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
+  D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -499,7 +558,7 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->step_chol.release(); p->date_ev_off.release(); p->ev_prod.release(); p->ev_flags.release();
   p->ev_data.release(); p->prod_x.release();
   p->date_expo.release(); p->date_metric.release(); p->set_flags.release(); p->set_lag.release();
-  p->xp.release(); p->set_threshold.release();
+  p->xp.release(); p->set_threshold.release(); p->sp_coef.release(); p->sp_src.release();
   delete p;
 }
 

@@ -111,6 +111,12 @@ struct NormalStream {
   }
   // two consecutive normals starting at an even index (noise_dim 2 fast path)
   __device__ inline void next2(double &z0, double &z1) { pair(n >> 1, z0, z1); n += 2; }
+  // both uniforms of block `block` (uniform #2 block and #2 block + 1)
+  __device__ inline void uniform_pair(uint32_t block, double &ua, double &ub) const {
+    uint32_t o[4];
+    ph(p_lo, p_hi, block, 1u, o);
+    ua = u52(o[0], o[1]); ub = u52(o[2], o[3]);
+  }
   __device__ inline double uniform(uint32_t m) const {
     uint32_t o[4];
     ph(p_lo, p_hi, m >> 1, 1u, o);

@@ -27,9 +27,9 @@ class PhiloxDraws:
         self.z = philox.normals(paths, n_sub, dim, seed, stream)
         self.u = None
         if with_uniforms:
-            # uniform #(s * n_uniform + a) of a path belongs to sub-step s, asset a
+            # uniform #(a * n_sub + s) of a path belongs to asset a, sub-step s
             u = philox.uniforms(paths, n_sub * n_uniform, seed, stream)
-            self.u = u if n_uniform == 1 else u.reshape(n_sub, n_uniform, n_paths).transpose(0, 2, 1).copy()
+            self.u = u if n_uniform == 1 else u.reshape(n_uniform, n_sub, n_paths).transpose(1, 2, 0).copy()
 
     def normals(self, s):
         return [self.z[s, :, j] for j in range(self.z.shape[2])]
