@@ -136,7 +136,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     pool = CpuPool()
-    per_worker = 1 << 14
+    per_worker = (1 << 15) if pool.workers <= 32 else (1 << 14)   # ~0.8 GB of path tensor per worker
     n = per_worker * pool.workers
     times = []
     for i in range(args.warmup + args.steps):
@@ -293,7 +293,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             pool = CpuPool()
-            per_worker = 1 << 14
+            per_worker = (1 << 15) if pool.workers <= 32 else (1 << 14)
             pool.step(per_worker, 0.3)
             rate, dt = max((pool.step(per_worker, 0.3) for _ in range(3)), key=lambda r: r[0])
             pool.close()
