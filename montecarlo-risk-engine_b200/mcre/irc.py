@@ -20,7 +20,7 @@ from common.enums import SimulationScheme
 from mcre import binding as B
 from mcre import runtime as RT
 from mcre.dual import D, cholesky_dual
-from mcre.lsm import backward_induction, solve_normal_equations, to_raw_basis
+from mcre.lsm import backward_induction, solve_normal_equations, solve_normal_equations_batch, to_raw_basis
 from mcre.timegrid import build_time_grid
 from metrics.metric import MetricType
 from models.cirpp import CIRPPModel
@@ -223,6 +223,15 @@ class IrcBackend:
         cached = getattr(self, "_step_cache", None)
         if cached is not None:
             step_vas, step_cir = cached
+        fast = cached is None and nt == 0 and self.has_cir and not self.cir.deterministic and self.scheme != SimulationScheme.ANALYTICAL
+        if fast:
+            # value-only plan: the per-step tables in one vectorised evaluation
+            psis = self.cir.psi_values([x.v for x in pc], grid.t1)
+            theta_t = [self.vas.mean_level(pv, t) for t in grid.t1]
+            for s in range(n_sub):
+                step_vas += [theta_t[s], zero]
+                step_cir += [D._val(float(psis[s])), zero]
+            cached = (step_vas, step_cir)
         for s in range(n_sub if cached is None else 0):
             if self.scheme == SimulationScheme.ANALYTICAL:
                 decay, _ = self.vas.exact_step_constants(pv, grid.dt[s])
@@ -359,12 +368,18 @@ class IrcBackend:
             acc |= B.ACC_CVA
             lgd = 1.0 - cva_metric.recovery_rate
             cva_coef = []
-            for m in range(n_metric):
-                if m < n_metric - 1:
-                    Ck, Bk = self.cir.conditional_survival_coefficients(pc, metric_times[m], metric_times[m + 1])
-                    cva_coef += [Ck, Bk]
-                else:
-                    cva_coef += [zero, zero]
+            if nt == 0 and not self.cir.deterministic and n_metric > 1:
+                Cs, Bs = self.cir.conditional_survival_values([x.v for x in pc], metric_times[:-1], metric_times[1:])
+                for Ck, Bk in zip(Cs, Bs):
+                    cva_coef += [D._val(float(Ck)), D._val(float(Bk))]
+                cva_coef += [zero, zero]
+            else:
+                for m in range(n_metric):
+                    if m < n_metric - 1:
+                        Ck, Bk = self.cir.conditional_survival_coefficients(pc, metric_times[m], metric_times[m + 1])
+                        cva_coef += [Ck, Bk]
+                    else:
+                        cva_coef += [zero, zero]
         set_thr = np.array([ns.threshold for ns in sets], dtype=np.float64)
         set_flags = np.zeros(len(sets), dtype=np.int32)
         set_lag = np.full((len(sets), max(n_metric, 1)), -1, dtype=np.int32)[:, :n_metric]
@@ -502,13 +517,9 @@ class IrcBackend:
                 L.mcre_irc_destroy(plan)
             nu = 1 if len(group) <= 1 else (2 if len(group) <= 2 else 4)
             assert mom.shape[1] == 5 + 3 * nu
+            G = mom[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]          # [n_expo, 3, 3] Gram matrices of [1, u, u^2]
             for u, prod in enumerate(group):
-                coefs = np.zeros((info["n_expo"], 3))
-                for k in range(info["n_expo"]):
-                    m = mom[k, :5]
-                    G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
-                    rhs = mom[k, 5 + 3 * u: 8 + 3 * u]
-                    coefs[k] = solve_normal_equations(G, rhs)
+                coefs = solve_normal_equations_batch(G, mom[:, 5 + 3 * u: 8 + 3 * u])
                 out[id(prod)] = (coefs, info["basis"])
         return out
 

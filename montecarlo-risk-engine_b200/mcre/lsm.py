@@ -42,6 +42,29 @@ def solve_normal_equations(G, rhs):
     return (vt2[keep].T * (1.0 / s2[keep])) @ (u2[:, keep].T @ rhs)
 
 
+def solve_normal_equations_batch(G, rhs):
+    """solve_normal_equations for a stack of systems: G [n,3,3], rhs [n,3] -> [n,3].  One batched SVD /
+    solve for the full-rank dates; rank-deficient ones (t = 0) go through the scalar routine."""
+    G, rhs = np.asarray(G, dtype=np.float64), np.asarray(rhs, dtype=np.float64)
+    n = G.shape[0]
+    out = np.zeros((n, 3))
+    if n == 0:
+        return out
+    d = np.sqrt(np.clip(np.diagonal(G, axis1=1, axis2=2), 0.0, None))
+    ok = np.isfinite(G).all(axis=(1, 2)) & (d[:, 0] > 0.0) & (d > 0.0).all(axis=1)
+    scale = np.where(d > 0.0, d, 1.0)
+    Gs = G / (scale[:, :, None] * scale[:, None, :])
+    Gs_safe = np.where(ok[:, None, None], Gs, np.eye(3)[None])
+    sv = np.linalg.svd(Gs_safe, compute_uv=False)
+    full = ok & (sv[:, 2] > 1e-10 * sv[:, 0])
+    if full.any():
+        sol = np.linalg.solve(Gs_safe[full], (rhs[full] / scale[full])[:, :, None])[:, :, 0]
+        out[full] = sol / scale[full]
+    for k in np.nonzero(~full)[0]:
+        out[k] = solve_normal_equations(G[k], rhs[k])
+    return out
+
+
 def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev):
     """xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product
     (exercise) dates; reg_times: regression dates (sorted, contain every product date);

@@ -5,6 +5,8 @@ All deterministic ingredients (market hazard, psi shift, CIR A/B functions, the
 conditional-survival prefactor) are scalars per date; they are evaluated here on
 the host as dual numbers and shipped to the kernels as per-step / per-date
 tables."""
+import math
+import numpy as np
 from models.model import *
 from mcre.dual import D, dexp, dsqrt, dlog, dval
 
@@ -109,6 +111,42 @@ class CIRPPModel(Model):
         Dt = (2.0 * kappa * theta / (sigma * sigma)) * (0.5 * (kappa + h) - (h * (kappa + h) * et) / den)
         Et = (4.0 * h * h * et) / (den * den)
         return self.market_hazard(t) + Dt - y0 * Et
+
+    # -- value-only, vectorised over dates (plans without sensitivities are lowered on every run) --
+    def _market_vec(self, ts, what):
+        f = self.market_hazard if what == "hazard" else self.market_survival
+        return np.array([f(float(t)) for t in ts])
+
+    def psi_values(self, pv, ts):
+        """psi(t) for an array of times, same formulas as psi()."""
+        kappa, theta, sigma, y0 = pv
+        ts = np.asarray(ts, dtype=np.float64)
+        h = math.sqrt(kappa * kappa + 2.0 * sigma * sigma)
+        et = np.exp(h * ts)
+        den = 2.0 * h + (kappa + h) * (et - 1.0)
+        Dt = (2.0 * kappa * theta / (sigma * sigma)) * (0.5 * (kappa + h) - (h * (kappa + h) * et) / den)
+        Et = (4.0 * h * h * et) / (den * den)
+        return self._market_vec(ts, "hazard") + Dt - y0 * Et
+
+    def conditional_survival_values(self, pv, t, T):
+        """(C, B) arrays of S(t,T | y) = C exp(-B y) for arrays of (t, T), same formulas as
+        conditional_survival_coefficients()."""
+        kappa, theta, sigma, y0 = pv
+        t, T = np.asarray(t, dtype=np.float64), np.asarray(T, dtype=np.float64)
+        h = math.sqrt(kappa * kappa + 2.0 * sigma * sigma)
+
+        def A(tau):
+            num = 2.0 * h * np.exp(0.5 * (kappa + h) * tau)
+            den = 2.0 * h + (kappa + h) * (np.exp(h * tau) - 1.0)
+            return (num / den) ** ((2.0 * kappa * theta) / (sigma * sigma))
+
+        def Bf(tau):
+            e = np.exp(h * tau) - 1.0
+            return (2.0 * e) / (2.0 * h + (kappa + h) * e)
+
+        pref = (self._market_vec(T, "survival") / self._market_vec(t, "survival")) * (A(t) / A(T)) \
+            * np.exp(Bf(T) * y0 - Bf(t) * y0)
+        return pref * A(T - t), Bf(T - t)
 
     def conditional_survival_coefficients(self, p, t, T):
         """(C, B) with S(t,T | y_t) = C * exp(-B * y_t) (reference: cirpp.py:246-285).
