@@ -57,6 +57,20 @@ def main():
                         diff=diff, sub=252, show=[("barrier", "pv"), ("asian", "pv")])
         raise SystemExit(f"unknown config {name}")
 
+    # algorithmic FP64 flop per path-step, derived like SURVEY 8(d) does for config 3 (add/mul 1, FMA 2,
+    # exp / log 20, sincos 30, sqrt / div 8):
+    #  1: one exact BS step + payoff + 3 tangents                                  ~ 64 + 30 + 3 * 30
+    #  2: Box-Muller pair 64 (one normal used) + Vasicek Euler 7 + date work 110 (numeraire exp, LIBOR exp,
+    #     2 coupons, 2 sets x (poly, threshold / MPoR, relu, sums))                = 181
+    #  2o: as 2 but only every second sub-step is a metric date                     ~ 64 + 7 + 60
+    #  4: 64 + 7 + exercise date: ~22 zero bonds x (exp 20 + 2) + payoff / decision 10 + exposure 30 + numeraire 20 = 615
+    #  5: 5 assets x (2 normals 64 + uniform 4 + ~90 algebraic + 2 exp + 1 log + 4 sqrt + 4 div = 60 + 64) ~ 5 x 282 + basket 20
+    flop_model = {"1": 184.0, "2": 181.0, "2o": 131.0, "4": 615.0, "5": 1430.0, "5g": 1430.0}
+    import ctypes as C
+    peak = C.c_double(0.0)
+    from mcre import runtime as RT
+    RT.compute_device()
+    B.check(B.lib().mcre_dfma_peak(C.byref(peak), RT.stream_ptr()))
     for name in args.configs:
         best, res = None, None
         for rep in range(args.repeats):
@@ -74,7 +88,10 @@ def main():
         out = {"config": name, "n_main": c["n_main"], "n_pre": c["n_pre"], "sub_steps": c["sub"], "differentiate": c["diff"],
                "seconds": best, "path_steps_per_s": c["n_main"] * c["sub"] / best, "launches": launches,
                "timings": {k: round(v, 4) for k, v in ctl.last_timings.items()},
-               "max_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}
+               "max_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+               "flop_per_path_step_model": flop_model[name],
+               "kernel_tflops_model": c["n_main"] * c["sub"] * flop_model[name] / max(ctl.last_timings["path_generation"], 1e-9) * 1e-12,
+               "dfma_peak_tflops": peak.value}
         for s, m in c["show"]:
             out[f"{s}|{m}"] = [float(res.get_results(s, m)[0]), float(res.get_mc_error(s, m)[0])]
             if c["diff"]:
