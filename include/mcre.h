@@ -304,14 +304,16 @@ typedef struct {
    * prod_x [n_prod][n_assets]: weights picking the explanatory variable x (spot of the option's asset). */
   const double *ev_data;
   const double *prod_x;
-  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op,
-   * 4 doubles: type (0 none, 1 analytic Black-Scholes value of a European option, european_option.py:123-145),
-   * time to maturity, 1/numeraire(t), pad.  Netting-set terms as in mcre_irc_desc.  acc_flags: MCRE_ACC_POS /
+  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op, 8 doubles:
+   * type 1 = analytic Black-Scholes value of a European option (european_option.py:123-145): [1, time to maturity,
+   * 1/numeraire(t), ...]; type 2 = regression proxy c(u) / numeraire (controller.py:438-447), u = (x - shift) scale,
+   * x = spot picked by prod_x: [2, c0, 1/numeraire(t), c1, c2, shift, scale, pad]; type 0 = none.
+   * Netting-set terms as in mcre_irc_desc.  acc_flags: MCRE_ACC_POS /
    * NEG / SPILL.  Adds [n_metric][NS][4] = sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2) to the slots. */
   int32_t n_expo, n_metric, acc_flags;
   const int32_t *date_expo;     /* [n_dates] internal exposure index or -1 */
   const int32_t *date_metric;   /* [n_dates] metric-date index or -1       */
-  const double *xp;             /* [n_expo][n_prod][4]                     */
+  const double *xp;             /* [n_expo][n_prod][8]                     */
   const double *set_threshold;  /* [n_sets]                                */
   const int32_t *set_flags;     /* [n_sets] bit0 collateralised            */
   const int32_t *set_lag;       /* [n_sets][n_metric] exposure-index lag of the collateral date, -1: none */
@@ -328,6 +330,14 @@ int64_t mcre_eq_slots(const mcre_eq_plan *plan);
 int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                     double *d_acc, double *d_shift, double *d_spill /* [n_sets][n_metric][n_paths] or NULL */,
                     void *stream);
+/* Pre-simulation pass of the regression-proxy exposures (replaces the path generation + request resolution +
+ * cashflow roll feeding controller._perform_regression_for_product, controller.py:294-351, for the equity
+ * products, which pay once): the same fused kernel run on the pre-simulation stream spills, date-major,
+ * d_x [n_expo][n_assets][n_paths] (spot of every asset per exposure date) and d_cf [n_prod][n_paths] (discounted
+ * cashflow of every product rounded to float32 like the reference's accumulators).  The moments / solve per
+ * (product, date) then go through mcre_lsm_step without an exercise update. */
+int mcre_eq_presim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                   double *d_shift, double *d_x, float *d_cf, void *stream);
 
 /* ================================================================================
  * Longstaff-Schwartz backward induction on spilled pre-simulation arrays: one call per

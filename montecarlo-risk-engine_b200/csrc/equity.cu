@@ -50,8 +50,12 @@ struct EqDev {
   // row is the identity (Heston QE variance draws are independent).  sp_n = 0: use the dense factor.
   int sp_n, n_sub_total;
   const double *sp_coef; const int *sp_src;
+  // pre-simulation spill (mcre_eq_presim): spot of every asset per exposure date, date-major, and the
+  // discounted cashflow of every product rounded to float32 (the reference's float32 accumulators)
+  double *ps_x;   // [n_expo][A][n_paths]
+  float *ps_cf;   // [n_prod][n_paths]
 };
-constexpr int EQ_XP = 4;
+constexpr int EQ_XP = 8;
 constexpr int EQ_MAX_LAG = 4;
 constexpr int EQ_SPNZ = 8;   // non-zeros kept per sparse correlation row
 
@@ -174,7 +178,11 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
       // exposure of the date (after its cashflows, controller.py:417-447), netting, collateral, metrics
       auto eval_exposure = [&](int di) {
         if (P.n_expo == 0) return;
-        const int xe = __ldg(P.date_expo + di), m = __ldg(P.date_metric + di);
+        const int xe = __ldg(P.date_expo + di), m = P.ps_x ? -1 : __ldg(P.date_metric + di);
+        if (xe >= 0 && P.ps_x) {
+          if (live) P.ps_x[((size_t)xe * A + a) * sh.n_paths + lpath] = val(spot_now());
+          return;     // pre-simulation pass: no exposures, no metrics
+        }
         if (xe >= 0) {
           const double Sv = val(spot_now());
           double expo[NS];
@@ -182,10 +190,25 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
           for (int s = 0; s < NS; ++s) expo[s] = 0.0;
           for (int pi = 0; pi < P.n_prod; ++pi) {
             const double *op = P.xp + ((size_t)xe * P.n_prod + pi) * EQ_XP;
-            if (__ldg(op) == 0.0) continue;
+            const int xtype = (int)__ldg(op);
+            if (xtype == 0) continue;
             const double *pr = P.prod + (size_t)pi * EQ_PR;
-            const double wgt = __ldg(P.prod_w + (size_t)pi * A + aa);
             double v = 0.0;
+            if (xtype == 2) {
+              // regression proxy: continuation(x) / numeraire with x the spot of the product's asset
+              // (controller.py:438-447), evaluated on the lane that owns that asset
+              const double xw = __ldg(P.prod_x + (size_t)pi * A + aa);
+              if (xw != 0.0) {
+                const double u = (Sv - __ldg(op + 5)) * __ldg(op + 6);
+                v = (__ldg(op + 1) + u * (__ldg(op + 3) + u * __ldg(op + 4))) * __ldg(op + 2);
+              }
+              const double tot2 = group_sum(v, base, A);
+              const int set2 = (int)__ldg(pr + 1);
+#pragma unroll
+              for (int s = 0; s < NS; ++s) if (s == set2) expo[s] += tot2;
+              continue;
+            }
+            const double wgt = __ldg(P.prod_w + (size_t)pi * A + aa);
             if (wgt != 0.0) {
               // Black-Scholes value of the remaining option at (S_t, T - t), over the numeraire
               // (european_option.py:70-100, 123-145); evaluated on the lane that owns the asset
@@ -327,6 +350,7 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             if (bt2 > 0) pay = pay * barrier_factor(mx, mn, __ldg(pr + 11), bt2);
           }
           const double invN = __ldg(pr + 4), dinvN = __ldg(pr + 5);
+          if (P.ps_cf && live && a == 0) P.ps_cf[(size_t)pi * sh.n_paths + lpath] = (float)(val(pay) * invN);
 #pragma unroll
           for (int s = 0; s < NS; ++s)
             if (s == set) { cf[s] = cf[s] + pay * invN; numtan[s] += val(pay) * dinvN; }
@@ -532,6 +556,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
+  D.ps_x = nullptr; D.ps_cf = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -573,6 +598,7 @@ template <int KIND, int ALT, int NT, int NS>
 static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
                      double *spill, cudaStream_t st) {
   const EqDev &d = p->d;
+  const bool presim = d.ps_x != nullptr;
   const int threads = 128, nw = threads / 32;
   constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVX = NS * 4;
   constexpr int NVMAX = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
@@ -588,8 +614,10 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   if (grid > n_chunks) grid = n_chunks;
   ShardDev pilot_sh{0, 1, sh.chunk};
   if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, spill, 1);
-  MCRE_LAUNCHED();
+  if (!presim) {   // the pre-simulation pass only spills; it needs no pilot shifts
+    k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, spill, 1);
+    MCRE_LAUNCHED();
+  }
   k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, shift, spill, 0);
   MCRE_LAUNCHED();
   return 0;
@@ -614,7 +642,8 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   int rc = check_shard(shard);
   if (rc) return rc;
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
-  if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill) return fail(-1, "spill requested but d_spill is null%s", "");
+  if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.ps_x)
+    return fail(-1, "spill requested but d_spill is null%s", "");
   if (rng->mode == MCRE_RNG_INJECT && p->d.kind == MCRE_EQ_HESTON && p->d.scheme == MCRE_SCHEME_QE && !rng->d_u)
     return fail(-1, "inject mode: QE needs uniforms%s", "");
   RngDev r = make_rng(rng);
@@ -637,4 +666,15 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   return mcre_tree_reduce(d_partial, n_chunks, mcre_eq_slots(p), d_acc, stream);
+}
+
+extern "C" int mcre_eq_presim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                              double *d_shift, double *d_x, float *d_cf, void *stream) {
+  if (!p || !rng || !d_partial || !d_shift || !d_x || !d_cf) return fail(-1, "null argument%s", "");
+  if (p->nt != 0) return fail(-4, "eq presim: tangents through the regression are not implemented%s", "");
+  if (p->d.n_expo <= 0) return fail(-1, "eq presim: the plan has no exposure dates%s", "");
+  p->d.ps_x = d_x; p->d.ps_cf = d_cf;
+  const int rc = mcre_eq_mainsim(p, rng, shard, d_partial, d_partial /* scratch: sums are not used */, d_shift, nullptr, stream);
+  p->d.ps_x = nullptr; p->d.ps_cf = nullptr;
+  return rc;
 }

@@ -43,7 +43,7 @@ CHUNK_PATHS = 4096
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
 P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
 EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
-EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS, EQ_XP, EQ_MAX_LAG = 16, 8, 2, 4, 4, 4
+EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS, EQ_XP, EQ_MAX_LAG = 16, 8, 2, 4, 8, 4
 _NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
 _BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
                  BarrierOptionType.UPANDIN: 3, BarrierOptionType.DOWNANDIN: 4}
@@ -137,9 +137,12 @@ class EquityBackend:
         if not all(_is_equity_product(p) for p in ctrl.products):
             return False
         if ctrl.risk_metrics.requires_exposure_profiles():
-            # exposure profiles: the analytic Black-Scholes exposure of European options
-            # (the reference's own no-regression branch, controller.py:204-229)
-            return all(ctrl._can_use_analytic_exposure_for_product(p) for p in ctrl.products)
+            # exposure profiles: the analytic Black-Scholes exposure of European options (the reference's
+            # own no-regression branch, controller.py:204-229), else the regression proxy of products that
+            # pay once; no CVA here (needs a credit model in the same ModelConfig: hybrid books are next)
+            if any(m.metric_type == MetricType.CVA for m in ctrl.risk_metrics.metrics):
+                return False
+            return all(ctrl._can_use_analytic_exposure_for_product(p) or not is_equity_exercise(p) for p in ctrl.products)
         return True
 
     def __init__(self, ctrl):
@@ -161,6 +164,7 @@ class EquityBackend:
         self.nt = self.npar if ctrl.differentiate else 0
         self.id_to_asset = {a.asset_id: i for i, a in enumerate(self.assets)}
         self.exercise_coef = {}   # id(product) -> (coef [n_ex, 3] standardised basis, basis [n_ex, 2])
+        self.expo_coef = {}       # id(product) -> (coef [n_expo, 3] standardised basis, basis [n_expo, 2])
         subs = _sub_models(ctrl.model)
         num_idx = ctrl.model.id_to_model["numeraire"] if isinstance(ctrl.model, ModelConfig) else 0
         self.num_model = subs[num_idx]
@@ -309,8 +313,12 @@ class EquityBackend:
             step_chol.append(seen[key])
         return 1, None, chol_dual, step_chol
 
-    def lower(self, set_indices):
+    def lower(self, set_indices, presim_products=None):
+        """Plan of the main pass for a group of netting sets, or (presim_products given) of the
+        pre-simulation spill pass for a group of products (all in one dummy set)."""
         c, nt, A = self.c, self.nt, self.A
+        if presim_products is not None:
+            nt = 0
         grid = build_time_grid(self.assets[0].model.t0(), c.simulation_timeline.tolist(), c.num_steps)
         dates = grid.dates
         date_idx = {t: i for i, t in enumerate(dates)}
@@ -338,8 +346,10 @@ class EquityBackend:
         recs, weights, xweights, events = [], [], [], [[] for _ in range(n_dates)]
         owners = []
         slot = 0
-        for r, si in enumerate(set_indices):
-            for p in c.netting_sets[si].products:
+        book = ([(0, p) for p in presim_products] if presim_products is not None else
+                [(r, p) for r, si in enumerate(set_indices) for p in c.netting_sets[si].products])
+        for r, p in book:
+            if True:
                 if c._can_skip_monte_carlo_for_product(p):
                     continue
                 use_slot = -1
@@ -351,8 +361,7 @@ class EquityBackend:
                 recs.append(rec)
                 weights.append(w)
                 xw = np.zeros(A)
-                if is_equity_exercise(p):
-                    xw[self._asset_index(p.get_asset_id())] = 1.0   # explanatory variable: spot of the option's asset
+                xw[self._asset_index(p.asset_ids[0])] = 1.0   # explanatory variable: spot of the product's first asset
                 xweights.append(xw)
                 owners.append(p)
                 for di, f in evs:
@@ -413,7 +422,7 @@ class EquityBackend:
         desc.n_prod = len(recs)
         desc.prod = fp("prod", np.stack(recs) if recs else np.zeros(EQ_PR))
         desc.prod_w = fp("prod_w", np.stack(weights) if weights else np.zeros(A))
-        desc.n_sets = len(set_indices)
+        desc.n_sets = len(set_indices) if presim_products is None else 1
         desc.ev_data = fp("ev_data", np.stack(ev_data) if ev_data else np.zeros(8))
         desc.prod_x = fp("prod_x", np.stack(xweights) if xweights else np.zeros(A))
 
@@ -434,9 +443,16 @@ class EquityBackend:
             for e, te in enumerate(expo_times):
                 inv = self._inv_numeraire(te)[0]
                 for pi, p in enumerate(owners):
-                    ttm = float(p.exercise_date) - te
-                    if ttm > 0.0:                       # matured options carry no exposure (european_option.py:129-131)
-                        xp[e, pi] = (1.0, ttm, inv, 0.0)
+                    if presim_products is not None:
+                        continue                        # the spill pass evaluates no exposures
+                    if c._can_use_analytic_exposure_for_product(p):
+                        ttm = float(p.exercise_date) - te
+                        if ttm > 0.0:                   # matured options carry no exposure (european_option.py:129-131)
+                            xp[e, pi, :3] = (1.0, ttm, inv)
+                    else:
+                        coef, basis = self.expo_coef[id(p)]
+                        if np.any(coef[e] != 0.0):
+                            xp[e, pi] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], 0.0)
             kinds = {m.metric_type for m in c.risk_metrics.metrics}
             if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
                 acc |= B.ACC_POS
@@ -444,11 +460,13 @@ class EquityBackend:
                 acc |= B.ACC_NEG
             if MetricType.PFE in kinds:
                 acc |= B.ACC_SPILL
-            sets = [c.netting_sets[i] for i in set_indices]
+            sets = [c.netting_sets[i] for i in set_indices] if presim_products is None else [c.netting_sets[0]]
+            if presim_products is not None:
+                set_indices, acc = [0], 0
             set_flags = np.zeros(len(sets), dtype=np.int32)
             set_lag = np.full((len(sets), n_metric), -1, dtype=np.int32)
             for r, (si, ns) in enumerate(zip(set_indices, sets)):
-                if ns.is_collateralized():
+                if ns.is_collateralized() and presim_products is None:
                     set_flags[r] |= 1
                     delayed = c.netting_set_delayed_exposure_indices[si].tolist()
                     for m in range(n_metric):
@@ -598,6 +616,96 @@ class EquityBackend:
         for j, t in enumerate(prod.regression_timeline.tolist()):
             prod.regression_coeffs[j, 1, :] = torch.tensor(raw[ridx[t]])
 
+    def presim_regression(self, products, dev):
+        """Regression-proxy exposure coefficients of products that pay once (controller.py:294-383): the
+        fused kernel run on the pre-simulation stream spills spots per exposure date and every product's
+        float32 discounted cashflow (mcre_eq_presim); per (product, exposure date before its payment) the 8
+        moments come from mcre_lsm_step, all solved in one batch after one all-reduce."""
+        from mcre.lsm import solve_normal_equations_batch, to_raw_basis
+        c, A = self.c, self.A
+        L = B.lib()
+        n_pre = c.num_paths_presim
+        if n_pre <= 0:
+            raise ValueError("Exposure metrics need a pre-simulation: num_paths_presim must be positive.")
+        expo_times = c.exposure_timeline.tolist()
+        n_expo = len(expo_times)
+        begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
+        n = max(count, 1)
+        n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
+        xs = torch.zeros((n_expo, A, n), dtype=torch.float64, device=dev)
+        cfs = {}
+        groups, cur, trk = [], [], 0
+        for p in products:
+            t = int(_is_path_dependent(p))
+            if cur and trk + t > EQ_NTRK:
+                groups.append(cur)
+                cur, trk = [], 0
+            cur.append(p)
+            trk += t
+        if cur:
+            groups.append(cur)
+        inj = c.injected_normals.get("pre") if c.injected_normals else None
+        for group in groups:
+            desc, keep, info = self.lower([], presim_products=group)
+            plan = C.c_void_p()
+            B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
+            try:
+                slots = L.mcre_eq_slots(plan)
+                cf = torch.zeros((len(group), n), dtype=torch.float32, device=dev)
+                partial = torch.empty(n_chunks * slots + slots + 1, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                rng = B.Rng()
+                rng.seed, rng.stream, rng.n_paths_total = 42, c.rng_stream, n_pre
+                if inj is not None:
+                    rng.mode, rng.d_z = B.RNG_INJECT, inj.data_ptr()
+                    iu = getattr(c, "injected_uniforms", None)
+                    iu = iu.get("pre") if iu else None
+                    if iu is not None:
+                        self._keep_u_pre = torch.as_tensor(iu, dtype=torch.float64).to(dev).contiguous()
+                        rng.d_u = self._keep_u_pre.data_ptr()
+                else:
+                    rng.mode = B.RNG_PHILOX
+                sh = B.Shard(begin, count, CHUNK_PATHS)
+                B.check(L.mcre_eq_presim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
+                                         xs.data_ptr(), cf.data_ptr(), RT.stream_ptr()))
+            finally:
+                L.mcre_eq_destroy(plan)
+            for u, p in enumerate(group):
+                cfs[id(p)] = cf[u]
+        # standardisation of each asset's spot per date: sample mean / std over all ranks
+        live = xs[:, :, :count]
+        mom = torch.stack([torch.full((n_expo, A), float(count), dtype=torch.float64, device=dev), live.sum(2), (live * live).sum(2)])
+        mom = RT.all_reduce_tree(mom).cpu().numpy()
+        mean = mom[1] / np.maximum(mom[0], 1.0)
+        std = np.sqrt(np.maximum(mom[2] / np.maximum(mom[0], 1.0) - mean * mean, 0.0))
+        scale = np.where(std > 1e-12 * np.maximum(np.abs(mean), 1.0), 1.0 / np.where(std > 0, std, 1.0), 1.0)
+        # moments per (product, date strictly before the payment)
+        jobs = [(p, k) for p in products for k, t in enumerate(expo_times) if t < float(p.product_timeline[-1])]
+        moments = torch.zeros((max(len(jobs), 1), 8), dtype=torch.float64, device=dev)
+        partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
+        nconst = torch.empty(n, dtype=torch.float64, device=dev)
+        t0 = self.num_model.t0()
+        last_k = None
+        for j, (p, k) in enumerate(jobs):
+            a = self._asset_index(p.asset_ids[0])
+            if k != last_k:
+                nconst.fill_(math.exp(self.num_rate * (expo_times[k] - t0)))
+                last_k = k
+            B.check(L.mcre_lsm_step(xs[k, a].data_ptr(), nconst.data_ptr(), float(mean[k, a]), float(scale[k, a]),
+                                    None, None, None, None, 0.0, 1.0, cfs[id(p)].data_ptr(), count, CHUNK_PATHS,
+                                    partial.data_ptr(), moments[j].data_ptr(), RT.stream_ptr()))
+        m = RT.all_reduce_tree(moments).cpu().numpy()
+        G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
+        sol = solve_normal_equations_batch(G, m[:, 5:8]) if jobs else np.zeros((0, 3))
+        for p in products:
+            a = self._asset_index(p.asset_ids[0])
+            self.expo_coef[id(p)] = (np.zeros((n_expo, 3)), np.stack([mean[:, a], scale[:, a]], axis=1))
+        for (p, k), cvec in zip(jobs, sol):
+            self.expo_coef[id(p)][0][k] = cvec
+        for p in products:
+            coef, basis = self.expo_coef[id(p)]
+            c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coef, basis, [t <= t0 for t in expo_times]))
+
     def run(self):
         c = self.c
         dev = RT.compute_device()
@@ -609,6 +717,10 @@ class EquityBackend:
         for p in c.products:
             if is_equity_exercise(p):
                 self.presim_exercise(p, dev)
+        if c.risk_metrics.requires_exposure_profiles():
+            reg = [p for p in c.products if not c._can_use_analytic_exposure_for_product(p)]
+            if reg:
+                self.presim_regression(reg, dev)
         t_pre = time.perf_counter() - t0
         results = [None] * n_sets
         group = EQ_MAX_SETS if self.nt == 0 else 2

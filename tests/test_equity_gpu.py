@@ -199,3 +199,57 @@ def test_bs_european_analytic_exposure_profiles_match_oracle():
     epe, err = np.array(big.get_results("call", "epe")), np.array(big.get_mc_error("call", "epe"))
     assert abs(epe[0] - pv) < 1e-10 and err[0] == 0.0
     assert np.all(np.abs(epe[1:4] - pv) <= 4.0 * err[1:4]) and epe[4] == 0.0
+
+
+@pytest.mark.parametrize("which", ["heston_qe", "bsm_full_metrics", "bs_euler_mixed"])
+def test_regression_proxy_exposure_profiles_match_oracle(which):
+    """Exposure profiles of equity products through the regression proxy (controller.py:294-471): the
+    pre-simulation spills spots and float32 discounted cashflows (mcre_eq_presim), per-date quadratic fits in
+    the spot of the product's first asset, then netting / threshold / MPoR collateral and CE / EPE / ENE /
+    EEPE / PFE in the fused kernel.  CUDA vs oracle on the same Philox streams."""
+    from oracle import risk
+    ns = cases.Namespace()
+    S = ns.SimulationScheme
+    full = [ns.PVMetric(), ns.CEMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.EEPEMetric(), ns.PFEMetric(0.9)]
+    if which == "heston_qe":
+        model = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+        sets = [ns.NettingSet(name="call", products=[ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)]),
+                ns.NettingSet(name="exotics", products=[ns.BarrierOption(0.0, 1.0, 100.0, 5, ns.OptionType.CALL, 140.0, ns.BarrierOptionType.UPANDOUT),
+                                                        ns.AsianOption(0.0, 0.75, 100.0, 4, ns.OptionType.PUT)], threshold=1.0),
+                ns.NettingSet(name="collateralised", products=[ns.BinaryOption(1.0, 100.0, 10.0, ns.OptionType.CALL),
+                                                               ns.EuropeanOption(ns.Equity(), 0.5, 95.0, ns.OptionType.PUT)],
+                              margin_period_of_risk=0.25)]
+        metrics, scheme, steps = full, S.QE, 3
+    elif which == "bsm_full_metrics":
+        model = ns.BlackScholesMulti(0.0, 0.03, ["a", "b", "c"], [100.0, 90.0, 110.0], [0.2, 0.3, 0.25],
+                                     np.array([[1.0, 0.5, 0.2], [0.5, 1.0, 0.3], [0.2, 0.3, 1.0]]))
+        w = [0.3, 0.3, 0.4]
+        sets = [ns.NettingSet(name="basket", products=[ns.BasketOption(1.0, ["a", "b", "c"], w, 100.0, ns.OptionType.CALL)]),
+                ns.NettingSet(name="single", products=[ns.EuropeanOption(ns.Equity("b"), 0.75, 90.0, ns.OptionType.CALL, asset_id="b"),
+                                                       ns.BinaryOption(1.0, 100.0, 5.0, ns.OptionType.PUT, asset_id="c")],
+                              margin_period_of_risk=0.5, threshold=0.5)]
+        metrics, scheme, steps = full, S.ANALYTICAL, 1     # ENE / CE / EEPE force the regression proxy even for Europeans
+    else:
+        model = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.2)
+        sets = [ns.NettingSet(name="mixed", products=[ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL),
+                                                      ns.AsianOption(0.25, 1.0, 100.0, 4, ns.OptionType.CALL, ns.AsianAveragingType.GEOMETRIC)])]
+        metrics, scheme, steps = [ns.PVMetric(), ns.EPEMetric(), ns.PFEMetric(0.95)], S.EULER, 2   # analytic + regression in one set
+    tl = np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    n = 6000
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, steps, scheme)
+    assert sc.requires_regression
+    res = sc.run_simulation()
+    out = risk.run(model, sets, metrics, tl, n, n, steps, scheme.name)
+    got, want = helpers.flatten_results(res), helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names())
+    for key in got:
+        scale = max(1.0, float(np.nanmax(np.abs(want[key][0]))))
+        helpers.assert_close(got[key][0], want[key][0], 1e-7, 1e-8 * scale, f"{which} {key} value")
+        helpers.assert_close(got[key][1], want[key][1], 1e-5, 1e-8 * scale, f"{which} {key} mc error")
+    # regression coefficients exposed like the reference's controller.regression_coeffs (raw basis)
+    for k, p in enumerate(sc.products):
+        if sc._product_requires_regression(p):
+            gotc = sc.regression_coeffs[k][:, 0, :].numpy()
+            wantc = np.stack([np.asarray(cc)[0] for cc in out["expo_coeffs"][k]])
+            x0 = 100.0
+            fit = lambda cfs: cfs[:, 0] + cfs[:, 1] * x0 + cfs[:, 2] * x0 * x0     # compare fitted values near the money
+            helpers.assert_close(fit(gotc), fit(wantc), 1e-6, 1e-7, f"{which} product {k} fitted continuation")
