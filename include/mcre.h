@@ -209,10 +209,17 @@ int64_t mcre_irc_partial_bytes(const mcre_irc_plan *plan, int64_t n_paths, int32
  * the least-squares solve): accumulates for every regression date k the Gram moments
  * sum u^0..u^4 and, per unit, sum u^j * Y_k with Y_k = N(t_k) * fp32 suffix sum of the
  * discounted future cashflows (the FP32 accumulation of controller.py:312-351 is
- * reproduced bit for bit).  d_moments: [n_reg][5 + 3*n_units] (+ tangents when nt>0).
+ * reproduced bit for bit).  d_moments: [n_reg][5 + 3*n_units].
+ * Plans with tangents (nt > 0, differentiate=True): the reference's regression coefficients stay
+ * inside the autograd graph (controller.py:118-119, 368-383), so sensitivities of exposure metrics
+ * contain d(coefficients)/d(parameters).  The forward pass then propagates the pathwise tangents of
+ * x, N and the windowed cashflows and d_tmoments receives [n_units][nt][n_reg][9] =
+ * sum u^m du (m = 0..3), sum u^i dY (i = 0..2), sum du Y, sum 2 u du Y, from which the host
+ * differentiates the normal equations.  d_tmoments may be NULL for nt = 0.
  * d_scratch / d_partial sized by the helpers above. */
+int64_t mcre_irc_presim_tangent_slots(const mcre_irc_plan *plan);
 int mcre_irc_presim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard,
-                    void *d_scratch, double *d_partial, double *d_moments, void *stream);
+                    void *d_scratch, double *d_partial, double *d_moments, double *d_tmoments, void *stream);
 
 /* Upload regression coefficients (after the host solved the normal equations). */
 int mcre_irc_set_coefficients(mcre_irc_plan *plan, const double *expo_coef /* host, dual[n_expo][n_sets][3] */,

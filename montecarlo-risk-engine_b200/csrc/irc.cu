@@ -319,11 +319,15 @@ extern "C" int64_t mcre_irc_presim_slots(const mcre_irc_plan *p) {
   return (int64_t)p->d.n_reg * (5 + 3 * nu_template(p->d.n_units));
 }
 extern "C" int64_t mcre_irc_presim_scratch_bytes(const mcre_irc_plan *p, int64_t n_paths) {
-  return (int64_t)p->d.n_reg * n_paths * (16 + 4 * (int64_t)p->d.n_units) + 256;
+  // value buffers, then (plans with tangents) dx, dN, dW: see irc_tan.cu
+  const int64_t tangents = (int64_t)p->d.n_reg * p->d.nt * n_paths * 8 * (2 + (int64_t)p->d.n_units);
+  return (int64_t)p->d.n_reg * n_paths * (16 + 4 * (int64_t)p->d.n_units) + tangents + 256;
 }
 extern "C" int64_t mcre_irc_partial_bytes(const mcre_irc_plan *p, int64_t n_paths, int32_t chunk, int presim) {
   int64_t n_chunks = (n_paths + chunk - 1) / chunk;
-  return n_chunks * (presim ? mcre_irc_presim_slots(p) : mcre_irc_main_slots(p)) * 8;
+  int64_t slots = presim ? mcre_irc_presim_slots(p) : mcre_irc_main_slots(p);
+  if (presim && p->d.nt > 0) slots = std::max<int64_t>(slots, mcre_irc_presim_tangent_slots(p));
+  return n_chunks * slots * 8;
 }
 
 extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, void *stream) {
@@ -414,12 +418,16 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
   return mcre_tree_reduce(d_partial, n_chunks, mcre_irc_main_slots(p), d_acc, stream);
 }
 
+// defined in irc_tan.cu
+int irc_presim_tangent_pass(mcre_irc_plan *p, const mcre::RngDev &r, const mcre::ShardDev &sh, void *d_scratch,
+                            double *d_partial, double *d_tmoments, cudaStream_t st);
+
 extern "C" int mcre_irc_presim(mcre_irc_plan *p, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
-                               double *d_partial, double *d_moments, void *stream) {
+                               double *d_partial, double *d_moments, double *d_tmoments, void *stream) {
   if (!p || !rng || !d_scratch || !d_partial || !d_moments) return fail(-1, "null argument%s", "");
   int rc = check_shard(shard);
   if (rc) return rc;
-  if (p->d.nt != 0) return fail(-4, "irc presim: tangents through the regression are not implemented%s", "");
+  if (p->d.nt != 0 && !d_tmoments) return fail(-1, "irc presim: the plan carries tangents but d_tmoments is null%s", "");
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   const IrcDev &d = p->d;
   if (d.n_reg == 0 || shard->n_paths == 0) return 0;
@@ -432,11 +440,17 @@ extern "C" int mcre_irc_presim(mcre_irc_plan *p, const mcre_rng *rng, const mcre
   float *wbuf = (float *)(nbuf + (size_t)d.n_reg * n);
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  if (d.has_cir) irc_presim_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
-  else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
-    irc_presim_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
-  else irc_presim_forward_kernel<false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
-  MCRE_LAUNCHED();
+  if (d.nt != 0 && d.n_units > 0) {
+    // forward pass with tangents (fills the value buffers too) + tangent moments
+    rc = irc_presim_tangent_pass(p, r, sh, d_scratch, d_partial, d_tmoments, st);
+    if (rc) return rc;
+  } else {
+    if (d.has_cir) irc_presim_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
+    else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
+      irc_presim_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
+    else irc_presim_forward_kernel<false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
+    MCRE_LAUNCHED();
+  }
   const int nu = nu_template(d.n_units);
   const int nv = 5 + 3 * nu, nw = threads / 32;
   const size_t smem = ((size_t)d.n_reg * nv + 2 * nw * nv) * sizeof(double);

@@ -62,7 +62,7 @@ _lib = None
 SYMBOLS = [
     "mcre_generate_paths",
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
-    "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim",
+    "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim", "mcre_irc_presim_tangent_slots",
     "mcre_irc_set_coefficients", "mcre_irc_mainsim",
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step",
     "mcre_lsm_prepare_equity",
@@ -97,7 +97,9 @@ def lib():
     L.mcre_irc_destroy.argtypes = [C.c_void_p]
     L.mcre_irc_destroy.restype = None
     L.mcre_irc_presim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_irc_presim_tangent_slots.restype = C.c_int64
+    L.mcre_irc_presim_tangent_slots.argtypes = [C.c_void_p]
     L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
     L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]

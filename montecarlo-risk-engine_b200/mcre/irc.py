@@ -20,7 +20,8 @@ from common.enums import SimulationScheme
 from mcre import binding as B
 from mcre import runtime as RT
 from mcre.dual import D, cholesky_dual
-from mcre.lsm import backward_induction, solve_normal_equations, solve_normal_equations_batch, to_raw_basis
+from mcre.lsm import (backward_induction, regression_tangents, solve_normal_equations, solve_normal_equations_batch,
+                      to_raw_basis)
 from mcre.timegrid import build_time_grid
 from metrics.metric import MetricType
 from models.cirpp import CIRPPModel
@@ -496,31 +497,43 @@ class IrcBackend:
             try:
                 begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
                 slots = L.mcre_irc_presim_slots(plan)
-                moments = torch.zeros(slots, dtype=torch.float64, device=dev)
+                tslots = L.mcre_irc_presim_tangent_slots(plan) if self.nt else 0
+                moments = torch.zeros(slots + tslots, dtype=torch.float64, device=dev)
                 # bound the scratch: process the local paths in batches of whole chunks
-                batch = max(CHUNK_PATHS, (c.presim_batch_paths // CHUNK_PATHS) * CHUNK_PATHS)
+                per_path = L.mcre_irc_presim_scratch_bytes(plan, CHUNK_PATHS) // CHUNK_PATHS
+                batch = c.presim_batch_paths * 20 * max(info["n_expo"], 1) // max(per_path, 1) if self.nt else c.presim_batch_paths
+                batch = max(CHUNK_PATHS, (batch // CHUNK_PATHS) * CHUNK_PATHS)
                 for b0 in range(0, count, batch):
                     bn = min(batch, count - b0)
                     scratch = torch.empty(L.mcre_irc_presim_scratch_bytes(plan, bn), dtype=torch.uint8, device=dev)
                     partial = torch.empty(L.mcre_irc_partial_bytes(plan, bn, CHUNK_PATHS, 1) // 8 + 1,
                                           dtype=torch.float64, device=dev)
-                    part_m = torch.zeros(slots, dtype=torch.float64, device=dev)
+                    part_m = torch.zeros(slots + tslots, dtype=torch.float64, device=dev)
                     rng = self._rng(42, inject, n_pre)
                     sh = B.Shard(begin + b0, bn, CHUNK_PATHS)
                     B.check(L.mcre_irc_presim(plan, C.byref(rng), C.byref(sh), scratch.data_ptr(),
-                                              partial.data_ptr(), part_m.data_ptr(), RT.stream_ptr()))
+                                              partial.data_ptr(), part_m.data_ptr(),
+                                              part_m[slots:].data_ptr() if tslots else None, RT.stream_ptr()))
                     moments += part_m
                     del scratch, partial
                 moments = RT.all_reduce_tree(moments)
-                mom = moments.cpu().numpy().reshape(info["n_expo"], -1)
+                mom_all = moments.cpu().numpy()
+                mom = mom_all[:slots].reshape(info["n_expo"], -1)
+                tmom = mom_all[slots:].reshape(len(group), self.nt, info["n_expo"], 9) if tslots else None
             finally:
                 L.mcre_irc_destroy(plan)
             nu = 1 if len(group) <= 1 else (2 if len(group) <= 2 else 4)
             assert mom.shape[1] == 5 + 3 * nu
             G = mom[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]          # [n_expo, 3, 3] Gram matrices of [1, u, u^2]
             for u, prod in enumerate(group):
-                coefs = solve_normal_equations_batch(G, mom[:, 5 + 3 * u: 8 + 3 * u])
-                out[id(prod)] = (coefs, info["basis"])
+                rhs = mom[:, 5 + 3 * u: 8 + 3 * u]
+                coefs = solve_normal_equations_batch(G, rhs)
+                dcoefs = None
+                if tmom is not None:
+                    # d(coefficients)/d(model parameters): the reference differentiates through lstsq
+                    dcoefs = np.stack([regression_tangents(G[k], rhs[k], coefs[k], tmom[u, :, k, :])
+                                       for k in range(info["n_expo"])])            # [n_expo, nt, 3]
+                out[id(prod)] = (coefs, info["basis"], dcoefs)
         return out
 
     def presim_bermudan(self, prod, dev):
@@ -579,7 +592,7 @@ class IrcBackend:
             # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
             for p in prods:
                 if id(p) in coef_by_product:
-                    coefs, basis = coef_by_product[id(p)]
+                    coefs, basis, _ = coef_by_product[id(p)]
                     degen = [t <= self.vas.t0() for t in c.exposure_timeline.tolist()]
                     c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coefs, basis, degen))
             expo_times = c.exposure_timeline.tolist() if need_expo else []
@@ -611,6 +624,8 @@ class IrcBackend:
                 for p in c.netting_sets[si].products:
                     if id(p) in coef_by_product:
                         coef[:n_expo, r, :, 0] += coef_by_product[id(p)][0]
+                        if self.nt and coef_by_product[id(p)][2] is not None:
+                            coef[:n_expo, r, :, 1:] += np.transpose(coef_by_product[id(p)][2], (0, 2, 1))
             plan = C.c_void_p()
             B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
             try:

@@ -65,6 +65,46 @@ def solve_normal_equations_batch(G, rhs):
     return out
 
 
+def gram_pinv(G):
+    """Pseudo-inverse of a Gram matrix with the rank decision of solve_normal_equations."""
+    d = np.sqrt(np.clip(np.diag(G), 0.0, None))
+    if not np.all(np.isfinite(G)) or d[0] == 0.0:
+        return np.zeros((3, 3))
+    scale = np.where(d > 0.0, d, 1.0)
+    Gs = G / np.outer(scale, scale)
+    s = np.linalg.svd(Gs, compute_uv=False)
+    if s[2] > 1e-10 * s[0]:
+        return np.linalg.inv(Gs) / np.outer(scale, scale)
+    u2, s2, vt2 = np.linalg.svd(G)
+    keep = s2 > 1e-10 * s2[0]
+    return (vt2[keep].T * (1.0 / s2[keep])) @ u2[:, keep].T
+
+
+def regression_tangents(G, rhs, coef, tm):
+    """d(coefficients)/d(parameter) of the least-squares fit c = pinv(A) Y from moment sums.
+
+    The reference keeps torch.linalg.lstsq inside the autograd graph (controller.py:368-383), whose
+    backward is the derivative of the pseudo-inverse.  With A = [1, u, u^2] per path and everything
+    expressed through sums over paths (G = A^T A, G+ = pinv(G), A+ = G+ A^T):
+        dc = G+ (A^T dY - A^T dA c) + G+ (dA^T Y - dA^T A c) + (I - G+ G) dA^T A G+ c
+    where A^T dA [i][j] = j sum u^(i+j-1) du.  The last term only matters on rank-deficient dates
+    (t = 0: every path has the same x).
+    G [3,3], rhs [3], coef [3], tm [nt, 9] (mcre_irc_presim tangent moments) -> [nt, 3]."""
+    Gp = gram_pinv(G)
+    nt = tm.shape[0]
+    out = np.zeros((nt, 3))
+    proj = np.eye(3) - Gp @ G
+    for p in range(nt):
+        mu, r, q1, q2 = tm[p, 0:4], tm[p, 4:7], tm[p, 7], tm[p, 8]
+        AtdA = np.zeros((3, 3))
+        for i in range(3):
+            for j in (1, 2):
+                AtdA[i, j] = j * mu[i + j - 1]
+        dAtY = np.array([0.0, q1, q2])
+        out[p] = Gp @ (r - AtdA @ coef) + Gp @ (dAtY - AtdA.T @ coef) + proj @ (AtdA.T @ (Gp @ coef))
+    return out
+
+
 def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev):
     """xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product
     (exercise) dates; reg_times: regression dates (sorted, contain every product date);

@@ -84,6 +84,64 @@ def test_pv_greeks_match_reference_golden():
     helpers.assert_close(got, out["grads"][0][0][0], 1e-9, 1e-9, "pv greeks")
 
 
+def _derivative_rows(res, s, m):
+    return np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives(s, m)])
+
+
+def test_exposure_metric_greeks_through_the_regression_match_reference_golden():
+    """CVA / EPE / PV sensitivities with differentiate=True.  The reference keeps the regression
+    coefficients in the autograd graph (controller.py:118-119, 368-383), so CVA and EPE Greeks contain
+    d(coefficients)/d(parameters): the tangent pre-simulation (csrc/irc_tan.cu) + the differentiated normal
+    equations (mcre/lsm.py:regression_tangents) reproduce it.  Injected reference draws; tolerance 2e-5
+    against the reference's autograd (its backward runs through float32 accumulators, SURVEY A-19) and
+    1e-7 against the oracle's forward-mode duals (same float64 tangents)."""
+    name = "wwr_cva_greeks"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _compare(flat, ref, RTOL, name)
+    out, _ = helpers.run_oracle(name, draws="torch")
+    for si, s in enumerate(gold["sets"]):
+        for mi, m in enumerate(gold["metrics"]):
+            got = _derivative_rows(res, s, m)
+            want = np.array([[0.0 if g is None else g for g in row] for row in gold["derivatives"][f"{s}|{m}"]])
+            scale = max(1.0, float(np.max(np.abs(want))))
+            rtol = 1e-9 if m == "pv" else 2e-5
+            helpers.assert_close(got, want, rtol, rtol * scale, f"{name} {s}|{m} derivatives vs reference")
+            orc = np.array([np.zeros(want.shape[1]) if g is None else np.asarray(g) for g in out["grads"][si][mi]])
+            helpers.assert_close(got, orc, 1e-7, 1e-7 * scale, f"{name} {s}|{m} derivatives vs oracle")
+
+
+@pytest.mark.parametrize("which", ["vasicek_collateral", "two_units_philox"])
+def test_exposure_metric_greeks_match_oracle(which):
+    """Other shapes of the same path: Vasicek alone (4 tangents) with MPoR collateral and a threshold, and a
+    netting set of two linear products (two regression units) under native Philox, vs the oracle."""
+    from oracle import risk
+    ns = cases.Namespace()
+    if which == "vasicek_collateral":
+        model, sets, metrics, tl = cases.vasicek_irs_collateral(ns, mpor=0.25, threshold=0.002, n_dates=9, maturity=2.0)
+        metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.EEPEMetric()]
+        n = 3000
+    else:
+        model, sets, metrics, tl = cases.wwr_cva(ns, rho=-0.4, n_expo=9, maturity=2.0)
+        extra = cases.wwr_cva(ns, rho=-0.4, n_expo=9, maturity=1.5)[1][0].products[0]
+        sets = [ns.NettingSet(name="book", products=[sets[0].products[0], extra], counterparty_id=sets[0].counterparty_id)]
+        n = 2500
+    rm = ns.RiskMetrics(metrics, exposure_timeline=tl)
+    sc = ns.SimulationController(sets, model, rm, n, n, 1, ns.SimulationScheme.EULER, True)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, metrics, tl, n, n, 1, "EULER", differentiate=True)
+    names, mnames = res.get_netting_set_names(), res.get_metric_names()
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, names, mnames), 1e-8, which, err_rtol=1e-6)
+    for si, s in enumerate(names):
+        for mi, m in enumerate(mnames):
+            got = _derivative_rows(res, s, m)
+            orc = np.array([np.zeros(got.shape[1]) if g is None else np.asarray(g) for g in out["grads"][si][mi]])
+            scale = max(1.0, float(np.max(np.abs(orc))))
+            helpers.assert_close(got, orc, 1e-6, 1e-7 * scale, f"{which} {s}|{m} derivatives vs oracle")
+
+
 def test_results_do_not_depend_on_sharding():
     """Chunked tree reduction: the same run split as 1 or 2 'ranks' gives identical bits."""
     from mcre import runtime
