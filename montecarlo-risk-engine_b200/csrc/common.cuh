@@ -33,19 +33,54 @@ inline int cuda_fail(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return mcre::cuda_fail(e__, "kernel launch"); \
   } while (0)
 
-// Device buffer filled from a host array (plan tables are tiny; cudaMalloc is fine).
+// One device allocation + one host-to-device copy for all tables of a plan: cudaMalloc / cudaFree
+// cost ~0.1 ms each and a plan has ~40 tables, which showed up as several ms per run_simulation()
+// call.  While an arena is open (ArenaScope) DevArray::upload stages into it; commit() allocates,
+// copies once and patches every staged array's device pointer.
+struct DevArena {
+  struct Item { void **slot; size_t off; };
+  std::vector<unsigned char> stage;
+  std::vector<Item> items;
+  void *base = nullptr;
+  void add(const void *host, size_t bytes, void **slot) {
+    const size_t off = (stage.size() + 255) & ~(size_t)255;
+    stage.resize(off + bytes);
+    memcpy(stage.data() + off, host, bytes);
+    items.push_back({slot, off});
+  }
+  int commit() {
+    if (stage.empty()) return 0;
+    MCRE_CUDA(cudaMalloc(&base, stage.size()));
+    MCRE_CUDA(cudaMemcpy(base, stage.data(), stage.size(), cudaMemcpyHostToDevice));
+    for (const Item &it : items) *it.slot = (unsigned char *)base + it.off;
+    std::vector<unsigned char>().swap(stage);
+    items.clear();
+    return 0;
+  }
+  void release() { if (base) cudaFree(base); base = nullptr; }
+};
+extern thread_local DevArena *g_arena;
+struct ArenaScope {
+  explicit ArenaScope(DevArena *a) { g_arena = a; }
+  ~ArenaScope() { g_arena = nullptr; }
+};
+
+// Device buffer filled from a host array (staged into the open arena, else its own allocation).
 template <typename T>
 struct DevArray {
   T *p = nullptr;
   size_t n = 0;
+  bool owned = false;
   int upload(const T *host, size_t count) {
     n = count;
     if (count == 0 || host == nullptr) { p = nullptr; n = 0; return 0; }
+    if (g_arena) { g_arena->add(host, count * sizeof(T), (void **)&p); return 0; }
     MCRE_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    owned = true;
     MCRE_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = false; }
 };
 
 int sm_count();

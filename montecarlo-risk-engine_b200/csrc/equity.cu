@@ -479,6 +479,7 @@ using namespace mcre;
 struct mcre_eq_plan {
   EqDev d;
   int nt = 0;
+  DevArena arena;   // all plan tables live in one device allocation
   DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w, ev_data, prod_x;
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
   DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src;
@@ -508,6 +509,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
     if (set < 0 || set >= c->n_sets) return fail(-1, "eq: product set index out of range%s", "");
   }
   mcre_eq_plan *p = new mcre_eq_plan();
+  ArenaScope arena_scope(&p->arena);
   p->nt = c->nt;
   const int A = c->n_assets, d = c->noise_dim, n_ev = c->date_ev_off[c->n_dates];
   int rc = 0;
@@ -553,6 +555,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
     if (sp_n > 0) { UP(sp_coef, coef.data(), coef.size()); UP(sp_src, src.data(), src.size()); }
   }
 #undef UP
+  if (!rc) rc = p->arena.commit();
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
@@ -584,6 +587,7 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->ev_data.release(); p->prod_x.release();
   p->date_expo.release(); p->date_metric.release(); p->set_flags.release(); p->set_lag.release();
   p->xp.release(); p->set_threshold.release(); p->sp_coef.release(); p->sp_src.release();
+  p->arena.release();
   delete p;
 }
 

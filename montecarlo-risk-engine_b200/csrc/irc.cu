@@ -204,6 +204,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   if (c->scheme == MCRE_SCHEME_ANALYTICAL && c->has_cir)
     return fail(-1, "irc: ANALYTICAL is not defined for the Vasicek+CIR++ hybrid (model_config.py:216-221)%s", "");
   mcre_irc_plan *p = new mcre_irc_plan();
+  ArenaScope arena_scope(&p->arena);
   const int w = 1 + c->nt;
   const int n_float = c->date_float_off ? c->date_float_off[c->n_dates] : 0;
   int rc = 0;
@@ -269,6 +270,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
                   c->set_threshold[0] == 0.0 && (c->set_flags[0] & 1) == 0 && (c->set_flags[0] & 2) != 0;
   }
 #undef UP
+  if (!rc) rc = p->arena.commit();
   if (rc) { mcre_irc_destroy(p); return rc; }
   IrcDev &d = p->d;
   d.nt = c->nt; d.scheme = c->scheme; d.has_cir = c->has_cir; d.cir_det = c->cir_deterministic;
@@ -307,6 +309,7 @@ extern "C" void mcre_irc_destroy(mcre_irc_plan *p) {
   p->berm_set.release(); p->date_ex_off.release(); p->ex_unit.release(); p->ex_last.release(); p->ex_term_off.release();
   p->berm_strike.release(); p->berm_sign.release(); p->ex_const.release(); p->term_coef.release(); p->term_w.release();
   p->ex_basis.release(); p->ex_coef.release(); p->berm_expo_coef.release();
+  p->arena.release();
   delete p;
 }
 

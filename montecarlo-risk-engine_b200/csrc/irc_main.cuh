@@ -508,8 +508,8 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
         }
         if (!pilot) block_accumulate<NVB>(vals, acc, P.n_metric * NVB, stage, NVB, parity);
       }
+      if (pilot) return;   // the pilot launch simulates global path 0 only: one pass is enough
     }
-    if (pilot) return;
     __syncthreads();
     for (int i = threadIdx.x; i < n_slots; i += blockDim.x) partial[(size_t)chunk * n_slots + i] = acc[i];
     __syncthreads();
@@ -523,6 +523,7 @@ using namespace mcre;
 
 struct mcre_irc_plan {
   IrcDev d;
+  DevArena arena;   // all plan tables live in one device allocation
   DevArray<double> vas, cir, cir_init, chol, step_dt, step_vas, step_cir, float_coef, float_inv_tau, set_fix,
       set_float, set_threshold, expo_coef, expo_basis, cva_coef, unit_fix, unit_float, reg_basis;
   DevArray<int> step_date, date_flags, date_expo, date_metric, date_reg, date_float_off, set_flags, set_lag;

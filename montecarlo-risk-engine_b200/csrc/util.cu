@@ -1,10 +1,15 @@
 // Library-wide utilities: error state, launch accounting, the fixed-order tree reduction
 // of per-chunk partial sums, and the FP64 FMA peak probe used as roofline denominator.
 #include "common.cuh"
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mcre {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+thread_local DevArena *g_arena = nullptr;
 
 int sm_count() {
   static int cached = 0;
@@ -17,32 +22,63 @@ int sm_count() {
   return cached;
 }
 
-// Balanced pairwise sum over chunks with a binary-counter stack: element i is pushed at
-// level 0 and equal-level neighbours are merged immediately.  For a power-of-two count
-// this is exactly the balanced binary tree over chunk indices, so a rank that owns an
-// aligned power-of-two block of chunks produces a node of the global tree and the result
-// is independent of how many GPUs the chunks were spread over.
-__global__ void tree_reduce_kernel(const double *partial, long long n_chunks, long long n_slots, double *out) {
-  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_slots) return;
-  double stack[48];
+// Balanced pairwise sum over chunks, defined by a binary-counter stack: element i is pushed at
+// level 0 and equal-level neighbours are merged immediately; leftover levels (non power-of-two
+// counts) fold from the most recent to the oldest.  For a power-of-two count this is exactly the
+// balanced binary tree over chunk indices, so a rank that owns an aligned power-of-two block of
+// chunks produces a node of the global tree and the result is independent of how many GPUs the
+// chunks were spread over.
+//
+// The tree is evaluated level by level, 32 elements at a time, so the loads of one thread are
+// independent (the first version walked the chunks serially per slot: 2 ms of dependent-load
+// latency per 4096-chunk reduction).  A full group of 32 aligned elements is a balanced subtree
+// -> one element of the next level; the ragged tail of a level is the most recent part of the
+// stack and is folded into the running `carry` before any older block, level by level.
+constexpr int TREE_G = 32;
+
+__device__ __forceinline__ double counter_fold(const double *v, int cnt, double carry, bool carry_valid) {
+  double stack[8];
   int top = 0;
-  for (long long c = 0; c < n_chunks; ++c) {
-    double v = partial[c * n_slots + slot];
-    long long idx = c + 1;
-    // merge while the low bit of the running count is clear: (c+1) has trailing zeros
-    while ((idx & 1) == 0) { v = stack[--top] + v; idx >>= 1; }
-    stack[top++] = v;
+  for (int c = 0; c < cnt; ++c) {
+    double x = v[c];
+    int idx = c + 1;
+    while ((idx & 1) == 0) { x = stack[--top] + x; idx >>= 1; }
+    stack[top++] = x;
   }
-  double s = 0.0;
-  bool first = true;
-  // leftover levels (non power-of-two counts): fold from the most recent to the oldest
+  double s = carry;
+  bool first = !carry_valid;
   while (top > 0) {
-    double v = stack[--top];
-    s = first ? v : v + s;
+    const double x = stack[--top];
+    s = first ? x : x + s;
     first = false;
   }
-  out[slot] = s;
+  return s;
+}
+
+// in: [n_in][n_slots].  Groups g < n_full: balanced sum of 32 rows -> next[g][slot].
+// Group n_full (launched when there is a tail, or as the last level with n_full = 0):
+// counter-fold of rows [32 n_full, n_in) with the incoming carry -> carry[slot].
+__global__ void __launch_bounds__(128) tree_level_kernel(const double *in, long long n_in, long long n_slots,
+                                                         long long n_full, double *next, double *carry,
+                                                         int carry_valid) {
+  const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const long long g = blockIdx.y;
+  double v[2 * TREE_G];
+  if (g < n_full) {
+#pragma unroll
+    for (int i = 0; i < TREE_G; ++i) v[i] = in[(g * TREE_G + i) * n_slots + slot];
+#pragma unroll
+    for (int w = 1; w < TREE_G; w <<= 1)
+#pragma unroll
+      for (int i = 0; i < TREE_G; i += 2 * w) v[i] = v[i] + v[i + w];
+    next[g * n_slots + slot] = v[0];
+    return;
+  }
+  const int cnt = (int)(n_in - n_full * TREE_G);   // < 2 * TREE_G
+#pragma unroll
+  for (int i = 0; i < 2 * TREE_G; ++i) v[i] = i < cnt ? in[(n_full * TREE_G + i) * n_slots + slot] : 0.0;
+  carry[slot] = counter_fold(v, cnt, carry_valid ? carry[slot] : 0.0, carry_valid != 0);
 }
 
 // Register-resident DFMA chains: 16 independent accumulators per thread.
@@ -63,14 +99,60 @@ __global__ void dfma_peak_kernel(double *sink, int iters, double a, double b) {
 
 using namespace mcre;
 
+// Level buffers of mcre_tree_reduce: one grow-only device buffer per (device, stream); work queued on a
+// stream is ordered, so consecutive reductions on it can share the buffer.  (cudaMallocAsync was tried and
+// cost more than the reduction: the default pool hands its memory back at every synchronisation.)
+static int tree_scratch(cudaStream_t st, size_t bytes, double **out) {
+  struct Buf { void *p = nullptr; size_t cap = 0; };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  int dev = 0;
+  MCRE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  Buf &b = bufs[std::make_pair(dev, st)];
+  if (b.cap < bytes) {
+    if (b.p) { MCRE_CUDA(cudaStreamSynchronize(st)); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t cap = std::max(bytes, (size_t)4 << 20);
+    MCRE_CUDA(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+  }
+  *out = (double *)b.p;
+  return 0;
+}
+
 extern "C" int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64_t n_slots, double *d_out,
                                 void *stream) {
   if (!d_partial || !d_out) return fail(-1, "null argument%s", "");
   if (n_slots <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_chunks <= 0) { MCRE_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_slots * sizeof(double), st)); return 0; }
   const int threads = 128;
-  const unsigned blocks = (unsigned)((n_slots + threads - 1) / threads);
-  tree_reduce_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_partial, n_chunks, n_slots, d_out);
-  MCRE_LAUNCHED();
+  const unsigned bx = (unsigned)((n_slots + threads - 1) / threads);
+  // level buffers: n/32 + n/1024 + ... rows, from a grow-only scratch kept per stream
+  double *scratch = nullptr;
+  size_t rows = 0;
+  for (long long n = n_chunks; n >= 2 * TREE_G; n /= TREE_G) rows += (size_t)(n / TREE_G);
+  if (rows) {
+    const int rc = tree_scratch(st, rows * (size_t)n_slots * sizeof(double), &scratch);
+    if (rc) return rc;
+  }
+  const double *in = d_partial;
+  double *next = scratch;
+  long long n = n_chunks;
+  int carry_valid = 0;
+  while (true) {
+    const bool last = n < 2 * TREE_G;
+    const long long n_full = last ? 0 : n / TREE_G;
+    const bool tail = last || (n % TREE_G) != 0;
+    dim3 grid(bx, (unsigned)(n_full + (tail ? 1 : 0)));
+    tree_level_kernel<<<grid, threads, 0, st>>>(in, n, n_slots, n_full, next, d_out, carry_valid);
+    MCRE_LAUNCHED();
+    if (tail) carry_valid = 1;
+    if (last) break;
+    in = next;
+    next += (size_t)n_full * n_slots;
+    n = n_full;
+  }
   return 0;
 }
 

@@ -361,7 +361,9 @@ class EquityBackend:
                 recs.append(rec)
                 weights.append(w)
                 xw = np.zeros(A)
-                xw[self._asset_index(p.asset_ids[0])] = 1.0   # explanatory variable: spot of the product's first asset
+                aid = p.asset_ids[0] if getattr(p, "asset_ids", None) else None
+                if self.A == 1 or aid in self.id_to_asset:
+                    xw[self._asset_index(aid)] = 1.0   # explanatory variable: spot of the product's first asset
                 xweights.append(xw)
                 owners.append(p)
                 for di, f in evs:

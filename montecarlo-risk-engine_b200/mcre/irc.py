@@ -10,6 +10,7 @@ simulation.  What it takes the place of in the reference:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 
@@ -36,7 +37,11 @@ CHUNK_PATHS = 4096
 
 
 def _packs(duals):
-    return np.concatenate([d.pack() for d in duals]) if duals else np.zeros(0)
+    if not duals:
+        return np.zeros(0)
+    if duals[0].t.shape[0] == 0:
+        return np.array([d.v for d in duals], dtype=np.float64)      # value-only plan
+    return np.concatenate([d.pack() for d in duals])
 
 
 class LinearLeg:
@@ -183,14 +188,21 @@ class IrcBackend:
     def basis_at(self, t):
         """Standardisation (shift, scale) of the explanatory variable r(t): its Vasicek mean /
         std (pure conditioning aid; the fitted values do not depend on it)."""
+        cache = self.__dict__.setdefault("_basis_cache", {})
+        hit = cache.get(t)
+        if hit is not None:
+            return hit
         pv, _ = self._dual_params()
         r0, sig, th, a = (x.v for x in pv)
         tau = t - self.vas.t0()
         if tau <= 0:
-            return (r0, 1.0)
-        mean = th + (r0 - th) * math.exp(-a * tau)
-        std = sig * math.sqrt((1.0 - math.exp(-2.0 * a * tau)) / (2.0 * a))
-        return (mean, 1.0 / std if std > 0 else 1.0)
+            out = (r0, 1.0)
+        else:
+            mean = th + (r0 - th) * math.exp(-a * tau)
+            std = sig * math.sqrt((1.0 - math.exp(-2.0 * a * tau)) / (2.0 * a))
+            out = (mean, 1.0 / std if std > 0 else 1.0)
+        cache[t] = out
+        return out
 
     def lower(self, set_indices, unit_products, berm_units=None, reg_times=None):
         """Build the descriptor for a group of netting sets (main) and regression units
@@ -480,8 +492,10 @@ class IrcBackend:
             r.n_paths_total = n_total
         return r
 
-    def presim_coefficients(self, products, dev):
-        """Regression coefficients [product][n_expo][3] in the standardised basis."""
+    def presim_coefficients(self, products, dev, while_running=None):
+        """Regression coefficients [product][n_expo][3] in the standardised basis.
+        `while_running`: host work to do after the first group's kernels are queued and before
+        their moments are read back (the main plan's lowering overlaps the pre-simulation)."""
         c = self.c
         L = B.lib()
         n_pre = c.num_paths_presim
@@ -516,6 +530,9 @@ class IrcBackend:
                                               part_m[slots:].data_ptr() if tslots else None, RT.stream_ptr()))
                     moments += part_m
                     del scratch, partial
+                if while_running is not None:
+                    while_running()
+                    while_running = None
                 moments = RT.all_reduce_tree(moments)
                 mom_all = moments.cpu().numpy()
                 mom = mom_all[:slots].reshape(info["n_expo"], -1)
@@ -536,6 +553,18 @@ class IrcBackend:
                 out[id(prod)] = (coefs, info["basis"], dcoefs)
         return out
 
+    @contextlib.contextmanager
+    def _value_only(self):
+        """Lower without tangents: the Longstaff-Schwartz policy enters the main pass through hard
+        exercise indicators only (bermudan_option.py:121), whose derivative is zero, so its
+        pre-simulation needs no tangents even when differentiate=True."""
+        saved = (self.nt, getattr(self, "_dual_cache", None), getattr(self, "_step_cache", None))
+        self.nt, self._dual_cache, self._step_cache = 0, None, None
+        try:
+            yield
+        finally:
+            self.nt, self._dual_cache, self._step_cache = saved
+
     def presim_bermudan(self, prod, dev):
         """Longstaff-Schwartz pre-simulation of one Bermudan option (controller.py:294-383):
         forward pass spills x, numeraire and immediate values; one fused moments(+exercise
@@ -550,7 +579,8 @@ class IrcBackend:
         expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
         ptl = prod.product_timeline.tolist()
         reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
-        desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
+        with self._value_only():
+            desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
         n_reg, n_ex = len(reg_times), info["n_ex"]
         basis = info["reg_basis"]
         inject = c.injected_normals.get("pre") if c.injected_normals else None
@@ -585,10 +615,19 @@ class IrcBackend:
         t0 = time.perf_counter()
         coef_by_product = {}
         berm_coef = {}
+        group_size = B.IRC_MAX_SETS if self.nt == 0 else 2
+        groups = [list(range(g0, min(g0 + group_size, n_sets))) for g0 in range(0, n_sets, group_size)]
+        lowered = {}
+
+        def lower_main():
+            for gi, idxs in enumerate(groups):
+                lowered[gi] = self.lower(idxs, [])
+
         if c.requires_regression:
             prods = [p for p in c.products if c._product_requires_regression(p) and is_linear(p)]
             if prods and need_expo:
-                coef_by_product = self.presim_coefficients(prods, dev)
+                # the main plans are lowered on the host while the pre-simulation kernels run
+                coef_by_product = self.presim_coefficients(prods, dev, while_running=lower_main)
             # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
             for p in prods:
                 if id(p) in coef_by_product:
@@ -599,6 +638,10 @@ class IrcBackend:
             for p in c.products:
                 if not is_rate_bermudan(p):
                     continue
+                if self.nt and need_expo:
+                    raise NotImplementedError(
+                        "sensitivities of exposure profiles of exercise products (tangents of the alive-state "
+                        "regression coefficients) are not implemented; PV sensitivities are")
                 coef, reg_times, basis = self.presim_bermudan(p, dev)
                 berm_coef[id(p)] = (coef, {t: k for k, t in enumerate(reg_times)}, basis)
                 raw = to_raw_basis(coef, basis, [t <= self.vas.t0() for t in reg_times])
@@ -613,10 +656,10 @@ class IrcBackend:
 
         results = [None] * n_sets
         inject = c.injected_normals.get("main") if c.injected_normals else None
-        group_size = B.IRC_MAX_SETS if self.nt == 0 else 2
-        for g0 in range(0, n_sets, group_size):
-            idxs = list(range(g0, min(g0 + group_size, n_sets)))
-            desc, keep, info = self.lower(idxs, [])
+        if not lowered:
+            lower_main()
+        for gi, idxs in enumerate(groups):
+            desc, keep, info = lowered[gi]
             w = 1 + self.nt
             n_expo, n_metric = info["n_expo"], info["n_metric"]
             coef = np.zeros((max(n_expo, 1), len(idxs), 3, w))

@@ -77,3 +77,53 @@ def test_shard_range_partitions_the_path_range():
                     assert b == covered
                 covered += c
             assert covered == n_paths
+
+
+def _level_tree_sum(vals, group=32):
+    """Python mirror of csrc/util.cu:mcre_tree_reduce (level-by-level evaluation of the binary-counter tree)."""
+    def counter_fold(v, carry):
+        stack = []
+        for c, x in enumerate(v):
+            idx = c + 1
+            while idx % 2 == 0:
+                x = stack.pop() + x
+                idx //= 2
+            stack.append(x)
+        s = carry
+        while stack:
+            x = stack.pop()
+            s = x if s is None else x + s
+        return s
+
+    cur, carry = list(vals), None
+    while True:
+        n = len(cur)
+        last = n < 2 * group
+        n_full = 0 if last else n // group
+        nxt = []
+        for g in range(n_full):
+            v = cur[g * group:(g + 1) * group]
+            w = 1
+            while w < group:
+                for i in range(0, group, 2 * w):
+                    v[i] = v[i] + v[i + w]
+                w *= 2
+            nxt.append(v[0])
+        if last or n % group:
+            carry = counter_fold(cur[n_full * group:], carry)
+        if last:
+            return carry
+        cur = nxt
+
+
+def test_level_tree_reduction_equals_the_binary_counter_tree():
+    """The device reduction evaluates the summation tree 32 elements per level; the tree itself (and so every
+    bit of the result) must stay the binary-counter tree that RT.tree_sum defines for any chunk count."""
+    import importlib
+    importlib.import_module("montecarlo-risk-engine_b200")
+    from mcre import runtime as RT
+    rng = np.random.default_rng(5)
+    for n in list(range(1, 140)) + [255, 256, 257, 1000, 1023, 1024, 1025, 2047, 2048, 2049, 4096, 4097, 5000, 33000]:
+        vals = list(rng.standard_normal(n) * 10.0 ** rng.integers(-8, 8, n))
+        a, b = RT.tree_sum(vals), _level_tree_sum(vals)
+        assert a == b, (n, a, b)

@@ -177,3 +177,22 @@ def test_edge_cases():
                                 256, 256, 1, ns.SimulationScheme.EULER)
     with pytest.raises(ValueError):
         ns.SimulationController([], model, rm, 16, 16, 1, ns.SimulationScheme.EULER)
+
+
+def test_tree_reduce_is_the_binary_counter_tree_bit_for_bit():
+    """mcre_tree_reduce evaluates the fixed summation tree level by level (csrc/util.cu); every bit must equal
+    the host definition of the tree (mcre/runtime.py:tree_sum) for ragged and power-of-two chunk counts."""
+    import ctypes as C
+    import torch
+    from mcre import binding as B, runtime as RT
+    L = B.lib()
+    dev = RT.compute_device()
+    rng = np.random.default_rng(11)
+    for n_chunks, n_slots in [(1, 5), (2, 3), (31, 7), (32, 130), (33, 4), (63, 4), (64, 9), (65, 2), (1000, 17),
+                              (1024, 3), (2049, 2), (4096, 964), (4097, 11)]:
+        host = rng.standard_normal((n_chunks, n_slots)) * 10.0 ** rng.integers(-6, 6, (n_chunks, n_slots))
+        part = torch.tensor(host, dtype=torch.float64, device=dev)
+        out = torch.full((n_slots,), float("nan"), dtype=torch.float64, device=dev)
+        B.check(L.mcre_tree_reduce(part.data_ptr(), n_chunks, n_slots, out.data_ptr(), RT.stream_ptr()))
+        want = RT.tree_sum([host[c] for c in range(n_chunks)])
+        assert np.array_equal(out.cpu().numpy(), want), (n_chunks, n_slots)

@@ -50,6 +50,26 @@ def test_bermudan_swaption_philox_matches_oracle(kwargs):
     assert np.all(np.abs(got - want) <= 1e-6 * fit_scale), "exposure regression coefficients"
 
 
+def test_bermudan_swaption_pv_greeks_match_oracle():
+    """PV sensitivities of a Bermudan swaption (differentiate=True): the exercise policy is a hard indicator
+    (bermudan_option.py:121, zero derivative), so the Greeks are the pathwise tangents of the exercised cashflow."""
+    from oracle import risk
+    ns = cases.Namespace()
+    model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=6)
+    n = 3000
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics([ns.PVMetric()]), n, n, 1, ns.SimulationScheme.EULER, True)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, [ns.PVMetric()], None, n, n, 1, "EULER", differentiate=True)
+    helpers.assert_close(res.get_results("bermudan", "pv"), [out["results"][0][0][0][0]], 1e-8, 1e-12, "pv")
+    got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives("bermudan", "pv")[0]])
+    want = np.asarray(out["grads"][0][0][0])
+    helpers.assert_close(got, want, 1e-7, 1e-8 * max(1.0, float(np.abs(want).max())), "pv greeks")
+    assert np.all(np.isfinite(got)) and np.any(got != 0.0)
+    with pytest.raises(NotImplementedError):
+        ns.SimulationController(sets, model, ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), n, n, 1,
+                                ns.SimulationScheme.EULER, True).run_simulation()
+
+
 def test_bermudan_pv_only_and_mixed_book():
     """PV-only run (regression dates = exercise dates only) and a netting set mixing a swap
     with a Bermudan swaption, collateralised, all exposure metrics."""
