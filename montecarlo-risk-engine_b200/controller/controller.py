@@ -13,6 +13,7 @@ Flow of run_simulation():
 from __future__ import annotations
 
 import logging
+import os
 import time
 from collections import defaultdict
 from typing import Sequence
@@ -32,6 +33,13 @@ from products.netting_set import NettingSet
 logger = logging.getLogger(__name__)
 
 _SINGLE_EVAL = {MetricType.PV, MetricType.CVA, MetricType.EEPE, MetricType.CE}
+
+
+def _merge_grads(a, b):
+    """Sum two per-parameter gradient lists where None means "not connected"."""
+    if a is None:
+        return list(b)
+    return [y if x is None else (x if y is None else x + y) for x, y in zip(a, b)]
 
 
 class SimulationController:
@@ -100,6 +108,9 @@ class SimulationController:
         self.rng_stream = 0
         #: parity mode: {"pre": Tensor[n_sub, N_pre, d], "main": Tensor[n_sub, N_main, d]} on the GPU
         self.injected_normals = None
+        #: "philox" (default: counter-based draws made in registers) or "torch": the reference's own
+        #: torch.randn stream (seeds 42 / 43) regenerated on the host and injected (mcre/compat.py)
+        self.rng_compat = os.environ.get("MCRE_RNG", "philox").lower()
         #: pre-simulation scratch is bounded by processing this many local paths at a time
         self.presim_batch_paths = 1 << 22
         self.last_timings = {}
@@ -183,20 +194,62 @@ class SimulationController:
             f"No CUDA backend for model {type(self.model).__name__} with products "
             f"{sorted({type(p).__name__ for p in self.products})}")
 
+    def _analytic_pv(self, product):
+        """Closed-form PV of a product the Monte Carlo can skip (controller.py:204-229) and, with
+        differentiate=True, its first (and on request second) derivatives with respect to the model
+        parameters: a scalar closed form evaluated on the host with torch autograd, like the reference."""
+        params = self.model.get_model_params()
+        if not self.differentiate:
+            return float(product.compute_pv_analytically(self.model).squeeze()), None, None
+        for q in params:
+            q.requires_grad_(True)
+        try:
+            pv = product.compute_pv_analytically(self.model).squeeze()
+            second = self.requires_higher_order_derivatives
+            g = torch.autograd.grad(pv, params, retain_graph=second, create_graph=second, allow_unused=True)
+            hess = None
+            if second:
+                hess = []
+                for gi in g:
+                    if gi is None or not gi.requires_grad:
+                        hess.append(tuple(None for _ in params))
+                        continue
+                    row = torch.autograd.grad(gi, params, retain_graph=True, allow_unused=True)
+                    hess.append(tuple(None if h is None else h.detach().cpu().numpy() for h in row))
+            grads = [None if gi is None else gi.detach().cpu().numpy() for gi in g]
+            return float(pv.detach()), grads, hess
+        finally:
+            for q in params:
+                q.requires_grad_(False)
+
     def run_simulation(self) -> SimulationResults:
         t0 = time.perf_counter()
-        if self.requires_higher_order_derivatives:
-            raise NotImplementedError("second-order sensitivities are not implemented (SURVEY §8f item 4)")
         mc_products = [p for p in self.products if not self._can_skip_monte_carlo_for_product(p)]
+        if self.requires_higher_order_derivatives and mc_products:
+            raise NotImplementedError("second-order sensitivities are implemented for analytic PVs only "
+                                      "(pathwise Hessians: SURVEY §8f item 4)")
+        n_params = len(self.model.get_model_params())
         analytic = [[0.0 for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
+        analytic_grads = [[None for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
+        analytic_hess = [[None for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
         has_pathwise = [False] * len(self.netting_sets)
         for pi, p in enumerate(self.products):
             si = self.product_to_netting_set_idx[pi]
             if self._can_skip_monte_carlo_for_product(p):
+                pv, g, h = self._analytic_pv(p)
                 for mi, _ in enumerate(self.risk_metrics.metrics):
-                    analytic[si][mi] += float(p.compute_pv_analytically(self.model).squeeze())
+                    analytic[si][mi] += pv
+                    if g is not None:
+                        analytic_grads[si][mi] = _merge_grads(analytic_grads[si][mi], g)
+                    if h is not None:
+                        cur = analytic_hess[si][mi]
+                        analytic_hess[si][mi] = h if cur is None else [tuple(_merge_grads(list(a), list(b))) for a, b in zip(cur, h)]
             else:
                 has_pathwise[si] = True
+        self._analytic_grads = analytic_grads
+        if mc_products and self.injected_normals is None and self.rng_compat == "torch":
+            from mcre.compat import inject_reference_stream
+            inject_reference_stream(self)
         raw, timings = None, {"preprocessing": 0.0, "path_generation": 0.0, "request_resolution": 0.0}
         if mc_products:
             backend = self._select_backend()
@@ -213,8 +266,14 @@ class SimulationController:
             "preprocessing=%.6fs path_generation=%.6fs request_resolution=%.6fs valuation=%.6fs total=%.6fs",
             len(self.netting_sets), len(self.products), timings["preprocessing"], timings["path_generation"],
             timings["request_resolution"], timings["valuation"], timings["total"])
+        higher = []
+        if self.requires_higher_order_derivatives:
+            # [set][metric][evaluation][parameter i] -> tuple over parameters (simulation_results.py:5-338)
+            higher = [[[analytic_hess[si][mi] if analytic_hess[si][mi] is not None
+                        else [tuple(None for _ in range(n_params)) for _ in range(n_params)]]
+                       for mi in range(len(self.risk_metrics.metrics))] for si in range(len(self.netting_sets))]
         return SimulationResults(
-            results, grads, [],
+            results, grads, higher,
             netting_set_names=self._make_unique_names([ns.get_name() for ns in self.netting_sets]),
             metric_names=self._make_unique_names([m.get_name() for m in self.risk_metrics.metrics]),
             model_param_names=self.model.get_model_param_names())

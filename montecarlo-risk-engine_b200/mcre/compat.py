@@ -33,3 +33,42 @@ def single_step(model, scheme, time1, time2, state, corr_randn):
                          init_state=uniq[k].tolist(), identity_chol=True)
         out[sel] = paths[:, 0, :].cpu()
     return out
+
+
+def torch_reference_draws(seed, n_paths, n_sub, dim, qe=False):
+    """The reference's own random stream for one engine run, regenerated on the host: it seeds the
+    (global) torch generator in MonteCarloEngine.__init__ (engine.py:25: 42 for the pre-simulation, 43 for
+    the main simulation), then draws per sub-step one torch.randn(N, d) (model.py:47) and, under the Heston QE
+    scheme, one torch.rand_like(m) after it (heston.py:191-192).  A private generator with the same seed
+    yields the same numbers without touching the caller's global RNG state.
+    -> (z [n_sub, N, d], u [n_sub, N] or None), float64 host tensors."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    z = torch.empty((n_sub, n_paths, dim), dtype=torch.float64)
+    u = torch.empty((n_sub, n_paths), dtype=torch.float64) if qe else None
+    for s in range(n_sub):
+        torch.randn(n_paths, dim, generator=g, dtype=torch.float64, out=z[s])
+        if qe:
+            u[s] = torch.rand(n_paths, 1, generator=g, dtype=torch.float64)[:, 0]
+    return z, u
+
+
+def inject_reference_stream(ctrl):
+    """RNG compatibility mode (`SimulationController.rng_compat = "torch"` or MCRE_RNG=torch): feed the
+    kernels the reference's torch.randn stream instead of Philox, so seeded known answers of the reference
+    (tests/pytests/test_american_option.py:61, test_cva.py:188-189) are reproduced digit for digit.  Only
+    the normals are made on the host; stepping, payoffs, regressions and metrics stay on the GPU."""
+    from common.enums import SimulationScheme
+    from mcre.timegrid import build_time_grid
+    model = ctrl.model
+    t0 = float(model.calibration_date[0]) if not hasattr(model, "models") else float(model.models[0].calibration_date[0])
+    n_sub = build_time_grid(t0, ctrl.simulation_timeline.tolist(), ctrl.num_steps).n_sub
+    dim = int(model.simulation_dim)
+    qe = ctrl.simulation_scheme == SimulationScheme.QE
+    pre = None
+    if ctrl.requires_regression and ctrl.num_paths_presim > 0:
+        pre = torch_reference_draws(42, ctrl.num_paths_presim, n_sub, dim, qe)
+    main = torch_reference_draws(43, ctrl.num_paths_mainsim, n_sub, dim, qe)
+    ctrl.inject_normals(pre=None if pre is None else pre[0], main=main[0])
+    if qe:
+        ctrl.injected_uniforms = {"pre": None if pre is None else pre[1], "main": main[1]}

@@ -77,12 +77,19 @@ def finish_results(ctrl, raw, analytic, has_pathwise):
             set_results.append(vals)
             if ctrl.differentiate:
                 used = r["param_used"](kind) if r is not None else [False] * n_params
+                # closed-form part of an analytic PV (controller._analytic_pv): host autograd gradients
+                ag = None
+                if kind == MetricType.PV and metric.evaluation_type == Metric.EvaluationType.ANALYTICAL:
+                    ag = getattr(ctrl, "_analytic_grads", None)
+                    ag = ag[si][mi] if ag is not None else None
                 per_eval = []
                 for t in tans:
-                    if t is None:
-                        per_eval.append(tuple(None for _ in range(n_params)))
-                    else:
-                        per_eval.append(tuple(np.asarray(t[i]) if used[i] else None for i in range(n_params)))
+                    row = [None] * n_params
+                    if t is not None:
+                        row = [np.asarray(t[i]) if used[i] else None for i in range(n_params)]
+                    if ag is not None:
+                        row = [a if b is None else (b if a is None else np.asarray(a + b)) for a, b in zip(ag, row)]
+                    per_eval.append(tuple(row))
                 set_grads.append(per_eval)
         results.append(set_results)
         if ctrl.differentiate:

@@ -1,10 +1,11 @@
 """European option on an equity, bond or swap underlying
 (reference: src/products/european_option.py:15-145).
 
-The semi-analytic Heston and Vasicek bond-option pricers of the reference are
-host-side validation helpers and out of scope; the
-Black-Scholes closed form is kept because the controller's analytic PV /
-analytic exposure shortcuts depend on it."""
+The Black-Scholes closed form drives the controller's analytic PV / analytic exposure
+shortcuts.  The semi-analytic Heston price (a host-side validation helper of the
+reference, european_option.py:146-242, used by tests/pytests/test_pv_european_option_heston.py)
+is provided through one characteristic function of log S_T in the branch-cut-free form;
+the Vasicek bond-option pricer stays out of scope."""
 import math
 from products.product import *
 from products.product import _ft
@@ -47,6 +48,60 @@ class EuropeanOption(Product):
         if self.option_type == OptionType.CALL:
             return spot * _norm_cdf(d1) - disc_k * _norm_cdf(d2)
         return disc_k * _norm_cdf(-d2) - spot * _norm_cdf(-d1)
+
+    # -- semi-analytic Heston price (validation helper, host only) --------------
+    def compute_pv_analytically_heston(self, model):
+        """Call/put under Heston by Fourier inversion of the characteristic function of log S_T:
+        C = S0 P1 - K exp(-rT) P2,  P2 = 1/2 + 1/pi int_0^inf Re[exp(-iu ln K) phi(u) / (iu)] du and
+        P1 the same with phi(u - i) / phi(-i).  phi is written with the root d and ratio g that keep
+        exp(-dT) decaying, so the complex logarithm never crosses its branch cut."""
+        from models.heston import HestonModel
+        if not isinstance(model, HestonModel):
+            raise TypeError("Expected model to be of type HestonModel")
+        import numpy as np
+        from scipy.integrate import quad
+        s0, sig, r, rho, kappa, theta, v0 = (float(q) for q in model.model_params)
+        K, T = float(self.strike[0]), float(self.exercise_date[0])
+        lnk, fwd = math.log(K), math.log(s0) + r * T
+
+        def phi(u):
+            iu = 1j * u
+            beta = kappa - rho * sig * iu
+            d = np.sqrt(beta * beta + sig * sig * (iu + u * u))
+            if d.real < 0:
+                d = -d
+            g = (beta - d) / (beta + d)
+            e = np.exp(-d * T)
+            A = kappa * theta / (sig * sig) * ((beta - d) * T - 2.0 * np.log((1.0 - g * e) / (1.0 - g)))
+            Bv = (beta - d) / (sig * sig) * (1.0 - e) / (1.0 - g * e)
+            return np.exp(iu * fwd + A + Bv * v0)
+
+        norm = s0 * math.exp(r * T)          # phi(-i): the forward
+        p2 = 0.5 + quad(lambda u: (np.exp(-1j * u * lnk) * phi(u) / (1j * u)).real, 1e-12, 200.0, limit=400)[0] / math.pi
+        p1 = 0.5 + quad(lambda u: (np.exp(-1j * u * lnk) * phi(u - 1j) / (1j * u * norm)).real, 1e-12, 200.0,
+                        limit=400)[0] / math.pi
+        call = s0 * p1 - K * math.exp(-r * T) * p2
+        if self.option_type == OptionType.CALL:
+            return call
+        return call - s0 + K * math.exp(-r * T)      # put-call parity
+
+    # -- closed-form second-order Greeks (validation helpers; reference: european_option.py:290-320) --
+    def _bs_d1_d2(self, model):
+        spot, sigma = self._bs_spot_vol(model)
+        vol_t = sigma * torch.sqrt(self.exercise_date)
+        d1 = (torch.log(spot / self.strike) + (model.get_rate() + 0.5 * sigma ** 2) * self.exercise_date) / vol_t
+        return spot, sigma, vol_t, d1, d1 - vol_t
+
+    def compute_dDeltadSpot_analytically(self, model):
+        """Black-Scholes gamma  phi(d1) / (S sigma sqrt(T))."""
+        spot, sigma, vol_t, d1, _ = self._bs_d1_d2(model)
+        return torch.exp(-0.5 * d1 ** 2) / math.sqrt(2.0 * math.pi) / (spot * vol_t)
+
+    def compute_dVegadSigma_analytically(self, model):
+        """Black-Scholes vomma  vega d1 d2 / sigma,  vega = S phi(d1) sqrt(T)."""
+        spot, sigma, vol_t, d1, d2 = self._bs_d1_d2(model)
+        vega = spot * torch.exp(-0.5 * d1 ** 2) / math.sqrt(2.0 * math.pi) * torch.sqrt(self.exercise_date)
+        return vega * d1 * d2 / sigma
 
     def compute_pv_analytically(self, model):
         spot, sigma = self._bs_spot_vol(model)

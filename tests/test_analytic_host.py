@@ -1,0 +1,96 @@
+"""Analytic PV shortcut of the controller (controller.py:204-229, 609-648): products with a closed form under
+the model skip the Monte Carlo; with differentiate=True first and (compute_higher_derivatives) second derivatives
+come from host autograd on the scalar closed form, like the reference.  No GPU needed: nothing is simulated.
+Mirrors tests/pytests/test_european_option_hessian.py:65-108 and test_simulation_results_named_access.py:17-95."""
+import math
+
+import numpy as np
+import pytest
+
+import cases
+
+
+def _bs_hessian(S, r, sig, T, K):
+    """Closed-form second derivatives of the Black-Scholes call in (spot, volatility, rate)."""
+    sq = math.sqrt(T)
+    d1 = (math.log(S / K) + (r + 0.5 * sig * sig) * T) / (sig * sq)
+    d2 = d1 - sig * sq
+    pdf = math.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi)
+    pdf2 = math.exp(-0.5 * d2 * d2) / math.sqrt(2 * math.pi)
+    disc = K * math.exp(-r * T)
+    gamma = pdf / (S * sig * sq)
+    vega = S * pdf * sq
+    return {("spot", "spot"): gamma, ("volatility", "volatility"): vega * d1 * d2 / sig,
+            ("spot", "volatility"): -pdf * d2 / sig, ("spot", "rate"): pdf * sq / sig,
+            ("volatility", "rate"): -T * disc * pdf2 * d1 / sig,
+            ("rate", "rate"): T * disc * (pdf2 * sq / sig - T * 0.5 * math.erfc(-d2 / math.sqrt(2)))}
+
+
+def _controller(ns, products_by_set, differentiate=True):
+    model = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.3)
+    from metrics.metric import Metric
+    rm = ns.RiskMetrics(metrics=[ns.PVMetric(evaluation_type=Metric.EvaluationType.ANALYTICAL)])
+    sets = [ns.NettingSet(name=ps[0].get_name(), products=ps) for ps in products_by_set]
+    return model, ns.SimulationController(sets, model, rm, 1, 0, 1, ns.SimulationScheme.ANALYTICAL, differentiate)
+
+
+def test_analytic_pv_second_derivatives_match_closed_form():
+    ns = cases.Namespace()
+    prod = ns.EuropeanOption(ns.Equity("id"), 2.0, 100.0, ns.OptionType.CALL)
+    model, sc = _controller(ns, [[prod]])
+    sc.compute_higher_derivatives()
+    res = sc.run_simulation()
+    assert res.get_product_names() == ["EuropeanOption"] and res.get_metric_names() == ["pv"]
+    assert res.get_model_param_names() == ["spot", "volatility", "rate"]
+    hess = res.get_second_derivatives("EuropeanOption", "pv", evaluation_idx=0)
+    for (a, b), want in _bs_hessian(100.0, 0.05, 0.3, 2.0, 100.0).items():
+        assert float(hess[a][b]) == pytest.approx(want, rel=1e-9, abs=1e-9), (a, b)
+        assert float(hess[b][a]) == pytest.approx(want, rel=1e-9, abs=1e-9), (b, a)
+    assert float(hess["spot"]["spot"]) == pytest.approx(float(prod.compute_dDeltadSpot_analytically(model)), rel=1e-9)
+    assert float(hess["volatility"]["volatility"]) == pytest.approx(float(prod.compute_dVegadSigma_analytically(model)), rel=1e-9)
+
+
+def test_named_access_of_analytic_results_and_first_derivatives():
+    ns = cases.Namespace()
+    p1 = ns.EuropeanOption(ns.Equity("id_1"), 2.0, 100.0, ns.OptionType.CALL)
+    p2 = ns.EuropeanOption(ns.Equity("id_2"), 2.0, 120.0, ns.OptionType.CALL)
+    model, sc = _controller(ns, [[p1], [p2]])
+    res = sc.run_simulation()
+    assert res.get_product_names() == ["EuropeanOption", "EuropeanOption#2"]
+    pv1 = float(res.get_results("EuropeanOption", "pv", evaluation_idx=0))
+    pv2 = float(res.get_results("EuropeanOption#2", "pv", evaluation_idx=0))
+    assert pv1 == pytest.approx(float(p1.compute_pv_analytically(model)), rel=1e-14) and pv1 != pv2
+    # legacy keyword aliases (simulation_results.py)
+    assert float(res.get_results(prod_idx="EuropeanOption", metric_idx="pv", evaluation_index=0)) == pv1
+    vega = float(res.get_derivatives("EuropeanOption", "pv", "volatility", evaluation_idx=0))
+    sq, d1 = math.sqrt(2.0), (0.05 + 0.045) * 2.0 / (0.3 * math.sqrt(2.0))
+    assert vega == pytest.approx(100.0 * math.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi) * sq, rel=1e-10)
+    grads = res.get_derivatives("EuropeanOption#2", "pv", evaluation_idx=0)
+    assert set(grads) == {"spot", "volatility", "rate"} and all(np.isfinite(float(v)) for v in grads.values())
+
+
+def test_netting_set_analytic_pv_sums_products_and_gradients():
+    ns = cases.Namespace()
+    a = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
+    b = ns.EuropeanOption(ns.Equity(), 2.0, 90.0, ns.OptionType.PUT)
+    model, sc = _controller(ns, [[a, b]])
+    res = sc.run_simulation()
+    name = res.get_product_names()[0]
+    want = float(a.compute_pv_analytically(model)) + float(b.compute_pv_analytically(model))
+    assert float(res.get_results(name, "pv", evaluation_idx=0)) == pytest.approx(want, rel=1e-14)
+    _, one = _controller(ns, [[ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)]])
+    _, two = _controller(ns, [[ns.EuropeanOption(ns.Equity(), 2.0, 90.0, ns.OptionType.PUT)]])
+    d1 = float(one.run_simulation().get_derivatives(0, "pv", "spot", evaluation_idx=0))
+    d2 = float(two.run_simulation().get_derivatives(0, "pv", "spot", evaluation_idx=0))
+    assert float(res.get_derivatives(name, "pv", "spot", evaluation_idx=0)) == pytest.approx(d1 + d2, rel=1e-12)
+
+
+def test_heston_semi_analytic_price_limits():
+    """Heston with vanishing vol-of-vol and v0 = theta is Black-Scholes with sigma = sqrt(theta)."""
+    ns = cases.Namespace()
+    model = ns.HestonModel(0.0, 100.0, 0.03, 1e-4, 0.0, 1.5, 0.04, 0.04)
+    call = ns.EuropeanOption(ns.Equity(), 1.0, 105.0, ns.OptionType.CALL)
+    put = ns.EuropeanOption(ns.Equity(), 1.0, 105.0, ns.OptionType.PUT)
+    bs = ns.BlackScholesModel(0.0, 100.0, 0.03, 0.2)
+    assert float(call.compute_pv_analytically_heston(model)) == pytest.approx(float(call.compute_pv_analytically(bs)), abs=1e-6)
+    assert float(put.compute_pv_analytically_heston(model)) == pytest.approx(float(put.compute_pv_analytically(bs)), abs=1e-6)
