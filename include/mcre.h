@@ -306,21 +306,26 @@ typedef struct {
                                    4 DI), barrier2, type2 (0: none), n observations, tracker slot, reserved  */
   const double *prod_w;         /* [n_prod][n_assets] weights of the composite underlying                 */
   int32_t n_sets;
-  /* exercise products: per event (same indexing as ev_prod) 8 doubles: c0, c1, c2 of the continuation
-   * value in u = (x - shift) * scale, shift, scale, 1/numeraire(t), d(1/numeraire)/d rate, last-date flag;
+  /* exercise products (Bermudan / American: 1 right, bermudan_option.py:93-188; FlexiCall: up to 3 rights,
+   * flexicall.py:56-160; prod[13] = number of rights, the tracker holds the rights left): per event (same
+   * indexing as ev_prod) 16 doubles: [0..2] c0, c1, c2 of the continuation value of state 1 in
+   * u = (x - shift) * scale, [3] shift, [4] scale, [5] 1/numeraire(t), [6] d(1/numeraire)/d rate, [7] last-date
+   * flag, [8..10] / [11..13] coefficients of states 2 / 3, [14] strike of this exercise date;
    * prod_x [n_prod][n_assets]: weights picking the explanatory variable x (spot of the option's asset). */
   const double *ev_data;
   const double *prod_x;
-  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op, 8 doubles:
+  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op, 16 doubles:
    * type 1 = analytic Black-Scholes value of a European option (european_option.py:123-145): [1, time to maturity,
    * 1/numeraire(t), ...]; type 2 = regression proxy c(u) / numeraire (controller.py:438-447), u = (x - shift) scale,
-   * x = spot picked by prod_x: [2, c0, 1/numeraire(t), c1, c2, shift, scale, pad]; type 0 = none.
+   * x = spot picked by prod_x: [2, c0, 1/numeraire(t), c1, c2, shift, scale, pad]; type 3 = the same for an exercise
+   * product, with the coefficients of its current state (rights left; [8..10] / [11..13] for states 2 / 3; no
+   * exposure in state 0); type 0 = none.
    * Netting-set terms as in mcre_irc_desc.  acc_flags: MCRE_ACC_POS /
    * NEG / SPILL.  Adds [n_metric][NS][4] = sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2) to the slots. */
   int32_t n_expo, n_metric, acc_flags;
   const int32_t *date_expo;     /* [n_dates] internal exposure index or -1 */
   const int32_t *date_metric;   /* [n_dates] metric-date index or -1       */
-  const double *xp;             /* [n_expo][n_prod][8]                     */
+  const double *xp;             /* [n_expo][n_prod][16]                    */
   const double *set_threshold;  /* [n_sets]                                */
   const int32_t *set_flags;     /* [n_sets] bit0 collateralised            */
   const int32_t *set_lag;       /* [n_sets][n_metric] exposure-index lag of the collateral date, -1: none */
@@ -365,17 +370,27 @@ int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double
                   const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i /* host[3] or NULL */,
                   double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
                   double *d_partial, double *d_moments, void *stream);
+/* The same with n_rights = 1..3 exercise rights (FlexiCall, src/products/flexicall.py:56-160): the product state
+ * is the number of rights left, d_value is [n_rights][n] (state s at row s-1; state 0 carries nothing),
+ * coef_i host [n_rights][3] (continuation of state s at product date i), d_moments [5 + 3 n_rights]:
+ *   ex_s = imm_i + cont_i(s-1) > cont_i(s), cont(0) = 0;  V_s <- fp32(fp32(ex_s ? imm_i/N_i : 0) + (ex_s ? V_{s-1} : V_s))
+ * n_rights = 1 is mcre_lsm_step. */
+int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const double *d_nk, double shift_k, double scale_k,
+                         const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i,
+                         double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
+                         double *d_partial, double *d_moments, void *stream);
 
 /* LSM pre-simulation arrays of an exercise product on equity underlyings, gathered date-major from
  * materialised pre-simulation paths (mcre_generate_paths with seed 42; the pre-simulation is a small
  * fraction of the run): x[k][n] explanatory spot and numeraire[k][n] per regression date k,
- * imm[i][n] = max(sign (U - K), 0) per exercise date i with U = sum_j w_j spot_j.  Spots are state
- * columns, exponentiated where the model keeps log-spot (Heston, Schwartz).  Host arrays unless d_*. */
+ * imm[i][n] = max(sign (U - K_i), 0) per exercise date i with U = sum_j w_j spot_j and K_i = ex_strike[i]
+ * (NULL: the same strike on every date).  Spots are state columns, exponentiated where the model keeps
+ * log-spot (Heston, Schwartz).  Host arrays unless d_*. */
 int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, int32_t n_dates, int32_t state_dim,
                             int32_t n_reg, const int32_t *reg_date, const double *reg_numeraire,
                             int32_t n_ex, const int32_t *ex_date, int32_t x_col, int32_t x_is_log,
                             int32_t n_under, const int32_t *under_col, const double *under_w,
-                            const int32_t *under_is_log, double strike, double sign,
+                            const int32_t *under_is_log, double strike, const double *ex_strike, double sign,
                             double *d_x, double *d_n, double *d_imm, void *stream);
 
 /* ================================================================================

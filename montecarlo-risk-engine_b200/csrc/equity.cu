@@ -26,7 +26,9 @@
 namespace mcre {
 
 constexpr int EQ_PR = 16;     // doubles per product record
-constexpr int EQ_NTRK = 2;    // path-dependent trackers per launch
+// path-dependent / exercise trackers per launch: 4 in the value-only builds (mixed books), 2 when the
+// trackers carry tangents (register budget)
+__host__ __device__ constexpr int eq_ntrk(int nt) { return nt == 0 ? 4 : 2; }
 constexpr int EQ_PAR = 8;     // doubles per asset parameter row
 
 struct EqDev {
@@ -55,7 +57,8 @@ struct EqDev {
   double *ps_x;   // [n_expo][A][n_paths]
   float *ps_cf;   // [n_prod][n_paths]
 };
-constexpr int EQ_XP = 8;
+constexpr int EQ_XP = 16;
+constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
 constexpr int EQ_MAX_LAG = 4;
 constexpr int EQ_SPNZ = 8;   // non-zeros kept per sparse correlation row
 
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
       else if constexpr (KIND == MCRE_EQ_HESTON) { s0 = r_log(par[0]); s1 = par[6]; }
       else { s0 = T::zero(); s1 = T::zero(); }
       double logF = KIND == MCRE_EQ_SCHWARTZ ? __ldg(P.init_aux + aa) : 0.0;
-      R cf[NS], trk_a[EQ_NTRK], trk_b[EQ_NTRK];
+      constexpr int NTRK = eq_ntrk(NT);
+      R cf[NS], trk_a[NTRK], trk_b[NTRK];
       double numtan[NS], hist[NS][EQ_MAX_LAG];
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -166,7 +170,16 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
 #pragma unroll
       for (int s = 0; s < NS; ++s) { cf[s] = T::zero(); numtan[s] = 0.0; }
 #pragma unroll
-      for (int k = 0; k < EQ_NTRK; ++k) { trk_a[k] = T::zero(); trk_b[k] = T::zero(); }
+      for (int k = 0; k < NTRK; ++k) { trk_a[k] = T::zero(); trk_b[k] = T::zero(); }
+      // exercise products start with all their rights (state = rights left): exposure dates before the
+      // first exercise date already look the state up
+      for (int pi = 0; pi < P.n_prod; ++pi) {
+        const double *pr = P.prod + (size_t)pi * EQ_PR;
+        if ((int)__ldg(pr + 0) != EQ_EXERCISE) continue;
+        const int slot = (int)__ldg(pr + 14);
+#pragma unroll
+        for (int k = 0; k < NTRK; ++k) if (k == slot) trk_a[k] = T::lift(__ldg(pr + 13));
+      }
 
       auto spot_now = [&]() -> R {
         if (KIND == MCRE_EQ_BS) return s0;
@@ -194,13 +207,23 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             if (xtype == 0) continue;
             const double *pr = P.prod + (size_t)pi * EQ_PR;
             double v = 0.0;
-            if (xtype == 2) {
+            if (xtype == 2 || xtype == 3) {
               // regression proxy: continuation(x) / numeraire with x the spot of the product's asset
-              // (controller.py:438-447), evaluated on the lane that owns that asset
+              // (controller.py:438-447), evaluated on the lane that owns that asset; type 3 (exercise
+              // products): the coefficients of the product's current state = rights left, none in state 0
               const double xw = __ldg(P.prod_x + (size_t)pi * A + aa);
-              if (xw != 0.0) {
+              int st = 1;
+              if (xtype == 3) {
+                const int slot = (int)__ldg(pr + 14);
+#pragma unroll
+                for (int k = 0; k < NTRK; ++k) if (k == slot) st = (int)val(trk_a[k]);
+              }
+              if (xw != 0.0 && st > 0) {
                 const double u = (Sv - __ldg(op + 5)) * __ldg(op + 6);
-                v = (__ldg(op + 1) + u * (__ldg(op + 3) + u * __ldg(op + 4))) * __ldg(op + 2);
+                const double c0 = st == 1 ? __ldg(op + 1) : __ldg(op + 8 + 3 * (st - 2));
+                const double c1 = st == 1 ? __ldg(op + 3) : __ldg(op + 9 + 3 * (st - 2));
+                const double c2 = st == 1 ? __ldg(op + 4) : __ldg(op + 10 + 3 * (st - 2));
+                v = (c0 + u * (c1 + u * c2)) * __ldg(op + 2);
               }
               const double tot2 = group_sum(v, base, A);
               const int set2 = (int)__ldg(pr + 1);
@@ -291,18 +314,25 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             // Bermudan / American exercise date (bermudan_option.py:93-131): exercise iff the
             // immediate value beats the regressed continuation value (hard indicator) and the right
             // is still alive; tracker a of the product's slot is the alive flag.
-            const double *ed = P.ev_data + (size_t)e * 8;
+            // FlexiCall (flexicall.py:56-160): tracker a holds the number of rights left (state s); a path in
+            // state s > 0 exercises iff immediate + continuation(s - 1) > continuation(s), strike per date.
+            const double *ed = P.ev_data + (size_t)e * EQ_EVD;
             const double xw = __ldg(P.prod_x + (size_t)pi * A + aa);
             const double X = group_sum(val(S) * xw, base, A);          // explanatory spot
             const double u = (X - __ldg(ed + 3)) * __ldg(ed + 4);
-            const double cont = __ldg(ed + 7) != 0.0 ? 0.0 : __ldg(ed + 0) + u * (__ldg(ed + 1) + u * __ldg(ed + 2));
-            const R imm = option_payoff(U, strike, sign);
+            const bool lastd = __ldg(ed + 7) != 0.0;                   // no continuation after the last date
+            auto cont_of = [&](int st) -> double {
+              if (lastd || st <= 0) return 0.0;
+              const double *c = st == 1 ? ed : ed + 8 + 3 * (st - 2);
+              return __ldg(c + 0) + u * (__ldg(c + 1) + u * __ldg(c + 2));
+            };
+            const R imm = option_payoff(U, __ldg(ed + 14), sign);
 #pragma unroll
-            for (int k = 0; k < EQ_NTRK; ++k) {
+            for (int k = 0; k < NTRK; ++k) {
               if (k != slot) continue;
-              if (ef & EQ_EV_FIRST) trk_a[k] = T::lift(1.0);
-              if (val(trk_a[k]) > 0.5 && val(imm) > cont) {
-                trk_a[k] = T::zero();
+              const int st = (int)val(trk_a[k]);
+              if (st > 0 && val(imm) + cont_of(st - 1) > cont_of(st)) {
+                trk_a[k] = T::lift((double)(st - 1));
 #pragma unroll
                 for (int s = 0; s < NS; ++s)
                   if (s == set) { cf[s] = cf[s] + imm * __ldg(ed + 5); numtan[s] += val(imm) * __ldg(ed + 6); }
@@ -312,7 +342,7 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
           }
           if (ef & EQ_EV_OBSERVE) {
 #pragma unroll
-            for (int k = 0; k < EQ_NTRK; ++k) {
+            for (int k = 0; k < NTRK; ++k) {
               if (k != slot) continue;
               if (kind == EQ_ASIAN) {
                 const R x = (pflags & 1) ? r_log(U + 1e-10) : U;     // asian_option.py:51-69
@@ -338,13 +368,13 @@ __global__ void __launch_bounds__(128) eq_main_kernel(EqDev P, RngDev rng, Shard
             const double inv_n = 1.0 / __ldg(pr + 13);
             R avg = T::zero();
 #pragma unroll
-            for (int k = 0; k < EQ_NTRK; ++k) if (k == slot) avg = trk_a[k] * inv_n;
+            for (int k = 0; k < NTRK; ++k) if (k == slot) avg = trk_a[k] * inv_n;
             if (pflags & 1) avg = r_exp(avg);
             pay = option_payoff(avg, strike, sign);
           } else {
             R mx = T::zero(), mn = T::zero();
 #pragma unroll
-            for (int k = 0; k < EQ_NTRK; ++k) if (k == slot) { mx = trk_a[k]; mn = trk_b[k]; }
+            for (int k = 0; k < NTRK; ++k) if (k == slot) { mx = trk_a[k]; mn = trk_b[k]; }
             pay = option_payoff(U, strike, sign) * barrier_factor(mx, mn, __ldg(pr + 9), (int)__ldg(pr + 10));
             const int bt2 = (int)__ldg(pr + 12);
             if (bt2 > 0) pay = pay * barrier_factor(mx, mn, __ldg(pr + 11), bt2);
@@ -502,8 +532,8 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (!scheme_ok) return fail(-1, "eq: scheme not defined for this model%s", "");
   for (int p = 0; p < c->n_prod; ++p) {
     const int slot = (int)c->prod[(size_t)p * EQ_PR + 14], kind = (int)c->prod[(size_t)p * EQ_PR];
-    if ((kind == EQ_ASIAN || kind == EQ_BARRIER || kind == EQ_EXERCISE) && (slot < 0 || slot >= EQ_NTRK))
-      return fail(-3, "eq: at most 2 path-dependent / exercise products per launch%s", "");
+    if ((kind == EQ_ASIAN || kind == EQ_BARRIER || kind == EQ_EXERCISE) && (slot < 0 || slot >= eq_ntrk(c->nt)))
+      return fail(-3, "eq: too many path-dependent / exercise products per launch (4, or 2 with tangents)%s", "");
     if (kind == EQ_EXERCISE && (!c->ev_data || !c->prod_x)) return fail(-1, "eq: exercise product without event data%s", "");
     const int set = (int)c->prod[(size_t)p * EQ_PR + 1];
     if (set < 0 || set >= c->n_sets) return fail(-1, "eq: product set index out of range%s", "");
@@ -523,7 +553,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   UP(chol_dual, c->chol_dual, c->corr_mode == 1 ? (size_t)c->n_chol * 4 * (c->nt + 1) : 0);
   UP(date_ev_off, c->date_ev_off, c->n_dates + 1); UP(ev_prod, c->ev_prod, n_ev); UP(ev_flags, c->ev_flags, n_ev);
   UP(prod, c->prod, (size_t)c->n_prod * EQ_PR); UP(prod_w, c->prod_w, (size_t)c->n_prod * A);
-  UP(ev_data, c->ev_data, c->ev_data ? (size_t)n_ev * 8 : 0); UP(prod_x, c->prod_x, c->prod_x ? (size_t)c->n_prod * A : 0);
+  UP(ev_data, c->ev_data, c->ev_data ? (size_t)n_ev * EQ_EVD : 0); UP(prod_x, c->prod_x, c->prod_x ? (size_t)c->n_prod * A : 0);
   if (c->n_expo > 0) {
     UP(date_expo, c->date_expo, c->n_dates); UP(date_metric, c->date_metric, c->n_dates);
     UP(xp, c->xp, (size_t)c->n_expo * c->n_prod * EQ_XP);

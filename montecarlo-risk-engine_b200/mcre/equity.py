@@ -37,13 +37,19 @@ from products.bermudan_option import BermudanOption
 from products.binary_option import BinaryOption
 from products.equity import Equity
 from products.european_option import EuropeanOption
+from products.flexicall import FlexiCall
 from products.product import OptionType
 
 CHUNK_PATHS = 4096
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
 P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
 EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
-EQ_PR, EQ_PAR, EQ_NTRK, EQ_MAX_SETS, EQ_XP, EQ_MAX_LAG = 16, 8, 2, 4, 8, 4
+EQ_PR, EQ_PAR, EQ_MAX_SETS, EQ_XP, EQ_EVD, EQ_MAX_LAG, EQ_MAX_RIGHTS = 16, 8, 4, 16, 16, 4, 3
+
+
+def eq_ntrk(nt):
+    """Path-dependent / exercise trackers per launch (csrc/equity.cu:eq_ntrk)."""
+    return 4 if nt == 0 else 2
 _NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
 _BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
                  BarrierOptionType.UPANDIN: 3, BarrierOptionType.DOWNANDIN: 4}
@@ -114,7 +120,14 @@ def family_of(model):
 
 
 def is_equity_exercise(p):
-    return isinstance(p, BermudanOption) and isinstance(p.underlying, Equity)
+    return isinstance(p, (BermudanOption, FlexiCall)) and isinstance(p.underlying, Equity)
+
+
+def exercise_strikes(p):
+    """Strike per exercise date: one strike (Bermudan / American) or the strip's strikes (FlexiCall)."""
+    if isinstance(p, FlexiCall):
+        return list(p.strikes)
+    return [float(p.strike)] * len(p.product_timeline)
 
 
 def _is_path_dependent(p):
@@ -142,7 +155,7 @@ class EquityBackend:
             # pay once; no CVA here (needs a credit model in the same ModelConfig: hybrid books are next)
             if any(m.metric_type == MetricType.CVA for m in ctrl.risk_metrics.metrics):
                 return False
-            return all(ctrl._can_use_analytic_exposure_for_product(p) or not is_equity_exercise(p) for p in ctrl.products)
+            return True
         return True
 
     def __init__(self, ctrl):
@@ -163,7 +176,8 @@ class EquityBackend:
         self.npar = _NPAR[self.kind]
         self.nt = self.npar if ctrl.differentiate else 0
         self.id_to_asset = {a.asset_id: i for i, a in enumerate(self.assets)}
-        self.exercise_coef = {}   # id(product) -> (coef [n_ex, 3] standardised basis, basis [n_ex, 2])
+        self.exercise_coef = {}        # id(product) -> (coef [n_ex, rights, 3] standardised basis, basis [n_ex, 2])
+        self.exercise_expo_coef = {}   # id(product) -> (coef [n_expo, rights, 3], basis [n_expo, 2]) per exposure date
         self.expo_coef = {}       # id(product) -> (coef [n_expo, 3] standardised basis, basis [n_expo, 2])
         subs = _sub_models(ctrl.model)
         num_idx = ctrl.model.id_to_model["numeraire"] if isinstance(ctrl.model, ModelConfig) else 0
@@ -202,7 +216,7 @@ class EquityBackend:
         rec[1] = set_local
         rec[14] = -1
         sign = 1.0 if p.option_type == OptionType.CALL else -1.0
-        rec[2], rec[3] = float(p.strike), sign
+        rec[2], rec[3] = (0.0 if isinstance(p, FlexiCall) else float(p.strike)), sign
         basket = getattr(p, "basket", None)   # extension: path-dependent payoffs on a weighted basket
         if isinstance(p, EuropeanOption):
             rec[0] = P_EUROPEAN
@@ -253,7 +267,9 @@ class EquityBackend:
             t_num = obs[0]
         elif is_equity_exercise(p):
             rec[0] = P_EXERCISE
-            rec[14] = slot
+            rec[13], rec[14] = p.num_exercise_rights, slot
+            if p.num_exercise_rights > EQ_MAX_RIGHTS:
+                raise NotImplementedError(f"at most {EQ_MAX_RIGHTS} exercise rights per product")
             w[self._asset_index(p.underlying.get_asset_id())] = 1.0
             ex = [float(t) for t in p.product_timeline]
             events = [(date_idx[t], EV_EXERCISE | (EV_FIRST if i == 0 else 0)) for i, t in enumerate(ex)]
@@ -368,23 +384,26 @@ class EquityBackend:
                 owners.append(p)
                 for di, f in evs:
                     events[di].append((pi, f))
-        if slot > EQ_NTRK:
-            raise NotImplementedError(f"at most {EQ_NTRK} path-dependent products per launch group")
+        if slot > eq_ntrk(nt):
+            raise NotImplementedError(f"at most {eq_ntrk(nt)} path-dependent / exercise products per launch group")
         ev_off, ev_prod, ev_flags, ev_data = [0], [], [], []
         ex_count = {}
         for di in range(n_dates):
             for pi, f in events[di]:
                 ev_prod.append(pi)
                 ev_flags.append(f)
-                row = np.zeros(8)
+                row = np.zeros(EQ_EVD)
                 if f & EV_EXERCISE:
                     p = owners[pi]
                     i = ex_count.get(pi, 0)
                     ex_count[pi] = i + 1
-                    coef, basis = self.exercise_coef[id(p)]
-                    row[0:3], row[3:5] = coef[i], basis[i]
+                    coef, basis = self.exercise_coef[id(p)]          # [n_ex, rights, 3], [n_ex, 2]
+                    row[0:3], row[3:5] = coef[i, 0], basis[i]
+                    for st in range(1, coef.shape[1]):
+                        row[8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[i, st]
                     row[5], row[6] = self._inv_numeraire(dates[di])
                     row[7] = 1.0 if i == len(p.product_timeline) - 1 else 0.0
+                    row[14] = exercise_strikes(p)[i]
                 ev_data.append(row)
             ev_off.append(len(ev_prod))
 
@@ -425,7 +444,7 @@ class EquityBackend:
         desc.prod = fp("prod", np.stack(recs) if recs else np.zeros(EQ_PR))
         desc.prod_w = fp("prod_w", np.stack(weights) if weights else np.zeros(A))
         desc.n_sets = len(set_indices) if presim_products is None else 1
-        desc.ev_data = fp("ev_data", np.stack(ev_data) if ev_data else np.zeros(8))
+        desc.ev_data = fp("ev_data", np.stack(ev_data) if ev_data else np.zeros(EQ_EVD))
         desc.prod_x = fp("prod_x", np.stack(xweights) if xweights else np.zeros(A))
 
         # ---- exposure profiles ---------------------------------------------------------------
@@ -451,10 +470,16 @@ class EquityBackend:
                         ttm = float(p.exercise_date) - te
                         if ttm > 0.0:                   # matured options carry no exposure (european_option.py:129-131)
                             xp[e, pi, :3] = (1.0, ttm, inv)
+                    elif is_equity_exercise(p):
+                        coef, basis = self.exercise_expo_coef[id(p)]     # [n_expo, rights, 3], [n_expo, 2]
+                        if np.any(coef[e] != 0.0):
+                            xp[e, pi, :8] = (3.0, coef[e, 0, 0], inv, coef[e, 0, 1], coef[e, 0, 2], basis[e, 0], basis[e, 1], 0.0)
+                            for st in range(1, coef.shape[1]):
+                                xp[e, pi, 8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[e, st]
                     else:
                         coef, basis = self.expo_coef[id(p)]
                         if np.any(coef[e] != 0.0):
-                            xp[e, pi] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], 0.0)
+                            xp[e, pi, :8] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], 0.0)
             kinds = {m.metric_type for m in c.risk_metrics.metrics}
             if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
                 acc |= B.ACC_POS
@@ -563,7 +588,9 @@ class EquityBackend:
         if n_pre <= 0:
             raise ValueError("Exercise products need a pre-simulation: num_paths_presim must be positive.")
         ptl = prod.product_timeline.tolist()
-        reg_times = sorted(set(prod.regression_timeline.tolist()))
+        expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
+        reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
+        R = int(prod.num_exercise_rights)
         sim = c.simulation_timeline.tolist()
         date_idx = {t: i for i, t in enumerate(sim)}
         begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
@@ -594,12 +621,12 @@ class EquityBackend:
 
         L.mcre_lsm_prepare_equity.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, B.c_ip, B.c_dp, C.c_int32,
                                               B.c_ip, C.c_int32, C.c_int32, C.c_int32, B.c_ip, B.c_dp, B.c_ip, C.c_double,
-                                              C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                              B.c_dp, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         sign = 1.0 if prod.option_type == OptionType.CALL else -1.0
         B.check(L.mcre_lsm_prepare_equity(
             paths.data_ptr(), count, len(sim), paths.shape[2], n_reg, ip([date_idx[t] for t in reg_times]),
             fp([math.exp(self.num_rate * (t - t0)) for t in reg_times]), n_ex, ip([date_idx[t] for t in ptl]),
-            cols[xi][0], cols[xi][1], 1, ip([cols[ui][0]]), fp([1.0]), ip([cols[ui][1]]), float(prod.strike), sign,
+            cols[xi][0], cols[xi][1], 1, ip([cols[ui][0]]), fp([1.0]), ip([cols[ui][1]]), 0.0, fp(exercise_strikes(prod)), sign,
             xs.data_ptr(), nums.data_ptr(), imm.data_ptr(), RT.stream_ptr()))
         del paths
         # standardisation of the explanatory variable per date: sample mean / std over all ranks
@@ -610,13 +637,20 @@ class EquityBackend:
         var = np.maximum(mom[2] / np.maximum(mom[0], 1.0) - mean * mean, 0.0)
         std = np.sqrt(var)
         basis = np.stack([mean, np.where(std > 1e-12 * np.maximum(np.abs(mean), 1.0), 1.0 / np.where(std > 0, std, 1.0), 1.0)], axis=1)
-        coef = backward_induction(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev)
+        coef = backward_induction(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R)
+        coef = coef.reshape(n_reg, R, 3)
         ridx = {t: k for k, t in enumerate(reg_times)}
         rows = [ridx[t] for t in ptl]
         self.exercise_coef[id(prod)] = (coef[rows], basis[rows])
-        raw = to_raw_basis(coef, basis, [t <= t0 for t in reg_times])
+        degen = [t <= t0 for t in reg_times]
+        raw = np.stack([to_raw_basis(coef[:, st, :], basis, degen) for st in range(R)], axis=1)   # [n_reg, R, 3]
+        # state s = rights left keeps its coefficients at row s, like the reference's [date, state, basis] tensors
         for j, t in enumerate(prod.regression_timeline.tolist()):
-            prod.regression_coeffs[j, 1, :] = torch.tensor(raw[ridx[t]])
+            prod.regression_coeffs[j, 1:R + 1, :] = torch.tensor(raw[ridx[t]])
+        if expo_times:
+            erows = [ridx[t] for t in expo_times]
+            self.exercise_expo_coef[id(prod)] = (coef[erows], basis[erows])
+            c.regression_coeffs[prod.product_id][:, 1:R + 1, :] = torch.tensor(raw[erows])
 
     def presim_regression(self, products, dev):
         """Regression-proxy exposure coefficients of products that pay once (controller.py:294-383): the
@@ -639,7 +673,7 @@ class EquityBackend:
         groups, cur, trk = [], [], 0
         for p in products:
             t = int(_is_path_dependent(p))
-            if cur and trk + t > EQ_NTRK:
+            if cur and trk + t > eq_ntrk(0):
                 groups.append(cur)
                 cur, trk = [], 0
             cur.append(p)
@@ -720,17 +754,17 @@ class EquityBackend:
             if is_equity_exercise(p):
                 self.presim_exercise(p, dev)
         if c.risk_metrics.requires_exposure_profiles():
-            reg = [p for p in c.products if not c._can_use_analytic_exposure_for_product(p)]
+            reg = [p for p in c.products if not c._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
             if reg:
                 self.presim_regression(reg, dev)
         t_pre = time.perf_counter() - t0
         results = [None] * n_sets
         group = EQ_MAX_SETS if self.nt == 0 else 2
-        # launch groups: up to `group` netting sets and EQ_NTRK path-dependent products each
+        # launch groups: up to `group` netting sets and eq_ntrk(nt) path-dependent / exercise products each
         groups, cur, cur_trk = [], [], 0
         for si, ns in enumerate(c.netting_sets):
             trk = sum(_is_path_dependent(p) for p in ns.products)
-            if cur and (len(cur) >= group or cur_trk + trk > EQ_NTRK):
+            if cur and (len(cur) >= group or cur_trk + trk > eq_ntrk(self.nt)):
                 groups.append(cur)
                 cur, cur_trk = [], 0
             cur.append(si)

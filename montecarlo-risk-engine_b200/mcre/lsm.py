@@ -105,19 +105,22 @@ def regression_tangents(G, rhs, coef, tm):
     return out
 
 
-def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev):
+def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
     """xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product
     (exercise) dates; reg_times: regression dates (sorted, contain every product date);
-    basis: [n_reg, 2] (shift, scale).  -> coefficients [n_reg, 3] in the standardised basis."""
+    basis: [n_reg, 2] (shift, scale).  -> coefficients in the standardised basis: [n_reg, 3] for one
+    exercise right, [n_reg, n_rights, 3] (state s = rights left at row s-1) for a FlexiCall."""
     L = B.lib()
     n_reg = len(reg_times)
     n = xs.shape[1]
+    R = int(n_rights)
+    nv = 5 + 3 * R
     reg_idx = {t: k for k, t in enumerate(reg_times)}
-    coef = np.zeros((n_reg, 3))
-    value = torch.zeros(n, dtype=torch.float32, device=dev)
+    coef = np.zeros((n_reg, R, 3))
+    value = torch.zeros((R, n), dtype=torch.float32, device=dev)
     n_chunks = (n + chunk_paths - 1) // chunk_paths
-    partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
-    moments = torch.zeros(8, dtype=torch.float64, device=dev)
+    partial = torch.empty(n_chunks * nv + 1, dtype=torch.float64, device=dev)
+    moments = torch.zeros(nv, dtype=torch.float64, device=dev)
     keep = {}
 
     def step(k, i):
@@ -127,12 +130,12 @@ def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
             ki = reg_idx[ptl[i]]
             cptr = None
             if i < len(ptl) - 1:
-                keep["c"], cptr = B.as_dp(coef[ki])
+                keep["c"], cptr = B.as_dp(coef[ki].reshape(-1))
             args_i = (xs[ki].data_ptr(), nums[ki].data_ptr(), imm[i].data_ptr(), cptr,
                       float(basis[ki, 0]), float(basis[ki, 1]))
-        B.check(L.mcre_lsm_step(xs[k].data_ptr(), nums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
-                                *args_i, value.data_ptr(), count, chunk_paths, partial.data_ptr(),
-                                moments.data_ptr(), RT.stream_ptr()))
+        B.check(L.mcre_lsm_step_states(R, xs[k].data_ptr(), nums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
+                                       *args_i, value.data_ptr(), count, chunk_paths, partial.data_ptr(),
+                                       moments.data_ptr(), RT.stream_ptr()))
 
     last = len(ptl)
     for k in range(n_reg - 1, -1, -1):
@@ -150,8 +153,9 @@ def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
             step(k, None)
         m = RT.all_reduce_tree(moments).cpu().numpy()
         G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
-        coef[k] = solve_normal_equations(G, m[5:8])
-    return coef
+        for s in range(R):
+            coef[k, s] = solve_normal_equations(G, m[5 + 3 * s:8 + 3 * s])
+    return coef[:, 0, :] if R == 1 else coef
 
 
 def to_raw_basis(coefs, basis, degenerate=None):

@@ -83,10 +83,14 @@ def regression_timeline(prod):
 
 
 def num_states(prod):
+    if kind(prod) == "FlexiCall":        # flexicall.py:50-54: states = rights left
+        return int(prod.num_exercise_rights) + 1
     return 2 if kind(prod) in ("BermudanOption", "AmericanOption") else 1
 
 
 def initial_state(prod):
+    if kind(prod) == "FlexiCall":
+        return int(prod.num_exercise_rights)
     return 1 if kind(prod) in ("BermudanOption", "AmericanOption") else 0
 
 
@@ -281,6 +285,32 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
             exercise = (ad.val(imm) > cont) & (st > 0)
             cols.append(imm * exercise.astype(np.float64) / numeraire)
             next_state[:, s] = np.where(exercise, np.where(st > 0, st - 1, st), st)
+        return next_state, cols
+    if k == "FlexiCall":               # flexicall.py:56-186
+        tl = product_timeline(prod)
+        t = tl[i]
+        opt = prod.underlyings[i]
+        u = underlying_value(opt.underlying, t, ctx)
+        sign = 1.0 if prod.underlyings[0].option_type.name == "CALL" else -1.0
+        imm = ad.clamp_min(sign * (u - _f(opt.strike)), 0.0)
+        x = ctx.spot(asset_of(prod), t)
+        numeraire = ctx.numeraire(t)
+        coeffs = None if i == len(tl) - 1 else coeffs_of(i)   # [S, degree]
+        next_state = state_matrix.copy()
+        cols = []
+        for s in range(S):
+            st = state_matrix[:, s]
+            after = np.where(st > 0, st - 1, st)               # state_after_exercise (flexicall.py:72-77)
+            if coeffs is None:
+                keep = exd = 0.0 * ad.val(imm)
+            else:
+                cval = ad.val(coeffs) if isinstance(coeffs, ad.Dual) else coeffs
+                basis = np.stack([ad.val(x) ** j for j in range(regfn_degree)], axis=1)
+                keep = np.einsum("nj,nj->n", basis, cval[st])
+                exd = np.einsum("nj,nj->n", basis, cval[after])
+            exercise = (ad.val(imm) + exd > keep) & (st > 0)    # flexicall.py:139-142
+            cols.append(imm * exercise.astype(np.float64) / numeraire)
+            next_state[:, s] = np.where(exercise, after, st)
         return next_state, cols
     raise NotImplementedError(k)
 

@@ -106,6 +106,49 @@ def bs_basket(ns_module, euler=False):
 
 
 #: name -> (builder, builder kwargs, run kwargs)
+def flexicall_bs(ns_module, exposure=False):
+    """FlexiCall on Black-Scholes: 3 European calls, 2 exercise rights
+    (tests/pytests/test_single_product_executor_parity.py "flexicall" case)."""
+    m = ns_module
+    model = m.BlackScholesModel(0.0, 100.0, 0.03, 0.2, asset_id="asset")
+    flexi = m.FlexiCall(underlyings=[m.EuropeanOption(m.Equity("asset"), 0.5, 95.0, m.OptionType.CALL, asset_id="asset"),
+                                     m.EuropeanOption(m.Equity("asset"), 1.0, 100.0, m.OptionType.CALL, asset_id="asset"),
+                                     m.EuropeanOption(m.Equity("asset"), 1.5, 105.0, m.OptionType.CALL, asset_id="asset")],
+                        num_exercise_rights=2, asset_id="asset")
+    sets = [m.NettingSet(name="flexicall", products=[flexi])]
+    if exposure:
+        return model, sets, [m.PVMetric(), m.EPEMetric(), m.PFEMetric(0.9)], np.linspace(0.0, 1.5, 7)
+    return model, sets, [m.PVMetric()], None
+
+
+def mixed_book(ns_module, exposure=True):
+    """Mixed equity book on a 2-asset BlackScholesMulti: Europeans, Americans, a FlexiCall and a barrier option in
+    one netting set (tests/pytests/test_netting_sets.py:375-528)."""
+    m = ns_module
+    ids = ["asset_1", "asset_2"]
+    model = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    products = [
+        m.EuropeanOption(m.Equity("asset_1"), 1.0, 95.0, m.OptionType.CALL, asset_id="asset_1"),
+        m.EuropeanOption(m.Equity("asset_2"), 1.5, 110.0, m.OptionType.PUT, asset_id="asset_2"),
+        m.AmericanOption(underlying=m.Equity("asset_1"), maturity=1.0, num_exercise_dates=8, strike=100.0,
+                         option_type=m.OptionType.PUT, asset_id="asset_1"),
+        m.AmericanOption(underlying=m.Equity("asset_2"), maturity=1.5, num_exercise_dates=12, strike=102.5,
+                         option_type=m.OptionType.CALL, asset_id="asset_2"),
+        m.FlexiCall(underlyings=[m.EuropeanOption(m.Equity("asset_1"), 0.5, 95.0, m.OptionType.CALL, asset_id="asset_1"),
+                                 m.EuropeanOption(m.Equity("asset_1"), 1.0, 100.0, m.OptionType.CALL, asset_id="asset_1"),
+                                 m.EuropeanOption(m.Equity("asset_1"), 1.5, 105.0, m.OptionType.CALL, asset_id="asset_1")],
+                    num_exercise_rights=2, asset_id="asset_1"),
+        m.BarrierOption(startdate=0.0, maturity=1.25, strike=100.0, num_observation_timepoints=12,
+                        option_type=m.OptionType.CALL, barrier1=130.0,
+                        barrier_option_type1=m.BarrierOptionType.UPANDOUT, asset_id="asset_2"),
+    ]
+    sets = [m.NettingSet(name="mixed_ns", products=products)]
+    if exposure:
+        return model, sets, [m.EPEMetric(), m.PFEMetric(0.95)], np.linspace(0.0, 1.5, 6)
+    return model, sets, [m.PVMetric()], None
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -121,6 +164,10 @@ GOLDEN_CASES = {
     "heston_european_greeks": (heston_european, dict(), dict(n_main=4096, n_pre=0, num_steps=10, scheme="QE", differentiate=True)),
     "heston_path_dependent": (heston_path_dependent, dict(), dict(n_main=4096, n_pre=0, num_steps=4, scheme="QE", differentiate=True)),
     "bs_basket": (bs_basket, dict(), dict(n_main=8192, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "flexicall_pv": (flexicall_bs, dict(), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "flexicall_exposure": (flexicall_bs, dict(exposure=True), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
+    "mixed_book_pv": (mixed_book, dict(exposure=False), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "mixed_book_exposure": (mixed_book, dict(exposure=True), dict(n_main=512, n_pre=512, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
 }
 
@@ -143,7 +190,6 @@ class Namespace:
         from models.black_scholes_multi import BlackScholesMulti
         from models.cirpp import CIRPPModel
         from models.heston import HestonModel
-        from models.hull_white import HullWhiteModel
         from models.model_config import ModelConfig
         from models.vasicek import VasicekModel
         from products.asian_option import AsianAveragingType, AsianOption
@@ -154,10 +200,16 @@ class Namespace:
         from products.bond import Bond
         from products.equity import Equity
         from products.european_option import EuropeanOption
+        from products.flexicall import FlexiCall
         from products.netting_set import NettingSet
         from products.product import OptionType
         from products.swap import InterestRateSwap, IRSType
         self.__dict__.update({k: v for k, v in locals().items() if k != "self"})
+        try:   # dead code in the reference; an extension in this package
+            from models.hull_white import HullWhiteModel
+            self.HullWhiteModel = HullWhiteModel
+        except Exception:  # pragma: no cover
+            pass
         try:
             from models.schwartz_two_factor import SchwartzTwoFactorModel
             self.SchwartzTwoFactorModel = SchwartzTwoFactorModel

@@ -13,8 +13,13 @@ import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, "/root/reference/src")
 sys.path.insert(0, os.path.dirname(HERE))  # tests/ for cases.py
+sys.path.insert(0, "/root/reference/src")  # first: the reference has its own `helpers` package
+
+# the reference's `helpers` is a namespace package (no __init__.py) and would lose against tests/helpers.py
+_helpers = types.ModuleType("helpers")
+_helpers.__path__ = ["/root/reference/src/helpers"]
+sys.modules["helpers"] = _helpers
 
 # matplotlib is imported by some reference modules but absent here
 mpl = types.ModuleType("matplotlib")

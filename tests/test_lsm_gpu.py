@@ -171,3 +171,30 @@ def test_hull_white_bermudan_swaption_extension_matches_oracle():
     out = risk.run(model, sets, metrics, tl, n, n, 2, "EULER")
     _compare(helpers.flatten_results(res), helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names()),
              1e-8, "hull-white bermudan", err_rtol=1e-6)
+
+
+FLEXI_CASES = ["flexicall_pv", "flexicall_exposure", "mixed_book_pv", "mixed_book_exposure"]
+
+
+@pytest.mark.parametrize("name", FLEXI_CASES)
+def test_flexicall_and_mixed_book_match_reference_golden(name):
+    """FlexiCall (src/products/flexicall.py: up to 3 exercise rights, state = rights left) alone and in the
+    reference's mixed equity book (tests/pytests/test_netting_sets.py:375-528: Europeans, Americans, FlexiCall,
+    barrier in one netting set), PV and EPE / PFE through state-dependent regression proxies.  The reference's
+    own draws injected, outputs of the unmodified reference (tests/golden)."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    assert res.get_netting_set_names() == gold["sets"] and res.get_metric_names() == gold["metrics"]
+    assert [float(t) for t in sc.simulation_timeline] == gold["simulation_timeline"]
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _compare(flat, ref, 1e-9, name)
+
+
+@pytest.mark.parametrize("name", FLEXI_CASES)
+def test_flexicall_and_mixed_book_philox_match_oracle(name):
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8,
+             name + " philox", err_rtol=1e-6)
