@@ -94,3 +94,21 @@ def test_heston_semi_analytic_price_limits():
     bs = ns.BlackScholesModel(0.0, 100.0, 0.03, 0.2)
     assert float(call.compute_pv_analytically_heston(model)) == pytest.approx(float(call.compute_pv_analytically(bs)), abs=1e-6)
     assert float(put.compute_pv_analytically_heston(model)) == pytest.approx(float(put.compute_pv_analytically(bs)), abs=1e-6)
+
+
+def test_netting_set_collateral_profile_uses_exact_delayed_indices():
+    """tests/pytests/test_netting_sets.py:209-264: the host-side tensor helpers of NettingSet."""
+    import torch
+    ns = cases.Namespace()
+    prod = ns.EuropeanOption(ns.Equity("eq"), 1.0, 100.0, ns.OptionType.CALL)
+    nset = ns.NettingSet(name="collateral_ns", products=[prod], margin_period_of_risk=0.5)
+    tl = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0], dtype=torch.float64)
+    netted = torch.tensor([[0.0, 0.0], [5.0, 10.0], [10.0, 20.0], [15.0, 30.0], [20.0, 40.0]], dtype=torch.float64)
+    metric_idx, delayed_idx = torch.tensor([0, 2, 4]), torch.tensor([-1, 1, 3])
+    coll = nset.compute_collateral_profile(netted, tl, metric_idx, delayed_idx)
+    unsec = nset.compute_unsecured_exposure_profiles(netted, tl, metric_idx, delayed_idx)
+    assert torch.equal(coll, torch.tensor([[0.0, 0.0], [5.0, 10.0], [15.0, 30.0]], dtype=torch.float64))
+    assert torch.equal(unsec, torch.tensor([[0.0, 0.0], [5.0, 10.0], [5.0, 10.0]], dtype=torch.float64))
+    banded = ns.NettingSet(name="t", products=[ns.EuropeanOption(ns.Equity("eq"), 1.0, 100.0, ns.OptionType.CALL)], threshold=7.0)
+    assert torch.equal(banded.apply_threshold(torch.tensor([-10.0, -3.0, 0.0, 7.0, 12.0], dtype=torch.float64)),
+                       torch.tensor([-3.0, 0.0, 0.0, 0.0, 5.0], dtype=torch.float64))
