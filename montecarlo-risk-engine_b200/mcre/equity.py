@@ -209,6 +209,39 @@ class EquityBackend:
         inv = math.exp(-self.num_rate * tau)
         return inv, -tau * inv
 
+    def basis_at(self, a, t):
+        """Standardisation (shift, scale) of the spot of asset a at time t from the model's own first two moments
+        (log-normal with the model's average variance).  A pure conditioning aid: the fitted values do not depend
+        on it, and - unlike sample statistics - it does not depend on how the paths are sharded over GPUs, so
+        results stay bit-identical across GPU counts."""
+        asset = self.assets[a]
+        m, par = asset.model, asset.par
+        tau = t - m.t0()
+        if self.kind == EQ_BS:
+            s0, sig, r = par
+            mean, var_log = s0 * math.exp(r * max(tau, 0.0)), sig * sig * tau
+        elif self.kind == EQ_HESTON:
+            s0, _, r, _, kappa, theta, v0 = par
+            kt = kappa * tau
+            avg = theta + (v0 - theta) * ((1.0 - math.exp(-kt)) / kt if kt > 1e-12 else 1.0)
+            mean, var_log = s0 * math.exp(r * max(tau, 0.0)), max(avg, 1e-12) * tau
+        else:
+            _, ks, ss, _, sl, rho = par
+            mean = m.curve_value(t)
+            e1 = (1.0 - math.exp(-ks * tau)) / ks if ks > 1e-12 else tau
+            e2 = (1.0 - math.exp(-2.0 * ks * tau)) / (2.0 * ks) if ks > 1e-12 else tau
+            var_log = ss * ss * e2 + sl * sl * tau + 2.0 * rho * ss * sl * e1
+        if tau <= 0.0 or var_log <= 0.0:
+            return (mean if tau > 0.0 else self._spot0(a), 1.0)
+        std = mean * math.sqrt(math.expm1(min(var_log, 50.0)))
+        return (mean, 1.0 / std if std > 0.0 else 1.0)
+
+    def _spot0(self, a):
+        asset = self.assets[a]
+        if self.kind == EQ_SCHWARTZ:
+            return asset.model.curve_value(asset.model.t0())
+        return asset.par[0]
+
     def _product_record(self, p, set_local, slot, date_idx):
         """-> (record[16], weights[A], events [(date index, flags)])."""
         rec = np.zeros(EQ_PR)
@@ -629,14 +662,8 @@ class EquityBackend:
             cols[xi][0], cols[xi][1], 1, ip([cols[ui][0]]), fp([1.0]), ip([cols[ui][1]]), 0.0, fp(exercise_strikes(prod)), sign,
             xs.data_ptr(), nums.data_ptr(), imm.data_ptr(), RT.stream_ptr()))
         del paths
-        # standardisation of the explanatory variable per date: sample mean / std over all ranks
-        live = xs[:, :count] if count else xs[:, :0]
-        mom = torch.stack([torch.full((n_reg,), float(count), dtype=torch.float64, device=dev), live.sum(1), (live * live).sum(1)])
-        mom = RT.all_reduce_tree(mom).cpu().numpy()
-        mean = mom[1] / np.maximum(mom[0], 1.0)
-        var = np.maximum(mom[2] / np.maximum(mom[0], 1.0) - mean * mean, 0.0)
-        std = np.sqrt(var)
-        basis = np.stack([mean, np.where(std > 1e-12 * np.maximum(np.abs(mean), 1.0), 1.0 / np.where(std > 0, std, 1.0), 1.0)], axis=1)
+        # standardisation of the explanatory variable per date: model moments (shard independent)
+        basis = np.array([self.basis_at(xi, t) for t in reg_times]).reshape(n_reg, 2)
         coef = backward_induction(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R)
         coef = coef.reshape(n_reg, R, 3)
         ridx = {t: k for k, t in enumerate(reg_times)}
@@ -708,13 +735,9 @@ class EquityBackend:
                 L.mcre_eq_destroy(plan)
             for u, p in enumerate(group):
                 cfs[id(p)] = cf[u]
-        # standardisation of each asset's spot per date: sample mean / std over all ranks
-        live = xs[:, :, :count]
-        mom = torch.stack([torch.full((n_expo, A), float(count), dtype=torch.float64, device=dev), live.sum(2), (live * live).sum(2)])
-        mom = RT.all_reduce_tree(mom).cpu().numpy()
-        mean = mom[1] / np.maximum(mom[0], 1.0)
-        std = np.sqrt(np.maximum(mom[2] / np.maximum(mom[0], 1.0) - mean * mean, 0.0))
-        scale = np.where(std > 1e-12 * np.maximum(np.abs(mean), 1.0), 1.0 / np.where(std > 0, std, 1.0), 1.0)
+        # standardisation of each asset's spot per date: model moments (shard independent)
+        bs = np.array([[self.basis_at(a, t) for a in range(A)] for t in expo_times]).reshape(n_expo, A, 2)
+        mean, scale = bs[:, :, 0], bs[:, :, 1]
         # moments per (product, date strictly before the payment)
         jobs = [(p, k) for p in products for k, t in enumerate(expo_times) if t < float(p.product_timeline[-1])]
         moments = torch.zeros((max(len(jobs), 1), 8), dtype=torch.float64, device=dev)

@@ -49,8 +49,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.paths_log2
     out = {}
-    for name in ["wwr_cva", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption", "heston_path_dependent",
-                 "bs_basket_euler"]:
+    for name in ["wwr_cva", "wwr_cva_greeks", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption",
+                 "heston_path_dependent", "bs_basket_euler", "flexicall_exposure", "mixed_book_exposure"]:
         res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0))
         vals = []
         for s in res.get_netting_set_names():
