@@ -127,11 +127,15 @@ __global__ void __launch_bounds__(128) irc_lsm_forward_kernel(IrcDev P, RngDev r
 // FP32 tails in registers; per regression date it sums its own paths first and the block
 // reduces once - 16x fewer shuffle / barrier rounds than reducing every 256 paths, and the
 // loads of one date stay coalesced.  HBM-bound: 20 B per (path, date).
-constexpr int MOM_IT = 16;
+// The loads of date k-1 are issued before the block reduction of date k (software pipeline): the first
+// version waited for memory and for the barrier in turn with 8 warps per SM (175 registers, one block per SM,
+// 1.1 TB/s; profiles/r01_other_kernels_ncu_summary.md).
+constexpr int MOM_IT = 8;
 template <int NU>
-__global__ void __launch_bounds__(256) irc_presim_moments_kernel(IrcDev P, ShardDev sh, const double *xbuf,
-                                                                 const double *nbuf, const float *wbuf,
-                                                                 double *partial) {
+__global__ void __launch_bounds__(256, 2) irc_presim_moments_kernel(IrcDev P, ShardDev sh, const double *__restrict__ xbuf,
+                                                                    const double *__restrict__ nbuf,
+                                                                    const float *__restrict__ wbuf,
+                                                                    double *__restrict__ partial) {
   constexpr int NV = 5 + 3 * NU;
   extern __shared__ double smem[];
   const int nw = blockDim.x >> 5;
@@ -157,27 +161,46 @@ __global__ void __launch_bounds__(256) irc_presim_moments_kernel(IrcDev P, Shard
 #pragma unroll
         for (int u = 0; u < NU; ++u) S[i][u] = 0.0f;
       }
+      double xc[MOM_IT], nc[MOM_IT], xn[MOM_IT], nn[MOM_IT];
+      float wc[MOM_IT][NU], wn[MOM_IT][NU];
+      auto load = [&](int k, double (&x)[MOM_IT], double (&num)[MOM_IT], float (&w)[MOM_IT][NU]) {
+#pragma unroll
+        for (int i = 0; i < MOM_IT; ++i) {
+          x[i] = __ldg(xbuf + (size_t)k * n + path[i]);
+          num[i] = __ldg(nbuf + (size_t)k * n + path[i]);
+#pragma unroll
+          for (int u = 0; u < NU; ++u)
+            w[i][u] = u < P.n_units ? __ldg(wbuf + ((size_t)u * P.n_reg + k) * n + path[i]) : 0.0f;
+        }
+      };
+      load(P.n_reg - 1, xc, nc, wc);
       for (int k = P.n_reg - 1; k >= 0; --k) {
+        if (k > 0) load(k - 1, xn, nn, wn);
         const double bs = __ldg(P.reg_basis + k * 2), bc = __ldg(P.reg_basis + k * 2 + 1);
         double vals[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) vals[j] = 0.0;
 #pragma unroll
         for (int i = 0; i < MOM_IT; ++i) {
-          const double x = xbuf[(size_t)k * n + path[i]], numeraire = nbuf[(size_t)k * n + path[i]];
           const double keep = live[i] ? 1.0 : 0.0;
-          const double uu = (x - bs) * bc;
+          const double uu = (xc[i] - bs) * bc;
           const double u1 = keep * uu, u2 = u1 * uu;
           vals[0] += keep; vals[1] += u1; vals[2] += u2; vals[3] += u2 * uu; vals[4] += u2 * uu * uu;
 #pragma unroll
           for (int u = 0; u < NU; ++u) {
             // total = step_value + tail_value, both float32 (controller.py:349)
-            if (u < P.n_units) S[i][u] = wbuf[((size_t)u * P.n_reg + k) * n + path[i]] + S[i][u];
-            const double Y = keep * (numeraire * (double)S[i][u]);  // numeraire.unsqueeze(1) * total_cfs (controller.py:368)
+            if (u < P.n_units) S[i][u] = wc[i][u] + S[i][u];
+            const double Y = keep * (nc[i] * (double)S[i][u]);  // numeraire.unsqueeze(1) * total_cfs (controller.py:368)
             vals[5 + 3 * u] += Y; vals[6 + 3 * u] += Y * uu; vals[7 + 3 * u] += Y * uu * uu;
           }
         }
         block_accumulate<NV>(vals, acc, k * NV, stage, NV, parity);
+#pragma unroll
+        for (int i = 0; i < MOM_IT; ++i) {
+          xc[i] = xn[i]; nc[i] = nn[i];
+#pragma unroll
+          for (int u = 0; u < NU; ++u) wc[i][u] = wn[i][u];
+        }
       }
     }
     __syncthreads();

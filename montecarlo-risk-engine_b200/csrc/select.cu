@@ -23,41 +23,66 @@ __device__ __forceinline__ double value_of(unsigned long long k) {
 constexpr int SEL_MAX_R = 4;
 
 // grid: (blocks_x, n_rows).  hist: [n_rows][R][256].
-__global__ void __launch_bounds__(256) select_count_kernel(const double *values, long long row_stride,
+// The first version spent 76 instructions per element (a loop over rank slots reading its tables from shared
+// memory, 2.2 TB/s, issue bound - profiles/r01_other_kernels_ncu_summary.md); now the distinct prefixes of the
+// row sit in registers, the match is one AND + compare against the already-found high bits, and four
+// independent loads are in flight per thread.
+__global__ void __launch_bounds__(256) select_count_kernel(const double *__restrict__ values, long long row_stride,
                                                            long long n_local, int R, int pass,
-                                                           const unsigned long long *prefix,
+                                                           const unsigned long long *__restrict__ prefix,
                                                            unsigned long long *hist) {
   __shared__ unsigned int sh[SEL_MAX_R][256];
-  __shared__ unsigned long long pre[SEL_MAX_R];
-  __shared__ int rep[SEL_MAX_R];
   const int row = blockIdx.y;
   for (int i = threadIdx.x; i < SEL_MAX_R * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
-  if (threadIdx.x < R) pre[threadIdx.x] = prefix[(size_t)row * R + threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // rank slots that share a prefix are counted once (adjacent ranks usually do)
-    for (int r = 0; r < R; ++r) {
-      rep[r] = r;
-      for (int q = 0; q < r; ++q) if (pre[q] == pre[r]) { rep[r] = q; break; }
+  // rank slots that share a prefix are counted once (adjacent ranks usually do): distinct prefixes pd[0..nd),
+  // slot r reads the histogram of rep[r]
+  unsigned long long pd[SEL_MAX_R];
+  int rep[SEL_MAX_R];
+  int nd = 0;
+#pragma unroll
+  for (int r = 0; r < SEL_MAX_R; ++r) {
+    pd[r] = ~0ull; rep[r] = 0;
+    if (r < R) {
+      const unsigned long long pr = prefix[(size_t)row * R + r];
+      int found = -1;
+#pragma unroll
+      for (int q = 0; q < SEL_MAX_R; ++q) if (q < nd && found < 0 && pd[q] == pr) found = q;
+      if (found < 0) {
+#pragma unroll
+        for (int q = 0; q < SEL_MAX_R; ++q) if (q == nd) pd[q] = pr;
+        found = nd++;
+      }
+      rep[r] = found;
     }
   }
   __syncthreads();
   const int shift = 56 - 8 * pass;
+  // bits above the current digit (none in pass 0); the prefixes only have those bits set
+  const unsigned long long high = pass == 0 ? 0ull : (~0ull << (shift + 8));
   const double *v = values + (size_t)row * row_stride;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local;
-       i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long k = key_of(v[i]);
+  auto count = [&](double x) {
+    const unsigned long long k = key_of(x);
     const unsigned int digit = (unsigned int)(k >> shift) & 0xffu;
-    for (int r = 0; r < R; ++r) {
-      if (rep[r] != r) continue;
-      const bool match = pass == 0 || ((k ^ pre[r]) >> (shift + 8)) == 0ull;
-      if (match) atomicAdd(&sh[r][digit], 1u);
-    }
+    const unsigned long long kh = k & high;
+#pragma unroll
+    for (int q = 0; q < SEL_MAX_R; ++q)
+      if (q < nd && kh == pd[q]) atomicAdd(&sh[q][digit], 1u);
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n_local; i += 4 * stride) {
+    const double x0 = __ldg(v + i), x1 = __ldg(v + i + stride), x2 = __ldg(v + i + 2 * stride),
+                 x3 = __ldg(v + i + 3 * stride);
+    count(x0); count(x1); count(x2); count(x3);
   }
+  for (; i < n_local; i += stride) count(__ldg(v + i));
   __syncthreads();
-  for (int i = threadIdx.x; i < R * 256; i += blockDim.x) {
-    const int r = i >> 8, d = i & 255;
-    const unsigned int c = sh[rep[r]][d];
+  for (int j = threadIdx.x; j < R * 256; j += blockDim.x) {
+    const int r = j >> 8, d = j & 255;
+    int q = 0;
+#pragma unroll
+    for (int t = 0; t < SEL_MAX_R; ++t) if (t == r) q = rep[t];
+    const unsigned int c = sh[q][d];
     if (c) atomicAdd(&hist[((size_t)row * R + r) * 256 + d], (unsigned long long)c);
   }
 }
