@@ -260,8 +260,12 @@ def main():
     B.check(L.mcre_dfma_peak(C.byref(peak), RT.stream_ptr()))
     achieved = per_gpu * FLOP_PER_PATH_STEP * 1e-12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-                "note": "algorithmic 225 FP64 flop/path-step (SURVEY 8d) x path-steps/s per GPU; peak = DFMA loop measured in this run"}
+                "frac": achieved / peak.value if peak.value > 0 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the main kernel, from the ncu --set full
+                # capture summarised in profiles/r01_irc_main_v5_ncu_summary.md: the state lives in registers
+                "traffic": 253.44, "traffic_unit": "bytes per launch (ncu, 2^22 paths x 240 steps)",
+                "note": "algorithmic 225 FP64 flop/path-step (SURVEY 8d) x path-steps/s per GPU; peak = DFMA loop measured in this run; "
+                        "the path is FP64-pipe / issue bound, not HBM or tensor-core bound (SURVEY 8d)"}
 
     # ---- end to end through the public API (host objects in, numpy results out) ------------
     e2e_times, h2d, d2h = [], 0, 0
