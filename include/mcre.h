@@ -342,6 +342,18 @@ int64_t mcre_eq_slots(const mcre_eq_plan *plan);
 int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                     double *d_acc, double *d_shift, double *d_spill /* [n_sets][n_metric][n_paths] or NULL */,
                     void *stream);
+/* Book splitting: a netting set with more path-dependent / exercise products than one launch can track
+ * (4 value-only, 2 with tangents) is evaluated in several launches over the same Philox streams; each launch
+ * ADDS its per-path discounted cashflow totals to d_accum [n_sets][n_paths] (NULL: off) and mcre_sum_stats
+ * turns the accumulated per-path PVs into the sums of metric.py:26-35.  Replaces the reference's loop over
+ * the products of a netting set (controller.py:506-563) for books of thousands of products
+ * (tests/pv_tests/pv_performance_large_netting_set.py). */
+int mcre_eq_set_pv_accumulator(mcre_eq_plan *plan, double *d_accum);
+/* d_out [n_rows][2] = sum(x - c), sum((x - c)^2) per row of d_x [n_rows][n], c = d_shift[row]; fixed-order
+ * chunk partials (d_partial: [ceil(n / chunk_paths)][n_rows][2]) + tree, like the simulation kernels. */
+int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,
+                   double *d_partial, double *d_out, void *stream);
+
 /* Pre-simulation pass of the regression-proxy exposures (replaces the path generation + request resolution +
  * cashflow roll feeding controller._perform_regression_for_product, controller.py:294-351, for the equity
  * products, which pay once): the same fused kernel run on the pre-simulation stream spills, date-major,

@@ -56,6 +56,10 @@ struct EqDev {
   // discounted cashflow of every product rounded to float32 (the reference's float32 accumulators)
   double *ps_x;   // [n_expo][A][n_paths]
   float *ps_cf;   // [n_prod][n_paths]
+  // book splitting (mcre_eq_set_pv_accumulator): per-path discounted cashflow totals of the launch are ADDED
+  // to pv_accum [n_sets][n_paths], so a netting set with more path-dependent products than one launch can
+  // track is evaluated in several launches over the same Philox streams and finished by mcre_sum_stats
+  double *pv_accum;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -475,6 +479,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           if (pilot) { if (threadIdx.x == 0) shift[s] = val(cf[s]); }
+          if (P.pv_accum && !pilot && live && a == 0 && s < P.n_sets) P.pv_accum[(size_t)s * sh.n_paths + lpath] += val(cf[s]);
           const double x = val(cf[s]) - (pilot ? 0.0 : shift[s]);
           vals[s * 3 + 0] = keep1 * x; vals[s * 3 + 1] = keep1 * x * x; vals[s * 3 + 2] = keep1 * numtan[s];
         }
@@ -589,7 +594,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
-  D.ps_x = nullptr; D.ps_cf = nullptr;
+  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -700,6 +705,12 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   return mcre_tree_reduce(d_partial, n_chunks, mcre_eq_slots(p), d_acc, stream);
+}
+
+extern "C" int mcre_eq_set_pv_accumulator(mcre_eq_plan *p, double *d_accum) {
+  if (!p) return fail(-1, "null argument%s", "");
+  p->d.pv_accum = d_accum;
+  return 0;
 }
 
 extern "C" int mcre_eq_presim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,

@@ -81,6 +81,34 @@ __global__ void __launch_bounds__(128) tree_level_kernel(const double *in, long 
   carry[slot] = counter_fold(v, cnt, carry_valid ? carry[slot] : 0.0, carry_valid != 0);
 }
 
+// sum(x - c), sum((x - c)^2) of rows of x [n_rows][n] with c = shift[row]: per-chunk block sums in a fixed order
+// (the same chunks as the simulation kernels), combined by mcre_tree_reduce.  partial: [chunk][n_rows][2].
+__global__ void __launch_bounds__(256) sum_stats_kernel(const double *__restrict__ x, long long n, int n_rows, int chunk,
+                                                        const double *__restrict__ shift, double *__restrict__ partial) {
+  __shared__ double stage[2 * 8];
+  const long long ch = blockIdx.x;
+  const int row = blockIdx.y;
+  const double c = shift[row];
+  double s1 = 0.0, s2 = 0.0;
+  for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
+    const long long p = ch * chunk + it;
+    if (p < n) { const double d = x[(size_t)row * n + p] - c; s1 += d; s2 += d * d; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { stage[warp * 2] = s1; stage[warp * 2 + 1] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += stage[w * 2 + threadIdx.x];
+    partial[((size_t)ch * n_rows + row) * 2 + threadIdx.x] = t;
+  }
+}
+
 // Register-resident DFMA chains: 16 independent accumulators per thread.
 __global__ void dfma_peak_kernel(double *sink, int iters, double a, double b) {
   double x[16];
@@ -154,6 +182,19 @@ extern "C" int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64
     n = n_full;
   }
   return 0;
+}
+
+extern "C" int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,
+                              double *d_partial, double *d_out, void *stream) {
+  if (!d_x || !d_shift || !d_partial || !d_out) return fail(-1, "null argument%s", "");
+  if (n_rows <= 0 || chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "sum_stats: bad shape%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) { MCRE_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_rows * 2 * sizeof(double), st)); return 0; }
+  const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
+  dim3 grid((unsigned)n_chunks, (unsigned)n_rows);
+  sum_stats_kernel<<<grid, 256, 0, st>>>(d_x, n, n_rows, chunk_paths, d_shift, d_partial);
+  MCRE_LAUNCHED();
+  return mcre_tree_reduce(d_partial, n_chunks, (int64_t)n_rows * 2, d_out, stream);
 }
 
 extern "C" int mcre_dfma_peak(double *tflops_out, void *stream) {

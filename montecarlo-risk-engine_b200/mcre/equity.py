@@ -362,9 +362,10 @@ class EquityBackend:
             step_chol.append(seen[key])
         return 1, None, chol_dual, step_chol
 
-    def lower(self, set_indices, presim_products=None):
+    def lower(self, set_indices, presim_products=None, subset=None):
         """Plan of the main pass for a group of netting sets, or (presim_products given) of the
-        pre-simulation spill pass for a group of products (all in one dummy set)."""
+        pre-simulation spill pass for a group of products (all in one dummy set).  `subset`: ids of the
+        products to keep (book splitting: one launch evaluates a part of a large netting set)."""
         c, nt, A = self.c, self.nt, self.A
         if presim_products is not None:
             nt = 0
@@ -396,7 +397,8 @@ class EquityBackend:
         owners = []
         slot = 0
         book = ([(0, p) for p in presim_products] if presim_products is not None else
-                [(r, p) for r, si in enumerate(set_indices) for p in c.netting_sets[si].products])
+                [(r, p) for r, si in enumerate(set_indices) for p in c.netting_sets[si].products
+                 if subset is None or id(p) in subset])
         for r, p in book:
             if True:
                 if c._can_skip_monte_carlo_for_product(p):
@@ -631,8 +633,13 @@ class EquityBackend:
         inj = c.injected_normals.get("pre") if c.injected_normals else None
         inj_u = getattr(c, "injected_uniforms", None)
         inj_u = inj_u.get("pre") if inj_u else None
-        paths = P.generate(c.model, sim, n, c.num_steps, self.scheme, 42, inject_z=inj, inject_u=inj_u,
-                           stream_id=c.rng_stream, path_begin=begin, n_total=n_pre)
+        paths = getattr(self, "_presim_paths", None)
+        if paths is None:
+            # one set of pre-simulation paths serves every exercise product of the run (the reference
+            # generates them once per run too, controller.py:272-292)
+            paths = P.generate(c.model, sim, n, c.num_steps, self.scheme, 42, inject_z=inj, inject_u=inj_u,
+                               stream_id=c.rng_stream, path_begin=begin, n_total=n_pre)
+            self._presim_paths = paths
         cols = self._state_columns()
         xi = self._asset_index(prod.get_asset_id())
         ui = self._asset_index(prod.underlying.get_asset_id())
@@ -765,6 +772,63 @@ class EquityBackend:
             coef, basis = self.expo_coef[id(p)]
             c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coef, basis, [t <= t0 for t in expo_times]))
 
+    def _run_split_book(self, si, dev, n_main, n_params):
+        """PV (and pathwise Greeks) of one netting set with more path-dependent / exercise products than a launch
+        can track: the products are split over launches that replay the same Philox streams; every launch adds
+        its per-path discounted cashflows to one accumulator (mcre_eq_set_pv_accumulator), the pilot shifts and
+        the tangent sums add up linearly, and mcre_sum_stats finishes mean / standard error."""
+        c = self.c
+        L = B.lib()
+        ntrk = eq_ntrk(self.nt)
+        prods = [p for p in c.netting_sets[si].products if not c._can_skip_monte_carlo_for_product(p)]
+        tracked = [p for p in prods if _is_path_dependent(p)]
+        plain = [p for p in prods if not _is_path_dependent(p)]
+        books = [tracked[i:i + ntrk] for i in range(0, len(tracked), ntrk)]
+        if plain and books:
+            books[0] = books[0] + plain
+        elif plain:
+            books = [plain]
+        begin, count = RT.shard_range(n_main, CHUNK_PATHS)
+        n = max(count, 1)
+        n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
+        accum = torch.zeros(n, dtype=torch.float64, device=dev)
+        shift_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
+        for book in books:
+            desc, keep, info = self.lower([si], subset={id(p) for p in book})
+            plan = C.c_void_p()
+            B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
+            try:
+                slots = L.mcre_eq_slots(plan)
+                acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
+                B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
+                rng = self._rng(43, n_main)
+                sh = B.Shard(begin, count, CHUNK_PATHS)
+                B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                          shift.data_ptr(), None, RT.stream_ptr()))
+                if self.nt:
+                    acc_h = RT.all_reduce_tree(acc).cpu().numpy()
+                    tang = acc_h[3:3 + self.A * self.nt].reshape(self.A, 1, self.nt)
+                    for a, asset in enumerate(self.assets):
+                        for k, g in enumerate(asset.gmap):
+                            grad[g] += tang[a, 0, k] / n_main
+                    numtan += acc_h[2] / n_main
+                    grad += self._control_variate_gradient(info["owners"], info["recs"], 0, n_params)
+                shift_sum += shift[0:1]      # pilot values add up: the book's value on global path 0
+            finally:
+                L.mcre_eq_destroy(plan)
+        partial = torch.empty(n_chunks * 2 + 1, dtype=torch.float64, device=dev)
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+        B.check(L.mcre_sum_stats(accum.data_ptr(), count, 1, CHUNK_PATHS, shift_sum.data_ptr(), partial.data_ptr(),
+                                 out.data_ptr(), RT.stream_ptr()))
+        s = RT.all_reduce_tree(out).cpu().numpy()
+        pv = mean_and_error(s[0], s[1], float(shift_sum[0]), n_main)
+        if self.nt:
+            grad[self.num_rate_global] += numtan
+        return {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+
     def run(self):
         c = self.c
         dev = RT.compute_device()
@@ -776,6 +840,7 @@ class EquityBackend:
         for p in c.products:
             if is_equity_exercise(p):
                 self.presim_exercise(p, dev)
+        self._presim_paths = None
         if c.risk_metrics.requires_exposure_profiles():
             reg = [p for p in c.products if not c._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
             if reg:
@@ -783,11 +848,22 @@ class EquityBackend:
         t_pre = time.perf_counter() - t0
         results = [None] * n_sets
         group = EQ_MAX_SETS if self.nt == 0 else 2
-        # launch groups: up to `group` netting sets and eq_ntrk(nt) path-dependent / exercise products each
+        # launch groups: up to `group` netting sets and eq_ntrk(nt) path-dependent / exercise products each;
+        # a netting set with more tracked products than one launch holds is split over several launches
+        ntrk = eq_ntrk(self.nt)
+        oversized = [si for si, ns in enumerate(c.netting_sets) if sum(_is_path_dependent(p) for p in ns.products) > ntrk]
+        if oversized and c.risk_metrics.requires_exposure_profiles():
+            raise NotImplementedError(
+                f"exposure profiles of a netting set with more than {ntrk} path-dependent / exercise products "
+                "are not implemented (PV is: the book is split over launches)")
+        for si in oversized:
+            results[si] = self._run_split_book(si, dev, n_main, n_params)
         groups, cur, cur_trk = [], [], 0
         for si, ns in enumerate(c.netting_sets):
+            if si in oversized:
+                continue
             trk = sum(_is_path_dependent(p) for p in ns.products)
-            if cur and (len(cur) >= group or cur_trk + trk > eq_ntrk(self.nt)):
+            if cur and (len(cur) >= group or cur_trk + trk > ntrk):
                 groups.append(cur)
                 cur, cur_trk = [], 0
             cur.append(si)

@@ -198,3 +198,44 @@ def test_flexicall_and_mixed_book_philox_match_oracle(name):
     out, _ = helpers.run_oracle(name, draws="philox")
     _compare(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8,
              name + " philox", err_rtol=1e-6)
+
+
+@pytest.mark.parametrize("differentiate", [False, True])
+def test_large_mixed_book_is_split_over_launches(differentiate):
+    """A netting set with more path-dependent / exercise products than one launch tracks (4, or 2 with tangents):
+    the book is evaluated in several launches that replay the same Philox streams and accumulate per-path
+    cashflows (mcre_eq_set_pv_accumulator + mcre_sum_stats).  PV, MC error and pathwise Greeks vs the oracle,
+    which evaluates the whole book at once like the reference (tests/pv_tests/pv_performance_large_netting_set.py)."""
+    from oracle import risk
+    ns = cases.Namespace()
+    ids = ["asset_1", "asset_2"]
+    model = ns.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                 volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    prods = []
+    for k in range(3):
+        a = ids[k % 2]
+        prods.append(ns.AmericanOption(underlying=ns.Equity(a), maturity=1.0 + 0.25 * k, num_exercise_dates=5 + k,
+                                       strike=95.0 + 5.0 * k, option_type=ns.OptionType.PUT if k % 2 else ns.OptionType.CALL,
+                                       asset_id=a))
+        prods.append(ns.BarrierOption(startdate=0.0, maturity=1.0 + 0.25 * k, strike=100.0, num_observation_timepoints=6,
+                                      option_type=ns.OptionType.CALL, barrier1=130.0 + 5 * k,
+                                      barrier_option_type1=ns.BarrierOptionType.UPANDOUT, asset_id=a))
+        prods.append(ns.AsianOption(0.0, 1.0, 100.0 + 2 * k, 4 + k, ns.OptionType.CALL, asset_id=a))
+        prods.append(ns.EuropeanOption(ns.Equity(a), 0.5 + 0.5 * k, 100.0, ns.OptionType.PUT, asset_id=a))
+    prods.append(ns.FlexiCall(underlyings=[ns.EuropeanOption(ns.Equity("asset_1"), 0.5 * (j + 1), 95.0 + 5 * j, ns.OptionType.CALL,
+                                                             asset_id="asset_1") for j in range(3)],
+                              num_exercise_rights=2, asset_id="asset_1"))
+    sets = [ns.NettingSet(name="big", products=prods),
+            ns.NettingSet(name="small", products=[ns.EuropeanOption(ns.Equity("asset_2"), 1.0, 105.0, ns.OptionType.CALL, asset_id="asset_2")])]
+    n = 3000
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics([ns.PVMetric()]), n, n, 1, ns.SimulationScheme.ANALYTICAL, differentiate)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, [ns.PVMetric()], None, n, n, 1, "ANALYTICAL", differentiate=differentiate)
+    for si, name in enumerate(["big", "small"]):
+        want_v, want_e = out["results"][si][0][0]
+        helpers.assert_close(res.get_results(name, "pv"), [want_v], 1e-8, 1e-10, f"{name} pv")
+        helpers.assert_close(res.get_mc_error(name, "pv"), [want_e], 1e-6, 1e-10, f"{name} pv error")
+        if differentiate:
+            got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(name, "pv")[0]])
+            want = np.asarray(out["grads"][si][0][0])
+            helpers.assert_close(got, want, 1e-6, 1e-7 * max(1.0, float(np.abs(want).max())), f"{name} pv greeks")
