@@ -26,9 +26,14 @@
 namespace mcre {
 
 constexpr int EQ_PR = 16;     // doubles per product record
-// path-dependent / exercise trackers per launch: 4 in the value-only builds (mixed books), 2 when the
-// trackers carry tangents (register budget)
-__host__ __device__ constexpr int eq_ntrk(int nt) { return nt == 0 ? 4 : 2; }
+// path-dependent / exercise trackers per launch.  Value-only builds keep 64 of them in dynamically indexed
+// per-thread arrays (local memory, touched only at product events): large mixed books need few launches.
+// Tangent builds keep 2 in registers (compile-time selects; the trackers carry the tangents).
+__host__ __device__ constexpr int eq_ntrk(int nt) { return nt == 0 ? 64 : 2; }
+// visits tracker `slot` (none if slot < 0): one dynamic access (NT = 0) or an unrolled compare-select
+#define MCRE_TRK_FOR(k, slot)                                                                         \
+  for (int k = (NT == 0 ? ((slot) > 0 ? (slot) : 0) : 0), k##_end = (NT == 0 ? (slot) + 1 : NTRK); k < k##_end; ++k) \
+    if (k == (slot))
 constexpr int EQ_PAR = 8;     // doubles per asset parameter row
 
 struct EqDev {
@@ -173,8 +178,10 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
         for (int l = 0; l < EQ_MAX_LAG; ++l) hist[s][l] = 0.0;
 #pragma unroll
       for (int s = 0; s < NS; ++s) { cf[s] = T::zero(); numtan[s] = 0.0; }
+      if constexpr (NT > 0) {   // (value-only builds: every tracker is set by its FIRST event / the loop below)
 #pragma unroll
-      for (int k = 0; k < NTRK; ++k) { trk_a[k] = T::zero(); trk_b[k] = T::zero(); }
+        for (int k = 0; k < NTRK; ++k) { trk_a[k] = T::zero(); trk_b[k] = T::zero(); }
+      }
       // exercise products start with all their rights (state = rights left): exposure dates before the
       // first exercise date already look the state up
       for (int pi = 0; pi < P.n_prod; ++pi) {
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
         if ((int)__ldg(pr + 0) != EQ_EXERCISE) continue;
         const int slot = (int)__ldg(pr + 14);
 #pragma unroll
-        for (int k = 0; k < NTRK; ++k) if (k == slot) trk_a[k] = T::lift(__ldg(pr + 13));
+        MCRE_TRK_FOR(k, slot) trk_a[k] = T::lift(__ldg(pr + 13));
       }
 
       auto spot_now = [&]() -> R {
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
               if (xtype == 3) {
                 const int slot = (int)__ldg(pr + 14);
 #pragma unroll
-                for (int k = 0; k < NTRK; ++k) if (k == slot) st = (int)val(trk_a[k]);
+                MCRE_TRK_FOR(k, slot) st = (int)val(trk_a[k]);
               }
               if (xw != 0.0 && st > 0) {
                 const double u = (Sv - __ldg(op + 5)) * __ldg(op + 6);
@@ -332,8 +339,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
             };
             const R imm = option_payoff(U, __ldg(ed + 14), sign);
 #pragma unroll
-            for (int k = 0; k < NTRK; ++k) {
-              if (k != slot) continue;
+            MCRE_TRK_FOR(k, slot) {
               const int st = (int)val(trk_a[k]);
               if (st > 0 && val(imm) + cont_of(st - 1) > cont_of(st)) {
                 trk_a[k] = T::lift((double)(st - 1));
@@ -346,8 +352,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
           }
           if (ef & EQ_EV_OBSERVE) {
 #pragma unroll
-            for (int k = 0; k < NTRK; ++k) {
-              if (k != slot) continue;
+            MCRE_TRK_FOR(k, slot) {
               if (kind == EQ_ASIAN) {
                 const R x = (pflags & 1) ? r_log(U + 1e-10) : U;     // asian_option.py:51-69
                 trk_a[k] = (ef & EQ_EV_FIRST) ? x : trk_a[k] + x;
@@ -372,13 +377,13 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
             const double inv_n = 1.0 / __ldg(pr + 13);
             R avg = T::zero();
 #pragma unroll
-            for (int k = 0; k < NTRK; ++k) if (k == slot) avg = trk_a[k] * inv_n;
+            MCRE_TRK_FOR(k, slot) avg = trk_a[k] * inv_n;
             if (pflags & 1) avg = r_exp(avg);
             pay = option_payoff(avg, strike, sign);
           } else {
             R mx = T::zero(), mn = T::zero();
 #pragma unroll
-            for (int k = 0; k < NTRK; ++k) if (k == slot) { mx = trk_a[k]; mn = trk_b[k]; }
+            MCRE_TRK_FOR(k, slot) { mx = trk_a[k]; mn = trk_b[k]; }
             pay = option_payoff(U, strike, sign) * barrier_factor(mx, mn, __ldg(pr + 9), (int)__ldg(pr + 10));
             const int bt2 = (int)__ldg(pr + 12);
             if (bt2 > 0) pay = pay * barrier_factor(mx, mn, __ldg(pr + 11), bt2);
@@ -538,7 +543,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   for (int p = 0; p < c->n_prod; ++p) {
     const int slot = (int)c->prod[(size_t)p * EQ_PR + 14], kind = (int)c->prod[(size_t)p * EQ_PR];
     if ((kind == EQ_ASIAN || kind == EQ_BARRIER || kind == EQ_EXERCISE) && (slot < 0 || slot >= eq_ntrk(c->nt)))
-      return fail(-3, "eq: too many path-dependent / exercise products per launch (4, or 2 with tangents)%s", "");
+      return fail(-3, "eq: too many path-dependent / exercise products per launch (64, or 2 with tangents)%s", "");
     if (kind == EQ_EXERCISE && (!c->ev_data || !c->prod_x)) return fail(-1, "eq: exercise product without event data%s", "");
     const int set = (int)c->prod[(size_t)p * EQ_PR + 1];
     if (set < 0 || set >= c->n_sets) return fail(-1, "eq: product set index out of range%s", "");
@@ -678,8 +683,11 @@ static int eq_dispatch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, d
 extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                                double *d_acc, double *d_shift, double *d_spill, void *stream) {
   if (!p || !rng || !d_partial || !d_acc || !d_shift) return fail(-1, "null argument%s", "");
-  int rc = check_shard(shard);
-  if (rc) return rc;
+  // the equity kernel takes any chunk that is a multiple of a warp (small runs use small chunks)
+  if (!shard || shard->n_paths < 0 || shard->chunk_paths <= 0 || shard->chunk_paths % 32 != 0)
+    return fail(-2, "invalid shard: chunk_paths must be a positive multiple of 32%s", "");
+  if (shard->path_begin % shard->chunk_paths != 0) return fail(-2, "invalid shard: path_begin not chunk aligned%s", "");
+  int rc = 0;
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.ps_x)
     return fail(-1, "spill requested but d_spill is null%s", "");

@@ -133,6 +133,8 @@ extern "C" int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, i
   cudaStream_t st = (cudaStream_t)stream;
   DevArray<int> rd, ed, uc, ul;
   DevArray<double> rn, uw, xs;
+  DevArena arena;   // the index tables travel in one allocation + one copy
+  ArenaScope arena_scope(&arena);
   int rc = rd.upload(reg_date, n_reg);
   if (!rc && ex_strike) rc = xs.upload(ex_strike, n_ex);
   if (!rc) rc = ed.upload(ex_date, n_ex);
@@ -140,6 +142,7 @@ extern "C" int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, i
   if (!rc) rc = ul.upload(under_is_log, n_under);
   if (!rc) rc = rn.upload(reg_numeraire, n_reg);
   if (!rc) rc = uw.upload(under_w, n_under);
+  if (!rc) rc = arena.commit();
   if (!rc) {
     lsm_prepare_equity_kernel<<<(unsigned)((n_paths + 255) / 256), 256, 0, st>>>(
         d_paths, n_paths, n_dates, state_dim, n_reg, rd.p, rn.p, n_ex, ed.p, x_col, x_is_log, n_under, uc.p, uw.p, ul.p,
@@ -150,6 +153,7 @@ extern "C" int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, i
     else cudaStreamSynchronize(st);   // the temporary index tables are freed below
   }
   rd.release(); ed.release(); uc.release(); ul.release(); rn.release(); uw.release(); xs.release();
+  arena.release();
   return rc;
 }
 

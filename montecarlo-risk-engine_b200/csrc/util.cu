@@ -187,7 +187,7 @@ extern "C" int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64
 extern "C" int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,
                               double *d_partial, double *d_out, void *stream) {
   if (!d_x || !d_shift || !d_partial || !d_out) return fail(-1, "null argument%s", "");
-  if (n_rows <= 0 || chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "sum_stats: bad shape%s", "");
+  if (n_rows <= 0 || chunk_paths <= 0 || chunk_paths % 32 != 0) return fail(-2, "sum_stats: bad shape%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) { MCRE_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_rows * 2 * sizeof(double), st)); return 0; }
   const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;

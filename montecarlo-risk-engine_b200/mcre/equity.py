@@ -41,6 +41,15 @@ from products.flexicall import FlexiCall
 from products.product import OptionType
 
 CHUNK_PATHS = 4096
+
+
+def main_chunk(n_total):
+    """Paths per reduction chunk (= per block pass) of the main pass: a pure function of the TOTAL path count, so
+    the summation tree - and every bit of the result - does not depend on the number of GPUs.  Small runs
+    (books of many products on ~1000 paths) use small chunks, otherwise one block would do all the work."""
+    if n_total >= (1 << 18):
+        return CHUNK_PATHS
+    return 256 if n_total >= (1 << 14) else 32
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
 P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
 EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
@@ -49,7 +58,7 @@ EQ_PR, EQ_PAR, EQ_MAX_SETS, EQ_XP, EQ_EVD, EQ_MAX_LAG, EQ_MAX_RIGHTS = 16, 8, 4,
 
 def eq_ntrk(nt):
     """Path-dependent / exercise trackers per launch (csrc/equity.cu:eq_ntrk)."""
-    return 4 if nt == 0 else 2
+    return 64 if nt == 0 else 2
 _NPAR = {EQ_BS: 3, EQ_HESTON: 7, EQ_SCHWARTZ: 6}
 _BARRIER_CODE = {BarrierOptionType.UPANDOUT: 1, BarrierOptionType.DOWNANDOUT: 2,
                  BarrierOptionType.UPANDIN: 3, BarrierOptionType.DOWNANDIN: 4}
@@ -611,12 +620,34 @@ class EquityBackend:
             off += m.state_dim
         return cols
 
-    def presim_exercise(self, prod, dev):
-        """Longstaff-Schwartz pre-simulation of a Bermudan / American option on equity underlyings
+    def presim_exercise_all(self, prods, dev):
+        """Longstaff-Schwartz pre-simulation of every exercise product of the run: the backward inductions of
+        the products advance in lock-step (one moment all-reduce + one device-to-host read per step for all
+        of them, mcre/lsm.py:run_backward_inductions) instead of one synchronisation per product and date.
+        Memory is bounded by processing the products in batches."""
+        from mcre.lsm import run_backward_inductions
+        if not prods:
+            return
+        c = self.c
+        n_expo = len(c.exposure_timeline) if c.risk_metrics.requires_exposure_profiles() else 0
+        _, count = RT.shard_range(c.num_paths_presim, CHUNK_PATHS)
+        per_product = max((3 * (len(p.product_timeline) + n_expo) + 2) * max(count, 1) * 8 for p in prods)
+        batch = max(1, min(64, int(6e9 // per_product)))
+        for b0 in range(0, len(prods), batch):
+            group = prods[b0:b0 + batch]
+            prepared = [self.presim_exercise(p, dev, prepare_only=True) for p in group]
+            coefs = run_backward_inductions([g for g, _ in prepared])
+            for (_, finish), coef in zip(prepared, coefs):
+                finish(coef)
+        self._presim_paths = None
+
+    def presim_exercise(self, prod, dev, prepare_only=False):
+        """Longstaff-Schwartz pre-simulation of a Bermudan / American / FlexiCall option on equity underlyings
         (controller.py:294-383): pre-simulation paths from the path generator (seed 42), gathered
-        date-major by mcre_lsm_prepare_equity, then the shared backward induction (mcre/lsm.py)."""
+        date-major by mcre_lsm_prepare_equity, then the shared backward induction (mcre/lsm.py).
+        prepare_only: return (generator of the backward induction, finish(coef)) for the lock-step driver."""
         from mcre import paths as P
-        from mcre.lsm import backward_induction, to_raw_basis
+        from mcre.lsm import backward_induction_steps, run_backward_inductions, to_raw_basis
         c = self.c
         L = B.lib()
         n_pre = c.num_paths_presim
@@ -671,20 +702,26 @@ class EquityBackend:
         del paths
         # standardisation of the explanatory variable per date: model moments (shard independent)
         basis = np.array([self.basis_at(xi, t) for t in reg_times]).reshape(n_reg, 2)
-        coef = backward_induction(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R)
-        coef = coef.reshape(n_reg, R, 3)
-        ridx = {t: k for k, t in enumerate(reg_times)}
-        rows = [ridx[t] for t in ptl]
-        self.exercise_coef[id(prod)] = (coef[rows], basis[rows])
-        degen = [t <= t0 for t in reg_times]
-        raw = np.stack([to_raw_basis(coef[:, st, :], basis, degen) for st in range(R)], axis=1)   # [n_reg, R, 3]
-        # state s = rights left keeps its coefficients at row s, like the reference's [date, state, basis] tensors
-        for j, t in enumerate(prod.regression_timeline.tolist()):
-            prod.regression_coeffs[j, 1:R + 1, :] = torch.tensor(raw[ridx[t]])
-        if expo_times:
-            erows = [ridx[t] for t in expo_times]
-            self.exercise_expo_coef[id(prod)] = (coef[erows], basis[erows])
-            c.regression_coeffs[prod.product_id][:, 1:R + 1, :] = torch.tensor(raw[erows])
+        gen = backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R)
+
+        def finish(coef):
+            coef = coef.reshape(n_reg, R, 3)
+            ridx = {t: k for k, t in enumerate(reg_times)}
+            rows = [ridx[t] for t in ptl]
+            self.exercise_coef[id(prod)] = (coef[rows], basis[rows])
+            degen = [t <= t0 for t in reg_times]
+            raw = np.stack([to_raw_basis(coef[:, st, :], basis, degen) for st in range(R)], axis=1)   # [n_reg, R, 3]
+            # state s = rights left keeps its coefficients at row s, like the reference's [date, state, basis] tensors
+            for j, t in enumerate(prod.regression_timeline.tolist()):
+                prod.regression_coeffs[j, 1:R + 1, :] = torch.tensor(raw[ridx[t]])
+            if expo_times:
+                erows = [ridx[t] for t in expo_times]
+                self.exercise_expo_coef[id(prod)] = (coef[erows], basis[erows])
+                c.regression_coeffs[prod.product_id][:, 1:R + 1, :] = torch.tensor(raw[erows])
+
+        if prepare_only:
+            return gen, finish
+        finish(run_backward_inductions([gen])[0])
 
     def presim_regression(self, products, dev):
         """Regression-proxy exposure coefficients of products that pay once (controller.py:294-383): the
@@ -788,9 +825,10 @@ class EquityBackend:
             books[0] = books[0] + plain
         elif plain:
             books = [plain]
-        begin, count = RT.shard_range(n_main, CHUNK_PATHS)
+        chunk = main_chunk(n_main)
+        begin, count = RT.shard_range(n_main, chunk)
         n = max(count, 1)
-        n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
+        n_chunks = (n + chunk - 1) // chunk
         accum = torch.zeros(n, dtype=torch.float64, device=dev)
         shift_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
@@ -805,7 +843,7 @@ class EquityBackend:
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
                 rng = self._rng(43, n_main)
-                sh = B.Shard(begin, count, CHUNK_PATHS)
+                sh = B.Shard(begin, count, chunk)
                 B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
                                           shift.data_ptr(), None, RT.stream_ptr()))
                 if self.nt:
@@ -821,7 +859,7 @@ class EquityBackend:
                 L.mcre_eq_destroy(plan)
         partial = torch.empty(n_chunks * 2 + 1, dtype=torch.float64, device=dev)
         out = torch.zeros(2, dtype=torch.float64, device=dev)
-        B.check(L.mcre_sum_stats(accum.data_ptr(), count, 1, CHUNK_PATHS, shift_sum.data_ptr(), partial.data_ptr(),
+        B.check(L.mcre_sum_stats(accum.data_ptr(), count, 1, chunk, shift_sum.data_ptr(), partial.data_ptr(),
                                  out.data_ptr(), RT.stream_ptr()))
         s = RT.all_reduce_tree(out).cpu().numpy()
         pv = mean_and_error(s[0], s[1], float(shift_sum[0]), n_main)
@@ -837,10 +875,7 @@ class EquityBackend:
         n_sets = len(c.netting_sets)
         n_params = len(c.model.model_params)
         t0 = time.perf_counter()
-        for p in c.products:
-            if is_equity_exercise(p):
-                self.presim_exercise(p, dev)
-        self._presim_paths = None
+        self.presim_exercise_all([p for p in c.products if is_equity_exercise(p)], dev)
         if c.risk_metrics.requires_exposure_profiles():
             reg = [p for p in c.products if not c._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
             if reg:
@@ -876,13 +911,14 @@ class EquityBackend:
             B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
             try:
                 slots = L.mcre_eq_slots(plan)
-                begin, count = RT.shard_range(n_main, CHUNK_PATHS)
-                n_chunks = max((count + CHUNK_PATHS - 1) // CHUNK_PATHS, 1)
+                chunk = main_chunk(n_main)
+                begin, count = RT.shard_range(n_main, chunk)
+                n_chunks = max((count + chunk - 1) // chunk, 1)
                 acc = torch.zeros(slots, dtype=torch.float64, device=dev)
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 rng = self._rng(43, n_main)
-                sh = B.Shard(begin, count, CHUNK_PATHS)
+                sh = B.Shard(begin, count, chunk)
                 n_metric = info["n_metric"]
                 spill = None
                 if info["acc"] & B.ACC_SPILL:

@@ -105,11 +105,20 @@ def regression_tangents(G, rhs, coef, tm):
     return out
 
 
-def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
-    """xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product
-    (exercise) dates; reg_times: regression dates (sorted, contain every product date);
-    basis: [n_reg, 2] (shift, scale).  -> coefficients in the standardised basis: [n_reg, 3] for one
-    exercise right, [n_reg, n_rights, 3] (state s = rights left at row s-1) for a FlexiCall."""
+LSM_MAX_NV = 5 + 3 * 3   # moments of the widest step (3 exercise rights)
+
+
+def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
+    """Generator form of the backward induction: queues the kernels of one regression date, yields the device
+    tensor that will hold its moments and expects the solved coefficients of that date back (`send`: [3, 3],
+    one row per state, from the driver's all-reduce + batched normal-equation solve).  Returns the
+    coefficients (StopIteration.value).  Lets a driver run many products in lock-step with ONE all-reduce and
+    ONE device-to-host read per step for all of them (run_backward_inductions).
+
+    xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product (exercise)
+    dates; reg_times: regression dates (sorted, contain every product date); basis: [n_reg, 2] (shift, scale).
+    -> coefficients in the standardised basis: [n_reg, 3] for one exercise right, [n_reg, n_rights, 3]
+    (state s = rights left at row s-1) for a FlexiCall."""
     L = B.lib()
     n_reg = len(reg_times)
     n = xs.shape[1]
@@ -120,7 +129,7 @@ def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
     value = torch.zeros((R, n), dtype=torch.float32, device=dev)
     n_chunks = (n + chunk_paths - 1) // chunk_paths
     partial = torch.empty(n_chunks * nv + 1, dtype=torch.float64, device=dev)
-    moments = torch.zeros(nv, dtype=torch.float64, device=dev)
+    moments = torch.zeros(LSM_MAX_NV, dtype=torch.float64, device=dev)
     keep = {}
 
     def step(k, i):
@@ -151,11 +160,41 @@ def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
             last = t_next
         else:
             step(k, None)
-        m = RT.all_reduce_tree(moments).cpu().numpy()
-        G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
-        for s in range(R):
-            coef[k, s] = solve_normal_equations(G, m[5 + 3 * s:8 + 3 * s])
+        solved = yield moments          # [3 states, 3] from the driver's batched solve of this round
+        coef[k] = solved[:R]
     return coef[:, 0, :] if R == 1 else coef
+
+
+def run_backward_inductions(gens):
+    """Drive backward_induction_steps generators in lock-step: per round every live generator queues its next
+    step, then the moments of all of them are all-reduced over the ranks and read back together.
+    -> list of coefficient arrays in the order of `gens`."""
+    results = [None] * len(gens)
+    pending = {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration as e:
+            results[i] = e.value
+    while pending:
+        keys = list(pending)
+        m = RT.all_reduce_tree(torch.stack([pending[k] for k in keys])).cpu().numpy()      # [K, LSM_MAX_NV]
+        G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
+        # one batched solve per state for all products of the round (states a product does not have carry zeros)
+        host = np.stack([solve_normal_equations_batch(G, m[:, 5 + 3 * s:8 + 3 * s]) for s in range(3)], axis=1)
+        for k, row in zip(keys, host):
+            try:
+                pending[k] = gens[k].send(row)
+            except StopIteration as e:
+                results[k] = e.value
+                del pending[k]
+    return results
+
+
+def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
+    """One product: see backward_induction_steps."""
+    return run_backward_inductions([backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
+                                                             dev, n_rights=n_rights)])[0]
 
 
 def to_raw_basis(coefs, basis, degenerate=None):
