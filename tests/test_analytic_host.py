@@ -112,3 +112,34 @@ def test_netting_set_collateral_profile_uses_exact_delayed_indices():
     banded = ns.NettingSet(name="t", products=[ns.EuropeanOption(ns.Equity("eq"), 1.0, 100.0, ns.OptionType.CALL)], threshold=7.0)
     assert torch.equal(banded.apply_threshold(torch.tensor([-10.0, -3.0, 0.0, 7.0, 12.0], dtype=torch.float64)),
                        torch.tensor([-3.0, 0.0, 0.0, 0.0, 5.0], dtype=torch.float64))
+
+
+def test_constructor_error_behaviour_matches_the_reference():
+    """controller.py:40-48, 89-97 and netting_set.py:23-34: what the boundary rejects, with the reference's
+    exception types."""
+    ns = cases.Namespace()
+    model = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.3)
+    opt = lambda: ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)   # noqa: E731
+    rm = ns.RiskMetrics([ns.PVMetric()])
+    S = ns.SimulationScheme.ANALYTICAL
+    with pytest.raises(ValueError):
+        ns.SimulationController([], model, rm, 10, 0, 1, S)
+    shared = opt()
+    with pytest.raises(ValueError):
+        ns.SimulationController([ns.NettingSet(name="a", products=[shared]), ns.NettingSet(name="b", products=[shared])],
+                                model, rm, 10, 0, 1, S)
+    with pytest.raises(ValueError):
+        ns.NettingSet(name="empty", products=[])
+    with pytest.raises(ValueError):
+        ns.NettingSet(name="neg", products=[opt()], threshold=-1.0)
+    with pytest.raises(ValueError):
+        ns.NettingSet(name="neg", products=[opt()], margin_period_of_risk=-0.1)
+    # CVA needs a ModelConfig that contains the counterparty's credit model
+    cva = ns.RiskMetrics([ns.CVAMetric("cp", 0.4)], exposure_timeline=np.linspace(0.0, 1.0, 3))
+    with pytest.raises(Exception):
+        ns.SimulationController([ns.NettingSet(name="a", products=[opt()], counterparty_id="cp")], model, cva, 10, 10, 1, S)
+    with pytest.raises(AssertionError):
+        ns.FlexiCall(underlyings=[opt()], num_exercise_rights=2)
+    with pytest.raises(NotImplementedError):
+        from products.storage import Storage
+        Storage(asset_id="gas", start_date=0.0, end_date=1.0)
