@@ -301,7 +301,7 @@ typedef struct {
   const int32_t *ev_flags;      /* [n_ev] MCRE_EQ_EV_*                                                   */
   int32_t n_prod;
   const double *prod;           /* [n_prod][16]: kind, set, strike, sign(+1 call / -1 put), 1/numeraire,
-                                   d(1/numeraire)/d rate, flags(bit0 geometric, bit1 control variate),
+                                   d(1/numeraire)/d rate, flags(bit0 geometric, bit1 control variate, bit2 Brownian-bridge barrier),
                                    control-variate constant, payment amount, barrier1, type1 (1 UO, 2 DO, 3 UI,
                                    4 DI), barrier2, type2 (0: none), n observations, tracker slot, reserved  */
   const double *prod_w;         /* [n_prod][n_assets] weights of the composite underlying                 */
@@ -349,6 +349,12 @@ int mcre_eq_mainsim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *s
  * the products of a netting set (controller.py:506-563) for books of thousands of products
  * (tests/pv_tests/pv_performance_large_netting_set.py). */
 int mcre_eq_set_pv_accumulator(mcre_eq_plan *plan, double *d_accum);
+/* Brownian-bridge barrier monitoring (barrier_option.py:138-222; product flag bit 2, value-only plans): the
+ * observation events of such a product carry in their ev_data row [0] the Philox block of their (product,
+ * interval) uniforms (stream kind 2; element 0 / 1 = first / second barrier), [1] -2 / (sigma^2 maturity / n_obs),
+ * [2] the interval index.  In RNG compatibility mode the reference's numpy uniforms replace Philox:
+ * d_u [tracker slot][barrier][n_paths_total][stride] (NULL: Philox). */
+int mcre_eq_set_bridge_uniforms(mcre_eq_plan *plan, const double *d_u, int32_t stride);
 /* d_out [n_rows][2] = sum(x - c), sum((x - c)^2) per row of d_x [n_rows][n], c = d_shift[row]; fixed-order
  * chunk partials (d_partial: [ceil(n / chunk_paths)][n_rows][2]) + tree, like the simulation kernels. */
 int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,

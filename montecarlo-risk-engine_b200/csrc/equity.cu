@@ -65,6 +65,10 @@ struct EqDev {
   // to pv_accum [n_sets][n_paths], so a netting set with more path-dependent products than one launch can
   // track is evaluated in several launches over the same Philox streams and finished by mcre_sum_stats
   double *pv_accum;
+  // Brownian-bridge barrier monitoring in RNG compatibility mode: the reference's numpy uniforms,
+  // [tracker slot][barrier 0/1][n_paths_total][bridge_stride] (NULL: Philox kind 2)
+  const double *bridge_u;
+  int bridge_stride;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -171,6 +175,8 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
       double logF = KIND == MCRE_EQ_SCHWARTZ ? __ldg(P.init_aux + aa) : 0.0;
       constexpr int NTRK = eq_ntrk(NT);
       R cf[NS], trk_a[NTRK], trk_b[NTRK];
+      // Brownian-bridge barriers (value-only builds): previous monitored spot, running no-hit products
+      double trk_c[NT == 0 ? NTRK : 1], trk_d[NT == 0 ? NTRK : 1], trk_e[NT == 0 ? NTRK : 1];
       double numtan[NS], hist[NS][EQ_MAX_LAG];
 #pragma unroll
       for (int s = 0; s < NS; ++s)
@@ -359,6 +365,36 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
               } else {                                                // running max / min
                 if ((ef & EQ_EV_FIRST) || val(U) > val(trk_a[k])) trk_a[k] = U;
                 if ((ef & EQ_EV_FIRST) || val(U) < val(trk_b[k])) trk_b[k] = U;
+                if constexpr (NT == 0) {
+                  if (pflags & 4) {
+                    // Brownian bridge between monitoring dates (barrier_option.py:138-222): crossing probability
+                    // exp(coef ln(S_prev / B) ln(S / B)), coef = -2 / (sigma^2 maturity / n_obs), against one
+                    // uniform per (path, interval); fuzzy indicator eps 0.05 like the rest of the product
+                    const double *ed = P.ev_data + (size_t)e * EQ_EVD;   // [0] Philox block, [1] coef, [2] interval
+                    const double Uv = val(U);
+                    if (ef & EQ_EV_FIRST) { trk_d[k] = 1.0; trk_e[k] = 1.0; }
+                    else {
+                      double ua, ub;
+                      if (P.bridge_u) {
+                        const size_t per = (size_t)rng.n_total * P.bridge_stride;
+                        const double *bu = P.bridge_u + (size_t)slot * 2 * per + (size_t)gpath * P.bridge_stride + (int)__ldg(ed + 2);
+                        ua = bu[0]; ub = bu[per];
+                      } else {
+                        ns.uniform_pair_kind((uint32_t)__ldg(ed + 0), 2u, ua, ub);
+                      }
+                      const double coef = __ldg(ed + 1), prev = trk_c[k];
+                      const double b1 = __ldg(pr + 9);
+                      const double p1 = exp(coef * log(prev / b1) * log(Uv / b1));
+                      trk_d[k] *= 1.0 - r_fuzzy(p1 - ua, true, 0.05);
+                      if ((int)__ldg(pr + 12) > 0) {
+                        const double b2 = __ldg(pr + 11);
+                        const double p2 = exp(coef * log(prev / b2) * log(Uv / b2));
+                        trk_e[k] *= 1.0 - r_fuzzy(p2 - ub, true, 0.05);
+                      }
+                    }
+                    trk_c[k] = Uv;
+                  }
+                }
               }
             }
           }
@@ -387,6 +423,20 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
             pay = option_payoff(U, strike, sign) * barrier_factor(mx, mn, __ldg(pr + 9), (int)__ldg(pr + 10));
             const int bt2 = (int)__ldg(pr + 12);
             if (bt2 > 0) pay = pay * barrier_factor(mx, mn, __ldg(pr + 11), bt2);
+            if constexpr (NT == 0) {
+              if (pflags & 4) {
+                // knock-out: also no crossing between the dates; knock-in: (1 - indicator)(1 - no-hit)
+                double nh1 = 1.0, nh2 = 1.0;
+                MCRE_TRK_FOR(k, slot) { nh1 = trk_d[k]; nh2 = trk_e[k]; }
+                auto bridged = [&](double barrier, int bt, double nh) -> double {
+                  const double out = val(barrier_factor(mx, mn, barrier, bt <= 2 ? bt : bt - 2));   // the "out" indicator
+                  return bt <= 2 ? out * nh : (1.0 - out) * (1.0 - nh);
+                };
+                double f = bridged(__ldg(pr + 9), (int)__ldg(pr + 10), nh1);
+                if (bt2 > 0) f *= bridged(__ldg(pr + 11), bt2, nh2);
+                pay = option_payoff(U, strike, sign) * f;
+              }
+            }
           }
           const double invN = __ldg(pr + 4), dinvN = __ldg(pr + 5);
           if (P.ps_cf && live && a == 0) P.ps_cf[(size_t)pi * sh.n_paths + lpath] = (float)(val(pay) * invN);
@@ -599,7 +649,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
-  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr;
+  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -713,6 +763,12 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   return mcre_tree_reduce(d_partial, n_chunks, mcre_eq_slots(p), d_acc, stream);
+}
+
+extern "C" int mcre_eq_set_bridge_uniforms(mcre_eq_plan *p, const double *d_u, int32_t stride) {
+  if (!p) return fail(-1, "null argument%s", "");
+  p->d.bridge_u = d_u; p->d.bridge_stride = stride;
+  return 0;
 }
 
 extern "C" int mcre_eq_set_pv_accumulator(mcre_eq_plan *p, double *d_accum) {

@@ -117,6 +117,12 @@ struct NormalStream {
     ph(p_lo, p_hi, block, 1u, o);
     ua = u52(o[0], o[1]); ub = u52(o[2], o[3]);
   }
+  // both uniforms of block `block` of stream kind `kind` (kind 2: Brownian-bridge draws of barrier options)
+  __device__ inline void uniform_pair_kind(uint32_t block, uint32_t kind, double &ua, double &ub) const {
+    uint32_t o[4];
+    ph(p_lo, p_hi, block, kind, o);
+    ua = u52(o[0], o[1]); ub = u52(o[2], o[3]);
+  }
   __device__ inline double uniform(uint32_t m) const {
     uint32_t o[4];
     ph(p_lo, p_hi, m >> 1, 1u, o);

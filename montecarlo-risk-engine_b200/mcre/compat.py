@@ -72,3 +72,24 @@ def inject_reference_stream(ctrl):
     ctrl.inject_normals(pre=None if pre is None else pre[0], main=main[0])
     if qe:
         ctrl.injected_uniforms = {"pre": None if pre is None else pre[1], "main": main[1]}
+    # Brownian-bridge barrier options draw from their own numpy default_rng(12345) at every payoff call
+    # (barrier_option.py:49-50, 174, 200): once in the pre-simulation if the product is regressed, then in the
+    # main simulation; first barrier before second
+    import numpy as np
+    bridge = {"pre": {}, "main": {}}
+    for prod in ctrl.products:
+        if not getattr(prod, "use_brownian_bridge", False):
+            continue
+        gen = np.random.default_rng(12345)
+        n_int = len(prod.modeling_timeline) - 1
+        double = prod.barrier2 is not None and prod.barrier_option_type2 is not None
+        passes = []
+        if pre is not None and ctrl._product_requires_regression(prod):
+            passes.append(("pre", ctrl.num_paths_presim))
+        passes.append(("main", ctrl.num_paths_mainsim))
+        for which, n in passes:
+            u1 = gen.uniform(0, 1, size=(n, n_int))
+            u2 = gen.uniform(0, 1, size=(n, n_int)) if double else None
+            bridge[which][prod.product_id] = (u1, u2)
+    if bridge["main"]:
+        ctrl.injected_bridge = bridge

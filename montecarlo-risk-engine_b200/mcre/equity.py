@@ -297,6 +297,11 @@ class EquityBackend:
                 rec[6] = 1 if p.averaging_type == AsianAveragingType.GEOMETRIC else 0
             else:
                 rec[0] = P_BARRIER
+                if getattr(p, "use_brownian_bridge", False):
+                    if self.nt or basket is not None or not isinstance(self.c.model, BlackScholesModel):
+                        raise NotImplementedError("Brownian-bridge barrier monitoring: single Black-Scholes model, "
+                                                  "one monitored asset, value-only runs")
+                    rec[6] = 4
                 rec[9], rec[10] = float(p.barrier1), _BARRIER_CODE[p.barrier_option_type1]
                 if p.barrier2 is not None and p.barrier_option_type2 is not None:
                     rec[11], rec[12] = float(p.barrier2), _BARRIER_CODE[p.barrier_option_type2]
@@ -432,6 +437,7 @@ class EquityBackend:
             raise NotImplementedError(f"at most {eq_ntrk(nt)} path-dependent / exercise products per launch group")
         ev_off, ev_prod, ev_flags, ev_data = [0], [], [], []
         ex_count = {}
+        bridge = []   # (tracker slot, product id, intervals) of Brownian-bridge barrier options
         for di in range(n_dates):
             for pi, f in events[di]:
                 ev_prod.append(pi)
@@ -448,6 +454,18 @@ class EquityBackend:
                     row[5], row[6] = self._inv_numeraire(dates[di])
                     row[7] = 1.0 if i == len(p.product_timeline) - 1 else 0.0
                     row[14] = exercise_strikes(p)[i]
+                elif (f & EV_OBSERVE) and getattr(owners[pi], "use_brownian_bridge", False):
+                    # Brownian-bridge draws of the interval ending at this observation (csrc/equity.cu)
+                    p = owners[pi]
+                    i = ex_count.get(pi, 0)
+                    ex_count[pi] = i + 1
+                    n_obs = len(p.modeling_timeline)
+                    sigma = self.assets[self._asset_index(p.get_asset_id())].par[1]
+                    row[0] = float(p.product_id * 4096 + max(i - 1, 0))
+                    row[1] = -2.0 / (sigma * sigma * float(p.maturity) / n_obs)
+                    row[2] = float(max(i - 1, 0))
+                    if i == 0:
+                        bridge.append((int(recs[pi][14]), int(p.product_id), n_obs - 1))
                 ev_data.append(row)
             ev_off.append(len(ev_prod))
 
@@ -552,7 +570,8 @@ class EquityBackend:
             desc.set_threshold = fp("set_thr", np.array([ns.threshold for ns in sets], dtype=np.float64))
             desc.set_flags, desc.set_lag = ip("set_flags", set_flags), ip("set_lag", set_lag)
         desc.n_expo, desc.n_metric, desc.acc_flags = n_expo, n_metric, acc
-        info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs, n_metric=n_metric, acc=acc)
+        info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs, n_metric=n_metric, acc=acc,
+                    bridge=bridge)
         return desc, t, info
 
     # ------------------------------------------------------------------ execution
@@ -772,6 +791,7 @@ class EquityBackend:
                         rng.d_u = self._keep_u_pre.data_ptr()
                 else:
                     rng.mode = B.RNG_PHILOX
+                keep_bridge = self._set_bridge_uniforms(plan, info, "pre", n_pre, dev)
                 sh = B.Shard(begin, count, CHUNK_PATHS)
                 B.check(L.mcre_eq_presim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
                                          xs.data_ptr(), cf.data_ptr(), RT.stream_ptr()))
@@ -809,6 +829,23 @@ class EquityBackend:
             coef, basis = self.expo_coef[id(p)]
             c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coef, basis, [t <= t0 for t in expo_times]))
 
+    def _set_bridge_uniforms(self, plan, info, which, n_total, dev):
+        """RNG compatibility mode: hand the launch the reference's numpy uniforms of its Brownian-bridge barrier
+        options (mcre/compat.py:inject_reference_stream); returns the device table to keep alive, or None."""
+        inj = getattr(self.c, "injected_bridge", None)
+        if not inj or not info["bridge"] or which not in inj:
+            return None
+        stride = max(n_int for _, _, n_int in info["bridge"])
+        table = torch.zeros((max(sl for sl, _, _ in info["bridge"]) + 1, 2, n_total, stride), dtype=torch.float64)
+        for slot, pid, n_int in info["bridge"]:
+            u1, u2 = inj[which][pid]
+            table[slot, 0, :, :n_int] = torch.as_tensor(u1)
+            if u2 is not None:
+                table[slot, 1, :, :n_int] = torch.as_tensor(u2)
+        table = table.to(dev).contiguous()
+        B.check(B.lib().mcre_eq_set_bridge_uniforms(plan, table.data_ptr(), stride))
+        return table
+
     def _run_split_book(self, si, dev, n_main, n_params):
         """PV (and pathwise Greeks) of one netting set with more path-dependent / exercise products than a launch
         can track: the products are split over launches that replay the same Philox streams; every launch adds
@@ -842,6 +879,7 @@ class EquityBackend:
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
+                keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
                 rng = self._rng(43, n_main)
                 sh = B.Shard(begin, count, chunk)
                 B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
@@ -918,6 +956,7 @@ class EquityBackend:
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 rng = self._rng(43, n_main)
+                keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
                 sh = B.Shard(begin, count, chunk)
                 n_metric = info["n_metric"]
                 spill = None

@@ -35,6 +35,9 @@ class BarrierOption(Product):
         self.use_brownian_bridge = False
 
     def set_use_brownian_bridge(self):
-        # Brownian-bridge correction draws from a numpy RNG in the reference
-        # (barrier_option.py:49-50, 138-222); SURVEY §8f item 4 ("next").
-        raise NotImplementedError("Brownian-bridge barrier monitoring is not implemented yet.")
+        """Brownian-bridge correction between monitoring dates (reference: barrier_option.py:62-63, 138-222):
+        per interval the crossing probability exp(-2 ln(S_i/B) ln(S_i+1/B) / (sigma^2 maturity / n_obs)) is
+        compared (fuzzy, eps 0.05) with one uniform per path and interval.  The kernel draws those uniforms from
+        Philox (kind 2); in RNG compatibility mode the reference's numpy default_rng(12345) stream is injected.
+        Single Black-Scholes model, value-only runs."""
+        self.use_brownian_bridge = True

@@ -440,6 +440,14 @@ def _rate(model, p):
     raise NotImplementedError(k)
 
 
+def volatility(model, p, asset_id):
+    """model.get_volatility() as the Brownian-bridge barrier uses it (barrier_option.py:149): defined for a single
+    Black-Scholes model only."""
+    if kind(model) == "BlackScholesModel":
+        return p[1]
+    raise NotImplementedError("Brownian-bridge barrier monitoring: single Black-Scholes model only")
+
+
 def spot(model, p, asset_id, state):
     m, mp, so = route(model, p, asset_id)
     k = kind(m)

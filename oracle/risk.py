@@ -50,9 +50,12 @@ def asset_of(product):
 class Ctx:
     """Per-simulation context: simulated states per date + model access."""
 
-    def __init__(self, model, p, timeline, paths, n):
+    def __init__(self, model, p, timeline, paths, n, bridge=None):
         self.model, self.p, self.timeline, self.paths, self.n = model, p, timeline, paths, n
         self.idx = {float(t): i for i, t in enumerate(timeline)}
+        #: bridge(product, n_intervals, second_barrier) -> [N, n_intervals] uniforms of the Brownian-bridge
+        #: crossing draws of a barrier option (barrier_option.py:174, 200)
+        self.bridge = bridge
 
     def state(self, t):
         return self.paths[self.idx[float(t)]]
@@ -259,6 +262,33 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
             above = ad.fuzzy(mn - barrier, True, 0.05)
             return {"UPANDOUT": below, "DOWNANDOUT": above, "UPANDIN": 1.0 - below, "DOWNANDIN": 1.0 - above}[btype.name]
 
+        if getattr(prod, "use_brownian_bridge", False):
+            # barrier_option.py:138-222: per interval the probability that the bridge between two monitored spots
+            # crossed the barrier, exp(-2 ln(S_i / B) ln(S_i+1 / B) / (sigma^2 maturity / n_obs)), against one
+            # uniform per (path, interval) - fuzzy (eps 0.05) like every indicator of this product
+            sigma = ad.val(M.volatility(ctx.model, ctx.p, asset_of(prod)))
+            dt_b = _f(prod.maturity) / len(obs)
+            sv = [ad.val(x) for x in spots]
+
+            def nohit(barrier, second):
+                u = ctx.bridge(prod, len(obs) - 1, second)
+                keep = np.ones_like(sv[0])
+                for i in range(len(obs) - 1):
+                    prob = np.exp(-2.0 * np.log(sv[i] / barrier) * np.log(sv[i + 1] / barrier) / (sigma ** 2 * dt_b))
+                    keep = keep * (1.0 - ad.val(ad.fuzzy(prob - u[:, i], True, 0.05)))
+                return keep
+
+            def bfactor(barrier, btype, second):
+                below = ad.val(ad.fuzzy(barrier - mx, True, 0.05))
+                above = ad.val(ad.fuzzy(mn - barrier, True, 0.05))
+                nh = nohit(barrier, second)
+                return {"UPANDOUT": below * nh, "DOWNANDOUT": above * nh, "UPANDIN": (1.0 - below) * (1.0 - nh),
+                        "DOWNANDIN": (1.0 - above) * (1.0 - nh)}[btype.name]
+
+            pay = ad.val(pay) * bfactor(_f(prod.barrier1), prod.barrier_option_type1, False)
+            if prod.barrier2 is not None and prod.barrier_option_type2 is not None:
+                pay = pay * bfactor(_f(prod.barrier2), prod.barrier_option_type2, True)
+            return state_matrix, [pay / ad.val(ctx.numeraire(obs[0]))] * S
         pay = pay * factor(_f(prod.barrier1), prod.barrier_option_type1)
         if prod.barrier2 is not None and prod.barrier_option_type2 is not None:
             pay = pay * factor(_f(prod.barrier2), prod.barrier_option_type2)
@@ -523,11 +553,30 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     dim = M.noise_dim(model)
     qe = scheme == "QE"
 
+    bridge_rngs = {}
+
+    def bridge_provider(draws, seed, n):
+        """Uniforms of the Brownian-bridge draws: under Philox block pid * 4096 + interval of kind 2 (element 0 /
+        1 = first / second barrier), like csrc/equity.cu; with the reference's draws each product's own
+        numpy default_rng(12345), consumed call after call (barrier_option.py:49-50, 174, 200)."""
+        philox_mode = isinstance(draws, E.PhiloxDraws) or draws is None
+
+        def get(prod, n_int, second):
+            pid = [id(q) for q in products].index(id(prod))
+            if philox_mode:
+                from oracle import philox
+                paths_ = np.arange(n, dtype=np.uint64)
+                cols = [philox._blocks(paths_, pid * 4096 + i, 2, seed, 0)[1 if second else 0] for i in range(n_int)]
+                return np.stack(cols, axis=1)
+            rng = bridge_rngs.setdefault(id(prod), np.random.default_rng(12345))
+            return rng.uniform(0, 1, size=(n, n_int))
+        return get
+
     if any(needs_regression(pr) for pr in products):
         if draws_pre is None:
             draws_pre = E.PhiloxDraws(42, n_pre, n_sub, dim, with_uniforms=qe)
         paths = E.generate_paths(model, p, sim_tl, n_pre, num_steps, scheme, draws_pre, smoothing)
-        ctx = Ctx(model, p, sim_tl, paths, n_pre)
+        ctx = Ctx(model, p, sim_tl, paths, n_pre, bridge=bridge_provider(draws_pre, 42, n_pre))
         for k, pr in enumerate(products):
             if needs_regression(pr):
                 regress_product(pr, ctx, expo_tl, degree, prod_coeffs[k], expo_coeffs[k])
@@ -536,7 +585,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
         n_uni = len(M.submodels(model)) if qe else 1
         draws_main = E.PhiloxDraws(43, n_main, n_sub, dim, with_uniforms=qe, n_uniform=n_uni)
     paths = E.generate_paths(model, p, sim_tl, n_main, num_steps, scheme, draws_main, smoothing)
-    ctx = Ctx(model, p, sim_tl, paths, n_main)
+    ctx = Ctx(model, p, sim_tl, paths, n_main, bridge=bridge_provider(draws_main, 43, n_main))
 
     # ---- _evaluate_product (controller.py:385-471) -------------------------------------
     set_cfs = [None] * len(netting_sets)

@@ -121,6 +121,22 @@ def flexicall_bs(ns_module, exposure=False):
     return model, sets, [m.PVMetric()], None
 
 
+def bs_bridge_barrier(ns_module):
+    """Barrier options with the Brownian-bridge correction between monitoring dates (barrier_option.py:138-222):
+    single and double barrier, knock-out and knock-in, on one Black-Scholes asset."""
+    m = ns_module
+    model = m.BlackScholesModel(0.0, 100.0, 0.03, 0.25)
+    B = m.BarrierOptionType
+    specs = [("up_out", m.OptionType.CALL, 125.0, B.UPANDOUT, None, None), ("down_in", m.OptionType.PUT, 85.0, B.DOWNANDIN, None, None),
+             ("double", m.OptionType.CALL, 130.0, B.UPANDOUT, 80.0, B.DOWNANDOUT), ("up_in", m.OptionType.CALL, 115.0, B.UPANDIN, None, None)]
+    sets = []
+    for name, ot, b1, t1, b2, t2 in specs:
+        opt = m.BarrierOption(0.0, 1.0, 100.0, 7, ot, b1, t1, b2, t2)
+        opt.set_use_brownian_bridge()
+        sets.append(m.NettingSet(name=name, products=[opt]))
+    return model, sets, [m.PVMetric()], None
+
+
 def mixed_book(ns_module, exposure=True):
     """Mixed equity book on a 2-asset BlackScholesMulti: Europeans, Americans, a FlexiCall and a barrier option in
     one netting set (tests/pytests/test_netting_sets.py:375-528)."""
@@ -164,6 +180,7 @@ GOLDEN_CASES = {
     "heston_european_greeks": (heston_european, dict(), dict(n_main=4096, n_pre=0, num_steps=10, scheme="QE", differentiate=True)),
     "heston_path_dependent": (heston_path_dependent, dict(), dict(n_main=4096, n_pre=0, num_steps=4, scheme="QE", differentiate=True)),
     "bs_basket": (bs_basket, dict(), dict(n_main=8192, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "bs_bridge_barrier": (bs_bridge_barrier, dict(), dict(n_main=4096, n_pre=0, num_steps=2, scheme="EULER", differentiate=False)),
     "flexicall_pv": (flexicall_bs, dict(), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "flexicall_exposure": (flexicall_bs, dict(exposure=True), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "mixed_book_pv": (mixed_book, dict(exposure=False), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="ANALYTICAL", differentiate=False)),

@@ -253,3 +253,32 @@ def test_regression_proxy_exposure_profiles_match_oracle(which):
             x0 = 100.0
             fit = lambda cfs: cfs[:, 0] + cfs[:, 1] * x0 + cfs[:, 2] * x0 * x0     # compare fitted values near the money
             helpers.assert_close(fit(gotc), fit(wantc), 1e-6, 1e-7, f"{which} product {k} fitted continuation")
+
+
+def test_brownian_bridge_barrier_matches_reference_golden_and_oracle():
+    """Barrier options with the Brownian-bridge correction between monitoring dates (barrier_option.py:138-222):
+    up-and-out, down-and-in, double knock-out, up-and-in.  (1) RNG compatibility mode - the reference's torch.randn
+    normals AND its numpy default_rng(12345) bridge uniforms injected - against the outputs of the unmodified
+    reference; (2) native Philox (bridge uniforms from stream kind 2) against the oracle on the same streams."""
+    name = "bs_bridge_barrier"
+    gold = helpers.load_golden(name)
+    ns, model, sets, metrics, tl, rkw = helpers.build(name)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), rkw["n_main"], rkw["n_pre"], rkw["num_steps"],
+                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"])
+    sc.rng_compat = "torch"
+    res = sc.run_simulation()
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _check_values(helpers.flatten_results(res), ref, RTOL, name)
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    _check_values(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8, name + " philox",
+                  err_rtol=1e-6)
+    # the correction removes knock-out paths that crossed between the dates; the reference's knock-in variant
+    # multiplies the discrete knock-in indicator by the bridge-hit indicator, so it can only stay or shrink
+    plain_sets = cases.bs_bridge_barrier(ns)[1]
+    for s in plain_sets:
+        s.products[0].use_brownian_bridge = False
+    plain = ns.SimulationController(plain_sets, model, ns.RiskMetrics(metrics), rkw["n_main"], 0, rkw["num_steps"],
+                                    ns.SimulationScheme.EULER, False).run_simulation()
+    assert float(res.get_results("up_out", "pv")[0]) < float(plain.get_results("up_out", "pv")[0])
+    assert float(res.get_results("up_in", "pv")[0]) <= float(plain.get_results("up_in", "pv")[0]) + 1e-12
