@@ -355,10 +355,19 @@ int mcre_eq_set_pv_accumulator(mcre_eq_plan *plan, double *d_accum);
  * [2] the interval index.  In RNG compatibility mode the reference's numpy uniforms replace Philox:
  * d_u [tracker slot][barrier][n_paths_total][stride] (NULL: Philox). */
 int mcre_eq_set_bridge_uniforms(mcre_eq_plan *plan, const double *d_u, int32_t stride);
-/* d_out [n_rows][2] = sum(x - c), sum((x - c)^2) per row of d_x [n_rows][n], c = d_shift[row]; fixed-order
- * chunk partials (d_partial: [ceil(n / chunk_paths)][n_rows][2]) + tree, like the simulation kernels. */
+/* The same for exposure profiles: each launch ADDS the netted exposure of its products to
+ * d_accum [n_sets][n_expo][n_paths] (and evaluates no netting terms or metrics); mcre_eq_unsecured_exposures then
+ * applies threshold / MPoR collateral (netting_set.py:48-72, 136-184) to one set's accumulated exposures:
+ * d_expo [n_expo][n_paths] -> d_out [n_metric][n_paths], metric_expo[m] = exposure index of metric date m,
+ * lag[m] = exposure indices back to its collateral date (-1: none).  Host index arrays. */
+int mcre_eq_set_exposure_accumulator(mcre_eq_plan *plan, double *d_accum);
+int mcre_eq_unsecured_exposures(const double *d_expo, int64_t n_paths, int32_t n_metric, const int32_t *metric_expo,
+                                const int32_t *lag, int32_t collateralised, double threshold, double *d_out, void *stream);
+/* d_out [n_rows][2] = sum(v - c), sum((v - c)^2) per row of d_x [n_rows][n], c = d_shift[row], v = x (mode 0),
+ * max(x, 0) (mode 1) or -max(-x, 0) (mode 2); fixed-order chunk partials (d_partial:
+ * [ceil(n / chunk_paths)][n_rows][2]) + tree, like the simulation kernels. */
 int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,
-                   double *d_partial, double *d_out, void *stream);
+                   int32_t mode, double *d_partial, double *d_out, void *stream);
 
 /* Pre-simulation pass of the regression-proxy exposures (replaces the path generation + request resolution +
  * cashflow roll feeding controller._perform_regression_for_product, controller.py:294-351, for the equity

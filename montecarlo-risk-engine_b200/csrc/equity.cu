@@ -69,6 +69,10 @@ struct EqDev {
   // [tracker slot][barrier 0/1][n_paths_total][bridge_stride] (NULL: Philox kind 2)
   const double *bridge_u;
   int bridge_stride;
+  // book splitting with exposure profiles (mcre_eq_set_exposure_accumulator): the netted exposure of the
+  // launch's products is ADDED to expo_accum [n_sets][n_expo][n_paths]; netting terms / metrics are applied
+  // afterwards by mcre_eq_unsecured_exposures + mcre_sum_stats
+  double *expo_accum;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -266,6 +270,14 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
 #pragma unroll
             for (int s = 0; s < NS; ++s) if (s == set) expo[s] += tot;
           }
+          if (P.expo_accum) {
+            if (live && a == 0 && !pilot) {
+#pragma unroll
+              for (int s = 0; s < NS; ++s)
+                if (s < P.n_sets) P.expo_accum[((size_t)s * P.n_expo + xe) * sh.n_paths + lpath] += expo[s];
+            }
+            return;   // netting terms and metrics are applied once all launches of the book have added up
+          }
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
 #pragma unroll
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P
             hist[s][0] = expo[s];
           }
         }
+        if (P.expo_accum) return;
         if (m >= 0) {
           double vals[NVX];
 #pragma unroll
@@ -649,7 +662,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
-  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0;
+  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -739,7 +752,7 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (shard->path_begin % shard->chunk_paths != 0) return fail(-2, "invalid shard: path_begin not chunk aligned%s", "");
   int rc = 0;
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
-  if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.ps_x)
+  if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.ps_x && !p->d.expo_accum)
     return fail(-1, "spill requested but d_spill is null%s", "");
   if (rng->mode == MCRE_RNG_INJECT && p->d.kind == MCRE_EQ_HESTON && p->d.scheme == MCRE_SCHEME_QE && !rng->d_u)
     return fail(-1, "inject mode: QE needs uniforms%s", "");
@@ -763,6 +776,64 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (rc) return rc;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   return mcre_tree_reduce(d_partial, n_chunks, mcre_eq_slots(p), d_acc, stream);
+}
+
+extern "C" int mcre_eq_set_exposure_accumulator(mcre_eq_plan *p, double *d_accum) {
+  if (!p) return fail(-1, "null argument%s", "");
+  p->d.expo_accum = d_accum;
+  return 0;
+}
+
+namespace mcre {
+// Netting-set terms on accumulated exposures (netting_set.py:48-72, 136-184): one thread per (path, metric date).
+// expo [n_expo][n], metric_expo [n_metric] = exposure index of the metric date, lag [n_metric] = exposure indices
+// back to the collateral date (-1: none), out [n_metric][n] unsecured exposure.
+__global__ void __launch_bounds__(256) eq_unsecured_kernel(const double *__restrict__ expo, long long n, int n_metric,
+                                                           const int *__restrict__ metric_expo, const int *__restrict__ lag,
+                                                           int collateralised, double h, double *__restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (p >= n || m >= n_metric) return;
+  auto thr = [h](double x) { return x > h ? x - h : (x < -h ? x + h : 0.0); };
+  const int xe = metric_expo[m];
+  const double now = expo[(size_t)xe * n + p];
+  double unsec;
+  if (collateralised) {
+    const int l = lag[m];
+    const double delayed = l >= 0 ? expo[(size_t)(xe - l) * n + p] : 0.0;
+    unsec = now - thr(delayed);
+  } else {
+    unsec = thr(now);
+  }
+  out[(size_t)m * n + p] = unsec;
+}
+}  // namespace mcre
+
+extern "C" int mcre_eq_unsecured_exposures(const double *d_expo, int64_t n_paths, int32_t n_metric, const int32_t *metric_expo,
+                                           const int32_t *lag, int32_t collateralised, double threshold, double *d_out,
+                                           void *stream) {
+  if (!d_expo || !metric_expo || !lag || !d_out) return fail(-1, "null argument%s", "");
+  if (n_paths <= 0 || n_metric <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DevArray<int> me, lg;
+  DevArena arena;
+  int rc = 0;
+  {
+    ArenaScope scope(&arena);
+    rc = me.upload(metric_expo, n_metric);
+    if (!rc) rc = lg.upload(lag, n_metric);
+    if (!rc) rc = arena.commit();
+  }
+  if (!rc) {
+    dim3 grid((unsigned)((n_paths + 255) / 256), (unsigned)n_metric);
+    eq_unsecured_kernel<<<grid, 256, 0, st>>>(d_expo, n_paths, n_metric, me.p, lg.p, collateralised, threshold, d_out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch");
+    else cudaStreamSynchronize(st);   // the index tables are freed below
+  }
+  arena.release();
+  return rc;
 }
 
 extern "C" int mcre_eq_set_bridge_uniforms(mcre_eq_plan *p, const double *d_u, int32_t stride) {

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(128) tree_level_kernel(const double *in, long 
 
 // sum(x - c), sum((x - c)^2) of rows of x [n_rows][n] with c = shift[row]: per-chunk block sums in a fixed order
 // (the same chunks as the simulation kernels), combined by mcre_tree_reduce.  partial: [chunk][n_rows][2].
+// mode 0: x, 1: max(x, 0), 2: -max(-x, 0)   (EPE / ENE integrands of spilled exposures)
 __global__ void __launch_bounds__(256) sum_stats_kernel(const double *__restrict__ x, long long n, int n_rows, int chunk,
-                                                        const double *__restrict__ shift, double *__restrict__ partial) {
+                                                        const double *__restrict__ shift, int mode,
+                                                        double *__restrict__ partial) {
   __shared__ double stage[2 * 8];
   const long long ch = blockIdx.x;
   const int row = blockIdx.y;
@@ -92,7 +94,11 @@ __global__ void __launch_bounds__(256) sum_stats_kernel(const double *__restrict
   double s1 = 0.0, s2 = 0.0;
   for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
     const long long p = ch * chunk + it;
-    if (p < n) { const double d = x[(size_t)row * n + p] - c; s1 += d; s2 += d * d; }
+    if (p < n) {
+      double v = x[(size_t)row * n + p];
+      if (mode == 1) v = fmax(v, 0.0); else if (mode == 2) v = -fmax(-v, 0.0);
+      const double d = v - c; s1 += d; s2 += d * d;
+    }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -185,14 +191,14 @@ extern "C" int mcre_tree_reduce(const double *d_partial, int64_t n_chunks, int64
 }
 
 extern "C" int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_paths, const double *d_shift,
-                              double *d_partial, double *d_out, void *stream) {
+                              int32_t mode, double *d_partial, double *d_out, void *stream) {
   if (!d_x || !d_shift || !d_partial || !d_out) return fail(-1, "null argument%s", "");
   if (n_rows <= 0 || chunk_paths <= 0 || chunk_paths % 32 != 0) return fail(-2, "sum_stats: bad shape%s", "");
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) { MCRE_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n_rows * 2 * sizeof(double), st)); return 0; }
   const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
   dim3 grid((unsigned)n_chunks, (unsigned)n_rows);
-  sum_stats_kernel<<<grid, 256, 0, st>>>(d_x, n, n_rows, chunk_paths, d_shift, d_partial);
+  sum_stats_kernel<<<grid, 256, 0, st>>>(d_x, n, n_rows, chunk_paths, d_shift, mode, d_partial);
   MCRE_LAUNCHED();
   return mcre_tree_reduce(d_partial, n_chunks, (int64_t)n_rows * 2, d_out, stream);
 }

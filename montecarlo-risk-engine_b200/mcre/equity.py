@@ -866,7 +866,11 @@ class EquityBackend:
         begin, count = RT.shard_range(n_main, chunk)
         n = max(count, 1)
         n_chunks = (n + chunk - 1) // chunk
+        need_expo = c.risk_metrics.requires_exposure_profiles()
+        kinds = {m.metric_type for m in c.risk_metrics.metrics}
+        n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
         accum = torch.zeros(n, dtype=torch.float64, device=dev)
+        accum_e = torch.zeros((n_expo, n), dtype=torch.float64, device=dev) if need_expo else None
         shift_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
         for book in books:
@@ -879,6 +883,8 @@ class EquityBackend:
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
+                if need_expo:
+                    B.check(L.mcre_eq_set_exposure_accumulator(plan, accum_e.data_ptr()))
                 keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
                 rng = self._rng(43, n_main)
                 sh = B.Shard(begin, count, chunk)
@@ -895,15 +901,49 @@ class EquityBackend:
                 shift_sum += shift[0:1]      # pilot values add up: the book's value on global path 0
             finally:
                 L.mcre_eq_destroy(plan)
-        partial = torch.empty(n_chunks * 2 + 1, dtype=torch.float64, device=dev)
+        partial = torch.empty(n_chunks * 2 * max(n_metric, 1) + 1, dtype=torch.float64, device=dev)
         out = torch.zeros(2, dtype=torch.float64, device=dev)
-        B.check(L.mcre_sum_stats(accum.data_ptr(), count, 1, chunk, shift_sum.data_ptr(), partial.data_ptr(),
+        B.check(L.mcre_sum_stats(accum.data_ptr(), count, 1, chunk, shift_sum.data_ptr(), 0, partial.data_ptr(),
                                  out.data_ptr(), RT.stream_ptr()))
         s = RT.all_reduce_tree(out).cpu().numpy()
         pv = mean_and_error(s[0], s[1], float(shift_sum[0]), n_main)
         if self.nt:
             grad[self.num_rate_global] += numtan
-        return {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+        res = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+        if need_expo:
+            # netting-set terms on the accumulated exposures, then the metric sums (shift = the value on global path 0,
+            # which lives on rank 0: summed over the ranks so that every rank uses the same one)
+            ns = c.netting_sets[si]
+            metric_expo = np.asarray(c.metric_exposure_indices.tolist(), dtype=np.int32)
+            lag = np.full(n_metric, -1, dtype=np.int32)
+            if ns.is_collateralized():
+                delayed = c.netting_set_delayed_exposure_indices[si].tolist()
+                for m in range(n_metric):
+                    if delayed[m] >= 0:
+                        lag[m] = int(metric_expo[m]) - delayed[m]
+            spill = torch.zeros((1, n_metric, n), dtype=torch.float64, device=dev)
+            me_k, me_p = B.as_ip(metric_expo)
+            lg_k, lg_p = B.as_ip(lag)
+            B.check(L.mcre_eq_unsecured_exposures(accum_e.data_ptr(), count, n_metric, me_p, lg_p,
+                                                  int(ns.is_collateralized()), float(ns.threshold), spill.data_ptr(),
+                                                  RT.stream_ptr()))
+            first = spill[0, :, 0].clone() if (RT.dist_info()[0] == 0 and count > 0) else torch.zeros(n_metric, dtype=torch.float64, device=dev)
+            first = RT.all_reduce_tree(first)
+            for key, mode, flag in (("pos", 1, B.ACC_POS), ("neg", 2, B.ACC_NEG)):
+                want = (kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}) if key == "pos" else (MetricType.ENE in kinds)
+                if not want:
+                    continue
+                c_shift = torch.clamp(first, min=0.0) if mode == 1 else -torch.clamp(-first, min=0.0)
+                out_m = torch.zeros(n_metric * 2, dtype=torch.float64, device=dev)
+                B.check(L.mcre_sum_stats(spill.data_ptr(), count, n_metric, chunk, c_shift.data_ptr(), mode,
+                                         partial.data_ptr(), out_m.data_ptr(), RT.stream_ptr()))
+                sm = RT.all_reduce_tree(out_m).cpu().numpy().reshape(n_metric, 2)
+                ch = c_shift.cpu().numpy()
+                res[key] = ([mean_and_error(sm[m, 0], sm[m, 1], ch[m], n_main) for m in range(n_metric)], [None] * n_metric)
+            if MetricType.PFE in kinds:
+                from mcre.select import order_statistics
+                res["pfe"] = order_statistics(c, spill, count, n_main)[0]
+        return res
 
     def run(self):
         c = self.c
@@ -925,10 +965,6 @@ class EquityBackend:
         # a netting set with more tracked products than one launch holds is split over several launches
         ntrk = eq_ntrk(self.nt)
         oversized = [si for si, ns in enumerate(c.netting_sets) if sum(_is_path_dependent(p) for p in ns.products) > ntrk]
-        if oversized and c.risk_metrics.requires_exposure_profiles():
-            raise NotImplementedError(
-                f"exposure profiles of a netting set with more than {ntrk} path-dependent / exercise products "
-                "are not implemented (PV is: the book is split over launches)")
         for si in oversized:
             results[si] = self._run_split_book(si, dev, n_main, n_params)
         groups, cur, cur_trk = [], [], 0

@@ -239,3 +239,38 @@ def test_large_mixed_book_is_split_over_launches(differentiate):
             got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(name, "pv")[0]])
             want = np.asarray(out["grads"][si][0][0])
             helpers.assert_close(got, want, 1e-6, 1e-7 * max(1.0, float(np.abs(want).max())), f"{name} pv greeks")
+
+
+def test_large_mixed_book_exposure_profiles_are_split_over_launches():
+    """More path-dependent / exercise products than the 64 trackers of one value-only launch, with exposure metrics:
+    every launch adds its products' netted exposures per (exposure date, path) to one accumulator
+    (mcre_eq_set_exposure_accumulator), threshold / MPoR collateral are applied afterwards
+    (mcre_eq_unsecured_exposures), EPE / ENE from mcre_sum_stats, PFE from the radix select.  Vs the oracle, which
+    nets the whole book at once like the reference (tests/exposure_tests/ee_performance_large_netting_set.py)."""
+    from oracle import risk
+    ns = cases.Namespace()
+    ids = ["asset_1", "asset_2"]
+    model = ns.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                 volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    prods = []
+    for k in range(66):
+        a = ids[k % 2]
+        if k % 3 == 0:
+            prods.append(ns.AsianOption(0.0, 0.5 + 0.25 * (k % 3), 95.0 + (k % 7), 3 + k % 3, ns.OptionType.CALL if k % 2 else ns.OptionType.PUT,
+                                        asset_id=a))
+        else:
+            prods.append(ns.BarrierOption(startdate=0.0, maturity=0.5 + 0.25 * (k % 4), strike=100.0, num_observation_timepoints=3 + k % 4,
+                                          option_type=ns.OptionType.CALL, barrier1=125.0 + k % 11,
+                                          barrier_option_type1=ns.BarrierOptionType.UPANDOUT, asset_id=a))
+    prods.append(ns.AmericanOption(underlying=ns.Equity("asset_1"), maturity=1.0, num_exercise_dates=5, strike=100.0,
+                                   option_type=ns.OptionType.PUT, asset_id="asset_1"))
+    prods.append(ns.EuropeanOption(ns.Equity("asset_2"), 1.0, 100.0, ns.OptionType.CALL, asset_id="asset_2"))
+    sets = [ns.NettingSet(name="big", products=prods, margin_period_of_risk=0.25, threshold=2.0)]
+    metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.PFEMetric(0.9)]
+    tl = np.linspace(0.0, 1.25, 6)
+    n = 2048
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.ANALYTICAL)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, metrics, tl, n, n, 1, "ANALYTICAL")
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, ["big"], res.get_metric_names()), 1e-7, "big book exposures",
+             err_rtol=1e-5)
