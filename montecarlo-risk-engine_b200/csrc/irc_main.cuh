@@ -174,6 +174,10 @@ __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 #ifndef MCRE_IRC_MINB
 #define MCRE_IRC_MINB 2
 #endif
+// 1: the Philox rounds of sub-step s+1 are issued inside the iteration of sub-step s (CVA-only build)
+#ifndef MCRE_IRC_PREFETCH
+#define MCRE_IRC_PREFETCH 0
+#endif
 __host__ __device__ constexpr int irc_pp(int nt, int ns, int mode) {
   return nt > 0 ? 1 : (mode == 1 ? MCRE_IRC_PP : (ns == 1 ? 4 : 2));
 }
@@ -406,6 +410,11 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
       };
 
       for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+      constexpr bool PREFETCH = MCRE_IRC_PREFETCH && CIR && MODE == 1;
+      uint32_t q0[PREFETCH ? PP : 1], q1[PREFETCH ? PP : 1], q2[PREFETCH ? PP : 1], q3[PREFETCH ? PP : 1];
+      if constexpr (PREFETCH) {
+        if (rng.mode != MCRE_RNG_INJECT && P.n_sub > 0) nsv.raw(q0, q1, q2, q3);
+      }
 #if defined(MCRE_IRC_UNROLL) && MCRE_IRC_UNROLL > 1
 #pragma unroll 2
 #else
@@ -427,6 +436,11 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
             z0[p] = zp[0];
             z1[p] = CIR ? zp[1] : 0.0;
           }
+        } else if constexpr (PREFETCH) {
+          uint32_t w0[PP], w1[PP], w2[PP], w3[PP];
+          MCRE_VP { w0[p] = q0[p]; w1[p] = q1[p]; w2[p] = q2[p]; w3[p] = q3[p]; }
+          if (is + 1 < P.n_sub) nsv.raw(q0, q1, q2, q3);     // integer work of the next sub-step, independent of this one
+          NormalStreamV<PP>::box_muller(w0, w1, w2, w3, z0, z1);
         } else if constexpr (CIR) {
           nsv.next2(z0, z1);
         } else {

@@ -144,9 +144,10 @@ struct NormalStreamV {
     k0 = r.k0; k1 = r.k1; n = 0;
     MCRE_VP { p_lo[p] = (uint32_t)gpath[p]; p_hi[p] = (uint32_t)((unsigned long long)gpath[p] >> 32); }
   }
-  // two consecutive normals of every path (noise_dim 2)
-  __device__ inline void next2(double (&z0)[PP], double (&z1)[PP]) {
-    uint32_t c0[PP], c1[PP], c2[PP], c3[PP];
+  // the integer half of next2: ten Philox rounds for the block of the next normal pair of every path.
+  // Split from the floating-point half so that a kernel can issue the rounds of step s+1 next to the FP64
+  // work of step s (the FP64 pipe and the integer pipe then overlap inside one warp).
+  __device__ inline void raw(uint32_t (&c0)[PP], uint32_t (&c1)[PP], uint32_t (&c2)[PP], uint32_t (&c3)[PP]) {
     const uint32_t block = n >> 1;
     MCRE_VP { c0[p] = p_lo[p]; c1[p] = p_hi[p]; c2[p] = block; c3[p] = 0u; }
     uint32_t a = k0, b = k1;
@@ -155,6 +156,11 @@ struct NormalStreamV {
       MCRE_VP Philox::round(c0[p], c1[p], c2[p], c3[p], a, b);
       a += 0x9E3779B9u; b += 0xBB67AE85u;
     }
+    n += 2;
+  }
+  // the floating-point half: Box-Muller on the raw words
+  __device__ static inline void box_muller(const uint32_t (&c0)[PP], const uint32_t (&c1)[PP], const uint32_t (&c2)[PP],
+                                           const uint32_t (&c3)[PP], double (&z0)[PP], double (&z1)[PP]) {
     double u1[PP], d2[PP], lg[PP], rad[PP];
     MCRE_VP u1[p] = u52(c0[p], c1[p]);
     MCRE_VP d2[p] = mant52(c2[p], c3[p]);
@@ -162,7 +168,12 @@ struct NormalStreamV {
     MCRE_VP lg[p] = -2.0 * lg[p];
     fm_sqrt_posv<PP>(lg, rad);          // u1 < 1: the argument is strictly positive
     fm_polar_tv<PP>(d2, rad, z0, z1);
-    n += 2;
+  }
+  // two consecutive normals of every path (noise_dim 2)
+  __device__ inline void next2(double (&z0)[PP], double (&z1)[PP]) {
+    uint32_t c0[PP], c1[PP], c2[PP], c3[PP];
+    raw(c0, c1, c2, c3);
+    box_muller(c0, c1, c2, c3, z0, z1);
   }
 };
 #endif

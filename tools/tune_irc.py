@@ -27,8 +27,11 @@ def main():
         from mcre import build
         for v in variants:
             pp, rest = v.split("x")
+            prefetch = rest.endswith("p")
+            rest = rest.rstrip("p")
             minb, _, unroll = rest.partition("u")
             flags = [f"-DMCRE_IRC_PP={pp}", f"-DMCRE_IRC_MINB={minb}"] + ([f"-DMCRE_IRC_UNROLL={unroll}"] if unroll else [])
+            flags += ["-DMCRE_IRC_PREFETCH=1"] if prefetch else []
             build.build(force=True, extra_flags=flags, lib=lib_of(v), tag="_" + v)
             print("built", lib_of(v))
     else:
