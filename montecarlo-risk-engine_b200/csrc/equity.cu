@@ -118,7 +118,7 @@ __device__ __forceinline__ R barrier_factor(const R &mx, const R &mn, double bar
 // slot layout: [NS][3] = sum(cf - c), sum((cf - c)^2), sum(payoff * d invN / d r)   then
 //              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p
 template <int KIND, int ALT, int NT, int NS>
-__global__ void __launch_bounds__(128, (NT == 0 ? 4 : 3)) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
+__global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
                                                       double *shift, double *spill, int pilot) {
   typedef typename RealOf<NT>::type R;
   typedef RealTraits<R> T;
