@@ -234,7 +234,9 @@ int mcre_irc_set_exercise_coefficients(mcre_irc_plan *plan, const double *ex_coe
 /* Pre-simulation of a Bermudan unit, forward pass (replaces the path generation + request
  * resolution feeding controller._perform_regression_for_product, controller.py:294-383):
  * spills x [n_reg][n], numeraire [n_reg][n] and the immediate exercise values imm [n_ex][n]
- * (all f64, date-major) for the backward induction of mcre_lsm_step. */
+ * (all f64, date-major) for the backward induction of mcre_lsm_step.
+ * Plans with tangents (nt > 0): dx [n_reg][nt][n], dN [n_reg][nt][n] and dimm [n_ex][nt][n] follow, for the
+ * sensitivities of exposure metrics of exercise products (mcre_lsm_step_tangents). */
 int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *plan, int64_t n_paths);
 int mcre_irc_lsm_forward(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
                          void *stream);
@@ -406,6 +408,18 @@ int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const double *d_n
                          const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i,
                          double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
                          double *d_partial, double *d_moments, void *stream);
+
+/* Tangent companion of mcre_lsm_step (one exercise right), called after it for the same regression date: applies
+ * the same hard exercise decision to the running pathwise tangents d_dvalue [nt][n] of the deflated value,
+ *   dV <- ex ? (dimm_i - (imm_i / N_i) dN_i) / N_i : dV,
+ * and accumulates d_tmoments [nt][9] = sum u^m du (m = 0..3), sum u^i dY (i = 0..2), sum du Y, sum 2 u du Y with
+ * Y = N_k V, dY = dN_k V + N_k dV, from which the host differentiates the normal equations (the reference keeps
+ * torch.linalg.lstsq inside the autograd graph, controller.py:368-383).  d_dxk, d_dnk, d_dni, d_dimm: [nt][n]. */
+int mcre_lsm_step_tangents(int32_t nt, const double *d_xk, const double *d_nk, const double *d_dxk, const double *d_dnk,
+                           double shift_k, double scale_k, const double *d_xi, const double *d_ni, const double *d_imm,
+                           const double *d_dni, const double *d_dimm, const double *coef_i, double shift_i, double scale_i,
+                           const float *d_value, double *d_dvalue, int64_t n, int32_t chunk_paths, double *d_partial,
+                           double *d_tmoments, void *stream);
 
 /* LSM pre-simulation arrays of an exercise product on equity underlyings, gathered date-major from
  * materialised pre-simulation paths (mcre_generate_paths with seed 42; the pre-simulation is a small

@@ -397,15 +397,19 @@ extern "C" int mcre_irc_set_exercise_coefficients(mcre_irc_plan *p, const double
 }
 
 extern "C" int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *p, int64_t n_paths) {
-  return ((int64_t)2 * p->d.n_reg + p->d.n_ex) * n_paths * 8 + 256;
+  // x, N, imm and (plans with tangents) dx, dN, dimm: see irc_tan.cu
+  return ((int64_t)2 * p->d.n_reg + p->d.n_ex) * n_paths * 8 * (1 + p->d.nt) + 256;
 }
+
+// defined in irc_tan.cu
+int irc_lsm_forward_tangent_pass(mcre_irc_plan *p, const mcre::RngDev &r, const mcre::ShardDev &sh, void *d_scratch,
+                                 cudaStream_t st);
 
 extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
                                     void *stream) {
   if (!p || !rng || !d_scratch) return fail(-1, "null argument%s", "");
   int rc = check_shard(shard);
   if (rc) return rc;
-  if (p->d.nt != 0) return fail(-4, "irc lsm: tangents through the regression are not implemented%s", "");
   if (p->d.n_berm < 1) return fail(-1, "irc lsm: plan has no exercise unit%s", "");
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   const IrcDev &d = p->d;
@@ -417,6 +421,7 @@ extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const
   double *xbuf = (double *)d_scratch;
   double *nbuf = xbuf + (size_t)d.n_reg * n;
   double *ibuf = nbuf + (size_t)d.n_reg * n;
+  if (d.nt != 0) return irc_lsm_forward_tangent_pass(p, r, sh, d_scratch, st);
   const int threads = 128;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   if (d.has_cir) irc_lsm_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);

@@ -162,9 +162,175 @@ __global__ void __launch_bounds__(256) irc_presim_tangent_moments_kernel(IrcDev 
   }
 }
 
+// Pre-simulation of a Bermudan unit with tangents: like irc_lsm_forward_kernel, plus the pathwise tangents of the
+// explanatory variable, the numeraire and the immediate exercise values.
+// scratch: x [n_reg][n] | N [n_reg][n] | imm [n_ex][n] | dx [n_reg][NT][n] | dN [n_reg][NT][n] | dimm [n_ex][NT][n]
+template <int NT, bool CIR, int SCHEME>
+__global__ void __launch_bounds__(128) irc_lsm_forward_tan_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
+                                                                  double *nbuf, double *ibuf, double *dxbuf, double *dnbuf,
+                                                                  double *dibuf) {
+  typedef Dual<NT> R;
+  typedef RealTraits<R> T;
+  fm_tables_init();
+  const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lpath >= sh.n_paths) return;
+  const long long gpath = sh.path_begin + lpath;
+  const long long n = sh.n_paths;
+  IrcParams<R, CIR> mp;
+  irc_load_params<R, CIR>(P, mp);
+  NormalStream ns; ns.init(rng, (unsigned long long)gpath);
+  IrcState<R> st;
+  st.r = mp.r0; st.logB = T::zero(); st.y = mp.y0; st.logBl = T::zero();
+  auto eval_date = [&](int di) {
+    const int flags = __ldg(P.date_flags + di);
+    if (flags & MCRE_DATE_HAS_REGRESSION) {
+      const int k = __ldg(P.date_reg + di);
+      const R num = r_exp(st.logB);
+      xbuf[(size_t)k * n + lpath] = st.r.v;
+      nbuf[(size_t)k * n + lpath] = num.v;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        dxbuf[((size_t)k * NT + i) * n + lpath] = st.r.d[i];
+        dnbuf[((size_t)k * NT + i) * n + lpath] = num.d[i];
+      }
+    }
+    if (flags & MCRE_DATE_HAS_EXERCISE) {
+      const int x0 = __ldg(P.date_ex_off + di), x1 = __ldg(P.date_ex_off + di + 1);
+      for (int x = x0; x < x1; ++x) {
+        const R imm = irc_exercise_value<R>(P, x, st.r);
+        ibuf[(size_t)x * n + lpath] = imm.v;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) dibuf[((size_t)x * NT + i) * n + lpath] = imm.d[i];
+      }
+    }
+  };
+  for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+  for (int is = 0; is < P.n_sub; ++is) {
+    double z0, z1;
+    irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
+    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    const int di = __ldg(P.step_date + is);
+    if (di >= 0) eval_date(di);
+  }
+}
+
+// Tangent companion of lsm_step_kernel<1> (csrc/lsm.cu), one exercise right: for parameter blockIdx.y it applies
+// the SAME exercise decision as the value pass (hard indicator, no derivative) to the running tangent
+//     dV <- ex ? d(imm_i / N_i) : dV,   d(imm / N) = (dimm - (imm / N) dN) / N
+// and accumulates the nine tangent moments of regression date k (see the header of this file) with Y = N_k V,
+// dY = dN_k V + N_k dV, V the float32 running value the value pass has already updated for this date.
+// dvalue: [nt][n] f64; partial: [chunk][nt][9].
+__global__ void __launch_bounds__(256) lsm_step_tan_kernel(int nt, const double *__restrict__ xk, const double *__restrict__ nk,
+                                                           const double *__restrict__ dxk, const double *__restrict__ dnk,
+                                                           double shift_k, double scale_k, const double *__restrict__ xi,
+                                                           const double *__restrict__ ni, const double *__restrict__ imm,
+                                                           const double *__restrict__ dni, const double *__restrict__ dimm,
+                                                           int has_coef, double c0, double c1, double c2, double shift_i,
+                                                           double scale_i, const float *__restrict__ value,
+                                                           double *__restrict__ dvalue, long long n, int chunk,
+                                                           double *__restrict__ partial) {
+  __shared__ double acc[TM_NV];
+  __shared__ double stage[2 * 8 * TM_NV];
+  const int ip = blockIdx.y;
+  const long long n_chunks = (n + chunk - 1) / chunk;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    if (threadIdx.x < TM_NV) acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    int parity = 0;
+    double vals[TM_NV];
+#pragma unroll
+    for (int j = 0; j < TM_NV; ++j) vals[j] = 0.0;
+    for (int it = 0; it < chunk; it += blockDim.x) {
+      const long long p = ch * chunk + it + threadIdx.x;
+      if (it + (int)threadIdx.x < chunk && p < n) {
+        double dv = dvalue[(size_t)ip * n + p];
+        if (imm) {
+          const double im = imm[p];
+          double cont = 0.0;
+          if (has_coef) {
+            const double ui = (xi[p] - shift_i) * scale_i;
+            cont = c0 + ui * (c1 + ui * c2);
+          }
+          if (im > cont) {
+            const double inv = 1.0 / ni[p];
+            dv = (dimm[(size_t)ip * n + p] - im * inv * dni[(size_t)ip * n + p]) * inv;
+          }
+          dvalue[(size_t)ip * n + p] = dv;
+        }
+        const double uu = (xk[p] - shift_k) * scale_k, du = dxk[(size_t)ip * n + p] * scale_k;
+        const double V = (double)value[p];
+        const double Y = nk[p] * V, dY = dnk[(size_t)ip * n + p] * V + nk[p] * dv;
+        const double u2 = uu * uu;
+        vals[0] += du; vals[1] += uu * du; vals[2] += u2 * du; vals[3] += u2 * uu * du;
+        vals[4] += dY; vals[5] += uu * dY; vals[6] += u2 * dY;
+        vals[7] += du * Y; vals[8] += 2.0 * uu * du * Y;
+      }
+    }
+    block_accumulate<TM_NV>(vals, acc, 0, stage, TM_NV, parity);
+    __syncthreads();
+    if (threadIdx.x < TM_NV) partial[((size_t)ch * nt + ip) * TM_NV + threadIdx.x] = acc[threadIdx.x];
+    __syncthreads();
+  }
+}
+
 }  // namespace mcre
 
 using namespace mcre;
+
+extern "C" int mcre_lsm_step_tangents(int32_t nt, const double *d_xk, const double *d_nk, const double *d_dxk,
+                                      const double *d_dnk, double shift_k, double scale_k, const double *d_xi,
+                                      const double *d_ni, const double *d_imm, const double *d_dni, const double *d_dimm,
+                                      const double *coef_i, double shift_i, double scale_i, const float *d_value,
+                                      double *d_dvalue, int64_t n, int32_t chunk_paths, double *d_partial,
+                                      double *d_tmoments, void *stream) {
+  if (!d_xk || !d_nk || !d_dxk || !d_dnk || !d_value || !d_dvalue || !d_partial || !d_tmoments)
+    return fail(-1, "null argument%s", "");
+  if (nt < 1) return fail(-1, "lsm tangents: nt must be positive%s", "");
+  if (d_imm && (!d_xi || !d_ni || !d_dni || !d_dimm)) return fail(-1, "lsm tangents: exercise update needs its arrays%s", "");
+  if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {
+    MCRE_CUDA(cudaMemsetAsync(d_tmoments, 0, (size_t)nt * TM_NV * sizeof(double), st));
+    return 0;
+  }
+  const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
+  long long gx = (long long)sm_count() * 4;
+  if (gx > n_chunks) gx = n_chunks;
+  dim3 grid((unsigned)gx, (unsigned)nt);
+  lsm_step_tan_kernel<<<grid, 256, 0, st>>>(nt, d_xk, d_nk, d_dxk, d_dnk, shift_k, scale_k, d_xi, d_ni, d_imm, d_dni, d_dimm,
+                                            coef_i != nullptr, coef_i ? coef_i[0] : 0.0, coef_i ? coef_i[1] : 0.0,
+                                            coef_i ? coef_i[2] : 0.0, shift_i, scale_i, d_value, d_dvalue, n, chunk_paths,
+                                            d_partial);
+  MCRE_LAUNCHED();
+  return mcre_tree_reduce(d_partial, n_chunks, (int64_t)nt * TM_NV, d_tmoments, stream);
+}
+
+template <int NT>
+static int launch_lsm_forward_tan(const IrcDev &d, const RngDev &r, const ShardDev &sh, double *x, double *nn, double *im,
+                                  double *dx, double *dn, double *di, cudaStream_t st) {
+  const int threads = 128;
+  const unsigned blocks = (unsigned)((sh.n_paths + threads - 1) / threads);
+  if (d.has_cir) irc_lsm_forward_tan_kernel<NT, true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, x, nn, im, dx, dn, di);
+  else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
+    irc_lsm_forward_tan_kernel<NT, false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, x, nn, im, dx, dn, di);
+  else irc_lsm_forward_tan_kernel<NT, false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, x, nn, im, dx, dn, di);
+  MCRE_LAUNCHED();
+  return 0;
+}
+
+// called by mcre_irc_lsm_forward when the plan carries tangents
+int irc_lsm_forward_tangent_pass(mcre_irc_plan *p, const RngDev &r, const ShardDev &sh, void *d_scratch, cudaStream_t st) {
+  const IrcDev &d = p->d;
+  const long long n = sh.n_paths;
+  double *x = (double *)d_scratch;
+  double *nn = x + (size_t)d.n_reg * n;
+  double *im = nn + (size_t)d.n_reg * n;
+  double *dx = im + (size_t)d.n_ex * n;
+  double *dn = dx + (size_t)d.n_reg * d.nt * n;
+  double *di = dn + (size_t)d.n_reg * d.nt * n;
+  return d.nt == 4 ? launch_lsm_forward_tan<4>(d, r, sh, x, nn, im, dx, dn, di, st)
+                   : launch_lsm_forward_tan<8>(d, r, sh, x, nn, im, dx, dn, di, st);
+}
 
 extern "C" int64_t mcre_irc_presim_tangent_slots(const mcre_irc_plan *p) {
   return (int64_t)p->d.n_units * p->d.nt * p->d.n_reg * TM_NV;

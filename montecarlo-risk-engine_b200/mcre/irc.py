@@ -579,8 +579,14 @@ class IrcBackend:
         expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
         ptl = prod.product_timeline.tolist()
         reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
-        with self._value_only():
+        # tangents are needed only where the coefficients enter smoothly: the alive-state exposure proxies.  The
+        # exercise policy is a hard indicator (zero derivative), so PV-only runs pre-simulate values only.
+        with_tan = bool(self.nt) and bool(expo_times)
+        if with_tan:
             desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
+        else:
+            with self._value_only():
+                desc, keep, info = self.lower([], [], berm_units=[(prod, 0)], reg_times=reg_times)
         n_reg, n_ex = len(reg_times), info["n_ex"]
         basis = info["reg_basis"]
         inject = c.injected_normals.get("pre") if c.injected_normals else None
@@ -589,7 +595,7 @@ class IrcBackend:
         try:
             begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
             n = max(count, 1)
-            scratch = torch.empty(L.mcre_irc_lsm_scratch_bytes(plan, n) // 8 + 1, dtype=torch.float64, device=dev)
+            scratch = torch.zeros(L.mcre_irc_lsm_scratch_bytes(plan, n) // 8 + 1, dtype=torch.float64, device=dev)
             rng = self._rng(42, inject, n_pre)
             sh = B.Shard(begin, count, CHUNK_PATHS)
             B.check(L.mcre_irc_lsm_forward(plan, C.byref(rng), C.byref(sh), scratch.data_ptr(), RT.stream_ptr()))
@@ -600,8 +606,16 @@ class IrcBackend:
         imm_all = scratch[2 * n_reg * n:(2 * n_reg + n_ex) * n].view(n_ex, n)
         assert [info["ex_index"][(0, i)] for i in range(len(ptl))] == list(range(len(ptl)))  # one unit: date order
         imm = imm_all
-        coef = backward_induction(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev)
-        return coef, reg_times, basis
+        tangents = None
+        if with_tan:
+            nt, off = self.nt, (2 * n_reg + n_ex) * n
+            dxs = scratch[off:off + n_reg * nt * n].view(n_reg, nt, n)
+            dns = scratch[off + n_reg * nt * n:off + 2 * n_reg * nt * n].view(n_reg, nt, n)
+            dim_ = scratch[off + 2 * n_reg * nt * n:off + (2 * n_reg + n_ex) * nt * n].view(n_ex, nt, n)
+            tangents = dict(nt=nt, dxs=dxs, dnums=dns, dimm=dim_)
+        out = backward_induction(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, tangents=tangents)
+        coef, dcoef = out if with_tan else (out, None)
+        return coef, reg_times, basis, dcoef
 
     def run(self):
         c = self.c
@@ -638,12 +652,8 @@ class IrcBackend:
             for p in c.products:
                 if not is_rate_bermudan(p):
                     continue
-                if self.nt and need_expo:
-                    raise NotImplementedError(
-                        "sensitivities of exposure profiles of exercise products (tangents of the alive-state "
-                        "regression coefficients) are not implemented; PV sensitivities are")
-                coef, reg_times, basis = self.presim_bermudan(p, dev)
-                berm_coef[id(p)] = (coef, {t: k for k, t in enumerate(reg_times)}, basis)
+                coef, reg_times, basis, dcoef = self.presim_bermudan(p, dev)
+                berm_coef[id(p)] = (coef, {t: k for k, t in enumerate(reg_times)}, basis, dcoef)
                 raw = to_raw_basis(coef, basis, [t <= self.vas.t0() for t in reg_times])
                 ridx = {t: k for k, t in enumerate(reg_times)}
                 for j, t in enumerate(p.regression_timeline.tolist()):
@@ -679,11 +689,13 @@ class IrcBackend:
                     exc = np.zeros((max(info["n_ex"], 1), 3, w))
                     bex = np.zeros((max(n_expo, 1), len(units), 3, w))
                     for b, (p, _) in enumerate(units):
-                        bc, ridx, _ = berm_coef[id(p)]
+                        bc, ridx, _, dbc = berm_coef[id(p)]
                         for i, t in enumerate(p.product_timeline.tolist()):
                             exc[info["ex_index"][(b, i)], :, 0] = bc[ridx[t]]
                         for e, t in enumerate(info["expo_times"]):
                             bex[e, b, :, 0] = bc[ridx[t]]
+                            if dbc is not None:      # d(alive-state exposure coefficients)/d(parameters)
+                                bex[e, b, :, 1:] = dbc[ridx[t]].T
                     exc_k, exc_ptr = B.as_dp(exc)
                     bex_k, bex_ptr = B.as_dp(bex)
                     B.check(L.mcre_irc_set_exercise_coefficients(plan, exc_ptr, bex_ptr, RT.stream_ptr()))

@@ -108,7 +108,7 @@ def regression_tangents(G, rhs, coef, tm):
 LSM_MAX_NV = 5 + 3 * 3   # moments of the widest step (3 exercise rights)
 
 
-def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
+def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1, tangents=None):
     """Generator form of the backward induction: queues the kernels of one regression date, yields the device
     tensor that will hold its moments and expects the solved coefficients of that date back (`send`: [3, 3],
     one row per state, from the driver's all-reduce + batched normal-equation solve).  Returns the
@@ -118,7 +118,10 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
     xs, nums: device [n_reg, n]; imm: device [n_ex, n] (row i = product date i); ptl: product (exercise)
     dates; reg_times: regression dates (sorted, contain every product date); basis: [n_reg, 2] (shift, scale).
     -> coefficients in the standardised basis: [n_reg, 3] for one exercise right, [n_reg, n_rights, 3]
-    (state s = rights left at row s-1) for a FlexiCall."""
+    (state s = rights left at row s-1) for a FlexiCall.
+    tangents (one exercise right): dict(nt, dxs [n_reg, nt, n], dnums [n_reg, nt, n], dimm [n_ex, nt, n]) - the
+    pathwise tangents of the spilled arrays; the generator then also returns d(coefficients)/d(parameters)
+    [n_reg, nt, 3] (mcre_lsm_step_tangents + regression_tangents): -> (coef, dcoef)."""
     L = B.lib()
     n_reg = len(reg_times)
     n = xs.shape[1]
@@ -131,6 +134,14 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
     partial = torch.empty(n_chunks * nv + 1, dtype=torch.float64, device=dev)
     moments = torch.zeros(LSM_MAX_NV, dtype=torch.float64, device=dev)
     keep = {}
+    if tangents is not None:
+        assert R == 1, "tangents of the regression: one exercise right"
+        nt = int(tangents["nt"])
+        dxs, dnums, dimm = tangents["dxs"], tangents["dnums"], tangents["dimm"]
+        dvalue = torch.zeros((nt, n), dtype=torch.float64, device=dev)
+        tpartial = torch.empty(n_chunks * nt * 9 + 1, dtype=torch.float64, device=dev)
+        tmoments = torch.zeros(nt * 9, dtype=torch.float64, device=dev)
+        dcoef = np.zeros((n_reg, nt, 3))
 
     def step(k, i):
         """moments of regression date k, after the exercise update at product date i (or None)."""
@@ -145,6 +156,16 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
         B.check(L.mcre_lsm_step_states(R, xs[k].data_ptr(), nums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
                                        *args_i, value.data_ptr(), count, chunk_paths, partial.data_ptr(),
                                        moments.data_ptr(), RT.stream_ptr()))
+        if tangents is not None:
+            # same exercise decision applied to the running tangents, then the tangent moments of date k
+            targs = (None, None, None, None, None, None, 0.0, 1.0)
+            if i is not None:
+                targs = (args_i[0], args_i[1], args_i[2], dnums[ki].data_ptr(), dimm[i].data_ptr(), args_i[3],
+                         args_i[4], args_i[5])
+            B.check(L.mcre_lsm_step_tangents(nt, xs[k].data_ptr(), nums[k].data_ptr(), dxs[k].data_ptr(),
+                                             dnums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]), *targs,
+                                             value.data_ptr(), dvalue.data_ptr(), count, chunk_paths,
+                                             tpartial.data_ptr(), tmoments.data_ptr(), RT.stream_ptr()))
 
     last = len(ptl)
     for k in range(n_reg - 1, -1, -1):
@@ -160,8 +181,14 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
             last = t_next
         else:
             step(k, None)
-        solved = yield moments          # [3 states, 3] from the driver's batched solve of this round
+        solved, m = yield moments       # [3 states, 3] from the driver's batched solve of this round, host moments
         coef[k] = solved[:R]
+        if tangents is not None:
+            tm = RT.all_reduce_tree(tmoments).cpu().numpy().reshape(nt, 9)
+            G = np.array([[m[0], m[1], m[2]], [m[1], m[2], m[3]], [m[2], m[3], m[4]]])
+            dcoef[k] = regression_tangents(G, m[5:8], coef[k, 0], tm)
+    if tangents is not None:
+        return coef[:, 0, :], dcoef
     return coef[:, 0, :] if R == 1 else coef
 
 
@@ -182,19 +209,19 @@ def run_backward_inductions(gens):
         G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
         # one batched solve per state for all products of the round (states a product does not have carry zeros)
         host = np.stack([solve_normal_equations_batch(G, m[:, 5 + 3 * s:8 + 3 * s]) for s in range(3)], axis=1)
-        for k, row in zip(keys, host):
+        for j, (k, row) in enumerate(zip(keys, host)):
             try:
-                pending[k] = gens[k].send(row)
+                pending[k] = gens[k].send((row, m[j]))
             except StopIteration as e:
                 results[k] = e.value
                 del pending[k]
     return results
 
 
-def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1):
+def backward_induction(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1, tangents=None):
     """One product: see backward_induction_steps."""
     return run_backward_inductions([backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths,
-                                                             dev, n_rights=n_rights)])[0]
+                                                             dev, n_rights=n_rights, tangents=tangents)])[0]
 
 
 def to_raw_basis(coefs, basis, degenerate=None):

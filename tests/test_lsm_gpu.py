@@ -65,9 +65,29 @@ def test_bermudan_swaption_pv_greeks_match_oracle():
     want = np.asarray(out["grads"][0][0][0])
     helpers.assert_close(got, want, 1e-7, 1e-8 * max(1.0, float(np.abs(want).max())), "pv greeks")
     assert np.all(np.isfinite(got)) and np.any(got != 0.0)
-    with pytest.raises(NotImplementedError):
-        ns.SimulationController(sets, model, ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), n, n, 1,
-                                ns.SimulationScheme.EULER, True).run_simulation()
+
+
+def test_bermudan_swaption_exposure_greeks_match_oracle():
+    """EPE / ENE / PV sensitivities of a Bermudan swaption (differentiate=True): the alive-state exposure proxies
+    carry d(coefficients)/d(parameters) from the tangent Longstaff-Schwartz pass (irc_lsm_forward_tan_kernel,
+    mcre_lsm_step_tangents, regression_tangents); exercise decisions stay hard.  Vs the oracle's forward-mode duals
+    through the same regression chain."""
+    from oracle import risk
+    ns = cases.Namespace()
+    model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=6)
+    metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric()]
+    n = 2500
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.EULER, True)
+    res = sc.run_simulation()
+    out = risk.run(model, sets, metrics, tl, n, n, 1, "EULER", differentiate=True)
+    _compare(helpers.flatten_results(res), helpers.oracle_flat(out, ["bermudan"], res.get_metric_names()), 1e-8, "values",
+             err_rtol=1e-6)
+    for mi, m in enumerate(res.get_metric_names()):
+        got = np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives("bermudan", m)])
+        want = np.array([np.zeros(got.shape[1]) if g is None else np.asarray(g) for g in out["grads"][0][mi]])
+        scale = max(1.0, float(np.abs(want).max()))
+        helpers.assert_close(got, want, 1e-6, 1e-7 * scale, f"bermudan {m} derivatives")
+    assert np.any(np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives("bermudan", "epe")]) != 0.0)
 
 
 def test_bermudan_pv_only_and_mixed_book():
