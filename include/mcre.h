@@ -241,6 +241,16 @@ int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *plan, int64_t n_paths);
 int mcre_irc_lsm_forward(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard, void *d_scratch,
                          void *stream);
 
+/* Path replay for the sensitivities of PFE: under autograd the gradient of the reference's order statistic
+ * (pfe_metric.py:59-71) is the pathwise gradient of the selected path.  With a path list set, the next
+ * mcre_irc_mainsim on a plan with tangents simulates the listed global path ids (shard: path_begin 0, n_paths =
+ * list length) and writes d_tan_spill [path][n_metric][n_sets][nt], the tangents of every unsecured exposure.
+ * NULL, NULL switches it off.  mcre_select_locate finds the paths: per row the smallest local index whose value
+ * equals d_targets[row] bit for bit (an index >= n_local: not on this rank). */
+int mcre_irc_set_path_replay(mcre_irc_plan *plan, const int64_t *d_paths, double *d_tan_spill);
+int mcre_select_locate(const double *d_values, int64_t row_stride, int64_t n_local, int32_t n_rows,
+                       const double *d_targets, int64_t *d_index, void *stream);
+
 /* Main simulation.  d_acc, d_shift: [mcre_irc_main_slots]; d_spill [n_sets][n_metric][n_paths]
  * or NULL.  Slot layout (NS = n_sets rounded up to 1, 2 or 4; w = 4 + 2*nt):
  *   [n_metric][NS][w] : sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2), d pos[nt], d neg[nt]

@@ -316,6 +316,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   d.date_ex_off = p->date_ex_off.p; d.ex_unit = p->ex_unit.p; d.ex_term_off = p->ex_term_off.p; d.ex_last = p->ex_last.p;
   d.ex_const = p->ex_const.p; d.term_coef = p->term_coef.p; d.term_w = p->term_w.p; d.ex_basis = p->ex_basis.p;
   d.ex_coef = p->ex_coef.p; d.berm_expo_coef = p->berm_expo_coef.p;
+  d.path_list = nullptr; d.tan_spill = nullptr;
   *out = p;
   return 0;
 }
@@ -396,6 +397,15 @@ extern "C" int mcre_irc_set_exercise_coefficients(mcre_irc_plan *p, const double
   return 0;
 }
 
+extern "C" int mcre_irc_set_path_replay(mcre_irc_plan *p, const int64_t *d_paths, double *d_tan_spill) {
+  if (!p) return fail(-1, "null argument%s", "");
+  if ((d_paths == nullptr) != (d_tan_spill == nullptr)) return fail(-1, "path replay needs both the path list and the output%s", "");
+  if (d_paths && p->d.nt == 0) return fail(-1, "path replay writes tangents: the plan has none%s", "");
+  p->d.path_list = (const long long *)d_paths;
+  p->d.tan_spill = d_tan_spill;
+  return 0;
+}
+
 extern "C" int64_t mcre_irc_lsm_scratch_bytes(const mcre_irc_plan *p, int64_t n_paths) {
   // x, N, imm and (plans with tangents) dx, dN, dimm: see irc_tan.cu
   return ((int64_t)2 * p->d.n_reg + p->d.n_ex) * n_paths * 8 * (1 + p->d.nt) + 256;
@@ -437,7 +447,7 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
   if (!p || !rng || !d_partial || !d_acc || !d_shift) return fail(-1, "null argument%s", "");
   int rc = check_shard(shard);
   if (rc) return rc;
-  if ((p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill) return fail(-1, "spill requested but d_spill is null%s", "");
+  if ((p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.tan_spill) return fail(-1, "spill requested but d_spill is null%s", "");
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   RngDev r = make_rng(rng);
   ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};

@@ -34,6 +34,11 @@ struct IrcDev {
   const double *ex_const, *term_coef, *term_w, *ex_basis;
   double *ex_coef;         // dual[n_ex][3] continuation coefficients (uploaded after the regression)
   double *berm_expo_coef;  // dual[n_expo][n_berm][3] alive-state exposure coefficients
+  // path replay (mcre_irc_set_path_replay): simulate the listed global path ids instead of a contiguous
+  // range and write the tangents of every unsecured exposure, [path][n_metric][n_sets][nt] - the gradient
+  // of a PFE order statistic is the pathwise gradient of the selected path (pfe_metric.py:59-71 under autograd)
+  const long long *path_list;
+  double *tan_spill;
 };
 
 // Underlying value of an exercise record at short rate r: const + sum_j w_j P(t, T_j; r) with
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
         lpath[p] = chunk * sh.chunk + it + p * (int)blockDim.x + threadIdx.x;
         // (PP that does not divide chunk / blockDim: the tail lanes of the last pass idle)
         live[p] = lpath[p] < sh.n_paths && it + p * (int)blockDim.x + (int)threadIdx.x < sh.chunk;
-        gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
+        gpath[p] = P.path_list ? P.path_list[live[p] ? lpath[p] : 0] : sh.path_begin + (live[p] ? lpath[p] : 0);
         ns[p].init(rng, (unsigned long long)gpath[p]);
         st[p].r = mp.r0; st[p].logB = T::zero(); st[p].y = mp.y0; st[p].logBl = T::zero();
         alive[p] = BERM ? ((1u << P.n_berm) - 1u) : 0u;
@@ -400,8 +405,15 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
                 vals[s * NV + 4 + k] += keep * tan_of(pos, k);
                 vals[s * NV + 4 + NT + k] += keep * tan_of(neg, k);
               }
-              if ((acc_flags & MCRE_ACC_SPILL) && live[p] && s < P.n_sets)
+              if ((acc_flags & MCRE_ACC_SPILL) && live[p] && s < P.n_sets && !P.tan_spill)
                 spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath[p]] = val(unsec);
+              if constexpr (NT > 0) {
+                if (P.tan_spill && live[p] && s < P.n_sets && !pilot) {
+#pragma unroll
+                  for (int k = 0; k < NT; ++k)
+                    P.tan_spill[(((size_t)lpath[p] * P.n_metric + m) * P.n_sets + s) * NT + k] = tan_of(unsec, k);
+                }
+              }
             }
           }
           if ((acc_flags & (MCRE_ACC_POS | MCRE_ACC_NEG)) && !pilot)

@@ -109,9 +109,38 @@ __global__ void select_finish_kernel(int n, const unsigned long long *prefix, do
   if (i < n) out[i] = value_of(prefix[i]);
 }
 
+// smallest local index whose value equals the row's target bit for bit (LLONG_MAX: none here)
+__global__ void __launch_bounds__(256) select_locate_kernel(const double *__restrict__ values, long long row_stride,
+                                                            long long n_local, const double *__restrict__ target,
+                                                            long long *index) {
+  const int row = blockIdx.y;
+  const unsigned long long want = key_of(target[row]);
+  const double *v = values + (size_t)row * row_stride;
+  long long best = 0x7fffffffffffffffll;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (long long)gridDim.x * blockDim.x)
+    if (key_of(v[i]) == want && i < best) best = i;
+  if (best != 0x7fffffffffffffffll) atomicMin(index + row, best);
+}
+
 }  // namespace mcre
 
 using namespace mcre;
+
+extern "C" int mcre_select_locate(const double *d_values, int64_t row_stride, int64_t n_local, int32_t n_rows,
+                                  const double *d_targets, int64_t *d_index, void *stream) {
+  if (!d_targets || !d_index || n_rows <= 0) return fail(-1, "select locate: bad argument%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  MCRE_CUDA(cudaMemsetAsync(d_index, 0x7f, (size_t)n_rows * 8, st));   // 0x7f7f...: larger than any index
+  if (n_local <= 0) return 0;
+  if (!d_values) return fail(-1, "select locate: null values%s", "");
+  long long bx = (n_local + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (long long)sm_count() * 16 / n_rows + 1;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)n_rows);
+  select_locate_kernel<<<grid, 256, 0, st>>>(d_values, row_stride, n_local, d_targets, (long long *)d_index);
+  MCRE_LAUNCHED();
+  return 0;
+}
 
 struct mcre_select_plan {
   int n_rows, R;

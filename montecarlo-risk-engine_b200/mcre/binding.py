@@ -63,7 +63,7 @@ SYMBOLS = [
     "mcre_generate_paths",
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim", "mcre_irc_presim_tangent_slots",
-    "mcre_irc_set_coefficients", "mcre_irc_mainsim",
+    "mcre_irc_set_coefficients", "mcre_irc_mainsim", "mcre_irc_set_path_replay", "mcre_select_locate",
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_step_tangents",
     "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
@@ -103,6 +103,8 @@ def lib():
     L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
     L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_irc_set_path_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_select_locate.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_irc_set_exercise_coefficients.argtypes = [C.c_void_p, c_dp, c_dp, C.c_void_p]
     L.mcre_irc_lsm_scratch_bytes.restype = C.c_int64
     L.mcre_irc_lsm_scratch_bytes.argtypes = [C.c_void_p, C.c_int64]

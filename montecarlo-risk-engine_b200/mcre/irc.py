@@ -617,6 +617,42 @@ class IrcBackend:
         coef, dcoef = out if with_tan else (out, None)
         return coef, reg_times, basis, dcoef
 
+    def _pfe_sensitivities(self, plan, quant, spill, begin, count, n_main, n_metric, n_sets, inject, dev):
+        """Gradient of the PFE order statistics: the reference differentiates torch.sort(...)[index]
+        (pfe_metric.py:59-71), i.e. the pathwise gradient of the selected path.  The selected paths are located
+        in the spilled exposures (smallest global path id among ties, whose tangents agree anyway), replayed with
+        tangents on every rank (Philox is counter based) and their unsecured-exposure tangents picked per date."""
+        L = B.lib()
+        for q, (vals, tans) in ((q, quant[0][q]) for q in list(quant[0])):
+            targets = torch.tensor([[quant[r][q][0][m][0] for m in range(n_metric)] for r in range(n_sets)],
+                                   dtype=torch.float64, device=dev).reshape(-1)
+            index = torch.empty(n_sets * n_metric, dtype=torch.int64, device=dev)
+            B.check(L.mcre_select_locate(spill.data_ptr(), spill.stride(1), count, n_sets * n_metric, targets.data_ptr(),
+                                         index.data_ptr(), RT.stream_ptr()))
+            gidx = torch.where(index < count, index + begin, torch.full_like(index, torch.iinfo(torch.int64).max))
+            _, world = RT.dist_info()
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(gidx, op=dist.ReduceOp.MIN)
+            paths, inverse = torch.unique(gidx, return_inverse=True)
+            n_list = int(paths.numel())
+            tan = torch.zeros((n_list, n_metric, n_sets, self.nt), dtype=torch.float64, device=dev)
+            B.check(L.mcre_irc_set_path_replay(plan, paths.data_ptr(), tan.data_ptr()))
+            try:
+                slots = L.mcre_irc_main_slots(plan)
+                acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                partial = torch.empty(L.mcre_irc_partial_bytes(plan, n_list, CHUNK_PATHS, 0) // 8 + 1, dtype=torch.float64, device=dev)
+                rng = self._rng(43, inject, n_main)
+                sh = B.Shard(0, n_list, CHUNK_PATHS)
+                B.check(L.mcre_irc_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                           shift.data_ptr(), None, RT.stream_ptr()))
+            finally:
+                B.check(L.mcre_irc_set_path_replay(plan, None, None))
+            tan_h, inv_h = tan.cpu().numpy(), inverse.cpu().numpy().reshape(n_sets, n_metric)
+            for r in range(n_sets):
+                quant[r][q] = (quant[r][q][0], [tan_h[inv_h[r, m], m, r, :] for m in range(n_metric)])
+
     def run(self):
         c = self.c
         dev = RT.compute_device()
@@ -720,6 +756,8 @@ class IrcBackend:
                 if spill is not None:
                     from mcre.select import order_statistics
                     quant = order_statistics(c, spill, count, n_main)
+                    if self.nt:
+                        self._pfe_sensitivities(plan, quant, spill, begin, count, n_main, n_metric, len(idxs), inject, dev)
             finally:
                 L.mcre_irc_destroy(plan)
             ns_t = 1 if len(idxs) <= 1 else (2 if len(idxs) <= 2 else 4)

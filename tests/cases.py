@@ -169,6 +169,7 @@ GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
     "wwr_cva_greeks": (wwr_cva, dict(rho=0.5, n_expo=11, maturity=2.5), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=True)),
+    "irs_collateral_greeks": (vasicek_irs_collateral, dict(mpor=0.25, threshold=0.002, n_dates=9, maturity=2.0), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=True)),
     "cva_deterministic": (wwr_cva, dict(rho=0.0, deterministic=True, n_expo=21, maturity=5.0), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
     "irs_collateral": (vasicek_irs_collateral, dict(mpor=0.25), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="EULER", differentiate=False)),
     "irs_collateral_offgrid": (vasicek_irs_collateral, dict(mpor=10 / 252, threshold=0.005), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="EULER", differentiate=False)),

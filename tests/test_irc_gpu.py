@@ -88,14 +88,16 @@ def _derivative_rows(res, s, m):
     return np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives(s, m)])
 
 
-def test_exposure_metric_greeks_through_the_regression_match_reference_golden():
+@pytest.mark.parametrize("name", ["wwr_cva_greeks", "irs_collateral_greeks"])
+def test_exposure_metric_greeks_through_the_regression_match_reference_golden(name):
     """CVA / EPE / PV sensitivities with differentiate=True.  The reference keeps the regression
     coefficients in the autograd graph (controller.py:118-119, 368-383), so CVA and EPE Greeks contain
     d(coefficients)/d(parameters): the tangent pre-simulation (csrc/irc_tan.cu) + the differentiated normal
     equations (mcre/lsm.py:regression_tangents) reproduce it.  Injected reference draws; tolerance 2e-5
     against the reference's autograd (its backward runs through float32 accumulators, SURVEY A-19) and
-    1e-7 against the oracle's forward-mode duals (same float64 tangents)."""
-    name = "wwr_cva_greeks"
+    1e-7 against the oracle's forward-mode duals (same float64 tangents).  The second case has two netting sets
+    (threshold, MPoR collateral) and the full metric list incl. PFE, whose gradient is the pathwise gradient of the
+    selected path (path replay)."""
     gold = helpers.load_golden(name)
     res, sc = helpers.run_cuda(name, draws="torch")
     flat = helpers.flatten_results(res)
@@ -121,7 +123,7 @@ def test_exposure_metric_greeks_match_oracle(which):
     ns = cases.Namespace()
     if which == "vasicek_collateral":
         model, sets, metrics, tl = cases.vasicek_irs_collateral(ns, mpor=0.25, threshold=0.002, n_dates=9, maturity=2.0)
-        metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.EEPEMetric()]
+        metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.EEPEMetric(), ns.PFEMetric(0.9)]   # PFE: path replay
         n = 3000
     else:
         model, sets, metrics, tl = cases.wwr_cva(ns, rho=-0.4, n_expo=9, maturity=2.0)

@@ -75,7 +75,7 @@ def test_bermudan_swaption_exposure_greeks_match_oracle():
     from oracle import risk
     ns = cases.Namespace()
     model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=6)
-    metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric()]
+    metrics = [ns.PVMetric(), ns.EPEMetric(), ns.ENEMetric(), ns.PFEMetric(0.95)]
     n = 2500
     sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.EULER, True)
     res = sc.run_simulation()
