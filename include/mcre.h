@@ -458,6 +458,12 @@ int mcre_select_begin(mcre_select_plan *p, const int64_t *ranks, void *stream);
 /* one pass = count (fills d_hist [n_rows][n_ranks_per_row][256] uint64) then scan. */
 int mcre_select_count(mcre_select_plan *p, const double *d_values, int64_t row_stride, int64_t n_local,
                       int32_t pass, uint64_t *d_hist, void *stream);
+/* Optional shortcut after `passes_done` >= 2 count + scan rounds: compacts, per row, the elements that still match
+ * one of the row's prefixes; later mcre_select_count calls read those instead of the full rows (rows with more
+ * than n_local / 8 candidates keep reading everything).  Exact: only elements that cannot be a wanted order
+ * statistic are dropped. */
+int mcre_select_compact(mcre_select_plan *plan, const double *d_values, int64_t row_stride, int64_t n_local,
+                        int32_t passes_done, void *stream);
 int mcre_select_scan(mcre_select_plan *p, int32_t pass, const uint64_t *d_hist, void *stream);
 /* after 8 passes: d_out [n_rows][n_ranks_per_row] the selected values. */
 int mcre_select_finish(mcre_select_plan *p, double *d_out, void *stream);

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) irc_presim_forward_kernel(IrcDev P, RngDe
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
     irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) irc_lsm_forward_kernel(IrcDev P, RngDev r
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
     irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }

@@ -73,7 +73,9 @@ struct IrcParams {
 // One sub-step of the joint model (src/models/vasicek.py:52-112, cirpp.py:155-198,
 // model_config.py:223-276).  z0/z1 are the independent draws; the correlated noise is
 // z @ L^T with L the lower Cholesky factor (model.py:46-48).
-template <typename R, bool CIR, int SCHEME>
+// STEP_CIR = false: the credit factor is not advanced (the pre-simulations of rate products only read the short
+// rate and the numeraire; its normal is still drawn so that the streams stay aligned).
+template <typename R, bool CIR, int SCHEME, bool STEP_CIR = CIR>
 __device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR> &mp, IrcState<R> &s, int is,
                                          double z0, double z1) {
   typedef RealTraits<R> T;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR
     const R theta_t = T::load(P.step_vas, is * 2 + 0);  // mean level at t1 (constant for Vasicek)
     s.r = s.r + mp.a * (theta_t - s.r) * dt + mp.sigma * sq * wv;
   }
-  if (CIR) {
+  if (CIR && STEP_CIR) {
     const R wc = (P.cir_noise == 1) ? w1 : w0;
     if (P.cir_det) {
       R lam1 = T::load(P.step_cir, is * 2 + 0), lam2 = T::load(P.step_cir, is * 2 + 1);

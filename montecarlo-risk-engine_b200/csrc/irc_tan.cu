@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) irc_presim_forward_tan_kernel(IrcDev P, R
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
     irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) irc_lsm_forward_tan_kernel(IrcDev P, RngD
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
     irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME>(P, mp, st, is, z0, z1);
+    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }

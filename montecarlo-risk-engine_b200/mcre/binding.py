@@ -68,7 +68,7 @@ SYMBOLS = [
     "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
-    "mcre_select_scan", "mcre_select_finish",
+    "mcre_select_scan", "mcre_select_compact", "mcre_select_finish",
     "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
 ]
 

@@ -23,6 +23,7 @@ def select_rows(values, n_local, ranks):
     L.mcre_select_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     L.mcre_select_scan.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.mcre_select_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_select_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     rows, R = ranks.shape
     dev = values.device
     plan = C.c_void_p()
@@ -40,6 +41,9 @@ def select_rows(values, n_local, ranks):
                 import torch.distributed as dist
                 dist.all_reduce(hist)  # integer sum: exact and order independent
             B.check(L.mcre_select_scan(plan, p, hist.data_ptr(), st))
+            if p == 1:
+                # 16 bits fixed: keep only the elements that can still be a wanted order statistic
+                B.check(L.mcre_select_compact(plan, values.data_ptr(), stride, n_local, 2, st))
         out = torch.empty(rows * R, dtype=torch.float64, device=dev)
         B.check(L.mcre_select_finish(plan, out.data_ptr(), st))
         return out.cpu().numpy().reshape(rows, R)
