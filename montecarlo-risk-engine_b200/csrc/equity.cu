@@ -115,8 +115,27 @@ __device__ __forceinline__ R barrier_factor(const R &mx, const R &mn, double bar
   }
 }
 
+// standard normal CDF of a dual number (tangent = density)
+template <int N>
+__device__ __forceinline__ Dual<N> dual_ncdf(const Dual<N> &x) {
+  Dual<N> r;
+  r.v = 0.5 * erfc(-x.v * 0.70710678118654752440);
+  const double pdf = 0.39894228040143267794 * exp(-0.5 * x.v * x.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = pdf * x.d[i];
+  return r;
+}
+
+// Sensitivities of exposure profiles (controller.py:609-627 on EPE / ENE / CE / EEPE): Black-Scholes builds with
+// tangents carry the exposures as duals (lane-local tangents like the cashflows); other models keep doubles.
+template <int KIND, int NT> struct EqExpoTan { static const bool on = (KIND == MCRE_EQ_BS) && (NT > 0); };
+template <bool ON, typename R> struct EqExpoReal { typedef double type; };
+template <typename R> struct EqExpoReal<true, R> { typedef R type; };
+
 // slot layout: [NS][3] = sum(cf - c), sum((cf - c)^2), sum(payoff * d invN / d r)   then
-//              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p
+//              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p             then
+//              [n_metric][NS][4] exposure sums                                          then (exposure tangents on)
+//              [n_metric][A][NS][2][NT] lane-local tangents of sum relu(E), sum -relu(-E)
 template <int KIND, int ALT, int NT, int NS>
 __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
                                                       double *shift, double *spill, int pilot) {
@@ -128,12 +147,17 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
   constexpr int NVH = NS * 3;
   constexpr int NVT = NS * (NT > 0 ? NT : 1);
   constexpr int NVX = NS * 4;                 // exposure values per metric date
-  constexpr int NVMAX = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
+  constexpr bool XT = EqExpoTan<KIND, NT>::on;
+  typedef typename EqExpoReal<XT, R>::type XR;
+  constexpr int NVXT = XT ? NS * 2 * NT : 1;  // exposure tangents per (metric date, asset)
+  constexpr int NVMAX0 = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
+  constexpr int NVMAX = NVMAX0 > NVXT ? NVMAX0 : NVXT;
   extern __shared__ double smem[];
   const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int A = P.n_assets, ppw = 32 / A;
   const int expo_base = NS * 3 + A * NS * NT;
-  const int n_slots = expo_base + P.n_metric * NVX;
+  const int xt_base = expo_base + P.n_metric * NVX;
+  const int n_slots = xt_base + (XT ? P.n_metric * A * NVXT : 0);
   double *acc = smem;                 // [n_slots]
   double *stage = smem + n_slots;     // [2][nw][NVMAX]
   const int g = lane / A, a = lane - g * A, base = g * A;
@@ -181,11 +205,12 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
       R cf[NS], trk_a[NTRK], trk_b[NTRK];
       // Brownian-bridge barriers (value-only builds): previous monitored spot, running no-hit products
       double trk_c[NT == 0 ? NTRK : 1], trk_d[NT == 0 ? NTRK : 1], trk_e[NT == 0 ? NTRK : 1];
-      double numtan[NS], hist[NS][EQ_MAX_LAG];
+      double numtan[NS];
+      XR hist[NS][EQ_MAX_LAG];
 #pragma unroll
       for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int l = 0; l < EQ_MAX_LAG; ++l) hist[s][l] = 0.0;
+        for (int l = 0; l < EQ_MAX_LAG; ++l) hist[s][l] = RealTraits<XR>::zero();
 #pragma unroll
       for (int s = 0; s < NS; ++s) { cf[s] = T::zero(); numtan[s] = 0.0; }
       if constexpr (NT > 0) {   // (value-only builds: every tracker is set by its FIRST event / the loop below)
@@ -219,9 +244,9 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
         }
         if (xe >= 0) {
           const double Sv = val(spot_now());
-          double expo[NS];
+          XR expo[NS];
 #pragma unroll
-          for (int s = 0; s < NS; ++s) expo[s] = 0.0;
+          for (int s = 0; s < NS; ++s) expo[s] = RealTraits<XR>::zero();
           for (int pi = 0; pi < P.n_prod; ++pi) {
             const double *op = P.xp + ((size_t)xe * P.n_prod + pi) * EQ_XP;
             const int xtype = (int)__ldg(op);
@@ -253,28 +278,44 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
               continue;
             }
             const double wgt = __ldg(P.prod_w + (size_t)pi * A + aa);
+            XR vx = RealTraits<XR>::zero();
             if (wgt != 0.0) {
               // Black-Scholes value of the remaining option at (S_t, T - t), over the numeraire
               // (european_option.py:70-100, 123-145); evaluated on the lane that owns the asset
               const double ttm = __ldg(op + 1), K = __ldg(pr + 2), sign = __ldg(pr + 3);
-              const double sigma = val(par[1]), rate = val(par[2]);
-              const double vol_t = sigma * sqrt(ttm);
-              const double d1 = (log(Sv / K) + (rate + 0.5 * sigma * sigma) * ttm) / vol_t, d2 = d1 - vol_t;
-              const double disc = K * exp(-rate * ttm);
-              const double price = sign > 0.0 ? Sv * 0.5 * erfc(-d1 * 0.70710678118654752440) - disc * 0.5 * erfc(-d2 * 0.70710678118654752440)
-                                              : disc * 0.5 * erfc(d2 * 0.70710678118654752440) - Sv * 0.5 * erfc(d1 * 0.70710678118654752440);
-              v = wgt * price * __ldg(op + 2);
+              if constexpr (XT) {
+                // the same closed form on duals: tangents through the spot, the volatility and the rate (drift,
+                // discounting inside the formula, and the numeraire 1 / N(t): d invN / d r in op[7])
+                const R Sr = spot_now();
+                const R &sg = par[1], &rt = par[2];
+                const R vol_t = sg * sqrt(ttm);
+                const R d1 = (r_log(Sr / K) + (rt + 0.5 * sg * sg) * ttm) / vol_t, d2 = d1 - vol_t;
+                const R disc = r_exp(-(rt * ttm)) * K;
+                const R price = sign > 0.0 ? Sr * dual_ncdf(d1) - disc * dual_ncdf(d2)
+                                           : disc * dual_ncdf(-d2) - Sr * dual_ncdf(-d1);
+                vx = price * (wgt * __ldg(op + 2));
+                vx.d[2] += wgt * val(price) * __ldg(op + 7);
+              } else {
+                const double sigma = val(par[1]), rate = val(par[2]);
+                const double vol_t = sigma * sqrt(ttm);
+                const double d1 = (log(Sv / K) + (rate + 0.5 * sigma * sigma) * ttm) / vol_t, d2 = d1 - vol_t;
+                const double disc = K * exp(-rate * ttm);
+                const double price = sign > 0.0 ? Sv * 0.5 * erfc(-d1 * 0.70710678118654752440) - disc * 0.5 * erfc(-d2 * 0.70710678118654752440)
+                                                : disc * 0.5 * erfc(d2 * 0.70710678118654752440) - Sv * 0.5 * erfc(d1 * 0.70710678118654752440);
+                vx = RealTraits<XR>::lift(wgt * price * __ldg(op + 2));
+              }
             }
-            const double tot = group_sum(v, base, A);
+            // value: the group's total; tangents: the part flowing through this lane's asset
+            const XR tot = r_with_value(vx, group_sum(val(vx), base, A));
             const int set = (int)__ldg(pr + 1);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) if (s == set) expo[s] += tot;
+            for (int s = 0; s < NS; ++s) if (s == set) expo[s] = expo[s] + tot;
           }
           if (P.expo_accum) {
             if (live && a == 0 && !pilot) {
 #pragma unroll
               for (int s = 0; s < NS; ++s)
-                if (s < P.n_sets) P.expo_accum[((size_t)s * P.n_expo + xe) * sh.n_paths + lpath] += expo[s];
+                if (s < P.n_sets) P.expo_accum[((size_t)s * P.n_expo + xe) * sh.n_paths + lpath] += val(expo[s]);
             }
             return;   // netting terms and metrics are applied once all launches of the book have added up
           }
@@ -288,22 +329,26 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
         if (P.expo_accum) return;
         if (m >= 0) {
           double vals[NVX];
+          XR xpos[NS], xneg[NS];
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
             const bool coll = s < P.n_sets && (__ldg(P.set_flags + s) & 1);
             const double h = s < P.n_sets ? __ldg(P.set_threshold + s) : 0.0;
             const int lag = coll ? __ldg(P.set_lag + (size_t)s * P.n_metric + m) : -1;
-            auto thr = [h](double x) { return x > h ? x - h : (x < -h ? x + h : 0.0); };   // netting_set.py:48-72
-            double unsec;
+            auto thr = [h](const XR &x) -> XR {    // netting_set.py:48-72
+              return val(x) > h ? x - h : (val(x) < -h ? x + h : RealTraits<XR>::zero());
+            };
+            XR unsec;
             if (coll) {
-              double delayed = 0.0;
+              XR delayed = RealTraits<XR>::zero();
 #pragma unroll
               for (int l = 0; l < EQ_MAX_LAG; ++l) if (l == lag) delayed = hist[s][l];
               unsec = hist[s][0] - thr(delayed);
             } else {
               unsec = thr(hist[s][0]);
             }
-            const double pos = fmax(unsec, 0.0), neg = -fmax(-unsec, 0.0);
+            xpos[s] = r_relu(unsec); xneg[s] = -r_relu(-unsec);
+            const double pos = val(xpos[s]), neg = val(xneg[s]);
             const int sb = expo_base + m * NVX + s * 4;
             if (pilot) { if (threadIdx.x == 0) { shift[sb + 0] = pos; shift[sb + 2] = neg; } }
             const double dp = pos - (pilot ? 0.0 : shift[sb + 0]), dn = neg - (pilot ? 0.0 : shift[sb + 2]);
@@ -311,9 +356,25 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
             vals[s * 4 + 0] = keep * dp; vals[s * 4 + 1] = keep * dp * dp;
             vals[s * 4 + 2] = keep * dn; vals[s * 4 + 3] = keep * dn * dn;
             if ((P.acc_flags & MCRE_ACC_SPILL) && live && a == 0 && s < P.n_sets && !pilot)
-              spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath] = unsec;
+              spill[((size_t)s * P.n_metric + m) * sh.n_paths + lpath] = val(unsec);
           }
           if (!pilot) block_accumulate<NVX>(vals, acc, expo_base + m * NVX, stage, NVMAX, parity);
+          if constexpr (XT) {
+            if (!pilot) {
+              for (int ap = 0; ap < A; ++ap) {
+                const double keep = (live && a == ap) ? 1.0 : 0.0;
+                double tv[NVXT];
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+#pragma unroll
+                  for (int k = 0; k < NT; ++k) {
+                    tv[(s * 2 + 0) * NT + k] = keep * tan_of(xpos[s], k);
+                    tv[(s * 2 + 1) * NT + k] = keep * tan_of(xneg[s], k);
+                  }
+                block_accumulate<NVXT>(tv, acc, xt_base + (m * A + ap) * NVXT, stage, NVMAX, parity);
+              }
+            }
+          }
         }
       };
 
@@ -597,7 +658,12 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (np < 0) return fail(-1, "eq: unknown model kind%s", "");
   if (c->nt != 0 && c->nt != np) return fail(-1, "eq: nt must be 0 or the model's parameter count%s", "");
   if (c->nt != 0 && c->n_sets > 2) return fail(-3, "eq: at most 2 netting sets per launch when tangents are on%s", "");
-  if (c->nt != 0 && c->n_expo > 0) return fail(-4, "eq: sensitivities of exposure profiles are not implemented%s", "");
+  if (c->nt != 0 && c->n_expo > 0) {
+    if (c->kind != MCRE_EQ_BS) return fail(-4, "eq: sensitivities of exposure profiles need a Black-Scholes model%s", "");
+    for (size_t i = 0; i < (size_t)c->n_expo * c->n_prod; ++i)
+      if (c->xp[i * EQ_XP] > 1.0)
+        return fail(-4, "eq: sensitivities of regression-proxy exposures are not implemented%s", "");
+  }
   if (c->corr_mode == 1 && (c->n_assets != 1 || c->noise_dim != 2))
     return fail(-1, "eq: dual Cholesky needs one asset with two noise sources%s", "");
   const bool scheme_ok = (c->kind == MCRE_EQ_HESTON) ? (c->scheme == MCRE_SCHEME_EULER || c->scheme == MCRE_SCHEME_QE)
@@ -698,7 +764,9 @@ static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 
 
 extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
   const int ns = eq_ns_template(p->d.n_sets);
-  return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4;
+  const bool xt = p->d.kind == MCRE_EQ_BS && p->nt > 0;
+  return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4 +
+         (xt ? (int64_t)p->d.n_metric * p->d.n_assets * ns * 2 * p->nt : 0);
 }
 
 template <int KIND, int ALT, int NT, int NS>
@@ -708,8 +776,11 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   const bool presim = d.ps_x != nullptr;
   const int threads = 128, nw = threads / 32;
   constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVX = NS * 4;
-  constexpr int NVMAX = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
-  const int n_slots = NS * 3 + d.n_assets * NS * NT + d.n_metric * NVX;
+  constexpr bool XT = EqExpoTan<KIND, NT>::on;
+  constexpr int NVXT = XT ? NS * 2 * NT : 1;
+  constexpr int NVMAX0 = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
+  constexpr int NVMAX = NVMAX0 > NVXT ? NVMAX0 : NVXT;
+  const int n_slots = NS * 3 + d.n_assets * NS * NT + d.n_metric * NVX + (XT ? d.n_metric * d.n_assets * NVXT : 0);
   const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0) return 0;

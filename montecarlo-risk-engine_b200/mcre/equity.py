@@ -512,8 +512,18 @@ class EquityBackend:
         # ---- exposure profiles ---------------------------------------------------------------
         n_expo = n_metric = acc = 0
         if c.risk_metrics.requires_exposure_profiles():
-            if nt:
-                raise NotImplementedError("sensitivities of exposure profiles are not implemented for equity books")
+            if nt and presim_products is None:
+                # sensitivities of EPE / ENE / CE through the analytic Black-Scholes exposure: tangents in the fused kernel
+                # (csrc/equity.cu, exposure tangents).  The numeraire term lands on the lane-local rate, so every asset
+                # must share the numeraire's rate parameter (BlackScholesModel, BlackScholesMulti).
+                if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
+                    raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
+                                              "model (single or multi-asset)")
+                if any(not c._can_use_analytic_exposure_for_product(p) for p in owners):
+                    raise NotImplementedError("sensitivities of regression-proxy exposures are not implemented for "
+                                              "equity books (analytic Black-Scholes exposures of European options only)")
+                if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
+                    raise NotImplementedError("PFE sensitivities are not implemented for equity books")
             expo_times, metric_times = c.exposure_timeline.tolist(), c.metric_exposure_timeline.tolist()
             n_expo, n_metric = len(expo_times), len(metric_times)
             date_expo = np.full(n_dates, -1, dtype=np.int32)
@@ -524,7 +534,7 @@ class EquityBackend:
                 date_metric[date_idx[tm]] = m
             xp = np.zeros((n_expo, max(len(recs), 1), EQ_XP))
             for e, te in enumerate(expo_times):
-                inv = self._inv_numeraire(te)[0]
+                inv, dinv = self._inv_numeraire(te)
                 for pi, p in enumerate(owners):
                     if presim_products is not None:
                         continue                        # the spill pass evaluates no exposures
@@ -532,6 +542,7 @@ class EquityBackend:
                         ttm = float(p.exercise_date) - te
                         if ttm > 0.0:                   # matured options carry no exposure (european_option.py:129-131)
                             xp[e, pi, :3] = (1.0, ttm, inv)
+                            xp[e, pi, 7] = dinv             # d (1 / N(t)) / d rate, for the exposure tangents
                     elif is_equity_exercise(p):
                         coef, basis = self.exercise_expo_coef[id(p)]     # [n_expo, rights, 3], [n_expo, 2]
                         if np.any(coef[e] != 0.0):
@@ -867,6 +878,8 @@ class EquityBackend:
         n = max(count, 1)
         n_chunks = (n + chunk - 1) // chunk
         need_expo = c.risk_metrics.requires_exposure_profiles()
+        if need_expo and self.nt:
+            raise NotImplementedError("sensitivities of exposure profiles of books split over several launches")
         kinds = {m.metric_type for m in c.risk_metrics.metrics}
         n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
         accum = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -1013,8 +1026,25 @@ class EquityBackend:
             head = acc_h[:ns_t * 3].reshape(ns_t, 3)
             expo_base = ns_t * 3 + self.A * ns_t * self.nt
             tang = acc_h[ns_t * 3:expo_base].reshape(self.A, ns_t, self.nt) if self.nt else None
-            xacc = acc_h[expo_base:].reshape(n_metric, ns_t, 4)
-            xshift = shift_h[expo_base:].reshape(n_metric, ns_t, 4)
+            xt_base = expo_base + n_metric * ns_t * 4
+            xacc = acc_h[expo_base:xt_base].reshape(n_metric, ns_t, 4)
+            xshift = shift_h[expo_base:xt_base].reshape(n_metric, ns_t, 4)
+            # exposure tangents [metric date][asset][set][pos / neg][lane-local parameter] (Black-Scholes builds)
+            xtan = None
+            if self.nt and n_metric and self.kind == EQ_BS:
+                xtan = acc_h[xt_base:].reshape(n_metric, self.A, ns_t, 2, self.nt)
+
+            def expo_grads(r, which):
+                if xtan is None:
+                    return [None] * n_metric
+                out = []
+                for m in range(n_metric):
+                    g = np.zeros(n_params)
+                    for a, asset in enumerate(self.assets):
+                        for k, gi in enumerate(asset.gmap):
+                            g[gi] += xtan[m, a, r, which, k] / n_main
+                    out.append(g)
+                return out
             for r, si in enumerate(idxs):
                 pv = mean_and_error(head[r, 0], head[r, 1], shift_h[r], n_main)
                 grad = None
@@ -1028,10 +1058,10 @@ class EquityBackend:
                 res = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
                 if info["acc"] & B.ACC_POS:
                     res["pos"] = ([mean_and_error(xacc[m, r, 0], xacc[m, r, 1], xshift[m, r, 0], n_main) for m in range(n_metric)],
-                                  [None] * n_metric)
+                                  expo_grads(r, 0))
                 if info["acc"] & B.ACC_NEG:
                     res["neg"] = ([mean_and_error(xacc[m, r, 2], xacc[m, r, 3], xshift[m, r, 2], n_main) for m in range(n_metric)],
-                                  [None] * n_metric)
+                                  expo_grads(r, 1))
                 if quant is not None:
                     res["pfe"] = quant[r]
                 results[si] = res

@@ -165,6 +165,27 @@ def mixed_book(ns_module, exposure=True):
     return model, sets, [m.PVMetric()], None
 
 
+def bs_exposure_greeks(ns_module, multi=True):
+    """EPE / PV sensitivities of European options through the analytic Black-Scholes exposure
+    (european_option.py:123-145, controller.py:609-627; the shape of tests/exposure_tests/eepe_simulation.py with the
+    metric set that keeps the analytic branch): thresholded and MPoR-collateralised netting sets."""
+    m = ns_module
+    if multi:
+        ids = ["asset_1", "asset_2"]
+        model = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                    volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    else:
+        ids = ["asset", "asset"]
+        model = m.BlackScholesModel(0.0, 100.0, 0.05, 0.2, asset_id="asset")
+
+    def book():
+        return [m.EuropeanOption(m.Equity(ids[0]), 1.0, 95.0, m.OptionType.CALL, asset_id=ids[0]),
+                m.EuropeanOption(m.Equity(ids[1]), 1.5, 110.0, m.OptionType.PUT, asset_id=ids[1])]
+    sets = [m.NettingSet(name="thresholded", products=book(), threshold=12.0),
+            m.NettingSet(name="collateralised", products=book(), margin_period_of_risk=0.25, threshold=1.0)]
+    return model, sets, [m.PVMetric(), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -186,6 +207,8 @@ GOLDEN_CASES = {
     "flexicall_exposure": (flexicall_bs, dict(exposure=True), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "mixed_book_pv": (mixed_book, dict(exposure=False), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "mixed_book_exposure": (mixed_book, dict(exposure=True), dict(n_main=512, n_pre=512, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "bs_exposure_greeks": (bs_exposure_greeks, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
+    "bs_exposure_greeks_euler": (bs_exposure_greeks, dict(multi=False), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
 }
 

@@ -15,7 +15,7 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 EQ_CASES = ["bs_european", "bs_european_euler", "heston_european", "heston_european_greeks",
-            "heston_path_dependent", "bs_basket", "bs_basket_euler"]
+            "heston_path_dependent", "bs_basket", "bs_basket_euler", "bs_exposure_greeks", "bs_exposure_greeks_euler"]
 RTOL = 1e-10
 
 
@@ -60,10 +60,10 @@ def test_philox_matches_oracle_and_reference_statistically(name):
     if gold["run"]["differentiate"]:
         for si, s in enumerate(gold["sets"]):
             for mi, m in enumerate(gold["metrics"]):
-                want = out["grads"][si][mi][0]
-                got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, m)[0]])
-                helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))),
-                                     f"{name} {s}|{m} philox derivatives")
+                for ev, want in enumerate(out["grads"][si][mi]):      # every evaluation (metric date) of the metric
+                    got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, m)[ev]])
+                    helpers.assert_close(got, want, 1e-7, 1e-7 * max(1.0, float(np.max(np.abs(want)))),
+                                         f"{name} {s}|{m}[{ev}] philox derivatives")
 
 
 def _run(ns, model, sets, metrics, n, steps, scheme, differentiate=False):
