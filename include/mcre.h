@@ -389,6 +389,19 @@ int mcre_sum_stats(const double *d_x, int64_t n, int32_t n_rows, int32_t chunk_p
  * (product, date) then go through mcre_lsm_step without an exercise update. */
 int mcre_eq_presim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                    double *d_shift, double *d_x, float *d_cf, void *stream);
+/* Sensitivities of exposure profiles of equity books (controller.py:609-627 on EPE / ENE / CE / EEPE; Black-Scholes
+ * plans with nt = 3).  The accumulator gains [n_metric][n_assets][NS][2][nt] lane-local tangents of sum relu(E) and
+ * sum -relu(-E) after the exposure sums (counted by mcre_eq_slots).  Analytic Black-Scholes exposures
+ * (european_option.py:123-145) need nothing else; regression proxies need the tangents of their coefficients:
+ *  - mcre_eq_presim_tangents: the pre-simulation spill pass on a plan with tangents also writes
+ *    d_dx [n_expo][n_assets][nt][n_paths] and d_dcf [n_prod][nt][n_paths] (tangents of the spots and of the deflated
+ *    cashflows with respect to the parameters of the product's asset), which feed mcre_lsm_step_tangents;
+ *  - mcre_eq_set_exposure_coef_tangents: host xp_tan [n_expo][n_prod][3][nt], d(c0, c1, c2)/d(lane parameters) from the
+ *    differentiated normal equations (the reference keeps torch.linalg.lstsq in the autograd graph,
+ *    controller.py:368-383); copied to the device. */
+int mcre_eq_presim_tangents(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                            double *d_shift, double *d_x, float *d_cf, double *d_dx, double *d_dcf, void *stream);
+int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *plan, const double *xp_tan);
 
 /* ================================================================================
  * Longstaff-Schwartz backward induction on spilled pre-simulation arrays: one call per

@@ -73,6 +73,12 @@ struct EqDev {
   // launch's products is ADDED to expo_accum [n_sets][n_expo][n_paths]; netting terms / metrics are applied
   // afterwards by mcre_eq_unsecured_exposures + mcre_sum_stats
   double *expo_accum;
+  // tangent builds (Black-Scholes): tangents of the regression-proxy coefficients with respect to the lane-local
+  // parameters of the product's asset, [n_expo][n_prod][3 coefficients][nt] (mcre_eq_set_exposure_coef_tangents),
+  // and the tangent spill of the pre-simulation pass (mcre_eq_presim_tangents): ps_dx [n_expo][A][nt][n_paths],
+  // ps_dcf [n_prod][nt][n_paths] (f64: the reference's float32 rounding touches values only under autograd's chain)
+  const double *xp_tan;
+  double *ps_dx, *ps_dcf;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -239,7 +245,16 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
         if (P.n_expo == 0) return;
         const int xe = __ldg(P.date_expo + di), m = P.ps_x ? -1 : __ldg(P.date_metric + di);
         if (xe >= 0 && P.ps_x) {
-          if (live) P.ps_x[((size_t)xe * A + a) * sh.n_paths + lpath] = val(spot_now());
+          if (live) {
+            const R Sp = spot_now();
+            P.ps_x[((size_t)xe * A + a) * sh.n_paths + lpath] = val(Sp);
+            if constexpr (NT > 0) {
+              if (P.ps_dx) {
+#pragma unroll
+                for (int k = 0; k < NT; ++k) P.ps_dx[(((size_t)xe * A + a) * NT + k) * sh.n_paths + lpath] = tan_of(Sp, k);
+              }
+            }
+          }
           return;     // pre-simulation pass: no exposures, no metrics
         }
         if (xe >= 0) {
@@ -263,6 +278,30 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
                 const int slot = (int)__ldg(pr + 14);
 #pragma unroll
                 MCRE_TRK_FOR(k, slot) st = (int)val(trk_a[k]);
+              }
+              if constexpr (XT) {
+                if (xtype == 2 && P.xp_tan) {
+                  // the same quadratic on duals: tangents through the spot, the fitted coefficients (differentiated
+                  // normal equations of the pre-simulation, mcre/lsm.py:regression_tangents) and the numeraire
+                  XR vq = RealTraits<XR>::zero();
+                  if (xw != 0.0) {
+                    const R uq = (spot_now() - __ldg(op + 5)) * __ldg(op + 6);
+                    R q0 = T::lift(__ldg(op + 1)), q1 = T::lift(__ldg(op + 3)), q2 = T::lift(__ldg(op + 4));
+                    const double *ct = P.xp_tan + ((size_t)xe * P.n_prod + pi) * 3 * NT;
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) {
+                      q0.d[k] = __ldg(ct + k); q1.d[k] = __ldg(ct + NT + k); q2.d[k] = __ldg(ct + 2 * NT + k);
+                    }
+                    const R poly = q0 + uq * (q1 + uq * q2);
+                    vq = poly * __ldg(op + 2);
+                    vq.d[2] += val(poly) * __ldg(op + 7);
+                  }
+                  const XR totq = r_with_value(vq, group_sum(val(vq), base, A));
+                  const int setq = (int)__ldg(pr + 1);
+#pragma unroll
+                  for (int s = 0; s < NS; ++s) if (s == setq) expo[s] = expo[s] + totq;
+                  continue;
+                }
               }
               if (xw != 0.0 && st > 0) {
                 const double u = (Sv - __ldg(op + 5)) * __ldg(op + 6);
@@ -514,6 +553,15 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
           }
           const double invN = __ldg(pr + 4), dinvN = __ldg(pr + 5);
           if (P.ps_cf && live && a == 0) P.ps_cf[(size_t)pi * sh.n_paths + lpath] = (float)(val(pay) * invN);
+          if constexpr (NT > 0) {
+            // tangents of the deflated cashflow with respect to the parameters of the product's asset, written by
+            // the lane that owns it (single-asset products; index 2 = the rate also carries the numeraire term)
+            if (P.ps_dcf && live && __ldg(P.prod_x + (size_t)pi * A + aa) != 0.0) {
+#pragma unroll
+              for (int k = 0; k < NT; ++k)
+                P.ps_dcf[((size_t)pi * NT + k) * sh.n_paths + lpath] = tan_of(pay, k) * invN + (k == 2 ? val(pay) * dinvN : 0.0);
+            }
+          }
 #pragma unroll
           for (int s = 0; s < NS; ++s)
             if (s == set) { cf[s] = cf[s] + pay * invN; numtan[s] += val(pay) * dinvN; }
@@ -648,6 +696,8 @@ struct mcre_eq_plan {
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
   DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src;
   DevArray<double> xp, set_threshold, sp_coef;
+  double *xp_tan = nullptr;   // own allocation (set after mcre_eq_create)
+  bool has_proxy = false;     // some exposure is a regression proxy (type 2)
 };
 
 extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
@@ -661,8 +711,8 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (c->nt != 0 && c->n_expo > 0) {
     if (c->kind != MCRE_EQ_BS) return fail(-4, "eq: sensitivities of exposure profiles need a Black-Scholes model%s", "");
     for (size_t i = 0; i < (size_t)c->n_expo * c->n_prod; ++i)
-      if (c->xp[i * EQ_XP] > 1.0)
-        return fail(-4, "eq: sensitivities of regression-proxy exposures are not implemented%s", "");
+      if (c->xp[i * EQ_XP] > 2.0)
+        return fail(-4, "eq: sensitivities of the exposures of exercise products are not implemented%s", "");
   }
   if (c->corr_mode == 1 && (c->n_assets != 1 || c->noise_dim != 2))
     return fail(-1, "eq: dual Cholesky needs one asset with two noise sources%s", "");
@@ -680,6 +730,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   mcre_eq_plan *p = new mcre_eq_plan();
   ArenaScope arena_scope(&p->arena);
   p->nt = c->nt;
+  for (size_t i = 0; c->n_expo > 0 && i < (size_t)c->n_expo * c->n_prod; ++i) p->has_proxy = p->has_proxy || c->xp[i * EQ_XP] == 2.0;
   const int A = c->n_assets, d = c->noise_dim, n_ev = c->date_ev_off[c->n_dates];
   int rc = 0;
 #define UP(field, host, count) if (!rc) rc = p->field.upload(host, (size_t)(count))
@@ -728,6 +779,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (rc) { mcre_eq_destroy(p); return rc; }
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
+  D.xp_tan = nullptr; D.ps_dx = nullptr; D.ps_dcf = nullptr;
   D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
@@ -757,7 +809,19 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->date_expo.release(); p->date_metric.release(); p->set_flags.release(); p->set_lag.release();
   p->xp.release(); p->set_threshold.release(); p->sp_coef.release(); p->sp_src.release();
   p->arena.release();
+  if (p->xp_tan) cudaFree(p->xp_tan);
   delete p;
+}
+
+extern "C" int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *p, const double *xp_tan) {
+  if (!p || !xp_tan) return fail(-1, "null argument%s", "");
+  if (p->nt <= 0 || p->d.kind != MCRE_EQ_BS || p->d.n_expo <= 0)
+    return fail(-4, "eq: coefficient tangents need a Black-Scholes plan with tangents and exposure dates%s", "");
+  const size_t n = (size_t)p->d.n_expo * p->d.n_prod * 3 * p->nt;
+  if (!p->xp_tan) MCRE_CUDA(cudaMalloc((void **)&p->xp_tan, n * sizeof(double)));
+  MCRE_CUDA(cudaMemcpy(p->xp_tan, xp_tan, n * sizeof(double), cudaMemcpyHostToDevice));
+  p->d.xp_tan = p->xp_tan;
+  return 0;
 }
 
 static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 2 : 4); }
@@ -825,6 +889,8 @@ extern "C" int mcre_eq_mainsim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_
   if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
   if (p->d.n_expo > 0 && (p->d.acc_flags & MCRE_ACC_SPILL) && !d_spill && !p->d.ps_x && !p->d.expo_accum)
     return fail(-1, "spill requested but d_spill is null%s", "");
+  if (p->nt > 0 && p->has_proxy && !p->d.xp_tan && !p->d.ps_x)
+    return fail(-1, "eq: plan with tangents and regression-proxy exposures: call mcre_eq_set_exposure_coef_tangents first%s", "");
   if (rng->mode == MCRE_RNG_INJECT && p->d.kind == MCRE_EQ_HESTON && p->d.scheme == MCRE_SCHEME_QE && !rng->d_u)
     return fail(-1, "inject mode: QE needs uniforms%s", "");
   RngDev r = make_rng(rng);
@@ -917,6 +983,17 @@ extern "C" int mcre_eq_set_pv_accumulator(mcre_eq_plan *p, double *d_accum) {
   if (!p) return fail(-1, "null argument%s", "");
   p->d.pv_accum = d_accum;
   return 0;
+}
+
+extern "C" int mcre_eq_presim_tangents(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
+                                       double *d_shift, double *d_x, float *d_cf, double *d_dx, double *d_dcf, void *stream) {
+  if (!p || !rng || !d_partial || !d_shift || !d_x || !d_cf || !d_dx || !d_dcf) return fail(-1, "null argument%s", "");
+  if (p->nt <= 0 || p->d.kind != MCRE_EQ_BS) return fail(-4, "eq presim tangents: Black-Scholes plans with tangents only%s", "");
+  if (p->d.n_expo <= 0) return fail(-1, "eq presim: the plan has no exposure dates%s", "");
+  p->d.ps_x = d_x; p->d.ps_cf = d_cf; p->d.ps_dx = d_dx; p->d.ps_dcf = d_dcf;
+  const int rc = mcre_eq_mainsim(p, rng, shard, d_partial, d_partial /* scratch: sums are not used */, d_shift, nullptr, stream);
+  p->d.ps_x = nullptr; p->d.ps_cf = nullptr; p->d.ps_dx = nullptr; p->d.ps_dcf = nullptr;
+  return rc;
 }
 
 extern "C" int mcre_eq_presim(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,

@@ -188,6 +188,7 @@ class EquityBackend:
         self.exercise_coef = {}        # id(product) -> (coef [n_ex, rights, 3] standardised basis, basis [n_ex, 2])
         self.exercise_expo_coef = {}   # id(product) -> (coef [n_expo, rights, 3], basis [n_expo, 2]) per exposure date
         self.expo_coef = {}       # id(product) -> (coef [n_expo, 3] standardised basis, basis [n_expo, 2])
+        self.expo_dcoef = {}      # id(product) -> d coef / d (lane parameters of the product's asset) [n_expo, nt, 3]
         subs = _sub_models(ctrl.model)
         num_idx = ctrl.model.id_to_model["numeraire"] if isinstance(ctrl.model, ModelConfig) else 0
         self.num_model = subs[num_idx]
@@ -376,12 +377,12 @@ class EquityBackend:
             step_chol.append(seen[key])
         return 1, None, chol_dual, step_chol
 
-    def lower(self, set_indices, presim_products=None, subset=None):
+    def lower(self, set_indices, presim_products=None, subset=None, presim_tangents=False):
         """Plan of the main pass for a group of netting sets, or (presim_products given) of the
         pre-simulation spill pass for a group of products (all in one dummy set).  `subset`: ids of the
         products to keep (book splitting: one launch evaluates a part of a large netting set)."""
         c, nt, A = self.c, self.nt, self.A
-        if presim_products is not None:
+        if presim_products is not None and not presim_tangents:
             nt = 0
         grid = build_time_grid(self.assets[0].model.t0(), c.simulation_timeline.tolist(), c.num_steps)
         dates = grid.dates
@@ -519,9 +520,13 @@ class EquityBackend:
                 if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
                     raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
                                               "model (single or multi-asset)")
-                if any(not c._can_use_analytic_exposure_for_product(p) for p in owners):
-                    raise NotImplementedError("sensitivities of regression-proxy exposures are not implemented for "
-                                              "equity books (analytic Black-Scholes exposures of European options only)")
+                for p in owners:
+                    if c._can_use_analytic_exposure_for_product(p):
+                        continue
+                    if is_equity_exercise(p) or id(p) not in self.expo_dcoef:
+                        raise NotImplementedError("sensitivities of exposure profiles of equity books: European "
+                                                  "options (analytic exposure) and single-asset products that pay once "
+                                                  "(regression proxy); not exercise products or baskets")
                 if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
                     raise NotImplementedError("PFE sensitivities are not implemented for equity books")
             expo_times, metric_times = c.exposure_timeline.tolist(), c.metric_exposure_timeline.tolist()
@@ -533,6 +538,7 @@ class EquityBackend:
             for m, tm in enumerate(metric_times):
                 date_metric[date_idx[tm]] = m
             xp = np.zeros((n_expo, max(len(recs), 1), EQ_XP))
+            xp_tan = np.zeros((n_expo, max(len(recs), 1), 3, max(nt, 1))) if (nt and presim_products is None) else None
             for e, te in enumerate(expo_times):
                 inv, dinv = self._inv_numeraire(te)
                 for pi, p in enumerate(owners):
@@ -552,7 +558,9 @@ class EquityBackend:
                     else:
                         coef, basis = self.expo_coef[id(p)]
                         if np.any(coef[e] != 0.0):
-                            xp[e, pi, :8] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], 0.0)
+                            xp[e, pi, :8] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], dinv)
+                            if xp_tan is not None:
+                                xp_tan[e, pi] = self.expo_dcoef[id(p)][e].T      # [nt, 3] -> [3, nt]
             kinds = {m.metric_type for m in c.risk_metrics.metrics}
             if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
                 acc |= B.ACC_POS
@@ -582,7 +590,7 @@ class EquityBackend:
             desc.set_flags, desc.set_lag = ip("set_flags", set_flags), ip("set_lag", set_lag)
         desc.n_expo, desc.n_metric, desc.acc_flags = n_expo, n_metric, acc
         info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs, n_metric=n_metric, acc=acc,
-                    bridge=bridge)
+                    bridge=bridge, xp_tan=xp_tan if (n_expo and presim_products is None) else None)
         return desc, t, info
 
     # ------------------------------------------------------------------ execution
@@ -771,10 +779,22 @@ class EquityBackend:
         n_chunks = (n + CHUNK_PATHS - 1) // CHUNK_PATHS
         xs = torch.zeros((n_expo, A, n), dtype=torch.float64, device=dev)
         cfs = {}
+        # sensitivities through the regression (differentiate=True): the spill pass runs on a plan with tangents and
+        # also writes the tangents of spots and deflated cashflows; the normal equations are differentiated below
+        nt = self.nt
+        if nt:
+            if self.kind != EQ_BS:
+                raise NotImplementedError("sensitivities of regression-proxy exposures: Black-Scholes models only")
+            for p in products:
+                ids = set(getattr(p, "asset_ids", None) or [])
+                if len(ids) > 1 or getattr(p, "basket", None) is not None:
+                    raise NotImplementedError("sensitivities of regression-proxy exposures: single-asset products only")
+            dxs = torch.zeros((n_expo, A, nt, n), dtype=torch.float64, device=dev)
+            dcfs = {}
         groups, cur, trk = [], [], 0
         for p in products:
             t = int(_is_path_dependent(p))
-            if cur and trk + t > eq_ntrk(0):
+            if cur and trk + t > eq_ntrk(nt):
                 groups.append(cur)
                 cur, trk = [], 0
             cur.append(p)
@@ -783,12 +803,13 @@ class EquityBackend:
             groups.append(cur)
         inj = c.injected_normals.get("pre") if c.injected_normals else None
         for group in groups:
-            desc, keep, info = self.lower([], presim_products=group)
+            desc, keep, info = self.lower([], presim_products=group, presim_tangents=bool(nt))
             plan = C.c_void_p()
             B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
             try:
                 slots = L.mcre_eq_slots(plan)
                 cf = torch.zeros((len(group), n), dtype=torch.float32, device=dev)
+                dcf = torch.zeros((len(group), nt, n), dtype=torch.float64, device=dev) if nt else None
                 partial = torch.empty(n_chunks * slots + slots + 1, dtype=torch.float64, device=dev)
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 rng = B.Rng()
@@ -804,12 +825,19 @@ class EquityBackend:
                     rng.mode = B.RNG_PHILOX
                 keep_bridge = self._set_bridge_uniforms(plan, info, "pre", n_pre, dev)
                 sh = B.Shard(begin, count, CHUNK_PATHS)
-                B.check(L.mcre_eq_presim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
-                                         xs.data_ptr(), cf.data_ptr(), RT.stream_ptr()))
+                if nt:
+                    B.check(L.mcre_eq_presim_tangents(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
+                                                      xs.data_ptr(), cf.data_ptr(), dxs.data_ptr(), dcf.data_ptr(),
+                                                      RT.stream_ptr()))
+                else:
+                    B.check(L.mcre_eq_presim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
+                                             xs.data_ptr(), cf.data_ptr(), RT.stream_ptr()))
             finally:
                 L.mcre_eq_destroy(plan)
             for u, p in enumerate(group):
                 cfs[id(p)] = cf[u]
+                if nt:
+                    dcfs[id(p)] = dcf[u]
         # standardisation of each asset's spot per date: model moments (shard independent)
         bs = np.array([[self.basis_at(a, t) for a in range(A)] for t in expo_times]).reshape(n_expo, A, 2)
         mean, scale = bs[:, :, 0], bs[:, :, 1]
@@ -818,19 +846,40 @@ class EquityBackend:
         moments = torch.zeros((max(len(jobs), 1), 8), dtype=torch.float64, device=dev)
         partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
         nconst = torch.empty(n, dtype=torch.float64, device=dev)
+        if nt:
+            # the numeraire exp(r (t - t0)) is deterministic: its only tangent is the rate's (lane parameter 2)
+            dnconst = torch.zeros((nt, n), dtype=torch.float64, device=dev)
+            tmoments = torch.zeros((max(len(jobs), 1), nt * 9), dtype=torch.float64, device=dev)
+            tpartial = torch.empty(n_chunks * nt * 9 + 1, dtype=torch.float64, device=dev)
         t0 = self.num_model.t0()
         last_k = None
         for j, (p, k) in enumerate(jobs):
             a = self._asset_index(p.asset_ids[0])
             if k != last_k:
-                nconst.fill_(math.exp(self.num_rate * (expo_times[k] - t0)))
+                nk = math.exp(self.num_rate * (expo_times[k] - t0))
+                nconst.fill_(nk)
+                if nt:
+                    dnconst[2].fill_((expo_times[k] - t0) * nk)
                 last_k = k
             B.check(L.mcre_lsm_step(xs[k, a].data_ptr(), nconst.data_ptr(), float(mean[k, a]), float(scale[k, a]),
                                     None, None, None, None, 0.0, 1.0, cfs[id(p)].data_ptr(), count, CHUNK_PATHS,
                                     partial.data_ptr(), moments[j].data_ptr(), RT.stream_ptr()))
+            if nt:
+                B.check(L.mcre_lsm_step_tangents(nt, xs[k, a].data_ptr(), nconst.data_ptr(), dxs[k, a].data_ptr(),
+                                                 dnconst.data_ptr(), float(mean[k, a]), float(scale[k, a]),
+                                                 None, None, None, None, None, None, 0.0, 1.0, cfs[id(p)].data_ptr(),
+                                                 dcfs[id(p)].data_ptr(), count, CHUNK_PATHS, tpartial.data_ptr(),
+                                                 tmoments[j].data_ptr(), RT.stream_ptr()))
         m = RT.all_reduce_tree(moments).cpu().numpy()
         G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
         sol = solve_normal_equations_batch(G, m[:, 5:8]) if jobs else np.zeros((0, 3))
+        if nt:
+            from mcre.lsm import regression_tangents
+            tm = RT.all_reduce_tree(tmoments).cpu().numpy().reshape(-1, nt, 9)
+            for p in products:
+                self.expo_dcoef[id(p)] = np.zeros((n_expo, nt, 3))
+            for j, ((p, k), cvec) in enumerate(zip(jobs, sol)):
+                self.expo_dcoef[id(p)][k] = regression_tangents(G[j], m[j, 5:8], cvec, tm[j])
         for p in products:
             a = self._asset_index(p.asset_ids[0])
             self.expo_coef[id(p)] = (np.zeros((n_expo, 3)), np.stack([mean[:, a], scale[:, a]], axis=1))
@@ -1006,6 +1055,9 @@ class EquityBackend:
                 partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 rng = self._rng(43, n_main)
                 keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
+                if info.get("xp_tan") is not None and self.nt:
+                    keep_xt, xt_ptr = B.as_dp(info["xp_tan"].reshape(-1))
+                    B.check(L.mcre_eq_set_exposure_coef_tangents(plan, xt_ptr))
                 sh = B.Shard(begin, count, chunk)
                 n_metric = info["n_metric"]
                 spill = None

@@ -409,20 +409,36 @@ def bs_analytic_exposure(prod, model, p, t, spot, numeraire):
 # ------------------------------------------------------------------------------------
 def lstsq_dual(A, Y):
     """min-norm least squares c = pinv(A) Y with forward-mode tangents (pinv derivative for
-    constant rank).  A: [N,p] (ndarray or Dual), Y: [N,S] -> c: [p,S]."""
+    constant rank).  A: [N,p] (ndarray or Dual), Y: [N,S] -> c: [p,S].
+
+    The values come from the raw basis [1, x, x^2] like the reference's torch.linalg.lstsq.  The TANGENTS are
+    evaluated in the basis of the standardised variable u = (x - mean) / std (A' = A T with a constant T, c = T c'):
+    the same function in exact arithmetic, but the residual term (A^T A)^-1 dA^T r loses ~7 digits to the 1e10
+    condition number of the raw Gram matrix (x ~ 100), which is more than the 1e-6 the CUDA path is checked to."""
     Av, Yv = ad.val(A), ad.val(Y)
     c, *_ = np.linalg.lstsq(Av, Yv, rcond=None)
     if not isinstance(A, ad.Dual) and not isinstance(Y, ad.Dual):
         return c
     P = A.P if isinstance(A, ad.Dual) else Y.P
     dA, dY = ad.tan(A, P), ad.tan(Y, P)
-    Ap = np.linalg.pinv(Av)                    # [p,N]
-    resid = Yv - Av @ c
-    proj = np.eye(Av.shape[1]) - Ap @ Av       # I - A+ A
-    ApT_c = Ap.T @ c                           # [N,S]
+    p = Av.shape[1]
+    T = np.eye(p)
+    if p >= 2 and all(np.allclose(Av[:, j], Av[:, 1] ** j, rtol=1e-12, atol=0.0) for j in range(p)):
+        m, sd = float(np.mean(Av[:, 1])), float(np.std(Av[:, 1]))
+        if sd > 1e-10 * max(abs(m), 1.0):      # (rank-deficient dates, all x equal: raw basis, min-norm like the reference)
+            for j in range(p):
+                for i in range(j + 1):
+                    T[i, j] = math.comb(j, i) * (-m) ** (j - i) / sd ** j
+    As = Av @ T                                # [N,p] standardised basis
+    dAs = dA @ T
+    cs = np.linalg.solve(T, c)                 # coefficients in the standardised basis
+    Ap = np.linalg.pinv(As)                    # [p,N]
+    resid = Yv - As @ cs
+    proj = np.eye(p) - Ap @ As                 # I - A+ A
+    ApT_c = Ap.T @ cs                          # [N,S]
     dc = np.empty((P,) + c.shape)
     for k in range(P):
-        dc[k] = (Ap @ (dY[k] - dA[k] @ c) + (Ap @ Ap.T) @ (dA[k].T @ resid) + proj @ (dA[k].T @ ApT_c))
+        dc[k] = T @ (Ap @ (dY[k] - dAs[k] @ cs) + (Ap @ Ap.T) @ (dAs[k].T @ resid) + proj @ (dAs[k].T @ ApT_c))
     return ad.Dual(c, dc)
 
 

@@ -186,6 +186,29 @@ def bs_exposure_greeks(ns_module, multi=True):
     return model, sets, [m.PVMetric(), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
 
 
+def bs_eepe_greeks(ns_module, book="european"):
+    """Sensitivities of exposure metrics through the regression proxy (controller.py:294-383, 438-447, 609-627).
+    book "european": tests/exposure_tests/eepe_simulation.py (EEPE of a Black-Scholes call; EEPE switches the analytic
+    exposure branch off).  book "mixed": single-asset products that pay once on a 2-asset BlackScholesMulti in a
+    thresholded and an MPoR-collateralised netting set."""
+    m = ns_module
+    if book == "european":
+        model = m.BlackScholesModel(0, 100.0, 0.05, 0.2)
+        opt = m.EuropeanOption(underlying=m.Equity("id"), exercise_date=2.0, strike=100, option_type=m.OptionType.CALL)
+        return model, [m.NettingSet(name="eepe_option_ns", products=[opt])], [m.EEPEMetric(), m.EPEMetric(), m.PVMetric()], np.linspace(0.0, 2.0, 10)
+    ids = ["asset_1", "asset_2"]
+    model = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+
+    def products():
+        return [m.EuropeanOption(m.Equity("asset_1"), 1.0, 95.0, m.OptionType.CALL, asset_id="asset_1"),
+                m.BinaryOption(1.5, 100.0, 10.0, m.OptionType.PUT, asset_id="asset_2"),
+                m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, asset_id="asset_1")]
+    sets = [m.NettingSet(name="thresholded", products=products(), threshold=6.0),
+            m.NettingSet(name="collateralised", products=products(), margin_period_of_risk=0.25, threshold=1.0)]
+    return model, sets, [m.PVMetric(), m.CEMetric(), m.EPEMetric(), m.ENEMetric(), m.EEPEMetric()], np.linspace(0.0, 1.5, 7)
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -209,6 +232,8 @@ GOLDEN_CASES = {
     "mixed_book_exposure": (mixed_book, dict(exposure=True), dict(n_main=512, n_pre=512, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "bs_exposure_greeks": (bs_exposure_greeks, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_exposure_greeks_euler": (bs_exposure_greeks, dict(multi=False), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
+    "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
+    "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
 }
 
