@@ -399,6 +399,22 @@ int mcre_eq_presim(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *sh
  *  - mcre_eq_set_exposure_coef_tangents: host xp_tan [n_expo][n_prod][3][nt], d(c0, c1, c2)/d(lane parameters) from the
  *    differentiated normal equations (the reference keeps torch.linalg.lstsq in the autograd graph,
  *    controller.py:368-383); copied to the device. */
+/* Hybrid ModelConfig of Black-Scholes market models + the CIR++ credit model of a counterparty (the reference's
+ * tests/exposure_tests/cva_perfprmance_large_netting_set.py): the fused equity kernel also steps the intensity
+ * (cirpp.py:155-198, Euler with full truncation or the deterministic mode) on the noise column `noise_col` of the joint
+ * draw, correlated with the equity draws through chol_row [noise_dim] = the credit row of the Cholesky factor of the
+ * joint correlation (model_config.py:101-142), and accumulates per path
+ *     CVA = lgd * sum_{k < n_metric-1} relu(E_k) exp(-logB_lambda(t_k)) (1 - C_k exp(-B_k y_k))     (cva_metric.py:62-100)
+ * for the sets with set_cva != 0.  step_cir [n_sub][2] = psi(t1), unused (deterministic: lambda(t1), lambda(t2));
+ * cva_coef [n_metric][2] = (C_k, B_k).  Adds [NS][2] = sum(cva - c), sum((cva - c)^2) at the end of the accumulator
+ * (counted by mcre_eq_slots).  Value-only plans; host arrays, copied. */
+typedef struct {
+  int32_t deterministic, noise_col;
+  double kappa, theta, sigma, y0, lgd;
+  const double *step_cir, *chol_row, *cva_coef;
+  const int32_t *set_cva;
+} mcre_eq_credit;
+int mcre_eq_set_credit(mcre_eq_plan *plan, const mcre_eq_credit *credit);
 int mcre_eq_presim_tangents(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                             double *d_shift, double *d_x, float *d_cf, double *d_dx, double *d_dcf, void *stream);
 int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *plan, const double *xp_tan);

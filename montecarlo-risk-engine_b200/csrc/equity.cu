@@ -79,6 +79,14 @@ struct EqDev {
   // ps_dcf [n_prod][nt][n_paths] (f64: the reference's float32 rounding touches values only under autograd's chain)
   const double *xp_tan;
   double *ps_dx, *ps_dcf;
+  // credit factor of a hybrid ModelConfig (mcre_eq_set_credit): CIR++ intensity of the counterparty stepped next to
+  // the equity assets (cirpp.py:155-198), its normal = noise column cir_col correlated through cir_row [noise_dim]
+  // (the credit row of the joint Cholesky factor); CVA weights per metric date cva_coef [n_metric][2] = (C_k, B_k)
+  // of S(t_k, t_k+1 | y) = C exp(-B y) (cirpp.py:246-285); set_cva [n_sets]: the metric's counterparty faces the set
+  int has_cir, cir_det, cir_col;
+  double cir_kappa, cir_theta, cir_sigma, cir_y0, lgd;
+  const double *step_cir, *cir_row, *cva_coef;
+  const int *set_cva;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -163,7 +171,8 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
   const int A = P.n_assets, ppw = 32 / A;
   const int expo_base = NS * 3 + A * NS * NT;
   const int xt_base = expo_base + P.n_metric * NVX;
-  const int n_slots = xt_base + (XT ? P.n_metric * A * NVXT : 0);
+  const int cva_base = xt_base + (XT ? P.n_metric * A * NVXT : 0);      // [NS][2] sum(cva - c), sum((cva - c)^2)
+  const int n_slots = cva_base + ((KIND == MCRE_EQ_BS && P.has_cir) ? NS * 2 : 0);
   double *acc = smem;                 // [n_slots]
   double *stage = smem + n_slots;     // [2][nw][NVMAX]
   const int g = lane / A, a = lane - g * A, base = g * A;
@@ -207,6 +216,9 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
       else if constexpr (KIND == MCRE_EQ_HESTON) { s0 = r_log(par[0]); s1 = par[6]; }
       else { s0 = T::zero(); s1 = T::zero(); }
       double logF = KIND == MCRE_EQ_SCHWARTZ ? __ldg(P.init_aux + aa) : 0.0;
+      double cy = P.cir_y0, clogB = 0.0, cva_path[NS];     // credit factor: every lane of the group carries a copy
+#pragma unroll
+      for (int s = 0; s < NS; ++s) cva_path[s] = 0.0;
       constexpr int NTRK = eq_ntrk(NT);
       R cf[NS], trk_a[NTRK], trk_b[NTRK];
       // Brownian-bridge barriers (value-only builds): previous monitored spot, running no-hit products
@@ -388,6 +400,11 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
             }
             xpos[s] = r_relu(unsec); xneg[s] = -r_relu(-unsec);
             const double pos = val(xpos[s]), neg = val(xneg[s]);
+            if (KIND == MCRE_EQ_BS && P.has_cir && m < P.n_metric - 1 && s < P.n_sets && __ldg(P.set_cva + s)) {
+              // cva_metric.py:62-100: relu(E_k) S(0, t_k) (1 - S(t_k, t_k+1 | y_k)), S(0, t) = exp(-logB_lambda)
+              const double Ck = __ldg(P.cva_coef + 2 * m), Bk = __ldg(P.cva_coef + 2 * m + 1);
+              cva_path[s] = fma(pos, exp(-clogB) * (1.0 - Ck * exp(-Bk * cy)), cva_path[s]);
+            }
             const int sb = expo_base + m * NVX + s * 4;
             if (pilot) { if (threadIdx.x == 0) { shift[sb + 0] = pos; shift[sb + 2] = neg; } }
             const double dp = pos - (pilot ? 0.0 : shift[sb + 0]), dn = neg - (pilot ? 0.0 : shift[sb + 2]);
@@ -645,6 +662,31 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
           }
           logF = __ldg(P.step_aux + (size_t)is * A + aa);
         }
+        if (KIND == MCRE_EQ_BS && P.has_cir) {
+          // correlated credit normal: its own draw plus the equity draws of the group (row of the joint factor)
+          double zc;
+          if (rng.mode == MCRE_RNG_INJECT) zc = rng.z[((size_t)is * rng.n_total + gpath) * d + P.cir_col];
+          else {
+            const uint32_t nc = (uint32_t)(is * d + P.cir_col);
+            double p0, p1;
+            ns.pair(nc >> 1, p0, p1);
+            zc = (nc & 1u) ? p1 : p0;
+          }
+          double wc = __ldg(P.cir_row + P.cir_col) * zc;
+          for (int j = 0; j < d; ++j) {
+            if (j == P.cir_col) continue;
+            const double zj = __shfl_sync(0xffffffffu, __ldg(P.col_elem + j) ? z1 : z0, (base + __ldg(P.col_asset + j)) & 31);
+            wc = fma(__ldg(P.cir_row + j), zj, wc);
+          }
+          if (P.cir_det) {
+            clogB += __ldg(P.step_cir + 2 * is) * dt;
+            cy = __ldg(P.step_cir + 2 * is + 1);
+          } else {      // Euler with full truncation (cirpp.py:174-198)
+            const double yn = cy + P.cir_kappa * (P.cir_theta - cy) * dt + P.cir_sigma * sqrt(fmax(cy, 0.0)) * sq * wc;
+            clogB += (cy + __ldg(P.step_cir + 2 * is)) * dt;
+            cy = fmax(yn, 1e-12);
+          }
+        }
         const int di = __ldg(P.step_date + is);
         if (di >= 0) { eval_date(di); eval_exposure(di); }
       }
@@ -661,6 +703,17 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
           vals[s * 3 + 0] = keep1 * x; vals[s * 3 + 1] = keep1 * x * x; vals[s * 3 + 2] = keep1 * numtan[s];
         }
         if (!pilot) block_accumulate<NVH>(vals, acc, 0, stage, NVMAX, parity);
+      }
+      if (KIND == MCRE_EQ_BS && P.has_cir) {
+        double cv[NS * 2];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const double c = cva_path[s] * P.lgd;
+          if (pilot) { if (threadIdx.x == 0) shift[cva_base + 2 * s] = c; }
+          const double x = c - (pilot ? 0.0 : shift[cva_base + 2 * s]);
+          cv[2 * s] = keep1 * x; cv[2 * s + 1] = keep1 * x * x;
+        }
+        if (!pilot) block_accumulate<NS * 2>(cv, acc, cva_base, stage, NVMAX, parity);
       }
       if (NT > 0 && !pilot) {
         for (int ap = 0; ap < A; ++ap) {
@@ -697,6 +750,7 @@ struct mcre_eq_plan {
   DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src;
   DevArray<double> xp, set_threshold, sp_coef;
   double *xp_tan = nullptr;   // own allocation (set after mcre_eq_create)
+  double *credit = nullptr;   // own allocation (mcre_eq_set_credit): step_cir, cir_row, cva_coef, set_cva
   bool has_proxy = false;     // some exposure is a regression proxy (type 2)
 };
 
@@ -780,6 +834,8 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   EqDev &D = p->d;
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
   D.xp_tan = nullptr; D.ps_dx = nullptr; D.ps_dcf = nullptr;
+  D.has_cir = 0; D.cir_det = 0; D.cir_col = 0; D.cir_kappa = D.cir_theta = D.cir_sigma = D.cir_y0 = D.lgd = 0.0;
+  D.step_cir = D.cir_row = D.cva_coef = nullptr; D.set_cva = nullptr;
   D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
@@ -810,6 +866,7 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->xp.release(); p->set_threshold.release(); p->sp_coef.release(); p->sp_src.release();
   p->arena.release();
   if (p->xp_tan) cudaFree(p->xp_tan);
+  if (p->credit) cudaFree(p->credit);
   delete p;
 }
 
@@ -824,13 +881,39 @@ extern "C" int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *p, const double 
   return 0;
 }
 
+extern "C" int mcre_eq_set_credit(mcre_eq_plan *p, const mcre_eq_credit *c) {
+  if (!p || !c || !c->step_cir || !c->chol_row || !c->set_cva) return fail(-1, "null argument%s", "");
+  if (p->nt != 0) return fail(-4, "eq: sensitivities of hybrid equity + credit runs are not implemented%s", "");
+  if (p->d.kind != MCRE_EQ_BS) return fail(-4, "eq: the credit factor rides with Black-Scholes market models%s", "");
+  if (c->noise_col < 0 || c->noise_col >= p->d.noise_dim) return fail(-1, "eq: credit noise column out of range%s", "");
+  if (p->d.n_metric > 0 && !c->cva_coef) return fail(-1, "eq: credit factor without CVA coefficients%s", "");
+  const EqDev &D0 = p->d;
+  const size_t n_step = (size_t)2 * (D0.n_sub > 0 ? D0.n_sub : 1), n_row = (size_t)D0.noise_dim,
+               n_cva = (size_t)2 * (D0.n_metric > 0 ? D0.n_metric : 1), n_set = (size_t)D0.n_sets;
+  std::vector<double> host(n_step + n_row + n_cva + n_set, 0.0);   // set flags ride as doubles' storage (ints behind)
+  for (size_t i = 0; i < (size_t)2 * D0.n_sub; ++i) host[i] = c->step_cir[i];
+  for (size_t i = 0; i < n_row; ++i) host[n_step + i] = c->chol_row[i];
+  for (size_t i = 0; i < (size_t)2 * D0.n_metric; ++i) host[n_step + n_row + i] = c->cva_coef[i];
+  int *flags = reinterpret_cast<int *>(host.data() + n_step + n_row + n_cva);
+  for (size_t i = 0; i < n_set; ++i) flags[i] = c->set_cva[i];
+  if (p->credit) { cudaFree(p->credit); p->credit = nullptr; }
+  MCRE_CUDA(cudaMalloc((void **)&p->credit, host.size() * sizeof(double)));
+  MCRE_CUDA(cudaMemcpy(p->credit, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  EqDev &D = p->d;
+  D.has_cir = 1; D.cir_det = c->deterministic; D.cir_col = c->noise_col;
+  D.cir_kappa = c->kappa; D.cir_theta = c->theta; D.cir_sigma = c->sigma; D.cir_y0 = c->y0; D.lgd = c->lgd;
+  D.step_cir = p->credit; D.cir_row = p->credit + n_step; D.cva_coef = p->credit + n_step + n_row;
+  D.set_cva = reinterpret_cast<const int *>(p->credit + n_step + n_row + n_cva);
+  return 0;
+}
+
 static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 2 : 4); }
 
 extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
   const int ns = eq_ns_template(p->d.n_sets);
   const bool xt = p->d.kind == MCRE_EQ_BS && p->nt > 0;
   return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4 +
-         (xt ? (int64_t)p->d.n_metric * p->d.n_assets * ns * 2 * p->nt : 0);
+         (xt ? (int64_t)p->d.n_metric * p->d.n_assets * ns * 2 * p->nt : 0) + (p->d.has_cir ? ns * 2 : 0);
 }
 
 template <int KIND, int ALT, int NT, int NS>
@@ -844,7 +927,8 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   constexpr int NVXT = XT ? NS * 2 * NT : 1;
   constexpr int NVMAX0 = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
   constexpr int NVMAX = NVMAX0 > NVXT ? NVMAX0 : NVXT;
-  const int n_slots = NS * 3 + d.n_assets * NS * NT + d.n_metric * NVX + (XT ? d.n_metric * d.n_assets * NVXT : 0);
+  const int n_slots = NS * 3 + d.n_assets * NS * NT + d.n_metric * NVX + (XT ? d.n_metric * d.n_assets * NVXT : 0) +
+                      (d.has_cir ? NS * 2 : 0);
   const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0) return 0;

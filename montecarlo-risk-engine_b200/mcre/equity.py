@@ -27,6 +27,7 @@ from mcre.timegrid import build_time_grid
 from metrics.metric import MetricType
 from models.black_scholes import BlackScholesModel
 from models.black_scholes_multi import BlackScholesMulti
+from models.cirpp import CIRPPModel
 from models.heston import HestonModel
 from models.model_config import ModelConfig
 from models.schwartz_two_factor import SchwartzTwoFactorModel
@@ -83,6 +84,21 @@ class EqDesc(C.Structure):
     ]
 
 
+class EqCredit(C.Structure):
+    """mcre_eq_credit (include/mcre.h)."""
+    _fields_ = [("deterministic", C.c_int32), ("noise_col", C.c_int32),
+                ("kappa", C.c_double), ("theta", C.c_double), ("sigma", C.c_double), ("y0", C.c_double), ("lgd", C.c_double),
+                ("step_cir", B.c_dp), ("chol_row", B.c_dp), ("cva_coef", B.c_dp), ("set_cva", B.c_ip)]
+
+
+def credit_of(model):
+    """(CIR++ credit model, its index in the ModelConfig) of a hybrid equity + credit ModelConfig, else (None, None):
+    the credit model rides after the market models (the joint Cholesky factor keeps the reference's asset order)."""
+    if isinstance(model, ModelConfig) and len(model.models) >= 2 and isinstance(model.models[-1], CIRPPModel):
+        return model.models[-1], len(model.models) - 1
+    return None, None
+
+
 class Asset:
     """One simulated asset = one lane of a path group."""
 
@@ -101,6 +117,9 @@ def family_of(model):
     subs = _sub_models(model)
     offs = model.param_offsets() if isinstance(model, ModelConfig) else [0]
     kinds, assets = set(), []
+    credit, _ = credit_of(model)
+    if credit is not None:
+        subs = subs[:-1]
     for m, off in zip(subs, offs):
         pv = m.param_values()
         if isinstance(m, BlackScholesModel):
@@ -125,6 +144,8 @@ def family_of(model):
     kind = kinds.pop()
     if kind == EQ_SCHWARTZ and len(assets) != 1:
         return None
+    if credit is not None and kind != EQ_BS:
+        return None      # the credit factor rides with Black-Scholes market models
     return kind, assets
 
 
@@ -163,7 +184,10 @@ class EquityBackend:
             # own no-regression branch, controller.py:204-229), else the regression proxy of products that
             # pay once; no CVA here (needs a credit model in the same ModelConfig: hybrid books are next)
             if any(m.metric_type == MetricType.CVA for m in ctrl.risk_metrics.metrics):
-                return False
+                # CVA of equity books: hybrid ModelConfig of Black-Scholes market models + the counterparty's CIR++
+                credit, _ = credit_of(ctrl.model)
+                return credit is not None and all(m.counterparty_id in credit.asset_ids for m in ctrl.risk_metrics.metrics
+                                                  if m.metric_type == MetricType.CVA)
             return True
         return True
 
@@ -171,6 +195,13 @@ class EquityBackend:
         self.c = ctrl
         self.kind, self.assets = family_of(ctrl.model)
         self.A = len(self.assets)
+        self.credit, self.credit_idx = credit_of(ctrl.model)
+        if self.credit is not None:
+            if ctrl.differentiate:
+                raise NotImplementedError("sensitivities of hybrid equity + credit runs are not implemented")
+            if ctrl.simulation_scheme != SimulationScheme.EULER:
+                # same restriction as the reference: only Black-Scholes pairs have a joint exact covariance (model_config.py:216-221)
+                raise NotImplementedError("Analytical covariance is currently only supported for Black-Scholes-type model pairs.")
         if self.A > 32:
             raise NotImplementedError("at most 32 jointly simulated assets per path group")
         scheme = ctrl.simulation_scheme
@@ -333,7 +364,7 @@ class EquityBackend:
         n_sub = grid.n_sub
         zero_idx = [0] * n_sub
         if self.kind == EQ_BS:
-            if self.A == 1:
+            if self.A == 1 and self.credit is None:
                 return 0, None, None, zero_idx
             # ANALYTICAL: chol(diag(s) C diag(s) dt) = diag(s sqrt(dt)) chol(C): one factor for all steps
             if isinstance(model, ModelConfig):
@@ -389,9 +420,9 @@ class EquityBackend:
         date_idx = {t: i for i, t in enumerate(dates)}
         n_dates, n_sub = len(dates), grid.n_sub
         two = self.kind != EQ_BS
-        d = (2 if two else 1) * A
+        d = (2 if two else 1) * A + (1 if self.credit is not None else 0)     # the credit factor draws the last column
         asset_noise = np.array([[2 * a, 2 * a + 1] if two else [a, -1] for a in range(A)], dtype=np.int32)
-        col_asset = np.array([j // 2 if two else j for j in range(d)], dtype=np.int32)
+        col_asset = np.array([min(j // 2 if two else j, A - 1) for j in range(d)], dtype=np.int32)
         col_elem = np.array([j % 2 if two else 0 for j in range(d)], dtype=np.int32)
         par = np.zeros((A, EQ_PAR))
         for a, asset in enumerate(self.assets):
@@ -590,8 +621,51 @@ class EquityBackend:
             desc.set_flags, desc.set_lag = ip("set_flags", set_flags), ip("set_lag", set_lag)
         desc.n_expo, desc.n_metric, desc.acc_flags = n_expo, n_metric, acc
         info = dict(grid=grid, noise_dim=d, n_uniform=desc.n_uniform, owners=owners, recs=recs, n_metric=n_metric, acc=acc,
-                    bridge=bridge, xp_tan=xp_tan if (n_expo and presim_products is None) else None)
+                    bridge=bridge, chol=chol, set_indices=list(set_indices), xp_tan=xp_tan if (n_expo and presim_products is None) else None)
         return desc, t, info
+
+    def _set_credit(self, plan, info):
+        """Hands the plan the CIR++ credit factor of a hybrid ModelConfig and the CVA weights (mcre_eq_set_credit);
+        returns the CVA metric or None.  Closed forms from models/cirpp.py (psi, conditional survival coefficients)."""
+        c, cir = self.c, self.credit
+        cvas = [m for m in c.risk_metrics.metrics if m.metric_type == MetricType.CVA]
+        if cir is None or not cvas or not info["n_metric"]:
+            return None
+        if len({m.counterparty_id for m in cvas}) > 1 or len({m.recovery_rate for m in cvas}) > 1:
+            raise NotImplementedError("one CVA counterparty / recovery per run is supported for now")
+        metric = cvas[0]
+        grid, d = info["grid"], info["noise_dim"]
+        pv = cir.param_values()                   # [kappa, theta, sigma, y0]
+        metric_times = c.metric_exposure_timeline.tolist()
+        n_metric = len(metric_times)
+        t0 = cir.t0()
+        step = np.zeros((max(grid.n_sub, 1), 2))
+        coef = np.zeros((n_metric, 2))
+        if cir.deterministic:
+            for s_ in range(grid.n_sub):
+                step[s_] = (cir.market_hazard(grid.t1[s_]), cir.market_hazard(grid.t2[s_]))
+            for m in range(n_metric - 1):
+                coef[m] = (cir.market_survival(metric_times[m + 1]) / cir.market_survival(metric_times[m]), 0.0)
+            y0 = cir.market_hazard(t0)
+        else:
+            if grid.n_sub:
+                step[:grid.n_sub, 0] = cir.psi_values(pv, grid.t1)
+            if n_metric > 1:
+                Cs, Bs = cir.conditional_survival_values(pv, metric_times[:-1], metric_times[1:])
+                coef[:-1, 0], coef[:-1, 1] = Cs, Bs
+            y0 = pv[3]
+        cr = EqCredit()
+        cr.deterministic, cr.noise_col = int(cir.deterministic), d - 1
+        cr.kappa, cr.theta, cr.sigma, cr.y0, cr.lgd = pv[0], pv[1], pv[2], y0, 1.0 - metric.recovery_rate
+        keep = {}
+        keep["step"], cr.step_cir = B.as_dp(step.reshape(-1))
+        keep["row"], cr.chol_row = B.as_dp(np.asarray(info["chol"])[0, d - 1, :])
+        keep["coef"], cr.cva_coef = B.as_dp(coef.reshape(-1))
+        flags = [int(c.netting_sets[si].counterparty_id is None or c.netting_sets[si].counterparty_id == metric.counterparty_id)
+                 for si in info["set_indices"]]
+        keep["flags"], cr.set_cva = B.as_ip(flags)
+        B.check(B.lib().mcre_eq_set_credit(plan, C.byref(cr)))
+        return metric
 
     # ------------------------------------------------------------------ execution
     def _rng(self, seed, n_total):
@@ -929,6 +1003,8 @@ class EquityBackend:
         need_expo = c.risk_metrics.requires_exposure_profiles()
         if need_expo and self.nt:
             raise NotImplementedError("sensitivities of exposure profiles of books split over several launches")
+        if any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
+            raise NotImplementedError("CVA of books split over several launches")
         kinds = {m.metric_type for m in c.risk_metrics.metrics}
         n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
         accum = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -1046,6 +1122,7 @@ class EquityBackend:
             plan = C.c_void_p()
             B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
             try:
+                cva_metric = self._set_credit(plan, info)
                 slots = L.mcre_eq_slots(plan)
                 chunk = main_chunk(n_main)
                 begin, count = RT.shard_range(n_main, chunk)
@@ -1085,6 +1162,9 @@ class EquityBackend:
             xtan = None
             if self.nt and n_metric and self.kind == EQ_BS:
                 xtan = acc_h[xt_base:].reshape(n_metric, self.A, ns_t, 2, self.nt)
+            cva_acc = cva_shift = None
+            if cva_metric is not None:
+                cva_acc, cva_shift = acc_h[-ns_t * 2:].reshape(ns_t, 2), shift_h[-ns_t * 2:].reshape(ns_t, 2)
 
             def expo_grads(r, which):
                 if xtan is None:
@@ -1116,6 +1196,8 @@ class EquityBackend:
                                   expo_grads(r, 1))
                 if quant is not None:
                     res["pfe"] = quant[r]
+                if cva_acc is not None:
+                    res["cva"] = (mean_and_error(cva_acc[r, 0], cva_acc[r, 1], cva_shift[r, 0], n_main), None)
                 results[si] = res
         torch.cuda.synchronize(dev)
         timings = {"preprocessing": t_pre, "path_generation": time.perf_counter() - t0 - t_pre, "request_resolution": 0.0}

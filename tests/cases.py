@@ -209,6 +209,34 @@ def bs_eepe_greeks(ns_module, book="european"):
     return model, sets, [m.PVMetric(), m.CEMetric(), m.EPEMetric(), m.ENEMetric(), m.EEPEMetric()], np.linspace(0.0, 1.5, 7)
 
 
+def equity_cva(ns_module, rho=0.2, deterministic=False, single=False):
+    """CVA of an equity book: Black-Scholes market model + CIR++ credit model of the counterparty in one ModelConfig
+    (tests/exposure_tests/cva_perfprmance_large_netting_set.py:69-193, reduced), regression-proxy exposures,
+    MPoR-collateralised and uncollateralised netting sets."""
+    m = ns_module
+    if single:
+        ids = ["asset_0", "asset_0"]
+        market = m.BlackScholesModel(0.0, 100.0, 0.03, 0.2, asset_id="asset_0")
+        inter = [np.array([rho])]
+    else:
+        ids = ["asset_0", "asset_1"]
+        market = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[95.0, 102.5],
+                                     volatilities=[0.18, 0.21], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+        inter = [np.full((2, 1), rho, dtype=float)]
+    credit = m.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=HAZARDS, kappa=0.10, theta=0.01,
+                          volatility=0.02, y0=0.0001, deterministic=deterministic)
+    model = m.ModelConfig(models=[market, credit], inter_asset_correlation_matrix=inter)
+
+    def products():
+        return [m.EuropeanOption(m.Equity(ids[0]), 1.0, 95.0, m.OptionType.CALL, asset_id=ids[0]),
+                m.EuropeanOption(m.Equity(ids[1]), 1.5, 110.0, m.OptionType.PUT, asset_id=ids[1]),
+                m.BinaryOption(1.25, 100.0, 10.0, m.OptionType.CALL, asset_id=ids[1]),
+                m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, asset_id=ids[0])]
+    sets = [m.NettingSet(name="collateralised", products=products(), counterparty_id="cp", margin_period_of_risk=0.25),
+            m.NettingSet(name="open", products=products(), counterparty_id="cp", threshold=2.0)]
+    return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric(), m.PVMetric()], np.linspace(0.0, 1.5, 7)
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -234,6 +262,8 @@ GOLDEN_CASES = {
     "bs_exposure_greeks_euler": (bs_exposure_greeks, dict(multi=False), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
     "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
+    "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
+    "equity_cva_single_det": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=False)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
 }
 

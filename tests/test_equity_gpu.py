@@ -316,3 +316,26 @@ def test_regression_proxy_exposure_greeks_match_reference_and_oracle(name):
                 got = np.array([0.0 if g is None else float(g) for g in res.get_derivatives(s, m)[ev]])
                 helpers.assert_close(got, want, 1e-6, 1e-6 * max(1.0, float(np.max(np.abs(want)))),
                                      f"{name} {s}|{m}[{ev}] philox derivatives")
+
+
+HYBRID_CVA_CASES = ["equity_cva", "equity_cva_single_det"]
+
+
+@pytest.mark.parametrize("name", HYBRID_CVA_CASES)
+def test_equity_book_cva_matches_reference_and_oracle(name):
+    """CVA of equity books (tests/exposure_tests/cva_perfprmance_large_netting_set.py, reduced): ModelConfig of a
+    Black-Scholes market model and the counterparty's CIR++ intensity, stepped in the fused equity kernel on the last
+    column of the joint draw (mcre_eq_set_credit); regression-proxy exposures, collateralised and thresholded sets,
+    stochastic (correlated) and deterministic credit.  Reference golden with its own draws injected 1e-9; native
+    Philox vs the oracle 1e-8."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    assert res.get_netting_set_names() == gold["sets"] and res.get_metric_names() == gold["metrics"]
+    assert res.get_model_param_names() == gold["params"]
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _check_values(flat, ref, 1e-9, name)
+    res, sc = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    _check_values(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8,
+                  name + " philox", err_rtol=1e-6)
