@@ -415,6 +415,13 @@ typedef struct {
   const int32_t *set_cva;
 } mcre_eq_credit;
 int mcre_eq_set_credit(mcre_eq_plan *plan, const mcre_eq_credit *credit);
+/* CVA of books split over several launches: the launch that carries the credit factor also writes the default
+ * weights d_w [n_metric][n_paths] = exp(-logB_lambda(t_k)) (1 - C_k exp(-B_k y_k)) (0 on the last date); once every
+ * launch has added its exposures and mcre_eq_unsecured_exposures has netted them, mcre_eq_cva_paths gives the per-path
+ * d_out [n_paths] = lgd * sum_k relu(unsec_k) w_k, finished by mcre_sum_stats. */
+int mcre_eq_set_cva_weight_spill(mcre_eq_plan *plan, double *d_w);
+int mcre_eq_cva_paths(const double *d_unsec, const double *d_w, int64_t n_paths, int32_t n_metric, double lgd,
+                      double *d_out, void *stream);
 int mcre_eq_presim_tangents(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                             double *d_shift, double *d_x, float *d_cf, double *d_dx, double *d_dcf, void *stream);
 int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *plan, const double *xp_tan);

@@ -87,6 +87,9 @@ struct EqDev {
   double cir_kappa, cir_theta, cir_sigma, cir_y0, lgd;
   const double *step_cir, *cir_row, *cva_coef;
   const int *set_cva;
+  // book splitting with CVA (mcre_eq_set_cva_weight_spill): the default weights S(0, t_k) (1 - S(t_k, t_k+1 | y_k)) of
+  // every path per metric date, [n_metric][n_paths]; mcre_eq_cva_paths combines them with the unsecured exposures
+  double *cva_w;
 };
 constexpr int EQ_XP = 16;
 constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
@@ -256,6 +259,10 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
       auto eval_exposure = [&](int di) {
         if (P.n_expo == 0) return;
         const int xe = __ldg(P.date_expo + di), m = P.ps_x ? -1 : __ldg(P.date_metric + di);
+        if (KIND == MCRE_EQ_BS && P.has_cir && P.cva_w && m >= 0 && live && a == 0 && !pilot) {
+          const double Ck = __ldg(P.cva_coef + 2 * m), Bk = __ldg(P.cva_coef + 2 * m + 1);
+          P.cva_w[(size_t)m * sh.n_paths + lpath] = m < P.n_metric - 1 ? exp(-clogB) * (1.0 - Ck * exp(-Bk * cy)) : 0.0;
+        }
         if (xe >= 0 && P.ps_x) {
           if (live) {
             const R Sp = spot_now();
@@ -835,7 +842,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   D.sp_n = sp_n; D.sp_coef = p->sp_coef.p; D.sp_src = p->sp_src.p; D.n_sub_total = c->n_sub;
   D.xp_tan = nullptr; D.ps_dx = nullptr; D.ps_dcf = nullptr;
   D.has_cir = 0; D.cir_det = 0; D.cir_col = 0; D.cir_kappa = D.cir_theta = D.cir_sigma = D.cir_y0 = D.lgd = 0.0;
-  D.step_cir = D.cir_row = D.cva_coef = nullptr; D.set_cva = nullptr;
+  D.step_cir = D.cir_row = D.cva_coef = nullptr; D.set_cva = nullptr; D.cva_w = nullptr;
   D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
@@ -1055,6 +1062,35 @@ extern "C" int mcre_eq_unsecured_exposures(const double *d_expo, int64_t n_paths
   }
   arena.release();
   return rc;
+}
+
+extern "C" int mcre_eq_set_cva_weight_spill(mcre_eq_plan *p, double *d_w) {
+  if (!p) return fail(-1, "null argument%s", "");
+  if (d_w && !p->d.has_cir) return fail(-1, "eq: CVA weight spill without a credit factor (mcre_eq_set_credit)%s", "");
+  p->d.cva_w = d_w;
+  return 0;
+}
+
+namespace mcre {
+// per-path CVA of a netting set from its unsecured exposures and the default weights, both [n_metric][n]
+// (cva_metric.py:62-100): out[p] = lgd * sum_m relu(unsec[m][p]) * w[m][p]
+__global__ void __launch_bounds__(256) eq_cva_paths_kernel(const double *__restrict__ unsec, const double *__restrict__ w,
+                                                           long long n, int n_metric, double lgd, double *__restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double tot = 0.0;
+  for (int m = 0; m < n_metric - 1; ++m) tot = fma(fmax(unsec[(size_t)m * n + p], 0.0), w[(size_t)m * n + p], tot);
+  out[p] = tot * lgd;
+}
+}  // namespace mcre
+
+extern "C" int mcre_eq_cva_paths(const double *d_unsec, const double *d_w, int64_t n_paths, int32_t n_metric, double lgd,
+                                 double *d_out, void *stream) {
+  if (!d_unsec || !d_w || !d_out) return fail(-1, "null argument%s", "");
+  if (n_paths <= 0) return 0;
+  eq_cva_paths_kernel<<<(unsigned)((n_paths + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_unsec, d_w, n_paths, n_metric, lgd, d_out);
+  MCRE_LAUNCHED();
+  return 0;
 }
 
 extern "C" int mcre_eq_set_bridge_uniforms(mcre_eq_plan *p, const double *d_u, int32_t stride) {

@@ -1003,15 +1003,14 @@ class EquityBackend:
         need_expo = c.risk_metrics.requires_exposure_profiles()
         if need_expo and self.nt:
             raise NotImplementedError("sensitivities of exposure profiles of books split over several launches")
-        if any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
-            raise NotImplementedError("CVA of books split over several launches")
         kinds = {m.metric_type for m in c.risk_metrics.metrics}
         n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
         accum = torch.zeros(n, dtype=torch.float64, device=dev)
         accum_e = torch.zeros((n_expo, n), dtype=torch.float64, device=dev) if need_expo else None
         shift_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
-        for book in books:
+        cva_metric, cva_w = None, None
+        for bi, book in enumerate(books):
             desc, keep, info = self.lower([si], subset={id(p) for p in book})
             plan = C.c_void_p()
             B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
@@ -1023,6 +1022,16 @@ class EquityBackend:
                 B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
                 if need_expo:
                     B.check(L.mcre_eq_set_exposure_accumulator(plan, accum_e.data_ptr()))
+                if bi == 0 and need_expo and MetricType.CVA in kinds:
+                    # the first launch carries the credit factor and spills the default weights per (metric date, path)
+                    cva_metric = self._set_credit(plan, info)
+                    if cva_metric is not None:
+                        cva_w = torch.zeros((n_metric, n), dtype=torch.float64, device=dev)
+                        B.check(L.mcre_eq_set_cva_weight_spill(plan, cva_w.data_ptr()))
+                        slots = L.mcre_eq_slots(plan)
+                        acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                        shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                        partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
                 keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
                 rng = self._rng(43, n_main)
                 sh = B.Shard(begin, count, chunk)
@@ -1081,6 +1090,21 @@ class EquityBackend:
             if MetricType.PFE in kinds:
                 from mcre.select import order_statistics
                 res["pfe"] = order_statistics(c, spill, count, n_main)[0]
+            if cva_metric is not None:
+                cp = ns.counterparty_id
+                if cp is None or cp == cva_metric.counterparty_id:
+                    cva_paths = torch.zeros(n, dtype=torch.float64, device=dev)
+                    B.check(L.mcre_eq_cva_paths(spill.data_ptr(), cva_w.data_ptr(), count, n_metric,
+                                                1.0 - cva_metric.recovery_rate, cva_paths.data_ptr(), RT.stream_ptr()))
+                    first_c = cva_paths[0:1].clone() if (RT.dist_info()[0] == 0 and count > 0) else torch.zeros(1, dtype=torch.float64, device=dev)
+                    first_c = RT.all_reduce_tree(first_c)
+                    out_c = torch.zeros(2, dtype=torch.float64, device=dev)
+                    B.check(L.mcre_sum_stats(cva_paths.data_ptr(), count, 1, chunk, first_c.data_ptr(), 0, partial.data_ptr(),
+                                             out_c.data_ptr(), RT.stream_ptr()))
+                    sc_ = RT.all_reduce_tree(out_c).cpu().numpy()
+                    res["cva"] = (mean_and_error(sc_[0], sc_[1], float(first_c[0]), n_main), None)
+                else:
+                    res["cva"] = ((0.0, 0.0), None)
         return res
 
     def run(self):

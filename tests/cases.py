@@ -237,6 +237,19 @@ def equity_cva(ns_module, rho=0.2, deterministic=False, single=False):
     return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric(), m.PVMetric()], np.linspace(0.0, 1.5, 7)
 
 
+def equity_cva_exercise(ns_module):
+    """The mixed equity book of tests/pytests/test_netting_sets.py:375-528 (Europeans, Americans, a FlexiCall, a
+    barrier option) facing a counterparty with a CIR++ intensity: CVA + EPE of an MPoR-collateralised netting set, the
+    product mix of tests/exposure_tests/cva_perfprmance_large_netting_set.py."""
+    m = ns_module
+    model0, sets0, _, _ = mixed_book(ns_module, exposure=True)
+    credit = m.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=HAZARDS, kappa=0.10, theta=0.01,
+                          volatility=0.02, y0=0.0001)
+    model = m.ModelConfig(models=[model0, credit], inter_asset_correlation_matrix=[np.full((2, 1), 0.2, dtype=float)])
+    sets = [m.NettingSet(name="mixed_cva", products=sets0[0].products, counterparty_id="cp", margin_period_of_risk=0.25)]
+    return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -264,6 +277,7 @@ GOLDEN_CASES = {
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "equity_cva_single_det": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=False)),
+    "equity_cva_exercise": (equity_cva_exercise, dict(), dict(n_main=512, n_pre=512, num_steps=1, scheme="EULER", differentiate=False)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
 }
 

@@ -318,7 +318,7 @@ def test_regression_proxy_exposure_greeks_match_reference_and_oracle(name):
                                      f"{name} {s}|{m}[{ev}] philox derivatives")
 
 
-HYBRID_CVA_CASES = ["equity_cva", "equity_cva_single_det"]
+HYBRID_CVA_CASES = ["equity_cva", "equity_cva_single_det", "equity_cva_exercise"]
 
 
 @pytest.mark.parametrize("name", HYBRID_CVA_CASES)
