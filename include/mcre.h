@@ -445,6 +445,13 @@ int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double
                   const double *d_xi, const double *d_ni, const double *d_imm, const double *coef_i /* host[3] or NULL */,
                   double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
                   double *d_partial, double *d_moments, void *stream);
+/* Step 2 of mcre_lsm_step (no exercise update, constant numeraire nk) for MANY (product, regression date) pairs in
+ * one launch: d_moments [n_jobs][8], bit-identical to the per-pair calls; d_partial [ceil(n / chunk_paths)][n_jobs][8].
+ * For the regression proxies of books of thousands of products (controller.py:294-383 per product and exposure date).
+ * `jobs` is a host array; x and v are device arrays of length n. */
+typedef struct { const double *x; const float *v; double nk, shift, scale; } mcre_lsm_job;
+int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, int64_t n, int32_t chunk_paths,
+                           double *d_partial, double *d_moments, void *stream);
 /* The same with n_rights = 1..3 exercise rights (FlexiCall, src/products/flexicall.py:56-160): the product state
  * is the number of rights left, d_value is [n_rights][n] (state s at row s-1; state 0 carries nothing),
  * coef_i host [n_rights][3] (continuation of state s at product date i), d_moments [5 + 3 n_rights]:

@@ -89,6 +89,44 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
   }
 }
 
+// Moments of many (product, regression date) pairs in ONE launch: books of thousands of products on ~1000
+// pre-simulation paths are launch-bound when every pair costs a kernel + a tree reduction (380k launches for the
+// reference's 5000-product exposure book).  Work item = (job, chunk); per item exactly the arithmetic of
+// lsm_step_kernel<1> without an exercise update and with a constant numeraire, so the sums are bit-identical to
+// the per-job calls.  partial: [chunk][job][8].
+struct LsmJob { const double *x; const float *v; double nk, shift, scale; };
+__global__ void __launch_bounds__(256) lsm_moments_batch_kernel(const LsmJob *__restrict__ jobs, long long n_jobs, long long n,
+                                                                int chunk, double *__restrict__ partial) {
+  constexpr int NV = 8;
+  __shared__ double acc[NV];
+  __shared__ double stage[2 * 8 * NV];
+  const long long n_chunks = (n + chunk - 1) / chunk;
+  for (long long w = blockIdx.x; w < n_jobs * n_chunks; w += gridDim.x) {
+    const long long j = w / n_chunks, ch = w - j * n_chunks;
+    const LsmJob job = jobs[j];
+    if (threadIdx.x < NV) acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    int parity = 0;
+    double vals[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+    for (int it = 0; it < chunk; it += blockDim.x) {
+      const long long p = ch * chunk + it + threadIdx.x;
+      if (it + (int)threadIdx.x < chunk && p < n) {
+        const double u = (job.x[p] - job.shift) * job.scale;
+        const double u2 = u * u;
+        vals[0] += 1.0; vals[1] += u; vals[2] += u2; vals[3] += u2 * u; vals[4] += u2 * u2;
+        const double y = job.nk * (double)job.v[p];
+        vals[5] += y; vals[6] += y * u; vals[7] += y * u2;
+      }
+    }
+    block_accumulate<NV>(vals, acc, 0, stage, NV, parity);
+    __syncthreads();
+    if (threadIdx.x < NV) partial[((size_t)ch * n_jobs + j) * NV + threadIdx.x] = acc[threadIdx.x];
+    __syncthreads();
+  }
+}
+
 // Gathers the regression / exercise inputs of an equity exercise product from materialised paths
 // [n_paths][n_dates][state_dim]: one thread per path, date-major outputs (coalesced writes).
 __global__ void __launch_bounds__(256) lsm_prepare_equity_kernel(const double *__restrict__ paths, long long n, int n_dates,
@@ -185,6 +223,33 @@ extern "C" int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const 
 #undef LSM_LAUNCH
   MCRE_LAUNCHED();
   return mcre_tree_reduce(d_partial, n_chunks, nv, d_moments, stream);
+}
+
+extern "C" int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, int64_t n, int32_t chunk_paths,
+                                      double *d_partial, double *d_moments, void *stream) {
+  if (n_jobs <= 0) return 0;
+  if (!jobs || !d_partial || !d_moments) return fail(-1, "null argument%s", "");
+  if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
+  static_assert(sizeof(LsmJob) == sizeof(mcre_lsm_job), "job record layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {
+    MCRE_CUDA(cudaMemsetAsync(d_moments, 0, (size_t)n_jobs * 8 * sizeof(double), st));
+    return 0;
+  }
+  LsmJob *d_jobs = nullptr;
+  MCRE_CUDA(cudaMalloc((void **)&d_jobs, (size_t)n_jobs * sizeof(LsmJob)));
+  cudaError_t e = cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmJob), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFree(d_jobs); return cuda_fail(e, "job table upload"); }
+  const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
+  long long grid = (long long)sm_count() * 8;
+  if (grid > n_jobs * n_chunks) grid = n_jobs * n_chunks;
+  lsm_moments_batch_kernel<<<(unsigned)grid, 256, 0, st>>>(d_jobs, n_jobs, n, chunk_paths, d_partial);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  e = cudaGetLastError();
+  int rc = e != cudaSuccess ? cuda_fail(e, "kernel launch") : mcre_tree_reduce(d_partial, n_chunks, n_jobs * 8, d_moments, stream);
+  cudaStreamSynchronize(st);   // the job table is freed below
+  cudaFree(d_jobs);
+  return rc;
 }
 
 extern "C" int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double scale_k, const double *d_xi,

@@ -570,28 +570,35 @@ class EquityBackend:
                 date_metric[date_idx[tm]] = m
             xp = np.zeros((n_expo, max(len(recs), 1), EQ_XP))
             xp_tan = np.zeros((n_expo, max(len(recs), 1), 3, max(nt, 1))) if (nt and presim_products is None) else None
-            for e, te in enumerate(expo_times):
-                inv, dinv = self._inv_numeraire(te)
-                for pi, p in enumerate(owners):
-                    if presim_products is not None:
-                        continue                        # the spill pass evaluates no exposures
-                    if c._can_use_analytic_exposure_for_product(p):
-                        ttm = float(p.exercise_date) - te
-                        if ttm > 0.0:                   # matured options carry no exposure (european_option.py:129-131)
-                            xp[e, pi, :3] = (1.0, ttm, inv)
-                            xp[e, pi, 7] = dinv             # d (1 / N(t)) / d rate, for the exposure tangents
-                    elif is_equity_exercise(p):
-                        coef, basis = self.exercise_expo_coef[id(p)]     # [n_expo, rights, 3], [n_expo, 2]
-                        if np.any(coef[e] != 0.0):
-                            xp[e, pi, :8] = (3.0, coef[e, 0, 0], inv, coef[e, 0, 1], coef[e, 0, 2], basis[e, 0], basis[e, 1], 0.0)
-                            for st in range(1, coef.shape[1]):
-                                xp[e, pi, 8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[e, st]
-                    else:
-                        coef, basis = self.expo_coef[id(p)]
-                        if np.any(coef[e] != 0.0):
-                            xp[e, pi, :8] = (2.0, coef[e, 0], inv, coef[e, 1], coef[e, 2], basis[e, 0], basis[e, 1], dinv)
-                            if xp_tan is not None:
-                                xp_tan[e, pi] = self.expo_dcoef[id(p)][e].T      # [nt, 3] -> [3, nt]
+            # per product, all exposure dates at once (books of thousands of products x ~100 dates: no Python in the
+            # (date, product) loop)
+            te_arr = np.asarray(expo_times, dtype=np.float64)
+            invs = np.array([self._inv_numeraire(te) for te in expo_times]).reshape(n_expo, 2)
+            inv, dinv = invs[:, 0], invs[:, 1]
+            for pi, p in enumerate(owners):
+                if presim_products is not None:
+                    break                           # the spill pass evaluates no exposures
+                if c._can_use_analytic_exposure_for_product(p):
+                    ttm = float(p.exercise_date) - te_arr
+                    on = ttm > 0.0                  # matured options carry no exposure (european_option.py:129-131)
+                    xp[on, pi, 0], xp[on, pi, 1], xp[on, pi, 2] = 1.0, ttm[on], inv[on]
+                    xp[on, pi, 7] = dinv[on]        # d (1 / N(t)) / d rate, for the exposure tangents
+                elif is_equity_exercise(p):
+                    coef, basis = self.exercise_expo_coef[id(p)]     # [n_expo, rights, 3], [n_expo, 2]
+                    on = np.any(coef != 0.0, axis=(1, 2))
+                    xp[on, pi, 0], xp[on, pi, 1], xp[on, pi, 2] = 3.0, coef[on, 0, 0], inv[on]
+                    xp[on, pi, 3], xp[on, pi, 4] = coef[on, 0, 1], coef[on, 0, 2]
+                    xp[on, pi, 5], xp[on, pi, 6] = basis[on, 0], basis[on, 1]
+                    for st in range(1, coef.shape[1]):
+                        xp[on, pi, 8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[on, st]
+                else:
+                    coef, basis = self.expo_coef[id(p)]              # [n_expo, 3], [n_expo, 2]
+                    on = np.any(coef != 0.0, axis=1)
+                    xp[on, pi, 0], xp[on, pi, 1], xp[on, pi, 2] = 2.0, coef[on, 0], inv[on]
+                    xp[on, pi, 3], xp[on, pi, 4] = coef[on, 1], coef[on, 2]
+                    xp[on, pi, 5], xp[on, pi, 6], xp[on, pi, 7] = basis[on, 0], basis[on, 1], dinv[on]
+                    if xp_tan is not None:
+                        xp_tan[on, pi] = np.transpose(self.expo_dcoef[id(p)][on], (0, 2, 1))   # [nt, 3] -> [3, nt]
             kinds = {m.metric_type for m in c.risk_metrics.metrics}
             if kinds & {MetricType.CE, MetricType.EPE, MetricType.EEPE}:
                 acc |= B.ACC_POS
@@ -916,29 +923,43 @@ class EquityBackend:
         bs = np.array([[self.basis_at(a, t) for a in range(A)] for t in expo_times]).reshape(n_expo, A, 2)
         mean, scale = bs[:, :, 0], bs[:, :, 1]
         # moments per (product, date strictly before the payment)
-        jobs = [(p, k) for p in products for k, t in enumerate(expo_times) if t < float(p.product_timeline[-1])]
+        te_arr = np.asarray(expo_times, dtype=np.float64)
+        n_before = [int(np.searchsorted(te_arr, float(p.product_timeline[-1]), side="left")) for p in products]
+        jobs = [(p, k) for p, nb in zip(products, n_before) for k in range(nb)]   # expo_times is sorted
         moments = torch.zeros((max(len(jobs), 1), 8), dtype=torch.float64, device=dev)
-        partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
-        nconst = torch.empty(n, dtype=torch.float64, device=dev)
+        t0 = self.num_model.t0()
+        nk_of = [math.exp(self.num_rate * (t - t0)) for t in expo_times]
+        if jobs:
+            # all (product, date) moments in one launch (mcre_lsm_moments_batch): job = device pointers of the date's
+            # spots of the product's asset and of the product's float32 cashflows + numeraire / standardisation
+            table = np.zeros(len(jobs), dtype=[("x", "u8"), ("v", "u8"), ("nk", "f8"), ("shift", "f8"), ("scale", "f8")])
+            x_base, row_bytes = xs.data_ptr(), n * 8
+            nk_arr, j0 = np.asarray(nk_of), 0
+            for p, nb in zip(products, n_before):
+                if nb == 0:
+                    continue
+                a, ks = self._asset_index(p.asset_ids[0]), np.arange(nb)
+                seg = table[j0:j0 + nb]
+                seg["x"] = x_base + (ks * A + a) * row_bytes
+                seg["v"] = cfs[id(p)].data_ptr()
+                seg["nk"], seg["shift"], seg["scale"] = nk_arr[:nb], mean[:nb, a], scale[:nb, a]
+                j0 += nb
+            partial = torch.empty(n_chunks * len(jobs) * 8 + 1, dtype=torch.float64, device=dev)
+            B.check(L.mcre_lsm_moments_batch(len(jobs), table.ctypes.data, count, CHUNK_PATHS, partial.data_ptr(),
+                                             moments.data_ptr(), RT.stream_ptr()))
         if nt:
             # the numeraire exp(r (t - t0)) is deterministic: its only tangent is the rate's (lane parameter 2)
+            nconst = torch.empty(n, dtype=torch.float64, device=dev)
             dnconst = torch.zeros((nt, n), dtype=torch.float64, device=dev)
             tmoments = torch.zeros((max(len(jobs), 1), nt * 9), dtype=torch.float64, device=dev)
             tpartial = torch.empty(n_chunks * nt * 9 + 1, dtype=torch.float64, device=dev)
-        t0 = self.num_model.t0()
-        last_k = None
-        for j, (p, k) in enumerate(jobs):
-            a = self._asset_index(p.asset_ids[0])
-            if k != last_k:
-                nk = math.exp(self.num_rate * (expo_times[k] - t0))
-                nconst.fill_(nk)
-                if nt:
-                    dnconst[2].fill_((expo_times[k] - t0) * nk)
-                last_k = k
-            B.check(L.mcre_lsm_step(xs[k, a].data_ptr(), nconst.data_ptr(), float(mean[k, a]), float(scale[k, a]),
-                                    None, None, None, None, 0.0, 1.0, cfs[id(p)].data_ptr(), count, CHUNK_PATHS,
-                                    partial.data_ptr(), moments[j].data_ptr(), RT.stream_ptr()))
-            if nt:
+            last_k = None
+            for j, (p, k) in enumerate(jobs):
+                a = self._asset_index(p.asset_ids[0])
+                if k != last_k:
+                    nconst.fill_(nk_of[k])
+                    dnconst[2].fill_((expo_times[k] - t0) * nk_of[k])
+                    last_k = k
                 B.check(L.mcre_lsm_step_tangents(nt, xs[k, a].data_ptr(), nconst.data_ptr(), dxs[k, a].data_ptr(),
                                                  dnconst.data_ptr(), float(mean[k, a]), float(scale[k, a]),
                                                  None, None, None, None, None, None, 0.0, 1.0, cfs[id(p)].data_ptr(),
@@ -957,8 +978,10 @@ class EquityBackend:
         for p in products:
             a = self._asset_index(p.asset_ids[0])
             self.expo_coef[id(p)] = (np.zeros((n_expo, 3)), np.stack([mean[:, a], scale[:, a]], axis=1))
-        for (p, k), cvec in zip(jobs, sol):
-            self.expo_coef[id(p)][0][k] = cvec
+        j0 = 0
+        for p, nb in zip(products, n_before):
+            self.expo_coef[id(p)][0][:nb] = sol[j0:j0 + nb]
+            j0 += nb
         for p in products:
             coef, basis = self.expo_coef[id(p)]
             c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coef, basis, [t <= t0 for t in expo_times]))

@@ -69,6 +69,9 @@ def main():
     ap.add_argument("--exposure-points", type=int, default=0,
                     help="> 0: EPE + PFE(0.95) on that many exposure dates over 2.5y "
                          "(tests/exposure_tests/ee_performance_large_netting_set.py) instead of PV")
+    ap.add_argument("--cva", action="store_true",
+                    help="CVA of the book against a counterparty with a CIR++ intensity, 80 exposure dates over the book's "
+                         "horizon, MPoR 10 days, EULER (tests/exposure_tests/cva_perfprmance_large_netting_set.py:69-193)")
     args = ap.parse_args()
     importlib.import_module("montecarlo-risk-engine_b200")
     import torch
@@ -83,22 +86,37 @@ def main():
                                  volatilities=[0.18 + 0.03 * i for i in range(4)], correlation_matrix=corr)
     prods = build_book(ns, ids, counts)
     nset = ns.NettingSet(name="mixed_state_dependent_book", products=prods)
-    if args.exposure_points > 0:
+    scheme = ns.SimulationScheme.ANALYTICAL
+    if args.cva:
+        credit = ns.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=cases.HAZARDS, kappa=0.10, theta=0.01,
+                               volatility=0.02, y0=0.0001)
+        market = model
+        model = ns.ModelConfig(models=[market, credit], inter_asset_correlation_matrix=[np.full((4, 1), 0.2, dtype=float)])
+        horizon = max(float(p.modeling_timeline[-1]) for p in prods)
+        nset = ns.NettingSet(name="mixed_state_dependent_book_cva", products=prods, counterparty_id="cp",
+                             margin_period_of_risk=10 / 252)
+        rm = ns.RiskMetrics([ns.CVAMetric("cp", 0.4)], exposure_timeline=np.linspace(0.0, horizon, args.exposure_points or 80))
+        scheme = ns.SimulationScheme.EULER
+    elif args.exposure_points > 0:
         rm = ns.RiskMetrics([ns.EPEMetric(), ns.PFEMetric(0.95)], exposure_timeline=np.linspace(0.0, 2.5, args.exposure_points))
     else:
         rm = ns.RiskMetrics([ns.PVMetric()])
-    sc = ns.SimulationController([nset], model, rm, args.paths, args.paths, 1, ns.SimulationScheme.ANALYTICAL, False)
+    sc = ns.SimulationController([nset], model, rm, args.paths, args.paths, 1, scheme, False)
     # warm-up on a tiny book of the same kinds: CUDA module loading and allocator growth are not product work
     warm = build_book(ns, ids, {k: 2 for k in base})
     ns.SimulationController([ns.NettingSet(name="warm", products=warm)], model, ns.RiskMetrics([ns.PVMetric()]), args.paths,
-                            args.paths, 1, ns.SimulationScheme.ANALYTICAL, False).run_simulation()
+                            args.paths, 1, scheme, False).run_simulation()
     torch.cuda.synchronize()
     l0 = B.launch_count()
     t0 = time.perf_counter()
     res = sc.run_simulation()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    if args.exposure_points > 0:
+    if args.cva:
+        shown = {"exposure_points": args.exposure_points or 80,
+                 "cva": float(res.get_results(nset.get_name(), "cva[cp]", evaluation_idx=0)),
+                 "mc_error": float(res.get_mc_error(nset.get_name(), "cva[cp]", evaluation_idx=0))}
+    elif args.exposure_points > 0:
         epe = np.asarray(res.get_results(nset.get_name(), "epe"))
         shown = {"exposure_points": args.exposure_points, "epe_mean": float(epe.mean()), "epe_max": float(epe.max()),
                  "pfe_max": float(np.asarray(res.get_results(nset.get_name(), "pfe[0.95]")).max())}
