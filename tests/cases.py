@@ -250,6 +250,33 @@ def equity_cva_exercise(ns_module):
     return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
 
 
+def big_cva_book(ns_module):
+    """More tracked products (Asians, barriers, an American) than one value-only launch holds, facing a counterparty
+    with a CIR++ intensity: CVA + EPE + PV of an MPoR-collateralised, thresholded netting set (book splitting)."""
+    m = ns_module
+    ids = ["asset_1", "asset_2"]
+    market = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                 volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    credit = m.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=HAZARDS, kappa=0.10, theta=0.01,
+                          volatility=0.02, y0=0.0001)
+    model = m.ModelConfig(models=[market, credit], inter_asset_correlation_matrix=[np.full((2, 1), 0.2, dtype=float)])
+    prods = []
+    for k in range(66):
+        a = ids[k % 2]
+        if k % 3 == 0:
+            prods.append(m.AsianOption(0.0, 0.5 + 0.25 * (k % 3), 95.0 + (k % 7), 3 + k % 3, m.OptionType.CALL if k % 2 else m.OptionType.PUT,
+                                       asset_id=a))
+        else:
+            prods.append(m.BarrierOption(startdate=0.0, maturity=0.5 + 0.25 * (k % 4), strike=100.0, num_observation_timepoints=3 + k % 4,
+                                         option_type=m.OptionType.CALL, barrier1=125.0 + k % 11,
+                                         barrier_option_type1=m.BarrierOptionType.UPANDOUT, asset_id=a))
+    prods.append(m.AmericanOption(underlying=m.Equity("asset_1"), maturity=1.0, num_exercise_dates=5, strike=100.0,
+                                  option_type=m.OptionType.PUT, asset_id="asset_1"))
+    prods.append(m.EuropeanOption(m.Equity("asset_2"), 1.0, 100.0, m.OptionType.CALL, asset_id="asset_2"))
+    sets = [m.NettingSet(name="big", products=prods, counterparty_id="cp", margin_period_of_risk=0.25, threshold=2.0)]
+    return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric(), m.PVMetric()], np.linspace(0.0, 1.25, 6)
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),

@@ -303,28 +303,7 @@ def test_large_mixed_book_cva_is_split_over_launches():
     mcre_eq_cva_paths + mcre_sum_stats finish.  Vs the oracle, which nets the whole book at once."""
     from oracle import risk
     ns = cases.Namespace()
-    ids = ["asset_1", "asset_2"]
-    market = ns.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
-                                  volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
-    credit = ns.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=cases.HAZARDS, kappa=0.10, theta=0.01,
-                           volatility=0.02, y0=0.0001)
-    model = ns.ModelConfig(models=[market, credit], inter_asset_correlation_matrix=[np.full((2, 1), 0.2, dtype=float)])
-    prods = []
-    for k in range(66):
-        a = ids[k % 2]
-        if k % 3 == 0:
-            prods.append(ns.AsianOption(0.0, 0.5 + 0.25 * (k % 3), 95.0 + (k % 7), 3 + k % 3, ns.OptionType.CALL if k % 2 else ns.OptionType.PUT,
-                                        asset_id=a))
-        else:
-            prods.append(ns.BarrierOption(startdate=0.0, maturity=0.5 + 0.25 * (k % 4), strike=100.0, num_observation_timepoints=3 + k % 4,
-                                          option_type=ns.OptionType.CALL, barrier1=125.0 + k % 11,
-                                          barrier_option_type1=ns.BarrierOptionType.UPANDOUT, asset_id=a))
-    prods.append(ns.AmericanOption(underlying=ns.Equity("asset_1"), maturity=1.0, num_exercise_dates=5, strike=100.0,
-                                   option_type=ns.OptionType.PUT, asset_id="asset_1"))
-    prods.append(ns.EuropeanOption(ns.Equity("asset_2"), 1.0, 100.0, ns.OptionType.CALL, asset_id="asset_2"))
-    sets = [ns.NettingSet(name="big", products=prods, counterparty_id="cp", margin_period_of_risk=0.25, threshold=2.0)]
-    metrics = [ns.CVAMetric("cp", 0.4), ns.EPEMetric(), ns.PVMetric()]
-    tl = np.linspace(0.0, 1.25, 6)
+    model, sets, metrics, tl = cases.big_cva_book(ns)
     n = 2048
     sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.EULER)
     res = sc.run_simulation()

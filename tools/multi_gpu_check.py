@@ -50,7 +50,8 @@ def main():
     n = 1 << args.paths_log2
     out = {}
     for name in ["wwr_cva", "wwr_cva_greeks", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption",
-                 "heston_path_dependent", "bs_basket_euler", "flexicall_exposure", "mixed_book_exposure"]:
+                 "heston_path_dependent", "bs_basket_euler", "flexicall_exposure", "mixed_book_exposure",
+                 "bs_exposure_greeks", "bs_proxy_greeks_mixed", "equity_cva", "equity_cva_exercise"]:
         res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0))
         vals = []
         for s in res.get_netting_set_names():
@@ -66,6 +67,11 @@ def main():
     res = sc.run_simulation()
     out["heston_basket5"] = [bits(res.get_results(s, "pv")[0]) for s in res.get_netting_set_names()] + \
         [bits(g) for s in res.get_netting_set_names() for g in res.get_derivatives(s, "pv")[0]]
+    # CVA of a book split over launches (default weights spilled by the first launch)
+    model, sets, metrics, tl = cases.big_cva_book(ns)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), n, n, 1, ns.SimulationScheme.EULER)
+    res = sc.run_simulation()
+    out["big_cva_book"] = [bits(v) for m in res.get_metric_names() for v in list(res.get_results("big", m)) + list(res.get_mc_error("big", m))]
     if RT.dist_info()[0] == 0:
         with open(args.out, "w") as f:
             json.dump(out, f)
