@@ -37,6 +37,13 @@ inline int cuda_fail(cudaError_t e, const char *what) {
 // cost ~0.1 ms each and a plan has ~40 tables, which showed up as several ms per run_simulation()
 // call.  While an arena is open (ArenaScope) DevArray::upload stages into it; commit() allocates,
 // copies once and patches every staged array's device pointer.
+// Plan arenas come from a small process-wide cache of device blocks (power-of-two size classes): books of thousands
+// of products create and destroy hundreds of plans and temporary tables per run, and cudaFree / cudaMalloc cost
+// milliseconds each once the process holds GBs of device memory (measured: 5 - 50 ms per call in the large-book runs).
+// A block goes back to the cache only after the device has drained (what cudaFree would have waited for, too).
+int arena_cache_get(size_t bytes, void **out, size_t *cap);
+void arena_cache_put(void *p, size_t cap);
+
 struct DevArena {
   struct Item { void **slot; size_t off; };
   std::vector<unsigned char> stage;
@@ -48,16 +55,18 @@ struct DevArena {
     memcpy(stage.data() + off, host, bytes);
     items.push_back({slot, off});
   }
+  size_t cap = 0;
   int commit() {
     if (stage.empty()) return 0;
-    MCRE_CUDA(cudaMalloc(&base, stage.size()));
+    const int rc = arena_cache_get(stage.size(), &base, &cap);
+    if (rc) return rc;
     MCRE_CUDA(cudaMemcpy(base, stage.data(), stage.size(), cudaMemcpyHostToDevice));
     for (const Item &it : items) *it.slot = (unsigned char *)base + it.off;
     std::vector<unsigned char>().swap(stage);
     items.clear();
     return 0;
   }
-  void release() { if (base) cudaFree(base); base = nullptr; }
+  void release() { if (base) arena_cache_put(base, cap); base = nullptr; cap = 0; }
 };
 extern thread_local DevArena *g_arena;
 struct ArenaScope {

@@ -128,23 +128,28 @@ __global__ void __launch_bounds__(256) lsm_moments_batch_kernel(const LsmJob *__
 }
 
 // Gathers the regression / exercise inputs of an equity exercise product from materialised paths
-// [n_paths][n_dates][state_dim]: one thread per path, date-major outputs (coalesced writes).
+// [n_paths][n_dates][state_dim]: blockIdx.y = output row (n_reg regression dates, then n_ex exercise dates), threads
+// over paths: date-major outputs (coalesced writes) and enough threads in flight for books on ~1000 paths (one
+// thread per path walking all dates was latency bound: 8 ms per product).
 __global__ void __launch_bounds__(256) lsm_prepare_equity_kernel(const double *__restrict__ paths, long long n, int n_dates,
-                                                                 int state_dim, int n_reg, const int *reg_date,
-                                                                 const double *reg_num, int n_ex, const int *ex_date,
-                                                                 int x_col, int x_is_log, int n_under, const int *ucol,
-                                                                 const double *uw, const int *ulog, double strike,
-                                                                 const double *ex_strike, double sign, double *x,
-                                                                 double *num, double *imm) {
+                                                                 int state_dim, int n_reg, const int *__restrict__ reg_date,
+                                                                 const double *__restrict__ reg_num, int n_ex,
+                                                                 const int *__restrict__ ex_date, int x_col, int x_is_log,
+                                                                 int n_under, const int *__restrict__ ucol,
+                                                                 const double *__restrict__ uw, const int *__restrict__ ulog,
+                                                                 double strike, const double *__restrict__ ex_strike,
+                                                                 double sign, double *__restrict__ x, double *__restrict__ num,
+                                                                 double *__restrict__ imm) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const double *row = paths + (size_t)p * n_dates * state_dim;
-  for (int k = 0; k < n_reg; ++k) {
+  const int k = blockIdx.y;
+  if (k < n_reg) {
     const double v = row[(size_t)reg_date[k] * state_dim + x_col];
     x[(size_t)k * n + p] = x_is_log ? exp(v) : v;
     num[(size_t)k * n + p] = reg_num[k];
-  }
-  for (int i = 0; i < n_ex; ++i) {
+  } else {
+    const int i = k - n_reg;
     const double *st = row + (size_t)ex_date[i] * state_dim;
     double U = 0.0;
     for (int j = 0; j < n_under; ++j) {
@@ -182,7 +187,7 @@ extern "C" int mcre_lsm_prepare_equity(const double *d_paths, int64_t n_paths, i
   if (!rc) rc = uw.upload(under_w, n_under);
   if (!rc) rc = arena.commit();
   if (!rc) {
-    lsm_prepare_equity_kernel<<<(unsigned)((n_paths + 255) / 256), 256, 0, st>>>(
+    lsm_prepare_equity_kernel<<<dim3((unsigned)((n_paths + 255) / 256), (unsigned)(n_reg + n_ex)), 256, 0, st>>>(
         d_paths, n_paths, n_dates, state_dim, n_reg, rd.p, rn.p, n_ex, ed.p, x_col, x_is_log, n_under, uc.p, uw.p, ul.p,
         strike, xs.p, sign, d_x, d_n, d_imm);
     g_launches.fetch_add(1, std::memory_order_relaxed);

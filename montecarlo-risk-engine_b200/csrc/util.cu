@@ -133,6 +133,59 @@ __global__ void dfma_peak_kernel(double *sink, int iters, double a, double b) {
 
 using namespace mcre;
 
+namespace mcre {
+namespace {
+std::mutex g_arena_mu;
+std::map<std::pair<int, size_t>, std::vector<void *>> g_arena_free;   // (device, size class) -> blocks
+size_t g_arena_cached = 0;
+constexpr size_t ARENA_CACHE_MAX = (size_t)1 << 30;                  // keep at most 1 GiB of idle blocks
+}  // namespace
+
+int arena_cache_get(size_t bytes, void **out, size_t *cap) {
+  size_t c = 4096;
+  while (c < bytes) c <<= 1;
+  int dev = 0;
+  MCRE_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(g_arena_mu);
+    auto it = g_arena_free.find(std::make_pair(dev, c));
+    if (it != g_arena_free.end() && !it->second.empty()) {
+      *out = it->second.back();
+      it->second.pop_back();
+      g_arena_cached -= c;
+      *cap = c;
+      return 0;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, c);
+  if (e != cudaSuccess) {
+    // out of memory with idle blocks around: hand them back and retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lock(g_arena_mu);
+      for (auto &kv : g_arena_free)
+        for (void *p : kv.second) cudaFree(p);
+      g_arena_free.clear();
+      g_arena_cached = 0;
+    }
+    MCRE_CUDA(cudaMalloc(out, c));
+  }
+  *cap = c;
+  return 0;
+}
+
+void arena_cache_put(void *p, size_t cap) {
+  if (!p) return;
+  int dev = 0;
+  if (cap == 0 || cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
+  cudaDeviceSynchronize();      // kernels that read the block have finished (cudaFree would wait for them as well)
+  std::lock_guard<std::mutex> lock(g_arena_mu);
+  if (g_arena_cached + cap > ARENA_CACHE_MAX) { cudaFree(p); return; }
+  g_arena_free[std::make_pair(dev, cap)].push_back(p);
+  g_arena_cached += cap;
+}
+}  // namespace mcre
+
 // Level buffers of mcre_tree_reduce: one grow-only device buffer per (device, stream); work queued on a
 // stream is ordered, so consecutive reductions on it can share the buffer.  (cudaMallocAsync was tried and
 // cost more than the reduction: the default pool hands its memory back at every synchronisation.)

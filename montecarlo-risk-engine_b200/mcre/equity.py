@@ -891,7 +891,10 @@ class EquityBackend:
                 slots = L.mcre_eq_slots(plan)
                 cf = torch.zeros((len(group), n), dtype=torch.float32, device=dev)
                 dcf = torch.zeros((len(group), nt, n), dtype=torch.float64, device=dev) if nt else None
-                partial = torch.empty(n_chunks * slots + slots + 1, dtype=torch.float64, device=dev)
+                # the spill pass uses none of the kernel's sums, so its reduction chunk is free: small chunks for small
+                # pre-simulations (one 4096-path chunk would put a 1000-path book on a single SM)
+                spill_chunk = main_chunk(n_pre)
+                partial = torch.empty(((n + spill_chunk - 1) // spill_chunk) * slots + slots + 1, dtype=torch.float64, device=dev)
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
                 rng = B.Rng()
                 rng.seed, rng.stream, rng.n_paths_total = 42, c.rng_stream, n_pre
@@ -905,7 +908,7 @@ class EquityBackend:
                 else:
                     rng.mode = B.RNG_PHILOX
                 keep_bridge = self._set_bridge_uniforms(plan, info, "pre", n_pre, dev)
-                sh = B.Shard(begin, count, CHUNK_PATHS)
+                sh = B.Shard(begin, count, spill_chunk)
                 if nt:
                     B.check(L.mcre_eq_presim_tangents(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), shift.data_ptr(),
                                                       xs.data_ptr(), cf.data_ptr(), dxs.data_ptr(), dcf.data_ptr(),

@@ -123,6 +123,7 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
     pathwise tangents of the spilled arrays; the generator then also returns d(coefficients)/d(parameters)
     [n_reg, nt, 3] (mcre_lsm_step_tangents + regression_tangents): -> (coef, dcoef)."""
     L = B.lib()
+    stream = RT.stream_ptr()      # once per induction: tens of thousands of steps per book
     n_reg = len(reg_times)
     n = xs.shape[1]
     R = int(n_rights)
@@ -155,7 +156,7 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
                       float(basis[ki, 0]), float(basis[ki, 1]))
         B.check(L.mcre_lsm_step_states(R, xs[k].data_ptr(), nums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]),
                                        *args_i, value.data_ptr(), count, chunk_paths, partial.data_ptr(),
-                                       moments.data_ptr(), RT.stream_ptr()))
+                                       moments.data_ptr(), stream))
         if tangents is not None:
             # same exercise decision applied to the running tangents, then the tangent moments of date k
             targs = (None, None, None, None, None, None, 0.0, 1.0)
@@ -165,7 +166,7 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
             B.check(L.mcre_lsm_step_tangents(nt, xs[k].data_ptr(), nums[k].data_ptr(), dxs[k].data_ptr(),
                                              dnums[k].data_ptr(), float(basis[k, 0]), float(basis[k, 1]), *targs,
                                              value.data_ptr(), dvalue.data_ptr(), count, chunk_paths,
-                                             tpartial.data_ptr(), tmoments.data_ptr(), RT.stream_ptr()))
+                                             tpartial.data_ptr(), tmoments.data_ptr(), stream))
 
     last = len(ptl)
     for k in range(n_reg - 1, -1, -1):
