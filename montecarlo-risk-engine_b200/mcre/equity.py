@@ -226,6 +226,13 @@ class EquityBackend:
         offs = ctrl.model.param_offsets() if isinstance(ctrl.model, ModelConfig) else [0]
         self.num_rate_global = offs[num_idx] + self._rate_index(self.num_model)
         self.num_rate = self.num_model.param_values()[self._rate_index(self.num_model)]
+        if ctrl.differentiate and ctrl.risk_metrics.requires_exposure_profiles():
+            # checked before any device work (the same conditions guard the lowering)
+            if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
+                raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
+                                          "model (single or multi-asset)")
+            if any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics):
+                raise NotImplementedError("PFE sensitivities are not implemented for equity books")
 
     @staticmethod
     def _rate_index(m):

@@ -143,3 +143,34 @@ def test_constructor_error_behaviour_matches_the_reference():
     with pytest.raises(NotImplementedError):
         from products.storage import Storage
         Storage(asset_id="gas", start_date=0.0, end_date=1.0)
+
+
+def test_unsupported_combinations_raise_instead_of_falling_back():
+    """what the CUDA backends do not cover raises NotImplementedError when the backend is chosen (before any
+    device work, so this runs without a GPU); nothing falls back to a CPU path."""
+    ns = cases.Namespace()
+    S = ns.SimulationScheme
+    tl = np.linspace(0.0, 1.5, 4)
+
+    # hybrid equity + credit: value-only, EULER only (the reference's ModelConfig has the same scheme restriction)
+    def hybrid(differentiate, scheme):
+        model, sets, metrics, tl_ = cases.equity_cva(ns)
+        return ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl_), 64, 64, 1, scheme, differentiate)
+    for differentiate, scheme in ((True, S.EULER), (False, S.ANALYTICAL)):
+        with pytest.raises(NotImplementedError):
+            hybrid(differentiate, scheme).run_simulation()
+
+    # sensitivities of exposure profiles of equity books: Black-Scholes only, no PFE, no exercise products
+    heston = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    opt = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
+    sc = ns.SimulationController([ns.NettingSet(name="h", products=[opt])], heston,
+                                 ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), 64, 64, 2, S.QE, True)
+    with pytest.raises(NotImplementedError):
+        sc.run_simulation()
+    bs = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.2)
+    opt = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
+    sc = ns.SimulationController([ns.NettingSet(name="p", products=[opt])], bs,
+                                 ns.RiskMetrics([ns.EPEMetric(), ns.PFEMetric(0.95)], exposure_timeline=tl), 64, 0, 1,
+                                 S.ANALYTICAL, True)
+    with pytest.raises(NotImplementedError):
+        sc.run_simulation()
