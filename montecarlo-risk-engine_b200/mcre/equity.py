@@ -417,7 +417,7 @@ class EquityBackend:
 
     def lower(self, set_indices, presim_products=None, subset=None, presim_tangents=False):
         """Plan of the main pass for a group of netting sets, or (presim_products given) of the
-        pre-simulation spill pass for a group of products (all in one dummy set).  `subset`: ids of the
+        pre-simulation spill pass for a group of products (all in one dummy set).  `subset`: the
         products to keep (book splitting: one launch evaluates a part of a large netting set)."""
         c, nt, A = self.c, self.nt, self.A
         if presim_products is not None and not presim_tangents:
@@ -449,9 +449,12 @@ class EquityBackend:
         recs, weights, xweights, events = [], [], [], [[] for _ in range(n_dates)]
         owners = []
         slot = 0
-        book = ([(0, p) for p in presim_products] if presim_products is not None else
-                [(r, p) for r, si in enumerate(set_indices) for p in c.netting_sets[si].products
-                 if subset is None or id(p) in subset])
+        if presim_products is not None:
+            book = [(0, p) for p in presim_products]
+        elif subset is not None:
+            book = [(0, p) for p in subset]      # book splitting: one netting set, products in netting-set order
+        else:
+            book = [(r, p) for r, si in enumerate(set_indices) for p in c.netting_sets[si].products]
         for r, p in book:
             if True:
                 if c._can_skip_monte_carlo_for_product(p):
@@ -838,8 +841,9 @@ class EquityBackend:
             degen = [t <= t0 for t in reg_times]
             raw = np.stack([to_raw_basis(coef[:, st, :], basis, degen) for st in range(R)], axis=1)   # [n_reg, R, 3]
             # state s = rights left keeps its coefficients at row s, like the reference's [date, state, basis] tensors
-            for j, t in enumerate(prod.regression_timeline.tolist()):
-                prod.regression_coeffs[j, 1:R + 1, :] = torch.tensor(raw[ridx[t]])
+            rrows = [ridx[t] for t in prod.regression_timeline.tolist()]
+            if rrows:
+                prod.regression_coeffs[:len(rrows), 1:R + 1, :] = torch.from_numpy(raw[rrows])
             if expo_times:
                 erows = [ridx[t] for t in expo_times]
                 self.exercise_expo_coef[id(prod)] = (coef[erows], basis[erows])
@@ -1022,6 +1026,7 @@ class EquityBackend:
         L = B.lib()
         ntrk = eq_ntrk(self.nt)
         prods = [p for p in c.netting_sets[si].products if not c._can_skip_monte_carlo_for_product(p)]
+        order = {id(p): i for i, p in enumerate(c.netting_sets[si].products)}
         tracked = [p for p in prods if _is_path_dependent(p)]
         plain = [p for p in prods if not _is_path_dependent(p)]
         books = [tracked[i:i + ntrk] for i in range(0, len(tracked), ntrk)]
@@ -1044,7 +1049,7 @@ class EquityBackend:
         grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
         cva_metric, cva_w = None, None
         for bi, book in enumerate(books):
-            desc, keep, info = self.lower([si], subset={id(p) for p in book})
+            desc, keep, info = self.lower([si], subset=sorted(book, key=lambda p: order[id(p)]))
             plan = C.c_void_p()
             B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
             try:
