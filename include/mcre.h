@@ -452,6 +452,21 @@ int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double
 typedef struct { const double *x; const float *v; double nk, shift, scale; } mcre_lsm_job;
 int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, int64_t n, int32_t chunk_paths,
                            double *d_partial, double *d_moments, void *stream);
+/* mcre_lsm_step_states for MANY products in one launch (the lock-step backward inductions of a book: one job per
+ * product and round): d_moments [n_jobs][14] (row layout of the 3-rights step, unused tail zero), bit-identical to the
+ * per-product calls; d_partial [ceil(n / chunk_paths)][n_jobs][14].  coef: [3][3] continuation coefficients of the
+ * product date (has_coef = 0: none); imm NULL: no exercise update.  `jobs` is a host array of device pointers. */
+typedef struct {
+  int32_t n_rights, has_coef;
+  const double *xk, *nk;
+  double shift_k, scale_k;
+  const double *xi, *ni, *imm;
+  double coef[9];
+  double shift_i, scale_i;
+  float *value;
+} mcre_lsm_step_job;
+int mcre_lsm_step_batch(int64_t n_jobs, const mcre_lsm_step_job *jobs, int64_t n, int32_t chunk_paths,
+                        double *d_partial, double *d_moments, void *stream);
 /* The same with n_rights = 1..3 exercise rights (FlexiCall, src/products/flexicall.py:56-160): the product state
  * is the number of rights left, d_value is [n_rights][n] (state s at row s-1; state 0 carries nothing),
  * coef_i host [n_rights][3] (continuation of state s at product date i), d_moments [5 + 3 n_rights]:

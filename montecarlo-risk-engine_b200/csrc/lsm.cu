@@ -13,6 +13,9 @@
 // HBM-bound, 5 coalesced f64 streams + the f32 value array (36 B / path / date).
 #include "common.cuh"
 #include "reduce.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mcre {
 
@@ -26,6 +29,65 @@ struct LsmCoef { double c[LSM_MAX_RIGHTS][3]; };
 //     ex_s = imm_i + cont_i(s-1) > cont_i(s)                       (hard indicator, cont(0) = 0)
 //     V_s <- fp32( fp32(ex_s ? imm_i / N_i : 0) + (ex_s ? V_{s-1} : V_s) )
 // then the moments of regression date k: sum u^0..u^4 and per state sum u^0..u^2 N_k V_s  (5 + 3R).
+// One (chunk) work item of the step: shared by the per-product kernel and the batched one, so both produce the same
+// bits.  out: NV partial sums of this chunk.
+template <int R>
+__device__ __forceinline__ void lsm_step_item(const double *__restrict__ xk, const double *__restrict__ nk, double shift_k,
+                                              double scale_k, const double *__restrict__ xi, const double *__restrict__ ni,
+                                              const double *__restrict__ imm, int has_coef, const LsmCoef &cf, double shift_i,
+                                              double scale_i, float *__restrict__ value, long long n, int chunk, long long ch,
+                                              double *acc, double *stage, double *__restrict__ out) {
+  constexpr int NV = 5 + 3 * R;
+  if (threadIdx.x < NV) acc[threadIdx.x] = 0.0;
+  __syncthreads();
+  int parity = 0;
+  // each thread first sums its own paths of the chunk (stride blockDim), the block reduces once
+  double vals[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) vals[i] = 0.0;
+  for (int it = 0; it < chunk; it += blockDim.x) {
+    const long long p = ch * chunk + it + threadIdx.x;
+    if (it + (int)threadIdx.x < chunk && p < n) {
+      float v[R];
+#pragma unroll
+      for (int s = 0; s < R; ++s) v[s] = value[(size_t)s * n + p];
+      if (imm) {
+        const double im = imm[p];
+        double cont[R + 1];
+        cont[0] = 0.0;
+        const double ui = has_coef ? (xi[p] - shift_i) * scale_i : 0.0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) cont[s + 1] = has_coef ? cf.c[s][0] + ui * (cf.c[s][1] + ui * cf.c[s][2]) : 0.0;
+        const double pay = im / ni[p];
+        float nv[R];
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          const bool ex = im + cont[s] > cont[s + 1];
+          // float32 step value updated with a float64 cashflow, then float32 + float32
+          // (controller.py:330-349)
+          const float step = (float)(ex ? pay : 0.0);
+          const float prev = s > 0 ? v[s - 1] : 0.0f;
+          nv[s] = step + (ex ? prev : v[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) { v[s] = nv[s]; value[(size_t)s * n + p] = nv[s]; }
+      }
+      const double u = (xk[p] - shift_k) * scale_k;
+      const double u2 = u * u;
+      vals[0] += 1.0; vals[1] += u; vals[2] += u2; vals[3] += u2 * u; vals[4] += u2 * u2;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const double y = nk[p] * (double)v[s];   // numeraire * total cashflows (controller.py:368)
+        vals[5 + 3 * s] += y; vals[6 + 3 * s] += y * u; vals[7 + 3 * s] += y * u2;
+      }
+    }
+  }
+  block_accumulate<NV>(vals, acc, 0, stage, NV, parity);
+  __syncthreads();
+  if (threadIdx.x < NV) out[threadIdx.x] = acc[threadIdx.x];
+  __syncthreads();
+}
+
 template <int R>
 __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict__ xk, const double *__restrict__ nk,
                                                        double shift_k, double scale_k, const double *__restrict__ xi,
@@ -37,55 +99,44 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
   __shared__ double acc[NV];
   __shared__ double stage[2 * 8 * NV];
   const long long n_chunks = (n + chunk - 1) / chunk;
-  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-    if (threadIdx.x < NV) acc[threadIdx.x] = 0.0;
-    __syncthreads();
-    int parity = 0;
-    // each thread first sums its own paths of the chunk (stride blockDim), the block reduces once
-    double vals[NV];
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x)
+    lsm_step_item<R>(xk, nk, shift_k, scale_k, xi, ni, imm, has_coef, cf, shift_i, scale_i, value, n, chunk, ch, acc, stage,
+                     partial + ch * NV);
+}
+
+// The steps of MANY exercise products in one launch (the lock-step backward inductions of a book: one job per
+// product and round).  Work item = (job, chunk); the moments of every job sit in a row of LSM_NV_MAX doubles
+// (unused tail zero).  partial: [chunk][job][LSM_NV_MAX].
+constexpr int LSM_NV_MAX = 5 + 3 * LSM_MAX_RIGHTS;
+struct LsmStepJob {
+  int n_rights, has_coef;
+  const double *xk, *nk;
+  double shift_k, scale_k;
+  const double *xi, *ni, *imm;
+  double coef[9];
+  double shift_i, scale_i;
+  float *value;
+};
+__global__ void __launch_bounds__(256) lsm_step_batch_kernel(const LsmStepJob *__restrict__ jobs, long long n_jobs, long long n,
+                                                             int chunk, double *__restrict__ partial) {
+  __shared__ double acc[LSM_NV_MAX];
+  __shared__ double stage[2 * 8 * LSM_NV_MAX];
+  const long long n_chunks = (n + chunk - 1) / chunk;
+  for (long long w = blockIdx.x; w < n_jobs * n_chunks; w += gridDim.x) {
+    const long long j = w / n_chunks, ch = w - j * n_chunks;
+    const LsmStepJob *job = jobs + j;
+    LsmCoef cf;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) vals[i] = 0.0;
-    for (int it = 0; it < chunk; it += blockDim.x) {
-      const long long p = ch * chunk + it + threadIdx.x;
-      if (it + (int)threadIdx.x < chunk && p < n) {
-        float v[R];
+    for (int s = 0; s < LSM_MAX_RIGHTS; ++s)
 #pragma unroll
-        for (int s = 0; s < R; ++s) v[s] = value[(size_t)s * n + p];
-        if (imm) {
-          const double im = imm[p];
-          double cont[R + 1];
-          cont[0] = 0.0;
-          const double ui = has_coef ? (xi[p] - shift_i) * scale_i : 0.0;
-#pragma unroll
-          for (int s = 0; s < R; ++s) cont[s + 1] = has_coef ? cf.c[s][0] + ui * (cf.c[s][1] + ui * cf.c[s][2]) : 0.0;
-          const double pay = im / ni[p];
-          float nv[R];
-#pragma unroll
-          for (int s = 0; s < R; ++s) {
-            const bool ex = im + cont[s] > cont[s + 1];
-            // float32 step value updated with a float64 cashflow, then float32 + float32
-            // (controller.py:330-349)
-            const float step = (float)(ex ? pay : 0.0);
-            const float prev = s > 0 ? v[s - 1] : 0.0f;
-            nv[s] = step + (ex ? prev : v[s]);
-          }
-#pragma unroll
-          for (int s = 0; s < R; ++s) { v[s] = nv[s]; value[(size_t)s * n + p] = nv[s]; }
-        }
-        const double u = (xk[p] - shift_k) * scale_k;
-        const double u2 = u * u;
-        vals[0] += 1.0; vals[1] += u; vals[2] += u2; vals[3] += u2 * u; vals[4] += u2 * u2;
-#pragma unroll
-        for (int s = 0; s < R; ++s) {
-          const double y = nk[p] * (double)v[s];   // numeraire * total cashflows (controller.py:368)
-          vals[5 + 3 * s] += y; vals[6 + 3 * s] += y * u; vals[7 + 3 * s] += y * u2;
-        }
-      }
-    }
-    block_accumulate<NV>(vals, acc, 0, stage, NV, parity);
-    __syncthreads();
-    if (threadIdx.x < NV) partial[ch * NV + threadIdx.x] = acc[threadIdx.x];
-    __syncthreads();
+      for (int q = 0; q < 3; ++q) cf.c[s][q] = job->coef[s * 3 + q];
+    double *out = partial + ((size_t)ch * n_jobs + j) * LSM_NV_MAX;
+    const int R = job->n_rights;
+    if (threadIdx.x >= 5 + 3 * R && threadIdx.x < LSM_NV_MAX) out[threadIdx.x] = 0.0;
+#define LSM_ITEM(RV) lsm_step_item<RV>(job->xk, job->nk, job->shift_k, job->scale_k, job->xi, job->ni, job->imm, job->has_coef, \
+                                       cf, job->shift_i, job->scale_i, job->value, n, chunk, ch, acc, stage, out)
+    if (R == 1) LSM_ITEM(1); else if (R == 2) LSM_ITEM(2); else LSM_ITEM(3);
+#undef LSM_ITEM
   }
 }
 
@@ -230,6 +281,55 @@ extern "C" int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const 
   return mcre_tree_reduce(d_partial, n_chunks, nv, d_moments, stream);
 }
 
+// Job tables of the batched launches: one grow-only device buffer per (device, stream); the upload is ordered on
+// the stream after the previous launch that read the buffer.
+static int job_scratch(cudaStream_t st, size_t bytes, void **out) {
+  struct Buf { void *p = nullptr; size_t cap = 0; };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  int dev = 0;
+  MCRE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  Buf &b = bufs[std::make_pair(dev, st)];
+  if (b.cap < bytes) {
+    if (b.p) { MCRE_CUDA(cudaStreamSynchronize(st)); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t cap = (size_t)1 << 20;
+    while (cap < bytes) cap <<= 1;
+    MCRE_CUDA(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+  }
+  *out = b.p;
+  return 0;
+}
+
+extern "C" int mcre_lsm_step_batch(int64_t n_jobs, const mcre_lsm_step_job *jobs, int64_t n, int32_t chunk_paths,
+                                   double *d_partial, double *d_moments, void *stream) {
+  if (n_jobs <= 0) return 0;
+  if (!jobs || !d_partial || !d_moments) return fail(-1, "null argument%s", "");
+  if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
+  static_assert(sizeof(LsmStepJob) == sizeof(mcre_lsm_step_job), "job record layout");
+  for (int64_t j = 0; j < n_jobs; ++j) {
+    if (jobs[j].n_rights < 1 || jobs[j].n_rights > LSM_MAX_RIGHTS) return fail(-3, "lsm: 1..3 exercise rights are supported%s", "");
+    if (!jobs[j].xk || !jobs[j].nk || !jobs[j].value) return fail(-1, "lsm batch: null job array%s", "");
+    if (jobs[j].imm && (!jobs[j].xi || !jobs[j].ni)) return fail(-1, "lsm: exercise update needs x_i and N_i%s", "");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {
+    MCRE_CUDA(cudaMemsetAsync(d_moments, 0, (size_t)n_jobs * LSM_NV_MAX * sizeof(double), st));
+    return 0;
+  }
+  void *d_jobs = nullptr;
+  int rc = job_scratch(st, (size_t)n_jobs * sizeof(LsmStepJob), &d_jobs);
+  if (rc) return rc;
+  MCRE_CUDA(cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmStepJob), cudaMemcpyHostToDevice, st));
+  const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
+  long long grid = (long long)sm_count() * 8;
+  if (grid > n_jobs * n_chunks) grid = n_jobs * n_chunks;
+  lsm_step_batch_kernel<<<(unsigned)grid, 256, 0, st>>>((const LsmStepJob *)d_jobs, n_jobs, n, chunk_paths, d_partial);
+  MCRE_LAUNCHED();
+  return mcre_tree_reduce(d_partial, n_chunks, n_jobs * LSM_NV_MAX, d_moments, stream);
+}
+
 extern "C" int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, int64_t n, int32_t chunk_paths,
                                       double *d_partial, double *d_moments, void *stream) {
   if (n_jobs <= 0) return 0;
@@ -241,20 +341,17 @@ extern "C" int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, 
     MCRE_CUDA(cudaMemsetAsync(d_moments, 0, (size_t)n_jobs * 8 * sizeof(double), st));
     return 0;
   }
-  LsmJob *d_jobs = nullptr;
-  MCRE_CUDA(cudaMalloc((void **)&d_jobs, (size_t)n_jobs * sizeof(LsmJob)));
-  cudaError_t e = cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmJob), cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) { cudaFree(d_jobs); return cuda_fail(e, "job table upload"); }
+  void *d_jobs_v = nullptr;
+  int rc = job_scratch(st, (size_t)n_jobs * sizeof(LsmJob), &d_jobs_v);
+  if (rc) return rc;
+  LsmJob *d_jobs = (LsmJob *)d_jobs_v;
+  MCRE_CUDA(cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmJob), cudaMemcpyHostToDevice, st));
   const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
   long long grid = (long long)sm_count() * 8;
   if (grid > n_jobs * n_chunks) grid = n_jobs * n_chunks;
   lsm_moments_batch_kernel<<<(unsigned)grid, 256, 0, st>>>(d_jobs, n_jobs, n, chunk_paths, d_partial);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  e = cudaGetLastError();
-  int rc = e != cudaSuccess ? cuda_fail(e, "kernel launch") : mcre_tree_reduce(d_partial, n_chunks, n_jobs * 8, d_moments, stream);
-  cudaStreamSynchronize(st);   // the job table is freed below
-  cudaFree(d_jobs);
-  return rc;
+  MCRE_LAUNCHED();
+  return mcre_tree_reduce(d_partial, n_chunks, n_jobs * 8, d_moments, stream);
 }
 
 extern "C" int mcre_lsm_step(const double *d_xk, const double *d_nk, double shift_k, double scale_k, const double *d_xi,

@@ -831,7 +831,8 @@ class EquityBackend:
         del paths
         # standardisation of the explanatory variable per date: model moments (shard independent)
         basis = np.array([self.basis_at(xi, t) for t in reg_times]).reshape(n_reg, 2)
-        gen = backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R)
+        gen = backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, n_rights=R,
+                                       batched=prepare_only)
 
         def finish(coef):
             coef = coef.reshape(n_reg, R, 3)

@@ -108,7 +108,23 @@ def regression_tangents(G, rhs, coef, tm):
 LSM_MAX_NV = 5 + 3 * 3   # moments of the widest step (3 exercise rights)
 
 
-def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1, tangents=None):
+#: mcre_lsm_step_job (include/mcre.h)
+STEP_JOB = np.dtype([("n_rights", "i4"), ("has_coef", "i4"), ("xk", "u8"), ("nk", "u8"), ("shift_k", "f8"), ("scale_k", "f8"),
+                     ("xi", "u8"), ("ni", "u8"), ("imm", "u8"), ("coef", "f8", (9,)), ("shift_i", "f8"), ("scale_i", "f8"),
+                     ("value", "u8")])
+assert STEP_JOB.itemsize == 160
+
+
+class DeferredSteps:
+    """What a generator yields in batched mode: the step jobs of its current round (to be run in order) instead of
+    launching them itself; the driver runs the j-th jobs of all products in one launch (mcre_lsm_step_batch)."""
+
+    def __init__(self, jobs, count, chunk_paths):
+        self.jobs, self.count, self.chunk_paths = jobs, count, chunk_paths
+
+
+def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev, n_rights=1, tangents=None,
+                             batched=False):
     """Generator form of the backward induction: queues the kernels of one regression date, yields the device
     tensor that will hold its moments and expects the solved coefficients of that date back (`send`: [3, 3],
     one row per state, from the driver's all-reduce + batched normal-equation solve).  Returns the
@@ -144,8 +160,26 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
         tmoments = torch.zeros(nt * 9, dtype=torch.float64, device=dev)
         dcoef = np.zeros((n_reg, nt, 3))
 
+    batched = batched and tangents is None
+    queue = []
+    xs_ptr, nums_ptr, imm_ptr, value_ptr, row = xs.data_ptr(), nums.data_ptr(), imm.data_ptr(), value.data_ptr(), n * 8
+
     def step(k, i):
         """moments of regression date k, after the exercise update at product date i (or None)."""
+        if batched:
+            # the same call as below, recorded for the driver's batched launch
+            job = np.zeros((), dtype=STEP_JOB)
+            job["n_rights"], job["xk"], job["nk"] = R, xs_ptr + k * row, nums_ptr + k * row
+            job["shift_k"], job["scale_k"], job["scale_i"], job["value"] = basis[k, 0], basis[k, 1], 1.0, value_ptr
+            if i is not None:
+                ki = reg_idx[ptl[i]]
+                job["xi"], job["ni"], job["imm"] = xs_ptr + ki * row, nums_ptr + ki * row, imm_ptr + i * row
+                job["shift_i"], job["scale_i"] = basis[ki, 0], basis[ki, 1]
+                if i < len(ptl) - 1:
+                    job["has_coef"] = 1
+                    job["coef"][:3 * R] = coef[ki].reshape(-1)
+            queue.append(job)
+            return
         args_i = (None, None, None, None, 0.0, 1.0)
         if i is not None:
             ki = reg_idx[ptl[i]]
@@ -182,7 +216,12 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
             last = t_next
         else:
             step(k, None)
-        solved, m = yield moments       # [3 states, 3] from the driver's batched solve of this round, host moments
+        if batched:
+            jobs = list(queue)
+            del queue[:]
+            solved, m = yield DeferredSteps(jobs, count, chunk_paths)
+        else:
+            solved, m = yield moments   # [3 states, 3] from the driver's batched solve of this round, host moments
         coef[k] = solved[:R]
         if tangents is not None:
             tm = RT.all_reduce_tree(tmoments).cpu().numpy().reshape(nt, 9)
@@ -204,8 +243,33 @@ def run_backward_inductions(gens):
             pending[i] = next(g)
         except StopIteration as e:
             results[i] = e.value
+    L = B.lib()
     while pending:
         keys = list(pending)
+        deferred = [k for k in keys if isinstance(pending[k], DeferredSteps)]
+        if deferred:
+            # wave w = the w-th step of every product of the round, one launch per wave; a product's moments are those
+            # of its last step
+            dev = RT.compute_device()
+            stream = RT.stream_ptr()
+            first = pending[deferred[0]]
+            n_chunks = max((first.count + first.chunk_paths - 1) // first.chunk_paths, 1)
+            out_rows = {}
+            w = 0
+            while True:
+                wave = [k for k in deferred if len(pending[k].jobs) > w]
+                if not wave:
+                    break
+                table = np.array([pending[k].jobs[w] for k in wave], dtype=STEP_JOB)
+                mom = torch.zeros((len(wave), LSM_MAX_NV), dtype=torch.float64, device=dev)
+                partial = torch.empty(n_chunks * len(wave) * LSM_MAX_NV + 1, dtype=torch.float64, device=dev)
+                B.check(L.mcre_lsm_step_batch(len(wave), table.ctypes.data, first.count, first.chunk_paths,
+                                              partial.data_ptr(), mom.data_ptr(), stream))
+                for j, k in enumerate(wave):
+                    out_rows[k] = mom[j]
+                w += 1
+            for k in deferred:
+                pending[k] = out_rows[k]
         m = RT.all_reduce_tree(torch.stack([pending[k] for k in keys])).cpu().numpy()      # [K, LSM_MAX_NV]
         G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
         # one batched solve per state for all products of the round (states a product does not have carry zeros)
