@@ -60,7 +60,8 @@ def solve_normal_equations_batch(G, rhs):
     if full.any():
         sol = np.linalg.solve(Gs_safe[full], (rhs[full] / scale[full])[:, :, None])[:, :, 0]
         out[full] = sol / scale[full]
-    for k in np.nonzero(~full)[0]:
+    todo = ~full & np.any(rhs != 0.0, axis=1)      # a zero right-hand side has the zero solution in every branch
+    for k in np.nonzero(todo)[0]:
         out[k] = solve_normal_equations(G[k], rhs[k])
     return out
 
