@@ -78,6 +78,9 @@ struct EqDev {
   // and the tangent spill of the pre-simulation pass (mcre_eq_presim_tangents): ps_dx [n_expo][A][nt][n_paths],
   // ps_dcf [n_prod][nt][n_paths] (f64: the reference's float32 rounding touches values only under autograd's chain)
   const double *xp_tan;
+  // per exposure date the products whose record carries an exposure (type != 0), ascending: xact[xact_off[e] .. xact_off[e+1])
+  // (built by mcre_eq_create from xp; matured products and the other launches' products are never visited)
+  const int *xact_off, *xact;
   double *ps_dx, *ps_dcf;
   // credit factor of a hybrid ModelConfig (mcre_eq_set_credit): CIR++ intensity of the counterparty stepped next to
   // the equity assets (cirpp.py:155-198), its normal = noise column cir_col correlated through cir_row [noise_dim]
@@ -288,10 +291,12 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
           // (ncu: long_scoreboard 9 of 14 cycles per issue, half of all stall samples on the record's first load).
           // One 128-byte record = one line: prefetch EQ_PF records ahead into L1.
           const double *xrow = P.xp + (size_t)xe * P.n_prod * EQ_XP;
-          for (int pi = 0; pi < EQ_PF && pi < P.n_prod; ++pi) prefetch_l1(xrow + (size_t)pi * EQ_XP);
-          for (int pi = 0; pi < P.n_prod; ++pi) {
+          const int q0 = __ldg(P.xact_off + xe), q1 = __ldg(P.xact_off + xe + 1);
+          for (int q = q0; q < q0 + EQ_PF && q < q1; ++q) prefetch_l1(xrow + (size_t)__ldg(P.xact + q) * EQ_XP);
+          for (int q = q0; q < q1; ++q) {
+            const int pi = __ldg(P.xact + q);
             const double *op = xrow + (size_t)pi * EQ_XP;
-            if (pi + EQ_PF < P.n_prod) prefetch_l1(op + EQ_PF * EQ_XP);
+            if (q + EQ_PF < q1) prefetch_l1(xrow + (size_t)__ldg(P.xact + q + EQ_PF) * EQ_XP);
             const int xtype = (int)__ldg(op);
             if (xtype == 0) continue;
             const double *pr = P.prod + (size_t)pi * EQ_PR;
@@ -763,7 +768,7 @@ struct mcre_eq_plan {
   DevArena arena;   // all plan tables live in one device allocation
   DevArray<double> asset_par, step_dt, step_sq, step_aux, init_aux, chol, chol_dual, prod, prod_w, ev_data, prod_x;
   DevArray<int> asset_noise, asset_uniform, col_asset, col_elem, step_date, step_chol, date_ev_off, ev_prod, ev_flags;
-  DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src;
+  DevArray<int> date_expo, date_metric, set_flags, set_lag, sp_src, xact_off, xact;
   DevArray<double> xp, set_threshold, sp_coef;
   double *xp_tan = nullptr;   // own allocation (set after mcre_eq_create)
   double *credit = nullptr;   // own allocation (mcre_eq_set_credit): step_cir, cir_row, cva_coef, set_cva
@@ -819,6 +824,15 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
     UP(xp, c->xp, (size_t)c->n_expo * c->n_prod * EQ_XP);
     UP(set_threshold, c->set_threshold, c->n_sets); UP(set_flags, c->set_flags, c->n_sets);
     UP(set_lag, c->set_lag, (size_t)c->n_sets * c->n_metric);
+    // products with an exposure per date (see EqDev)
+    std::vector<int> off(c->n_expo + 1, 0), act;
+    for (int e = 0; e < c->n_expo; ++e) {
+      for (int pi = 0; pi < c->n_prod; ++pi)
+        if (c->xp[((size_t)e * c->n_prod + pi) * EQ_XP] != 0.0) act.push_back(pi);
+      off[e + 1] = (int)act.size();
+    }
+    if (act.empty()) act.push_back(0);
+    UP(xact_off, off.data(), off.size()); UP(xact, act.data(), act.size());
   }
   // sparse rows of the joint Cholesky factor (see EqDev)
   int sp_n = 0;
@@ -867,6 +881,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   D.n_expo = c->n_expo; D.n_metric = c->n_expo > 0 ? c->n_metric : 0; D.acc_flags = c->acc_flags;
   D.date_expo = p->date_expo.p; D.date_metric = p->date_metric.p; D.xp = p->xp.p;
   D.set_threshold = p->set_threshold.p; D.set_flags = p->set_flags.p; D.set_lag = p->set_lag.p;
+  D.xact_off = p->xact_off.p; D.xact = p->xact.p;
   *out = p;
   return 0;
 }
@@ -880,6 +895,7 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
   p->ev_data.release(); p->prod_x.release();
   p->date_expo.release(); p->date_metric.release(); p->set_flags.release(); p->set_lag.release();
   p->xp.release(); p->set_threshold.release(); p->sp_coef.release(); p->sp_src.release();
+  p->xact_off.release(); p->xact.release();
   p->arena.release();
   if (p->xp_tan) cudaFree(p->xp_tan);
   if (p->credit) cudaFree(p->credit);
