@@ -14,6 +14,7 @@
 
 namespace mcre {
 
+#ifndef MCRE_HOST_EMU   // (tests/host/fastmath_host.cpp compiles this header for the CPU with its own models of these two)
 __device__ __forceinline__ double fm_rcp_approx(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -24,6 +25,7 @@ __device__ __forceinline__ double fm_rsqrt_approx(double x) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   return y;
 }
+#endif
 
 // a / b for normal, finite b (|b| in [1e-300, 1e300]): MUFU seed + 2 Newton steps + residual fix.
 __device__ __forceinline__ double fm_div(double a, double b) {
@@ -36,28 +38,21 @@ __device__ __forceinline__ double fm_div(double a, double b) {
   return fma(fma(-b, q, a), y, q);
 }
 
-// sqrt(x) for x >= 0 (0 -> 0), normal range.
-__device__ __forceinline__ double fm_sqrt(double x) {
-  const double xs = x > 0.0 ? x : 1.0;
-  double y = fm_rsqrt_approx(xs);
-  double g = xs * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  g = fma(fma(-g, g, xs), h, g);
-  return x > 0.0 ? g : 0.0;
-}
-
-// sqrt(x) for x > 0 (normal range): no zero guard.  MUFU seed (2^-22) + two coupled
-// Goldschmidt iterations; the last step is the residual correction g + (x - g^2) h with the
-// first-iteration h (relative error 2^-44: enough for a correction of relative size 2^-44).
+// sqrt(x) for x > 0 (normal range): no zero guard.  y = MUFU.RSQ64H(x) reads the high word only (relative
+// error e <= 2^-20); g = x y = sqrt(x) (1 + e), r = 1 - g y = -2e - e^2 and
+// sqrt(x) = g (1 - r)^(-1/2) = g + g r (1/2 + 3/8 r) + O(r^3): 5 FP64 instructions, 2^-60 relative truncation,
+// the rounding of g is absorbed by r.
 __device__ __forceinline__ double fm_sqrt_pos(double x) {
   const double y = fm_rsqrt_approx(x);
-  double g = x * y, h = 0.5 * y;
-  const double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  return fma(fma(-g, g, x), h, g);
+  const double g = x * y;
+  const double r = fma(-g, y, 1.0);
+  return fma(g * r, fma(r, 0.375, 0.5), g);
+}
+
+// sqrt(x) for x >= 0 (0 -> 0), normal range.
+__device__ __forceinline__ double fm_sqrt(double x) {
+  const double g = fm_sqrt_pos(x > 0.0 ? x : 1.0);
+  return x > 0.0 ? g : 0.0;
 }
 
 
@@ -162,50 +157,58 @@ __device__ __forceinline__ void fm_sincos2pi(double u, double &sn, double &cs) {
 
 #if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
 // =====================================================================================
-// Table-driven variants (second ncu pass, profiles/r01_irc_main_v1_*): the v1 kernel spent
-// ~100 of its 148 FP64 instructions per path-step in the long Taylor polynomials above and
-// 77 instructions materialising their coefficients.  Here the argument is reduced against
-// small tables in SHARED memory (4.6 KB per block, built by fm_tables_init at kernel start
-// with libdevice), so the polynomials shrink to degree 5-7, and the coefficients sit in
-// __constant__ memory (one LDCU.128 per two coefficients instead of four UMOV).
-//   exp   : 2^(n/64)            64 doubles     19 -> 11 FP64 instructions
-//   log   : (1/c_j, log c_j)    128 pairs      25 -> 13
-//   sincos: (sin, cos)(2 pi n/128) 128 pairs   24 -> 14
+// Table-driven variants.  History: the v1 kernel spent ~100 of its 148 FP64 instructions per
+// path-step in the long Taylor polynomials above and 77 instructions materialising their
+// coefficients (profiles/r01_irc_main_v1_*); round 1 reduced the arguments against small tables
+// in SHARED memory.  Round 2 (profiles/r02_issue_mix_probe.log): an FP64 instruction holds the
+// issue port of its scheduler for ~2.2 cycles and integer instructions do NOT issue in its shadow,
+// so every FP64 instruction removed is worth two integer ones.  The tables were doubled / quadrupled
+// (14 KB per block, built by fm_tables_init at kernel start with libdevice) so that each polynomial
+// loses one or two degrees, and every non-immediate coefficient sits in __constant__ memory:
+//   exp    : 2^(n/256)              256 doubles    9 FP64 instructions
+//   -2 log : (-2/c_j, -2 log c_j)   256 pairs     10  (the Box-Muller radius wants -2 log u)
+//   sincos : (sin, cos)(2 pi n/512) 512 pairs     15 for the fused Box-Muller rotation
+//   sqrt   : MUFU seed + second-order correction   5
 // Every kernel that calls these must call fm_tables_init() first.
 // =====================================================================================
 struct FmShared {
-  double exp2t[64];
-  double2 logt[128];
-  double2 sct[128];
+  double exp2t[256];
+  double2 logt[256];
+  double2 sct[512];
 };
 static __shared__ FmShared s_fm;
 
-static __constant__ double FM_C[24] = {
-    // exp: 1/120, 1/24, 1/6, 1/2   (index 0..3)
-    8.3333333333333332e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
-    // exp reduction: 64/ln2, ln2/64 hi, ln2/64 lo, pad   (4..7)
-    92.33248261689366, 0.01083042469326756, 2.9815858271643302e-12, 0.0,
-    // log1p(f)/f - 1: -1/2, 1/3, -1/4, 1/5, -1/6, 1/7, -1/8, pad   (8..15)
-    -0.5, 3.3333333333333331e-01, -0.25, 0.2, -1.6666666666666666e-01, 1.4285714285714285e-01, -0.125, 0.0,
-    // sin: -1/6, 1/120, -1/5040 ; cos: -1/2, 1/24, -1/720 ; 2 pi ; pad   (16..23)
-    -1.6666666666666666e-01, 8.3333333333333332e-03, -1.984126984126984e-04,
-    -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 6.283185307179586, 0.0};
+static __constant__ double FM_C[32] = {
+    // exp: 1/24, 1/6, 256/ln2, ln2/256 hi (21 trailing zero bits), ln2/256 lo   (index 0..4), pad
+    4.1666666666666664e-02, 1.6666666666666666e-01, 369.3299304675746, 0.00270760617331689, 7.453964567463233e-13,
+    0.0, 0.0, 0.0,
+    // -2 log1p(-g/2) = g + g^2 (1/4 + g/12 + g^2/32 + g^3/80 + g^4/192): 1/192, 1/80, 1/32, 1/12   (8..11);
+    // -2 ln2 (12); 2^52 + 1023 (13); 1 - 2^-53 (14); 1.5 2^52 - 512 (15)
+    0.005208333333333333, 0.0125, 0.03125, 0.08333333333333333, -1.3862943611198906, 4503599627371519.0,
+    0.99999999999999988898, 6755399441055232.0,
+    // sin(2 pi x) = x (S1 + z (S3 + z S5)), cos(2 pi x) - 1 = z (C2 + z C4), z = x^2, |x| <= 2^-10 turns   (16..20)
+    6.283185307179586, -41.34170224039976, 81.60524927607506, -19.739208802178716, 64.9393940226683,
+    // exp(x), |x| <= 2^-6: 1/720, 1/120 (21, 22); 1e-12 (23)
+    1.3888888888888889e-03, 8.3333333333333332e-03, 1e-12,
+    0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 
 // Builds the shared tables (all threads of the block; ends with a barrier).
 __device__ __forceinline__ void fm_tables_init() {
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_fm.exp2t[i] = exp2((double)i * (1.0 / 64.0));
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_fm.exp2t[i] = exp2((double)i * (1.0 / 256.0));
     // interval j of the mantissa m in [1,2): centre c_j, except the two intervals that touch
-    // u = 1 (j = 0: c = 1, j = 127: c = 2) so that log(u) keeps its relative accuracy there.
-    // Intervals with m >= 1 + 53/128 (~sqrt 2) are folded down by a factor 2 (exponent + 1).
-    double c = 1.0 + ((double)i + 0.5) * (1.0 / 128.0);
+    // u = 1 (j = 0: c = 1, j = 255: c = 2) so that log(u) keeps its relative accuracy there.
+    // Intervals with m >= 1 + 106/256 (~sqrt 2) are folded down by a factor 2 (exponent + 1).
+    double c = 1.0 + ((double)i + 0.5) * (1.0 / 256.0);
     if (i == 0) c = 1.0;
-    if (i == 127) c = 2.0;
+    if (i == 255) c = 2.0;
     const double rc = 1.0 / c;
-    double L = (i == 0 || i == 127) ? 0.0 : -log(i >= 53 ? rc * 2.0 : rc);
-    s_fm.logt[i] = make_double2(rc, L);
+    const double L = (i == 0 || i == 255) ? 0.0 : -log(i >= 106 ? rc * 2.0 : rc);
+    s_fm.logt[i] = make_double2(-2.0 * rc, -2.0 * L);
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     double sn, cs;
-    sincospi((double)i * (1.0 / 64.0), &sn, &cs);
+    sincospi((double)i * (1.0 / 256.0), &sn, &cs);
     s_fm.sct[i] = make_double2(sn, cs);
   }
   __syncthreads();
@@ -219,26 +222,26 @@ __device__ __forceinline__ void fm_tables_init() {
 // operations interleaved in source order; the scalar entry points are the PP = 1 instances.
 #define MCRE_VP _Pragma("unroll") for (int p = 0; p < PP; ++p)
 
-// exp(x) for |x| <= 700: n = round(64 x / ln2), exp(x) = 2^(n>>6) * T[n&63] * exp(r), |r| <= ln2/128.
+// exp(x) for |x| <= 700: n = round(256 x / ln2), exp(x) = 2^(n>>8) * T[n&255] * exp(r), |r| <= ln2/512
+// (r^5/120 < 4e-17: the series stops at r^4).
 template <int PP>
 __device__ __forceinline__ void fm_exp_tv(const double (&x)[PP], double (&out)[PP]) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
   double t[PP], r[PP], T[PP], q[PP], tr[PP];
   int n[PP];
-  MCRE_VP t[p] = fma(x[p], FM_C[4], MAGIC);
+  MCRE_VP t[p] = fma(x[p], FM_C[2], MAGIC);
   MCRE_VP n[p] = __double2loint(t[p]);
   MCRE_VP t[p] -= MAGIC;
-  MCRE_VP T[p] = s_fm.exp2t[n[p] & 63];
-  MCRE_VP r[p] = fma(t[p], -FM_C[5], x[p]);
-  MCRE_VP r[p] = fma(t[p], -FM_C[6], r[p]);
+  MCRE_VP T[p] = s_fm.exp2t[n[p] & 255];
+  MCRE_VP r[p] = fma(t[p], -FM_C[3], x[p]);
+  MCRE_VP r[p] = fma(t[p], -FM_C[4], r[p]);
   MCRE_VP q[p] = fma(r[p], FM_C[0], FM_C[1]);
-  MCRE_VP q[p] = fma(q[p], r[p], FM_C[2]);
-  MCRE_VP q[p] = fma(q[p], r[p], FM_C[3]);
-  MCRE_VP q[p] = fma(q[p], r[p], 1.0);          // 1 + r/2 + r^2/6 + r^3/24 + r^4/120
+  MCRE_VP q[p] = fma(q[p], r[p], 0.5);
+  MCRE_VP q[p] = fma(q[p], r[p], 1.0);          // 1 + r/2 + r^2/6 + r^3/24
   MCRE_VP tr[p] = T[p] * r[p];
   MCRE_VP q[p] = fma(tr[p], q[p], T[p]);        // T (1 + r q)
-  // scale by 2^(n>>6) in the exponent field (result stays normal for |x| <= 700)
-  MCRE_VP out[p] = __hiloint2double(__double2hiint(q[p]) + ((n[p] >> 6) << 20), __double2loint(q[p]));
+  // scale by 2^(n>>8) in the exponent field (result stays normal for |x| <= 700)
+  MCRE_VP out[p] = __hiloint2double(__double2hiint(q[p]) + ((n[p] >> 8) << 20), __double2loint(q[p]));
 }
 __device__ __forceinline__ double fm_exp_t(double x) {
   const double a[1] = {x};
@@ -251,9 +254,9 @@ __device__ __forceinline__ double fm_exp_t(double x) {
 template <int PP>
 __device__ __forceinline__ void fm_exp_smallv(const double (&x)[PP], double (&out)[PP]) {
   double q[PP];
-  MCRE_VP q[p] = fma(x[p], 1.3888888888888889e-03, 8.3333333333333332e-03);
-  MCRE_VP q[p] = fma(q[p], x[p], 4.1666666666666664e-02);
-  MCRE_VP q[p] = fma(q[p], x[p], 1.6666666666666666e-01);
+  MCRE_VP q[p] = fma(x[p], FM_C[21], FM_C[22]);
+  MCRE_VP q[p] = fma(q[p], x[p], FM_C[0]);
+  MCRE_VP q[p] = fma(q[p], x[p], FM_C[1]);
   MCRE_VP q[p] = fma(q[p], x[p], 0.5);
   MCRE_VP q[p] = fma(q[p], x[p], 1.0);
   MCRE_VP out[p] = fma(q[p], x[p], 1.0);
@@ -266,32 +269,43 @@ __device__ __forceinline__ double fm_exp_small(double x) {
   return o[0];
 }
 
-// log(u) for u in [2^-60, 2).
-template <int PP>
-__device__ __forceinline__ void fm_log_tv(const double (&u)[PP], double (&out)[PP]) {
-  const double LN2 = 6.931471805599453094e-01;
-  int hi[PP], e[PP];
-  double m[PP], f[PP], q[PP], ff[PP], ed[PP], a[PP];
+// -2 log(u) for u in [2^-60, 2): u = 2^e m, m / c_j - 1 = -g/2 with the table holding -2/c_j, so
+//   -2 log u = e (-2 ln2) - 2 log c_j + (g + g^2/4 + g^3/12 + g^4/32 + g^5/80 + g^6/192),  |g| <= 2^-8
+// (2^-7 in the interval that touches 1 from above, u in [1, 1 + 2^-8): uniforms never get there; the general
+// logarithm, ABOVE_ONE = true, carries the g^7/448 term for it).
+template <int PP, bool ABOVE_ONE = false>
+__device__ __forceinline__ void fm_neg2log_tv(const double (&u)[PP], double (&out)[PP]) {
+  int hi[PP], E[PP];
+  double m[PP], g[PP], q[PP], gg[PP], ed[PP], a[PP];
   double2 tb[PP];
   MCRE_VP hi[p] = __double2hiint(u[p]);
-  MCRE_VP tb[p] = s_fm.logt[(hi[p] >> 13) & 127];
-  MCRE_VP e[p] = ((hi[p] + 0x96000) >> 20) - 1023;     // exponent, +1 when m >= 1 + 53/128
+  MCRE_VP tb[p] = s_fm.logt[(hi[p] >> 12) & 255];
+  MCRE_VP E[p] = (hi[p] + 0x96000) >> 20;              // biased exponent, +1 when m >= 1 + 106/256
   MCRE_VP m[p] = __hiloint2double((hi[p] & 0x000fffff) | 0x3ff00000, __double2loint(u[p]));
-  // (double)e through the 2^52 + 2^31 bias: one integer op + one FP64 add
-  MCRE_VP ed[p] = __hiloint2double(0x43300000, e[p] ^ 0x80000000) - 4503601774854144.0;
-  MCRE_VP f[p] = fma(m[p], tb[p].x, -1.0);             // m / c_j - 1, |f| <= 1/128
-  MCRE_VP q[p] = fma(f[p], FM_C[14], FM_C[13]);
-  MCRE_VP ff[p] = f[p] * f[p];
-  MCRE_VP q[p] = fma(q[p], f[p], FM_C[12]);
-  // e ln2 + log c_j: |e| <= 60, so the rounding of ln2 costs at most 60 * 2^-54 absolute -
+  // (double)(E - 1023) through the 2^52 bias: one FP64 add
+  MCRE_VP ed[p] = __hiloint2double(0x43300000, E[p]) - FM_C[13];
+  MCRE_VP g[p] = fma(m[p], tb[p].x, 2.0);              // -2 (m / c_j - 1)
+  if (ABOVE_ONE) {
+    MCRE_VP q[p] = fma(g[p], 0.002232142857142857, FM_C[8]);
+    MCRE_VP q[p] = fma(q[p], g[p], FM_C[9]);
+  } else {
+    MCRE_VP q[p] = fma(g[p], FM_C[8], FM_C[9]);
+  }
+  MCRE_VP gg[p] = g[p] * g[p];
+  MCRE_VP q[p] = fma(q[p], g[p], FM_C[10]);
+  // e (-2 ln2) - 2 log c_j: |e| <= 60, so the rounding of ln2 costs at most 60 * 2^-53 absolute -
   // below half an ulp of the result whenever e != 0; for e = 0 the term vanishes
-  MCRE_VP a[p] = fma(ed[p], LN2, tb[p].y);
-  MCRE_VP q[p] = fma(q[p], f[p], FM_C[11]);
-  MCRE_VP q[p] = fma(q[p], f[p], FM_C[10]);
-  MCRE_VP q[p] = fma(q[p], f[p], FM_C[9]);
-  MCRE_VP q[p] = fma(q[p], f[p], FM_C[8]);             // -1/2 + f/3 - f^2/4 ...
-  MCRE_VP q[p] = fma(ff[p], q[p], f[p]);               // log1p(f)
+  MCRE_VP a[p] = fma(ed[p], FM_C[12], tb[p].y);
+  MCRE_VP q[p] = fma(q[p], g[p], FM_C[11]);
+  MCRE_VP q[p] = fma(q[p], g[p], 0.25);
+  MCRE_VP q[p] = fma(gg[p], q[p], g[p]);
   MCRE_VP out[p] = a[p] + q[p];
+}
+// log(u) for u in [2^-60, 2)
+template <int PP>
+__device__ __forceinline__ void fm_log_tv(const double (&u)[PP], double (&out)[PP]) {
+  fm_neg2log_tv<PP, true>(u, out);
+  MCRE_VP out[p] *= -0.5;
 }
 __device__ __forceinline__ double fm_log_t(double u) {
   const double a[1] = {u};
@@ -300,39 +314,36 @@ __device__ __forceinline__ double fm_log_t(double u) {
   return o[0];
 }
 
-// sqrt(x) for x > 0, PP-wide (same arithmetic as fm_sqrt_pos).
+// sqrt(x) for x > 0 (normal range), PP-wide.  y = MUFU.RSQ64H(x) reads the high word only: relative error
+// e <= 2^-20; with g = x y = sqrt(x) (1 + e) and r = 1 - g y = -2e - e^2:  sqrt(x) = g (1 - r)^(-1/2)
+// = g + g r (1/2 + 3/8 r) + O(r^3) (2^-60 relative).  The rounding of g is absorbed by r.
 template <int PP>
 __device__ __forceinline__ void fm_sqrt_posv(const double (&x)[PP], double (&out)[PP]) {
-  double y[PP], g[PP], h[PP], r[PP];
+  double y[PP], g[PP], r[PP], q[PP], t[PP];
   MCRE_VP y[p] = fm_rsqrt_approx(x[p]);
   MCRE_VP g[p] = x[p] * y[p];
-  MCRE_VP h[p] = 0.5 * y[p];
-  MCRE_VP r[p] = fma(-h[p], g[p], 0.5);
-  MCRE_VP g[p] = fma(g[p], r[p], g[p]);
-  MCRE_VP h[p] = fma(h[p], r[p], h[p]);
-  MCRE_VP r[p] = fma(-g[p], g[p], x[p]);
-  MCRE_VP out[p] = fma(r[p], h[p], g[p]);
+  MCRE_VP r[p] = fma(-g[p], y[p], 1.0);
+  MCRE_VP q[p] = fma(r[p], 0.375, 0.5);
+  MCRE_VP t[p] = g[p] * r[p];
+  MCRE_VP out[p] = fma(t[p], q[p], g[p]);
 }
 
-// (sin(2 pi u), cos(2 pi u)) for u in [0, 1): n = round(128 u), angle = 2 pi n/128 + x, |x| <= pi/128.
+// (sin(2 pi u), cos(2 pi u)) for u in [0, 1): n = round(512 u), angle = 2 pi (n/512 + x), |x| <= 2^-10.
 template <int PP>
 __device__ __forceinline__ void fm_sincos2pi_tv(const double (&u)[PP], double (&sn)[PP], double (&cs)[PP]) {
   const double MAGIC = 6755399441055744.0;
-  double t[PP], x[PP], z[PP], ps[PP], pc[PP], xz[PP], a[PP], b[PP];
+  double t[PP], x[PP], z[PP], ps[PP], pc[PP], a[PP], b[PP];
   double2 tb[PP];
-  MCRE_VP t[p] = fma(u[p], 128.0, MAGIC);
-  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 127];
+  MCRE_VP t[p] = fma(u[p], 512.0, MAGIC);
+  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 511];
   MCRE_VP t[p] -= MAGIC;
-  MCRE_VP x[p] = fma(t[p], -0.0078125, u[p]);          // exact, [-1/256, 1/256]
-  MCRE_VP x[p] = x[p] * FM_C[22];
+  MCRE_VP x[p] = fma(t[p], -0.001953125, u[p]);        // exact, [-2^-10, 2^-10]
   MCRE_VP z[p] = x[p] * x[p];
   MCRE_VP ps[p] = fma(z[p], FM_C[18], FM_C[17]);
-  MCRE_VP pc[p] = fma(z[p], FM_C[21], FM_C[20]);
-  MCRE_VP xz[p] = x[p] * z[p];
+  MCRE_VP pc[p] = fma(z[p], FM_C[20], FM_C[19]);
   MCRE_VP ps[p] = fma(ps[p], z[p], FM_C[16]);
-  MCRE_VP pc[p] = fma(pc[p], z[p], FM_C[19]);
-  MCRE_VP ps[p] = fma(xz[p], ps[p], x[p]);             // sin x
-  MCRE_VP pc[p] = z[p] * pc[p];                        // cos x - 1
+  MCRE_VP pc[p] = z[p] * pc[p];                        // cos - 1
+  MCRE_VP ps[p] = x[p] * ps[p];                        // sin
   // rotate: sin(a + x) = S + (C sx + S cm),  cos(a + x) = C + (C cm - S sx)
   MCRE_VP a[p] = tb[p].x * pc[p];
   MCRE_VP b[p] = tb[p].y * pc[p];
@@ -347,24 +358,20 @@ __device__ __forceinline__ void fm_sincos2pi_tv(const double (&u)[PP], double (&
 template <int PP>
 __device__ __forceinline__ void fm_polar_tv(const double (&d)[PP], const double (&rad)[PP], double (&zc)[PP],
                                             double (&zs)[PP]) {
-  const double MAGIC = 6755399441055744.0;
-  double t[PP], x[PP], z[PP], ps[PP], pc[PP], xz[PP], rc[PP], rs[PP];
+  double t[PP], x[PP], z[PP], ps[PP], pc[PP], rc[PP], rs[PP];
   double2 tb[PP];
-  MCRE_VP t[p] = fma(d[p], 128.0, MAGIC - 128.0);       // MAGIC + round(128 v)
-  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 127];
-  MCRE_VP t[p] -= MAGIC - 128.0;                        // round(128 v) + 128
-  MCRE_VP x[p] = fma(t[p], -0.0078125, d[p]);          // v - n/128, exact, [-1/256, 1/256]
-  MCRE_VP x[p] = x[p] * FM_C[22];
+  MCRE_VP t[p] = fma(d[p], 512.0, FM_C[15]);            // 1.5 2^52 + round(512 v)
+  MCRE_VP tb[p] = s_fm.sct[__double2loint(t[p]) & 511];
+  MCRE_VP t[p] -= FM_C[15];                             // round(512 v) + 512
+  MCRE_VP x[p] = fma(t[p], -0.001953125, d[p]);        // v - n/512, exact, [-2^-10, 2^-10]
   MCRE_VP rc[p] = rad[p] * tb[p].y;
   MCRE_VP rs[p] = rad[p] * tb[p].x;
   MCRE_VP z[p] = x[p] * x[p];
   MCRE_VP ps[p] = fma(z[p], FM_C[18], FM_C[17]);
-  MCRE_VP pc[p] = fma(z[p], FM_C[21], FM_C[20]);
-  MCRE_VP xz[p] = x[p] * z[p];
+  MCRE_VP pc[p] = fma(z[p], FM_C[20], FM_C[19]);
   MCRE_VP ps[p] = fma(ps[p], z[p], FM_C[16]);
-  MCRE_VP pc[p] = fma(pc[p], z[p], FM_C[19]);
-  MCRE_VP ps[p] = fma(xz[p], ps[p], x[p]);             // sin x
-  MCRE_VP pc[p] = z[p] * pc[p];                        // cos x - 1
+  MCRE_VP pc[p] = z[p] * pc[p];                        // cos - 1
+  MCRE_VP ps[p] = x[p] * ps[p];                        // sin
   MCRE_VP zc[p] = fma(rc[p], pc[p], rc[p]);
   MCRE_VP zs[p] = fma(rs[p], pc[p], rs[p]);
   MCRE_VP zc[p] = fma(-rs[p], ps[p], zc[p]);

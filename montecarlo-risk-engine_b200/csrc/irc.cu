@@ -288,9 +288,29 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
     }
     UP(step_rec, srec.data(), srec.size());
     UP(date_rec, p->h_date_rec.data(), p->h_date_rec.size());
-    // "CVA only" fast mode: one set, CVA the only accumulator, no threshold / collateral
-    p->cva_only = c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA &&
-                  c->set_threshold[0] == 0.0 && (c->set_flags[0] & 1) == 0 && (c->set_flags[0] & 2) != 0;
+    // "CVA only" kernel (irc_cva.cu): one set, CVA the only accumulator, no threshold / collateral, stochastic
+    // intensity started above zero; everything else runs the general kernel
+    p->cva_only = c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA && n_berm == 0 &&
+                  c->set_threshold[0] == 0.0 && (c->set_flags[0] & 1) == 0 && (c->set_flags[0] & 2) != 0 &&
+                  !c->cir_deterministic && c->cir_init[0] > 0.0 && c->scheme == MCRE_SCHEME_EULER;
+    if (p->cva_only) {
+      CvaHost &h = p->cva;
+      h.n_sub = c->n_sub; h.n_pre_dates = c->n_pre_dates; h.n_metric = c->n_metric;
+      h.vas_noise = c->vas_noise; h.cir_noise = c->cir_noise;
+      for (int k = 0; k < 4; ++k) { h.vas[k] = c->vas[k]; h.chol[k] = c->chol[k]; }
+      for (int k = 0; k < 3; ++k) h.cir[k] = c->cir[k];
+      h.y0 = c->cir_init[0]; h.lgd = c->lgd;
+      h.step_dt.assign(c->step_dt, c->step_dt + c->n_sub);
+      h.step_date.assign(c->step_date, c->step_date + c->n_sub);
+      h.step_theta.resize(c->n_sub); h.step_psi.resize(c->n_sub);
+      for (int s = 0; s < c->n_sub; ++s) { h.step_theta[s] = c->step_vas[(size_t)s * 2]; h.step_psi[s] = c->step_cir[(size_t)s * 2]; }
+      h.date_flags.assign(c->date_flags, c->date_flags + c->n_dates);
+      h.date_metric.assign(c->date_metric, c->date_metric + c->n_dates);
+      std::vector<double> zrec((size_t)(c->n_pre_dates + c->n_sub) * CVA_REC + 2, 0.0);
+      std::vector<int> zsync(4, 0);
+      UP(cva_rec, zrec.data(), zrec.size());
+      UP(cva_sync, zsync.data(), zsync.size());
+    }
   }
 #undef UP
   if (!rc) rc = p->arena.commit();
@@ -317,6 +337,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   d.ex_const = p->ex_const.p; d.term_coef = p->term_coef.p; d.term_w = p->term_w.p; d.ex_basis = p->ex_basis.p;
   d.ex_coef = p->ex_coef.p; d.berm_expo_coef = p->berm_expo_coef.p;
   d.path_list = nullptr; d.tan_spill = nullptr;
+  p->cva_rec_dev = p->cva_rec.p; p->cva_sync_dev = (unsigned *)p->cva_sync.p;
   *out = p;
   return 0;
 }
@@ -333,6 +354,7 @@ extern "C" void mcre_irc_destroy(mcre_irc_plan *p) {
   p->berm_set.release(); p->date_ex_off.release(); p->ex_unit.release(); p->ex_last.release(); p->ex_term_off.release();
   p->berm_strike.release(); p->berm_sign.release(); p->ex_const.release(); p->term_coef.release(); p->term_w.release();
   p->ex_basis.release(); p->ex_coef.release(); p->berm_expo_coef.release();
+  p->cva_rec.release(); p->cva_sync.release();
   p->arena.release();
   delete p;
 }
@@ -380,6 +402,10 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
   }
   MCRE_CUDA(cudaMemcpyAsync((void *)p->d.date_rec, p->h_date_rec.data(), p->h_date_rec.size() * sizeof(double),
                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  if (p->cva_only) {
+    const int rc = irc_cva_build_records(p, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   MCRE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // host staging buffers may be reused by the caller
   return 0;
 }
@@ -452,6 +478,14 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
   RngDev r = make_rng(rng);
   ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->cva_only) {
+    // per-chunk partials of the tail row only: [chunk][pv, pv^2, cva, cva^2]; the date rows of the accumulator stay 0
+    const int64_t slots = mcre_irc_main_slots(p);
+    rc = irc_cva_launch(p, r, sh, d_partial, d_shift, st);
+    if (rc) return rc;
+    MCRE_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)slots * sizeof(double), st));
+    return mcre_tree_reduce(d_partial, (sh.n_paths + sh.chunk - 1) / sh.chunk, 4, d_acc + (slots - 4), stream);
+  }
   rc = p->d.n_berm > 0 ? irc_dispatch_main_berm(p, r, sh, d_partial, d_spill, d_shift, st)
                        : irc_dispatch_main<false>(p, r, sh, d_partial, d_spill, d_shift, st);
   if (rc) return rc;

@@ -1,0 +1,295 @@
+// Vasicek + CIR++ "CVA only" kernel: the headline path (BASELINE config 3: wrong-way-risk CVA of a payer swap,
+// one netting set, no threshold / collateral, CVA the only metric, value-only build).
+//
+// What it replaces in the reference, per path and sub-step: MonteCarloEngine.generate_paths (engine.py:27-123) for
+// ModelConfig([Vasicek, CIR++]) under EULER (vasicek.py:88-112, cirpp.py:174-198, model_config.py:223-276), the
+// request resolution of numeraire / spot / survival probabilities (request_interface.py:115-130), the regression-proxy
+// exposure (controller.py:438-447) and CVAMetric.evaluate (cva_metric.py:62-100).
+//
+// Round-2 rewrite of the MODE 1 branch of irc_main_kernel.  The probe tools/probes/issue_mix.cu showed that on this
+// GPU an FP64 instruction occupies the issue port of its scheduler for ~2.2 cycles and integer instructions do not
+// issue in its shadow, so the kernel is bound by (2.2 x FP64 + 1 x other) instructions per path-step.  Everything
+// below is about removing instructions (84 FP64 + 96 other per path-step in round 1):
+//  * every per-step scalar that does not depend on the path is folded on the host into one packed record per
+//    sub-step (mcre_irc_plan::build_cva_records):
+//      r'  = r (1 - a dt) + a theta_t dt + (sigma sqrt(dt) L_v.) z            2-3 FMA   (was 4-5)
+//      y'  = y (1 - kappa dt) + kappa theta dt + sqrt(y) (sigma_c sqrt(dt) L_c.) z
+//      A  -= (r + y) dt    the only integral the CVA integrand needs: logB + logB_lambda = -A + sum psi dt, and the
+//                          deterministic shift integral sum psi dt is folded into the exposure coefficients
+//  * the integrand relu(E_k) S(0,t_k) (1 - S(t_k,t_k+1 | y)) / N_k becomes
+//      (E' + |E'|) exp(A) H(y),   E' = 1/2 exp(-sum psi dt) (c0 + c1 r + c2 r^2),
+//      H(y) = 1 - C exp(-B y) = (1 - C) + C B y - C B^2 y^2 / 2 ... to y^5 while B y <= 2^-9 (warp vote on the high
+//      word of y; otherwise the table exponential): one exponential per date instead of two;
+//  * max(y', 1e-12) and the validity tests are integer compares on the high words + one warp vote (an FP64 max is a
+//    DSETP and two selects); relu(x) = (x + |x|) / 2 is one DADD;
+//  * Box-Muller on the shortened elementary functions of fastmath.cuh (31 FP64 instructions per normal pair);
+//  * per-path CVA totals are summed per thread over the passes of a chunk and block-reduced ONCE per chunk;
+//  * the pilot launch is gone: block 0 simulates global path 0 first and publishes its value (the common shift c of
+//    sum(x - c), sum((x - c)^2)); the other blocks accumulate against the first path of their own chunk and convert
+//    to c when they store the chunk partial (exact algebra, fixed order, so results stay independent of timing and
+//    of the number of GPUs); chunks are handed out by an atomic counter, so block 0's late start costs nothing.
+#include "irc_main.cuh"
+
+#ifndef MCRE_CVA_PP
+#define MCRE_CVA_PP 4
+#endif
+#ifndef MCRE_CVA_MINB
+#define MCRE_CVA_MINB 3
+#endif
+
+namespace mcre {
+
+constexpr int CVA_EV_KV1 = 1;      // the short rate also loads on the second normal
+constexpr int CVA_EV_KC1 = 2;      // the intensity also loads on the second normal
+constexpr int CVA_EV_DATE = 4;     // a metric date k < n_metric - 1 follows the step: CVA contribution
+constexpr int CVA_EV_NOSTEP = 8;   // date at the calibration date: no step, no draw
+constexpr int HI_1E_12 = 0x3D719799;   // high word of 1e-12
+
+struct CvaDev {
+  const double *rec;   // [n_events][CVA_REC]
+  int n_events;
+  double r0, y0, lgd;
+  unsigned *sync;      // [0]: next chunk, [1]: pilot value published
+};
+
+template <int PP>
+__global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(CvaDev P, RngDev rng, ShardDev sh,
+                                                                      double *__restrict__ partial,
+                                                                      double *shift_tail) {
+  fm_tables_init();
+  __shared__ double s_stage[2][4];
+  __shared__ double s_first;
+  __shared__ long long s_chunk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  const bool inject = rng.mode == MCRE_RNG_INJECT;
+  bool pilot = blockIdx.x == 0;
+  bool have_shift = false;
+  double gshift = 0.0;
+
+  while (true) {
+    long long chunk = 0;
+    if (!pilot) {
+      if (tid == 0) s_chunk = (long long)atomicAdd(P.sync, 1u);
+      __syncthreads();
+      chunk = s_chunk;
+      __syncthreads();
+      if (chunk >= n_chunks) break;
+    }
+    double s1 = 0.0, s2 = 0.0, first = 0.0;
+    const int span = pilot ? 1 : sh.chunk;
+    for (int it = 0; it < span; it += 128 * PP) {
+      long long gpath[PP];
+      double keep[PP];
+      MCRE_VP {
+        const int in_chunk = it + p * 128 + tid;
+        const long long lpath = chunk * sh.chunk + in_chunk;
+        const bool live = !pilot && lpath < sh.n_paths && in_chunk < sh.chunk;
+        keep[p] = live ? 1.0 : 0.0;
+        gpath[p] = pilot ? 0 : sh.path_begin + (live ? lpath : 0);
+      }
+      NormalStreamV<PP> nsv;
+      nsv.init(rng, gpath);
+      double r[PP], y[PP], A[PP], cva[PP];
+      MCRE_VP { r[p] = P.r0; y[p] = P.y0; A[p] = 0.0; cva[p] = 0.0; }
+      int is = 0;   // sub-step counter (row of the injected normals)
+#pragma unroll 1
+      for (int ev = 0; ev < P.n_events; ++ev) {
+        const double2 *rec = (const double2 *)(P.rec + (size_t)ev * CVA_REC);
+        const double2 g4 = __ldg(rec + 4);
+        const int flags = __double2loint(g4.y);
+        if (!(flags & CVA_EV_NOSTEP)) {
+          const double2 g0 = __ldg(rec), g1 = __ldg(rec + 1), g2 = __ldg(rec + 2), g3 = __ldg(rec + 3);
+          const double ndt = g0.x, om_v = g0.y, c_v = g1.x, kv0 = g1.y, kv1 = g2.x, om_c = g2.y, c_c = g3.x,
+                       kc0 = g3.y, kc1 = g4.x;
+          double z0[PP], z1[PP];
+          if (inject) {
+            MCRE_VP {
+              const double *zp = rng.z + ((size_t)is * rng.n_total + gpath[p]) * 2;
+              z0[p] = zp[0]; z1[p] = zp[1];
+            }
+          } else {
+            nsv.next2(z0, z1);
+          }
+          ++is;
+          // integrals with the pre-step state (left Riemann sums, vasicek.py:80,107, cirpp.py:196-197)
+          MCRE_VP A[p] = fma(r[p], ndt, A[p]);
+          MCRE_VP A[p] = fma(y[p], ndt, A[p]);
+          double sy[PP], wn[PP], yn[PP];
+          fm_sqrt_posv<PP>(y, sy);                  // y >= 1e-12 after every step and y0 > 0
+          MCRE_VP r[p] = fma(r[p], om_v, c_v);
+          MCRE_VP r[p] = fma(kv0, z0[p], r[p]);
+          if (flags & CVA_EV_KV1) { MCRE_VP r[p] = fma(kv1, z1[p], r[p]); }
+          MCRE_VP wn[p] = kc0 * z0[p];
+          if (flags & CVA_EV_KC1) { MCRE_VP wn[p] = fma(kc1, z1[p], wn[p]); }
+          MCRE_VP yn[p] = fma(y[p], om_c, c_c);
+          MCRE_VP yn[p] = fma(sy[p], wn[p], yn[p]);
+          // y' = max(yn, 1e-12) (cirpp.py:198): high word above that of 1e-12 <=> certainly larger
+          bool above = true;
+          MCRE_VP above = above && (__double2hiint(yn[p]) > HI_1E_12);
+          if (__all_sync(0xffffffffu, above)) { MCRE_VP y[p] = yn[p]; }
+          else { MCRE_VP y[p] = fmax(yn[p], 1e-12); }
+        }
+        if (flags & CVA_EV_DATE) {
+          const double2 h0 = __ldg(rec + 5), h1 = __ldg(rec + 6), h2 = __ldg(rec + 7), h3 = __ldg(rec + 8),
+                        h4 = __ldg(rec + 9);
+          const double c0 = h0.x, c1 = h0.y, c2 = h1.x, d0 = h1.y, d1 = h2.x, d2 = h2.y, d3 = h3.x, d4 = h3.y,
+                       d5 = h4.x;
+          const int thr = __double2loint(h4.y);
+          double e[PP], ea[PP], h[PP];
+          MCRE_VP e[p] = fma(r[p], c2, c1);
+          MCRE_VP e[p] = fma(r[p], e[p], c0);
+          bool small = true;
+          MCRE_VP small = small && (__double2hiint(y[p]) < thr);
+          fm_exp_tv<PP>(A, ea);
+          MCRE_VP e[p] = e[p] + fabs(e[p]);          // relu of the exposure proxy (the 1/2 sits in c0..c2)
+          if (__all_sync(0xffffffffu, small)) {
+            MCRE_VP h[p] = fma(y[p], d5, d4);
+            MCRE_VP h[p] = fma(h[p], y[p], d3);
+            MCRE_VP h[p] = fma(h[p], y[p], d2);
+            MCRE_VP h[p] = fma(h[p], y[p], d1);
+            MCRE_VP h[p] = fma(h[p], y[p], d0);
+          } else {
+            const double2 h5 = __ldg(rec + 10);
+            double xb[PP], eb[PP];
+            MCRE_VP xb[p] = h5.y * y[p];             // -B y
+            fm_exp_tv<PP>(xb, eb);
+            MCRE_VP h[p] = fma(-h5.x, eb[p], 1.0);   // 1 - C exp(-B y)   (cirpp.py:298-317)
+          }
+          MCRE_VP e[p] = e[p] * ea[p];
+          MCRE_VP cva[p] = fma(e[p], h[p], cva[p]);
+        }
+      }
+      // ---- per-path totals ----------------------------------------------------------------------
+      if (pilot) {
+        if (tid == 0) {
+          shift_tail[0] = 0.0; shift_tail[1] = 0.0; shift_tail[2] = cva[0] * P.lgd; shift_tail[3] = 0.0;
+          __threadfence();
+          atomicExch(P.sync + 1, 1u);
+        }
+        break;
+      }
+      if (it == 0) {
+        if (tid == 0) s_first = cva[0] * P.lgd;
+        __syncthreads();
+        first = s_first;
+      }
+      MCRE_VP {
+        const double d = fma(cva[p], P.lgd, -first) * keep[p];
+        s1 += d;
+        s2 = fma(d, d, s2);
+      }
+    }
+    if (pilot) { pilot = false; continue; }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { s_stage[0][warp] = s1; s_stage[1][warp] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+      double t1 = 0.0, t2 = 0.0;
+      for (int w = 0; w < 4; ++w) { t1 += s_stage[0][w]; t2 += s_stage[1][w]; }
+      if (!have_shift) {
+        while (atomicAdd(P.sync + 1, 0u) == 0u) __nanosleep(100);
+        __threadfence();
+        gshift = *(volatile double *)(shift_tail + 2);
+        have_shift = true;
+      }
+      // sums against the chunk's first path -> sums against the common shift (global path 0):
+      //   sum(x - c) = sum(x - f) + n (f - c),  sum((x - c)^2) = sum((x - f)^2) + (f - c) (2 sum(x - f) + n (f - c))
+      const long long left = sh.n_paths - chunk * sh.chunk;
+      const double n = (double)(left < sh.chunk ? left : sh.chunk);
+      const double dl = first - gshift;
+      double *out = partial + (size_t)chunk * 4;
+      out[0] = 0.0; out[1] = 0.0;
+      out[2] = fma(n, dl, t1);
+      out[3] = fma(dl, fma(n, dl, 2.0 * t1), t2);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace mcre
+
+using namespace mcre;
+
+// Packs the event records from the plan's host copies.  Called from mcre_irc_set_coefficients (the exposure
+// coefficients of the regression enter the records).
+int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st) {
+  const CvaHost &h = p->cva;
+  const int n_events = h.n_pre_dates + h.n_sub;
+  std::vector<double> &rec = p->cva_rec_host;
+  rec.assign((size_t)n_events * CVA_REC + 2, 0.0);
+  const double sigma = h.vas[1], a = h.vas[3];
+  const double kappa = h.cir[0], ctheta = h.cir[1], csigma = h.cir[2];
+  const double *Lv = h.chol + 2 * h.vas_noise, *Lc = h.chol + 2 * h.cir_noise;   // rows of the lower Cholesky factor
+  const int DR = p->date_stride;
+  double psi_int = 0.0;   // sum psi(t1) dt over the sub-steps so far: the deterministic part of logB_lambda
+  auto date_part = [&](double *r, int di) {
+    if (di < 0) return;
+    const int m = h.date_metric[di];
+    if (!(h.date_flags[di] & MCRE_DATE_HAS_METRIC) || m < 0 || m >= h.n_metric - 1) return;
+    const double *dr = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR;   // C, B, c0, c1, c2 (raw basis)
+    const double C = dr[0], Bc = dr[1];
+    const double g = 0.5 * exp(-psi_int);
+    r[10] = g * dr[2]; r[11] = g * dr[3]; r[12] = g * dr[4];
+    double term = -C;           // d_j = -C (-B)^j / j!
+    r[13] = 1.0 - C;
+    for (int j = 1; j <= 5; ++j) { term *= -Bc / (double)j; r[13 + j] = term; }
+    int thr = 0;                // high word below which B y <= 2^-9 for certain
+    if (Bc > 0.0) {
+      const double ymax = 0.001953125 / Bc;
+      long long bits; memcpy(&bits, &ymax, 8);
+      thr = (int)(bits >> 32);
+    }
+    r[19] = pack2(thr, 0);
+    r[20] = C; r[21] = -Bc;
+    long long fb; memcpy(&fb, &r[9], 8);
+    r[9] = pack2((int)(fb & 0xffffffff) | CVA_EV_DATE, 0);
+  };
+  for (int ev = 0; ev < n_events; ++ev) {
+    double *r = rec.data() + (size_t)ev * CVA_REC;
+    if (ev < h.n_pre_dates) {
+      r[9] = pack2(CVA_EV_NOSTEP, 0);
+      date_part(r, ev);
+      continue;
+    }
+    const int s = ev - h.n_pre_dates;
+    const double dt = h.step_dt[s], sq = sqrt(dt);
+    int flags = 0;
+    r[0] = -dt;
+    r[1] = 1.0 - a * dt; r[2] = a * h.step_theta[s] * dt;
+    r[3] = sigma * sq * Lv[0]; r[4] = sigma * sq * Lv[1];
+    r[5] = 1.0 - kappa * dt; r[6] = kappa * ctheta * dt;
+    r[7] = csigma * sq * Lc[0]; r[8] = csigma * sq * Lc[1];
+    if (r[4] != 0.0) flags |= CVA_EV_KV1;
+    if (r[8] != 0.0) flags |= CVA_EV_KC1;
+    r[9] = pack2(flags, 0);
+    psi_int += h.step_psi[s] * dt;
+    date_part(r, h.step_date[s]);
+  }
+  MCRE_CUDA(cudaMemcpyAsync(p->cva_rec_dev, rec.data(), (size_t)n_events * CVA_REC * sizeof(double),
+                            cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+int irc_cva_launch(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
+                   cudaStream_t st) {
+  const CvaHost &h = p->cva;
+  CvaDev d;
+  d.rec = p->cva_rec_dev; d.n_events = h.n_pre_dates + h.n_sub;
+  d.r0 = h.vas[0]; d.y0 = h.y0; d.lgd = h.lgd;
+  d.sync = p->cva_sync_dev;
+  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  auto k = irc_cva_kernel<MCRE_CVA_PP>;
+  int per_sm = 1;
+  MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
+  if (per_sm < 1) return fail(-3, "irc cva kernel does not fit%s", "");
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > n_chunks) grid = n_chunks;
+  if (grid < 1) grid = 1;      // a rank without paths still publishes the common shift (global path 0)
+  MCRE_CUDA(cudaMemsetAsync(d.sync, 0, 2 * sizeof(unsigned), st));
+  // shift layout [n_metric + 1][4]: only the tail row (pv, -, cva, -) is used by this mode
+  k<<<(unsigned)grid, 128, 0, st>>>(d, rng, sh, partial, shift + (size_t)p->d.n_metric * 4);
+  MCRE_LAUNCHED();
+  return 0;
+}

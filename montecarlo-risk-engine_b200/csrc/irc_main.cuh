@@ -162,8 +162,8 @@ __device__ __forceinline__ R apply_threshold(const R &x, double h) {
 //    arithmetic are shared by the PP paths and their Horner chains interleave;
 //  * every per-step / per-date scalar sits in one packed record (mcre_irc_create packs
 //    them), read with a handful of wide uniform loads instead of ~45 scalar loads;
-//  * MODE 1 ("CVA only": one netting set, no threshold / collateral, no other metric):
-//    relu(E_k) S(0,t_k) = relu(poly) exp(-(logB + logB_lambda)) - two exponentials per date.
+//  * the "CVA only" case (one netting set, no threshold / collateral, no other metric, stochastic intensity)
+//    has its own kernel: irc_cva.cu.
 // =====================================================================================
 constexpr int STEP_HDR = 4;   // dt, sqrt(dt), bits(date index), pad
 constexpr int DATE_HDR = 6;   // bits(flags|(expo+1)<<32), bits((metric+1)|float_off<<32), bits(float_cnt), pad, shift, scale
@@ -172,27 +172,12 @@ __device__ __forceinline__ int lo32(double x) { return __double2loint(x); }
 __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 
 // Paths per thread / resident 128-thread blocks per SM of each build.  The FP64 pipe needs
-// in-warp ILP (fastmath.cuh, MCRE_VP): the CVA-only mode (few live values per path) runs 8 paths
-// per thread with 2 blocks per SM (255 registers); the general value-only builds carry
-// per-set cashflow / exposure-history state, so fewer paths fit; tangent builds run one path.
-#ifndef MCRE_IRC_PP
-#define MCRE_IRC_PP 8
-#endif
-#ifndef MCRE_IRC_MINB
-#define MCRE_IRC_MINB 2
-#endif
-// 1: the Philox rounds of sub-step s+1 are issued inside the iteration of sub-step s (CVA-only build)
-#ifndef MCRE_IRC_PREFETCH
-#define MCRE_IRC_PREFETCH 0
-#endif
-__host__ __device__ constexpr int irc_pp(int nt, int ns, int mode) {
-  return nt > 0 ? 1 : (mode == 1 ? MCRE_IRC_PP : (ns == 1 ? 4 : 2));
-}
-__host__ __device__ constexpr int irc_minb(int nt, int ns, int mode) {
-  return nt > 0 ? 1 : (mode == 1 ? MCRE_IRC_MINB : (ns == 1 ? 2 : 4));
-}
-template <int NT, int NS, bool CIR, int SCHEME, int PP, int MODE, bool BERM>
-__global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
+// in-warp ILP (fastmath.cuh, MCRE_VP): the value-only builds carry per-set cashflow / exposure-history
+// state for several paths per thread; tangent builds run one path.
+__host__ __device__ constexpr int irc_pp(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 4 : 2); }
+__host__ __device__ constexpr int irc_minb(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 2 : 4); }
+template <int NT, int NS, bool CIR, int SCHEME, int PP, bool BERM>
+__global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
                                                                          double *partial, double *spill,
                                                                          double *shift, int pilot) {
   typedef typename RealOf<NT>::type R;
@@ -232,7 +217,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
       NormalStream ns[PP];          // Vasicek only: one normal per step
       NormalStreamV<PP> nsv;        // Vasicek + CIR++: two normals per step, paths in lock-step
       IrcState<R> st[PP];
-      R pv[PP][NS], cva[PP][NS], hist[PP][NS][MODE == 1 ? 1 : MCRE_IRC_MAX_LAG];
+      R pv[PP][NS], cva[PP][NS], hist[PP][NS][MCRE_IRC_MAX_LAG];
       unsigned alive[PP];   // bit b: Bermudan unit b still holds its exercise right
 #pragma unroll
       for (int p = 0; p < PP; ++p) {
@@ -247,7 +232,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
         for (int s = 0; s < NS; ++s) {
           pv[p][s] = T::zero(); cva[p][s] = T::zero();
 #pragma unroll
-          for (int l = 0; l < (MODE == 1 ? 1 : MCRE_IRC_MAX_LAG); ++l) hist[p][s][l] = T::zero();
+          for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l) hist[p][s][l] = T::zero();
         }
       }
       nsv.init(rng, gpath);
@@ -262,32 +247,6 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
           return;
         const double bshift = h2.x, bscale = h2.y;
         const double *dc = dr + DATE_HDR;   // C[w], B[w], coef[set][3][w]
-        if constexpr (MODE == 1) {
-          // CVA-only fast path (value-only build, R = double): contribution at metric dates
-          // k < n_metric-1 only; every operation runs over the PP paths in lock-step.
-          if (!(flags & MCRE_DATE_HAS_METRIC) || m >= P.n_metric - 1) return;
-          // (the host side rewrites the coefficients of this mode in the raw basis [1, r, r^2]:
-          // mcre_irc_set_coefficients)
-          const double C = __ldg(dc + 0), Bc = __ldg(dc + 1);
-          const double c0 = __ldg(dc + 2), c1 = __ldg(dc + 3), c2 = __ldg(dc + 4);
-          double xa[PP], xb[PP], ea[PP], eb[PP], pos[PP];
-          bool small = true;
-          MCRE_VP xb[p] = -(Bc * st[p].y);
-          MCRE_VP small = small && fabs(xb[p]) <= 0.015625;
-          // S(t_k, t_k+1 | y) = C exp(-B y): B y is tiny for any sane intensity, so the whole warp
-          // normally takes the reduction-free Taylor form (uniform branch)
-          const bool all_small = __all_sync(0xffffffffu, small);
-          MCRE_VP xa[p] = -(st[p].logB + st[p].logBl);
-          MCRE_VP pos[p] = fma(st[p].r, c2, c1);
-          fm_exp_tv<PP>(xa, ea);
-          if (all_small) fm_exp_smallv<PP>(xb, eb);
-          else fm_exp_tv<PP>(xb, eb);
-          MCRE_VP pos[p] = fmax(fma(st[p].r, pos[p], c0), 0.0);
-          MCRE_VP eb[p] = fma(-C, eb[p], 1.0);
-          MCRE_VP pos[p] = pos[p] * ea[p];
-          MCRE_VP cva[p][0] = fma(pos[p], eb[p], cva[p][0]);
-          return;
-        }
         R invN[PP];
 #pragma unroll
         for (int p = 0; p < PP; ++p) invN[p] = r_exp(-st[p].logB);  // 1 / numeraire (vasicek.py:154-156)
@@ -424,16 +383,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
       };
 
       for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
-      constexpr bool PREFETCH = MCRE_IRC_PREFETCH && CIR && MODE == 1;
-      uint32_t q0[PREFETCH ? PP : 1], q1[PREFETCH ? PP : 1], q2[PREFETCH ? PP : 1], q3[PREFETCH ? PP : 1];
-      if constexpr (PREFETCH) {
-        if (rng.mode != MCRE_RNG_INJECT && P.n_sub > 0) nsv.raw(q0, q1, q2, q3);
-      }
-#if defined(MCRE_IRC_UNROLL) && MCRE_IRC_UNROLL > 1
-#pragma unroll 2
-#else
 #pragma unroll 1
-#endif
       for (int is = 0; is < P.n_sub; ++is) {
         const double *sr = P.step_rec + (size_t)is * SR;
         const double2 g0 = __ldg((const double2 *)sr), g1 = __ldg((const double2 *)sr + 1);
@@ -450,11 +400,6 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
             z0[p] = zp[0];
             z1[p] = CIR ? zp[1] : 0.0;
           }
-        } else if constexpr (PREFETCH) {
-          uint32_t w0[PP], w1[PP], w2[PP], w3[PP];
-          MCRE_VP { w0[p] = q0[p]; w1[p] = q1[p]; w2[p] = q2[p]; w3[p] = q3[p]; }
-          if (is + 1 < P.n_sub) nsv.raw(q0, q1, q2, q3);     // integer work of the next sub-step, independent of this one
-          NormalStreamV<PP>::box_muller(w0, w1, w2, w3, z0, z1);
         } else if constexpr (CIR) {
           nsv.next2(z0, z1);
         } else {
@@ -549,8 +494,23 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS, MODE)) irc_main_kernel(I
 // ---- host side shared by irc.cu and irc_berm.cu ----------------------------------------
 using namespace mcre;
 
+// Host copies of what the CVA-only kernel's event records are built from (irc_cva.cu)
+constexpr int CVA_REC = 24;        // doubles per event record
+struct CvaHost {
+  int n_sub = 0, n_pre_dates = 0, n_metric = 0, vas_noise = 0, cir_noise = 1;
+  double vas[4] = {0, 0, 0, 0}, cir[3] = {0, 0, 0}, chol[4] = {1, 0, 0, 1}, y0 = 0.0, lgd = 0.0;
+  std::vector<double> step_dt, step_theta, step_psi;
+  std::vector<int> step_date, date_flags, date_metric;
+};
+
 struct mcre_irc_plan {
   IrcDev d;
+  CvaHost cva;
+  std::vector<double> cva_rec_host;
+  double *cva_rec_dev = nullptr;
+  unsigned *cva_sync_dev = nullptr;
+  DevArray<double> cva_rec;
+  DevArray<int> cva_sync;
   DevArena arena;   // all plan tables live in one device allocation
   DevArray<double> vas, cir, cir_init, chol, step_dt, step_vas, step_cir, float_coef, float_inv_tau, set_fix,
       set_float, set_threshold, expo_coef, expo_basis, cva_coef, unit_fix, unit_float, reg_basis;
@@ -577,10 +537,11 @@ static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, 
   const int nvb = NS * (4 + 2 * NT);
   const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
-  if (n_chunks == 0) return 0;
-#define LAUNCH(CIRV, SCH, MODEV)                                                                       \
+  // The pilot launch (global path 0 -> the common shift of the shifted sums) runs on every rank, also on one whose
+  // shard is empty: all ranks must finish their all-reduced sums with the same shift.
+#define LAUNCH(CIRV, SCH)                                                                              \
   do {                                                                                                 \
-    auto k = irc_main_kernel<NT, NS, CIRV, SCH, irc_pp(NT, NS, MODEV), MODEV, BERM>;                         \
+    auto k = irc_main_kernel<NT, NS, CIRV, SCH, irc_pp(NT, NS), BERM>;                                 \
     if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                    \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));               \
@@ -590,14 +551,14 @@ static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, 
     ShardDev pilot_sh{0, 1, sh.chunk};                                                                 \
     k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, spill, shift, 1);                           \
     MCRE_LAUNCHED();                                                                                   \
-    k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, spill, shift, 0);                    \
-    MCRE_LAUNCHED();                                                                                   \
+    if (n_chunks > 0) {                                                                                \
+      k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, spill, shift, 0);                  \
+      MCRE_LAUNCHED();                                                                                 \
+    }                                                                                                  \
   } while (0)
-  if (d.has_cir) {
-    if (NT == 0 && NS == 1 && !BERM && p->cva_only) LAUNCH(true, MCRE_SCHEME_EULER, (NT == 0 && NS == 1 && !BERM ? 1 : 0));
-    else LAUNCH(true, MCRE_SCHEME_EULER, 0);
-  } else if (d.scheme == MCRE_SCHEME_ANALYTICAL) LAUNCH(false, MCRE_SCHEME_ANALYTICAL, 0);
-  else LAUNCH(false, MCRE_SCHEME_EULER, 0);
+  if (d.has_cir) LAUNCH(true, MCRE_SCHEME_EULER);
+  else if (d.scheme == MCRE_SCHEME_ANALYTICAL) LAUNCH(false, MCRE_SCHEME_ANALYTICAL);
+  else LAUNCH(false, MCRE_SCHEME_EULER);
 #undef LAUNCH
   return 0;
 }
@@ -625,6 +586,10 @@ static int irc_dispatch_main(mcre_irc_plan *p, const RngDev &r, const ShardDev &
   return ns == 1 ? launch_main<8, 1, BERM>(p, r, sh, d_partial, d_spill, d_shift, st)
                  : launch_main<8, 2, BERM>(p, r, sh, d_partial, d_spill, d_shift, st);
 }
+// defined in irc_cva.cu (the CVA-only kernel)
+int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st);
+int irc_cva_launch(mcre_irc_plan *p, const mcre::RngDev &rng, const mcre::ShardDev &sh, double *partial, double *shift,
+                   cudaStream_t st);
 // defined in irc_berm.cu (books with Bermudan exercise units)
 int irc_dispatch_main_berm(mcre_irc_plan *p, const mcre::RngDev &r, const mcre::ShardDev &sh, double *d_partial,
                            double *d_spill, double *d_shift, cudaStream_t st);

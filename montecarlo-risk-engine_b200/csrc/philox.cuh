@@ -4,7 +4,8 @@
 //   key     = (low 32 bits of seed, low 32 bits of stream)
 //   counter = (path_lo, path_hi, block, kind)      kind 0: normals, 1: uniforms
 //   normal  #n of a path = element (n & 1) of BoxMuller(block n >> 1):
-//             sqrt(-2 log u1) (cos, sin)(2 pi u2), u1 = (k1 + 1/2) 2^-52, u2 = k2 2^-52, k = top 52 bits
+//             sqrt(-2 log u1) (cos, sin)(2 pi u2), u1 = (k1 + 1/2) 2^-52, u2 = k2 2^-52,
+//             k = (low 20 bits of the first word):(second word) of a word pair
 //   uniform #m of a path = element (m & 1) of the two 52-bit uniforms of block m >> 1
 // so a draw depends only on (seed, stream, global path id, draw index): sharding paths
 // over GPUs or replaying a path in a second pass reproduces it exactly.  Takes the place
@@ -40,22 +41,23 @@ struct Philox {
   }
 };
 
-// 52-bit uniform in (0,1): (k + 0.5) * 2^-52, k = the top 52 bits of (hi:lo).  Built in the
-// mantissa of a double in [1,2) and shifted down with one exact subtraction - no int -> double
-// conversion (I2F.F64.U64 was the longest stall of the v2 profile).
+// 52-bit uniform in (0,1): (k + 0.5) * 2^-52 with k = (low 20 bits of hi):(lo).  Built in the
+// mantissa of a double in [1,2) with ONE logic instruction (the exponent is OR-ed over the 12 unused
+// bits of hi, lo is the low word as it is) and shifted down with one exact subtraction - no
+// int -> double conversion, no funnel shifts.  (Round 1 used the top 52 bits of hi:lo, 4 instructions.)
 __host__ __device__ inline double u52(uint32_t hi, uint32_t lo) {
 #ifdef __CUDA_ARCH__
-  const double d = __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+  const double d = __hiloint2double((int)(0x3ff00000u | (hi & 0x000fffffu)), (int)lo);
   return d - 0.99999999999999988898;   // 1 - 2^-53: exact, result (2k + 1) * 2^-53
 #else
-  uint64_t k = (((uint64_t)hi << 32) | lo) >> 12;
+  uint64_t k = (((uint64_t)(hi & 0x000fffffu)) << 32) | lo;
   return ((double)k + 0.5) * 2.220446049250313e-16;
 #endif
 }
 
-// mantissa double in [1, 2) from the top 52 bits of (hi:lo): 1 + k 2^-52
+// mantissa double in [1, 2) from the same 52 bits: 1 + k 2^-52
 __device__ inline double mant52(uint32_t hi, uint32_t lo) {
-  return __hiloint2double((int)(0x3ff00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+  return __hiloint2double((int)(0x3ff00000u | (hi & 0x000fffffu)), (int)lo);
 }
 
 struct RngDev {
@@ -86,7 +88,10 @@ struct NormalStream {
 #if defined(MCRE_FAST_MATH) && MCRE_FAST_MATH >= 2
     // same arithmetic as NormalStreamV::next2 (the angle reduction works on the mantissa double)
     const double dd[1] = {mant52(o[2], o[3])};
-    const double rr[1] = {fm_sqrt_pos(-2.0 * fm_log_t(u1))};   // u1 < 1: the argument is strictly positive
+    const double uu[1] = {u1};
+    double lg[1];
+    fm_neg2log_tv<1>(uu, lg);
+    const double rr[1] = {fm_sqrt_pos(lg[0])};   // u1 < 1: the argument is strictly positive
     double zc[1], zs[1];
     fm_polar_tv<1>(dd, rr, zc, zs);
     z0 = zc[0]; z1 = zs[0];
@@ -164,8 +169,7 @@ struct NormalStreamV {
     double u1[PP], d2[PP], lg[PP], rad[PP];
     MCRE_VP u1[p] = u52(c0[p], c1[p]);
     MCRE_VP d2[p] = mant52(c2[p], c3[p]);
-    fm_log_tv<PP>(u1, lg);
-    MCRE_VP lg[p] = -2.0 * lg[p];
+    fm_neg2log_tv<PP>(u1, lg);
     fm_sqrt_posv<PP>(lg, rad);          // u1 < 1: the argument is strictly positive
     fm_polar_tv<PP>(d2, rad, z0, z1);
   }

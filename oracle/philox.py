@@ -21,8 +21,8 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
 
 
 def u52(hi, lo):
-    """(k + 0.5) * 2^-52 with k the top 52 bits of (hi:lo) - same definition as csrc/philox.cuh."""
-    k = ((hi << np.uint64(32)) | lo) >> np.uint64(12)
+    """(k + 0.5) * 2^-52 with k = (low 20 bits of hi):(lo) - same definition as csrc/philox.cuh."""
+    k = ((hi & np.uint64(0xFFFFF)) << np.uint64(32)) | lo
     return (k.astype(np.float64) + 0.5) * 2.220446049250313e-16
 
 

@@ -153,7 +153,13 @@ def test_bs_european_call_with_aad_matches_black_scholes(rng):
     res = sc.run_simulation()
     price = float(res.get_results(prod.get_name(), "pv")[0])
     exact = float(prod.compute_pv_analytically(model))
-    assert abs(price - exact) / exact < 1e-3
+    if rng == "torch":
+        assert abs(price - exact) / exact < 1e-3            # the reference's own threshold, on the reference's draws
+    else:
+        # 1e-3 relative is 0.7 standard errors at this size (the reference passes on its seed): under Philox
+        # the bound is 4 standard errors
+        err = float(res.get_mc_error(prod.get_name(), "pv")[0])
+        assert abs(price - exact) < 4.0 * err, (price, exact, err)
     d1 = (math.log(100.0 / 100.0) + (0.05 + 0.02) * 1.0) / 0.2
     delta, vega = 0.5 * math.erfc(-d1 / math.sqrt(2)), 100.0 * math.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi)
     g = res.get_derivatives(prod.get_name(), "pv", evaluation_idx=0)

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Builds tuning variants of the library (paths per thread x resident blocks per SM of the
-IRC main kernel) into montecarlo-risk-engine_b200/variants/ so one GPU call can time them:
+CVA-only kernel, csrc/irc_cva.cu) into montecarlo-risk-engine_b200/variants/ so one GPU call can time them:
 
-    python tools/tune_irc.py build 2x4 2x5 2x6 1x8 4x2           (here, no GPU)
-    python tools/tune_irc.py run 2x4 2x5 ...                      (on the GPU box)
+    python tools/tune_irc.py build 8x2 4x3 4x4 6x2           (here, no GPU)
+    python tools/tune_irc.py run 8x2 4x3 ...                  (on the GPU box)
+
+Only irc_cva.cu is recompiled per variant; the other objects come from the product build.
 """
 import json
 import os
@@ -25,15 +27,22 @@ def main():
     os.makedirs(VAR, exist_ok=True)
     if mode == "build":
         from mcre import build
+        build.build()
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        objs = [os.path.join(PKG, "build", os.path.basename(s)[:-3] + ".o") for s in build.sources()]
         for v in variants:
-            pp, rest = v.split("x")
-            prefetch = rest.endswith("p")
-            rest = rest.rstrip("p")
-            minb, _, unroll = rest.partition("u")
-            flags = [f"-DMCRE_IRC_PP={pp}", f"-DMCRE_IRC_MINB={minb}"] + ([f"-DMCRE_IRC_UNROLL={unroll}"] if unroll else [])
-            flags += ["-DMCRE_IRC_PREFETCH=1"] if prefetch else []
-            build.build(force=True, extra_flags=flags, lib=lib_of(v), tag="_" + v)
-            print("built", lib_of(v))
+            pp, _, rest = v.partition("x")
+            minb, _, extra = rest.partition("_")
+            flags = [f"-DMCRE_CVA_PP={pp}", f"-DMCRE_CVA_MINB={minb}"] + ([f"-D{e}" for e in extra.split("_") if e])
+            obj = os.path.join(VAR, f"irc_cva_{v}.o")
+            out = subprocess.run([nvcc, *build.NVCC_FLAGS, *flags, "-Xptxas", "-v", "-c", os.path.join(build.CSRC, "irc_cva.cu"), "-o", obj],
+                                 capture_output=True, text=True)
+            if out.returncode:
+                sys.exit(out.stderr)
+            regs = [l for l in out.stderr.splitlines() if "registers" in l]
+            link = [o if not o.endswith("irc_cva.o") else obj for o in objs]
+            subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_of(v), *link, "-lcudart"])
+            print("built", lib_of(v), regs[-1].strip() if regs else "")
     else:
         for v in variants:
             env = dict(os.environ, MCRE_LIB_PATH=lib_of(v))
