@@ -131,10 +131,89 @@ class CpuPool:
         self.pool.shutdown()
 
 
+REF_SRC = os.path.join(ROOT, "oracle", "_ref", "src")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_SRC, "controller", "controller.py"))
+
+
 def run_reference_arm(args):
+    """`--impl reference`: the UNMODIFIED reference (oracle/_ref/src, copied from /root/reference/src by
+    oracle/make_ref.py) through its own public API: SimulationController(...).run_simulation() of config 3 on all host
+    cores (torch intra-op threads), on a bounded sample of the paths.  `value` follows SURVEY 8d: main-simulation
+    pipeline (the controller's own phase log: path_generation + request_resolution + valuation); `e2e` is the whole
+    call including the pre-simulation, whose path count keeps the 1/16 ratio of the GPU arm.
+    Falls back to the oracle port (kind "port") only when oracle/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not reference_available():
+        return run_port_arm(args)
+    import logging
+    import types
+    import torch
+    # the reference's module names (controller, models, ...) are the ones this repo's package uses too: this process
+    # imports the reference only
+    sys.path.insert(0, REF_SRC)
+    _helpers = types.ModuleType("helpers")          # namespace package in the reference; tests/helpers.py would win
+    _helpers.__path__ = [os.path.join(REF_SRC, "helpers")]
+    sys.modules["helpers"] = _helpers
+    import cases
+    ns = cases.Namespace()
+    assert os.path.realpath(sys.modules["controller.controller"].__file__).startswith(os.path.realpath(REF_SRC))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_main = 1 << args.ref_paths_log2
+    n_pre = max(n_main >> 4, 1024)
+
+    class Grab(logging.Handler):
+        def __init__(self):
+            super().__init__()
+            self.phases = None
+
+        def emit(self, record):
+            if isinstance(record.args, tuple) and len(record.args) == 7:
+                self.phases = dict(zip(("preprocessing", "path_generation", "request_resolution", "valuation", "total"),
+                                       (float(x) for x in record.args[2:])))
+
+    grab = Grab()
+    lg = logging.getLogger("controller.controller")
+    lg.setLevel(logging.INFO)
+    lg.addHandler(grab)
+    main_t, total_t, phases, cva = [], [], None, None
+    for i in range(args.warmup + args.steps):
+        model, sets, metrics, tl = build_case(ns, float(RHOS[i % len(RHOS)]))
+        rm = ns.RiskMetrics(metrics, exposure_timeline=tl)
+        t0 = time.perf_counter()
+        sc = ns.SimulationController(sets, model, rm, n_main, n_pre, 1, ns.SimulationScheme.EULER)
+        res = sc.run_simulation()
+        wall = time.perf_counter() - t0
+        ph = grab.phases
+        if i >= args.warmup:
+            main_t.append(ph["path_generation"] + ph["request_resolution"] + ph["valuation"])
+            total_t.append(wall)
+            phases = ph
+            cva = float(res.get_results("irs", "cva[GM]")[0])
+    ms = 1e3 * float(np.mean(main_t))
+    value = n_main * N_STEPS_SIM / (ms * 1e-3)
+    e2e_value = n_main * N_STEPS_SIM / float(np.mean(total_t))
+    sample = (f"{n_main} main + {n_pre} pre-simulation paths x {N_STEPS_SIM} steps per step, unmodified reference "
+              f"(oracle/_ref/src = /root/reference/src) SimulationController.run_simulation(), torch {torch.__version__} CPU, "
+              f"{cores} intra-op threads; value = path_generation + request_resolution + valuation of its phase log")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: Vasicek+CIR++ WWR CVA payer swap, 2^24 paths x 240 steps (bounded CPU sample)",
+                       "paths_per_step": n_main, "presim_paths": n_pre, "sub_steps": N_STEPS_SIM},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "phases_last_step_s": phases, "cva_last_step": cva}
+    print(json.dumps(line))
+
+
+def run_port_arm(args):
+    """The oracle port (numpy restatement) on all host cores: one single-threaded worker process per core."""
     pool = CpuPool()
     per_worker = (1 << 15) if pool.workers <= 32 else (1 << 14)   # ~0.8 GB of path tensor per worker
     n = per_worker * pool.workers
@@ -148,7 +227,8 @@ def run_reference_arm(args):
     value = n * N_STEPS_SIM / (ms * 1e-3)
     sample = (f"{n} paths x {N_STEPS_SIM} steps per step ({per_worker} per worker process, {pool.workers} workers = host cores), "
               "main simulation incl. normal generation: torch.randn draws + numpy FP64 restatement of the reference")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference" if args.impl == "reference" else "port", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[2]: Vasicek+CIR++ WWR CVA payer swap, 2^24 paths x 240 steps (bounded CPU sample)",
@@ -168,9 +248,12 @@ def main():
     ap.add_argument("--presim-log2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the end-to-end leg")
+    ap.add_argument("--ref-paths-log2", type=int, default=17, help="main-simulation paths per step of the reference arm")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "port":
+        return run_port_arm(args) if int(os.environ.get("RANK", "0")) == 0 else None
 
     import torch
     import torch.distributed as dist

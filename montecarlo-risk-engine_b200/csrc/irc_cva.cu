@@ -47,14 +47,40 @@ constexpr int HI_1E_12 = 0x3D719799;   // high word of 1e-12
 
 struct CvaDev {
   const double *rec;   // [n_events][CVA_REC]
-  int n_events;
+  int n_pre, n_sub;    // events: n_pre dates at the calibration date (no step), then one per sub-step
   double r0, y0, lgd;
   unsigned *sync;      // [0]: next chunk, [1]: pilot value published
+  // Philox round keys (key + i * Weyl constant): kernel parameters sit in the constant bank and feed the
+  // round's LOP3 directly - no key-schedule instructions in the loop
+  uint32_t rk0[10], rk1[10];
+  // USTEP builds: all sub-steps share their scalars (constant dt, constant mean levels): parameters, not loads
+  double st[9];
+  int st_flags;
 };
 
+// 1: the Philox rounds of draw block s+1 are issued inside event s (software pipeline, draw words ping-pong between
+// two register sets).  Measured (profiles/r02_cva_kernel.md): ptxas still emits the rounds as one cluster next to
+// long DFMA runs, 2 % slower than 0 because of the 16 extra live registers - off.
+#ifndef MCRE_CVA_PF
+#define MCRE_CVA_PF 0
+#endif
+
+// Ten Philox rounds for the draw block `block` of PP paths in lock-step (the paths of one pass share the high word
+// of their global id: a pass never leaves its 4096-aligned chunk).
 template <int PP>
-__global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(CvaDev P, RngDev rng, ShardDev sh,
-                                                                      double *__restrict__ partial,
+__device__ __forceinline__ void cva_philox(const CvaDev &P, const uint32_t (&plo)[PP], uint32_t phi, uint32_t block,
+                                           uint32_t (&c0)[PP], uint32_t (&c1)[PP], uint32_t (&c2)[PP],
+                                           uint32_t (&c3)[PP]) {
+  MCRE_VP { c0[p] = plo[p]; c1[p] = phi; c2[p] = block; c3[p] = 0u; }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    MCRE_VP Philox::round(c0[p], c1[p], c2[p], c3[p], P.rk0[i], P.rk1[i]);
+  }
+}
+
+template <int PP, bool USTEP, bool PF>
+__global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(const __grid_constant__ CvaDev P, RngDev rng,
+                                                                      ShardDev sh, double *__restrict__ partial,
                                                                       double *shift_tail) {
   fm_tables_init();
   __shared__ double s_stage[2][4];
@@ -79,87 +105,129 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(CvaDev P, R
     double s1 = 0.0, s2 = 0.0, first = 0.0;
     const int span = pilot ? 1 : sh.chunk;
     for (int it = 0; it < span; it += 128 * PP) {
-      long long gpath[PP];
-      double keep[PP];
+      // global id of path p of this thread: g0 + 128 p (the pilot pass simulates global path 0 in every lane);
+      // lanes past the end of the shard simulate ids nobody owns and are masked out of the sums
+      const long long l0 = chunk * sh.chunk + it + tid;
+      const long long g0 = pilot ? 0 : sh.path_begin + l0;
+      const int stride = pilot ? 0 : 128;
+      unsigned live = 0u;
+      uint32_t plo[PP];
       MCRE_VP {
-        const int in_chunk = it + p * 128 + tid;
-        const long long lpath = chunk * sh.chunk + in_chunk;
-        const bool live = !pilot && lpath < sh.n_paths && in_chunk < sh.chunk;
-        keep[p] = live ? 1.0 : 0.0;
-        gpath[p] = pilot ? 0 : sh.path_begin + (live ? lpath : 0);
+        if (!pilot && l0 + p * 128 < sh.n_paths && it + p * 128 + tid < sh.chunk) live |= 1u << p;
+        plo[p] = (uint32_t)(g0 + p * stride);
       }
-      NormalStreamV<PP> nsv;
-      nsv.init(rng, gpath);
+      const uint32_t phi = (uint32_t)((unsigned long long)g0 >> 32);
       double r[PP], y[PP], A[PP], cva[PP];
       MCRE_VP { r[p] = P.r0; y[p] = P.y0; A[p] = 0.0; cva[p] = 0.0; }
-      int is = 0;   // sub-step counter (row of the injected normals)
-#pragma unroll 1
-      for (int ev = 0; ev < P.n_events; ++ev) {
-        const double2 *rec = (const double2 *)(P.rec + (size_t)ev * CVA_REC);
-        const double2 g4 = __ldg(rec + 4);
-        const int flags = __double2loint(g4.y);
-        if (!(flags & CVA_EV_NOSTEP)) {
-          const double2 g0 = __ldg(rec), g1 = __ldg(rec + 1), g2 = __ldg(rec + 2), g3 = __ldg(rec + 3);
-          const double ndt = g0.x, om_v = g0.y, c_v = g1.x, kv0 = g1.y, kv1 = g2.x, om_c = g2.y, c_c = g3.x,
-                       kc0 = g3.y, kc1 = g4.x;
-          double z0[PP], z1[PP];
-          if (inject) {
-            MCRE_VP {
-              const double *zp = rng.z + ((size_t)is * rng.n_total + gpath[p]) * 2;
-              z0[p] = zp[0]; z1[p] = zp[1];
-            }
-          } else {
-            nsv.next2(z0, z1);
-          }
-          ++is;
-          // integrals with the pre-step state (left Riemann sums, vasicek.py:80,107, cirpp.py:196-197)
-          MCRE_VP A[p] = fma(r[p], ndt, A[p]);
-          MCRE_VP A[p] = fma(y[p], ndt, A[p]);
-          double sy[PP], wn[PP], yn[PP];
-          fm_sqrt_posv<PP>(y, sy);                  // y >= 1e-12 after every step and y0 > 0
-          MCRE_VP r[p] = fma(r[p], om_v, c_v);
-          MCRE_VP r[p] = fma(kv0, z0[p], r[p]);
-          if (flags & CVA_EV_KV1) { MCRE_VP r[p] = fma(kv1, z1[p], r[p]); }
-          MCRE_VP wn[p] = kc0 * z0[p];
-          if (flags & CVA_EV_KC1) { MCRE_VP wn[p] = fma(kc1, z1[p], wn[p]); }
-          MCRE_VP yn[p] = fma(y[p], om_c, c_c);
-          MCRE_VP yn[p] = fma(sy[p], wn[p], yn[p]);
-          // y' = max(yn, 1e-12) (cirpp.py:198): high word above that of 1e-12 <=> certainly larger
-          bool above = true;
-          MCRE_VP above = above && (__double2hiint(yn[p]) > HI_1E_12);
-          if (__all_sync(0xffffffffu, above)) { MCRE_VP y[p] = yn[p]; }
-          else { MCRE_VP y[p] = fmax(yn[p], 1e-12); }
+
+      // ---- CVA contribution of the metric date that closes event `ev` ---------------------------------------
+      auto date_part = [&](const double *rec) {
+        const double2 *rd = (const double2 *)(rec + 10);
+        const double2 h0 = __ldg(rd), h1 = __ldg(rd + 1), h2 = __ldg(rd + 2), h3 = __ldg(rd + 3), h4 = __ldg(rd + 4);
+        const double c0 = h0.x, c1 = h0.y, c2 = h1.x, d0 = h1.y, d1 = h2.x, d2 = h2.y, d3 = h3.x, d4 = h3.y,
+                     d5 = h4.x;
+        const int thr = __double2loint(h4.y);
+        double e[PP], ea[PP], h[PP];
+        MCRE_VP e[p] = fma(r[p], c2, c1);
+        MCRE_VP e[p] = fma(r[p], e[p], c0);
+        bool small = true;
+        MCRE_VP small = small && (__double2hiint(y[p]) < thr);
+        fm_exp_tv<PP>(A, ea);
+        MCRE_VP e[p] = e[p] + fabs(e[p]);          // relu of the exposure proxy (the 1/2 sits in c0..c2)
+        if (__all_sync(0xffffffffu, small)) {
+          MCRE_VP h[p] = fma(y[p], d5, d4);
+          MCRE_VP h[p] = fma(h[p], y[p], d3);
+          MCRE_VP h[p] = fma(h[p], y[p], d2);
+          MCRE_VP h[p] = fma(h[p], y[p], d1);
+          MCRE_VP h[p] = fma(h[p], y[p], d0);
+        } else {
+          __syncwarp();                              // (a real branch, see the clamp above)
+          const double2 h5 = __ldg(rd + 5);
+          double xb[PP], eb[PP];
+          MCRE_VP xb[p] = h5.y * y[p];             // -B y
+          fm_exp_tv<PP>(xb, eb);
+          // 1 - C exp(-B y)   (cirpp.py:298-317); volatile: not to be merged with the polynomial branch
+          MCRE_VP asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(h[p]) : "d"(-h5.x), "d"(eb[p]), "d"(1.0));
         }
-        if (flags & CVA_EV_DATE) {
-          const double2 h0 = __ldg(rec + 5), h1 = __ldg(rec + 6), h2 = __ldg(rec + 7), h3 = __ldg(rec + 8),
-                        h4 = __ldg(rec + 9);
-          const double c0 = h0.x, c1 = h0.y, c2 = h1.x, d0 = h1.y, d1 = h2.x, d2 = h2.y, d3 = h3.x, d4 = h3.y,
-                       d5 = h4.x;
-          const int thr = __double2loint(h4.y);
-          double e[PP], ea[PP], h[PP];
-          MCRE_VP e[p] = fma(r[p], c2, c1);
-          MCRE_VP e[p] = fma(r[p], e[p], c0);
-          bool small = true;
-          MCRE_VP small = small && (__double2hiint(y[p]) < thr);
-          fm_exp_tv<PP>(A, ea);
-          MCRE_VP e[p] = e[p] + fabs(e[p]);          // relu of the exposure proxy (the 1/2 sits in c0..c2)
-          if (__all_sync(0xffffffffu, small)) {
-            MCRE_VP h[p] = fma(y[p], d5, d4);
-            MCRE_VP h[p] = fma(h[p], y[p], d3);
-            MCRE_VP h[p] = fma(h[p], y[p], d2);
-            MCRE_VP h[p] = fma(h[p], y[p], d1);
-            MCRE_VP h[p] = fma(h[p], y[p], d0);
-          } else {
-            const double2 h5 = __ldg(rec + 10);
-            double xb[PP], eb[PP];
-            MCRE_VP xb[p] = h5.y * y[p];             // -B y
-            fm_exp_tv<PP>(xb, eb);
-            MCRE_VP h[p] = fma(-h5.x, eb[p], 1.0);   // 1 - C exp(-B y)   (cirpp.py:298-317)
-          }
-          MCRE_VP e[p] = e[p] * ea[p];
-          MCRE_VP cva[p] = fma(e[p], h[p], cva[p]);
+        MCRE_VP e[p] = e[p] * ea[p];
+        MCRE_VP cva[p] = fma(e[p], h[p], cva[p]);
+      };
+
+      // ---- one sub-step: draws (words `w` were produced one event earlier when PF), SDE step, date ----------
+      auto step_event = [&](int is, uint32_t (&w0)[PP], uint32_t (&w1)[PP], uint32_t (&w2)[PP], uint32_t (&w3)[PP],
+                            uint32_t (&n0)[PP], uint32_t (&n1)[PP], uint32_t (&n2)[PP], uint32_t (&n3)[PP]) {
+        const double *rec = P.rec + (size_t)(P.n_pre + is) * CVA_REC;
+        double ndt, om_v, c_v, kv0, kv1, om_c, c_c, kc0, kc1;
+        int flags;
+        if (USTEP) {
+          ndt = P.st[0]; om_v = P.st[1]; c_v = P.st[2]; kv0 = P.st[3]; kv1 = P.st[4]; om_c = P.st[5]; c_c = P.st[6];
+          kc0 = P.st[7]; kc1 = P.st[8];
+          flags = P.st_flags | (__double2loint(__ldg(rec + 9)) & CVA_EV_DATE);
+        } else {
+          const double2 *rs = (const double2 *)rec;
+          const double2 g0_ = __ldg(rs), g1 = __ldg(rs + 1), g2 = __ldg(rs + 2), g3 = __ldg(rs + 3), g4 = __ldg(rs + 4);
+          ndt = g0_.x; om_v = g0_.y; c_v = g1.x; kv0 = g1.y; kv1 = g2.x; om_c = g2.y; c_c = g3.x; kc0 = g3.y; kc1 = g4.x;
+          flags = __double2loint(g4.y);
         }
+        double z0[PP], z1[PP];
+        if (inject) {
+          MCRE_VP {
+            long long g = g0 + p * stride;
+            if (!((live >> p) & 1u) && !pilot) g = sh.path_begin;
+            const double *zp = rng.z + ((size_t)is * rng.n_total + g) * 2;
+            z0[p] = zp[0]; z1[p] = zp[1];
+          }
+        } else {
+          if (PF) {
+            // the integer rounds of the NEXT draw block are independent of everything below: issued here so that
+            // they interleave with the FP64 work of this event inside one warp
+            cva_philox<PP>(P, plo, phi, (uint32_t)is + 1u, n0, n1, n2, n3);
+          } else {
+            cva_philox<PP>(P, plo, phi, (uint32_t)is, w0, w1, w2, w3);
+          }
+          NormalStreamV<PP>::box_muller(w0, w1, w2, w3, z0, z1);
+        }
+        // integrals with the pre-step state (left Riemann sums, vasicek.py:80,107, cirpp.py:196-197)
+        MCRE_VP A[p] = fma(r[p], ndt, A[p]);
+        MCRE_VP A[p] = fma(y[p], ndt, A[p]);
+        double sy[PP], wn[PP], yn[PP];
+        fm_sqrt_posv<PP>(y, sy);                  // y >= 1e-12 after every step and y0 > 0
+        MCRE_VP r[p] = fma(r[p], om_v, c_v);
+        MCRE_VP r[p] = fma(kv0, z0[p], r[p]);
+        if (flags & CVA_EV_KV1) { MCRE_VP r[p] = fma(kv1, z1[p], r[p]); }
+        MCRE_VP wn[p] = kc0 * z0[p];
+        if (flags & CVA_EV_KC1) { MCRE_VP wn[p] = fma(kc1, z1[p], wn[p]); }
+        MCRE_VP yn[p] = fma(y[p], om_c, c_c);
+        MCRE_VP yn[p] = fma(sy[p], wn[p], yn[p]);
+        // y' = max(yn, 1e-12) (cirpp.py:198): high word above that of 1e-12 <=> certainly larger
+        bool above = true;
+        MCRE_VP above = above && (__double2hiint(yn[p]) > HI_1E_12);
+        if (__all_sync(0xffffffffu, above)) {
+          MCRE_VP y[p] = yn[p];
+        } else {
+          // rare.  (__syncwarp + volatile: a real branch - the compiler otherwise predicates this side into
+          // the instruction stream of every step, or folds both sides into an unconditional FP64 max)
+          __syncwarp();
+          MCRE_VP asm volatile("max.f64 %0, %1, %2;" : "=d"(y[p]) : "d"(yn[p]), "d"(1e-12));
+        }
+        if (flags & CVA_EV_DATE) date_part(rec);
+      };
+
+      for (int ev = 0; ev < P.n_pre; ++ev) {
+        const double *rec = P.rec + (size_t)ev * CVA_REC;
+        if (__double2loint(__ldg(rec + 9)) & CVA_EV_DATE) date_part(rec);
       }
+      uint32_t qa0[PP], qa1[PP], qa2[PP], qa3[PP], qb0[PP], qb1[PP], qb2[PP], qb3[PP];
+      if (PF && !inject) cva_philox<PP>(P, plo, phi, 0u, qa0, qa1, qa2, qa3);
+      int is = 0;
+      // two events per trip: the draw words ping-pong between two register sets (no copies)
+#pragma unroll 1
+      for (; is + 1 < P.n_sub; is += 2) {
+        step_event(is, qa0, qa1, qa2, qa3, qb0, qb1, qb2, qb3);
+        step_event(is + 1, qb0, qb1, qb2, qb3, qa0, qa1, qa2, qa3);
+      }
+      if (is < P.n_sub) step_event(is, qa0, qa1, qa2, qa3, qb0, qb1, qb2, qb3);
+
       // ---- per-path totals ----------------------------------------------------------------------
       if (pilot) {
         if (tid == 0) {
@@ -175,7 +243,7 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(CvaDev P, R
         first = s_first;
       }
       MCRE_VP {
-        const double d = fma(cva[p], P.lgd, -first) * keep[p];
+        const double d = ((live >> p) & 1u) ? fma(cva[p], P.lgd, -first) : 0.0;
         s1 += d;
         s2 = fma(d, d, s2);
       }
@@ -276,11 +344,25 @@ int irc_cva_launch(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, doub
                    cudaStream_t st) {
   const CvaHost &h = p->cva;
   CvaDev d;
-  d.rec = p->cva_rec_dev; d.n_events = h.n_pre_dates + h.n_sub;
+  d.rec = p->cva_rec_dev; d.n_pre = h.n_pre_dates; d.n_sub = h.n_sub;
   d.r0 = h.vas[0]; d.y0 = h.y0; d.lgd = h.lgd;
   d.sync = p->cva_sync_dev;
+  for (int i = 0; i < 10; ++i) { d.rk0[i] = rng.k0 + (uint32_t)i * 0x9E3779B9u; d.rk1[i] = rng.k1 + (uint32_t)i * 0xBB67AE85u; }
+  // all sub-steps alike (constant dt and mean level)?  Then their scalars travel as kernel parameters.
+  const std::vector<double> &rec = p->cva_rec_host;
+  bool ustep = h.n_sub > 0;
+  const double *first = rec.data() + (size_t)h.n_pre_dates * CVA_REC;
+  long long f0 = 0;
+  if (ustep) memcpy(&f0, first + 9, 8);
+  for (int s = 1; s < h.n_sub && ustep; ++s) {
+    const double *r = first + (size_t)s * CVA_REC;
+    long long fs; memcpy(&fs, r + 9, 8);
+    ustep = memcmp(r, first, 9 * sizeof(double)) == 0 && ((fs ^ f0) & ~(long long)CVA_EV_DATE) == 0;
+  }
+  for (int k = 0; k < 9; ++k) d.st[k] = ustep ? first[k] : 0.0;
+  d.st_flags = ustep ? (int)(f0 & ~(long long)CVA_EV_DATE) : 0;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
-  auto k = irc_cva_kernel<MCRE_CVA_PP>;
+  auto k = ustep ? irc_cva_kernel<MCRE_CVA_PP, true, MCRE_CVA_PF != 0> : irc_cva_kernel<MCRE_CVA_PP, false, MCRE_CVA_PF != 0>;
   int per_sm = 1;
   MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));
   if (per_sm < 1) return fail(-3, "irc cva kernel does not fit%s", "");

@@ -18,8 +18,12 @@ sys.path.insert(0, PKG)
 VAR = os.path.join(PKG, "variants")
 
 
+def safe(v):
+    return "".join(ch if ch.isalnum() else "_" for ch in v)
+
+
 def lib_of(v):
-    return os.path.join(VAR, f"libmcre_b200_{v}.so")
+    return os.path.join(VAR, f"libmcre_b200_{safe(v)}.so")
 
 
 def main():
@@ -32,9 +36,9 @@ def main():
         objs = [os.path.join(PKG, "build", os.path.basename(s)[:-3] + ".o") for s in build.sources()]
         for v in variants:
             pp, _, rest = v.partition("x")
-            minb, _, extra = rest.partition("_")
-            flags = [f"-DMCRE_CVA_PP={pp}", f"-DMCRE_CVA_MINB={minb}"] + ([f"-D{e}" for e in extra.split("_") if e])
-            obj = os.path.join(VAR, f"irc_cva_{v}.o")
+            minb, _, extra = rest.partition(",")          # e.g. 4x3,MCRE_CVA_PF=0
+            flags = [f"-DMCRE_CVA_PP={pp}", f"-DMCRE_CVA_MINB={minb}"] + ([f"-D{e}" for e in extra.split(",") if e])
+            obj = os.path.join(VAR, f"irc_cva_{safe(v)}.o")
             out = subprocess.run([nvcc, *build.NVCC_FLAGS, *flags, "-Xptxas", "-v", "-c", os.path.join(build.CSRC, "irc_cva.cu"), "-o", obj],
                                  capture_output=True, text=True)
             if out.returncode:
