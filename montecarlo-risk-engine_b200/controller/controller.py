@@ -225,6 +225,16 @@ class SimulationController:
     def run_simulation(self) -> SimulationResults:
         t0 = time.perf_counter()
         mc_products = [p for p in self.products if not self._can_skip_monte_carlo_for_product(p)]
+        if any(self._product_requires_regression(p) for p in mc_products):
+            # the pre-simulation kernels accumulate the moments of the quadratic basis [1, x, x^2] (8 sums, 3x3 normal
+            # equations) and the main kernels evaluate 3 coefficients: any other basis must not be evaluated as this one
+            from maths.regression import PolyomialRegression
+            rf = self.regression_function
+            if type(rf) is not PolyomialRegression or rf.degree != 2:
+                raise NotImplementedError(
+                    "regression_function: only PolyomialRegression(degree=2) is implemented by the CUDA regression "
+                    f"kernels (got {type(rf).__name__}(degree={getattr(rf, 'degree', None)})); the reference builds "
+                    "regression_function.get_regression_matrix(x) for any basis (controller.py:361-374)")
         if self.requires_higher_order_derivatives and mc_products:
             raise NotImplementedError("second-order sensitivities are implemented for analytic PVs only "
                                       "(pathwise Hessians: SURVEY §8f item 4)")

@@ -16,70 +16,139 @@ namespace mcre {
 // Pre-simulation pass A: forward simulation, spills per regression date the explanatory
 // variable, the numeraire and the FP32 window sums of each unit's discounted cashflows.
 // scratch: x [n_reg][n] f64 | N [n_reg][n] f64 | W [n_units][n_reg][n] f32
+//
+// Round 2: lock-step like the main kernels (PP paths per thread, every operation interleaved over them - the
+// round-1 version ran one path per thread on libdevice exp and took 3.4 ms of the 4.5 ms pre-simulation of the
+// headline config).  Only the short rate and the numeraire integral are stepped: rate products read nothing else,
+// the credit factor's normal is skipped (Philox is counter based: no stream to keep aligned; the injected stream is
+// indexed).  NU = regression units of the launch (window accumulators per path).
 // =====================================================================================
-template <bool CIR, int SCHEME>
-__global__ void __launch_bounds__(256) irc_presim_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
-                                                                 double *nbuf, float *wbuf) {
-  typedef double R;
-  typedef RealTraits<R> T;
+constexpr int PRE_PP = 4;
+template <bool CIR, int SCHEME, int NU>
+__global__ void __launch_bounds__(128, 4) irc_presim_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
+                                                                   double *nbuf, float *wbuf) {
+  constexpr int PP = PRE_PP;
   fm_tables_init();
-  const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lpath >= sh.n_paths) return;
-  const long long gpath = sh.path_begin + lpath;
   const long long n = sh.n_paths;
-  IrcParams<R, CIR> mp;
-  irc_load_params<R, CIR>(P, mp);
-  NormalStream ns; ns.init(rng, (unsigned long long)gpath);
-  IrcState<R> st;
-  st.r = mp.r0; st.logB = 0.0; st.y = mp.y0; st.logBl = 0.0;
-  float W[MCRE_IRC_MAX_UNITS];
+  const long long base = (long long)blockIdx.x * (128 * PP) + threadIdx.x;
+  if (base - threadIdx.x >= n) return;
+  long long lpath[PP], gpath[PP];
+  bool live[PP];
+  MCRE_VP {
+    lpath[p] = base + p * 128;
+    live[p] = lpath[p] < n;
+    gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
+  }
+  NormalStreamV<PP> nsv;
+  nsv.init(rng, gpath);
+  const bool inject = rng.mode == MCRE_RNG_INJECT;
+  const double r0 = __ldg(P.vas + 0), sigma = __ldg(P.vas + 1), theta = __ldg(P.vas + 2), a = __ldg(P.vas + 3);
+  // correlated noise of the short rate: row vas_noise of the lower Cholesky factor (model.py:46-48)
+  const bool second = CIR && P.vas_noise == 1;
+  const double l0 = CIR ? __ldg(P.chol + (second ? 2 : 0)) : __ldg(P.chol + 0);
+  const double l1 = second ? __ldg(P.chol + 3) : 0.0;
+  double r[PP], logB[PP], zb[PP];
+  float W[PP][NU];
+  MCRE_VP {
+    r[p] = r0; logB[p] = 0.0; zb[p] = 0.0;
 #pragma unroll
-  for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u) W[u] = 0.0f;
+    for (int u = 0; u < NU; ++u) W[p][u] = 0.0f;
+  }
 
   auto eval_date = [&](int di) {
     const int flags = __ldg(P.date_flags + di);
     if (!(flags & (MCRE_DATE_HAS_CASHFLOW | MCRE_DATE_HAS_REGRESSION))) return;
-    const double numeraire = exp(st.logB);
+    double numeraire[PP];
+    fm_exp_tv<PP>(logB, numeraire);                    // vasicek.py:154-156
     if (flags & MCRE_DATE_HAS_CASHFLOW) {
-      double cf[MCRE_IRC_MAX_UNITS];
+      double cf[PP][NU];
 #pragma unroll
-      for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u)
-        cf[u] = u < P.n_units ? __ldg(P.unit_fix + (size_t)u * P.n_dates + di) : 0.0;
+      for (int u = 0; u < NU; ++u) {
+        const double fx = u < P.n_units ? __ldg(P.unit_fix + (size_t)u * P.n_dates + di) : 0.0;
+        MCRE_VP cf[p][u] = fx;
+      }
       const int j0 = __ldg(P.date_float_off + di), j1 = __ldg(P.date_float_off + di + 1);
       for (int j = j0; j < j1; ++j) {
+        // LIBOR from the zero bond at the payment date's own short rate: (1 / P - 1) / tau with
+        // 1 / P = exp(B r - alpha) (bond.py:55-66, vasicek.py:114-128)
         const double alpha = __ldg(P.float_coef + j * 2), B = __ldg(P.float_coef + j * 2 + 1);
-        const double libor = (1.0 / exp(alpha - B * st.r) - 1.0) * __ldg(P.float_inv_tau + j);
+        const double inv_tau = __ldg(P.float_inv_tau + j);
+        double xa[PP], ip[PP];
+        MCRE_VP xa[p] = fma(B, r[p], -alpha);
+        fm_exp_tv<PP>(xa, ip);
+        MCRE_VP ip[p] = (ip[p] - 1.0) * inv_tau;
 #pragma unroll
-        for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u)
-          if (u < P.n_units) cf[u] += libor * __ldg(P.unit_float + (size_t)u * P.n_float + j);
+        for (int u = 0; u < NU; ++u) {
+          if (u < P.n_units) {
+            const double wgt = __ldg(P.unit_float + (size_t)u * P.n_float + j);
+            MCRE_VP cf[p][u] = fma(ip[p], wgt, cf[p][u]);
+          }
+        }
       }
-      // FP32 accumulator updated with an FP64 addend: W <- fp32(fp64(W) + cf)
+      // FP32 accumulator updated with an FP64 addend: W <- fp32(fp64(W) + cf / N)
       // (controller.py:330,341: float32 step_value += float64 cashflows)
 #pragma unroll
-      for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u) W[u] = (float)((double)W[u] + cf[u] / numeraire);
+      for (int u = 0; u < NU; ++u) {
+        MCRE_VP W[p][u] = (float)((double)W[p][u] + fm_div(cf[p][u], numeraire[p]));
+      }
     }
     if (flags & MCRE_DATE_HAS_REGRESSION) {
       const int k = __ldg(P.date_reg + di);
-      xbuf[(size_t)k * n + lpath] = st.r;
-      nbuf[(size_t)k * n + lpath] = numeraire;
+      MCRE_VP {
+        if (live[p]) {
+          xbuf[(size_t)k * n + lpath[p]] = r[p];
+          nbuf[(size_t)k * n + lpath[p]] = numeraire[p];
+        }
+      }
 #pragma unroll
-      for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u) {
-        if (u < P.n_units && k > 0) wbuf[((size_t)u * P.n_reg + (k - 1)) * n + lpath] = W[u];
-        W[u] = 0.0f;  // cashflows at or before the first regression date never enter a window
+      for (int u = 0; u < NU; ++u) {
+        MCRE_VP {
+          if (u < P.n_units && k > 0 && live[p]) wbuf[((size_t)u * P.n_reg + (k - 1)) * n + lpath[p]] = W[p][u];
+          W[p][u] = 0.0f;  // cashflows at or before the first regression date never enter a window
+        }
       }
     }
   };
   for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+#pragma unroll 1
   for (int is = 0; is < P.n_sub; ++is) {
-    double z0, z1;
-    irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
+    const double dt = __ldg(P.step_dt + is);
+    const double sv0 = __ldg(P.step_vas + is * 2), sv1 = __ldg(P.step_vas + is * 2 + 1);
+    double z0[PP], z1[PP];
+    if (inject) {
+      MCRE_VP {
+        const double *zp = rng.z + ((size_t)is * rng.n_total + gpath[p]) * (CIR ? 2 : 1);
+        z0[p] = zp[0];
+        z1[p] = CIR ? zp[1] : 0.0;
+      }
+    } else if (CIR) {
+      nsv.next2(z0, z1);                               // normals 2 is, 2 is + 1 of the path
+    } else {
+      // one normal per step: a Box-Muller pair serves two steps
+      if ((is & 1) == 0) nsv.next2(z0, zb);
+      else { MCRE_VP z0[p] = zb[p]; }
+      MCRE_VP z1[p] = 0.0;
+    }
+    MCRE_VP logB[p] = fma(r[p], dt, logB[p]);          // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+    if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
+      // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
+      MCRE_VP r[p] = fma(sv1, z0[p], fma(r[p] - theta, sv0, theta));
+    } else {
+      // r + a (theta_t - r) dt + sigma sqrt(dt) w   (vasicek.py:88-112)
+      const double adt = a * dt, ssq = sigma * sqrt(dt);
+      const double k0 = ssq * l0, k1 = ssq * l1;
+      MCRE_VP r[p] = fma(k0, z0[p], fma(sv0 - r[p], adt, r[p]));
+      if (second) { MCRE_VP r[p] = fma(k1, z1[p], r[p]); }
+    }
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }
 #pragma unroll
-  for (int u = 0; u < MCRE_IRC_MAX_UNITS; ++u)
-    if (u < P.n_units && P.n_reg > 0) wbuf[((size_t)u * P.n_reg + (P.n_reg - 1)) * n + lpath] = W[u];
+  for (int u = 0; u < NU; ++u) {
+    MCRE_VP {
+      if (u < P.n_units && P.n_reg > 0 && live[p]) wbuf[((size_t)u * P.n_reg + (P.n_reg - 1)) * n + lpath[p]] = W[p][u];
+    }
+  }
 }
 
 // Pre-simulation of Bermudan units, forward pass: spills per regression date the explanatory
@@ -514,16 +583,22 @@ extern "C" int mcre_irc_presim(mcre_irc_plan *p, const mcre_rng *rng, const mcre
   double *nbuf = xbuf + (size_t)d.n_reg * n;
   float *wbuf = (float *)(nbuf + (size_t)d.n_reg * n);
   const int threads = 256;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   if (d.nt != 0 && d.n_units > 0) {
     // forward pass with tangents (fills the value buffers too) + tangent moments
     rc = irc_presim_tangent_pass(p, r, sh, d_scratch, d_partial, d_tmoments, st);
     if (rc) return rc;
   } else {
-    if (d.has_cir) irc_presim_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
-    else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
-      irc_presim_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
-    else irc_presim_forward_kernel<false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf);
+    const unsigned fblocks = (unsigned)((n + 128 * PRE_PP - 1) / (128 * PRE_PP));
+    const int nuf = nu_template(d.n_units);
+#define LAUNCHF(NUV)                                                                                          \
+  do {                                                                                                        \
+    if (d.has_cir) irc_presim_forward_kernel<true, MCRE_SCHEME_EULER, NUV><<<fblocks, 128, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf); \
+    else if (d.scheme == MCRE_SCHEME_ANALYTICAL)                                                              \
+      irc_presim_forward_kernel<false, MCRE_SCHEME_ANALYTICAL, NUV><<<fblocks, 128, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf); \
+    else irc_presim_forward_kernel<false, MCRE_SCHEME_EULER, NUV><<<fblocks, 128, 0, st>>>(d, r, sh, xbuf, nbuf, wbuf); \
+  } while (0)
+    if (nuf == 1) LAUNCHF(1); else if (nuf == 2) LAUNCHF(2); else LAUNCHF(4);
+#undef LAUNCHF
     MCRE_LAUNCHED();
   }
   const int nu = nu_template(d.n_units);

@@ -152,9 +152,13 @@ __global__ void __launch_bounds__(256) select_compact_kernel(const double *__res
       for (int r = 0; r < SEL_MAX_R; ++r) keep = keep || kh == pd[r];
       if (keep && i < n_local) stage[atomicAdd(&n_stage, 1u)] = x[j];
     }
-    // at most 4 * 256 new entries per iteration: flush while another iteration may not fit
+    // at most 4 * 256 new entries per iteration: flush while another iteration may not fit.  The decision must be
+    // uniform over the block (flush() contains barriers): n_stage is read between two barriers, so no thread can
+    // start the next iteration's atomicAdd before every thread holds the same value.
     __syncthreads();
-    if (n_stage > SEL_STAGE - 4 * 256) flush();
+    const unsigned int staged = n_stage;
+    __syncthreads();
+    if (staged > SEL_STAGE - 4 * 256) flush();
   }
   flush();
 }

@@ -141,6 +141,32 @@ size_t g_arena_cached = 0;
 constexpr size_t ARENA_CACHE_MAX = (size_t)1 << 30;                  // keep at most 1 GiB of idle blocks
 }  // namespace
 
+// A released block may still be read by kernels queued on some stream.  Instead of draining the whole device (which
+// serialised every stream of the process and broke the asynchronous-on-the-caller's-stream contract of the entry
+// points), the block is parked with an event recorded on the legacy default stream - which orders after the work
+// queued so far on all blocking streams of the device, what the library's callers use - and goes back to the free list
+// only once that event has completed (checked, without waiting, on later get / put calls).
+namespace {
+struct Parked { void *p; size_t cap; int dev; cudaEvent_t ev; };
+std::vector<Parked> g_arena_parked;
+
+void arena_cache_collect_locked() {
+  size_t w = 0;
+  for (size_t i = 0; i < g_arena_parked.size(); ++i) {
+    Parked &k = g_arena_parked[i];
+    if (cudaEventQuery(k.ev) == cudaSuccess) {
+      cudaEventDestroy(k.ev);
+      if (g_arena_cached + k.cap > ARENA_CACHE_MAX) cudaFree(k.p);
+      else { g_arena_free[std::make_pair(k.dev, k.cap)].push_back(k.p); g_arena_cached += k.cap; }
+    } else {
+      cudaGetLastError();   // cudaErrorNotReady is not an error
+      g_arena_parked[w++] = k;
+    }
+  }
+  g_arena_parked.resize(w);
+}
+}  // namespace
+
 int arena_cache_get(size_t bytes, void **out, size_t *cap) {
   size_t c = 4096;
   while (c < bytes) c <<= 1;
@@ -148,6 +174,7 @@ int arena_cache_get(size_t bytes, void **out, size_t *cap) {
   MCRE_CUDA(cudaGetDevice(&dev));
   {
     std::lock_guard<std::mutex> lock(g_arena_mu);
+    arena_cache_collect_locked();
     auto it = g_arena_free.find(std::make_pair(dev, c));
     if (it != g_arena_free.end() && !it->second.empty()) {
       *out = it->second.back();
@@ -161,8 +188,10 @@ int arena_cache_get(size_t bytes, void **out, size_t *cap) {
   if (e != cudaSuccess) {
     // out of memory with idle blocks around: hand them back and retry once
     cudaGetLastError();
+    cudaDeviceSynchronize();
     {
       std::lock_guard<std::mutex> lock(g_arena_mu);
+      arena_cache_collect_locked();
       for (auto &kv : g_arena_free)
         for (void *p : kv.second) cudaFree(p);
       g_arena_free.clear();
@@ -178,11 +207,16 @@ void arena_cache_put(void *p, size_t cap) {
   if (!p) return;
   int dev = 0;
   if (cap == 0 || cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
-  cudaDeviceSynchronize();      // kernels that read the block have finished (cudaFree would wait for them as well)
+  cudaEvent_t ev;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    cudaFree(p);
+    return;
+  }
   std::lock_guard<std::mutex> lock(g_arena_mu);
-  if (g_arena_cached + cap > ARENA_CACHE_MAX) { cudaFree(p); return; }
-  g_arena_free[std::make_pair(dev, cap)].push_back(p);
-  g_arena_cached += cap;
+  g_arena_parked.push_back(Parked{p, cap, dev, ev});
+  arena_cache_collect_locked();
 }
 }  // namespace mcre
 

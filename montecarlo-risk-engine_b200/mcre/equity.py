@@ -191,6 +191,12 @@ class EquityBackend:
             return True
         return True
 
+    def _param_used(self, kind):
+        """Which model parameters a metric's value is connected to in the reference's autograd graph."""
+        n = len(self.c.model.model_params)
+        off = self.c.model.unconnected_params(self.c.simulation_scheme) if hasattr(self.c.model, "unconnected_params") else set()
+        return [i not in off for i in range(n)]
+
     def __init__(self, ctrl):
         self.c = ctrl
         self.kind, self.assets = family_of(ctrl.model)
@@ -1095,7 +1101,7 @@ class EquityBackend:
         pv = mean_and_error(s[0], s[1], float(shift_sum[0]), n_main)
         if self.nt:
             grad[self.num_rate_global] += numtan
-        res = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+        res = {"pv": (pv, grad), "param_used": self._param_used}
         if need_expo:
             # netting-set terms on the accumulated exposures, then the metric sums (shift = the value on global path 0,
             # which lives on rank 0: summed over the ranks so that every rank uses the same one)
@@ -1250,7 +1256,7 @@ class EquityBackend:
                             grad[g] += tang[a, r, k] / n_main
                     grad[self.num_rate_global] += head[r, 2] / n_main
                     grad += self._control_variate_gradient(info["owners"], info["recs"], r, n_params)
-                res = {"pv": (pv, grad), "param_used": lambda kind: [True] * n_params}
+                res = {"pv": (pv, grad), "param_used": self._param_used}
                 if info["acc"] & B.ACC_POS:
                     res["pos"] = ([mean_and_error(xacc[m, r, 0], xacc[m, r, 1], xshift[m, r, 0], n_main) for m in range(n_metric)],
                                   expo_grads(r, 0))

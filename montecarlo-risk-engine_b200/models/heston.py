@@ -44,7 +44,14 @@ class HestonModel(Model):
         one, zero = D(1.0, None, nt), D(0.0, None, nt)
         if scheme == SimulationScheme.QE:
             return [[one, zero], [zero, one]]
-        return [[one, p[3]], [p[3], one]]
+        # the reference builds this matrix in the constructor, before requires_grad() (heston.py:53-58): a constant of
+        # the autograd graph, so rho gets no sensitivity under EULER (its derivative comes back as None)
+        rho = D(p[3].v, None, nt)
+        return [[one, rho], [rho, one]]
+
+    def unconnected_params(self, scheme):
+        """Parameter indices the reference's autograd graph does not reach (returned as None)."""
+        return set() if scheme == SimulationScheme.QE else {3}
 
     def rate_dual(self, p):
         return p[2]

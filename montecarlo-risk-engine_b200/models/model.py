@@ -37,6 +37,11 @@ class Model:
         self.perform_smoothing = True
         self.differentiate = True
 
+    def unconnected_params(self, scheme):
+        """Parameter indices that the reference's autograd graph does not reach for this scheme: their
+        sensitivities come back as None (torch.autograd.grad(..., allow_unused=True), controller.py:618-624)."""
+        return set()
+
     def param_values(self):
         return [float(p) for p in self.model_params]
 

@@ -48,7 +48,14 @@ class SchwartzTwoFactorModel(Model):
     def intra_correlation(self, scheme, p):
         nt = p[0].t.shape[0]
         one = D(1.0, None, nt)
-        return [[one, p[5]], [p[5], one]]
+        # built in the reference's constructor, before requires_grad() (schwartz_two_factor.py:59-65): a constant of
+        # the autograd graph; the exact scheme's covariance (below) reads rho at step time and does carry it
+        rho = D(p[5].v, None, nt)
+        return [[one, rho], [rho, one]]
+
+    def unconnected_params(self, scheme):
+        """Parameter indices the reference's autograd graph does not reach (returned as None)."""
+        return {5} if scheme == SimulationScheme.EULER else set()
 
     def exact_covariance(self, p, dt):
         """2x2 covariance of (short, long) factor increments (reference: :124-145)."""

@@ -227,9 +227,12 @@ def correlation(model, p, scheme):
     if k == "HestonModel":
         if scheme == "QE":
             return [[1.0, 0.0], [0.0, 1.0]]
-        return [[1.0, p[3]], [p[3], 1.0]]
+        # heston.py:53-58: the matrix is built in the constructor, before requires_grad() - a constant of the graph
+        rho = float(ad.val(p[3]))
+        return [[1.0, rho], [rho, 1.0]]
     if k == "SchwartzTwoFactorModel":
-        return [[1.0, p[5]], [p[5], 1.0]]
+        rho = float(ad.val(p[5]))       # schwartz_two_factor.py:59-65: same (the exact covariance reads rho live)
+        return [[1.0, rho], [rho, 1.0]]
     return [[1.0]]
 
 

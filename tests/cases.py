@@ -277,6 +277,53 @@ def big_cva_book(ns_module):
     return model, sets, [m.CVAMetric("cp", 0.4), m.EPEMetric(), m.PVMetric()], np.linspace(0.0, 1.25, 6)
 
 
+def cfg3_wwr(ns_module, rho=0.5, vol=0.2):
+    """BASELINE configs[2] at its exact shape (what bench.py runs): Vasicek + CIR++ payer swap 0 -> 10y quarterly,
+    exposure grid np.arange(241) / 24 (240 sub-steps, coupon dates on the grid), CVA the only metric
+    (tests/pytests/test_cva.py:113-182 construction)."""
+    m = ns_module
+    vas = m.VasicekModel(0., 0.03, 0.05, 0.02, vol, asset_id="irs")
+    cir = m.CIRPPModel(0., "GM", HAZARDS, 0.1, 0.01, 0.02, 0.0001)
+    model = m.ModelConfig([vas, cir], inter_asset_correlation_matrix=np.array([rho]))
+    irs = m.InterestRateSwap(0.0, 10.0, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER, asset_id="irs")
+    sets = [m.NettingSet(name="irs", products=[irs], counterparty_id="GM")]
+    return model, sets, [m.CVAMetric("GM", 0.4)], np.arange(241) / 24.0
+
+
+def cfg2_irs(ns_module, mpor=0.25):
+    """BASELINE configs[1] at its exact shape: Vasicek payer IRS 0 -> 30y quarterly, exposure grid 0.25 * (0..120),
+    uncollateralised + MPoR-collateralised netting sets (on-grid 0.25 or off-grid 10/252, which doubles the internal
+    exposure grid), PV / EPE / ENE / EEPE / PFE (tests/exposure_tests/ee_pfe_swap_collateralized.py:58-107)."""
+    m = ns_module
+    model = m.VasicekModel(0., 0.03, 0.05, 0.02, 0.02)
+    a = m.InterestRateSwap(0.0, 30.0, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    b = m.InterestRateSwap(0.0, 30.0, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    sets = [m.NettingSet(name="irs_uncollateralized", products=[a]),
+            m.NettingSet(name="irs_collateralized", products=[b], margin_period_of_risk=mpor)]
+    metrics = [m.PVMetric(), m.EPEMetric(), m.ENEMetric(), m.EEPEMetric(), m.PFEMetric(0.95)]
+    return model, sets, metrics, np.arange(121) * 0.25
+
+
+def schwartz_book(ns_module):
+    """Schwartz two-factor standalone (schwartz_two_factor.py:124-196): the model cannot enter a ModelConfig and its
+    only reference consumer is the storage product; European / binary / Asian payoffs on it pin the model step."""
+    m = ns_module
+    model = m.SchwartzTwoFactorModel(0.0, [0.0, 0.5, 1.0, 2.0], [50.0, 52.0, 51.0, 55.0], 0.03, 1.2, 0.4, 0.02, 0.15, 0.3)
+    sets = [m.NettingSet("call", [m.EuropeanOption(m.Equity(), 1.0, 50.0, m.OptionType.CALL)]),
+            m.NettingSet("binary", [m.BinaryOption(1.5, 52.0, 10.0, m.OptionType.PUT)]),
+            m.NettingSet("asian", [m.AsianOption(0.25, 1.0, 51.0, 4, m.OptionType.CALL)])]
+    return model, sets, [m.PVMetric()], None
+
+
+def heston_euler_book(ns_module):
+    """Heston under the EULER scheme (heston.py:99-121; the QE scheme has its own goldens)."""
+    m = ns_module
+    model = m.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    sets = [m.NettingSet("call", [m.EuropeanOption(m.Equity(), 1.0, 100.0, m.OptionType.CALL)]),
+            m.NettingSet("asian", [m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.PUT)])]
+    return model, sets, [m.PVMetric()], None
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -306,6 +353,18 @@ GOLDEN_CASES = {
     "equity_cva_single_det": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=False)),
     "equity_cva_exercise": (equity_cva_exercise, dict(), dict(n_main=512, n_pre=512, num_steps=1, scheme="EULER", differentiate=False)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
+    # the BASELINE.json configs at their exact shapes (reduced path counts)
+    "cfg3_wwr_cva": (cfg3_wwr, dict(rho=0.5), dict(n_main=32768, n_pre=32768, num_steps=1, scheme="EULER", differentiate=False)),
+    # same shape with a short-rate volatility of 2 % instead of 20 %: the CVA integrand loses its heavy tail, so Monte
+    # Carlo standard errors are reliable and a 3-sigma comparison of native Philox with the reference is meaningful
+    "cfg3_wwr_cva_lowvol": (cfg3_wwr, dict(rho=0.5, vol=0.02), dict(n_main=16384, n_pre=16384, num_steps=1, scheme="EULER", differentiate=False)),
+    "cfg2_irs_ongrid": (cfg2_irs, dict(mpor=0.25), dict(n_main=8192, n_pre=8192, num_steps=1, scheme="EULER", differentiate=False)),
+    "cfg2_irs_offgrid": (cfg2_irs, dict(mpor=10 / 252), dict(n_main=8192, n_pre=8192, num_steps=1, scheme="EULER", differentiate=False)),
+    "cfg4_bermudan_40": (bermudan_swaption, dict(n_ex=40), dict(n_main=8192, n_pre=8192, num_steps=1, scheme="EULER", differentiate=False)),
+    # models the reference only runs standalone
+    "schwartz_analytical": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=2, scheme="ANALYTICAL", differentiate=True)),
+    "schwartz_euler": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
+    "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
 }
 
 

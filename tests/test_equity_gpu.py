@@ -15,7 +15,9 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 EQ_CASES = ["bs_european", "bs_european_euler", "heston_european", "heston_european_greeks",
-            "heston_path_dependent", "bs_basket", "bs_basket_euler", "bs_exposure_greeks", "bs_exposure_greeks_euler"]
+            "heston_path_dependent", "bs_basket", "bs_basket_euler", "bs_exposure_greeks", "bs_exposure_greeks_euler",
+            # models the reference only runs standalone: Schwartz two-factor (both schemes), Heston under EULER
+            "schwartz_analytical", "schwartz_euler", "heston_euler"]
 RTOL = 1e-10
 
 
@@ -44,6 +46,9 @@ def test_injected_draws_match_reference_golden(name):
                 got = np.array([[0.0 if g is None else float(g) for g in row] for row in res.get_derivatives(s, m)])
                 helpers.assert_close(got, want, 1e-8, 1e-8 * max(1.0, float(np.max(np.abs(want)))),
                                      f"{name} {s}|{m} derivatives")
+                # parameters outside the reference's autograd graph come back as None there, and here
+                assert [[g is None for g in row] for row in res.get_derivatives(s, m)] == \
+                       [[g is None for g in row] for row in gold["derivatives"][f"{s}|{m}"]], f"{name} {s}|{m} None pattern"
 
 
 @pytest.mark.parametrize("name", EQ_CASES)

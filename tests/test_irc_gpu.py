@@ -16,7 +16,10 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 IRC_CASES = ["wwr_cva", "wwr_cva_neg", "cva_deterministic", "irs_collateral", "irs_collateral_offgrid",
-             "irs_analytical"]
+             "irs_analytical",
+             # the BASELINE.json configs at their exact shapes (241-date grid / 10y swap / CVA only; 30y swap / 121 dates
+             # with on- and off-grid MPoR), reduced path counts
+             "cfg3_wwr_cva", "cfg3_wwr_cva_lowvol", "cfg2_irs_ongrid", "cfg2_irs_offgrid"]
 RTOL = 1e-10
 
 
@@ -47,10 +50,10 @@ def test_philox_matches_oracle_and_reference_statistically(name):
     out, _ = helpers.run_oracle(name, draws="philox")
     flat = helpers.flatten_results(res)
     _compare(flat, helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8, name + " philox", err_rtol=1e-6)
-    if name.startswith("wwr") or name == "cva_deterministic":
-        # sigma = 0.2 on the short rate makes exp(int r) heavy tailed: the sample standard
-        # errors at these path counts are themselves unreliable, so the 3-sigma comparison
-        # against the torch-seeded reference run is only made on the moderate-vol cases.
+    if name.startswith("wwr") or name in ("cva_deterministic", "cfg3_wwr_cva"):
+        # sigma = 0.2 on the short rate makes exp(int r) heavy tailed: the sample standard errors are themselves
+        # unreliable at any feasible path count (see test_wwr_family_philox_within_three_sigma_of_reference, which
+        # makes the 3-sigma comparison of this kernel against the reference on the low-volatility twin of the config)
         return
     for key, (v, e) in flat.items():
         rv, re_ = np.array(gold["values"][key]), np.array(gold["errors"][key])
@@ -62,6 +65,29 @@ def test_philox_matches_oracle_and_reference_statistically(name):
             # regression-proxy profiles also carry the pre-simulation's sampling error, which the
             # reported MC error does not include: compare the profile as a whole
             assert np.linalg.norm(v - rv) <= 0.15 * np.linalg.norm(rv) + 1e-12, f"{name} {key}"
+
+
+def test_wwr_family_philox_within_three_sigma_of_reference():
+    """North star: native Philox within 3 Monte Carlo standard errors of the reference - for the wrong-way-risk CVA
+    kernel.  With the headline parameters (sigma = 0.2 on the short rate over 10 years) the integrand
+    relu(E) exp(-int r) is heavy tailed: int r has a standard deviation of ~3.6, the sample mean is carried by rare
+    paths and the SAMPLE standard error is itself wrong by factors (measured in round 2: 2^22 Philox paths give CVA
+    1.43 against 0.92 +- 0.004 of the reference's 2^15-path golden, and 1.40 - 1.55 at 2^24) - no sigma-based
+    comparison of two runs of that config means anything, for the reference itself included.  Those cases are
+    compared draw for draw instead (injected reference draws 1e-10, Philox vs oracle 1e-8, above).
+    The statistical check runs on the SAME code path (same grid, swap, CVA-only kernel) with sigma = 0.02, where the
+    central limit theorem applies: 2^22 Philox paths on the GPU against the reference's torch-seeded golden
+    (2^14 paths), within 4 combined standard errors (3 + 1 for the regression proxy's pre-simulation error, which
+    neither reported error includes)."""
+    name = "cfg3_wwr_cva_lowvol"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="philox", n_main=1 << 22, n_pre=1 << 20)
+    flat = helpers.flatten_results(res)
+    for key, (v, e) in flat.items():
+        rv, re_ = np.array(gold["values"][key]), np.array(gold["errors"][key])
+        se = np.sqrt(e ** 2 + re_ ** 2)
+        assert np.all(np.abs(v - rv) <= 4.0 * se + 1e-12), f"{name} {key}: {v} vs {rv} (se {se})"
+        assert np.all(e < 0.2 * re_), f"{name} {key}: standard error {e} at 2^22 paths vs {re_} at 2^14"
 
 
 def test_pv_greeks_match_reference_golden():
@@ -198,3 +224,58 @@ def test_tree_reduce_is_the_binary_counter_tree_bit_for_bit():
         B.check(L.mcre_tree_reduce(part.data_ptr(), n_chunks, n_slots, out.data_ptr(), RT.stream_ptr()))
         want = RT.tree_sum([host[c] for c in range(n_chunks)])
         assert np.array_equal(out.cpu().numpy(), want), (n_chunks, n_slots)
+
+
+@pytest.mark.parametrize("name", ["wwr_cva_neg", "irs_collateral"])
+def test_rank_with_an_empty_shard_still_gets_the_common_shift(name):
+    """Sharding contract: the sums sum(x - c), sum((x - c)^2) of all ranks are all-reduced and finished with
+    the rank-local shift c, so every rank must hold the same c = the value on GLOBAL path 0 - also a rank whose shard is
+    empty (n_main < world * chunk; round-1 advisor finding: such a rank kept c = 0).  One process stands in for both
+    ranks: the same plan is run on the full range and on an empty shard; the shifts must agree bit for bit and the
+    empty shard's sums must be zero.  Covers the CVA-only kernel (block 0 publishes the shift) and the general
+    kernel (pilot launch)."""
+    import ctypes as C
+    import torch
+    from mcre import binding as B
+    from mcre import runtime as RT
+    from mcre.irc import CHUNK_PATHS, IrcBackend
+    ns, model, sets, metrics, tl, rkw = helpers.build(name)
+    rm = ns.RiskMetrics(metrics, exposure_timeline=tl)
+    n = CHUNK_PATHS
+    sc = ns.SimulationController(sets, model, rm, n, n, rkw["num_steps"], ns.SimulationScheme.EULER)
+    dev = RT.compute_device()
+    L = B.lib()
+    be = IrcBackend(sc)
+    coefs = be.presim_coefficients(sc.products, dev)
+    idxs = list(range(len(sets)))
+    desc, keep, info = be.lower(idxs, [])
+    plan = C.c_void_p()
+    B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
+    try:
+        coef = np.zeros((info["n_expo"], len(idxs), 3, 1))
+        for r, s in enumerate(sets):
+            for p in s.products:
+                coef[:, r, :, 0] += coefs[id(p)][0]
+        arr, ptr = B.as_dp(coef)
+        B.check(L.mcre_irc_set_coefficients(plan, ptr, RT.stream_ptr()))
+        slots = L.mcre_irc_main_slots(plan)
+        out = []
+        for begin, count in ((0, n), (n, 0)):
+            acc = torch.full((slots,), 7.0, dtype=torch.float64, device=dev)
+            shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+            partial = torch.empty(L.mcre_irc_partial_bytes(plan, max(count, 1), CHUNK_PATHS, 0) // 8 + 1, dtype=torch.float64, device=dev)
+            spill = torch.empty((len(idxs), info["n_metric"], max(count, 1)), dtype=torch.float64, device=dev)
+            rng = B.Rng()
+            rng.mode, rng.seed, rng.stream, rng.n_paths_total = B.RNG_PHILOX, 43, 0, n
+            sh = B.Shard(begin, count, CHUNK_PATHS)
+            B.check(L.mcre_irc_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                       shift.data_ptr(), spill.data_ptr(), RT.stream_ptr()))
+            torch.cuda.synchronize()
+            out.append((acc.cpu().numpy(), shift.cpu().numpy()))
+    finally:
+        L.mcre_irc_destroy(plan)
+    (acc_full, shift_full), (acc_empty, shift_empty) = out
+    assert np.any(shift_full != 0.0)
+    assert np.array_equal(shift_full, shift_empty)
+    assert np.all(acc_empty == 0.0)
+    assert np.any(acc_full != 0.0)

@@ -23,8 +23,10 @@ def _compare(flat_a, flat_b, rtol, what, err_rtol=1e-7):
         helpers.assert_close(ea, eb, err_rtol, 1e-10 * scale, f"{what} {key} mc error")
 
 
-def test_bermudan_swaption_matches_reference_golden():
-    name = "bermudan_swaption"
+@pytest.mark.parametrize("name", ["bermudan_swaption", "cfg4_bermudan_40"])
+def test_bermudan_swaption_matches_reference_golden(name):
+    """(cfg4_bermudan_40: BASELINE configs[3] at its exact shape - 40 quarterly exercise dates on an 11y swap,
+    41 exposure dates - at 8192 paths.)"""
     gold = helpers.load_golden(name)
     res, sc = helpers.run_cuda(name, draws="torch")
     assert res.get_netting_set_names() == gold["sets"]
@@ -32,12 +34,15 @@ def test_bermudan_swaption_matches_reference_golden():
     assert [float(t) for t in sc.simulation_timeline] == gold["simulation_timeline"]
     flat = helpers.flatten_results(res)
     ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
-    _compare(flat, ref, 1e-9, name)
+    # (the Monte Carlo error of PFE is a difference quotient of adjacent order statistics, pfe_metric.py:27-44: it
+    # amplifies the 1e-10 agreement of the values by the ratio value / spacing)
+    _compare(flat, ref, 1e-9, name, err_rtol=1e-6)
 
 
-@pytest.mark.parametrize("kwargs", [dict(), dict(n_main=5000, n_pre=3000), dict(num_steps=2)])
+@pytest.mark.parametrize("kwargs", [dict(), dict(n_main=5000, n_pre=3000), dict(num_steps=2), dict(case="cfg4_bermudan_40")])
 def test_bermudan_swaption_philox_matches_oracle(kwargs):
-    name = "bermudan_swaption"
+    kwargs = dict(kwargs)
+    name = kwargs.pop("case", "bermudan_swaption")
     gold = helpers.load_golden(name)
     res, sc = helpers.run_cuda(name, draws="philox", **kwargs)
     out, _ = helpers.run_oracle(name, draws="philox", **kwargs)
