@@ -64,9 +64,10 @@ class SimulationController:
         # exposure grids: metric dates, plus (t - MPoR) look-back dates of collateralised sets
         self.metric_exposure_timeline = risk_metrics.exposure_timeline.clone()
         self.exposure_timeline = self._build_internal_exposure_timeline()
-        self._exposure_time_to_idx = {float(t): i for i, t in enumerate(self.exposure_timeline)}
+        # (.tolist(): iterating a tensor element by element costs microseconds per element)
+        self._exposure_time_to_idx = {t: i for i, t in enumerate(self.exposure_timeline.tolist())}
         self.metric_exposure_indices = torch.tensor(
-            [self._exposure_time_to_idx[float(t)] for t in self.metric_exposure_timeline],
+            [self._exposure_time_to_idx[t] for t in self.metric_exposure_timeline.tolist()],
             dtype=torch.long, device=device)
         self.netting_set_delayed_exposure_indices = self._build_netting_set_delayed_exposure_indices()
 
@@ -98,8 +99,8 @@ class SimulationController:
                 dtype=FLOAT, device=device))
 
         # simulation grid = product modelling dates U exposure dates, merged on float equality
-        times = {float(t) for p in self.products for t in p.modeling_timeline}
-        times |= {float(t) for t in self.exposure_timeline}
+        times = {t for p in self.products for t in p.modeling_timeline.tolist()}
+        times |= set(self.exposure_timeline.tolist())
         self.simulation_timeline = torch.tensor(sorted(times), dtype=FLOAT, device=device)
         self.requires_regression = any(self._product_requires_regression(p) for p in self.products)
 
@@ -119,10 +120,10 @@ class SimulationController:
     def _build_internal_exposure_timeline(self):
         if not self.risk_metrics.requires_exposure_profiles():
             return self.risk_metrics.exposure_timeline.clone()
-        times = {float(t) for t in self.risk_metrics.exposure_timeline}
+        times = set(self.risk_metrics.exposure_timeline.tolist())
         for ns in self.netting_sets:
             if ns.is_collateralized():
-                times.update(float(t) for t in ns.get_collateral_query_times(self.risk_metrics.exposure_timeline))
+                times.update(ns.get_collateral_query_times(self.risk_metrics.exposure_timeline).tolist())
         return torch.tensor(sorted(times), dtype=FLOAT, device=device)
 
     def _build_netting_set_delayed_exposure_indices(self):
@@ -131,10 +132,9 @@ class SimulationController:
         for ns in self.netting_sets:
             idx = torch.full((n,), -1, dtype=torch.long, device=device)
             if ns.is_collateralized():
-                delayed = self.metric_exposure_timeline - ns.margin_period_of_risk
-                for m in range(n):
-                    if float(delayed[m]) >= 0.0:
-                        idx[m] = self._exposure_time_to_idx[float(delayed[m])]
+                delayed = (self.metric_exposure_timeline - ns.margin_period_of_risk).tolist()
+                vals = [self._exposure_time_to_idx[d] if d >= 0.0 else -1 for d in delayed]
+                idx = torch.tensor(vals, dtype=torch.long, device=device)
             out.append(idx)
         return out
 

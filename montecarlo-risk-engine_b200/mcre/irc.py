@@ -10,9 +10,11 @@ simulation.  What it takes the place of in the reference:
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -34,6 +36,30 @@ from products.product import OptionType
 from products.swap import InterestRateSwap, IRSType
 
 CHUNK_PATHS = 4096
+
+# Lowered plans of runs that differ only in the inter-model correlation (the rho sweep of the wrong-way-risk CVA
+# config): every table except the Cholesky factor is a function of (model parameters, schedules, timelines, metric
+# list), so it is built once and reused.  Keyed on the VALUES of everything lower() reads (never on object identity);
+# value-only plans of linear products on plain Vasicek (+ CIR++) models only.  MCRE_PLAN_CACHE=0 switches it off.
+_PLAN_CACHE = collections.OrderedDict()
+_PLAN_CACHE_MAX = 64
+
+
+def plan_cache_enabled():
+    return os.environ.get("MCRE_PLAN_CACHE", "1") != "0"
+
+
+def _sig_bond(b):
+    return ("B", float(b.startdate), float(b.maturity), float(b.notional), float(b.tenor),
+            None if b.fixed_rate is None else float(b.fixed_rate), bool(b.pays_notional), tuple(b.payment_dates.tolist()))
+
+
+def _sig_product(p):
+    if type(p) is Bond:
+        return _sig_bond(p)
+    if type(p) is InterestRateSwap:
+        return ("S", p.irs_type.name, _sig_bond(p.fixed_leg), _sig_bond(p.floating_leg))
+    return None
 
 
 def _packs(duals):
@@ -210,6 +236,69 @@ class IrcBackend:
         options of the given sets); `reg_times`: regression dates of the pre-simulation
         (default: the internal exposure dates).
         Returns (desc, tables) with `tables` keeping numpy arrays alive."""
+        key = self._lower_key(set_indices, unit_products, berm_units, reg_times)
+        if key is not None:
+            hit = _PLAN_CACHE.get(key)
+            if hit is not None:
+                _PLAN_CACHE.move_to_end(key)
+                return self._lower_from_cache(hit)
+        out = self._lower_uncached(set_indices, unit_products, berm_units, reg_times)
+        if key is not None:
+            _PLAN_CACHE[key] = out
+            while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+                _PLAN_CACHE.popitem(last=False)
+        return out
+
+    def _lower_key(self, set_indices, unit_products, berm_units, reg_times):
+        """Hashable value signature of everything _lower_uncached reads except the inter-model correlation; None when
+        the plan is not cacheable (tangents, exercise units, model extensions)."""
+        c = self.c
+        if not plan_cache_enabled() or self.nt != 0 or berm_units or reg_times is not None:
+            return None
+        if type(self.vas) is not VasicekModel or (self.has_cir and type(self.cir) is not CIRPPModel):
+            return None
+        sets = [c.netting_sets[i] for i in set_indices]
+        prods = [p for ns in sets for p in ns.products] + list(unit_products)
+        sigs = [_sig_product(p) for p in prods]
+        if any(sg is None for sg in sigs):
+            return None
+        model_sig = (tuple(self.vas.param_values()), float(self.vas.t0()), self.vas_idx, self.cir_idx)
+        if self.has_cir:
+            model_sig += (tuple(self.cir.param_values()), float(self.cir.t0()), tuple(self.cir.tenors.tolist()),
+                          tuple(self.cir.hazard_rates.tolist()), bool(self.cir.deterministic), tuple(self.cir.asset_ids))
+        rm = c.risk_metrics
+        metric_sig = tuple((m.metric_type.name, getattr(m, "counterparty_id", None), getattr(m, "recovery_rate", None))
+                           for m in rm.metrics)
+        set_sig = tuple((float(ns.threshold), ns.margin_period_of_risk, ns.counterparty_id, len(ns.products),
+                         tuple(c.netting_set_delayed_exposure_indices[i].tolist()))
+                        for i, ns in zip(set_indices, sets))
+        return (model_sig, self.scheme.name, int(c.num_steps), tuple(c.simulation_timeline.tolist()),
+                tuple(c.exposure_timeline.tolist()), tuple(c.metric_exposure_timeline.tolist()),
+                tuple(c.metric_exposure_indices.tolist()), metric_sig, set_sig, tuple(sigs), len(unit_products))
+
+    def _cholesky(self):
+        """Lower Cholesky factor of the joint correlation as [L00, L01, L10, L11] duals (model.py:50-73)."""
+        nt = self.nt
+        zero = D(0.0, None, nt)
+        if isinstance(self.c.model, ModelConfig) and self.has_cir:
+            pv, pc = self._dual_params()
+            sub = [None, None]
+            sub[self.vas_idx], sub[self.cir_idx] = pv, pc
+            corr = self.c.model.joint_correlation(self.scheme, sub)
+            L = cholesky_dual(corr)
+            return [L[0][0], L[0][1], L[1][0], L[1][1]]
+        one = D(1.0, None, nt)
+        return [one, zero, zero, one]
+
+    def _lower_from_cache(self, hit):
+        """A cached plan with this run's Cholesky factor: copy of the descriptor, shared (read-only) tables."""
+        desc, keep, info = hit
+        d = B.IrcDesc.from_buffer_copy(desc)
+        t = dict(keep)
+        t["chol"], d.chol = B.as_dp(_packs(self._cholesky()))
+        return d, t, info
+
+    def _lower_uncached(self, set_indices, unit_products, berm_units=None, reg_times=None):
         c, nt = self.c, self.nt
         w = 1 + nt
         pv, pc = self._dual_params()
@@ -221,15 +310,7 @@ class IrcBackend:
         zero = D(0.0, None, nt)
 
         # ---- correlation / Cholesky -------------------------------------------------
-        if isinstance(c.model, ModelConfig) and self.has_cir:
-            sub = [None, None]
-            sub[self.vas_idx], sub[self.cir_idx] = pv, pc
-            corr = c.model.joint_correlation(self.scheme, sub)
-            L = cholesky_dual(corr)
-            chol = [L[0][0], L[0][1], L[1][0], L[1][1]]
-        else:
-            one = D(1.0, None, nt)
-            chol = [one, zero, zero, one]
+        chol = self._cholesky()
 
         # ---- per-step model scalars (shared by the pre-simulation and main plans) ---------
         step_vas, step_cir = [], []
