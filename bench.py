@@ -245,7 +245,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--paths-log2", type=int, default=24, help="paths per GPU (weak scaling)")
+    ap.add_argument("--paths-log2", type=int, default=24, help="paths per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: 2^paths-log2 paths per GPU (default, what the driver's scaling run uses); strong: "
+                         "2^paths-log2 paths in total = BASELINE's 2^24-path config split over the GPUs")
     ap.add_argument("--presim-log2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel tuning runs: skip the end-to-end leg")
@@ -270,8 +273,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ns = cases.Namespace()
-    n_per_gpu = 1 << args.paths_log2
-    n_total = n_per_gpu * world
+    strong = args.scaling == "strong"
+    n_total = (1 << args.paths_log2) if strong else (1 << args.paths_log2) * world
+    n_per_gpu = n_total // world
     n_pre = 1 << args.presim_log2
     L = B.lib()
 
@@ -357,6 +361,7 @@ def main():
     for i in range(0 if args.no_e2e else 2):
         model, sets, metrics, tl = build_case(ns, float(RHOS[(i + 7) % len(RHOS)]))
         barrier()
+        h2d0, d2h0 = B.h2d_bytes(), RT.d2h_bytes
         t0 = time.perf_counter()
         rm = ns.RiskMetrics(metrics, exposure_timeline=tl)
         sc = ns.SimulationController(sets, model, rm, n_total, n_pre, 1, ns.SimulationScheme.EULER)
@@ -365,10 +370,7 @@ def main():
         cva = float(res.get_results("irs", "cva[GM]")[0])
         barrier()
         e2e_times.append(time.perf_counter() - t0)
-    be = IrcBackend(plans[0][2])
-    desc, keep, info = be.lower([0], [])
-    h2d = int(sum(a.nbytes for a in keep.values())) * 2 + info["n_expo"] * 3 * 8
-    d2h = int(slots * 8 * 2 + info["n_expo"] * 8 * 8)
+        h2d, d2h = B.h2d_bytes() - h2d0, RT.d2h_bytes - d2h0      # measured: counted where the copies are made
     e2e_dt = min(e2e_times) if e2e_times else float("inf")
     tt = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
@@ -423,9 +425,10 @@ def main():
             else:
                 cpu = {"value": rate, "unit": UNIT, "cores": pool.workers, "kind": "port", "sample": port["sample"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "configs[2]: Vasicek+CIR++ WWR CVA payer swap, rho sweep, 2^%d paths/GPU x 240 steps" % args.paths_log2,
+                "config": {"workload": "configs[2]: Vasicek+CIR++ WWR CVA payer swap, rho sweep, 2^%d paths%s x 240 steps"
+                                       % (args.paths_log2, " in total" if strong else "/GPU"),
                            "paths_per_gpu": n_per_gpu, "sub_steps": N_STEPS_SIM, "presim_paths": n_pre,
                            "l2": "no HBM-resident inputs: state in registers; each step re-reads only KB-sized plan tables"},
                 "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

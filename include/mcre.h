@@ -221,6 +221,17 @@ int64_t mcre_irc_presim_tangent_slots(const mcre_irc_plan *plan);
 int mcre_irc_presim(mcre_irc_plan *plan, const mcre_rng *rng, const mcre_shard *shard,
                     void *d_scratch, double *d_partial, double *d_moments, double *d_tmoments, void *stream);
 
+/* Device side of the exposure regression of value-only plans of linear products (takes the place of
+ * torch.linalg.lstsq, controller.py:368-374, with the minimum-norm convention of its gelsy driver): solves the 3x3
+ * normal equations of every regression date from d_moments (mcre_irc_presim, all-reduced over the ranks) without
+ * leaving the device.  unit_set[u] (host): netting-set row of unit u in the main plan, or -1.
+ * d_coef_unit: [n_units][n_reg][3], d_coef_sum: [n_reg][n_sets][3] (standardised basis), both device. */
+int mcre_irc_solve_coefficients(const mcre_irc_plan *presim_plan, const double *d_moments, const int32_t *unit_set,
+                                int32_t n_sets, double *d_coef_unit, double *d_coef_sum, void *stream);
+/* Same as mcre_irc_set_coefficients for value-only plans, from DEVICE coefficients [n_expo][n_sets][3]
+ * (mcre_irc_solve_coefficients): pre-simulation -> solve -> main simulation then is one stream of kernels. */
+int mcre_irc_set_coefficients_device(mcre_irc_plan *plan, const double *d_expo_coef, void *stream);
+
 /* Upload regression coefficients (after the host solved the normal equations). */
 int mcre_irc_set_coefficients(mcre_irc_plan *plan, const double *expo_coef /* host, dual[n_expo][n_sets][3] */,
                               void *stream);
@@ -539,6 +550,9 @@ int mcre_dfma_peak(double *tflops_out, void *stream);
 int mcre_fastmath_probe(int32_t fn, const double *d_x, double *d_y, int64_t n, void *stream);
 /* Kernel launches issued by this library since load (bench.py "gpu_launches"). */
 int64_t mcre_launch_count(void);
+/* Bytes this library has copied host -> device so far (plan arenas, coefficient uploads, job tables): what
+ * bench.py reports as h2d_bytes_per_step of the end-to-end leg (measured, not computed). */
+int64_t mcre_h2d_bytes(void);
 const char *mcre_last_error(void);
 int mcre_abi_version(void);
 

@@ -12,6 +12,8 @@ namespace mcre {
 
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_h2d_bytes;   // bytes this library copied host -> device (mcre_h2d_bytes)
+#define MCRE_H2D(bytes) mcre::g_h2d_bytes.fetch_add((long long)(bytes), std::memory_order_relaxed)
 
 inline int fail(int code, const char *fmt, const char *a = "", long long b = 0) {
   snprintf(g_err, sizeof(g_err), fmt, a, b);
@@ -61,6 +63,7 @@ struct DevArena {
     const int rc = arena_cache_get(stage.size(), &base, &cap);
     if (rc) return rc;
     MCRE_CUDA(cudaMemcpy(base, stage.data(), stage.size(), cudaMemcpyHostToDevice));
+    MCRE_H2D(stage.size());
     for (const Item &it : items) *it.slot = (unsigned char *)base + it.off;
     std::vector<unsigned char>().swap(stage);
     items.clear();
@@ -87,6 +90,7 @@ struct DevArray {
     MCRE_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
     owned = true;
     MCRE_CUDA(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    MCRE_H2D(count * sizeof(T));
     return 0;
   }
   void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = false; }

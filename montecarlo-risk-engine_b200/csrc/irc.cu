@@ -375,9 +375,9 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
       for (int s = 0; s < c->n_sub; ++s) { h.step_theta[s] = c->step_vas[(size_t)s * 2]; h.step_psi[s] = c->step_cir[(size_t)s * 2]; }
       h.date_flags.assign(c->date_flags, c->date_flags + c->n_dates);
       h.date_metric.assign(c->date_metric, c->date_metric + c->n_dates);
-      std::vector<double> zrec((size_t)(c->n_pre_dates + c->n_sub) * CVA_REC + 2, 0.0);
+      irc_cva_fill_static(p);
       std::vector<int> zsync(4, 0);
-      UP(cva_rec, zrec.data(), zrec.size());
+      UP(cva_rec, p->cva_rec_host.data(), p->cva_rec_host.size());
       UP(cva_sync, zsync.data(), zsync.size());
     }
   }
@@ -453,6 +453,7 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
   if (p->expo_coef_count == 0) return 0;
   MCRE_CUDA(cudaMemcpyAsync(p->d.expo_coef, coef, p->expo_coef_count * sizeof(double), cudaMemcpyHostToDevice,
                             (cudaStream_t)stream));
+  MCRE_H2D(p->expo_coef_count * sizeof(double) + p->h_date_rec.size() * sizeof(double));
   const int w = 1 + p->d.nt, per_date = 3 * w * p->d.n_sets, DR = p->date_stride;
   for (int di = 0; di < p->d.n_dates; ++di) {
     const int e = p->h_date_expo[di];
@@ -472,7 +473,7 @@ extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, v
   MCRE_CUDA(cudaMemcpyAsync((void *)p->d.date_rec, p->h_date_rec.data(), p->h_date_rec.size() * sizeof(double),
                             cudaMemcpyHostToDevice, (cudaStream_t)stream));
   if (p->cva_only) {
-    const int rc = irc_cva_build_records(p, (cudaStream_t)stream);
+    const int rc = irc_cva_apply_coefficients(p, (cudaStream_t)stream);
     if (rc) return rc;
   }
   MCRE_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // host staging buffers may be reused by the caller
@@ -485,6 +486,8 @@ extern "C" int mcre_irc_set_exercise_coefficients(mcre_irc_plan *p, const double
   cudaStream_t st = (cudaStream_t)stream;
   if (p->ex_coef_count && ex_coef)
     MCRE_CUDA(cudaMemcpyAsync(p->d.ex_coef, ex_coef, p->ex_coef_count * sizeof(double), cudaMemcpyHostToDevice, st));
+  MCRE_H2D((p->ex_coef_count && ex_coef ? p->ex_coef_count : 0) * sizeof(double) +
+           (p->berm_expo_count && expo_coef ? p->berm_expo_count : 0) * sizeof(double));
   if (p->berm_expo_count && expo_coef)
     MCRE_CUDA(cudaMemcpyAsync(p->d.berm_expo_coef, expo_coef, p->berm_expo_count * sizeof(double),
                               cudaMemcpyHostToDevice, st));

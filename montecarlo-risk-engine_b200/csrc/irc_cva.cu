@@ -280,9 +280,11 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(const __gri
 
 using namespace mcre;
 
-// Packs the event records from the plan's host copies.  Called from mcre_irc_set_coefficients (the exposure
-// coefficients of the regression enter the records).
-int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st) {
+// Packs the event records from the plan's host copies: everything that does not depend on the regression (called
+// from mcre_irc_create, the records travel with the plan arena).  Slots 10..12 (the exposure polynomial) are filled
+// later, on the host (irc_cva_apply_coefficients) or on the device (irc_patch_coefficients_kernel, irc_solve.cu):
+// slot 22 keeps g_k = 1/2 exp(-sum psi dt), slot 23 the date the event closes (+1).
+void irc_cva_fill_static(mcre_irc_plan *p) {
   const CvaHost &h = p->cva;
   const int n_events = h.n_pre_dates + h.n_sub;
   std::vector<double> &rec = p->cva_rec_host;
@@ -296,10 +298,8 @@ int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st) {
     if (di < 0) return;
     const int m = h.date_metric[di];
     if (!(h.date_flags[di] & MCRE_DATE_HAS_METRIC) || m < 0 || m >= h.n_metric - 1) return;
-    const double *dr = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR;   // C, B, c0, c1, c2 (raw basis)
+    const double *dr = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR;   // C, B of the date
     const double C = dr[0], Bc = dr[1];
-    const double g = 0.5 * exp(-psi_int);
-    r[10] = g * dr[2]; r[11] = g * dr[3]; r[12] = g * dr[4];
     double term = -C;           // d_j = -C (-B)^j / j!
     r[13] = 1.0 - C;
     for (int j = 1; j <= 5; ++j) { term *= -Bc / (double)j; r[13 + j] = term; }
@@ -311,6 +311,8 @@ int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st) {
     }
     r[19] = pack2(thr, 0);
     r[20] = C; r[21] = -Bc;
+    r[22] = 0.5 * exp(-psi_int);
+    r[23] = pack2(di + 1, 0);
     long long fb; memcpy(&fb, &r[9], 8);
     r[9] = pack2((int)(fb & 0xffffffff) | CVA_EV_DATE, 0);
   };
@@ -335,8 +337,25 @@ int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st) {
     psi_int += h.step_psi[s] * dt;
     date_part(r, h.step_date[s]);
   }
+}
+
+// Host path of the coefficients (mcre_irc_set_coefficients): the raw-basis polynomial of h_date_rec, scaled by g_k.
+int irc_cva_apply_coefficients(mcre_irc_plan *p, cudaStream_t st) {
+  const CvaHost &h = p->cva;
+  const int n_events = h.n_pre_dates + h.n_sub;
+  std::vector<double> &rec = p->cva_rec_host;
+  const int DR = p->date_stride;
+  for (int ev = 0; ev < n_events; ++ev) {
+    double *r = rec.data() + (size_t)ev * CVA_REC;
+    long long db; memcpy(&db, &r[23], 8);
+    const int di = (int)(db & 0xffffffff) - 1;
+    if (di < 0) continue;
+    const double *dr = p->h_date_rec.data() + (size_t)di * DR + DATE_HDR;   // C, B, c0, c1, c2 (raw basis)
+    r[10] = r[22] * dr[2]; r[11] = r[22] * dr[3]; r[12] = r[22] * dr[4];
+  }
   MCRE_CUDA(cudaMemcpyAsync(p->cva_rec_dev, rec.data(), (size_t)n_events * CVA_REC * sizeof(double),
                             cudaMemcpyHostToDevice, st));
+  MCRE_H2D((size_t)n_events * CVA_REC * sizeof(double));
   return 0;
 }
 

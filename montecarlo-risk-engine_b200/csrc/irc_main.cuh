@@ -587,7 +587,8 @@ static int irc_dispatch_main(mcre_irc_plan *p, const RngDev &r, const ShardDev &
                  : launch_main<8, 2, BERM>(p, r, sh, d_partial, d_spill, d_shift, st);
 }
 // defined in irc_cva.cu (the CVA-only kernel)
-int irc_cva_build_records(mcre_irc_plan *p, cudaStream_t st);
+void irc_cva_fill_static(mcre_irc_plan *p);
+int irc_cva_apply_coefficients(mcre_irc_plan *p, cudaStream_t st);
 int irc_cva_launch(mcre_irc_plan *p, const mcre::RngDev &rng, const mcre::ShardDev &sh, double *partial, double *shift,
                    cudaStream_t st);
 // defined in irc_berm.cu (books with Bermudan exercise units)

@@ -322,6 +322,7 @@ extern "C" int mcre_lsm_step_batch(int64_t n_jobs, const mcre_lsm_step_job *jobs
   int rc = job_scratch(st, (size_t)n_jobs * sizeof(LsmStepJob), &d_jobs);
   if (rc) return rc;
   MCRE_CUDA(cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmStepJob), cudaMemcpyHostToDevice, st));
+  MCRE_H2D((size_t)n_jobs * sizeof(LsmStepJob));
   const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
   long long grid = (long long)sm_count() * 8;
   if (grid > n_jobs * n_chunks) grid = n_jobs * n_chunks;
@@ -346,6 +347,7 @@ extern "C" int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, 
   if (rc) return rc;
   LsmJob *d_jobs = (LsmJob *)d_jobs_v;
   MCRE_CUDA(cudaMemcpyAsync(d_jobs, jobs, (size_t)n_jobs * sizeof(LsmJob), cudaMemcpyHostToDevice, st));
+  MCRE_H2D((size_t)n_jobs * sizeof(LsmJob));
   const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
   long long grid = (long long)sm_count() * 8;
   if (grid > n_jobs * n_chunks) grid = n_jobs * n_chunks;

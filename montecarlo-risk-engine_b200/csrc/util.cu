@@ -9,6 +9,7 @@
 namespace mcre {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_h2d_bytes{0};
 thread_local DevArena *g_arena = nullptr;
 
 int sm_count() {
@@ -320,5 +321,6 @@ extern "C" int mcre_dfma_peak(double *tflops_out, void *stream) {
 }
 
 extern "C" int64_t mcre_launch_count(void) { return g_launches.load(); }
+extern "C" int64_t mcre_h2d_bytes(void) { return g_h2d_bytes.load(); }
 extern "C" const char *mcre_last_error(void) { return g_err; }
 extern "C" int mcre_abi_version(void) { return MCRE_ABI_VERSION; }

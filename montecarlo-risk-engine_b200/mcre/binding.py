@@ -63,13 +63,13 @@ SYMBOLS = [
     "mcre_generate_paths",
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim", "mcre_irc_presim_tangent_slots",
-    "mcre_irc_set_coefficients", "mcre_irc_mainsim", "mcre_irc_set_path_replay", "mcre_select_locate",
+    "mcre_irc_set_coefficients", "mcre_irc_solve_coefficients", "mcre_irc_set_coefficients_device", "mcre_irc_mainsim", "mcre_irc_set_path_replay", "mcre_select_locate",
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_moments_batch", "mcre_lsm_step_batch", "mcre_lsm_step_tangents",
     "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_presim_tangents", "mcre_eq_set_exposure_coef_tangents", "mcre_eq_set_credit", "mcre_eq_set_cva_weight_spill", "mcre_eq_cva_paths", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_compact", "mcre_select_finish",
-    "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_last_error", "mcre_abi_version",
+    "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_h2d_bytes", "mcre_last_error", "mcre_abi_version",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.mcre_last_error.restype = C.c_char_p
     L.mcre_launch_count.restype = C.c_int64
+    L.mcre_h2d_bytes.restype = C.c_int64
     L.mcre_irc_main_slots.restype = C.c_int64
     L.mcre_irc_main_slots.argtypes = [C.c_void_p]
     L.mcre_irc_presim_slots.restype = C.c_int64
@@ -101,6 +102,8 @@ def lib():
     L.mcre_irc_presim_tangent_slots.restype = C.c_int64
     L.mcre_irc_presim_tangent_slots.argtypes = [C.c_void_p]
     L.mcre_irc_set_coefficients.argtypes = [C.c_void_p, c_dp, C.c_void_p]
+    L.mcre_irc_solve_coefficients.argtypes = [C.c_void_p, C.c_void_p, c_ip, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_irc_set_coefficients_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_irc_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_irc_set_path_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -165,3 +168,8 @@ def as_ip(a):
 
 def launch_count():
     return int(lib().mcre_launch_count())
+
+
+def h2d_bytes():
+    """Bytes the library has copied host -> device so far."""
+    return int(lib().mcre_h2d_bytes())

@@ -615,7 +615,7 @@ class IrcBackend:
                     while_running()
                     while_running = None
                 moments = RT.all_reduce_tree(moments)
-                mom_all = moments.cpu().numpy()
+                mom_all = RT.to_host(moments)
                 mom = mom_all[:slots].reshape(info["n_expo"], -1)
                 tmom = mom_all[slots:].reshape(len(group), self.nt, info["n_expo"], 9) if tslots else None
             finally:
@@ -633,6 +633,57 @@ class IrcBackend:
                                        for k in range(info["n_expo"])])            # [n_expo, nt, 3]
                 out[id(prod)] = (coefs, info["basis"], dcoefs)
         return out
+
+    def _device_regression_ok(self, prods, groups):
+        """Pre-simulation -> normal equations -> main simulation as one stream of kernels (no read-back in between):
+        value-only runs of linear products whose regression units fit one launch and whose sets fit one group."""
+        c = self.c
+        return (os.environ.get("MCRE_DEVICE_SOLVE", "1") != "0" and self.nt == 0 and len(groups) == 1
+                and 0 < len(prods) <= B.IRC_MAX_UNITS and all(is_linear(p) for p in c.products))
+
+    def presim_on_device(self, prods, dev, while_running=None):
+        """Like presim_coefficients, but the moments never leave the device: they are all-reduced and solved there
+        (mcre_irc_solve_coefficients).  -> (coef_unit [n_units][n_expo][3], coef_sum [n_expo][n_sets][3]) device
+        tensors in the standardised basis, and the basis."""
+        c = self.c
+        L = B.lib()
+        n_pre = c.num_paths_presim
+        if n_pre <= 0:
+            raise ValueError("Exposure metrics need a pre-simulation: num_paths_presim must be positive.")
+        inject = c.injected_normals.get("pre") if c.injected_normals else None
+        desc, keep, info = self.lower([], prods)
+        n_expo, n_sets = info["n_expo"], len(c.netting_sets)
+        plan = C.c_void_p()
+        B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
+        try:
+            begin, count = RT.shard_range(n_pre, CHUNK_PATHS)
+            slots = L.mcre_irc_presim_slots(plan)
+            moments = torch.zeros(slots, dtype=torch.float64, device=dev)
+            batch = max(CHUNK_PATHS, (c.presim_batch_paths // CHUNK_PATHS) * CHUNK_PATHS)
+            for b0 in range(0, count, batch):
+                bn = min(batch, count - b0)
+                scratch = torch.empty(L.mcre_irc_presim_scratch_bytes(plan, bn), dtype=torch.uint8, device=dev)
+                partial = torch.empty(L.mcre_irc_partial_bytes(plan, bn, CHUNK_PATHS, 1) // 8 + 1, dtype=torch.float64, device=dev)
+                part_m = moments if count <= batch else torch.zeros(slots, dtype=torch.float64, device=dev)
+                rng = self._rng(42, inject, n_pre)
+                sh = B.Shard(begin + b0, bn, CHUNK_PATHS)
+                B.check(L.mcre_irc_presim(plan, C.byref(rng), C.byref(sh), scratch.data_ptr(), partial.data_ptr(),
+                                          part_m.data_ptr(), None, RT.stream_ptr()))
+                if part_m is not moments:
+                    moments += part_m
+                del scratch, partial
+            if while_running is not None:
+                while_running()
+            moments = RT.all_reduce_tree(moments)
+            set_of = {id(p): si for si, ns in enumerate(c.netting_sets) for p in ns.products}
+            unit_set, unit_ptr = B.as_ip(np.array([set_of[id(p)] for p in prods], dtype=np.int32))
+            coef_unit = torch.empty((len(prods), n_expo, 3), dtype=torch.float64, device=dev)
+            coef_sum = torch.empty((n_expo, n_sets, 3), dtype=torch.float64, device=dev)
+            B.check(L.mcre_irc_solve_coefficients(plan, moments.data_ptr(), unit_ptr, n_sets, coef_unit.data_ptr(),
+                                                  coef_sum.data_ptr(), RT.stream_ptr()))
+        finally:
+            L.mcre_irc_destroy(plan)
+        return coef_unit, coef_sum, info["basis"]
 
     @contextlib.contextmanager
     def _value_only(self):
@@ -754,9 +805,17 @@ class IrcBackend:
             for gi, idxs in enumerate(groups):
                 lowered[gi] = self.lower(idxs, [])
 
+        dev_reg = None          # (coef_unit, coef_sum, basis, products): regression solved on the device
+        events = None
         if c.requires_regression:
             prods = [p for p in c.products if c._product_requires_regression(p) and is_linear(p)]
-            if prods and need_expo:
+            if prods and need_expo and self._device_regression_ok(prods, groups):
+                # no host synchronisation until the results are read: phases are timed with CUDA events
+                events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                events[0].record()
+                dev_reg = self.presim_on_device(prods, dev, while_running=lower_main) + (prods,)
+                events[1].record()
+            elif prods and need_expo:
                 # the main plans are lowered on the host while the pre-simulation kernels run
                 coef_by_product = self.presim_coefficients(prods, dev, while_running=lower_main)
             # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
@@ -777,7 +836,8 @@ class IrcBackend:
                     p.regression_coeffs[j, 1, :] = torch.tensor(raw[ridx[t]])
                 for e, t in enumerate(expo_times):
                     c.regression_coeffs[p.product_id][e, 1, :] = torch.tensor(raw[ridx[t]])
-        torch.cuda.synchronize(dev)
+        if dev_reg is None:
+            torch.cuda.synchronize(dev)
         timings["preprocessing"] = time.perf_counter() - t0
         t1 = time.perf_counter()
 
@@ -799,8 +859,11 @@ class IrcBackend:
             plan = C.c_void_p()
             B.check(L.mcre_irc_create(C.byref(desc), C.byref(plan)))
             try:
-                coef_flat, coef_ptr = B.as_dp(coef[:n_expo])
-                B.check(L.mcre_irc_set_coefficients(plan, coef_ptr, RT.stream_ptr()))
+                if dev_reg is not None:
+                    B.check(L.mcre_irc_set_coefficients_device(plan, dev_reg[1].data_ptr(), RT.stream_ptr()))
+                else:
+                    coef_flat, coef_ptr = B.as_dp(coef[:n_expo])
+                    B.check(L.mcre_irc_set_coefficients(plan, coef_ptr, RT.stream_ptr()))
                 if info["berm_units"]:
                     units = info["berm_units"]
                     exc = np.zeros((max(info["n_ex"], 1), 3, w))
@@ -831,8 +894,10 @@ class IrcBackend:
                                            shift.data_ptr(), spill.data_ptr() if spill is not None else None,
                                            RT.stream_ptr()))
                 acc = RT.all_reduce_tree(acc)
-                acc_h = acc.cpu().numpy()
-                shift_h = shift.cpu().numpy()
+                if events is not None:
+                    events[2].record()
+                acc_h = RT.to_host(acc)
+                shift_h = RT.to_host(shift)
                 quant = None
                 if spill is not None:
                     from mcre.select import order_statistics
@@ -855,4 +920,17 @@ class IrcBackend:
         torch.cuda.synchronize(dev)
         timings["path_generation"] = time.perf_counter() - t1
         timings["request_resolution"] = 0.0
+        if dev_reg is not None:
+            # expose the coefficients in the reference's raw monomial basis (controller.regression_coeffs)
+            coef_unit, _, basis, prods = dev_reg
+            coef_h = RT.to_host(coef_unit)
+            degen = [t <= self.vas.t0() for t in c.exposure_timeline.tolist()]
+            for u, p in enumerate(prods):
+                c.regression_coeffs[p.product_id][:, 0, :] = torch.tensor(to_raw_basis(coef_h[u], basis, degen))
+            # phase split on the device clock (the host never waited between the phases)
+            pre_s = events[0].elapsed_time(events[1]) * 1e-3
+            main_s = events[1].elapsed_time(events[2]) * 1e-3
+            total = timings["preprocessing"] + timings["path_generation"]
+            timings["preprocessing"] = pre_s
+            timings["path_generation"] = max(total - pre_s, main_s)
         return results, timings

@@ -27,6 +27,17 @@ def compute_device():
     return _device
 
 
+#: bytes read back device -> host through to_host() (bench.py: d2h_bytes_per_step of the end-to-end leg)
+d2h_bytes = 0
+
+
+def to_host(t):
+    """Device tensor -> numpy array (synchronises on the tensor's stream); counts the bytes."""
+    global d2h_bytes
+    d2h_bytes += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 

@@ -279,3 +279,27 @@ def test_rank_with_an_empty_shard_still_gets_the_common_shift(name):
     assert np.array_equal(shift_full, shift_empty)
     assert np.all(acc_empty == 0.0)
     assert np.any(acc_full != 0.0)
+
+
+@pytest.mark.parametrize("name", ["cfg3_wwr_cva", "irs_collateral_offgrid", "irs_analytical"])
+def test_device_side_regression_equals_host_solve(name, monkeypatch):
+    """Value-only runs of linear products solve the normal equations of the exposure regression on the device
+    (mcre_irc_solve_coefficients: equilibrated Gaussian elimination, minimum-norm pseudo-inverse on rank-deficient
+    dates) and patch the coefficients into the main plan there, so that nothing is read back between pre-simulation
+    and main simulation.  Must agree with the host solver path (numpy, mcre/lsm.py:solve_normal_equations) - which
+    tangent / Bermudan plans keep using - far inside the parity tolerance, including the t = 0 date (rank 1) and the
+    exposed raw-basis coefficients."""
+    monkeypatch.setenv("MCRE_DEVICE_SOLVE", "1")
+    res_d, sc_d = helpers.run_cuda(name, draws="philox")
+    monkeypatch.setenv("MCRE_DEVICE_SOLVE", "0")
+    res_h, sc_h = helpers.run_cuda(name, draws="philox")
+    fd, fh = helpers.flatten_results(res_d), helpers.flatten_results(res_h)
+    for key in fh:
+        scale = max(1.0, float(np.nanmax(np.abs(fh[key][0]))))
+        helpers.assert_close(fd[key][0], fh[key][0], 1e-11, 1e-12 * scale, f"{name} {key} value")
+        helpers.assert_close(fd[key][1], fh[key][1], 1e-8, 1e-12 * scale, f"{name} {key} mc error")
+    for cd, ch in zip(sc_d.regression_coeffs, sc_h.regression_coeffs):
+        cd, ch = cd.numpy(), ch.numpy()
+        fit = np.abs(ch).max(axis=(1, 2), keepdims=True) + 1e-30
+        assert np.all(np.abs(cd - ch) <= 1e-7 * fit)
+    assert set(sc_d.last_timings) >= {"preprocessing", "path_generation"}
