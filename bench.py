@@ -358,7 +358,8 @@ def main():
     # ---- end to end through the public API (host objects in, numpy results out) ------------
     e2e_times, h2d, d2h = [], 0, 0
     cva = None
-    for i in range(0 if args.no_e2e else 2):
+    # one untimed call first (first-use costs: NCCL connections of the moment all-gather, allocator growth), then best of 2
+    for i in range(0 if args.no_e2e else 3):
         model, sets, metrics, tl = build_case(ns, float(RHOS[(i + 7) % len(RHOS)]))
         barrier()
         h2d0, d2h0 = B.h2d_bytes(), RT.d2h_bytes
@@ -369,14 +370,17 @@ def main():
         res = sc.run_simulation()
         cva = float(res.get_results("irs", "cva[GM]")[0])
         barrier()
-        e2e_times.append(time.perf_counter() - t0)
+        if i > 0:
+            e2e_times.append(time.perf_counter() - t0)
+        if os.environ.get("MCRE_BENCH_DEBUG") and e2e_times:
+            sys.stderr.write(f"rank {rank} e2e {i}: {e2e_times[-1] * 1e3:.2f} ms {sc.last_timings}\n")
         h2d, d2h = B.h2d_bytes() - h2d0, RT.d2h_bytes - d2h0      # measured: counted where the copies are made
     e2e_dt = min(e2e_times) if e2e_times else float("inf")
     tt = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = {"value": n_total * N_STEPS_SIM / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "includes": f"plan lowering + pre-simulation of 2^{args.presim_log2} paths + main pass",
+           "d2h_bytes_per_step": d2h, "includes": f"plan lowering + pre-simulation of 2^{args.presim_log2} paths + main pass; best of 2 calls after one untimed call",
            "cva": cva}
 
     # ---- parity guard: the same config on a small Philox stream, CUDA vs the oracle (checker only, not timed) ----

@@ -488,6 +488,16 @@ int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const double *d_n
                          double shift_i, double scale_i, float *d_value, int64_t n, int32_t chunk_paths,
                          double *d_partial, double *d_moments, void *stream);
 
+/* Single-right step like mcre_lsm_step_states, with the continuation coefficients of product date i read from
+ * DEVICE memory (d_coef_i: 3 doubles, or NULL), and the 3x3 solve of one regression date on the device
+ * (d_moments: the 8 moments, all-reduced over the ranks; d_coef: 3 doubles; the minimum-norm convention of
+ * torch.linalg.lstsq's gelsy driver, controller.py:368-374): the backward induction of one Bermudan option is then
+ * a stream of kernels without a per-date read-back. */
+int mcre_lsm_step_dev(const double *d_xk, const double *d_nk, double shift_k, double scale_k, const double *d_xi,
+                      const double *d_ni, const double *d_imm, const double *d_coef_i, double shift_i, double scale_i,
+                      float *d_value, int64_t n, int32_t chunk_paths, double *d_partial, double *d_moments, void *stream);
+int mcre_lsm_solve_dev(const double *d_moments, double *d_coef, void *stream);
+
 /* Tangent companion of mcre_lsm_step (one exercise right), called after it for the same regression date: applies
  * the same hard exercise decision to the running pathwise tangents d_dvalue [nt][n] of the deflated value,
  *   dV <- ex ? (dimm_i - (imm_i / N_i) dN_i) / N_i : dV,

@@ -154,37 +154,93 @@ __global__ void __launch_bounds__(128, 4) irc_presim_forward_kernel(IrcDev P, Rn
 // Pre-simulation of Bermudan units, forward pass: spills per regression date the explanatory
 // variable and the numeraire, and per exercise record the immediate exercise value.
 // scratch: x [n_reg][n] | N [n_reg][n] | imm [n_ex][n], all f64
+// Lock-step like irc_presim_forward_kernel (PRE_PP paths per thread; the zero-bond exponentials of the underlying,
+// ~20 per exercise date of a 10y swap, are evaluated PP-wide on the table-driven exp).
 template <bool CIR, int SCHEME>
-__global__ void __launch_bounds__(128) irc_lsm_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
-                                                              double *nbuf, double *ibuf) {
-  typedef double R;
+__global__ void __launch_bounds__(128, 4) irc_lsm_forward_kernel(IrcDev P, RngDev rng, ShardDev sh, double *xbuf,
+                                                                 double *nbuf, double *ibuf) {
+  constexpr int PP = PRE_PP;
   fm_tables_init();
-  const long long lpath = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lpath >= sh.n_paths) return;
-  const long long gpath = sh.path_begin + lpath;
   const long long n = sh.n_paths;
-  IrcParams<R, CIR> mp;
-  irc_load_params<R, CIR>(P, mp);
-  NormalStream ns; ns.init(rng, (unsigned long long)gpath);
-  IrcState<R> st;
-  st.r = mp.r0; st.logB = 0.0; st.y = mp.y0; st.logBl = 0.0;
+  const long long base = (long long)blockIdx.x * (128 * PP) + threadIdx.x;
+  if (base - threadIdx.x >= n) return;
+  long long lpath[PP], gpath[PP];
+  bool live[PP];
+  MCRE_VP {
+    lpath[p] = base + p * 128;
+    live[p] = lpath[p] < n;
+    gpath[p] = sh.path_begin + (live[p] ? lpath[p] : 0);
+  }
+  NormalStreamV<PP> nsv;
+  nsv.init(rng, gpath);
+  const bool inject = rng.mode == MCRE_RNG_INJECT;
+  const double r0 = __ldg(P.vas + 0), sigma = __ldg(P.vas + 1), theta = __ldg(P.vas + 2), a = __ldg(P.vas + 3);
+  const bool second = CIR && P.vas_noise == 1;
+  const double l0 = CIR ? __ldg(P.chol + (second ? 2 : 0)) : __ldg(P.chol + 0);
+  const double l1 = second ? __ldg(P.chol + 3) : 0.0;
+  double r[PP], logB[PP], zb[PP];
+  MCRE_VP { r[p] = r0; logB[p] = 0.0; zb[p] = 0.0; }
   auto eval_date = [&](int di) {
     const int flags = __ldg(P.date_flags + di);
     if (flags & MCRE_DATE_HAS_REGRESSION) {
       const int k = __ldg(P.date_reg + di);
-      xbuf[(size_t)k * n + lpath] = st.r;
-      nbuf[(size_t)k * n + lpath] = exp(st.logB);
+      double numeraire[PP];
+      fm_exp_tv<PP>(logB, numeraire);
+      MCRE_VP {
+        if (live[p]) {
+          xbuf[(size_t)k * n + lpath[p]] = r[p];
+          nbuf[(size_t)k * n + lpath[p]] = numeraire[p];
+        }
+      }
     }
     if (flags & MCRE_DATE_HAS_EXERCISE) {
       const int x0 = __ldg(P.date_ex_off + di), x1 = __ldg(P.date_ex_off + di + 1);
-      for (int x = x0; x < x1; ++x) ibuf[(size_t)x * n + lpath] = irc_exercise_value<R>(P, x, st.r);
+      for (int x = x0; x < x1; ++x) {
+        // underlying = const + sum_j w_j P(t, T_j; r), P = exp(alpha_j - B_j r); immediate value max(sign (U - K), 0)
+        // (bond.py:115-163, swap.py:129-140, bermudan_option.py:60-70) - same arithmetic as irc_exercise_value
+        const int t0 = __ldg(P.ex_term_off + x), t1 = __ldg(P.ex_term_off + x + 1), b = __ldg(P.ex_unit + x);
+        double U[PP];
+        MCRE_VP U[p] = __ldg(P.ex_const + x);
+        for (int t = t0; t < t1; ++t) {
+          const double alpha = __ldg(P.term_coef + 2 * t), B = __ldg(P.term_coef + 2 * t + 1), wgt = __ldg(P.term_w + t);
+          double xa[PP], e[PP];
+          MCRE_VP xa[p] = alpha - B * r[p];
+          fm_exp_tv<PP>(xa, e);
+          MCRE_VP U[p] = U[p] + e[p] * wgt;
+        }
+        const double K = __ldg(P.berm_strike + b), sg = __ldg(P.berm_sign + b);
+        MCRE_VP { if (live[p]) ibuf[(size_t)x * n + lpath[p]] = fmax((U[p] - K) * sg, 0.0); }
+      }
     }
   };
   for (int di = 0; di < P.n_pre_dates; ++di) eval_date(di);
+#pragma unroll 1
   for (int is = 0; is < P.n_sub; ++is) {
-    double z0, z1;
-    irc_draw<R, CIR>(rng, ns, is, lpath, gpath, z0, z1);
-    irc_step<R, CIR, SCHEME, false>(P, mp, st, is, z0, z1);
+    const double dt = __ldg(P.step_dt + is);
+    const double sv0 = __ldg(P.step_vas + is * 2), sv1 = __ldg(P.step_vas + is * 2 + 1);
+    double z0[PP], z1[PP];
+    if (inject) {
+      MCRE_VP {
+        const double *zp = rng.z + ((size_t)is * rng.n_total + gpath[p]) * (CIR ? 2 : 1);
+        z0[p] = zp[0];
+        z1[p] = CIR ? zp[1] : 0.0;
+      }
+    } else if (CIR) {
+      nsv.next2(z0, z1);
+    } else {
+      if ((is & 1) == 0) nsv.next2(z0, zb);
+      else { MCRE_VP z0[p] = zb[p]; }
+      MCRE_VP z1[p] = 0.0;
+    }
+    MCRE_VP logB[p] = fma(r[p], dt, logB[p]);
+    if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
+      MCRE_VP r[p] = fma(sv1, z0[p], fma(r[p] - theta, sv0, theta));
+    } else {
+      const double adt = a * dt, ssq = sigma * sqrt(dt);
+      const double k0 = ssq * l0, k1 = ssq * l1;
+      MCRE_VP r[p] = fma(k0, z0[p], fma(sv0 - r[p], adt, r[p]));
+      if (second) { MCRE_VP r[p] = fma(k1, z1[p], r[p]); }
+    }
     const int di = __ldg(P.step_date + is);
     if (di >= 0) eval_date(di);
   }
@@ -531,7 +587,7 @@ extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const
   double *ibuf = nbuf + (size_t)d.n_reg * n;
   if (d.nt != 0) return irc_lsm_forward_tangent_pass(p, r, sh, d_scratch, st);
   const int threads = 128;
-  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const unsigned blocks = (unsigned)((n + threads * PRE_PP - 1) / (threads * PRE_PP));
   if (d.has_cir) irc_lsm_forward_kernel<true, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
   else if (d.scheme == MCRE_SCHEME_ANALYTICAL)
     irc_lsm_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);

@@ -13,6 +13,7 @@
 // HBM-bound, 5 coalesced f64 streams + the f32 value array (36 B / path / date).
 #include "common.cuh"
 #include "reduce.cuh"
+#include "solve3.cuh"
 #include <map>
 #include <mutex>
 #include <utility>
@@ -102,6 +103,38 @@ __global__ void __launch_bounds__(256) lsm_step_kernel(const double *__restrict_
   for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x)
     lsm_step_item<R>(xk, nk, shift_k, scale_k, xi, ni, imm, has_coef, cf, shift_i, scale_i, value, n, chunk, ch, acc, stage,
                      partial + ch * NV);
+}
+
+// Single-right step with the continuation coefficients of product date i read from DEVICE memory (d_coef, 3 doubles,
+// or NULL): the backward induction of one Bermudan option then runs as a stream of kernels - step, tree reduction,
+// (all-reduce,) 3x3 solve - without reading the moments back per date (mcre/lsm.py:backward_induction_device).
+__global__ void __launch_bounds__(256) lsm_step_dev_kernel(const double *__restrict__ xk, const double *__restrict__ nk,
+                                                           double shift_k, double scale_k, const double *__restrict__ xi,
+                                                           const double *__restrict__ ni, const double *__restrict__ imm,
+                                                           const double *__restrict__ d_coef, double shift_i, double scale_i,
+                                                           float *__restrict__ value, long long n, int chunk,
+                                                           double *__restrict__ partial) {
+  constexpr int NV = 8;
+  __shared__ double acc[NV];
+  __shared__ double stage[2 * 8 * NV];
+  LsmCoef cf;
+#pragma unroll
+  for (int s = 0; s < LSM_MAX_RIGHTS; ++s)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) cf.c[s][q] = (d_coef && s == 0) ? d_coef[q] : 0.0;
+  const long long n_chunks = (n + chunk - 1) / chunk;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x)
+    lsm_step_item<1>(xk, nk, shift_k, scale_k, xi, ni, imm, d_coef != nullptr, cf, shift_i, scale_i, value, n, chunk, ch, acc,
+                     stage, partial + ch * NV);
+}
+
+// coefficients of one regression date from its 8 moments (sum u^0..u^4, sum u^0..u^2 Y)
+__global__ void lsm_solve_dev_kernel(const double *__restrict__ moments, double *__restrict__ coef) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double c[3];
+    solve_normal_equations_dev(moments, moments + 5, c);
+    coef[0] = c[0]; coef[1] = c[1]; coef[2] = c[2];
+  }
 }
 
 // The steps of MANY exercise products in one launch (the lock-step backward inductions of a book: one job per
@@ -279,6 +312,34 @@ extern "C" int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const 
 #undef LSM_LAUNCH
   MCRE_LAUNCHED();
   return mcre_tree_reduce(d_partial, n_chunks, nv, d_moments, stream);
+}
+
+extern "C" int mcre_lsm_step_dev(const double *d_xk, const double *d_nk, double shift_k, double scale_k, const double *d_xi,
+                                 const double *d_ni, const double *d_imm, const double *d_coef_i, double shift_i,
+                                 double scale_i, float *d_value, int64_t n, int32_t chunk_paths, double *d_partial,
+                                 double *d_moments, void *stream) {
+  if (!d_xk || !d_nk || !d_value || !d_partial || !d_moments) return fail(-1, "null argument%s", "");
+  if (d_imm && (!d_xi || !d_ni)) return fail(-1, "lsm: exercise update needs x_i and N_i%s", "");
+  if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) {   // a rank without pre-simulation paths contributes zero moments
+    MCRE_CUDA(cudaMemsetAsync(d_moments, 0, 8 * sizeof(double), st));
+    return 0;
+  }
+  const long long n_chunks = (n + chunk_paths - 1) / chunk_paths;
+  long long grid = (long long)sm_count() * 8;
+  if (grid > n_chunks) grid = n_chunks;
+  lsm_step_dev_kernel<<<(unsigned)grid, 256, 0, st>>>(d_xk, d_nk, shift_k, scale_k, d_xi, d_ni, d_imm, d_coef_i, shift_i,
+                                                      scale_i, d_value, n, chunk_paths, d_partial);
+  MCRE_LAUNCHED();
+  return mcre_tree_reduce(d_partial, n_chunks, 8, d_moments, stream);
+}
+
+extern "C" int mcre_lsm_solve_dev(const double *d_moments, double *d_coef, void *stream) {
+  if (!d_moments || !d_coef) return fail(-1, "null argument%s", "");
+  lsm_solve_dev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_moments, d_coef);
+  MCRE_LAUNCHED();
+  return 0;
 }
 
 // Job tables of the batched launches: one grow-only device buffer per (device, stream); the upload is ordered on

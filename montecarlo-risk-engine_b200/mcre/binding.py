@@ -64,7 +64,7 @@ SYMBOLS = [
     "mcre_irc_create", "mcre_irc_destroy", "mcre_irc_main_slots", "mcre_irc_presim_slots",
     "mcre_irc_presim_scratch_bytes", "mcre_irc_partial_bytes", "mcre_irc_presim", "mcre_irc_presim_tangent_slots",
     "mcre_irc_set_coefficients", "mcre_irc_solve_coefficients", "mcre_irc_set_coefficients_device", "mcre_irc_mainsim", "mcre_irc_set_path_replay", "mcre_select_locate",
-    "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_moments_batch", "mcre_lsm_step_batch", "mcre_lsm_step_tangents",
+    "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_step_dev", "mcre_lsm_solve_dev", "mcre_lsm_moments_batch", "mcre_lsm_step_batch", "mcre_lsm_step_tangents",
     "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_presim_tangents", "mcre_eq_set_exposure_coef_tangents", "mcre_eq_set_credit", "mcre_eq_set_cva_weight_spill", "mcre_eq_cva_paths", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
@@ -116,6 +116,10 @@ def lib():
                                 c_dp, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p]
     L.mcre_lsm_step_states.argtypes = [C.c_int32] + list(L.mcre_lsm_step.argtypes)
+    L.mcre_lsm_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    L.mcre_lsm_solve_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_lsm_step_batch.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_lsm_moments_batch.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_lsm_step_tangents.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,

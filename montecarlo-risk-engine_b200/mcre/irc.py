@@ -23,7 +23,7 @@ from common.enums import SimulationScheme
 from mcre import binding as B
 from mcre import runtime as RT
 from mcre.dual import D, cholesky_dual
-from mcre.lsm import (backward_induction, regression_tangents, solve_normal_equations, solve_normal_equations_batch,
+from mcre.lsm import (backward_induction, backward_induction_device, regression_tangents, solve_normal_equations, solve_normal_equations_batch,
                       to_raw_basis)
 from mcre.timegrid import build_time_grid
 from metrics.metric import MetricType
@@ -745,7 +745,10 @@ class IrcBackend:
             dns = scratch[off + n_reg * nt * n:off + 2 * n_reg * nt * n].view(n_reg, nt, n)
             dim_ = scratch[off + 2 * n_reg * nt * n:off + (2 * n_reg + n_ex) * nt * n].view(n_ex, nt, n)
             tangents = dict(nt=nt, dxs=dxs, dnums=dns, dimm=dim_)
-        out = backward_induction(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, tangents=tangents)
+        if not with_tan and os.environ.get("MCRE_DEVICE_SOLVE", "1") != "0":
+            out = backward_induction_device(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev)
+        else:
+            out = backward_induction(xs, ns_, imm, ptl, reg_times, basis, count, CHUNK_PATHS, dev, tangents=tangents)
         coef, dcoef = out if with_tan else (out, None)
         return coef, reg_times, basis, dcoef
 

@@ -233,6 +233,54 @@ def backward_induction_steps(xs, nums, imm, ptl, reg_times, basis, count, chunk_
     return coef[:, 0, :] if R == 1 else coef
 
 
+def backward_induction_device(xs, nums, imm, ptl, reg_times, basis, count, chunk_paths, dev):
+    """Backward induction of ONE single-right exercise product (value-only) as a stream of kernels: per regression
+    date the fused step launch (exercise update + 8 moments, mcre_lsm_step_dev with the continuation coefficients
+    read from device memory), the all-reduce of the moments over the ranks (on the stream) and the 3x3 solve on the
+    device (mcre_lsm_solve_dev).  Same schedule and arithmetic as backward_induction_steps; the host reads the
+    coefficients back once at the end instead of once per date (round 1: 0.7 ms of round trip per exercise date).
+    -> coefficients [n_reg, 3] in the standardised basis (numpy)."""
+    L = B.lib()
+    stream = RT.stream_ptr()
+    n_reg = len(reg_times)
+    n = xs.shape[1]
+    reg_idx = {t: k for k, t in enumerate(reg_times)}
+    coef = torch.zeros((n_reg, 3), dtype=torch.float64, device=dev)
+    value = torch.zeros((1, n), dtype=torch.float32, device=dev)
+    n_chunks = (n + chunk_paths - 1) // chunk_paths
+    partial = torch.empty(n_chunks * 8 + 1, dtype=torch.float64, device=dev)
+    moments = torch.zeros(8, dtype=torch.float64, device=dev)
+    xs_ptr, nums_ptr, imm_ptr, coef_ptr, row = xs.data_ptr(), nums.data_ptr(), imm.data_ptr(), coef.data_ptr(), n * 8
+    _, world = RT.dist_info()
+
+    def step(k, i):
+        args_i = (None, None, None, None, 0.0, 1.0)
+        if i is not None:
+            ki = reg_idx[ptl[i]]
+            cptr = coef_ptr + ki * 24 if i < len(ptl) - 1 else None
+            args_i = (xs_ptr + ki * row, nums_ptr + ki * row, imm_ptr + i * row, cptr, float(basis[ki, 0]), float(basis[ki, 1]))
+        B.check(L.mcre_lsm_step_dev(xs_ptr + k * row, nums_ptr + k * row, float(basis[k, 0]), float(basis[k, 1]), *args_i,
+                                    value.data_ptr(), count, chunk_paths, partial.data_ptr(), moments.data_ptr(), stream))
+
+    last = len(ptl)
+    for k in range(n_reg - 1, -1, -1):
+        t_reg = reg_times[k]
+        pidx = bisect_left(ptl, t_reg)
+        if pidx >= len(ptl):
+            continue      # after the last exercise date: no continuation value (controller.py:303-305)
+        t_next = pidx + 1 if ptl[pidx] == t_reg else pidx
+        if t_next < last:
+            for i in range(last - 1, t_next, -1):   # product dates that are not regression dates
+                step(k, i)
+            step(k, t_next)
+            last = t_next
+        else:
+            step(k, None)
+        m = RT.all_reduce_tree(moments) if world > 1 else moments
+        B.check(L.mcre_lsm_solve_dev(m.data_ptr(), coef_ptr + k * 24, stream))
+    return RT.to_host(coef)
+
+
 def run_backward_inductions(gens):
     """Drive backward_induction_steps generators in lock-step: per round every live generator queues its next
     step, then the moments of all of them are all-reduced over the ranks and read back together.

@@ -315,3 +315,22 @@ def test_large_mixed_book_cva_is_split_over_launches():
     out = risk.run(model, sets, metrics, tl, n, n, 1, "EULER")
     _compare(helpers.flatten_results(res), helpers.oracle_flat(out, ["big"], res.get_metric_names()), 1e-7, "big book cva",
              err_rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["bermudan_swaption", "cfg4_bermudan_40"])
+def test_device_side_backward_induction_equals_host_driven_one(name, monkeypatch):
+    """The Longstaff-Schwartz backward induction of a rate Bermudan runs as a stream of kernels (fused step with the
+    continuation coefficients read from device memory, 3x3 solve on the device: mcre_lsm_step_dev /
+    mcre_lsm_solve_dev) instead of one device-to-host round trip per exercise date.  Same schedule, same arithmetic:
+    every path must take the same exercise decisions as with the host-driven induction (numpy solve), so all results
+    agree far inside the parity tolerance."""
+    monkeypatch.setenv("MCRE_DEVICE_SOLVE", "1")
+    res_d, sc_d = helpers.run_cuda(name, draws="philox")
+    monkeypatch.setenv("MCRE_DEVICE_SOLVE", "0")
+    res_h, sc_h = helpers.run_cuda(name, draws="philox")
+    fd, fh = helpers.flatten_results(res_d), helpers.flatten_results(res_h)
+    _compare(fd, fh, 1e-11, name + " device vs host induction", err_rtol=1e-6)
+    for cd, ch in zip(sc_d.regression_coeffs, sc_h.regression_coeffs):
+        cd, ch = cd.numpy(), ch.numpy()
+        fit = np.abs(ch).max(axis=(1, 2), keepdims=True) + 1e-30
+        assert np.all(np.abs(cd - ch) <= 1e-7 * fit)

@@ -49,7 +49,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = 1 << args.paths_log2
     out = {}
-    for name in ["wwr_cva", "wwr_cva_greeks", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption",
+    for name in ["cfg3_wwr_cva", "cfg2_irs_offgrid", "wwr_cva", "wwr_cva_greeks", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption",
                  "heston_path_dependent", "bs_basket_euler", "flexicall_exposure", "mixed_book_exposure",
                  "bs_exposure_greeks", "bs_proxy_greeks_mixed", "equity_cva", "equity_cva_exercise"]:
         res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0))
