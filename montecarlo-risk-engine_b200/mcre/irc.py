@@ -423,7 +423,12 @@ class IrcBackend:
         ex_index = {}
         for di in range(n_dates):
             for b, i, t, last in ex_by_date[di]:
-                const, terms = underlying_terms(berm_units[b][0].underlying, t)
+                # (memoised per backend: the pre-simulation plan and the main plan ask for the same decompositions)
+                memo = self.__dict__.setdefault("_terms_cache", {})
+                key_ut = (id(berm_units[b][0].underlying), t)
+                if key_ut not in memo:
+                    memo[key_ut] = underlying_terms(berm_units[b][0].underlying, t)
+                const, terms = memo[key_ut]
                 ex_index[(b, i)] = len(ex_unit)
                 ex_unit.append(b)
                 ex_last.append(int(last))

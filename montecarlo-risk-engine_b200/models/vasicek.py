@@ -1,5 +1,7 @@
 """Vasicek short rate with money-market numeraire
 (reference: src/models/vasicek.py:5-156)."""
+import math
+
 from models.model import *
 from mcre.dual import D, dexp, dsqrt, dval
 
@@ -37,6 +39,13 @@ class VasicekModel(Model):
         """(alpha, B) with P(t1,t2;r) = exp(alpha - B r)."""
         sigma, theta, a = p[1], p[2], p[3]
         tau = t2 - t1
+        if sigma.t.shape[0] == 0:
+            # value-only plans: the same expression on plain floats (plans of exercise products evaluate this for
+            # every zero bond of every exercise date - thousands of calls)
+            sg, th, av = sigma.v, theta.v, a.v
+            Bv = (1.0 - math.exp(-av * tau)) / av
+            al = (th - sg * sg / (2.0 * av * av)) * (Bv - tau) - (sg * sg / (4.0 * av)) * Bv * Bv
+            return D._val(al), D._val(Bv)
         B = (1.0 - dexp(-a * tau)) / a
         alpha = (theta - sigma * sigma / (2.0 * a * a)) * (B - tau) - (sigma * sigma / (4.0 * a)) * B * B
         return alpha, B
