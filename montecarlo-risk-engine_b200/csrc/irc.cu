@@ -501,7 +501,9 @@ extern "C" int64_t mcre_irc_partial_bytes(const mcre_irc_plan *p, int64_t n_path
   int64_t n_chunks = (n_paths + chunk - 1) / chunk;
   int64_t slots = presim ? mcre_irc_presim_slots(p) : mcre_irc_main_slots(p);
   if (presim && p->d.nt > 0) slots = std::max<int64_t>(slots, mcre_irc_presim_tangent_slots(p));
-  return n_chunks * slots * 8;
+  int64_t doubles = n_chunks * slots;
+  if (!presim && p->cva_only) doubles = std::max<int64_t>(doubles, irc_cva_units(n_paths) * 4);   // per-pass partials
+  return doubles * 8;
 }
 
 extern "C" int mcre_irc_set_coefficients(mcre_irc_plan *p, const double *coef, void *stream) {
@@ -607,12 +609,12 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
   ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
   cudaStream_t st = (cudaStream_t)stream;
   if (p->cva_only) {
-    // per-chunk partials of the tail row only: [chunk][pv, pv^2, cva, cva^2]; the date rows of the accumulator stay 0
+    // per-pass partials of the tail row only: [pass][pv, pv^2, cva, cva^2]; the date rows of the accumulator stay 0
     const int64_t slots = mcre_irc_main_slots(p);
     rc = irc_cva_launch(p, r, sh, d_partial, d_shift, st);
     if (rc) return rc;
     MCRE_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)slots * sizeof(double), st));
-    return mcre_tree_reduce(d_partial, (sh.n_paths + sh.chunk - 1) / sh.chunk, 4, d_acc + (slots - 4), stream);
+    return mcre_tree_reduce(d_partial, irc_cva_units(sh.n_paths), 4, d_acc + (slots - 4), stream);
   }
   rc = p->d.n_berm > 0 ? irc_dispatch_main_berm(p, r, sh, d_partial, d_spill, d_shift, st)
                        : irc_dispatch_main<false>(p, r, sh, d_partial, d_spill, d_shift, st);

@@ -23,7 +23,9 @@
 //  * max(y', 1e-12) and the validity tests are integer compares on the high words + one warp vote (an FP64 max is a
 //    DSETP and two selects); relu(x) = (x + |x|) / 2 is one DADD;
 //  * Box-Muller on the shortened elementary functions of fastmath.cuh (31 FP64 instructions per normal pair);
-//  * per-path CVA totals are summed per thread over the passes of a chunk and block-reduced ONCE per chunk;
+//  * the unit of work and of deterministic summation is one PASS (128 threads x PP paths = 512 paths): per-path CVA
+//    totals are block-reduced once per pass into partial[pass], passes are handed out by an atomic counter (a whole
+//    4096-path chunk per hand-out left 1.15 chunks per block on a strong-scaled 8-GPU pass: 58 % of the SMs busy);
 //  * the pilot launch is gone: block 0 simulates global path 0 first and publishes its value (the common shift c of
 //    sum(x - c), sum((x - c)^2)); the other blocks accumulate against the first path of their own chunk and convert
 //    to c when they store the chunk partial (exact algebra, fixed order, so results stay independent of timing and
@@ -93,27 +95,29 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(const __gri
   bool have_shift = false;
   double gshift = 0.0;
 
+  static_assert((PP & (PP - 1)) == 0, "a pass (128 x PP paths) must divide the 256-aligned chunk size");
+  const int unit = 128 * PP;                                   // paths per pass
+  const long long n_units = (sh.n_paths + unit - 1) / unit;
   while (true) {
-    long long chunk = 0;
+    long long u = 0;
     if (!pilot) {
       if (tid == 0) s_chunk = (long long)atomicAdd(P.sync, 1u);
       __syncthreads();
-      chunk = s_chunk;
+      u = s_chunk;
       __syncthreads();
-      if (chunk >= n_chunks) break;
+      if (u >= n_units) break;
     }
     double s1 = 0.0, s2 = 0.0, first = 0.0;
-    const int span = pilot ? 1 : sh.chunk;
-    for (int it = 0; it < span; it += 128 * PP) {
+    {
       // global id of path p of this thread: g0 + 128 p (the pilot pass simulates global path 0 in every lane);
       // lanes past the end of the shard simulate ids nobody owns and are masked out of the sums
-      const long long l0 = chunk * sh.chunk + it + tid;
+      const long long l0 = u * unit + tid;
       const long long g0 = pilot ? 0 : sh.path_begin + l0;
       const int stride = pilot ? 0 : 128;
       unsigned live = 0u;
       uint32_t plo[PP];
       MCRE_VP {
-        if (!pilot && l0 + p * 128 < sh.n_paths && it + p * 128 + tid < sh.chunk) live |= 1u << p;
+        if (!pilot && l0 + p * 128 < sh.n_paths) live |= 1u << p;
         plo[p] = (uint32_t)(g0 + p * stride);
       }
       const uint32_t phi = (uint32_t)((unsigned long long)g0 >> 32);
@@ -235,20 +239,18 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(const __gri
           __threadfence();
           atomicExch(P.sync + 1, 1u);
         }
-        break;
+        pilot = false;
+        continue;
       }
-      if (it == 0) {
-        if (tid == 0) s_first = cva[0] * P.lgd;
-        __syncthreads();
-        first = s_first;
-      }
+      if (tid == 0) s_first = cva[0] * P.lgd;
+      __syncthreads();
+      first = s_first;
       MCRE_VP {
         const double d = ((live >> p) & 1u) ? fma(cva[p], P.lgd, -first) : 0.0;
         s1 += d;
         s2 = fma(d, d, s2);
       }
     }
-    if (pilot) { pilot = false; continue; }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     if (lane == 0) { s_stage[0][warp] = s1; s_stage[1][warp] = s2; }
@@ -262,12 +264,12 @@ __global__ void __launch_bounds__(128, MCRE_CVA_MINB) irc_cva_kernel(const __gri
         gshift = *(volatile double *)(shift_tail + 2);
         have_shift = true;
       }
-      // sums against the chunk's first path -> sums against the common shift (global path 0):
+      // sums against the pass's first path -> sums against the common shift (global path 0):
       //   sum(x - c) = sum(x - f) + n (f - c),  sum((x - c)^2) = sum((x - f)^2) + (f - c) (2 sum(x - f) + n (f - c))
-      const long long left = sh.n_paths - chunk * sh.chunk;
-      const double n = (double)(left < sh.chunk ? left : sh.chunk);
+      const long long left = sh.n_paths - u * unit;
+      const double n = (double)(left < unit ? left : unit);
       const double dl = first - gshift;
-      double *out = partial + (size_t)chunk * 4;
+      double *out = partial + (size_t)u * 4;
       out[0] = 0.0; out[1] = 0.0;
       out[2] = fma(n, dl, t1);
       out[3] = fma(dl, fma(n, dl, 2.0 * t1), t2);
@@ -359,6 +361,8 @@ int irc_cva_apply_coefficients(mcre_irc_plan *p, cudaStream_t st) {
   return 0;
 }
 
+long long irc_cva_units(long long n_paths) { return (n_paths + 128 * MCRE_CVA_PP - 1) / (128 * MCRE_CVA_PP); }
+
 int irc_cva_launch(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
                    cudaStream_t st) {
   const CvaHost &h = p->cva;
@@ -380,7 +384,7 @@ int irc_cva_launch(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, doub
   }
   for (int k = 0; k < 9; ++k) d.st[k] = ustep ? first[k] : 0.0;
   d.st_flags = ustep ? (int)(f0 & ~(long long)CVA_EV_DATE) : 0;
-  const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+  const long long n_chunks = (sh.n_paths + 128 * MCRE_CVA_PP - 1) / (128 * MCRE_CVA_PP);   // passes
   auto k = ustep ? irc_cva_kernel<MCRE_CVA_PP, true, MCRE_CVA_PF != 0> : irc_cva_kernel<MCRE_CVA_PP, false, MCRE_CVA_PF != 0>;
   int per_sm = 1;
   MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, 0));

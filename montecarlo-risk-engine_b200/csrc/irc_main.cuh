@@ -589,6 +589,7 @@ static int irc_dispatch_main(mcre_irc_plan *p, const RngDev &r, const ShardDev &
 // defined in irc_cva.cu (the CVA-only kernel)
 void irc_cva_fill_static(mcre_irc_plan *p);
 int irc_cva_apply_coefficients(mcre_irc_plan *p, cudaStream_t st);
+long long irc_cva_units(long long n_paths);   // summation units (passes) of a shard
 int irc_cva_launch(mcre_irc_plan *p, const mcre::RngDev &rng, const mcre::ShardDev &sh, double *partial, double *shift,
                    cudaStream_t st);
 // defined in irc_berm.cu (books with Bermudan exercise units)
