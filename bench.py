@@ -32,6 +32,10 @@ METRIC = "path-steps/sec (paths×steps) for Vasicek+CIR++ CVA"
 UNIT = "path-steps/s"
 N_STEPS_SIM = 240
 FLOP_PER_PATH_STEP = 225.0  # SURVEY §8(d) algorithmic FP64 flop model for config 3
+# what irc_cva_kernel executes per path-step: 45 DFMA + 13 DMUL + 6 DADD (profiles/r02_cva_kernel.md)
+EXECUTED_FLOP_PER_PATH_STEP = 45 * 2 + 13 + 6
+NCU_FP64_PIPE_PCT = 52.9          # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active, final build
+NCU_DRAM_BYTES_PER_LAUNCH = 101.6  # dram__bytes_read.sum + dram__bytes_write.sum of one launch: the state lives in registers
 RHOS = np.linspace(-0.9, 0.9, 19)
 
 
@@ -347,13 +351,19 @@ def main():
     peak = C.c_double(0.0)
     B.check(L.mcre_dfma_peak(C.byref(peak), RT.stream_ptr()))
     achieved = per_gpu * FLOP_PER_PATH_STEP * 1e-12
+    executed = per_gpu * EXECUTED_FLOP_PER_PATH_STEP * 1e-12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the main kernel, from the ncu --set full
-                # capture summarised in profiles/r01_irc_main_v5_ncu_summary.md: the state lives in registers
-                "traffic": 253.44, "traffic_unit": "bytes per launch (ncu, 2^22 paths x 240 steps)",
-                "note": "algorithmic 225 FP64 flop/path-step (SURVEY 8d) x path-steps/s per GPU; peak = DFMA loop measured in this run; "
-                        "the path is FP64-pipe / issue bound, not HBM or tensor-core bound (SURVEY 8d)"}
+                # what the hardware counts (profiles/r02_cva_kernel.md, ncu --set full of this build, 2^22 paths x 240 steps):
+                "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT,
+                "executed_fp64_instr_per_path_step": 64, "executed_flop_per_path_step": EXECUTED_FLOP_PER_PATH_STEP,
+                "executed_tflops": executed, "executed_frac": executed / peak.value if peak.value > 0 else None,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu, 2^22 paths x 240 steps)",
+                "note": "frac: algorithmic 225 FP64 flop/path-step of SURVEY 8d (exp/log/sincos/sqrt/div weighted 20-30 flop) x path-steps/s / "
+                        "DFMA peak measured in this run.  The kernel EXECUTES 64 FP64 instructions = 109 flop per path-step "
+                        "(executed_frac, equal to ncu's sm__pipe_fp64_cycles_active within a point) next to 79 integer / other "
+                        "instructions, 37 of them the ten Philox rounds; an FP64 instruction holds the issue port ~2.2 cycles, so "
+                        "the path is issue bound at (2.2 x 64 + 79) slots per path-step, not HBM or tensor-core bound"}
 
     # ---- end to end through the public API (host objects in, numpy results out) ------------
     e2e_times, h2d, d2h = [], 0, 0

@@ -965,13 +965,15 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0) return 0;
   auto k = eq_main_kernel<KIND, ALT, NT, NS>;
+  // (14 KB of static function tables: static + dynamic shared memory beyond 48 KB needs the opt-in, before the query)
+  if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
   if (per_sm < 1) return fail(-3, "eq main kernel does not fit%s", "");
   long long grid = (long long)sm_count() * per_sm;
   if (grid > n_chunks) grid = n_chunks;
   ShardDev pilot_sh{0, 1, sh.chunk};
-  if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (!presim) {   // the pre-simulation pass only spills; it needs no pilot shifts
     k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, spill, 1);
     MCRE_LAUNCHED();

@@ -669,7 +669,7 @@ extern "C" int mcre_irc_presim(mcre_irc_plan *p, const mcre_rng *rng, const mcre
 #define LAUNCHB(NUV)                                                                                     \
   do {                                                                                                   \
     auto k = irc_presim_moments_kernel<NUV>;                                                             \
-    if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                      \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));                 \
     if (per_sm < 1) return fail(-3, "irc presim kernel does not fit: too many regression dates%s", "");  \

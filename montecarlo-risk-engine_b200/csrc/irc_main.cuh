@@ -174,8 +174,14 @@ __device__ __forceinline__ int hi32(double x) { return __double2hiint(x); }
 // Paths per thread / resident 128-thread blocks per SM of each build.  The FP64 pipe needs
 // in-warp ILP (fastmath.cuh, MCRE_VP): the value-only builds carry per-set cashflow / exposure-history
 // state for several paths per thread; tangent builds run one path.
-__host__ __device__ constexpr int irc_pp(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 4 : 2); }
-__host__ __device__ constexpr int irc_minb(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 2 : 4); }
+#ifndef MCRE_IRC_PP2
+#define MCRE_IRC_PP2 4     // paths per thread of the 2-set value-only build
+#endif
+#ifndef MCRE_IRC_MINB2
+#define MCRE_IRC_MINB2 2
+#endif
+__host__ __device__ constexpr int irc_pp(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 4 : (ns == 2 ? MCRE_IRC_PP2 : 2)); }
+__host__ __device__ constexpr int irc_minb(int nt, int ns) { return nt > 0 ? 1 : (ns == 1 ? 2 : (ns == 2 ? MCRE_IRC_MINB2 : 4)); }
 template <int NT, int NS, bool CIR, int SCHEME, int PP, bool BERM>
 __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev P, RngDev rng, ShardDev sh,
                                                                          double *partial, double *spill,
@@ -378,7 +384,10 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev 
             }
           }
           if ((acc_flags & (MCRE_ACC_POS | MCRE_ACC_NEG)) && !pilot)
-            block_accumulate<NVB>(vals, acc, m * NVB, stage, NVB, parity);
+            {
+              if constexpr (NT == 0 && NVB >= 4) block_accumulate_t128<NVB>(vals, acc, m * NVB, stage, parity);
+              else block_accumulate<NVB>(vals, acc, m * NVB, stage, NVB, parity);
+            }
         }
       };
 
@@ -479,7 +488,10 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev 
             }
           }
         }
-        if (!pilot) block_accumulate<NVB>(vals, acc, P.n_metric * NVB, stage, NVB, parity);
+        if (!pilot) {
+          if constexpr (NT == 0 && NVB >= 4) block_accumulate_t128<NVB>(vals, acc, P.n_metric * NVB, stage, parity);
+          else block_accumulate<NVB>(vals, acc, P.n_metric * NVB, stage, NVB, parity);
+        }
       }
       if (pilot) return;   // the pilot launch simulates global path 0 only: one pass is enough
     }
@@ -535,14 +547,16 @@ static int launch_main(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh, 
 
   const int threads = 128, nw = threads / 32;
   const int nvb = NS * (4 + 2 * NT);
-  const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * nw * nvb) * sizeof(double);
+  // accumulators + reduction stage: [2][nw][nvb] (shuffle trees) or [2][nvb][128] (transposed reduction, value-only)
+  const size_t smem = ((size_t)(d.n_metric + 1) * nvb + 2 * (NT == 0 ? 128 : nw) * nvb) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   // The pilot launch (global path 0 -> the common shift of the shifted sums) runs on every rank, also on one whose
   // shard is empty: all ranks must finish their all-reduced sums with the same shift.
 #define LAUNCH(CIRV, SCH)                                                                              \
   do {                                                                                                 \
     auto k = irc_main_kernel<NT, NS, CIRV, SCH, irc_pp(NT, NS), BERM>;                                 \
-    if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    /* (static shared memory: 14 KB of function tables; static + dynamic beyond 48 KB needs the opt-in) */ \
+    if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                    \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));               \
     if (per_sm < 1) return fail(-3, "irc main kernel does not fit: too many metric dates x tangents%s", ""); \

@@ -371,7 +371,7 @@ int irc_presim_tangent_pass(mcre_irc_plan *p, const RngDev &r, const ShardDev &s
   const size_t smem = ((size_t)d.n_reg * TM_NV + 2 * nw * TM_NV) * sizeof(double);
   const long long n_chunks = (n + sh.chunk - 1) / sh.chunk;
   auto k = irc_presim_tangent_moments_kernel;
-  if (smem > 48 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem));
   if (per_sm < 1) return fail(-3, "irc tangent presim kernel does not fit: too many regression dates%s", "");

@@ -37,4 +37,32 @@ __device__ __forceinline__ void block_accumulate(const double (&vals)[NV], doubl
   parity ^= 1;
 }
 
+// Transposed variant for 128-thread blocks and few values per call (the value-only interest-rate kernel: 4 - 16 sums
+// per metric date): every thread stores its NV values to shared memory, then G = 128 / NV' threads per value
+// (NV' = NV rounded up to a power of two) each add 128 / G staged entries in a fixed order and finish with log2(G)
+// shuffles - 2 NV + 128 / G + log2 G instructions per thread instead of the 10 NV of NV shuffle trees, and the same
+// single barrier per call.  stage: [2][NV][128].  Summation order fixed => reproducible bit for bit.
+template <int NV>
+__device__ __forceinline__ void block_accumulate_t128(const double (&vals)[NV], double *acc, int slot, double *stage,
+                                                      int &parity) {
+  constexpr int NVP = NV <= 4 ? 4 : NV <= 8 ? 8 : NV <= 16 ? 16 : 32;
+  constexpr int G = 128 / NVP;          // threads per value: 32, 16, 8 or 4 (a group never spans warps)
+  constexpr int PER = 128 / G;          // staged entries per thread
+  static_assert(NV >= 4 && NV <= 32, "block_accumulate_t128: 4..32 values per call");
+  const int tid = threadIdx.x;
+  double *st = stage + (size_t)parity * NV * 128;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) st[i * 128 + tid] = vals[i];
+  __syncthreads();
+  const int v = tid / G, g = tid % G;
+  const int vr = v < NV ? v : NV - 1;   // (idle groups of a non-power-of-two NV redo the last value: all lanes shuffle)
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) s += st[vr * 128 + g + j * G];
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, G);
+  if (g == 0 && v < NV) acc[slot + v] += s;
+  parity ^= 1;
+}
+
 }  // namespace mcre
