@@ -7,7 +7,9 @@
 // Only block-reduced sums ever reach HBM.  See include/mcre.h for what each entry point
 // replaces in the reference.
 #include <algorithm>
+#include <cstdlib>
 #include "irc_main.cuh"
+#include "irc_value.cuh"
 
 namespace mcre {
 
@@ -413,6 +415,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
     }
     UP(step_rec, srec.data(), srec.size());
     UP(date_rec, p->h_date_rec.data(), p->h_date_rec.size());
+    for (int k = 0; k < c->n_sets; ++k) p->any_collateral = p->any_collateral || (c->set_flags[k] & 1);
     // "CVA only" kernel (irc_cva.cu): one set, CVA the only accumulator, no threshold / collateral, stochastic
     // intensity started above zero; everything else runs the general kernel
     p->cva_only = c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA && n_berm == 0 &&
@@ -615,6 +618,17 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
     if (rc) return rc;
     MCRE_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)slots * sizeof(double), st));
     return mcre_tree_reduce(d_partial, irc_cva_units(sh.n_paths), 4, d_acc + (slots - 4), stream);
+  }
+  // value-only plans without exercise units: the lean kernel of irc_value.cuh (MCRE_IRC_GENERIC=1: the general template)
+  static const bool force_generic = getenv("MCRE_IRC_GENERIC") && getenv("MCRE_IRC_GENERIC")[0] == '1';
+  if (p->d.nt == 0 && p->d.n_berm == 0 && !p->d.path_list && !force_generic) {
+    const int ns = ns_template(p->d.n_sets);
+    rc = ns == 1 ? launch_value<1>(p, r, sh, d_partial, d_spill, d_shift, st)
+       : ns == 2 ? launch_value<2>(p, r, sh, d_partial, d_spill, d_shift, st)
+                 : launch_value<4>(p, r, sh, d_partial, d_spill, d_shift, st);
+    if (rc) return rc;
+    const long long n_chunks_v = (sh.n_paths + sh.chunk - 1) / sh.chunk;
+    return mcre_tree_reduce(d_partial, n_chunks_v, mcre_irc_main_slots(p), d_acc, stream);
   }
   rc = p->d.n_berm > 0 ? irc_dispatch_main_berm(p, r, sh, d_partial, d_spill, d_shift, st)
                        : irc_dispatch_main<false>(p, r, sh, d_partial, d_spill, d_shift, st);

@@ -533,6 +533,7 @@ struct mcre_irc_plan {
   int date_stride = 0;
   size_t expo_coef_count = 0;
   bool cva_only = false;
+  bool any_collateral = false;   // some netting set of the plan is MPoR-collateralised
   DevArray<int> berm_set, date_ex_off, ex_unit, ex_last, ex_term_off;
   DevArray<double> berm_strike, berm_sign, ex_const, term_coef, term_w, ex_basis, ex_coef, berm_expo_coef;
   size_t ex_coef_count = 0, berm_expo_count = 0;

@@ -4,7 +4,7 @@
 wall time of the call, path-steps/s and a few result values.  Not the headline bench
 (bench.py is); used to size and sanity-check the other configs.
 
-    python tools/run_configs.py [1 2 2o 4 5] [--scale-log2 -2]   # --scale shrinks the path counts
+    python tools/run_configs.py [1 2 2o 3 3g 4 5 5g] [--scale-log2 -2]   # --scale shrinks the path counts
 """
 import argparse
 import importlib
@@ -46,6 +46,14 @@ def main():
             model, sets, metrics, tl = cases.vasicek_irs_collateral(ns, mpor=mpor, n_dates=121, maturity=30.0)
             return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(22), n_pre=n(22), steps=1, scheme=S.EULER,
                         diff=False, sub=120 if name == "2" else 240, show=[("irs_collateralized", "eepe"), ("irs_uncollateralized", "eepe")])
+        if name in ("3", "3g"):
+            # config 3 through the public API: value-only at full size; with all 8 first-order sensitivities of the CVA
+            # (through the regression: tangent pre-simulation + differentiated normal equations) at 2^22 paths
+            import bench
+            model, sets, metrics, tl = bench.build_case(ns, 0.3)
+            g = name == "3g"
+            return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(22 if g else 24), n_pre=n(18 if g else 20), steps=1,
+                        scheme=S.EULER, diff=g, sub=240, show=[("irs", "cva[GM]")])
         if name == "4":
             model, sets, metrics, tl = cases.bermudan_swaption(ns, n_ex=40)
             return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(22), n_pre=n(22), steps=1, scheme=S.EULER,
@@ -65,7 +73,7 @@ def main():
     #  2o: as 2 but only every second sub-step is a metric date                     ~ 64 + 7 + 60
     #  4: 64 + 7 + exercise date: ~22 zero bonds x (exp 20 + 2) + payoff / decision 10 + exposure 30 + numeraire 20 = 615
     #  5: 5 assets x (2 normals 64 + uniform 4 + ~90 algebraic + 2 exp + 1 log + 4 sqrt + 4 div = 60 + 64) ~ 5 x 282 + basket 20
-    flop_model = {"1": 184.0, "2": 181.0, "2o": 131.0, "4": 615.0, "5": 1430.0, "5g": 1430.0}
+    flop_model = {"1": 184.0, "2": 181.0, "2o": 131.0, "3": 225.0, "3g": 225.0, "4": 615.0, "5": 1430.0, "5g": 1430.0}
     import ctypes as C
     peak = C.c_double(0.0)
     from mcre import runtime as RT
