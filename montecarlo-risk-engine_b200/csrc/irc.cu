@@ -257,13 +257,15 @@ __global__ void __launch_bounds__(128, 4) irc_lsm_forward_kernel(IrcDev P, RngDe
 // The loads of date k-1 are issued before the block reduction of date k (software pipeline): the first
 // version waited for memory and for the barrier in turn with 8 warps per SM (175 registers, one block per SM,
 // 1.1 TB/s; profiles/r01_other_kernels_ncu_summary.md).
-constexpr int MOM_IT = 8;
+// (paths per thread: 8 with one regression unit; fewer with more units, whose per-path window sums and tails would
+// otherwise spill - the two-unit build ran at 2.1 TB/s with 120 bytes of spills, profiles/r02_other_kernels.md)
 template <int NU>
 __global__ void __launch_bounds__(256, 2) irc_presim_moments_kernel(IrcDev P, ShardDev sh, const double *__restrict__ xbuf,
                                                                     const double *__restrict__ nbuf,
                                                                     const float *__restrict__ wbuf,
                                                                     double *__restrict__ partial) {
   constexpr int NV = 5 + 3 * NU;
+  constexpr int MOM_IT = NU == 1 ? 8 : (NU == 2 ? 4 : 2);
   extern __shared__ double smem[];
   const int nw = blockDim.x >> 5;
   const int n_slots = P.n_reg * NV;

@@ -330,7 +330,7 @@ class EquityBackend:
             events = [(date_idx[t_pay], EV_PAY)]
             t_num = t_pay
         elif isinstance(p, (AsianOption, BarrierOption)):
-            obs = [float(t) for t in p.modeling_timeline]
+            obs = p.modeling_timeline.tolist()        # (iterating a tensor element by element costs microseconds each)
             if basket is not None:
                 for aid, wi in zip(*basket):
                     w[self._asset_index(aid)] += float(wi)
@@ -363,7 +363,7 @@ class EquityBackend:
             if p.num_exercise_rights > EQ_MAX_RIGHTS:
                 raise NotImplementedError(f"at most {EQ_MAX_RIGHTS} exercise rights per product")
             w[self._asset_index(p.underlying.get_asset_id())] = 1.0
-            ex = [float(t) for t in p.product_timeline]
+            ex = p.product_timeline.tolist()
             events = [(date_idx[t], EV_EXERCISE | (EV_FIRST if i == 0 else 0)) for i, t in enumerate(ex)]
             t_num = ex[0]
         else:

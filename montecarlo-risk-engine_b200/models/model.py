@@ -54,7 +54,11 @@ class Model:
         return [D.var(v, offset + i, n_total) for i, v in enumerate(vals)]
 
     def t0(self):
-        return float(self.calibration_date[0])
+        # (cached: plan compilers call this per product record - tensor -> float costs microseconds)
+        v = self.__dict__.get("_t0_cache")
+        if v is None:
+            v = self.__dict__["_t0_cache"] = float(self.calibration_date[0])
+        return v
 
     # -- correlation description (reference: model.py:75-81) ------------------
     def intra_correlation(self, scheme, p):
