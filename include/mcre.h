@@ -548,6 +548,68 @@ int mcre_select_scan(mcre_select_plan *p, int32_t pass, const uint64_t *d_hist, 
 int mcre_select_finish(mcre_select_plan *p, double *d_out, void *stream);
 
 /* ================================================================================
+ * Gas storage on a two-factor log-price model
+ * replaces Storage.compute_normalized_cashflows (src/products/storage.py:215-308: inventory moves of the three
+ * actions, interpolated continuation grid, arg-max, realised cashflow) and the controller loops that drive it:
+ * the backward induction of _perform_regression_for_product (src/controller/controller.py:294-383) and the PV branch
+ * of _evaluate_product (:399-410), for SchwartzTwoFactorModel (src/models/schwartz_two_factor.py:147-196).
+ * ============================================================================== */
+#define MCRE_STORAGE_MAX_KNOTS 8   /* knots per injection / withdrawal rate curve                      */
+#define MCRE_STORAGE_RECORD 48     /* doubles per action-date record                                    */
+#define MCRE_STORAGE_MAX_STATES 16 /* inventory grid states                                             */
+#define MCRE_STORAGE_STEP 10       /* doubles per sub-step record                                       */
+#define MCRE_STORAGE_MAX_BASIS 6   /* regression basis functions (polynomial degree + 1)                */
+
+typedef struct {
+  int32_t n_sub;            /* sub-steps of the simulation grid (engine.py:36-123)                         */
+  int32_t n_dates;          /* action dates of the storage                                                 */
+  int32_t n_pre_dates;      /* leading action dates reached without stepping (at the calibration date)     */
+  int32_t n_states;         /* inventory grid states                                                       */
+  int32_t n_basis;          /* regression basis functions                                                  */
+  double log_spot0;         /* log of the forward curve at the calibration date                            */
+  const double *step;       /* [n_sub][MCRE_STORAGE_STEP] a, k, dt, m, cx, b00, cy, b10, b11, log F(t2):
+                               x' = (a x - (k x) dt) + cx (b00 z0);  y' = (y + m) + cy (b10 z0 + b11 z1);
+                               log S = log F(t2) + x' + y'
+                               ANALYTICAL: a = exp(-kappa dt), k = 0, cx = cy = 1, b = Cholesky factor of the step
+                               covariance (schwartz_two_factor.py:124-168); EULER: a = 1, k = kappa, cx / cy = vol
+                               sqrt(dt), b = Cholesky factor of the correlation (:170-196)                    */
+  const int32_t *step_date; /* [n_sub] action-date index completed by the sub-step, or -1                  */
+  const double *date_rec;   /* [n_dates][MCRE_STORAGE_RECORD] per action date:
+                               0 vmin of the date's band, 1 inventory per state index, 2 / 3 vmin / vmax of the next
+                               date's band, 4 state index per unit inventory on the next date (0: degenerate band),
+                               5 period to the next action date, 6 / 7 injection / withdrawal cost, 8 / 9 number of
+                               injection / withdrawal knots, 10 non-zero on the last action date (no continuation),
+                               16.. injection knots (level, rate) x 8, then withdrawal knots x 8
+                               (storage_helpers.py:56-127, storage.py:114-190)                              */
+  const double *numeraire;  /* [n_dates] numeraire at the action dates                                     */
+} mcre_storage_desc;
+
+typedef struct mcre_storage_plan mcre_storage_plan;
+int mcre_storage_create(const mcre_storage_desc *desc, mcre_storage_plan **out);
+void mcre_storage_destroy(mcre_storage_plan *plan);
+/* Pre-simulation forward pass: d_spot [n_dates][shard->n_paths] = spot at every action date. */
+int mcre_storage_spots(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_spot, void *stream);
+/* One date of the backward induction (controller.py:322-352) for all n paths and all grid states:
+ * d_value [n_states][n] holds the normalised value from the next action date on, per state entering it, and is
+ * replaced by the same quantity for `date`: float32(best action's cashflow / numeraire) + the float64 tail interpolated
+ * at the state the action leads to.  d_coef [2 + n_states * n_basis] (device) = centre, inverse scale and per-state
+ * coefficients of the continuation polynomial in u = (spot - centre) * inverse scale at `date` (raw basis of the
+ * reference: centre 0, scale 1); ignored on the last action date.  d_spot_row [n] = spot at `date`. */
+int mcre_storage_backward(mcre_storage_plan *plan, int32_t date, const double *d_coef, const double *d_spot_row,
+                          double *d_value, int64_t n, void *stream);
+/* Regression moments of `date` (the Gram / right-hand-side sums of controller.py:361-374 for y_s = numeraire x
+ * d_value[s]): d_out [n_states * n_basis + 2 n_basis - 1] = sum u^k y_s (s major), then sum u^q, q < 2 n_basis - 1;
+ * fixed-order chunk partials d_partial [ceil(n / chunk_paths)][slots] + tree. */
+int64_t mcre_storage_moment_slots(const mcre_storage_plan *plan);
+int mcre_storage_moments(mcre_storage_plan *plan, int32_t date, double centre, double inv_scale, const double *d_spot_row,
+                         const double *d_value, int64_t n, int32_t chunk_paths, double *d_partial, double *d_out,
+                         void *stream);
+/* Valuation pass, fused (path stepping + decisions + cashflows): ADDS each local path's discounted cashflows to d_cfs
+ * [shard->n_paths]; d_coef [n_dates][2 + n_states * n_basis] (device); d_final_state [n_paths] or NULL. */
+int mcre_storage_mainsim(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, const double *d_coef,
+                         double initial_state, double *d_cfs, double *d_final_state, void *stream);
+
+/* ================================================================================
  * Utilities
  * ============================================================================== */
 /* Fixed-order binary-tree sum over chunks: d_partial [n_chunks][n_slots] -> d_out [n_slots]. */

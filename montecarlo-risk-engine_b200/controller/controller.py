@@ -114,6 +114,9 @@ class SimulationController:
         self.rng_compat = os.environ.get("MCRE_RNG", "philox").lower()
         #: pre-simulation scratch is bounded by processing this many local paths at a time
         self.presim_batch_paths = 1 << 22
+        #: least-squares solver of gas-storage regressions: "auto", "lapack" (the reference's own routine on the host,
+        #: reproduces its rank decisions) or "moments" (device moments + small normal equations); mcre/storage.py
+        self.storage_regression = "auto"
         self.last_timings = {}
 
     # ------------------------------------------------------------------ timelines
@@ -184,6 +187,9 @@ class SimulationController:
 
     # ------------------------------------------------------------------ run
     def _select_backend(self):
+        from mcre.storage import StorageBackend
+        if StorageBackend.supports(self):
+            return StorageBackend(self)
         from mcre.irc import IrcBackend
         if IrcBackend.supports(self):
             return IrcBackend(self)
@@ -225,7 +231,9 @@ class SimulationController:
     def run_simulation(self) -> SimulationResults:
         t0 = time.perf_counter()
         mc_products = [p for p in self.products if not self._can_skip_monte_carlo_for_product(p)]
-        if any(self._product_requires_regression(p) for p in mc_products):
+        from products.storage import Storage
+        if any(self._product_requires_regression(p) and not isinstance(p, Storage) for p in mc_products):
+            # (gas storages regress on any polynomial degree: mcre/storage.py)
             # the pre-simulation kernels accumulate the moments of the quadratic basis [1, x, x^2] (8 sums, 3x3 normal
             # equations) and the main kernels evaluate 3 coefficients: any other basis must not be evaluated as this one
             from maths.regression import PolyomialRegression

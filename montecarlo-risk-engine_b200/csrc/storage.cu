@@ -1,0 +1,414 @@
+// Gas storage on a two-factor log-price model: the reference's Storage.compute_normalized_cashflows
+// (src/products/storage.py:215-308) and the controller loops around it (src/controller/controller.py:294-383 for the
+// backward induction, :399-410 for the valuation pass) as four kernels:
+//
+//   storage_spots_kernel     pre-simulation forward pass: the spot of every action date, [date][path]
+//   storage_backward_kernel  one date of the backward induction for all paths x all grid states in one launch:
+//                            continuation grid (polynomial in the spot per state), the three actions, arg-max,
+//                            float32 cashflow accumulator + interpolated float64 tail (controller.py:331-352)
+//   storage_moments_kernel   Gram / right-hand-side moments of the regression of one date (large path counts)
+//   storage_main_kernel      valuation pass, fused: path stepping + decision + realised cashflows per path; no
+//                            path or state tensor is materialised
+//
+// The inventory arithmetic (volume <-> state, rate-curve interpolation, clamps) uses explicit unfused
+// multiplies and adds: it is pure +,-,*,/ on contract data and reproduces the reference's doubles bit for bit,
+// so a path sits in exactly the reference's state unless a decision differs.
+#include "common.cuh"
+#include "launch.cuh"
+#include "philox.cuh"
+
+namespace mcre {
+
+constexpr int ST_REC = MCRE_STORAGE_RECORD;
+constexpr int ST_KNOTS = MCRE_STORAGE_MAX_KNOTS;
+constexpr int ST_MAX_S = MCRE_STORAGE_MAX_STATES;
+constexpr int ST_MAX_B = MCRE_STORAGE_MAX_BASIS;
+constexpr int ST_THREADS = 128;
+
+struct StorageDev {
+  int n_sub, n_dates, n_pre_dates, n_states, n_basis;
+  double log_spot0;
+  const double *step;       // [n_sub][ST_STEP]: a, k, dt, m, cx, b00, cy, b10, b11, log curve(t2)
+  const int *step_date;     // [n_sub]
+  const double *rec;        // [n_dates][ST_REC]
+  const double *numeraire;  // [n_dates]
+};
+
+}  // namespace mcre
+
+struct mcre_storage_plan {
+  mcre::StorageDev d;
+  mcre::DevArena arena;
+  mcre::DevArray<double> step, rec, numeraire;
+  mcre::DevArray<int> step_date;
+};
+
+namespace mcre {
+
+// storage_helpers.py:96-127: torch.bucketize(point, xp) counts the knots strictly below the point; the segment is
+// clamped to the curve, the weight is zero on a degenerate segment (torch.isclose: rtol 1e-5, atol 1e-8), and the
+// end rates apply at and beyond the end knots.
+__device__ __forceinline__ double curve_rate_dev(double point, const double *__restrict__ kn, int n) {
+  if (n == 1) return __ldg(kn + 1);
+  int below = 0;
+  for (int j = 0; j < n; ++j) below += (__ldg(kn + 2 * j) < point) ? 1 : 0;
+  int left = below - 1;
+  left = left < 0 ? 0 : (left > n - 2 ? n - 2 : left);
+  const double x0 = __ldg(kn + 2 * left), y0 = __ldg(kn + 2 * left + 1);
+  const double x1 = __ldg(kn + 2 * left + 2), y1 = __ldg(kn + 2 * left + 3);
+  const bool close = fabs(x0 - x1) <= 1e-8 + 1e-5 * fabs(x1);
+  const double w = close ? 0.0 : __ddiv_rn(__dsub_rn(point, x0), __dsub_rn(x1, x0));
+  double out = __dadd_rn(y0, __dmul_rn(w, __dsub_rn(y1, y0)));
+  if (point <= __ldg(kn)) out = __ldg(kn + 1);
+  if (point >= __ldg(kn + 2 * (n - 1))) out = __ldg(kn + 2 * (n - 1) + 1);
+  return out;
+}
+
+struct Moves {
+  double ns[3], dv[3];   // next state, volume difference of inject / hold / withdraw
+};
+
+// _transition_volume + _state_from_volume (storage.py:114-190) for the three actions from one state
+__device__ __forceinline__ Moves transitions(const double *__restrict__ r, double state) {
+  const double vmin = __ldg(r + 0), step = __ldg(r + 1), nmin = __ldg(r + 2), nmax = __ldg(r + 3);
+  const double scale = __ldg(r + 4), period = __ldg(r + 5);
+  const int n_inj = (int)__ldg(r + 8), n_wd = (int)__ldg(r + 9);
+  const double vol = __dadd_rn(vmin, __dmul_rn(state, step));
+  const double up = __dadd_rn(vol, __dmul_rn(curve_rate_dev(vol, r + 16, n_inj), period));
+  const double dn = __dsub_rn(vol, __dmul_rn(curve_rate_dev(vol, r + 16 + 2 * ST_KNOTS, n_wd), period));
+  double nv[3];
+  nv[0] = fmin(up, nmax);
+  nv[1] = fmin(fmax(vol, nmin), nmax);
+  nv[2] = fmax(dn, nmin);
+  Moves m;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    m.ns[a] = scale == 0.0 ? 0.0 : __dmul_rn(__dsub_rn(nv[a], nmin), scale);
+    m.dv[a] = __dsub_rn(nv[a], vol);
+  }
+  return m;
+}
+
+// payoffs of the three actions (storage.py:246-253)
+__device__ __forceinline__ void payoffs(const double *__restrict__ r, const Moves &m, double spot, double (&pay)[3]) {
+  const double ci = __ldg(r + 6), cw = __ldg(r + 7);
+  pay[0] = -m.dv[0] * (spot + ci);
+  pay[1] = -m.dv[1] * (m.dv[1] >= 0.0 ? spot + ci : spot - cw);
+  pay[2] = -m.dv[2] * (spot - cw);
+}
+
+// lookup_state_values (storage.py:200-213): weights of the two neighbouring grid states
+__device__ __forceinline__ void neighbours(double state, int S, int &lo, int &hi, double &w) {
+  const double b = fmin(fmax(state, 0.0), (double)(S - 1));
+  const double f = floor(b);
+  lo = (int)f; hi = (int)ceil(b);
+  w = b - f;
+}
+
+// polynomial of the standardised spot u = (x - centre) * inv_scale; raw basis: centre 0, scale 1
+__device__ __forceinline__ double poly(const double *__restrict__ c, int nb, double u) {
+  double acc = __ldg(c), p = u;
+  for (int k = 1; k < nb; ++k) { acc = fma(__ldg(c + k), p, acc); p *= u; }
+  return acc;
+}
+
+// first maximum of (inject, hold, withdraw) like torch.argmax (storage.py:286)
+__device__ __forceinline__ int best_of(const double (&v)[3]) {
+  int a = 0;
+  if (v[1] > v[a]) a = 1;
+  if (v[2] > v[a]) a = 2;
+  return a;
+}
+
+// One path of the two-factor model (schwartz_two_factor.py:147-196), both schemes in one form with the reference's
+// association of operations (unfused):
+//   x' = (a x - (k x) dt) + cx (b00 z0)         ANALYTICAL: a = exp(-kappa dt), k = 0, cx = 1, b = chol(step covariance)
+//   y' = (y + m) + cy (b10 z0 + b11 z1)         EULER:      a = 1, k = kappa, cx = sigma_s sqrt(dt), cy = sigma_l sqrt(dt),
+//   log S = log F(t2) + x' + y'                             b = chol(correlation)
+constexpr int ST_STEP = MCRE_STORAGE_STEP;
+struct TwoFactor {
+  double x = 0.0, y = 0.0;
+  __device__ __forceinline__ double advance(const double *__restrict__ st, double z0, double z1) {
+    const double w0 = __dmul_rn(__ldg(st + 5), z0);
+    const double w1 = __dadd_rn(__dmul_rn(__ldg(st + 7), z0), __dmul_rn(__ldg(st + 8), z1));
+    const double drift = __dsub_rn(__dmul_rn(__ldg(st + 0), x), __dmul_rn(__dmul_rn(__ldg(st + 1), x), __ldg(st + 2)));
+    x = __dadd_rn(drift, __dmul_rn(__ldg(st + 4), w0));
+    y = __dadd_rn(__dadd_rn(y, __ldg(st + 3)), __dmul_rn(__ldg(st + 6), w1));
+    return __dadd_rn(__dadd_rn(__ldg(st + 9), x), y);
+  }
+};
+
+__device__ __forceinline__ void draw2(const RngDev &rng, NormalStream &ns, int is, long long gpath, double &z0, double &z1) {
+  if (rng.mode == MCRE_RNG_INJECT) {
+    const double *zp = rng.z + ((size_t)is * rng.n_total + gpath) * 2;
+    z0 = zp[0]; z1 = zp[1];
+  } else {
+    ns.next2(z0, z1);
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P, RngDev rng, long long path_begin,
+                                                                   long long n_paths, double *__restrict__ spot) {
+  const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= n_paths) return;
+  const long long gp = path_begin + lp;
+  NormalStream ns; ns.init(rng, (unsigned long long)gp);
+  TwoFactor f;
+  const double s0 = exp(P.log_spot0);
+  for (int d = 0; d < P.n_pre_dates; ++d) spot[(size_t)d * n_paths + lp] = s0;
+  for (int is = 0; is < P.n_sub; ++is) {
+    double z0, z1;
+    draw2(rng, ns, is, gp, z0, z1);
+    const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
+    const int d = __ldg(P.step_date + is);
+    if (d >= 0) spot[(size_t)d * n_paths + lp] = exp(ls);
+  }
+}
+
+// One date of the backward induction.  value [S][n]: on entry the normalised value from the NEXT action date on per
+// state entering it, on exit the same for THIS date (in place: a thread owns its path's column).
+// coef: [2 + S * NB] = centre, inverse scale, coefficients per state of this date's continuation; unused on the last date.
+__global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev P, int date, const double *__restrict__ coef,
+                                                                      const double *__restrict__ x, double *__restrict__ value,
+                                                                      long long n) {
+  __shared__ double s_ns[3 * ST_MAX_S], s_dv[3 * ST_MAX_S];
+  __shared__ double s_val[ST_MAX_S * ST_THREADS], s_grid[ST_MAX_S * ST_THREADS];
+  const int S = P.n_states, NB = P.n_basis, tid = threadIdx.x;
+  const double *r = P.rec + (size_t)date * ST_REC;
+  const bool last = __ldg(r + 10) != 0.0;
+  if (tid < S) {     // on-grid states: the moves do not depend on the path
+    const Moves m = transitions(r, (double)tid);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { s_ns[a * ST_MAX_S + tid] = m.ns[a]; s_dv[a * ST_MAX_S + tid] = m.dv[a]; }
+  }
+  const long long p = (long long)blockIdx.x * blockDim.x + tid;
+  const bool live = p < n;
+  double spot = 0.0;
+  if (live) {
+    spot = x[p];
+    const double u = last ? 0.0 : (spot - __ldg(coef)) * __ldg(coef + 1);
+    for (int s = 0; s < S; ++s) {
+      s_val[s * ST_THREADS + tid] = value[(size_t)s * n + p];
+      s_grid[s * ST_THREADS + tid] = last ? 0.0 : poly(coef + 2 + s * NB, NB, u);
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const double num = __ldg(P.numeraire + date);
+  for (int s = 0; s < S; ++s) {
+    Moves m;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { m.ns[a] = s_ns[a * ST_MAX_S + s]; m.dv[a] = s_dv[a * ST_MAX_S + s]; }
+    double pay[3], v[3];
+    payoffs(r, m, spot, pay);
+    int lo[3], hi[3];
+    double w[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      neighbours(m.ns[a], S, lo[a], hi[a], w[a]);
+      const double gl = s_grid[lo[a] * ST_THREADS + tid], gh = s_grid[hi[a] * ST_THREADS + tid];
+      v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(w[a], __dsub_rn(gh, gl)));
+    }
+    const int a = best_of(v);
+    const int l = a == 0 ? lo[0] : a == 1 ? lo[1] : lo[2], h = a == 0 ? hi[0] : a == 1 ? hi[1] : hi[2];
+    const double ww = a == 0 ? w[0] : a == 1 ? w[1] : w[2], pa = a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2];
+    const double tl = s_val[l * ST_THREADS + tid], th = s_val[h * ST_THREADS + tid];
+    const double tail = __dadd_rn(tl, __dmul_rn(ww, __dsub_rn(th, tl)));
+    const double step = (double)(float)__ddiv_rn(pa, num);     // float32 accumulator of the window (controller.py:331, 342)
+    value[(size_t)s * n + p] = step + tail;
+  }
+}
+
+// Moments of the regression of `date`: y_s = numeraire(date) * value[s], basis u^k, u = (x - centre) * inv_scale.
+// blockIdx.y < S: sum u^k y_s, k < NB -> slots [s * NB + k]; blockIdx.y == S: sum u^q, q < 2 NB - 1 -> slots [S * NB + q].
+// One block per (chunk of paths, row); fixed summation order inside the block, chunks combined by mcre_tree_reduce.
+__global__ void __launch_bounds__(256) storage_moments_kernel(StorageDev P, int date, double centre, double inv_scale,
+                                                              const double *__restrict__ x, const double *__restrict__ value,
+                                                              long long n, int chunk, double *__restrict__ partial) {
+  __shared__ double stage[8][2 * ST_MAX_B];
+  const int S = P.n_states, NB = P.n_basis, row = blockIdx.y;
+  const int nv = row < S ? NB : 2 * NB - 1;
+  const double num = __ldg(P.numeraire + date);
+  double acc[2 * ST_MAX_B];
+#pragma unroll
+  for (int k = 0; k < 2 * ST_MAX_B; ++k) acc[k] = 0.0;
+  const long long base = (long long)blockIdx.x * chunk;
+  for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
+    const long long p = base + it;
+    if (p >= n) break;
+    const double u = (x[p] - centre) * inv_scale;
+    double w = row < S ? num * value[(size_t)row * n + p] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 2 * ST_MAX_B; ++k)
+      if (k < nv) { acc[k] += w; w *= u; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 2 * ST_MAX_B; ++k) {
+    double v = acc[k];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) stage[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nv) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += stage[w][threadIdx.x];
+    const int n_slots = S * NB + 2 * NB - 1;
+    partial[(size_t)blockIdx.x * n_slots + (row < S ? row * NB : S * NB) + threadIdx.x] = s;
+  }
+}
+
+// Valuation pass (controller.py:399-410 with storage.py:215-308 inlined): one thread per path carries the two factors,
+// the inventory state and the running sum of discounted cashflows.  coef: [n_dates][2 + S * NB].
+__global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, RngDev rng, long long path_begin,
+                                                                  long long n_paths, const double *__restrict__ coef,
+                                                                  double initial_state, double *__restrict__ cfs,
+                                                                  double *__restrict__ final_state) {
+  const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lp >= n_paths) return;
+  const long long gp = path_begin + lp;
+  NormalStream ns; ns.init(rng, (unsigned long long)gp);
+  TwoFactor f;
+  const int S = P.n_states, NB = P.n_basis, row = 2 + S * NB;
+  double state = initial_state, total = 0.0;
+
+  auto act = [&](int d, double spot) {
+    const double *r = P.rec + (size_t)d * ST_REC;
+    const Moves m = transitions(r, state);
+    double pay[3], v[3];
+    payoffs(r, m, spot, pay);
+    if (__ldg(r + 10) != 0.0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) v[a] = pay[a];
+    } else {
+      const double *c = coef + (size_t)d * row;
+      const double u = (spot - __ldg(c)) * __ldg(c + 1);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        int lo, hi;
+        double w;
+        neighbours(m.ns[a], S, lo, hi, w);
+        const double gl = poly(c + 2 + lo * NB, NB, u);
+        const double gh = hi == lo ? gl : poly(c + 2 + hi * NB, NB, u);
+        v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(w, __dsub_rn(gh, gl)));
+      }
+    }
+    const int a = best_of(v);
+    state = a == 0 ? m.ns[0] : a == 1 ? m.ns[1] : m.ns[2];
+    total += __ddiv_rn(a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2], __ldg(P.numeraire + d));
+  };
+
+  const double s0 = exp(P.log_spot0);
+  for (int d = 0; d < P.n_pre_dates; ++d) act(d, s0);
+  for (int is = 0; is < P.n_sub; ++is) {
+    double z0, z1;
+    draw2(rng, ns, is, gp, z0, z1);
+    const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
+    const int d = __ldg(P.step_date + is);
+    if (d >= 0) act(d, exp(ls));
+  }
+  cfs[lp] += total;
+  if (final_state) final_state[lp] = state;
+}
+
+}  // namespace mcre
+
+using namespace mcre;
+
+extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan **out) {
+  if (!c || !out) return fail(-1, "null argument%s", "");
+  if (c->n_states < 2 || c->n_states > ST_MAX_S) return fail(-2, "storage: 2..%s%lld inventory states", "", ST_MAX_S);
+  if (c->n_basis < 1 || c->n_basis > ST_MAX_B) return fail(-2, "storage: 1..%s%lld basis functions", "", ST_MAX_B);
+  if (c->n_dates <= 0 || c->n_sub < 0 || c->n_pre_dates < 0 || c->n_pre_dates > c->n_dates)
+    return fail(-2, "storage: bad date / step counts%s", "");
+  for (int d = 0; d < c->n_dates; ++d) {
+    const double *r = c->date_rec + (size_t)d * ST_REC;
+    if (r[8] < 1 || r[8] > ST_KNOTS || r[9] < 1 || r[9] > ST_KNOTS) return fail(-2, "storage: 1..8 knots per rate curve%s", "");
+  }
+  mcre_storage_plan *p = new mcre_storage_plan();
+  int rc = 0;
+  {
+    ArenaScope scope(&p->arena);
+    if (!rc) rc = p->step.upload(c->step, (size_t)c->n_sub * ST_STEP);
+    if (!rc) rc = p->step_date.upload(c->step_date, (size_t)c->n_sub);
+    if (!rc) rc = p->rec.upload(c->date_rec, (size_t)c->n_dates * ST_REC);
+    if (!rc) rc = p->numeraire.upload(c->numeraire, (size_t)c->n_dates);
+    if (!rc) rc = p->arena.commit();
+  }
+  if (rc) { p->arena.release(); delete p; return rc; }
+  StorageDev &d = p->d;
+  d.n_sub = c->n_sub; d.n_dates = c->n_dates; d.n_pre_dates = c->n_pre_dates; d.n_states = c->n_states;
+  d.n_basis = c->n_basis; d.log_spot0 = c->log_spot0;
+  d.step = p->step.p; d.step_date = p->step_date.p; d.rec = p->rec.p; d.numeraire = p->numeraire.p;
+  *out = p;
+  return 0;
+}
+
+extern "C" void mcre_storage_destroy(mcre_storage_plan *p) {
+  if (!p) return;
+  p->arena.release();
+  delete p;
+}
+
+static int storage_rng_ok(const mcre_rng *rng) {
+  if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
+  return 0;
+}
+
+extern "C" int mcre_storage_spots(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_spot,
+                                  void *stream) {
+  if (!p || !rng || !shard || !d_spot) return fail(-1, "null argument%s", "");
+  if (int rc = storage_rng_ok(rng)) return rc;
+  if (shard->n_paths <= 0) return 0;
+  const unsigned blocks = (unsigned)((shard->n_paths + ST_THREADS - 1) / ST_THREADS);
+  storage_spots_kernel<<<blocks, ST_THREADS, 0, (cudaStream_t)stream>>>(p->d, make_rng(rng), shard->path_begin,
+                                                                         shard->n_paths, d_spot);
+  MCRE_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcre_storage_backward(mcre_storage_plan *p, int32_t date, const double *d_coef, const double *d_spot_row,
+                                     double *d_value, int64_t n, void *stream) {
+  if (!p || !d_spot_row || !d_value) return fail(-1, "null argument%s", "");
+  if (date < 0 || date >= p->d.n_dates) return fail(-2, "storage: date index out of range%s", "");
+  if (n <= 0) return 0;
+  const unsigned blocks = (unsigned)((n + ST_THREADS - 1) / ST_THREADS);
+  storage_backward_kernel<<<blocks, ST_THREADS, 0, (cudaStream_t)stream>>>(p->d, date, d_coef, d_spot_row, d_value, n);
+  MCRE_LAUNCHED();
+  return 0;
+}
+
+extern "C" int64_t mcre_storage_moment_slots(const mcre_storage_plan *p) {
+  return p ? (int64_t)p->d.n_states * p->d.n_basis + 2 * p->d.n_basis - 1 : 0;
+}
+
+extern "C" int mcre_storage_moments(mcre_storage_plan *p, int32_t date, double centre, double inv_scale,
+                                    const double *d_spot_row, const double *d_value, int64_t n, int32_t chunk_paths,
+                                    double *d_partial, double *d_out, void *stream) {
+  if (!p || !d_spot_row || !d_value || !d_partial || !d_out) return fail(-1, "null argument%s", "");
+  if (date < 0 || date >= p->d.n_dates) return fail(-2, "storage: date index out of range%s", "");
+  if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "storage: chunk_paths must be a multiple of 256%s", "");
+  const int64_t slots = mcre_storage_moment_slots(p);
+  const long long n_chunks = n > 0 ? (n + chunk_paths - 1) / chunk_paths : 0;
+  if (n_chunks > 0) {
+    dim3 grid((unsigned)n_chunks, (unsigned)(p->d.n_states + 1));
+    storage_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->d, date, centre, inv_scale, d_spot_row, d_value, n,
+                                                                   chunk_paths, d_partial);
+    MCRE_LAUNCHED();
+  }
+  return mcre_tree_reduce(d_partial, n_chunks, slots, d_out, stream);
+}
+
+extern "C" int mcre_storage_mainsim(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard,
+                                    const double *d_coef, double initial_state, double *d_cfs, double *d_final_state,
+                                    void *stream) {
+  if (!p || !rng || !shard || !d_coef || !d_cfs) return fail(-1, "null argument%s", "");
+  if (int rc = storage_rng_ok(rng)) return rc;
+  if (shard->n_paths <= 0) return 0;
+  const unsigned blocks = (unsigned)((shard->n_paths + ST_THREADS - 1) / ST_THREADS);
+  storage_main_kernel<<<blocks, ST_THREADS, 0, (cudaStream_t)stream>>>(p->d, make_rng(rng), shard->path_begin,
+                                                                        shard->n_paths, d_coef, initial_state, d_cfs,
+                                                                        d_final_state);
+  MCRE_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,267 @@
+"""Backend for books of gas storages on a Schwartz two-factor model (csrc/storage.cu).
+
+Replaces, for `products.storage.Storage`, the reference's pre-simulation + backward induction
+(src/controller/controller.py:272-383) and valuation pass (:385-471, PV branch) with
+
+  pre-simulation : one forward launch spilling the spot of every action date, then one launch per action date
+                   (backwards) that advances the value grid [state][path] of ALL paths and states;
+  regression     : per action date a tall least squares of the value grid on the polynomial basis of the spot.
+                   Two solvers (`SimulationController.storage_regression`):
+                     "lapack"  - the design matrix and the value grid are read back and solved by LAPACK gelsy
+                                 through torch.linalg.lstsq, the very routine the reference calls.  Default up to
+                                 LAPACK_MAX_PATHS pre-simulation paths, because the reference's results depend on that
+                                 routine's rank decisions wherever prices are (nearly) deterministic: on the
+                                 reference's own `storage1` known answer a mathematically equivalent solver moves the
+                                 PV by 1.7e-3 (exact ties between "inject today" and "inject tomorrow" are broken
+                                 by the least-squares noise).  Only the [N x basis] solve runs on the host - paths,
+                                 decisions and value grids stay on the GPU;
+                     "moments" - Gram / right-hand-side moments of the standardised basis accumulated on the device
+                                 (fixed-order chunk tree, all-reduced over ranks), (basis x basis) normal equations
+                                 solved on the host; paths are sharded over the GPUs.  Default above that size;
+  main simulation: one fused launch per product (stepping + decisions + cashflows), per-path totals of a netting
+                   set accumulated on the device, mean and standard error by mcre_sum_stats.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+import torch
+
+from common.enums import SimulationScheme
+from mcre import binding as B
+from mcre import runtime as RT
+from mcre.finish import mean_and_error
+from mcre.timegrid import build_time_grid
+
+#: largest pre-simulation for which the regression is solved by LAPACK on the host by default
+LAPACK_MAX_PATHS = 1 << 16
+STEP = 10
+
+
+def _is_storage(p):
+    from products.storage import Storage
+    return isinstance(p, Storage)
+
+
+def step_table(model, grid, scheme):
+    """[n_sub][STEP] coefficients of csrc/storage.cu:TwoFactor::advance (schwartz_two_factor.py:124-196)."""
+    rate, kappa, sig_s, mu, sig_l, rho = model.param_values()
+    out = np.zeros((max(grid.n_sub, 1), STEP))
+    chol = {}
+    for s in range(grid.n_sub):
+        dt = grid.dt[s]
+        if scheme == SimulationScheme.ANALYTICAL:
+            key = grid.dt_nominal[s]            # the reference caches the factor per nominal dt (model.py:45-64)
+            if key not in chol:
+                if abs(kappa) <= 1e-12:
+                    var_s = sig_s * sig_s * key
+                else:
+                    var_s = sig_s * sig_s * (1.0 - math.exp(-2.0 * kappa * key)) / (2.0 * kappa)
+                var_l = sig_l * sig_l * key
+                cov = rho * math.sqrt(max(var_s * var_l, 0.0))
+                l00 = math.sqrt(var_s)
+                l10 = cov / l00
+                chol[key] = (l00, l10, math.sqrt(var_l - l10 * l10))
+            a = 1.0 if abs(kappa) <= 1e-12 else math.exp(-kappa * dt)
+            out[s, :9] = (a, 0.0, dt, mu * dt, 1.0, chol[key][0], 1.0, chol[key][1], chol[key][2])
+        elif scheme == SimulationScheme.EULER:
+            sq = math.sqrt(dt)
+            out[s, :9] = (1.0, kappa, dt, mu * dt, sig_s * sq, 1.0, sig_l * sq, rho, math.sqrt(1.0 - rho * rho))
+        else:
+            raise NotImplementedError(f"storage: scheme {scheme} is not defined for the Schwartz two-factor model")
+        out[s, 9] = math.log(model.curve_value(grid.t2[s]))
+    return out
+
+
+def log_spot_scale(model, t):
+    """Standard deviation of log S(t) under the model: a per-date scale for the standardised basis."""
+    _, kappa, sig_s, _, sig_l, rho = model.param_values()
+    tau = max(t - model.t0(), 0.0)
+    if abs(kappa) <= 1e-12:
+        var_s, cov = sig_s * sig_s * tau, rho * sig_s * sig_l * tau
+    else:
+        var_s = sig_s * sig_s * (1.0 - math.exp(-2.0 * kappa * tau)) / (2.0 * kappa)
+        cov = rho * sig_s * sig_l * (1.0 - math.exp(-kappa * tau)) / kappa
+    return math.sqrt(max(var_s + sig_l * sig_l * tau + 2.0 * cov, 0.0))
+
+
+class StorageBackend:
+    @staticmethod
+    def supports(ctrl):
+        return any(_is_storage(p) for p in ctrl.products)
+
+    def __init__(self, ctrl):
+        from maths.regression import PolyomialRegression
+        from metrics.metric import MetricType
+        from models.schwartz_two_factor import SchwartzTwoFactorModel
+        self.c = c = ctrl
+        if not all(_is_storage(p) for p in c.products):
+            raise NotImplementedError("gas storages are valued in books of their own (no mixing with other products)")
+        if not isinstance(c.model, SchwartzTwoFactorModel):
+            raise NotImplementedError("gas storage: only SchwartzTwoFactorModel is implemented "
+                                      f"(got {type(c.model).__name__})")
+        if any(m.metric_type != MetricType.PV for m in c.risk_metrics.metrics):
+            raise NotImplementedError("gas storage: PV is the only implemented metric")
+        if c.differentiate:
+            raise NotImplementedError("gas storage: sensitivities are not implemented")
+        rf = c.regression_function
+        if type(rf) is not PolyomialRegression or not 0 <= rf.degree < B_MAX_BASIS:
+            raise NotImplementedError(f"gas storage: PolyomialRegression of degree 0..{B_MAX_BASIS - 1} (the kernels "
+                                      "evaluate monomials of the spot)")
+        self.n_basis = rf.degree + 1
+        mode = getattr(c, "storage_regression", "auto")
+        if mode not in ("auto", "lapack", "moments"):
+            raise ValueError("storage_regression must be 'auto', 'lapack' or 'moments'")
+        if mode == "auto":
+            mode = "lapack" if c.num_paths_presim <= LAPACK_MAX_PATHS else "moments"
+        self.mode = mode
+
+    # ------------------------------------------------------------------ plan
+    def _create(self, prod, grid, steps):
+        c = self.c
+        sim_dates = {t: i for i, t in enumerate(grid.dates)}
+        acts = prod.product_timeline.tolist()
+        date_of = {sim_dates[t]: k for k, t in enumerate(acts)}
+        step_date = np.array([date_of.get(d, -1) if d >= 0 else -1 for d in grid.date_after], dtype=np.int32)
+        n_pre = sum(1 for t in acts if sim_dates[t] < grid.n_pre_dates)
+        rec = prod.lower()
+        t0 = c.model.t0()
+        rate = c.model.param_values()[0]
+        numeraire = np.array([math.exp(rate * (t - t0)) for t in acts])
+        keep = []
+        d = B.StorageDesc()
+        d.n_sub, d.n_dates, d.n_pre_dates = grid.n_sub, len(acts), n_pre
+        d.n_states, d.n_basis = prod.num_states, self.n_basis
+        d.log_spot0 = math.log(c.model.curve_value(t0))
+        for name, arr, conv in (("step", steps, B.as_dp), ("step_date", step_date if grid.n_sub else np.zeros(1, np.int32), B.as_ip),
+                                ("date_rec", rec, B.as_dp), ("numeraire", numeraire, B.as_dp)):
+            a, ptr = conv(arr)
+            keep.append(a)
+            setattr(d, name, ptr)
+        plan = C.c_void_p()
+        B.check(B.lib().mcre_storage_create(C.byref(d), C.byref(plan)))
+        return plan, numeraire, acts
+
+    def _rng(self, which, seed, n_total):
+        c = self.c
+        rng = B.Rng()
+        rng.seed, rng.stream, rng.n_paths_total = seed, c.rng_stream, n_total
+        z = c.injected_normals.get(which) if c.injected_normals else None
+        if z is not None:
+            if z.shape[1] != n_total or z.shape[2] != 2:
+                raise ValueError(f"injected {which} normals must be [n_sub, {n_total}, 2]")
+            rng.mode, rng.d_z = B.RNG_INJECT, z.data_ptr()
+        else:
+            rng.mode = B.RNG_PHILOX
+        return rng, z
+
+    # ------------------------------------------------------------------ pre-simulation + regression
+    def _regress(self, prod, plan, numeraire, acts, dev):
+        """-> device tensor [n_dates][2 + S * NB]: (centre, inverse scale, coefficients per state) per action date."""
+        c, L = self.c, B.lib()
+        S, NB, n_dates = prod.num_states, self.n_basis, len(acts)
+        row = 2 + S * NB
+        n_total = c.num_paths_presim
+        rank, world = RT.dist_info()
+        chunk = 256 if n_total < (1 << 18) else 4096
+        if self.mode == "lapack" or world == 1:
+            begin, count = 0, n_total            # (lapack: every rank solves the same full-size systems)
+        else:
+            begin, count = RT.shard_range(n_total, chunk)
+        rng, _keep = self._rng("pre", 42, n_total)
+        shard = B.Shard(begin, count, chunk)
+        spot = torch.empty((n_dates, max(count, 1)), dtype=torch.float64, device=dev)
+        B.check(L.mcre_storage_spots(plan, C.byref(rng), C.byref(shard), spot.data_ptr(), RT.stream_ptr()))
+        coef_h = np.zeros((n_dates, row))
+        coef_h[:, 1] = 1.0
+        if self.mode == "moments":
+            for k, t in enumerate(acts):
+                f = c.model.curve_value(t)
+                sd = f * log_spot_scale(c.model, t)
+                coef_h[k, 0], coef_h[k, 1] = f, (1.0 / sd if sd > 1e-300 else 0.0)
+        coef = torch.from_numpy(coef_h.copy()).to(dev)
+        value = torch.zeros((S, max(count, 1)), dtype=torch.float64, device=dev)
+        if self.mode == "lapack":
+            spot_h = RT.to_host(spot)
+        else:
+            slots = L.mcre_storage_moment_slots(plan)
+            n_chunks = (count + chunk - 1) // chunk
+            partial = torch.empty(max(n_chunks, 1) * slots, dtype=torch.float64, device=dev)
+            mom = torch.zeros(slots, dtype=torch.float64, device=dev)
+        for k in range(n_dates - 1, 0, -1):
+            B.check(L.mcre_storage_backward(plan, k, coef[k].data_ptr(), spot[k].data_ptr(), value.data_ptr(), count,
+                                            RT.stream_ptr()))
+            j = k - 1
+            if self.mode == "lapack":
+                # controller.py:361-374: A = [x^0 .. x^degree], solution of min |A c - numeraire * value| by gelsy
+                x = torch.from_numpy(spot_h[j])
+                A = c.regression_function.get_regression_matrix(x)
+                Y = torch.from_numpy(RT.to_host(value)).transpose(0, 1) * float(numeraire[j])
+                sol = torch.linalg.lstsq(A, Y).solution            # [NB, S]
+                coef_h[j, 2:] = sol.transpose(0, 1).reshape(-1).numpy()
+            else:
+                B.check(L.mcre_storage_moments(plan, j, coef_h[j, 0], coef_h[j, 1], spot[j].data_ptr(), value.data_ptr(),
+                                               count, chunk, partial.data_ptr(), mom.data_ptr(), RT.stream_ptr()))
+                m = RT.to_host(RT.all_reduce_tree(mom))
+                rhs = m[:S * NB].reshape(S, NB).T                  # [NB, S]
+                pw = m[S * NB:]
+                G = np.array([[pw[a + b] for b in range(NB)] for a in range(NB)])
+                sol, *_ = np.linalg.lstsq(G, rhs, rcond=1e-12)      # minimum norm where the spot is deterministic
+                coef_h[j, 2:] = sol.T.reshape(-1)
+            coef[j].copy_(torch.from_numpy(coef_h[j]), non_blocking=False)
+        # regression coefficients of the product, as the reference stores them ([date][state][basis]); in "moments"
+        # mode they refer to the standardised spot (spot - centre) * inverse scale, kept next to them
+        prod.regression_coeffs = torch.from_numpy(coef_h[:, 2:].reshape(n_dates, S, NB).copy())
+        prod.regression_basis_shift_scale = torch.from_numpy(coef_h[:, :2].copy())
+        return coef
+
+    # ------------------------------------------------------------------ run
+    def run(self):
+        c, L = self.c, B.lib()
+        dev = RT.compute_device()
+        t_start = time.perf_counter()
+        grid = build_time_grid(c.model.t0(), c.simulation_timeline.tolist(), c.num_steps)
+        steps = step_table(c.model, grid, c.simulation_scheme)
+        n_main = c.num_paths_mainsim
+        chunk = 256 if n_main < (1 << 18) else 4096
+        begin, count = RT.shard_range(n_main, chunk)
+        rng_main, _keep = self._rng("main", 43, n_main)
+        shard = B.Shard(begin, count, chunk)
+        plans, t_pre = [], 0.0
+        cfs = [torch.zeros(max(count, 1), dtype=torch.float64, device=dev) for _ in c.netting_sets]
+        try:
+            for pi, prod in enumerate(c.products):
+                plan, numeraire, acts = self._create(prod, grid, steps)
+                plans.append(plan)
+                t0 = time.perf_counter()
+                coef = self._regress(prod, plan, numeraire, acts, dev)
+                torch.cuda.current_stream().synchronize()
+                t_pre += time.perf_counter() - t0
+                si = c.product_to_netting_set_idx[pi]
+                B.check(L.mcre_storage_mainsim(plan, C.byref(rng_main), C.byref(shard), coef.data_ptr(),
+                                               float(prod.get_initial_state()), cfs[si].data_ptr(), None, RT.stream_ptr()))
+            raw = []
+            n_chunks = max((count + chunk - 1) // chunk, 1)
+            partial = torch.empty(n_chunks * 2 + 1, dtype=torch.float64, device=dev)
+            for si in range(len(c.netting_sets)):
+                # shift = the set's value on global path 0 (lives on the rank that owns it; summed over the ranks)
+                shift = cfs[si][0:1].clone() if (begin == 0 and count > 0) else torch.zeros(1, dtype=torch.float64, device=dev)
+                shift = RT.all_reduce_tree(shift)
+                out = torch.zeros(2, dtype=torch.float64, device=dev)
+                B.check(L.mcre_sum_stats(cfs[si].data_ptr(), count, 1, chunk, shift.data_ptr(), 0, partial.data_ptr(),
+                                         out.data_ptr(), RT.stream_ptr()))
+                s = RT.to_host(RT.all_reduce_tree(out))
+                pv = mean_and_error(float(s[0]), float(s[1]), float(RT.to_host(shift)[0]), n_main)
+                raw.append({"pv": (pv, None), "param_used": lambda kind: [False] * len(c.model.model_params)})
+        finally:
+            torch.cuda.current_stream().synchronize()
+            for plan in plans:
+                L.mcre_storage_destroy(plan)
+        total = time.perf_counter() - t_start
+        return raw, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}
+
+
+B_MAX_BASIS = 6

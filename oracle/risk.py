@@ -530,7 +530,7 @@ def pfe_quantile_index(q, n):
 
 
 def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_steps, scheme,
-        differentiate=False, draws_pre=None, draws_main=None, degree=3):
+        differentiate=False, draws_pre=None, draws_main=None, degree=3, storage_solver="gelsy"):
     """Restatement of SimulationController.__init__ + run_simulation (controller.py:26-151, 663-709).
     Returns dict(results=[set][metric] -> [(value, err)], grads=[set][metric][eval] -> array[P] or None,
     coeffs=[product] -> [T_e] of [S,degree])."""
@@ -587,6 +587,10 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
             rng = bridge_rngs.setdefault(id(prod), np.random.default_rng(12345))
             return rng.uniform(0, 1, size=(n, n_int))
         return get
+
+    if any(kind(pr) == "Storage" for pr in products):
+        return _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_main, n_pre, num_steps, scheme,
+                            draws_pre, draws_main, degree, n_sub, dim, storage_solver)
 
     if any(needs_regression(pr) for pr in products):
         if draws_pre is None:
@@ -718,3 +722,44 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
         grads.append(mgrads)
     return dict(results=results, grads=grads, expo_coeffs=expo_coeffs, prod_coeffs=prod_coeffs,
                 sim_timeline=sim_tl, exposure_timeline=expo_tl, n_sub=n_sub, noise_dim=dim)
+
+
+def _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_main, n_pre, num_steps, scheme,
+                 draws_pre, draws_main, degree, n_sub, dim, solver="gelsy"):
+    """Books of gas storages, PV only (oracle/storage.py; controller.py:294-383 for the regression pass,
+    :399-410 for the valuation pass)."""
+    from oracle import storage as ST
+    if any(kind(pr) != "Storage" for pr in products) or any(t != "PV" for t in mtypes):
+        raise NotImplementedError("oracle: storages are valued on their own, PV only")
+    if draws_pre is None:
+        draws_pre = E.PhiloxDraws(42, n_pre, n_sub, dim)
+    if draws_main is None:
+        draws_main = E.PhiloxDraws(43, n_main, n_sub, dim)
+    ctx_pre = Ctx(model, p, sim_tl, E.generate_paths(model, p, sim_tl, n_pre, num_steps, scheme, draws_pre), n_pre)
+    ctx_main = Ctx(model, p, sim_tl, E.generate_paths(model, p, sim_tl, n_main, num_steps, scheme, draws_main), n_main)
+    set_cfs = [None] * len(netting_sets)
+    all_coeffs = []
+    for k, pr in enumerate(products):
+        tl = product_timeline(pr)
+        asset = asset_of(pr)
+
+        def market(ctx):
+            spots = [np.asarray(ad.val(ctx.spot(asset, t)), dtype=float) for t in tl]
+            nums = [float(np.asarray(ad.val(ctx.numeraire(t))).reshape(-1)[0]) for t in tl]
+            return spots, nums
+        std = None
+        if solver == "moments":      # standardised basis (spot - F(t)) / (F(t) sd(log S(t))), mcre/storage.py
+            std = []
+            for t in tl:
+                f = M.schwartz_curve(model, t)
+                sd = f * ST.log_spot_std(model, t)
+                std.append((f, 1.0 / sd if sd > 1e-300 else 0.0))
+        coeffs = ST.regress(pr, *market(ctx_pre), degree, solver=ST.gelsy if solver == "gelsy" else ST.normal_equations,
+                            std=std)
+        cfs = ST.evaluate(pr, *market(ctx_main), coeffs, degree, std=std)
+        all_coeffs.append(coeffs)
+        si = prod_set[k]
+        set_cfs[si] = cfs if set_cfs[si] is None else set_cfs[si] + cfs
+    results = [[[tuple(float(v) for v in mc_mean_and_error(set_cfs[si]))] for _ in mtypes] for si in range(len(netting_sets))]
+    grads = [[[None] for _ in mtypes] for _ in netting_sets]
+    return dict(results=results, grads=grads, prod_coeffs=all_coeffs, sim_timeline=sim_tl, n_sub=n_sub, noise_dim=dim)

@@ -1,5 +1,7 @@
 """Shared scenario builders for the tests: each returns this repo's host objects for one
 of the reference's test / benchmark configurations."""
+import math
+
 import numpy as np
 
 HAZARDS = {0.5: 0.006402303360855854, 1.0: 0.01553038972325307, 2.0: 0.009729741230773657,
@@ -324,6 +326,64 @@ def heston_euler_book(ns_module):
     return model, sets, [m.PVMetric()], None
 
 
+def _days(a, b):
+    import datetime
+    return float((datetime.date(*b) - datetime.date(*a)).days)
+
+
+def storage_s2f(ns_module, which="storage1", end_day=None, num_states=10, vols=None):
+    """Gas storage on a Schwartz two-factor curve, daily decisions (tests/storage_s2f_cases.py:139-214 and
+    tests/pytests/test_storage_s2f_pv.py:23-52): "storage1" = two months, one flat 90-unit band, nearly
+    deterministic prices; "storage2" = 15 months, five inventory bands, level-dependent rate curves.
+    `end_day` cuts the contract short (smaller cases); `vols` = (short-term, long-term) annual volatilities."""
+    m = ns_module
+    if which == "storage1":
+        start, end = (2024, 12, 1), (2025, 1, 31)
+        n_days = _days(start, end)
+        bands = [((2024, 12, 1), (2025, 2, 1), 0.0, 90.0)]
+        inj = [((2024, 12, 1), (2025, 2, 1), 0.0, 90.0)]
+        wd = [((2024, 12, 1), (2025, 2, 1), 0.0, 90.0)]
+        costs = (0.2, 0.0)
+        curve = [(0.0, 100.0), (float(int(round(n_days * 0.25))), 100.0), (float(int(round(n_days * 0.55))), 110.0),
+                 (n_days, 112.0)]
+        kappa, sig_s, sig_l = 8.0, 0.00001, 0.00005
+    else:
+        start, end = (2025, 1, 1), (2026, 3, 31)
+        n_days = _days(start, end)
+        bands = [((2025, 1, 1), (2025, 7, 1), 0.0, 200000.0), ((2025, 7, 1), (2025, 10, 1), 50000.0, 260000.0),
+                 ((2025, 10, 1), (2026, 1, 1), 180000.0, 280000.0), ((2026, 1, 1), (2026, 3, 1), 40000.0, 260000.0),
+                 ((2026, 3, 1), (2026, 4, 1), 0.0, 260000.0)]
+        levels = (0.0, 60000.0, 150000.0, 225000.0)
+        first, second = ((2025, 1, 1), (2025, 10, 1)), ((2025, 10, 1), (2026, 4, 1))
+        inj = [(*first, lv, r) for lv, r in zip(levels, (3400.0, 2920.0, 2200.0, 1480.0))] + \
+              [(*second, lv, r) for lv, r in zip(levels, (5800.0, 4840.0, 3400.0, 1960.0))]
+        wd = [(*first, lv, r) for lv, r in zip(levels, (1720.0, 2800.0, 3880.0, 4600.0))] + \
+             [(*second, lv, r) for lv, r in zip(levels, (2200.0, 4000.0, 5800.0, 7000.0))]
+        costs = (0.35, 0.12)
+        curve = [(0.0, 90.0), (_days(start, (2025, 4, 1)), 94.0), (_days(start, (2025, 7, 1)), 88.0),
+                 (_days(start, (2025, 10, 1)), 96.0), (_days(start, (2026, 1, 1)), 104.0), (n_days, 98.0)]
+        kappa, sig_s, sig_l = 1.5, 0.18, 0.08
+    if vols is not None:
+        sig_s, sig_l = vols
+    cfg = m.StorageConfig()
+    for a, b, lo, hi in bands:
+        cfg.add_volume_constraint(_days(start, a), _days(start, b), lo, hi, 0.0)
+    for a, b, level, rate in inj:
+        cfg.add_injection_flexibility(_days(start, a), _days(start, b), level, rate)
+    for a, b, level, rate in wd:
+        cfg.add_withdrawal_flexibility(_days(start, a), _days(start, b), level, rate)
+    cfg.add_variable_injection_cost(0.0, costs[0])
+    cfg.add_variable_withdrawal_cost(0.0, costs[1])
+    storage = m.Storage(asset_id="thegasprice", start_date=0.0, end_date=n_days if end_day is None else float(end_day),
+                        initial_amount=0.0, storage_config=cfg, num_states=num_states, rollout_interval=1.0)
+    model = m.SchwartzTwoFactorModel(calibration_date=0.0, curve_times=[t for t, _ in curve],
+                                     curve_values=[v for _, v in curve], rate=0.0 / 365.0,
+                                     short_term_mean_reversion=kappa / 365.0, short_term_vol=sig_s / math.sqrt(365.0),
+                                     long_term_drift=0.0 / 365.0, long_term_vol=sig_l / math.sqrt(365.0), rho=0.2,
+                                     asset_id="thegasprice")
+    return model, [m.NettingSet(name=storage.get_name(), products=[storage])], [m.PVMetric()], None
+
+
 GOLDEN_CASES = {
     "wwr_cva": (wwr_cva, dict(rho=0.3), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "wwr_cva_neg": (wwr_cva, dict(rho=-0.9, extra_metrics=False), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="EULER", differentiate=False)),
@@ -364,6 +424,12 @@ GOLDEN_CASES = {
     # models the reference only runs standalone
     "schwartz_analytical": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=2, scheme="ANALYTICAL", differentiate=True)),
     "schwartz_euler": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
+    # gas storage (the reference's tests/pytests/test_storage_s2f_pv.py at its own sizes, and cut-down twins);
+    # "degree" = polynomial degree of the regression basis (PolyomialRegression(degree), default 2)
+    "storage1": (storage_s2f, dict(which="storage1"), dict(n_main=2000, n_pre=4000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
+    "storage2": (storage_s2f, dict(which="storage2"), dict(n_main=2000, n_pre=4000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
+    "storage2_short_euler": (storage_s2f, dict(which="storage2", end_day=100, num_states=6), dict(n_main=1024, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False, degree=2)),
+    "storage1_vol": (storage_s2f, dict(which="storage1", vols=(0.9, 0.3), num_states=5), dict(n_main=3000, n_pre=3000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=4)),
     "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
 }
 
@@ -404,6 +470,13 @@ class Namespace:
         try:   # dead code in the reference; an extension in this package
             from models.hull_white import HullWhiteModel
             self.HullWhiteModel = HullWhiteModel
+        except Exception:  # pragma: no cover
+            pass
+        try:
+            from maths.regression import PolyomialRegression
+            from products.storage import Storage
+            from products.storage_helpers import StorageConfig
+            self.PolyomialRegression, self.Storage, self.StorageConfig = PolyomialRegression, Storage, StorageConfig
         except Exception:  # pragma: no cover
             pass
         try:

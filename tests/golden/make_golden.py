@@ -44,8 +44,9 @@ def run_case(name):
     ns = cases.Namespace()
     model, sets, metrics, tl = builder(ns, **bkw)
     rm = ns.RiskMetrics(metrics, exposure_timeline=tl) if tl is not None else ns.RiskMetrics(metrics)
+    extra = dict(regression_function=ns.PolyomialRegression(degree=rkw["degree"])) if "degree" in rkw else {}
     sc = ns.SimulationController(sets, model, rm, rkw["n_main"], rkw["n_pre"], rkw["num_steps"],
-                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"])
+                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"], **extra)
     res = sc.run_simulation()
     out = dict(case=name, builder=builder.__name__, builder_kwargs=bkw, run=rkw,
                torch=torch.__version__, sets=res.get_netting_set_names(), metrics=res.get_metric_names(),

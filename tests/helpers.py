@@ -54,7 +54,8 @@ def run_oracle(name, draws="torch", **override):
     if draws == "torch":
         pre, main = reference_draws(model, sets, tl, metrics, rkw)
     out = risk.run(model, sets, metrics, tl, rkw["n_main"], rkw["n_pre"], rkw["num_steps"], rkw["scheme"],
-                   differentiate=rkw["differentiate"], draws_pre=pre, draws_main=main)
+                   differentiate=rkw["differentiate"], draws_pre=pre, draws_main=main,
+                   degree=rkw.get("degree", 2) + 1, storage_solver=rkw.get("storage_solver", "gelsy"))
     return out, (ns, model, sets, metrics, tl, rkw)
 
 
@@ -62,8 +63,11 @@ def run_cuda(name, draws="torch", **override):
     """Run the scenario through this repo's SimulationController (CUDA kernels)."""
     ns, model, sets, metrics, tl, rkw = build(name, **override)
     rm = ns.RiskMetrics(metrics, exposure_timeline=tl) if tl is not None else ns.RiskMetrics(metrics)
+    extra = dict(regression_function=ns.PolyomialRegression(degree=rkw["degree"])) if "degree" in rkw else {}
     sc = ns.SimulationController(sets, model, rm, rkw["n_main"], rkw["n_pre"], rkw["num_steps"],
-                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"])
+                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"], **extra)
+    if "storage_solver" in rkw:
+        sc.storage_regression = "lapack" if rkw["storage_solver"] == "gelsy" else rkw["storage_solver"]
     if draws == "torch":
         pre, main = reference_draws(model, sets, tl, metrics, rkw)
         sc.inject_normals(pre=None if pre is None else pre.z, main=main.z)

@@ -164,3 +164,19 @@ def test_bs_european_call_with_aad_matches_black_scholes(rng):
     delta, vega = 0.5 * math.erfc(-d1 / math.sqrt(2)), 100.0 * math.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi)
     g = res.get_derivatives(prod.get_name(), "pv", evaluation_idx=0)
     assert abs(float(g["spot"]) - delta) < 3e-3 and abs(float(g["volatility"]) - vega) < 0.2
+
+
+@pytest.mark.parametrize("which,expected", [("storage1", 1055.330006881181), ("storage2", 3769746.378205333)])
+def test_storage_s2f_pv_known_answers(which, expected):
+    """tests/pytests/test_storage_s2f_pv.py:23-52: gas storage on the Schwartz two-factor model, 2000 / 4000 paths,
+    one ANALYTICAL step per day, cubic regression: the pinned PVs at the reference's own tolerance (abs 1e-6)."""
+    ns = cases.Namespace()
+    model, sets, metrics, _ = cases.storage_s2f(ns, which=which)
+    product = sets[0].products[0]
+    pv_metric = metrics[0]
+    sc = _compat(ns.SimulationController(netting_sets=sets, model=model, risk_metrics=ns.RiskMetrics(metrics=[pv_metric]),
+                                         num_paths_mainsim=2000, num_paths_presim=4000, num_steps=1,
+                                         simulation_scheme=ns.SimulationScheme.ANALYTICAL, differentiate=False,
+                                         regression_function=ns.PolyomialRegression(degree=3)))
+    pv = sc.run_simulation().get_results(product.get_name(), pv_metric.get_name(), evaluation_idx=0)
+    assert float(pv) == pytest.approx(expected, abs=1e-6)

@@ -1,0 +1,91 @@
+"""Gas storage on the GPU (csrc/storage.cu through mcre/storage.py) against goldens of the unmodified reference,
+against the oracle on the same draws, and through size-independent properties at large path counts."""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+STORAGE_CASES = ["storage1", "storage2", "storage2_short_euler", "storage1_vol"]
+
+
+@pytest.mark.parametrize("name", STORAGE_CASES)
+def test_storage_pv_matches_reference_golden(name):
+    """The reference's torch.randn stream injected: PV and its standard error to 1e-9 / 1e-7 relative.  storage1 and
+    storage2 are tests/pytests/test_storage_s2f_pv.py at its own sizes (1055.330006881181 / 3769746.378205333)."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    for key, ref in gold["values"].items():
+        vals, errs = flat[key]
+        helpers.assert_close(vals, ref, 1e-9, 1e-9, f"{name} {key}")
+        helpers.assert_close(errs, gold["errors"][key], 1e-7, 1e-9, f"{name} {key} mc error")
+    prod = sc.products[0]
+    assert tuple(prod.regression_coeffs.shape) == (len(prod.product_timeline), prod.num_states, sc.regression_function.get_degree())
+
+
+@pytest.mark.parametrize("name", ["storage2_short_euler", "storage1_vol"])
+def test_storage_native_philox_matches_oracle_philox(name):
+    res, sc = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    v, e = out["results"][0][0][0]
+    got = helpers.flatten_results(res)["Storage|pv"]
+    helpers.assert_close(got[0], [v], 1e-9, 1e-9, f"{name} philox value")
+    helpers.assert_close(got[1], [e], 1e-7, 1e-9, f"{name} philox error")
+    # regression coefficients of the product: the LAPACK solve sees the device's spots and value grid
+    coeffs = np.stack(out["prod_coeffs"][0])
+    mine = sc.products[0].regression_coeffs.numpy()
+    scale = np.abs(coeffs).max(axis=(1, 2), keepdims=True) + 1e-300
+    assert np.max(np.abs(mine - coeffs) / scale) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["storage2_short_euler", "storage1_vol", "storage2"])
+def test_storage_device_moments_solver_matches_oracle_normal_equations(name):
+    """storage_regression = "moments": Gram moments of the standardised basis accumulated on the device."""
+    res, sc = helpers.run_cuda(name, draws="torch", storage_solver="moments")
+    out, _ = helpers.run_oracle(name, draws="torch", storage_solver="moments")
+    v, e = out["results"][0][0][0]
+    got = helpers.flatten_results(res)["Storage|pv"]
+    helpers.assert_close(got[0], [v], 1e-8, 1e-8, f"{name} moments value")
+    helpers.assert_close(got[1], [e], 1e-6, 1e-8, f"{name} moments error")
+
+
+def test_two_storages_in_two_netting_sets_and_one_set_of_two():
+    """Per-set accumulation: PV(set of two storages) = PV(a) + PV(b) on the same paths; each product has its own
+    action dates inside the common simulation grid."""
+    ns = cases.Namespace()
+    model, sets_a, metrics, _ = cases.storage_s2f(ns, which="storage2", end_day=50, num_states=6)
+    _, sets_b, _, _ = cases.storage_s2f(ns, which="storage2", end_day=35, num_states=8)
+    a, b = sets_a[0].products[0], sets_b[0].products[0]
+
+    def run(sets):
+        sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), 4096, 4096, 1, ns.SimulationScheme.ANALYTICAL,
+                                     False, regression_function=ns.PolyomialRegression(degree=3))
+        return sc.run_simulation()
+    r2 = run([ns.NettingSet(name="a", products=[a]), ns.NettingSet(name="b", products=[b])])
+    pa, pb = float(r2.get_results("a", "pv")[0]), float(r2.get_results("b", "pv")[0])
+    _, sets_a2, _, _ = cases.storage_s2f(ns, which="storage2", end_day=50, num_states=6)
+    _, sets_b2, _, _ = cases.storage_s2f(ns, which="storage2", end_day=35, num_states=8)
+    r1 = run([ns.NettingSet(name="ab", products=[sets_a2[0].products[0], sets_b2[0].products[0]])])
+    assert abs(float(r1.get_results("ab", "pv")[0]) - (pa + pb)) <= 1e-9 * abs(pa + pb)
+
+
+def test_storage_large_run_is_deterministic_and_consistent_with_the_small_one():
+    """2^18 paths in both passes, device moments solver, native Philox: bit-identical when repeated, and within
+    4 standard errors of the 4096-path LAPACK run (policy bias is far below that at these sizes)."""
+    ns = cases.Namespace()
+
+    def run(n, mode):
+        model, sets, metrics, _ = cases.storage_s2f(ns, which="storage2", end_day=90, num_states=8)
+        sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), n, n, 1, ns.SimulationScheme.ANALYTICAL,
+                                     False, regression_function=ns.PolyomialRegression(degree=3))
+        sc.storage_regression = mode
+        r = sc.run_simulation()
+        return float(r.get_results("Storage", "pv")[0]), float(r.get_mc_error("Storage", "pv")[0])
+    big1, big2 = run(1 << 18, "moments"), run(1 << 18, "moments")
+    assert big1 == big2
+    small = run(4096, "lapack")
+    assert abs(big1[0] - small[0]) < 4.0 * np.hypot(big1[1], small[1])
+    assert big1[1] < small[1] / 6.0            # standard error shrinks like 1 / sqrt(64)

@@ -1,0 +1,122 @@
+"""Host side of the gas storage (products/storage.py, products/storage_helpers.py, mcre/storage.py) against the
+reference's own outputs (tests/golden/storage_envelope.json, made by tests/golden/make_storage_envelope.py with the
+unmodified reference).  CPU only: contract logic and table lowering, no simulation."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import helpers
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(helpers.GOLDEN_DIR, "storage_envelope.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("which", ["storage1", "storage2"])
+def test_envelope_rates_and_costs_equal_the_reference_bit_for_bit(golden, which):
+    g = golden[which]
+    ns = cases.Namespace()
+    _, sets, _, _ = cases.storage_s2f(ns, which=which)
+    st = sets[0].products[0]
+    cfg = st.storage_config
+    env = [[w.start_date, w.end_date, w.vmin, w.vmax] for w in cfg.volume_constraints]
+    assert env == g["envelope"]                      # the bisection of the envelope is reproduced operation by operation
+    assert st.product_timeline.tolist() == g["action_dates"]
+    assert st.next_action_dates.tolist() == g["next_dates"]
+    levels = torch.tensor(g["levels"], dtype=torch.float64)
+    for t, inj, wd, cost in zip(g["dates"], g["injection"], g["withdrawal"], g["costs"]):
+        assert cfg.interpolate_rate_tensor(levels, cfg.get_injection_flexibility_slice(t)).tolist() == inj
+        assert [cfg.get_withdrawal_flexibility_rate(t, float(v)) for v in g["levels"]] == wd
+        assert [cfg.get_variable_injection_cost(t), cfg.get_variable_withdrawal_cost(t)] == cost
+    assert [[cfg.grid_step(0.0, 90.0, 10), cfg.state_scale(0.0, 90.0, 10)],
+            [cfg.grid_step(5.0, 5.0, 10), cfg.state_scale(5.0, 5.0, 10)]] == g["grid"]
+    assert st.state_to_volume(200.0, torch.tensor([0.0, 2.5, 9.0])).tolist() == g["volume_of_state"]
+
+
+def test_lowered_date_records_restate_the_contract():
+    ns = cases.Namespace()
+    _, sets, _, _ = cases.storage_s2f(ns, which="storage2")
+    st = sets[0].products[0]
+    cfg = st.storage_config
+    rec = st.lower()
+    acts, nxt = st.product_timeline.tolist(), st.next_action_dates.tolist()
+    assert rec.shape == (len(acts), 48)
+    for i in (0, 1, 180, 181, 272, 273, 400, len(acts) - 1):
+        now, after = cfg.get_volume_constraint(acts[i]), cfg.get_volume_constraint(nxt[i])
+        assert rec[i, 0] == now.vmin and rec[i, 1] == cfg.grid_step(now.vmin, now.vmax, 10)
+        assert (rec[i, 2], rec[i, 3]) == (after.vmin, after.vmax)
+        assert rec[i, 4] == cfg.state_scale(after.vmin, after.vmax, 10)
+        assert rec[i, 5] == nxt[i] - acts[i] and (rec[i, 6], rec[i, 7]) == (0.35, 0.12)
+        knots = cfg.get_injection_flexibility_slice(acts[i])
+        assert rec[i, 8] == len(knots) and [rec[i, 16 + 2 * k] for k in range(len(knots))] == [k.point for k in knots]
+        assert rec[i, 10] == (1.0 if i == len(acts) - 1 else 0.0)
+
+
+def test_invalid_contracts_raise_like_the_reference():
+    ns = cases.Namespace()
+    cfg = ns.StorageConfig()
+    with pytest.raises(ValueError):
+        cfg.get_volume_constraint(0.0)
+    cfg.add_volume_constraint(0.0, 10.0, 0.0, 10.0)
+    cfg.add_injection_flexibility(0.0, 10.0, 0.0, 1.0)
+    cfg.add_withdrawal_flexibility(0.0, 10.0, 0.0, 1.0)
+    with pytest.raises(ValueError):
+        ns.Storage("gas", 0.0, 5.0, 0.0, cfg, num_states=1)
+    with pytest.raises(ValueError):
+        ns.Storage("gas", 0.0, 5.0, 0.0, cfg, num_states=4, rollout_interval=0.0)
+    # the initial inventory lies outside the contract's band: no feasible envelope (storage_helpers.py:418-431)
+    with pytest.raises(ValueError):
+        ns.Storage("gas", 0.0, 5.0, 50.0, cfg, num_states=4)
+
+
+@pytest.mark.parametrize("scheme", ["ANALYTICAL", "EULER"])
+def test_step_table_reproduces_the_oracle_model_step(scheme):
+    """mcre/storage.py:step_table folded into csrc/storage.cu's two-factor step = the oracle's Schwartz step."""
+    from mcre.storage import step_table
+    from mcre.timegrid import build_time_grid
+    from oracle import engine as E, models as M, ad
+    ns = cases.Namespace()
+    model, sets, _, _ = cases.storage_s2f(ns, which="storage2", end_day=30)
+    tl = sets[0].products[0].product_timeline.tolist()
+    grid = build_time_grid(0.0, tl, 2)
+    tab = step_table(model, grid, getattr(ns.SimulationScheme, scheme))
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal((grid.n_sub, 64, 2))
+    p = ad.params(M.param_values(model), False)
+    paths = E.generate_paths(model, p, tl, 64, 2, scheme, E.InjectedDraws(z))
+    x = np.zeros(64)
+    y = np.zeros(64)
+    for s in range(grid.n_sub):
+        a, k, dt, m, cx, b00, cy, b10, b11, lf = tab[s]
+        x = (a * x - (k * x) * dt) + cx * (b00 * z[s, :, 0])
+        y = (y + m) + cy * (b10 * z[s, :, 0] + b11 * z[s, :, 1])
+        d = grid.date_after[s]
+        if d >= 0:
+            np.testing.assert_allclose(lf + x + y, np.asarray(paths[d][0]), rtol=0, atol=1e-13)
+
+
+def test_unsupported_storage_runs_raise_before_any_device_work():
+    ns = cases.Namespace()
+    model, sets, metrics, _ = cases.storage_s2f(ns, which="storage1")
+    from mcre.storage import StorageBackend
+
+    def ctrl(**kw):
+        args = dict(netting_sets=sets, model=model, risk_metrics=ns.RiskMetrics(metrics), num_paths_mainsim=256,
+                    num_paths_presim=256, num_steps=1, simulation_scheme=ns.SimulationScheme.ANALYTICAL)
+        args.update(kw)
+        return ns.SimulationController(**args)
+    assert StorageBackend(ctrl(regression_function=ns.PolyomialRegression(3))).mode == "lapack"
+    assert StorageBackend(ctrl(num_paths_presim=1 << 17)).mode == "moments"
+    with pytest.raises(NotImplementedError):
+        StorageBackend(ctrl(differentiate=True))
+    with pytest.raises(NotImplementedError):
+        StorageBackend(ctrl(regression_function=ns.PolyomialRegression(7)))
+    with pytest.raises(NotImplementedError):
+        StorageBackend(ctrl(model=ns.BlackScholesModel(0.0, 100.0, 0.0, 0.2)))
