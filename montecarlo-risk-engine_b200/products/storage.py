@@ -69,6 +69,43 @@ class Storage(Product):
         w = self.storage_config.get_volume_constraint(float(date))
         return w.vmin + torch.as_tensor(state, dtype=FLOAT) * StorageConfig.grid_step(w.vmin, w.vmax, self.num_states)
 
+    # -- host-side views of the inventory moves (storage.py:114-213): the API the reference's unit tests exercise.
+    #    The simulation does not call them; csrc/storage.cu:transitions evaluates the same rule per path and state.
+    def _move(self, date, next_date, action, state):
+        cfg = self.storage_config
+        now, nxt = cfg.get_volume_constraint(date), cfg.get_volume_constraint(next_date)
+        state = torch.as_tensor(state, dtype=FLOAT)
+        vol = now.vmin + state * StorageConfig.grid_step(now.vmin, now.vmax, self.num_states)
+        period = max(next_date - date, 0.0)
+        if action == StorageAction.INJECTION:
+            rate = cfg.interpolate_rate_tensor(vol, cfg.get_injection_flexibility_slice(date))
+            new = torch.clamp(vol + rate * period, max=nxt.vmax)
+        elif action == StorageAction.WITHDRAWAL:
+            rate = cfg.interpolate_rate_tensor(vol, cfg.get_withdrawal_flexibility_slice(date))
+            new = torch.clamp(vol - rate * period, min=nxt.vmin)
+        else:
+            new = torch.clamp(vol, min=nxt.vmin, max=nxt.vmax)
+        return vol, new, nxt
+
+    def compute_next_state(self, date, next_date, action_type):
+        def mapping(previous_state):
+            _, new, nxt = self._move(date, next_date, action_type, previous_state)
+            scale = StorageConfig.state_scale(nxt.vmin, nxt.vmax, self.num_states)
+            return torch.zeros_like(new) if scale == 0.0 else (new - nxt.vmin) * scale
+        return mapping
+
+    def compute_volume_difference(self, date, next_date, action_type):
+        def mapping(previous_state):
+            vol, new, _ = self._move(date, next_date, action_type, previous_state)
+            return new - vol
+        return mapping
+
+    def lookup_state_values(self, values_by_state, state_matrix):
+        b = torch.clamp(state_matrix.to(dtype=FLOAT), 0.0, self.num_states - 1.0)
+        lo, hi = torch.floor(b).long(), torch.ceil(b).long()
+        v_lo, v_hi = values_by_state.gather(dim=1, index=lo), values_by_state.gather(dim=1, index=hi)
+        return v_lo + (b - lo.to(dtype=FLOAT)) * (v_hi - v_lo)
+
     def lower(self):
         """-> float64 array [n_dates, RECORD], one record per action date (layout shared with csrc/storage.cu):
              0 vmin of the date's band        1 inventory per state index (storage_helpers.py:56-60)

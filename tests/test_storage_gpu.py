@@ -98,3 +98,22 @@ def test_storage_large_run_is_deterministic_and_consistent_with_the_small_one():
     small = run(4096, "lapack")
     assert abs(big1[0] - small[0]) < 4.0 * np.hypot(big1[1], small[1])
     assert big1[1] < small[1] / 6.0            # standard error shrinks like 1 / sqrt(64)
+
+
+def test_storage_pv_withdraws_initial_inventory():
+    """tests/pytests/test_storage.py:116-166: one unit in store, price pinned at 10, default quadratic basis: PV = 10."""
+    ns = cases.Namespace()
+    cfg = ns.StorageConfig()
+    cfg.add_volume_constraint(0.0, 2.0, 0.0, 2.0, 0.0)
+    cfg.add_injection_flexibility(0.0, 2.0, 0.0, 1.0)
+    cfg.add_withdrawal_flexibility(0.0, 2.0, 0.0, 1.0)
+    cfg.add_variable_injection_cost(0.0, 0.0)
+    cfg.add_variable_withdrawal_cost(0.0, 0.0)
+    product = ns.Storage("thegasprice", 0.0, 2.0, 1.0, cfg, num_states=3)
+    model = ns.SchwartzTwoFactorModel(0.0, [0.0, 2.0], [10.0, 10.0], 0.0, 1.0, 1e-8, 0.0, 1e-8, 0.0, asset_id="thegasprice")
+    for compat in ("torch", "philox"):
+        sc = ns.SimulationController([ns.NettingSet(name=product.get_name(), products=[product])], model,
+                                     ns.RiskMetrics([ns.PVMetric()]), 2000, 2000, 1, ns.SimulationScheme.ANALYTICAL, False)
+        sc.rng_compat = compat
+        pv = sc.run_simulation().get_results(product.get_name(), "pv", evaluation_idx=0)
+        assert abs(float(pv) - 10.0) < 1e-3

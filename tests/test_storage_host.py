@@ -120,3 +120,47 @@ def test_unsupported_storage_runs_raise_before_any_device_work():
         StorageBackend(ctrl(regression_function=ns.PolyomialRegression(7)))
     with pytest.raises(NotImplementedError):
         StorageBackend(ctrl(model=ns.BlackScholesModel(0.0, 100.0, 0.0, 0.2)))
+
+
+# ---- the reference's own unit tests of the inventory moves (tests/pytests/test_storage.py:19-113), restated ----------
+def _window_storage(ns, shifting=False):
+    cfg = ns.StorageConfig()
+    if shifting:
+        for a, b, lo, hi in ((0.0, 2.0, 0.0, 12.0), (2.0, 3.0, 0.0, 12.0), (3.0, 4.0, 3.0, 9.0)):
+            cfg.add_volume_constraint(a, b, lo, hi, 0.0)
+        cfg.add_injection_flexibility(0.0, 4.0, 0.0, 3.0)
+        cfg.add_withdrawal_flexibility(0.0, 4.0, 0.0, 3.0)
+        cfg.add_variable_injection_cost(0.0, 0.0)
+        cfg.add_variable_withdrawal_cost(0.0, 0.0)
+        return ns.Storage("thegasprice", 0.0, 4.0, 6.0, cfg, num_states=4)
+    cfg.add_volume_constraint(0.0, 4.0, 0.0, 12.0, 0.0)
+    for level, rate in ((0.0, 3.0), (6.0, 1.5)):
+        cfg.add_injection_flexibility(0.0, 4.0, level, rate)
+    for level, rate in ((0.0, 1.0), (6.0, 2.5)):
+        cfg.add_withdrawal_flexibility(0.0, 4.0, level, rate)
+    cfg.add_variable_injection_cost(0.0, 1.0)
+    cfg.add_variable_withdrawal_cost(0.0, 1.0)
+    return ns.Storage("thegasprice", 0.0, 4.0, 4.0, cfg, num_states=4)
+
+
+def test_reference_unit_tests_of_the_inventory_moves():
+    from products.storage import StorageAction
+    ns = cases.Namespace()
+    st = _window_storage(ns)
+    states = torch.tensor([0.0, 1.0, 2.0, 3.0], dtype=torch.float64)
+    now = st.state_to_volume(1.0, states)
+    nxt_s = st.compute_next_state(1.0, 2.0, StorageAction.INJECTION)(states)
+    nxt_v = st.state_to_volume(2.0, nxt_s)
+    assert torch.all(nxt_s[1:] >= nxt_s[:-1]) and torch.all(nxt_v >= now)
+    assert torch.allclose(nxt_v, torch.tensor([4.5, 5.5, 6.5, 7.5], dtype=torch.float64), atol=1e-10, rtol=0.0)
+    assert nxt_v[-1].item() == st.storage_config.get_volume_constraint(2.0).vmax
+    for action in StorageAction:
+        s2 = st.compute_next_state(1.0, 2.0, action)(states)
+        delta = st.compute_volume_difference(1.0, 2.0, action)(states)
+        assert torch.allclose(delta, st.state_to_volume(2.0, s2) - now, atol=1e-10, rtol=0.0)
+    sh = _window_storage(ns, shifting=True)
+    held = sh.compute_next_state(2.0, 3.0, StorageAction.DO_NOTHING)(states)
+    assert torch.allclose(sh.state_to_volume(3.0, held), torch.tensor([3.0, 4.0, 8.0, 9.0], dtype=torch.float64), atol=1e-10, rtol=0.0)
+    assert held[1].item() == 0.5 and held[2].item() == 2.5
+    grid = torch.tensor([[0.0, 10.0, 20.0, 30.0]], dtype=torch.float64)
+    assert sh.lookup_state_values(grid, torch.tensor([[0.5, 2.5, 7.0]], dtype=torch.float64)).tolist() == [[5.0, 25.0, 30.0]]
