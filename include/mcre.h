@@ -191,12 +191,22 @@ typedef struct {
   const double *term_coef;     /* dual[n_term][2] alpha, B of P(t_ex, T_j; r) = exp(alpha - B r) */
   const double *term_w;        /* [n_term] weight of the zero bond in the underlying's value */
   const double *ex_basis;      /* [n_ex][2] shift, scale of the explanatory variable         */
+  /* ---- hybrid books: numeraire of another model (model_config.py:44-47, numeraire_model_idx) ---- */
+  int32_t ext_numeraire;       /* 1: numeraire = exp(ext_rate (t - t0)) instead of the short rate's own account;
+                                  value-only plans (nt = 0)                                     */
+  double ext_rate;
 } mcre_irc_desc;
 
 typedef struct mcre_irc_plan mcre_irc_plan;
 
 int mcre_irc_create(const mcre_irc_desc *desc, mcre_irc_plan **out);
 void mcre_irc_destroy(mcre_irc_plan *plan);
+/* Per-path discounted cashflow totals of the main simulation: d_pv [n_sets][shard->n_paths] is WRITTEN by the next
+ * mcre_irc_mainsim (value-only plans of linear products with MCRE_ACC_PV).  With MCRE_ACC_SPILL on a plan whose
+ * metric dates are all its exposure dates this gives per-path cashflows and exposures of the rate products of a book
+ * that also holds products of another model family (mcre/hybrid.py; the reference nets them in one loop over
+ * products, controller.py:506-563).  NULL: off. */
+int mcre_irc_set_pv_spill(mcre_irc_plan *plan, double *d_pv);
 
 /* Number of accumulator slots of the main simulation / pre-simulation moments. */
 int64_t mcre_irc_main_slots(const mcre_irc_plan *plan);
@@ -546,6 +556,14 @@ int mcre_select_compact(mcre_select_plan *plan, const double *d_values, int64_t 
 int mcre_select_scan(mcre_select_plan *p, int32_t pass, const uint64_t *d_hist, void *stream);
 /* after 8 passes: d_out [n_rows][n_ranks_per_row] the selected values. */
 int mcre_select_finish(mcre_select_plan *p, double *d_out, void *stream);
+
+/* Correlated joint noise of a ModelConfig, materialised: d_out [n_sub][n_paths][dim] = L z per (sub-step, global path
+ * 0 .. n_paths-1) with z the Philox stream of `rng` (normal number sub-step * dim + column of the path) or its injected
+ * draws, and chol [dim][dim] (host) the lower Cholesky factor of the joint correlation (model.py:46-73,
+ * model_config.py:101-142).  For netting sets that mix products of model families whose fused kernels run separately
+ * on columns of one joint draw (mcre/hybrid.py); the fused kernels themselves never materialise noise. */
+int mcre_correlated_normals(const mcre_rng *rng, int32_t n_sub, int32_t dim, const double *chol, int64_t n_paths,
+                            double *d_out, void *stream);
 
 /* ================================================================================
  * Gas storage on a two-factor log-price model

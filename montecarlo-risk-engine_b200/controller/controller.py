@@ -196,6 +196,9 @@ class SimulationController:
         from mcre.equity import EquityBackend
         if EquityBackend.supports(self):
             return EquityBackend(self)
+        from mcre.hybrid import HybridBackend
+        if HybridBackend.supports(self):
+            return HybridBackend(self)
         raise NotImplementedError(
             f"No CUDA backend for model {type(self.model).__name__} with products "
             f"{sorted({type(p).__name__ for p in self.products})}")

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128, 4) irc_presim_forward_kernel(IrcDev P, Rn
       else { MCRE_VP z0[p] = zb[p]; }
       MCRE_VP z1[p] = 0.0;
     }
-    MCRE_VP logB[p] = fma(r[p], dt, logB[p]);          // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+    MCRE_VP logB[p] = fma(P.ext_num ? P.ext_rate : r[p], dt, logB[p]);          // left Riemann sum with the pre-step rate (vasicek.py:80,107)
     if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
       // exact OU transition; the 1x1 Cholesky factor of the step covariance is sv1 (vasicek.py:52-86)
       MCRE_VP r[p] = fma(sv1, z0[p], fma(r[p] - theta, sv0, theta));
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(128, 4) irc_lsm_forward_kernel(IrcDev P, RngDe
       else { MCRE_VP z0[p] = zb[p]; }
       MCRE_VP z1[p] = 0.0;
     }
-    MCRE_VP logB[p] = fma(r[p], dt, logB[p]);
+    MCRE_VP logB[p] = fma(P.ext_num ? P.ext_rate : r[p], dt, logB[p]);
     if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
       MCRE_VP r[p] = fma(sv1, z0[p], fma(r[p] - theta, sv0, theta));
     } else {
@@ -348,6 +348,7 @@ using namespace mcre;
 extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   if (!c || !out) return fail(-1, "null argument%s", "");
   if (c->nt != 0 && c->nt != 4 && c->nt != 8) return fail(-1, "irc: nt must be 0, 4 or 8%s", "");
+  if (c->ext_numeraire && c->nt != 0) return fail(-3, "irc: an external numeraire is implemented for value-only plans%s", "");
   if (c->n_sets < 0 || c->n_sets > MCRE_IRC_MAX_SETS) return fail(-1, "irc: n_sets out of range%s", "");
   if (c->n_units < 0 || c->n_units > MCRE_IRC_MAX_UNITS) return fail(-1, "irc: n_units out of range%s", "");
   if (c->n_berm < 0 || c->n_berm > MCRE_IRC_MAX_BERM) return fail(-1, "irc: n_berm out of range%s", "");
@@ -420,7 +421,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
     for (int k = 0; k < c->n_sets; ++k) p->any_collateral = p->any_collateral || (c->set_flags[k] & 1);
     // "CVA only" kernel (irc_cva.cu): one set, CVA the only accumulator, no threshold / collateral, stochastic
     // intensity started above zero; everything else runs the general kernel
-    p->cva_only = c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA && n_berm == 0 &&
+    p->cva_only = !c->ext_numeraire && c->has_cir && c->nt == 0 && c->n_sets == 1 && c->acc_flags == MCRE_ACC_CVA && n_berm == 0 &&
                   c->set_threshold[0] == 0.0 && (c->set_flags[0] & 1) == 0 && (c->set_flags[0] & 2) != 0 &&
                   !c->cir_deterministic && c->cir_init[0] > 0.0 && c->scheme == MCRE_SCHEME_EULER;
     if (p->cva_only) {
@@ -448,6 +449,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   IrcDev &d = p->d;
   d.nt = c->nt; d.scheme = c->scheme; d.has_cir = c->has_cir; d.cir_det = c->cir_deterministic;
   d.vas_noise = c->vas_noise; d.cir_noise = c->cir_noise;
+  d.ext_num = c->ext_numeraire; d.ext_rate = c->ext_rate; d.pv_spill = nullptr;
   d.vas = p->vas.p; d.cir = p->cir.p; d.cir_init = p->cir_init.p; d.chol = p->chol.p;
   d.n_sub = c->n_sub; d.n_dates = c->n_dates; d.n_pre_dates = c->n_pre_dates;
   d.step_dt = p->step_dt.p; d.step_date = p->step_date.p; d.step_vas = p->step_vas.p; d.step_cir = p->step_cir.p;
@@ -600,6 +602,14 @@ extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const
     irc_lsm_forward_kernel<false, MCRE_SCHEME_ANALYTICAL><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
   else irc_lsm_forward_kernel<false, MCRE_SCHEME_EULER><<<blocks, threads, 0, st>>>(d, r, sh, xbuf, nbuf, ibuf);
   MCRE_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcre_irc_set_pv_spill(mcre_irc_plan *p, double *d_pv) {
+  if (!p) return fail(-1, "null argument%s", "");
+  if (p->cva_only) return fail(-3, "pv spill: not available on the CVA-only plan%s", "");
+  if (p->d.nt != 0 || p->d.n_berm != 0) return fail(-3, "pv spill: value-only plans of linear products%s", "");
+  p->d.pv_spill = d_pv;
   return 0;
 }
 

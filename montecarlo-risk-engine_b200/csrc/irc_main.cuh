@@ -39,6 +39,12 @@ struct IrcDev {
   // of a PFE order statistic is the pathwise gradient of the selected path (pfe_metric.py:59-71 under autograd)
   const long long *path_list;
   double *tan_spill;
+  // hybrid books (mcre/hybrid.py): the numeraire is another model's deterministic money-market account,
+  // exp(ext_rate (t - t0)) (model_config.py:44-47, numeraire_model_idx), accumulated step by step like the path's own;
+  // pv_spill [n_sets][n_paths]: per-path discounted cashflow totals (mcre_irc_set_pv_spill)
+  int ext_num;
+  double ext_rate;
+  double *pv_spill;
 };
 
 // Underlying value of an exercise record at short rate r: const + sum_j w_j P(t, T_j; r) with
@@ -86,7 +92,7 @@ __device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR
   if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
   const R wv = (CIR && P.vas_noise == 1) ? w1 : w0;
   // numeraire integral uses the pre-step rate (left Riemann sum)
-  s.logB = s.logB + s.r * dt;
+  s.logB = s.logB + (P.ext_num ? T::lift(P.ext_rate) : s.r) * dt;
   if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
     R decay = T::load(P.step_vas, is * 2 + 0), nstd = T::load(P.step_vas, is * 2 + 1);
     // exact OU transition; the 1x1 Cholesky factor of the step covariance is nstd (vasicek.py:52-86)
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev 
             MCRE_VP st[p].r = st[p].r + kv1 * z1[p];
           }
         }
-        MCRE_VP st[p].logB = st[p].logB + rate0[p] * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+        MCRE_VP st[p].logB = st[p].logB + (P.ext_num ? T::lift(P.ext_rate) : rate0[p]) * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
         if constexpr (CIR) {
           if (cir_det) {                      // cirpp.py:155-172
             MCRE_VP { st[p].logBl = st[p].logBl + sc0 * dt; st[p].y = sc1; }
@@ -477,6 +483,7 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev 
           for (int p = 0; p < PP; ++p) {
             const R c = cva[p][s] * P.lgd;
             if (pilot && p == 0 && threadIdx.x == 0) { shift[sb + 0] = val(pv[p][s]); shift[sb + 2] = val(c); }
+            if (P.pv_spill && !pilot && live[p] && s < P.n_sets) P.pv_spill[(size_t)s * sh.n_paths + lpath[p]] = val(pv[p][s]);
             const double keep = live[p] ? 1.0 : 0.0;
             const double dp = val(pv[p][s]) - sh_pv, dcv = val(c) - sh_cva;
             vals[s * NV + 0] += keep * dp; vals[s * NV + 1] += keep * dp * dp;

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
           const double adt = a * dt, ssq = sigma * sq;
           om_v = 1.0 - adt; c_v = sv0 * adt; kv0 = ssq * lv0; kv1 = ssq * lv1;
         }
-        MCRE_VP logB[p] = fma(r[p], dt, logB[p]);      // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+        MCRE_VP logB[p] = fma(P.ext_num ? P.ext_rate : r[p], dt, logB[p]);      // left Riemann sum with the pre-step rate (vasicek.py:80,107)
         MCRE_VP r[p] = fma(kv0, z0[p], fma(r[p], om_v, c_v));
         if (kv1 != 0.0) { MCRE_VP r[p] = fma(kv1, z1[p], r[p]); }
         if (CIR) {
@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
           double sh_pv = 0.0, sh_cva = 0.0;
           if (!pilot) { sh_pv = shift[sb + 0]; sh_cva = shift[sb + 2]; }
           if (pilot && tid == 0) { shift[sb + 0] = pv[0][s]; shift[sb + 2] = cva[0][s] * P.lgd; }
+          if (P.pv_spill && !pilot && s < P.n_sets) {
+            MCRE_VP { if (live[p]) P.pv_spill[(size_t)s * sh.n_paths + lpath[p]] = pv[p][s]; }
+          }
           MCRE_VP {
             const double dp = live[p] ? pv[p][s] - sh_pv : 0.0, dcv = live[p] ? cva[p][s] * P.lgd - sh_cva : 0.0;
             vals[s * NV + 0] += dp; vals[s * NV + 1] = fma(dp, dp, vals[s * NV + 1]);

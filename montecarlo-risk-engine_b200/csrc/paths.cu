@@ -9,6 +9,7 @@
 #include "philox.cuh"
 #include "dual.cuh"
 #include "heston.cuh"
+#include "launch.cuh"
 
 namespace mcre {
 
@@ -131,9 +132,53 @@ __global__ void __launch_bounds__(128) paths_kernel(PathsDev P, RngDev rng, long
   }
 }
 
+// Correlated joint noise w = L z of every (sub-step, path), materialised: [n_sub][n_paths][dim].  z is the Philox
+// stream (normal # is * dim + j of the path) or the injected reference stream.  Used by hybrid books whose model
+// families run in separate fused kernels on slices of one joint draw (mcre/hybrid.py).
+__global__ void __launch_bounds__(128) correlated_normals_kernel(RngDev rng, int n_sub, int dim, const double *__restrict__ chol,
+                                                                 long long n_paths, double *__restrict__ out) {
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= n_paths) return;
+  NormalStream ns; ns.init(rng, (unsigned long long)gp);
+  double z[PATHS_MAX_DIM];
+  for (int is = 0; is < n_sub; ++is) {
+    if (rng.mode == MCRE_RNG_INJECT) {
+      const double *zp = rng.z + ((size_t)is * rng.n_total + gp) * dim;
+      for (int j = 0; j < dim; ++j) z[j] = zp[j];
+    } else {
+      for (int j = 0; j < dim; ++j) z[j] = ns.next();
+    }
+    double *o = out + ((size_t)is * n_paths + gp) * dim;
+    for (int i = 0; i < dim; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc += chol[i * dim + j] * z[j];
+      o[i] = acc;
+    }
+  }
+}
+
 }  // namespace mcre
 
 using namespace mcre;
+
+extern "C" int mcre_correlated_normals(const mcre_rng *rng, int32_t n_sub, int32_t dim, const double *chol,
+                                       int64_t n_paths, double *d_out, void *stream) {
+  if (!rng || !chol || !d_out) return fail(-1, "null argument%s", "");
+  if (dim < 1 || dim > PATHS_MAX_DIM || n_sub < 0) return fail(-2, "correlated normals: 1..16 noise dimensions%s", "");
+  if (rng->mode == MCRE_RNG_INJECT && (!rng->d_z || rng->n_paths_total < n_paths))
+    return fail(-1, "inject mode without (enough) normals%s", "");
+  if (n_paths <= 0 || n_sub == 0) return 0;
+  DevArray<double> L;
+  int rc = L.upload(chol, (size_t)dim * dim);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((n_paths + 127) / 128);
+  correlated_normals_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(make_rng(rng), n_sub, dim, L.p, n_paths, d_out);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);   // the factor is freed below
+  L.release();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "correlated normals kernel");
+}
 
 extern "C" int mcre_generate_paths(const mcre_paths_desc *c, const mcre_rng *rng, const mcre_shard *shard,
                                    double *d_paths, void *stream) {

@@ -1024,11 +1024,15 @@ class EquityBackend:
         B.check(B.lib().mcre_eq_set_bridge_uniforms(plan, table.data_ptr(), stride))
         return table
 
-    def _run_split_book(self, si, dev, n_main, n_params):
+    def _run_split_book(self, si, dev, n_main, n_params, chunk=None, extra_expo=None, extra_pv=None):
         """PV (and pathwise Greeks) of one netting set with more path-dependent / exercise products than a launch
         can track: the products are split over launches that replay the same Philox streams; every launch adds
         its per-path discounted cashflows to one accumulator (mcre_eq_set_pv_accumulator), the pilot shifts and
-        the tangent sums add up linearly, and mcre_sum_stats finishes mean / standard error."""
+        the tangent sums add up linearly, and mcre_sum_stats finishes mean / standard error.
+        `extra_expo` [n_expo][n] / `extra_pv` [n]: per-path netted exposures / discounted cashflows of products of
+        ANOTHER model family of the same netting set, on the same paths (mcre/hybrid.py): the accumulators start from
+        them, so that threshold / collateral, the positive parts and the CVA integrand see the whole netting set
+        (controller.py:506-563 sums all products of a set before netting_set.compute_unsecured_exposure_profiles)."""
         c = self.c
         L = B.lib()
         ntrk = eq_ntrk(self.nt)
@@ -1041,18 +1045,27 @@ class EquityBackend:
             books[0] = books[0] + plain
         elif plain:
             books = [plain]
-        chunk = main_chunk(n_main)
+        chunk = main_chunk(n_main) if chunk is None else chunk
         begin, count = RT.shard_range(n_main, chunk)
         n = max(count, 1)
         n_chunks = (n + chunk - 1) // chunk
         need_expo = c.risk_metrics.requires_exposure_profiles()
         if need_expo and self.nt:
             raise NotImplementedError("sensitivities of exposure profiles of books split over several launches")
+        if need_expo and MetricType.CVA in {m.metric_type for m in c.risk_metrics.metrics} and not books:
+            raise NotImplementedError("CVA of a netting set without simulated equity products in a hybrid ModelConfig: "
+                                      "the default weights ride with the first equity launch")
         kinds = {m.metric_type for m in c.risk_metrics.metrics}
         n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
-        accum = torch.zeros(n, dtype=torch.float64, device=dev)
-        accum_e = torch.zeros((n_expo, n), dtype=torch.float64, device=dev) if need_expo else None
+        accum = torch.zeros(n, dtype=torch.float64, device=dev) if extra_pv is None else extra_pv.clone()
+        accum_e = None
+        if need_expo:
+            accum_e = torch.zeros((n_expo, n), dtype=torch.float64, device=dev) if extra_expo is None else extra_expo.clone()
+        # (the shift of the PV sums is the book's value on global path 0, which lives on the rank that owns it)
         shift_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        if extra_pv is not None:
+            first_pv = extra_pv[0:1].clone() if (begin == 0 and count > 0) else torch.zeros(1, dtype=torch.float64, device=dev)
+            shift_sum += RT.all_reduce_tree(first_pv)
         grad, numtan = (np.zeros(n_params) if self.nt else None), 0.0
         cva_metric, cva_w = None, None
         for bi, book in enumerate(books):

@@ -1,0 +1,227 @@
+"""Netting sets that mix equity and interest-rate products under one ModelConfig of Black-Scholes market models
+(the numeraire), a Vasicek short rate and optionally the counterparty's CIR++ intensity - the reference's
+tests/exposure_tests/cva_large_netting_set_derivatives.py (model_config.py:8-276; the controller sums all products of a
+set before the netting terms, controller.py:506-563).
+
+The two product families have their own fused kernels.  Here they run on column slices of ONE joint correlated draw:
+
+  1. mcre_correlated_normals materialises w = L z per (sub-step, path) for the pre-simulation (key 42) and the main
+     simulation (key 43): L = Cholesky factor of the joint correlation, z = Philox or the injected reference stream;
+  2. the rate products run through the interest-rate backend on the Vasicek column with the numeraire of the
+     Black-Scholes model (`ext_numeraire`), spilling per-path netted exposures [exposure date][path] and discounted
+     cashflows instead of finishing metrics;
+  3. the equity products run through the equity backend's accumulating launches on the equity (+ credit) columns,
+     starting from those spills: threshold / MPoR collateral, positive parts, PFE order statistics and the CVA integrand
+     then see the whole netting set.
+
+Value-only.  The noise tensor is O(sub-steps x paths x factors): these books run on thousands to a few million paths.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from common.enums import SimulationScheme
+from mcre import binding as B
+from mcre import runtime as RT
+from mcre.timegrid import build_time_grid
+
+#: largest joint noise tensor (bytes) this backend materialises per simulation pass
+MAX_NOISE_BYTES = 24 << 30
+
+
+def _families(model):
+    """(black-scholes indices, vasicek index, credit index or None) of a hybrid ModelConfig, or None."""
+    from models.black_scholes import BlackScholesModel
+    from models.cirpp import CIRPPModel
+    from models.model_config import ModelConfig
+    from models.vasicek import VasicekModel
+    if not isinstance(model, ModelConfig):
+        return None
+    bs = [i for i, m in enumerate(model.models) if type(m) is BlackScholesModel]
+    vas = [i for i, m in enumerate(model.models) if isinstance(m, VasicekModel)]
+    cir = [i for i, m in enumerate(model.models) if isinstance(m, CIRPPModel)]
+    if not bs or len(vas) != 1 or len(cir) > 1 or len(bs) + len(vas) + len(cir) != len(model.models):
+        return None
+    if model.id_to_model["numeraire"] not in bs:
+        return None
+    return bs, vas[0], (cir[0] if cir else None)
+
+
+class HybridBackend:
+    @staticmethod
+    def supports(ctrl):
+        return _families(ctrl.model) is not None
+
+    def __init__(self, ctrl):
+        from mcre.irc import is_linear
+        self.c = c = ctrl
+        self.bs_idx, self.vas_idx, self.cir_idx = _families(c.model)
+        if c.differentiate:
+            raise NotImplementedError("sensitivities of netting sets that mix rate and equity products "
+                                      "(three-model ModelConfig): value-only for now")
+        if c.simulation_scheme != SimulationScheme.EULER:
+            # the reference defines inter-model covariances for Black-Scholes pairs only (model_config.py:201-221)
+            raise NotImplementedError("Inter covariance not implemented for the requested pair of models.")
+        models = c.model.models
+        vas_assets = set(models[self.vas_idx].asset_ids)
+        eq_assets = {a for i in self.bs_idx for a in models[i].asset_ids}
+        self.rate_products, self.equity_products = [], []
+        for p in c.products:
+            a = p.get_asset_id()
+            if a in vas_assets:
+                if not is_linear(p):
+                    raise NotImplementedError("hybrid books: bonds and swaps on the short-rate model")
+                self.rate_products.append(p)
+            elif a in eq_assets:
+                self.equity_products.append(p)
+            else:
+                raise NotImplementedError(f"hybrid books: no market model for asset {a!r}")
+
+    # ------------------------------------------------------------------ joint noise
+    def _joint_noise(self, which, seed, n_total, n_sub, dev):
+        """-> device tensor [n_sub][n_total][dim] of correlated draws."""
+        from mcre.dual import D, cholesky_dual
+        from mcre.paths import joint_matrix
+        c = self.c
+        dim = int(c.model.simulation_dim)
+        if n_sub * n_total * dim * 8 > MAX_NOISE_BYTES:
+            raise NotImplementedError(f"hybrid books materialise the joint noise: {n_sub} sub-steps x {n_total} paths x "
+                                      f"{dim} factors exceeds {MAX_NOISE_BYTES >> 30} GB")
+        corr = joint_matrix(c.model, c.simulation_scheme, None)
+        Lm = cholesky_dual([[D(x, None, 0) for x in row] for row in corr])
+        chol, chol_p = B.as_dp(np.array([[x.v for x in row] for row in Lm]))
+        rng = B.Rng()
+        rng.seed, rng.stream, rng.n_paths_total = seed, c.rng_stream, n_total
+        z = c.injected_normals.get(which) if c.injected_normals else None
+        if z is not None:
+            if tuple(z.shape) != (n_sub, n_total, dim):
+                raise ValueError(f"injected {which} normals must be [{n_sub}, {n_total}, {dim}]")
+            rng.mode, rng.d_z = B.RNG_INJECT, z.data_ptr()
+        else:
+            rng.mode = B.RNG_PHILOX
+        out = torch.empty((max(n_sub, 1), n_total, dim), dtype=torch.float64, device=dev)
+        B.check(B.lib().mcre_correlated_normals(C.byref(rng), n_sub, dim, chol_p, n_total, out.data_ptr(), RT.stream_ptr()))
+        return out
+
+    def _columns(self):
+        """Noise columns of (equity models, vasicek, credit) in the joint draw."""
+        off, cols = 0, []
+        for m in self.c.model.models:
+            cols.append(off)
+            off += m.simulation_dim
+        return [cols[i] for i in self.bs_idx], cols[self.vas_idx], (cols[self.cir_idx] if self.cir_idx is not None else None)
+
+    # ------------------------------------------------------------------ sub-controllers
+    def _sub(self, model, netting_sets, risk_metrics=None):
+        c = self.c
+        sub = copy.copy(c)
+        sub.model = model
+        sub.netting_sets = netting_sets
+        sub.products = [p for ns in netting_sets for p in ns.products]
+        sub.product_to_netting_set_idx = [i for i, ns in enumerate(netting_sets) for _ in ns.products]
+        if risk_metrics is not None:
+            n = len(c.exposure_timeline)
+            sub.risk_metrics = risk_metrics
+            sub.metric_exposure_timeline = c.exposure_timeline.clone()
+            sub.metric_exposure_indices = torch.arange(n, dtype=torch.long)
+            sub.netting_set_delayed_exposure_indices = [torch.full((n,), -1, dtype=torch.long) for _ in netting_sets]
+        sub.requires_regression = any(sub._product_requires_regression(p) for p in sub.products)
+        sub.injected_normals = {}
+        sub.last_timings = {}
+        return sub
+
+    def run(self):
+        from metrics.metric import MetricType
+        from metrics.pfe_metric import PFEMetric
+        from metrics.pv_metric import PVMetric
+        from metrics.risk_metrics import RiskMetrics
+        from models.model_config import ModelConfig
+        from mcre.equity import EquityBackend
+        from mcre.irc import IrcBackend
+        from products.netting_set import NettingSet
+        c = self.c
+        dev = RT.compute_device()
+        t_start = time.perf_counter()
+        models = c.model.models
+        n_main, n_pre = c.num_paths_mainsim, c.num_paths_presim
+        t0 = float(models[0].calibration_date[0])
+        n_sub = build_time_grid(t0, c.simulation_timeline.tolist(), c.num_steps).n_sub
+        need_expo = c.risk_metrics.requires_exposure_profiles()
+        need_pv = c.risk_metrics.requires_discounted_cashflows()
+        kinds = {m.metric_type for m in c.risk_metrics.metrics}
+        eq_cols, vas_col, cir_col = self._columns()
+        with_credit = MetricType.CVA in kinds and self.cir_idx is not None
+        chunk = 256 if n_main < (1 << 18) else 4096
+
+        # ---- one joint draw per pass, sliced per family (contiguous copies: the kernels index [sub-step][path][column])
+        w_main = self._joint_noise("main", 43, n_main, n_sub, dev)
+        eq_take = eq_cols + ([cir_col] if with_credit else [])
+        noise_eq = {"main": w_main[:, :, eq_take].contiguous()}
+        noise_ir = {"main": w_main[:, :, [vas_col]].contiguous()}
+        del w_main
+        if c.requires_regression and n_pre > 0:
+            w_pre = self._joint_noise("pre", 42, n_pre, n_sub, dev)
+            noise_eq["pre"] = w_pre[:, :, eq_take].contiguous()
+            noise_ir["pre"] = w_pre[:, :, [vas_col]].contiguous()
+            del w_pre
+
+        # ---- rate products: per-path exposures and cashflows under the Black-Scholes numeraire --------------------------
+        n_expo = len(c.exposure_timeline)
+        n_sets = len(c.netting_sets)
+        rate_of_set = [[p for p in ns.products if p in self.rate_products] for ns in c.netting_sets]
+        extra_expo, extra_pv = [None] * n_sets, [None] * n_sets
+        t_pre = 0.0
+        if self.rate_products:
+            rows = [si for si in range(n_sets) if rate_of_set[si]]
+            ir_sets = [NettingSet(name=f"rates_{si}", products=rate_of_set[si]) for si in rows]
+            ir_metrics = ([PFEMetric(0.5)] if need_expo else []) + ([PVMetric()] if need_pv or not need_expo else [])
+            rm = RiskMetrics(ir_metrics, exposure_timeline=c.exposure_timeline.tolist() if need_expo else None)
+            sub = self._sub(models[self.vas_idx], ir_sets, rm)
+            sub.injected_normals = noise_ir
+            ib = IrcBackend(sub)
+            num_model = models[c.model.id_to_model["numeraire"]]
+            ib.hybrid = {"ext_rate": float(num_model.param_values()[2]), "chunk": chunk, "captured": []}
+            _, t_ir = ib.run()
+            t_pre += t_ir.get("preprocessing", 0.0)
+            for idxs, spill, pv_spill in ib.hybrid["captured"]:
+                for r, k in enumerate(idxs):
+                    si = rows[k]
+                    if spill is not None:
+                        extra_expo[si] = spill[r]
+                    if pv_spill is not None:
+                        extra_pv[si] = pv_spill[r]
+
+        # ---- equity products + netting-set terms + metrics on the combined accumulators ------------------------------------
+        eq_models = [models[i] for i in self.bs_idx] + ([models[self.cir_idx]] if with_credit else [])
+        eq_model = eq_models[0] if len(eq_models) == 1 else ModelConfig(models=eq_models)
+        eq_sets = []
+        for ns in c.netting_sets:
+            view = copy.copy(ns)
+            view.products = [p for p in ns.products if p in self.equity_products]
+            eq_sets.append(view)
+        sub = self._sub(eq_model, eq_sets)
+        sub.injected_normals = noise_eq
+        eb = EquityBackend(sub)
+        t1 = time.perf_counter()
+        from mcre.equity import is_equity_exercise
+        eb.presim_exercise_all([p for p in sub.products if is_equity_exercise(p)], dev)
+        if need_expo:
+            reg = [p for p in sub.products if not sub._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
+            if reg:
+                eb.presim_regression(reg, dev)
+        torch.cuda.synchronize(dev)
+        t_pre += time.perf_counter() - t1
+        n_params = len(sub.model.model_params)
+        results = []
+        for si in range(n_sets):
+            res = eb._run_split_book(si, dev, n_main, n_params, chunk=chunk, extra_expo=extra_expo[si], extra_pv=extra_pv[si])
+            res["param_used"] = lambda kind: [False] * len(c.model.model_params)
+            results.append(res)
+        torch.cuda.synchronize(dev)
+        total = time.perf_counter() - t_start
+        return results, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}

@@ -194,6 +194,9 @@ class IrcBackend:
         self.scheme = scheme
         self.nt = len(ctrl.model.model_params) if ctrl.differentiate else 0
         self._keep = []
+        #: set by mcre/hybrid.py: {"ext_rate": rate of the numeraire model, "chunk": reduction chunk shared with the
+        #: equity launches, "captured": [(set indices, exposure spill, pv spill, pv shift)] filled by run()}
+        self.hybrid = None
 
     # ------------------------------------------------------------------ lowering
     def _dual_params(self):
@@ -262,7 +265,8 @@ class IrcBackend:
         sigs = [_sig_product(p) for p in prods]
         if any(sg is None for sg in sigs):
             return None
-        model_sig = (tuple(self.vas.param_values()), float(self.vas.t0()), self.vas_idx, self.cir_idx)
+        model_sig = (tuple(self.vas.param_values()), float(self.vas.t0()), self.vas_idx, self.cir_idx,
+                     None if self.hybrid is None else float(self.hybrid["ext_rate"]))
         if self.has_cir:
             model_sig += (tuple(self.cir.param_values()), float(self.cir.t0()), tuple(self.cir.tenors.tolist()),
                           tuple(self.cir.hazard_rates.tolist()), bool(self.cir.deterministic), tuple(self.cir.asset_ids))
@@ -503,6 +507,10 @@ class IrcBackend:
         d.cir_deterministic = int(self.has_cir and self.cir.deterministic)
         d.vas_noise = self.vas_idx if self.has_cir else 0
         d.cir_noise = self.cir_idx if self.has_cir else 0
+        if self.hybrid is not None:
+            if nt:
+                raise NotImplementedError("sensitivities of books that mix rate and equity products")
+            d.ext_numeraire, d.ext_rate = 1, float(self.hybrid["ext_rate"])
 
         def fp(name, arr):
             t[name], ptr = B.as_dp(arr)
@@ -887,17 +895,22 @@ class IrcBackend:
                     exc_k, exc_ptr = B.as_dp(exc)
                     bex_k, bex_ptr = B.as_dp(bex)
                     B.check(L.mcre_irc_set_exercise_coefficients(plan, exc_ptr, bex_ptr, RT.stream_ptr()))
-                begin, count = RT.shard_range(n_main, CHUNK_PATHS)
+                chunk_paths = CHUNK_PATHS if self.hybrid is None else self.hybrid["chunk"]
+                begin, count = RT.shard_range(n_main, chunk_paths)
                 slots = L.mcre_irc_main_slots(plan)
                 acc = torch.zeros(slots, dtype=torch.float64, device=dev)
                 shift = torch.zeros(slots, dtype=torch.float64, device=dev)
-                partial = torch.empty(L.mcre_irc_partial_bytes(plan, max(count, 1), CHUNK_PATHS, 0) // 8 + 1,
+                partial = torch.empty(L.mcre_irc_partial_bytes(plan, max(count, 1), chunk_paths, 0) // 8 + 1,
                                       dtype=torch.float64, device=dev)
                 spill = None
                 if info["acc"] & B.ACC_SPILL:
                     spill = torch.empty((len(idxs), n_metric, max(count, 1)), dtype=torch.float64, device=dev)
+                pv_spill = None
+                if self.hybrid is not None and (info["acc"] & B.ACC_PV):
+                    pv_spill = torch.zeros((len(idxs), max(count, 1)), dtype=torch.float64, device=dev)
+                    B.check(L.mcre_irc_set_pv_spill(plan, pv_spill.data_ptr()))
                 rng = self._rng(43, inject, n_main)
-                sh = B.Shard(begin, count, CHUNK_PATHS)
+                sh = B.Shard(begin, count, chunk_paths)
                 B.check(L.mcre_irc_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
                                            shift.data_ptr(), spill.data_ptr() if spill is not None else None,
                                            RT.stream_ptr()))
@@ -907,6 +920,10 @@ class IrcBackend:
                 acc_h = RT.to_host(acc)
                 shift_h = RT.to_host(shift)
                 quant = None
+                if self.hybrid is not None:
+                    # per-path exposures / cashflows handed to the combining backend; no metric is finished here
+                    self.hybrid["captured"].append((list(idxs), spill, pv_spill))
+                    spill = None
                 if spill is not None:
                     from mcre.select import order_statistics
                     quant = order_statistics(c, spill, count, n_main)

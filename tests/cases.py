@@ -326,6 +326,53 @@ def heston_euler_book(ns_module):
     return model, sets, [m.PVMetric()], None
 
 
+def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_level=0.03, deterministic=True,
+               rho=(0.0, 0.0, 0.0), horizon=4.0, n_expo=30, extra_metrics=False, collateral=False):
+    """Equity options + bonds + swaps in ONE netting set against a three-model ModelConfig: Black-Scholes (numeraire),
+    Vasicek, CIR++ credit (tests/exposure_tests/cva_large_netting_set_derivatives.py:58-175, the book of
+    tests/pytests/test_cva_large_netting_set_aad_vs_fd.py:26-57).  rho = inter-model correlations in the reference's
+    order (equity-rates, equity-credit, rates-credit)."""
+    m = ns_module
+    cp = "large_counterparty"
+    prods = []
+    mats, strikes = np.linspace(0.5, 3.0, 8), np.linspace(0.85, 1.15, 10)
+    for i in range(n_euro):
+        o = m.EuropeanOption(m.Equity("equity"), float(mats[i % 8]), 100.0 * float(strikes[i % 10]), m.OptionType.CALL, asset_id="equity")
+        o.name = f"large_european_call_{i}"
+        prods.append(o)
+    bmats, coupons = np.linspace(2.0, 6.0, 8), np.linspace(0.018, 0.030, 5)
+    for i in range(n_bonds):
+        b = m.Bond(startdate=0.0, maturity=float(bmats[i % 8]), notional=2.0, tenor=0.5, pays_notional=True,
+                   fixed_rate=float(coupons[i % 5]), asset_id="rates")
+        b.name = f"large_bond_{i}"
+        prods.append(b)
+    fixed = np.linspace(0.019, 0.031, 6)
+    for i in range(n_swaps):
+        sw = m.InterestRateSwap(startdate=0.0, enddate=float(bmats[i % 8]), notional=25.0, fixed_rate=float(fixed[i % 6]),
+                                tenor_fixed=0.5, tenor_float=0.25, irs_type=m.IRSType.PAYER, asset_id="rates")
+        sw.name = f"large_swap_{i}"
+        prods.append(sw)
+    eq = m.BlackScholesModel(calibration_date=0.0, spot=spot, rate=rate_level, sigma=0.22, asset_id="equity")
+    rates = m.VasicekModel(calibration_date=0.0, rate=rate_level, mean=0.03, mean_reversion_speed=1.0, volatility=0.01,
+                           asset_id="rates")
+    credit = m.CIRPPModel(calibration_date=0.0, asset_id=cp, hazard_rates=HAZARDS, kappa=0.10, theta=0.01, volatility=0.02,
+                          y0=0.0001, deterministic=deterministic)
+    model = m.ModelConfig(models=[eq, rates, credit], inter_asset_correlation_matrix=[np.array([r]) for r in rho])
+    metrics = [m.CVAMetric(counterparty_id=cp, recovery_rate=0.4)]
+    if extra_metrics:
+        metrics += [m.EPEMetric(), m.PVMetric()]
+    if collateral:
+        # the same book twice: thresholded, and MPoR-collateralised with a threshold; more metrics
+        metrics += [m.ENEMetric(), m.PFEMetric(0.9)]
+        tl = np.linspace(0.0, horizon, n_expo)
+        _, twin, _, _ = hybrid_cva(ns_module, n_euro, n_bonds, n_swaps, spot, rate_level, deterministic, rho, horizon, n_expo)
+        sets = [m.NettingSet(name="open", products=prods, counterparty_id=cp, threshold=1.5),
+                m.NettingSet(name="margined", products=twin[0].products, counterparty_id=cp, threshold=0.5,
+                             margin_period_of_risk=float(tl[1] - tl[0]))]
+        return model, sets, metrics, tl
+    return model, [m.NettingSet(name="large_cva_ns", products=prods, counterparty_id=cp)], metrics, np.linspace(0.0, horizon, n_expo)
+
+
 def _days(a, b):
     import datetime
     return float((datetime.date(*b) - datetime.date(*a)).days)
@@ -424,6 +471,13 @@ GOLDEN_CASES = {
     # models the reference only runs standalone
     "schwartz_analytical": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=2, scheme="ANALYTICAL", differentiate=True)),
     "schwartz_euler": (schwartz_book, dict(), dict(n_main=4096, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
+    # three-model hybrid: equity + rates products netted in one set (test_cva_large_netting_set_aad_vs_fd.py at its
+    # own sizes, value-only; a stochastic-credit, correlated twin with more metrics)
+    "hybrid_cva": (hybrid_cva, dict(), dict(n_main=1024, n_pre=1024, num_steps=4, scheme="EULER", differentiate=False)),
+    "hybrid_cva_corr": (hybrid_cva, dict(n_euro=3, n_bonds=2, n_swaps=5, deterministic=False, rho=(0.3, -0.2, 0.4), horizon=2.0, n_expo=9, extra_metrics=True),
+                        dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
+    "hybrid_collateral": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, deterministic=False, rho=(0.25, 0.1, -0.3), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True),
+                          dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=False)),
     # gas storage (the reference's tests/pytests/test_storage_s2f_pv.py at its own sizes, and cut-down twins);
     # "degree" = polynomial degree of the regression basis (PolyomialRegression(degree), default 2)
     "storage1": (storage_s2f, dict(which="storage1"), dict(n_main=2000, n_pre=4000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
