@@ -622,6 +622,12 @@ int64_t mcre_storage_moment_slots(const mcre_storage_plan *plan);
 int mcre_storage_moments(mcre_storage_plan *plan, int32_t date, double centre, double inv_scale, const double *d_spot_row,
                          const double *d_value, int64_t n, int32_t chunk_paths, double *d_partial, double *d_out,
                          void *stream);
+/* Minimum-norm solution of the normal equations of one regression date on the device: d_mom = the (all-reduced) sums of
+ * mcre_storage_moments, d_coef_row [2 + n_states * n_basis]: the coefficients are written behind the (centre, inverse
+ * scale) pair the caller keeps in its first two entries.  Eigenvalues of the Gram matrix below rcond x the largest are
+ * cut off (numpy.linalg.lstsq(G, rhs, rcond): a date with a deterministic spot fits the mean).  No host synchronisation:
+ * the backward induction is one stream of kernels. */
+int mcre_storage_solve(mcre_storage_plan *plan, const double *d_mom, double rcond, double *d_coef_row, void *stream);
 /* Valuation pass, fused (path stepping + decisions + cashflows): ADDS each local path's discounted cashflows to d_cfs
  * [shard->n_paths]; d_coef [n_dates][2 + n_states * n_basis] (device); d_final_state [n_paths] or NULL. */
 int mcre_storage_mainsim(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, const double *d_coef,

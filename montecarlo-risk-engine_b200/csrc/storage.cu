@@ -13,6 +13,7 @@
 // The inventory arithmetic (volume <-> state, rate-curve interpolation, clamps) uses explicit unfused
 // multiplies and adds: it is pure +,-,*,/ on contract data and reproduces the reference's doubles bit for bit,
 // so a path sits in exactly the reference's state unless a decision differs.
+#define MCRE_FAST_MATH 2   // table-driven exp / log / sincos of fastmath.cuh (<= 2 ulp), like the other fused kernels
 #include "common.cuh"
 #include "launch.cuh"
 #include "philox.cuh"
@@ -149,6 +150,7 @@ __device__ __forceinline__ void draw2(const RngDev &rng, NormalStream &ns, int i
 
 __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P, RngDev rng, long long path_begin,
                                                                    long long n_paths, double *__restrict__ spot) {
+  fm_tables_init();
   const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n_paths) return;
   const long long gp = path_begin + lp;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P,
     draw2(rng, ns, is, gp, z0, z1);
     const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
     const int d = __ldg(P.step_date + is);
-    if (d >= 0) spot[(size_t)d * n_paths + lp] = exp(ls);
+    if (d >= 0) spot[(size_t)d * n_paths + lp] = fm_exp_t(ls);
   }
 }
 
@@ -171,15 +173,25 @@ __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P,
 __global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev P, int date, const double *__restrict__ coef,
                                                                       const double *__restrict__ x, double *__restrict__ value,
                                                                       long long n) {
-  __shared__ double s_ns[3 * ST_MAX_S], s_dv[3 * ST_MAX_S];
+  // per (action, on-grid state): volume difference, interpolation weight and the two neighbouring states of the state
+  // the action leads to - none of them depends on the path (first profile: 315 warp instructions per (path, state)
+  // with the moves recomputed per path, profiles/r02_storage_kernels.md)
+  __shared__ double s_dv[3 * ST_MAX_S], s_w[3 * ST_MAX_S];
+  __shared__ int s_lo[3 * ST_MAX_S], s_hi[3 * ST_MAX_S];
   __shared__ double s_val[ST_MAX_S * ST_THREADS], s_grid[ST_MAX_S * ST_THREADS];
   const int S = P.n_states, NB = P.n_basis, tid = threadIdx.x;
   const double *r = P.rec + (size_t)date * ST_REC;
   const bool last = __ldg(r + 10) != 0.0;
-  if (tid < S) {     // on-grid states: the moves do not depend on the path
+  if (tid < S) {
     const Moves m = transitions(r, (double)tid);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { s_ns[a * ST_MAX_S + tid] = m.ns[a]; s_dv[a * ST_MAX_S + tid] = m.dv[a]; }
+    for (int a = 0; a < 3; ++a) {
+      int lo, hi;
+      double w;
+      neighbours(m.ns[a], S, lo, hi, w);
+      s_dv[a * ST_MAX_S + tid] = m.dv[a]; s_w[a * ST_MAX_S + tid] = w;
+      s_lo[a * ST_MAX_S + tid] = lo; s_hi[a * ST_MAX_S + tid] = hi;
+    }
   }
   const long long p = (long long)blockIdx.x * blockDim.x + tid;
   const bool live = p < n;
@@ -195,26 +207,25 @@ __global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev
   __syncthreads();
   if (!live) return;
   const double num = __ldg(P.numeraire + date);
+  const double ci = __ldg(r + 6), cw = __ldg(r + 7);
+  const double buy = spot + ci, sell = spot - cw;      // storage.py:246-253
   for (int s = 0; s < S; ++s) {
-    Moves m;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { m.ns[a] = s_ns[a * ST_MAX_S + s]; m.dv[a] = s_dv[a * ST_MAX_S + s]; }
     double pay[3], v[3];
-    payoffs(r, m, spot, pay);
-    int lo[3], hi[3];
-    double w[3];
+    const double dv1 = s_dv[ST_MAX_S + s];
+    pay[0] = -s_dv[s] * buy;
+    pay[1] = -dv1 * (dv1 >= 0.0 ? buy : sell);
+    pay[2] = -s_dv[2 * ST_MAX_S + s] * sell;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      neighbours(m.ns[a], S, lo[a], hi[a], w[a]);
-      const double gl = s_grid[lo[a] * ST_THREADS + tid], gh = s_grid[hi[a] * ST_THREADS + tid];
-      v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(w[a], __dsub_rn(gh, gl)));
+      const double gl = s_grid[s_lo[a * ST_MAX_S + s] * ST_THREADS + tid], gh = s_grid[s_hi[a * ST_MAX_S + s] * ST_THREADS + tid];
+      v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(s_w[a * ST_MAX_S + s], __dsub_rn(gh, gl)));
     }
     const int a = best_of(v);
-    const int l = a == 0 ? lo[0] : a == 1 ? lo[1] : lo[2], h = a == 0 ? hi[0] : a == 1 ? hi[1] : hi[2];
-    const double ww = a == 0 ? w[0] : a == 1 ? w[1] : w[2], pa = a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2];
-    const double tl = s_val[l * ST_THREADS + tid], th = s_val[h * ST_THREADS + tid];
-    const double tail = __dadd_rn(tl, __dmul_rn(ww, __dsub_rn(th, tl)));
-    const double step = (double)(float)__ddiv_rn(pa, num);     // float32 accumulator of the window (controller.py:331, 342)
+    const double pa = a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2];
+    const double tl = s_val[s_lo[a * ST_MAX_S + s] * ST_THREADS + tid], th = s_val[s_hi[a * ST_MAX_S + s] * ST_THREADS + tid];
+    const double tail = __dadd_rn(tl, __dmul_rn(s_w[a * ST_MAX_S + s], __dsub_rn(th, tl)));
+    // float32 accumulator of the window (controller.py:331, 342); x / 1 is exact, so the division is skipped there
+    const double step = (double)(float)(num == 1.0 ? pa : __ddiv_rn(pa, num));
     value[(size_t)s * n + p] = step + tail;
   }
 }
@@ -258,12 +269,110 @@ __global__ void __launch_bounds__(256) storage_moments_kernel(StorageDev P, int 
   }
 }
 
+
+// Minimum-norm solution of the normal equations of one regression date on the device (the host solver of the
+// "moments" mode was one synchronisation per action date: 0.3 ms x 454 dates).  mom: the all-reduced sums of
+// storage_moments_kernel.  Thread 0 diagonalises the (NB x NB) Gram matrix by cyclic Jacobi rotations (symmetric positive
+// semi-definite: eigenvalues = singular values), threads s < S apply the pseudo-inverse with the cut-off
+// lambda_i > rcond * lambda_max to their right-hand side - numpy.linalg.lstsq(G, rhs, rcond) in exact arithmetic,
+// including the rank-1 system of a date with a deterministic spot (all u equal -> the mean).
+__global__ void __launch_bounds__(32) storage_solve_kernel(int S, int NB, const double *__restrict__ mom, double rcond,
+                                                           double *__restrict__ coef) {
+  __shared__ double V[ST_MAX_B][ST_MAX_B], lam[ST_MAX_B];
+  __shared__ int use_chol;
+  __shared__ double Lc[ST_MAX_B][ST_MAX_B];
+  if (threadIdx.x == 0) {
+    double G[ST_MAX_B][ST_MAX_B];
+    double dmax = 0.0;
+    for (int a = 0; a < NB; ++a)
+      for (int b = 0; b < NB; ++b) { G[a][b] = mom[S * NB + a + b]; V[a][b] = a == b ? 1.0 : 0.0; }
+    for (int a = 0; a < NB; ++a) dmax = fmax(dmax, G[a][a]);
+    // fast path: a Cholesky factorisation whose pivots stay above 1e-8 of the largest diagonal entry - the matrix is
+    // then far from the rcond cut-off and the pseudo-inverse is the inverse (all but the deterministic-spot dates;
+    // the single-thread Jacobi sweeps below cost 80 us, as much as the backward and moments kernels together)
+    int ok = 1;
+    for (int j = 0; j < NB && ok; ++j) {
+      double d = G[j][j];
+      for (int k = 0; k < j; ++k) d -= Lc[j][k] * Lc[j][k];
+      if (!(d > 1e-8 * dmax)) { ok = 0; break; }
+      const double lj = sqrt(d);
+      Lc[j][j] = lj;
+      for (int i = j + 1; i < NB; ++i) {
+        double v = G[i][j];
+        for (int k = 0; k < j; ++k) v -= Lc[i][k] * Lc[j][k];
+        Lc[i][j] = v / lj;
+      }
+    }
+    use_chol = ok;
+    for (int sweep = 0; sweep < 12 && !ok; ++sweep) {
+      double off = 0.0, diag = 0.0;
+      for (int a = 0; a < NB; ++a) { diag += G[a][a] * G[a][a]; for (int b = a + 1; b < NB; ++b) off += G[a][b] * G[a][b]; }
+      if (off <= 1e-34 * diag) break;
+      for (int p = 0; p < NB; ++p)
+        for (int q = p + 1; q < NB; ++q) {
+          if (G[p][q] == 0.0) continue;
+          const double theta = (G[q][q] - G[p][p]) / (2.0 * G[p][q]);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+          for (int k = 0; k < NB; ++k) {       // columns p, q
+            const double gkp = G[k][p], gkq = G[k][q];
+            G[k][p] = c * gkp - sn * gkq; G[k][q] = sn * gkp + c * gkq;
+          }
+          for (int k = 0; k < NB; ++k) {       // rows p, q
+            const double gpk = G[p][k], gqk = G[q][k];
+            G[p][k] = c * gpk - sn * gqk; G[q][k] = sn * gpk + c * gqk;
+          }
+          for (int k = 0; k < NB; ++k) {
+            const double vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq;
+          }
+        }
+    }
+    double top = 0.0;
+    for (int a = 0; a < NB; ++a) { lam[a] = G[a][a]; top = fmax(top, fabs(G[a][a])); }
+    for (int a = 0; a < NB; ++a) lam[a] = lam[a] > rcond * top ? 1.0 / lam[a] : 0.0;   // (inverse, 0 = cut off)
+  }
+  __syncthreads();
+  if (use_chol) {
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+      double y[ST_MAX_B];
+      for (int i = 0; i < NB; ++i) {           // L y = b
+        double v = mom[s * NB + i];
+        for (int k = 0; k < i; ++k) v -= Lc[i][k] * y[k];
+        y[i] = v / Lc[i][i];
+      }
+      for (int i = NB - 1; i >= 0; --i) {      // L^T c = y
+        double v = y[i];
+        for (int k = i + 1; k < NB; ++k) v -= Lc[k][i] * y[k];
+        y[i] = v / Lc[i][i];
+      }
+      for (int k = 0; k < NB; ++k) coef[2 + s * NB + k] = y[k];
+    }
+    return;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    double y[ST_MAX_B];
+    for (int i = 0; i < NB; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < NB; ++k) acc += V[k][i] * mom[s * NB + k];
+      y[i] = acc * lam[i];
+    }
+    for (int k = 0; k < NB; ++k) {
+      double acc = 0.0;
+      for (int i = 0; i < NB; ++i) acc += V[k][i] * y[i];
+      coef[2 + s * NB + k] = acc;
+    }
+  }
+}
+
 // Valuation pass (controller.py:399-410 with storage.py:215-308 inlined): one thread per path carries the two factors,
 // the inventory state and the running sum of discounted cashflows.  coef: [n_dates][2 + S * NB].
 __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, RngDev rng, long long path_begin,
                                                                   long long n_paths, const double *__restrict__ coef,
                                                                   double initial_state, double *__restrict__ cfs,
                                                                   double *__restrict__ final_state) {
+  fm_tables_init();
   const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n_paths) return;
   const long long gp = path_begin + lp;
@@ -305,7 +414,7 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
     draw2(rng, ns, is, gp, z0, z1);
     const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
     const int d = __ldg(P.step_date + is);
-    if (d >= 0) act(d, exp(ls));
+    if (d >= 0) act(d, fm_exp_t(ls));
   }
   cfs[lp] += total;
   if (final_state) final_state[lp] = state;
@@ -397,6 +506,14 @@ extern "C" int mcre_storage_moments(mcre_storage_plan *p, int32_t date, double c
     MCRE_LAUNCHED();
   }
   return mcre_tree_reduce(d_partial, n_chunks, slots, d_out, stream);
+}
+
+extern "C" int mcre_storage_solve(mcre_storage_plan *p, const double *d_mom, double rcond, double *d_coef_row,
+                                  void *stream) {
+  if (!p || !d_mom || !d_coef_row) return fail(-1, "null argument%s", "");
+  storage_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p->d.n_states, p->d.n_basis, d_mom, rcond, d_coef_row);
+  MCRE_LAUNCHED();
+  return 0;
 }
 
 extern "C" int mcre_storage_mainsim(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard,

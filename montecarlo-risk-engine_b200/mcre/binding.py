@@ -74,7 +74,7 @@ SYMBOLS = [
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_step_dev", "mcre_lsm_solve_dev", "mcre_lsm_moments_batch", "mcre_lsm_step_batch", "mcre_lsm_step_tangents",
     "mcre_lsm_prepare_equity",
     "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_presim_tangents", "mcre_eq_set_exposure_coef_tangents", "mcre_eq_set_credit", "mcre_eq_set_cva_weight_spill", "mcre_eq_cva_paths", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
-    "mcre_storage_create", "mcre_storage_destroy", "mcre_storage_spots", "mcre_storage_backward", "mcre_storage_moment_slots", "mcre_storage_moments", "mcre_storage_mainsim",
+    "mcre_storage_create", "mcre_storage_destroy", "mcre_storage_spots", "mcre_storage_backward", "mcre_storage_moment_slots", "mcre_storage_moments", "mcre_storage_solve", "mcre_storage_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_compact", "mcre_select_finish",
     "mcre_tree_reduce", "mcre_dfma_peak", "mcre_fastmath_probe", "mcre_launch_count", "mcre_h2d_bytes", "mcre_last_error", "mcre_abi_version",
@@ -167,6 +167,7 @@ def lib():
     L.mcre_storage_moment_slots.restype = C.c_int64
     L.mcre_storage_moments.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_storage_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     L.mcre_storage_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_double, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]

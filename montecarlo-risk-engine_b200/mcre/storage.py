@@ -17,7 +17,9 @@ Replaces, for `products.storage.Storage`, the reference's pre-simulation + backw
                                  decisions and value grids stay on the GPU;
                      "moments" - Gram / right-hand-side moments of the standardised basis accumulated on the device
                                  (fixed-order chunk tree, all-reduced over ranks), (basis x basis) normal equations
-                                 solved on the host; paths are sharded over the GPUs.  Default above that size;
+                                 solved on the device by Jacobi diagonalisation with a minimum-norm cut-off: the whole
+                                 induction is one stream of kernels; paths are sharded over the GPUs.  Default above
+                                 that size;
   main simulation: one fused launch per product (stepping + decisions + cashflows), per-path totals of a netting
                    set accumulated on the device, mean and standard error by mcre_sum_stats.
 """
@@ -205,13 +207,14 @@ class StorageBackend:
             else:
                 B.check(L.mcre_storage_moments(plan, j, coef_h[j, 0], coef_h[j, 1], spot[j].data_ptr(), value.data_ptr(),
                                                count, chunk, partial.data_ptr(), mom.data_ptr(), RT.stream_ptr()))
-                m = RT.to_host(RT.all_reduce_tree(mom))
-                rhs = m[:S * NB].reshape(S, NB).T                  # [NB, S]
-                pw = m[S * NB:]
-                G = np.array([[pw[a + b] for b in range(NB)] for a in range(NB)])
-                sol, *_ = np.linalg.lstsq(G, rhs, rcond=1e-12)      # minimum norm where the spot is deterministic
-                coef_h[j, 2:] = sol.T.reshape(-1)
+                # normal equations solved on the device, coefficients written straight into the row the next backward
+                # step reads: no host synchronisation inside the induction (NCCL's all-gather is stream ordered)
+                B.check(L.mcre_storage_solve(plan, RT.all_reduce_tree(mom).data_ptr(), 1e-12, coef[j].data_ptr(),
+                                             RT.stream_ptr()))
+                continue
             coef[j].copy_(torch.from_numpy(coef_h[j]), non_blocking=False)
+        if self.mode == "moments":
+            coef_h = RT.to_host(coef)
         # regression coefficients of the product, as the reference stores them ([date][state][basis]); in "moments"
         # mode they refer to the standardised spot (spot - centre) * inverse scale, kept next to them
         prod.regression_coeffs = torch.from_numpy(coef_h[:, 2:].reshape(n_dates, S, NB).copy())

@@ -118,8 +118,16 @@ class Storage(Product):
         cfg, S = self.storage_config, self.num_states
         acts, nexts = self.product_timeline.tolist(), self.next_action_dates.tolist()
         rec = np.zeros((len(acts), RECORD))
+        env = cfg.volume_constraints
+
+        def band(i, t):
+            # the envelope has one window per action date, in order: the linear search of get_volume_constraint
+            # (454 x 455 window tests for a 15-month contract) finds exactly this one
+            if i < len(env) and env[i].contains(t):
+                return env[i]
+            return cfg.get_volume_constraint(t)
         for i, (t, t_next) in enumerate(zip(acts, nexts)):
-            now, nxt = cfg.get_volume_constraint(t), cfg.get_volume_constraint(t_next)
+            now, nxt = band(i, t), band(i + 1, t_next)
             inj, wd = cfg.get_injection_flexibility_slice(t), cfg.get_withdrawal_flexibility_slice(t)
             if len(inj) > MAX_KNOTS or len(wd) > MAX_KNOTS:
                 raise NotImplementedError(f"at most {MAX_KNOTS} knots per injection / withdrawal curve")

@@ -63,6 +63,22 @@ def main():
             diff = name == "5g"
             return dict(model=model, sets=sets, metrics=metrics, tl=None, n_main=n(24), n_pre=0, steps=21, scheme=S.QE,
                         diff=diff, sub=252, show=[("barrier", "pv"), ("asian", "pv")])
+        if name in ("st", "stL"):
+            # gas storage on the Schwartz two-factor model (tests/pytests/test_storage_s2f_pv.py: "storage2", 454 daily
+            # decisions, 10 inventory states, cubic regression): "st" at the reference's own 4000 / 2000 paths (LAPACK
+            # solve of the regressions), "stL" at 2^20 paths in both passes (device moments)
+            model, sets, metrics, tl = cases.storage_s2f(ns, which="storage2")
+            big = name == "stL"
+            return dict(model=model, sets=sets, metrics=metrics, tl=None, n_main=n(20) if big else 2000,
+                        n_pre=n(20) if big else 4000, steps=1, scheme=S.ANALYTICAL, diff=False, sub=454,
+                        show=[("Storage", "pv")], extra=dict(regression_function=ns.PolyomialRegression(degree=3)))
+        if name in ("hy", "hyL"):
+            # three-model hybrid book of tests/pytests/test_cva_large_netting_set_aad_vs_fd.py (8 calls, 4 bonds, 40 swaps,
+            # 30 exposure dates x 4 sub-steps): at its own 1024 paths and at 2^20
+            model, sets, metrics, tl = cases.hybrid_cva(ns)
+            big = name == "hyL"
+            return dict(model=model, sets=sets, metrics=metrics, tl=tl, n_main=n(20) if big else 1024, n_pre=n(20) if big else 1024,
+                        steps=4, scheme=S.EULER, diff=False, sub=116, show=[("large_cva_ns", "cva[large_counterparty]")])
         raise SystemExit(f"unknown config {name}")
 
     # algorithmic FP64 flop per path-step, derived like SURVEY 8(d) does for config 3 (add/mul 1, FMA 2,
@@ -73,7 +89,11 @@ def main():
     #  2o: as 2 but only every second sub-step is a metric date                     ~ 64 + 7 + 60
     #  4: 64 + 7 + exercise date: ~22 zero bonds x (exp 20 + 2) + payoff / decision 10 + exposure 30 + numeraire 20 = 615
     #  5: 5 assets x (2 normals 64 + uniform 4 + ~90 algebraic + 2 exp + 1 log + 4 sqrt + 4 div = 60 + 64) ~ 5 x 282 + basket 20
-    flop_model = {"1": 184.0, "2": 181.0, "2o": 131.0, "3": 225.0, "3g": 225.0, "4": 615.0, "5": 1430.0, "5g": 1430.0}
+    #  st / stL: Box-Muller pair 64 + two-factor step 12 + exp 20 + decision (3 rate-curve interpolations ~30, 6 cubics 36,
+    #     payoffs / arg-max / division ~20)                                          ~ 180
+    #  hy / hyL: 3 normals 96 + correlation 9 + BS / Vasicek / credit steps ~25 + per exposure date (every 4th sub-step)
+    #     numeraire exp 20 + 2 polynomials + netting 20                              ~ 150
+    flop_model = {"st": 180.0, "stL": 180.0, "hy": 150.0, "hyL": 150.0, "1": 184.0, "2": 181.0, "2o": 131.0, "3": 225.0, "3g": 225.0, "4": 615.0, "5": 1430.0, "5g": 1430.0}
     import ctypes as C
     peak = C.c_double(0.0)
     from mcre import runtime as RT
@@ -87,7 +107,8 @@ def main():
             torch.cuda.synchronize()
             l0 = B.launch_count()
             t0 = time.perf_counter()
-            ctl = ns.SimulationController(c["sets"], c["model"], rm, c["n_main"], c["n_pre"], c["steps"], c["scheme"], c["diff"])
+            ctl = ns.SimulationController(c["sets"], c["model"], rm, c["n_main"], c["n_pre"], c["steps"], c["scheme"], c["diff"],
+                                          **c.get("extra", {}))
             res = ctl.run_simulation()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
