@@ -600,6 +600,13 @@ typedef struct {
                                16.. injection knots (level, rate) x 8, then withdrawal knots x 8
                                (storage_helpers.py:56-127, storage.py:114-190)                              */
   const double *numeraire;  /* [n_dates] numeraire at the action dates                                     */
+  int32_t noise_dim;        /* normals per sub-step: 2 (Schwartz two-factor) or 1 (Black-Scholes: b10 = b11 = 0, the
+                               log-price accumulates in x, its drift in m; black_scholes.py:50-67)              */
+  int32_t n_tan;            /* 0, or 3 / 6: pathwise PV sensitivities with respect to that many model parameters   */
+  const double *step_tan;   /* [n_sub][n_tan][6] d(A, B00, M, B10, B11, log F)/d parameter of the effective recursion
+                               x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (A = a - k dt, B00 = cx b00, ...);
+                               entry [0][.][5] also holds d log F(t0)                                          */
+  const double *dlog_num;   /* [n_dates][n_tan] d log numeraire / d parameter                                  */
 } mcre_storage_desc;
 
 typedef struct mcre_storage_plan mcre_storage_plan;
@@ -629,9 +636,12 @@ int mcre_storage_moments(mcre_storage_plan *plan, int32_t date, double centre, d
  * the backward induction is one stream of kernels. */
 int mcre_storage_solve(mcre_storage_plan *plan, const double *d_mom, double rcond, double *d_coef_row, void *stream);
 /* Valuation pass, fused (path stepping + decisions + cashflows): ADDS each local path's discounted cashflows to d_cfs
- * [shard->n_paths]; d_coef [n_dates][2 + n_states * n_basis] (device); d_final_state [n_paths] or NULL. */
+ * [shard->n_paths]; d_coef [n_dates][2 + n_states * n_basis] (device); d_final_state [n_paths] or NULL.  Plans with
+ * n_tan > 0 also ADD the path's pathwise sensitivities to d_tan [n_tan][n_paths]: what torch.autograd.grad of the PV
+ * gives in the reference (controller.py:609-627) - decisions and inventory moves carry no gradient, cashflows
+ * differentiate through the spot and the numeraire. */
 int mcre_storage_mainsim(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, const double *d_coef,
-                         double initial_state, double *d_cfs, double *d_final_state, void *stream);
+                         double initial_state, double *d_cfs, double *d_final_state, double *d_tan, void *stream);
 
 /* ================================================================================
  * Utilities

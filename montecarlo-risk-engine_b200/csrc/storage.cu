@@ -33,6 +33,11 @@ struct StorageDev {
   const int *step_date;     // [n_sub]
   const double *rec;        // [n_dates][ST_REC]
   const double *numeraire;  // [n_dates]
+  // pathwise PV sensitivities (n_tan > 0): tangents of the effective linear recursion per sub-step and parameter,
+  // [n_sub][n_tan][6] = d(A, B00, M, B10, B11, log F) with x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1, and
+  // d log numeraire / d parameter per action date [n_dates][n_tan]
+  int noise_dim, n_tan;
+  const double *step_tan, *dlog_num;
 };
 
 }  // namespace mcre
@@ -40,7 +45,7 @@ struct StorageDev {
 struct mcre_storage_plan {
   mcre::StorageDev d;
   mcre::DevArena arena;
-  mcre::DevArray<double> step, rec, numeraire;
+  mcre::DevArray<double> step, rec, numeraire, step_tan, dlog_num;
   mcre::DevArray<int> step_date;
 };
 
@@ -139,12 +144,16 @@ struct TwoFactor {
   }
 };
 
-__device__ __forceinline__ void draw2(const RngDev &rng, NormalStream &ns, int is, long long gpath, double &z0, double &z1) {
+// the model's draws of one sub-step: two normals (Schwartz two-factor) or one (Black-Scholes: z1 = 0)
+__device__ __forceinline__ void draw2(const RngDev &rng, NormalStream &ns, int dim, int is, long long gpath, double &z0,
+                                      double &z1) {
   if (rng.mode == MCRE_RNG_INJECT) {
-    const double *zp = rng.z + ((size_t)is * rng.n_total + gpath) * 2;
-    z0 = zp[0]; z1 = zp[1];
-  } else {
+    const double *zp = rng.z + ((size_t)is * rng.n_total + gpath) * dim;
+    z0 = zp[0]; z1 = dim > 1 ? zp[1] : 0.0;
+  } else if (dim > 1) {
     ns.next2(z0, z1);
+  } else {
+    z0 = ns.next(); z1 = 0.0;
   }
 }
 
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P,
   for (int d = 0; d < P.n_pre_dates; ++d) spot[(size_t)d * n_paths + lp] = s0;
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
-    draw2(rng, ns, is, gp, z0, z1);
+    draw2(rng, ns, P.noise_dim, is, gp, z0, z1);
     const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
     const int d = __ldg(P.step_date + is);
     if (d >= 0) spot[(size_t)d * n_paths + lp] = fm_exp_t(ls);
@@ -368,10 +377,15 @@ __global__ void __launch_bounds__(32) storage_solve_kernel(int S, int NB, const 
 
 // Valuation pass (controller.py:399-410 with storage.py:215-308 inlined): one thread per path carries the two factors,
 // the inventory state and the running sum of discounted cashflows.  coef: [n_dates][2 + S * NB].
+// NT > 0: pathwise sensitivities of the PV with respect to the NT model parameters, the way the reference's autograd sees
+// them (controller.py:609-627): the arg-max and the inventory moves carry no gradient, a cashflow
+// -dV (S +- cost) / N differentiates to -dV dS / N - cashflow dlogN, and dS = S dlogS follows the tangent recursion of
+// the factors.  Per-path tangents are ADDED to tan [NT][n_paths].
+template <int NT>
 __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, RngDev rng, long long path_begin,
                                                                   long long n_paths, const double *__restrict__ coef,
                                                                   double initial_state, double *__restrict__ cfs,
-                                                                  double *__restrict__ final_state) {
+                                                                  double *__restrict__ final_state, double *__restrict__ tan) {
   fm_tables_init();
   const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n_paths) return;
@@ -380,6 +394,9 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
   TwoFactor f;
   const int S = P.n_states, NB = P.n_basis, row = 2 + S * NB;
   double state = initial_state, total = 0.0;
+  double dx[NT > 0 ? NT : 1], dy[NT > 0 ? NT : 1], dls[NT > 0 ? NT : 1], dtot[NT > 0 ? NT : 1];
+#pragma unroll
+  for (int k = 0; k < NT; ++k) { dx[k] = 0.0; dy[k] = 0.0; dls[k] = 0.0; dtot[k] = 0.0; }
 
   auto act = [&](int d, double spot) {
     const double *r = P.rec + (size_t)d * ST_REC;
@@ -404,20 +421,53 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
     }
     const int a = best_of(v);
     state = a == 0 ? m.ns[0] : a == 1 ? m.ns[1] : m.ns[2];
-    total += __ddiv_rn(a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2], __ldg(P.numeraire + d));
+    const double num = __ldg(P.numeraire + d);
+    const double cf = __ddiv_rn(a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2], num);
+    total += cf;
+    if constexpr (NT > 0) {
+      const double dvb = a == 0 ? m.dv[0] : a == 1 ? m.dv[1] : m.dv[2];
+      const double g = -dvb * spot / num;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) dtot[k] += g * dls[k] - cf * __ldg(P.dlog_num + (size_t)d * NT + k);
+    }
   };
 
   const double s0 = exp(P.log_spot0);
+  if constexpr (NT > 0) {
+    // at the calibration date only log F0 depends on the parameters (Black-Scholes: log of the spot parameter);
+    // its tangent is stored with the first sub-step
+    if (P.n_sub > 0) {
+#pragma unroll
+      for (int k = 0; k < NT; ++k) dls[k] = __ldg(P.step_tan + (size_t)k * 6 + 5);
+    }
+  }
   for (int d = 0; d < P.n_pre_dates; ++d) act(d, s0);
   for (int is = 0; is < P.n_sub; ++is) {
     double z0, z1;
-    draw2(rng, ns, is, gp, z0, z1);
-    const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
+    draw2(rng, ns, P.noise_dim, is, gp, z0, z1);
+    const double x_old = f.x;
+    const double *st = P.step + (size_t)is * ST_STEP;
+    const double ls = f.advance(st, z0, z1);
+    if constexpr (NT > 0) {
+      const double A = __ldg(st + 0) - __ldg(st + 1) * __ldg(st + 2);
+      const double *tt = P.step_tan + (size_t)is * NT * 6;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const double *t6 = tt + k * 6;
+        dx[k] = A * dx[k] + __ldg(t6 + 0) * x_old + __ldg(t6 + 1) * z0;
+        dy[k] = dy[k] + __ldg(t6 + 2) + __ldg(t6 + 3) * z0 + __ldg(t6 + 4) * z1;
+        dls[k] = __ldg(t6 + 5) + dx[k] + dy[k];
+      }
+    }
     const int d = __ldg(P.step_date + is);
     if (d >= 0) act(d, fm_exp_t(ls));
   }
   cfs[lp] += total;
   if (final_state) final_state[lp] = state;
+  if constexpr (NT > 0) {
+#pragma unroll
+    for (int k = 0; k < NT; ++k) tan[(size_t)k * n_paths + lp] += dtot[k];
+  }
 }
 
 }  // namespace mcre
@@ -428,6 +478,9 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
   if (!c || !out) return fail(-1, "null argument%s", "");
   if (c->n_states < 2 || c->n_states > ST_MAX_S) return fail(-2, "storage: 2..%s%lld inventory states", "", ST_MAX_S);
   if (c->n_basis < 1 || c->n_basis > ST_MAX_B) return fail(-2, "storage: 1..%s%lld basis functions", "", ST_MAX_B);
+  if (c->noise_dim != 1 && c->noise_dim != 2) return fail(-2, "storage: one or two noise factors%s", "");
+  if (c->n_tan != 0 && c->n_tan != 3 && c->n_tan != 6) return fail(-2, "storage: 0, 3 or 6 tangent directions%s", "");
+  if (c->n_tan > 0 && (!c->step_tan || !c->dlog_num)) return fail(-1, "storage: tangent tables missing%s", "");
   if (c->n_dates <= 0 || c->n_sub < 0 || c->n_pre_dates < 0 || c->n_pre_dates > c->n_dates)
     return fail(-2, "storage: bad date / step counts%s", "");
   for (int d = 0; d < c->n_dates; ++d) {
@@ -442,6 +495,8 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
     if (!rc) rc = p->step_date.upload(c->step_date, (size_t)c->n_sub);
     if (!rc) rc = p->rec.upload(c->date_rec, (size_t)c->n_dates * ST_REC);
     if (!rc) rc = p->numeraire.upload(c->numeraire, (size_t)c->n_dates);
+    if (!rc && c->n_tan > 0) rc = p->step_tan.upload(c->step_tan, (size_t)c->n_sub * c->n_tan * 6);
+    if (!rc && c->n_tan > 0) rc = p->dlog_num.upload(c->dlog_num, (size_t)c->n_dates * c->n_tan);
     if (!rc) rc = p->arena.commit();
   }
   if (rc) { p->arena.release(); delete p; return rc; }
@@ -449,6 +504,7 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
   d.n_sub = c->n_sub; d.n_dates = c->n_dates; d.n_pre_dates = c->n_pre_dates; d.n_states = c->n_states;
   d.n_basis = c->n_basis; d.log_spot0 = c->log_spot0;
   d.step = p->step.p; d.step_date = p->step_date.p; d.rec = p->rec.p; d.numeraire = p->numeraire.p;
+  d.noise_dim = c->noise_dim; d.n_tan = c->n_tan; d.step_tan = p->step_tan.p; d.dlog_num = p->dlog_num.p;
   *out = p;
   return 0;
 }
@@ -518,14 +574,20 @@ extern "C" int mcre_storage_solve(mcre_storage_plan *p, const double *d_mom, dou
 
 extern "C" int mcre_storage_mainsim(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard,
                                     const double *d_coef, double initial_state, double *d_cfs, double *d_final_state,
-                                    void *stream) {
+                                    double *d_tan, void *stream) {
   if (!p || !rng || !shard || !d_coef || !d_cfs) return fail(-1, "null argument%s", "");
+  if (p->d.n_tan > 0 && !d_tan) return fail(-1, "storage: plan with tangents but d_tan is null%s", "");
   if (int rc = storage_rng_ok(rng)) return rc;
   if (shard->n_paths <= 0) return 0;
   const unsigned blocks = (unsigned)((shard->n_paths + ST_THREADS - 1) / ST_THREADS);
-  storage_main_kernel<<<blocks, ST_THREADS, 0, (cudaStream_t)stream>>>(p->d, make_rng(rng), shard->path_begin,
-                                                                        shard->n_paths, d_coef, initial_state, d_cfs,
-                                                                        d_final_state);
+  const RngDev r = make_rng(rng);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GO(NT) storage_main_kernel<NT><<<blocks, ST_THREADS, 0, st>>>(p->d, r, shard->path_begin, shard->n_paths, d_coef, \
+                                                                     initial_state, d_cfs, d_final_state, d_tan)
+  if (p->d.n_tan == 0) GO(0);
+  else if (p->d.n_tan == 3) GO(3);
+  else GO(6);
+#undef GO
   MCRE_LAUNCHED();
   return 0;
 }

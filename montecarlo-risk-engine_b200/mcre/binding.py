@@ -54,7 +54,8 @@ class IrcDesc(C.Structure):
 class StorageDesc(C.Structure):
     _fields_ = [("n_sub", C.c_int32), ("n_dates", C.c_int32), ("n_pre_dates", C.c_int32), ("n_states", C.c_int32),
                 ("n_basis", C.c_int32), ("log_spot0", C.c_double), ("step", c_dp), ("step_date", c_ip),
-                ("date_rec", c_dp), ("numeraire", c_dp)]
+                ("date_rec", c_dp), ("numeraire", c_dp), ("noise_dim", C.c_int32), ("n_tan", C.c_int32),
+                ("step_tan", c_dp), ("dlog_num", c_dp)]
 
 
 RNG_PHILOX, RNG_INJECT = 0, 1
@@ -169,7 +170,7 @@ def lib():
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_storage_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     L.mcre_storage_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_double, C.c_void_p,
-                                       C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
     L.mcre_fastmath_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L

@@ -48,40 +48,76 @@ def _is_storage(p):
     return isinstance(p, Storage)
 
 
-def step_table(model, grid, scheme):
-    """[n_sub][STEP] coefficients of csrc/storage.cu:TwoFactor::advance (schwartz_two_factor.py:124-196)."""
-    rate, kappa, sig_s, mu, sig_l, rho = model.param_values()
+def _is_bs(model):
+    from models.black_scholes import BlackScholesModel
+    return type(model) is BlackScholesModel
+
+
+def step_table(model, grid, scheme, nt=0):
+    """-> (steps [n_sub][STEP], tangents [n_sub][nt][6] or None): coefficients of csrc/storage.cu:TwoFactor::advance
+    and, for pathwise sensitivities, d(A, B00, M, B10, B11, log F) / d(parameter) of the effective recursion
+    x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (host duals, mcre/dual.py).
+    Schwartz two-factor (schwartz_two_factor.py:124-196), parameters [rate, kappa, sigma_s, mu_l, sigma_l, rho]:
+      ANALYTICAL  a = exp(-kappa dt), b = Cholesky factor of the step covariance (cached per nominal dt, model.py:45-64)
+      EULER       a = 1, k = kappa, cx / cy = sigma sqrt(dt), b = Cholesky factor of the correlation - which the
+                  reference builds before requires_grad(): rho is a constant of its autograd graph there
+    Black-Scholes (black_scholes.py:50-67, ANALYTICAL only; parameters [spot, sigma, rate]): the log-price accumulates in
+    x (b00 = sqrt(sigma^2 dt)), its drift (rate - sigma^2 / 2) dt in m, log F = log spot."""
+    from mcre.dual import D, dexp, dlog, dsqrt
+    p = model.dual_params(0, nt)
+    zero, one = D(0.0, None, nt), D(1.0, None, nt)
     out = np.zeros((max(grid.n_sub, 1), STEP))
+    tan = np.zeros((max(grid.n_sub, 1), nt, 6)) if nt else None
     chol = {}
     for s in range(grid.n_sub):
         dt = grid.dt[s]
-        if scheme == SimulationScheme.ANALYTICAL:
-            key = grid.dt_nominal[s]            # the reference caches the factor per nominal dt (model.py:45-64)
-            if key not in chol:
-                if abs(kappa) <= 1e-12:
-                    var_s = sig_s * sig_s * key
-                else:
-                    var_s = sig_s * sig_s * (1.0 - math.exp(-2.0 * kappa * key)) / (2.0 * kappa)
-                var_l = sig_l * sig_l * key
-                cov = rho * math.sqrt(max(var_s * var_l, 0.0))
-                l00 = math.sqrt(var_s)
-                l10 = cov / l00
-                chol[key] = (l00, l10, math.sqrt(var_l - l10 * l10))
-            a = 1.0 if abs(kappa) <= 1e-12 else math.exp(-kappa * dt)
-            out[s, :9] = (a, 0.0, dt, mu * dt, 1.0, chol[key][0], 1.0, chol[key][1], chol[key][2])
-        elif scheme == SimulationScheme.EULER:
-            sq = math.sqrt(dt)
-            out[s, :9] = (1.0, kappa, dt, mu * dt, sig_s * sq, 1.0, sig_l * sq, rho, math.sqrt(1.0 - rho * rho))
+        if _is_bs(model):
+            if scheme != SimulationScheme.ANALYTICAL:
+                raise NotImplementedError("gas storage on Black-Scholes: the ANALYTICAL scheme (the Euler step is not "
+                                          "additive in the log-price)")
+            spot, sig, rate = p
+            a, k, m = one, zero, rate * dt - 0.5 * dt * sig * sig
+            cx, b00, cy, b10, b11 = one, dsqrt(sig * sig * grid.dt_nominal[s]), zero, zero, zero
+            lf = dlog(spot)
         else:
-            raise NotImplementedError(f"storage: scheme {scheme} is not defined for the Schwartz two-factor model")
-        out[s, 9] = math.log(model.curve_value(grid.t2[s]))
-    return out
+            rate, kappa, sig_s, mu, sig_l, rho = p
+            if scheme == SimulationScheme.ANALYTICAL:
+                key = grid.dt_nominal[s]            # the reference caches the factor per nominal dt
+                if key not in chol:
+                    if abs(kappa.v) <= 1e-12:
+                        var_s = sig_s * sig_s * key
+                    else:
+                        var_s = sig_s * sig_s * (1.0 - dexp(-2.0 * kappa * key)) / (2.0 * kappa)
+                    var_l = sig_l * sig_l * key
+                    cov = rho * dsqrt(var_s * var_l)
+                    l00 = dsqrt(var_s)
+                    l10 = cov / l00
+                    chol[key] = (l00, l10, dsqrt(var_l - l10 * l10))
+                a = one if abs(kappa.v) <= 1e-12 else dexp(-kappa * dt)
+                k, m, cx, cy = zero, mu * dt, one, one
+                b00, b10, b11 = chol[key]
+            elif scheme == SimulationScheme.EULER:
+                sq = math.sqrt(dt)
+                rho_c = rho.v                         # constant of the reference's graph under EULER
+                a, k, m = one, kappa, mu * dt
+                cx, b00, cy, b10, b11 = sig_s * sq, one, sig_l * sq, D(rho_c, None, nt), D(math.sqrt(1.0 - rho_c * rho_c), None, nt)
+            else:
+                raise NotImplementedError(f"storage: scheme {scheme} is not defined for the Schwartz two-factor model")
+            lf = D(math.log(model.curve_value(grid.t2[s])), None, nt)
+        out[s] = [x.v if isinstance(x, D) else x for x in (a, k, dt, m, cx, b00, cy, b10, b11, lf)]
+        if nt:
+            eff = (a - k * dt, cx * b00, m, cy * b10, cy * b11, lf)
+            for j, e in enumerate(eff):
+                tan[s, :, j] = D.lift(e, nt).t
+    return out, tan
 
 
 def log_spot_scale(model, t):
     """Standard deviation of log S(t) under the model: a per-date scale for the standardised basis."""
-    _, kappa, sig_s, _, sig_l, rho = model.param_values()
     tau = max(t - model.t0(), 0.0)
+    if _is_bs(model):
+        return model.param_values()[1] * math.sqrt(tau)
+    _, kappa, sig_s, _, sig_l, rho = model.param_values()
     if abs(kappa) <= 1e-12:
         var_s, cov = sig_s * sig_s * tau, rho * sig_s * sig_l * tau
     else:
@@ -102,13 +138,14 @@ class StorageBackend:
         self.c = c = ctrl
         if not all(_is_storage(p) for p in c.products):
             raise NotImplementedError("gas storages are valued in books of their own (no mixing with other products)")
-        if not isinstance(c.model, SchwartzTwoFactorModel):
-            raise NotImplementedError("gas storage: only SchwartzTwoFactorModel is implemented "
+        if not isinstance(c.model, SchwartzTwoFactorModel) and not _is_bs(c.model):
+            raise NotImplementedError("gas storage: SchwartzTwoFactorModel and BlackScholesModel are implemented "
                                       f"(got {type(c.model).__name__})")
         if any(m.metric_type != MetricType.PV for m in c.risk_metrics.metrics):
             raise NotImplementedError("gas storage: PV is the only implemented metric")
-        if c.differentiate:
-            raise NotImplementedError("gas storage: sensitivities are not implemented")
+        self.nt = len(c.model.model_params) if c.differentiate else 0
+        self.rate_index = 2 if _is_bs(c.model) else 0
+        self.noise_dim = 1 if _is_bs(c.model) else 2
         rf = c.regression_function
         if type(rf) is not PolyomialRegression or not 0 <= rf.degree < B_MAX_BASIS:
             raise NotImplementedError(f"gas storage: PolyomialRegression of degree 0..{B_MAX_BASIS - 1} (the kernels "
@@ -122,7 +159,7 @@ class StorageBackend:
         self.mode = mode
 
     # ------------------------------------------------------------------ plan
-    def _create(self, prod, grid, steps):
+    def _create(self, prod, grid, steps, steps_tan):
         c = self.c
         sim_dates = {t: i for i, t in enumerate(grid.dates)}
         acts = prod.product_timeline.tolist()
@@ -131,14 +168,19 @@ class StorageBackend:
         n_pre = sum(1 for t in acts if sim_dates[t] < grid.n_pre_dates)
         rec = prod.lower()
         t0 = c.model.t0()
-        rate = c.model.param_values()[0]
+        rate = c.model.param_values()[self.rate_index]
         numeraire = np.array([math.exp(rate * (t - t0)) for t in acts])
+        dlog_num = np.zeros((len(acts), max(self.nt, 1)))
+        if self.nt:
+            dlog_num[:, self.rate_index] = [t - t0 for t in acts]
         keep = []
         d = B.StorageDesc()
         d.n_sub, d.n_dates, d.n_pre_dates = grid.n_sub, len(acts), n_pre
         d.n_states, d.n_basis = prod.num_states, self.n_basis
-        d.log_spot0 = math.log(c.model.curve_value(t0))
-        for name, arr, conv in (("step", steps, B.as_dp), ("step_date", step_date if grid.n_sub else np.zeros(1, np.int32), B.as_ip),
+        d.log_spot0 = math.log(c.model.param_values()[0] if _is_bs(c.model) else c.model.curve_value(t0))
+        d.noise_dim, d.n_tan = self.noise_dim, self.nt
+        for name, arr, conv in (("step_tan", steps_tan if self.nt else np.zeros(1), B.as_dp), ("dlog_num", dlog_num, B.as_dp),
+                                ("step", steps, B.as_dp), ("step_date", step_date if grid.n_sub else np.zeros(1, np.int32), B.as_ip),
                                 ("date_rec", rec, B.as_dp), ("numeraire", numeraire, B.as_dp)):
             a, ptr = conv(arr)
             keep.append(a)
@@ -153,8 +195,8 @@ class StorageBackend:
         rng.seed, rng.stream, rng.n_paths_total = seed, c.rng_stream, n_total
         z = c.injected_normals.get(which) if c.injected_normals else None
         if z is not None:
-            if z.shape[1] != n_total or z.shape[2] != 2:
-                raise ValueError(f"injected {which} normals must be [n_sub, {n_total}, 2]")
+            if z.shape[1] != n_total or z.shape[2] != self.noise_dim:
+                raise ValueError(f"injected {which} normals must be [n_sub, {n_total}, {self.noise_dim}]")
             rng.mode, rng.d_z = B.RNG_INJECT, z.data_ptr()
         else:
             rng.mode = B.RNG_PHILOX
@@ -181,7 +223,8 @@ class StorageBackend:
         coef_h[:, 1] = 1.0
         if self.mode == "moments":
             for k, t in enumerate(acts):
-                f = c.model.curve_value(t)
+                f = c.model.param_values()[0] * math.exp(c.model.param_values()[2] * (t - c.model.t0())) if _is_bs(c.model) \
+                    else c.model.curve_value(t)
                 sd = f * log_spot_scale(c.model, t)
                 coef_h[k, 0], coef_h[k, 1] = f, (1.0 / sd if sd > 1e-300 else 0.0)
         coef = torch.from_numpy(coef_h.copy()).to(dev)
@@ -227,7 +270,7 @@ class StorageBackend:
         dev = RT.compute_device()
         t_start = time.perf_counter()
         grid = build_time_grid(c.model.t0(), c.simulation_timeline.tolist(), c.num_steps)
-        steps = step_table(c.model, grid, c.simulation_scheme)
+        steps, steps_tan = step_table(c.model, grid, c.simulation_scheme, self.nt)
         n_main = c.num_paths_mainsim
         chunk = 256 if n_main < (1 << 18) else 4096
         begin, count = RT.shard_range(n_main, chunk)
@@ -235,9 +278,11 @@ class StorageBackend:
         shard = B.Shard(begin, count, chunk)
         plans, t_pre = [], 0.0
         cfs = [torch.zeros(max(count, 1), dtype=torch.float64, device=dev) for _ in c.netting_sets]
+        tans = [torch.zeros((self.nt, max(count, 1)), dtype=torch.float64, device=dev) if self.nt else None
+                for _ in c.netting_sets]
         try:
             for pi, prod in enumerate(c.products):
-                plan, numeraire, acts = self._create(prod, grid, steps)
+                plan, numeraire, acts = self._create(prod, grid, steps, steps_tan)
                 plans.append(plan)
                 t0 = time.perf_counter()
                 coef = self._regress(prod, plan, numeraire, acts, dev)
@@ -245,10 +290,13 @@ class StorageBackend:
                 t_pre += time.perf_counter() - t0
                 si = c.product_to_netting_set_idx[pi]
                 B.check(L.mcre_storage_mainsim(plan, C.byref(rng_main), C.byref(shard), coef.data_ptr(),
-                                               float(prod.get_initial_state()), cfs[si].data_ptr(), None, RT.stream_ptr()))
+                                               float(prod.get_initial_state()), cfs[si].data_ptr(), None,
+                                               tans[si].data_ptr() if self.nt else None, RT.stream_ptr()))
             raw = []
             n_chunks = max((count + chunk - 1) // chunk, 1)
-            partial = torch.empty(n_chunks * 2 + 1, dtype=torch.float64, device=dev)
+            partial = torch.empty(n_chunks * 2 * max(self.nt, 1) + 1, dtype=torch.float64, device=dev)
+            unconnected = c.model.unconnected_params(c.simulation_scheme)
+            used = [i not in unconnected for i in range(len(c.model.model_params))]
             for si in range(len(c.netting_sets)):
                 # shift = the set's value on global path 0 (lives on the rank that owns it; summed over the ranks)
                 shift = cfs[si][0:1].clone() if (begin == 0 and count > 0) else torch.zeros(1, dtype=torch.float64, device=dev)
@@ -258,7 +306,15 @@ class StorageBackend:
                                          out.data_ptr(), RT.stream_ptr()))
                 s = RT.to_host(RT.all_reduce_tree(out))
                 pv = mean_and_error(float(s[0]), float(s[1]), float(RT.to_host(shift)[0]), n_main)
-                raw.append({"pv": (pv, None), "param_used": lambda kind: [False] * len(c.model.model_params)})
+                grad = None
+                if self.nt:
+                    # sums of the per-path tangents in the same fixed chunk order (shift 0); mean = sum / n
+                    zero = torch.zeros(self.nt, dtype=torch.float64, device=dev)
+                    out_t = torch.zeros(self.nt * 2, dtype=torch.float64, device=dev)
+                    B.check(L.mcre_sum_stats(tans[si].data_ptr(), count, self.nt, chunk, zero.data_ptr(), 0,
+                                             partial.data_ptr(), out_t.data_ptr(), RT.stream_ptr()))
+                    grad = RT.to_host(RT.all_reduce_tree(out_t)).reshape(self.nt, 2)[:, 0] / n_main
+                raw.append({"pv": (pv, grad), "param_used": lambda kind: used})
         finally:
             torch.cuda.current_stream().synchronize()
             for plan in plans:

@@ -738,6 +738,7 @@ def _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_m
     ctx_pre = Ctx(model, p, sim_tl, E.generate_paths(model, p, sim_tl, n_pre, num_steps, scheme, draws_pre), n_pre)
     ctx_main = Ctx(model, p, sim_tl, E.generate_paths(model, p, sim_tl, n_main, num_steps, scheme, draws_main), n_main)
     set_cfs = [None] * len(netting_sets)
+    set_tan = [np.zeros(len(M.param_values(model))) for _ in netting_sets]
     all_coeffs = []
     for k, pr in enumerate(products):
         tl = product_timeline(pr)
@@ -756,10 +757,17 @@ def _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_m
                 std.append((f, 1.0 / sd if sd > 1e-300 else 0.0))
         coeffs = ST.regress(pr, *market(ctx_pre), degree, solver=ST.gelsy if solver == "gelsy" else ST.normal_equations,
                             std=std)
-        cfs = ST.evaluate(pr, *market(ctx_main), coeffs, degree, std=std)
+        P = len(M.param_values(model))
+        if isinstance(p[0], ad.Dual):
+            s_t = [np.broadcast_to(ad.tan(ctx_main.spot(asset, t), P), (P, n_main)) for t in tl]
+            n_t = [np.asarray(ad.tan(ctx_main.numeraire(t), P), dtype=float).reshape(P, -1)[:, 0] for t in tl]
+            cfs, tans = ST.evaluate(pr, *market(ctx_main), coeffs, degree, std=std, spot_tangents=s_t, numeraire_tangents=n_t)
+            set_tan[prod_set[k]] = set_tan[prod_set[k]] + tans.mean(axis=1)
+        else:
+            cfs = ST.evaluate(pr, *market(ctx_main), coeffs, degree, std=std)
         all_coeffs.append(coeffs)
         si = prod_set[k]
         set_cfs[si] = cfs if set_cfs[si] is None else set_cfs[si] + cfs
     results = [[[tuple(float(v) for v in mc_mean_and_error(set_cfs[si]))] for _ in mtypes] for si in range(len(netting_sets))]
-    grads = [[[None] for _ in mtypes] for _ in netting_sets]
+    grads = [[[set_tan[si] if isinstance(p[0], ad.Dual) else None] for _ in mtypes] for si in range(len(netting_sets))]
     return dict(results=results, grads=grads, prod_coeffs=all_coeffs, sim_timeline=sim_tl, n_sub=n_sub, noise_dim=dim)

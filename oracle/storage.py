@@ -64,7 +64,7 @@ def basis(x, n_basis):
     return np.stack([x ** k for k in range(n_basis)], axis=1)
 
 
-def cashflows(prod, i, spot, numeraire, state, coeffs_i, n_basis, std=(0.0, 1.0)):
+def cashflows(prod, i, spot, numeraire, state, coeffs_i, n_basis, std=(0.0, 1.0), want_delta=False):
     """compute_normalized_cashflows (storage.py:215-308): state [N, B] -> (next state [N, B], cashflows / numeraire).
     std = (centre, inverse scale) of the basis variable (the reference's raw basis: (0, 1))."""
     S = prod.num_states
@@ -87,6 +87,8 @@ def cashflows(prod, i, spot, numeraire, state, coeffs_i, n_basis, std=(0.0, 1.0)
     best = np.argmax(values, axis=2)[..., None]                # first maximum, like torch.argmax on these sizes
     nstate = np.take_along_axis(np.stack([inj_s, no_s, wd_s], axis=2), best, axis=2)[..., 0]
     cf = np.take_along_axis(np.stack([inj_pay, no_pay, wd_pay], axis=2), best, axis=2)[..., 0]
+    if want_delta:
+        return nstate, cf / numeraire[:, None], np.take_along_axis(np.stack([inj_d, no_d, wd_d], axis=2), best, axis=2)[..., 0]
     return nstate, cf / numeraire[:, None]
 
 
@@ -147,13 +149,20 @@ def regress(prod, spots, numeraires, n_basis, solver=gelsy, std=None):
     return coeffs
 
 
-def evaluate(prod, spots, numeraires, coeffs, n_basis, std=None):
-    """_evaluate_product, PV-only branch (controller.py:399-410): realised cashflows of the regression policy."""
+def evaluate(prod, spots, numeraires, coeffs, n_basis, std=None, spot_tangents=None, numeraire_tangents=None):
+    """_evaluate_product, PV-only branch (controller.py:399-410): realised cashflows of the regression policy.
+    With spot_tangents [n_dates][P, N] and numeraire_tangents [n_dates][P] also the pathwise sensitivities [P, N] the
+    reference's autograd yields (controller.py:609-627): torch.argmax / gather and the inventory moves carry no gradient,
+    a cashflow -dV (S +- cost) / N differentiates through S and N only."""
     n = spots[0].shape[0]
     std = std or [(0.0, 1.0)] * len(prod.product_timeline)
     sm = np.full((n, 1), float(prod.get_initial_state()))
     cfs = np.zeros(n)
+    tans = None if spot_tangents is None else np.zeros((spot_tangents[0].shape[0], n))
     for i in range(len(prod.product_timeline)):
-        sm, cf = cashflows(prod, i, spots[i], np.full(n, numeraires[i]), sm, coeffs[i], n_basis, std[i])
+        sm, cf, dv = cashflows(prod, i, spots[i], np.full(n, numeraires[i]), sm, coeffs[i], n_basis, std[i], want_delta=True)
         cfs = cfs + cf[:, 0]
-    return cfs
+        if tans is not None:
+            tans = tans + (-dv[:, 0] / numeraires[i]) * spot_tangents[i] \
+                - cf[:, 0] * (numeraire_tangents[i] / numeraires[i])[:, None]
+    return cfs if tans is None else (cfs, tans)

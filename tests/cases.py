@@ -373,6 +373,26 @@ def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_leve
     return model, [m.NettingSet(name="large_cva_ns", products=prods, counterparty_id=cp)], metrics, np.linspace(0.0, horizon, n_expo)
 
 
+def storage_small(ns_module, model_kind="bs", num_states=4, end_day=2.0):
+    """The storage of tests/pytests/test_single_product_executor_parity.py:43-60 / 162-168 (Black-Scholes "gas" price,
+    PV with pathwise sensitivities), and the same contract over 12 days on a Schwartz two-factor curve."""
+    m = ns_module
+    cfg = m.StorageConfig()
+    cfg.add_volume_constraint(0.0, end_day, 0.0, 6.0, 0.0)
+    cfg.add_injection_flexibility(0.0, end_day, 0.0, 2.0)
+    cfg.add_withdrawal_flexibility(0.0, end_day, 0.0, 2.0)
+    cfg.add_variable_injection_cost(0.0, 0.1)
+    cfg.add_variable_withdrawal_cost(0.0, 0.1)
+    st = m.Storage(asset_id="gas", start_date=0.0, end_date=end_day, initial_amount=1.0, storage_config=cfg, num_states=num_states)
+    st.name = "storage"
+    if model_kind == "bs":
+        model = m.BlackScholesModel(0.0, 100.0, 0.03, 0.2, asset_id="gas")
+    else:
+        model = m.SchwartzTwoFactorModel(0.0, [0.0, 4.0, 9.0, 12.0], [20.0, 23.0, 19.0, 22.0], 0.002, 0.35, 0.08, 0.001, 0.03, 0.3,
+                                         asset_id="gas")
+    return model, [m.NettingSet(name="storage", products=[st])], [m.PVMetric()], None
+
+
 def _days(a, b):
     import datetime
     return float((datetime.date(*b) - datetime.date(*a)).days)
@@ -484,6 +504,10 @@ GOLDEN_CASES = {
     "storage2": (storage_s2f, dict(which="storage2"), dict(n_main=2000, n_pre=4000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
     "storage2_short_euler": (storage_s2f, dict(which="storage2", end_day=100, num_states=6), dict(n_main=1024, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False, degree=2)),
     "storage1_vol": (storage_s2f, dict(which="storage1", vols=(0.9, 0.3), num_states=5), dict(n_main=3000, n_pre=3000, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=4)),
+    # pathwise PV sensitivities of storages (realised cashflows of the regression policy; decisions carry no gradient)
+    "storage_bs_greeks": (storage_small, dict(), dict(n_main=256, n_pre=256, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
+    "storage_s2f_greeks": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="ANALYTICAL", differentiate=True, degree=3)),
+    "storage_s2f_greeks_euler": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="EULER", differentiate=True)),
     "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
 }
 

@@ -117,3 +117,36 @@ def test_storage_pv_withdraws_initial_inventory():
         sc.rng_compat = compat
         pv = sc.run_simulation().get_results(product.get_name(), "pv", evaluation_idx=0)
         assert abs(float(pv) - 10.0) < 1e-3
+
+
+GREEK_CASES = ["storage_bs_greeks", "storage_s2f_greeks", "storage_s2f_greeks_euler"]
+
+
+@pytest.mark.parametrize("name", GREEK_CASES)
+def test_storage_pathwise_greeks_match_reference_autograd(name):
+    """differentiate=True: PV and its sensitivities to every model parameter against torch.autograd of the unmodified
+    reference (storage_bs_greeks is the storage case of tests/pytests/test_single_product_executor_parity.py:162-168);
+    parameters outside the reference's graph (rho under EULER) come back as None."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    helpers.assert_close(flat["storage|pv"][0], gold["values"]["storage|pv"], 1e-9, 1e-9, f"{name} pv")
+    helpers.assert_close(flat["storage|pv"][1], gold["errors"]["storage|pv"], 1e-7, 1e-9, f"{name} pv error")
+    got = res.get_derivatives("storage", "pv")[0]
+    want = gold["derivatives"]["storage|pv"][0]
+    for pname, g, w in zip(gold["params"], got, want):
+        if w is None:
+            assert g is None, f"{name} d/d{pname}: expected None"
+        else:
+            assert g is not None and abs(float(g) - w) <= 1e-8 * max(1.0, abs(w)), f"{name} d/d{pname}: {float(g)} vs {w}"
+
+
+@pytest.mark.parametrize("name", ["storage_bs_greeks", "storage_s2f_greeks"])
+def test_storage_greeks_native_philox_match_oracle(name):
+    res, sc = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    v, e = out["results"][0][0][0]
+    got = helpers.flatten_results(res)["storage|pv"]
+    helpers.assert_close(got[0], [v], 1e-9, 1e-9, f"{name} philox value")
+    grads = np.array([float(g) for g in res.get_derivatives("storage", "pv")[0]])
+    helpers.assert_close(grads, out["grads"][0][0][0], 1e-8, 1e-8, f"{name} philox greeks")

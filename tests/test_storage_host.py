@@ -86,7 +86,7 @@ def test_step_table_reproduces_the_oracle_model_step(scheme):
     model, sets, _, _ = cases.storage_s2f(ns, which="storage2", end_day=30)
     tl = sets[0].products[0].product_timeline.tolist()
     grid = build_time_grid(0.0, tl, 2)
-    tab = step_table(model, grid, getattr(ns.SimulationScheme, scheme))
+    tab, _ = step_table(model, grid, getattr(ns.SimulationScheme, scheme))
     rng = np.random.default_rng(5)
     z = rng.standard_normal((grid.n_sub, 64, 2))
     p = ad.params(M.param_values(model), False)
@@ -114,12 +114,43 @@ def test_unsupported_storage_runs_raise_before_any_device_work():
         return ns.SimulationController(**args)
     assert StorageBackend(ctrl(regression_function=ns.PolyomialRegression(3))).mode == "lapack"
     assert StorageBackend(ctrl(num_paths_presim=1 << 17)).mode == "moments"
-    with pytest.raises(NotImplementedError):
-        StorageBackend(ctrl(differentiate=True))
+    assert StorageBackend(ctrl(differentiate=True)).nt == 6
+    assert StorageBackend(ctrl(model=ns.BlackScholesModel(0.0, 100.0, 0.0, 0.2, asset_id="thegasprice"))).noise_dim == 1
     with pytest.raises(NotImplementedError):
         StorageBackend(ctrl(regression_function=ns.PolyomialRegression(7)))
     with pytest.raises(NotImplementedError):
-        StorageBackend(ctrl(model=ns.BlackScholesModel(0.0, 100.0, 0.0, 0.2)))
+        StorageBackend(ctrl(model=ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)))
+    with pytest.raises(NotImplementedError):     # exposure metrics of a storage
+        StorageBackend(ctrl(risk_metrics=ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=[0.0, 1.0])))
+
+
+def test_step_tangent_table_equals_finite_differences_of_the_step_table():
+    """d(A, B00, M, B10, B11, log F)/d(parameter) from the host duals against central differences of the value table."""
+    from mcre.storage import step_table
+    from mcre.timegrid import build_time_grid
+    ns = cases.Namespace()
+    for kind, scheme in (("s2f", "ANALYTICAL"), ("s2f", "EULER"), ("bs", "ANALYTICAL")):
+        model, sets, _, _ = cases.storage_small(ns, model_kind=kind, end_day=5.0)
+        grid = build_time_grid(0.0, sets[0].products[0].product_timeline.tolist(), 2)
+        sch = getattr(ns.SimulationScheme, scheme)
+        nt = len(model.model_params)
+        _, tan = step_table(model, grid, sch, nt)
+
+        def eff(m):
+            t, _ = step_table(m, grid, sch)
+            return np.stack([t[:, 0] - t[:, 1] * t[:, 2], t[:, 4] * t[:, 5], t[:, 3], t[:, 6] * t[:, 7], t[:, 6] * t[:, 8], t[:, 9]], axis=1)
+        for k in range(nt):
+            if k in model.unconnected_params(sch):
+                assert np.all(tan[:, k, :] == 0.0)
+                continue
+            v0 = float(model.model_params[k])
+            h = 1e-6 * max(abs(v0), 1e-3)
+            model.model_params[k] = torch.tensor(v0 + h, dtype=torch.float64)
+            up = eff(model)
+            model.model_params[k] = torch.tensor(v0 - h, dtype=torch.float64)
+            dn = eff(model)
+            model.model_params[k] = torch.tensor(v0, dtype=torch.float64)
+            np.testing.assert_allclose(tan[:grid.n_sub, k, :], (up - dn)[:grid.n_sub] / (2 * h), rtol=2e-6, atol=1e-9)
 
 
 # ---- the reference's own unit tests of the inventory moves (tests/pytests/test_storage.py:19-113), restated ----------
