@@ -192,9 +192,9 @@ typedef struct {
   const double *term_w;        /* [n_term] weight of the zero bond in the underlying's value */
   const double *ex_basis;      /* [n_ex][2] shift, scale of the explanatory variable         */
   /* ---- hybrid books: numeraire of another model (model_config.py:44-47, numeraire_model_idx) ---- */
-  int32_t ext_numeraire;       /* 1: numeraire = exp(ext_rate (t - t0)) instead of the short rate's own account;
-                                  value-only plans (nt = 0)                                     */
+  int32_t ext_numeraire;       /* 1: numeraire = exp(ext_rate (t - t0)) instead of the short rate's own account */
   double ext_rate;
+  int32_t ext_slot;            /* plans with tangents: the tangent slot that stands for ext_rate, -1: a constant   */
 } mcre_irc_desc;
 
 typedef struct mcre_irc_plan mcre_irc_plan;
@@ -202,7 +202,7 @@ typedef struct mcre_irc_plan mcre_irc_plan;
 int mcre_irc_create(const mcre_irc_desc *desc, mcre_irc_plan **out);
 void mcre_irc_destroy(mcre_irc_plan *plan);
 /* Per-path discounted cashflow totals of the main simulation: d_pv [n_sets][shard->n_paths] is WRITTEN by the next
- * mcre_irc_mainsim (value-only plans of linear products with MCRE_ACC_PV).  With MCRE_ACC_SPILL on a plan whose
+ * mcre_irc_mainsim (plans of linear products with MCRE_ACC_PV).  With MCRE_ACC_SPILL on a plan whose
  * metric dates are all its exposure dates this gives per-path cashflows and exposures of the rate products of a book
  * that also holds products of another model family (mcre/hybrid.py; the reference nets them in one loop over
  * products, controller.py:506-563).  NULL: off. */
@@ -394,6 +394,21 @@ int mcre_eq_set_bridge_uniforms(mcre_eq_plan *plan, const double *d_u, int32_t s
  * d_expo [n_expo][n_paths] -> d_out [n_metric][n_paths], metric_expo[m] = exposure index of metric date m,
  * lag[m] = exposure indices back to its collateral date (-1: none).  Host index arrays. */
 int mcre_eq_set_exposure_accumulator(mcre_eq_plan *plan, double *d_accum);
+/* Black-Scholes plans with tangents in accumulating mode: the lane-local tangents of the netted exposures are ADDED to
+ * d_accum_tan [n_sets][n_expo][n_assets][nt][n_paths] (nt = 3: spot, volatility, rate of the lane's asset).  With the
+ * per-path tangents of the other product family of a hybrid book (mcre_irc_set_path_replay) they feed
+ * mcre_exposure_tangent_sums.  NULL: off. */
+int mcre_eq_set_exposure_tangent_accumulator(mcre_eq_plan *plan, double *d_accum_tan);
+/* Pathwise sensitivities of exposure metrics from per-path exposures and their tangents (what torch.autograd gives
+ * through netting_set.py:48-72, 136-184, epe_metric.py / ene_metric.py / cva_metric.py:62-100 for weights that do not
+ * depend on the parameters): d_expo [n_expo][n], d_tan [n_par][n_expo][n]; per metric date m and parameter g
+ *   U = unsecured exposure (threshold / collateral like mcre_eq_unsecured_exposures), dU its tangent,
+ *   d_out [n_metric][n_par][3] = sum 1{U > 0} dU, sum 1{U < 0} dU, sum w_m 1{U > 0} dU   (w: host [n_metric]).
+ * Fixed-order chunk partials d_partial [ceil(n / chunk_paths)][n_metric * n_par * 3] + tree. */
+int mcre_exposure_tangent_sums(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo, int32_t n_par,
+                               int32_t n_metric, const int32_t *metric_expo, const int32_t *lag, int32_t collateralised,
+                               double threshold, const double *weights, int32_t chunk_paths, double *d_partial,
+                               double *d_out, void *stream);
 int mcre_eq_unsecured_exposures(const double *d_expo, int64_t n_paths, int32_t n_metric, const int32_t *metric_expo,
                                 const int32_t *lag, int32_t collateralised, double threshold, double *d_out, void *stream);
 /* d_out [n_rows][2] = sum(v - c), sum((v - c)^2) per row of d_x [n_rows][n], c = d_shift[row], v = x (mode 0),

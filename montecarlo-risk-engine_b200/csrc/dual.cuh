@@ -67,6 +67,12 @@ template <> __device__ __forceinline__ double r_load<double>(const double *p, in
 // ---- Dual<N> ----------------------------------------------------------------------
 #define MCRE_DUAL_LOOP for (int i = 0; i < N; ++i)
 template <int N> __device__ __forceinline__ double val(const Dual<N> &x) { return x.v; }
+// makes x the independent variable of tangent slot `slot` (slot < 0: a constant)
+__device__ __forceinline__ void r_seed(double &, int) {}
+template <int N> __device__ __forceinline__ void r_seed(Dual<N> &x, int slot) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) x.d[i] = i == slot ? 1.0 : 0.0;
+}
 template <int N> __device__ __forceinline__ double tan_of(const Dual<N> &x, int i) { return x.d[i]; }
 
 template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N> &a, const Dual<N> &b) {

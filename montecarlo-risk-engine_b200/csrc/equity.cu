@@ -73,6 +73,9 @@ struct EqDev {
   // launch's products is ADDED to expo_accum [n_sets][n_expo][n_paths]; netting terms / metrics are applied
   // afterwards by mcre_eq_unsecured_exposures + mcre_sum_stats
   double *expo_accum;
+  // ... and the lane-local tangents of those exposures to expo_accum_tan [n_sets][n_expo][A][nt][n_paths]
+  // (mcre_eq_set_exposure_tangent_accumulator; hybrid books, mcre/hybrid.py)
+  double *expo_accum_tan;
   // tangent builds (Black-Scholes): tangents of the regression-proxy coefficients with respect to the lane-local
   // parameters of the product's asset, [n_expo][n_prod][3 coefficients][nt] (mcre_eq_set_exposure_coef_tangents),
   // and the tangent spill of the pre-simulation pass (mcre_eq_presim_tangents): ps_dx [n_expo][A][nt][n_paths],
@@ -388,6 +391,17 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
 #pragma unroll
               for (int s = 0; s < NS; ++s)
                 if (s < P.n_sets) P.expo_accum[((size_t)s * P.n_expo + xe) * sh.n_paths + lpath] += val(expo[s]);
+            }
+            if constexpr (XT) {
+              if (P.expo_accum_tan && live && !pilot) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                  if (s < P.n_sets) {
+#pragma unroll
+                    for (int k = 0; k < NT; ++k)
+                      P.expo_accum_tan[((((size_t)s * P.n_expo + xe) * A + a) * NT + k) * sh.n_paths + lpath] += tan_of(expo[s], k);
+                  }
+              }
             }
             return;   // netting terms and metrics are applied once all launches of the book have added up
           }
@@ -866,7 +880,7 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   D.xp_tan = nullptr; D.ps_dx = nullptr; D.ps_dcf = nullptr;
   D.has_cir = 0; D.cir_det = 0; D.cir_col = 0; D.cir_kappa = D.cir_theta = D.cir_sigma = D.cir_y0 = D.lgd = 0.0;
   D.step_cir = D.cir_row = D.cva_coef = nullptr; D.set_cva = nullptr; D.cva_w = nullptr;
-  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr;
+  D.ps_x = nullptr; D.ps_cf = nullptr; D.pv_accum = nullptr; D.bridge_u = nullptr; D.bridge_stride = 0; D.expo_accum = nullptr; D.expo_accum_tan = nullptr;
   D.kind = c->kind; D.scheme = c->scheme; D.smoothing = c->smoothing; D.n_assets = A; D.noise_dim = d;
   D.n_uniform = c->n_uniform > 0 ? c->n_uniform : 1;
   D.asset_par = p->asset_par.p; D.asset_noise = p->asset_noise.p; D.asset_uniform = p->asset_uniform.p;
@@ -1037,6 +1051,97 @@ extern "C" int mcre_eq_set_exposure_accumulator(mcre_eq_plan *p, double *d_accum
   if (!p) return fail(-1, "null argument%s", "");
   p->d.expo_accum = d_accum;
   return 0;
+}
+
+extern "C" int mcre_eq_set_exposure_tangent_accumulator(mcre_eq_plan *p, double *d_accum_tan) {
+  if (!p) return fail(-1, "null argument%s", "");
+  if (d_accum_tan && (p->d.kind != MCRE_EQ_BS || p->nt <= 0))
+    return fail(-3, "eq: exposure tangents exist in Black-Scholes plans with tangents%s", "");
+  p->d.expo_accum_tan = d_accum_tan;
+  return 0;
+}
+
+namespace mcre {
+// Tangent sums of the exposure metrics of one netting set from per-path exposures and tangents: one block per
+// (chunk of paths, parameter, metric date); fixed summation order inside the block.
+__global__ void __launch_bounds__(128) exposure_tangent_sums_kernel(const double *__restrict__ expo, const double *__restrict__ tan,
+                                                                    long long n, int n_expo, int n_par, int n_metric,
+                                                                    const int *__restrict__ metric_expo,
+                                                                    const int *__restrict__ lag, int collateralised, double h,
+                                                                    const double *__restrict__ w, int chunk,
+                                                                    double *__restrict__ partial) {
+  __shared__ double stage[4][3];
+  const int g = blockIdx.y, m = blockIdx.z;
+  const int xe = metric_expo[m];
+  const int l = collateralised ? lag[m] : -1;
+  const double *tg = tan + (size_t)g * n_expo * n;
+  double s_pos = 0.0, s_neg = 0.0;
+  const long long base = (long long)blockIdx.x * chunk;
+  for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
+    const long long p = base + it;
+    if (p >= n) break;
+    const double now = expo[(size_t)xe * n + p], dnow = tg[(size_t)xe * n + p];
+    auto thr = [h](double x) { return x > h ? x - h : (x < -h ? x + h : 0.0); };
+    auto dthr = [h](double x) { return (x > h || x < -h) ? 1.0 : 0.0; };
+    double u, du;
+    if (collateralised) {
+      const double delayed = l >= 0 ? expo[(size_t)(xe - l) * n + p] : 0.0;
+      const double ddel = l >= 0 ? tg[(size_t)(xe - l) * n + p] : 0.0;
+      u = now - thr(delayed); du = dnow - dthr(delayed) * ddel;
+    } else {
+      u = thr(now); du = dthr(now) * dnow;
+    }
+    if (u > 0.0) s_pos += du;
+    if (u < 0.0) s_neg += du;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 16; off > 0; off >>= 1) {
+    s_pos += __shfl_xor_sync(0xffffffffu, s_pos, off);
+    s_neg += __shfl_xor_sync(0xffffffffu, s_neg, off);
+  }
+  if (lane == 0) { stage[warp][0] = s_pos; stage[warp][1] = s_neg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < 4; ++k) { a += stage[k][0]; b += stage[k][1]; }
+    double *o = partial + ((size_t)blockIdx.x * n_metric * n_par + (size_t)m * n_par + g) * 3;
+    o[0] = a; o[1] = b; o[2] = w[m] * a;
+  }
+}
+}  // namespace mcre
+
+extern "C" int mcre_exposure_tangent_sums(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo,
+                                          int32_t n_par, int32_t n_metric, const int32_t *metric_expo, const int32_t *lag,
+                                          int32_t collateralised, double threshold, const double *weights,
+                                          int32_t chunk_paths, double *d_partial, double *d_out, void *stream) {
+  if (!d_expo || !d_tan || !metric_expo || !lag || !weights || !d_partial || !d_out) return fail(-1, "null argument%s", "");
+  if (n_par <= 0 || n_metric <= 0 || n_expo <= 0 || chunk_paths <= 0) return fail(-2, "tangent sums: bad shape%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t slots = (int64_t)n_metric * n_par * 3;
+  const long long n_chunks = n_paths > 0 ? (n_paths + chunk_paths - 1) / chunk_paths : 0;
+  DevArray<int> me, lg;
+  DevArray<double> wd;
+  DevArena arena;
+  int rc = 0;
+  {
+    ArenaScope scope(&arena);
+    rc = me.upload(metric_expo, n_metric);
+    if (!rc) rc = lg.upload(lag, n_metric);
+    if (!rc) rc = wd.upload(weights, n_metric);
+    if (!rc) rc = arena.commit();
+  }
+  if (!rc && n_chunks > 0) {
+    dim3 grid((unsigned)n_chunks, (unsigned)n_par, (unsigned)n_metric);
+    exposure_tangent_sums_kernel<<<grid, 128, 0, st>>>(d_expo, d_tan, n_paths, n_expo, n_par, n_metric, me.p, lg.p,
+                                                       collateralised, threshold, wd.p, chunk_paths, d_partial);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch");
+  }
+  if (!rc) rc = mcre_tree_reduce(d_partial, n_chunks, slots, d_out, stream);
+  if (!rc) cudaStreamSynchronize(st);   // the index tables are freed below
+  arena.release();
+  return rc;
 }
 
 namespace mcre {

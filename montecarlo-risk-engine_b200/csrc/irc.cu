@@ -348,7 +348,6 @@ using namespace mcre;
 extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   if (!c || !out) return fail(-1, "null argument%s", "");
   if (c->nt != 0 && c->nt != 4 && c->nt != 8) return fail(-1, "irc: nt must be 0, 4 or 8%s", "");
-  if (c->ext_numeraire && c->nt != 0) return fail(-3, "irc: an external numeraire is implemented for value-only plans%s", "");
   if (c->n_sets < 0 || c->n_sets > MCRE_IRC_MAX_SETS) return fail(-1, "irc: n_sets out of range%s", "");
   if (c->n_units < 0 || c->n_units > MCRE_IRC_MAX_UNITS) return fail(-1, "irc: n_units out of range%s", "");
   if (c->n_berm < 0 || c->n_berm > MCRE_IRC_MAX_BERM) return fail(-1, "irc: n_berm out of range%s", "");
@@ -449,7 +448,7 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   IrcDev &d = p->d;
   d.nt = c->nt; d.scheme = c->scheme; d.has_cir = c->has_cir; d.cir_det = c->cir_deterministic;
   d.vas_noise = c->vas_noise; d.cir_noise = c->cir_noise;
-  d.ext_num = c->ext_numeraire; d.ext_rate = c->ext_rate; d.pv_spill = nullptr;
+  d.ext_num = c->ext_numeraire; d.ext_rate = c->ext_rate; d.ext_slot = c->ext_numeraire ? c->ext_slot : -1; d.pv_spill = nullptr;
   d.vas = p->vas.p; d.cir = p->cir.p; d.cir_init = p->cir_init.p; d.chol = p->chol.p;
   d.n_sub = c->n_sub; d.n_dates = c->n_dates; d.n_pre_dates = c->n_pre_dates;
   d.step_dt = p->step_dt.p; d.step_date = p->step_date.p; d.step_vas = p->step_vas.p; d.step_cir = p->step_cir.p;
@@ -608,7 +607,7 @@ extern "C" int mcre_irc_lsm_forward(mcre_irc_plan *p, const mcre_rng *rng, const
 extern "C" int mcre_irc_set_pv_spill(mcre_irc_plan *p, double *d_pv) {
   if (!p) return fail(-1, "null argument%s", "");
   if (p->cva_only) return fail(-3, "pv spill: not available on the CVA-only plan%s", "");
-  if (p->d.nt != 0 || p->d.n_berm != 0) return fail(-3, "pv spill: value-only plans of linear products%s", "");
+  if (p->d.n_berm != 0) return fail(-3, "pv spill: plans of linear products%s", "");
   p->d.pv_spill = d_pv;
   return 0;
 }

@@ -42,7 +42,7 @@ struct IrcDev {
   // hybrid books (mcre/hybrid.py): the numeraire is another model's deterministic money-market account,
   // exp(ext_rate (t - t0)) (model_config.py:44-47, numeraire_model_idx), accumulated step by step like the path's own;
   // pv_spill [n_sets][n_paths]: per-path discounted cashflow totals (mcre_irc_set_pv_spill)
-  int ext_num;
+  int ext_num, ext_slot;   // ext_slot: tangent slot of the external rate (-1: none)
   double ext_rate;
   double *pv_spill;
 };
@@ -92,7 +92,13 @@ __device__ __forceinline__ void irc_step(const IrcDev &P, const IrcParams<R, CIR
   if (CIR) w1 = mp.L10 * z0 + mp.L11 * z1;
   const R wv = (CIR && P.vas_noise == 1) ? w1 : w0;
   // numeraire integral uses the pre-step rate (left Riemann sum)
-  s.logB = s.logB + (P.ext_num ? T::lift(P.ext_rate) : s.r) * dt;
+  if (P.ext_num) {
+    R e = T::lift(P.ext_rate);
+    r_seed(e, P.ext_slot);
+    s.logB = s.logB + e * dt;
+  } else {
+    s.logB = s.logB + s.r * dt;
+  }
   if (SCHEME == MCRE_SCHEME_ANALYTICAL) {
     R decay = T::load(P.step_vas, is * 2 + 0), nstd = T::load(P.step_vas, is * 2 + 1);
     // exact OU transition; the 1x1 Cholesky factor of the step covariance is nstd (vasicek.py:52-86)
@@ -437,7 +443,12 @@ __global__ void __launch_bounds__(128, irc_minb(NT, NS)) irc_main_kernel(IrcDev 
             MCRE_VP st[p].r = st[p].r + kv1 * z1[p];
           }
         }
-        MCRE_VP st[p].logB = st[p].logB + (P.ext_num ? T::lift(P.ext_rate) : rate0[p]) * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
+        if (P.ext_num) {
+          R e_num = T::lift(P.ext_rate);
+          r_seed(e_num, P.ext_slot);
+          MCRE_VP st[p].logB = st[p].logB + e_num * dt;
+        } else
+        MCRE_VP st[p].logB = st[p].logB + rate0[p] * dt;   // left Riemann sum with the pre-step rate (vasicek.py:80,107)
         if constexpr (CIR) {
           if (cir_det) {                      // cirpp.py:155-172
             MCRE_VP { st[p].logBl = st[p].logBl + sc0 * dt; st[p].y = sc1; }

@@ -1114,7 +1114,7 @@ class EquityBackend:
         pv = mean_and_error(s[0], s[1], float(shift_sum[0]), n_main)
         if self.nt:
             grad[self.num_rate_global] += numtan
-        res = {"pv": (pv, grad), "param_used": self._param_used}
+        res = {"pv": (pv, grad), "param_used": self._param_used, "_expo": accum_e, "_cva_w": cva_w}
         if need_expo:
             # netting-set terms on the accumulated exposures, then the metric sums (shift = the value on global path 0,
             # which lives on rank 0: summed over the ranks so that every rank uses the same one)
@@ -1164,6 +1164,64 @@ class EquityBackend:
                 else:
                     res["cva"] = ((0.0, 0.0), None)
         return res
+
+    def exposure_tangent_pass(self, si, dev, n_main, chunk):
+        """Tangent twin of _run_split_book for hybrid books (mcre/hybrid.py): the launches of netting set `si` in
+        accumulating mode on a plan with tangents.  -> (per-path tangents of the netted exposure of the set's equity
+        products [n_expo][assets][nt][n] w.r.t. the lane-local parameters (spot, volatility, rate) of each asset,
+        PV gradient [parameters of this backend's model] or None)."""
+        c = self.c
+        L = B.lib()
+        ntrk = eq_ntrk(self.nt)
+        prods = [p for p in c.netting_sets[si].products if not c._can_skip_monte_carlo_for_product(p)]
+        order = {id(p): i for i, p in enumerate(c.netting_sets[si].products)}
+        tracked = [p for p in prods if _is_path_dependent(p)]
+        plain = [p for p in prods if not _is_path_dependent(p)]
+        books = [tracked[i:i + ntrk] for i in range(0, len(tracked), ntrk)]
+        if plain and books:
+            books[0] = books[0] + plain
+        elif plain:
+            books = [plain]
+        begin, count = RT.shard_range(n_main, chunk)
+        n = max(count, 1)
+        n_chunks = (n + chunk - 1) // chunk
+        n_expo = len(c.exposure_timeline)
+        n_params = len(c.model.model_params)
+        accum = torch.zeros(n, dtype=torch.float64, device=dev)
+        accum_e = torch.zeros((n_expo, n), dtype=torch.float64, device=dev)
+        accum_t = torch.zeros((n_expo, self.A, self.nt, n), dtype=torch.float64, device=dev)
+        grad, numtan = np.zeros(n_params), 0.0
+        for book in books:
+            desc, keep, info = self.lower([si], subset=sorted(book, key=lambda p: order[id(p)]))
+            plan = C.c_void_p()
+            B.check(L.mcre_eq_create(C.byref(desc), C.byref(plan)))
+            try:
+                slots = L.mcre_eq_slots(plan)
+                acc = torch.zeros(slots, dtype=torch.float64, device=dev)
+                shift = torch.zeros(slots, dtype=torch.float64, device=dev)
+                partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
+                B.check(L.mcre_eq_set_pv_accumulator(plan, accum.data_ptr()))
+                B.check(L.mcre_eq_set_exposure_accumulator(plan, accum_e.data_ptr()))
+                B.check(L.mcre_eq_set_exposure_tangent_accumulator(plan, accum_t.data_ptr()))
+                if info.get("xp_tan") is not None:
+                    keep_xt, xt_ptr = B.as_dp(info["xp_tan"].reshape(-1))
+                    B.check(L.mcre_eq_set_exposure_coef_tangents(plan, xt_ptr))
+                keep_bridge = self._set_bridge_uniforms(plan, info, "main", n_main, dev)
+                rng = self._rng(43, n_main)
+                sh = B.Shard(begin, count, chunk)
+                B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
+                                          shift.data_ptr(), None, RT.stream_ptr()))
+                acc_h = RT.all_reduce_tree(acc).cpu().numpy()
+                tang = acc_h[3:3 + self.A * self.nt].reshape(self.A, 1, self.nt)
+                for a, asset in enumerate(self.assets):
+                    for k, g in enumerate(asset.gmap):
+                        grad[g] += tang[a, 0, k] / n_main
+                numtan += acc_h[2] / n_main
+                grad += self._control_variate_gradient(info["owners"], info["recs"], 0, n_params)
+            finally:
+                L.mcre_eq_destroy(plan)
+        grad[self.num_rate_global] += numtan
+        return accum_t, grad
 
     def run(self):
         c = self.c

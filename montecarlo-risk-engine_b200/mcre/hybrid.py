@@ -14,7 +14,10 @@ The two product families have their own fused kernels.  Here they run on column 
      starting from those spills: threshold / MPoR collateral, positive parts, PFE order statistics and the CVA integrand
      then see the whole netting set.
 
-Value-only.  The noise tensor is O(sub-steps x paths x factors): these books run on thousands to a few million paths.
+Sensitivities (differentiate=True): a second pass on plans with tangents leaves per-path tangents of both families'
+exposures (interest-rate kernels: the path-replay spill; equity kernel: mcre_eq_set_exposure_tangent_accumulator), and
+mcre_exposure_tangent_sums differentiates the netting terms and positive parts on the combined duals.
+The noise tensor is O(sub-steps x paths x factors): these books run on thousands to a few million paths.
 """
 from __future__ import annotations
 
@@ -60,10 +63,18 @@ class HybridBackend:
     def __init__(self, ctrl):
         from mcre.irc import is_linear
         self.c = c = ctrl
+        self.differentiate = bool(c.differentiate)
         self.bs_idx, self.vas_idx, self.cir_idx = _families(c.model)
         if c.differentiate:
-            raise NotImplementedError("sensitivities of netting sets that mix rate and equity products "
-                                      "(three-model ModelConfig): value-only for now")
+            from metrics.metric import MetricType
+            cir = c.model.models[self.cir_idx] if self.cir_idx is not None else None
+            if len(self.bs_idx) != 1:
+                raise NotImplementedError("sensitivities of hybrid books: one Black-Scholes market model")
+            if cir is not None and not cir.deterministic and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
+                raise NotImplementedError("sensitivities of the CVA of hybrid books: deterministic credit (the default "
+                                          "weights of a stochastic intensity carry tangents the equity launch does not have)")
+            if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
+                raise NotImplementedError("PFE sensitivities of hybrid books")
         if c.simulation_scheme != SimulationScheme.EULER:
             # the reference defines inter-model covariances for Black-Scholes pairs only (model_config.py:201-221)
             raise NotImplementedError("Inter covariance not implemented for the requested pair of models.")
@@ -117,7 +128,7 @@ class HybridBackend:
         return [cols[i] for i in self.bs_idx], cols[self.vas_idx], (cols[self.cir_idx] if self.cir_idx is not None else None)
 
     # ------------------------------------------------------------------ sub-controllers
-    def _sub(self, model, netting_sets, risk_metrics=None):
+    def _sub(self, model, netting_sets, risk_metrics=None, differentiate=False):
         c = self.c
         sub = copy.copy(c)
         sub.model = model
@@ -131,9 +142,130 @@ class HybridBackend:
             sub.metric_exposure_indices = torch.arange(n, dtype=torch.long)
             sub.netting_set_delayed_exposure_indices = [torch.full((n,), -1, dtype=torch.long) for _ in netting_sets]
         sub.requires_regression = any(sub._product_requires_regression(p) for p in sub.products)
+        sub.differentiate = differentiate
         sub.injected_normals = {}
         sub.last_timings = {}
         return sub
+
+    # ------------------------------------------------------------------ sensitivities
+    def _tangent_pass(self, noise_eq, noise_ir, values, chunk, dev):
+        """First-order sensitivities of every metric (the reference: torch.autograd through the whole run,
+        controller.py:609-627).  Both families run once more on plans with tangents and leave per-path tangents of their
+        netted exposures; mcre_exposure_tangent_sums applies the netting-set terms and the positive / negative parts to
+        the combined duals.  `values`: the value run's per-set dicts (exposures before netting terms, default weights).
+        -> per set {"pv": grad, "pos": [grad per metric date], "neg": [...], "cva": grad} over the flattened parameters."""
+        from metrics.metric import MetricType
+        from metrics.pfe_metric import PFEMetric
+        from metrics.pv_metric import PVMetric
+        from metrics.risk_metrics import RiskMetrics
+        from mcre.equity import EquityBackend, is_equity_exercise
+        from mcre.irc import IrcBackend
+        from products.netting_set import NettingSet
+        c = self.c
+        L = B.lib()
+        models = c.model.models
+        offs = c.model.param_offsets()
+        n_par = len(c.model.model_params)
+        n_main = c.num_paths_mainsim
+        n_sets = len(c.netting_sets)
+        n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
+        need_expo = c.risk_metrics.requires_exposure_profiles()
+        need_pv = c.risk_metrics.requires_discounted_cashflows()
+        num_rate = offs[c.model.id_to_model["numeraire"]] + 2
+        begin, count = RT.shard_range(n_main, chunk)
+        n = max(count, 1)
+        # per-path tangents of the netted exposure of every set with respect to the flattened parameters
+        tan = [torch.zeros((n_par, n_expo, n), dtype=torch.float64, device=dev) if need_expo else None for _ in range(n_sets)]
+        pv_grad = [np.zeros(n_par) for _ in range(n_sets)]
+
+        # ---- rate products: tangent build with 8 slots = 4 Vasicek parameters, the numeraire model's rate, 3 unused
+        rate_of_set = [[p for p in ns.products if p in self.rate_products] for ns in c.netting_sets]
+        if self.rate_products:
+            rows = [si for si in range(n_sets) if rate_of_set[si]]
+            ir_sets = [NettingSet(name=f"rates_{si}", products=rate_of_set[si]) for si in rows]
+            ir_metrics = ([PFEMetric(0.5)] if need_expo else []) + ([PVMetric()] if need_pv or not need_expo else [])
+            rm = RiskMetrics(ir_metrics, exposure_timeline=c.exposure_timeline.tolist() if need_expo else None)
+            sub = self._sub(models[self.vas_idx], ir_sets, rm, differentiate=True)
+            sub.injected_normals = noise_ir
+            sub.regression_coeffs = [rc.clone() for rc in c.regression_coeffs]     # (the value run's stay as they are)
+            ib = IrcBackend(sub)
+            ib.nt = 8
+            num_model = models[c.model.id_to_model["numeraire"]]
+            ib.hybrid = {"ext_rate": float(num_model.param_values()[2]), "ext_slot": 4, "chunk": chunk, "captured": []}
+            ib.run()
+            slot_to_global = [offs[self.vas_idx] + k for k in range(4)] + [num_rate]
+            for cap in ib.hybrid["captured"]:
+                for r, k in enumerate(cap["idxs"]):
+                    si = rows[k]
+                    if cap["tan"] is not None:
+                        t = cap["tan"][:, :, r, :].permute(2, 1, 0)          # [path][date][slot] -> [slot][date][path]
+                        for slot, g in enumerate(slot_to_global):
+                            tan[si][g] += t[slot]
+                    if cap["pv_tan"] is not None:
+                        for slot, g in enumerate(slot_to_global):
+                            pv_grad[si][g] += cap["pv_tan"][r][slot]
+
+        # ---- equity products: Black-Scholes plan with lane-local tangents (spot, volatility, rate) ----------------
+        b = self.bs_idx[0]
+        eq_sets = []
+        for ns in c.netting_sets:
+            view = copy.copy(ns)
+            view.products = [p for p in ns.products if p in self.equity_products]
+            eq_sets.append(view)
+        sub = self._sub(models[b], eq_sets, differentiate=True)
+        sub.injected_normals = {k: v[:, :, :1].contiguous() for k, v in noise_eq.items()}
+        sub.regression_coeffs = [rc.clone() for rc in c.regression_coeffs]
+        eb = EquityBackend(sub)
+        eb.presim_exercise_all([p for p in sub.products if is_equity_exercise(p)], dev)
+        if need_expo:
+            reg = [p for p in sub.products if not sub._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
+            if reg:
+                eb.presim_regression(reg, dev)
+        for si in range(n_sets):
+            if not eq_sets[si].products:
+                continue
+            accum_t, g_pv = eb.exposure_tangent_pass(si, dev, n_main, chunk)
+            for k in range(3):
+                if need_expo:
+                    tan[si][offs[b] + k] += accum_t[:, 0, k, :]
+                pv_grad[si][offs[b] + k] += g_pv[k]
+
+        # ---- netting-set terms and metric parts on the combined duals ---------------------------------------------
+        out = []
+        kinds = {m.metric_type for m in c.risk_metrics.metrics}
+        cva_metric = next((m for m in c.risk_metrics.metrics if m.metric_type == MetricType.CVA), None)
+        metric_expo = np.asarray(c.metric_exposure_indices.tolist(), dtype=np.int32)
+        for si, ns in enumerate(c.netting_sets):
+            res = {"pv": pv_grad[si]}
+            if need_expo:
+                lag = np.full(n_metric, -1, dtype=np.int32)
+                if ns.is_collateralized():
+                    delayed = c.netting_set_delayed_exposure_indices[si].tolist()
+                    for m in range(n_metric):
+                        if delayed[m] >= 0:
+                            lag[m] = int(metric_expo[m]) - delayed[m]
+                w = np.zeros(n_metric)
+                cva_w = values[si].get("_cva_w")
+                if cva_metric is not None and cva_w is not None:
+                    # deterministic credit: the same weights on every path; every rank reads its first local path
+                    w_local = cva_w[:, 0].clone() if count > 0 else torch.zeros(n_metric, dtype=torch.float64, device=dev)
+                    w = RT.to_host(w_local) * (1.0 - cva_metric.recovery_rate)
+                n_chunks = (n + chunk - 1) // chunk
+                slots = n_metric * n_par * 3
+                partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
+                sums = torch.zeros(slots, dtype=torch.float64, device=dev)
+                me_k, me_p = B.as_ip(metric_expo)
+                lg_k, lg_p = B.as_ip(lag)
+                w_k, w_p = B.as_dp(w)
+                B.check(L.mcre_exposure_tangent_sums(values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par,
+                                                     n_metric, me_p, lg_p, int(ns.is_collateralized()), float(ns.threshold),
+                                                     w_p, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
+                sm = RT.to_host(RT.all_reduce_tree(sums)).reshape(n_metric, n_par, 3) / n_main
+                res["pos"] = [sm[m, :, 0] for m in range(n_metric)]
+                res["neg"] = [sm[m, :, 1] for m in range(n_metric)]
+                res["cva"] = sm[:n_metric - 1, :, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
+            out.append(res)
+        return out
 
     def run(self):
         from metrics.metric import MetricType
@@ -188,13 +320,13 @@ class HybridBackend:
             ib.hybrid = {"ext_rate": float(num_model.param_values()[2]), "chunk": chunk, "captured": []}
             _, t_ir = ib.run()
             t_pre += t_ir.get("preprocessing", 0.0)
-            for idxs, spill, pv_spill in ib.hybrid["captured"]:
-                for r, k in enumerate(idxs):
+            for cap in ib.hybrid["captured"]:
+                for r, k in enumerate(cap["idxs"]):
                     si = rows[k]
-                    if spill is not None:
-                        extra_expo[si] = spill[r]
-                    if pv_spill is not None:
-                        extra_pv[si] = pv_spill[r]
+                    if cap["spill"] is not None:
+                        extra_expo[si] = cap["spill"][r]
+                    if cap["pv_spill"] is not None:
+                        extra_pv[si] = cap["pv_spill"][r]
 
         # ---- equity products + netting-set terms + metrics on the combined accumulators ------------------------------------
         eq_models = [models[i] for i in self.bs_idx] + ([models[self.cir_idx]] if with_credit else [])
@@ -222,6 +354,24 @@ class HybridBackend:
             res = eb._run_split_book(si, dev, n_main, n_params, chunk=chunk, extra_expo=extra_expo[si], extra_pv=extra_pv[si])
             res["param_used"] = lambda kind: [False] * len(c.model.model_params)
             results.append(res)
+        if self.differentiate:
+            grads = self._tangent_pass(noise_eq, noise_ir, results, chunk, dev)
+            # parameters of the credit model: its deterministic mode reads the market hazard curve only, the reference's
+            # autograd graph does not reach them (None); everything else is connected
+            offs = c.model.param_offsets()
+            used = [True] * len(c.model.model_params)
+            if self.cir_idx is not None:
+                for k in range(len(models[self.cir_idx].model_params)):
+                    used[offs[self.cir_idx] + k] = False
+            for res, g in zip(results, grads):
+                res["pv"] = (res["pv"][0], g["pv"])
+                if "pos" in res:
+                    res["pos"] = (res["pos"][0], g["pos"])
+                if "neg" in res:
+                    res["neg"] = (res["neg"][0], g["neg"])
+                if "cva" in res and res["cva"][0] != (0.0, 0.0):
+                    res["cva"] = (res["cva"][0], g["cva"])
+                res["param_used"] = lambda kind, used=used: used
         torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start
         return results, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}

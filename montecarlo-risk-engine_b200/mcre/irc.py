@@ -508,9 +508,8 @@ class IrcBackend:
         d.vas_noise = self.vas_idx if self.has_cir else 0
         d.cir_noise = self.cir_idx if self.has_cir else 0
         if self.hybrid is not None:
-            if nt:
-                raise NotImplementedError("sensitivities of books that mix rate and equity products")
             d.ext_numeraire, d.ext_rate = 1, float(self.hybrid["ext_rate"])
+            d.ext_slot = int(self.hybrid.get("ext_slot", -1)) if nt else -1
 
         def fp(name, arr):
             t[name], ptr = B.as_dp(arr)
@@ -920,9 +919,24 @@ class IrcBackend:
                 acc_h = RT.to_host(acc)
                 shift_h = RT.to_host(shift)
                 quant = None
+                cap = None
                 if self.hybrid is not None:
                     # per-path exposures / cashflows handed to the combining backend; no metric is finished here
-                    self.hybrid["captured"].append((list(idxs), spill, pv_spill))
+                    cap = dict(idxs=list(idxs), spill=spill, pv_spill=pv_spill, tan=None, pv_tan=None)
+                    if self.nt and spill is not None:
+                        # tangents of every path's exposures: the replay mode of the tangent build (made for the
+                        # gradient of PFE order statistics) over the whole shard, [path][exposure date][set][nt]
+                        paths = torch.arange(begin, begin + max(count, 1), dtype=torch.int64, device=dev)
+                        cap["tan"] = torch.zeros((max(count, 1), n_metric, len(idxs), self.nt), dtype=torch.float64, device=dev)
+                        B.check(L.mcre_irc_set_path_replay(plan, paths.data_ptr(), cap["tan"].data_ptr()))
+                        try:
+                            acc2, shift2 = torch.zeros_like(acc), torch.zeros_like(shift)
+                            sh2 = B.Shard(0, count, chunk_paths)
+                            B.check(L.mcre_irc_mainsim(plan, C.byref(rng), C.byref(sh2), partial.data_ptr(), acc2.data_ptr(),
+                                                       shift2.data_ptr(), None, RT.stream_ptr()))
+                        finally:
+                            B.check(L.mcre_irc_set_path_replay(plan, None, None))
+                    self.hybrid["captured"].append(cap)
                     spill = None
                 if spill is not None:
                     from mcre.select import order_statistics
@@ -935,6 +949,8 @@ class IrcBackend:
             nv = 4 + 2 * self.nt
             acc_h = acc_h.reshape(n_metric + 1, ns_t, nv)
             shift_h = shift_h.reshape(n_metric + 1, ns_t, nv)
+            if cap is not None and self.nt and (info["acc"] & B.ACC_PV):
+                cap["pv_tan"] = [acc_h[n_metric, r, 4:4 + self.nt] / n_main for r in range(len(idxs))]
             from mcre.finish import irc_raw_to_neutral
             for r, si in enumerate(idxs):
                 res = irc_raw_to_neutral(acc_h[:, r, :], shift_h[:, r, :], n_main, self.nt, n_metric, info["acc"])

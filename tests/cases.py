@@ -327,7 +327,7 @@ def heston_euler_book(ns_module):
 
 
 def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_level=0.03, deterministic=True,
-               rho=(0.0, 0.0, 0.0), horizon=4.0, n_expo=30, extra_metrics=False, collateral=False):
+               rho=(0.0, 0.0, 0.0), horizon=4.0, n_expo=30, extra_metrics=False, collateral=False, pfe=True):
     """Equity options + bonds + swaps in ONE netting set against a three-model ModelConfig: Black-Scholes (numeraire),
     Vasicek, CIR++ credit (tests/exposure_tests/cva_large_netting_set_derivatives.py:58-175, the book of
     tests/pytests/test_cva_large_netting_set_aad_vs_fd.py:26-57).  rho = inter-model correlations in the reference's
@@ -363,7 +363,7 @@ def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_leve
         metrics += [m.EPEMetric(), m.PVMetric()]
     if collateral:
         # the same book twice: thresholded, and MPoR-collateralised with a threshold; more metrics
-        metrics += [m.ENEMetric(), m.PFEMetric(0.9)]
+        metrics += [m.ENEMetric()] + ([m.PFEMetric(0.9)] if pfe else [])
         tl = np.linspace(0.0, horizon, n_expo)
         _, twin, _, _ = hybrid_cva(ns_module, n_euro, n_bonds, n_swaps, spot, rate_level, deterministic, rho, horizon, n_expo)
         sets = [m.NettingSet(name="open", products=prods, counterparty_id=cp, threshold=1.5),
@@ -496,6 +496,11 @@ GOLDEN_CASES = {
     "hybrid_cva": (hybrid_cva, dict(), dict(n_main=1024, n_pre=1024, num_steps=4, scheme="EULER", differentiate=False)),
     "hybrid_cva_corr": (hybrid_cva, dict(n_euro=3, n_bonds=2, n_swaps=5, deterministic=False, rho=(0.3, -0.2, 0.4), horizon=2.0, n_expo=9, extra_metrics=True),
                         dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
+    # first-order sensitivities of a hybrid book: the AAD leg of test_cva_large_netting_set_aad_vs_fd.py at its own
+    # sizes, and a smaller book with threshold / MPoR sets and more metrics (deterministic credit)
+    "hybrid_cva_greeks": (hybrid_cva, dict(), dict(n_main=1024, n_pre=1024, num_steps=4, scheme="EULER", differentiate=True)),
+    "hybrid_collateral_greeks": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, rho=(0.25, 0.0, 0.0), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True, pfe=False),
+                                 dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "hybrid_collateral": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, deterministic=False, rho=(0.25, 0.1, -0.3), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True),
                           dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=False)),
     # gas storage (the reference's tests/pytests/test_storage_s2f_pv.py at its own sizes, and cut-down twins);

@@ -57,10 +57,60 @@ def test_hybrid_cva_is_positive_and_moves_with_spot_and_rate():
     assert np.isfinite(d_spot) and np.isfinite(d_rate) and d_spot > 0.0      # calls gain with the spot
 
 
-def test_hybrid_sensitivities_raise():
+@pytest.mark.parametrize("name", ["hybrid_cva_greeks", "hybrid_collateral_greeks"])
+def test_hybrid_sensitivities_match_reference_autograd(name):
+    """differentiate=True on a hybrid book: every metric's gradient with respect to the 11 parameters of the three models
+    against torch.autograd of the unmodified reference.  Exposure metrics pass through the float32 regression chain on
+    the reference's side (2e-5 like the other exposure Greeks), PV is pathwise (1e-8); the credit model's parameters are
+    outside the reference's graph in deterministic mode (None)."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    for key, ref in gold["values"].items():
+        scale = max(1.0, float(np.max(np.abs(ref))))
+        helpers.assert_close(flat[key][0], ref, 1e-9, 1e-10 * scale, f"{name} {key}")
+    for key, rows in gold["derivatives"].items():
+        s, m = key.split("|")
+        got = res.get_derivatives(s, m)
+        rtol = 1e-8 if m == "pv" else 2e-5
+        for ev, row in enumerate(rows):
+            scale = max(1.0, max(abs(w) for w in row if w is not None))
+            for pname, g, w in zip(gold["params"], got[ev], row):
+                if w is None:
+                    assert g is None, f"{name} {key}[{ev}] d/d{pname}: expected None, got {g}"
+                else:
+                    assert g is not None, f"{name} {key}[{ev}] d/d{pname} is None"
+                    assert abs(float(g) - w) <= rtol * scale, f"{name} {key}[{ev}] d/d{pname}: {float(g)} vs {w}"
+
+
+def test_large_netting_set_cva_aad_matches_finite_differences():
+    """tests/pytests/test_cva_large_netting_set_aad_vs_fd.py:26-57 restated: the AAD sensitivities of the CVA to the spot
+    and to both initial rates against bump-and-revalue on common random numbers, the reference's tolerances."""
     ns = cases.Namespace()
-    model, sets, metrics, tl = cases.hybrid_cva(ns, n_euro=1, n_bonds=1, n_swaps=1)
+
+    def run(spot, rate, diff):
+        model, sets, metrics, tl = cases.hybrid_cva(ns, spot=spot, rate_level=rate)
+        sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), 1024, 1024, 4,
+                                     ns.SimulationScheme.EULER, diff)
+        r = sc.run_simulation()
+        name = metrics[0].get_name()
+        cva = float(r.get_results("large_cva_ns", name, evaluation_idx=0))
+        if not diff:
+            return cva
+        d = r.get_derivatives("large_cva_ns", name, evaluation_idx=0)
+        return cva, float(d["equity.spot"]), float(d["equity.rate"]) + float(d["rates.rate"])
+    cva, d_spot, d_rate = run(100.0, 0.03, True)
+    base = run(100.0, 0.03, False)
+    assert abs(cva - base) <= 1e-12 * abs(base)
+    fd_spot = (run(101.0, 0.03, False) - base) / 1.0
+    fd_rate = (run(100.0, 0.0325, False) - base) / 0.0025
+    assert abs(d_spot - fd_spot) < 2e-3 and abs(d_rate - fd_rate) < 0.1
+
+
+def test_unsupported_hybrid_sensitivities_raise():
+    ns = cases.Namespace()
+    model, sets, metrics, tl = cases.hybrid_cva(ns, n_euro=1, n_bonds=1, n_swaps=1, deterministic=False)
     sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), 256, 256, 1,
                                  ns.SimulationScheme.EULER, True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # CVA sensitivities under a stochastic intensity
         sc.run_simulation()
