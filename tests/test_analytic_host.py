@@ -140,9 +140,13 @@ def test_constructor_error_behaviour_matches_the_reference():
         ns.SimulationController([ns.NettingSet(name="a", products=[opt()], counterparty_id="cp")], model, cva, 10, 10, 1, S)
     with pytest.raises(AssertionError):
         ns.FlexiCall(underlyings=[opt()], num_exercise_rights=2)
-    with pytest.raises(NotImplementedError):
-        from products.storage import Storage
-        Storage(asset_id="gas", start_date=0.0, end_date=1.0)
+    # gas storage (storage.py:28-31): at least two inventory states, a positive roll-out interval
+    from products.storage import Storage
+    from products.storage_helpers import StorageConfig
+    cfg = StorageConfig()
+    cfg.add_volume_constraint(0.0, 1.0, 0.0, 1.0)
+    with pytest.raises(ValueError):
+        Storage(asset_id="gas", start_date=0.0, end_date=1.0, initial_amount=0.0, storage_config=cfg, num_states=1)
 
 
 def test_unsupported_combinations_raise_instead_of_falling_back():
