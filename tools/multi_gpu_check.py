@@ -51,8 +51,17 @@ def main():
     out = {}
     for name in ["cfg3_wwr_cva", "cfg2_irs_offgrid", "wwr_cva", "wwr_cva_greeks", "irs_collateral", "irs_collateral_offgrid", "bermudan_swaption",
                  "heston_path_dependent", "bs_basket_euler", "flexicall_exposure", "mixed_book_exposure",
-                 "bs_exposure_greeks", "bs_proxy_greeks_mixed", "equity_cva", "equity_cva_exercise"]:
-        res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0))
+                 "bs_exposure_greeks", "bs_proxy_greeks_mixed", "equity_cva", "equity_cva_exercise",
+                 # round 2: three-model hybrid books (values and sensitivities), gas storage with the device-moments
+                 # solver (pre-simulation sharded) and with the LAPACK solver (pre-simulation replicated), storage Greeks
+                 "hybrid_cva_corr", "hybrid_collateral", "hybrid_collateral_greeks", "storage2_short_euler",
+                 "storage2_short_euler:gelsy", "storage_s2f_greeks"]:
+        extra = {}
+        if ":" in name:
+            name, solver = name.split(":")
+            extra["storage_solver"] = solver
+        key = name + ("".join(f":{v}" for v in extra.values()))
+        res, sc = helpers.run_cuda(name, draws="philox", n_main=n, n_pre=(n if cases.GOLDEN_CASES[name][2]["n_pre"] else 0), **extra)
         vals = []
         for s in res.get_netting_set_names():
             for m in res.get_metric_names():
@@ -60,7 +69,7 @@ def main():
                 if cases.GOLDEN_CASES[name][2]["differentiate"]:
                     for row in res.get_derivatives(s, m):
                         vals += [bits(0.0 if g is None else g) for g in row]
-        out[name] = vals
+        out[key] = vals
     ns = cases.Namespace()
     model, sets, metrics, _ = cases.heston_basket5(ns)
     sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), n, 0, 2, ns.SimulationScheme.QE, True)
