@@ -590,7 +590,8 @@ int mcre_correlated_normals(const mcre_rng *rng, int32_t n_sub, int32_t dim, con
 #define MCRE_STORAGE_MAX_KNOTS 8   /* knots per injection / withdrawal rate curve                      */
 #define MCRE_STORAGE_RECORD 48     /* doubles per action-date record                                    */
 #define MCRE_STORAGE_MAX_STATES 16 /* inventory grid states                                             */
-#define MCRE_STORAGE_STEP 10       /* doubles per sub-step record                                       */
+#define MCRE_STORAGE_STEP 24       /* doubles per sub-step record                                       */
+#define MCRE_STORAGE_MAX_NOISE 8   /* normals per sub-step of the price model's joint draw              */
 #define MCRE_STORAGE_MAX_BASIS 6   /* regression basis functions (polynomial degree + 1)                */
 
 typedef struct {
@@ -600,12 +601,16 @@ typedef struct {
   int32_t n_states;         /* inventory grid states                                                       */
   int32_t n_basis;          /* regression basis functions                                                  */
   double log_spot0;         /* log of the forward curve at the calibration date                            */
-  const double *step;       /* [n_sub][MCRE_STORAGE_STEP] a, k, dt, m, cx, b00, cy, b10, b11, log F(t2):
-                               x' = (a x - (k x) dt) + cx (b00 z0);  y' = (y + m) + cy (b10 z0 + b11 z1);
-                               log S = log F(t2) + x' + y'
-                               ANALYTICAL: a = exp(-kappa dt), k = 0, cx = cy = 1, b = Cholesky factor of the step
-                               covariance (schwartz_two_factor.py:124-168); EULER: a = 1, k = kappa, cx / cy = vol
-                               sqrt(dt), b = Cholesky factor of the correlation (:170-196)                    */
+  const double *step;       /* [n_sub][MCRE_STORAGE_STEP]: [0] a, [1] k, [2] dt, [3] m, [4] cx, [5] cy, [6] log F(t2),
+                               [8 + j] bx_j, [16 + j] by_j (j < noise_dim):
+                                 w0 = sum_j bx_j z_j, w1 = sum_j by_j z_j   (the model's rows of the joint draw z @ L^T)
+                                 x' = (a x - (k x) dt) + cx w0;  y' = (y + m) + cy w1;  log S = log F(t2) + x' + y'
+                               Schwartz ANALYTICAL: a = exp(-kappa dt), k = 0, cx = cy = 1, b = rows of the Cholesky
+                               factor of the step covariance (schwartz_two_factor.py:124-168); EULER: a = 1, k = kappa,
+                               cx / cy = vol sqrt(dt), b = rows of the Cholesky factor of the correlation (:170-196);
+                               Black-Scholes single / multi-asset, ANALYTICAL: a = 1, k = 0, cx = 1, cy = 0, m = (rate -
+                               sigma^2 / 2) dt, bx = the asset's row of the Cholesky factor of the step covariance of
+                               all assets (black_scholes.py:50-67, black_scholes_multi.py:63-79), log F = log spot  */
   const int32_t *step_date; /* [n_sub] action-date index completed by the sub-step, or -1                  */
   const double *date_rec;   /* [n_dates][MCRE_STORAGE_RECORD] per action date:
                                0 vmin of the date's band, 1 inventory per state index, 2 / 3 vmin / vmax of the next
@@ -615,12 +620,12 @@ typedef struct {
                                16.. injection knots (level, rate) x 8, then withdrawal knots x 8
                                (storage_helpers.py:56-127, storage.py:114-190)                              */
   const double *numeraire;  /* [n_dates] numeraire at the action dates                                     */
-  int32_t noise_dim;        /* normals per sub-step: 2 (Schwartz two-factor) or 1 (Black-Scholes: b10 = b11 = 0, the
-                               log-price accumulates in x, its drift in m; black_scholes.py:50-67)              */
+  int32_t noise_dim;        /* normals per sub-step of the model's joint draw: 2 (Schwartz two-factor), 1 (Black-Scholes),
+                               number of assets (Black-Scholes multi-asset), <= MCRE_STORAGE_MAX_NOISE         */
   int32_t n_tan;            /* 0, or 3 / 6: pathwise PV sensitivities with respect to that many model parameters   */
   const double *step_tan;   /* [n_sub][n_tan][6] d(A, B00, M, B10, B11, log F)/d parameter of the effective recursion
-                               x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (A = a - k dt, B00 = cx b00, ...);
-                               entry [0][.][5] also holds d log F(t0)                                          */
+                               x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (A = a - k dt, B00 = cx bx_0, B10 = cy by_0,
+                               B11 = cy by_1; noise_dim <= 2); entry [0][.][5] also holds d log F(t0)           */
   const double *dlog_num;   /* [n_dates][n_tan] d log numeraire / d parameter                                  */
 } mcre_storage_desc;
 

@@ -29,7 +29,7 @@ constexpr int ST_THREADS = 128;
 struct StorageDev {
   int n_sub, n_dates, n_pre_dates, n_states, n_basis;
   double log_spot0;
-  const double *step;       // [n_sub][ST_STEP]: a, k, dt, m, cx, b00, cy, b10, b11, log curve(t2)
+  const double *step;       // [n_sub][ST_STEP]: see TwoFactor
   const int *step_date;     // [n_sub]
   const double *rec;        // [n_dates][ST_REC]
   const double *numeraire;  // [n_dates]
@@ -126,34 +126,41 @@ __device__ __forceinline__ int best_of(const double (&v)[3]) {
   return a;
 }
 
-// One path of the two-factor model (schwartz_two_factor.py:147-196), both schemes in one form with the reference's
-// association of operations (unfused):
-//   x' = (a x - (k x) dt) + cx (b00 z0)         ANALYTICAL: a = exp(-kappa dt), k = 0, cx = 1, b = chol(step covariance)
-//   y' = (y + m) + cy (b10 z0 + b11 z1)         EULER:      a = 1, k = kappa, cx = sigma_s sqrt(dt), cy = sigma_l sqrt(dt),
-//   log S = log F(t2) + x' + y'                             b = chol(correlation)
+// One path of the two-factor log-price model, every scheme / price model in one form with the reference's association
+// of operations (unfused):
+//   w0 = sum_j bx_j z_j,  w1 = sum_j by_j z_j            (the model's rows of the joint draw z @ L^T, model.py:46-73)
+//   x' = (a x - (k x) dt) + cx w0                        y' = (y + m) + cy w1            log S = log F + x' + y'
+// Schwartz two-factor (schwartz_two_factor.py:147-196): ANALYTICAL a = exp(-kappa dt), k = 0, cx = cy = 1, b = rows of the
+// Cholesky factor of the step covariance; EULER a = 1, k = kappa, cx / cy = sigma sqrt(dt), b = rows of the Cholesky
+// factor of the correlation.  Black-Scholes single / multi-asset (black_scholes.py:50-67, black_scholes_multi.py:63-79,
+// ANALYTICAL): the log-price accumulates in x (bx = the asset's row of the Cholesky factor of the step covariance over
+// ALL assets of the model: the draw is the joint one), its drift in m, log F = log spot.
+// Step record: [0] a, [1] k, [2] dt, [3] m, [4] cx, [5] cy, [6] log F, [8 + j] bx_j, [16 + j] by_j.
 constexpr int ST_STEP = MCRE_STORAGE_STEP;
+constexpr int ST_NOISE = MCRE_STORAGE_MAX_NOISE;
 struct TwoFactor {
   double x = 0.0, y = 0.0;
-  __device__ __forceinline__ double advance(const double *__restrict__ st, double z0, double z1) {
-    const double w0 = __dmul_rn(__ldg(st + 5), z0);
-    const double w1 = __dadd_rn(__dmul_rn(__ldg(st + 7), z0), __dmul_rn(__ldg(st + 8), z1));
+  __device__ __forceinline__ double advance(const double *__restrict__ st, double w0, double w1) {
     const double drift = __dsub_rn(__dmul_rn(__ldg(st + 0), x), __dmul_rn(__dmul_rn(__ldg(st + 1), x), __ldg(st + 2)));
     x = __dadd_rn(drift, __dmul_rn(__ldg(st + 4), w0));
-    y = __dadd_rn(__dadd_rn(y, __ldg(st + 3)), __dmul_rn(__ldg(st + 6), w1));
-    return __dadd_rn(__dadd_rn(__ldg(st + 9), x), y);
+    y = __dadd_rn(__dadd_rn(y, __ldg(st + 3)), __dmul_rn(__ldg(st + 5), w1));
+    return __dadd_rn(__dadd_rn(__ldg(st + 6), x), y);
   }
 };
 
-// the model's draws of one sub-step: two normals (Schwartz two-factor) or one (Black-Scholes: z1 = 0)
-__device__ __forceinline__ void draw2(const RngDev &rng, NormalStream &ns, int dim, int is, long long gpath, double &z0,
-                                      double &z1) {
-  if (rng.mode == MCRE_RNG_INJECT) {
-    const double *zp = rng.z + ((size_t)is * rng.n_total + gpath) * dim;
-    z0 = zp[0]; z1 = dim > 1 ? zp[1] : 0.0;
-  } else if (dim > 1) {
-    ns.next2(z0, z1);
-  } else {
-    z0 = ns.next(); z1 = 0.0;
+// the model's draws of one sub-step (normals number is * dim + j of the path, or the injected stream) folded into the two
+// factor noises; z0, z1: the first two draws (tangent recursion of the one- and two-factor price models)
+__device__ __forceinline__ void draw_w(const RngDev &rng, NormalStream &ns, int dim, int is, long long gpath,
+                                       const double *__restrict__ st, double &w0, double &w1, double &z0, double &z1) {
+  w0 = 0.0; w1 = 0.0; z0 = 0.0; z1 = 0.0;
+  const double *zp = rng.mode == MCRE_RNG_INJECT ? rng.z + ((size_t)is * rng.n_total + gpath) * dim : nullptr;
+  for (int j = 0; j < dim; ++j) {
+    const double z = zp ? zp[j] : ns.next();
+    if (j == 0) z0 = z;
+    if (j == 1) z1 = z;
+    const double tx = __dmul_rn(__ldg(st + 8 + j), z), ty = __dmul_rn(__ldg(st + 16 + j), z);
+    w0 = j == 0 ? tx : __dadd_rn(w0, tx);
+    w1 = j == 0 ? ty : __dadd_rn(w1, ty);
   }
 }
 
@@ -168,9 +175,10 @@ __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P,
   const double s0 = exp(P.log_spot0);
   for (int d = 0; d < P.n_pre_dates; ++d) spot[(size_t)d * n_paths + lp] = s0;
   for (int is = 0; is < P.n_sub; ++is) {
-    double z0, z1;
-    draw2(rng, ns, P.noise_dim, is, gp, z0, z1);
-    const double ls = f.advance(P.step + (size_t)is * ST_STEP, z0, z1);
+    double w0, w1, z0, z1;
+    const double *st = P.step + (size_t)is * ST_STEP;
+    draw_w(rng, ns, P.noise_dim, is, gp, st, w0, w1, z0, z1);
+    const double ls = f.advance(st, w0, w1);
     const int d = __ldg(P.step_date + is);
     if (d >= 0) spot[(size_t)d * n_paths + lp] = fm_exp_t(ls);
   }
@@ -443,11 +451,11 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
   }
   for (int d = 0; d < P.n_pre_dates; ++d) act(d, s0);
   for (int is = 0; is < P.n_sub; ++is) {
-    double z0, z1;
-    draw2(rng, ns, P.noise_dim, is, gp, z0, z1);
+    double w0, w1, z0, z1;
     const double x_old = f.x;
     const double *st = P.step + (size_t)is * ST_STEP;
-    const double ls = f.advance(st, z0, z1);
+    draw_w(rng, ns, P.noise_dim, is, gp, st, w0, w1, z0, z1);
+    const double ls = f.advance(st, w0, w1);
     if constexpr (NT > 0) {
       const double A = __ldg(st + 0) - __ldg(st + 1) * __ldg(st + 2);
       const double *tt = P.step_tan + (size_t)is * NT * 6;
@@ -478,7 +486,8 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
   if (!c || !out) return fail(-1, "null argument%s", "");
   if (c->n_states < 2 || c->n_states > ST_MAX_S) return fail(-2, "storage: 2..%s%lld inventory states", "", ST_MAX_S);
   if (c->n_basis < 1 || c->n_basis > ST_MAX_B) return fail(-2, "storage: 1..%s%lld basis functions", "", ST_MAX_B);
-  if (c->noise_dim != 1 && c->noise_dim != 2) return fail(-2, "storage: one or two noise factors%s", "");
+  if (c->noise_dim < 1 || c->noise_dim > ST_NOISE) return fail(-2, "storage: 1..8 noise factors%s", "");
+  if (c->n_tan > 0 && c->noise_dim > 2) return fail(-3, "storage: sensitivities for one- and two-factor price models%s", "");
   if (c->n_tan != 0 && c->n_tan != 3 && c->n_tan != 6) return fail(-2, "storage: 0, 3 or 6 tangent directions%s", "");
   if (c->n_tan > 0 && (!c->step_tan || !c->dlog_num)) return fail(-1, "storage: tangent tables missing%s", "");
   if (c->n_dates <= 0 || c->n_sub < 0 || c->n_pre_dates < 0 || c->n_pre_dates > c->n_dates)

@@ -40,7 +40,8 @@ from mcre.timegrid import build_time_grid
 
 #: largest pre-simulation for which the regression is solved by LAPACK on the host by default
 LAPACK_MAX_PATHS = 1 << 16
-STEP = 10
+STEP = 24
+MAX_NOISE = 8
 
 
 def _is_storage(p):
@@ -53,31 +54,50 @@ def _is_bs(model):
     return type(model) is BlackScholesModel
 
 
-def step_table(model, grid, scheme, nt=0):
-    """-> (steps [n_sub][STEP], tangents [n_sub][nt][6] or None): coefficients of csrc/storage.cu:TwoFactor::advance
-    and, for pathwise sensitivities, d(A, B00, M, B10, B11, log F) / d(parameter) of the effective recursion
-    x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (host duals, mcre/dual.py).
+def _is_bsm(model):
+    from models.black_scholes_multi import BlackScholesMulti
+    return isinstance(model, BlackScholesMulti)
+
+
+def step_table(model, grid, scheme, nt=0, asset_id=None):
+    """-> (steps [n_sub][STEP], tangents [n_sub][nt][6] or None): records of csrc/storage.cu:TwoFactor and, for pathwise
+    sensitivities, d(A, B00, M, B10, B11, log F) / d(parameter) of the effective recursion x' = A x + B00 z0,
+    y' = y + M + B10 z0 + B11 z1 (host duals, mcre/dual.py; one- and two-factor models).
     Schwartz two-factor (schwartz_two_factor.py:124-196), parameters [rate, kappa, sigma_s, mu_l, sigma_l, rho]:
       ANALYTICAL  a = exp(-kappa dt), b = Cholesky factor of the step covariance (cached per nominal dt, model.py:45-64)
       EULER       a = 1, k = kappa, cx / cy = sigma sqrt(dt), b = Cholesky factor of the correlation - which the
                   reference builds before requires_grad(): rho is a constant of its autograd graph there
     Black-Scholes (black_scholes.py:50-67, ANALYTICAL only; parameters [spot, sigma, rate]): the log-price accumulates in
-    x (b00 = sqrt(sigma^2 dt)), its drift (rate - sigma^2 / 2) dt in m, log F = log spot."""
+    x (bx_0 = sqrt(sigma^2 dt)), its drift (rate - sigma^2 / 2) dt in m, log F = log spot.
+    Black-Scholes multi-asset (black_scholes_multi.py:63-79, ANALYTICAL, value-only): the same for the asset `asset_id`
+    with bx = its row of the Cholesky factor of the step covariance of all assets - the draw is the model's joint one."""
     from mcre.dual import D, dexp, dlog, dsqrt
     p = model.dual_params(0, nt)
     zero, one = D(0.0, None, nt), D(1.0, None, nt)
     out = np.zeros((max(grid.n_sub, 1), STEP))
     tan = np.zeros((max(grid.n_sub, 1), nt, 6)) if nt else None
     chol = {}
+    if (_is_bs(model) or _is_bsm(model)) and scheme != SimulationScheme.ANALYTICAL:
+        raise NotImplementedError("gas storage on Black-Scholes models: the ANALYTICAL scheme (the Euler step is not "
+                                  "additive in the log-price)")
     for s in range(grid.n_sub):
         dt = grid.dt[s]
-        if _is_bs(model):
-            if scheme != SimulationScheme.ANALYTICAL:
-                raise NotImplementedError("gas storage on Black-Scholes: the ANALYTICAL scheme (the Euler step is not "
-                                          "additive in the log-price)")
+        bx, by = [zero] * MAX_NOISE, [zero] * MAX_NOISE
+        if _is_bsm(model):
+            from mcre.paths import joint_matrix
+            n = model.num_assets
+            ai = model.asset_ids.index(asset_id)
+            key = grid.dt_nominal[s]
+            if key not in chol:
+                chol[key] = np.linalg.cholesky(np.array(joint_matrix(model, scheme, key)))
+            sig, rate = p[n + ai], p[2 * n]
+            a, k, m, cx, cy = one, zero, (rate - 0.5 * sig * sig) * dt, one, zero
+            bx = [D(float(chol[key][ai, j]), None, nt) if j <= ai else zero for j in range(MAX_NOISE)]
+            lf = dlog(p[ai])
+        elif _is_bs(model):
             spot, sig, rate = p
-            a, k, m = one, zero, rate * dt - 0.5 * dt * sig * sig
-            cx, b00, cy, b10, b11 = one, dsqrt(sig * sig * grid.dt_nominal[s]), zero, zero, zero
+            a, k, m, cx, cy = one, zero, rate * dt - 0.5 * dt * sig * sig, one, zero
+            bx = [dsqrt(sig * sig * grid.dt_nominal[s])] + [zero] * (MAX_NOISE - 1)
             lf = dlog(spot)
         else:
             rate, kappa, sig_s, mu, sig_l, rho = p
@@ -95,18 +115,24 @@ def step_table(model, grid, scheme, nt=0):
                     chol[key] = (l00, l10, dsqrt(var_l - l10 * l10))
                 a = one if abs(kappa.v) <= 1e-12 else dexp(-kappa * dt)
                 k, m, cx, cy = zero, mu * dt, one, one
-                b00, b10, b11 = chol[key]
+                bx = [chol[key][0]] + [zero] * (MAX_NOISE - 1)
+                by = [chol[key][1], chol[key][2]] + [zero] * (MAX_NOISE - 2)
             elif scheme == SimulationScheme.EULER:
                 sq = math.sqrt(dt)
                 rho_c = rho.v                         # constant of the reference's graph under EULER
                 a, k, m = one, kappa, mu * dt
-                cx, b00, cy, b10, b11 = sig_s * sq, one, sig_l * sq, D(rho_c, None, nt), D(math.sqrt(1.0 - rho_c * rho_c), None, nt)
+                cx, cy = sig_s * sq, sig_l * sq
+                bx = [one] + [zero] * (MAX_NOISE - 1)
+                by = [D(rho_c, None, nt), D(math.sqrt(1.0 - rho_c * rho_c), None, nt)] + [zero] * (MAX_NOISE - 2)
             else:
                 raise NotImplementedError(f"storage: scheme {scheme} is not defined for the Schwartz two-factor model")
             lf = D(math.log(model.curve_value(grid.t2[s])), None, nt)
-        out[s] = [x.v if isinstance(x, D) else x for x in (a, k, dt, m, cx, b00, cy, b10, b11, lf)]
+        val = lambda x: x.v if isinstance(x, D) else x   # noqa: E731
+        out[s, :7] = [val(x) for x in (a, k, dt, m, cx, cy, lf)]
+        out[s, 8:8 + MAX_NOISE] = [val(x) for x in bx]
+        out[s, 16:16 + MAX_NOISE] = [val(x) for x in by]
         if nt:
-            eff = (a - k * dt, cx * b00, m, cy * b10, cy * b11, lf)
+            eff = (a - k * dt, cx * bx[0], m, cy * by[0], cy * by[1], lf)
             for j, e in enumerate(eff):
                 tan[s, :, j] = D.lift(e, nt).t
     return out, tan
@@ -117,6 +143,8 @@ def log_spot_scale(model, t):
     tau = max(t - model.t0(), 0.0)
     if _is_bs(model):
         return model.param_values()[1] * math.sqrt(tau)
+    if _is_bsm(model):
+        return max(model.param_values()[model.num_assets:2 * model.num_assets]) * math.sqrt(tau)
     _, kappa, sig_s, _, sig_l, rho = model.param_values()
     if abs(kappa) <= 1e-12:
         var_s, cov = sig_s * sig_s * tau, rho * sig_s * sig_l * tau
@@ -136,16 +164,26 @@ class StorageBackend:
         from metrics.metric import MetricType
         from models.schwartz_two_factor import SchwartzTwoFactorModel
         self.c = c = ctrl
-        if not all(_is_storage(p) for p in c.products):
-            raise NotImplementedError("gas storages are valued in books of their own (no mixing with other products)")
-        if not isinstance(c.model, SchwartzTwoFactorModel) and not _is_bs(c.model):
-            raise NotImplementedError("gas storage: SchwartzTwoFactorModel and BlackScholesModel are implemented "
-                                      f"(got {type(c.model).__name__})")
+        #: storages next to other equity products in the same run (the reference's 50k-product book,
+        #: tests/pv_tests/pv_performance_large_netting_set.py): the storages' per-path cashflows start the PV
+        #: accumulators of the equity launches (mcre/equity.py:_run_split_book, extra_pv)
+        self.mixed = not all(_is_storage(p) for p in c.products)
+        if not isinstance(c.model, SchwartzTwoFactorModel) and not _is_bs(c.model) and not _is_bsm(c.model):
+            raise NotImplementedError("gas storage: SchwartzTwoFactorModel, BlackScholesModel and BlackScholesMulti are "
+                                      f"implemented (got {type(c.model).__name__})")
         if any(m.metric_type != MetricType.PV for m in c.risk_metrics.metrics):
             raise NotImplementedError("gas storage: PV is the only implemented metric")
+        if c.differentiate and (self.mixed or _is_bsm(c.model)):
+            raise NotImplementedError("gas storage: sensitivities for books of storages on a one- or two-factor price model")
         self.nt = len(c.model.model_params) if c.differentiate else 0
-        self.rate_index = 2 if _is_bs(c.model) else 0
-        self.noise_dim = 1 if _is_bs(c.model) else 2
+        self.rate_index = 2 if _is_bs(c.model) else (2 * c.model.num_assets if _is_bsm(c.model) else 0)
+        self.noise_dim = 1 if _is_bs(c.model) else (c.model.num_assets if _is_bsm(c.model) else 2)
+        if self.noise_dim > MAX_NOISE:
+            raise NotImplementedError(f"gas storage: price models with at most {MAX_NOISE} noise factors")
+        if _is_bsm(c.model):
+            for p in c.products:
+                if _is_storage(p) and p.get_asset_id() not in c.model.asset_ids:
+                    raise ValueError(f"Asset id '{p.get_asset_id()}' not found in model asset ids {list(c.model.asset_ids)}.")
         rf = c.regression_function
         if type(rf) is not PolyomialRegression or not 0 <= rf.degree < B_MAX_BASIS:
             raise NotImplementedError(f"gas storage: PolyomialRegression of degree 0..{B_MAX_BASIS - 1} (the kernels "
@@ -159,6 +197,12 @@ class StorageBackend:
         self.mode = mode
 
     # ------------------------------------------------------------------ plan
+    def _spot0(self, prod):
+        c = self.c
+        if _is_bsm(c.model):
+            return c.model.param_values()[c.model.asset_ids.index(prod.get_asset_id())]
+        return c.model.param_values()[0] if _is_bs(c.model) else c.model.curve_value(c.model.t0())
+
     def _create(self, prod, grid, steps, steps_tan):
         c = self.c
         sim_dates = {t: i for i, t in enumerate(grid.dates)}
@@ -177,7 +221,7 @@ class StorageBackend:
         d = B.StorageDesc()
         d.n_sub, d.n_dates, d.n_pre_dates = grid.n_sub, len(acts), n_pre
         d.n_states, d.n_basis = prod.num_states, self.n_basis
-        d.log_spot0 = math.log(c.model.param_values()[0] if _is_bs(c.model) else c.model.curve_value(t0))
+        d.log_spot0 = math.log(self._spot0(prod))
         d.noise_dim, d.n_tan = self.noise_dim, self.nt
         for name, arr, conv in (("step_tan", steps_tan if self.nt else np.zeros(1), B.as_dp), ("dlog_num", dlog_num, B.as_dp),
                                 ("step", steps, B.as_dp), ("step_date", step_date if grid.n_sub else np.zeros(1, np.int32), B.as_ip),
@@ -223,8 +267,10 @@ class StorageBackend:
         coef_h[:, 1] = 1.0
         if self.mode == "moments":
             for k, t in enumerate(acts):
-                f = c.model.param_values()[0] * math.exp(c.model.param_values()[2] * (t - c.model.t0())) if _is_bs(c.model) \
-                    else c.model.curve_value(t)
+                if _is_bs(c.model) or _is_bsm(c.model):
+                    f = self._spot0(prod) * math.exp(c.model.param_values()[self.rate_index] * (t - c.model.t0()))
+                else:
+                    f = c.model.curve_value(t)
                 sd = f * log_spot_scale(c.model, t)
                 coef_h[k, 0], coef_h[k, 1] = f, (1.0 / sd if sd > 1e-300 else 0.0)
         coef = torch.from_numpy(coef_h.copy()).to(dev)
@@ -270,9 +316,19 @@ class StorageBackend:
         dev = RT.compute_device()
         t_start = time.perf_counter()
         grid = build_time_grid(c.model.t0(), c.simulation_timeline.tolist(), c.num_steps)
-        steps, steps_tan = step_table(c.model, grid, c.simulation_scheme, self.nt)
+        step_cache = {}
+
+        def steps_of(prod):
+            key = prod.get_asset_id() if _is_bsm(c.model) else None
+            if key not in step_cache:
+                step_cache[key] = step_table(c.model, grid, c.simulation_scheme, self.nt, asset_id=key)
+            return step_cache[key]
         n_main = c.num_paths_mainsim
-        chunk = 256 if n_main < (1 << 18) else 4096
+        if self.mixed:
+            from mcre.equity import main_chunk
+            chunk = main_chunk(n_main)       # the equity launches' reduction chunk: one summation tree for the whole set
+        else:
+            chunk = 256 if n_main < (1 << 18) else 4096
         begin, count = RT.shard_range(n_main, chunk)
         rng_main, _keep = self._rng("main", 43, n_main)
         shard = B.Shard(begin, count, chunk)
@@ -282,7 +338,9 @@ class StorageBackend:
                 for _ in c.netting_sets]
         try:
             for pi, prod in enumerate(c.products):
-                plan, numeraire, acts = self._create(prod, grid, steps, steps_tan)
+                if not _is_storage(prod):
+                    continue
+                plan, numeraire, acts = self._create(prod, grid, *steps_of(prod))
                 plans.append(plan)
                 t0 = time.perf_counter()
                 coef = self._regress(prod, plan, numeraire, acts, dev)
@@ -292,6 +350,8 @@ class StorageBackend:
                 B.check(L.mcre_storage_mainsim(plan, C.byref(rng_main), C.byref(shard), coef.data_ptr(),
                                                float(prod.get_initial_state()), cfs[si].data_ptr(), None,
                                                tans[si].data_ptr() if self.nt else None, RT.stream_ptr()))
+            if self.mixed:
+                return self._finish_mixed(cfs, chunk, dev, t_start, t_pre)
             raw = []
             n_chunks = max((count + chunk - 1) // chunk, 1)
             partial = torch.empty(n_chunks * 2 * max(self.nt, 1) + 1, dtype=torch.float64, device=dev)
@@ -319,6 +379,36 @@ class StorageBackend:
             torch.cuda.current_stream().synchronize()
             for plan in plans:
                 L.mcre_storage_destroy(plan)
+        total = time.perf_counter() - t_start
+        return raw, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}
+
+
+    def _finish_mixed(self, cfs, chunk, dev, t_start, t_pre):
+        """The other products of the run through the equity backend's accumulating launches, starting from the
+        storages' per-path discounted cashflows (same Philox streams: the draw is the model's joint one)."""
+        import copy
+        from mcre.equity import EquityBackend, is_equity_exercise
+        c = self.c
+        sub = copy.copy(c)
+        sub.netting_sets = []
+        for ns in c.netting_sets:
+            view = copy.copy(ns)
+            view.products = [p for p in ns.products if not _is_storage(p)]
+            sub.netting_sets.append(view)
+        sub.products = [p for ns in sub.netting_sets for p in ns.products]
+        sub.product_to_netting_set_idx = [i for i, ns in enumerate(sub.netting_sets) for _ in ns.products]
+        sub.requires_regression = any(sub._product_requires_regression(p) for p in sub.products)
+        eb = EquityBackend(sub)
+        t1 = time.perf_counter()
+        eb.presim_exercise_all([p for p in sub.products if is_equity_exercise(p)], dev)
+        torch.cuda.synchronize(dev)
+        t_pre += time.perf_counter() - t1
+        n_params = len(c.model.model_params)
+        raw = []
+        for si in range(len(c.netting_sets)):
+            res = eb._run_split_book(si, dev, c.num_paths_mainsim, n_params, chunk=chunk, extra_pv=cfs[si])
+            raw.append(res)
+        torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start
         return raw, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}
 

@@ -570,6 +570,17 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     qe = scheme == "QE"
 
     bridge_rngs = {}
+    from oracle import storage as ST
+    storage_coeffs = {}
+    n_storage = sum(kind(pr) == "Storage" for pr in products)
+    if 0 < n_storage < len(products) and (need_expo or differentiate):
+        raise NotImplementedError("oracle: storages in mixed books are valued for PV, value-only")
+
+    def storage_market(pr, ctx):
+        tl_ = product_timeline(pr)
+        spots = [np.asarray(ad.val(ctx.spot(asset_of(pr), t)), dtype=float) for t in tl_]
+        nums = [float(np.asarray(ad.val(ctx.numeraire(t))).reshape(-1)[0]) for t in tl_]
+        return spots, nums
 
     def bridge_provider(draws, seed, n):
         """Uniforms of the Brownian-bridge draws: under Philox block pid * 4096 + interval of kind 2 (element 0 /
@@ -588,7 +599,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
             return rng.uniform(0, 1, size=(n, n_int))
         return get
 
-    if any(kind(pr) == "Storage" for pr in products):
+    if all(kind(pr) == "Storage" for pr in products):
         return _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_main, n_pre, num_steps, scheme,
                             draws_pre, draws_main, degree, n_sub, dim, storage_solver)
 
@@ -598,7 +609,9 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
         paths = E.generate_paths(model, p, sim_tl, n_pre, num_steps, scheme, draws_pre, smoothing)
         ctx = Ctx(model, p, sim_tl, paths, n_pre, bridge=bridge_provider(draws_pre, 42, n_pre))
         for k, pr in enumerate(products):
-            if needs_regression(pr):
+            if kind(pr) == "Storage":       # storages next to other products (pv_performance_large_netting_set.py)
+                storage_coeffs[k] = ST.regress(pr, *storage_market(pr, ctx), degree)
+            elif needs_regression(pr):
                 regress_product(pr, ctx, expo_tl, degree, prod_coeffs[k], expo_coeffs[k])
 
     if draws_main is None:
@@ -613,6 +626,10 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     zero_path = 0.0 * ctx.numeraire(sim_tl[0])
     for k, pr in enumerate(products):
         si = prod_set[k]
+        if kind(pr) == "Storage":
+            cfs = ST.evaluate(pr, *storage_market(pr, ctx), storage_coeffs[k], degree)
+            set_cfs[si] = cfs if set_cfs[si] is None else set_cfs[si] + cfs
+            continue
         sm = np.full((n_main, 1), initial_state(pr), dtype=np.int64)
         ptl = product_timeline(pr)
         cfs, t_start = zero_path, 0

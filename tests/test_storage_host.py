@@ -94,9 +94,10 @@ def test_step_table_reproduces_the_oracle_model_step(scheme):
     x = np.zeros(64)
     y = np.zeros(64)
     for s in range(grid.n_sub):
-        a, k, dt, m, cx, b00, cy, b10, b11, lf = tab[s]
-        x = (a * x - (k * x) * dt) + cx * (b00 * z[s, :, 0])
-        y = (y + m) + cy * (b10 * z[s, :, 0] + b11 * z[s, :, 1])
+        a, k, dt, m, cx, cy, lf = tab[s, :7]
+        bx, by = tab[s, 8:10], tab[s, 16:18]
+        x = (a * x - (k * x) * dt) + cx * (bx[0] * z[s, :, 0] + bx[1] * z[s, :, 1])
+        y = (y + m) + cy * (by[0] * z[s, :, 0] + by[1] * z[s, :, 1])
         d = grid.date_after[s]
         if d >= 0:
             np.testing.assert_allclose(lf + x + y, np.asarray(paths[d][0]), rtol=0, atol=1e-13)
@@ -138,7 +139,7 @@ def test_step_tangent_table_equals_finite_differences_of_the_step_table():
 
         def eff(m):
             t, _ = step_table(m, grid, sch)
-            return np.stack([t[:, 0] - t[:, 1] * t[:, 2], t[:, 4] * t[:, 5], t[:, 3], t[:, 6] * t[:, 7], t[:, 6] * t[:, 8], t[:, 9]], axis=1)
+            return np.stack([t[:, 0] - t[:, 1] * t[:, 2], t[:, 4] * t[:, 8], t[:, 3], t[:, 5] * t[:, 16], t[:, 5] * t[:, 17], t[:, 6]], axis=1)
         for k in range(nt):
             if k in model.unconnected_params(sch):
                 assert np.all(tan[:, k, :] == 0.0)
@@ -195,3 +196,31 @@ def test_reference_unit_tests_of_the_inventory_moves():
     assert held[1].item() == 0.5 and held[2].item() == 2.5
     grid = torch.tensor([[0.0, 10.0, 20.0, 30.0]], dtype=torch.float64)
     assert sh.lookup_state_values(grid, torch.tensor([[0.5, 2.5, 7.0]], dtype=torch.float64)).tolist() == [[5.0, 25.0, 30.0]]
+
+
+def test_step_table_of_a_multi_asset_model_reproduces_the_oracle_model_step():
+    """A storage on asset 2 of a three-asset Black-Scholes model: the asset's row of the Cholesky factor of the joint step
+    covariance applied to the joint draw = the oracle's multi-asset step (black_scholes_multi.py:63-79)."""
+    from mcre.storage import step_table
+    from mcre.timegrid import build_time_grid
+    from oracle import engine as E, models as M, ad
+    ns = cases.Namespace()
+    model, sets, _, _ = cases.storage_mixed_book(ns)
+    st = sets[0].products[3]
+    tl = st.product_timeline.tolist()[1:]
+    grid = build_time_grid(0.0, tl, 2)
+    tab, _ = step_table(model, grid, ns.SimulationScheme.ANALYTICAL, asset_id=st.get_asset_id())
+    rng = np.random.default_rng(11)
+    z = rng.standard_normal((grid.n_sub, 32, 3))
+    p = ad.params(M.param_values(model), False)
+    paths = E.generate_paths(model, p, tl, 32, 2, "ANALYTICAL", E.InjectedDraws(z))
+    x = np.zeros(32)
+    y = np.zeros(32)
+    for s in range(grid.n_sub):
+        a, k, dt, m, cx, cy, lf = tab[s, :7]
+        w0 = sum(tab[s, 8 + j] * z[s, :, j] for j in range(3))
+        x = (a * x - (k * x) * dt) + cx * w0
+        y = (y + m) + cy * 0.0
+        d = grid.date_after[s]
+        if d >= 0:
+            np.testing.assert_allclose(np.exp(lf + x + y), np.asarray(paths[d][2]), rtol=1e-13, atol=0)
