@@ -393,6 +393,30 @@ def storage_small(ns_module, model_kind="bs", num_states=4, end_day=2.0):
     return model, [m.NettingSet(name="storage", products=[st])], [m.PVMetric()], None
 
 
+def book_storage(m, i, asset, maturity, capacity, rollout, states, initial, inj_cost, wd_cost):
+    """One storage of the reference's large mixed book (tests/pv_tests/pv_performance_large_netting_set.py:43-90): three
+    inventory bands, two-knot rate curves that change at the band edges, costs stepping up by 10 %."""
+    cfg = m.StorageConfig()
+    up, flat = 0.35 * maturity, 0.70 * maturity
+    cfg.add_volume_constraint(0.0, up, 0.0, 0.55 * capacity, 0.0)
+    cfg.add_volume_constraint(up, flat, 0.10 * capacity, 0.85 * capacity, 0.0)
+    cfg.add_volume_constraint(flat, maturity, 0.0, capacity, 0.0)
+    for a, b, lo, hi in ((0.0, up, 0.30, 0.18), (up, maturity, 0.22, 0.12)):
+        cfg.add_injection_flexibility(a, b, 0.0, lo * capacity)
+        cfg.add_injection_flexibility(a, b, 0.60 * capacity, hi * capacity)
+    for a, b, lo, hi in ((0.0, flat, 0.16, 0.24), (flat, maturity, 0.24, 0.32)):
+        cfg.add_withdrawal_flexibility(a, b, 0.0, lo * capacity)
+        cfg.add_withdrawal_flexibility(a, b, 0.60 * capacity, hi * capacity)
+    cfg.add_variable_injection_cost(0.0, inj_cost)
+    cfg.add_variable_injection_cost(flat, inj_cost * 1.10)
+    cfg.add_variable_withdrawal_cost(0.0, wd_cost)
+    cfg.add_variable_withdrawal_cost(flat, wd_cost * 1.10)
+    st = m.Storage(asset_id=asset, start_date=0.0, end_date=maturity, initial_amount=initial, storage_config=cfg,
+                   num_states=states, rollout_interval=rollout)
+    st.name = f"storage_{i}"
+    return st
+
+
 def storage_mixed_book(ns_module):
     """Storages next to European / American / Asian options in ONE netting set on a multi-asset Black-Scholes model: the
     shape of tests/pv_tests/pv_performance_large_netting_set.py:43-90, 228-251 (three inventory bands, two-knot rate
@@ -404,25 +428,7 @@ def storage_mixed_book(ns_module):
                                 correlation_matrix=np.array([[1.0, 0.35, 0.35], [0.35, 1.0, 0.35], [0.35, 0.35, 1.0]]))
 
     def storage(i, asset, maturity, capacity, rollout, states):
-        cfg = m.StorageConfig()
-        up, flat = 0.35 * maturity, 0.70 * maturity
-        cfg.add_volume_constraint(0.0, up, 0.0, 0.55 * capacity, 0.0)
-        cfg.add_volume_constraint(up, flat, 0.10 * capacity, 0.85 * capacity, 0.0)
-        cfg.add_volume_constraint(flat, maturity, 0.0, capacity, 0.0)
-        for a, b, lo, hi in ((0.0, up, 0.30, 0.18), (up, maturity, 0.22, 0.12)):
-            cfg.add_injection_flexibility(a, b, 0.0, lo * capacity)
-            cfg.add_injection_flexibility(a, b, 0.60 * capacity, hi * capacity)
-        for a, b, lo, hi in ((0.0, flat, 0.16, 0.24), (flat, maturity, 0.24, 0.32)):
-            cfg.add_withdrawal_flexibility(a, b, 0.0, lo * capacity)
-            cfg.add_withdrawal_flexibility(a, b, 0.60 * capacity, hi * capacity)
-        cfg.add_variable_injection_cost(0.0, 0.10 + 0.02 * i)
-        cfg.add_variable_injection_cost(flat, (0.10 + 0.02 * i) * 1.10)
-        cfg.add_variable_withdrawal_cost(0.0, 0.08 + 0.015 * i)
-        cfg.add_variable_withdrawal_cost(flat, (0.08 + 0.015 * i) * 1.10)
-        st = m.Storage(asset_id=asset, start_date=0.0, end_date=maturity, initial_amount=2.0 + 0.5 * i, storage_config=cfg,
-                       num_states=states, rollout_interval=rollout)
-        st.name = f"storage_{i}"
-        return st
+        return book_storage(m, i, asset, maturity, capacity, rollout, states, 2.0 + 0.5 * i, 0.10 + 0.02 * i, 0.08 + 0.015 * i)
     prods = [m.EuropeanOption(m.Equity(ids[0]), 1.0, 95.0, m.OptionType.CALL, asset_id=ids[0]),
              storage(0, ids[1], 1.0, 18.0, 0.05, 6),
              m.AmericanOption(underlying=m.Equity(ids[2]), maturity=1.0, num_exercise_dates=6, strike=108.0,

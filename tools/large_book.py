@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Products-per-second of one large mixed netting set on BlackScholesMulti: the shape of the
 reference's tests/pv_tests/pv_performance_large_netting_set.py (Europeans, binaries, baskets, Asians, barriers,
-Americans, FlexiCalls in ONE netting set, PV metric, 1000 paths), without its gas-storage products (out of scope).
+Americans, FlexiCalls and gas storages in ONE netting set, PV metric, 1000 paths).
 The path-dependent / exercise products exceed what one launch tracks, so the book is split over launches
 (mcre/equity.py:_run_split_book).
 
@@ -59,6 +59,11 @@ def build_book(ns, ids, counts):
         unders = [ns.EuropeanOption(ns.Equity(a), float(t), 92.0 + 4.0 * j, ns.OptionType.CALL, asset_id=a)
                   for j, t in enumerate(np.linspace(mat / m, mat, m))]
         prods.append(ns.FlexiCall(underlyings=unders, num_exercise_rights=min(2, m - 1), asset_id=a))
+    import cases
+    for i in range(counts.get("storage", 0)):       # pv_performance_large_netting_set.py:235-251
+        prods.append(cases.book_storage(ns, i, cyc(ids, i), cyc([1.0, 1.5, 2.0, 2.5], i), cyc([18.0, 26.0, 34.0, 42.0], i),
+                                        cyc([0.05, 0.10, 0.125], i), 6 + i % 5, 2.0 + 0.5 * (i % 5), 0.10 + 0.02 * (i % 4),
+                                        0.08 + 0.015 * (i % 4)))
     return prods
 
 
@@ -79,6 +84,8 @@ def main():
     from mcre import binding as B
     ns = cases.Namespace()
     base = dict(european=39400, binary=1000, basket=1000, asian=2000, barrier=4000, american=1800, flexicall=700)
+    if not args.cva and args.exposure_points == 0:
+        base["storage"] = 100        # the PV book of the reference carries 100 gas storages (PV is their only metric here)
     counts = {k: max(1, int(round(v * args.scale))) for k, v in base.items()}
     ids = [f"asset_{i}" for i in range(4)]
     corr = np.full((4, 4), 0.35) + 0.65 * np.eye(4)
