@@ -627,13 +627,20 @@ typedef struct {
                                x' = A x + B00 z0, y' = y + M + B10 z0 + B11 z1 (A = a - k dt, B00 = cx bx_0, B10 = cy by_0,
                                B11 = cy by_1; noise_dim <= 2); entry [0][.][5] also holds d log F(t0)           */
   const double *dlog_num;   /* [n_dates][n_tan] d log numeraire / d parameter                                  */
+  /* ---- exposure dates (controller.py:412-447); n_expo = 0: none ---- */
+  int32_t n_expo;           /* internal exposure dates                                                         */
+  int32_t n_pre_expo;       /* leading exposure dates at the calibration date                                  */
+  const int32_t *step_expo; /* [n_sub] exposure index completed by the sub-step, or -1                         */
+  const double *expo_numeraire; /* [n_expo]                                                                    */
 } mcre_storage_desc;
 
 typedef struct mcre_storage_plan mcre_storage_plan;
 int mcre_storage_create(const mcre_storage_desc *desc, mcre_storage_plan **out);
 void mcre_storage_destroy(mcre_storage_plan *plan);
-/* Pre-simulation forward pass: d_spot [n_dates][shard->n_paths] = spot at every action date. */
-int mcre_storage_spots(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_spot, void *stream);
+/* Pre-simulation forward pass: d_spot [n_dates][shard->n_paths] = spot at every action date; d_spot_expo
+ * [n_expo][n_paths] = spot at every exposure date (NULL: not wanted). */
+int mcre_storage_spots(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_spot,
+                       double *d_spot_expo, void *stream);
 /* One date of the backward induction (controller.py:322-352) for all n paths and all grid states:
  * d_value [n_states][n] holds the normalised value from the next action date on, per state entering it, and is
  * replaced by the same quantity for `date`: float32(best action's cashflow / numeraire) + the float64 tail interpolated
@@ -642,11 +649,12 @@ int mcre_storage_spots(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_
  * reference: centre 0, scale 1); ignored on the last action date.  d_spot_row [n] = spot at `date`. */
 int mcre_storage_backward(mcre_storage_plan *plan, int32_t date, const double *d_coef, const double *d_spot_row,
                           double *d_value, int64_t n, void *stream);
-/* Regression moments of `date` (the Gram / right-hand-side sums of controller.py:361-374 for y_s = numeraire x
- * d_value[s]): d_out [n_states * n_basis + 2 n_basis - 1] = sum u^k y_s (s major), then sum u^q, q < 2 n_basis - 1;
+/* Regression moments of one regression date - an action date or an exposure date in front of the action date whose value
+ * grid d_value holds (the Gram / right-hand-side sums of controller.py:353-374 for y_s = numeraire x d_value[s], numeraire
+ * and d_spot_row taken at the regression date): d_out [n_states * n_basis + 2 n_basis - 1] = sum u^k y_s (s major), then sum u^q, q < 2 n_basis - 1;
  * fixed-order chunk partials d_partial [ceil(n / chunk_paths)][slots] + tree. */
 int64_t mcre_storage_moment_slots(const mcre_storage_plan *plan);
-int mcre_storage_moments(mcre_storage_plan *plan, int32_t date, double centre, double inv_scale, const double *d_spot_row,
+int mcre_storage_moments(mcre_storage_plan *plan, double numeraire, double centre, double inv_scale, const double *d_spot_row,
                          const double *d_value, int64_t n, int32_t chunk_paths, double *d_partial, double *d_out,
                          void *stream);
 /* Minimum-norm solution of the normal equations of one regression date on the device: d_mom = the (all-reduced) sums of
@@ -659,9 +667,14 @@ int mcre_storage_solve(mcre_storage_plan *plan, const double *d_mom, double rcon
  * [shard->n_paths]; d_coef [n_dates][2 + n_states * n_basis] (device); d_final_state [n_paths] or NULL.  Plans with
  * n_tan > 0 also ADD the path's pathwise sensitivities to d_tan [n_tan][n_paths]: what torch.autograd.grad of the PV
  * gives in the reference (controller.py:609-627) - decisions and inventory moves carry no gradient, cashflows
- * differentiate through the spot and the numeraire. */
+ * differentiate through the spot and the numeraire.  d_coef_expo [n_expo][2 + n_states * n_basis] + d_expo
+ * [n_expo][n_paths] (both or neither): the path's exposure at every exposure date - the continuation polynomials of that
+ * date interpolated at the inventory state after the actions up to it, over the numeraire (controller.py:432-447) - is
+ * ADDED to d_expo, for the netting-set terms and exposure metrics of mcre_eq_unsecured_exposures / mcre_sum_stats /
+ * mcre_select_*. */
 int mcre_storage_mainsim(mcre_storage_plan *plan, const mcre_rng *rng, const mcre_shard *shard, const double *d_coef,
-                         double initial_state, double *d_cfs, double *d_final_state, double *d_tan, void *stream);
+                         double initial_state, double *d_cfs, double *d_final_state, double *d_tan,
+                         const double *d_coef_expo, double *d_expo, void *stream);
 
 /* ================================================================================
  * Utilities

@@ -38,6 +38,11 @@ struct StorageDev {
   // d log numeraire / d parameter per action date [n_dates][n_tan]
   int noise_dim, n_tan;
   const double *step_tan, *dlog_num;
+  // exposure dates (controller.py:412-447): n_expo internal exposure dates, the first n_pre_expo at the calibration date;
+  // step_expo [n_sub]: exposure index completed by the sub-step or -1; expo_num [n_expo]: numeraire there
+  int n_expo, n_pre_expo;
+  const int *step_expo;
+  const double *expo_num;
 };
 
 }  // namespace mcre
@@ -45,8 +50,8 @@ struct StorageDev {
 struct mcre_storage_plan {
   mcre::StorageDev d;
   mcre::DevArena arena;
-  mcre::DevArray<double> step, rec, numeraire, step_tan, dlog_num;
-  mcre::DevArray<int> step_date;
+  mcre::DevArray<double> step, rec, numeraire, step_tan, dlog_num, expo_num;
+  mcre::DevArray<int> step_date, step_expo;
 };
 
 namespace mcre {
@@ -165,7 +170,8 @@ __device__ __forceinline__ void draw_w(const RngDev &rng, NormalStream &ns, int 
 }
 
 __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P, RngDev rng, long long path_begin,
-                                                                   long long n_paths, double *__restrict__ spot) {
+                                                                   long long n_paths, double *__restrict__ spot,
+                                                                   double *__restrict__ spot_expo) {
   fm_tables_init();
   const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n_paths) return;
@@ -174,13 +180,20 @@ __global__ void __launch_bounds__(ST_THREADS) storage_spots_kernel(StorageDev P,
   TwoFactor f;
   const double s0 = exp(P.log_spot0);
   for (int d = 0; d < P.n_pre_dates; ++d) spot[(size_t)d * n_paths + lp] = s0;
+  if (spot_expo)
+    for (int e = 0; e < P.n_pre_expo; ++e) spot_expo[(size_t)e * n_paths + lp] = s0;
   for (int is = 0; is < P.n_sub; ++is) {
     double w0, w1, z0, z1;
     const double *st = P.step + (size_t)is * ST_STEP;
     draw_w(rng, ns, P.noise_dim, is, gp, st, w0, w1, z0, z1);
     const double ls = f.advance(st, w0, w1);
     const int d = __ldg(P.step_date + is);
-    if (d >= 0) spot[(size_t)d * n_paths + lp] = fm_exp_t(ls);
+    const int e = spot_expo ? __ldg(P.step_expo + is) : -1;
+    if (d >= 0 || e >= 0) {
+      const double sp = fm_exp_t(ls);
+      if (d >= 0) spot[(size_t)d * n_paths + lp] = sp;
+      if (e >= 0) spot_expo[(size_t)e * n_paths + lp] = sp;
+    }
   }
 }
 
@@ -250,13 +263,12 @@ __global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev
 // Moments of the regression of `date`: y_s = numeraire(date) * value[s], basis u^k, u = (x - centre) * inv_scale.
 // blockIdx.y < S: sum u^k y_s, k < NB -> slots [s * NB + k]; blockIdx.y == S: sum u^q, q < 2 NB - 1 -> slots [S * NB + q].
 // One block per (chunk of paths, row); fixed summation order inside the block, chunks combined by mcre_tree_reduce.
-__global__ void __launch_bounds__(256) storage_moments_kernel(StorageDev P, int date, double centre, double inv_scale,
+__global__ void __launch_bounds__(256) storage_moments_kernel(StorageDev P, double num, double centre, double inv_scale,
                                                               const double *__restrict__ x, const double *__restrict__ value,
                                                               long long n, int chunk, double *__restrict__ partial) {
   __shared__ double stage[8][2 * ST_MAX_B];
   const int S = P.n_states, NB = P.n_basis, row = blockIdx.y;
   const int nv = row < S ? NB : 2 * NB - 1;
-  const double num = __ldg(P.numeraire + date);
   double acc[2 * ST_MAX_B];
 #pragma unroll
   for (int k = 0; k < 2 * ST_MAX_B; ++k) acc[k] = 0.0;
@@ -393,7 +405,9 @@ template <int NT>
 __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, RngDev rng, long long path_begin,
                                                                   long long n_paths, const double *__restrict__ coef,
                                                                   double initial_state, double *__restrict__ cfs,
-                                                                  double *__restrict__ final_state, double *__restrict__ tan) {
+                                                                  double *__restrict__ final_state, double *__restrict__ tan,
+                                                                  const double *__restrict__ coef_expo,
+                                                                  double *__restrict__ expo) {
   fm_tables_init();
   const long long lp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (lp >= n_paths) return;
@@ -440,6 +454,20 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
     }
   };
 
+  // exposure at an exposure date (controller.py:432-447): the continuation polynomials of that date, interpolated at the
+  // inventory state the path is in after the actions up to that date, over the numeraire; ADDED to expo [n_expo][n_paths]
+  auto exposure = [&](int e, double spot) {
+    const double *c = coef_expo + (size_t)e * row;
+    const double u = (spot - __ldg(c)) * __ldg(c + 1);
+    int lo, hi;
+    double w;
+    neighbours(state, S, lo, hi, w);
+    const double gl = poly(c + 2 + lo * NB, NB, u);
+    const double gh = hi == lo ? gl : poly(c + 2 + hi * NB, NB, u);
+    const double cont = __dadd_rn(gl, __dmul_rn(w, __dsub_rn(gh, gl)));
+    expo[(size_t)e * n_paths + lp] += __ddiv_rn(cont, __ldg(P.expo_num + e));
+  };
+
   const double s0 = exp(P.log_spot0);
   if constexpr (NT > 0) {
     // at the calibration date only log F0 depends on the parameters (Black-Scholes: log of the spot parameter);
@@ -450,6 +478,8 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
     }
   }
   for (int d = 0; d < P.n_pre_dates; ++d) act(d, s0);
+  if (expo)
+    for (int e = 0; e < P.n_pre_expo; ++e) exposure(e, s0);
   for (int is = 0; is < P.n_sub; ++is) {
     double w0, w1, z0, z1;
     const double x_old = f.x;
@@ -468,7 +498,12 @@ __global__ void __launch_bounds__(ST_THREADS) storage_main_kernel(StorageDev P, 
       }
     }
     const int d = __ldg(P.step_date + is);
-    if (d >= 0) act(d, fm_exp_t(ls));
+    const int e = expo ? __ldg(P.step_expo + is) : -1;
+    if (d >= 0 || e >= 0) {
+      const double sp = fm_exp_t(ls);
+      if (d >= 0) act(d, sp);          // the action of a date comes before the exposure of the same date (:417-430)
+      if (e >= 0) exposure(e, sp);
+    }
   }
   cfs[lp] += total;
   if (final_state) final_state[lp] = state;
@@ -490,6 +525,8 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
   if (c->n_tan > 0 && c->noise_dim > 2) return fail(-3, "storage: sensitivities for one- and two-factor price models%s", "");
   if (c->n_tan != 0 && c->n_tan != 3 && c->n_tan != 6) return fail(-2, "storage: 0, 3 or 6 tangent directions%s", "");
   if (c->n_tan > 0 && (!c->step_tan || !c->dlog_num)) return fail(-1, "storage: tangent tables missing%s", "");
+  if (c->n_expo < 0 || c->n_pre_expo < 0 || c->n_pre_expo > c->n_expo || (c->n_expo > 0 && (!c->expo_numeraire || (c->n_sub > 0 && !c->step_expo))))
+    return fail(-2, "storage: bad exposure tables%s", "");
   if (c->n_dates <= 0 || c->n_sub < 0 || c->n_pre_dates < 0 || c->n_pre_dates > c->n_dates)
     return fail(-2, "storage: bad date / step counts%s", "");
   for (int d = 0; d < c->n_dates; ++d) {
@@ -504,6 +541,8 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
     if (!rc) rc = p->step_date.upload(c->step_date, (size_t)c->n_sub);
     if (!rc) rc = p->rec.upload(c->date_rec, (size_t)c->n_dates * ST_REC);
     if (!rc) rc = p->numeraire.upload(c->numeraire, (size_t)c->n_dates);
+    if (!rc && c->n_expo > 0) rc = p->step_expo.upload(c->step_expo, (size_t)c->n_sub);
+    if (!rc && c->n_expo > 0) rc = p->expo_num.upload(c->expo_numeraire, (size_t)c->n_expo);
     if (!rc && c->n_tan > 0) rc = p->step_tan.upload(c->step_tan, (size_t)c->n_sub * c->n_tan * 6);
     if (!rc && c->n_tan > 0) rc = p->dlog_num.upload(c->dlog_num, (size_t)c->n_dates * c->n_tan);
     if (!rc) rc = p->arena.commit();
@@ -514,6 +553,7 @@ extern "C" int mcre_storage_create(const mcre_storage_desc *c, mcre_storage_plan
   d.n_basis = c->n_basis; d.log_spot0 = c->log_spot0;
   d.step = p->step.p; d.step_date = p->step_date.p; d.rec = p->rec.p; d.numeraire = p->numeraire.p;
   d.noise_dim = c->noise_dim; d.n_tan = c->n_tan; d.step_tan = p->step_tan.p; d.dlog_num = p->dlog_num.p;
+  d.n_expo = c->n_expo; d.n_pre_expo = c->n_pre_expo; d.step_expo = p->step_expo.p; d.expo_num = p->expo_num.p;
   *out = p;
   return 0;
 }
@@ -530,13 +570,14 @@ static int storage_rng_ok(const mcre_rng *rng) {
 }
 
 extern "C" int mcre_storage_spots(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_spot,
-                                  void *stream) {
+                                  double *d_spot_expo, void *stream) {
   if (!p || !rng || !shard || !d_spot) return fail(-1, "null argument%s", "");
+  if (d_spot_expo && p->d.n_expo <= 0) return fail(-2, "storage: exposure spots requested on a plan without exposure dates%s", "");
   if (int rc = storage_rng_ok(rng)) return rc;
   if (shard->n_paths <= 0) return 0;
   const unsigned blocks = (unsigned)((shard->n_paths + ST_THREADS - 1) / ST_THREADS);
   storage_spots_kernel<<<blocks, ST_THREADS, 0, (cudaStream_t)stream>>>(p->d, make_rng(rng), shard->path_begin,
-                                                                         shard->n_paths, d_spot);
+                                                                         shard->n_paths, d_spot, d_spot_expo);
   MCRE_LAUNCHED();
   return 0;
 }
@@ -556,17 +597,16 @@ extern "C" int64_t mcre_storage_moment_slots(const mcre_storage_plan *p) {
   return p ? (int64_t)p->d.n_states * p->d.n_basis + 2 * p->d.n_basis - 1 : 0;
 }
 
-extern "C" int mcre_storage_moments(mcre_storage_plan *p, int32_t date, double centre, double inv_scale,
+extern "C" int mcre_storage_moments(mcre_storage_plan *p, double numeraire, double centre, double inv_scale,
                                     const double *d_spot_row, const double *d_value, int64_t n, int32_t chunk_paths,
                                     double *d_partial, double *d_out, void *stream) {
   if (!p || !d_spot_row || !d_value || !d_partial || !d_out) return fail(-1, "null argument%s", "");
-  if (date < 0 || date >= p->d.n_dates) return fail(-2, "storage: date index out of range%s", "");
   if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "storage: chunk_paths must be a multiple of 256%s", "");
   const int64_t slots = mcre_storage_moment_slots(p);
   const long long n_chunks = n > 0 ? (n + chunk_paths - 1) / chunk_paths : 0;
   if (n_chunks > 0) {
     dim3 grid((unsigned)n_chunks, (unsigned)(p->d.n_states + 1));
-    storage_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->d, date, centre, inv_scale, d_spot_row, d_value, n,
+    storage_moments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->d, numeraire, centre, inv_scale, d_spot_row, d_value, n,
                                                                    chunk_paths, d_partial);
     MCRE_LAUNCHED();
   }
@@ -583,8 +623,10 @@ extern "C" int mcre_storage_solve(mcre_storage_plan *p, const double *d_mom, dou
 
 extern "C" int mcre_storage_mainsim(mcre_storage_plan *p, const mcre_rng *rng, const mcre_shard *shard,
                                     const double *d_coef, double initial_state, double *d_cfs, double *d_final_state,
-                                    double *d_tan, void *stream) {
+                                    double *d_tan, const double *d_coef_expo, double *d_expo, void *stream) {
   if (!p || !rng || !shard || !d_coef || !d_cfs) return fail(-1, "null argument%s", "");
+  if ((d_expo != nullptr) != (d_coef_expo != nullptr) || (d_expo && p->d.n_expo <= 0))
+    return fail(-2, "storage: exposures need both the coefficient table and the output, on a plan with exposure dates%s", "");
   if (p->d.n_tan > 0 && !d_tan) return fail(-1, "storage: plan with tangents but d_tan is null%s", "");
   if (int rc = storage_rng_ok(rng)) return rc;
   if (shard->n_paths <= 0) return 0;
@@ -592,7 +634,7 @@ extern "C" int mcre_storage_mainsim(mcre_storage_plan *p, const mcre_rng *rng, c
   const RngDev r = make_rng(rng);
   cudaStream_t st = (cudaStream_t)stream;
 #define GO(NT) storage_main_kernel<NT><<<blocks, ST_THREADS, 0, st>>>(p->d, r, shard->path_begin, shard->n_paths, d_coef, \
-                                                                     initial_state, d_cfs, d_final_state, d_tan)
+                                                                     initial_state, d_cfs, d_final_state, d_tan, d_coef_expo, d_expo)
   if (p->d.n_tan == 0) GO(0);
   else if (p->d.n_tan == 3) GO(3);
   else GO(6);

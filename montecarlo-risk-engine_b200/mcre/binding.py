@@ -55,7 +55,8 @@ class StorageDesc(C.Structure):
     _fields_ = [("n_sub", C.c_int32), ("n_dates", C.c_int32), ("n_pre_dates", C.c_int32), ("n_states", C.c_int32),
                 ("n_basis", C.c_int32), ("log_spot0", C.c_double), ("step", c_dp), ("step_date", c_ip),
                 ("date_rec", c_dp), ("numeraire", c_dp), ("noise_dim", C.c_int32), ("n_tan", C.c_int32),
-                ("step_tan", c_dp), ("dlog_num", c_dp)]
+                ("step_tan", c_dp), ("dlog_num", c_dp), ("n_expo", C.c_int32), ("n_pre_expo", C.c_int32),
+                ("step_expo", c_ip), ("expo_numeraire", c_dp)]
 
 
 RNG_PHILOX, RNG_INJECT = 0, 1
@@ -165,15 +166,15 @@ def lib():
     L.mcre_storage_create.argtypes = [C.POINTER(StorageDesc), C.POINTER(C.c_void_p)]
     L.mcre_storage_destroy.argtypes = [C.c_void_p]
     L.mcre_storage_destroy.restype = None
-    L.mcre_storage_spots.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p]
+    L.mcre_storage_spots.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_storage_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.mcre_storage_moment_slots.argtypes = [C.c_void_p]
     L.mcre_storage_moment_slots.restype = C.c_int64
-    L.mcre_storage_moments.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
+    L.mcre_storage_moments.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_storage_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     L.mcre_storage_mainsim.argtypes = [C.c_void_p, C.POINTER(Rng), C.POINTER(Shard), C.c_void_p, C.c_double, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mcre_dfma_peak.argtypes = [c_dp, C.c_void_p]
     L.mcre_fastmath_probe.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L

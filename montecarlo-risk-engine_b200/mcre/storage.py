@@ -171,10 +171,12 @@ class StorageBackend:
         if not isinstance(c.model, SchwartzTwoFactorModel) and not _is_bs(c.model) and not _is_bsm(c.model):
             raise NotImplementedError("gas storage: SchwartzTwoFactorModel, BlackScholesModel and BlackScholesMulti are "
                                       f"implemented (got {type(c.model).__name__})")
-        if any(m.metric_type != MetricType.PV for m in c.risk_metrics.metrics):
-            raise NotImplementedError("gas storage: PV is the only implemented metric")
-        if c.differentiate and (self.mixed or _is_bsm(c.model)):
-            raise NotImplementedError("gas storage: sensitivities for books of storages on a one- or two-factor price model")
+        if any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
+            raise NotImplementedError("gas storage: CVA (a credit model next to the price model) is not implemented")
+        self.need_expo = c.risk_metrics.requires_exposure_profiles()
+        if c.differentiate and (self.mixed or _is_bsm(c.model) or self.need_expo):
+            raise NotImplementedError("gas storage: sensitivities of the PV of books of storages on a one- or two-factor "
+                                      "price model")
         self.nt = len(c.model.model_params) if c.differentiate else 0
         self.rate_index = 2 if _is_bs(c.model) else (2 * c.model.num_assets if _is_bsm(c.model) else 0)
         self.noise_dim = 1 if _is_bs(c.model) else (c.model.num_assets if _is_bsm(c.model) else 2)
@@ -223,7 +225,15 @@ class StorageBackend:
         d.n_states, d.n_basis = prod.num_states, self.n_basis
         d.log_spot0 = math.log(self._spot0(prod))
         d.noise_dim, d.n_tan = self.noise_dim, self.nt
-        for name, arr, conv in (("step_tan", steps_tan if self.nt else np.zeros(1), B.as_dp), ("dlog_num", dlog_num, B.as_dp),
+        expo_times = c.exposure_timeline.tolist() if self.need_expo else []
+        expo_of = {sim_dates[t]: e for e, t in enumerate(expo_times)}
+        step_expo = np.array([expo_of.get(di, -1) if di >= 0 else -1 for di in grid.date_after], dtype=np.int32)
+        d.n_expo = len(expo_times)
+        d.n_pre_expo = sum(1 for t in expo_times if sim_dates[t] < grid.n_pre_dates)
+        expo_num = np.array([math.exp(rate * (t - t0)) for t in expo_times]) if expo_times else np.zeros(1)
+        for name, arr, conv in (("step_expo", step_expo if (grid.n_sub and expo_times) else np.zeros(1, np.int32), B.as_ip),
+                                ("expo_numeraire", expo_num, B.as_dp),
+                                ("step_tan", steps_tan if self.nt else np.zeros(1), B.as_dp), ("dlog_num", dlog_num, B.as_dp),
                                 ("step", steps, B.as_dp), ("step_date", step_date if grid.n_sub else np.zeros(1, np.int32), B.as_ip),
                                 ("date_rec", rec, B.as_dp), ("numeraire", numeraire, B.as_dp)):
             a, ptr = conv(arr)
@@ -231,7 +241,7 @@ class StorageBackend:
             setattr(d, name, ptr)
         plan = C.c_void_p()
         B.check(B.lib().mcre_storage_create(C.byref(d), C.byref(plan)))
-        return plan, numeraire, acts
+        return plan, numeraire, acts, expo_num
 
     def _rng(self, which, seed, n_total):
         c = self.c
@@ -247,8 +257,18 @@ class StorageBackend:
         return rng, z
 
     # ------------------------------------------------------------------ pre-simulation + regression
-    def _regress(self, prod, plan, numeraire, acts, dev):
-        """-> device tensor [n_dates][2 + S * NB]: (centre, inverse scale, coefficients per state) per action date."""
+    def _forward(self, t, prod):
+        c = self.c
+        if _is_bs(c.model) or _is_bsm(c.model):
+            return self._spot0(prod) * math.exp(c.model.param_values()[self.rate_index] * (t - c.model.t0()))
+        return c.model.curve_value(t)
+
+    def _regress(self, prod, plan, numeraire, acts, expo_num, dev):
+        """-> (coef [n_dates][2 + S * NB], coef_expo [n_expo][2 + S * NB] or None) on the device: (centre, inverse scale,
+        coefficients per state) of the continuation polynomials per action date and per exposure date.
+        controller.py:294-383: walking the dates backwards, the value grid of action date k (per state entering it) is
+        regressed on the spot of the action date before it and on the spot of every exposure date in (T_k-1, T_k)
+        (and of one equal to T_k-1: the same system); exposure dates from the last action date on get zeros."""
         c, L = self.c, B.lib()
         S, NB, n_dates = prod.num_states, self.n_basis, len(acts)
         row = 2 + S * NB
@@ -261,54 +281,78 @@ class StorageBackend:
             begin, count = RT.shard_range(n_total, chunk)
         rng, _keep = self._rng("pre", 42, n_total)
         shard = B.Shard(begin, count, chunk)
+        expo_times = c.exposure_timeline.tolist() if self.need_expo else []
+        n_expo = len(expo_times)
+        # value grid each exposure date is regressed on: the first action date AFTER it (an action on the exposure date
+        # itself has been taken when the exposure is read, controller.py:417-430)
+        next_action = [int(np.searchsorted(acts, t, side="right")) for t in expo_times]
+        expo_of_k = {}
+        for e, k in enumerate(next_action):
+            expo_of_k.setdefault(k, []).append(e)
         spot = torch.empty((n_dates, max(count, 1)), dtype=torch.float64, device=dev)
-        B.check(L.mcre_storage_spots(plan, C.byref(rng), C.byref(shard), spot.data_ptr(), RT.stream_ptr()))
-        coef_h = np.zeros((n_dates, row))
-        coef_h[:, 1] = 1.0
-        if self.mode == "moments":
-            for k, t in enumerate(acts):
-                if _is_bs(c.model) or _is_bsm(c.model):
-                    f = self._spot0(prod) * math.exp(c.model.param_values()[self.rate_index] * (t - c.model.t0()))
-                else:
-                    f = c.model.curve_value(t)
-                sd = f * log_spot_scale(c.model, t)
-                coef_h[k, 0], coef_h[k, 1] = f, (1.0 / sd if sd > 1e-300 else 0.0)
+        spot_e = torch.empty((n_expo, max(count, 1)), dtype=torch.float64, device=dev) if n_expo else None
+        B.check(L.mcre_storage_spots(plan, C.byref(rng), C.byref(shard), spot.data_ptr(),
+                                     spot_e.data_ptr() if n_expo else None, RT.stream_ptr()))
+
+        def basis_rows(times):
+            h = np.zeros((len(times), row))
+            h[:, 1] = 1.0
+            if self.mode == "moments":
+                for i, t in enumerate(times):
+                    f = self._forward(t, prod)
+                    sd = f * log_spot_scale(c.model, t)
+                    h[i, 0], h[i, 1] = f, (1.0 / sd if sd > 1e-300 else 0.0)
+            return h
+        coef_h, coef_eh = basis_rows(acts), basis_rows(expo_times)
         coef = torch.from_numpy(coef_h.copy()).to(dev)
+        coef_e = torch.from_numpy(coef_eh.copy()).to(dev) if n_expo else None
         value = torch.zeros((S, max(count, 1)), dtype=torch.float64, device=dev)
         if self.mode == "lapack":
             spot_h = RT.to_host(spot)
+            spot_eh = RT.to_host(spot_e) if n_expo else None
         else:
             slots = L.mcre_storage_moment_slots(plan)
             n_chunks = (count + chunk - 1) // chunk
             partial = torch.empty(max(n_chunks, 1) * slots, dtype=torch.float64, device=dev)
             mom = torch.zeros(slots, dtype=torch.float64, device=dev)
-        for k in range(n_dates - 1, 0, -1):
-            B.check(L.mcre_storage_backward(plan, k, coef[k].data_ptr(), spot[k].data_ptr(), value.data_ptr(), count,
-                                            RT.stream_ptr()))
-            j = k - 1
+        value_h = [None]
+
+        def solve(x_host, x_dev, num, host_row, dev_row):
+            """Regression of numeraire x value grid on the basis of one date's spot -> host_row / dev_row [2 + S NB]."""
             if self.mode == "lapack":
                 # controller.py:361-374: A = [x^0 .. x^degree], solution of min |A c - numeraire * value| by gelsy
-                x = torch.from_numpy(spot_h[j])
-                A = c.regression_function.get_regression_matrix(x)
-                Y = torch.from_numpy(RT.to_host(value)).transpose(0, 1) * float(numeraire[j])
-                sol = torch.linalg.lstsq(A, Y).solution            # [NB, S]
-                coef_h[j, 2:] = sol.transpose(0, 1).reshape(-1).numpy()
+                if value_h[0] is None:
+                    value_h[0] = torch.from_numpy(RT.to_host(value)).transpose(0, 1)
+                A = c.regression_function.get_regression_matrix(torch.from_numpy(x_host))
+                sol = torch.linalg.lstsq(A, value_h[0] * float(num)).solution            # [NB, S]
+                host_row[2:] = sol.transpose(0, 1).reshape(-1).numpy()
+                dev_row.copy_(torch.from_numpy(host_row), non_blocking=False)
             else:
-                B.check(L.mcre_storage_moments(plan, j, coef_h[j, 0], coef_h[j, 1], spot[j].data_ptr(), value.data_ptr(),
+                B.check(L.mcre_storage_moments(plan, float(num), host_row[0], host_row[1], x_dev.data_ptr(), value.data_ptr(),
                                                count, chunk, partial.data_ptr(), mom.data_ptr(), RT.stream_ptr()))
                 # normal equations solved on the device, coefficients written straight into the row the next backward
                 # step reads: no host synchronisation inside the induction (NCCL's all-gather is stream ordered)
-                B.check(L.mcre_storage_solve(plan, RT.all_reduce_tree(mom).data_ptr(), 1e-12, coef[j].data_ptr(),
+                B.check(L.mcre_storage_solve(plan, RT.all_reduce_tree(mom).data_ptr(), 1e-12, dev_row.data_ptr(),
                                              RT.stream_ptr()))
-                continue
-            coef[j].copy_(torch.from_numpy(coef_h[j]), non_blocking=False)
+        first = 0 if 0 in expo_of_k else 1
+        for k in range(n_dates - 1, first - 1, -1):
+            B.check(L.mcre_storage_backward(plan, k, coef[k].data_ptr(), spot[k].data_ptr(), value.data_ptr(), count,
+                                            RT.stream_ptr()))
+            value_h[0] = None
+            if k >= 1:
+                solve(spot_h[k - 1] if self.mode == "lapack" else None, spot[k - 1], numeraire[k - 1], coef_h[k - 1], coef[k - 1])
+            for e in expo_of_k.get(k, []):
+                solve(spot_eh[e] if self.mode == "lapack" else None, spot_e[e], expo_num[e], coef_eh[e], coef_e[e])
         if self.mode == "moments":
             coef_h = RT.to_host(coef)
+            coef_eh = RT.to_host(coef_e) if n_expo else coef_eh
         # regression coefficients of the product, as the reference stores them ([date][state][basis]); in "moments"
         # mode they refer to the standardised spot (spot - centre) * inverse scale, kept next to them
         prod.regression_coeffs = torch.from_numpy(coef_h[:, 2:].reshape(n_dates, S, NB).copy())
         prod.regression_basis_shift_scale = torch.from_numpy(coef_h[:, :2].copy())
-        return coef
+        if n_expo:
+            c.regression_coeffs[prod.product_id] = torch.from_numpy(coef_eh[:, 2:].reshape(n_expo, S, NB).copy())
+        return coef, coef_e
 
     # ------------------------------------------------------------------ run
     def run(self):
@@ -324,7 +368,7 @@ class StorageBackend:
                 step_cache[key] = step_table(c.model, grid, c.simulation_scheme, self.nt, asset_id=key)
             return step_cache[key]
         n_main = c.num_paths_mainsim
-        if self.mixed:
+        if self.mixed or self.need_expo:
             from mcre.equity import main_chunk
             chunk = main_chunk(n_main)       # the equity launches' reduction chunk: one summation tree for the whole set
         else:
@@ -334,24 +378,29 @@ class StorageBackend:
         shard = B.Shard(begin, count, chunk)
         plans, t_pre = [], 0.0
         cfs = [torch.zeros(max(count, 1), dtype=torch.float64, device=dev) for _ in c.netting_sets]
+        n_expo = len(c.exposure_timeline) if self.need_expo else 0
+        expos = [torch.zeros((n_expo, max(count, 1)), dtype=torch.float64, device=dev) if n_expo else None
+                 for _ in c.netting_sets]
         tans = [torch.zeros((self.nt, max(count, 1)), dtype=torch.float64, device=dev) if self.nt else None
                 for _ in c.netting_sets]
         try:
             for pi, prod in enumerate(c.products):
                 if not _is_storage(prod):
                     continue
-                plan, numeraire, acts = self._create(prod, grid, *steps_of(prod))
+                plan, numeraire, acts, expo_num = self._create(prod, grid, *steps_of(prod))
                 plans.append(plan)
                 t0 = time.perf_counter()
-                coef = self._regress(prod, plan, numeraire, acts, dev)
+                coef, coef_e = self._regress(prod, plan, numeraire, acts, expo_num, dev)
                 torch.cuda.current_stream().synchronize()
                 t_pre += time.perf_counter() - t0
                 si = c.product_to_netting_set_idx[pi]
                 B.check(L.mcre_storage_mainsim(plan, C.byref(rng_main), C.byref(shard), coef.data_ptr(),
                                                float(prod.get_initial_state()), cfs[si].data_ptr(), None,
-                                               tans[si].data_ptr() if self.nt else None, RT.stream_ptr()))
-            if self.mixed:
-                return self._finish_mixed(cfs, chunk, dev, t_start, t_pre)
+                                               tans[si].data_ptr() if self.nt else None,
+                                               coef_e.data_ptr() if n_expo else None,
+                                               expos[si].data_ptr() if n_expo else None, RT.stream_ptr()))
+            if self.mixed or self.need_expo:
+                return self._finish_mixed(cfs, expos, chunk, dev, t_start, t_pre)
             raw = []
             n_chunks = max((count + chunk - 1) // chunk, 1)
             partial = torch.empty(n_chunks * 2 * max(self.nt, 1) + 1, dtype=torch.float64, device=dev)
@@ -383,9 +432,10 @@ class StorageBackend:
         return raw, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}
 
 
-    def _finish_mixed(self, cfs, chunk, dev, t_start, t_pre):
+    def _finish_mixed(self, cfs, expos, chunk, dev, t_start, t_pre):
         """The other products of the run through the equity backend's accumulating launches, starting from the
-        storages' per-path discounted cashflows (same Philox streams: the draw is the model's joint one)."""
+        storages' per-path discounted cashflows and exposures (same Philox streams: the draw is the model's joint one);
+        that path also applies threshold / collateral and finishes EPE / ENE / PFE - for books of storages alone, too."""
         import copy
         from mcre.equity import EquityBackend, is_equity_exercise
         c = self.c
@@ -401,12 +451,17 @@ class StorageBackend:
         eb = EquityBackend(sub)
         t1 = time.perf_counter()
         eb.presim_exercise_all([p for p in sub.products if is_equity_exercise(p)], dev)
+        if self.need_expo:
+            reg = [p for p in sub.products if not sub._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
+            if reg:
+                eb.presim_regression(reg, dev)
         torch.cuda.synchronize(dev)
         t_pre += time.perf_counter() - t1
         n_params = len(c.model.model_params)
         raw = []
         for si in range(len(c.netting_sets)):
-            res = eb._run_split_book(si, dev, c.num_paths_mainsim, n_params, chunk=chunk, extra_pv=cfs[si])
+            res = eb._run_split_book(si, dev, c.num_paths_mainsim, n_params, chunk=chunk, extra_pv=cfs[si],
+                                     extra_expo=expos[si])
             raw.append(res)
         torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start

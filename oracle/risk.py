@@ -572,12 +572,13 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     bridge_rngs = {}
     from oracle import storage as ST
     storage_coeffs = {}
+    storage_expo_coeffs = {}
     n_storage = sum(kind(pr) == "Storage" for pr in products)
-    if 0 < n_storage < len(products) and (need_expo or differentiate):
-        raise NotImplementedError("oracle: storages in mixed books are valued for PV, value-only")
+    if n_storage and differentiate and (n_storage < len(products) or need_expo):
+        raise NotImplementedError("oracle: storages in mixed books / with exposure metrics are valued without sensitivities")
 
-    def storage_market(pr, ctx):
-        tl_ = product_timeline(pr)
+    def storage_market(pr, ctx, times=None):
+        tl_ = product_timeline(pr) if times is None else times
         spots = [np.asarray(ad.val(ctx.spot(asset_of(pr), t)), dtype=float) for t in tl_]
         nums = [float(np.asarray(ad.val(ctx.numeraire(t))).reshape(-1)[0]) for t in tl_]
         return spots, nums
@@ -599,7 +600,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
             return rng.uniform(0, 1, size=(n, n_int))
         return get
 
-    if all(kind(pr) == "Storage" for pr in products):
+    if all(kind(pr) == "Storage" for pr in products) and not need_expo:
         return _run_storage(model, netting_sets, products, prod_set, mtypes, p, sim_tl, n_main, n_pre, num_steps, scheme,
                             draws_pre, draws_main, degree, n_sub, dim, storage_solver)
 
@@ -610,7 +611,11 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
         ctx = Ctx(model, p, sim_tl, paths, n_pre, bridge=bridge_provider(draws_pre, 42, n_pre))
         for k, pr in enumerate(products):
             if kind(pr) == "Storage":       # storages next to other products (pv_performance_large_netting_set.py)
-                storage_coeffs[k] = ST.regress(pr, *storage_market(pr, ctx), degree)
+                if need_expo:
+                    expo = (expo_tl,) + storage_market(pr, ctx, expo_tl)
+                    storage_coeffs[k], storage_expo_coeffs[k] = ST.regress(pr, *storage_market(pr, ctx), degree, expo=expo)
+                else:
+                    storage_coeffs[k] = ST.regress(pr, *storage_market(pr, ctx), degree)
             elif needs_regression(pr):
                 regress_product(pr, ctx, expo_tl, degree, prod_coeffs[k], expo_coeffs[k])
 
@@ -627,7 +632,14 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     for k, pr in enumerate(products):
         si = prod_set[k]
         if kind(pr) == "Storage":
-            cfs = ST.evaluate(pr, *storage_market(pr, ctx), storage_coeffs[k], degree)
+            if need_expo:
+                expo = (expo_tl,) + storage_market(pr, ctx, expo_tl)
+                cfs, expos = ST.evaluate_with_exposures(pr, *storage_market(pr, ctx), storage_coeffs[k], degree, expo,
+                                                        storage_expo_coeffs[k])
+                for i, e in enumerate(expos):
+                    set_expo[si][i] = e if set_expo[si][i] is None else set_expo[si][i] + e
+            else:
+                cfs = ST.evaluate(pr, *storage_market(pr, ctx), storage_coeffs[k], degree)
             set_cfs[si] = cfs if set_cfs[si] is None else set_cfs[si] + cfs
             continue
         sm = np.full((n_main, 1), initial_state(pr), dtype=np.int64)

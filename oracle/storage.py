@@ -121,32 +121,71 @@ def log_spot_std(model, t):
     return math.sqrt(max(vs + sl * sl * tau + 2.0 * cov, 0.0))
 
 
-def regress(prod, spots, numeraires, n_basis, solver=gelsy, std=None):
-    """_perform_regression_for_product for a Storage valued on its own dates (controller.py:294-383):
+def regress(prod, spots, numeraires, n_basis, solver=gelsy, std=None, expo=None):
+    """_perform_regression_for_product for a Storage (controller.py:294-383):
     spots [n_dates][N], numeraires [n_dates] -> coeffs [n_dates][S, n_basis].
-    The window between two regression dates is one action date; its cashflows pass through a float32
-    accumulator (controller.py:331, 342) before the float64 tail is added (:345-352)."""
-    n_dates, S, n = len(prod.product_timeline), prod.num_states, spots[0].shape[0]
+    The regression dates are the action dates and, with expo = (times, spots [n_expo][N], numeraires [n_expo]), the
+    exposure dates; walking them backwards, the window between two regression dates holds at most one action date, whose
+    cashflows pass through a float32 accumulator (controller.py:331, 342) before the float64 tail is added (:345-352).
+    With `expo` -> (coeffs, exposure coeffs [n_expo][S, n_basis])."""
+    ptl = [float(t) for t in prod.product_timeline]
+    n_dates, S, n = len(ptl), prod.num_states, spots[0].shape[0]
     std = std or [(0.0, 1.0)] * n_dates
     coeffs = [np.zeros((S, n_basis)) for _ in range(n_dates)]
-    tail = np.zeros((n, S))
+    e_times, e_spots, e_nums = expo if expo is not None else ([], [], [])
+    e_coeffs = [np.zeros((S, n_basis)) for _ in e_times]
+    reg_tl = sorted(set(ptl) | set(float(t) for t in e_times))
+    e_index = {float(t): i for i, t in enumerate(e_times)}
+    cache = {n_dates: np.zeros((n, S))}
     last = n_dates
-    for j in reversed(range(n_dates)):
-        t_next = j + 1
+    for t_reg in reversed(reg_tl):
+        pidx = int(np.searchsorted(np.asarray(ptl), t_reg, side="left"))
+        if pidx >= n_dates:
+            continue
+        t_next = pidx + 1 if ptl[pidx] == t_reg else pidx
         if t_next < last:
             sm = np.tile(np.arange(S, dtype=float), (n, 1))
             step = np.zeros((n, S), dtype=np.float32)
             for i in range(t_next, last):
                 sm, cf = cashflows(prod, i, spots[i], np.full(n, numeraires[i]), sm, coeffs[i], n_basis, std[i])
                 step = (step.astype(np.float64) + cf).astype(np.float32)
-            tail = step.astype(np.float64) + lookup(tail, sm, S)
+            cache[t_next] = step.astype(np.float64) + lookup(cache[last], sm, S)
             last = t_next
-            total = tail
+        total = cache[t_next]
+        if t_reg in ptl:
+            j = ptl.index(t_reg)
+            A = basis((spots[j] - std[j][0]) * std[j][1], n_basis)
+            sol = solver(A, numeraires[j] * total).T.copy()
+            coeffs[j] = sol
+            if t_reg in e_index:
+                e_coeffs[e_index[t_reg]] = sol
         else:
-            total = tail
-        A = basis((spots[j] - std[j][0]) * std[j][1], n_basis)
-        coeffs[j] = solver(A, numeraires[j] * total).T.copy()
-    return coeffs
+            e = e_index[t_reg]
+            e_coeffs[e] = solver(basis(e_spots[e], n_basis), e_nums[e] * total).T.copy()
+    return coeffs if expo is None else (coeffs, e_coeffs)
+
+
+def evaluate_with_exposures(prod, spots, numeraires, coeffs, n_basis, expo, e_coeffs):
+    """_evaluate_product, exposure branch (controller.py:412-458): per exposure date the actions of all action dates up
+    to it are taken first, then exposure = continuation polynomials of that date interpolated at the realised inventory
+    state, over the numeraire.  expo = (times, spots, numeraires) -> (cashflows [N], exposures [n_expo][N])."""
+    ptl = [float(t) for t in prod.product_timeline]
+    S, n = prod.num_states, spots[0].shape[0]
+    e_times, e_spots, e_nums = expo
+    sm = np.full((n, 1), float(prod.get_initial_state()))
+    cfs, t_start, out = np.zeros(n), 0, []
+    for e, t in enumerate(e_times):
+        while t_start < len(ptl) and ptl[t_start] <= t:
+            sm, cf = cashflows(prod, t_start, spots[t_start], np.full(n, numeraires[t_start]), sm, coeffs[t_start], n_basis)
+            cfs = cfs + cf[:, 0]
+            t_start += 1
+        grid = basis(e_spots[e], n_basis) @ e_coeffs[e].T
+        out.append(lookup(grid, sm, S)[:, 0] / e_nums[e])
+    while t_start < len(ptl):
+        sm, cf = cashflows(prod, t_start, spots[t_start], np.full(n, numeraires[t_start]), sm, coeffs[t_start], n_basis)
+        cfs = cfs + cf[:, 0]
+        t_start += 1
+    return cfs, out
 
 
 def evaluate(prod, spots, numeraires, coeffs, n_basis, std=None, spot_tangents=None, numeraire_tangents=None):

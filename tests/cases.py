@@ -373,6 +373,26 @@ def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_leve
     return model, [m.NettingSet(name="large_cva_ns", products=prods, counterparty_id=cp)], metrics, np.linspace(0.0, horizon, n_expo)
 
 
+def storage_exposure(ns_module, mixed=False):
+    """Exposure profiles of a storage (tests/exposure_tests/ee_pfe_storage.py: EPE + PFE on an exposure grid that does not
+    coincide with the daily decisions), here with ENE and PV, an MPoR-collateralised twin set, and - `mixed` - the storages
+    netted with equity options on a multi-asset Black-Scholes model (tests/exposure_tests/ee_performance_large_netting_set.py)."""
+    m = ns_module
+    if mixed:
+        model, sets, _, _ = storage_mixed_book(ns_module)
+        _, twin, _, _ = storage_mixed_book(ns_module)
+        sets = [m.NettingSet(name="open", products=sets[0].products, threshold=5.0),
+                m.NettingSet(name="margined", products=twin[0].products, margin_period_of_risk=0.125)]
+        tl = np.linspace(0.0, 1.5, 13)
+    else:
+        model, sets, _, _ = storage_s2f(ns_module, which="storage2", end_day=40, num_states=6, vols=(0.5, 0.2))
+        _, twin, _, _ = storage_s2f(ns_module, which="storage2", end_day=40, num_states=6, vols=(0.5, 0.2))
+        sets = [m.NettingSet(name="open", products=sets[0].products),
+                m.NettingSet(name="margined", products=twin[0].products, margin_period_of_risk=4.0, threshold=1000.0)]
+        tl = np.linspace(0.0, 44.0, 12)      # 4-day grid against daily decisions; the last dates lie beyond the contract
+    return model, sets, [m.EPEMetric(), m.ENEMetric(), m.PFEMetric(0.95), m.PVMetric()], tl
+
+
 def storage_small(ns_module, model_kind="bs", num_states=4, end_day=2.0):
     """The storage of tests/pytests/test_single_product_executor_parity.py:43-60 / 162-168 (Black-Scholes "gas" price,
     PV with pathwise sensitivities), and the same contract over 12 days on a Schwartz two-factor curve."""
@@ -562,6 +582,8 @@ GOLDEN_CASES = {
     "storage_bs_greeks": (storage_small, dict(), dict(n_main=256, n_pre=256, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "storage_s2f_greeks": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="ANALYTICAL", differentiate=True, degree=3)),
     "storage_s2f_greeks_euler": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="EULER", differentiate=True)),
+    "storage_exposure": (storage_exposure, dict(), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
+    "storage_exposure_mixed": (storage_exposure, dict(mixed=True), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "storage_mixed_book": (storage_mixed_book, dict(), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
 }

@@ -168,3 +168,25 @@ def test_storages_next_to_equity_products_in_one_netting_set(draws):
         v, e = [out["results"][0][0][0][0]], [out["results"][0][0][0][1]]
     helpers.assert_close(got[0], v, 1e-9, 1e-9, f"{name} {draws} value")
     helpers.assert_close(got[1], e, 1e-7, 1e-9, f"{name} {draws} mc error")
+
+
+@pytest.mark.parametrize("name", ["storage_exposure", "storage_exposure_mixed"])
+@pytest.mark.parametrize("draws", ["torch", "philox"])
+def test_storage_exposure_profiles(name, draws):
+    """EPE / ENE / PFE / PV of storages (tests/exposure_tests/ee_pfe_storage.py) on an exposure grid that does not coincide
+    with the decisions, open and MPoR-collateralised sets; alone on the Schwartz model and netted with equity options on a
+    multi-asset Black-Scholes model: the reference's golden with its injected draws, the oracle under native Philox."""
+    res, sc = helpers.run_cuda(name, draws=draws)
+    flat = helpers.flatten_results(res)
+    if draws == "torch":
+        gold = helpers.load_golden(name)
+        want = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    else:
+        out, _ = helpers.run_oracle(name, draws="philox")
+        want = helpers.oracle_flat(out, res.get_netting_set_names(), res.get_metric_names())
+    for key, (vals, errs) in want.items():
+        scale = max(1.0, float(np.max(np.abs(vals))))
+        # (regression proxies of the equity products pass through the reference's float32 chain: 1e-9 like the other goldens)
+        helpers.assert_close(flat[key][0], vals, 1e-9, 1e-9 * scale, f"{name} {draws} {key}")
+        if not key.split("|")[1].startswith("pfe"):
+            helpers.assert_close(flat[key][1], errs, 1e-6, 1e-9 * scale, f"{name} {draws} {key} mc error")

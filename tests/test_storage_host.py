@@ -121,8 +121,9 @@ def test_unsupported_storage_runs_raise_before_any_device_work():
         StorageBackend(ctrl(regression_function=ns.PolyomialRegression(7)))
     with pytest.raises(NotImplementedError):
         StorageBackend(ctrl(model=ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)))
-    with pytest.raises(NotImplementedError):     # exposure metrics of a storage
-        StorageBackend(ctrl(risk_metrics=ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=[0.0, 1.0])))
+    assert StorageBackend(ctrl(risk_metrics=ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=[0.0, 1.0]))).need_expo
+    with pytest.raises(NotImplementedError):     # sensitivities of exposure metrics of a storage
+        StorageBackend(ctrl(risk_metrics=ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=[0.0, 1.0]), differentiate=True))
 
 
 def test_step_tangent_table_equals_finite_differences_of_the_step_table():
