@@ -602,7 +602,9 @@ typedef struct {
   int32_t n_basis;          /* regression basis functions                                                  */
   double log_spot0;         /* log of the forward curve at the calibration date                            */
   const double *step;       /* [n_sub][MCRE_STORAGE_STEP]: [0] a, [1] k, [2] dt, [3] m, [4] cx, [5] cy, [6] log F(t2),
-                               [8 + j] bx_j, [16 + j] by_j (j < noise_dim):
+                               [7] non-zero: Black-Scholes EULER step x' = x + log1p(m + cx w0), log S = log F + x'
+                               (m = rate dt, cx = sigma sqrt(dt); black_scholes.py:69-85), [8 + j] bx_j, [16 + j] by_j
+                               (j < noise_dim):
                                  w0 = sum_j bx_j z_j, w1 = sum_j by_j z_j   (the model's rows of the joint draw z @ L^T)
                                  x' = (a x - (k x) dt) + cx w0;  y' = (y + m) + cy w1;  log S = log F(t2) + x' + y'
                                Schwartz ANALYTICAL: a = exp(-kappa dt), k = 0, cx = cy = 1, b = rows of the Cholesky

@@ -140,12 +140,19 @@ __device__ __forceinline__ int best_of(const double (&v)[3]) {
 // factor of the correlation.  Black-Scholes single / multi-asset (black_scholes.py:50-67, black_scholes_multi.py:63-79,
 // ANALYTICAL): the log-price accumulates in x (bx = the asset's row of the Cholesky factor of the step covariance over
 // ALL assets of the model: the draw is the joint one), its drift in m, log F = log spot.
-// Step record: [0] a, [1] k, [2] dt, [3] m, [4] cx, [5] cy, [6] log F, [8 + j] bx_j, [16 + j] by_j.
+// Step record: [0] a, [1] k, [2] dt, [3] m, [4] cx, [5] cy, [6] log F, [7] 1: Euler Black-Scholes step (below),
+// [8 + j] bx_j, [16 + j] by_j.
 constexpr int ST_STEP = MCRE_STORAGE_STEP;
 constexpr int ST_NOISE = MCRE_STORAGE_MAX_NOISE;
 struct TwoFactor {
   double x = 0.0, y = 0.0;
   __device__ __forceinline__ double advance(const double *__restrict__ st, double w0, double w1) {
+    if (__ldg(st + 7) != 0.0) {
+      // Black-Scholes under EULER (black_scholes.py:69-85, black_scholes_multi.py:81-97): S' = S + (r S dt + sigma S
+      // sqrt(dt) w) = S (1 + m + cx w0), carried in the log
+      x = x + log1p(__dadd_rn(__ldg(st + 3), __dmul_rn(__ldg(st + 4), w0)));
+      return __ldg(st + 6) + x;
+    }
     const double drift = __dsub_rn(__dmul_rn(__ldg(st + 0), x), __dmul_rn(__dmul_rn(__ldg(st + 1), x), __ldg(st + 2)));
     x = __dadd_rn(drift, __dmul_rn(__ldg(st + 4), w0));
     y = __dadd_rn(__dadd_rn(y, __ldg(st + 3)), __dmul_rn(__ldg(st + 5), w1));

@@ -430,7 +430,7 @@ class EquityBackend:
             nt = 0
         grid = build_time_grid(self.assets[0].model.t0(), c.simulation_timeline.tolist(), c.num_steps)
         dates = grid.dates
-        date_idx = {t: i for i, t in enumerate(dates)}
+        date_idx = grid.index_map()
         n_dates, n_sub = len(dates), grid.n_sub
         two = self.kind != EQ_BS
         d = (2 if two else 1) * A + (1 if self.credit is not None else 0)     # the credit factor draws the last column

@@ -309,7 +309,7 @@ class IrcBackend:
         t0 = self.vas.t0()
         grid = build_time_grid(t0, c.simulation_timeline.tolist(), c.num_steps)
         dates = grid.dates
-        date_idx = {t: i for i, t in enumerate(dates)}
+        date_idx = grid.index_map()
         n_dates, n_sub = len(dates), grid.n_sub
         zero = D(0.0, None, nt)
 

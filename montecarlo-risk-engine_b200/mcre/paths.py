@@ -200,4 +200,6 @@ def generate(model, timeline, n_paths, num_steps, scheme, seed, inject_z=None, i
     out = torch.empty((n_paths, n_dates, state_dim), dtype=torch.float64, device=dev)
     sh = B.Shard(path_begin, n_paths, 256)
     B.check(L.mcre_generate_paths(C.byref(d), C.byref(rng), C.byref(sh), out.data_ptr(), RT.stream_ptr()))
+    for di in grid.zero_dt_dates:        # dates the running time had already reached: state unchanged (engine.py:48-60)
+        out[:, di, :] = out[:, grid.alias[di], :]
     return out

@@ -59,6 +59,26 @@ def _is_bsm(model):
     return isinstance(model, BlackScholesMulti)
 
 
+def price_model_of(model, asset_id):
+    """(sub-model that simulates `asset_id`, its first noise column in the model's joint draw, joint noise dimension,
+    numeraire model).  A plain model is its own price and numeraire model; in a ModelConfig (model_config.py:8-77) the
+    sub-models' draws are concatenated."""
+    from models.model_config import ModelConfig
+    if not isinstance(model, ModelConfig):
+        return model, 0, int(model.simulation_dim), model
+    off = 0
+    for m in model.models:
+        if asset_id in m.asset_ids:
+            return m, off, int(model.simulation_dim), model.models[model.id_to_model["numeraire"]]
+        off += int(m.simulation_dim)
+    raise ValueError(f"Asset id '{asset_id}' not found in model asset ids {list(model.asset_ids)}.")
+
+
+def rate_of(model):
+    """Rate parameter of a (numeraire) model."""
+    return model.param_values()[2 * model.num_assets if _is_bsm(model) else (2 if _is_bs(model) else 0)]
+
+
 def step_table(model, grid, scheme, nt=0, asset_id=None):
     """-> (steps [n_sub][STEP], tangents [n_sub][nt][6] or None): records of csrc/storage.cu:TwoFactor and, for pathwise
     sensitivities, d(A, B00, M, B10, B11, log F) / d(parameter) of the effective recursion x' = A x + B00 z0,
@@ -72,33 +92,53 @@ def step_table(model, grid, scheme, nt=0, asset_id=None):
     Black-Scholes multi-asset (black_scholes_multi.py:63-79, ANALYTICAL, value-only): the same for the asset `asset_id`
     with bx = its row of the Cholesky factor of the step covariance of all assets - the draw is the model's joint one."""
     from mcre.dual import D, dexp, dlog, dsqrt
+    from models.model_config import ModelConfig
+    joint = model
+    model, noise_off, noise_dim, _ = price_model_of(joint, asset_id)
+    if noise_dim > MAX_NOISE:
+        raise NotImplementedError(f"gas storage: price models with at most {MAX_NOISE} noise factors")
+    if nt and joint is not model:
+        raise NotImplementedError("gas storage: sensitivities on a stand-alone price model")
     p = model.dual_params(0, nt)
     zero, one = D(0.0, None, nt), D(1.0, None, nt)
     out = np.zeros((max(grid.n_sub, 1), STEP))
     tan = np.zeros((max(grid.n_sub, 1), nt, 6)) if nt else None
     chol = {}
-    if (_is_bs(model) or _is_bsm(model)) and scheme != SimulationScheme.ANALYTICAL:
-        raise NotImplementedError("gas storage on Black-Scholes models: the ANALYTICAL scheme (the Euler step is not "
-                                  "additive in the log-price)")
+    black_scholes = _is_bs(model) or _is_bsm(model)
+    if black_scholes and scheme not in (SimulationScheme.ANALYTICAL, SimulationScheme.EULER):
+        raise NotImplementedError(f"gas storage on Black-Scholes models: scheme {scheme}")
+    if black_scholes and scheme == SimulationScheme.EULER and nt:
+        raise NotImplementedError("gas storage: sensitivities under the ANALYTICAL scheme for Black-Scholes price models")
+
+    def joint_factor(key):
+        """Lower Cholesky factor of the joint step covariance (ANALYTICAL) / correlation (EULER) of the whole draw
+        (model.py:50-73, model_config.py:101-221; raises like the reference for pairs without a joint covariance)."""
+        from mcre.paths import joint_matrix
+        if key not in chol:
+            chol[key] = np.linalg.cholesky(np.array(joint_matrix(joint, scheme, key)))
+        return chol[key]
     for s in range(grid.n_sub):
         dt = grid.dt[s]
         bx, by = [zero] * MAX_NOISE, [zero] * MAX_NOISE
-        if _is_bsm(model):
-            from mcre.paths import joint_matrix
-            n = model.num_assets
-            ai = model.asset_ids.index(asset_id)
-            key = grid.dt_nominal[s]
-            if key not in chol:
-                chol[key] = np.linalg.cholesky(np.array(joint_matrix(model, scheme, key)))
-            sig, rate = p[n + ai], p[2 * n]
-            a, k, m, cx, cy = one, zero, (rate - 0.5 * sig * sig) * dt, one, zero
-            bx = [D(float(chol[key][ai, j]), None, nt) if j <= ai else zero for j in range(MAX_NOISE)]
-            lf = dlog(p[ai])
-        elif _is_bs(model):
-            spot, sig, rate = p
-            a, k, m, cx, cy = one, zero, rate * dt - 0.5 * dt * sig * sig, one, zero
-            bx = [dsqrt(sig * sig * grid.dt_nominal[s])] + [zero] * (MAX_NOISE - 1)
-            lf = dlog(spot)
+        euler_bs = 0.0
+        if black_scholes:
+            n = model.num_assets if _is_bsm(model) else 1
+            ai = model.asset_ids.index(asset_id) if _is_bsm(model) else 0
+            spot, sig, rate = (p[ai], p[n + ai], p[2 * n]) if _is_bsm(model) else p
+            col = noise_off + ai
+            a, k, cx, cy, lf = one, zero, one, zero, dlog(spot)
+            if scheme == SimulationScheme.EULER:
+                # S' = S + (r S dt + sigma S sqrt(dt) w): multiplicative, carried as log1p in the kernel
+                L = joint_factor(None)
+                m, cx, euler_bs = rate * dt, sig * math.sqrt(dt), 1.0
+                bx = [D(float(L[col, j]), None, nt) if j <= col else zero for j in range(MAX_NOISE)]
+            elif _is_bs(model) and joint is model:
+                m = rate * dt - 0.5 * dt * sig * sig
+                bx = [dsqrt(sig * sig * grid.dt_nominal[s])] + [zero] * (MAX_NOISE - 1)
+            else:
+                L = joint_factor(grid.dt_nominal[s])
+                m = (rate - 0.5 * sig * sig) * dt if _is_bsm(model) else rate * dt - 0.5 * dt * sig * sig
+                bx = [D(float(L[col, j]), None, nt) if j <= col else zero for j in range(MAX_NOISE)]
         else:
             rate, kappa, sig_s, mu, sig_l, rho = p
             if scheme == SimulationScheme.ANALYTICAL:
@@ -129,6 +169,7 @@ def step_table(model, grid, scheme, nt=0, asset_id=None):
             lf = D(math.log(model.curve_value(grid.t2[s])), None, nt)
         val = lambda x: x.v if isinstance(x, D) else x   # noqa: E731
         out[s, :7] = [val(x) for x in (a, k, dt, m, cx, cy, lf)]
+        out[s, 7] = euler_bs
         out[s, 8:8 + MAX_NOISE] = [val(x) for x in bx]
         out[s, 16:16 + MAX_NOISE] = [val(x) for x in by]
         if nt:
@@ -140,6 +181,9 @@ def step_table(model, grid, scheme, nt=0, asset_id=None):
 
 def log_spot_scale(model, t):
     """Standard deviation of log S(t) under the model: a per-date scale for the standardised basis."""
+    from models.model_config import ModelConfig
+    if isinstance(model, ModelConfig):
+        return max(log_spot_scale(m, t) for m in model.models if _is_bs(m) or _is_bsm(m))
     tau = max(t - model.t0(), 0.0)
     if _is_bs(model):
         return model.param_values()[1] * math.sqrt(tau)
@@ -168,24 +212,34 @@ class StorageBackend:
         #: tests/pv_tests/pv_performance_large_netting_set.py): the storages' per-path cashflows start the PV
         #: accumulators of the equity launches (mcre/equity.py:_run_split_book, extra_pv)
         self.mixed = not all(_is_storage(p) for p in c.products)
-        if not isinstance(c.model, SchwartzTwoFactorModel) and not _is_bs(c.model) and not _is_bsm(c.model):
-            raise NotImplementedError("gas storage: SchwartzTwoFactorModel, BlackScholesModel and BlackScholesMulti are "
-                                      f"implemented (got {type(c.model).__name__})")
-        if any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
-            raise NotImplementedError("gas storage: CVA (a credit model next to the price model) is not implemented")
+        from models.cirpp import CIRPPModel
+        from models.model_config import ModelConfig
+        subs = list(c.model.models) if isinstance(c.model, ModelConfig) else [c.model]
+        self.standalone = not isinstance(c.model, ModelConfig)
+        for m in subs:
+            ok = _is_bs(m) or _is_bsm(m) or (isinstance(m, SchwartzTwoFactorModel) and self.standalone) \
+                or (isinstance(m, CIRPPModel) and not self.standalone)
+            if not ok:
+                raise NotImplementedError("gas storage: SchwartzTwoFactorModel, BlackScholesModel, BlackScholesMulti, or a "
+                                          f"ModelConfig of Black-Scholes models and a credit model (got {type(m).__name__})")
+        kinds = {m.metric_type for m in c.risk_metrics.metrics}
+        if MetricType.CVA in kinds and not self.mixed:
+            raise NotImplementedError("gas storage: CVA of a book of storages alone (the default weights ride with an equity "
+                                      "launch of the same netting set)")
         self.need_expo = c.risk_metrics.requires_exposure_profiles()
-        if c.differentiate and (self.mixed or _is_bsm(c.model) or self.need_expo):
+        if c.differentiate and (self.mixed or not self.standalone or _is_bsm(c.model) or self.need_expo):
             raise NotImplementedError("gas storage: sensitivities of the PV of books of storages on a one- or two-factor "
                                       "price model")
         self.nt = len(c.model.model_params) if c.differentiate else 0
-        self.rate_index = 2 if _is_bs(c.model) else (2 * c.model.num_assets if _is_bsm(c.model) else 0)
-        self.noise_dim = 1 if _is_bs(c.model) else (c.model.num_assets if _is_bsm(c.model) else 2)
+        for p in c.products:
+            if _is_storage(p):
+                price_model_of(c.model, p.get_asset_id())      # raises for an unknown asset id
+        num_model = price_model_of(c.model, [p for p in c.products if _is_storage(p)][0].get_asset_id())[3]
+        self.num_rate = rate_of(num_model)
+        self.rate_index = 2 if _is_bs(c.model) else 0           # (tangent slot of the rate: stand-alone one- / two-factor models)
+        self.noise_dim = int(c.model.simulation_dim)
         if self.noise_dim > MAX_NOISE:
             raise NotImplementedError(f"gas storage: price models with at most {MAX_NOISE} noise factors")
-        if _is_bsm(c.model):
-            for p in c.products:
-                if _is_storage(p) and p.get_asset_id() not in c.model.asset_ids:
-                    raise ValueError(f"Asset id '{p.get_asset_id()}' not found in model asset ids {list(c.model.asset_ids)}.")
         rf = c.regression_function
         if type(rf) is not PolyomialRegression or not 0 <= rf.degree < B_MAX_BASIS:
             raise NotImplementedError(f"gas storage: PolyomialRegression of degree 0..{B_MAX_BASIS - 1} (the kernels "
@@ -200,21 +254,21 @@ class StorageBackend:
 
     # ------------------------------------------------------------------ plan
     def _spot0(self, prod):
-        c = self.c
-        if _is_bsm(c.model):
-            return c.model.param_values()[c.model.asset_ids.index(prod.get_asset_id())]
-        return c.model.param_values()[0] if _is_bs(c.model) else c.model.curve_value(c.model.t0())
+        m = price_model_of(self.c.model, prod.get_asset_id())[0]
+        if _is_bsm(m):
+            return m.param_values()[m.asset_ids.index(prod.get_asset_id())]
+        return m.param_values()[0] if _is_bs(m) else m.curve_value(m.t0())
 
     def _create(self, prod, grid, steps, steps_tan):
         c = self.c
-        sim_dates = {t: i for i, t in enumerate(grid.dates)}
+        sim_dates = grid.index_map()
         acts = prod.product_timeline.tolist()
         date_of = {sim_dates[t]: k for k, t in enumerate(acts)}
         step_date = np.array([date_of.get(d, -1) if d >= 0 else -1 for d in grid.date_after], dtype=np.int32)
         n_pre = sum(1 for t in acts if sim_dates[t] < grid.n_pre_dates)
         rec = prod.lower()
-        t0 = c.model.t0()
-        rate = c.model.param_values()[self.rate_index]
+        t0 = self._t0()
+        rate = self.num_rate
         numeraire = np.array([math.exp(rate * (t - t0)) for t in acts])
         dlog_num = np.zeros((len(acts), max(self.nt, 1)))
         if self.nt:
@@ -226,6 +280,11 @@ class StorageBackend:
         d.log_spot0 = math.log(self._spot0(prod))
         d.noise_dim, d.n_tan = self.noise_dim, self.nt
         expo_times = c.exposure_timeline.tolist() if self.need_expo else []
+        for t in expo_times:
+            # two dates one rounding error apart share a simulation date; the kernel acts before it reads the exposure of
+            # that date, which is the reference's order only if the action date is not the later of the two
+            if any(sim_dates[ta] == sim_dates[t] and ta > t for ta in acts):
+                raise NotImplementedError(f"exposure date {t!r} lies one rounding error before an action date of a storage")
         expo_of = {sim_dates[t]: e for e, t in enumerate(expo_times)}
         step_expo = np.array([expo_of.get(di, -1) if di >= 0 else -1 for di in grid.date_after], dtype=np.int32)
         d.n_expo = len(expo_times)
@@ -257,11 +316,15 @@ class StorageBackend:
         return rng, z
 
     # ------------------------------------------------------------------ pre-simulation + regression
+    def _t0(self):
+        m = self.c.model
+        return (m if self.standalone else m.models[0]).t0()
+
     def _forward(self, t, prod):
-        c = self.c
-        if _is_bs(c.model) or _is_bsm(c.model):
-            return self._spot0(prod) * math.exp(c.model.param_values()[self.rate_index] * (t - c.model.t0()))
-        return c.model.curve_value(t)
+        m = price_model_of(self.c.model, prod.get_asset_id())[0]
+        if _is_bs(m) or _is_bsm(m):
+            return self._spot0(prod) * math.exp(rate_of(m) * (t - m.t0()))
+        return m.curve_value(t)
 
     def _regress(self, prod, plan, numeraire, acts, expo_num, dev):
         """-> (coef [n_dates][2 + S * NB], coef_expo [n_expo][2 + S * NB] or None) on the device: (centre, inverse scale,
@@ -359,11 +422,11 @@ class StorageBackend:
         c, L = self.c, B.lib()
         dev = RT.compute_device()
         t_start = time.perf_counter()
-        grid = build_time_grid(c.model.t0(), c.simulation_timeline.tolist(), c.num_steps)
+        grid = build_time_grid(self._t0(), c.simulation_timeline.tolist(), c.num_steps)
         step_cache = {}
 
         def steps_of(prod):
-            key = prod.get_asset_id() if _is_bsm(c.model) else None
+            key = None if (self.standalone and not _is_bsm(c.model)) else prod.get_asset_id()
             if key not in step_cache:
                 step_cache[key] = step_table(c.model, grid, c.simulation_scheme, self.nt, asset_id=key)
             return step_cache[key]

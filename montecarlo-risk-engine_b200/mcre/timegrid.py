@@ -20,10 +20,18 @@ class TimeGrid:
     dt: list = field(default_factory=list)        # time2 - time1 as the models see it
     date_after: list = field(default_factory=list)  # date index completed by the sub-step, or -1
     zero_dt_dates: list = field(default_factory=list)  # non-leading dates with dt <= 0 (state unchanged)
+    alias: dict = field(default_factory=dict)         # zero-dt date index -> index of the date whose state it shares
 
     @property
     def n_sub(self):
         return len(self.dt)
+
+    def index_map(self):
+        """time -> index of the simulation date whose state is the state at that time.  Dates the running time has
+        already reached or passed (dt <= 0: two dates one rounding error apart, e.g. 0.15 from np.linspace and
+        0.15000000000000002 from repeated addition of 0.05) are not stepped to by the reference (engine.py:48-60: the
+        state is unchanged) - their events join the date before them."""
+        return {t: self.alias.get(i, i) for i, t in enumerate(self.dates)}
 
 
 def build_time_grid(calibration_date, dates, num_steps):
@@ -47,7 +55,5 @@ def build_time_grid(calibration_date, dates, num_steps):
             g.n_pre_dates = di + 1
         else:
             g.zero_dt_dates.append(di)
-    if g.zero_dt_dates:
-        # cannot happen for a sorted, de-duplicated timeline after the first positive step
-        raise NotImplementedError("simulation date not after the running time: unsupported timeline")
+            g.alias[di] = g.alias.get(di - 1, di - 1)
     return g

@@ -393,6 +393,18 @@ def storage_exposure(ns_module, mixed=False):
     return model, sets, [m.EPEMetric(), m.ENEMetric(), m.PFEMetric(0.95), m.PVMetric()], tl
 
 
+def storage_cva_mixed(ns_module):
+    """CVA + EPE of the mixed book (storages + equity options) against a counterparty with a CIR++ intensity correlated
+    with the assets, MPoR-collateralised, EULER scheme: the shape of tests/exposure_tests/cva_perfprmance_large_netting_set.py."""
+    m = ns_module
+    market, sets, _, _ = storage_mixed_book(ns_module)
+    credit = m.CIRPPModel(calibration_date=0.0, asset_id="cp", hazard_rates=HAZARDS, kappa=0.10, theta=0.01, volatility=0.02,
+                          y0=0.0001)
+    model = m.ModelConfig(models=[market, credit], inter_asset_correlation_matrix=[np.full((3, 1), 0.2, dtype=float)])
+    nset = m.NettingSet(name="mixed_cva", products=sets[0].products, counterparty_id="cp", margin_period_of_risk=10 / 252)
+    return model, [nset], [m.CVAMetric("cp", 0.4), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
+
+
 def storage_small(ns_module, model_kind="bs", num_states=4, end_day=2.0):
     """The storage of tests/pytests/test_single_product_executor_parity.py:43-60 / 162-168 (Black-Scholes "gas" price,
     PV with pathwise sensitivities), and the same contract over 12 days on a Schwartz two-factor curve."""
@@ -584,6 +596,7 @@ GOLDEN_CASES = {
     "storage_s2f_greeks_euler": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="EULER", differentiate=True)),
     "storage_exposure": (storage_exposure, dict(), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
     "storage_exposure_mixed": (storage_exposure, dict(mixed=True), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "storage_cva_mixed": (storage_cva_mixed, dict(), dict(n_main=1000, n_pre=1000, num_steps=2, scheme="EULER", differentiate=False)),
     "storage_mixed_book": (storage_mixed_book, dict(), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),
 }

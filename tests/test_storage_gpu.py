@@ -170,12 +170,14 @@ def test_storages_next_to_equity_products_in_one_netting_set(draws):
     helpers.assert_close(got[1], e, 1e-7, 1e-9, f"{name} {draws} mc error")
 
 
-@pytest.mark.parametrize("name", ["storage_exposure", "storage_exposure_mixed"])
+@pytest.mark.parametrize("name", ["storage_exposure", "storage_exposure_mixed", "storage_cva_mixed"])
 @pytest.mark.parametrize("draws", ["torch", "philox"])
 def test_storage_exposure_profiles(name, draws):
     """EPE / ENE / PFE / PV of storages (tests/exposure_tests/ee_pfe_storage.py) on an exposure grid that does not coincide
     with the decisions, open and MPoR-collateralised sets; alone on the Schwartz model and netted with equity options on a
-    multi-asset Black-Scholes model: the reference's golden with its injected draws, the oracle under native Philox."""
+    multi-asset Black-Scholes model; storage_cva_mixed: CVA + EPE of that mixed book against a CIR++ counterparty under EULER
+    (tests/exposure_tests/cva_perfprmance_large_netting_set.py): the reference's golden with its injected draws, the oracle
+    under native Philox."""
     res, sc = helpers.run_cuda(name, draws=draws)
     flat = helpers.flatten_results(res)
     if draws == "torch":

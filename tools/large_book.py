@@ -84,8 +84,9 @@ def main():
     from mcre import binding as B
     ns = cases.Namespace()
     base = dict(european=39400, binary=1000, basket=1000, asian=2000, barrier=4000, american=1800, flexicall=700)
-    if not args.cva and args.exposure_points == 0:
-        base["storage"] = 100        # the PV book of the reference carries 100 gas storages (PV is their only metric here)
+    # the reference's PV book carries 100 gas storages, its exposure and CVA books 10 of their 5000 products
+    # (ee_performance_large_netting_set.py:36, cva_perfprmance_large_netting_set.py:78)
+    base["storage"] = 100
     counts = {k: max(1, int(round(v * args.scale))) for k, v in base.items()}
     ids = [f"asset_{i}" for i in range(4)]
     corr = np.full((4, 4), 0.35) + 0.65 * np.eye(4)
