@@ -207,9 +207,12 @@ class SimulationController:
         from mcre.storage import StorageBackend
         if StorageBackend.supports(self):
             return StorageBackend(self)
-        from mcre.irc import IrcBackend
-        if IrcBackend.supports(self):
-            return IrcBackend(self)
+        from mcre.irc import IrcBackend, with_single_exercise_proxies
+        view = with_single_exercise_proxies(self)
+        if view is not self:
+            view._proxy_parent = self
+        if IrcBackend.supports(view):
+            return IrcBackend(view)
         from mcre.equity import EquityBackend
         if EquityBackend.supports(self):
             return EquityBackend(self)

@@ -458,6 +458,17 @@ extern "C" int mcre_irc_create(const mcre_irc_desc *c, mcre_irc_plan **out) {
   d.n_sets = c->n_sets; d.n_expo = c->n_expo; d.n_metric = c->n_metric; d.acc_flags = c->acc_flags;
   d.set_fix = p->set_fix.p; d.set_float = p->set_float.p; d.set_threshold = p->set_threshold.p;
   d.set_flags = p->set_flags.p; d.set_lag = p->set_lag.p;
+  {
+    int max_lag = 0;
+    for (size_t k = 0; k < (size_t)c->n_sets * c->n_metric; ++k) max_lag = std::max(max_lag, (int)c->set_lag[k]);
+    // the general template keeps MCRE_IRC_MAX_LAG exposures per path in registers; the value-only kernel a ring in shared memory
+    const bool general = c->nt != 0 || n_berm != 0;
+    if (max_lag >= (general ? MCRE_IRC_MAX_LAG : 64)) { mcre_irc_destroy(p); return fail(-3, "irc: MPoR look-back of %s%lld exposure dates is too long for this plan", "", max_lag); }
+    p->max_lag = max_lag;
+    d.ring_depth = 2;
+    while (d.ring_depth <= max_lag) d.ring_depth *= 2;
+    if (general && d.ring_depth < MCRE_IRC_MAX_LAG) d.ring_depth = MCRE_IRC_MAX_LAG;
+  }
   d.expo_coef = p->expo_coef.p; d.expo_basis = p->expo_basis.p; d.cva_coef = p->cva_coef.p; d.lgd = c->lgd;
   d.n_units = c->n_units; d.n_reg = c->n_reg;
   d.unit_fix = p->unit_fix.p; d.unit_float = p->unit_float.p; d.reg_basis = p->reg_basis.p;
@@ -641,6 +652,7 @@ extern "C" int mcre_irc_mainsim(mcre_irc_plan *p, const mcre_rng *rng, const mcr
     const long long n_chunks_v = (sh.n_paths + sh.chunk - 1) / sh.chunk;
     return mcre_tree_reduce(d_partial, n_chunks_v, mcre_irc_main_slots(p), d_acc, stream);
   }
+  if (p->max_lag >= MCRE_IRC_MAX_LAG) return fail(-3, "irc: MPoR look-back too long for the general kernel%s", "");
   rc = p->d.n_berm > 0 ? irc_dispatch_main_berm(p, r, sh, d_partial, d_spill, d_shift, st)
                        : irc_dispatch_main<false>(p, r, sh, d_partial, d_spill, d_shift, st);
   if (rc) return rc;

@@ -42,6 +42,7 @@ struct IrcDev {
   // hybrid books (mcre/hybrid.py): the numeraire is another model's deterministic money-market account,
   // exp(ext_rate (t - t0)) (model_config.py:44-47, numeraire_model_idx), accumulated step by step like the path's own;
   // pv_spill [n_sets][n_paths]: per-path discounted cashflow totals (mcre_irc_set_pv_spill)
+  int ring_depth;          // value-only kernel: slots of the exposure look-back ring (power of two > largest MPoR lag)
   int ext_num, ext_slot;   // ext_slot: tangent slot of the external rate (-1: none)
   double ext_rate;
   double *pv_spill;
@@ -552,6 +553,7 @@ struct mcre_irc_plan {
   size_t expo_coef_count = 0;
   bool cva_only = false;
   bool any_collateral = false;   // some netting set of the plan is MPoR-collateralised
+  int max_lag = 0;               // largest MPoR look-back of the plan, in exposure dates
   DevArray<int> berm_set, date_ex_off, ex_unit, ex_last, ex_term_off;
   DevArray<double> berm_strike, berm_sign, ex_const, term_coef, term_w, ex_basis, ex_coef, berm_expo_coef;
   size_t ex_coef_count = 0, berm_expo_count = 0;

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
   const int n_slots = (P.n_metric + 1) * NVB;
   double *acc = smem;                           // [n_slots]
   double *stage = acc + n_slots;                // [2][NVR][128]
-  double *ring = stage + 2 * NVR * 128;         // [MCRE_IRC_MAX_LAG][NS][128 * PP]: exposure look-back
+  double *ring = stage + 2 * NVR * 128;         // [P.ring_depth][NS][128 * PP]: exposure look-back
+  const int ring_mask = P.ring_depth - 1;       // (depth: a power of two above the largest MPoR lag of the plan)
   const int tid = threadIdx.x;
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   const int DR = (DATE_HDR + 2 * W + 3 * W * P.n_sets + 1) & ~1;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
       if (any_coll) {
         // exposures before the first exposure date count as zero (netting_set.py:139-146)
 #pragma unroll
-        for (int l = 0; l < MCRE_IRC_MAX_LAG; ++l)
+        for (int l = 0; l < P.ring_depth; ++l)
 #pragma unroll
           for (int s = 0; s < NS; ++s)
             MCRE_VP ring[(l * NS + s) * (128 * PP) + p * 128 + tid] = 0.0;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
           for (int s = 0; s < NS; ++s) {
             // continuation / numeraire (controller.py:438-447)
             MCRE_VP cur[p][s] = fma(u[p], fma(u[p], cc[s][2], cc[s][1]), cc[s][0]) * invN[p];
-            if (sflags[s] & 1) { MCRE_VP ring[((e & (MCRE_IRC_MAX_LAG - 1)) * NS + s) * (128 * PP) + p * 128 + tid] = cur[p][s]; }
+            if (sflags[s] & 1) { MCRE_VP ring[((e & ring_mask) * NS + s) * (128 * PP) + p * 128 + tid] = cur[p][s]; }
           }
         }
         if (flags & MCRE_DATE_HAS_METRIC) {
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? 3 : 2) irc_value_kernel(IrcDev 
               // collateral = thresholded exposure at t_k - MPoR, looked up by exposure index; none before t0
               // (netting_set.py:136-146, 175-176)
               if (lag >= 0) {
-                const int slot = (e - lag) & (MCRE_IRC_MAX_LAG - 1);
+                const int slot = (e - lag) & ring_mask;
                 MCRE_VP {
                   const double delayed = ring[(slot * NS + s) * (128 * PP) + p * 128 + tid];
                   unsec[p] = cur[p][s] - (thr[s] != 0.0 ? val_threshold(delayed, thr[s]) : delayed);
@@ -319,7 +320,7 @@ static int launch_value(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh,
   constexpr int NVB = NS * 4, NVR = NVB < 4 ? 4 : NVB;
   // (the look-back ring is only there when a set is collateralised)
   const size_t smem = ((size_t)(d.n_metric + 1) * NVB + 2 * NVR * 128 +
-                       (p->any_collateral ? (size_t)MCRE_IRC_MAX_LAG * NS * 128 * VAL_PP : 0)) * sizeof(double);
+                       (p->any_collateral ? (size_t)d.ring_depth * NS * 128 * VAL_PP : 0)) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
 #define LAUNCHV(CIRV)                                                                                     \
   do {                                                                                                    \
@@ -327,7 +328,7 @@ static int launch_value(mcre_irc_plan *p, const RngDev &rng, const ShardDev &sh,
     if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     int per_sm = 1;                                                                                       \
     MCRE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, 128, smem));                      \
-    if (per_sm < 1) return fail(-3, "irc value kernel does not fit: too many metric dates%s", "");        \
+    if (per_sm < 1) return fail(-3, "irc value kernel does not fit: too many metric dates / too long an MPoR look-back%s", "");        \
     long long grid = (long long)sm_count() * per_sm;                                                      \
     if (grid > n_chunks) grid = n_chunks;                                                                 \
     ShardDev pilot_sh{0, 1, sh.chunk};                                                                    \

@@ -160,6 +160,47 @@ def is_rate_bermudan(p):
     return isinstance(p, BermudanOption) and isinstance(p.underlying, (Bond, InterestRateSwap))
 
 
+def is_rate_european(p):
+    from products.european_option import EuropeanOption
+    return isinstance(p, EuropeanOption) and isinstance(p.underlying, (Bond, InterestRateSwap))
+
+
+def with_single_exercise_proxies(ctrl):
+    """European options on bonds / swaps (european_option.py:45-68 with a rate underlying; the reference's
+    pv_european_bond_option.py, ee_pfe_swaption.py) are the one-date case of the exercise units the kernels have: the
+    payoff max(+-(U - K), 0) is "exercise iff positive" with no continuation after the only date, the exposure proxy before
+    it is the alive-state regression, and there is none from the exercise date on - the same numbers the reference's
+    one-state European product gives.  -> a view of the controller whose rate Europeans are replaced by one-date
+    BermudanOption proxies (own coefficient tensors), or the controller itself if it has none."""
+    import copy
+    if not any(is_rate_european(p) for p in ctrl.products):
+        return ctrl
+    view = copy.copy(ctrl)
+    view.regression_coeffs = list(ctrl.regression_coeffs)
+    proxies, sets = [], []
+    for ns in ctrl.netting_sets:
+        ns_view = copy.copy(ns)
+        ns_view.products = []
+        for p in ns.products:
+            if is_rate_european(p):
+                q = BermudanOption(p.underlying, [float(p.exercise_date[0])], float(p.strike[0]), p.option_type,
+                                   asset_id=p.asset_ids[0])
+                q.name, q.product_id = p.name if p.name else "EuropeanOption", p.product_id
+                # (quadratic basis of the kernels; a run that regresses with another basis is refused by the controller, a
+                # PV run - nothing regressed - may carry any regression_function, pv_european_bond_option.py:53)
+                q.regression_coeffs = torch.zeros((1, 2, 3), dtype=torch.float64)
+                view.regression_coeffs[p.product_id] = torch.zeros((len(ctrl.exposure_timeline), 2, 3), dtype=torch.float64)
+                proxies.append((p, q))
+                p = q
+            ns_view.products.append(p)
+        sets.append(ns_view)
+    view.netting_sets = sets
+    view.products = [p for ns in sets for p in ns.products]
+    view.requires_regression = any(view._product_requires_regression(p) for p in view.products)
+    view._european_proxies = proxies
+    return view
+
+
 def split_model(model):
     """(vasicek, cir or None, vas_index, cir_index) or None if not an IRC model."""
     if isinstance(model, VasicekModel):
@@ -493,9 +534,12 @@ class IrcBackend:
                 for m in range(n_metric):
                     if delayed[m] >= 0:
                         lag = int(c.metric_exposure_indices[m]) - delayed[m]
-                        if lag >= B.IRC_MAX_LAG:
+                        # the general template (tangents, exercise units) keeps the last IRC_MAX_LAG exposures of a path in
+                        # registers; the value-only kernel a ring in shared memory sized for the plan's largest lag
+                        general = nt != 0 or bool(berm_units)
+                        if lag >= (B.IRC_MAX_LAG if general else 64):
                             raise NotImplementedError(
-                                f"MPoR look-back spans {lag} exposure dates; the fused kernel keeps {B.IRC_MAX_LAG - 1}")
+                                f"MPoR look-back spans {lag} exposure dates; this kernel keeps {(B.IRC_MAX_LAG if general else 64) - 1}")
                         set_lag[r, m] = lag
             if cva_metric is not None and (ns.counterparty_id is None or ns.counterparty_id == cva_metric.counterparty_id):
                 set_flags[r] |= 2
@@ -718,11 +762,15 @@ class IrcBackend:
         c = self.c
         L = B.lib()
         n_pre = c.num_paths_presim
-        if n_pre <= 0:
-            raise ValueError("Exercise products need a pre-simulation: num_paths_presim must be positive.")
         expo_times = c.exposure_timeline.tolist() if c.risk_metrics.requires_exposure_profiles() else []
         ptl = prod.product_timeline.tolist()
         reg_times = sorted(set(prod.regression_timeline.tolist()) | set(expo_times))
+        if len(ptl) == 1 and not expo_times:
+            # one exercise date and no exposure dates (a European option's proxy in a PV run): nothing is regressed -
+            # there is no continuation after the only date - and the reference does not pre-simulate either
+            return np.zeros((len(reg_times), 3)), reg_times, np.array([self.basis_at(t) for t in reg_times]), None
+        if n_pre <= 0:
+            raise ValueError("Exercise products need a pre-simulation: num_paths_presim must be positive.")
         # tangents are needed only where the coefficients enter smoothly: the alive-state exposure proxies.  The
         # exercise policy is a hard indicator (zero derivative), so PV-only runs pre-simulate values only.
         with_tan = bool(self.nt) and bool(expo_times)
@@ -959,6 +1007,11 @@ class IrcBackend:
                 res["param_used"] = self.param_used
                 results[si] = res
         torch.cuda.synchronize(dev)
+        for orig, proxy in getattr(c, "_european_proxies", []):
+            # the one state of the European product = the alive state of its proxy
+            orig_coeffs = c.regression_coeffs[proxy.product_id]
+            if orig_coeffs.shape[0]:
+                c._proxy_parent.regression_coeffs[orig.product_id][:, 0, :] = orig_coeffs[:, 1, :]
         timings["path_generation"] = time.perf_counter() - t1
         timings["request_resolution"] = 0.0
         if dev_reg is not None:

@@ -66,6 +66,11 @@ class CIRPPModel(Model):
             surv *= math.exp(-haz[idx] * dt)
         return surv
 
+    def _market_survival_probability(self, t):
+        """Tensor form of market_survival under the reference's (private) name, which its scenario script calls
+        (tests/exposure_tests/cirpp_scenarios_vs_deterministic_hazard.py:93)."""
+        return torch.tensor(self.market_survival(float(torch.as_tensor(t).reshape(-1)[0])), dtype=FLOAT, device=device)
+
     # -- CIR building blocks (reference: cirpp.py:85-142) ---------------------
     @staticmethod
     def _h(p):
@@ -101,6 +106,14 @@ class CIRPPModel(Model):
         e = dexp(h * tau) - 1.0
         memo[tau] = (2.0 * e) / (2.0 * h + (kappa + h) * e)
         return memo[tau]
+
+    def lambda_t(self, t, y_t):
+        """Model intensity lambda(t) = y(t) + psi(t); in deterministic mode the state already is the market hazard
+        (reference: cirpp.py:240-244).  Host helper."""
+        y_t = torch.as_tensor(y_t, dtype=FLOAT)
+        if self.deterministic:
+            return y_t
+        return y_t + float(self.psi(self.dual_params(), float(torch.as_tensor(t).reshape(-1)[0])).v)
 
     def psi(self, p, t):
         """Deterministic shift psi(t) = lambda_mkt(t) + D(t) - y0 E(t)."""

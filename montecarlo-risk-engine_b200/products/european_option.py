@@ -5,7 +5,7 @@ The Black-Scholes closed form drives the controller's analytic PV / analytic exp
 shortcuts.  The semi-analytic Heston price (a host-side validation helper of the
 reference, european_option.py:146-242, used by tests/pytests/test_pv_european_option_heston.py)
 is provided through one characteristic function of log S_T in the branch-cut-free form;
-the Vasicek bond-option pricer stays out of scope."""
+the Vasicek bond-option closed form is a host helper next to it."""
 import math
 from products.product import *
 from products.product import _ft
@@ -48,6 +48,25 @@ class EuropeanOption(Product):
         if self.option_type == OptionType.CALL:
             return spot * _norm_cdf(d1) - disc_k * _norm_cdf(d2)
         return disc_k * _norm_cdf(-d2) - spot * _norm_cdf(-d1)
+
+    # -- option on a zero-coupon bond under Vasicek (reference: european_option.py:264-288) ----------------------
+    def compute_pv_bond_option_analytically(self, model):
+        """Jamshidian's closed form: with P(0,T) the discount bond to the exercise date T, P(0,S) to the bond's maturity
+        S and v = sigma sqrt((1 - exp(-2aT)) / (2a)) (1 - exp(-a(S - T))) / a the volatility of the forward bond price,
+        call = P(0,S) N(d1) - K P(0,T) N(d2), d1 = ln(P(0,S) / (K P(0,T))) / v + v / 2, d2 = d1 - v.  Host helper."""
+        from products.bond import Bond
+        if not isinstance(self.underlying, Bond):
+            raise TypeError("Expected self.underlying to be of type Bond")
+        a, r0, sigma, t0 = model.get_mean_reversion_speed(), model.get_rate(), model.get_volatility(), model.calibration_date
+        expiry, maturity = self.exercise_date, self.underlying.maturity
+        p_expiry = model.compute_bond_price(t0, expiry, r0)
+        p_maturity = model.compute_bond_price(t0, maturity, r0)
+        v = sigma * torch.sqrt((1.0 - torch.exp(-2.0 * a * (expiry - t0))) / (2.0 * a)) * (1.0 - torch.exp(-a * (maturity - expiry))) / a
+        d1 = torch.log(p_maturity / (p_expiry * self.strike)) / v + 0.5 * v
+        d2 = d1 - v
+        if self.option_type == OptionType.CALL:
+            return p_maturity * _norm_cdf(d1) - self.strike * p_expiry * _norm_cdf(d2)
+        return self.strike * p_expiry * _norm_cdf(-d2) - p_maturity * _norm_cdf(-d1)
 
     # -- semi-analytic Heston price (validation helper, host only) --------------
     def compute_pv_analytically_heston(self, model):

@@ -373,6 +373,28 @@ def hybrid_cva(ns_module, n_euro=8, n_bonds=4, n_swaps=40, spot=100.0, rate_leve
     return model, [m.NettingSet(name="large_cva_ns", products=prods, counterparty_id=cp)], metrics, np.linspace(0.0, horizon, n_expo)
 
 
+def rate_european(ns_module, kind="bond_option"):
+    """European options on rate underlyings under Vasicek: "bond_option" = a call on a zero-coupon bond, PV with pathwise
+    Greeks (tests/pv_tests/pv_european_bond_option.py:41-63); "swaption" = a European receiver swaption with EPE / PFE / PV
+    (tests/exposure_tests/ee_pfe_swaption.py:23-60), netted with a payer swap in a second, collateralised set."""
+    m = ns_module
+    if kind == "bond_option":
+        model = m.VasicekModel(calibration_date=0., rate=0.03, mean=0.05, mean_reversion_speed=0.02, volatility=0.02)
+        bond = m.Bond(startdate=0.0, maturity=2.0, notional=1.0, tenor=2.0, pays_notional=True, fixed_rate=0.0)
+        opt = m.EuropeanOption(underlying=bond, exercise_date=1.0, strike=0.93, option_type=m.OptionType.CALL)
+        return model, [m.NettingSet(name=opt.get_name(), products=[opt])], [m.PVMetric()], None
+    model = m.VasicekModel(calibration_date=0., rate=0.03, mean=0.05, mean_reversion_speed=0.02, volatility=0.02)
+
+    def swaption():
+        und = m.InterestRateSwap(startdate=0.0, enddate=2.0, notional=1.0, fixed_rate=0.03, tenor_fixed=0.25, tenor_float=0.25,
+                                 irs_type=m.IRSType.RECEIVER)
+        return m.EuropeanOption(underlying=und, exercise_date=1.5, strike=0.0, option_type=m.OptionType.CALL)
+    swap = m.InterestRateSwap(0.0, 2.0, 1.0, 0.03, 0.25, 0.25, m.IRSType.PAYER)
+    sets = [m.NettingSet(name="swaption_ns", products=[swaption()]),
+            m.NettingSet(name="hedged", products=[swaption(), swap], margin_period_of_risk=0.25, threshold=0.001)]
+    return model, sets, [m.EPEMetric(), m.PFEMetric(0.9), m.PVMetric()], np.linspace(0.0, 3.0, 25)
+
+
 def storage_exposure(ns_module, mixed=False):
     """Exposure profiles of a storage (tests/exposure_tests/ee_pfe_storage.py: EPE + PFE on an exposure grid that does not
     coincide with the daily decisions), here with ENE and PV, an MPoR-collateralised twin set, and - `mixed` - the storages
@@ -596,6 +618,8 @@ GOLDEN_CASES = {
     "storage_s2f_greeks_euler": (storage_small, dict(model_kind="s2f", num_states=5, end_day=12.0), dict(n_main=512, n_pre=512, num_steps=2, scheme="EULER", differentiate=True)),
     "storage_exposure": (storage_exposure, dict(), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="ANALYTICAL", differentiate=False, degree=3)),
     "storage_exposure_mixed": (storage_exposure, dict(mixed=True), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "bond_option_european": (rate_european, dict(), dict(n_main=8192, n_pre=0, num_steps=10, scheme="EULER", differentiate=True)),
+    "swaption_european": (rate_european, dict(kind="swaption"), dict(n_main=4096, n_pre=4096, num_steps=2, scheme="EULER", differentiate=False)),
     "storage_cva_mixed": (storage_cva_mixed, dict(), dict(n_main=1000, n_pre=1000, num_steps=2, scheme="EULER", differentiate=False)),
     "storage_mixed_book": (storage_mixed_book, dict(), dict(n_main=1000, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "heston_euler": (heston_euler_book, dict(), dict(n_main=4096, n_pre=0, num_steps=8, scheme="EULER", differentiate=True)),

@@ -5,6 +5,7 @@ Mirrors tests/pytests/test_european_option_hessian.py:65-108 and test_simulation
 import math
 
 import numpy as np
+import torch
 import pytest
 
 import cases
@@ -199,3 +200,21 @@ def test_regression_basis_other_than_quadratic_raises():
     sc = ns.SimulationController([ns.NettingSet(name="c", products=[opt])], bs, ns.RiskMetrics([ns.PVMetric()]), 64, 0, 1,
                                  ns.SimulationScheme.ANALYTICAL, regression_function=PolyomialRegression(3))
     assert not any(sc._product_requires_regression(p) for p in sc.products)
+
+
+def test_host_helpers_of_rate_and_credit_models_match_the_reference():
+    """Jamshidian's bond-option closed form (european_option.py:264-288) and the CIR++ intensity lambda(t) = y + psi(t)
+    (cirpp.py:240-244): values computed with the unmodified reference."""
+    ns = cases.Namespace()
+    m = ns.VasicekModel(calibration_date=0., rate=0.03, mean=0.05, mean_reversion_speed=0.02, volatility=0.02)
+    b = ns.Bond(startdate=0.0, maturity=2.0, notional=1.0, tenor=2.0, pays_notional=True, fixed_rate=0.0)
+    for ot, want in ((ns.OptionType.CALL, 0.03921194857833765), (ns.OptionType.PUT, 9.768465960734857e-05)):
+        o = ns.EuropeanOption(underlying=b, exercise_date=1.0, strike=0.93, option_type=ot)
+        assert abs(float(o.compute_pv_bond_option_analytically(m)) - want) < 1e-13
+    c = ns.CIRPPModel(calibration_date=0., asset_id="cp", hazard_rates=cases.HAZARDS, kappa=0.1, theta=0.01, volatility=0.02,
+                      y0=0.0001)
+    got = c.lambda_t(torch.tensor(1.7), torch.tensor([0.002, 0.01])).tolist()
+    assert np.allclose(got, [0.0100823457359637, 0.01808234541745138], rtol=1e-12, atol=0)
+    det = ns.CIRPPModel(calibration_date=0., asset_id="cp", hazard_rates=cases.HAZARDS, kappa=0.1, theta=0.01,
+                        volatility=0.02, y0=0.0001, deterministic=True)
+    assert det.lambda_t(1.7, torch.tensor([0.3], dtype=torch.float64)).tolist() == [0.3]
