@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
       R cf[NS], trk_a[NTRK], trk_b[NTRK];
       // Brownian-bridge barriers (value-only builds): previous monitored spot, running no-hit products
       double trk_c[NT == 0 ? NTRK : 1], trk_d[NT == 0 ? NTRK : 1], trk_e[NT == 0 ? NTRK : 1];
+      // ... tangent builds (Black-Scholes): the same three as duals, dynamically indexed - they live in local memory and are
+      // touched at the observation events of bridge-monitored barriers only
+      R brg_c[NT > 0 ? NTRK : 1], brg_d[NT > 0 ? NTRK : 1], brg_e[NT > 0 ? NTRK : 1];
       double numtan[NS];
       XR hist[NS][EQ_MAX_LAG];
 #pragma unroll
@@ -562,6 +565,36 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
                 }
               }
             }
+            if constexpr (NT > 0 && KIND == MCRE_EQ_BS) {
+              if (kind == EQ_BARRIER && (pflags & 4) && slot >= 0 && slot < NTRK) {
+                // the same crossing probabilities on duals: through both monitored spots and, in coef = -2 / (sigma^2
+                // maturity / n_obs), through the volatility (lane parameter 1): d coef / d sigma = -2 coef / sigma
+                const double *ed = P.ev_data + (size_t)e * EQ_EVD;
+                if (ef & EQ_EV_FIRST) { brg_d[slot] = T::lift(1.0); brg_e[slot] = T::lift(1.0); }
+                else {
+                  double ua, ub;
+                  if (P.bridge_u) {
+                    const size_t per = (size_t)rng.n_total * P.bridge_stride;
+                    const double *bu = P.bridge_u + (size_t)slot * 2 * per + (size_t)gpath * P.bridge_stride + (int)__ldg(ed + 2);
+                    ua = bu[0]; ub = bu[per];
+                  } else {
+                    ns.uniform_pair_kind((uint32_t)__ldg(ed + 0), 2u, ua, ub);
+                  }
+                  R coef = T::lift(__ldg(ed + 1));
+                  coef.d[1] = -2.0 * __ldg(ed + 1) / val(par[1]);
+                  const R prev = brg_c[slot];
+                  const double b1 = __ldg(pr + 9);
+                  const R p1 = r_exp(coef * r_log(prev / b1) * r_log(U / b1));
+                  brg_d[slot] = brg_d[slot] * (1.0 - r_fuzzy(p1 - ua, true, 0.05));
+                  if ((int)__ldg(pr + 12) > 0) {
+                    const double b2 = __ldg(pr + 11);
+                    const R p2 = r_exp(coef * r_log(prev / b2) * r_log(U / b2));
+                    brg_e[slot] = brg_e[slot] * (1.0 - r_fuzzy(p2 - ub, true, 0.05));
+                  }
+                }
+                brg_c[slot] = U;
+              }
+            }
           }
           if (!(ef & EQ_EV_PAY)) continue;
           R pay;
@@ -599,6 +632,17 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
                 };
                 double f = bridged(__ldg(pr + 9), (int)__ldg(pr + 10), nh1);
                 if (bt2 > 0) f *= bridged(__ldg(pr + 11), bt2, nh2);
+                pay = option_payoff(U, strike, sign) * f;
+              }
+            }
+            if constexpr (NT > 0 && KIND == MCRE_EQ_BS) {
+              if ((pflags & 4) && slot >= 0 && slot < NTRK) {
+                auto bridged = [&](double barrier, int bt, const R &nh) -> R {
+                  const R out = barrier_factor(mx, mn, barrier, bt <= 2 ? bt : bt - 2);
+                  return bt <= 2 ? out * nh : (1.0 - out) * (1.0 - nh);
+                };
+                R f = bridged(__ldg(pr + 9), (int)__ldg(pr + 10), brg_d[slot]);
+                if (bt2 > 0) f = f * bridged(__ldg(pr + 11), bt2, brg_e[slot]);
                 pay = option_payoff(U, strike, sign) * f;
               }
             }

@@ -343,9 +343,9 @@ class EquityBackend:
             else:
                 rec[0] = P_BARRIER
                 if getattr(p, "use_brownian_bridge", False):
-                    if self.nt or basket is not None or not isinstance(self.c.model, BlackScholesModel):
+                    if basket is not None or not isinstance(self.c.model, BlackScholesModel):
                         raise NotImplementedError("Brownian-bridge barrier monitoring: single Black-Scholes model, "
-                                                  "one monitored asset, value-only runs")
+                                                  "one monitored asset")
                     rec[6] = 4
                 rec[9], rec[10] = float(p.barrier1), _BARRIER_CODE[p.barrier_option_type1]
                 if p.barrier2 is not None and p.barrier_option_type2 is not None:

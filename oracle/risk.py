@@ -266,29 +266,30 @@ def cashflows(prod, i, ctx, state_matrix, regfn_degree, coeffs_of):
             # barrier_option.py:138-222: per interval the probability that the bridge between two monitored spots
             # crossed the barrier, exp(-2 ln(S_i / B) ln(S_i+1 / B) / (sigma^2 maturity / n_obs)), against one
             # uniform per (path, interval) - fuzzy (eps 0.05) like every indicator of this product
-            sigma = ad.val(M.volatility(ctx.model, ctx.p, asset_of(prod)))
+            # (all of it differentiable: the reference's autograd sees the spots and the volatility inside the crossing
+            # probabilities and the band-limited indicators)
+            sigma = M.volatility(ctx.model, ctx.p, asset_of(prod))
             dt_b = _f(prod.maturity) / len(obs)
-            sv = [ad.val(x) for x in spots]
 
             def nohit(barrier, second):
                 u = ctx.bridge(prod, len(obs) - 1, second)
-                keep = np.ones_like(sv[0])
+                keep = 1.0
                 for i in range(len(obs) - 1):
-                    prob = np.exp(-2.0 * np.log(sv[i] / barrier) * np.log(sv[i + 1] / barrier) / (sigma ** 2 * dt_b))
-                    keep = keep * (1.0 - ad.val(ad.fuzzy(prob - u[:, i], True, 0.05)))
+                    prob = ad.exp(-2.0 * ad.log(spots[i] / barrier) * ad.log(spots[i + 1] / barrier) / (sigma ** 2 * dt_b))
+                    keep = keep * (1.0 - ad.fuzzy(prob - u[:, i], True, 0.05))
                 return keep
 
             def bfactor(barrier, btype, second):
-                below = ad.val(ad.fuzzy(barrier - mx, True, 0.05))
-                above = ad.val(ad.fuzzy(mn - barrier, True, 0.05))
+                below = ad.fuzzy(barrier - mx, True, 0.05)
+                above = ad.fuzzy(mn - barrier, True, 0.05)
                 nh = nohit(barrier, second)
                 return {"UPANDOUT": below * nh, "DOWNANDOUT": above * nh, "UPANDIN": (1.0 - below) * (1.0 - nh),
                         "DOWNANDIN": (1.0 - above) * (1.0 - nh)}[btype.name]
 
-            pay = ad.val(pay) * bfactor(_f(prod.barrier1), prod.barrier_option_type1, False)
+            pay = pay * bfactor(_f(prod.barrier1), prod.barrier_option_type1, False)
             if prod.barrier2 is not None and prod.barrier_option_type2 is not None:
                 pay = pay * bfactor(_f(prod.barrier2), prod.barrier_option_type2, True)
-            return state_matrix, [pay / ad.val(ctx.numeraire(obs[0]))] * S
+            return state_matrix, [pay / ctx.numeraire(obs[0])] * S
         pay = pay * factor(_f(prod.barrier1), prod.barrier_option_type1)
         if prod.barrier2 is not None and prod.barrier_option_type2 is not None:
             pay = pay * factor(_f(prod.barrier2), prod.barrier_option_type2)

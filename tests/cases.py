@@ -568,6 +568,8 @@ GOLDEN_CASES = {
     "heston_path_dependent": (heston_path_dependent, dict(), dict(n_main=4096, n_pre=0, num_steps=4, scheme="QE", differentiate=True)),
     "bs_basket": (bs_basket, dict(), dict(n_main=8192, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "bs_bridge_barrier": (bs_bridge_barrier, dict(), dict(n_main=4096, n_pre=0, num_steps=2, scheme="EULER", differentiate=False)),
+    # ... with pathwise Greeks: the crossing probabilities and fuzzy hit indicators are differentiable (tests/pv_tests/pv_barrier_option.py)
+    "bs_bridge_barrier_greeks": (bs_bridge_barrier, dict(), dict(n_main=4096, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "flexicall_pv": (flexicall_bs, dict(), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "flexicall_exposure": (flexicall_bs, dict(exposure=True), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "mixed_book_pv": (mixed_book, dict(exposure=False), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="ANALYTICAL", differentiate=False)),

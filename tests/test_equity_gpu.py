@@ -289,6 +289,33 @@ def test_brownian_bridge_barrier_matches_reference_golden_and_oracle():
     assert float(res.get_results("up_in", "pv")[0]) <= float(plain.get_results("up_in", "pv")[0]) + 1e-12
 
 
+def test_brownian_bridge_barrier_greeks_match_reference_autograd_and_oracle():
+    """The same four options with differentiate=True (tests/pv_tests/pv_barrier_option.py): the crossing probabilities and
+    band-limited hit indicators carry tangents through both monitored spots and the volatility.  RNG compatibility mode
+    against the reference's autograd; native Philox against the oracle's duals."""
+    name = "bs_bridge_barrier_greeks"
+    gold = helpers.load_golden(name)
+    ns, model, sets, metrics, tl, rkw = helpers.build(name)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics), rkw["n_main"], rkw["n_pre"], rkw["num_steps"],
+                                 getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"])
+    sc.rng_compat = "torch"
+    res = sc.run_simulation()
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _check_values(helpers.flatten_results(res), ref, RTOL, name)
+    for s_ in gold["sets"]:
+        want = np.array(gold["derivatives"][f"{s_}|pv"][0])
+        got = np.array([float(g) for g in res.get_derivatives(s_, "pv")[0]])
+        helpers.assert_close(got, want, 1e-8, 1e-8 * float(np.max(np.abs(want))), f"{name} {s_} greeks")
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    _check_values(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8, name + " philox",
+                  err_rtol=1e-6)
+    for si, s_ in enumerate(gold["sets"]):
+        want = out["grads"][si][0][0]
+        got = np.array([float(g) for g in res.get_derivatives(s_, "pv")[0]])
+        helpers.assert_close(got, want, 1e-7, 1e-7 * float(np.max(np.abs(want))), f"{name} {s_} philox greeks")
+
+
 PROXY_GREEK_CASES = ["bs_eepe_greeks", "bs_proxy_greeks_mixed"]
 
 
