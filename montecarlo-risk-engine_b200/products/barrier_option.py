@@ -41,3 +41,33 @@ class BarrierOption(Product):
         Philox (kind 2); in RNG compatibility mode the reference's numpy default_rng(12345) stream is injected.
         Single Black-Scholes model, value-only runs."""
         self.use_brownian_bridge = True
+
+    def compute_pv_analytically(self, model):
+        """Continuously monitored single-barrier calls under Black-Scholes (Reiner-Rubinstein; reference:
+        barrier_option.py:245-301, the benchmark of tests/pv_tests/pv_barrier_option.py): up-and-out with strike below
+        the barrier, down-and-out with strike above it.  With x -> d(x) = (ln x + (r + sigma^2 / 2) T) / (sigma sqrt T),
+        N+ = N(d(.)), N- = N(d(.) - sigma sqrt T) and the reflection image B^2 / (K S):
+          up-and-out    S [N+(S/K) - N+(S/B)] - S (B/S)^(1 + 2r/s^2) [N+(B^2/(KS)) - N+(B/S)]
+                        - K e^(-rT) {[N-(S/K) - N-(S/B)] - (S/B)^(1 - 2r/s^2) [N-(B^2/(KS)) - N-(B/S)]}      (S < B)
+          down-and-out  vanilla call - S (B/S)^(2r/s^2) [(B/S) N+(B^2/(KS)) - (K/S) e^(-rT) N-(B^2/(KS))]     (S > B)
+        Host helper; other barrier types return NotImplementedError like the reference."""
+        import math
+        S, r, sig = model.get_spot(), model.get_rate(), model.get_volatility()
+        B, K, T = self.barrier1, self.strike, self.maturity
+        vol = sig * torch.sqrt(T)
+        ncdf = lambda x: 0.5 * torch.erfc(-x / math.sqrt(2.0))   # noqa: E731
+        plus = lambda x: ncdf((torch.log(x) + (r + 0.5 * sig ** 2) * T) / vol)   # noqa: E731
+        minus = lambda x: ncdf((torch.log(x) + (r + 0.5 * sig ** 2) * T) / vol - vol)   # noqa: E731
+        disc_k = K * torch.exp(-r * T)
+        image = B ** 2 / (K * S)
+        if self.option_type != OptionType.CALL:
+            return NotImplementedError(f"Analytical method for {self.barrier_option_type1} {self.option_type} not yet implemented")
+        if self.barrier_option_type1 == BarrierOptionType.UPANDOUT:
+            spot_leg = S * ((plus(S / K) - plus(S / B)) - (B / S) ** (1.0 + 2.0 * r / sig ** 2) * (plus(image) - plus(B / S)))
+            strike_leg = disc_k * ((minus(S / K) - minus(S / B)) - (S / B) ** (1.0 - 2.0 * r / sig ** 2) * (minus(image) - minus(B / S)))
+            return (S < B) * (spot_leg - strike_leg)
+        if self.barrier_option_type1 == BarrierOptionType.DOWNANDOUT:
+            vanilla = S * plus(S / K) - disc_k * minus(S / K)
+            mirror = (B / S) * plus(image) - (K / S) * torch.exp(-r * T) * minus(image)
+            return (S > B) * (vanilla - S * (B / S) ** (2.0 * r / sig ** 2) * mirror)
+        return NotImplementedError(f"Analytical method for {self.barrier_option_type1} not yet implemented")

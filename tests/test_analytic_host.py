@@ -218,3 +218,15 @@ def test_host_helpers_of_rate_and_credit_models_match_the_reference():
     det = ns.CIRPPModel(calibration_date=0., asset_id="cp", hazard_rates=cases.HAZARDS, kappa=0.1, theta=0.01,
                         volatility=0.02, y0=0.0001, deterministic=True)
     assert det.lambda_t(1.7, torch.tensor([0.3], dtype=torch.float64)).tolist() == [0.3]
+
+
+def test_barrier_closed_forms_match_the_reference():
+    """Reiner-Rubinstein up-and-out / down-and-out calls (barrier_option.py:245-301): values of the unmodified reference."""
+    ns = cases.Namespace()
+    B = ns.BarrierOptionType
+    for S0, bar, K, bt, want in ((100.0, 120.0, 100.0, B.UPANDOUT, 0.4093649419852321), (110.0, 130.0, 95.0, B.UPANDOUT, 1.773254975855977),
+                                 (100.0, 85.0, 100.0, B.DOWNANDOUT, 9.679474963397013), (125.0, 120.0, 100.0, B.UPANDOUT, 0.0)):
+        m = ns.BlackScholesModel(0, S0, 0.03, 0.25)
+        p = ns.BarrierOption(startdate=0.0, maturity=1.5, strike=K, num_observation_timepoints=10, option_type=ns.OptionType.CALL,
+                             barrier1=bar, barrier_option_type1=bt)
+        assert abs(float(p.compute_pv_analytically(m)) - want) < 1e-12
