@@ -343,22 +343,22 @@ typedef struct {
    * flexicall.py:56-160; prod[13] = number of rights, the tracker holds the rights left): per event (same
    * indexing as ev_prod) 16 doubles: [0..2] c0, c1, c2 of the continuation value of state 1 in
    * u = (x - shift) * scale, [3] shift, [4] scale, [5] 1/numeraire(t), [6] d(1/numeraire)/d rate, [7] last-date
-   * flag, [8..10] / [11..13] coefficients of states 2 / 3, [14] strike of this exercise date;
+   * flag, [14] strike of this exercise date, [16 + 3 (s - 2) ..] coefficients of states s = 2 .. 6 (32 doubles per event);
    * prod_x [n_prod][n_assets]: weights picking the explanatory variable x (spot of the option's asset). */
   const double *ev_data;
   const double *prod_x;
-  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op, 16 doubles:
+  /* exposure profiles (n_expo = 0: PV only).  Per internal exposure date and product an exposure op, 32 doubles:
    * type 1 = analytic Black-Scholes value of a European option (european_option.py:123-145): [1, time to maturity,
    * 1/numeraire(t), ...]; type 2 = regression proxy c(u) / numeraire (controller.py:438-447), u = (x - shift) scale,
    * x = spot picked by prod_x: [2, c0, 1/numeraire(t), c1, c2, shift, scale, pad]; type 3 = the same for an exercise
-   * product, with the coefficients of its current state (rights left; [8..10] / [11..13] for states 2 / 3; no
+   * product, with the coefficients of its current state (rights left; [16 + 3 (s - 2) ..] for states s = 2 .. 6; no
    * exposure in state 0); type 0 = none.
    * Netting-set terms as in mcre_irc_desc.  acc_flags: MCRE_ACC_POS /
    * NEG / SPILL.  Adds [n_metric][NS][4] = sum(pos-c), sum((pos-c)^2), sum(neg-c'), sum((neg-c')^2) to the slots. */
   int32_t n_expo, n_metric, acc_flags;
   const int32_t *date_expo;     /* [n_dates] internal exposure index or -1 */
   const int32_t *date_metric;   /* [n_dates] metric-date index or -1       */
-  const double *xp;             /* [n_expo][n_prod][16]                    */
+  const double *xp;             /* [n_expo][n_prod][32]                    */
   const double *set_threshold;  /* [n_sets]                                */
   const int32_t *set_flags;     /* [n_sets] bit0 collateralised            */
   const int32_t *set_lag;       /* [n_sets][n_metric] exposure-index lag of the collateral date, -1: none */
@@ -489,21 +489,22 @@ typedef struct { const double *x; const float *v; double nk, shift, scale; } mcr
 int mcre_lsm_moments_batch(int64_t n_jobs, const mcre_lsm_job *jobs, int64_t n, int32_t chunk_paths,
                            double *d_partial, double *d_moments, void *stream);
 /* mcre_lsm_step_states for MANY products in one launch (the lock-step backward inductions of a book: one job per
- * product and round): d_moments [n_jobs][14] (row layout of the 3-rights step, unused tail zero), bit-identical to the
- * per-product calls; d_partial [ceil(n / chunk_paths)][n_jobs][14].  coef: [3][3] continuation coefficients of the
+ * product and round): d_moments [n_jobs][23] (row layout of the 6-rights step, unused tail zero), bit-identical to the
+ * per-product calls; d_partial [ceil(n / chunk_paths)][n_jobs][23].  coef: [6][3] continuation coefficients of the
  * product date (has_coef = 0: none); imm NULL: no exercise update.  `jobs` is a host array of device pointers. */
+#define MCRE_LSM_MAX_RIGHTS 6   /* exercise rights of a product (FlexiCall); state = rights left */
 typedef struct {
   int32_t n_rights, has_coef;
   const double *xk, *nk;
   double shift_k, scale_k;
   const double *xi, *ni, *imm;
-  double coef[9];
+  double coef[3 * MCRE_LSM_MAX_RIGHTS];
   double shift_i, scale_i;
   float *value;
 } mcre_lsm_step_job;
 int mcre_lsm_step_batch(int64_t n_jobs, const mcre_lsm_step_job *jobs, int64_t n, int32_t chunk_paths,
                         double *d_partial, double *d_moments, void *stream);
-/* The same with n_rights = 1..3 exercise rights (FlexiCall, src/products/flexicall.py:56-160): the product state
+/* The same with n_rights = 1..6 exercise rights (FlexiCall, src/products/flexicall.py:56-160): the product state
  * is the number of rights left, d_value is [n_rights][n] (state s at row s-1; state 0 carries nothing),
  * coef_i host [n_rights][3] (continuation of state s at product date i), d_moments [5 + 3 n_rights]:
  *   ex_s = imm_i + cont_i(s-1) > cont_i(s), cont(0) = 0;  V_s <- fp32(fp32(ex_s ? imm_i/N_i : 0) + (ex_s ? V_{s-1} : V_s))

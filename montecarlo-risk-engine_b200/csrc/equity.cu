@@ -97,10 +97,10 @@ struct EqDev {
   // every path per metric date, [n_metric][n_paths]; mcre_eq_cva_paths combines them with the unsecured exposures
   double *cva_w;
 };
-constexpr int EQ_XP = 16;
+constexpr int EQ_XP = 32;      // doubles per exposure record: [0..7] type, state-1 coefficients, basis, numeraire; [16 + 3 (st - 2)] states 2..6
 constexpr int EQ_PF = 8;     // exposure records prefetched ahead of the walk (measured: 8 ahead -7 % on the 5k-product CVA book, 32 ahead no gain)
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int EQ_EVD = 16;  // doubles per event record (exercise events: see mcre_eq_desc.ev_data)
+constexpr int EQ_EVD = 32;  // doubles per event record ([16 + 3 (st - 2)]: continuation coefficients of states 2..6) (exercise events: see mcre_eq_desc.ev_data)
 constexpr int EQ_MAX_LAG = 4;
 constexpr int EQ_SPNZ = 8;   // non-zeros kept per sparse correlation row
 
@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
               }
               if (xw != 0.0 && st > 0) {
                 const double u = (Sv - __ldg(op + 5)) * __ldg(op + 6);
-                const double c0 = st == 1 ? __ldg(op + 1) : __ldg(op + 8 + 3 * (st - 2));
-                const double c1 = st == 1 ? __ldg(op + 3) : __ldg(op + 9 + 3 * (st - 2));
-                const double c2 = st == 1 ? __ldg(op + 4) : __ldg(op + 10 + 3 * (st - 2));
+                const double c0 = st == 1 ? __ldg(op + 1) : __ldg(op + 16 + 3 * (st - 2));
+                const double c1 = st == 1 ? __ldg(op + 3) : __ldg(op + 17 + 3 * (st - 2));
+                const double c2 = st == 1 ? __ldg(op + 4) : __ldg(op + 18 + 3 * (st - 2));
                 v = (c0 + u * (c1 + u * c2)) * __ldg(op + 2);
               }
               const double tot2 = group_sum(v, base, A);
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
             const bool lastd = __ldg(ed + 7) != 0.0;                   // no continuation after the last date
             auto cont_of = [&](int st) -> double {
               if (lastd || st <= 0) return 0.0;
-              const double *c = st == 1 ? ed : ed + 8 + 3 * (st - 2);
+              const double *c = st == 1 ? ed : ed + 16 + 3 * (st - 2);
               return __ldg(c + 0) + u * (__ldg(c + 1) + u * __ldg(c + 2));
             };
             const R imm = option_payoff(U, __ldg(ed + 14), sign);

@@ -20,11 +20,11 @@
 
 namespace mcre {
 
-constexpr int LSM_MAX_RIGHTS = 3;
+constexpr int LSM_MAX_RIGHTS = MCRE_LSM_MAX_RIGHTS;
 
 struct LsmCoef { double c[LSM_MAX_RIGHTS][3]; };
 
-// R exercise rights (1: Bermudan / American, up to 3: FlexiCall, src/products/flexicall.py:56-160).  The
+// R exercise rights (1: Bermudan / American, up to 6: FlexiCall, src/products/flexicall.py:56-160).  The
 // product state is the number of rights left; the roll keeps one float32 running value per path and state
 // s = 1..R (value[s-1][n]; state 0 carries nothing).  Exercise update of product date i:
 //     ex_s = imm_i + cont_i(s-1) > cont_i(s)                       (hard indicator, cont(0) = 0)
@@ -146,7 +146,7 @@ struct LsmStepJob {
   const double *xk, *nk;
   double shift_k, scale_k;
   const double *xi, *ni, *imm;
-  double coef[9];
+  double coef[3 * LSM_MAX_RIGHTS];
   double shift_i, scale_i;
   float *value;
 };
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256) lsm_step_batch_kernel(const LsmStepJob *_
     if (threadIdx.x >= 5 + 3 * R && threadIdx.x < LSM_NV_MAX) out[threadIdx.x] = 0.0;
 #define LSM_ITEM(RV) lsm_step_item<RV>(job->xk, job->nk, job->shift_k, job->scale_k, job->xi, job->ni, job->imm, job->has_coef, \
                                        cf, job->shift_i, job->scale_i, job->value, n, chunk, ch, acc, stage, out)
-    if (R == 1) LSM_ITEM(1); else if (R == 2) LSM_ITEM(2); else LSM_ITEM(3);
+    if (R == 1) LSM_ITEM(1); else if (R == 2) LSM_ITEM(2); else if (R == 3) LSM_ITEM(3); else if (R == 4) LSM_ITEM(4);
+    else if (R == 5) LSM_ITEM(5); else LSM_ITEM(6);
 #undef LSM_ITEM
   }
 }
@@ -289,7 +290,7 @@ extern "C" int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const 
                                     const double *coef_i, double shift_i, double scale_i, float *d_value, int64_t n,
                                     int32_t chunk_paths, double *d_partial, double *d_moments, void *stream) {
   if (!d_xk || !d_nk || !d_value || !d_partial || !d_moments) return fail(-1, "null argument%s", "");
-  if (n_rights < 1 || n_rights > LSM_MAX_RIGHTS) return fail(-3, "lsm: 1..3 exercise rights are supported%s", "");
+  if (n_rights < 1 || n_rights > LSM_MAX_RIGHTS) return fail(-3, "lsm: 1..6 exercise rights are supported%s", "");
   if (d_imm && (!d_xi || !d_ni)) return fail(-1, "lsm: exercise update needs x_i and N_i%s", "");
   if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
   cudaStream_t st = (cudaStream_t)stream;
@@ -308,7 +309,8 @@ extern "C" int mcre_lsm_step_states(int32_t n_rights, const double *d_xk, const 
   lsm_step_kernel<RV><<<(unsigned)grid, 256, 0, st>>>(d_xk, d_nk, shift_k, scale_k, d_xi, d_ni, d_imm,          \
                                                       coef_i != nullptr, cf, shift_i, scale_i, d_value, n,     \
                                                       chunk_paths, d_partial)
-  if (n_rights == 1) LSM_LAUNCH(1); else if (n_rights == 2) LSM_LAUNCH(2); else LSM_LAUNCH(3);
+  if (n_rights == 1) LSM_LAUNCH(1); else if (n_rights == 2) LSM_LAUNCH(2); else if (n_rights == 3) LSM_LAUNCH(3);
+  else if (n_rights == 4) LSM_LAUNCH(4); else if (n_rights == 5) LSM_LAUNCH(5); else LSM_LAUNCH(6);
 #undef LSM_LAUNCH
   MCRE_LAUNCHED();
   return mcre_tree_reduce(d_partial, n_chunks, nv, d_moments, stream);
@@ -370,7 +372,7 @@ extern "C" int mcre_lsm_step_batch(int64_t n_jobs, const mcre_lsm_step_job *jobs
   if (chunk_paths <= 0 || chunk_paths % 256 != 0) return fail(-2, "lsm: chunk_paths must be a positive multiple of 256%s", "");
   static_assert(sizeof(LsmStepJob) == sizeof(mcre_lsm_step_job), "job record layout");
   for (int64_t j = 0; j < n_jobs; ++j) {
-    if (jobs[j].n_rights < 1 || jobs[j].n_rights > LSM_MAX_RIGHTS) return fail(-3, "lsm: 1..3 exercise rights are supported%s", "");
+    if (jobs[j].n_rights < 1 || jobs[j].n_rights > LSM_MAX_RIGHTS) return fail(-3, "lsm: 1..6 exercise rights are supported%s", "");
     if (!jobs[j].xk || !jobs[j].nk || !jobs[j].value) return fail(-1, "lsm batch: null job array%s", "");
     if (jobs[j].imm && (!jobs[j].xi || !jobs[j].ni)) return fail(-1, "lsm: exercise update needs x_i and N_i%s", "");
   }

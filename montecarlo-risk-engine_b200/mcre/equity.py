@@ -54,7 +54,7 @@ def main_chunk(n_total):
 EQ_BS, EQ_HESTON, EQ_SCHWARTZ = 0, 1, 2
 P_EUROPEAN, P_BINARY, P_BASKET, P_ASIAN, P_BARRIER, P_EXERCISE = 0, 1, 2, 3, 4, 5
 EV_OBSERVE, EV_PAY, EV_FIRST, EV_EXERCISE = 1, 2, 4, 8
-EQ_PR, EQ_PAR, EQ_MAX_SETS, EQ_XP, EQ_EVD, EQ_MAX_LAG, EQ_MAX_RIGHTS = 16, 8, 4, 16, 16, 4, 3
+EQ_PR, EQ_PAR, EQ_MAX_SETS, EQ_XP, EQ_EVD, EQ_MAX_LAG, EQ_MAX_RIGHTS = 16, 8, 4, 32, 32, 4, 6
 
 
 def eq_ntrk(nt):
@@ -498,7 +498,7 @@ class EquityBackend:
                     coef, basis = self.exercise_coef[id(p)]          # [n_ex, rights, 3], [n_ex, 2]
                     row[0:3], row[3:5] = coef[i, 0], basis[i]
                     for st in range(1, coef.shape[1]):
-                        row[8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[i, st]
+                        row[16 + 3 * (st - 1):19 + 3 * (st - 1)] = coef[i, st]
                     row[5], row[6] = self._inv_numeraire(dates[di])
                     row[7] = 1.0 if i == len(p.product_timeline) - 1 else 0.0
                     row[14] = exercise_strikes(p)[i]
@@ -606,7 +606,7 @@ class EquityBackend:
                     xp[on, pi, 3], xp[on, pi, 4] = coef[on, 0, 1], coef[on, 0, 2]
                     xp[on, pi, 5], xp[on, pi, 6] = basis[on, 0], basis[on, 1]
                     for st in range(1, coef.shape[1]):
-                        xp[on, pi, 8 + 3 * (st - 1):11 + 3 * (st - 1)] = coef[on, st]
+                        xp[on, pi, 16 + 3 * (st - 1):19 + 3 * (st - 1)] = coef[on, st]
                 else:
                     coef, basis = self.expo_coef[id(p)]              # [n_expo, 3], [n_expo, 2]
                     on = np.any(coef != 0.0, axis=1)

@@ -113,14 +113,15 @@ def regression_tangents(G, rhs, coef, tm):
     return out
 
 
-LSM_MAX_NV = 5 + 3 * 3   # moments of the widest step (3 exercise rights)
+LSM_MAX_RIGHTS = 6         # MCRE_LSM_MAX_RIGHTS (include/mcre.h)
+LSM_MAX_NV = 5 + 3 * LSM_MAX_RIGHTS   # moments of the widest step
 
 
 #: mcre_lsm_step_job (include/mcre.h)
 STEP_JOB = np.dtype([("n_rights", "i4"), ("has_coef", "i4"), ("xk", "u8"), ("nk", "u8"), ("shift_k", "f8"), ("scale_k", "f8"),
-                     ("xi", "u8"), ("ni", "u8"), ("imm", "u8"), ("coef", "f8", (9,)), ("shift_i", "f8"), ("scale_i", "f8"),
+                     ("xi", "u8"), ("ni", "u8"), ("imm", "u8"), ("coef", "f8", (3 * LSM_MAX_RIGHTS,)), ("shift_i", "f8"), ("scale_i", "f8"),
                      ("value", "u8")])
-assert STEP_JOB.itemsize == 160
+assert STEP_JOB.itemsize == 88 + 24 * LSM_MAX_RIGHTS
 
 
 class DeferredSteps:
@@ -329,7 +330,7 @@ def run_backward_inductions(gens):
         m = RT.all_reduce_tree(torch.stack([pending[k] for k in keys])).cpu().numpy()      # [K, LSM_MAX_NV]
         G = m[:, [[0, 1, 2], [1, 2, 3], [2, 3, 4]]]
         # one batched solve per state for all products of the round (states a product does not have carry zeros)
-        host = np.stack([solve_normal_equations_batch(G, m[:, 5 + 3 * s:8 + 3 * s]) for s in range(3)], axis=1)
+        host = np.stack([solve_normal_equations_batch(G, m[:, 5 + 3 * s:8 + 3 * s]) for s in range(LSM_MAX_RIGHTS)], axis=1)
         for j, (k, row) in enumerate(zip(keys, host)):
             try:
                 pending[k] = gens[k].send((row, m[j]))

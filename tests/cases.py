@@ -108,11 +108,18 @@ def bs_basket(ns_module, euler=False):
 
 
 #: name -> (builder, builder kwargs, run kwargs)
-def flexicall_bs(ns_module, exposure=False):
+def flexicall_bs(ns_module, exposure=False, rights=2):
     """FlexiCall on Black-Scholes: 3 European calls, 2 exercise rights
-    (tests/pytests/test_single_product_executor_parity.py "flexicall" case)."""
+    (tests/pytests/test_single_product_executor_parity.py "flexicall" case); rights > 2: 8 calls of alternating strikes, of
+    which `rights` may be exercised (tests/exposure_tests/ee_pfe_flexicall.py: 4 rights)."""
     m = ns_module
     model = m.BlackScholesModel(0.0, 100.0, 0.03, 0.2, asset_id="asset")
+    if rights > 2:
+        unders = [m.EuropeanOption(m.Equity("asset"), 0.25 * (i + 1), 96.0 + 3.0 * (i % 4), m.OptionType.CALL, asset_id="asset")
+                  for i in range(8)]
+        flexi = m.FlexiCall(underlyings=unders, num_exercise_rights=rights, asset_id="asset")
+        sets = [m.NettingSet(name="flexicall", products=[flexi])]
+        return model, sets, [m.PVMetric(), m.EPEMetric(), m.PFEMetric(0.9)], np.linspace(0.0, 2.0, 9)
     flexi = m.FlexiCall(underlyings=[m.EuropeanOption(m.Equity("asset"), 0.5, 95.0, m.OptionType.CALL, asset_id="asset"),
                                      m.EuropeanOption(m.Equity("asset"), 1.0, 100.0, m.OptionType.CALL, asset_id="asset"),
                                      m.EuropeanOption(m.Equity("asset"), 1.5, 105.0, m.OptionType.CALL, asset_id="asset")],
@@ -572,6 +579,8 @@ GOLDEN_CASES = {
     "bs_bridge_barrier_greeks": (bs_bridge_barrier, dict(), dict(n_main=4096, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "flexicall_pv": (flexicall_bs, dict(), dict(n_main=4096, n_pre=4096, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "flexicall_exposure": (flexicall_bs, dict(exposure=True), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
+    "flexicall_4_rights": (flexicall_bs, dict(rights=4), dict(n_main=2048, n_pre=2048, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
+    "flexicall_6_rights": (flexicall_bs, dict(rights=6), dict(n_main=1024, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "mixed_book_pv": (mixed_book, dict(exposure=False), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "mixed_book_exposure": (mixed_book, dict(exposure=True), dict(n_main=512, n_pre=512, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "bs_exposure_greeks": (bs_exposure_greeks, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),

@@ -198,12 +198,12 @@ def test_hull_white_bermudan_swaption_extension_matches_oracle():
              1e-8, "hull-white bermudan", err_rtol=1e-6)
 
 
-FLEXI_CASES = ["flexicall_pv", "flexicall_exposure", "mixed_book_pv", "mixed_book_exposure"]
+FLEXI_CASES = ["flexicall_pv", "flexicall_exposure", "flexicall_4_rights", "flexicall_6_rights", "mixed_book_pv", "mixed_book_exposure"]
 
 
 @pytest.mark.parametrize("name", FLEXI_CASES)
 def test_flexicall_and_mixed_book_match_reference_golden(name):
-    """FlexiCall (src/products/flexicall.py: up to 3 exercise rights, state = rights left) alone and in the
+    """FlexiCall (src/products/flexicall.py: up to 6 exercise rights, state = rights left) alone and in the
     reference's mixed equity book (tests/pytests/test_netting_sets.py:375-528: Europeans, Americans, FlexiCall,
     barrier in one netting set), PV and EPE / PFE through state-dependent regression proxies.  The reference's
     own draws injected, outputs of the unmodified reference (tests/golden)."""
