@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev
   // the action leads to - none of them depends on the path (first profile: 315 warp instructions per (path, state)
   // with the moves recomputed per path, profiles/r02_storage_kernels.md)
   __shared__ double s_dv[3 * ST_MAX_S], s_w[3 * ST_MAX_S];
-  __shared__ int s_lo[3 * ST_MAX_S], s_hi[3 * ST_MAX_S];
+  __shared__ int s_lo[3 * ST_MAX_S], s_hi[3 * ST_MAX_S];      // (offsets of the neighbour states' rows in the tiles below)
   __shared__ double s_val[ST_MAX_S * ST_THREADS], s_grid[ST_MAX_S * ST_THREADS];
+  __shared__ double s_coef[2 + ST_MAX_S * ST_MAX_B];
   const int S = P.n_states, NB = P.n_basis, tid = threadIdx.x;
   const double *r = P.rec + (size_t)date * ST_REC;
   const bool last = __ldg(r + 10) != 0.0;
@@ -227,40 +228,60 @@ __global__ void __launch_bounds__(ST_THREADS) storage_backward_kernel(StorageDev
       double w;
       neighbours(m.ns[a], S, lo, hi, w);
       s_dv[a * ST_MAX_S + tid] = m.dv[a]; s_w[a * ST_MAX_S + tid] = w;
-      s_lo[a * ST_MAX_S + tid] = lo; s_hi[a * ST_MAX_S + tid] = hi;
+      s_lo[a * ST_MAX_S + tid] = lo * ST_THREADS; s_hi[a * ST_MAX_S + tid] = hi * ST_THREADS;
     }
   }
+  // the date's continuation coefficients once per block (second profile: 40 dependent read-only loads per path)
+  if (!last)
+    for (int i = tid; i < 2 + S * NB; i += ST_THREADS) s_coef[i] = coef[i];
   const long long p = (long long)blockIdx.x * blockDim.x + tid;
   const bool live = p < n;
   double spot = 0.0;
   if (live) {
     spot = x[p];
-    const double u = last ? 0.0 : (spot - __ldg(coef)) * __ldg(coef + 1);
-    for (int s = 0; s < S; ++s) {
-      s_val[s * ST_THREADS + tid] = value[(size_t)s * n + p];
-      s_grid[s * ST_THREADS + tid] = last ? 0.0 : poly(coef + 2 + s * NB, NB, u);
-    }
+    for (int s = 0; s < S; ++s) s_val[s * ST_THREADS + tid] = value[(size_t)s * n + p];   // (all loads in flight together)
   }
   __syncthreads();
   if (!live) return;
+  {
+    const double u = last ? 0.0 : (spot - s_coef[0]) * s_coef[1];
+    for (int s = 0; s < S; ++s) {
+      double g = 0.0;
+      if (!last) {
+        const double *c = s_coef + 2 + s * NB;
+        double pw = u;
+        g = c[0];
+        for (int k = 1; k < NB; ++k) { g = fma(c[k], pw, g); pw *= u; }
+      }
+      s_grid[s * ST_THREADS + tid] = g;
+    }
+  }
+  // (a thread reads only its own column of the tiles: no barrier needed between its writes and its reads)
   const double num = __ldg(P.numeraire + date);
   const double ci = __ldg(r + 6), cw = __ldg(r + 7);
   const double buy = spot + ci, sell = spot - cw;      // storage.py:246-253
+  const double *gcol = s_grid + tid, *vcol = s_val + tid;
+#pragma unroll 2
   for (int s = 0; s < S; ++s) {
     double pay[3], v[3];
     const double dv1 = s_dv[ST_MAX_S + s];
     pay[0] = -s_dv[s] * buy;
     pay[1] = -dv1 * (dv1 >= 0.0 ? buy : sell);
     pay[2] = -s_dv[2 * ST_MAX_S + s] * sell;
+    int lo[3], hi[3];
+    double w[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const double gl = s_grid[s_lo[a * ST_MAX_S + s] * ST_THREADS + tid], gh = s_grid[s_hi[a * ST_MAX_S + s] * ST_THREADS + tid];
-      v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(s_w[a * ST_MAX_S + s], __dsub_rn(gh, gl)));
+      lo[a] = s_lo[a * ST_MAX_S + s]; hi[a] = s_hi[a * ST_MAX_S + s]; w[a] = s_w[a * ST_MAX_S + s];
+      const double gl = gcol[lo[a]], gh = gcol[hi[a]];
+      v[a] = pay[a] + __dadd_rn(gl, __dmul_rn(w[a], __dsub_rn(gh, gl)));
     }
     const int a = best_of(v);
     const double pa = a == 0 ? pay[0] : a == 1 ? pay[1] : pay[2];
-    const double tl = s_val[s_lo[a * ST_MAX_S + s] * ST_THREADS + tid], th = s_val[s_hi[a * ST_MAX_S + s] * ST_THREADS + tid];
-    const double tail = __dadd_rn(tl, __dmul_rn(s_w[a * ST_MAX_S + s], __dsub_rn(th, tl)));
+    const int l = a == 0 ? lo[0] : a == 1 ? lo[1] : lo[2], h = a == 0 ? hi[0] : a == 1 ? hi[1] : hi[2];
+    const double ww = a == 0 ? w[0] : a == 1 ? w[1] : w[2];
+    const double tl = vcol[l], th = vcol[h];
+    const double tail = __dadd_rn(tl, __dmul_rn(ww, __dsub_rn(th, tl)));
     // float32 accumulator of the window (controller.py:331, 342); x / 1 is exact, so the division is skipped there
     const double step = (double)(float)(num == 1.0 ? pa : __ddiv_rn(pa, num));
     value[(size_t)s * n + p] = step + tail;
@@ -280,14 +301,26 @@ __global__ void __launch_bounds__(256) storage_moments_kernel(StorageDev P, doub
 #pragma unroll
   for (int k = 0; k < 2 * ST_MAX_B; ++k) acc[k] = 0.0;
   const long long base = (long long)blockIdx.x * chunk;
-  for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
-    const long long p = base + it;
-    if (p >= n) break;
-    const double u = (x[p] - centre) * inv_scale;
-    double w = row < S ? num * value[(size_t)row * n + p] : 1.0;
+  // four paths of a thread at a time: their loads are in flight together and their power chains interleave (one path at a
+  // time was a chain of dependent multiplies behind two dependent loads: 24 us for 2^18 paths, latency bound)
+  constexpr int IT = 4;
+  for (int it0 = threadIdx.x; it0 < chunk; it0 += IT * (int)blockDim.x) {
+    double u[IT], w[IT];
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+      const int it = it0 + j * (int)blockDim.x;
+      const long long p = base + it;
+      const bool ok = it < chunk && p < n;
+      u[j] = ok ? (x[p] - centre) * inv_scale : 0.0;
+      w[j] = ok ? (row < S ? num * value[(size_t)row * n + p] : 1.0) : 0.0;
+    }
 #pragma unroll
     for (int k = 0; k < 2 * ST_MAX_B; ++k)
-      if (k < nv) { acc[k] += w; w *= u; }
+      if (k < nv) {
+        acc[k] += (w[0] + w[1]) + (w[2] + w[3]);
+#pragma unroll
+        for (int j = 0; j < IT; ++j) w[j] *= u[j];
+      }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
