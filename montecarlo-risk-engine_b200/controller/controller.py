@@ -214,6 +214,9 @@ class SimulationController:
         if IrcBackend.supports(view):
             return IrcBackend(view)
         from mcre.equity import EquityBackend
+        from mcre.hybrid import EquityCreditGreeks
+        if EquityCreditGreeks.supports(self):
+            return EquityCreditGreeks(self)
         if EquityBackend.supports(self):
             return EquityBackend(self)
         from mcre.hybrid import HybridBackend

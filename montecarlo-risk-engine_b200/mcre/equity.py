@@ -203,7 +203,9 @@ class EquityBackend:
         self.A = len(self.assets)
         self.credit, self.credit_idx = credit_of(ctrl.model)
         if self.credit is not None:
-            if ctrl.differentiate:
+            if ctrl.differentiate and not getattr(ctrl, "_credit_passenger", False):
+                # (mcre/hybrid.py:EquityCreditGreeks runs the tangent pass with the credit factor as a value-only
+                # passenger of the joint draw and differentiates the metrics on per-path duals)
                 raise NotImplementedError("sensitivities of hybrid equity + credit runs are not implemented")
             if ctrl.simulation_scheme != SimulationScheme.EULER:
                 # same restriction as the reference: only Black-Scholes pairs have a joint exact covariance (model_config.py:216-221)

@@ -55,6 +55,150 @@ def _families(model):
     return bs, vas[0], (cir[0] if cir else None)
 
 
+def metric_gradients(c, values, tan, pv_grad, chunk, dev):
+    """Netting-set terms and metric parts on per-path duals (mcre_exposure_tangent_sums): `values[si]` = the value run's
+    dict of set si (exposures before netting terms "_expo", default weights "_cva_w"), tan[si] [parameters][exposure
+    date][path] the tangents of those exposures, pv_grad[si] the PV gradient.
+    -> per set {"pv": grad, "pos": [grad per metric date], "neg": [...], "cva": grad} over the flattened parameters."""
+    from metrics.metric import MetricType
+    L = B.lib()
+    n_par = len(c.model.model_params)
+    n_main = c.num_paths_mainsim
+    n_expo, n_metric = len(c.exposure_timeline), len(c.metric_exposure_timeline)
+    need_expo = c.risk_metrics.requires_exposure_profiles()
+    begin, count = RT.shard_range(n_main, chunk)
+    n = max(count, 1)
+    out = []
+    cva_metric = next((m for m in c.risk_metrics.metrics if m.metric_type == MetricType.CVA), None)
+    metric_expo = np.asarray(c.metric_exposure_indices.tolist(), dtype=np.int32)
+    for si, ns in enumerate(c.netting_sets):
+        res = {"pv": pv_grad[si]}
+        if need_expo:
+            lag = np.full(n_metric, -1, dtype=np.int32)
+            if ns.is_collateralized():
+                delayed = c.netting_set_delayed_exposure_indices[si].tolist()
+                for m in range(n_metric):
+                    if delayed[m] >= 0:
+                        lag[m] = int(metric_expo[m]) - delayed[m]
+            w = np.zeros(n_metric)
+            cva_w = values[si].get("_cva_w")
+            if cva_metric is not None and cva_w is not None:
+                # deterministic credit: the same weights on every path; every rank reads its first local path
+                w_local = cva_w[:, 0].clone() if count > 0 else torch.zeros(n_metric, dtype=torch.float64, device=dev)
+                w = RT.to_host(w_local) * (1.0 - cva_metric.recovery_rate)
+            n_chunks = (n + chunk - 1) // chunk
+            slots = n_metric * n_par * 3
+            partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
+            sums = torch.zeros(slots, dtype=torch.float64, device=dev)
+            me_k, me_p = B.as_ip(metric_expo)
+            lg_k, lg_p = B.as_ip(lag)
+            w_k, w_p = B.as_dp(w)
+            B.check(L.mcre_exposure_tangent_sums(values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par,
+                                                 n_metric, me_p, lg_p, int(ns.is_collateralized()), float(ns.threshold),
+                                                 w_p, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
+            sm = RT.to_host(RT.all_reduce_tree(sums)).reshape(n_metric, n_par, 3) / n_main
+            res["pos"] = [sm[m, :, 0] for m in range(n_metric)]
+            res["neg"] = [sm[m, :, 1] for m in range(n_metric)]
+            res["cva"] = sm[:n_metric - 1, :, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
+        out.append(res)
+    return out
+
+
+def attach_gradients(results, grads, used):
+    """Puts the gradients of metric_gradients next to the values of the value run's per-set dicts."""
+    for res, g in zip(results, grads):
+        res["pv"] = (res["pv"][0], g["pv"])
+        if "pos" in res:
+            res["pos"] = (res["pos"][0], g["pos"])
+        if "neg" in res:
+            res["neg"] = (res["neg"][0], g["neg"])
+        if "cva" in res and res["cva"][0] != (0.0, 0.0):
+            res["cva"] = (res["cva"][0], g["cva"])
+        res["param_used"] = lambda kind, used=used: used
+
+
+def _credit_checks(c, cir, what):
+    from metrics.metric import MetricType
+    if cir is not None and not cir.deterministic and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
+        raise NotImplementedError(f"sensitivities of the CVA of {what}: deterministic credit (the default weights of a "
+                                  "stochastic intensity carry tangents the equity launch does not have)")
+    if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
+        raise NotImplementedError(f"PFE sensitivities of {what}")
+
+
+class EquityCreditGreeks:
+    """differentiate=True on an equity book whose ModelConfig carries the counterparty's CIR++ model (CVA of equity
+    books, tests/exposure_tests/cva_perfprmance_large_netting_set.py with sensitivities): the value run is the equity
+    backend's accumulating path; a second pass on a plan with tangents - the credit factor rides along value-only, so the
+    joint draw and the paths are the same - leaves per-path exposure tangents, and metric_gradients differentiates netting
+    terms, positive parts and the CVA integrand.  The market parameters' sensitivities are complete; the credit model's
+    come back as None in its deterministic mode (outside the reference's autograd graph)."""
+
+    @staticmethod
+    def supports(ctrl):
+        from mcre.equity import EquityBackend, credit_of
+        return bool(ctrl.differentiate) and credit_of(ctrl.model)[0] is not None and EquityBackend.supports(ctrl)
+
+    def __init__(self, ctrl):
+        from mcre.equity import credit_of
+        self.c = ctrl
+        self.credit, self.credit_idx = credit_of(ctrl.model)
+        _credit_checks(ctrl, self.credit, "equity books against a credit model")
+
+    def _view(self, differentiate):
+        c = self.c
+        v = copy.copy(c)
+        v.differentiate = differentiate
+        v._credit_passenger = differentiate
+        v.regression_coeffs = list(c.regression_coeffs) if not differentiate else [rc.clone() for rc in c.regression_coeffs]
+        return v
+
+    def run(self):
+        from mcre.equity import EquityBackend, is_equity_exercise, main_chunk
+        c = self.c
+        dev = RT.compute_device()
+        t_start = time.perf_counter()
+        n_main, n_sets = c.num_paths_mainsim, len(c.netting_sets)
+        n_par = len(c.model.model_params)
+        n_expo = len(c.exposure_timeline)
+        need_expo = c.risk_metrics.requires_exposure_profiles()
+        chunk = main_chunk(n_main)
+        begin, count = RT.shard_range(n_main, chunk)
+        n = max(count, 1)
+
+        def presim(eb, view):
+            eb.presim_exercise_all([p for p in view.products if is_equity_exercise(p)], dev)
+            if need_expo:
+                reg = [p for p in view.products if not view._can_use_analytic_exposure_for_product(p) and not is_equity_exercise(p)]
+                if reg:
+                    eb.presim_regression(reg, dev)
+        view = self._view(False)
+        eb = EquityBackend(view)
+        presim(eb, view)
+        results = [eb._run_split_book(si, dev, n_main, n_par, chunk=chunk) for si in range(n_sets)]
+        tview = self._view(True)
+        et = EquityBackend(tview)
+        presim(et, tview)
+        tan = [torch.zeros((n_par, n_expo, n), dtype=torch.float64, device=dev) if need_expo else None for _ in range(n_sets)]
+        pv_grad = []
+        for si in range(n_sets):
+            accum_t, g_pv = et.exposure_tangent_pass(si, dev, n_main, chunk)
+            pv_grad.append(g_pv)
+            if need_expo:
+                for a, asset in enumerate(et.assets):
+                    for k, g in enumerate(asset.gmap):
+                        tan[si][g] += accum_t[:, a, k, :]
+        grads = metric_gradients(c, results, tan, pv_grad, chunk, dev)
+        used = [True] * n_par
+        offs = c.model.param_offsets()
+        for k in range(len(self.credit.model_params)):
+            used[offs[self.credit_idx] + k] = False
+        attach_gradients(results, grads, used)
+        torch.cuda.synchronize(dev)
+        total = time.perf_counter() - t_start
+        return results, {"preprocessing": 0.0, "path_generation": total, "request_resolution": 0.0}
+
+
 class HybridBackend:
     @staticmethod
     def supports(ctrl):
@@ -230,42 +374,7 @@ class HybridBackend:
                     tan[si][offs[b] + k] += accum_t[:, 0, k, :]
                 pv_grad[si][offs[b] + k] += g_pv[k]
 
-        # ---- netting-set terms and metric parts on the combined duals ---------------------------------------------
-        out = []
-        kinds = {m.metric_type for m in c.risk_metrics.metrics}
-        cva_metric = next((m for m in c.risk_metrics.metrics if m.metric_type == MetricType.CVA), None)
-        metric_expo = np.asarray(c.metric_exposure_indices.tolist(), dtype=np.int32)
-        for si, ns in enumerate(c.netting_sets):
-            res = {"pv": pv_grad[si]}
-            if need_expo:
-                lag = np.full(n_metric, -1, dtype=np.int32)
-                if ns.is_collateralized():
-                    delayed = c.netting_set_delayed_exposure_indices[si].tolist()
-                    for m in range(n_metric):
-                        if delayed[m] >= 0:
-                            lag[m] = int(metric_expo[m]) - delayed[m]
-                w = np.zeros(n_metric)
-                cva_w = values[si].get("_cva_w")
-                if cva_metric is not None and cva_w is not None:
-                    # deterministic credit: the same weights on every path; every rank reads its first local path
-                    w_local = cva_w[:, 0].clone() if count > 0 else torch.zeros(n_metric, dtype=torch.float64, device=dev)
-                    w = RT.to_host(w_local) * (1.0 - cva_metric.recovery_rate)
-                n_chunks = (n + chunk - 1) // chunk
-                slots = n_metric * n_par * 3
-                partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
-                sums = torch.zeros(slots, dtype=torch.float64, device=dev)
-                me_k, me_p = B.as_ip(metric_expo)
-                lg_k, lg_p = B.as_ip(lag)
-                w_k, w_p = B.as_dp(w)
-                B.check(L.mcre_exposure_tangent_sums(values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par,
-                                                     n_metric, me_p, lg_p, int(ns.is_collateralized()), float(ns.threshold),
-                                                     w_p, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
-                sm = RT.to_host(RT.all_reduce_tree(sums)).reshape(n_metric, n_par, 3) / n_main
-                res["pos"] = [sm[m, :, 0] for m in range(n_metric)]
-                res["neg"] = [sm[m, :, 1] for m in range(n_metric)]
-                res["cva"] = sm[:n_metric - 1, :, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
-            out.append(res)
-        return out
+        return metric_gradients(c, values, tan, pv_grad, chunk, dev)
 
     def run(self):
         from metrics.metric import MetricType
@@ -363,15 +472,7 @@ class HybridBackend:
             if self.cir_idx is not None:
                 for k in range(len(models[self.cir_idx].model_params)):
                     used[offs[self.cir_idx] + k] = False
-            for res, g in zip(results, grads):
-                res["pv"] = (res["pv"][0], g["pv"])
-                if "pos" in res:
-                    res["pos"] = (res["pos"][0], g["pos"])
-                if "neg" in res:
-                    res["neg"] = (res["neg"][0], g["neg"])
-                if "cva" in res and res["cva"][0] != (0.0, 0.0):
-                    res["cva"] = (res["cva"][0], g["cva"])
-                res["param_used"] = lambda kind, used=used: used
+            attach_gradients(results, grads, used)
         torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start
         return results, {"preprocessing": t_pre, "path_generation": total - t_pre, "request_resolution": 0.0}

@@ -589,6 +589,9 @@ GOLDEN_CASES = {
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "equity_cva_single_det": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=False)),
+    # sensitivities of CVA / EPE / PV of equity books against a counterparty with a deterministic intensity
+    "equity_cva_det_greeks": (equity_cva, dict(rho=0.0, deterministic=True), dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
+    "equity_cva_single_det_greeks": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=True)),
     "equity_cva_exercise": (equity_cva_exercise, dict(), dict(n_main=512, n_pre=512, num_steps=1, scheme="EULER", differentiate=False)),
     "bs_basket_euler": (bs_basket, dict(), dict(n_main=4096, n_pre=0, num_steps=5, scheme="EULER", differentiate=True)),
     # the BASELINE.json configs at their exact shapes (reduced path counts)

@@ -157,7 +157,8 @@ def test_unsupported_combinations_raise_instead_of_falling_back():
     S = ns.SimulationScheme
     tl = np.linspace(0.0, 1.5, 4)
 
-    # hybrid equity + credit: value-only, EULER only (the reference's ModelConfig has the same scheme restriction)
+    # hybrid equity + credit: sensitivities of the CVA only under a deterministic intensity, EULER only (the reference's
+    # ModelConfig has the same scheme restriction)
     def hybrid(differentiate, scheme):
         model, sets, metrics, tl_ = cases.equity_cva(ns)
         return ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl_), 64, 64, 1, scheme, differentiate)

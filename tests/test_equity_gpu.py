@@ -371,3 +371,43 @@ def test_equity_book_cva_matches_reference_and_oracle(name):
     out, _ = helpers.run_oracle(name, draws="philox")
     _check_values(helpers.flatten_results(res), helpers.oracle_flat(out, gold["sets"], gold["metrics"]), 1e-8,
                   name + " philox", err_rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["equity_cva_det_greeks", "equity_cva_single_det_greeks"])
+def test_equity_book_cva_sensitivities_match_reference_autograd(name):
+    """differentiate=True on the equity CVA books with a deterministic intensity (mcre/hybrid.py:EquityCreditGreeks): CVA,
+    EPE and PV gradients with respect to the market model's parameters against the reference's autograd (exposure metrics
+    through its float32 regression chain: 2e-5; PV pathwise: 1e-8); the credit model's parameters are outside the
+    reference's graph (None).  Native Philox against the oracle's duals."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    _check_values(flat, ref, 1e-9, name)
+
+    def check(res, rows_of, rtol_expo, what):
+        for s_ in gold["sets"]:
+            for m in gold["metrics"]:
+                rows, got = rows_of(s_, m), res.get_derivatives(s_, m)
+                rtol = 1e-8 if m == "pv" else rtol_expo
+                for ev, row in enumerate(rows):
+                    if row is None:
+                        continue
+                    scale = max(1.0, max(abs(w) for w in row if w is not None))
+                    for pname, g, w in zip(gold["params"], got[ev], row):
+                        if w is None:
+                            assert g is None, f"{what} {s_}|{m}[{ev}] d/d{pname}: expected None"
+                        else:
+                            assert g is not None and abs(float(g) - w) <= rtol * scale, f"{what} {s_}|{m}[{ev}] d/d{pname}: {g} vs {w}"
+    check(res, lambda s_, m: gold["derivatives"][f"{s_}|{m}"], 2e-5, name)
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    none_of = {(s_, m): [[w is None for w in row] for row in gold["derivatives"][f"{s_}|{m}"]] for s_ in gold["sets"] for m in gold["metrics"]}
+
+    def oracle_rows(s_, m):
+        si, mi = gold["sets"].index(s_), gold["metrics"].index(m)
+        rows = []
+        for ev, g in enumerate(out["grads"][si][mi]):
+            rows.append(None if g is None else [None if none_of[(s_, m)][ev][k] else float(g[k]) for k in range(len(g))])
+        return rows
+    check(res, oracle_rows, 1e-6, name + " philox")
