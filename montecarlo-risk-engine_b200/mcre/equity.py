@@ -239,7 +239,9 @@ class EquityBackend:
             if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
                 raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
                                           "model (single or multi-asset)")
-            if any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics):
+            if any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics) and not getattr(ctrl, "_credit_passenger", False):
+                # (the fused kernel reduces tangent sums; the gradient of an order statistic is the tangent of ONE path:
+                # mcre/hybrid.py:EquityCreditGreeks takes it from the per-path duals of the accumulating tangent pass)
                 raise NotImplementedError("PFE sensitivities are not implemented for equity books")
 
     @staticmethod
@@ -576,7 +578,7 @@ class EquityBackend:
                         raise NotImplementedError("sensitivities of exposure profiles of equity books: European "
                                                   "options (analytic exposure) and single-asset products that pay once "
                                                   "(regression proxy); not exercise products or baskets")
-                if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
+                if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics) and not getattr(c, "_credit_passenger", False):
                     raise NotImplementedError("PFE sensitivities are not implemented for equity books")
             expo_times, metric_times = c.exposure_timeline.tolist(), c.metric_exposure_timeline.tolist()
             n_expo, n_metric = len(expo_times), len(metric_times)
@@ -1147,6 +1149,7 @@ class EquityBackend:
                 sm = RT.all_reduce_tree(out_m).cpu().numpy().reshape(n_metric, 2)
                 ch = c_shift.cpu().numpy()
                 res[key] = ([mean_and_error(sm[m, 0], sm[m, 1], ch[m], n_main) for m in range(n_metric)], [None] * n_metric)
+            res["_unsec"] = spill
             if MetricType.PFE in kinds:
                 from mcre.select import order_statistics
                 res["pfe"] = order_statistics(c, spill, count, n_main)[0]

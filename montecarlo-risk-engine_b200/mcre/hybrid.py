@@ -100,6 +100,42 @@ def metric_gradients(c, values, tan, pv_grad, chunk, dev):
             res["pos"] = [sm[m, :, 0] for m in range(n_metric)]
             res["neg"] = [sm[m, :, 1] for m in range(n_metric)]
             res["cva"] = sm[:n_metric - 1, :, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
+            # PFE: the reference differentiates torch.sort(...)[index] (pfe_metric.py:59-71) = the pathwise gradient of the
+            # selected path.  The path is located in the value run's unsecured exposures (smallest global id among ties,
+            # like the interest-rate backend), its dual read from the per-path tensors on the rank that owns it.
+            res["pfe"] = {}
+            for q, (vals, _) in (values[si].get("pfe") or {}).items():
+                unsec = values[si]["_unsec"]                                       # [1][n_metric][n]
+                targets = torch.tensor([v for v, _ in vals], dtype=torch.float64, device=dev)
+                index = torch.empty(n_metric, dtype=torch.int64, device=dev)
+                B.check(L.mcre_select_locate(unsec.data_ptr(), unsec.stride(1), count, n_metric, targets.data_ptr(),
+                                             index.data_ptr(), RT.stream_ptr()))
+                gidx = torch.where(index < count, index + begin, torch.full_like(index, torch.iinfo(torch.int64).max))
+                _, world = RT.dist_info()
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(gidx, op=dist.ReduceOp.MIN)
+                expo_h = values[si]["_expo"]
+                grad = torch.zeros((n_metric, n_par), dtype=torch.float64, device=dev)
+                g_host = gidx.tolist()
+                h = float(ns.threshold)
+                for m in range(n_metric):
+                    lp = g_host[m] - begin
+                    if not (0 <= lp < count):
+                        continue                                                   # another rank owns the path
+                    xe = int(metric_expo[m])
+
+                    def dthr(x):
+                        return 1.0 if (x > h or x < -h) else 0.0
+                    if ns.is_collateralized():
+                        g = tan[si][:, xe, lp].clone()
+                        if lag[m] >= 0:
+                            g -= dthr(float(expo_h[xe - lag[m], lp])) * tan[si][:, xe - lag[m], lp]
+                    else:
+                        g = dthr(float(expo_h[xe, lp])) * tan[si][:, xe, lp]
+                    grad[m] = g
+                grad_h = RT.to_host(RT.all_reduce_tree(grad))
+                res["pfe"][q] = [grad_h[m] for m in range(n_metric)]
         out.append(res)
     return out
 
@@ -114,6 +150,8 @@ def attach_gradients(results, grads, used):
             res["neg"] = (res["neg"][0], g["neg"])
         if "cva" in res and res["cva"][0] != (0.0, 0.0):
             res["cva"] = (res["cva"][0], g["cva"])
+        for q, rows in (g.get("pfe") or {}).items():
+            res["pfe"][q] = (res["pfe"][q][0], rows)
         res["param_used"] = lambda kind, used=used: used
 
 
@@ -122,8 +160,6 @@ def _credit_checks(c, cir, what):
     if cir is not None and not cir.deterministic and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
         raise NotImplementedError(f"sensitivities of the CVA of {what}: deterministic credit (the default weights of a "
                                   "stochastic intensity carry tangents the equity launch does not have)")
-    if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
-        raise NotImplementedError(f"PFE sensitivities of {what}")
 
 
 class EquityCreditGreeks:
@@ -136,8 +172,16 @@ class EquityCreditGreeks:
 
     @staticmethod
     def supports(ctrl):
-        from mcre.equity import EquityBackend, credit_of
-        return bool(ctrl.differentiate) and credit_of(ctrl.model)[0] is not None and EquityBackend.supports(ctrl)
+        """Equity books whose sensitivities need per-path duals: a credit model in the ModelConfig, or a PFE metric (the
+        gradient of an order statistic is one path's tangent; the fused kernel only has tangent sums)."""
+        from metrics.metric import MetricType
+        from mcre.equity import EQ_BS, EquityBackend, credit_of, family_of
+        if not ctrl.differentiate or not EquityBackend.supports(ctrl):
+            return False
+        if credit_of(ctrl.model)[0] is not None:
+            return True
+        fam = family_of(ctrl.model)
+        return fam is not None and fam[0] == EQ_BS and any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics)
 
     def __init__(self, ctrl):
         from mcre.equity import credit_of
@@ -190,9 +234,10 @@ class EquityCreditGreeks:
                         tan[si][g] += accum_t[:, a, k, :]
         grads = metric_gradients(c, results, tan, pv_grad, chunk, dev)
         used = [True] * n_par
-        offs = c.model.param_offsets()
-        for k in range(len(self.credit.model_params)):
-            used[offs[self.credit_idx] + k] = False
+        if self.credit is not None:
+            offs = c.model.param_offsets()
+            for k in range(len(self.credit.model_params)):
+                used[offs[self.credit_idx] + k] = False
         attach_gradients(results, grads, used)
         torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start
@@ -217,8 +262,6 @@ class HybridBackend:
             if cir is not None and not cir.deterministic and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
                 raise NotImplementedError("sensitivities of the CVA of hybrid books: deterministic credit (the default "
                                           "weights of a stochastic intensity carry tangents the equity launch does not have)")
-            if any(m.metric_type == MetricType.PFE for m in c.risk_metrics.metrics):
-                raise NotImplementedError("PFE sensitivities of hybrid books")
         if c.simulation_scheme != SimulationScheme.EULER:
             # the reference defines inter-model covariances for Black-Scholes pairs only (model_config.py:201-221)
             raise NotImplementedError("Inter covariance not implemented for the requested pair of models.")
@@ -287,6 +330,7 @@ class HybridBackend:
             sub.netting_set_delayed_exposure_indices = [torch.full((n,), -1, dtype=torch.long) for _ in netting_sets]
         sub.requires_regression = any(sub._product_requires_regression(p) for p in sub.products)
         sub.differentiate = differentiate
+        sub._credit_passenger = differentiate     # per-path duals: the metrics are differentiated in metric_gradients
         sub.injected_normals = {}
         sub.last_timings = {}
         return sub

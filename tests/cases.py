@@ -174,7 +174,7 @@ def mixed_book(ns_module, exposure=True):
     return model, sets, [m.PVMetric()], None
 
 
-def bs_exposure_greeks(ns_module, multi=True):
+def bs_exposure_greeks(ns_module, multi=True, pfe=False):
     """EPE / PV sensitivities of European options through the analytic Black-Scholes exposure
     (european_option.py:123-145, controller.py:609-627; the shape of tests/exposure_tests/eepe_simulation.py with the
     metric set that keeps the analytic branch): thresholded and MPoR-collateralised netting sets."""
@@ -192,7 +192,7 @@ def bs_exposure_greeks(ns_module, multi=True):
                 m.EuropeanOption(m.Equity(ids[1]), 1.5, 110.0, m.OptionType.PUT, asset_id=ids[1])]
     sets = [m.NettingSet(name="thresholded", products=book(), threshold=12.0),
             m.NettingSet(name="collateralised", products=book(), margin_period_of_risk=0.25, threshold=1.0)]
-    return model, sets, [m.PVMetric(), m.EPEMetric()], np.linspace(0.0, 1.5, 7)
+    return model, sets, [m.PVMetric(), m.EPEMetric()] + ([m.PFEMetric(0.9)] if pfe else []), np.linspace(0.0, 1.5, 7)
 
 
 def bs_eepe_greeks(ns_module, book="european"):
@@ -585,6 +585,10 @@ GOLDEN_CASES = {
     "mixed_book_exposure": (mixed_book, dict(exposure=True), dict(n_main=512, n_pre=512, num_steps=1, scheme="ANALYTICAL", differentiate=False)),
     "bs_exposure_greeks": (bs_exposure_greeks, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_exposure_greeks_euler": (bs_exposure_greeks, dict(multi=False), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True)),
+    # sensitivities of PFE order statistics (pathwise gradient of the selected path): equity book, hybrid book
+    "bs_pfe_greeks": (bs_exposure_greeks, dict(pfe=True), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
+    "hybrid_pfe_greeks": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, rho=(0.25, 0.0, 0.0), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True, pfe=True),
+                          dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),

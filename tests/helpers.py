@@ -104,3 +104,20 @@ def assert_close(a, b, rtol, atol, what):
     tol = atol + rtol * np.maximum(np.abs(a), np.abs(b))
     bad = ~(both_nan | (err <= tol))
     assert not bad.any(), f"{what}: max abs diff {np.nanmax(err):.3e} (rtol {rtol}, atol {atol}); a={a[bad][:3]} b={b[bad][:3]}"
+
+
+def assert_gradients(res, gold_like, params, sets, metrics, rtol_of, what):
+    """Every metric's gradient rows against `gold_like[f"{set}|{metric}"]` (rows per evaluation, None = not connected)."""
+    for s_ in sets:
+        for m in metrics:
+            rows, got = gold_like[f"{s_}|{m}"], res.get_derivatives(s_, m)
+            for ev, row in enumerate(rows):
+                if row is None:
+                    continue
+                scale = max([1.0] + [abs(w) for w in row if w is not None])
+                for pname, g, w in zip(params, got[ev], row):
+                    if w is None:
+                        assert g is None, f"{what} {s_}|{m}[{ev}] d/d{pname}: expected None, got {g}"
+                    else:
+                        assert g is not None, f"{what} {s_}|{m}[{ev}] d/d{pname} is None"
+                        assert abs(float(g) - w) <= rtol_of(m) * scale, f"{what} {s_}|{m}[{ev}] d/d{pname}: {float(g)} vs {w}"

@@ -166,18 +166,11 @@ def test_unsupported_combinations_raise_instead_of_falling_back():
         with pytest.raises(NotImplementedError):
             hybrid(differentiate, scheme).run_simulation()
 
-    # sensitivities of exposure profiles of equity books: Black-Scholes only, no PFE, no exercise products
+    # sensitivities of exposure profiles of equity books: Black-Scholes only, no exercise products
     heston = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
     opt = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
     sc = ns.SimulationController([ns.NettingSet(name="h", products=[opt])], heston,
                                  ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), 64, 64, 2, S.QE, True)
-    with pytest.raises(NotImplementedError):
-        sc.run_simulation()
-    bs = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.2)
-    opt = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
-    sc = ns.SimulationController([ns.NettingSet(name="p", products=[opt])], bs,
-                                 ns.RiskMetrics([ns.EPEMetric(), ns.PFEMetric(0.95)], exposure_timeline=tl), 64, 0, 1,
-                                 S.ANALYTICAL, True)
     with pytest.raises(NotImplementedError):
         sc.run_simulation()
 

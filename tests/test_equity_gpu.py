@@ -411,3 +411,22 @@ def test_equity_book_cva_sensitivities_match_reference_autograd(name):
             rows.append(None if g is None else [None if none_of[(s_, m)][ev][k] else float(g[k]) for k in range(len(g))])
         return rows
     check(res, oracle_rows, 1e-6, name + " philox")
+
+
+def test_pfe_sensitivities_of_an_equity_book_match_reference_autograd():
+    """Gradient of PFE order statistics (pfe_metric.py:59-71 under autograd = the pathwise gradient of the selected path),
+    next to EPE and PV, for thresholded and MPoR-collateralised sets of European options (analytic exposures): against the
+    reference's autograd with its draws injected, against the oracle under native Philox."""
+    name = "bs_pfe_greeks"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    ref = {k: (np.array(v), np.array(gold["errors"][k])) for k, v in gold["values"].items()}
+    flat = helpers.flatten_results(res)
+    for key, (vb, eb) in ref.items():
+        helpers.assert_close(flat[key][0], vb, 1e-9, 1e-9, f"{name} {key}")
+    helpers.assert_gradients(res, gold["derivatives"], gold["params"], gold["sets"], gold["metrics"], lambda m: 1e-8, name)
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    like = {f"{s_}|{m}": [None if g is None else [float(x) for x in g] for g in out["grads"][si][mi]]
+            for si, s_ in enumerate(gold["sets"]) for mi, m in enumerate(gold["metrics"])}
+    helpers.assert_gradients(res, like, gold["params"], gold["sets"], gold["metrics"], lambda m: 1e-7, name + " philox")

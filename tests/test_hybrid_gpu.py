@@ -57,7 +57,7 @@ def test_hybrid_cva_is_positive_and_moves_with_spot_and_rate():
     assert np.isfinite(d_spot) and np.isfinite(d_rate) and d_spot > 0.0      # calls gain with the spot
 
 
-@pytest.mark.parametrize("name", ["hybrid_cva_greeks", "hybrid_collateral_greeks"])
+@pytest.mark.parametrize("name", ["hybrid_cva_greeks", "hybrid_collateral_greeks", "hybrid_pfe_greeks"])
 def test_hybrid_sensitivities_match_reference_autograd(name):
     """differentiate=True on a hybrid book: every metric's gradient with respect to the 11 parameters of the three models
     against torch.autograd of the unmodified reference.  Exposure metrics pass through the float32 regression chain on
