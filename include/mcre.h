@@ -310,7 +310,9 @@ enum { MCRE_EQ_EUROPEAN = 0, MCRE_EQ_BINARY = 1, MCRE_EQ_BASKET = 2, MCRE_EQ_ASI
 typedef struct {
   int32_t kind;          /* MCRE_EQ_*: every asset of a launch is of this kind                       */
   int32_t scheme;        /* MCRE_SCHEME_*                                                            */
-  int32_t nt;            /* tangents per lane: 0, or the kind's parameter count (BS 3, Heston 7, Schwartz 6) */
+  int32_t nt;            /* tangents per lane: 0, or the kind's parameter count (BS 3, Heston 7, Schwartz 6), or 9 =
+                            second order on Black-Scholes lanes: 3 first + 6 second derivatives (upper triangle,
+                            row-major), present values only; the tangent slots of the result hold all 9          */
   int32_t smoothing;     /* Heston fuzzy indicators on (the reference ties this to differentiate)    */
   int32_t n_assets, noise_dim, n_uniform;
   const double *asset_par;      /* [n_assets][8] lane parameters: BS spot, sigma, rate | Heston spot, sigma, rate,

@@ -269,9 +269,6 @@ class SimulationController:
                     "regression_function: only PolyomialRegression(degree=2) is implemented by the CUDA regression "
                     f"kernels (got {type(rf).__name__}(degree={getattr(rf, 'degree', None)})); the reference builds "
                     "regression_function.get_regression_matrix(x) for any basis (controller.py:361-374)")
-        if self.requires_higher_order_derivatives and mc_products:
-            raise NotImplementedError("second-order sensitivities are implemented for analytic PVs only "
-                                      "(pathwise Hessians: SURVEY §8f item 4)")
         n_params = len(self.model.get_model_params())
         analytic = [[0.0 for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
         analytic_grads = [[None for _ in self.risk_metrics.metrics] for _ in self.netting_sets]
@@ -297,6 +294,9 @@ class SimulationController:
         raw, timings = None, {"preprocessing": 0.0, "path_generation": 0.0, "request_resolution": 0.0}
         if mc_products:
             backend = self._select_backend()
+            if self.requires_higher_order_derivatives and not getattr(backend, "second", False):
+                raise NotImplementedError("second-order sensitivities of Monte Carlo values: present values of equity "
+                                          "books on one Black-Scholes model (mcre/equity.py); analytic PVs otherwise")
             raw, timings = backend.run()
         t3 = time.perf_counter()
         from mcre.finish import finish_results
@@ -313,9 +313,16 @@ class SimulationController:
         higher = []
         if self.requires_higher_order_derivatives:
             # [set][metric][evaluation][parameter i] -> tuple over parameters (simulation_results.py:5-338)
-            higher = [[[analytic_hess[si][mi] if analytic_hess[si][mi] is not None
-                        else [tuple(None for _ in range(n_params)) for _ in range(n_params)]]
-                       for mi in range(len(self.risk_metrics.metrics))] for si in range(len(self.netting_sets))]
+            def hessian_of(si, mi):
+                h = analytic_hess[si][mi]
+                mc = raw[si].get("pv_hess") if (raw is not None and raw[si] is not None) else None
+                if mc is not None and self.risk_metrics.metrics[mi].metric_type == MetricType.PV:
+                    # pathwise Hessian of the simulated part (mcre/equity.py, csrc/dual2.cuh) + the analytic part
+                    rows = [tuple(float(x) for x in row) for row in mc]
+                    h = rows if h is None else [tuple(_merge_grads(list(a), list(b))) for a, b in zip(h, rows)]
+                return h if h is not None else [tuple(None for _ in range(n_params)) for _ in range(n_params)]
+            higher = [[[hessian_of(si, mi)] for mi in range(len(self.risk_metrics.metrics))]
+                      for si in range(len(self.netting_sets))]
         return SimulationResults(
             results, grads, higher,
             netting_set_names=self._make_unique_names([ns.get_name() for ns in self.netting_sets]),

@@ -18,7 +18,7 @@
 #define MCRE_FAST_MATH 2
 #include "common.cuh"
 #include "philox.cuh"
-#include "dual.cuh"
+#include "dual2.cuh"
 #include "heston.cuh"
 #include "reduce.cuh"
 #include "launch.cuh"
@@ -140,6 +140,16 @@ __device__ __forceinline__ R barrier_factor(const R &mx, const R &mn, double bar
   }
 }
 
+// coef = -2 / (sigma^2 maturity / n_obs) of the Brownian-bridge crossing probability as a function of the volatility
+// (c0 = its value): d coef / d sigma = -2 coef / sigma
+template <int N> __device__ __forceinline__ Dual<N> bridge_coef(double c0, const Dual<N> &sigma) {
+  Dual<N> r = dual_zero<N>(); r.v = c0; r.d[1] = -2.0 * c0 / sigma.v;
+  return r;
+}
+template <int N> __device__ __forceinline__ Dual2<N> bridge_coef(double c0, const Dual2<N> &sigma) {
+  return (c0 * sigma.v * sigma.v) / (sigma * sigma);
+}
+
 // standard normal CDF of a dual number (tangent = density)
 template <int N>
 __device__ __forceinline__ Dual<N> dual_ncdf(const Dual<N> &x) {
@@ -153,7 +163,8 @@ __device__ __forceinline__ Dual<N> dual_ncdf(const Dual<N> &x) {
 
 // Sensitivities of exposure profiles (controller.py:609-627 on EPE / ENE / CE / EEPE): Black-Scholes builds with
 // tangents carry the exposures as duals (lane-local tangents like the cashflows); other models keep doubles.
-template <int KIND, int NT> struct EqExpoTan { static const bool on = (KIND == MCRE_EQ_BS) && (NT > 0); };
+// (NT = 9: the second-order build, Dual2<3> - present values only)
+template <int KIND, int NT> struct EqExpoTan { static const bool on = (KIND == MCRE_EQ_BS) && (NT > 0) && (NT != 9); };
 template <bool ON, typename R> struct EqExpoReal { typedef double type; };
 template <typename R> struct EqExpoReal<true, R> { typedef R type; };
 
@@ -580,8 +591,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
                   } else {
                     ns.uniform_pair_kind((uint32_t)__ldg(ed + 0), 2u, ua, ub);
                   }
-                  R coef = T::lift(__ldg(ed + 1));
-                  coef.d[1] = -2.0 * __ldg(ed + 1) / val(par[1]);
+                  const R coef = bridge_coef(__ldg(ed + 1), par[1]);
                   const R prev = brg_c[slot];
                   const double b1 = __ldg(pr + 9);
                   const R p1 = r_exp(coef * r_log(prev / b1) * r_log(U / b1));
@@ -660,7 +670,19 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
           }
 #pragma unroll
           for (int s = 0; s < NS; ++s)
-            if (s == set) { cf[s] = cf[s] + pay * invN; numtan[s] += val(pay) * dinvN; }
+            if (s == set) {
+              if constexpr (NT == 9) {
+                // second-order build: the numeraire 1 / N(T) = exp(-r T) as a function of the lane's rate (the host admits
+                // books whose assets share the numeraire's rate parameter), so the header's separate rate term stays 0
+                // (every lane of the group holds the payoff's value, the product's own lane its derivatives: the
+                // numeraire's derivatives ride with that lane alone)
+                R nrm = T::lift(invN);
+                if (wgt != 0.0) { nrm.d[2] = dinvN; nrm.h[5] = dinvN * dinvN / invN; }
+                cf[s] = cf[s] + pay * nrm;
+              } else {
+                cf[s] = cf[s] + pay * invN; numtan[s] += val(pay) * dinvN;
+              }
+            }
         }
       };
 
@@ -839,7 +861,11 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
   if (c->n_sets < 1 || c->n_sets > MCRE_EQ_MAX_SETS) return fail(-1, "eq: n_sets out of range%s", "");
   const int np = c->kind == MCRE_EQ_BS ? 3 : c->kind == MCRE_EQ_HESTON ? 7 : c->kind == MCRE_EQ_SCHWARTZ ? 6 : -1;
   if (np < 0) return fail(-1, "eq: unknown model kind%s", "");
-  if (c->nt != 0 && c->nt != np) return fail(-1, "eq: nt must be 0 or the model's parameter count%s", "");
+  const bool second = c->kind == MCRE_EQ_BS && c->nt == 9;   // value + 3 first + 6 second derivatives per lane (Dual2<3>)
+  if (c->nt != 0 && c->nt != np && !second)
+    return fail(-1, "eq: nt must be 0, the model's parameter count, or 9 (second order, Black-Scholes)%s", "");
+  if (second && c->n_expo > 0)
+    return fail(-4, "eq: the second-order build carries present values only%s", "");
   if (c->nt != 0 && c->n_sets > 2) return fail(-3, "eq: at most 2 netting sets per launch when tangents are on%s", "");
   if (c->nt != 0 && c->n_expo > 0) {
     if (c->kind != MCRE_EQ_BS) return fail(-4, "eq: sensitivities of exposure profiles need a Black-Scholes model%s", "");
@@ -1049,6 +1075,11 @@ static int eq_dispatch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, d
     return ns == 1 ? eq_launch<KIND, ALT, 0, 1>(p, rng, sh, partial, shift, spill, st)
          : ns == 2 ? eq_launch<KIND, ALT, 0, 2>(p, rng, sh, partial, shift, spill, st)
                    : eq_launch<KIND, ALT, 0, 4>(p, rng, sh, partial, shift, spill, st);
+  }
+  if constexpr (KIND == MCRE_EQ_BS) {
+    if (p->nt == 9)
+      return ns == 1 ? eq_launch<KIND, ALT, 9, 1>(p, rng, sh, partial, shift, spill, st)
+                     : eq_launch<KIND, ALT, 9, 2>(p, rng, sh, partial, shift, spill, st);
   }
   return ns == 1 ? eq_launch<KIND, ALT, NTK, 1>(p, rng, sh, partial, shift, spill, st)
                  : eq_launch<KIND, ALT, NTK, 2>(p, rng, sh, partial, shift, spill, st);

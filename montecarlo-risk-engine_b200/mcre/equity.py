@@ -234,6 +234,24 @@ class EquityBackend:
         offs = ctrl.model.param_offsets() if isinstance(ctrl.model, ModelConfig) else [0]
         self.num_rate_global = offs[num_idx] + self._rate_index(self.num_model)
         self.num_rate = self.num_model.param_values()[self._rate_index(self.num_model)]
+        #: pathwise Hessians (compute_higher_derivatives, controller.py:253-255, 631-648): Black-Scholes lanes carry
+        #: Dual2<3> numbers - value, 3 first and 6 second derivatives w.r.t. (spot, volatility, rate) of the lane's asset
+        self.second = bool(ctrl.differentiate and getattr(ctrl, "requires_higher_order_derivatives", False))
+        if self.second:
+            if (self.kind != EQ_BS or self.credit is not None or ctrl.risk_metrics.requires_exposure_profiles()
+                    or any(a.gmap[2] != self.num_rate_global for a in self.assets)):
+                raise NotImplementedError("second-order sensitivities of Monte Carlo values: present values of books on "
+                                          "one Black-Scholes model (single or multi-asset)")
+            for p in ctrl.products:
+                if ctrl._can_skip_monte_carlo_for_product(p):
+                    continue
+                if (is_equity_exercise(p) or isinstance(p, BasketOption) or getattr(p, "basket", None) is not None
+                        or getattr(p, "use_brownian_bridge", False)):
+                    # (second derivatives across assets do not live in one lane; exercise products would need the
+                    # second-order dependence of the regression coefficients)
+                    raise NotImplementedError("second-order sensitivities of Monte Carlo values: single-asset products "
+                                              "that pay once (European, binary, barrier, Asian options)")
+            self.nt = 9
         if ctrl.differentiate and ctrl.risk_metrics.requires_exposure_profiles():
             # checked before any device work (the same conditions guard the lowering)
             if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
@@ -1248,6 +1266,8 @@ class EquityBackend:
         # a netting set with more tracked products than one launch holds is split over several launches
         ntrk = eq_ntrk(self.nt)
         oversized = [si for si, ns in enumerate(c.netting_sets) if sum(_is_path_dependent(p) for p in ns.products) > ntrk]
+        if oversized and self.second:
+            raise NotImplementedError(f"second-order sensitivities: at most {ntrk} path-dependent products per netting set")
         for si in oversized:
             results[si] = self._run_split_book(si, dev, n_main, n_params)
         groups, cur, cur_trk = [], [], 0
@@ -1333,6 +1353,20 @@ class EquityBackend:
                     grad[self.num_rate_global] += head[r, 2] / n_main
                     grad += self._control_variate_gradient(info["owners"], info["recs"], r, n_params)
                 res = {"pv": (pv, grad), "param_used": self._param_used}
+                if self.second:
+                    # lane-local upper triangles (00 01 02 11 12 22 behind the 3 first derivatives) -> the model's
+                    # parameter order; entries across assets are structurally zero (single-asset products)
+                    hess = np.zeros((n_params, n_params))
+                    for a, asset in enumerate(self.assets):
+                        k = 3
+                        for i in range(3):
+                            for j in range(i, 3):
+                                gi, gj = asset.gmap[i], asset.gmap[j]
+                                hess[gi, gj] += tang[a, r, k] / n_main
+                                if gi != gj:
+                                    hess[gj, gi] += tang[a, r, k] / n_main
+                                k += 1
+                    res["pv_hess"] = hess
                 if info["acc"] & B.ACC_POS:
                     res["pos"] = ([mean_and_error(xacc[m, r, 0], xacc[m, r, 1], xshift[m, r, 0], n_main) for m in range(n_metric)],
                                   expo_grads(r, 0))

@@ -531,7 +531,7 @@ def pfe_quantile_index(q, n):
 
 
 def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_steps, scheme,
-        differentiate=False, draws_pre=None, draws_main=None, degree=3, storage_solver="gelsy"):
+        differentiate=False, draws_pre=None, draws_main=None, degree=3, storage_solver="gelsy", second_order=False):
     """Restatement of SimulationController.__init__ + run_simulation (controller.py:26-151, 663-709).
     Returns dict(results=[set][metric] -> [(value, err)], grads=[set][metric][eval] -> array[P] or None,
     coeffs=[product] -> [T_e] of [S,degree])."""
@@ -552,7 +552,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
     sim_tl = sorted({t for pr in products for t in modeling_timeline(pr)} | set(expo_tl))
     smoothing = bool(differentiate)
     pvals = M.param_values(model)
-    p = ad.params(pvals, differentiate)
+    p = ad.params(pvals, differentiate, second_order)   # second_order: compute_higher_derivatives (controller.py:253-255)
     P = len(pvals)
 
     def analytic_exposure_ok(pr):
@@ -687,7 +687,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
             set_expo[si][i] = e if set_expo[si][i] is None else set_expo[si][i] + e
 
     # ---- netting sets + metrics (controller.py:506-563, netting_set.py:156-184) ---------
-    results, grads = [], []
+    results, grads, hess = [], [], []
     for si, ns in enumerate(netting_sets):
         unsec = []
         if need_expo:
@@ -699,7 +699,7 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
                     td = float(np.asarray(metric_tl)[m] - ns.margin_period_of_risk)
                     coll = 0.0 * e if td < 0.0 else threshold(set_expo[si][expo_idx[td]], ns.threshold)
                     unsec.append(e - coll)
-        mres, mgrads = [], []
+        mres, mgrads, mhess = [], [], []
         for metric, mt in zip(metrics, mtypes):
             if (mt == "CVA" and ns.counterparty_id is not None
                     and getattr(metric, "counterparty_id", None) != ns.counterparty_id):
@@ -748,9 +748,12 @@ def run(model, netting_sets, metrics, exposure_timeline, n_main, n_pre, num_step
                 raise NotImplementedError(mt)
             mres.append([(float(ad.val(v)), float(e)) for v, e in vals])
             mgrads.append([np.array(v.t, dtype=float).reshape(P) if isinstance(v, ad.Dual) else None for v, _ in vals])
+            mhess.append([np.array(v.h, dtype=float).reshape(P, P) if isinstance(v, ad.Dual) and v.h is not None else None
+                          for v, _ in vals])
         results.append(mres)
         grads.append(mgrads)
-    return dict(results=results, grads=grads, expo_coeffs=expo_coeffs, prod_coeffs=prod_coeffs,
+        hess.append(mhess)
+    return dict(results=results, grads=grads, hess=hess, expo_coeffs=expo_coeffs, prod_coeffs=prod_coeffs,
                 sim_timeline=sim_tl, exposure_timeline=expo_tl, n_sub=n_sub, noise_dim=dim)
 
 

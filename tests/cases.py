@@ -195,6 +195,26 @@ def bs_exposure_greeks(ns_module, multi=True, pfe=False):
     return model, sets, [m.PVMetric(), m.EPEMetric()] + ([m.PFEMetric(0.9)] if pfe else []), np.linspace(0.0, 1.5, 7)
 
 
+def bs_hessian(ns_module, multi=False):
+    """Pathwise second-order sensitivities of Monte Carlo present values (compute_higher_derivatives, controller.py:253-255,
+    631-648: autograd of every first derivative): products that pay once, with the payoff smoothing differentiate=True
+    switches on (binary / barrier indicators become fuzzy), so that the Hessian has curvature to carry."""
+    m = ns_module
+    if multi:
+        ids = ["asset_1", "asset_2"]
+        model = m.BlackScholesMulti(calibration_date=0.0, rate=0.03, asset_ids=ids, spots=[100.0, 105.0],
+                                    volatilities=[0.20, 0.24], correlation_matrix=np.array([[1.0, 0.35], [0.35, 1.0]]))
+    else:
+        ids = ["asset", "asset"]
+        model = m.BlackScholesModel(0.0, 100.0, 0.05, 0.2, asset_id="asset")
+    vanilla = [m.EuropeanOption(m.Equity(ids[0]), 1.0, 95.0, m.OptionType.CALL, asset_id=ids[0]),
+               m.BinaryOption(1.5, 100.0, 10.0, m.OptionType.PUT, asset_id=ids[1])]
+    paths = [m.BarrierOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, 135.0, m.BarrierOptionType.UPANDOUT, asset_id=ids[1]),
+             m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, asset_id=ids[0])]
+    sets = [m.NettingSet(name="vanilla", products=vanilla), m.NettingSet(name="path_dependent", products=paths)]
+    return model, sets, [m.PVMetric()], None
+
+
 def bs_eepe_greeks(ns_module, book="european"):
     """Sensitivities of exposure metrics through the regression proxy (controller.py:294-383, 438-447, 609-627).
     book "european": tests/exposure_tests/eepe_simulation.py (EEPE of a Black-Scholes call; EEPE switches the analytic
@@ -589,6 +609,10 @@ GOLDEN_CASES = {
     "bs_pfe_greeks": (bs_exposure_greeks, dict(pfe=True), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "hybrid_pfe_greeks": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, rho=(0.25, 0.0, 0.0), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True, pfe=True),
                           dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
+    # pathwise Hessians of Monte Carlo present values (compute_higher_derivatives): exact and Euler steps, one and two assets
+    "bs_hessian": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True, second_order=True)),
+    "bs_hessian_euler": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True, second_order=True)),
+    "bs_hessian_multi": (bs_hessian, dict(multi=True), dict(n_main=2048, n_pre=0, num_steps=2, scheme="EULER", differentiate=True, second_order=True)),
     "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),

@@ -47,6 +47,8 @@ def run_case(name):
     extra = dict(regression_function=ns.PolyomialRegression(degree=rkw["degree"])) if "degree" in rkw else {}
     sc = ns.SimulationController(sets, model, rm, rkw["n_main"], rkw["n_pre"], rkw["num_steps"],
                                  getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"], **extra)
+    if rkw.get("second_order"):
+        sc.compute_higher_derivatives()
     res = sc.run_simulation()
     out = dict(case=name, builder=builder.__name__, builder_kwargs=bkw, run=rkw,
                torch=torch.__version__, sets=res.get_netting_set_names(), metrics=res.get_metric_names(),
@@ -60,6 +62,10 @@ def run_case(name):
             if rkw["differentiate"]:
                 d = res.get_derivatives(s, m)
                 out["derivatives"][key] = [[_num(g) for g in ev] for ev in d]
+            if rkw.get("second_order"):
+                # [evaluation][parameter i][parameter j]; None = not connected in the reference's autograd graph
+                h = res.second_derivatives[out["sets"].index(s)][out["metrics"].index(m)]
+                out.setdefault("second_derivatives", {})[key] = [[[_num(x) for x in row] for row in ev] for ev in h]
     return out
 
 

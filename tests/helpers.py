@@ -55,7 +55,8 @@ def run_oracle(name, draws="torch", **override):
         pre, main = reference_draws(model, sets, tl, metrics, rkw)
     out = risk.run(model, sets, metrics, tl, rkw["n_main"], rkw["n_pre"], rkw["num_steps"], rkw["scheme"],
                    differentiate=rkw["differentiate"], draws_pre=pre, draws_main=main,
-                   degree=rkw.get("degree", 2) + 1, storage_solver=rkw.get("storage_solver", "gelsy"))
+                   degree=rkw.get("degree", 2) + 1, storage_solver=rkw.get("storage_solver", "gelsy"),
+                   second_order=rkw.get("second_order", False))
     return out, (ns, model, sets, metrics, tl, rkw)
 
 
@@ -68,6 +69,8 @@ def run_cuda(name, draws="torch", **override):
                                  getattr(ns.SimulationScheme, rkw["scheme"]), rkw["differentiate"], **extra)
     if "storage_solver" in rkw:
         sc.storage_regression = "lapack" if rkw["storage_solver"] == "gelsy" else rkw["storage_solver"]
+    if rkw.get("second_order"):
+        sc.compute_higher_derivatives()
     if draws == "torch":
         pre, main = reference_draws(model, sets, tl, metrics, rkw)
         sc.inject_normals(pre=None if pre is None else pre.z, main=main.z)
@@ -121,3 +124,19 @@ def assert_gradients(res, gold_like, params, sets, metrics, rtol_of, what):
                     else:
                         assert g is not None, f"{what} {s_}|{m}[{ev}] d/d{pname} is None"
                         assert abs(float(g) - w) <= rtol_of(m) * scale, f"{what} {s_}|{m}[{ev}] d/d{pname}: {float(g)} vs {w}"
+
+
+def assert_hessians(hess_of, gold_like, sets, metrics, rtol, what):
+    """`hess_of(set index, metric index, evaluation)` -> [P][P] (entries may be None) against
+    `gold_like[f"{set}|{metric}"][evaluation][i][j]`.  The reference returns None or 0.0 for structurally zero entries
+    depending on its autograd graph's connectivity; both compare as zero."""
+    for si, s_ in enumerate(sets):
+        for mi, m in enumerate(metrics):
+            for ev, want in enumerate(gold_like[f"{s_}|{m}"]):
+                got = hess_of(si, mi, ev)
+                scale = max([1.0] + [abs(x) for row in want for x in row if x is not None])
+                for i, row in enumerate(want):
+                    for j, w in enumerate(row):
+                        g = got[i][j]
+                        g, w = (0.0 if g is None else float(g)), (0.0 if w is None else float(w))
+                        assert abs(g - w) <= rtol * scale, f"{what} {s_}|{m}[{ev}] d2/d{i}d{j}: {g} vs {w}"

@@ -430,3 +430,46 @@ def test_pfe_sensitivities_of_an_equity_book_match_reference_autograd():
     like = {f"{s_}|{m}": [None if g is None else [float(x) for x in g] for g in out["grads"][si][mi]]
             for si, s_ in enumerate(gold["sets"]) for mi, m in enumerate(gold["metrics"])}
     helpers.assert_gradients(res, like, gold["params"], gold["sets"], gold["metrics"], lambda m: 1e-7, name + " philox")
+
+
+@pytest.mark.parametrize("name", ["bs_hessian", "bs_hessian_euler", "bs_hessian_multi"])
+def test_pathwise_hessians_match_reference_double_backward(name):
+    """compute_higher_derivatives() on Monte Carlo present values (controller.py:253-255, 631-648): the kernel carries
+    Dual2<3> numbers per lane (csrc/dual2.cuh).  Against the reference's autograd-of-autograd with its draws injected,
+    and against the oracle's second-order forward mode under native Philox."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    for key, vb in gold["values"].items():
+        helpers.assert_close(flat[key][0], np.array(vb), 1e-9, 1e-9, f"{name} {key}")
+    helpers.assert_gradients(res, gold["derivatives"], gold["params"], gold["sets"], gold["metrics"], lambda m: 1e-9, name)
+    helpers.assert_hessians(lambda si, mi, ev: res.second_derivatives[si][mi][ev], gold["second_derivatives"], gold["sets"],
+                            gold["metrics"], 1e-9, name)
+    # the reference's accessor shapes (simulation_results.py:261-334)
+    s0, p = gold["sets"][0], gold["params"]
+    named = res.get_second_derivatives(s0, "pv", evaluation_idx=0)
+    assert abs(float(named[p[1]][p[-1]]) - gold["second_derivatives"][f"{s0}|pv"][0][1][len(p) - 1]) <= 1e-8 * 300
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    like = {f"{s_}|{m}": [out["hess"][si][mi][ev].tolist() for ev in range(len(out["hess"][si][mi]))]
+            for si, s_ in enumerate(gold["sets"]) for mi, m in enumerate(gold["metrics"])}
+    helpers.assert_hessians(lambda si, mi, ev: res.second_derivatives[si][mi][ev], like, gold["sets"], gold["metrics"], 1e-8,
+                            name + " philox")
+
+
+def test_second_order_requests_outside_the_supported_books_raise():
+    ns = cases.Namespace()
+    bs = ns.BlackScholesModel(0.0, 100.0, 0.05, 0.2)
+    am = ns.AmericanOption(ns.Equity("id"), 1.0, 4, 100.0, ns.OptionType.PUT)
+    sc = ns.SimulationController([ns.NettingSet(name="a", products=[am])], bs, ns.RiskMetrics([ns.PVMetric()]), 1024, 1024, 1,
+                                 ns.SimulationScheme.ANALYTICAL, True)
+    sc.compute_higher_derivatives()
+    with pytest.raises(NotImplementedError):
+        sc.run_simulation()
+    heston = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+    eu = ns.EuropeanOption(ns.Equity("id"), 1.0, 100.0, ns.OptionType.CALL)
+    sc = ns.SimulationController([ns.NettingSet(name="e", products=[eu])], heston, ns.RiskMetrics([ns.PVMetric()]), 1024, 0, 2,
+                                 ns.SimulationScheme.EULER, True)
+    sc.compute_higher_derivatives()
+    with pytest.raises(NotImplementedError):
+        sc.run_simulation()

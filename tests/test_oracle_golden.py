@@ -37,6 +37,10 @@ def test_oracle_matches_reference_golden(name):
                     rtol = 2e-5 if exposure_metric else 1e-8
                     helpers.assert_close(got, want, rtol, rtol * max(1.0, float(np.max(np.abs(want)))),
                                          f"{name} {s}|{m}[{ev}] derivatives")
+    if rkw.get("second_order"):
+        # the reference's double backward (controller.py:631-648) against the oracle's second-order forward mode
+        helpers.assert_hessians(lambda si, mi, ev: out["hess"][si][mi][ev], gold["second_derivatives"], gold["sets"],
+                                gold["metrics"], 1e-10, name)
 
 
 def test_reference_known_answer_uncorrelated_cva():
