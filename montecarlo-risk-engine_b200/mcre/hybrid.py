@@ -172,16 +172,23 @@ class EquityCreditGreeks:
 
     @staticmethod
     def supports(ctrl):
-        """Equity books whose sensitivities need per-path duals: a credit model in the ModelConfig, or a PFE metric (the
-        gradient of an order statistic is one path's tangent; the fused kernel only has tangent sums)."""
+        """Equity books whose sensitivities need per-path duals: a credit model in the ModelConfig, a PFE metric (the
+        gradient of an order statistic is one path's tangent; the fused kernel only has tangent sums), or a netting set
+        split over several launches."""
         from metrics.metric import MetricType
-        from mcre.equity import EQ_BS, EquityBackend, credit_of, family_of
+        from mcre.equity import EQ_BS, EquityBackend, _is_path_dependent, credit_of, eq_ntrk, family_of
         if not ctrl.differentiate or not EquityBackend.supports(ctrl):
             return False
         if credit_of(ctrl.model)[0] is not None:
             return True
         fam = family_of(ctrl.model)
-        return fam is not None and fam[0] == EQ_BS and any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics)
+        if fam is None or fam[0] != EQ_BS or not ctrl.risk_metrics.requires_exposure_profiles():
+            return False
+        if any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics):
+            return True
+        # exposure sensitivities of a netting set with more path-dependent products than one launch with tangents tracks:
+        # the book is split over launches, whose per-path exposures and duals are netted here
+        return any(sum(_is_path_dependent(p) for p in ns.products) > eq_ntrk(3) for ns in ctrl.netting_sets)
 
     def __init__(self, ctrl):
         from mcre.equity import credit_of

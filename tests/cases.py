@@ -215,6 +215,24 @@ def bs_hessian(ns_module, multi=False):
     return model, sets, [m.PVMetric()], None
 
 
+def bs_split_book_greeks(ns_module):
+    """Exposure sensitivities of a netting set with more path-dependent products than one launch with tangents tracks
+    (two), so that the book is split over launches: the reference nets whatever the set holds (controller.py:438-447)."""
+    m = ns_module
+    model = m.BlackScholesModel(0.0, 100.0, 0.04, 0.25, asset_id="asset")
+
+    def book():
+        return [m.EuropeanOption(m.Equity("asset"), 1.0, 95.0, m.OptionType.PUT, asset_id="asset"),
+                m.BarrierOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, 140.0, m.BarrierOptionType.UPANDOUT, asset_id="asset"),
+                m.BarrierOption(0.0, 1.0, 105.0, 5, m.OptionType.PUT, 75.0, m.BarrierOptionType.DOWNANDOUT, asset_id="asset"),
+                m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL, asset_id="asset"),
+                m.AsianOption(0.0, 0.75, 98.0, 4, m.OptionType.PUT, asset_id="asset"),
+                m.BinaryOption(0.5, 100.0, 10.0, m.OptionType.CALL, asset_id="asset")]
+    sets = [m.NettingSet(name="split", products=book(), threshold=4.0),
+            m.NettingSet(name="split_collateralised", products=book(), margin_period_of_risk=0.25, threshold=1.0)]
+    return model, sets, [m.PVMetric(), m.EPEMetric(), m.ENEMetric()], np.linspace(0.0, 1.0, 5)
+
+
 def bs_eepe_greeks(ns_module, book="european"):
     """Sensitivities of exposure metrics through the regression proxy (controller.py:294-383, 438-447, 609-627).
     book "european": tests/exposure_tests/eepe_simulation.py (EEPE of a Black-Scholes call; EEPE switches the analytic
@@ -613,6 +631,7 @@ GOLDEN_CASES = {
     "bs_hessian": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True, second_order=True)),
     "bs_hessian_euler": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True, second_order=True)),
     "bs_hessian_multi": (bs_hessian, dict(multi=True), dict(n_main=2048, n_pre=0, num_steps=2, scheme="EULER", differentiate=True, second_order=True)),
+    "bs_split_book_greeks": (bs_split_book_greeks, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),

@@ -224,3 +224,34 @@ def test_barrier_closed_forms_match_the_reference():
         p = ns.BarrierOption(startdate=0.0, maturity=1.5, strike=K, num_observation_timepoints=10, option_type=ns.OptionType.CALL,
                              barrier1=bar, barrier_option_type1=bt)
         assert abs(float(p.compute_pv_analytically(m)) - want) < 1e-12
+
+
+def test_cds_bootstrap_matches_the_reference_fixture():
+    """helpers/cs_helper.py (reference: src/helpers/cs_helper.py:9-107): hazards, legs and default probabilities against
+    tests/golden/cs_helper.json, written by the unmodified reference (tests/golden/make_cs_helper.py)."""
+    import json
+    import os
+    import importlib.util
+    from maths.maths import bisection_search
+    # (the package's `helpers` has the reference's name, which the test suite's own helpers.py shadows: load by path)
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "montecarlo-risk-engine_b200")
+    spec = importlib.util.spec_from_file_location("mcre_cs_helper", os.path.join(pkg, "helpers", "cs_helper.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    CSHelper = mod.CSHelper
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cs_helper.json")))
+    pay = np.arange(0.25, 20.0 + 1e-7, 0.25)
+    df = np.exp(-g["rate"] * pay)
+    h = CSHelper()
+    haz = h.bootstrap_hazards(credit_spreads=g["spreads"], maturities=g["tenors"], payment_days=pay,
+                              discount_factors_payment_days=df, recovery_rate=g["recovery"])
+    assert np.allclose(haz, g["hazards"], rtol=0, atol=1e-11)
+    legs = [h._compute_cds_legs(g["tenors"][:i + 1], pay, df, g["recovery"], haz[:i + 1]) for i in range(len(haz))]
+    assert np.allclose(legs, g["legs"], rtol=1e-12, atol=1e-13)
+    # the bootstrapped curve reprices every quote
+    assert np.allclose([b / a for a, b in legs], g["spreads"], rtol=0, atol=1e-10)
+    t64 = lambda x: torch.tensor(x, dtype=torch.float64)
+    pd = [float(h.probability_of_default(t64(haz), t64(g["tenors"]), t64(t))) for t in g["dates"]]
+    assert np.allclose(pd, g["default_probability"], rtol=0, atol=1e-14)
+    assert bisection_search(lambda x: x * x + 1.0) is None
+    assert abs(bisection_search(lambda x: x * x - 2.0) - 2.0 ** 0.5) < 1e-11

@@ -473,3 +473,17 @@ def test_second_order_requests_outside_the_supported_books_raise():
     sc.compute_higher_derivatives()
     with pytest.raises(NotImplementedError):
         sc.run_simulation()
+
+
+def test_exposure_sensitivities_of_a_book_split_over_launches():
+    """Six products, four of them path-dependent, per netting set: more than one launch with tangents tracks, so the
+    values and the per-path duals of several launches are netted (mcre/hybrid.py:EquityCreditGreeks) - thresholded and
+    MPoR-collateralised, against the reference's autograd."""
+    name = "bs_split_book_greeks"
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    for key, vb in gold["values"].items():
+        helpers.assert_close(flat[key][0], np.array(vb), 1e-9, 1e-9, f"{name} {key}")
+    helpers.assert_gradients(res, gold["derivatives"], gold["params"], gold["sets"], gold["metrics"],
+                             lambda m: 1e-8 if m.startswith("pv") else 2e-5, name)
