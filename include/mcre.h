@@ -411,6 +411,15 @@ int mcre_exposure_tangent_sums(const double *d_expo, const double *d_tan, int64_
                                int32_t n_metric, const int32_t *metric_expo, const int32_t *lag, int32_t collateralised,
                                double threshold, const double *weights, int32_t chunk_paths, double *d_partial,
                                double *d_out, void *stream);
+/* The same with default weights that differ per path (stochastic intensity, cva_metric.py:62-100 under autograd):
+ * d_w_paths [n_metric][n] replaces `weights`, slot 2 = lgd * sum w_m(path) 1{U > 0} dU.  With d_w_tan
+ * [n_metric][n_wtan][n] (mcre_eq_credit_weight_tangents) the output has n_par + n_wtan rows per metric date,
+ * d_out [n_metric][n_par + n_wtan][3]; row n_par + j: slot 2 = lgd * sum relu(U) d w_m / d (credit parameter j), the
+ * part of the CVA gradient that flows through the weights; slots 0 / 1 of those rows are 0. */
+int mcre_exposure_tangent_sums_paths(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo, int32_t n_par,
+                                     int32_t n_metric, const int32_t *metric_expo, const int32_t *lag, int32_t collateralised,
+                                     double threshold, const double *d_w_paths, double lgd, const double *d_w_tan,
+                                     int32_t n_wtan, int32_t chunk_paths, double *d_partial, double *d_out, void *stream);
 int mcre_eq_unsecured_exposures(const double *d_expo, int64_t n_paths, int32_t n_metric, const int32_t *metric_expo,
                                 const int32_t *lag, int32_t collateralised, double threshold, double *d_out, void *stream);
 /* d_out [n_rows][2] = sum(v - c), sum((v - c)^2) per row of d_x [n_rows][n], c = d_shift[row], v = x (mode 0),
@@ -458,6 +467,14 @@ int mcre_eq_set_credit(mcre_eq_plan *plan, const mcre_eq_credit *credit);
  * launch has added its exposures and mcre_eq_unsecured_exposures has netted them, mcre_eq_cva_paths gives the per-path
  * d_out [n_paths] = lgd * sum_k relu(unsec_k) w_k, finished by mcre_sum_stats. */
 int mcre_eq_set_cva_weight_spill(mcre_eq_plan *plan, double *d_w);
+/* Tangents of those per-path default weights w.r.t. the CIR++ model's own parameters (kappa, theta, sigma, y0) under a
+ * stochastic intensity (cirpp.py:174-198, 246-285 under torch.autograd): the credit factor is replayed from the plan's
+ * grid and the same draws (column noise_col of the joint draw through chol_row) with its Euler recursion differentiated
+ * by hand.  `credit` as for mcre_eq_set_credit (the plan itself need not carry the factor); dpsi host [n_sub][4] =
+ * d psi(t1) / d parameters, dcoef host [n_metric][2][4] = d (C_k, B_k) / d parameters.
+ * d_w_tan [n_metric][4][shard->n_paths] (0 on the last date). */
+int mcre_eq_credit_weight_tangents(mcre_eq_plan *plan, const mcre_eq_credit *credit, const double *dpsi, const double *dcoef,
+                                   const mcre_rng *rng, const mcre_shard *shard, double *d_w_tan, void *stream);
 int mcre_eq_cva_paths(const double *d_unsec, const double *d_w, int64_t n_paths, int32_t n_metric, double lgd,
                       double *d_out, void *stream);
 int mcre_eq_presim_tangents(mcre_eq_plan *plan, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,

@@ -1139,61 +1139,178 @@ extern "C" int mcre_eq_set_exposure_tangent_accumulator(mcre_eq_plan *p, double 
 namespace mcre {
 // Tangent sums of the exposure metrics of one netting set from per-path exposures and tangents: one block per
 // (chunk of paths, parameter, metric date); fixed summation order inside the block.
+// CVA weights: w [n_metric] shared by all paths, or per path wp [n_metric][n] (stochastic intensity) scaled by lgd; with
+// wt [n_metric][n_wtan][n] = tangents of the per-path weights w.r.t. the credit model's own parameters the grid's
+// y-dimension runs over n_par + n_wtan "parameters": for g >= n_par slot 2 = lgd * sum relu(U) d w / d credit_g.
 __global__ void __launch_bounds__(128) exposure_tangent_sums_kernel(const double *__restrict__ expo, const double *__restrict__ tan,
                                                                     long long n, int n_expo, int n_par, int n_metric,
                                                                     const int *__restrict__ metric_expo,
                                                                     const int *__restrict__ lag, int collateralised, double h,
-                                                                    const double *__restrict__ w, int chunk,
-                                                                    double *__restrict__ partial) {
+                                                                    const double *__restrict__ w, const double *__restrict__ wp,
+                                                                    double lgd, const double *__restrict__ wt, int n_wtan,
+                                                                    int chunk, double *__restrict__ partial) {
   __shared__ double stage[4][3];
   const int g = blockIdx.y, m = blockIdx.z;
   const int xe = metric_expo[m];
   const int l = collateralised ? lag[m] : -1;
-  const double *tg = tan + (size_t)g * n_expo * n;
-  double s_pos = 0.0, s_neg = 0.0;
+  const bool credit = g >= n_par;
+  const double *tg = tan + (size_t)(credit ? 0 : g) * n_expo * n;
+  const double *wtg = credit ? wt + ((size_t)m * n_wtan + (g - n_par)) * n : nullptr;
+  double s_pos = 0.0, s_neg = 0.0, s_cva = 0.0;
   const long long base = (long long)blockIdx.x * chunk;
   for (int it = threadIdx.x; it < chunk; it += blockDim.x) {
     const long long p = base + it;
     if (p >= n) break;
-    const double now = expo[(size_t)xe * n + p], dnow = tg[(size_t)xe * n + p];
+    const double now = expo[(size_t)xe * n + p], dnow = credit ? 0.0 : tg[(size_t)xe * n + p];
     auto thr = [h](double x) { return x > h ? x - h : (x < -h ? x + h : 0.0); };
     auto dthr = [h](double x) { return (x > h || x < -h) ? 1.0 : 0.0; };
     double u, du;
     if (collateralised) {
       const double delayed = l >= 0 ? expo[(size_t)(xe - l) * n + p] : 0.0;
-      const double ddel = l >= 0 ? tg[(size_t)(xe - l) * n + p] : 0.0;
+      const double ddel = (l >= 0 && !credit) ? tg[(size_t)(xe - l) * n + p] : 0.0;
       u = now - thr(delayed); du = dnow - dthr(delayed) * ddel;
     } else {
       u = thr(now); du = dthr(now) * dnow;
     }
-    if (u > 0.0) s_pos += du;
-    if (u < 0.0) s_neg += du;
+    if (credit) {
+      if (u > 0.0) s_cva += u * wtg[p];
+    } else {
+      if (u > 0.0) { s_pos += du; if (wp) s_cva += du * wp[(size_t)m * n + p]; }
+      if (u < 0.0) s_neg += du;
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int off = 16; off > 0; off >>= 1) {
     s_pos += __shfl_xor_sync(0xffffffffu, s_pos, off);
     s_neg += __shfl_xor_sync(0xffffffffu, s_neg, off);
+    s_cva += __shfl_xor_sync(0xffffffffu, s_cva, off);
   }
-  if (lane == 0) { stage[warp][0] = s_pos; stage[warp][1] = s_neg; }
+  if (lane == 0) { stage[warp][0] = s_pos; stage[warp][1] = s_neg; stage[warp][2] = s_cva; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < 4; ++k) { a += stage[k][0]; b += stage[k][1]; }
-    double *o = partial + ((size_t)blockIdx.x * n_metric * n_par + (size_t)m * n_par + g) * 3;
-    o[0] = a; o[1] = b; o[2] = w[m] * a;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int k = 0; k < 4; ++k) { a += stage[k][0]; b += stage[k][1]; c += stage[k][2]; }
+    const int np_tot = n_par + n_wtan;
+    double *o = partial + ((size_t)blockIdx.x * n_metric * np_tot + (size_t)m * np_tot + g) * 3;
+    o[0] = a; o[1] = b; o[2] = (wp || credit) ? lgd * c : w[m] * a;
+  }
+}
+
+// Tangents of the per-path default weights w_k = exp(-int lambda) (1 - C_k exp(-B_k y_k)) of a stochastic CIR++ credit
+// factor w.r.t. its own parameters (kappa, theta, sigma, y0): the factor is replayed from the same draws as in
+// eq_main_kernel (column cir_col of the joint draw, correlated through the credit row of the Cholesky factor) with the
+// Euler recursion differentiated by hand (cirpp.py:174-198, clamps pass the derivative like torch.clamp), one path per
+// thread.  psi [n_sub], dpsi [n_sub][4], coef [n_metric][2] = (C_k, B_k), dcoef [n_metric][2][4].
+struct CreditTanDev {
+  double kappa, theta, sigma, y0;
+  int cir_col;
+  const double *row, *psi, *dpsi, *coef, *dcoef;
+};
+__global__ void __launch_bounds__(128) credit_weight_tangents_kernel(EqDev P, RngDev rng, ShardDev sh, CreditTanDev ct,
+                                                                      double *__restrict__ w_tan) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= sh.n_paths) return;
+  const unsigned long long gpath = (unsigned long long)(sh.path_begin + p);
+  NormalStream ns; ns.init(rng, gpath);
+  const int d = P.noise_dim;
+  double cy = ct.y0, lb = 0.0, cyd[4] = {0.0, 0.0, 0.0, 1.0}, lbd[4] = {0.0, 0.0, 0.0, 0.0};
+  auto emit = [&](int di) {
+    const int m = __ldg(P.date_metric + di);
+    if (m < 0) return;
+    const double Ck = __ldg(ct.coef + 2 * m), Bk = __ldg(ct.coef + 2 * m + 1);
+    const double e1 = exp(-lb), e2 = exp(-Bk * cy), w = e1 * (1.0 - Ck * e2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double dC = __ldg(ct.dcoef + (size_t)m * 8 + j), dB = __ldg(ct.dcoef + (size_t)m * 8 + 4 + j);
+      const double dw = -w * lbd[j] + e1 * e2 * (Ck * (dB * cy + Bk * cyd[j]) - dC);
+      w_tan[((size_t)m * 4 + j) * sh.n_paths + p] = m < P.n_metric - 1 ? dw : 0.0;
+    }
+  };
+  for (int di = 0; di < P.n_pre_dates; ++di) emit(di);
+  for (int is = 0; is < P.n_sub; ++is) {
+    const double dt = __ldg(P.step_dt + is), sq = __ldg(P.step_sq + is);
+    double wc = 0.0;
+    for (int j = 0; j < d; ++j) {
+      double zj;
+      if (rng.mode == MCRE_RNG_INJECT) zj = rng.z[((size_t)is * rng.n_total + gpath) * d + j];
+      else {
+        const uint32_t nc = (uint32_t)(is * d + j);
+        double p0, p1;
+        ns.pair(nc >> 1, p0, p1);
+        zj = (nc & 1u) ? p1 : p0;
+      }
+      wc = fma(__ldg(ct.row + j), zj, wc);
+    }
+    const double sp = sqrt(fmax(cy, 0.0)), gsp = cy > 0.0 ? 0.5 / sp : 0.0;
+    const double yn = cy + ct.kappa * (ct.theta - cy) * dt + ct.sigma * sp * sq * wc;
+    const double carry = 1.0 - ct.kappa * dt + ct.sigma * sq * wc * gsp;
+    double dyn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dyn[j] = carry * cyd[j];
+    dyn[0] += (ct.theta - cy) * dt; dyn[1] += ct.kappa * dt; dyn[2] += sp * sq * wc;
+    lb += (cy + __ldg(ct.psi + is)) * dt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lbd[j] += (cyd[j] + __ldg(ct.dpsi + (size_t)is * 4 + j)) * dt;
+    const bool pass = yn >= 1e-12;
+    cy = fmax(yn, 1e-12);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cyd[j] = pass ? dyn[j] : 0.0;
+    const int di = __ldg(P.step_date + is);
+    if (di >= 0) emit(di);
   }
 }
 }  // namespace mcre
 
-extern "C" int mcre_exposure_tangent_sums(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo,
-                                          int32_t n_par, int32_t n_metric, const int32_t *metric_expo, const int32_t *lag,
-                                          int32_t collateralised, double threshold, const double *weights,
-                                          int32_t chunk_paths, double *d_partial, double *d_out, void *stream) {
-  if (!d_expo || !d_tan || !metric_expo || !lag || !weights || !d_partial || !d_out) return fail(-1, "null argument%s", "");
-  if (n_par <= 0 || n_metric <= 0 || n_expo <= 0 || chunk_paths <= 0) return fail(-2, "tangent sums: bad shape%s", "");
+extern "C" int mcre_eq_credit_weight_tangents(mcre_eq_plan *p, const mcre_eq_credit *c, const double *dpsi, const double *dcoef,
+                                              const mcre_rng *rng, const mcre_shard *shard, double *d_w_tan, void *stream) {
+  if (!p || !c || !dpsi || !dcoef || !rng || !shard || !d_w_tan || !c->step_cir || !c->chol_row || !c->cva_coef)
+    return fail(-1, "null argument%s", "");
+  if (c->deterministic) return fail(-4, "credit weight tangents: the deterministic intensity has no parameters%s", "");
+  if (p->d.n_metric <= 0 || !p->d.date_metric) return fail(-4, "credit weight tangents: the plan has no metric dates%s", "");
+  if (c->noise_col < 0 || c->noise_col >= p->d.noise_dim) return fail(-1, "eq: credit noise column out of range%s", "");
+  if (rng->mode == MCRE_RNG_INJECT && !rng->d_z) return fail(-1, "inject mode without normals%s", "");
+  const EqDev &D = p->d;
+  const size_t ns_ = (size_t)(D.n_sub > 0 ? D.n_sub : 1), nm = (size_t)D.n_metric, nd = (size_t)D.noise_dim;
+  std::vector<double> host(nd + ns_ + ns_ * 4 + nm * 2 + nm * 8, 0.0);
+  double *row = host.data(), *psi = row + nd, *dps = psi + ns_, *cf = dps + ns_ * 4, *dcf = cf + nm * 2;
+  for (size_t i = 0; i < nd; ++i) row[i] = c->chol_row[i];
+  for (size_t i = 0; i < (size_t)D.n_sub; ++i) psi[i] = c->step_cir[2 * i];
+  for (size_t i = 0; i < (size_t)D.n_sub * 4; ++i) dps[i] = dpsi[i];
+  for (size_t i = 0; i < nm * 2; ++i) cf[i] = c->cva_coef[i];
+  for (size_t i = 0; i < nm * 8; ++i) dcf[i] = dcoef[i];
+  double *dev = nullptr;
+  MCRE_CUDA(cudaMalloc((void **)&dev, host.size() * sizeof(double)));
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t slots = (int64_t)n_metric * n_par * 3;
+  cudaError_t e = cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? 0 : cuda_fail(e, "copy");
+  if (!rc && shard->n_paths > 0) {
+    CreditTanDev ct{c->kappa, c->theta, c->sigma, c->y0, c->noise_col, dev, dev + nd, dev + nd + ns_, dev + nd + ns_ * 5,
+                    dev + nd + ns_ * 5 + nm * 2};
+    RngDev r = make_rng(rng);
+    ShardDev sh{shard->path_begin, shard->n_paths, shard->chunk_paths};
+    credit_weight_tangents_kernel<<<(unsigned)((shard->n_paths + 127) / 128), 128, 0, st>>>(D, r, sh, ct, d_w_tan);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch");
+  }
+  cudaStreamSynchronize(st);   // the tables are freed below (pageable host source: the copy has completed too)
+  cudaFree(dev);
+  return rc;
+}
+
+static int exposure_tangent_sums_impl(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo,
+                                      int32_t n_par, int32_t n_metric, const int32_t *metric_expo, const int32_t *lag,
+                                      int32_t collateralised, double threshold, const double *weights,
+                                      const double *d_w_paths, double lgd, const double *d_w_tan, int32_t n_wtan,
+                                      int32_t chunk_paths, double *d_partial, double *d_out, void *stream) {
+  if (!d_expo || !d_tan || !metric_expo || !lag || (!weights && !d_w_paths) || !d_partial || !d_out)
+    return fail(-1, "null argument%s", "");
+  if (n_par <= 0 || n_metric <= 0 || n_expo <= 0 || chunk_paths <= 0 || n_wtan < 0 || (n_wtan > 0 && !d_w_tan))
+    return fail(-2, "tangent sums: bad shape%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t slots = (int64_t)n_metric * (n_par + n_wtan) * 3;
   const long long n_chunks = n_paths > 0 ? (n_paths + chunk_paths - 1) / chunk_paths : 0;
+  std::vector<double> zero_w((size_t)n_metric, 0.0);
   DevArray<int> me, lg;
   DevArray<double> wd;
   DevArena arena;
@@ -1202,13 +1319,14 @@ extern "C" int mcre_exposure_tangent_sums(const double *d_expo, const double *d_
     ArenaScope scope(&arena);
     rc = me.upload(metric_expo, n_metric);
     if (!rc) rc = lg.upload(lag, n_metric);
-    if (!rc) rc = wd.upload(weights, n_metric);
+    if (!rc) rc = wd.upload(weights ? weights : zero_w.data(), n_metric);
     if (!rc) rc = arena.commit();
   }
   if (!rc && n_chunks > 0) {
-    dim3 grid((unsigned)n_chunks, (unsigned)n_par, (unsigned)n_metric);
+    dim3 grid((unsigned)n_chunks, (unsigned)(n_par + n_wtan), (unsigned)n_metric);
     exposure_tangent_sums_kernel<<<grid, 128, 0, st>>>(d_expo, d_tan, n_paths, n_expo, n_par, n_metric, me.p, lg.p,
-                                                       collateralised, threshold, wd.p, chunk_paths, d_partial);
+                                                       collateralised, threshold, wd.p, d_w_paths, lgd, d_w_tan, n_wtan,
+                                                       chunk_paths, d_partial);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch");
@@ -1217,6 +1335,25 @@ extern "C" int mcre_exposure_tangent_sums(const double *d_expo, const double *d_
   if (!rc) cudaStreamSynchronize(st);   // the index tables are freed below
   arena.release();
   return rc;
+}
+
+extern "C" int mcre_exposure_tangent_sums(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo,
+                                          int32_t n_par, int32_t n_metric, const int32_t *metric_expo, const int32_t *lag,
+                                          int32_t collateralised, double threshold, const double *weights,
+                                          int32_t chunk_paths, double *d_partial, double *d_out, void *stream) {
+  if (!weights) return fail(-1, "null argument%s", "");
+  return exposure_tangent_sums_impl(d_expo, d_tan, n_paths, n_expo, n_par, n_metric, metric_expo, lag, collateralised,
+                                    threshold, weights, nullptr, 0.0, nullptr, 0, chunk_paths, d_partial, d_out, stream);
+}
+
+extern "C" int mcre_exposure_tangent_sums_paths(const double *d_expo, const double *d_tan, int64_t n_paths, int32_t n_expo,
+                                                int32_t n_par, int32_t n_metric, const int32_t *metric_expo,
+                                                const int32_t *lag, int32_t collateralised, double threshold,
+                                                const double *d_w_paths, double lgd, const double *d_w_tan, int32_t n_wtan,
+                                                int32_t chunk_paths, double *d_partial, double *d_out, void *stream) {
+  if (!d_w_paths) return fail(-1, "null argument%s", "");
+  return exposure_tangent_sums_impl(d_expo, d_tan, n_paths, n_expo, n_par, n_metric, metric_expo, lag, collateralised,
+                                    threshold, nullptr, d_w_paths, lgd, d_w_tan, n_wtan, chunk_paths, d_partial, d_out, stream);
 }
 
 namespace mcre {

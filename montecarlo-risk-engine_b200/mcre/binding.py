@@ -75,7 +75,7 @@ SYMBOLS = [
     "mcre_irc_set_coefficients", "mcre_irc_solve_coefficients", "mcre_irc_set_coefficients_device", "mcre_irc_mainsim", "mcre_irc_set_pv_spill", "mcre_irc_set_path_replay", "mcre_select_locate",
     "mcre_irc_set_exercise_coefficients", "mcre_irc_lsm_scratch_bytes", "mcre_irc_lsm_forward", "mcre_lsm_step", "mcre_lsm_step_states", "mcre_lsm_step_dev", "mcre_lsm_solve_dev", "mcre_lsm_moments_batch", "mcre_lsm_step_batch", "mcre_lsm_step_tangents",
     "mcre_lsm_prepare_equity",
-    "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_presim_tangents", "mcre_eq_set_exposure_coef_tangents", "mcre_eq_set_credit", "mcre_eq_set_cva_weight_spill", "mcre_eq_cva_paths", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_set_exposure_tangent_accumulator", "mcre_exposure_tangent_sums", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
+    "mcre_eq_create", "mcre_eq_destroy", "mcre_eq_slots", "mcre_eq_mainsim", "mcre_eq_presim", "mcre_eq_presim_tangents", "mcre_eq_set_exposure_coef_tangents", "mcre_eq_set_credit", "mcre_eq_set_cva_weight_spill", "mcre_eq_cva_paths", "mcre_eq_set_pv_accumulator", "mcre_eq_set_bridge_uniforms", "mcre_eq_set_exposure_accumulator", "mcre_eq_set_exposure_tangent_accumulator", "mcre_exposure_tangent_sums", "mcre_exposure_tangent_sums_paths", "mcre_eq_credit_weight_tangents", "mcre_eq_unsecured_exposures", "mcre_sum_stats",
     "mcre_storage_create", "mcre_storage_destroy", "mcre_storage_spots", "mcre_storage_backward", "mcre_storage_moment_slots", "mcre_storage_moments", "mcre_storage_solve", "mcre_storage_mainsim",
     "mcre_select_create", "mcre_select_destroy", "mcre_select_begin", "mcre_select_count",
     "mcre_select_scan", "mcre_select_compact", "mcre_select_finish",
@@ -159,6 +159,11 @@ def lib():
     L.mcre_eq_set_exposure_tangent_accumulator.argtypes = [C.c_void_p, C.c_void_p]
     L.mcre_exposure_tangent_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip,
                                              C.c_int32, C.c_double, c_dp, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_exposure_tangent_sums_paths.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip,
+                                                   C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_int32,
+                                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mcre_eq_credit_weight_tangents.argtypes = [C.c_void_p, C.c_void_p, c_dp, c_dp, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]
     L.mcre_eq_unsecured_exposures.argtypes = [C.c_void_p, C.c_int64, C.c_int32, c_ip, c_ip, C.c_int32, C.c_double,
                                               C.c_void_p, C.c_void_p]
     L.mcre_tree_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]

@@ -712,6 +712,40 @@ class EquityBackend:
         B.check(B.lib().mcre_eq_set_credit(plan, C.byref(cr)))
         return metric
 
+    def _credit_weight_tangents(self, plan, info, rng, sh, n, dev):
+        """d (per-path default weights) / d (kappa, theta, sigma, y0) of a stochastic CIR++ counterparty,
+        [n_metric][4][n] (mcre_eq_credit_weight_tangents): the closed forms psi(t) and (C_k, B_k) as host duals
+        (models/cirpp.py), the factor's Euler recursion differentiated in the kernel."""
+        c, cir = self.c, self.credit
+        grid, d = info["grid"], info["noise_dim"]
+        pv = cir.param_values()
+        pc = cir.dual_params(0, 4)
+        metric_times = c.metric_exposure_timeline.tolist()
+        n_metric = len(metric_times)
+        step = np.zeros((max(grid.n_sub, 1), 2))
+        dpsi = np.zeros((max(grid.n_sub, 1), 4))
+        for s_ in range(grid.n_sub):
+            ps = cir.psi(pc, grid.t1[s_])
+            step[s_, 0], dpsi[s_] = ps.v, ps.t
+        coef, dcoef = np.zeros((n_metric, 2)), np.zeros((n_metric, 2, 4))
+        for m in range(n_metric - 1):
+            Ck, Bk = cir.conditional_survival_coefficients(pc, metric_times[m], metric_times[m + 1])
+            coef[m] = (Ck.v, Bk.v)
+            dcoef[m, 0], dcoef[m, 1] = Ck.t, Bk.t
+        cr = EqCredit()
+        cr.deterministic, cr.noise_col = 0, d - 1
+        cr.kappa, cr.theta, cr.sigma, cr.y0, cr.lgd = pv[0], pv[1], pv[2], pv[3], 1.0
+        keep = {}
+        keep["step"], cr.step_cir = B.as_dp(step.reshape(-1))
+        keep["row"], cr.chol_row = B.as_dp(np.asarray(info["chol"])[0, d - 1, :])
+        keep["coef"], cr.cva_coef = B.as_dp(coef.reshape(-1))
+        keep["dpsi"], dpsi_p = B.as_dp(dpsi.reshape(-1))
+        keep["dcoef"], dcoef_p = B.as_dp(dcoef.reshape(-1))
+        w_tan = torch.zeros((n_metric, 4, n), dtype=torch.float64, device=dev)
+        B.check(B.lib().mcre_eq_credit_weight_tangents(plan, C.byref(cr), dpsi_p, dcoef_p, C.byref(rng), C.byref(sh),
+                                                       w_tan.data_ptr(), RT.stream_ptr()))
+        return w_tan
+
     # ------------------------------------------------------------------ execution
     def _rng(self, seed, n_total):
         c = self.c
@@ -1188,7 +1222,7 @@ class EquityBackend:
                     res["cva"] = ((0.0, 0.0), None)
         return res
 
-    def exposure_tangent_pass(self, si, dev, n_main, chunk):
+    def exposure_tangent_pass(self, si, dev, n_main, chunk, credit_out=None):
         """Tangent twin of _run_split_book for hybrid books (mcre/hybrid.py): the launches of netting set `si` in
         accumulating mode on a plan with tangents.  -> (per-path tangents of the netted exposure of the set's equity
         products [n_expo][assets][nt][n] w.r.t. the lane-local parameters (spot, volatility, rate) of each asset,
@@ -1234,6 +1268,9 @@ class EquityBackend:
                 sh = B.Shard(begin, count, chunk)
                 B.check(L.mcre_eq_mainsim(plan, C.byref(rng), C.byref(sh), partial.data_ptr(), acc.data_ptr(),
                                           shift.data_ptr(), None, RT.stream_ptr()))
+                if credit_out is not None and "w_tan" not in credit_out:
+                    # (the credit factor depends on the grid and the joint draw alone: any launch's plan will do)
+                    credit_out["w_tan"] = self._credit_weight_tangents(plan, info, rng, sh, n, dev)
                 acc_h = RT.all_reduce_tree(acc).cpu().numpy()
                 tang = acc_h[3:3 + self.A * self.nt].reshape(self.A, 1, self.nt)
                 for a, asset in enumerate(self.assets):

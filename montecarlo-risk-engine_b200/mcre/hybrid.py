@@ -55,10 +55,12 @@ def _families(model):
     return bs, vas[0], (cir[0] if cir else None)
 
 
-def metric_gradients(c, values, tan, pv_grad, chunk, dev):
+def metric_gradients(c, values, tan, pv_grad, chunk, dev, credit=None):
     """Netting-set terms and metric parts on per-path duals (mcre_exposure_tangent_sums): `values[si]` = the value run's
     dict of set si (exposures before netting terms "_expo", default weights "_cva_w"), tan[si] [parameters][exposure
     date][path] the tangents of those exposures, pv_grad[si] the PV gradient.
+    `credit` (stochastic intensity): {"w_tan": [n_metric][4][n] tangents of the per-path default weights w.r.t. the
+    credit model's parameters, "offset": index of its first parameter}; the weights themselves are the value run's.
     -> per set {"pv": grad, "pos": [grad per metric date], "neg": [...], "cva": grad} over the flattened parameters."""
     from metrics.metric import MetricType
     L = B.lib()
@@ -82,24 +84,37 @@ def metric_gradients(c, values, tan, pv_grad, chunk, dev):
                         lag[m] = int(metric_expo[m]) - delayed[m]
             w = np.zeros(n_metric)
             cva_w = values[si].get("_cva_w")
-            if cva_metric is not None and cva_w is not None:
+            per_path = credit is not None and cva_metric is not None and cva_w is not None
+            if cva_metric is not None and cva_w is not None and not per_path:
                 # deterministic credit: the same weights on every path; every rank reads its first local path
                 w_local = cva_w[:, 0].clone() if count > 0 else torch.zeros(n_metric, dtype=torch.float64, device=dev)
                 w = RT.to_host(w_local) * (1.0 - cva_metric.recovery_rate)
+            n_wtan = 4 if per_path else 0
             n_chunks = (n + chunk - 1) // chunk
-            slots = n_metric * n_par * 3
+            slots = n_metric * (n_par + n_wtan) * 3
             partial = torch.empty(n_chunks * slots + 1, dtype=torch.float64, device=dev)
             sums = torch.zeros(slots, dtype=torch.float64, device=dev)
             me_k, me_p = B.as_ip(metric_expo)
             lg_k, lg_p = B.as_ip(lag)
             w_k, w_p = B.as_dp(w)
-            B.check(L.mcre_exposure_tangent_sums(values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par,
-                                                 n_metric, me_p, lg_p, int(ns.is_collateralized()), float(ns.threshold),
-                                                 w_p, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
-            sm = RT.to_host(RT.all_reduce_tree(sums)).reshape(n_metric, n_par, 3) / n_main
-            res["pos"] = [sm[m, :, 0] for m in range(n_metric)]
-            res["neg"] = [sm[m, :, 1] for m in range(n_metric)]
-            res["cva"] = sm[:n_metric - 1, :, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
+            if per_path:
+                # stochastic intensity: per-path weights; the credit model's own parameters enter through the weights
+                # (rows n_par .. n_par + 3 of the result)
+                B.check(L.mcre_exposure_tangent_sums_paths(
+                    values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par, n_metric, me_p, lg_p,
+                    int(ns.is_collateralized()), float(ns.threshold), cva_w.data_ptr(), 1.0 - cva_metric.recovery_rate,
+                    credit["w_tan"].data_ptr(), n_wtan, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
+            else:
+                B.check(L.mcre_exposure_tangent_sums(values[si]["_expo"].data_ptr(), tan[si].data_ptr(), count, n_expo, n_par,
+                                                     n_metric, me_p, lg_p, int(ns.is_collateralized()), float(ns.threshold),
+                                                     w_p, chunk, partial.data_ptr(), sums.data_ptr(), RT.stream_ptr()))
+            sm = RT.to_host(RT.all_reduce_tree(sums)).reshape(n_metric, n_par + n_wtan, 3) / n_main
+            res["pos"] = [sm[m, :n_par, 0] for m in range(n_metric)]
+            res["neg"] = [sm[m, :n_par, 1] for m in range(n_metric)]
+            res["cva"] = sm[:n_metric - 1, :n_par, 2].sum(axis=0) if n_metric > 1 else np.zeros(n_par)
+            if per_path and n_metric > 1:
+                off = credit["offset"]
+                res["cva"][off:off + 4] += sm[:n_metric - 1, n_par:, 2].sum(axis=0)
             # PFE: the reference differentiates torch.sort(...)[index] (pfe_metric.py:59-71) = the pathwise gradient of the
             # selected path.  The path is located in the value run's unsecured exposures (smallest global id among ties,
             # like the interest-rate backend), its dual read from the per-path tensors on the rank that owns it.
@@ -140,8 +155,10 @@ def metric_gradients(c, values, tan, pv_grad, chunk, dev):
     return out
 
 
-def attach_gradients(results, grads, used):
-    """Puts the gradients of metric_gradients next to the values of the value run's per-set dicts."""
+def attach_gradients(results, grads, used, used_cva=None):
+    """Puts the gradients of metric_gradients next to the values of the value run's per-set dicts.  used / used_cva:
+    which parameters the metrics / the CVA are connected to in the reference's autograd graph."""
+    from metrics.metric import MetricType
     for res, g in zip(results, grads):
         res["pv"] = (res["pv"][0], g["pv"])
         if "pos" in res:
@@ -152,7 +169,7 @@ def attach_gradients(results, grads, used):
             res["cva"] = (res["cva"][0], g["cva"])
         for q, rows in (g.get("pfe") or {}).items():
             res["pfe"][q] = (res["pfe"][q][0], rows)
-        res["param_used"] = lambda kind, used=used: used
+        res["param_used"] = lambda kind, used=used, uc=used_cva: (uc if (uc is not None and kind == MetricType.CVA) else used)
 
 
 def _credit_checks(c, cir, what):
@@ -194,7 +211,6 @@ class EquityCreditGreeks:
         from mcre.equity import credit_of
         self.c = ctrl
         self.credit, self.credit_idx = credit_of(ctrl.model)
-        _credit_checks(ctrl, self.credit, "equity books against a credit model")
 
     def _view(self, differentiate):
         c = self.c
@@ -232,20 +248,31 @@ class EquityCreditGreeks:
         presim(et, tview)
         tan = [torch.zeros((n_par, n_expo, n), dtype=torch.float64, device=dev) if need_expo else None for _ in range(n_sets)]
         pv_grad = []
+        from metrics.metric import MetricType
+        stochastic_cva = (self.credit is not None and not self.credit.deterministic and need_expo
+                          and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics))
+        credit_out = {} if stochastic_cva else None
         for si in range(n_sets):
-            accum_t, g_pv = et.exposure_tangent_pass(si, dev, n_main, chunk)
+            accum_t, g_pv = et.exposure_tangent_pass(si, dev, n_main, chunk, credit_out=credit_out)
             pv_grad.append(g_pv)
             if need_expo:
                 for a, asset in enumerate(et.assets):
                     for k, g in enumerate(asset.gmap):
                         tan[si][g] += accum_t[:, a, k, :]
-        grads = metric_gradients(c, results, tan, pv_grad, chunk, dev)
+        credit = None
+        if stochastic_cva and "w_tan" in credit_out:
+            credit = {"w_tan": credit_out["w_tan"], "offset": c.model.param_offsets()[self.credit_idx]}
+        grads = metric_gradients(c, results, tan, pv_grad, chunk, dev, credit=credit)
         used = [True] * n_par
-        if self.credit is not None:
+        used_cva = list(used)
+        if self.credit is not None and self.credit.deterministic:
+            # the deterministic intensity is outside the reference's autograd graph (None); a stochastic one rides in the
+            # joint state tensor: its parameters come back as 0.0 for the metrics they do not move
             offs = c.model.param_offsets()
             for k in range(len(self.credit.model_params)):
                 used[offs[self.credit_idx] + k] = False
-        attach_gradients(results, grads, used)
+                used_cva[offs[self.credit_idx] + k] = False
+        attach_gradients(results, grads, used, used_cva)
         torch.cuda.synchronize(dev)
         total = time.perf_counter() - t_start
         return results, {"preprocessing": 0.0, "path_generation": total, "request_resolution": 0.0}

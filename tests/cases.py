@@ -637,6 +637,8 @@ GOLDEN_CASES = {
     "equity_cva": (equity_cva, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=False)),
     "equity_cva_single_det": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=False)),
     # sensitivities of CVA / EPE / PV of equity books against a counterparty with a deterministic intensity
+    # stochastic intensity correlated with the assets: the credit model's own parameters enter through the default weights
+    "equity_cva_greeks": (equity_cva, dict(rho=0.2), dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva_det_greeks": (equity_cva, dict(rho=0.0, deterministic=True), dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "equity_cva_single_det_greeks": (equity_cva, dict(rho=0.0, deterministic=True, single=True), dict(n_main=1024, n_pre=1024, num_steps=1, scheme="EULER", differentiate=True)),
     "equity_cva_exercise": (equity_cva_exercise, dict(), dict(n_main=512, n_pre=512, num_steps=1, scheme="EULER", differentiate=False)),

@@ -373,12 +373,14 @@ def test_equity_book_cva_matches_reference_and_oracle(name):
                   name + " philox", err_rtol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["equity_cva_det_greeks", "equity_cva_single_det_greeks"])
+@pytest.mark.parametrize("name", ["equity_cva_det_greeks", "equity_cva_single_det_greeks", "equity_cva_greeks"])
 def test_equity_book_cva_sensitivities_match_reference_autograd(name):
-    """differentiate=True on the equity CVA books with a deterministic intensity (mcre/hybrid.py:EquityCreditGreeks): CVA,
-    EPE and PV gradients with respect to the market model's parameters against the reference's autograd (exposure metrics
-    through its float32 regression chain: 2e-5; PV pathwise: 1e-8); the credit model's parameters are outside the
-    reference's graph (None).  Native Philox against the oracle's duals."""
+    """differentiate=True on the equity CVA books (mcre/hybrid.py:EquityCreditGreeks): CVA, EPE and PV gradients with
+    respect to the market model's parameters against the reference's autograd (exposure metrics through its float32
+    regression chain: 2e-5; PV pathwise: 1e-8).  Deterministic intensity: the credit model's parameters are outside the
+    reference's graph (None).  Stochastic intensity correlated with the assets (`equity_cva_greeks`): per-path default
+    weights, and the credit model's own parameters through the weights' tangents (mcre_eq_credit_weight_tangents).
+    Native Philox against the oracle's duals."""
     gold = helpers.load_golden(name)
     res, sc = helpers.run_cuda(name, draws="torch")
     flat = helpers.flatten_results(res)

@@ -55,7 +55,10 @@ def main():
                  # round 2: three-model hybrid books (values and sensitivities), gas storage with the device-moments
                  # solver (pre-simulation sharded) and with the LAPACK solver (pre-simulation replicated), storage Greeks
                  "hybrid_cva_corr", "hybrid_collateral", "hybrid_collateral_greeks", "storage2_short_euler",
-                 "storage2_short_euler:gelsy", "storage_s2f_greeks"]:
+                 "storage2_short_euler:gelsy", "storage_s2f_greeks",
+                 # sensitivities from per-path duals: PFE order statistics, equity + credit, books split over launches;
+                 # pathwise Hessians
+                 "bs_pfe_greeks", "hybrid_pfe_greeks", "equity_cva_det_greeks", "bs_split_book_greeks", "bs_hessian_multi"]:
         extra = {}
         if ":" in name:
             name, solver = name.split(":")
@@ -69,6 +72,9 @@ def main():
                 if cases.GOLDEN_CASES[name][2]["differentiate"]:
                     for row in res.get_derivatives(s, m):
                         vals += [bits(0.0 if g is None else g) for g in row]
+                if cases.GOLDEN_CASES[name][2].get("second_order"):
+                    si, mi = res.get_netting_set_names().index(s), res.get_metric_names().index(m)
+                    vals += [bits(0.0 if x is None else x) for ev in res.second_derivatives[si][mi] for row in ev for x in row]
         out[key] = vals
     ns = cases.Namespace()
     model, sets, metrics, _ = cases.heston_basket5(ns)
