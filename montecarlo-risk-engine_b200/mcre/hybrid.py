@@ -293,9 +293,6 @@ class HybridBackend:
             cir = c.model.models[self.cir_idx] if self.cir_idx is not None else None
             if len(self.bs_idx) != 1:
                 raise NotImplementedError("sensitivities of hybrid books: one Black-Scholes market model")
-            if cir is not None and not cir.deterministic and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics):
-                raise NotImplementedError("sensitivities of the CVA of hybrid books: deterministic credit (the default "
-                                          "weights of a stochastic intensity carry tangents the equity launch does not have)")
         if c.simulation_scheme != SimulationScheme.EULER:
             # the reference defines inter-model covariances for Black-Scholes pairs only (model_config.py:201-221)
             raise NotImplementedError("Inter covariance not implemented for the requested pair of models.")
@@ -434,8 +431,19 @@ class HybridBackend:
             view = copy.copy(ns)
             view.products = [p for p in ns.products if p in self.equity_products]
             eq_sets.append(view)
-        sub = self._sub(models[b], eq_sets, differentiate=True)
-        sub.injected_normals = {k: v[:, :, :1].contiguous() for k, v in noise_eq.items()}
+        cir = models[self.cir_idx] if self.cir_idx is not None else None
+        stochastic_cva = (cir is not None and not cir.deterministic and need_expo
+                          and any(m.metric_type == MetricType.CVA for m in c.risk_metrics.metrics))
+        if stochastic_cva:
+            # the credit factor as a passenger of the equity plan (the value run's layout: market model, then credit):
+            # its column of the joint draw feeds the tangents of the per-path default weights
+            from models.model_config import ModelConfig
+            sub = self._sub(ModelConfig(models=[models[b], cir]), eq_sets, differentiate=True)
+            sub.injected_normals = dict(noise_eq)
+        else:
+            sub = self._sub(models[b], eq_sets, differentiate=True)
+            sub.injected_normals = {k: v[:, :, :1].contiguous() for k, v in noise_eq.items()}
+        credit_out = {} if stochastic_cva else None
         sub.regression_coeffs = [rc.clone() for rc in c.regression_coeffs]
         eb = EquityBackend(sub)
         eb.presim_exercise_all([p for p in sub.products if is_equity_exercise(p)], dev)
@@ -446,13 +454,19 @@ class HybridBackend:
         for si in range(n_sets):
             if not eq_sets[si].products:
                 continue
-            accum_t, g_pv = eb.exposure_tangent_pass(si, dev, n_main, chunk)
+            accum_t, g_pv = eb.exposure_tangent_pass(si, dev, n_main, chunk, credit_out=credit_out)
             for k in range(3):
                 if need_expo:
                     tan[si][offs[b] + k] += accum_t[:, 0, k, :]
                 pv_grad[si][offs[b] + k] += g_pv[k]
 
-        return metric_gradients(c, values, tan, pv_grad, chunk, dev)
+        credit = None
+        if stochastic_cva:
+            if "w_tan" not in credit_out:
+                raise NotImplementedError("sensitivities of the CVA of hybrid books under a stochastic intensity: a netting "
+                                          "set with equity products (the weights' tangents ride with an equity launch)")
+            credit = {"w_tan": credit_out["w_tan"], "offset": offs[self.cir_idx]}
+        return metric_gradients(c, values, tan, pv_grad, chunk, dev, credit=credit)
 
     def run(self):
         from metrics.metric import MetricType
@@ -547,7 +561,8 @@ class HybridBackend:
             # autograd graph does not reach them (None); everything else is connected
             offs = c.model.param_offsets()
             used = [True] * len(c.model.model_params)
-            if self.cir_idx is not None:
+            if self.cir_idx is not None and models[self.cir_idx].deterministic:
+                # (a stochastic intensity rides in the joint state tensor: 0.0 where it moves nothing, numbers for the CVA)
                 for k in range(len(models[self.cir_idx].model_params)):
                     used[offs[self.cir_idx] + k] = False
             attach_gradients(results, grads, used)

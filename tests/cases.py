@@ -662,6 +662,9 @@ GOLDEN_CASES = {
     # first-order sensitivities of a hybrid book: the AAD leg of test_cva_large_netting_set_aad_vs_fd.py at its own
     # sizes, and a smaller book with threshold / MPoR sets and more metrics (deterministic credit)
     "hybrid_cva_greeks": (hybrid_cva, dict(), dict(n_main=1024, n_pre=1024, num_steps=4, scheme="EULER", differentiate=True)),
+    # stochastic intensity correlated with both market factors: sensitivities to all three models' parameters, PFE included
+    "hybrid_stochastic_greeks": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, deterministic=False, rho=(0.25, 0.1, -0.3), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True, pfe=True),
+                                 dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "hybrid_collateral_greeks": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, rho=(0.25, 0.0, 0.0), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True, pfe=False),
                                  dict(n_main=1024, n_pre=1024, num_steps=2, scheme="EULER", differentiate=True)),
     "hybrid_collateral": (hybrid_cva, dict(n_euro=2, n_bonds=1, n_swaps=3, deterministic=False, rho=(0.25, 0.1, -0.3), horizon=2.0, n_expo=9, extra_metrics=True, collateral=True),

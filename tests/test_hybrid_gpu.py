@@ -57,7 +57,7 @@ def test_hybrid_cva_is_positive_and_moves_with_spot_and_rate():
     assert np.isfinite(d_spot) and np.isfinite(d_rate) and d_spot > 0.0      # calls gain with the spot
 
 
-@pytest.mark.parametrize("name", ["hybrid_cva_greeks", "hybrid_collateral_greeks", "hybrid_pfe_greeks"])
+@pytest.mark.parametrize("name", ["hybrid_cva_greeks", "hybrid_collateral_greeks", "hybrid_pfe_greeks", "hybrid_stochastic_greeks"])
 def test_hybrid_sensitivities_match_reference_autograd(name):
     """differentiate=True on a hybrid book: every metric's gradient with respect to the 11 parameters of the three models
     against torch.autograd of the unmodified reference.  Exposure metrics pass through the float32 regression chain on
@@ -108,9 +108,17 @@ def test_large_netting_set_cva_aad_matches_finite_differences():
 
 
 def test_unsupported_hybrid_sensitivities_raise():
+    """Sensitivities of hybrid books are lowered for one Black-Scholes market model; two of them must raise, not fall back."""
     ns = cases.Namespace()
-    model, sets, metrics, tl = cases.hybrid_cva(ns, n_euro=1, n_bonds=1, n_swaps=1, deterministic=False)
-    sc = ns.SimulationController(sets, model, ns.RiskMetrics(metrics, exposure_timeline=tl), 256, 256, 1,
-                                 ns.SimulationScheme.EULER, True)
-    with pytest.raises(NotImplementedError):      # CVA sensitivities under a stochastic intensity
+    eq1 = ns.BlackScholesModel(calibration_date=0.0, spot=100.0, rate=0.03, sigma=0.22, asset_id="equity")
+    eq2 = ns.BlackScholesModel(calibration_date=0.0, spot=90.0, rate=0.03, sigma=0.3, asset_id="equity_2")
+    rates = ns.VasicekModel(calibration_date=0.0, rate=0.03, mean=0.03, mean_reversion_speed=1.0, volatility=0.01, asset_id="rates")
+    model = ns.ModelConfig(models=[eq1, eq2, rates], inter_asset_correlation_matrix=[np.array([0.0])] * 3)
+    prods = [ns.EuropeanOption(ns.Equity("equity"), 1.0, 100.0, ns.OptionType.CALL, asset_id="equity"),
+             ns.EuropeanOption(ns.Equity("equity_2"), 1.0, 90.0, ns.OptionType.PUT, asset_id="equity_2"),
+             ns.Bond(startdate=0.0, maturity=2.0, notional=2.0, tenor=0.5, pays_notional=True, fixed_rate=0.02, asset_id="rates")]
+    sc = ns.SimulationController([ns.NettingSet(name="s", products=prods)], model,
+                                 ns.RiskMetrics([ns.EPEMetric(), ns.PVMetric()], exposure_timeline=np.linspace(0.0, 2.0, 5)),
+                                 256, 256, 1, ns.SimulationScheme.EULER, True)
+    with pytest.raises(NotImplementedError):
         sc.run_simulation()
