@@ -1047,7 +1047,7 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
                       (d.has_cir ? NS * 2 : 0);
   const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
-  if (n_chunks == 0) return 0;
+  if (n_chunks == 0 && presim) return 0;
   auto k = eq_main_kernel<KIND, ALT, NT, NS>;
   // (14 KB of static function tables: static + dynamic shared memory beyond 48 KB needs the opt-in, before the query)
   if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1056,12 +1056,15 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   if (per_sm < 1) return fail(-3, "eq main kernel does not fit%s", "");
   long long grid = (long long)sm_count() * per_sm;
   if (grid > n_chunks) grid = n_chunks;
+  // The pilot launch (global path 0 -> the common shift of the shifted sums) runs on every rank, also on one whose
+  // shard is empty (fewer chunks than ranks): all ranks finish the all-reduced sums with the same shift.
   ShardDev pilot_sh{0, 1, sh.chunk};
   if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (!presim) {   // the pre-simulation pass only spills; it needs no pilot shifts
     k<<<1, threads, smem, st>>>(d, rng, pilot_sh, partial, shift, spill, 1);
     MCRE_LAUNCHED();
   }
+  if (n_chunks == 0) return 0;
   k<<<(unsigned)grid, threads, smem, st>>>(d, rng, sh, partial, shift, spill, 0);
   MCRE_LAUNCHED();
   return 0;

@@ -149,7 +149,7 @@ def metric_gradients(c, values, tan, pv_grad, chunk, dev, credit=None):
                     else:
                         g = dthr(float(expo_h[xe, lp])) * tan[si][:, xe, lp]
                     grad[m] = g
-                grad_h = RT.to_host(RT.all_reduce_tree(grad))
+                grad_h = RT.to_host(RT.all_reduce_tree(grad)) + 0.0     # (-0.0 of a masked tangent -> 0.0, as the sum over ranks gives)
                 res["pfe"][q] = [grad_h[m] for m in range(n_metric)]
         out.append(res)
     return out
@@ -211,6 +211,9 @@ class EquityCreditGreeks:
         from mcre.equity import credit_of
         self.c = ctrl
         self.credit, self.credit_idx = credit_of(ctrl.model)
+        if self.credit is not None and ctrl.simulation_scheme != SimulationScheme.EULER:
+            # same restriction as the reference: only Black-Scholes pairs have a joint exact covariance (model_config.py:216-221)
+            raise NotImplementedError("Analytical covariance is currently only supported for Black-Scholes-type model pairs.")
 
     def _view(self, differentiate):
         c = self.c

@@ -14,7 +14,7 @@ importlib.import_module("montecarlo-risk-engine_b200")
 import numpy as np  # noqa: E402
 
 import cases  # noqa: E402
-import helpers  # noqa: E402
+import parity_helpers as helpers  # noqa: E402
 from oracle import risk  # noqa: E402
 
 

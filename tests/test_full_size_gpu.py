@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import cases
-import helpers
+import parity_helpers as helpers
 
 pytestmark = pytest.mark.gpu
 

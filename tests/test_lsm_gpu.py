@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import cases
-import helpers
+import parity_helpers as helpers
 
 pytestmark = pytest.mark.gpu
 

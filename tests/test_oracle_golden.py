@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import cases
-import helpers
+import parity_helpers as helpers
 
 VALUE_RTOL = 1e-9
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import cases
-import helpers
+import parity_helpers as helpers
 
 pytestmark = pytest.mark.gpu
 

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import cases
-import helpers
+import parity_helpers as helpers
 
 
 @pytest.fixture(scope="module")
