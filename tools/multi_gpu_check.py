@@ -58,7 +58,9 @@ def main():
                  "storage2_short_euler:gelsy", "storage_s2f_greeks",
                  # sensitivities from per-path duals: PFE order statistics, equity + credit, books split over launches;
                  # pathwise Hessians
-                 "bs_pfe_greeks", "hybrid_pfe_greeks", "equity_cva_det_greeks", "bs_split_book_greeks", "bs_hessian_multi"]:
+                 "bs_pfe_greeks", "hybrid_pfe_greeks", "equity_cva_det_greeks", "bs_split_book_greeks", "bs_hessian_multi",
+                 # stochastic intensity: per-path default weights and their tangents
+                 "equity_cva_greeks", "hybrid_stochastic_greeks"]:
         extra = {}
         if ":" in name:
             name, solver = name.split(":")
