@@ -1211,6 +1211,7 @@ struct CreditTanDev {
 };
 __global__ void __launch_bounds__(128) credit_weight_tangents_kernel(EqDev P, RngDev rng, ShardDev sh, CreditTanDev ct,
                                                                       double *__restrict__ w_tan) {
+  fm_tables_init();      // (the Philox normals go through the table-driven elementary functions, like eq_main_kernel's)
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= sh.n_paths) return;
   const unsigned long long gpath = (unsigned long long)(sh.path_begin + p);
