@@ -1,0 +1,3 @@
+from unittest import mock
+def __getattr__(name):
+    return mock.MagicMock()
