@@ -164,7 +164,11 @@ __device__ __forceinline__ Dual<N> dual_ncdf(const Dual<N> &x) {
 // Sensitivities of exposure profiles (controller.py:609-627 on EPE / ENE / CE / EEPE): Black-Scholes builds with
 // tangents carry the exposures as duals (lane-local tangents like the cashflows); other models keep doubles.
 // (NT = 9: the second-order build, Dual2<3> - present values only)
-template <int KIND, int NT> struct EqExpoTan { static const bool on = (KIND == MCRE_EQ_BS) && (NT > 0) && (NT != 9); };
+// Heston builds too (every exposure a regression proxy on the spot; the analytic branch is Black-Scholes only).
+template <int KIND, int NT> struct EqExpoTan {
+  static const bool on = (KIND == MCRE_EQ_BS || KIND == MCRE_EQ_HESTON) && (NT > 0) && (NT != 9);
+};
+static inline bool eq_kind_has_exposure_tangents(int kind) { return kind == MCRE_EQ_BS || kind == MCRE_EQ_HESTON; }
 template <bool ON, typename R> struct EqExpoReal { typedef double type; };
 template <typename R> struct EqExpoReal<true, R> { typedef R type; };
 
@@ -868,7 +872,8 @@ extern "C" int mcre_eq_create(const mcre_eq_desc *c, mcre_eq_plan **out) {
     return fail(-4, "eq: the second-order build carries present values only%s", "");
   if (c->nt != 0 && c->n_sets > 2) return fail(-3, "eq: at most 2 netting sets per launch when tangents are on%s", "");
   if (c->nt != 0 && c->n_expo > 0) {
-    if (c->kind != MCRE_EQ_BS) return fail(-4, "eq: sensitivities of exposure profiles need a Black-Scholes model%s", "");
+    if (!eq_kind_has_exposure_tangents(c->kind))
+      return fail(-4, "eq: sensitivities of exposure profiles need a Black-Scholes or Heston model%s", "");
     for (size_t i = 0; i < (size_t)c->n_expo * c->n_prod; ++i)
       if (c->xp[i * EQ_XP] > 2.0)
         return fail(-4, "eq: sensitivities of the exposures of exercise products are not implemented%s", "");
@@ -988,8 +993,8 @@ extern "C" void mcre_eq_destroy(mcre_eq_plan *p) {
 
 extern "C" int mcre_eq_set_exposure_coef_tangents(mcre_eq_plan *p, const double *xp_tan) {
   if (!p || !xp_tan) return fail(-1, "null argument%s", "");
-  if (p->nt <= 0 || p->d.kind != MCRE_EQ_BS || p->d.n_expo <= 0)
-    return fail(-4, "eq: coefficient tangents need a Black-Scholes plan with tangents and exposure dates%s", "");
+  if (p->nt <= 0 || !eq_kind_has_exposure_tangents(p->d.kind) || p->d.n_expo <= 0)
+    return fail(-4, "eq: coefficient tangents need a Black-Scholes / Heston plan with tangents and exposure dates%s", "");
   const size_t n = (size_t)p->d.n_expo * p->d.n_prod * 3 * p->nt;
   if (!p->xp_tan) MCRE_CUDA(cudaMalloc((void **)&p->xp_tan, n * sizeof(double)));
   MCRE_CUDA(cudaMemcpy(p->xp_tan, xp_tan, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -1027,7 +1032,7 @@ static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 
 
 extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
   const int ns = eq_ns_template(p->d.n_sets);
-  const bool xt = p->d.kind == MCRE_EQ_BS && p->nt > 0;
+  const bool xt = eq_kind_has_exposure_tangents(p->d.kind) && p->nt > 0 && p->nt != 9;
   return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4 +
          (xt ? (int64_t)p->d.n_metric * p->d.n_assets * ns * 2 * p->nt : 0) + (p->d.has_cir ? ns * 2 : 0);
 }
@@ -1456,7 +1461,8 @@ extern "C" int mcre_eq_set_pv_accumulator(mcre_eq_plan *p, double *d_accum) {
 extern "C" int mcre_eq_presim_tangents(mcre_eq_plan *p, const mcre_rng *rng, const mcre_shard *shard, double *d_partial,
                                        double *d_shift, double *d_x, float *d_cf, double *d_dx, double *d_dcf, void *stream) {
   if (!p || !rng || !d_partial || !d_shift || !d_x || !d_cf || !d_dx || !d_dcf) return fail(-1, "null argument%s", "");
-  if (p->nt <= 0 || p->d.kind != MCRE_EQ_BS) return fail(-4, "eq presim tangents: Black-Scholes plans with tangents only%s", "");
+  if (p->nt <= 0 || !eq_kind_has_exposure_tangents(p->d.kind))
+    return fail(-4, "eq presim tangents: Black-Scholes / Heston plans with tangents only%s", "");
   if (p->d.n_expo <= 0) return fail(-1, "eq presim: the plan has no exposure dates%s", "");
   p->d.ps_x = d_x; p->d.ps_cf = d_cf; p->d.ps_dx = d_dx; p->d.ps_dcf = d_dcf;
   const int rc = mcre_eq_mainsim(p, rng, shard, d_partial, d_partial /* scratch: sums are not used */, d_shift, nullptr, stream);

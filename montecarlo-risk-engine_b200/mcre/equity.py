@@ -254,9 +254,9 @@ class EquityBackend:
             self.nt = 9
         if ctrl.differentiate and ctrl.risk_metrics.requires_exposure_profiles():
             # checked before any device work (the same conditions guard the lowering)
-            if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
+            if self.kind not in (EQ_BS, EQ_HESTON) or any(a.gmap[2] != self.num_rate_global for a in self.assets):
                 raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
-                                          "model (single or multi-asset)")
+                                          "model (single or multi-asset) or one Heston model")
             if any(m.metric_type == MetricType.PFE for m in ctrl.risk_metrics.metrics) and not getattr(ctrl, "_credit_passenger", False):
                 # (the fused kernel reduces tangent sums; the gradient of an order statistic is the tangent of ONE path:
                 # mcre/hybrid.py:EquityCreditGreeks takes it from the per-path duals of the accumulating tangent pass)
@@ -586,9 +586,9 @@ class EquityBackend:
                 # sensitivities of EPE / ENE / CE through the analytic Black-Scholes exposure: tangents in the fused kernel
                 # (csrc/equity.cu, exposure tangents).  The numeraire term lands on the lane-local rate, so every asset
                 # must share the numeraire's rate parameter (BlackScholesModel, BlackScholesMulti).
-                if self.kind != EQ_BS or any(a.gmap[2] != self.num_rate_global for a in self.assets):
+                if self.kind not in (EQ_BS, EQ_HESTON) or any(a.gmap[2] != self.num_rate_global for a in self.assets):
                     raise NotImplementedError("sensitivities of exposure profiles of equity books: one Black-Scholes "
-                                              "model (single or multi-asset)")
+                                              "model (single or multi-asset) or one Heston model")
                 for p in owners:
                     if c._can_use_analytic_exposure_for_product(p):
                         continue
@@ -938,8 +938,8 @@ class EquityBackend:
         # also writes the tangents of spots and deflated cashflows; the normal equations are differentiated below
         nt = self.nt
         if nt:
-            if self.kind != EQ_BS:
-                raise NotImplementedError("sensitivities of regression-proxy exposures: Black-Scholes models only")
+            if self.kind not in (EQ_BS, EQ_HESTON):
+                raise NotImplementedError("sensitivities of regression-proxy exposures: Black-Scholes and Heston models")
             for p in products:
                 ids = set(getattr(p, "asset_ids", None) or [])
                 if len(ids) > 1 or getattr(p, "basket", None) is not None:
@@ -1362,7 +1362,7 @@ class EquityBackend:
             xshift = shift_h[expo_base:xt_base].reshape(n_metric, ns_t, 4)
             # exposure tangents [metric date][asset][set][pos / neg][lane-local parameter] (Black-Scholes builds)
             xtan = None
-            if self.nt and n_metric and self.kind == EQ_BS:
+            if self.nt and n_metric and self.kind in (EQ_BS, EQ_HESTON) and not self.second:
                 xtan = acc_h[xt_base:].reshape(n_metric, self.A, ns_t, 2, self.nt)
             cva_acc = cva_shift = None
             if cva_metric is not None:

@@ -215,6 +215,22 @@ def bs_hessian(ns_module, multi=False):
     return model, sets, [m.PVMetric()], None
 
 
+def heston_exposure_greeks(ns_module):
+    """Sensitivities of exposure metrics under Heston (no closed-form exposure: every product goes through the regression
+    proxy on the spot, controller.py:294-383, 438-447, 609-627): a European put, a binary call and an Asian call in a
+    thresholded and an MPoR-collateralised netting set."""
+    m = ns_module
+    model = m.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
+
+    def book():
+        return [m.EuropeanOption(m.Equity("id"), 1.0, 105.0, m.OptionType.PUT),
+                m.BinaryOption(1.5, 100.0, 10.0, m.OptionType.CALL),
+                m.AsianOption(0.0, 1.0, 100.0, 5, m.OptionType.CALL)]
+    sets = [m.NettingSet(name="thresholded", products=book(), threshold=3.0),
+            m.NettingSet(name="collateralised", products=book(), margin_period_of_risk=0.25, threshold=1.0)]
+    return model, sets, [m.EEPEMetric(), m.EPEMetric(), m.ENEMetric(), m.PVMetric()], np.linspace(0.0, 1.5, 7)
+
+
 def bs_split_book_greeks(ns_module):
     """Exposure sensitivities of a netting set with more path-dependent products than one launch with tangents tracks
     (two), so that the book is split over launches: the reference nets whatever the set holds (controller.py:438-447)."""
@@ -631,6 +647,8 @@ GOLDEN_CASES = {
     "bs_hessian": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=1, scheme="ANALYTICAL", differentiate=True, second_order=True)),
     "bs_hessian_euler": (bs_hessian, dict(), dict(n_main=2048, n_pre=0, num_steps=3, scheme="EULER", differentiate=True, second_order=True)),
     "bs_hessian_multi": (bs_hessian, dict(multi=True), dict(n_main=2048, n_pre=0, num_steps=2, scheme="EULER", differentiate=True, second_order=True)),
+    "heston_exposure_greeks_qe": (heston_exposure_greeks, dict(), dict(n_main=2048, n_pre=2048, num_steps=3, scheme="QE", differentiate=True)),
+    "heston_exposure_greeks_euler": (heston_exposure_greeks, dict(), dict(n_main=2048, n_pre=2048, num_steps=3, scheme="EULER", differentiate=True)),
     "bs_split_book_greeks": (bs_split_book_greeks, dict(), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),
     "bs_eepe_greeks": (bs_eepe_greeks, dict(), dict(n_main=4096, n_pre=1000, num_steps=1, scheme="ANALYTICAL", differentiate=True)),
     "bs_proxy_greeks_mixed": (bs_eepe_greeks, dict(book="mixed"), dict(n_main=2048, n_pre=2048, num_steps=2, scheme="EULER", differentiate=True)),

@@ -166,11 +166,10 @@ def test_unsupported_combinations_raise_instead_of_falling_back():
         with pytest.raises(NotImplementedError):
             hybrid(differentiate, scheme).run_simulation()
 
-    # sensitivities of exposure profiles of equity books: Black-Scholes only, no exercise products
-    heston = ns.HestonModel(0.0, 100.0, 0.03, 0.4, -0.7, 2.0, 0.04, 0.04)
-    opt = ns.EuropeanOption(ns.Equity(), 1.0, 100.0, ns.OptionType.CALL)
-    sc = ns.SimulationController([ns.NettingSet(name="h", products=[opt])], heston,
-                                 ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), 64, 64, 2, S.QE, True)
+    # sensitivities of exposure profiles of equity books: Black-Scholes and Heston, not the Schwartz two-factor model
+    builder, kwargs, _ = cases.GOLDEN_CASES["schwartz_euler"]
+    model, sets, _, _ = builder(ns, **kwargs)
+    sc = ns.SimulationController(sets, model, ns.RiskMetrics([ns.EPEMetric()], exposure_timeline=tl), 64, 64, 2, S.EULER, True)
     with pytest.raises(NotImplementedError):
         sc.run_simulation()
 

@@ -489,3 +489,32 @@ def test_exposure_sensitivities_of_a_book_split_over_launches():
         helpers.assert_close(flat[key][0], np.array(vb), 1e-9, 1e-9, f"{name} {key}")
     helpers.assert_gradients(res, gold["derivatives"], gold["params"], gold["sets"], gold["metrics"],
                              lambda m: 1e-8 if m.startswith("pv") else 2e-5, name)
+
+
+@pytest.mark.parametrize("name", ["heston_exposure_greeks_qe", "heston_exposure_greeks_euler"])
+def test_exposure_sensitivities_under_heston_match_reference_autograd(name):
+    """EEPE / EPE / ENE / PV gradients w.r.t. the seven Heston parameters through the regression proxy (tangent
+    pre-simulation + differentiated normal equations, csrc/equity.cu exposure tangents on the Heston build): thresholded
+    and MPoR-collateralised sets, QE and Euler, against the reference's autograd with its draws injected and against the
+    oracle's duals under native Philox."""
+    gold = helpers.load_golden(name)
+    res, sc = helpers.run_cuda(name, draws="torch")
+    flat = helpers.flatten_results(res)
+    for key, vb in gold["values"].items():
+        helpers.assert_close(flat[key][0], np.array(vb), 1e-9, 1e-9, f"{name} {key}")
+    # (the reference regresses in float32: 2e-5 for the Black-Scholes books; the QE scheme's fuzzy branch weights
+    # amplify that noise a little - the worst entry here differs by 2.1e-5 of its row's scale)
+    helpers.assert_gradients(res, gold["derivatives"], gold["params"], gold["sets"], gold["metrics"],
+                             lambda m: 1e-8 if m.startswith("pv") else 5e-5, name)
+    res, _ = helpers.run_cuda(name, draws="philox")
+    out, _ = helpers.run_oracle(name, draws="philox")
+    # (parameters outside the reference's graph - rho under EULER - are None in the golden and here, 0.0 in the oracle)
+    like = {}
+    for si, s_ in enumerate(gold["sets"]):
+        for mi, m in enumerate(gold["metrics"]):
+            rows = []
+            for ev, g in enumerate(out["grads"][si][mi]):
+                ref_row = gold["derivatives"][f"{s_}|{m}"][ev]
+                rows.append(None if g is None else [None if r is None else float(x) for x, r in zip(g, ref_row)])
+            like[f"{s_}|{m}"] = rows
+    helpers.assert_gradients(res, like, gold["params"], gold["sets"], gold["metrics"], lambda m: 1e-6, name + " philox")
