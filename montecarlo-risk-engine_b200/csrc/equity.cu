@@ -164,9 +164,11 @@ __device__ __forceinline__ Dual<N> dual_ncdf(const Dual<N> &x) {
 // Sensitivities of exposure profiles (controller.py:609-627 on EPE / ENE / CE / EEPE): Black-Scholes builds with
 // tangents carry the exposures as duals (lane-local tangents like the cashflows); other models keep doubles.
 // (NT = 9: the second-order build, Dual2<3> - present values only)
-// Heston builds too (every exposure a regression proxy on the spot; the analytic branch is Black-Scholes only).
-template <int KIND, int NT> struct EqExpoTan {
-  static const bool on = (KIND == MCRE_EQ_BS || KIND == MCRE_EQ_HESTON) && (NT > 0) && (NT != 9);
+// Heston builds with XH (plans with exposure dates: every exposure a regression proxy on the spot; the analytic branch is
+// Black-Scholes only).  Heston plans without exposure dates keep the lean build: exposures as duals cost the 35-Greek
+// run of BASELINE config 5 45 % when they rode along unused.
+template <int KIND, int NT, bool XH> struct EqExpoTan {
+  static const bool on = (KIND == MCRE_EQ_BS && NT > 0 && NT != 9) || (KIND == MCRE_EQ_HESTON && NT > 0 && XH);
 };
 static inline bool eq_kind_has_exposure_tangents(int kind) { return kind == MCRE_EQ_BS || kind == MCRE_EQ_HESTON; }
 template <bool ON, typename R> struct EqExpoReal { typedef double type; };
@@ -176,7 +178,7 @@ template <typename R> struct EqExpoReal<true, R> { typedef R type; };
 //              [A][NS][NT] lane-local tangents of sum_p payoff_p * invN_p             then
 //              [n_metric][NS][4] exposure sums                                          then (exposure tangents on)
 //              [n_metric][A][NS][2][NT] lane-local tangents of sum relu(E), sum -relu(-E)
-template <int KIND, int ALT, int NT, int NS>
+template <int KIND, int ALT, int NT, int NS, bool XH = false>
 __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P, RngDev rng, ShardDev sh, double *partial,
                                                       double *shift, double *spill, int pilot) {
   typedef typename RealOf<NT>::type R;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(128, (NT == 0 ? 4 : 2)) eq_main_kernel(EqDev P
   constexpr int NVH = NS * 3;
   constexpr int NVT = NS * (NT > 0 ? NT : 1);
   constexpr int NVX = NS * 4;                 // exposure values per metric date
-  constexpr bool XT = EqExpoTan<KIND, NT>::on;
+  constexpr bool XT = EqExpoTan<KIND, NT, XH>::on;
   typedef typename EqExpoReal<XT, R>::type XR;
   constexpr int NVXT = XT ? NS * 2 * NT : 1;  // exposure tangents per (metric date, asset)
   constexpr int NVMAX0 = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
@@ -1032,19 +1034,19 @@ static int eq_ns_template(int n_sets) { return n_sets <= 1 ? 1 : (n_sets <= 2 ? 
 
 extern "C" int64_t mcre_eq_slots(const mcre_eq_plan *p) {
   const int ns = eq_ns_template(p->d.n_sets);
-  const bool xt = eq_kind_has_exposure_tangents(p->d.kind) && p->nt > 0 && p->nt != 9;
+  const bool xt = p->nt > 0 && ((p->d.kind == MCRE_EQ_BS && p->nt != 9) || (p->d.kind == MCRE_EQ_HESTON && p->d.n_expo > 0));
   return (int64_t)ns * 3 + (int64_t)p->d.n_assets * ns * p->nt + (int64_t)p->d.n_metric * ns * 4 +
          (xt ? (int64_t)p->d.n_metric * p->d.n_assets * ns * 2 * p->nt : 0) + (p->d.has_cir ? ns * 2 : 0);
 }
 
-template <int KIND, int ALT, int NT, int NS>
+template <int KIND, int ALT, int NT, int NS, bool XH = false>
 static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, double *partial, double *shift,
                      double *spill, cudaStream_t st) {
   const EqDev &d = p->d;
   const bool presim = d.ps_x != nullptr;
   const int threads = 128, nw = threads / 32;
   constexpr int NVH = NS * 3, NVT = NS * (NT > 0 ? NT : 1), NVX = NS * 4;
-  constexpr bool XT = EqExpoTan<KIND, NT>::on;
+  constexpr bool XT = EqExpoTan<KIND, NT, XH>::on;
   constexpr int NVXT = XT ? NS * 2 * NT : 1;
   constexpr int NVMAX0 = (NVH > NVT ? NVH : NVT) > NVX ? (NVH > NVT ? NVH : NVT) : NVX;
   constexpr int NVMAX = NVMAX0 > NVXT ? NVMAX0 : NVXT;
@@ -1053,7 +1055,7 @@ static int eq_launch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, dou
   const size_t smem = ((size_t)n_slots + 2 * nw * NVMAX) * sizeof(double);
   const long long n_chunks = (sh.n_paths + sh.chunk - 1) / sh.chunk;
   if (n_chunks == 0 && presim) return 0;
-  auto k = eq_main_kernel<KIND, ALT, NT, NS>;
+  auto k = eq_main_kernel<KIND, ALT, NT, NS, XH>;
   // (14 KB of static function tables: static + dynamic shared memory beyond 48 KB needs the opt-in, before the query)
   if (smem > 32 * 1024) MCRE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -1088,6 +1090,11 @@ static int eq_dispatch(mcre_eq_plan *p, const RngDev &rng, const ShardDev &sh, d
     if (p->nt == 9)
       return ns == 1 ? eq_launch<KIND, ALT, 9, 1>(p, rng, sh, partial, shift, spill, st)
                      : eq_launch<KIND, ALT, 9, 2>(p, rng, sh, partial, shift, spill, st);
+  }
+  if constexpr (KIND == MCRE_EQ_HESTON) {
+    if (p->d.n_expo > 0)     // exposures as duals (sensitivities of exposure metrics through the regression proxy)
+      return ns == 1 ? eq_launch<KIND, ALT, NTK, 1, true>(p, rng, sh, partial, shift, spill, st)
+                     : eq_launch<KIND, ALT, NTK, 2, true>(p, rng, sh, partial, shift, spill, st);
   }
   return ns == 1 ? eq_launch<KIND, ALT, NTK, 1>(p, rng, sh, partial, shift, spill, st)
                  : eq_launch<KIND, ALT, NTK, 2>(p, rng, sh, partial, shift, spill, st);
